@@ -1,0 +1,199 @@
+/* spliser_b200.h -- C ABI of libspliser_b200.so
+ *
+ * Drop-in boundary for the counting path of SpliSER v0.1.8 (`process`, and the re-count that
+ * `combine` performs for sites missing from a sample).  The reference has no FFI of its own;
+ * this seam replaces, inside /root/reference/SpliSER_v0_1_8.py ("S:"):
+ *
+ *   spl_process*   <- S:710-717  findAlphaCounts (S:227-362, after the BED text filters of
+ *                     S:255-288), findCompetitorPos (S:364-372), processSites (S:681-692) with
+ *                     checkBam (S:408-559), findBeta2Counts (S:581-623), calculateSSE (S:626-639)
+ *   spl_recount*   <- S:903 (and S:1145)  checkBam for a (site, sample) gap in combine mode
+ *
+ * Plain pointers and sizes only; no torch / C++ types.  All functions return 0 on success or a
+ * negative spl_status; the message is available from spl_last_error().  Nothing here ever calls
+ * exit() or throws across the boundary.  A context is not thread-safe: one call at a time per
+ * spl_ctx (the reference is single-threaded with module-global state, S:23-47); different
+ * contexts may be used concurrently.  There is NO CPU fallback: every entry point that counts
+ * fails with SPL_ERR_CUDA when no sm_100 device is usable.
+ *
+ * Conventions
+ *   positions   1-based int32, the reference's site convention (S:274-276, S:482-483)
+ *   strands     one raw byte per junction/site: the first byte of BED column 6 ('+', '-', '?', ...);
+ *               0 means the empty strand '' of combine's makeSingleSpliceSite (S:855)
+ *   chromosomes int32 index into the caller's chrom_index order (S:23, S:90, S:265)
+ *   counts      int64 at the ABI (device counters are u32 per launch, widened on the device)
+ *   ownership   inputs are borrowed for the duration of the call; spl_result is library-owned
+ *               until spl_result_free; spl_recount* outputs are caller-allocated
+ */
+#ifndef SPLISER_B200_H
+#define SPLISER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spl_ctx spl_ctx;
+typedef struct spl_result spl_result;
+
+typedef enum spl_status {
+    SPL_OK = 0,
+    SPL_ERR_ARG = -1,      /* bad argument (null pointer, negative size, unsorted input ...) */
+    SPL_ERR_CUDA = -2,     /* CUDA runtime / no usable device / kernel failure */
+    SPL_ERR_IO = -3,       /* BAM file cannot be opened / is truncated / is not BGZF-BAM */
+    SPL_ERR_NOMEM = -4,
+    SPL_ERR_RANGE = -5     /* input exceeds a 32-bit device index (e.g. > 2^32 CIGAR ops per call) */
+} spl_status;
+
+/* flags for spl_process* / spl_recount* (S:1314-1316; COMBINE mirrors sys.argv[1] at S:531) */
+#define SPL_FLAG_STRANDED 1u   /* --isStranded */
+#define SPL_FLAG_RF       2u   /* -s rf (else fr); only read when STRANDED */
+#define SPL_FLAG_CRYPTIC  4u   /* --beta2Cryptic: SSE includes beta2Cryptic_weighted (S:633-635) */
+#define SPL_FLAG_COMBINE  8u   /* checkBam runs under `combine`: flanking reads add beta2Simple (S:531-532) */
+
+/* ---- context ------------------------------------------------------------------------------- */
+/* device_ids: CUDA ordinals this context drives (one process per GPU: pass exactly one).
+ * tile_index / tile_count (spl_set_tile) select the genomic tile this context owns when a job
+ * is sharded over several processes: the context then counts only sites whose global index
+ * (reference list order) falls in its tile and zero-fills the rest. */
+int  spl_create(spl_ctx** out, const int* device_ids, int n_devices);
+void spl_destroy(spl_ctx* ctx);
+const char* spl_last_error(const spl_ctx* ctx);   /* NUL-terminated, valid until next call on ctx */
+int  spl_set_tile(spl_ctx* ctx, int tile_index, int tile_count);
+int  spl_set_threads(spl_ctx* ctx, int n_host_threads);   /* BGZF inflate / record parse workers */
+const char* spl_version(void);
+
+/* ---- process (S:710-717) ------------------------------------------------------------------- */
+/* Junction table = BED12 lines in file order AFTER the 12-column / -c / -g filters (S:259-288):
+ * j_left = int(col1)+blockSizes[0], j_right = int(col2)-blockSizes[1], j_score = int(col4),
+ * j_strand = first byte of col5 (S:272-277).  chrom_names[i] is chrom_index[i]. */
+int spl_process(spl_ctx* ctx, const char* bam_path,
+                int32_t n_chrom, const char* const* chrom_names,
+                int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right,
+                const int64_t* j_score, const uint8_t* j_strand,
+                uint32_t flags, spl_result** out);
+
+/* Same, with the alignment records already decoded into host arrays (what `samtools view`
+ * would print, S:429-437: FLAG, POS, CIGAR).  Records are grouped in segments of one chromosome
+ * each (a coordinate-sorted BAM has one segment per reference); coordinate-sorted input is
+ * fastest, but any record order inside a segment gives the same counts. */
+typedef struct spl_records_view {
+    int64_t n_rec;
+    int64_t n_cigar;              /* == cig_off[n_rec]; must be < 2^32 */
+    const int32_t*  pos;          /* [n_rec]   1-based leftmost position (SAM POS) */
+    const uint16_t* flag;         /* [n_rec]   SAM FLAG */
+    const uint32_t* cig_off;      /* [n_rec+1] offsets into cigar[] */
+    const uint32_t* cigar;        /* [n_cigar] BAM-encoded: len<<4 | op, op indexes "MIDNSHP=X" */
+    int32_t n_seg;
+    const int32_t*  seg_chrom;    /* [n_seg]   chrom_index of the segment; < 0 = not a known chromosome (skipped) */
+    const int64_t*  seg_off;      /* [n_seg+1] records [seg_off[k], seg_off[k+1]) form segment k */
+} spl_records_view;
+
+int spl_process_records(spl_ctx* ctx, const spl_records_view* rec,
+                        int32_t n_chrom,
+                        int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right,
+                        const int64_t* j_score, const uint8_t* j_strand,
+                        uint32_t flags, spl_result** out);
+
+/* ---- combine re-count (S:899-904) ---------------------------------------------------------- */
+/* One call per sample.  For gap site i: position s_pos[i] on chromosome s_chrom[i] with strand
+ * byte s_strand[i] (0 = ''), partner positions p_pos[p_off[i] .. p_off[i+1]) (keys of
+ * PartnerCounts, S:417-419) and competitor positions c_pos[c_off[i] .. c_off[i+1]).
+ * SPL_FLAG_COMBINE is implied.  Writes beta1_out[i], beta2simple_out[i]. */
+int spl_recount(spl_ctx* ctx, const char* bam_path, int32_t n_chrom, const char* const* chrom_names,
+                int64_t n_sites, const int32_t* s_chrom, const int32_t* s_pos, const uint8_t* s_strand,
+                const int64_t* p_off, const int32_t* p_pos, const int64_t* c_off, const int32_t* c_pos,
+                uint32_t flags, int64_t* beta1_out, int64_t* beta2simple_out);
+int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec,
+                        int32_t n_chrom,
+                        int64_t n_sites, const int32_t* s_chrom, const int32_t* s_pos, const uint8_t* s_strand,
+                        const int64_t* p_off, const int32_t* p_pos, const int64_t* c_off, const int32_t* c_pos,
+                        uint32_t flags, int64_t* beta1_out, int64_t* beta2simple_out);
+
+/* ---- result accessors ---------------------------------------------------------------------- */
+/* Sites are in the reference's output order: chrom_index order, then the per-chromosome list
+ * order of site2D_array (position ascending; '+' before '-' in a stranded run, G:123-136). */
+int64_t        spl_result_n_sites(const spl_result* r);
+const int32_t* spl_result_chrom(const spl_result* r);
+const int32_t* spl_result_pos(const spl_result* r);
+const uint8_t* spl_result_strand(const spl_result* r);
+const int64_t* spl_result_alpha(const spl_result* r);
+const int64_t* spl_result_beta1(const spl_result* r);
+const int64_t* spl_result_beta2simple(const spl_result* r);
+const int64_t* spl_result_beta2cryptic(const spl_result* r);
+const double*  spl_result_beta2weighted(const spl_result* r);
+const double*  spl_result_sse(const spl_result* r);
+/* index of the BED line (into the junction table passed in) that created each site: the caller
+ * assigns the Gene column with that line's strand (S:313) */
+const int64_t* spl_result_first_line(const spl_result* r);
+/* PartnerCounts in insertion order (TSV "Partners" column, S:662) and sorted CompetitorPos
+ * (TSV "Competitors" column, S:663) as CSR over sites */
+const int64_t* spl_result_partner_off(const spl_result* r);
+const int32_t* spl_result_partner_pos(const spl_result* r);
+const int64_t* spl_result_partner_cnt(const spl_result* r);
+const int64_t* spl_result_comp_off(const spl_result* r);
+const int32_t* spl_result_comp_pos(const spl_result* r);
+void spl_result_free(spl_result* r);
+
+/* ---- resident (benchmark) path -------------------------------------------------------------
+ * Roofline measurements need the read SoA already in HBM when the timed region starts:
+ *   spl_resident_load   uploads records + junction table, builds the site graph and expands
+ *                       the records into the structure-of-arrays the counting kernels stream
+ *   spl_resident_count  runs the counting kernels (alpha reduce, beta1 stabbing, spliced-read
+ *                       corrections, beta2 gather, SSE) `iters` times on the context's stream,
+ *                       timed with CUDA events on that stream; results stay in HBM
+ *   spl_resident_fetch  copies the last results to the host as an spl_result
+ * stats_out (may be NULL) receives SPL_NSTATS doubles, see SPL_STAT_* below. */
+int spl_resident_load(spl_ctx* ctx, const spl_records_view* rec,
+                      int32_t n_chrom,
+                      int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right,
+                      const int64_t* j_score, const uint8_t* j_strand, uint32_t flags);
+int spl_resident_count(spl_ctx* ctx, int iters, double* stats_out);
+int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
+
+#define SPL_STAT_MS_TOTAL      0   /* CUDA-event ms for all `iters` passes                      */
+#define SPL_STAT_MS_BETA1      1   /* summed ms of the beta1 stabbing kernel                    */
+#define SPL_STAT_MS_SPLICED    2   /* summed ms of the spliced-read kernel                      */
+#define SPL_STAT_MS_FINAL      3   /* summed ms of alpha reduce + scan + beta2 gather + SSE     */
+#define SPL_STAT_N_MBLOCKS_A   4   /* M/=/X blocks of unspliced reads                           */
+#define SPL_STAT_N_MBLOCKS_B   5   /* M/=/X blocks of spliced reads                             */
+#define SPL_STAT_N_JUNC_OPS    6   /* N operators                                               */
+#define SPL_STAT_N_SPLICED     7   /* reads with >= 1 N operator                                */
+#define SPL_STAT_N_SITES       8
+#define SPL_STAT_N_EDGES       9   /* directed site->partner entries                            */
+#define SPL_STAT_N_ALIGNED    10   /* records with >= 1 CIGAR op ("aligned reads")              */
+#define SPL_STAT_LAUNCHES     11   /* kernels launched per pass                                 */
+#define SPL_STAT_MS_EXPAND    12   /* ms of the record -> SoA expansion at load time            */
+#define SPL_NSTATS            16
+
+/* per-call statistics of the last spl_process* / spl_recount* call (same indices; MS_* are
+ * host wall-clock of the stages; extra indices below) */
+#define SPL_STAT_MS_DECODE    13   /* BAM inflate + parse (host wall ms)                        */
+#define SPL_STAT_H2D_BYTES    14
+#define SPL_STAT_D2H_BYTES    15
+int spl_last_stats(const spl_ctx* ctx, double* stats_out);
+
+/* ---- BAM utilities (used by tests / benchmarks to make synthetic inputs) -------------------- */
+/* Writes a coordinate-sorted BAM (BGZF, no index needed by this library) from record arrays;
+ * ref_len may be NULL (lengths written as 2^29).  SEQ/QUAL are omitted ('*'). */
+int spl_write_bam(const char* path, int32_t n_ref, const char* const* ref_names, const int32_t* ref_len,
+                  const spl_records_view* rec /* seg_chrom indexes ref_names */, int n_threads);
+/* Decodes a BAM into library-owned record arrays (host only; no GPU needed).  chrom_names maps
+ * BAM reference names to caller chromosome indices; records on other references are dropped. */
+typedef struct spl_records spl_records;
+int spl_read_bam(const char* path, int32_t n_chrom, const char* const* chrom_names, int n_threads,
+                 spl_records** out, char* err, int err_len);
+const spl_records_view* spl_records_get(const spl_records* r);
+void spl_records_free(spl_records* r);
+
+/* Page-locked host memory for callers that want full-speed host->device copies of their record
+ * arrays (numpy arrays can be built over it).  Needs a CUDA device. */
+void* spl_host_alloc(size_t bytes);
+void  spl_host_free(void* p);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPLISER_B200_H */

@@ -1,0 +1,362 @@
+"""Host-side API over the C ABI: numpy in, numpy out.
+
+The names mirror the reference's stages: `Context.process_*` is the body of `process`
+(SpliSER_v0_1_8.py:710-717: findAlphaCounts -> findCompetitorPos -> processSites) and
+`Context.recount_*` is the `checkBam` call `combine` makes for a site missing from a sample
+(S:899-904).  Everything that counts runs on the GPU behind libspliser_b200.so.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import re
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib as L
+
+FLAG_STRANDED, FLAG_RF, FLAG_CRYPTIC, FLAG_COMBINE = 1, 2, 4, 8
+
+_CIG = re.compile(r"(\d+)([MIDNSHP=X])")
+_OPS = {c: i for i, c in enumerate("MIDNSHP=X")}
+
+
+def mode_flags(is_stranded=False, stranded_type=None, beta2_cryptic=False, combine=False) -> int:
+    """CLI switches (S:1314-1316) -> ABI flags.  Mirrors check_strand's UnboundLocalError (S:378-406)
+    for a stranded run whose type is neither 'fr' nor 'rf'."""
+    f = 0
+    if is_stranded:
+        if stranded_type not in ("fr", "rf"):
+            raise UnboundLocalError("cannot access local variable 'readStrand': strandedType must be 'fr' or 'rf'")
+        f |= FLAG_STRANDED | (FLAG_RF if stranded_type == "rf" else 0)
+    if beta2_cryptic:
+        f |= FLAG_CRYPTIC
+    if combine:
+        f |= FLAG_COMBINE
+    return f
+
+
+def encode_cigar(cigar: str):
+    if cigar == "*" or not cigar:
+        return []
+    return [(int(n) << 4) | _OPS[op] for n, op in _CIG.findall(cigar)]
+
+
+def _ptr(a, ty):
+    return a.ctypes.data_as(ty)
+
+
+@dataclass
+class Junctions:
+    """Junction table in BED-line order after the text filters (S:259-288)."""
+    chrom: np.ndarray
+    left: np.ndarray
+    right: np.ndarray
+    score: np.ndarray
+    strand: np.ndarray
+
+    def __post_init__(self):
+        self.chrom = np.ascontiguousarray(self.chrom, dtype=np.int32)
+        self.left = np.ascontiguousarray(self.left, dtype=np.int32)
+        self.right = np.ascontiguousarray(self.right, dtype=np.int32)
+        self.score = np.ascontiguousarray(self.score, dtype=np.int64)
+        self.strand = np.ascontiguousarray(self.strand, dtype=np.uint8)
+        n = len(self.chrom)
+        if not (len(self.left) == len(self.right) == len(self.score) == len(self.strand) == n):
+            raise ValueError("junction arrays differ in length")
+
+    def __len__(self):
+        return len(self.chrom)
+
+    def args(self):
+        return (C.c_int64(len(self)), _ptr(self.chrom, L.c_i32p), _ptr(self.left, L.c_i32p), _ptr(self.right, L.c_i32p),
+                _ptr(self.score, L.c_i64p), _ptr(self.strand, L.c_u8p))
+
+
+class Records:
+    """Alignment records as flat arrays grouped in chromosome segments (spl_records_view)."""
+
+    def __init__(self, pos, flag, cig_off, cigar, seg_chrom, seg_off, _owner=None):
+        self.pos = np.ascontiguousarray(pos, dtype=np.int32)
+        self.flag = np.ascontiguousarray(flag, dtype=np.uint16)
+        self.cig_off = np.ascontiguousarray(cig_off, dtype=np.uint32)
+        self.cigar = np.ascontiguousarray(cigar, dtype=np.uint32)
+        self.seg_chrom = np.ascontiguousarray(seg_chrom, dtype=np.int32)
+        self.seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+        self._owner = _owner
+        if len(self.cig_off) != len(self.pos) + 1 or len(self.flag) != len(self.pos):
+            raise ValueError("record arrays differ in length")
+        if len(self.seg_off) != len(self.seg_chrom) + 1:
+            raise ValueError("seg_off must have n_seg+1 entries")
+
+    def __len__(self):
+        return len(self.pos)
+
+    def view(self) -> L.RecordsView:
+        v = L.RecordsView()
+        v.n_rec = len(self.pos)
+        v.n_cigar = len(self.cigar)
+        v.pos = _ptr(self.pos, L.c_i32p)
+        v.flag = _ptr(self.flag, L.c_u16p)
+        v.cig_off = _ptr(self.cig_off, L.c_u32p)
+        v.cigar = _ptr(self.cigar, L.c_u32p)
+        v.n_seg = len(self.seg_chrom)
+        v.seg_chrom = _ptr(self.seg_chrom, L.c_i32p)
+        v.seg_off = _ptr(self.seg_off, L.c_i64p)
+        return v
+
+    @classmethod
+    def from_reads(cls, chrom_names, reads):
+        """reads: iterable of (chrom_name, pos1, flag, cigar_string) in file order.  Reads on unknown
+        chromosomes become segments with chromosome -1 (skipped by the library)."""
+        index = {c: i for i, c in enumerate(chrom_names)}
+        pos, flag, off, cig, seg_chrom, seg_off = [], [], [0], [], [], []
+        cur = None
+        for chrom, p, f, cg in reads:
+            ci = index.get(chrom, -1)
+            if ci != cur:
+                seg_chrom.append(ci)
+                seg_off.append(len(pos))
+                cur = ci
+            pos.append(p)
+            flag.append(f)
+            cig.extend(encode_cigar(cg))
+            off.append(len(cig))
+        seg_off.append(len(pos))
+        if not seg_chrom:
+            seg_off = [0]
+        return cls(pos, flag, off, cig, seg_chrom, seg_off)
+
+    @classmethod
+    def from_bam(cls, path, chrom_names, threads=0):
+        lib = L.load()
+        names = (C.c_char_p * max(1, len(chrom_names)))(*[c.encode() for c in chrom_names])
+        h = C.c_void_p()
+        err = C.create_string_buffer(512)
+        rc = lib.spl_read_bam(str(path).encode(), len(chrom_names), names, threads, C.byref(h), err, 512)
+        if rc != 0:
+            raise IOError("spl_read_bam(%s): %s" % (path, err.value.decode()))
+        try:
+            v = lib.spl_records_get(h).contents
+            n, nc, ns = v.n_rec, v.n_cigar, v.n_seg
+
+            def arr(p, cnt, dt):
+                return np.ctypeslib.as_array(p, shape=(cnt,)).astype(dt, copy=True) if cnt else np.zeros(0, dt)
+            out = cls(arr(v.pos, n, np.int32), arr(v.flag, n, np.uint16),
+                      np.ctypeslib.as_array(v.cig_off, shape=(n + 1,)).astype(np.uint32, copy=True),
+                      arr(v.cigar, nc, np.uint32), arr(v.seg_chrom, ns, np.int32),
+                      np.ctypeslib.as_array(v.seg_off, shape=(ns + 1,)).astype(np.int64, copy=True))
+        finally:
+            lib.spl_records_free(h)
+        return out
+
+    def write_bam(self, path, ref_names, ref_len=None, threads=0):
+        lib = L.load()
+        names = (C.c_char_p * max(1, len(ref_names)))(*[c.encode() for c in ref_names])
+        rl = None
+        if ref_len is not None:
+            rl = np.ascontiguousarray(ref_len, dtype=np.int32)
+        v = self.view()
+        rc = lib.spl_write_bam(str(path).encode(), len(ref_names), names,
+                               _ptr(rl, L.c_i32p) if rl is not None else None, C.byref(v), threads)
+        if rc != 0:
+            raise IOError("spl_write_bam(%s) failed with %d" % (path, rc))
+
+
+@dataclass
+class SiteTable:
+    """Per-site results in the reference's output order (outputBedFile, S:645-663)."""
+    chrom: np.ndarray
+    pos: np.ndarray
+    strand: np.ndarray       # raw byte
+    alpha: np.ndarray
+    beta1: np.ndarray
+    beta2simple: np.ndarray
+    beta2cryptic: np.ndarray
+    beta2weighted: np.ndarray
+    sse: np.ndarray
+    first_line: np.ndarray
+    partner_off: np.ndarray
+    partner_pos: np.ndarray
+    partner_cnt: np.ndarray
+    comp_off: np.ndarray
+    comp_pos: np.ndarray
+
+    def __len__(self):
+        return len(self.pos)
+
+    def partners(self, i):
+        a, b = self.partner_off[i], self.partner_off[i + 1]
+        return {int(p): int(c) for p, c in zip(self.partner_pos[a:b], self.partner_cnt[a:b])}
+
+    def competitors(self, i):
+        a, b = self.comp_off[i], self.comp_off[i + 1]
+        return [int(c) for c in self.comp_pos[a:b]]
+
+    def strand_str(self, i):
+        b = int(self.strand[i])
+        return chr(b) if b else ""
+
+
+class SpliserError(RuntimeError):
+    pass
+
+
+class Context:
+    """One spl_ctx = one GPU (one process per GPU)."""
+
+    def __init__(self, device=0, tile=None, threads=0):
+        self._lib = L.load()
+        self._h = C.c_void_p()
+        dev = (C.c_int32 * 1)(device)
+        rc = self._lib.spl_create(C.byref(self._h), dev, 1)
+        if rc != 0:
+            msg = self._lib.spl_last_error(self._h).decode() if self._h else "spl_create failed"
+            if self._h:
+                self._lib.spl_destroy(self._h)
+                self._h = C.c_void_p()
+            raise SpliserError("spl_create: %s (code %d)" % (msg, rc))
+        if tile is not None:
+            self._check(self._lib.spl_set_tile(self._h, int(tile[0]), int(tile[1])), "spl_set_tile")
+        if threads:
+            self._lib.spl_set_threads(self._h, int(threads))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.spl_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise SpliserError("%s: %s (code %d)" % (what, self._lib.spl_last_error(self._h).decode(), rc))
+
+    def stats(self):
+        buf = (C.c_double * L.SPL_NSTATS)()
+        self._lib.spl_last_stats(self._h, buf)
+        return dict(zip(L.STAT_NAMES, list(buf)))
+
+    # ---- process -----------------------------------------------------------------------------
+    def _take(self, h) -> SiteTable:
+        lib = self._lib
+        try:
+            n = lib.spl_result_n_sites(h)
+
+            def arr(fn, cnt, dt):
+                if cnt == 0:
+                    return np.zeros(0, dt)
+                return np.ctypeslib.as_array(fn(h), shape=(cnt,)).astype(dt, copy=True)
+            poff = np.ctypeslib.as_array(lib.spl_result_partner_off(h), shape=(n + 1,)).astype(np.int64, copy=True)
+            coff = np.ctypeslib.as_array(lib.spl_result_comp_off(h), shape=(n + 1,)).astype(np.int64, copy=True)
+            ne, nc = int(poff[-1]), int(coff[-1])
+            return SiteTable(
+                chrom=arr(lib.spl_result_chrom, n, np.int32), pos=arr(lib.spl_result_pos, n, np.int32),
+                strand=arr(lib.spl_result_strand, n, np.uint8), alpha=arr(lib.spl_result_alpha, n, np.int64),
+                beta1=arr(lib.spl_result_beta1, n, np.int64), beta2simple=arr(lib.spl_result_beta2simple, n, np.int64),
+                beta2cryptic=arr(lib.spl_result_beta2cryptic, n, np.int64),
+                beta2weighted=arr(lib.spl_result_beta2weighted, n, np.float64), sse=arr(lib.spl_result_sse, n, np.float64),
+                first_line=arr(lib.spl_result_first_line, n, np.int64),
+                partner_off=poff, partner_pos=arr(lib.spl_result_partner_pos, ne, np.int32),
+                partner_cnt=arr(lib.spl_result_partner_cnt, ne, np.int64),
+                comp_off=coff, comp_pos=arr(lib.spl_result_comp_pos, nc, np.int32))
+        finally:
+            lib.spl_result_free(h)
+
+    def process_records(self, records: Records, n_chrom: int, junctions: Junctions, flags: int) -> SiteTable:
+        v = records.view()
+        h = C.c_void_p()
+        rc = self._lib.spl_process_records(self._h, C.byref(v), n_chrom, *junctions.args(), flags, C.byref(h))
+        self._check(rc, "spl_process_records")
+        return self._take(h)
+
+    def process_bam(self, bam_path, chrom_names, junctions: Junctions, flags: int) -> SiteTable:
+        names = (C.c_char_p * max(1, len(chrom_names)))(*[c.encode() for c in chrom_names])
+        h = C.c_void_p()
+        rc = self._lib.spl_process(self._h, str(bam_path).encode(), len(chrom_names), names, *junctions.args(), flags, C.byref(h))
+        self._check(rc, "spl_process")
+        return self._take(h)
+
+    # ---- combine re-count ----------------------------------------------------------------------
+    @staticmethod
+    def _gap_args(gaps):
+        """gaps: list of (chrom_idx, pos, strand_str, partner_positions, competitor_positions)."""
+        n = len(gaps)
+        s_chrom = np.array([g[0] for g in gaps], dtype=np.int32)
+        s_pos = np.array([g[1] for g in gaps], dtype=np.int32)
+        s_strand = np.array([(ord(g[2][0]) if g[2] else 0) for g in gaps], dtype=np.uint8)
+        p_off = np.zeros(n + 1, dtype=np.int64)
+        c_off = np.zeros(n + 1, dtype=np.int64)
+        pp, cp = [], []
+        for i, g in enumerate(gaps):
+            pp.extend(g[3])
+            cp.extend(g[4])
+            p_off[i + 1] = len(pp)
+            c_off[i + 1] = len(cp)
+        p_pos = np.array(pp, dtype=np.int32)
+        c_pos = np.array(cp, dtype=np.int32)
+        keep = (s_chrom, s_pos, s_strand, p_off, p_pos, c_off, c_pos)
+        args = (C.c_int64(n), _ptr(s_chrom, L.c_i32p), _ptr(s_pos, L.c_i32p), _ptr(s_strand, L.c_u8p),
+                _ptr(p_off, L.c_i64p), _ptr(p_pos, L.c_i32p), _ptr(c_off, L.c_i64p), _ptr(c_pos, L.c_i32p))
+        return keep, args
+
+    def recount_records(self, records: Records, n_chrom: int, gaps, flags: int):
+        keep, args = self._gap_args(gaps)
+        b1 = np.zeros(len(gaps), dtype=np.int64)
+        b2 = np.zeros(len(gaps), dtype=np.int64)
+        v = records.view()
+        rc = self._lib.spl_recount_records(self._h, C.byref(v), n_chrom, *args, flags, _ptr(b1, L.c_i64p), _ptr(b2, L.c_i64p))
+        self._check(rc, "spl_recount_records")
+        return b1, b2
+
+    def recount_bam(self, bam_path, chrom_names, gaps, flags: int):
+        keep, args = self._gap_args(gaps)
+        b1 = np.zeros(len(gaps), dtype=np.int64)
+        b2 = np.zeros(len(gaps), dtype=np.int64)
+        names = (C.c_char_p * max(1, len(chrom_names)))(*[c.encode() for c in chrom_names])
+        rc = self._lib.spl_recount(self._h, str(bam_path).encode(), len(chrom_names), names, *args, flags,
+                                   _ptr(b1, L.c_i64p), _ptr(b2, L.c_i64p))
+        self._check(rc, "spl_recount")
+        return b1, b2
+
+    # ---- resident (benchmark) path -------------------------------------------------------------
+    def resident_load(self, records: Records, n_chrom: int, junctions: Junctions, flags: int):
+        v = records.view()
+        self._check(self._lib.spl_resident_load(self._h, C.byref(v), n_chrom, *junctions.args(), flags), "spl_resident_load")
+
+    def resident_count(self, iters=1):
+        buf = (C.c_double * L.SPL_NSTATS)()
+        self._check(self._lib.spl_resident_count(self._h, iters, buf), "spl_resident_count")
+        return dict(zip(L.STAT_NAMES, list(buf)))
+
+    def resident_fetch(self) -> SiteTable:
+        h = C.c_void_p()
+        self._check(self._lib.spl_resident_fetch(self._h, C.byref(h)), "spl_resident_fetch")
+        return self._take(h)
+
+
+def pinned_empty(n, dtype):
+    """numpy array over page-locked memory from spl_host_alloc (full-speed host->device copies)."""
+    lib = L.load()
+    dt = np.dtype(dtype)
+    nbytes = max(1, int(n) * dt.itemsize)
+    p = lib.spl_host_alloc(nbytes)
+    if not p:
+        raise SpliserError("spl_host_alloc(%d) failed (no CUDA device?)" % nbytes)
+    buf = (C.c_uint8 * nbytes).from_address(p)
+    a = np.frombuffer(buf, dtype=dt, count=int(n))
+    _PINNED[id(buf)] = (buf, p)
+    return a
+
+
+_PINNED = {}

@@ -1,0 +1,96 @@
+// Device-side data layout shared by kernels.cu and pipeline.cu.  See DESIGN.md "Data layout in HBM".
+#pragma once
+#include <cstdint>
+
+namespace spl {
+
+// One work tile = up to CHUNK_READS consecutive records of one chromosome.  The expansion kernels
+// fill the bases/counts; the hint kernel fills the site windows.  K3 streams the chunk's A blocks,
+// K4 its spliced reads.
+struct Chunk {
+    int32_t  chrom;
+    uint32_t rec_lo, rec_hi;            // [rec_lo, rec_hi) records (host-filled)
+    uint32_t a_cnt, b_cnt, s_cnt, j_cnt;     // totals (expand pass 1)
+    uint32_t a_base, b_base, s_base, j_base; // exclusive scan of the totals
+    int32_t  a_lo, a_hi;                // min block start / max (block end - 2) over A blocks (empty: lo > hi)
+    int32_t  s_lo, s_hi;                // min / max position any lookup of the chunk's spliced reads can ask for
+    int32_t  a_site_lo, a_site_n;       // global site index range with a_lo <= pos <= a_hi
+    int32_t  s_site_lo, s_site_n;       // global site index range with s_lo <= pos <= s_hi
+};
+
+struct DevGraph {
+    int32_t n_chrom, n_sites, n_edges;
+    int32_t own_lo, own_hi;             // site index range this context owns (tile sharding)
+    const int32_t* cs_off;              // [n_chrom+1]
+    const int32_t* site_pos;            // [n_sites + 8], tail padded with INT32_MAX
+    const uint8_t* site_cls;            // [n_sites]
+    const int32_t *pt_off, *pt_site;    // Partners (site indices)
+    const int32_t *pc_off, *pc_pos;     // PartnerCounts keys
+    const int32_t *cp_off, *cp_pos;     // CompetitorPos (sorted)
+    const int32_t *rp_off, *rp_site;    // reverse partner index, anchored at first site of a position
+    const int32_t *inc_off, *inc_line;  // alpha reduction segments
+    const int32_t *einc_off, *einc_line;// PartnerCounts reduction segments
+    const int64_t* j_score;             // junction scores (device copy)
+};
+
+struct DevRecords {
+    uint32_t n_rec;
+    const int32_t*  pos;                // 1-based
+    const uint16_t* flag;
+    const uint32_t* cig_off;            // [n_rec+1]
+    const uint32_t* cigar;              // BAM-encoded ops
+};
+
+// Structure-of-arrays the counting kernels stream.
+struct DevSoA {
+    uint32_t nA, nB, nS, nJ;
+    int32_t* a_start; int32_t* a_end; uint8_t* a_cls;   // M/=/X blocks of unspliced reads, [start, end)
+    int32_t* b_start; int32_t* b_end;                   // blocks of spliced reads, contiguous per read
+    uint32_t* sr_boff; uint32_t* sr_joff;               // [nS+1] per spliced read
+    uint8_t* sr_cls;                                    // bit0 strand class, bit1 first advancing op is N
+    int32_t* jn_l; int32_t* jn_r;                       // junctions: last base before N, last base of N
+};
+
+// Per-pass counters, one contiguous u32 buffer (zeroed by one memset per pass).
+struct DevCounters {
+    uint32_t* cov;     // [2][S]   reads whose block covers site and site+1, by read strand class
+    uint32_t* span;    // [2][S+1] difference array: reads whose N strictly spans the site
+    uint32_t* covx;    // [S] covering reads that are beta1-type (moved from beta1 to beta2Simple)
+    uint32_t* spanx;   // [S] spanning reads that are flanking (removed from the mutually-exclusive count)
+    uint32_t* flank;   // [S] flanking reads (counted as beta2Simple in combine mode only)
+    uint32_t* dc;      // [E] PartnerBeta2DoubleCounts increments seen in the BAM
+};
+
+struct DevOutputs {
+    int64_t* alpha; int64_t* pc_cnt;    // [S], [E]
+    int64_t* beta1; int64_t* beta2s; int64_t* beta2c;
+    double* beta2w; double* sse;
+    int64_t* dc_tot; uint8_t* dc_present;   // [E] scratch of the beta2 gather
+    uint32_t* span_blk;                 // block sums for the span scan
+};
+
+constexpr int CHUNK_READS = 2048;       // records per chunk
+constexpr int EXPAND_THREADS = 512;     // 4 records per thread
+constexpr int K3_THREADS = 256;
+constexpr int K3_MAX_STAGED = 2048;     // site positions staged in shared memory per tile (8 KB)
+constexpr int K4_THREADS = 128;
+constexpr int K4_MAX_STAGED = 4096;
+constexpr int FIN_THREADS = 256;
+constexpr int FIN_ITEMS = 4;            // sites per thread in the span scan
+
+constexpr uint32_t FLAG_STRANDED = 1u, FLAG_RF = 2u, FLAG_CRYPTIC = 4u, FLAG_COMBINE = 8u;
+
+struct KernelTimes { float beta1_ms, spliced_ms, final_ms; };
+
+// launchers (kernels.cu); all asynchronous on `stream`
+void launch_expand_count(const DevRecords& rec, Chunk* chunks, int n_chunks, uint32_t flags, void* stream);
+void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals4, void* stream);
+void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream);
+void launch_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g, void* stream);
+void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream);
+void launch_beta1(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, void* stream);
+void launch_spliced(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t flags, void* stream);
+void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream);
+int  kernel_launch_count_per_pass();
+
+}  // namespace spl

@@ -1,0 +1,793 @@
+// Hand-written sm_100a kernels for the SpliSER counting path.
+//
+//   K0  expand_count / chunk_scan / expand_scatter / chunk_hints : BAM-style records -> SoA
+//   K1  alpha_reduce   : junction scores -> alpha[site], PartnerCounts[edge]   (SpliSER_v0_1_8.py:341,:353-355)
+//   K3  beta1_stab     : M-block vs site stabbing count                        (S:454-477)
+//   K4  spliced        : N-span range adds + compSplicing exceptions           (S:480-557)
+//   K5  span_blocksum / span_scan / finalize : prefix scan, beta2 gather (S:581-623), SSE (S:626-639)
+//
+// Nothing here is a dense contraction, so no tensor-core path: the kernels are HBM streaming
+// (K3) or L2/latency bound graph lookups (K4, K5).  Site tiles are staged into shared memory with
+// a 1-D TMA bulk copy (cp.async.bulk + mbarrier), blocks are loaded 128 bits at a time, matches
+// are aggregated per warp with redux.sync before a single RED per (warp, site).
+#include <cuda_runtime.h>
+#include <climits>
+#include <cstdint>
+
+#include "device_types.h"
+
+namespace spl {
+
+// ------------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ int4 ldg_stream(const int4* p) {   // streaming 128-bit load, no L1 allocation
+    int4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+
+// first index in [lo, hi) with a[idx] >= key
+__device__ __forceinline__ int lower_bound_i32(const int32_t* a, int lo, int hi, int32_t key) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// first index in [lo, hi) with a[idx] > key
+__device__ __forceinline__ int upper_bound_i32(const int32_t* a, int lo, int hi, int32_t key) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] <= key) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// strand class bit of a read: 0 = '+', 1 = '-' under check_strand (S:374-406); always 0 when unstranded
+__device__ __forceinline__ uint32_t read_class(uint32_t flag, uint32_t mode) {
+    if (!(mode & FLAG_STRANDED)) return 0u;
+    const bool first = (flag & 64u) || !(flag & 1u);
+    const bool rev = (flag & 16u) != 0;
+    bool plus = first != rev;               // fr
+    if (mode & FLAG_RF) plus = !plus;
+    return plus ? 0u : 1u;
+}
+
+// does a read of class k match a site of class c?  (CLS_ANY matches class 0 only because every
+// read of an unstranded run is class 0)
+__device__ __forceinline__ bool strand_ok(uint32_t site_cls, uint32_t k) {
+    return (site_cls == 0u && k == 0u) || (site_cls == 1u && k == 0u) || (site_cls == 2u && k == 1u);
+}
+
+struct Cnt4 { uint32_t a, b, s, j; };
+
+// ------------------------------------------------------------------------------------------------
+// K0: record expansion
+// ------------------------------------------------------------------------------------------------
+struct ReadShape {
+    uint32_t nM, nN;        // mapped (M,=,X) ops and N ops
+    int32_t  lo, hi;        // min block start, max (block end - 2) over M ops  (lo > hi when none)
+    int32_t  qlo, qhi;      // min / max position a site lookup of this read may ask for
+    bool     first_adv_is_N;
+};
+
+__device__ __forceinline__ ReadShape read_shape(const DevRecords& rec, uint32_t i) {
+    ReadShape s;
+    s.nM = s.nN = 0;
+    s.lo = INT_MAX; s.hi = INT_MIN; s.qlo = INT_MAX; s.qhi = INT_MIN;
+    s.first_adv_is_N = false;
+    int32_t cur = rec.pos[i];
+    bool seen = false;
+    const uint32_t c0 = rec.cig_off[i], c1 = rec.cig_off[i + 1];
+    for (uint32_t k = c0; k < c1; ++k) {
+        const uint32_t v = rec.cigar[k];
+        const uint32_t op = v & 15u;
+        const int32_t len = (int32_t)(v >> 4);
+        if (op == 0u || op == 7u || op == 8u) {           // M = X : mapped + advance (S:457-459)
+            s.nM++;
+            s.lo = min(s.lo, cur);
+            s.hi = max(s.hi, cur + len - 2);
+            s.qlo = min(s.qlo, cur);
+            s.qhi = max(s.qhi, cur + len);
+            cur += len; seen = true;
+        } else if (op == 3u) {                            // N : advance, junction (S:480-483)
+            if (!seen) s.first_adv_is_N = true;
+            s.nN++;
+            s.qlo = min(s.qlo, cur - 1);
+            s.qhi = max(s.qhi, cur + len);
+            cur += len; seen = true;
+        } else if (op == 2u) {                            // D : advance only (S:460-462)
+            cur += len; seen = true;
+        }                                                 // I S H P : no progression (S:463-464)
+    }
+    return s;
+}
+
+// block-wide exclusive scan of four counters (blockDim.x == EXPAND_THREADS); returns the block total
+__device__ __forceinline__ Cnt4 block_exscan4(Cnt4 v, Cnt4& total, Cnt4* warp_tot /* [32] shared */) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    Cnt4 inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, inc.a, d), b = __shfl_up_sync(0xffffffffu, inc.b, d);
+        const uint32_t s = __shfl_up_sync(0xffffffffu, inc.s, d), j = __shfl_up_sync(0xffffffffu, inc.j, d);
+        if (lane >= d) { inc.a += a; inc.b += b; inc.s += s; inc.j += j; }
+    }
+    if (lane == 31) warp_tot[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        const int nw = blockDim.x >> 5;
+        Cnt4 w = lane < nw ? warp_tot[lane] : Cnt4{0, 0, 0, 0};
+        Cnt4 wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, wi.a, d), b = __shfl_up_sync(0xffffffffu, wi.b, d);
+            const uint32_t s = __shfl_up_sync(0xffffffffu, wi.s, d), j = __shfl_up_sync(0xffffffffu, wi.j, d);
+            if (lane >= d) { wi.a += a; wi.b += b; wi.s += s; wi.j += j; }
+        }
+        if (lane < nw) warp_tot[lane] = Cnt4{wi.a - w.a, wi.b - w.b, wi.s - w.s, wi.j - w.j};   // exclusive
+        if (lane == nw - 1) warp_tot[32] = wi;                                                  // total
+    }
+    __syncthreads();
+    const Cnt4 base = warp_tot[warp];
+    total = warp_tot[32];
+    return Cnt4{base.a + inc.a - v.a, base.b + inc.b - v.b, base.s + inc.s - v.s, base.j + inc.j - v.j};
+}
+
+constexpr int RPT = CHUNK_READS / EXPAND_THREADS;   // records per thread, contiguous
+
+__global__ void __launch_bounds__(EXPAND_THREADS) k_expand_count(DevRecords rec, Chunk* chunks, uint32_t mode) {
+    Chunk& ck = chunks[blockIdx.x];
+    const uint32_t r0 = ck.rec_lo + threadIdx.x * RPT;
+    Cnt4 c{0, 0, 0, 0};
+    int32_t alo = INT_MAX, ahi = INT_MIN, slo = INT_MAX, shi = INT_MIN;
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        const uint32_t i = r0 + q;
+        if (i < ck.rec_hi) {
+            const ReadShape s = read_shape(rec, i);
+            if (s.nN == 0) {
+                c.a += s.nM;
+                alo = min(alo, s.lo); ahi = max(ahi, s.hi);
+            } else {
+                c.b += s.nM; c.s += 1; c.j += s.nN;
+                slo = min(slo, s.qlo); shi = max(shi, s.qhi);
+            }
+        }
+    }
+    __shared__ Cnt4 wt[33];
+    __shared__ int32_t red[4][EXPAND_THREADS / 32];
+    Cnt4 total;
+    (void)block_exscan4(c, total, wt);
+    alo = __reduce_min_sync(0xffffffffu, alo); ahi = __reduce_max_sync(0xffffffffu, ahi);
+    slo = __reduce_min_sync(0xffffffffu, slo); shi = __reduce_max_sync(0xffffffffu, shi);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { red[0][warp] = alo; red[1][warp] = ahi; red[2][warp] = slo; red[3][warp] = shi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < EXPAND_THREADS / 32; ++w) {
+            alo = min(alo, red[0][w]); ahi = max(ahi, red[1][w]);
+            slo = min(slo, red[2][w]); shi = max(shi, red[3][w]);
+        }
+        ck.a_cnt = total.a; ck.b_cnt = total.b; ck.s_cnt = total.s; ck.j_cnt = total.j;
+        ck.a_lo = alo; ck.a_hi = ahi; ck.s_lo = slo; ck.s_hi = shi;
+    }
+}
+
+// exclusive scan of the per-chunk totals; single CTA (n_chunks is R / 2048: at most ~1e5)
+__global__ void __launch_bounds__(1024) k_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals4) {
+    __shared__ Cnt4 wt[33];
+    __shared__ Cnt4 carry;
+    if (threadIdx.x == 0) carry = Cnt4{0, 0, 0, 0};
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < n_chunks; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        Cnt4 v{0, 0, 0, 0};
+        if (i < n_chunks) v = Cnt4{chunks[i].a_cnt, chunks[i].b_cnt, chunks[i].s_cnt, chunks[i].j_cnt};
+        Cnt4 inc = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, inc.a, d), b = __shfl_up_sync(0xffffffffu, inc.b, d);
+            const uint32_t s = __shfl_up_sync(0xffffffffu, inc.s, d), j = __shfl_up_sync(0xffffffffu, inc.j, d);
+            if (lane >= d) { inc.a += a; inc.b += b; inc.s += s; inc.j += j; }
+        }
+        if (lane == 31) wt[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            Cnt4 w = wt[lane];
+            Cnt4 wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t a = __shfl_up_sync(0xffffffffu, wi.a, d), b = __shfl_up_sync(0xffffffffu, wi.b, d);
+                const uint32_t s = __shfl_up_sync(0xffffffffu, wi.s, d), j = __shfl_up_sync(0xffffffffu, wi.j, d);
+                if (lane >= d) { wi.a += a; wi.b += b; wi.s += s; wi.j += j; }
+            }
+            wt[lane] = Cnt4{wi.a - w.a, wi.b - w.b, wi.s - w.s, wi.j - w.j};
+            if (lane == 31) wt[32] = wi;
+        }
+        __syncthreads();
+        const Cnt4 c = carry, wb = wt[warp];
+        if (i < n_chunks) {
+            chunks[i].a_base = c.a + wb.a + inc.a - v.a;
+            chunks[i].b_base = c.b + wb.b + inc.b - v.b;
+            chunks[i].s_base = c.s + wb.s + inc.s - v.s;
+            chunks[i].j_base = c.j + wb.j + inc.j - v.j;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const Cnt4 t = wt[32];
+            carry = Cnt4{c.a + t.a, c.b + t.b, c.s + t.s, c.j + t.j};
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        totals4[0] = carry.a; totals4[1] = carry.b; totals4[2] = carry.s; totals4[3] = carry.j;
+    }
+}
+
+__global__ void __launch_bounds__(EXPAND_THREADS)
+k_expand_scatter(DevRecords rec, const Chunk* chunks, DevSoA soa, uint32_t mode) {
+    const Chunk ck = chunks[blockIdx.x];
+    const uint32_t r0 = ck.rec_lo + threadIdx.x * RPT;
+    Cnt4 c{0, 0, 0, 0};
+    uint32_t nM[RPT], nN[RPT];
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        const uint32_t i = r0 + q;
+        nM[q] = nN[q] = 0;
+        if (i < ck.rec_hi) {
+            const uint32_t c0 = rec.cig_off[i], c1 = rec.cig_off[i + 1];
+            for (uint32_t k = c0; k < c1; ++k) {
+                const uint32_t op = rec.cigar[k] & 15u;
+                nM[q] += (op == 0u || op == 7u || op == 8u);
+                nN[q] += (op == 3u);
+            }
+            if (nN[q] == 0) c.a += nM[q]; else { c.b += nM[q]; c.s += 1; c.j += nN[q]; }
+        }
+    }
+    __shared__ Cnt4 wt[33];
+    Cnt4 total;
+    Cnt4 ex = block_exscan4(c, total, wt);
+    uint32_t ia = ck.a_base + ex.a, ib = ck.b_base + ex.b, is = ck.s_base + ex.s, ij = ck.j_base + ex.j;
+#pragma unroll
+    for (int q = 0; q < RPT; ++q) {
+        const uint32_t i = r0 + q;
+        if (i >= ck.rec_hi) break;
+        const uint32_t k = read_class(rec.flag[i], mode);
+        const bool spliced = nN[q] != 0;
+        int32_t cur = rec.pos[i];
+        bool seen = false, firstN = false;
+        if (spliced) { soa.sr_boff[is] = ib; soa.sr_joff[is] = ij; }
+        const uint32_t c0 = rec.cig_off[i], c1 = rec.cig_off[i + 1];
+        for (uint32_t kk = c0; kk < c1; ++kk) {
+            const uint32_t v = rec.cigar[kk];
+            const uint32_t op = v & 15u;
+            const int32_t len = (int32_t)(v >> 4);
+            if (op == 0u || op == 7u || op == 8u) {
+                if (spliced) { soa.b_start[ib] = cur; soa.b_end[ib] = cur + len; ++ib; }
+                else { soa.a_start[ia] = cur; soa.a_end[ia] = cur + len; soa.a_cls[ia] = (uint8_t)k; ++ia; }
+                cur += len; seen = true;
+            } else if (op == 3u) {
+                if (!seen) firstN = true;
+                soa.jn_l[ij] = cur - 1; soa.jn_r[ij] = cur + len - 1; ++ij;     // S:482-483
+                cur += len; seen = true;
+            } else if (op == 2u) {
+                cur += len; seen = true;
+            }
+        }
+        if (spliced) { soa.sr_cls[is] = (uint8_t)(k | (firstN ? 2u : 0u)); ++is; }
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // CSR sentinels
+        soa.sr_boff[ck.s_base + ck.s_cnt] = ck.b_base + ck.b_cnt;
+        soa.sr_joff[ck.s_base + ck.s_cnt] = ck.j_base + ck.j_cnt;
+    }
+}
+
+// per-chunk site windows: global index range of the chromosome's sites inside [lo, hi]
+__global__ void k_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_chunks) return;
+    Chunk& ck = chunks[i];
+    const int c = ck.chrom;
+    const int s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
+    if (ck.a_cnt && ck.a_lo <= ck.a_hi) {
+        const int lo = lower_bound_i32(g.site_pos, s0, s1, ck.a_lo);
+        const int hi = upper_bound_i32(g.site_pos, lo, s1, ck.a_hi);
+        ck.a_site_lo = lo; ck.a_site_n = hi - lo;
+    } else { ck.a_site_lo = s0; ck.a_site_n = 0; }
+    if (ck.s_cnt && ck.s_lo <= ck.s_hi) {
+        const int lo = lower_bound_i32(g.site_pos, s0, s1, ck.s_lo);
+        const int hi = upper_bound_i32(g.site_pos, lo, s1, ck.s_hi);
+        ck.s_site_lo = lo; ck.s_site_n = hi - lo;
+    } else { ck.s_site_lo = s0; ck.s_site_n = 0; }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: alpha and PartnerCounts as segmented reductions of the junction scores
+// ------------------------------------------------------------------------------------------------
+__global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < g.n_sites) {
+        int64_t a = 0;
+        for (int k = g.inc_off[i]; k < g.inc_off[i + 1]; ++k) a += g.j_score[g.inc_line[k]];
+        out.alpha[i] = a;
+    } else if (i < g.n_sites + g.n_edges) {
+        const int e = i - g.n_sites;
+        int64_t a = 0;
+        for (int k = g.einc_off[e]; k < g.einc_off[e + 1]; ++k) a += g.j_score[g.einc_line[k]];
+        out.pc_cnt[e] = a;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: beta1 stabbing count over the A stream (blocks of unspliced reads)
+//
+// One CTA per chunk.  The chunk's site window (positions inside [min block start, max block end-2])
+// is staged into shared memory by one TMA bulk copy while the threads issue their 128-bit block
+// loads.  Each warp narrows the window to [min start, max end-2] of its own 128..256 blocks with two
+// redux.sync and a warp-uniform binary search (broadcast LDS, no bank conflicts); almost always the
+// narrowed range is empty or 1-3 sites, which are then tested against the lane's blocks from
+// registers and summed across the warp with one redux.sync per site -> one RED per (warp, site, class).
+// ------------------------------------------------------------------------------------------------
+constexpr int K3_GROUPS = 2;     // int4 groups (4 blocks each) per thread and pass
+constexpr int K3_DENSE = 48;     // narrowed ranges longer than this use the per-lane search path
+
+__global__ void __launch_bounds__(K3_THREADS)
+k_beta1_stab(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounters cnt) {
+    const Chunk ck = chunks[blockIdx.x];
+    if (ck.a_cnt == 0 || ck.a_site_n == 0) return;     // zone-map prune: no site can be stabbed by this chunk
+    __shared__ __align__(16) int32_t s_sites[K3_MAX_STAGED + 8];
+    __shared__ __align__(8) uint64_t bar;
+
+    const bool staged = ck.a_site_n <= K3_MAX_STAGED;
+    const int al = ck.a_site_lo & ~3;                                  // 16-byte aligned source index
+    const int nst = ((ck.a_site_lo + ck.a_site_n + 3) & ~3) - al;      // entries copied (multiple of 4)
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (staged && threadIdx.x == 0) {
+        mbar_expect_tx(&bar, (uint32_t)nst * 4u);
+        bulk_g2s(s_sites, g.site_pos + al, (uint32_t)nst * 4u, &bar);
+    }
+    // window as a pointer indexed by (global site index - base)
+    const int32_t* sp = staged ? (s_sites - al) : g.site_pos;          // sp[global index]
+    const int w_lo = max(ck.a_site_lo, g.own_lo), w_hi = min(ck.a_site_lo + ck.a_site_n, g.own_hi);
+
+    const uint32_t e0 = ck.a_base, e1 = ck.a_base + ck.a_cnt;
+    const uint32_t g0 = e0 >> 2, g1 = (e1 + 3) >> 2;
+    const int lane = threadIdx.x & 31;
+    bool waited = false;
+    const uint32_t* cls32 = reinterpret_cast<const uint32_t*>(soa.a_cls);
+    for (uint32_t gb = g0 + threadIdx.x; gb - threadIdx.x < g1; gb += K3_THREADS * K3_GROUPS) {
+        int4 st[K3_GROUPS], en[K3_GROUPS];
+        uint32_t cl[K3_GROUPS];
+#pragma unroll
+        for (int u = 0; u < K3_GROUPS; ++u) {
+            const uint32_t gi = gb + u * K3_THREADS;
+            if (gi < g1) {
+                st[u] = ldg_stream(reinterpret_cast<const int4*>(soa.a_start) + gi);
+                en[u] = ldg_stream(reinterpret_cast<const int4*>(soa.a_end) + gi);
+                cl[u] = ldg_stream_u32(cls32 + gi);
+            } else {
+                st[u] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
+                en[u] = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
+                cl[u] = 0;
+            }
+        }
+        // turn [start, end) into the closed stabbing interval [start, end-2]; invalidate foreign elements
+        int lo = INT_MAX, hi = INT_MIN;
+#pragma unroll
+        for (int u = 0; u < K3_GROUPS; ++u) {
+            const uint32_t gi = gb + u * K3_THREADS;
+            int* s = &st[u].x; int* e = &en[u].x;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t idx = gi * 4 + q;
+                const bool valid = gi < g1 && idx >= e0 && idx < e1;
+                const int a = valid ? s[q] : INT_MAX;
+                const int b = valid ? e[q] - 2 : INT_MIN;
+                s[q] = a; e[q] = b;
+                if (a <= b) { lo = min(lo, a); hi = max(hi, b); }
+            }
+        }
+        const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
+        if (wlo > whi) continue;
+        if (staged && !waited) { mbar_wait(&bar, 0); waited = true; }
+        int i0 = lower_bound_i32(sp, w_lo, w_hi, wlo);
+        int i1 = upper_bound_i32(sp, i0, w_hi, whi);
+        if (i0 >= i1) continue;
+        if (i1 - i0 <= K3_DENSE) {
+            for (int s = i0; s < i1; ++s) {                           // warp-uniform loop
+                const int p = sp[s];
+                uint32_t c = 0;
+#pragma unroll
+                for (int u = 0; u < K3_GROUPS; ++u) {
+                    const int* a = &st[u].x; const int* b = &en[u].x;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const bool hit = a[q] <= p && p <= b[q];
+                        const uint32_t k = (cl[u] >> (8 * q)) & 1u;
+                        c += hit ? (k ? 0x10000u : 1u) : 0u;
+                    }
+                }
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (lane == 0 && c) {
+                    if (c & 0xffffu) atomicAdd(cnt.cov + s, c & 0xffffu);
+                    if (c >> 16) atomicAdd(cnt.cov + g.n_sites + s, c >> 16);
+                }
+            }
+        } else {                                                       // wide window (sparse / unsorted input)
+#pragma unroll
+            for (int u = 0; u < K3_GROUPS; ++u) {
+                const int* a = &st[u].x; const int* b = &en[u].x;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    if (a[q] > b[q]) continue;
+                    const uint32_t k = (cl[u] >> (8 * q)) & 1u;
+                    for (int s = lower_bound_i32(sp, i0, i1, a[q]); s < i1 && sp[s] <= b[q]; ++s)
+                        atomicAdd(cnt.cov + k * g.n_sites + s, 1u);
+                }
+            }
+        }
+    }
+    if (staged && !waited) mbar_wait(&bar, 0);   // never exit with the bulk copy still in flight
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: spliced reads.  One thread per spliced read; site window of the chunk staged by TMA.
+// ------------------------------------------------------------------------------------------------
+struct SiteWin {
+    const int32_t* sm;      // staged copy, indexed by global site index (already offset), or nullptr
+    const int32_t* gl;      // global site_pos
+    int lo, hi;             // staged global index range [lo, hi)
+    int32_t plo, phi;       // positions covered completely by the staged range
+    int c0, c1;             // the chromosome's site range
+    __device__ __forceinline__ int32_t at(int i) const { return (i >= lo && i < hi) ? sm[i] : gl[i]; }
+    __device__ __forceinline__ int lower(int32_t key) const {
+        if (key >= plo && key <= phi) return lower_bound_i32(sm, lo, hi, key);
+        return lower_bound_i32(gl, c0, c1, key);
+    }
+};
+
+__device__ __forceinline__ bool in_list(const int32_t* a, int lo, int hi, int32_t key) {
+    for (int i = lo; i < hi; ++i)
+        if (a[i] == key) return true;
+    return false;
+}
+__device__ __forceinline__ bool in_sorted(const int32_t* a, int lo, int hi, int32_t key) {
+    const int i = lower_bound_i32(a, lo, hi, key);
+    return i < hi && a[i] == key;
+}
+
+// is junction (l, r) a partner/competitor pair for site t?  (S:494-501)
+__device__ __forceinline__ bool pc_pair(const DevGraph& g, int t, int32_t l, int32_t r) {
+    const int p0 = g.pc_off[t], p1 = g.pc_off[t + 1], c0 = g.cp_off[t], c1 = g.cp_off[t + 1];
+    return (in_list(g.pc_pos, p0, p1, l) && in_sorted(g.cp_pos, c0, c1, r)) ||
+           (in_sorted(g.cp_pos, c0, c1, l) && in_list(g.pc_pos, p0, p1, r));
+}
+
+__global__ void __launch_bounds__(K4_THREADS)
+k_spliced(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t mode) {
+    const Chunk ck = chunks[blockIdx.x];
+    if (ck.s_cnt == 0) return;
+    __shared__ __align__(16) int32_t s_sites[K4_MAX_STAGED + 8];
+    __shared__ __align__(8) uint64_t bar;
+    const bool staged = ck.s_site_n > 0 && ck.s_site_n <= K4_MAX_STAGED;
+    const int al = ck.s_site_lo & ~3;
+    const int nst = ((ck.s_site_lo + ck.s_site_n + 3) & ~3) - al;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (staged) {
+        if (threadIdx.x == 0) {
+            mbar_expect_tx(&bar, (uint32_t)nst * 4u);
+            bulk_g2s(s_sites, g.site_pos + al, (uint32_t)nst * 4u, &bar);
+        }
+        mbar_wait(&bar, 0);
+    }
+    SiteWin w;
+    w.gl = g.site_pos;
+    w.c0 = g.cs_off[ck.chrom]; w.c1 = g.cs_off[ck.chrom + 1];
+    if (staged) { w.sm = s_sites - al; w.lo = ck.s_site_lo; w.hi = ck.s_site_lo + ck.s_site_n; w.plo = ck.s_lo; w.phi = ck.s_hi; }
+    else if (ck.s_site_n == 0) { w.sm = g.site_pos; w.lo = ck.s_site_lo; w.hi = ck.s_site_lo; w.plo = ck.s_lo; w.phi = ck.s_hi; }   // window proven empty
+    else { w.sm = g.site_pos; w.lo = 0; w.hi = 0; w.plo = INT_MAX; w.phi = INT_MIN; }                                          // too many sites: global search
+    const int S = g.n_sites;
+    const bool combine = (mode & FLAG_COMBINE) != 0;
+
+    for (uint32_t ri = ck.s_base + threadIdx.x; ri < ck.s_base + ck.s_cnt; ri += K4_THREADS) {
+        const uint32_t b0 = soa.sr_boff[ri], b1 = soa.sr_boff[ri + 1];
+        const uint32_t j0 = soa.sr_joff[ri], j1 = soa.sr_joff[ri + 1];
+        const uint32_t rc = soa.sr_cls[ri];
+        const uint32_t k = rc & 1u;
+        const bool firstN = (rc & 2u) != 0;
+        // (1) stabbing count of this read's own blocks (same rule as K3)
+        for (uint32_t b = b0; b < b1; ++b) {
+            const int32_t a = soa.b_start[b], e = soa.b_end[b] - 2;
+            if (a > e) continue;
+            for (int s = w.lower(a); s < w.c1 && w.at(s) <= e; ++s)
+                if (s >= g.own_lo && s < g.own_hi) atomicAdd(cnt.cov + k * S + s, 1u);
+        }
+        // (2) junctions: span range add + exceptions
+        for (uint32_t j = j0; j < j1; ++j) {
+            const int32_t l = soa.jn_l[j], r = soa.jn_r[j];
+            const int il = w.lower(l);
+            int iu = il;
+            while (iu < w.c1 && w.at(iu) == l) ++iu;                   // upper_bound(l)
+            const int ir = (r > l) ? w.lower(r) : il;
+            {   // sites strictly inside (l, r): S:503-512 range part
+                const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);
+                if (x0 < x1) {
+                    atomicAdd(cnt.span + k * (S + 1) + x0, 1u);
+                    atomicAdd(cnt.span + k * (S + 1) + x1, 0xffffffffu);   // -1
+                }
+            }
+            // exceptions: sites t for which (l, r) is a partner/competitor pair; they all hang off the
+            // reverse partner lists of the sites at l and at r
+#pragma unroll 1
+            for (int side = 0; side < 2; ++side) {
+                const int anchor = side == 0 ? il : ir;
+                const int32_t epos = side == 0 ? l : r;
+                if (anchor >= w.c1 || w.at(anchor) != epos) continue;
+                for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
+                    const int t = g.rp_site[q];
+                    if (t < g.own_lo || t >= g.own_hi) continue;
+                    if (g.cp_off[t + 1] == g.cp_off[t]) continue;         // no competitors: never a pair
+                    if (!pc_pair(g, t, l, r)) continue;
+                    if (side == 1 && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) continue;   // seen at side 0
+                    bool earlier = false;
+                    for (uint32_t jj = j0; jj < j && !earlier; ++jj) earlier = pc_pair(g, t, soa.jn_l[jj], soa.jn_r[jj]);
+                    if (earlier) continue;
+                    // --- first junction of this read that makes compSplicing true for t: classify the read at t
+                    const int32_t tp = g.site_pos[t];
+                    const bool ok = strand_ok(g.site_cls[t], k);
+                    bool alpha = false; int32_t partner_used = 0; int kstar = -1;
+                    for (uint32_t jj = j0; jj < j1; ++jj) {
+                        const int32_t ll = soa.jn_l[jj], rr = soa.jn_r[jj];
+                        if (ll == tp && !(jj == j0 && firstN)) { alpha = true; partner_used = rr; }   // POS <= t filter (S:435)
+                        if (rr == tp) { alpha = true; partner_used = ll; }
+                        if (ll < tp && tp < rr) kstar = (int)(jj - j0);
+                    }
+                    if (alpha) {                                           // S:519-527
+                        for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
+                            const int32_t pp = g.pc_pos[e];
+                            if (pp == partner_used) continue;
+                            bool in_read = false;
+                            for (uint32_t jj = j0; jj < j1 && !in_read; ++jj) in_read = soa.jn_l[jj] == pp || soa.jn_r[jj] == pp;
+                            if (in_read) atomicAdd(cnt.dc + e, 1u);
+                        }
+                    } else if (kstar >= 0) {
+                        if (kstar >= (int)(j - j0)) {                      // compSplicing already true at k*: flanking (S:503-505)
+                            if (ok) atomicAdd(cnt.spanx + t, 1u);
+                            if (combine) atomicAdd(cnt.flank + t, 1u);
+                        }
+                    } else if (ok) {
+                        bool covers = false;
+                        for (uint32_t b = b0; b < b1 && !covers; ++b) covers = soa.b_start[b] <= tp && soa.b_end[b] >= tp + 2;
+                        if (covers) {                                      // beta1-type, S:544-552
+                            atomicAdd(cnt.covx + t, 1u);
+                            for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
+                                const int32_t pp = g.pc_pos[e];
+                                bool in_read = false;
+                                for (uint32_t jj = j0; jj < j1 && !in_read; ++jj) in_read = soa.jn_l[jj] == pp || soa.jn_r[jj] == pp;
+                                if (in_read) atomicAdd(cnt.dc + e, 1u);
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: span prefix scan + beta2 gather + SSE
+// ------------------------------------------------------------------------------------------------
+constexpr int FIN_TILE = FIN_THREADS * FIN_ITEMS;
+
+__global__ void __launch_bounds__(FIN_THREADS) k_span_blocksum(DevCounters cnt, int S, uint32_t* blk) {
+    __shared__ uint32_t red[2][FIN_THREADS / 32];
+    uint32_t s0 = 0, s1 = 0;
+    const int base = blockIdx.x * FIN_TILE;
+    for (int q = 0; q < FIN_ITEMS; ++q) {
+        const int i = base + q * FIN_THREADS + threadIdx.x;
+        if (i < S) { s0 += cnt.span[i]; s1 += cnt.span[(S + 1) + i]; }
+    }
+    s0 = __reduce_add_sync(0xffffffffu, s0); s1 = __reduce_add_sync(0xffffffffu, s1);
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < FIN_THREADS / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
+        blk[2 * blockIdx.x] = s0; blk[2 * blockIdx.x + 1] = s1;
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_span_scan(uint32_t* blk, int nblk) {   // exclusive scan, single CTA
+    __shared__ uint32_t wt[2][32];
+    __shared__ uint32_t carry[2];
+    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nblk; base += 1024) {
+        const int i = base + (int)threadIdx.x;
+        const uint32_t v0 = i < nblk ? blk[2 * i] : 0, v1 = i < nblk ? blk[2 * i + 1] : 0;
+        uint32_t a0 = v0, a1 = v1;                                  // inclusive scan inside the warp
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t x0 = __shfl_up_sync(0xffffffffu, a0, d), x1 = __shfl_up_sync(0xffffffffu, a1, d);
+            if (lane >= d) { a0 += x0; a1 += x1; }
+        }
+        if (lane == 31) { wt[0][warp] = a0; wt[1][warp] = a1; }
+        __syncthreads();
+        if (warp == 0) {                                            // exclusive scan of the 32 warp totals
+            const uint32_t w0 = wt[0][lane], w1 = wt[1][lane];
+            uint32_t b0 = w0, b1 = w1;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t x0 = __shfl_up_sync(0xffffffffu, b0, d), x1 = __shfl_up_sync(0xffffffffu, b1, d);
+                if (lane >= d) { b0 += x0; b1 += x1; }
+            }
+            wt[0][lane] = b0 - w0; wt[1][lane] = b1 - w1;
+        }
+        __syncthreads();
+        const uint32_t e0 = carry[0] + wt[0][warp] + a0 - v0, e1 = carry[1] + wt[1][warp] + a1 - v1;
+        if (i < nblk) { blk[2 * i] = e0; blk[2 * i + 1] = e1; }
+        __syncthreads();
+        if (threadIdx.x == 1023) { carry[0] = e0 + v0; carry[1] = e1 + v1; }
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(FIN_THREADS)
+k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode) {
+    const int S = g.n_sites;
+    __shared__ uint32_t wt[2][FIN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // each thread owns FIN_ITEMS consecutive sites so that the in-thread running sum is in order
+    const int first = blockIdx.x * FIN_TILE + threadIdx.x * FIN_ITEMS;
+    uint32_t d0[FIN_ITEMS], d1[FIN_ITEMS];
+    uint32_t t0 = 0, t1 = 0;
+#pragma unroll
+    for (int q = 0; q < FIN_ITEMS; ++q) {
+        const int i = first + q;
+        d0[q] = i < S ? cnt.span[i] : 0; d1[q] = i < S ? cnt.span[(S + 1) + i] : 0;
+        t0 += d0[q]; t1 += d1[q];
+    }
+    uint32_t a0 = t0, a1 = t1;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t x0 = __shfl_up_sync(0xffffffffu, a0, d), x1 = __shfl_up_sync(0xffffffffu, a1, d);
+        if (lane >= d) { a0 += x0; a1 += x1; }
+    }
+    if (lane == 31) { wt[0][warp] = a0; wt[1][warp] = a1; }
+    __syncthreads();
+    uint32_t run0 = out.span_blk[2 * blockIdx.x] + a0 - t0, run1 = out.span_blk[2 * blockIdx.x + 1] + a1 - t1;
+    for (int w = 0; w < warp; ++w) { run0 += wt[0][w]; run1 += wt[1][w]; }
+
+    const bool stranded = (mode & FLAG_STRANDED) != 0, cryptic = (mode & FLAG_CRYPTIC) != 0, combine = (mode & FLAG_COMBINE) != 0;
+#pragma unroll 1
+    for (int q = 0; q < FIN_ITEMS; ++q) {
+        const int t = first + q;
+        if (t >= S) break;
+        run0 += d0[q]; run1 += d1[q];                       // inclusive prefix = reads whose N spans site t
+        const bool owned = t >= g.own_lo && t < g.own_hi;
+        const uint32_t c = g.site_cls[t];
+        uint32_t cov = 0, span = 0;
+        if (!stranded) { cov = cnt.cov[t]; span = run0; }
+        else if (c == 1u) { cov = cnt.cov[t]; span = run0; }
+        else if (c == 2u) { cov = cnt.cov[S + t]; span = run1; }
+        const uint32_t covx = cnt.covx[t], spanx = cnt.spanx[t];
+        int64_t b1 = (int64_t)cov - (int64_t)covx;
+        int64_t b2 = (int64_t)covx + (int64_t)span - (int64_t)spanx + (combine ? (int64_t)cnt.flank[t] : 0);
+        if (!owned || c == 4u) { b1 = 0; b2 = 0; }
+        // ---- findBeta2Counts, S:581-623
+        const int32_t tp = g.site_pos[t];
+        const int64_t alpha_t = out.alpha[t];
+        const int e_lo = g.pc_off[t], e_hi = g.pc_off[t + 1];
+        for (int e = e_lo; e < e_hi; ++e) { out.dc_tot[e] = cnt.dc[e]; out.dc_present[e] = cnt.dc[e] != 0; }
+        int64_t b2c = 0;
+        double b2w = 0.0;
+        for (int a = g.pt_off[t]; a < g.pt_off[t + 1]; ++a) {
+            const int p = g.pt_site[a];
+            const int32_t pp = g.site_pos[p];
+            int et = e_lo;
+            while (et < e_hi && g.pc_pos[et] != pp) ++et;                  // PartnerCounts[pSite.getPos()], S:604
+            int64_t tab = 0; bool hit = false;
+            for (int x = g.pc_off[p]; x < g.pc_off[p + 1]; ++x) {          // S:592-599
+                const int32_t cpos = g.pc_pos[x];
+                if ((pp > tp && cpos < tp) || (pp < tp && cpos > tp)) { tab += out.pc_cnt[x]; hit = true; }
+            }
+            b2 += tab;
+            if (et < e_hi) {
+                if (hit) { out.dc_tot[et] += tab; out.dc_present[et] = 1; }
+                const int64_t pcount = out.pc_cnt[et];
+                int64_t v = out.alpha[p] - pcount;                         // S:606
+                if (out.dc_present[et]) { v -= out.dc_tot[et]; if (v < 0) v = 0; }   // subIntNoNeg, S:608-611
+                b2c += v;
+                const double wgt = alpha_t > 0 ? __ddiv_rn((double)pcount, (double)alpha_t) : 0.0;   // S:615
+                b2w = __dadd_rn(b2w, __dmul_rn((double)v, wgt));           // mul then add, no FMA (S:617-619)
+            }
+        }
+        // ---- calculateSSE, S:626-639
+        double sse = 0.0;
+        if (cryptic) {
+            const double betas = __dadd_rn((double)(b1 + b2), b2w);
+            const double den = __dadd_rn((double)alpha_t, betas);
+            if (den > 0.0) sse = __ddiv_rn((double)alpha_t, den);
+        } else {
+            const int64_t den = alpha_t + b1 + b2;
+            if (den > 0) sse = __ddiv_rn((double)alpha_t, (double)den);
+        }
+        out.beta1[t] = b1; out.beta2s[t] = b2; out.beta2c[t] = b2c; out.beta2w[t] = b2w; out.sse[t] = sse;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+void launch_expand_count(const DevRecords& rec, Chunk* chunks, int n_chunks, uint32_t flags, void* stream) {
+    if (n_chunks > 0) k_expand_count<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, flags);
+}
+void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals4, void* stream) {
+    k_chunk_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(chunks, n_chunks, totals4);
+}
+void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream) {
+    if (n_chunks > 0) k_expand_scatter<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, soa, flags);
+}
+void launch_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g, void* stream) {
+    if (n_chunks > 0) k_chunk_hints<<<(n_chunks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(chunks, n_chunks, g);
+}
+void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream) {
+    const int n = g.n_sites + g.n_edges;
+    if (n > 0) k_alpha_reduce<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, out);
+}
+void launch_beta1(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, void* stream) {
+    if (n_chunks > 0 && g.n_sites > 0) k_beta1_stab<<<n_chunks, K3_THREADS, 0, (cudaStream_t)stream>>>(chunks, soa, g, cnt);
+}
+void launch_spliced(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
+    if (n_chunks > 0 && g.n_sites > 0) k_spliced<<<n_chunks, K4_THREADS, 0, (cudaStream_t)stream>>>(chunks, soa, g, cnt, flags);
+}
+void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
+    if (g.n_sites <= 0) return;
+    const int nblk = (g.n_sites + FIN_TILE - 1) / FIN_TILE;
+    k_span_blocksum<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(cnt, g.n_sites, out.span_blk);
+    k_span_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(out.span_blk, nblk);
+    k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags);
+}
+int kernel_launch_count_per_pass() { return 6; }   // alpha_reduce, beta1_stab, spliced, span_blocksum, span_scan, finalize
+
+}  // namespace spl

@@ -1,0 +1,613 @@
+// Context, device memory management, kernel orchestration and the C ABI of libspliser_b200.so.
+// See include/spliser_b200.h for the contract of every entry point.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/spliser_b200.h"
+#include "bam_io.h"
+#include "device_types.h"
+#include "site_graph.h"
+
+using namespace spl;
+
+namespace {
+
+double now_ms() {
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 4096;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// carve sub-arrays out of one allocation
+struct Carver {
+    size_t off = 0;
+    template <class T> size_t take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        const size_t o = off;
+        off += n * sizeof(T);
+        return o;
+    }
+};
+
+}  // namespace
+
+struct spl_result {
+    int64_t n = 0;
+    std::vector<int32_t> chrom, pos;
+    std::vector<uint8_t> strand;
+    std::vector<int64_t> alpha, beta1, beta2s, beta2c, first_line;
+    std::vector<double> beta2w, sse;
+    std::vector<int64_t> pc_off, pc_cnt, cp_off;
+    std::vector<int32_t> pc_pos, cp_pos;
+};
+
+struct spl_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int n_threads = 0;
+    int tile_index = 0, tile_count = 1;
+    double stats[SPL_NSTATS] = {0};
+
+    // device memory
+    DevBuf d_graph, d_rec, d_chunks, d_soa, d_cnt, d_out, d_tot;
+    uint32_t* h_tot = nullptr;      // pinned, 4 totals
+    std::vector<cudaEvent_t> events;
+
+    // state of the last load
+    SiteGraph hg;                   // host graph (structure) of the last load
+    DevGraph g{};
+    DevRecords rec{};
+    DevSoA soa{};
+    DevCounters cnt{};
+    DevOutputs out{};
+    Chunk* chunks = nullptr;
+    int n_chunks = 0;
+    size_t cnt_bytes = 0;
+    uint32_t flags = 0;
+    bool loaded = false;
+    int64_t n_aligned = 0;
+
+    int fail(int code, const char* fmt, ...) {
+        char buf[512];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t _e = (call);                                                                   \
+        if (_e != cudaSuccess)                                                                     \
+            return ctx->fail(SPL_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+namespace {
+
+template <class T> std::vector<int32_t> to_i32(const std::vector<T>& v) {
+    std::vector<int32_t> r(v.size());
+    for (size_t i = 0; i < v.size(); ++i) r[i] = (int32_t)v[i];
+    return r;
+}
+
+int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
+    const SiteGraph& h = ctx->hg;
+    const size_t S = (size_t)h.n_sites, E = h.pc_pos.size();
+    if (h.pt_site.size() >= (size_t)INT_MAX || h.inc_line.size() >= (size_t)INT_MAX || h.cp_pos.size() >= (size_t)INT_MAX)
+        return ctx->fail(SPL_ERR_RANGE, "site graph exceeds 2^31 entries");
+    Carver c;
+    const size_t o_cs = c.take<int32_t>((size_t)h.n_chrom + 1), o_pos = c.take<int32_t>(S + 8), o_cls = c.take<uint8_t>(S + 8);
+    const size_t o_pto = c.take<int32_t>(S + 1), o_pts = c.take<int32_t>(h.pt_site.size() + 1);
+    const size_t o_pco = c.take<int32_t>(S + 1), o_pcp = c.take<int32_t>(E + 1);
+    const size_t o_cpo = c.take<int32_t>(S + 1), o_cpp = c.take<int32_t>(h.cp_pos.size() + 1);
+    const size_t o_rpo = c.take<int32_t>(S + 1), o_rps = c.take<int32_t>(h.rp_site.size() + 1);
+    const size_t o_ino = c.take<int32_t>(S + 1), o_inl = c.take<int32_t>(h.inc_line.size() + 1);
+    const size_t o_eio = c.take<int32_t>(E + 1), o_eil = c.take<int32_t>(h.einc_line.size() + 1);
+    const size_t o_js = c.take<int64_t>((size_t)n_junc + 1);
+    const size_t total = c.off + 256;
+    CU(ctx->d_graph.reserve(total));
+    std::vector<uint8_t> stage(total, 0);
+    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) memcpy(stage.data() + off, src, bytes); };
+    auto put32 = [&](size_t off, const std::vector<int64_t>& v, size_t expect) {
+        std::vector<int32_t> t = to_i32(v);
+        t.resize(expect, t.empty() ? 0 : t.back());
+        put(off, t.data(), t.size() * 4);
+    };
+    put32(o_cs, h.cs_off, (size_t)h.n_chrom + 1);
+    {
+        std::vector<int32_t> p(h.pos);
+        p.resize(S + 8, INT_MAX);
+        put(o_pos, p.data(), p.size() * 4);
+    }
+    put(o_cls, h.cls.data(), S);
+    put32(o_pto, h.pt_off, S + 1); put(o_pts, h.pt_site.data(), h.pt_site.size() * 4);
+    put32(o_pco, h.pc_off, S + 1); put(o_pcp, h.pc_pos.data(), E * 4);
+    put32(o_cpo, h.cp_off, S + 1); put(o_cpp, h.cp_pos.data(), h.cp_pos.size() * 4);
+    put32(o_rpo, h.rp_off, S + 1); put(o_rps, h.rp_site.data(), h.rp_site.size() * 4);
+    put32(o_ino, h.inc_off, S + 1); put(o_inl, h.inc_line.data(), h.inc_line.size() * 4);
+    put32(o_eio, h.einc_off, E + 1); put(o_eil, h.einc_line.data(), h.einc_line.size() * 4);
+    if (n_junc) put(o_js, j_score, (size_t)n_junc * 8);
+    CU(cudaMemcpyAsync(ctx->d_graph.p, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // `stage` is pageable and dies at scope exit
+    ctx->stats[SPL_STAT_H2D_BYTES] += (double)total;
+    char* b = (char*)ctx->d_graph.p;
+    DevGraph& g = ctx->g;
+    g.n_chrom = h.n_chrom; g.n_sites = (int32_t)S; g.n_edges = (int32_t)E;
+    const int64_t tc = std::max(1, ctx->tile_count), ti = std::min<int64_t>(std::max(0, ctx->tile_index), tc - 1);
+    g.own_lo = (int32_t)((int64_t)S * ti / tc); g.own_hi = (int32_t)((int64_t)S * (ti + 1) / tc);
+    g.cs_off = (const int32_t*)(b + o_cs); g.site_pos = (const int32_t*)(b + o_pos); g.site_cls = (const uint8_t*)(b + o_cls);
+    g.pt_off = (const int32_t*)(b + o_pto); g.pt_site = (const int32_t*)(b + o_pts);
+    g.pc_off = (const int32_t*)(b + o_pco); g.pc_pos = (const int32_t*)(b + o_pcp);
+    g.cp_off = (const int32_t*)(b + o_cpo); g.cp_pos = (const int32_t*)(b + o_cpp);
+    g.rp_off = (const int32_t*)(b + o_rpo); g.rp_site = (const int32_t*)(b + o_rps);
+    g.inc_off = (const int32_t*)(b + o_ino); g.inc_line = (const int32_t*)(b + o_inl);
+    g.einc_off = (const int32_t*)(b + o_eio); g.einc_line = (const int32_t*)(b + o_eil);
+    g.j_score = (const int64_t*)(b + o_js);
+
+    // counters + outputs
+    Carver cc;
+    const size_t c_cov = cc.take<uint32_t>(2 * S + 2), c_span = cc.take<uint32_t>(2 * (S + 1) + 2);
+    const size_t c_covx = cc.take<uint32_t>(S + 1), c_spanx = cc.take<uint32_t>(S + 1), c_flank = cc.take<uint32_t>(S + 1);
+    const size_t c_dc = cc.take<uint32_t>(E + 1);
+    ctx->cnt_bytes = cc.off + 256;
+    CU(ctx->d_cnt.reserve(ctx->cnt_bytes));
+    char* cb = (char*)ctx->d_cnt.p;
+    ctx->cnt.cov = (uint32_t*)(cb + c_cov); ctx->cnt.span = (uint32_t*)(cb + c_span);
+    ctx->cnt.covx = (uint32_t*)(cb + c_covx); ctx->cnt.spanx = (uint32_t*)(cb + c_spanx);
+    ctx->cnt.flank = (uint32_t*)(cb + c_flank); ctx->cnt.dc = (uint32_t*)(cb + c_dc);
+    Carver oc;
+    const size_t nblk = (S + FIN_THREADS * FIN_ITEMS - 1) / (FIN_THREADS * FIN_ITEMS) + 1;
+    const size_t o_al = oc.take<int64_t>(S + 1), o_pc = oc.take<int64_t>(E + 1), o_b1 = oc.take<int64_t>(S + 1),
+                 o_b2 = oc.take<int64_t>(S + 1), o_b2c = oc.take<int64_t>(S + 1), o_b2w = oc.take<double>(S + 1),
+                 o_sse = oc.take<double>(S + 1), o_dct = oc.take<int64_t>(E + 1), o_dcp = oc.take<uint8_t>(E + 1),
+                 o_blk = oc.take<uint32_t>(2 * nblk + 2);
+    CU(ctx->d_out.reserve(oc.off + 256));
+    char* ob = (char*)ctx->d_out.p;
+    DevOutputs& o = ctx->out;
+    o.alpha = (int64_t*)(ob + o_al); o.pc_cnt = (int64_t*)(ob + o_pc); o.beta1 = (int64_t*)(ob + o_b1);
+    o.beta2s = (int64_t*)(ob + o_b2); o.beta2c = (int64_t*)(ob + o_b2c); o.beta2w = (double*)(ob + o_b2w);
+    o.sse = (double*)(ob + o_sse); o.dc_tot = (int64_t*)(ob + o_dct); o.dc_present = (uint8_t*)(ob + o_dcp);
+    o.span_blk = (uint32_t*)(ob + o_blk);
+    return SPL_OK;
+}
+
+int check_view(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
+    if (!v) return ctx->fail(SPL_ERR_ARG, "records view is NULL");
+    if (v->n_rec < 0 || v->n_cigar < 0 || v->n_seg < 0) return ctx->fail(SPL_ERR_ARG, "negative size in records view");
+    if (v->n_rec > 0 && (!v->pos || !v->flag || !v->cig_off)) return ctx->fail(SPL_ERR_ARG, "NULL record array");
+    if (v->n_cigar > 0 && !v->cigar) return ctx->fail(SPL_ERR_ARG, "NULL cigar array");
+    if (v->n_seg > 0 && (!v->seg_chrom || !v->seg_off)) return ctx->fail(SPL_ERR_ARG, "NULL segment array");
+    if (v->n_rec >= (int64_t)UINT32_MAX - 16 || v->n_cigar >= (int64_t)UINT32_MAX - 16)
+        return ctx->fail(SPL_ERR_RANGE, "more than 2^32 records or CIGAR operators in one call");
+    int64_t prev = 0;
+    for (int32_t k = 0; k < v->n_seg; ++k) {
+        if (v->seg_off[k] != prev || v->seg_off[k + 1] < prev) return ctx->fail(SPL_ERR_ARG, "segment offsets must start at 0 and be monotone");
+        prev = v->seg_off[k + 1];
+        if (v->seg_chrom[k] >= n_chrom) return ctx->fail(SPL_ERR_ARG, "segment chromosome index out of range");
+    }
+    if (v->n_seg > 0 && prev != v->n_rec) return ctx->fail(SPL_ERR_ARG, "segments do not cover all records");
+    if (v->n_seg == 0 && v->n_rec != 0) return ctx->fail(SPL_ERR_ARG, "records without segments");
+    if (v->n_rec > 0 && (int64_t)v->cig_off[v->n_rec] != v->n_cigar) return ctx->fail(SPL_ERR_ARG, "cig_off[n_rec] != n_cigar");
+    return SPL_OK;
+}
+
+// upload records, run the expansion kernels, leave the SoA + chunk table on the device
+int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
+    const double t0 = now_ms();
+    std::vector<Chunk> hc;
+    for (int32_t k = 0; k < v->n_seg; ++k) {
+        if (v->seg_chrom[k] < 0) continue;
+        for (int64_t lo = v->seg_off[k]; lo < v->seg_off[k + 1]; lo += CHUNK_READS) {
+            Chunk c{};
+            c.chrom = v->seg_chrom[k];
+            c.rec_lo = (uint32_t)lo;
+            c.rec_hi = (uint32_t)std::min<int64_t>(lo + CHUNK_READS, v->seg_off[k + 1]);
+            hc.push_back(c);
+        }
+    }
+    ctx->n_chunks = (int)hc.size();
+    const size_t R = (size_t)v->n_rec, NC = (size_t)v->n_cigar;
+    Carver c;
+    const size_t o_pos = c.take<int32_t>(R + 4), o_flag = c.take<uint16_t>(R + 4), o_off = c.take<uint32_t>(R + 4),
+                 o_cig = c.take<uint32_t>(NC + 4);
+    CU(ctx->d_rec.reserve(c.off + 256));
+    char* rb = (char*)ctx->d_rec.p;
+    if (R) {
+        CU(cudaMemcpyAsync(rb + o_pos, v->pos, R * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(rb + o_flag, v->flag, R * 2, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(rb + o_off, v->cig_off, (R + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (NC) CU(cudaMemcpyAsync(rb + o_cig, v->cigar, NC * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    ctx->stats[SPL_STAT_H2D_BYTES] += (double)(R * 10 + 4 + NC * 4 + hc.size() * sizeof(Chunk));
+    ctx->rec.n_rec = (uint32_t)R;
+    ctx->rec.pos = (const int32_t*)(rb + o_pos); ctx->rec.flag = (const uint16_t*)(rb + o_flag);
+    ctx->rec.cig_off = (const uint32_t*)(rb + o_off); ctx->rec.cigar = (const uint32_t*)(rb + o_cig);
+    CU(ctx->d_chunks.reserve((hc.size() + 1) * sizeof(Chunk)));
+    ctx->chunks = (Chunk*)ctx->d_chunks.p;
+    if (!hc.empty()) CU(cudaMemcpyAsync(ctx->chunks, hc.data(), hc.size() * sizeof(Chunk), cudaMemcpyHostToDevice, ctx->stream));
+    CU(ctx->d_tot.reserve(64));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, ctx->stream));
+    launch_expand_count(ctx->rec, ctx->chunks, ctx->n_chunks, flags, ctx->stream);
+    launch_chunk_scan(ctx->chunks, ctx->n_chunks, (uint32_t*)ctx->d_tot.p, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_tot, ctx->d_tot.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // also makes `hc` (pageable) safe to drop
+    const size_t nA = ctx->h_tot[0], nB = ctx->h_tot[1], nS = ctx->h_tot[2], nJ = ctx->h_tot[3];
+    Carver s;
+    const size_t o_as = s.take<int32_t>(nA + 16), o_ae = s.take<int32_t>(nA + 16), o_ac = s.take<uint8_t>(nA + 64);
+    const size_t o_bs = s.take<int32_t>(nB + 16), o_be = s.take<int32_t>(nB + 16);
+    const size_t o_sb = s.take<uint32_t>(nS + 16), o_sj = s.take<uint32_t>(nS + 16), o_sc = s.take<uint8_t>(nS + 16);
+    const size_t o_jl = s.take<int32_t>(nJ + 16), o_jr = s.take<int32_t>(nJ + 16);
+    CU(ctx->d_soa.reserve(s.off + 256));
+    char* sb = (char*)ctx->d_soa.p;
+    DevSoA& soa = ctx->soa;
+    soa.nA = (uint32_t)nA; soa.nB = (uint32_t)nB; soa.nS = (uint32_t)nS; soa.nJ = (uint32_t)nJ;
+    soa.a_start = (int32_t*)(sb + o_as); soa.a_end = (int32_t*)(sb + o_ae); soa.a_cls = (uint8_t*)(sb + o_ac);
+    soa.b_start = (int32_t*)(sb + o_bs); soa.b_end = (int32_t*)(sb + o_be);
+    soa.sr_boff = (uint32_t*)(sb + o_sb); soa.sr_joff = (uint32_t*)(sb + o_sj); soa.sr_cls = (uint8_t*)(sb + o_sc);
+    soa.jn_l = (int32_t*)(sb + o_jl); soa.jn_r = (int32_t*)(sb + o_jr);
+    launch_expand_scatter(ctx->rec, ctx->chunks, ctx->n_chunks, soa, flags, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaEventRecord(e1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    ctx->stats[SPL_STAT_MS_EXPAND] = ms;
+    ctx->stats[SPL_STAT_N_MBLOCKS_A] = (double)nA; ctx->stats[SPL_STAT_N_MBLOCKS_B] = (double)nB;
+    ctx->stats[SPL_STAT_N_SPLICED] = (double)nS; ctx->stats[SPL_STAT_N_JUNC_OPS] = (double)nJ;
+    int64_t aligned = 0;
+    for (int32_t k = 0; k < v->n_seg; ++k)
+        if (v->seg_chrom[k] >= 0) aligned += v->seg_off[k + 1] - v->seg_off[k];
+    ctx->n_aligned = aligned;
+    ctx->stats[SPL_STAT_N_ALIGNED] = (double)aligned;
+    (void)t0;
+    return SPL_OK;
+}
+
+// one counting pass over the resident SoA; events (if given) bracket the three kernel groups
+int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
+    if (ev) CU(cudaEventRecord(ev[0], ctx->stream));
+    if (ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->d_cnt.p, 0, ctx->cnt_bytes, ctx->stream));
+    launch_alpha_reduce(ctx->g, ctx->out, ctx->stream);
+    if (ev) CU(cudaEventRecord(ev[1], ctx->stream));
+    launch_beta1(ctx->chunks, ctx->n_chunks, ctx->soa, ctx->g, ctx->cnt, ctx->stream);
+    if (ev) CU(cudaEventRecord(ev[2], ctx->stream));
+    launch_spliced(ctx->chunks, ctx->n_chunks, ctx->soa, ctx->g, ctx->cnt, ctx->flags, ctx->stream);
+    if (ev) CU(cudaEventRecord(ev[3], ctx->stream));
+    launch_finalize(ctx->g, ctx->cnt, ctx->out, ctx->flags, ctx->stream);
+    if (ev) CU(cudaEventRecord(ev[4], ctx->stream));
+    CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+int fetch(spl_ctx* ctx, spl_result** out_r) {
+    const SiteGraph& h = ctx->hg;
+    const size_t S = (size_t)h.n_sites, E = h.pc_pos.size();
+    std::unique_ptr<spl_result> r(new spl_result());
+    r->n = (int64_t)S;
+    r->chrom = h.chrom; r->pos = h.pos; r->strand = h.strand; r->first_line = h.first_line;
+    r->pc_off = h.pc_off; r->pc_pos = h.pc_pos; r->cp_off = h.cp_off; r->cp_pos = h.cp_pos;
+    r->alpha.resize(S); r->beta1.resize(S); r->beta2s.resize(S); r->beta2c.resize(S);
+    r->beta2w.resize(S); r->sse.resize(S); r->pc_cnt.resize(E);
+    if (S) {
+        CU(cudaMemcpyAsync(r->alpha.data(), ctx->out.alpha, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(r->beta1.data(), ctx->out.beta1, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(r->beta2s.data(), ctx->out.beta2s, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(r->beta2c.data(), ctx->out.beta2c, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(r->beta2w.data(), ctx->out.beta2w, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(r->sse.data(), ctx->out.sse, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        if (E) CU(cudaMemcpyAsync(r->pc_cnt.data(), ctx->out.pc_cnt, E * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->stats[SPL_STAT_D2H_BYTES] += (double)(S * 48 + E * 8);
+    *out_r = r.release();
+    return SPL_OK;
+}
+
+void reset_stats(spl_ctx* ctx) { std::fill(ctx->stats, ctx->stats + SPL_NSTATS, 0.0); }
+
+int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
+                const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags) {
+    ctx->loaded = false;
+    int rc = check_view(ctx, rec, n_chrom);
+    if (rc) return rc;
+    if (n_junc > 0 && !j_score) return ctx->fail(SPL_ERR_ARG, "NULL j_score");
+    CU(cudaSetDevice(ctx->device));
+    reset_stats(ctx);
+    std::string e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, (flags & SPL_FLAG_STRANDED) != 0, ctx->hg);
+    if (!e.empty()) return ctx->fail(SPL_ERR_ARG, "%s", e.c_str());
+    ctx->flags = flags;
+    rc = upload_graph(ctx, j_score, n_junc);
+    if (rc) return rc;
+    rc = upload_and_expand(ctx, rec, flags);
+    if (rc) return rc;
+    launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
+    CU(cudaGetLastError());
+    ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
+    ctx->stats[SPL_STAT_N_EDGES] = (double)ctx->hg.pc_pos.size();
+    ctx->stats[SPL_STAT_LAUNCHES] = (double)kernel_launch_count_per_pass();
+    ctx->loaded = true;
+    return SPL_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// C ABI
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+
+const char* spl_version(void) { return "spliser_b200 0.1.0 (SpliSER v0.1.8 counting path, sm_100a)"; }
+
+int spl_create(spl_ctx** out, const int* device_ids, int n_devices) {
+    if (!out) return SPL_ERR_ARG;
+    *out = nullptr;
+    spl_ctx* ctx = new (std::nothrow) spl_ctx();
+    if (!ctx) return SPL_ERR_NOMEM;
+    *out = ctx;   // returned even on failure so that spl_last_error() can be read; caller destroys it
+    if (n_devices != 1 || !device_ids)
+        return ctx->fail(SPL_ERR_ARG, "this build drives exactly one GPU per context (one process per GPU); got n_devices=%d", n_devices);
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        return ctx->fail(SPL_ERR_CUDA, "no CUDA device available (%s); libspliser_b200 has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device_ids[0] < 0 || device_ids[0] >= count) return ctx->fail(SPL_ERR_ARG, "device %d out of range (%d devices)", device_ids[0], count);
+    ctx->device = device_ids[0];
+    CU(cudaSetDevice(ctx->device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, ctx->device));
+    if (prop.major != 10)
+        return ctx->fail(SPL_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", ctx->device, prop.major, prop.minor);
+    CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaHostAlloc((void**)&ctx->h_tot, 64, cudaHostAllocDefault));
+    return SPL_OK;
+}
+
+void spl_destroy(spl_ctx* ctx) {
+    if (!ctx) return;
+    if (ctx->stream) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+        for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
+        ctx->d_graph.release(); ctx->d_rec.release(); ctx->d_chunks.release(); ctx->d_soa.release();
+        ctx->d_cnt.release(); ctx->d_out.release(); ctx->d_tot.release();
+        if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
+        cudaStreamDestroy(ctx->stream);
+    }
+    delete ctx;
+}
+
+const char* spl_last_error(const spl_ctx* ctx) { return ctx ? ctx->err.c_str() : "NULL context"; }
+
+int spl_set_tile(spl_ctx* ctx, int tile_index, int tile_count) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (tile_count < 1 || tile_index < 0 || tile_index >= tile_count) return ctx->fail(SPL_ERR_ARG, "bad tile %d/%d", tile_index, tile_count);
+    ctx->tile_index = tile_index; ctx->tile_count = tile_count;
+    return SPL_OK;
+}
+
+int spl_set_threads(spl_ctx* ctx, int n) {
+    if (!ctx) return SPL_ERR_ARG;
+    ctx->n_threads = n < 0 ? 0 : n;
+    return SPL_OK;
+}
+
+int spl_last_stats(const spl_ctx* ctx, double* stats_out) {
+    if (!ctx || !stats_out) return SPL_ERR_ARG;
+    memcpy(stats_out, ctx->stats, sizeof ctx->stats);
+    return SPL_OK;
+}
+
+int spl_process_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
+                        const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand,
+                        uint32_t flags, spl_result** out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!out) return ctx->fail(SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    const double t0 = now_ms();
+    int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags);
+    if (rc) return rc;
+    rc = count_pass(ctx, nullptr);
+    if (rc) return rc;
+    rc = fetch(ctx, out);
+    ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
+    return rc;
+}
+
+int spl_process(spl_ctx* ctx, const char* bam_path, int32_t n_chrom, const char* const* chrom_names, int64_t n_junc,
+                const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right, const int64_t* j_score,
+                const uint8_t* j_strand, uint32_t flags, spl_result** out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!out) return ctx->fail(SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    if (!bam_path) return ctx->fail(SPL_ERR_ARG, "bam_path is NULL");
+    const double t0 = now_ms();
+    BamRecords recs;
+    std::string e = read_bam(bam_path, n_chrom, chrom_names, ctx->n_threads, recs);
+    if (!e.empty()) return ctx->fail(SPL_ERR_IO, "%s", e.c_str());
+    const double t1 = now_ms();
+    spl_records_view v = recs.view();
+    int rc = spl_process_records(ctx, &v, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, out);
+    ctx->stats[SPL_STAT_MS_DECODE] = t1 - t0;
+    ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
+    return rc;
+}
+
+int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_sites, const int32_t* s_chrom,
+                        const int32_t* s_pos, const uint8_t* s_strand, const int64_t* p_off, const int32_t* p_pos,
+                        const int64_t* c_off, const int32_t* c_pos, uint32_t flags, int64_t* beta1_out, int64_t* beta2simple_out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    if (n_sites > 0 && (!beta1_out || !beta2simple_out)) return ctx->fail(SPL_ERR_ARG, "NULL output array");
+    ctx->loaded = false;
+    int rc = check_view(ctx, rec, n_chrom);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    reset_stats(ctx);
+    const double t0 = now_ms();
+    flags |= SPL_FLAG_COMBINE;
+    flags &= ~SPL_FLAG_CRYPTIC;
+    std::string e = build_recount_graph(n_chrom, n_sites, s_chrom, s_pos, s_strand, p_off, p_pos, c_off, c_pos,
+                                        (flags & SPL_FLAG_STRANDED) != 0, ctx->hg);
+    if (!e.empty()) return ctx->fail(SPL_ERR_ARG, "%s", e.c_str());
+    ctx->flags = flags;
+    const int save_ti = ctx->tile_index, save_tc = ctx->tile_count;
+    ctx->tile_index = 0; ctx->tile_count = 1;          // a re-count is sharded by sample, never by tile
+    rc = upload_graph(ctx, nullptr, 0);
+    ctx->tile_index = save_ti; ctx->tile_count = save_tc;
+    if (rc) return rc;
+    rc = upload_and_expand(ctx, rec, flags);
+    if (rc) return rc;
+    launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
+    rc = count_pass(ctx, nullptr);
+    if (rc) return rc;
+    const size_t S = (size_t)ctx->hg.n_sites;
+    std::vector<int64_t> b1(S), b2(S);
+    if (S) {
+        CU(cudaMemcpyAsync(b1.data(), ctx->out.beta1, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(b2.data(), ctx->out.beta2s, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < n_sites; ++i) { beta1_out[i] = 0; beta2simple_out[i] = 0; }
+    for (size_t k = 0; k < S; ++k) {
+        const int64_t gi = ctx->hg.gap_index[k];
+        if (gi >= 0) { beta1_out[gi] = b1[k]; beta2simple_out[gi] = b2[k]; }
+    }
+    ctx->stats[SPL_STAT_D2H_BYTES] += (double)(S * 16);
+    ctx->stats[SPL_STAT_N_SITES] = (double)n_sites;
+    ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
+    return SPL_OK;
+}
+
+int spl_recount(spl_ctx* ctx, const char* bam_path, int32_t n_chrom, const char* const* chrom_names, int64_t n_sites,
+                const int32_t* s_chrom, const int32_t* s_pos, const uint8_t* s_strand, const int64_t* p_off, const int32_t* p_pos,
+                const int64_t* c_off, const int32_t* c_pos, uint32_t flags, int64_t* beta1_out, int64_t* beta2simple_out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    if (!bam_path) return ctx->fail(SPL_ERR_ARG, "bam_path is NULL");
+    const double t0 = now_ms();
+    BamRecords recs;
+    std::string e = read_bam(bam_path, n_chrom, chrom_names, ctx->n_threads, recs);
+    if (!e.empty()) return ctx->fail(SPL_ERR_IO, "%s", e.c_str());
+    const double t1 = now_ms();
+    spl_records_view v = recs.view();
+    int rc = spl_recount_records(ctx, &v, n_chrom, n_sites, s_chrom, s_pos, s_strand, p_off, p_pos, c_off, c_pos, flags,
+                                 beta1_out, beta2simple_out);
+    ctx->stats[SPL_STAT_MS_DECODE] = t1 - t0;
+    ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
+    return rc;
+}
+
+int spl_resident_load(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
+                      const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    // the raw records are not needed once expanded
+    ctx->d_rec.release();
+    return SPL_OK;
+}
+
+int spl_resident_count(spl_ctx* ctx, int iters, double* stats_out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!ctx->loaded) return ctx->fail(SPL_ERR_ARG, "spl_resident_count without a successful spl_resident_load");
+    if (iters < 1) return ctx->fail(SPL_ERR_ARG, "iters must be >= 1");
+    CU(cudaSetDevice(ctx->device));
+    while (ctx->events.size() < (size_t)iters * 5) {
+        cudaEvent_t e;
+        CU(cudaEventCreate(&e));
+        ctx->events.push_back(e);
+    }
+    for (int it = 0; it < iters; ++it) {
+        int rc = count_pass(ctx, ctx->events.data() + (size_t)it * 5);
+        if (rc) return rc;
+    }
+    CU(cudaStreamSynchronize(ctx->stream));
+    float total = 0, b1 = 0, sp = 0, fin = 0;
+    CU(cudaEventElapsedTime(&total, ctx->events[0], ctx->events[(size_t)(iters - 1) * 5 + 4]));
+    for (int it = 0; it < iters; ++it) {
+        cudaEvent_t* ev = ctx->events.data() + (size_t)it * 5;
+        float a, b, c, d;
+        CU(cudaEventElapsedTime(&a, ev[0], ev[1])); CU(cudaEventElapsedTime(&b, ev[1], ev[2]));
+        CU(cudaEventElapsedTime(&c, ev[2], ev[3])); CU(cudaEventElapsedTime(&d, ev[3], ev[4]));
+        b1 += b; sp += c; fin += a + d;
+    }
+    ctx->stats[SPL_STAT_MS_TOTAL] = total; ctx->stats[SPL_STAT_MS_BETA1] = b1;
+    ctx->stats[SPL_STAT_MS_SPLICED] = sp; ctx->stats[SPL_STAT_MS_FINAL] = fin;
+    if (stats_out) memcpy(stats_out, ctx->stats, sizeof ctx->stats);
+    return SPL_OK;
+}
+
+int spl_resident_fetch(spl_ctx* ctx, spl_result** out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!out) return ctx->fail(SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!ctx->loaded) return ctx->fail(SPL_ERR_ARG, "nothing loaded");
+    CU(cudaSetDevice(ctx->device));
+    return fetch(ctx, out);
+}
+
+int64_t spl_result_n_sites(const spl_result* r) { return r ? r->n : 0; }
+const int32_t* spl_result_chrom(const spl_result* r) { return r->chrom.data(); }
+const int32_t* spl_result_pos(const spl_result* r) { return r->pos.data(); }
+const uint8_t* spl_result_strand(const spl_result* r) { return r->strand.data(); }
+const int64_t* spl_result_alpha(const spl_result* r) { return r->alpha.data(); }
+const int64_t* spl_result_beta1(const spl_result* r) { return r->beta1.data(); }
+const int64_t* spl_result_beta2simple(const spl_result* r) { return r->beta2s.data(); }
+const int64_t* spl_result_beta2cryptic(const spl_result* r) { return r->beta2c.data(); }
+const double* spl_result_beta2weighted(const spl_result* r) { return r->beta2w.data(); }
+const double* spl_result_sse(const spl_result* r) { return r->sse.data(); }
+const int64_t* spl_result_first_line(const spl_result* r) { return r->first_line.data(); }
+const int64_t* spl_result_partner_off(const spl_result* r) { return r->pc_off.data(); }
+const int32_t* spl_result_partner_pos(const spl_result* r) { return r->pc_pos.data(); }
+const int64_t* spl_result_partner_cnt(const spl_result* r) { return r->pc_cnt.data(); }
+const int64_t* spl_result_comp_off(const spl_result* r) { return r->cp_off.data(); }
+const int32_t* spl_result_comp_pos(const spl_result* r) { return r->cp_pos.data(); }
+void spl_result_free(spl_result* r) { delete r; }
+
+void* spl_host_alloc(size_t bytes) {
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void spl_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+}  // extern "C"

@@ -1,0 +1,406 @@
+// Host-side construction of the site table and competing-site graph.
+//
+// Two regimes (SURVEY.md 8(a) "edge regimes"):
+//   clean  -- unstranded run, or stranded run whose junction rows all carry '+' or '-': a site is
+//             identified by position (resp. position + strand), so a hash lookup reproduces
+//             binary_site_search (SpliSER_v0_1_8.py:175-225) exactly;
+//   dirty  -- stranded run with other strand bytes (regtools '?'), or degenerate rows: the outcome
+//             depends on where the reference's hand-rolled bisection lands in the current list, so
+//             the list and the bisection are emulated step by step (S:186-221, S:347-350 with
+//             Site.__lt__ of Gene_Site_Iter_Graph_v0_1_8.py:123-136).
+// Only the *structure* is built here; alpha and PartnerCounts values are reduced on the GPU from
+// the junction scores using the inc_* / einc_* segments.
+#include "site_graph.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <numeric>
+#include <unordered_map>
+
+namespace spl {
+namespace {
+
+inline bool is_pm(uint8_t s) { return s == '+' || s == '-'; }
+
+struct PtKey {
+    uint32_t a, pos;
+    uint8_t strand;
+    bool operator==(const PtKey& o) const { return a == o.a && pos == o.pos && strand == o.strand; }
+};
+struct PtKeyHash {
+    size_t operator()(const PtKey& k) const {
+        uint64_t h = ((uint64_t)k.a << 32 | k.pos) * 0x9E3779B97F4A7C15ull;
+        return (size_t)(h ^ (h >> 29) ^ ((uint64_t)k.strand << 17));
+    }
+};
+
+struct Builder {
+    bool stranded = false;
+    bool emulate = false;
+    std::vector<int32_t> s_chrom, s_pos;
+    std::vector<uint8_t> s_strand;
+    std::vector<int64_t> s_line;
+    std::vector<std::vector<int32_t>> order;            // emulate: per-chrom list of site ids
+    std::unordered_map<uint64_t, int32_t> index;        // clean: key -> site id
+    // edges in creation order
+    std::vector<int32_t> pt_a, pt_b;                    // Partners entries (a has partner object b)
+    std::vector<int32_t> pc_a, pc_pos;                  // PartnerCounts keys
+    std::unordered_map<uint64_t, int32_t> pc_index;     // (a, pos) -> edge id
+    std::unordered_map<PtKey, char, PtKeyHash> pt_seen;  // (a, b.pos, b.strand) per Site.__eq__
+    std::vector<int32_t> inc_site, inc_line, einc_edge, einc_line;
+
+    uint64_t key(int32_t c, int32_t p, uint8_t st) const {
+        uint64_t sb = (stranded && st == '-') ? 1u : 0u;
+        return ((uint64_t)(uint32_t)c << 34) | ((uint64_t)(uint32_t)p << 1) | sb;
+    }
+
+    // strand compatibility test shared by S:199 and S:204
+    bool strand_ok(uint8_t q, uint8_t s) const { return q == s || !stranded || !is_pm(q); }
+
+    // binary_site_search, S:175-225 (control flow kept: the result depends on it in the dirty regime)
+    int32_t search(const std::vector<int32_t>& arr, int32_t pos, uint8_t strand) const {
+        const int64_t length = (int64_t)arr.size();
+        if (length == 0) return -1;
+        int64_t idx = length / 2, past_max = length, past_min = 0, last_idx = -1, new_idx = idx;
+        bool stuck = false, found = false;
+        while (!stuck && !found) {
+            const int32_t p = s_pos[arr[idx]];
+            if (pos == p) {
+                if (strand_ok(strand, s_strand[arr[idx]])) {
+                    found = true;
+                    break;
+                }
+                const int64_t cand[2] = {idx - 1, idx + 1};   // both computed from the landing index (S:203)
+                for (int k = 0; k < 2; ++k) {
+                    const int64_t a = cand[k];
+                    if (a >= 0 && a < length && pos == s_pos[arr[a]] && strand_ok(strand, s_strand[arr[a]])) {
+                        idx = a;
+                        found = true;
+                    }
+                }
+                break;
+            } else if (pos >= p) {
+                new_idx = idx + ((past_max - idx) / 2);
+                past_min = idx;
+            } else {
+                new_idx = idx - ((idx - past_min) / 2);
+                past_max = idx;
+                if (idx == 1) new_idx = 0;
+            }
+            if (idx != last_idx) {
+                last_idx = idx;
+                idx = new_idx;
+            } else {
+                stuck = true;
+            }
+        }
+        return found ? (int32_t)idx : -1;
+    }
+
+    // Site.__lt__, G:123-136 (a fall-through None is falsy)
+    bool lt(int32_t a, int32_t b) const {
+        if (stranded && s_pos[a] == s_pos[b]) {
+            if (s_strand[a] == s_strand[b]) return false;
+            return s_strand[a] == '+' && s_strand[b] == '-';
+        }
+        return s_pos[a] < s_pos[b];
+    }
+
+    void insort(std::vector<int32_t>& arr, int32_t x) const {   // bisect.insort_right, S:347-350
+        size_t lo = 0, hi = arr.size();
+        while (lo < hi) {
+            size_t mid = (lo + hi) / 2;
+            if (lt(x, arr[mid])) hi = mid; else lo = mid + 1;
+        }
+        arr.insert(arr.begin() + (ptrdiff_t)lo, x);
+    }
+
+    int32_t new_site(int32_t c, int32_t p, uint8_t st, int64_t line) {
+        s_chrom.push_back(c);
+        s_pos.push_back(p);
+        s_strand.push_back(st);
+        s_line.push_back(line);
+        return (int32_t)s_pos.size() - 1;
+    }
+
+    void link(int32_t a, int32_t b, int32_t line) {
+        // addPartner (G:260-262): `b not in a.Partners` is identity-or-__eq__; __eq__ (G:151-163) is
+        // position equality when unstranded, position + strand-byte equality when stranded
+        const PtKey pk{(uint32_t)a, (uint32_t)s_pos[b], stranded ? s_strand[b] : (uint8_t)0};
+        if (pt_seen.emplace(pk, 1).second) {
+            pt_a.push_back(a);
+            pt_b.push_back(b);
+        }
+        // addPartnerCount (G:243-246): keyed by position only
+        const uint64_t ck = ((uint64_t)(uint32_t)a << 32) | (uint32_t)s_pos[b];
+        auto ce = pc_index.find(ck);
+        int32_t e;
+        if (ce == pc_index.end()) {
+            e = (int32_t)pc_a.size();
+            pc_index.emplace(ck, e);
+            pc_a.push_back(a);
+            pc_pos.push_back(s_pos[b]);
+        } else {
+            e = ce->second;
+        }
+        einc_edge.push_back(e);
+        einc_line.push_back(line);
+    }
+};
+
+// stable counting sort of `n` items with integer keys in [0, n_keys): returns offsets and fills perm
+void group_by(const std::vector<int32_t>& keys, int64_t n_keys, std::vector<int64_t>& off, std::vector<int32_t>& perm) {
+    off.assign((size_t)n_keys + 1, 0);
+    for (int32_t k : keys) off[(size_t)k + 1]++;
+    for (int64_t i = 0; i < n_keys; ++i) off[(size_t)i + 1] += off[(size_t)i];
+    perm.resize(keys.size());
+    std::vector<int64_t> cur(off.begin(), off.end() - 1);
+    for (size_t i = 0; i < keys.size(); ++i) perm[(size_t)cur[(size_t)keys[i]]++] = (int32_t)i;
+}
+
+void build_rp(SiteGraph& g) {
+    // anchor = first site index of the chromosome whose position equals the partner position
+    std::vector<int32_t> anchor_of;   // per (t, e) pair
+    std::vector<int32_t> t_of;
+    anchor_of.reserve(g.pc_pos.size());
+    t_of.reserve(g.pc_pos.size());
+    for (int64_t t = 0; t < g.n_sites; ++t) {
+        const int32_t c = g.chrom[(size_t)t];
+        const int32_t* lo = g.pos.data() + g.cs_off[(size_t)c];
+        const int32_t* hi = g.pos.data() + g.cs_off[(size_t)c + 1];
+        for (int64_t e = g.pc_off[(size_t)t]; e < g.pc_off[(size_t)t + 1]; ++e) {
+            const int32_t* it = std::lower_bound(lo, hi, g.pc_pos[(size_t)e]);
+            if (it == hi || *it != g.pc_pos[(size_t)e]) continue;   // cannot happen: partners are rows
+            anchor_of.push_back((int32_t)(it - g.pos.data()));
+            t_of.push_back((int32_t)t);
+        }
+    }
+    std::vector<int32_t> perm;
+    group_by(anchor_of, g.n_sites, g.rp_off, perm);
+    g.rp_site.resize(perm.size());
+    for (size_t i = 0; i < perm.size(); ++i) g.rp_site[i] = t_of[(size_t)perm[i]];
+}
+
+}  // namespace
+
+std::string build_site_graph(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left,
+                             const int32_t* j_right, const uint8_t* j_strand, bool stranded, SiteGraph& g) {
+    if (n_chrom < 0 || n_junc < 0) return "negative size";
+    if (n_junc > 0 && (!j_chrom || !j_left || !j_right || !j_strand)) return "null junction array";
+    if (n_junc >= (int64_t)1 << 30) return "too many junction rows";
+    Builder b;
+    b.stranded = stranded;
+    for (int64_t i = 0; i < n_junc; ++i) {
+        if (j_chrom[i] < 0 || j_chrom[i] >= n_chrom) return "junction chromosome index out of range";
+        if ((stranded && !is_pm(j_strand[i])) || j_left[i] == j_right[i]) b.emulate = true;
+    }
+    if (const char* f = std::getenv("SPLISER_FORCE_EMULATION")) {
+        if (f[0] == '1') b.emulate = true;
+    }
+    if (b.emulate) b.order.resize((size_t)n_chrom);
+    b.index.reserve((size_t)n_junc * 2);
+    b.pc_index.reserve((size_t)n_junc * 2);
+    b.pt_seen.reserve((size_t)n_junc * 2);
+
+    for (int64_t i = 0; i < n_junc; ++i) {
+        const int32_t c = j_chrom[i], l = j_left[i], r = j_right[i];
+        const uint8_t st = j_strand[i];
+        int32_t sl = -1, sr = -1;
+        bool lnew = false, rnew = false;
+        if (b.emulate) {
+            auto& arr = b.order[(size_t)c];
+            const int32_t li = b.search(arr, l, st), ri = b.search(arr, r, st);   // both before any insert, S:291-292
+            sl = li >= 0 ? arr[(size_t)li] : -1;
+            sr = ri >= 0 ? arr[(size_t)ri] : -1;
+        } else {
+            auto it = b.index.find(b.key(c, l, st));
+            if (it != b.index.end()) sl = it->second;
+            it = b.index.find(b.key(c, r, st));
+            if (it != b.index.end()) sr = it->second;
+        }
+        if (sl < 0) { sl = b.new_site(c, l, st, i); lnew = true; }
+        if (sr < 0) { sr = b.new_site(c, r, st, i); rnew = true; }
+        b.inc_site.push_back(sl); b.inc_line.push_back((int32_t)i);     // addAlphaCount, S:341
+        b.inc_site.push_back(sr); b.inc_line.push_back((int32_t)i);
+        if (b.emulate) {
+            if (lnew) b.insort(b.order[(size_t)c], sl);
+            if (rnew) b.insort(b.order[(size_t)c], sr);
+        } else {
+            if (lnew) b.index.emplace(b.key(c, l, st), sl);
+            if (rnew) b.index.emplace(b.key(c, r, st), sr);
+        }
+        b.link(sl, sr, (int32_t)i);                                       // S:352-355
+        b.link(sr, sl, (int32_t)i);
+    }
+
+    // ---- creation id -> list order --------------------------------------------------------------
+    const int64_t S = (int64_t)b.s_pos.size();
+    std::vector<int32_t> new_of((size_t)S), old_of((size_t)S);
+    g = SiteGraph();
+    g.n_chrom = n_chrom;
+    g.n_sites = S;
+    g.dirty_regime = b.emulate;
+    g.cs_off.assign((size_t)n_chrom + 1, 0);
+    if (b.emulate) {
+        int64_t k = 0;
+        for (int32_t c = 0; c < n_chrom; ++c) {
+            g.cs_off[(size_t)c] = k;
+            for (int32_t id : b.order[(size_t)c]) old_of[(size_t)k++] = id;
+        }
+        g.cs_off[(size_t)n_chrom] = k;
+    } else {
+        std::iota(old_of.begin(), old_of.end(), 0);
+        std::stable_sort(old_of.begin(), old_of.end(), [&](int32_t x, int32_t y) {
+            if (b.s_chrom[x] != b.s_chrom[y]) return b.s_chrom[x] < b.s_chrom[y];
+            if (b.s_pos[x] != b.s_pos[y]) return b.s_pos[x] < b.s_pos[y];
+            if (stranded) return b.s_strand[x] == '+' && b.s_strand[y] == '-';
+            return false;
+        });
+        for (int64_t k = 0; k < S; ++k) g.cs_off[(size_t)b.s_chrom[old_of[(size_t)k]] + 1]++;
+        for (int32_t c = 0; c < n_chrom; ++c) g.cs_off[(size_t)c + 1] += g.cs_off[(size_t)c];
+    }
+    for (int64_t k = 0; k < S; ++k) new_of[(size_t)old_of[(size_t)k]] = (int32_t)k;
+    g.chrom.resize((size_t)S); g.pos.resize((size_t)S); g.strand.resize((size_t)S);
+    g.cls.resize((size_t)S); g.first_line.resize((size_t)S);
+    for (int64_t k = 0; k < S; ++k) {
+        const int32_t o = old_of[(size_t)k];
+        g.chrom[(size_t)k] = b.s_chrom[o];
+        g.pos[(size_t)k] = b.s_pos[o];
+        g.strand[(size_t)k] = b.s_strand[o];
+        g.first_line[(size_t)k] = b.s_line[o];
+        g.cls[(size_t)k] = !stranded ? CLS_ANY : b.s_strand[o] == '+' ? CLS_PLUS : b.s_strand[o] == '-' ? CLS_MINUS : CLS_NEVER;
+    }
+
+    std::vector<int32_t> keys, perm;
+    // Partners CSR
+    keys.resize(b.pt_a.size());
+    for (size_t i = 0; i < keys.size(); ++i) keys[i] = new_of[(size_t)b.pt_a[i]];
+    group_by(keys, S, g.pt_off, perm);
+    g.pt_site.resize(perm.size());
+    for (size_t i = 0; i < perm.size(); ++i) g.pt_site[i] = new_of[(size_t)b.pt_b[(size_t)perm[i]]];
+    // PartnerCounts CSR (+ old edge id -> new edge id)
+    keys.resize(b.pc_a.size());
+    for (size_t i = 0; i < keys.size(); ++i) keys[i] = new_of[(size_t)b.pc_a[i]];
+    group_by(keys, S, g.pc_off, perm);
+    const int64_t E = (int64_t)perm.size();
+    std::vector<int32_t> new_edge((size_t)E);
+    g.pc_pos.resize((size_t)E);
+    for (int64_t i = 0; i < E; ++i) {
+        new_edge[(size_t)perm[(size_t)i]] = (int32_t)i;
+        g.pc_pos[(size_t)i] = b.pc_pos[(size_t)perm[(size_t)i]];
+    }
+    // reduction segments
+    keys.resize(b.inc_site.size());
+    for (size_t i = 0; i < keys.size(); ++i) keys[i] = new_of[(size_t)b.inc_site[i]];
+    group_by(keys, S, g.inc_off, perm);
+    g.inc_line.resize(perm.size());
+    for (size_t i = 0; i < perm.size(); ++i) g.inc_line[i] = b.inc_line[(size_t)perm[i]];
+    keys.resize(b.einc_edge.size());
+    for (size_t i = 0; i < keys.size(); ++i) keys[i] = new_edge[(size_t)b.einc_edge[i]];
+    group_by(keys, E, g.einc_off, perm);
+    g.einc_line.resize(perm.size());
+    for (size_t i = 0; i < perm.size(); ++i) g.einc_line[i] = b.einc_line[(size_t)perm[i]];
+
+    // ---- competitors: positions of partners-of-partners other than own position (S:364-372) -------
+    g.cp_off.assign((size_t)S + 1, 0);
+    g.cp_pos.clear();
+    std::vector<int32_t> tmp;
+    for (int64_t t = 0; t < S; ++t) {
+        tmp.clear();
+        for (int64_t a = g.pt_off[(size_t)t]; a < g.pt_off[(size_t)t + 1]; ++a) {
+            const int32_t p = g.pt_site[(size_t)a];
+            for (int64_t q = g.pt_off[(size_t)p]; q < g.pt_off[(size_t)p + 1]; ++q) {
+                const int32_t cpos = g.pos[(size_t)g.pt_site[(size_t)q]];
+                if (cpos != g.pos[(size_t)t]) tmp.push_back(cpos);
+            }
+        }
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        g.cp_pos.insert(g.cp_pos.end(), tmp.begin(), tmp.end());
+        g.cp_off[(size_t)t + 1] = (int64_t)g.cp_pos.size();
+    }
+    build_rp(g);
+    return "";
+}
+
+std::string build_recount_graph(int32_t n_chrom, int64_t n_sites, const int32_t* s_chrom, const int32_t* s_pos,
+                                const uint8_t* s_strand, const int64_t* p_off, const int32_t* p_pos,
+                                const int64_t* c_off, const int32_t* c_pos, bool stranded, SiteGraph& g) {
+    if (n_chrom < 0 || n_sites < 0) return "negative size";
+    if (n_sites > 0 && (!s_chrom || !s_pos || !s_strand || !p_off || !c_off)) return "null site array";
+    if (n_sites >= (int64_t)1 << 30) return "too many sites";
+    struct Row { int32_t chrom, pos; int64_t gap; };
+    std::vector<Row> rows;
+    rows.reserve((size_t)n_sites * 2);
+    std::unordered_map<uint64_t, char> have;
+    have.reserve((size_t)n_sites * 2);
+    auto pk = [](int32_t c, int32_t p) { return ((uint64_t)(uint32_t)c << 32) | (uint32_t)p; };
+    for (int64_t i = 0; i < n_sites; ++i) {
+        if (p_off[i + 1] < p_off[i] || c_off[i + 1] < c_off[i]) return "offsets not monotone";
+        // a region unknown to this sample's BAM: the reference's samtools call yields no reads, so
+        // the gap keeps the zeros the caller initialised its outputs with
+        if (s_chrom[i] < 0 || s_chrom[i] >= n_chrom) continue;
+        rows.push_back({s_chrom[i], s_pos[i], i});
+        have.emplace(pk(s_chrom[i], s_pos[i]), 1);
+    }
+    const size_t n_real = rows.size();
+    for (size_t k = 0; k < n_real; ++k) {
+        const int64_t i = rows[k].gap;
+        for (int64_t e = p_off[i]; e < p_off[i + 1]; ++e) {
+            const uint64_t key = pk(rows[k].chrom, p_pos[e]);
+            if (have.find(key) == have.end()) {
+                have.emplace(key, 1);
+                rows.push_back({rows[k].chrom, p_pos[e], -1});
+            }
+        }
+    }
+    std::stable_sort(rows.begin(), rows.end(), [](const Row& a, const Row& b) {
+        if (a.chrom != b.chrom) return a.chrom < b.chrom;
+        return a.pos < b.pos;
+    });
+    const int64_t S = (int64_t)rows.size();
+    g = SiteGraph();
+    g.n_chrom = n_chrom;
+    g.n_sites = S;
+    g.cs_off.assign((size_t)n_chrom + 1, 0);
+    g.chrom.resize((size_t)S); g.pos.resize((size_t)S); g.strand.resize((size_t)S); g.cls.resize((size_t)S);
+    g.first_line.assign((size_t)S, -1);
+    g.gap_index.resize((size_t)S);
+    g.pt_off.assign((size_t)S + 1, 0);
+    g.inc_off.assign((size_t)S + 1, 0);
+    g.pc_off.assign((size_t)S + 1, 0);
+    g.cp_off.assign((size_t)S + 1, 0);
+    std::vector<int32_t> tmp;
+    for (int64_t k = 0; k < S; ++k) {
+        const Row& r = rows[(size_t)k];
+        g.cs_off[(size_t)r.chrom + 1]++;
+        g.chrom[(size_t)k] = r.chrom;
+        g.pos[(size_t)k] = r.pos;
+        g.gap_index[(size_t)k] = r.gap;
+        if (r.gap < 0) {
+            g.strand[(size_t)k] = 0;
+            g.cls[(size_t)k] = CLS_PSEUDO;
+        } else {
+            const uint8_t st = s_strand[r.gap];
+            g.strand[(size_t)k] = st;
+            g.cls[(size_t)k] = !stranded ? CLS_ANY : st == '+' ? CLS_PLUS : st == '-' ? CLS_MINUS : CLS_NEVER;
+            tmp.assign(p_pos + p_off[r.gap], p_pos + p_off[r.gap + 1]);
+            // keys of a dict: unique, order irrelevant for membership tests
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            g.pc_pos.insert(g.pc_pos.end(), tmp.begin(), tmp.end());
+            tmp.assign(c_pos + c_off[r.gap], c_pos + c_off[r.gap + 1]);
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+            g.cp_pos.insert(g.cp_pos.end(), tmp.begin(), tmp.end());
+        }
+        g.pc_off[(size_t)k + 1] = (int64_t)g.pc_pos.size();
+        g.cp_off[(size_t)k + 1] = (int64_t)g.cp_pos.size();
+    }
+    for (int32_t c = 0; c < n_chrom; ++c) g.cs_off[(size_t)c + 1] += g.cs_off[(size_t)c];
+    g.einc_off.assign(g.pc_pos.size() + 1, 0);
+    build_rp(g);
+    return "";
+}
+
+}  // namespace spl
