@@ -166,13 +166,16 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_N_ALIGNED    10   /* records with >= 1 CIGAR op ("aligned reads")              */
 #define SPL_STAT_LAUNCHES     11   /* kernels launched per pass                                 */
 #define SPL_STAT_MS_EXPAND    12   /* ms of the record -> SoA expansion at load time            */
-#define SPL_NSTATS            16
+#define SPL_NSTATS            24
 
 /* per-call statistics of the last spl_process* / spl_recount* call (same indices; MS_* are
  * host wall-clock of the stages; extra indices below) */
 #define SPL_STAT_MS_DECODE    13   /* BAM inflate + parse (host wall ms)                        */
 #define SPL_STAT_H2D_BYTES    14
 #define SPL_STAT_D2H_BYTES    15
+#define SPL_STAT_MS_GRAPH     16   /* host: site table + competing-site graph construction          */
+#define SPL_STAT_MS_UPLOAD    17   /* host wall ms until records are uploaded and expanded           */
+#define SPL_STAT_MS_COUNT     18   /* host wall ms of the counting pass + result download            */
 int spl_last_stats(const spl_ctx* ctx, double* stats_out);
 
 /* ---- BAM utilities (used by tests / benchmarks to make synthetic inputs) -------------------- */

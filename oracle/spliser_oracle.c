@@ -19,9 +19,13 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <stdio.h>
+#include <time.h>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
+
+static double now_s(void) { struct timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec + 1e-9 * ts.tv_nsec; }
 
 #define FLAG_STRANDED 1u
 #define FLAG_RF 2u
@@ -399,8 +403,11 @@ int oracle_process(const RecView* r, int32_t n_chrom, int64_t n_junc, const int3
     if (n_threads > 0) omp_set_num_threads(n_threads);
 #endif
     const int stranded = (mode & FLAG_STRANDED) != 0;
+    const double t0 = now_s();
     SiteList* lists = build_sites(n_chrom, n_junc, jc, jl, jr, js, jst, stranded);
+    const double t1 = now_s();
     ChromIndex* ix = build_index(r, n_chrom);
+    const double t2 = now_s();
     int64_t S = 0;
     for (int32_t c = 0; c < n_chrom; ++c) S += lists[c].n;
     for (int32_t c = 0; c < n_chrom; ++c) {                                  /* processSites, S:681-692 */
@@ -408,6 +415,7 @@ int oracle_process(const RecView* r, int32_t n_chrom, int64_t n_junc, const int3
         for (int64_t k = 0; k < lists[c].n; ++k) check_bam(lists[c].v[k], r, &ix[c], mode);
         for (int64_t k = 0; k < lists[c].n; ++k) beta2_and_sse(lists[c].v[k], mode);
     }
+    if (getenv("ORACLE_TIMING")) fprintf(stderr, "oracle: build_sites %.3fs build_index %.3fs count %.3fs\n", t1 - t0, t2 - t1, now_s() - t2);
     memset(out, 0, sizeof *out);
     out->n_sites = S;
     const size_t n1 = (size_t)S + 1;

@@ -345,13 +345,17 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     if (n_junc > 0 && !j_score) return ctx->fail(SPL_ERR_ARG, "NULL j_score");
     CU(cudaSetDevice(ctx->device));
     reset_stats(ctx);
+    const double tg0 = now_ms();
     std::string e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, (flags & SPL_FLAG_STRANDED) != 0, ctx->hg);
     if (!e.empty()) return ctx->fail(SPL_ERR_ARG, "%s", e.c_str());
     ctx->flags = flags;
     rc = upload_graph(ctx, j_score, n_junc);
     if (rc) return rc;
+    const double tg1 = now_ms();
+    ctx->stats[SPL_STAT_MS_GRAPH] = tg1 - tg0;
     rc = upload_and_expand(ctx, rec, flags);
     if (rc) return rc;
+    ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg1;
     launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
     CU(cudaGetLastError());
     ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
@@ -442,9 +446,11 @@ int spl_process_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     const double t0 = now_ms();
     int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags);
     if (rc) return rc;
+    const double tc0 = now_ms();
     rc = count_pass(ctx, nullptr);
     if (rc) return rc;
     rc = fetch(ctx, out);
+    ctx->stats[SPL_STAT_MS_COUNT] = now_ms() - tc0;
     ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
     return rc;
 }

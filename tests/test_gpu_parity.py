@@ -83,4 +83,85 @@ def test_empty_and_ragged_inputs(ctx):
     j = Junctions([0, 0], [100, 100], [200, 300], [5, 3], [ord("+"), ord("+")])
     t = ctx.process_records(Records.from_reads(["C", "D"], [("D", 90, 0, "30M"), ("Z", 5, 0, "10M"), ("C", 95, 0, "*")]), 2, j, 0)
     assert list(t.pos) == [100, 200, 300] and list(t.alpha) == [8, 5, 3] and int(t.beta1.sum()) == 0
-    assert [float(x) for x in t.sse] == [1.0, 1.0, 1.0]
+    assert [float(x) for x in t.sse] == [1.0, 0.625, 1.0]      # site 200: junction (100,300) flanks it -> beta2Simple 3 (S:594-599)
+    assert list(t.beta2simple) == [0, 3, 0]
+
+
+@pytest.mark.parametrize("stranded,paired,n", [(False, False, 150_000), (True, True, 400_000)])
+def test_synthetic_workload_vs_c_oracle(ctx, stranded, paired, n):
+    """Config-shaped synthetic sample (sizes the C oracle finishes in seconds), every output column."""
+    from oracle import c_oracle
+    from spliser_b200 import synth
+    w = synth.generate(synth.config_small(n, seed=21 + stranded, stranded=stranded, paired=paired))
+    for flags in (w.flags, w.flags | 4, w.flags | 8):
+        want = c_oracle.process(w.records, len(w.chroms), w.junctions, flags, threads=8)
+        got = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, flags))
+        assert c_oracle.diff_tables(got, want) is None, (flags, c_oracle.diff_tables(got, want))
+    assert int(want["beta1"].sum()) > 0 and int(want["beta2simple"].sum()) > 0
+
+
+def test_c1_shaped_workload_vs_c_oracle(ctx):
+    """BASELINE configs[0] shape at reduced depth (400k of the 2M records), unstranded."""
+    from oracle import c_oracle
+    from spliser_b200 import synth
+    cfg = synth.config_c1()
+    cfg.n_records = 400_000
+    w = synth.generate(cfg)
+    want = c_oracle.process(w.records, len(w.chroms), w.junctions, w.flags, threads=8)
+    got = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags))
+    assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
+
+
+def test_resident_path_equals_process_path(ctx):
+    from oracle import c_oracle
+    from spliser_b200 import synth
+    w = synth.generate(synth.config_small(120_000, seed=33, stranded=True, paired=True))
+    a = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags | 4))
+    ctx.resident_load(w.records, len(w.chroms), w.junctions, w.flags | 4)
+    st = ctx.resident_count(3)                 # idempotent: counters are re-zeroed every pass
+    b = c_oracle.table_dict(ctx.resident_fetch())
+    assert c_oracle.diff_tables(a, b) is None
+    assert st["n_aligned"] == len(w.records) and st["ms_total"] > 0
+
+
+def test_shuffled_records_give_identical_counts(ctx):
+    """Any record order inside a chromosome segment is exact (the sorted-input fast paths have fallbacks)."""
+    import numpy as np
+    from oracle import c_oracle
+    from spliser_b200 import Records, synth
+    w = synth.generate(synth.config_small(60_000, seed=44))
+    r = w.records
+    rng = np.random.default_rng(1)
+    pos, flag, ops = [], [], []
+    off = [0]
+    for s in range(len(r.seg_chrom)):
+        idx = np.arange(int(r.seg_off[s]), int(r.seg_off[s + 1]))
+        rng.shuffle(idx)
+        for i in idx:
+            pos.append(r.pos[i]); flag.append(r.flag[i])
+            ops.extend(r.cigar[int(r.cig_off[i]):int(r.cig_off[i + 1])])
+            off.append(len(ops))
+    sh = Records(pos, flag, off, ops, r.seg_chrom, r.seg_off)
+    a = c_oracle.table_dict(ctx.process_records(r, len(w.chroms), w.junctions, 4))
+    b = c_oracle.table_dict(ctx.process_records(sh, len(w.chroms), w.junctions, 4))
+    assert c_oracle.diff_tables(a, b) is None
+
+
+def test_tiles_concatenate_to_the_untiled_result(built_library):
+    """Genomic-tile sharding: each tile context counts only the sites it owns; owned slices concatenate
+    to the single-context result (run sequentially on one GPU)."""
+    import numpy as np
+    import spliser_b200
+    from spliser_b200 import synth
+    w = synth.generate(synth.config_small(80_000, seed=55, stranded=True, paired=True))
+    with spliser_b200.Context(0) as full:
+        ref = full.process_records(w.records, len(w.chroms), w.junctions, w.flags)
+    S = len(ref)
+    n_tiles = 3
+    b1 = np.zeros(S, np.int64); b2 = np.zeros(S, np.int64); sse = np.zeros(S)
+    for ti in range(n_tiles):
+        with spliser_b200.Context(0, tile=(ti, n_tiles)) as c:
+            t = c.process_records(w.records, len(w.chroms), w.junctions, w.flags)
+        lo, hi = S * ti // n_tiles, S * (ti + 1) // n_tiles
+        b1[lo:hi], b2[lo:hi], sse[lo:hi] = t.beta1[lo:hi], t.beta2simple[lo:hi], t.sse[lo:hi]
+    assert np.array_equal(b1, ref.beta1) and np.array_equal(b2, ref.beta2simple) and np.array_equal(sse, ref.sse)
