@@ -24,6 +24,7 @@ struct DevGraph {
     const int32_t* cs_off;              // [n_chrom+1]
     const int32_t* site_pos;            // [n_sites + 8], tail padded with INT32_MAX
     const uint8_t* site_cls;            // [n_sites]
+    const uint8_t* site_hot;            // [n_sites + 32] 1 = some site in the reverse-partner list anchored here has competitors
     const int32_t *pt_off, *pt_site;    // Partners (site indices)
     const int32_t *pc_off, *pc_pos;     // PartnerCounts keys
     const int32_t *cp_off, *cp_pos;     // CompetitorPos (sorted)
@@ -41,15 +42,22 @@ struct DevRecords {
     const uint32_t* cigar;              // BAM-encoded ops
 };
 
-// Structure-of-arrays the counting kernels stream.
+// Structure-of-arrays the counting kernels stream.  Positions are < 2^31, so bit 31 of the second
+// word of every element carries the read's strand class (0 = '+' / unstranded, 1 = '-'):
+//   blocks     (start, end | class<<31)            [start, end) of one M/=/X operator
+//   junctions  (l | firstN<<31, r | class<<31)     l = last base before the N, r = last base of the N;
+//                                                  firstN marks a read whose first advancing op is this N
+// Blocks of unspliced reads (stream A, sorted by start) come first, blocks of spliced reads (stream B,
+// contiguous per read) follow in the same arrays.
 struct DevSoA {
     uint32_t nA, nB, nS, nJ;
-    int32_t* a_start; int32_t* a_end; uint8_t* a_cls;   // M/=/X blocks of unspliced reads, [start, end)
-    int32_t* b_start; int32_t* b_end;                   // blocks of spliced reads, contiguous per read
-    uint32_t* sr_boff; uint32_t* sr_joff;               // [nS+1] per spliced read
-    uint8_t* sr_cls;                                    // bit0 strand class, bit1 first advancing op is N
-    int32_t* jn_l; int32_t* jn_r;                       // junctions: last base before N, last base of N
+    int32_t* m_start; uint32_t* m_endk;                 // [nA + nB] (+ padding); B stream starts at index bB
+    uint32_t bB;                                        // first element of stream B (multiple of 4)
+    uint32_t* sr_boff; uint32_t* sr_joff;               // [nS+1] per spliced read: offsets into stream B / junctions
+    uint32_t* jn_l; uint32_t* jn_rk;                    // [nJ]
+    uint32_t* jn_read;                                  // [nJ] owning spliced read; only touched for hot junctions
 };
+constexpr uint32_t POS_MASK = 0x7fffffffu;
 
 // Per-pass counters, one contiguous u32 buffer (zeroed by one memset per pass).
 struct DevCounters {
@@ -69,16 +77,17 @@ struct DevOutputs {
     uint32_t* span_blk;                 // block sums for the span scan
 };
 
-constexpr int CHUNK_READS = 2048;       // records per chunk
-constexpr int EXPAND_THREADS = 512;     // 4 records per thread
-constexpr int K3_THREADS = 256;
-constexpr int K3_MAX_STAGED = 2048;     // site positions staged in shared memory per tile (8 KB)
+constexpr int CHUNK_READS = 4096;       // records per chunk
+constexpr int EXPAND_THREADS = 512;     // one record per thread and round
+constexpr int K3_THREADS = 128;
+constexpr int K3_MAX_STAGED = 4096;     // site positions staged in shared memory per tile (16 KB)
 constexpr int K4_THREADS = 128;
-constexpr int K4_MAX_STAGED = 4096;
+constexpr int K4_MAX_STAGED = 2048;
 constexpr int FIN_THREADS = 256;
 constexpr int FIN_ITEMS = 4;            // sites per thread in the span scan
 
 constexpr uint32_t FLAG_STRANDED = 1u, FLAG_RF = 2u, FLAG_CRYPTIC = 4u, FLAG_COMBINE = 8u;
+constexpr uint32_t FLAG_DEBUG_SKIP_EXC = 0x10000u;   // set only by SPLISER_DEBUG_SKIP_EXC=1 (kernel timing experiments)
 
 struct KernelTimes { float beta1_ms, spliced_ms, final_ms; };
 

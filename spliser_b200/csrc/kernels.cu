@@ -98,22 +98,21 @@ __device__ __forceinline__ bool strand_ok(uint32_t site_cls, uint32_t k) {
 struct Cnt4 { uint32_t a, b, s, j; };
 
 // ------------------------------------------------------------------------------------------------
-// K0: record expansion
+// K0: record expansion (BAM-style records -> SoA).  One CTA per chunk, one record per thread and
+// round; the per-round exclusive scan keeps the output in record order, which is what makes the
+// A stream sorted by start and the chunk windows tight.
 // ------------------------------------------------------------------------------------------------
 struct ReadShape {
     uint32_t nM, nN;        // mapped (M,=,X) ops and N ops
     int32_t  lo, hi;        // min block start, max (block end - 2) over M ops  (lo > hi when none)
     int32_t  qlo, qhi;      // min / max position a site lookup of this read may ask for
-    bool     first_adv_is_N;
 };
 
 __device__ __forceinline__ ReadShape read_shape(const DevRecords& rec, uint32_t i) {
     ReadShape s;
     s.nM = s.nN = 0;
     s.lo = INT_MAX; s.hi = INT_MIN; s.qlo = INT_MAX; s.qhi = INT_MIN;
-    s.first_adv_is_N = false;
     int32_t cur = rec.pos[i];
-    bool seen = false;
     const uint32_t c0 = rec.cig_off[i], c1 = rec.cig_off[i + 1];
     for (uint32_t k = c0; k < c1; ++k) {
         const uint32_t v = rec.cigar[k];
@@ -125,22 +124,21 @@ __device__ __forceinline__ ReadShape read_shape(const DevRecords& rec, uint32_t 
             s.hi = max(s.hi, cur + len - 2);
             s.qlo = min(s.qlo, cur);
             s.qhi = max(s.qhi, cur + len);
-            cur += len; seen = true;
+            cur += len;
         } else if (op == 3u) {                            // N : advance, junction (S:480-483)
-            if (!seen) s.first_adv_is_N = true;
             s.nN++;
             s.qlo = min(s.qlo, cur - 1);
             s.qhi = max(s.qhi, cur + len);
-            cur += len; seen = true;
+            cur += len;
         } else if (op == 2u) {                            // D : advance only (S:460-462)
-            cur += len; seen = true;
+            cur += len;
         }                                                 // I S H P : no progression (S:463-464)
     }
     return s;
 }
 
-// block-wide exclusive scan of four counters (blockDim.x == EXPAND_THREADS); returns the block total
-__device__ __forceinline__ Cnt4 block_exscan4(Cnt4 v, Cnt4& total, Cnt4* warp_tot /* [32] shared */) {
+// block-wide exclusive scan of four counters; returns the exclusive prefix and the block total
+__device__ __forceinline__ Cnt4 block_exscan4(Cnt4 v, Cnt4& total, Cnt4* warp_tot /* [33] shared */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     Cnt4 inc = v;
 #pragma unroll
@@ -149,6 +147,7 @@ __device__ __forceinline__ Cnt4 block_exscan4(Cnt4 v, Cnt4& total, Cnt4* warp_to
         const uint32_t s = __shfl_up_sync(0xffffffffu, inc.s, d), j = __shfl_up_sync(0xffffffffu, inc.j, d);
         if (lane >= d) { inc.a += a; inc.b += b; inc.s += s; inc.j += j; }
     }
+    __syncthreads();                                      // previous use of warp_tot is over
     if (lane == 31) warp_tot[warp] = inc;
     __syncthreads();
     if (warp == 0) {
@@ -170,25 +169,18 @@ __device__ __forceinline__ Cnt4 block_exscan4(Cnt4 v, Cnt4& total, Cnt4* warp_to
     return Cnt4{base.a + inc.a - v.a, base.b + inc.b - v.b, base.s + inc.s - v.s, base.j + inc.j - v.j};
 }
 
-constexpr int RPT = CHUNK_READS / EXPAND_THREADS;   // records per thread, contiguous
-
 __global__ void __launch_bounds__(EXPAND_THREADS) k_expand_count(DevRecords rec, Chunk* chunks, uint32_t mode) {
     Chunk& ck = chunks[blockIdx.x];
-    const uint32_t r0 = ck.rec_lo + threadIdx.x * RPT;
     Cnt4 c{0, 0, 0, 0};
     int32_t alo = INT_MAX, ahi = INT_MIN, slo = INT_MAX, shi = INT_MIN;
-#pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-        const uint32_t i = r0 + q;
-        if (i < ck.rec_hi) {
-            const ReadShape s = read_shape(rec, i);
-            if (s.nN == 0) {
-                c.a += s.nM;
-                alo = min(alo, s.lo); ahi = max(ahi, s.hi);
-            } else {
-                c.b += s.nM; c.s += 1; c.j += s.nN;
-                slo = min(slo, s.qlo); shi = max(shi, s.qhi);
-            }
+    for (uint32_t i = ck.rec_lo + threadIdx.x; i < ck.rec_hi; i += EXPAND_THREADS) {
+        const ReadShape s = read_shape(rec, i);
+        if (s.nN == 0) {
+            c.a += s.nM;
+            alo = min(alo, s.lo); ahi = max(ahi, s.hi);
+        } else {
+            c.b += s.nM; c.s += 1; c.j += s.nN;
+            slo = min(slo, s.qlo); shi = max(shi, s.qhi);
         }
     }
     __shared__ Cnt4 wt[33];
@@ -210,51 +202,25 @@ __global__ void __launch_bounds__(EXPAND_THREADS) k_expand_count(DevRecords rec,
     }
 }
 
-// exclusive scan of the per-chunk totals; single CTA (n_chunks is R / 2048: at most ~1e5)
+// exclusive scan of the per-chunk totals; single CTA (n_chunks is R / 4096: at most ~1e5)
 __global__ void __launch_bounds__(1024) k_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals4) {
     __shared__ Cnt4 wt[33];
     __shared__ Cnt4 carry;
     if (threadIdx.x == 0) carry = Cnt4{0, 0, 0, 0};
     __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < n_chunks; base += 1024) {
         const int i = base + (int)threadIdx.x;
         Cnt4 v{0, 0, 0, 0};
         if (i < n_chunks) v = Cnt4{chunks[i].a_cnt, chunks[i].b_cnt, chunks[i].s_cnt, chunks[i].j_cnt};
-        Cnt4 inc = v;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t a = __shfl_up_sync(0xffffffffu, inc.a, d), b = __shfl_up_sync(0xffffffffu, inc.b, d);
-            const uint32_t s = __shfl_up_sync(0xffffffffu, inc.s, d), j = __shfl_up_sync(0xffffffffu, inc.j, d);
-            if (lane >= d) { inc.a += a; inc.b += b; inc.s += s; inc.j += j; }
-        }
-        if (lane == 31) wt[warp] = inc;
-        __syncthreads();
-        if (warp == 0) {
-            Cnt4 w = wt[lane];
-            Cnt4 wi = w;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t a = __shfl_up_sync(0xffffffffu, wi.a, d), b = __shfl_up_sync(0xffffffffu, wi.b, d);
-                const uint32_t s = __shfl_up_sync(0xffffffffu, wi.s, d), j = __shfl_up_sync(0xffffffffu, wi.j, d);
-                if (lane >= d) { wi.a += a; wi.b += b; wi.s += s; wi.j += j; }
-            }
-            wt[lane] = Cnt4{wi.a - w.a, wi.b - w.b, wi.s - w.s, wi.j - w.j};
-            if (lane == 31) wt[32] = wi;
-        }
-        __syncthreads();
-        const Cnt4 c = carry, wb = wt[warp];
+        Cnt4 total;
+        const Cnt4 ex = block_exscan4(v, total, wt);
+        const Cnt4 c = carry;
         if (i < n_chunks) {
-            chunks[i].a_base = c.a + wb.a + inc.a - v.a;
-            chunks[i].b_base = c.b + wb.b + inc.b - v.b;
-            chunks[i].s_base = c.s + wb.s + inc.s - v.s;
-            chunks[i].j_base = c.j + wb.j + inc.j - v.j;
+            chunks[i].a_base = c.a + ex.a; chunks[i].b_base = c.b + ex.b;
+            chunks[i].s_base = c.s + ex.s; chunks[i].j_base = c.j + ex.j;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            const Cnt4 t = wt[32];
-            carry = Cnt4{c.a + t.a, c.b + t.b, c.s + t.s, c.j + t.j};
-        }
+        if (threadIdx.x == 0) carry = Cnt4{c.a + total.a, c.b + total.b, c.s + total.s, c.j + total.j};
         __syncthreads();
     }
     if (threadIdx.x == 0) {
@@ -265,54 +231,50 @@ __global__ void __launch_bounds__(1024) k_chunk_scan(Chunk* chunks, int n_chunks
 __global__ void __launch_bounds__(EXPAND_THREADS)
 k_expand_scatter(DevRecords rec, const Chunk* chunks, DevSoA soa, uint32_t mode) {
     const Chunk ck = chunks[blockIdx.x];
-    const uint32_t r0 = ck.rec_lo + threadIdx.x * RPT;
-    Cnt4 c{0, 0, 0, 0};
-    uint32_t nM[RPT], nN[RPT];
-#pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-        const uint32_t i = r0 + q;
-        nM[q] = nN[q] = 0;
-        if (i < ck.rec_hi) {
-            const uint32_t c0 = rec.cig_off[i], c1 = rec.cig_off[i + 1];
+    __shared__ Cnt4 wt[33];
+    Cnt4 run{ck.a_base, soa.bB + ck.b_base, ck.s_base, ck.j_base};       // running output cursors of the chunk
+    for (uint32_t base = ck.rec_lo; base < ck.rec_hi; base += EXPAND_THREADS) {   // uniform trip count
+        const uint32_t i = base + threadIdx.x;
+        const bool live = i < ck.rec_hi;
+        uint32_t nM = 0, nN = 0, c0 = 0, c1 = 0;
+        if (live) {
+            c0 = rec.cig_off[i]; c1 = rec.cig_off[i + 1];
             for (uint32_t k = c0; k < c1; ++k) {
                 const uint32_t op = rec.cigar[k] & 15u;
-                nM[q] += (op == 0u || op == 7u || op == 8u);
-                nN[q] += (op == 3u);
-            }
-            if (nN[q] == 0) c.a += nM[q]; else { c.b += nM[q]; c.s += 1; c.j += nN[q]; }
-        }
-    }
-    __shared__ Cnt4 wt[33];
-    Cnt4 total;
-    Cnt4 ex = block_exscan4(c, total, wt);
-    uint32_t ia = ck.a_base + ex.a, ib = ck.b_base + ex.b, is = ck.s_base + ex.s, ij = ck.j_base + ex.j;
-#pragma unroll
-    for (int q = 0; q < RPT; ++q) {
-        const uint32_t i = r0 + q;
-        if (i >= ck.rec_hi) break;
-        const uint32_t k = read_class(rec.flag[i], mode);
-        const bool spliced = nN[q] != 0;
-        int32_t cur = rec.pos[i];
-        bool seen = false, firstN = false;
-        if (spliced) { soa.sr_boff[is] = ib; soa.sr_joff[is] = ij; }
-        const uint32_t c0 = rec.cig_off[i], c1 = rec.cig_off[i + 1];
-        for (uint32_t kk = c0; kk < c1; ++kk) {
-            const uint32_t v = rec.cigar[kk];
-            const uint32_t op = v & 15u;
-            const int32_t len = (int32_t)(v >> 4);
-            if (op == 0u || op == 7u || op == 8u) {
-                if (spliced) { soa.b_start[ib] = cur; soa.b_end[ib] = cur + len; ++ib; }
-                else { soa.a_start[ia] = cur; soa.a_end[ia] = cur + len; soa.a_cls[ia] = (uint8_t)k; ++ia; }
-                cur += len; seen = true;
-            } else if (op == 3u) {
-                if (!seen) firstN = true;
-                soa.jn_l[ij] = cur - 1; soa.jn_r[ij] = cur + len - 1; ++ij;     // S:482-483
-                cur += len; seen = true;
-            } else if (op == 2u) {
-                cur += len; seen = true;
+                nM += (op == 0u || op == 7u || op == 8u);
+                nN += (op == 3u);
             }
         }
-        if (spliced) { soa.sr_cls[is] = (uint8_t)(k | (firstN ? 2u : 0u)); ++is; }
+        const bool spliced = nN != 0;
+        Cnt4 v{spliced ? 0u : nM, spliced ? nM : 0u, spliced ? 1u : 0u, nN};
+        Cnt4 total;
+        const Cnt4 ex = block_exscan4(v, total, wt);
+        if (live) {
+            uint32_t im = spliced ? run.b + ex.b : run.a + ex.a;              // block cursor (A or B stream)
+            uint32_t ij = run.j + ex.j;
+            const uint32_t kbit = read_class(rec.flag[i], mode) << 31;
+            if (spliced) { soa.sr_boff[run.s + ex.s] = im - soa.bB; soa.sr_joff[run.s + ex.s] = ij; }
+            int32_t cur = rec.pos[i];
+            bool seen = false;
+            for (uint32_t kk = c0; kk < c1; ++kk) {
+                const uint32_t w = rec.cigar[kk];
+                const uint32_t op = w & 15u;
+                const int32_t len = (int32_t)(w >> 4);
+                if (op == 0u || op == 7u || op == 8u) {
+                    soa.m_start[im] = cur; soa.m_endk[im] = (uint32_t)(cur + len) | kbit; ++im;
+                    cur += len; seen = true;
+                } else if (op == 3u) {
+                    soa.jn_l[ij] = (uint32_t)(cur - 1) | (seen ? 0u : 0x80000000u);     // S:482; firstN flag (POS <= t filter, S:435)
+                    soa.jn_rk[ij] = (uint32_t)(cur + len - 1) | kbit;                   // S:483
+                    soa.jn_read[ij] = run.s + ex.s;                                     // owning spliced read (hot path only)
+                    ++ij;
+                    cur += len; seen = true;
+                } else if (op == 2u) {
+                    cur += len; seen = true;
+                }
+            }
+        }
+        run.a += total.a; run.b += total.b; run.s += total.s; run.j += total.j;
     }
     if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) {   // CSR sentinels
         soa.sr_boff[ck.s_base + ck.s_cnt] = ck.b_base + ck.b_cnt;
@@ -357,61 +319,45 @@ __global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: beta1 stabbing count over the A stream (blocks of unspliced reads)
+// K3: beta1 stabbing count over both block streams.
 //
-// One CTA per chunk.  The chunk's site window (positions inside [min block start, max block end-2])
-// is staged into shared memory by one TMA bulk copy while the threads issue their 128-bit block
-// loads.  Each warp narrows the window to [min start, max end-2] of its own 128..256 blocks with two
-// redux.sync and a warp-uniform binary search (broadcast LDS, no bank conflicts); almost always the
-// narrowed range is empty or 1-3 sites, which are then tested against the lane's blocks from
-// registers and summed across the warp with one redux.sync per site -> one RED per (warp, site, class).
+// grid = 2 x chunks: CTA (c, 0) streams the chunk's A blocks (unspliced reads, sorted by start),
+// CTA (c, 1) its B blocks (spliced reads).  The chunk's site window is staged into shared memory
+// by one TMA bulk copy while the threads issue their 128-bit block loads.  Each warp narrows the
+// window to [min start, max end-2] of the 256 blocks it holds with two redux.sync and a
+// warp-uniform binary search (broadcast LDS, no bank conflicts).  Short narrowed ranges (the common
+// case: 0-3 sites) are tested against the lane's blocks from registers and summed across the warp
+// with one redux.sync per site -> one RED per (warp, site, class); long ranges (sparse coverage,
+// displaced second blocks of spliced reads) fall back to a per-lane binary search.
 // ------------------------------------------------------------------------------------------------
 constexpr int K3_GROUPS = 2;     // int4 groups (4 blocks each) per thread and pass
-constexpr int K3_DENSE = 48;     // narrowed ranges longer than this use the per-lane search path
+constexpr int K3_DENSE = 12;     // narrowed ranges longer than this use the per-lane search path
 
-__global__ void __launch_bounds__(K3_THREADS)
-k_beta1_stab(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounters cnt) {
-    const Chunk ck = chunks[blockIdx.x];
-    if (ck.a_cnt == 0 || ck.a_site_n == 0) return;     // zone-map prune: no site can be stabbed by this chunk
-    __shared__ __align__(16) int32_t s_sites[K3_MAX_STAGED + 8];
-    __shared__ __align__(8) uint64_t bar;
-
-    const bool staged = ck.a_site_n <= K3_MAX_STAGED;
-    const int al = ck.a_site_lo & ~3;                                  // 16-byte aligned source index
-    const int nst = ((ck.a_site_lo + ck.a_site_n + 3) & ~3) - al;      // entries copied (multiple of 4)
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (staged && threadIdx.x == 0) {
-        mbar_expect_tx(&bar, (uint32_t)nst * 4u);
-        bulk_g2s(s_sites, g.site_pos + al, (uint32_t)nst * 4u, &bar);
-    }
-    // window as a pointer indexed by (global site index - base)
-    const int32_t* sp = staged ? (s_sites - al) : g.site_pos;          // sp[global index]
-    const int w_lo = max(ck.a_site_lo, g.own_lo), w_hi = min(ck.a_site_lo + ck.a_site_n, g.own_hi);
-
-    const uint32_t e0 = ck.a_base, e1 = ck.a_base + ck.a_cnt;
+template <bool SMEM>
+__device__ __forceinline__ void k3_body(const int32_t* __restrict__ sp, int w_lo, int w_hi, uint32_t e0, uint32_t e1,
+                                        const DevSoA& soa, const DevGraph& g, const DevCounters& cnt) {
     const uint32_t g0 = e0 >> 2, g1 = (e1 + 3) >> 2;
     const int lane = threadIdx.x & 31;
-    bool waited = false;
-    const uint32_t* cls32 = reinterpret_cast<const uint32_t*>(soa.a_cls);
-    for (uint32_t gb = g0 + threadIdx.x; gb - threadIdx.x < g1; gb += K3_THREADS * K3_GROUPS) {
-        int4 st[K3_GROUPS], en[K3_GROUPS];
-        uint32_t cl[K3_GROUPS];
+    const int4* gs = reinterpret_cast<const int4*>(soa.m_start);
+    const int4* ge = reinterpret_cast<const int4*>(soa.m_endk);
+    int4 nst[K3_GROUPS], nen[K3_GROUPS];                               // next pass, loaded one pass ahead
+    auto load_pass = [&](uint32_t gb) {
 #pragma unroll
         for (int u = 0; u < K3_GROUPS; ++u) {
             const uint32_t gi = gb + u * K3_THREADS;
-            if (gi < g1) {
-                st[u] = ldg_stream(reinterpret_cast<const int4*>(soa.a_start) + gi);
-                en[u] = ldg_stream(reinterpret_cast<const int4*>(soa.a_end) + gi);
-                cl[u] = ldg_stream_u32(cls32 + gi);
-            } else {
-                st[u] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX);
-                en[u] = make_int4(INT_MIN, INT_MIN, INT_MIN, INT_MIN);
-                cl[u] = 0;
-            }
+            if (gi < g1) { nst[u] = ldg_stream(gs + gi); nen[u] = ldg_stream(ge + gi); }
+            else { nst[u] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX); nen[u] = make_int4(0, 0, 0, 0); }
         }
-        // turn [start, end) into the closed stabbing interval [start, end-2]; invalidate foreign elements
+    };
+    load_pass(g0 + threadIdx.x);
+    for (uint32_t gb = g0 + threadIdx.x; gb - threadIdx.x < g1; gb += K3_THREADS * K3_GROUPS) {
+        int4 st[K3_GROUPS], en[K3_GROUPS];
+#pragma unroll
+        for (int u = 0; u < K3_GROUPS; ++u) { st[u] = nst[u]; en[u] = nen[u]; }
+        if (gb - threadIdx.x + K3_THREADS * K3_GROUPS < g1) load_pass(gb + K3_THREADS * K3_GROUPS);
+        // (start, end|class) -> start a, length-2 d (unsigned; huge when the block cannot stab), class increment
         int lo = INT_MAX, hi = INT_MIN;
+        uint32_t inc[K3_GROUPS][4];
 #pragma unroll
         for (int u = 0; u < K3_GROUPS; ++u) {
             const uint32_t gi = gb + u * K3_THREADS;
@@ -419,18 +365,18 @@ k_beta1_stab(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounte
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 const uint32_t idx = gi * 4 + q;
-                const bool valid = gi < g1 && idx >= e0 && idx < e1;
-                const int a = valid ? s[q] : INT_MAX;
-                const int b = valid ? e[q] - 2 : INT_MIN;
-                s[q] = a; e[q] = b;
-                if (a <= b) { lo = min(lo, a); hi = max(hi, b); }
+                const uint32_t ek = (uint32_t)e[q];
+                const int b = (int)(ek & POS_MASK) - 2;                 // last stabbed position
+                const bool valid = (idx - e0) < (e1 - e0) && s[q] <= b;
+                inc[u][q] = valid ? ((ek >> 31) ? 0x10000u : 1u) : 0u;    // invalid blocks add 0 whatever they "hit"
+                e[q] = b - s[q];                                        // d = b - a  (>= 0 when valid)
+                if (valid) { lo = min(lo, s[q]); hi = max(hi, b); }
             }
         }
         const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
         if (wlo > whi) continue;
-        if (staged && !waited) { mbar_wait(&bar, 0); waited = true; }
-        int i0 = lower_bound_i32(sp, w_lo, w_hi, wlo);
-        int i1 = upper_bound_i32(sp, i0, w_hi, whi);
+        const int i0 = lower_bound_i32(sp, w_lo, w_hi, wlo);
+        const int i1 = upper_bound_i32(sp, i0, w_hi, whi);
         if (i0 >= i1) continue;
         if (i1 - i0 <= K3_DENSE) {
             for (int s = i0; s < i1; ++s) {                           // warp-uniform loop
@@ -438,13 +384,10 @@ k_beta1_stab(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounte
                 uint32_t c = 0;
 #pragma unroll
                 for (int u = 0; u < K3_GROUPS; ++u) {
-                    const int* a = &st[u].x; const int* b = &en[u].x;
+                    const int* a = &st[u].x; const int* d = &en[u].x;
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const bool hit = a[q] <= p && p <= b[q];
-                        const uint32_t k = (cl[u] >> (8 * q)) & 1u;
-                        c += hit ? (k ? 0x10000u : 1u) : 0u;
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        c += ((uint32_t)p - (uint32_t)a[q] <= (uint32_t)d[q]) ? inc[u][q] : 0u;
                 }
                 c = __reduce_add_sync(0xffffffffu, c);
                 if (lane == 0 && c) {
@@ -452,39 +395,61 @@ k_beta1_stab(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounte
                     if (c >> 16) atomicAdd(cnt.cov + g.n_sites + s, c >> 16);
                 }
             }
-        } else {                                                       // wide window (sparse / unsorted input)
+        } else {                                                       // wide window: per-lane search
 #pragma unroll
             for (int u = 0; u < K3_GROUPS; ++u) {
-                const int* a = &st[u].x; const int* b = &en[u].x;
+                const int* a = &st[u].x; const int* d = &en[u].x;
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
-                    if (a[q] > b[q]) continue;
-                    const uint32_t k = (cl[u] >> (8 * q)) & 1u;
-                    for (int s = lower_bound_i32(sp, i0, i1, a[q]); s < i1 && sp[s] <= b[q]; ++s)
+                    if (!inc[u][q]) continue;
+                    const uint32_t k = inc[u][q] >> 16;
+                    const int b = a[q] + d[q];
+                    for (int s = lower_bound_i32(sp, i0, i1, a[q]); s < i1 && sp[s] <= b; ++s)
                         atomicAdd(cnt.cov + k * g.n_sites + s, 1u);
                 }
             }
         }
     }
-    if (staged && !waited) mbar_wait(&bar, 0);   // never exit with the bulk copy still in flight
+}
+
+__global__ void __launch_bounds__(K3_THREADS)
+k_beta1_stab(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounters cnt) {
+    const Chunk ck = chunks[blockIdx.x >> 1];
+    const bool bstream = blockIdx.x & 1;
+    const uint32_t n = bstream ? ck.b_cnt : ck.a_cnt;
+    const int site_lo = bstream ? ck.s_site_lo : ck.a_site_lo, site_n = bstream ? ck.s_site_n : ck.a_site_n;
+    if (n == 0 || site_n == 0) return;                 // zone-map prune: no site can be stabbed by these blocks
+    const int w_lo = max(site_lo, g.own_lo), w_hi = min(site_lo + site_n, g.own_hi);
+    if (w_lo >= w_hi) return;
+    const uint32_t e0 = bstream ? soa.bB + ck.b_base : ck.a_base, e1 = e0 + n;
+    __shared__ __align__(16) int32_t s_sites[K3_MAX_STAGED + 8];
+    __shared__ __align__(8) uint64_t bar;
+    if (site_n <= K3_MAX_STAGED) {
+        const int al = site_lo & ~3;                                   // 16-byte aligned source index
+        const int nst = ((site_lo + site_n + 3) & ~3) - al;            // entries copied (multiple of 4)
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)nst * 4u);
+            bulk_g2s(s_sites, g.site_pos + al, (uint32_t)nst * 4u, &bar);
+        }
+        __syncthreads();                                               // barrier initialised before anyone waits
+        mbar_wait(&bar, 0);
+        k3_body<true>(s_sites - al, w_lo, w_hi, e0, e1, soa, g, cnt);
+    } else {
+        k3_body<false>(g.site_pos, w_lo, w_hi, e0, e1, soa, g, cnt);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: spliced reads.  One thread per spliced read; site window of the chunk staged by TMA.
+// K4: junctions of spliced reads.  One thread per N operator; the chunk's site window (positions and
+// the "hot" flags) is staged by TMA.  Per junction (l, r):
+//   * range add of +1 over the sites strictly inside (l, r) into the span difference array
+//     (mutually-exclusive reads, S:507-512), aggregated across the warp with match.any because
+//     neighbouring reads usually carry the same junction;
+//   * if a site at l or r anchors a reverse-partner list with competitors ("hot"), the read may make
+//     compSplicing true for some site t (S:494-501): the owning read is located by a binary search in
+//     the junction offsets and the exception logic runs for this (read, junction) pair.
 // ------------------------------------------------------------------------------------------------
-struct SiteWin {
-    const int32_t* sm;      // staged copy, indexed by global site index (already offset), or nullptr
-    const int32_t* gl;      // global site_pos
-    int lo, hi;             // staged global index range [lo, hi)
-    int32_t plo, phi;       // positions covered completely by the staged range
-    int c0, c1;             // the chromosome's site range
-    __device__ __forceinline__ int32_t at(int i) const { return (i >= lo && i < hi) ? sm[i] : gl[i]; }
-    __device__ __forceinline__ int lower(int32_t key) const {
-        if (key >= plo && key <= phi) return lower_bound_i32(sm, lo, hi, key);
-        return lower_bound_i32(gl, c0, c1, key);
-    }
-};
-
 __device__ __forceinline__ bool in_list(const int32_t* a, int lo, int hi, int32_t key) {
     for (int i = lo; i < hi; ++i)
         if (a[i] == key) return true;
@@ -502,115 +467,166 @@ __device__ __forceinline__ bool pc_pair(const DevGraph& g, int t, int32_t l, int
            (in_sorted(g.cp_pos, c0, c1, l) && in_list(g.pc_pos, p0, p1, r));
 }
 
-__global__ void __launch_bounds__(K4_THREADS)
+// exception logic for read `ri`, junction j (global index), whose endpoint `epos` (side 0 = l, 1 = r) sits on
+// the anchor site `anchor`
+__device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, uint32_t ri, uint32_t j,
+                                           int anchor, int side, uint32_t k, bool combine) {
+    const uint32_t j0 = soa.sr_joff[ri], j1 = soa.sr_joff[ri + 1];
+    const int32_t l = (int32_t)(soa.jn_l[j] & POS_MASK), r = (int32_t)(soa.jn_rk[j] & POS_MASK);
+    for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
+        const int t = g.rp_site[q];
+        if (t < g.own_lo || t >= g.own_hi) continue;
+        if (g.cp_off[t + 1] == g.cp_off[t]) continue;                 // no competitors: never a pair
+        if (!pc_pair(g, t, l, r)) continue;
+        if (side == 1 && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) continue;   // already seen at side 0
+        bool earlier = false;
+        for (uint32_t jj = j0; jj < j && !earlier; ++jj)
+            earlier = pc_pair(g, t, (int32_t)(soa.jn_l[jj] & POS_MASK), (int32_t)(soa.jn_rk[jj] & POS_MASK));
+        if (earlier) continue;
+        // j is the first junction of this read that makes compSplicing true for t: classify the read at t
+        const int32_t tp = g.site_pos[t];
+        const bool ok = strand_ok(g.site_cls[t], k);
+        bool alpha = false; int32_t partner_used = 0; int kstar = -1;
+        for (uint32_t jj = j0; jj < j1; ++jj) {
+            const uint32_t lraw = soa.jn_l[jj];
+            const int32_t ll = (int32_t)(lraw & POS_MASK), rr = (int32_t)(soa.jn_rk[jj] & POS_MASK);
+            if (ll == tp && !(lraw >> 31)) { alpha = true; partner_used = rr; }   // firstN: POS > t, read skipped (S:435)
+            if (rr == tp) { alpha = true; partner_used = ll; }
+            if (ll < tp && tp < rr) kstar = (int)(jj - j0);
+        }
+        if (alpha) {                                                   // S:519-527
+            for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
+                const int32_t pp = g.pc_pos[e];
+                if (pp == partner_used) continue;
+                bool in_read = false;
+                for (uint32_t jj = j0; jj < j1 && !in_read; ++jj)
+                    in_read = (int32_t)(soa.jn_l[jj] & POS_MASK) == pp || (int32_t)(soa.jn_rk[jj] & POS_MASK) == pp;
+                if (in_read) atomicAdd(cnt.dc + e, 1u);
+            }
+        } else if (kstar >= 0) {
+            if (kstar >= (int)(j - j0)) {                              // compSplicing already true at k*: flanking (S:503-505)
+                if (ok) atomicAdd(cnt.spanx + t, 1u);
+                if (combine) atomicAdd(cnt.flank + t, 1u);
+            }
+        } else if (ok) {
+            const uint32_t b0 = soa.bB + soa.sr_boff[ri], b1 = soa.bB + soa.sr_boff[ri + 1];
+            bool covers = false;
+            for (uint32_t b = b0; b < b1 && !covers; ++b)
+                covers = soa.m_start[b] <= tp && (int32_t)(soa.m_endk[b] & POS_MASK) >= tp + 2;
+            if (covers) {                                              // beta1-type, S:544-552
+                atomicAdd(cnt.covx + t, 1u);
+                for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
+                    const int32_t pp = g.pc_pos[e];
+                    bool in_read = false;
+                    for (uint32_t jj = j0; jj < j1 && !in_read; ++jj)
+                        in_read = (int32_t)(soa.jn_l[jj] & POS_MASK) == pp || (int32_t)(soa.jn_rk[jj] & POS_MASK) == pp;
+                    if (in_read) atomicAdd(cnt.dc + e, 1u);
+                }
+            }
+        }
+    }
+}
+
+constexpr int K4_WORKLIST = 1024;
+
+// one work-list item: the exception logic for (read that owns junction j, junction j, endpoint)
+__device__ __forceinline__ void k4_item(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, const Chunk& ck, uint32_t j,
+                                        int anchor, int side, bool combine) {
+    (void)ck;
+    k4_exceptions(soa, g, cnt, soa.jn_read[j], j, anchor, side, soa.jn_rk[j] >> 31, combine);
+}
+
+template <bool SMEM>
+__device__ __forceinline__ void k4_body(const int32_t* __restrict__ sp, const uint8_t* __restrict__ hot, int w_lo, int w_hi,
+                                        const Chunk& ck, const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, bool combine,
+                                        bool skip_exc, uint32_t* wl_j, uint32_t* wl_a, uint32_t* wl_n) {
+    const int S = g.n_sites;
+    const uint32_t jb = ck.j_base, je = ck.j_base + ck.j_cnt;
+    uint32_t nl = 0, nr = 0;                                           // next iteration, loaded one iteration ahead
+    if (jb + threadIdx.x < je) { nl = ldg_stream_u32(soa.jn_l + jb + threadIdx.x); nr = ldg_stream_u32(soa.jn_rk + jb + threadIdx.x); }
+    for (uint32_t j = jb + threadIdx.x; j - threadIdx.x < je; j += K4_THREADS) {     // uniform trip count
+        const bool live = j < je;
+        const uint32_t lraw = nl, rraw = nr;
+        if (j + K4_THREADS < je) { nl = ldg_stream_u32(soa.jn_l + j + K4_THREADS); nr = ldg_stream_u32(soa.jn_rk + j + K4_THREADS); }
+        const int32_t l = live ? (int32_t)(lraw & POS_MASK) : INT_MAX, r = live ? (int32_t)(rraw & POS_MASK) : INT_MIN;
+        const uint32_t k = rraw >> 31;
+        // narrow the window to the positions this warp asks about (broadcast loads)
+        const int wlo = __reduce_min_sync(0xffffffffu, l), whi = __reduce_max_sync(0xffffffffu, live ? max(l, r) : INT_MIN);
+        if (wlo > whi) continue;                                       // no live lane in this warp
+        const int n0 = lower_bound_i32(sp, w_lo, w_hi, wlo);
+        const int n1 = upper_bound_i32(sp, n0, w_hi, whi);
+        int il = n0, iu = n0, ir = n0;
+        if (live) {
+            il = lower_bound_i32(sp, n0, n1, l);
+            iu = il;
+            while (iu < n1 && sp[iu] == l) ++iu;                       // upper_bound(l)
+            ir = (r > l) ? lower_bound_i32(sp, iu, n1, r) : il;
+        }
+        // span range add over sites strictly inside (l, r), aggregated over identical ranges in the warp
+        const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);
+        const bool add = live && x0 < x1;
+        const unsigned long long key = add ? (((unsigned long long)(uint32_t)x0 << 32) | ((uint32_t)x1 << 1) | k) : ~0ull;
+        const uint32_t grp = __match_any_sync(0xffffffffu, key);
+        if (add && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) {
+            const uint32_t c = (uint32_t)__popc(grp);
+            atomicAdd(cnt.span + k * (S + 1) + x0, c);
+            atomicAdd(cnt.span + k * (S + 1) + x1, 0u - c);
+        }
+        // exceptions only where a reverse-partner list with competitors hangs off an endpoint.  Hot
+        // (junction, endpoint) items are few and expensive (dependent graph lookups), so they are parked
+        // in a shared-memory work list and processed after the streaming loop with every lane busy.
+        const bool hl = live && !skip_exc && il < n1 && sp[il] == l && hot[il];
+        const bool hr = live && !skip_exc && ir < n1 && sp[ir] == r && hot[ir];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const bool h = side == 0 ? hl : hr;
+            const uint32_t bal = __ballot_sync(0xffffffffu, h);
+            if (!bal) continue;
+            uint32_t base = 0;
+            if ((threadIdx.x & 31) == 0) base = atomicAdd(wl_n, (uint32_t)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (h) {
+                const uint32_t slot = base + (uint32_t)__popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                const int anchor = side == 0 ? il : ir;
+                if (slot < K4_WORKLIST) { wl_j[slot] = j; wl_a[slot] = (uint32_t)anchor | ((uint32_t)side << 31); }
+                else k4_item(soa, g, cnt, ck, j, anchor, side, combine);      // list full: do it now
+            }
+        }
+    }
+    __syncthreads();
+    const uint32_t n_items = min(*wl_n, (uint32_t)K4_WORKLIST);
+    for (uint32_t i = threadIdx.x; i < n_items; i += K4_THREADS)
+        k4_item(soa, g, cnt, ck, wl_j[i], (int)(wl_a[i] & POS_MASK), (int)(wl_a[i] >> 31), combine);
+}
+
+__global__ void __launch_bounds__(K4_THREADS, 8)
 k_spliced(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t mode) {
     const Chunk ck = chunks[blockIdx.x];
-    if (ck.s_cnt == 0) return;
-    __shared__ __align__(16) int32_t s_sites[K4_MAX_STAGED + 8];
-    __shared__ __align__(8) uint64_t bar;
-    const bool staged = ck.s_site_n > 0 && ck.s_site_n <= K4_MAX_STAGED;
-    const int al = ck.s_site_lo & ~3;
-    const int nst = ((ck.s_site_lo + ck.s_site_n + 3) & ~3) - al;
-    if (threadIdx.x == 0) mbar_init(&bar, 1);
-    __syncthreads();
-    if (staged) {
-        if (threadIdx.x == 0) {
-            mbar_expect_tx(&bar, (uint32_t)nst * 4u);
-            bulk_g2s(s_sites, g.site_pos + al, (uint32_t)nst * 4u, &bar);
-        }
-        mbar_wait(&bar, 0);
-    }
-    SiteWin w;
-    w.gl = g.site_pos;
-    w.c0 = g.cs_off[ck.chrom]; w.c1 = g.cs_off[ck.chrom + 1];
-    if (staged) { w.sm = s_sites - al; w.lo = ck.s_site_lo; w.hi = ck.s_site_lo + ck.s_site_n; w.plo = ck.s_lo; w.phi = ck.s_hi; }
-    else if (ck.s_site_n == 0) { w.sm = g.site_pos; w.lo = ck.s_site_lo; w.hi = ck.s_site_lo; w.plo = ck.s_lo; w.phi = ck.s_hi; }   // window proven empty
-    else { w.sm = g.site_pos; w.lo = 0; w.hi = 0; w.plo = INT_MAX; w.phi = INT_MIN; }                                          // too many sites: global search
-    const int S = g.n_sites;
+    if (ck.j_cnt == 0) return;
     const bool combine = (mode & FLAG_COMBINE) != 0;
-
-    for (uint32_t ri = ck.s_base + threadIdx.x; ri < ck.s_base + ck.s_cnt; ri += K4_THREADS) {
-        const uint32_t b0 = soa.sr_boff[ri], b1 = soa.sr_boff[ri + 1];
-        const uint32_t j0 = soa.sr_joff[ri], j1 = soa.sr_joff[ri + 1];
-        const uint32_t rc = soa.sr_cls[ri];
-        const uint32_t k = rc & 1u;
-        const bool firstN = (rc & 2u) != 0;
-        // (1) stabbing count of this read's own blocks (same rule as K3)
-        for (uint32_t b = b0; b < b1; ++b) {
-            const int32_t a = soa.b_start[b], e = soa.b_end[b] - 2;
-            if (a > e) continue;
-            for (int s = w.lower(a); s < w.c1 && w.at(s) <= e; ++s)
-                if (s >= g.own_lo && s < g.own_hi) atomicAdd(cnt.cov + k * S + s, 1u);
+    const bool skip_exc = (mode & FLAG_DEBUG_SKIP_EXC) != 0;          // timing experiments only (wrong counts)
+    __shared__ __align__(16) int32_t s_sites[K4_MAX_STAGED + 32];
+    __shared__ __align__(16) uint8_t s_hot[K4_MAX_STAGED + 32];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ uint32_t wl_j[K4_WORKLIST], wl_a[K4_WORKLIST], wl_n;
+    if (threadIdx.x == 0) wl_n = 0;
+    const int w_lo = ck.s_site_lo, w_hi = ck.s_site_lo + ck.s_site_n;
+    if (ck.s_site_n > 0 && ck.s_site_n <= K4_MAX_STAGED) {
+        const int al = ck.s_site_lo & ~15;                             // 16-byte aligned for both element sizes
+        const int nst = ((ck.s_site_lo + ck.s_site_n + 15) & ~15) - al;
+        if (threadIdx.x == 0) {
+            mbar_init(&bar, 1);
+            mbar_expect_tx(&bar, (uint32_t)nst * 5u);
+            bulk_g2s(s_sites, g.site_pos + al, (uint32_t)nst * 4u, &bar);
+            bulk_g2s(s_hot, g.site_hot + al, (uint32_t)nst, &bar);
         }
-        // (2) junctions: span range add + exceptions
-        for (uint32_t j = j0; j < j1; ++j) {
-            const int32_t l = soa.jn_l[j], r = soa.jn_r[j];
-            const int il = w.lower(l);
-            int iu = il;
-            while (iu < w.c1 && w.at(iu) == l) ++iu;                   // upper_bound(l)
-            const int ir = (r > l) ? w.lower(r) : il;
-            {   // sites strictly inside (l, r): S:503-512 range part
-                const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);
-                if (x0 < x1) {
-                    atomicAdd(cnt.span + k * (S + 1) + x0, 1u);
-                    atomicAdd(cnt.span + k * (S + 1) + x1, 0xffffffffu);   // -1
-                }
-            }
-            // exceptions: sites t for which (l, r) is a partner/competitor pair; they all hang off the
-            // reverse partner lists of the sites at l and at r
-#pragma unroll 1
-            for (int side = 0; side < 2; ++side) {
-                const int anchor = side == 0 ? il : ir;
-                const int32_t epos = side == 0 ? l : r;
-                if (anchor >= w.c1 || w.at(anchor) != epos) continue;
-                for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
-                    const int t = g.rp_site[q];
-                    if (t < g.own_lo || t >= g.own_hi) continue;
-                    if (g.cp_off[t + 1] == g.cp_off[t]) continue;         // no competitors: never a pair
-                    if (!pc_pair(g, t, l, r)) continue;
-                    if (side == 1 && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) continue;   // seen at side 0
-                    bool earlier = false;
-                    for (uint32_t jj = j0; jj < j && !earlier; ++jj) earlier = pc_pair(g, t, soa.jn_l[jj], soa.jn_r[jj]);
-                    if (earlier) continue;
-                    // --- first junction of this read that makes compSplicing true for t: classify the read at t
-                    const int32_t tp = g.site_pos[t];
-                    const bool ok = strand_ok(g.site_cls[t], k);
-                    bool alpha = false; int32_t partner_used = 0; int kstar = -1;
-                    for (uint32_t jj = j0; jj < j1; ++jj) {
-                        const int32_t ll = soa.jn_l[jj], rr = soa.jn_r[jj];
-                        if (ll == tp && !(jj == j0 && firstN)) { alpha = true; partner_used = rr; }   // POS <= t filter (S:435)
-                        if (rr == tp) { alpha = true; partner_used = ll; }
-                        if (ll < tp && tp < rr) kstar = (int)(jj - j0);
-                    }
-                    if (alpha) {                                           // S:519-527
-                        for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
-                            const int32_t pp = g.pc_pos[e];
-                            if (pp == partner_used) continue;
-                            bool in_read = false;
-                            for (uint32_t jj = j0; jj < j1 && !in_read; ++jj) in_read = soa.jn_l[jj] == pp || soa.jn_r[jj] == pp;
-                            if (in_read) atomicAdd(cnt.dc + e, 1u);
-                        }
-                    } else if (kstar >= 0) {
-                        if (kstar >= (int)(j - j0)) {                      // compSplicing already true at k*: flanking (S:503-505)
-                            if (ok) atomicAdd(cnt.spanx + t, 1u);
-                            if (combine) atomicAdd(cnt.flank + t, 1u);
-                        }
-                    } else if (ok) {
-                        bool covers = false;
-                        for (uint32_t b = b0; b < b1 && !covers; ++b) covers = soa.b_start[b] <= tp && soa.b_end[b] >= tp + 2;
-                        if (covers) {                                      // beta1-type, S:544-552
-                            atomicAdd(cnt.covx + t, 1u);
-                            for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
-                                const int32_t pp = g.pc_pos[e];
-                                bool in_read = false;
-                                for (uint32_t jj = j0; jj < j1 && !in_read; ++jj) in_read = soa.jn_l[jj] == pp || soa.jn_r[jj] == pp;
-                                if (in_read) atomicAdd(cnt.dc + e, 1u);
-                            }
-                        }
-                    }
-                }
-            }
-        }
+        __syncthreads();
+        mbar_wait(&bar, 0);
+        k4_body<true>(s_sites - al, s_hot - al, w_lo, w_hi, ck, soa, g, cnt, combine, skip_exc, wl_j, wl_a, &wl_n);
+    } else {
+        // window proven empty (w_lo == w_hi: nothing is ever read) or too many sites to stage: global arrays
+        __syncthreads();                                               // wl_n = 0 visible
+        k4_body<false>(g.site_pos, g.site_hot, w_lo, w_hi, ck, soa, g, cnt, combine, skip_exc, wl_j, wl_a, &wl_n);
     }
 }
 
@@ -776,7 +792,7 @@ void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream) {
     if (n > 0) k_alpha_reduce<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, out);
 }
 void launch_beta1(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, void* stream) {
-    if (n_chunks > 0 && g.n_sites > 0) k_beta1_stab<<<n_chunks, K3_THREADS, 0, (cudaStream_t)stream>>>(chunks, soa, g, cnt);
+    if (n_chunks > 0 && g.n_sites > 0) k_beta1_stab<<<2 * n_chunks, K3_THREADS, 0, (cudaStream_t)stream>>>(chunks, soa, g, cnt);
 }
 void launch_spliced(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
     if (n_chunks > 0 && g.n_sites > 0) k_spliced<<<n_chunks, K4_THREADS, 0, (cudaStream_t)stream>>>(chunks, soa, g, cnt, flags);

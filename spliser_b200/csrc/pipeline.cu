@@ -7,6 +7,7 @@
 #include <climits>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <string>
@@ -124,7 +125,8 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     if (h.pt_site.size() >= (size_t)INT_MAX || h.inc_line.size() >= (size_t)INT_MAX || h.cp_pos.size() >= (size_t)INT_MAX)
         return ctx->fail(SPL_ERR_RANGE, "site graph exceeds 2^31 entries");
     Carver c;
-    const size_t o_cs = c.take<int32_t>((size_t)h.n_chrom + 1), o_pos = c.take<int32_t>(S + 8), o_cls = c.take<uint8_t>(S + 8);
+    const size_t o_cs = c.take<int32_t>((size_t)h.n_chrom + 1), o_pos = c.take<int32_t>(S + 64), o_cls = c.take<uint8_t>(S + 8);
+    const size_t o_hot = c.take<uint8_t>(S + 64);
     const size_t o_pto = c.take<int32_t>(S + 1), o_pts = c.take<int32_t>(h.pt_site.size() + 1);
     const size_t o_pco = c.take<int32_t>(S + 1), o_pcp = c.take<int32_t>(E + 1);
     const size_t o_cpo = c.take<int32_t>(S + 1), o_cpp = c.take<int32_t>(h.cp_pos.size() + 1);
@@ -144,10 +146,19 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     put32(o_cs, h.cs_off, (size_t)h.n_chrom + 1);
     {
         std::vector<int32_t> p(h.pos);
-        p.resize(S + 8, INT_MAX);
+        p.resize(S + 64, INT_MAX);
         put(o_pos, p.data(), p.size() * 4);
     }
     put(o_cls, h.cls.data(), S);
+    {   // hot[anchor] = some site of the reverse-partner list anchored here has competitors
+        std::vector<uint8_t> hot(S + 64, 0);
+        for (size_t a = 0; a < S; ++a)
+            for (int64_t q = h.rp_off[a]; q < h.rp_off[a + 1] && !hot[a]; ++q) {
+                const size_t t = (size_t)h.rp_site[(size_t)q];
+                hot[a] = h.cp_off[t + 1] > h.cp_off[t];
+            }
+        put(o_hot, hot.data(), hot.size());
+    }
     put32(o_pto, h.pt_off, S + 1); put(o_pts, h.pt_site.data(), h.pt_site.size() * 4);
     put32(o_pco, h.pc_off, S + 1); put(o_pcp, h.pc_pos.data(), E * 4);
     put32(o_cpo, h.cp_off, S + 1); put(o_cpp, h.cp_pos.data(), h.cp_pos.size() * 4);
@@ -164,6 +175,7 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     const int64_t tc = std::max(1, ctx->tile_count), ti = std::min<int64_t>(std::max(0, ctx->tile_index), tc - 1);
     g.own_lo = (int32_t)((int64_t)S * ti / tc); g.own_hi = (int32_t)((int64_t)S * (ti + 1) / tc);
     g.cs_off = (const int32_t*)(b + o_cs); g.site_pos = (const int32_t*)(b + o_pos); g.site_cls = (const uint8_t*)(b + o_cls);
+    g.site_hot = (const uint8_t*)(b + o_hot);
     g.pt_off = (const int32_t*)(b + o_pto); g.pt_site = (const int32_t*)(b + o_pts);
     g.pc_off = (const int32_t*)(b + o_pco); g.pc_pos = (const int32_t*)(b + o_pcp);
     g.cp_off = (const int32_t*)(b + o_cpo); g.cp_pos = (const int32_t*)(b + o_cpp);
@@ -264,18 +276,18 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
     CU(cudaStreamSynchronize(ctx->stream));   // also makes `hc` (pageable) safe to drop
     const size_t nA = ctx->h_tot[0], nB = ctx->h_tot[1], nS = ctx->h_tot[2], nJ = ctx->h_tot[3];
     Carver s;
-    const size_t o_as = s.take<int32_t>(nA + 16), o_ae = s.take<int32_t>(nA + 16), o_ac = s.take<uint8_t>(nA + 64);
-    const size_t o_bs = s.take<int32_t>(nB + 16), o_be = s.take<int32_t>(nB + 16);
-    const size_t o_sb = s.take<uint32_t>(nS + 16), o_sj = s.take<uint32_t>(nS + 16), o_sc = s.take<uint8_t>(nS + 16);
-    const size_t o_jl = s.take<int32_t>(nJ + 16), o_jr = s.take<int32_t>(nJ + 16);
+    const size_t bB = (nA + 3) & ~(size_t)3;                      // stream B starts on a 128-bit boundary
+    if (bB + nB >= (size_t)UINT32_MAX - 64) return ctx->fail(SPL_ERR_RANGE, "more than 2^32 mapped blocks in one call");
+    const size_t o_ms = s.take<int32_t>(bB + nB + 32), o_me = s.take<uint32_t>(bB + nB + 32);
+    const size_t o_sb = s.take<uint32_t>(nS + 16), o_sj = s.take<uint32_t>(nS + 16);
+    const size_t o_jl = s.take<uint32_t>(nJ + 16), o_jr = s.take<uint32_t>(nJ + 16), o_jq = s.take<uint32_t>(nJ + 16);
     CU(ctx->d_soa.reserve(s.off + 256));
     char* sb = (char*)ctx->d_soa.p;
     DevSoA& soa = ctx->soa;
     soa.nA = (uint32_t)nA; soa.nB = (uint32_t)nB; soa.nS = (uint32_t)nS; soa.nJ = (uint32_t)nJ;
-    soa.a_start = (int32_t*)(sb + o_as); soa.a_end = (int32_t*)(sb + o_ae); soa.a_cls = (uint8_t*)(sb + o_ac);
-    soa.b_start = (int32_t*)(sb + o_bs); soa.b_end = (int32_t*)(sb + o_be);
-    soa.sr_boff = (uint32_t*)(sb + o_sb); soa.sr_joff = (uint32_t*)(sb + o_sj); soa.sr_cls = (uint8_t*)(sb + o_sc);
-    soa.jn_l = (int32_t*)(sb + o_jl); soa.jn_r = (int32_t*)(sb + o_jr);
+    soa.m_start = (int32_t*)(sb + o_ms); soa.m_endk = (uint32_t*)(sb + o_me); soa.bB = (uint32_t)bB;
+    soa.sr_boff = (uint32_t*)(sb + o_sb); soa.sr_joff = (uint32_t*)(sb + o_sj);
+    soa.jn_l = (uint32_t*)(sb + o_jl); soa.jn_rk = (uint32_t*)(sb + o_jr); soa.jn_read = (uint32_t*)(sb + o_jq);
     launch_expand_scatter(ctx->rec, ctx->chunks, ctx->n_chunks, soa, flags, ctx->stream);
     CU(cudaGetLastError());
     CU(cudaEventRecord(e1, ctx->stream));
@@ -348,6 +360,9 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     const double tg0 = now_ms();
     std::string e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, (flags & SPL_FLAG_STRANDED) != 0, ctx->hg);
     if (!e.empty()) return ctx->fail(SPL_ERR_ARG, "%s", e.c_str());
+    flags &= 0xfu;
+    if (const char* dbg = std::getenv("SPLISER_DEBUG_SKIP_EXC"))
+        if (dbg[0] == '1') flags |= FLAG_DEBUG_SKIP_EXC;
     ctx->flags = flags;
     rc = upload_graph(ctx, j_score, n_junc);
     if (rc) return rc;
