@@ -67,6 +67,7 @@ struct DevCounters {
     uint32_t* spanx;   // [S] spanning reads that are flanking (removed from the mutually-exclusive count)
     uint32_t* flank;   // [S] flanking reads (counted as beta2Simple in combine mode only)
     uint32_t* dc;      // [E] PartnerBeta2DoubleCounts increments seen in the BAM
+    uint32_t* work;    // [2] work-item counters of the persistent kernels (K3, K4)
 };
 
 struct DevOutputs {
@@ -79,10 +80,6 @@ struct DevOutputs {
 
 constexpr int CHUNK_READS = 4096;       // records per chunk
 constexpr int EXPAND_THREADS = 512;     // one record per thread and round
-constexpr int K3_THREADS = 128;
-constexpr int K3_MAX_STAGED = 4096;     // site positions staged in shared memory per tile (16 KB)
-constexpr int K4_THREADS = 128;
-constexpr int K4_MAX_STAGED = 2048;
 constexpr int FIN_THREADS = 256;
 constexpr int FIN_ITEMS = 4;            // sites per thread in the span scan
 

@@ -319,55 +319,84 @@ __global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3: beta1 stabbing count over both block streams.
+// Persistent, warp-specialised streaming kernels (K3, K4).
 //
-// grid = 2 x chunks: CTA (c, 0) streams the chunk's A blocks (unspliced reads, sorted by start),
-// CTA (c, 1) its B blocks (spliced reads).  The chunk's site window is staged into shared memory
-// by one TMA bulk copy while the threads issue their 128-bit block loads.  Each warp narrows the
-// window to [min start, max end-2] of the 256 blocks it holds with two redux.sync and a
-// warp-uniform binary search (broadcast LDS, no bank conflicts).  Short narrowed ranges (the common
-// case: 0-3 sites) are tested against the lane's blocks from registers and summed across the warp
-// with one redux.sync per site -> one RED per (warp, site, class); long ranges (sparse coverage,
-// displaced second blocks of spliced reads) fall back to a per-lane binary search.
+// grid = SMs x resident CTAs; every CTA has one producer warp and four consumer warps.  The producer
+// (one elected lane) pulls work items from a global atomic counter (dynamic scheduling: chunks differ
+// a lot in cost), and for each piece of an item issues 1-D TMA bulk copies (cp.async.bulk) of the
+// SoA slices and of the chunk's site window into a ring of shared-memory stages, completion tracked
+// by mbarriers (full/empty pair per stage).  The consumers never touch HBM for streamed data: DRAM
+// latency is hidden by the ring, not by occupancy.
+// ------------------------------------------------------------------------------------------------
+constexpr int PS_STAGES = 3;
+constexpr int PS_CONSUMERS = 256;                  // 8 consumer warps
+constexpr int PS_THREADS = PS_CONSUMERS + 32;      // + 1 producer warp
+constexpr int K3_TILE = 2048;                      // blocks per stage (16 KB)
+constexpr int K3_SITES = 2048;                     // staged site positions per stage (8 KB)
+constexpr int K4_TILE = 1024;                      // junctions per stage (8 KB)
+constexpr int K4_SITES = 2048;
+constexpr int K4_WORKLIST = 1024;
+
+struct StageMeta {
+    uint32_t e0, e1;        // valid global element range of the item
+    uint32_t p0, n;         // global index of staged element 0 (multiple of 4), staged element count
+    int32_t  w_lo, w_hi;    // site window (global indices, already clamped to the owned range)
+    int32_t  al;            // global site index of staged site 0
+    uint32_t flags;         // PS_DONE | PS_GLOBAL_SITES
+    int32_t  chunk;
+    int32_t  pad[3];
+};
+constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u;
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PS_CONSUMERS) : "memory"); }
+
+struct K3Stage {
+    int32_t  start[K3_TILE];
+    uint32_t endk[K3_TILE];
+    int32_t  sites[K3_SITES + 8];
+};
+struct K3Smem {
+    K3Stage st[PS_STAGES];
+    StageMeta meta[PS_STAGES];
+    uint64_t full[PS_STAGES], empty[PS_STAGES];
+};
+
+// ------------------------------------------------------------------------------------------------
+// K3: beta1 stabbing count over both block streams (A: unspliced reads, sorted; B: spliced reads).
+// Each consumer warp narrows the staged site window to [min start, max end-2] of the 256 blocks it
+// holds with two redux.sync and a warp-uniform binary search (broadcast LDS, no bank conflicts).
+// Short narrowed ranges (the common case: 0-3 sites) are tested against the lane's blocks from
+// registers and summed across the warp with one redux.sync per site -> one RED per (warp, site,
+// class); long ranges (sparse coverage, displaced blocks of spliced reads) use a per-lane search.
 // ------------------------------------------------------------------------------------------------
 constexpr int K3_GROUPS = 2;     // int4 groups (4 blocks each) per thread and pass
 constexpr int K3_DENSE = 12;     // narrowed ranges longer than this use the per-lane search path
 
-template <bool SMEM>
-__device__ __forceinline__ void k3_body(const int32_t* __restrict__ sp, int w_lo, int w_hi, uint32_t e0, uint32_t e1,
-                                        const DevSoA& soa, const DevGraph& g, const DevCounters& cnt) {
-    const uint32_t g0 = e0 >> 2, g1 = (e1 + 3) >> 2;
+__device__ __forceinline__ void k3_consume(const K3Stage& stg, const StageMeta& m, const int32_t* __restrict__ sp,
+                                           const DevGraph& g, const DevCounters& cnt) {
     const int lane = threadIdx.x & 31;
-    const int4* gs = reinterpret_cast<const int4*>(soa.m_start);
-    const int4* ge = reinterpret_cast<const int4*>(soa.m_endk);
-    int4 nst[K3_GROUPS], nen[K3_GROUPS];                               // next pass, loaded one pass ahead
-    auto load_pass = [&](uint32_t gb) {
-#pragma unroll
-        for (int u = 0; u < K3_GROUPS; ++u) {
-            const uint32_t gi = gb + u * K3_THREADS;
-            if (gi < g1) { nst[u] = ldg_stream(gs + gi); nen[u] = ldg_stream(ge + gi); }
-            else { nst[u] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX); nen[u] = make_int4(0, 0, 0, 0); }
-        }
-    };
-    load_pass(g0 + threadIdx.x);
-    for (uint32_t gb = g0 + threadIdx.x; gb - threadIdx.x < g1; gb += K3_THREADS * K3_GROUPS) {
+    const uint32_t ng = m.n >> 2;
+    const int4* gs = reinterpret_cast<const int4*>(stg.start);
+    const int4* ge = reinterpret_cast<const int4*>(stg.endk);
+    for (uint32_t base = 0; base < ng; base += PS_CONSUMERS * K3_GROUPS) {       // uniform trip count
         int4 st[K3_GROUPS], en[K3_GROUPS];
-#pragma unroll
-        for (int u = 0; u < K3_GROUPS; ++u) { st[u] = nst[u]; en[u] = nen[u]; }
-        if (gb - threadIdx.x + K3_THREADS * K3_GROUPS < g1) load_pass(gb + K3_THREADS * K3_GROUPS);
-        // (start, end|class) -> start a, length-2 d (unsigned; huge when the block cannot stab), class increment
-        int lo = INT_MAX, hi = INT_MIN;
         uint32_t inc[K3_GROUPS][4];
+        int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll
         for (int u = 0; u < K3_GROUPS; ++u) {
-            const uint32_t gi = gb + u * K3_THREADS;
+            const uint32_t gi = base + u * PS_CONSUMERS + threadIdx.x;
+            if (gi < ng) { st[u] = gs[gi]; en[u] = ge[gi]; }
+            else { st[u] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX); en[u] = make_int4(0, 0, 0, 0); }
             int* s = &st[u].x; int* e = &en[u].x;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint32_t idx = gi * 4 + q;
+                const uint32_t idx = m.p0 + gi * 4 + q;
                 const uint32_t ek = (uint32_t)e[q];
                 const int b = (int)(ek & POS_MASK) - 2;                 // last stabbed position
-                const bool valid = (idx - e0) < (e1 - e0) && s[q] <= b;
+                const bool valid = gi < ng && (idx - m.e0) < (m.e1 - m.e0) && s[q] <= b;
                 inc[u][q] = valid ? ((ek >> 31) ? 0x10000u : 1u) : 0u;    // invalid blocks add 0 whatever they "hit"
                 e[q] = b - s[q];                                        // d = b - a  (>= 0 when valid)
                 if (valid) { lo = min(lo, s[q]); hi = max(hi, b); }
@@ -375,8 +404,8 @@ __device__ __forceinline__ void k3_body(const int32_t* __restrict__ sp, int w_lo
         }
         const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
         if (wlo > whi) continue;
-        const int i0 = lower_bound_i32(sp, w_lo, w_hi, wlo);
-        const int i1 = upper_bound_i32(sp, i0, w_hi, whi);
+        const int i0 = lower_bound_i32(sp, m.w_lo, m.w_hi, wlo);
+        const int i1 = upper_bound_i32(sp, i0, m.w_hi, whi);
         if (i0 >= i1) continue;
         if (i1 - i0 <= K3_DENSE) {
             for (int s = i0; s < i1; ++s) {                           // warp-uniform loop
@@ -412,43 +441,80 @@ __device__ __forceinline__ void k3_body(const int32_t* __restrict__ sp, int w_lo
     }
 }
 
-__global__ void __launch_bounds__(K3_THREADS)
-k_beta1_stab(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounters cnt) {
-    const Chunk ck = chunks[blockIdx.x >> 1];
-    const bool bstream = blockIdx.x & 1;
-    const uint32_t n = bstream ? ck.b_cnt : ck.a_cnt;
-    const int site_lo = bstream ? ck.s_site_lo : ck.a_site_lo, site_n = bstream ? ck.s_site_n : ck.a_site_n;
-    if (n == 0 || site_n == 0) return;                 // zone-map prune: no site can be stabbed by these blocks
-    const int w_lo = max(site_lo, g.own_lo), w_hi = min(site_lo + site_n, g.own_hi);
-    if (w_lo >= w_hi) return;
-    const uint32_t e0 = bstream ? soa.bB + ck.b_base : ck.a_base, e1 = e0 + n;
-    __shared__ __align__(16) int32_t s_sites[K3_MAX_STAGED + 8];
-    __shared__ __align__(8) uint64_t bar;
-    if (site_n <= K3_MAX_STAGED) {
-        const int al = site_lo & ~3;                                   // 16-byte aligned source index
-        const int nst = ((site_lo + site_n + 3) & ~3) - al;            // entries copied (multiple of 4)
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            mbar_expect_tx(&bar, (uint32_t)nst * 4u);
-            bulk_g2s(s_sites, g.site_pos + al, (uint32_t)nst * 4u, &bar);
+__global__ void __launch_bounds__(PS_THREADS)
+k_beta1_stab(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    K3Smem& sm = *reinterpret_cast<K3Smem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], PS_CONSUMERS / 32); }
+    }
+    __syncthreads();
+    if (warp == PS_CONSUMERS / 32) {
+        // ===== producer =====
+        if (lane != 0) return;
+        uint32_t it = 0;
+        // the next item's index and descriptor are fetched while the current item's copies are issued
+        uint32_t next = atomicAdd(cnt.work + 0, 1u);
+        Chunk nck = chunks[min(next >> 1, (uint32_t)n_chunks - 1u)];
+        for (;;) {
+            const uint32_t item = next;
+            if (item >= 2u * (uint32_t)n_chunks) break;
+            const Chunk ck = nck;
+            next = atomicAdd(cnt.work + 0, 1u);
+            nck = chunks[min(next >> 1, (uint32_t)n_chunks - 1u)];
+            const bool bstream = item & 1u;
+            const uint32_t n = bstream ? ck.b_cnt : ck.a_cnt;
+            const int site_lo = bstream ? ck.s_site_lo : ck.a_site_lo, site_n = bstream ? ck.s_site_n : ck.a_site_n;
+            if (n == 0 || site_n == 0) continue;         // zone-map prune: no site can be stabbed by these blocks
+            const int w_lo = max(site_lo, g.own_lo), w_hi = min(site_lo + site_n, g.own_hi);
+            if (w_lo >= w_hi) continue;
+            const uint32_t e0 = bstream ? soa.bB + ck.b_base : ck.a_base, e1 = e0 + n;
+            const bool staged = site_n <= K3_SITES;
+            const int al = site_lo & ~3;
+            const uint32_t nst = staged ? (uint32_t)(((site_lo + site_n + 3) & ~3) - al) : 0u;
+            for (uint32_t p = e0 & ~3u; p < e1; p += K3_TILE, ++it) {
+                const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
+                mbar_wait(&sm.empty[stage], parity ^ 1u);
+                const uint32_t np = min((uint32_t)K3_TILE, ((e1 + 3u) & ~3u) - p);
+                StageMeta& m = sm.meta[stage];
+                m.e0 = e0; m.e1 = e1; m.p0 = p; m.n = np; m.w_lo = w_lo; m.w_hi = w_hi; m.al = al;
+                m.flags = staged ? 0u : PS_GLOBAL_SITES; m.chunk = (int32_t)(item >> 1);
+                mbar_expect_tx(&sm.full[stage], np * 8u + nst * 4u);
+                bulk_g2s(sm.st[stage].start, soa.m_start + p, np * 4u, &sm.full[stage]);
+                bulk_g2s(sm.st[stage].endk, soa.m_endk + p, np * 4u, &sm.full[stage]);
+                if (nst) bulk_g2s(sm.st[stage].sites, g.site_pos + al, nst * 4u, &sm.full[stage]);
+            }
         }
-        __syncthreads();                                               // barrier initialised before anyone waits
-        mbar_wait(&bar, 0);
-        k3_body<true>(s_sites - al, w_lo, w_hi, e0, e1, soa, g, cnt);
-    } else {
-        k3_body<false>(g.site_pos, w_lo, w_hi, e0, e1, soa, g, cnt);
+        const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
+        mbar_wait(&sm.empty[stage], parity ^ 1u);
+        sm.meta[stage].flags = PS_DONE;
+        mbar_arrive(&sm.full[stage]);
+        return;
+    }
+    // ===== consumers =====
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
+        mbar_wait(&sm.full[stage], parity);
+        const StageMeta m = sm.meta[stage];
+        if (m.flags & PS_DONE) break;
+        if (m.flags & PS_GLOBAL_SITES) k3_consume(sm.st[stage], m, g.site_pos, g, cnt);
+        else k3_consume(sm.st[stage], m, sm.st[stage].sites - m.al, g, cnt);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4: junctions of spliced reads.  One thread per N operator; the chunk's site window (positions and
-// the "hot" flags) is staged by TMA.  Per junction (l, r):
+// K4: junctions of spliced reads.  One consumer thread per N operator; junction slices, the chunk's
+// site window and its "hot" flags are staged by the producer.  Per junction (l, r):
 //   * range add of +1 over the sites strictly inside (l, r) into the span difference array
 //     (mutually-exclusive reads, S:507-512), aggregated across the warp with match.any because
 //     neighbouring reads usually carry the same junction;
 //   * if a site at l or r anchors a reverse-partner list with competitors ("hot"), the read may make
-//     compSplicing true for some site t (S:494-501): the owning read is located by a binary search in
-//     the junction offsets and the exception logic runs for this (read, junction) pair.
+//     compSplicing true for some site t (S:494-501): the (junction, endpoint) item is parked in a
+//     shared-memory work list and processed after the streaming loop of the stage with every lane
+//     busy (the exception logic is a chain of dependent graph lookups).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool in_list(const int32_t* a, int lo, int hi, int32_t key) {
     for (int i = lo; i < hi; ++i)
@@ -467,10 +533,11 @@ __device__ __forceinline__ bool pc_pair(const DevGraph& g, int t, int32_t l, int
            (in_sorted(g.cp_pos, c0, c1, l) && in_list(g.pc_pos, p0, p1, r));
 }
 
-// exception logic for read `ri`, junction j (global index), whose endpoint `epos` (side 0 = l, 1 = r) sits on
-// the anchor site `anchor`
-__device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, uint32_t ri, uint32_t j,
-                                           int anchor, int side, uint32_t k, bool combine) {
+// exception logic for the read that owns junction j, whose endpoint (side 0 = l, 1 = r) sits on `anchor`
+__device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, uint32_t j,
+                                              int anchor, int side, bool combine) {
+    const uint32_t ri = soa.jn_read[j];
+    const uint32_t k = soa.jn_rk[j] >> 31;
     const uint32_t j0 = soa.sr_joff[ri], j1 = soa.sr_joff[ri + 1];
     const int32_t l = (int32_t)(soa.jn_l[j] & POS_MASK), r = (int32_t)(soa.jn_rk[j] & POS_MASK);
     for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
@@ -527,34 +594,37 @@ __device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph&
     }
 }
 
-constexpr int K4_WORKLIST = 1024;
+struct K4Stage {
+    uint32_t l[K4_TILE];
+    uint32_t rk[K4_TILE];
+    int32_t  sites[K4_SITES + 32];
+    uint8_t  hot[K4_SITES + 32];
+};
+struct K4Smem {
+    K4Stage st[PS_STAGES];
+    StageMeta meta[PS_STAGES];
+    uint64_t full[PS_STAGES], empty[PS_STAGES];
+    uint32_t wl_j[K4_WORKLIST], wl_a[K4_WORKLIST];
+    uint32_t wl_n;
+};
 
-// one work-list item: the exception logic for (read that owns junction j, junction j, endpoint)
-__device__ __forceinline__ void k4_item(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, const Chunk& ck, uint32_t j,
-                                        int anchor, int side, bool combine) {
-    (void)ck;
-    k4_exceptions(soa, g, cnt, soa.jn_read[j], j, anchor, side, soa.jn_rk[j] >> 31, combine);
-}
-
-template <bool SMEM>
-__device__ __forceinline__ void k4_body(const int32_t* __restrict__ sp, const uint8_t* __restrict__ hot, int w_lo, int w_hi,
-                                        const Chunk& ck, const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, bool combine,
-                                        bool skip_exc, uint32_t* wl_j, uint32_t* wl_a, uint32_t* wl_n) {
+__device__ __forceinline__ void k4_consume(const K4Stage& stg, const StageMeta& m, const int32_t* __restrict__ sp,
+                                           const uint8_t* __restrict__ hot, const DevSoA& soa, const DevGraph& g,
+                                           const DevCounters& cnt, bool combine, bool skip_exc, K4Smem& sm) {
     const int S = g.n_sites;
-    const uint32_t jb = ck.j_base, je = ck.j_base + ck.j_cnt;
-    uint32_t nl = 0, nr = 0;                                           // next iteration, loaded one iteration ahead
-    if (jb + threadIdx.x < je) { nl = ldg_stream_u32(soa.jn_l + jb + threadIdx.x); nr = ldg_stream_u32(soa.jn_rk + jb + threadIdx.x); }
-    for (uint32_t j = jb + threadIdx.x; j - threadIdx.x < je; j += K4_THREADS) {     // uniform trip count
-        const bool live = j < je;
-        const uint32_t lraw = nl, rraw = nr;
-        if (j + K4_THREADS < je) { nl = ldg_stream_u32(soa.jn_l + j + K4_THREADS); nr = ldg_stream_u32(soa.jn_rk + j + K4_THREADS); }
+    const int lane = threadIdx.x & 31;
+    for (uint32_t base = 0; base < m.n; base += PS_CONSUMERS) {       // uniform trip count
+        const uint32_t idx = base + threadIdx.x;
+        const uint32_t j = m.p0 + idx;
+        const bool live = idx < m.n && (j - m.e0) < (m.e1 - m.e0);
+        const uint32_t lraw = live ? stg.l[idx] : 0u, rraw = live ? stg.rk[idx] : 0u;
         const int32_t l = live ? (int32_t)(lraw & POS_MASK) : INT_MAX, r = live ? (int32_t)(rraw & POS_MASK) : INT_MIN;
         const uint32_t k = rraw >> 31;
         // narrow the window to the positions this warp asks about (broadcast loads)
         const int wlo = __reduce_min_sync(0xffffffffu, l), whi = __reduce_max_sync(0xffffffffu, live ? max(l, r) : INT_MIN);
         if (wlo > whi) continue;                                       // no live lane in this warp
-        const int n0 = lower_bound_i32(sp, w_lo, w_hi, wlo);
-        const int n1 = upper_bound_i32(sp, n0, w_hi, whi);
+        const int n0 = lower_bound_i32(sp, m.w_lo, m.w_hi, wlo);
+        const int n1 = upper_bound_i32(sp, n0, m.w_hi, whi);
         int il = n0, iu = n0, ir = n0;
         if (live) {
             il = lower_bound_i32(sp, n0, n1, l);
@@ -565,16 +635,16 @@ __device__ __forceinline__ void k4_body(const int32_t* __restrict__ sp, const ui
         // span range add over sites strictly inside (l, r), aggregated over identical ranges in the warp
         const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);
         const bool add = live && x0 < x1;
-        const unsigned long long key = add ? (((unsigned long long)(uint32_t)x0 << 32) | ((uint32_t)x1 << 1) | k) : ~0ull;
-        const uint32_t grp = __match_any_sync(0xffffffffu, key);
-        if (add && (int)(__ffs(grp) - 1) == (int)(threadIdx.x & 31)) {
-            const uint32_t c = (uint32_t)__popc(grp);
-            atomicAdd(cnt.span + k * (S + 1) + x0, c);
-            atomicAdd(cnt.span + k * (S + 1) + x1, 0u - c);
+        const uint32_t anyadd = __ballot_sync(0xffffffffu, add);
+        if (anyadd) {
+            const unsigned long long key = add ? (((unsigned long long)(uint32_t)x0 << 32) | ((uint32_t)x1 << 1) | k) : ~0ull;
+            const uint32_t grp = __match_any_sync(0xffffffffu, key);
+            if (add && (int)(__ffs(grp) - 1) == lane) {
+                const uint32_t c = (uint32_t)__popc(grp);
+                atomicAdd(cnt.span + k * (S + 1) + x0, c);
+                atomicAdd(cnt.span + k * (S + 1) + x1, 0u - c);
+            }
         }
-        // exceptions only where a reverse-partner list with competitors hangs off an endpoint.  Hot
-        // (junction, endpoint) items are few and expensive (dependent graph lookups), so they are parked
-        // in a shared-memory work list and processed after the streaming loop with every lane busy.
         const bool hl = live && !skip_exc && il < n1 && sp[il] == l && hot[il];
         const bool hr = live && !skip_exc && ir < n1 && sp[ir] == r && hot[ir];
 #pragma unroll
@@ -582,51 +652,88 @@ __device__ __forceinline__ void k4_body(const int32_t* __restrict__ sp, const ui
             const bool h = side == 0 ? hl : hr;
             const uint32_t bal = __ballot_sync(0xffffffffu, h);
             if (!bal) continue;
-            uint32_t base = 0;
-            if ((threadIdx.x & 31) == 0) base = atomicAdd(wl_n, (uint32_t)__popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t slot0 = 0;
+            if (lane == 0) slot0 = atomicAdd(&sm.wl_n, (uint32_t)__popc(bal));
+            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
             if (h) {
-                const uint32_t slot = base + (uint32_t)__popc(bal & ((1u << (threadIdx.x & 31)) - 1u));
+                const uint32_t slot = slot0 + (uint32_t)__popc(bal & ((1u << lane) - 1u));
                 const int anchor = side == 0 ? il : ir;
-                if (slot < K4_WORKLIST) { wl_j[slot] = j; wl_a[slot] = (uint32_t)anchor | ((uint32_t)side << 31); }
-                else k4_item(soa, g, cnt, ck, j, anchor, side, combine);      // list full: do it now
+                if (slot < K4_WORKLIST) { sm.wl_j[slot] = j; sm.wl_a[slot] = (uint32_t)anchor | ((uint32_t)side << 31); }
+                else k4_exceptions(soa, g, cnt, j, anchor, side, combine);    // list full: do it now
             }
         }
     }
-    __syncthreads();
-    const uint32_t n_items = min(*wl_n, (uint32_t)K4_WORKLIST);
-    for (uint32_t i = threadIdx.x; i < n_items; i += K4_THREADS)
-        k4_item(soa, g, cnt, ck, wl_j[i], (int)(wl_a[i] & POS_MASK), (int)(wl_a[i] >> 31), combine);
 }
 
-__global__ void __launch_bounds__(K4_THREADS, 8)
-k_spliced(const Chunk* __restrict__ chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t mode) {
-    const Chunk ck = chunks[blockIdx.x];
-    if (ck.j_cnt == 0) return;
+__global__ void __launch_bounds__(PS_THREADS)
+k_spliced(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t mode) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    K4Smem& sm = *reinterpret_cast<K4Smem*>(smem_raw);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool combine = (mode & FLAG_COMBINE) != 0;
     const bool skip_exc = (mode & FLAG_DEBUG_SKIP_EXC) != 0;          // timing experiments only (wrong counts)
-    __shared__ __align__(16) int32_t s_sites[K4_MAX_STAGED + 32];
-    __shared__ __align__(16) uint8_t s_hot[K4_MAX_STAGED + 32];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ uint32_t wl_j[K4_WORKLIST], wl_a[K4_WORKLIST], wl_n;
-    if (threadIdx.x == 0) wl_n = 0;
-    const int w_lo = ck.s_site_lo, w_hi = ck.s_site_lo + ck.s_site_n;
-    if (ck.s_site_n > 0 && ck.s_site_n <= K4_MAX_STAGED) {
-        const int al = ck.s_site_lo & ~15;                             // 16-byte aligned for both element sizes
-        const int nst = ((ck.s_site_lo + ck.s_site_n + 15) & ~15) - al;
-        if (threadIdx.x == 0) {
-            mbar_init(&bar, 1);
-            mbar_expect_tx(&bar, (uint32_t)nst * 5u);
-            bulk_g2s(s_sites, g.site_pos + al, (uint32_t)nst * 4u, &bar);
-            bulk_g2s(s_hot, g.site_hot + al, (uint32_t)nst, &bar);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], PS_CONSUMERS / 32); }
+        sm.wl_n = 0;
+    }
+    __syncthreads();
+    if (warp == PS_CONSUMERS / 32) {
+        // ===== producer =====
+        if (lane != 0) return;
+        uint32_t it = 0;
+        uint32_t next = atomicAdd(cnt.work + 1, 1u);
+        Chunk nck = chunks[min(next, (uint32_t)n_chunks - 1u)];
+        for (;;) {
+            const uint32_t item = next;
+            if (item >= (uint32_t)n_chunks) break;
+            const Chunk ck = nck;
+            next = atomicAdd(cnt.work + 1, 1u);
+            nck = chunks[min(next, (uint32_t)n_chunks - 1u)];
+            if (ck.j_cnt == 0 || ck.s_site_n == 0) continue;        // no site inside the chunk's window: nothing to count
+            const int w_lo = ck.s_site_lo, w_hi = ck.s_site_lo + ck.s_site_n;
+            const uint32_t e0 = ck.j_base, e1 = ck.j_base + ck.j_cnt;
+            const bool staged = ck.s_site_n <= K4_SITES;
+            const int al = ck.s_site_lo & ~15;                         // 16-byte aligned for both element sizes
+            const uint32_t nst = staged ? (uint32_t)(((w_hi + 15) & ~15) - al) : 0u;
+            for (uint32_t p = e0 & ~3u; p < e1; p += K4_TILE, ++it) {
+                const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
+                mbar_wait(&sm.empty[stage], parity ^ 1u);
+                const uint32_t np = min((uint32_t)K4_TILE, ((e1 + 3u) & ~3u) - p);
+                StageMeta& m = sm.meta[stage];
+                m.e0 = e0; m.e1 = e1; m.p0 = p; m.n = np; m.w_lo = w_lo; m.w_hi = w_hi; m.al = al;
+                m.flags = staged ? 0u : PS_GLOBAL_SITES; m.chunk = (int32_t)item;
+                mbar_expect_tx(&sm.full[stage], np * 8u + nst * 5u);
+                bulk_g2s(sm.st[stage].l, soa.jn_l + p, np * 4u, &sm.full[stage]);
+                bulk_g2s(sm.st[stage].rk, soa.jn_rk + p, np * 4u, &sm.full[stage]);
+                if (nst) {
+                    bulk_g2s(sm.st[stage].sites, g.site_pos + al, nst * 4u, &sm.full[stage]);
+                    bulk_g2s(sm.st[stage].hot, g.site_hot + al, nst, &sm.full[stage]);
+                }
+            }
         }
-        __syncthreads();
-        mbar_wait(&bar, 0);
-        k4_body<true>(s_sites - al, s_hot - al, w_lo, w_hi, ck, soa, g, cnt, combine, skip_exc, wl_j, wl_a, &wl_n);
-    } else {
-        // window proven empty (w_lo == w_hi: nothing is ever read) or too many sites to stage: global arrays
-        __syncthreads();                                               // wl_n = 0 visible
-        k4_body<false>(g.site_pos, g.site_hot, w_lo, w_hi, ck, soa, g, cnt, combine, skip_exc, wl_j, wl_a, &wl_n);
+        const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
+        mbar_wait(&sm.empty[stage], parity ^ 1u);
+        sm.meta[stage].flags = PS_DONE;
+        mbar_arrive(&sm.full[stage]);
+        return;
+    }
+    // ===== consumers =====
+    for (uint32_t it = 0;; ++it) {
+        const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
+        mbar_wait(&sm.full[stage], parity);
+        const StageMeta m = sm.meta[stage];
+        if (m.flags & PS_DONE) break;
+        if (m.flags & PS_GLOBAL_SITES) k4_consume(sm.st[stage], m, g.site_pos, g.site_hot, soa, g, cnt, combine, skip_exc, sm);
+        else k4_consume(sm.st[stage], m, sm.st[stage].sites - m.al, sm.st[stage].hot - m.al, soa, g, cnt, combine, skip_exc, sm);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.empty[stage]);                  // the stage can be refilled while the work list drains
+        consumer_sync();                                               // work list complete
+        const uint32_t n_items = min(sm.wl_n, (uint32_t)K4_WORKLIST);
+        for (uint32_t i = threadIdx.x; i < n_items; i += PS_CONSUMERS)
+            k4_exceptions(soa, g, cnt, sm.wl_j[i], (int)(sm.wl_a[i] & POS_MASK), (int)(sm.wl_a[i] >> 31), combine);
+        consumer_sync();                                               // everyone has read wl_n / the list
+        if (threadIdx.x == 0) sm.wl_n = 0;
+        consumer_sync();
     }
 }
 
@@ -791,11 +898,28 @@ void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream) {
     const int n = g.n_sites + g.n_edges;
     if (n > 0) k_alpha_reduce<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, out);
 }
+static int persistent_grid(const void* kernel, size_t smem) {
+    static int sms = 0;
+    if (!sms) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int per_sm = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PS_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    return sms * per_sm;                     // one resident CTA per slot: a multiple of the SM count
+}
 void launch_beta1(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, void* stream) {
-    if (n_chunks > 0 && g.n_sites > 0) k_beta1_stab<<<2 * n_chunks, K3_THREADS, 0, (cudaStream_t)stream>>>(chunks, soa, g, cnt);
+    if (n_chunks <= 0 || g.n_sites <= 0) return;
+    static const int grid = persistent_grid((const void*)k_beta1_stab, sizeof(K3Smem));
+    k_beta1_stab<<<grid, PS_THREADS, sizeof(K3Smem), (cudaStream_t)stream>>>(chunks, n_chunks, soa, g, cnt);
 }
 void launch_spliced(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
-    if (n_chunks > 0 && g.n_sites > 0) k_spliced<<<n_chunks, K4_THREADS, 0, (cudaStream_t)stream>>>(chunks, soa, g, cnt, flags);
+    if (n_chunks <= 0 || g.n_sites <= 0) return;
+    static const int grid = persistent_grid((const void*)k_spliced, sizeof(K4Smem));
+    k_spliced<<<grid, PS_THREADS, sizeof(K4Smem), (cudaStream_t)stream>>>(chunks, n_chunks, soa, g, cnt, flags);
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;

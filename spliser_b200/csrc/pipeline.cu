@@ -188,13 +188,13 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     Carver cc;
     const size_t c_cov = cc.take<uint32_t>(2 * S + 2), c_span = cc.take<uint32_t>(2 * (S + 1) + 2);
     const size_t c_covx = cc.take<uint32_t>(S + 1), c_spanx = cc.take<uint32_t>(S + 1), c_flank = cc.take<uint32_t>(S + 1);
-    const size_t c_dc = cc.take<uint32_t>(E + 1);
+    const size_t c_dc = cc.take<uint32_t>(E + 1), c_work = cc.take<uint32_t>(4);
     ctx->cnt_bytes = cc.off + 256;
     CU(ctx->d_cnt.reserve(ctx->cnt_bytes));
     char* cb = (char*)ctx->d_cnt.p;
     ctx->cnt.cov = (uint32_t*)(cb + c_cov); ctx->cnt.span = (uint32_t*)(cb + c_span);
     ctx->cnt.covx = (uint32_t*)(cb + c_covx); ctx->cnt.spanx = (uint32_t*)(cb + c_spanx);
-    ctx->cnt.flank = (uint32_t*)(cb + c_flank); ctx->cnt.dc = (uint32_t*)(cb + c_dc);
+    ctx->cnt.flank = (uint32_t*)(cb + c_flank); ctx->cnt.dc = (uint32_t*)(cb + c_dc); ctx->cnt.work = (uint32_t*)(cb + c_work);
     Carver oc;
     const size_t nblk = (S + FIN_THREADS * FIN_ITEMS - 1) / (FIN_THREADS * FIN_ITEMS) + 1;
     const size_t o_al = oc.take<int64_t>(S + 1), o_pc = oc.take<int64_t>(E + 1), o_b1 = oc.take<int64_t>(S + 1),
