@@ -112,6 +112,15 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec,
                         const int64_t* p_off, const int32_t* p_pos, const int64_t* c_off, const int32_t* c_pos,
                         uint32_t flags, int64_t* beta1_out, int64_t* beta2simple_out);
 
+/* Host-only half of findAlphaCounts + findCompetitorPos (S:289-372): the site table in output order,
+ * alpha, PartnerCounts and CompetitorPos from the junction table alone.  beta1 / beta2* / SSE are
+ * zero: they need the alignments and therefore the GPU.  Useful for tools that only need the site
+ * universe, and for testing the host logic on a machine without a GPU. */
+int spl_build_site_table(int32_t n_chrom,
+                         int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right,
+                         const int64_t* j_score, const uint8_t* j_strand,
+                         uint32_t flags, spl_result** out, char* err, int err_len);
+
 /* ---- result accessors ---------------------------------------------------------------------- */
 /* Sites are in the reference's output order: chrom_index order, then the per-chromosome list
  * order of site2D_array (position ascending; '+' before '-' in a stranded run, G:123-136). */

@@ -345,6 +345,23 @@ class Context:
         return self._take(h)
 
 
+def build_site_table(n_chrom: int, junctions: Junctions, flags: int) -> SiteTable:
+    """Host-only site table (findAlphaCounts + findCompetitorPos, S:289-372): alpha, Partners, Competitors.
+    beta / SSE columns are zero -- they need the alignments and the GPU."""
+    lib = L.load()
+    h = C.c_void_p()
+    err = C.create_string_buffer(512)
+    rc = lib.spl_build_site_table(n_chrom, *junctions.args(), flags, C.byref(h), err, 512)
+    if rc != 0:
+        raise SpliserError("spl_build_site_table: %s (code %d)" % (err.value.decode(), rc))
+    return Context._take(_LibOnly(lib), h)
+
+
+class _LibOnly:
+    def __init__(self, lib):
+        self._lib = lib
+
+
 def pinned_empty(n, dtype):
     """numpy array over page-locked memory from spl_host_alloc (full-speed host->device copies)."""
     lib = L.load()

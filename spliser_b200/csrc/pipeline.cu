@@ -11,6 +11,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/spliser_b200.h"
@@ -357,20 +358,27 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     if (n_junc > 0 && !j_score) return ctx->fail(SPL_ERR_ARG, "NULL j_score");
     CU(cudaSetDevice(ctx->device));
     reset_stats(ctx);
-    const double tg0 = now_ms();
-    std::string e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, (flags & SPL_FLAG_STRANDED) != 0, ctx->hg);
-    if (!e.empty()) return ctx->fail(SPL_ERR_ARG, "%s", e.c_str());
     flags &= 0xfu;
     if (const char* dbg = std::getenv("SPLISER_DEBUG_SKIP_EXC"))
         if (dbg[0] == '1') flags |= FLAG_DEBUG_SKIP_EXC;
     ctx->flags = flags;
+    // the site graph is built on a host thread while the records travel to the GPU and are expanded
+    const double tg0 = now_ms();
+    std::string e;
+    double graph_ms = 0;
+    std::thread builder([&]() {
+        e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, (flags & SPL_FLAG_STRANDED) != 0, ctx->hg);
+        graph_ms = now_ms() - tg0;
+    });
+    rc = upload_and_expand(ctx, rec, flags);
+    ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg0;
+    builder.join();
+    if (rc) return rc;
+    if (!e.empty()) return ctx->fail(SPL_ERR_ARG, "%s", e.c_str());
+    const double tu0 = now_ms();
     rc = upload_graph(ctx, j_score, n_junc);
     if (rc) return rc;
-    const double tg1 = now_ms();
-    ctx->stats[SPL_STAT_MS_GRAPH] = tg1 - tg0;
-    rc = upload_and_expand(ctx, rec, flags);
-    if (rc) return rc;
-    ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg1;
+    ctx->stats[SPL_STAT_MS_GRAPH] = graph_ms + (now_ms() - tu0);
     launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
     CU(cudaGetLastError());
     ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
@@ -604,6 +612,33 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out) {
     if (!ctx->loaded) return ctx->fail(SPL_ERR_ARG, "nothing loaded");
     CU(cudaSetDevice(ctx->device));
     return fetch(ctx, out);
+}
+
+int spl_build_site_table(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right,
+                         const int64_t* j_score, const uint8_t* j_strand, uint32_t flags, spl_result** out, char* err, int err_len) {
+    if (!out) return SPL_ERR_ARG;
+    *out = nullptr;
+    SiteGraph h;
+    std::string e = (n_junc > 0 && !j_score) ? std::string("NULL j_score")
+                                              : build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand,
+                                                                 (flags & SPL_FLAG_STRANDED) != 0, h);
+    if (!e.empty()) {
+        if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
+        return SPL_ERR_ARG;
+    }
+    std::unique_ptr<spl_result> r(new spl_result());
+    const size_t S = (size_t)h.n_sites, E = h.pc_pos.size();
+    r->n = (int64_t)S;
+    r->chrom = h.chrom; r->pos = h.pos; r->strand = h.strand; r->first_line = h.first_line;
+    r->pc_off = h.pc_off; r->pc_pos = h.pc_pos; r->cp_off = h.cp_off; r->cp_pos = h.cp_pos;
+    r->alpha.assign(S, 0); r->beta1.assign(S, 0); r->beta2s.assign(S, 0); r->beta2c.assign(S, 0);
+    r->beta2w.assign(S, 0.0); r->sse.assign(S, 0.0); r->pc_cnt.assign(E, 0);
+    for (size_t t = 0; t < S; ++t)
+        for (int64_t k = h.inc_off[t]; k < h.inc_off[t + 1]; ++k) r->alpha[t] += j_score[h.inc_line[(size_t)k]];
+    for (size_t x = 0; x < E; ++x)
+        for (int64_t k = h.einc_off[x]; k < h.einc_off[x + 1]; ++k) r->pc_cnt[x] += j_score[h.einc_line[(size_t)k]];
+    *out = r.release();
+    return SPL_OK;
 }
 
 int64_t spl_result_n_sites(const spl_result* r) { return r ? r->n : 0; }

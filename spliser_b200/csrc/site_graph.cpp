@@ -13,6 +13,8 @@
 #include "site_graph.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <numeric>
 #include <unordered_map>
@@ -164,11 +166,24 @@ void build_rp(SiteGraph& g) {
     std::vector<int32_t> t_of;
     anchor_of.reserve(g.pc_pos.size());
     t_of.reserve(g.pc_pos.size());
+    const bool direct = !g.dirty_regime && g.pt_site.size() == g.pc_pos.size() && g.gap_index.empty();
+    std::vector<int32_t> first_at;    // first site index sharing (chrom, pos) with site s
+    if (direct) {
+        first_at.resize((size_t)g.n_sites);
+        for (int64_t s = 0; s < g.n_sites; ++s)
+            first_at[(size_t)s] = (s > 0 && g.chrom[(size_t)s - 1] == g.chrom[(size_t)s] && g.pos[(size_t)s - 1] == g.pos[(size_t)s])
+                                      ? first_at[(size_t)s - 1] : (int32_t)s;
+    }
     for (int64_t t = 0; t < g.n_sites; ++t) {
         const int32_t c = g.chrom[(size_t)t];
         const int32_t* lo = g.pos.data() + g.cs_off[(size_t)c];
         const int32_t* hi = g.pos.data() + g.cs_off[(size_t)c + 1];
         for (int64_t e = g.pc_off[(size_t)t]; e < g.pc_off[(size_t)t + 1]; ++e) {
+            if (direct) {                                              // PartnerCounts entry e <-> partner object pt_site[e]
+                anchor_of.push_back(first_at[(size_t)g.pt_site[(size_t)e]]);
+                t_of.push_back((int32_t)t);
+                continue;
+            }
             const int32_t* it = std::lower_bound(lo, hi, g.pc_pos[(size_t)e]);
             if (it == hi || *it != g.pc_pos[(size_t)e]) continue;   // cannot happen: partners are rows
             anchor_of.push_back((int32_t)(it - g.pos.data()));
@@ -183,6 +198,227 @@ void build_rp(SiteGraph& g) {
 
 }  // namespace
 
+namespace {
+void build_rp(SiteGraph& g);
+
+// competitors: positions of partners-of-partners other than own position (S:364-372), then the reverse index
+void finish_graph(SiteGraph& g) {
+    const int64_t S = g.n_sites;
+    g.cp_off.assign((size_t)S + 1, 0);
+    g.cp_pos.clear();
+    std::vector<int32_t> tmp;
+    for (int64_t t = 0; t < S; ++t) {
+        tmp.clear();
+        for (int64_t a = g.pt_off[(size_t)t]; a < g.pt_off[(size_t)t + 1]; ++a) {
+            const int32_t p = g.pt_site[(size_t)a];
+            for (int64_t q = g.pt_off[(size_t)p]; q < g.pt_off[(size_t)p + 1]; ++q) {
+                const int32_t cpos = g.pos[(size_t)g.pt_site[(size_t)q]];
+                if (cpos != g.pos[(size_t)t]) tmp.push_back(cpos);
+            }
+        }
+        if (tmp.size() > 1) {
+            std::sort(tmp.begin(), tmp.end());
+            tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        }
+        g.cp_pos.insert(g.cp_pos.end(), tmp.begin(), tmp.end());
+        g.cp_off[(size_t)t + 1] = (int64_t)g.cp_pos.size();
+    }
+    build_rp(g);
+}
+}  // namespace
+
+namespace {
+
+// stable LSD radix sort of (key, val) pairs, 8-bit digits; digits on which all keys agree are skipped
+void radix_sort_pairs(std::vector<uint64_t>& key, std::vector<uint32_t>& val, int key_bits) {
+    const size_t n = key.size();
+    if (n < 2) return;
+    uint64_t all_or = 0, all_and = ~0ull;
+    bool sorted = true;
+    for (size_t i = 0; i < n; ++i) {
+        all_or |= key[i]; all_and &= key[i];
+        if (i && key[i] < key[i - 1]) sorted = false;
+    }
+    if (sorted) return;
+    const uint64_t differ = all_or ^ all_and;
+    std::vector<uint64_t> k2(n);
+    std::vector<uint32_t> v2(n);
+    size_t cnt[256];
+    for (int shift = 0; shift < key_bits; shift += 8) {
+        if (!((differ >> shift) & 0xff)) continue;
+        std::fill(cnt, cnt + 256, (size_t)0);
+        for (size_t i = 0; i < n; ++i) cnt[(key[i] >> shift) & 0xff]++;
+        size_t run = 0;
+        for (size_t b = 0; b < 256; ++b) { const size_t c = cnt[b]; cnt[b] = run; run += c; }
+        const uint64_t* ks = key.data(); const uint32_t* vs = val.data();
+        uint64_t* kd = k2.data(); uint32_t* vd = v2.data();
+        for (size_t i = 0; i < n; ++i) {
+            const size_t d = cnt[(ks[i] >> shift) & 0xff]++;
+            kd[d] = ks[i]; vd[d] = vs[i];
+        }
+        key.swap(k2); val.swap(v2);
+    }
+}
+
+// LSD radix sort of packed 64-bit words on bits [lo_bit, hi_bit); lower bits ride along (stable)
+void radix_sort_packed(std::vector<uint64_t>& a, int lo_bit, int hi_bit) {
+    const size_t n = a.size();
+    if (n < 2) return;
+    uint64_t all_or = 0, all_and = ~0ull;
+    bool sorted = true;
+    const uint64_t hmask = hi_bit >= 64 ? ~0ull : (((uint64_t)1 << hi_bit) - 1);
+    for (size_t i = 0; i < n; ++i) {
+        all_or |= a[i]; all_and &= a[i];
+        if (i && ((a[i] & hmask) >> lo_bit) < ((a[i - 1] & hmask) >> lo_bit)) sorted = false;
+    }
+    if (sorted) return;
+    const uint64_t differ = all_or ^ all_and;
+    std::vector<uint64_t> b(n);
+    size_t cnt[256];
+    for (int shift = lo_bit; shift < hi_bit; shift += 8) {
+        const int width = std::min(8, hi_bit - shift);
+        const uint64_t dm = ((uint64_t)1 << width) - 1;
+        if (!((differ >> shift) & dm)) continue;
+        std::fill(cnt, cnt + 256, (size_t)0);
+        for (size_t i = 0; i < n; ++i) cnt[(a[i] >> shift) & dm]++;
+        size_t run = 0;
+        for (size_t k = 0; k < 256; ++k) { const size_t c = cnt[k]; cnt[k] = run; run += c; }
+        const uint64_t* src = a.data(); uint64_t* dst = b.data();
+        for (size_t i = 0; i < n; ++i) dst[cnt[(src[i] >> shift) & dm]++] = src[i];
+        a.swap(b);
+    }
+}
+
+int bits_for(uint64_t max_value) {
+    int b = 1;
+    while (b < 64 && (max_value >> b)) ++b;
+    return b;
+}
+
+// Clean regime: a site is (chrom, pos[, '+'/'-']); everything is a sort / unique / group-by over the junction rows.
+// Produces exactly what the line-by-line construction of the reference produces (list order, first-seen
+// strand and line, Partners / PartnerCounts in first-appearance order).
+void build_clean_sorted(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right,
+                        const uint8_t* j_strand, bool stranded, SiteGraph& g) {
+    const size_t J = (size_t)n_junc;
+    g = SiteGraph();
+    g.n_chrom = n_chrom;
+    const bool timing = std::getenv("SPLISER_TIMING") != nullptr;
+    auto tprev = std::chrono::steady_clock::now();
+#define TICK(name) do { if (timing) { auto tn = std::chrono::steady_clock::now(); fprintf(stderr, "  %-16s %.2f ms\n", name, std::chrono::duration<double, std::milli>(tn - tprev).count()); tprev = tn; } } while (0)
+    // ---- endpoints -> sites
+    std::vector<uint64_t> key(2 * J);
+    std::vector<uint32_t> val(2 * J);
+    uint64_t kmax = 0;
+    for (size_t i = 0; i < J; ++i) {
+        const uint64_t sb = (stranded && j_strand[i] == '-') ? 1u : 0u;
+        const uint64_t c = (uint64_t)(uint32_t)j_chrom[i] << 33;
+        key[2 * i] = c | ((uint64_t)(uint32_t)j_left[i] << 1) | sb;
+        key[2 * i + 1] = c | ((uint64_t)(uint32_t)j_right[i] << 1) | sb;
+        val[2 * i] = (uint32_t)(2 * i); val[2 * i + 1] = (uint32_t)(2 * i + 1);
+        kmax |= key[2 * i] | key[2 * i + 1];
+    }
+    TICK("endpoint keys");
+    const int vb = bits_for(2 * J), kb = bits_for(kmax);
+    if (kb + vb <= 64) {                 // usual case: key and row id share one word -> one array to move
+        for (size_t e = 0; e < 2 * J; ++e) key[e] = (key[e] << vb) | val[e];
+        radix_sort_packed(key, vb, vb + kb);
+        const uint64_t vm = ((uint64_t)1 << vb) - 1;
+        for (size_t e = 0; e < 2 * J; ++e) { val[e] = (uint32_t)(key[e] & vm); key[e] >>= vb; }
+    } else {
+        radix_sort_pairs(key, val, kb);
+    }
+    TICK("endpoint sort");
+    std::vector<int32_t> site_of(2 * J);
+    g.chrom.reserve(2 * J); g.pos.reserve(2 * J); g.strand.reserve(2 * J); g.first_line.reserve(2 * J);
+    g.cls.reserve(2 * J); g.inc_off.reserve(2 * J + 1);
+    g.cs_off.assign((size_t)n_chrom + 1, 0);
+    g.inc_off.clear(); g.inc_line.resize(2 * J);
+    int64_t S = 0;
+    for (size_t e = 0; e < 2 * J; ++e) {
+        if (e == 0 || key[e] != key[e - 1]) {
+            const size_t line = val[e] >> 1;
+            g.chrom.push_back(j_chrom[line]);
+            g.pos.push_back((int32_t)((key[e] >> 1) & 0xffffffffu));
+            g.strand.push_back(j_strand[line]);                       // first-seen strand (stable sort keeps row order)
+            g.first_line.push_back((int64_t)line);
+            g.cls.push_back(!stranded ? CLS_ANY : j_strand[line] == '+' ? CLS_PLUS : j_strand[line] == '-' ? CLS_MINUS : CLS_NEVER);
+            g.inc_off.push_back((int64_t)e);
+            g.cs_off[(size_t)j_chrom[line] + 1]++;
+            ++S;
+        }
+        site_of[val[e]] = (int32_t)(S - 1);
+        g.inc_line[e] = (int32_t)(val[e] >> 1);
+    }
+    g.inc_off.push_back((int64_t)(2 * J));
+    g.n_sites = S;
+    for (int32_t c = 0; c < n_chrom; ++c) g.cs_off[(size_t)c + 1] += g.cs_off[(size_t)c];
+    TICK("sites");
+    // ---- directed edges -> PartnerCounts entries
+    const int sbits = bits_for((uint64_t)(S > 0 ? S - 1 : 0));
+    for (size_t i = 0; i < J; ++i) {
+        const uint64_t a = (uint64_t)(uint32_t)site_of[2 * i], b = (uint64_t)(uint32_t)site_of[2 * i + 1];
+        key[2 * i] = (a << 32) | b; key[2 * i + 1] = (b << 32) | a;
+        val[2 * i] = (uint32_t)i; val[2 * i + 1] = (uint32_t)i;       // row order == first-appearance order
+    }
+    TICK("edge keys");
+    const int lb = bits_for(J);
+    if (32 + sbits + lb <= 64) {
+        for (size_t e = 0; e < 2 * J; ++e) key[e] = (key[e] << lb) | val[e];
+        radix_sort_packed(key, lb, lb + 32 + sbits);
+        const uint64_t lm = ((uint64_t)1 << lb) - 1;
+        for (size_t e = 0; e < 2 * J; ++e) { val[e] = (uint32_t)(key[e] & lm); key[e] >>= lb; }
+    } else {
+        radix_sort_pairs(key, val, 32 + sbits);
+    }
+    TICK("edge sort");
+    std::vector<uint64_t> ukey;       // (src << 32) | first_line   -> order of Partners inside a site
+    std::vector<uint32_t> uidx;       // index of the unique edge
+    std::vector<int32_t> u_dst;
+    std::vector<int64_t> u_lo;        // segment [u_lo[u], u_lo[u+1]) of the sorted rows
+    ukey.reserve(2 * J); uidx.reserve(2 * J); u_dst.reserve(2 * J); u_lo.reserve(2 * J + 1);
+    for (size_t e = 0; e < 2 * J; ++e) {
+        if (e == 0 || key[e] != key[e - 1]) {
+            ukey.push_back((key[e] & 0xffffffff00000000ull) | val[e]);
+            uidx.push_back((uint32_t)u_dst.size());
+            u_dst.push_back((int32_t)(key[e] & 0xffffffffu));
+            u_lo.push_back((int64_t)e);
+        }
+    }
+    u_lo.push_back((int64_t)(2 * J));
+    const size_t E = u_dst.size();
+    TICK("unique edges");
+    const int eb = bits_for(E);
+    if (32 + sbits + eb <= 64) {
+        for (size_t x = 0; x < E; ++x) ukey[x] = (ukey[x] << eb) | uidx[x];
+        radix_sort_packed(ukey, eb, eb + 32 + sbits);
+        const uint64_t em = ((uint64_t)1 << eb) - 1;
+        for (size_t x = 0; x < E; ++x) { uidx[x] = (uint32_t)(ukey[x] & em); ukey[x] >>= eb; }
+    } else {
+        radix_sort_pairs(ukey, uidx, 32 + sbits);
+    }
+    TICK("edge order sort");
+    g.pt_off.assign((size_t)S + 1, 0);
+    g.pt_site.resize(E); g.pc_pos.resize(E);
+    g.einc_off.assign(E + 1, 0);
+    g.einc_line.resize(2 * J);
+    int64_t w = 0;
+    for (size_t x = 0; x < E; ++x) {
+        const uint32_t u = uidx[x];
+        const size_t src = (size_t)(ukey[x] >> 32);
+        g.pt_off[src + 1]++;
+        g.pt_site[x] = u_dst[u];
+        g.pc_pos[x] = g.pos[(size_t)u_dst[u]];
+        for (int64_t e = u_lo[u]; e < u_lo[u + 1]; ++e) g.einc_line[(size_t)w++] = (int32_t)val[(size_t)e];
+        g.einc_off[x + 1] = w;
+    }
+    for (int64_t t = 0; t < S; ++t) g.pt_off[(size_t)t + 1] += g.pt_off[(size_t)t];
+    g.pc_off = g.pt_off;              // clean regime: one PartnerCounts key per partner object
+    TICK("csr");
+}
+
+}  // namespace
+
 std::string build_site_graph(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left,
                              const int32_t* j_right, const uint8_t* j_strand, bool stranded, SiteGraph& g) {
     if (n_chrom < 0 || n_junc < 0) return "negative size";
@@ -192,43 +428,41 @@ std::string build_site_graph(int32_t n_chrom, int64_t n_junc, const int32_t* j_c
     b.stranded = stranded;
     for (int64_t i = 0; i < n_junc; ++i) {
         if (j_chrom[i] < 0 || j_chrom[i] >= n_chrom) return "junction chromosome index out of range";
-        if ((stranded && !is_pm(j_strand[i])) || j_left[i] == j_right[i]) b.emulate = true;
+        if ((stranded && !is_pm(j_strand[i])) || j_left[i] == j_right[i] || j_left[i] < 0 || j_right[i] < 0) b.emulate = true;
     }
     if (const char* f = std::getenv("SPLISER_FORCE_EMULATION")) {
         if (f[0] == '1') b.emulate = true;
     }
-    if (b.emulate) b.order.resize((size_t)n_chrom);
-    b.index.reserve((size_t)n_junc * 2);
+    if (!b.emulate) {
+        const auto t0 = std::chrono::steady_clock::now();
+        build_clean_sorted(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, stranded, g);
+        const auto t1 = std::chrono::steady_clock::now();
+        finish_graph(g);
+        if (std::getenv("SPLISER_TIMING")) {
+            const auto t2 = std::chrono::steady_clock::now();
+            fprintf(stderr, "site graph: sorted build %.2f ms, competitors+reverse index %.2f ms\n",
+                    std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+        }
+        return "";
+    }
+    b.order.resize((size_t)n_chrom);
     b.pc_index.reserve((size_t)n_junc * 2);
     b.pt_seen.reserve((size_t)n_junc * 2);
 
     for (int64_t i = 0; i < n_junc; ++i) {
         const int32_t c = j_chrom[i], l = j_left[i], r = j_right[i];
         const uint8_t st = j_strand[i];
-        int32_t sl = -1, sr = -1;
+        auto& arr = b.order[(size_t)c];
+        const int32_t li = b.search(arr, l, st), ri = b.search(arr, r, st);   // both before any insert, S:291-292
+        int32_t sl = li >= 0 ? arr[(size_t)li] : -1;
+        int32_t sr = ri >= 0 ? arr[(size_t)ri] : -1;
         bool lnew = false, rnew = false;
-        if (b.emulate) {
-            auto& arr = b.order[(size_t)c];
-            const int32_t li = b.search(arr, l, st), ri = b.search(arr, r, st);   // both before any insert, S:291-292
-            sl = li >= 0 ? arr[(size_t)li] : -1;
-            sr = ri >= 0 ? arr[(size_t)ri] : -1;
-        } else {
-            auto it = b.index.find(b.key(c, l, st));
-            if (it != b.index.end()) sl = it->second;
-            it = b.index.find(b.key(c, r, st));
-            if (it != b.index.end()) sr = it->second;
-        }
         if (sl < 0) { sl = b.new_site(c, l, st, i); lnew = true; }
         if (sr < 0) { sr = b.new_site(c, r, st, i); rnew = true; }
         b.inc_site.push_back(sl); b.inc_line.push_back((int32_t)i);     // addAlphaCount, S:341
         b.inc_site.push_back(sr); b.inc_line.push_back((int32_t)i);
-        if (b.emulate) {
-            if (lnew) b.insort(b.order[(size_t)c], sl);
-            if (rnew) b.insort(b.order[(size_t)c], sr);
-        } else {
-            if (lnew) b.index.emplace(b.key(c, l, st), sl);
-            if (rnew) b.index.emplace(b.key(c, r, st), sr);
-        }
+        if (lnew) b.insort(arr, sl);
+        if (rnew) b.insort(arr, sr);
         b.link(sl, sr, (int32_t)i);                                       // S:352-355
         b.link(sr, sl, (int32_t)i);
     }
@@ -239,25 +473,15 @@ std::string build_site_graph(int32_t n_chrom, int64_t n_junc, const int32_t* j_c
     g = SiteGraph();
     g.n_chrom = n_chrom;
     g.n_sites = S;
-    g.dirty_regime = b.emulate;
+    g.dirty_regime = true;
     g.cs_off.assign((size_t)n_chrom + 1, 0);
-    if (b.emulate) {
+    {
         int64_t k = 0;
         for (int32_t c = 0; c < n_chrom; ++c) {
             g.cs_off[(size_t)c] = k;
             for (int32_t id : b.order[(size_t)c]) old_of[(size_t)k++] = id;
         }
         g.cs_off[(size_t)n_chrom] = k;
-    } else {
-        std::iota(old_of.begin(), old_of.end(), 0);
-        std::stable_sort(old_of.begin(), old_of.end(), [&](int32_t x, int32_t y) {
-            if (b.s_chrom[x] != b.s_chrom[y]) return b.s_chrom[x] < b.s_chrom[y];
-            if (b.s_pos[x] != b.s_pos[y]) return b.s_pos[x] < b.s_pos[y];
-            if (stranded) return b.s_strand[x] == '+' && b.s_strand[y] == '-';
-            return false;
-        });
-        for (int64_t k = 0; k < S; ++k) g.cs_off[(size_t)b.s_chrom[old_of[(size_t)k]] + 1]++;
-        for (int32_t c = 0; c < n_chrom; ++c) g.cs_off[(size_t)c + 1] += g.cs_off[(size_t)c];
     }
     for (int64_t k = 0; k < S; ++k) new_of[(size_t)old_of[(size_t)k]] = (int32_t)k;
     g.chrom.resize((size_t)S); g.pos.resize((size_t)S); g.strand.resize((size_t)S);
@@ -300,26 +524,7 @@ std::string build_site_graph(int32_t n_chrom, int64_t n_junc, const int32_t* j_c
     group_by(keys, E, g.einc_off, perm);
     g.einc_line.resize(perm.size());
     for (size_t i = 0; i < perm.size(); ++i) g.einc_line[i] = b.einc_line[(size_t)perm[i]];
-
-    // ---- competitors: positions of partners-of-partners other than own position (S:364-372) -------
-    g.cp_off.assign((size_t)S + 1, 0);
-    g.cp_pos.clear();
-    std::vector<int32_t> tmp;
-    for (int64_t t = 0; t < S; ++t) {
-        tmp.clear();
-        for (int64_t a = g.pt_off[(size_t)t]; a < g.pt_off[(size_t)t + 1]; ++a) {
-            const int32_t p = g.pt_site[(size_t)a];
-            for (int64_t q = g.pt_off[(size_t)p]; q < g.pt_off[(size_t)p + 1]; ++q) {
-                const int32_t cpos = g.pos[(size_t)g.pt_site[(size_t)q]];
-                if (cpos != g.pos[(size_t)t]) tmp.push_back(cpos);
-            }
-        }
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        g.cp_pos.insert(g.cp_pos.end(), tmp.begin(), tmp.end());
-        g.cp_off[(size_t)t + 1] = (int64_t)g.cp_pos.size();
-    }
-    build_rp(g);
+    finish_graph(g);
     return "";
 }
 

@@ -93,3 +93,47 @@ def test_synth_is_deterministic_and_sorted():
     for s in range(len(r.seg_chrom)):
         assert (np.diff(r.pos[r.seg_off[s]:r.seg_off[s + 1]]) >= 0).all()
     assert len(a.junctions) > 50 and int(((r.cigar & 15) == 3).sum()) > 500
+
+
+def test_sorted_site_table_equals_line_by_line_emulation(monkeypatch, built_library):
+    """Clean regime: the sort/unique builder must reproduce the emulated reference construction
+    (list order, first-seen strand and row, Partners order, PartnerCounts, CompetitorPos)."""
+    from oracle import fuzzgen
+    from spliser_b200 import synth
+    from spliser_b200.api import build_site_table
+    from spliser_b200.bed import parse_bed12
+    fields = ("chrom", "pos", "strand", "alpha", "first_line", "partner_off", "partner_pos", "partner_cnt", "comp_off", "comp_pos")
+
+    def both(n_chrom, junc, flags):
+        monkeypatch.delenv("SPLISER_FORCE_EMULATION", raising=False)
+        a = build_site_table(n_chrom, junc, flags)
+        monkeypatch.setenv("SPLISER_FORCE_EMULATION", "1")
+        b = build_site_table(n_chrom, junc, flags)
+        monkeypatch.delenv("SPLISER_FORCE_EMULATION", raising=False)
+        for k in fields:
+            assert np.array_equal(getattr(a, k), getattr(b, k)), k
+        return a
+
+    for seed in range(120):
+        case = fuzzgen.gen_case(seed, n_chrom=1 + seed % 3, dirty=False)
+        chroms, junc, _ = parse_bed12(case["bed"].splitlines(True))
+        both(len(chroms), junc, 1 if case["stranded"] else 0)
+    for stranded in (False, True):
+        w = synth.generate(synth.config_small(40000, seed=70 + stranded, stranded=stranded, paired=stranded))
+        t = both(len(w.chroms), w.junctions, w.flags)
+        assert len(t) > 100 and int(t.alpha.sum()) == 2 * int(w.junctions.score.sum())
+
+
+def test_site_table_matches_reference_golden(built_library):
+    """Host-only site table (alpha, Partners, Competitors) against the reference's rows, incl. the dirty regime."""
+    from common import load_golden
+    from spliser_b200.api import build_site_table
+    from spliser_b200.bed import parse_bed12
+    cases = load_golden("process_fuzz.json.gz") + [c for c in load_golden("appendix_a.json.gz")["process"] if "qgene" not in c]
+    for case in cases:
+        chroms, junc, _ = parse_bed12(case["bed"].splitlines(True))
+        t = build_site_table(len(chroms), junc, 1 if case["stranded"] else 0)
+        got = [(chroms[int(t.chrom[i])], int(t.pos[i]), t.strand_str(i), int(t.alpha[i]), list(map(list, t.partners(i).items())), t.competitors(i))
+               for i in range(len(t))]
+        want = [(r["chrom"], r["pos"], r["strand"], r["alpha"], [list(p) for p in r["partners"]], r["competitors"]) for r in case["rows"]]
+        assert got == want, case.get("seed", case.get("name"))
