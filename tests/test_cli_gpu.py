@@ -1,0 +1,86 @@
+"""The SpliSER-compatible CLI end to end on the GPU: .SpliSER.tsv and .combined.tsv must be byte-identical
+to what the unmodified reference wrote for the same inputs (golden fixtures)."""
+import os
+
+import pytest
+
+from common import load_golden
+
+pytestmark = pytest.mark.gpu
+
+
+def _write_inputs(tmp, case, chroms_extra=()):
+    from spliser_b200 import Records
+    bed = os.path.join(tmp, "j.bed")
+    open(bed, "w").write(case["bed"])
+    reads = [tuple(r) for r in case["reads"]]
+    refs = sorted({r[0] for r in reads} | set(chroms_extra)) or ["C"]
+    bam = os.path.join(tmp, "x.bam")
+    Records.from_reads(refs, reads).write_bam(bam, refs)
+    gff = None
+    if case.get("gff"):
+        gff = os.path.join(tmp, "a.gff")
+        open(gff, "w").write(case["gff"])
+    return bam, bed, gff
+
+
+def test_process_cli_known_answers(ctx, tmp_path):
+    from spliser_b200 import cli
+    g = load_golden("appendix_a.json.gz")
+    for k, case in enumerate(g["process"]):
+        d = tmp_path / ("p%d" % k)
+        d.mkdir()
+        bam, bed, gff = _write_inputs(str(d), case)
+        out = str(d / "out")
+        cli.process(bam, bed, out, qGene=case.get("qgene", "All"), qChrom=case.get("qchrom", "All"),
+                    maxIntronSize=case.get("max_intron", 0), annotationFile=gff, isStranded=case["stranded"],
+                    strandedType=case["stype"], isbeta2Cryptic=case["cryptic"], ctx=ctx)
+        assert open(out + ".SpliSER.tsv").read() == case["tsv"], case["name"]
+
+
+def test_process_cli_fuzz_text(ctx, tmp_path):
+    from spliser_b200 import cli
+    cases = load_golden("process_fuzz.json.gz")[::6]
+    for k, case in enumerate(cases):
+        d = tmp_path / ("f%d" % k)
+        d.mkdir()
+        bam, bed, _ = _write_inputs(str(d), case)
+        out = str(d / "out")
+        cli.process(bam, bed, out, isStranded=case["stranded"], strandedType=case["stype"], isbeta2Cryptic=case["cryptic"], ctx=ctx)
+        assert open(out + ".SpliSER.tsv").read() == case["tsv"], case["seed"]
+
+
+def test_missing_query_gene_raises_like_the_reference(ctx, tmp_path):
+    from spliser_b200 import cli
+    case = [c for c in load_golden("appendix_a.json.gz")["process"] if c["name"] == "A.4-locus"][0]
+    bam, bed, gff = _write_inputs(str(tmp_path), case)
+    with pytest.raises(AttributeError):
+        cli.process(bam, bed, str(tmp_path / "o"), qGene="NOPE", qChrom="C", maxIntronSize=50, annotationFile=gff, ctx=ctx)
+    with pytest.raises(UnboundLocalError):
+        cli.process(bam, bed, str(tmp_path / "o"), isStranded=True, strandedType="xx", ctx=ctx)
+
+
+def _run_combine(ctx, tmp, case, cryptic=False):
+    from spliser_b200 import Records, cli
+    lines = []
+    for i, s in enumerate(case["samples"]):
+        p = os.path.join(tmp, "s%d.SpliSER.tsv" % i)
+        open(p, "w").write(s["tsv"])
+        bam = os.path.join(tmp, "s%d.bam" % i)
+        reads = [tuple(r) for r in s["reads"]]
+        Records.from_reads(["C"], reads).write_bam(bam, ["C"])
+        lines.append("%s\t%s\t%s\n" % (s["title"], p, bam))
+    sf = os.path.join(tmp, "samples.tsv")
+    open(sf, "w").writelines(lines)
+    out = os.path.join(tmp, "out")
+    cli.combine(sf, out, isStranded=case["stranded"], strandedType=case["stype"], isbeta2Cryptic=cryptic, ctx=ctx)
+    return open(out + ".combined.tsv").read()
+
+
+def test_combine_cli_matches_reference(ctx, tmp_path):
+    cases = load_golden("appendix_a.json.gz")["combine"] + load_golden("combine_fuzz.json.gz")
+    for k, case in enumerate(cases):
+        d = tmp_path / ("c%d" % k)
+        d.mkdir()
+        got = _run_combine(ctx, str(d), case)
+        assert got == case["combined"], case.get("name", case.get("seed"))

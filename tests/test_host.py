@@ -137,3 +137,20 @@ def test_site_table_matches_reference_golden(built_library):
                for i in range(len(t))]
         want = [(r["chrom"], r["pos"], r["strand"], r["alpha"], [list(p) for p in r["partners"]], r["competitors"]) for r in case["rows"]]
         assert got == want, case.get("seed", case.get("name"))
+
+
+def test_gene_assignment_matches_reference_golden(tmp_path):
+    """Gene column (createGenes + binary_gene_search, S:50-173) for the annotated known-answer scenario."""
+    from common import load_golden
+    from spliser_b200.genes import gene_name, load_annotation
+    case = [c for c in load_golden("appendix_a.json.gz")["process"] if c["name"] == "A.4-annot"][0]
+    p = tmp_path / "a.gff"
+    p.write_text(case["gff"])
+    ann = load_annotation(str(p))
+    assert ann.chrom_index == ["C"] and [g.name for g in ann.genes[0]] == ["G1", "G2"]
+    assert (ann.genes[0][0].left, ann.genes[0][0].right) == (89, 320)
+    for r in case["rows"]:
+        assert gene_name(ann, 0, r["pos"], r["strand"], False) == r["gene"]
+    q = load_annotation(str(p), "G2")
+    assert q.query_gene.name == "G2" and len(q.genes[0]) == 1
+    assert load_annotation(str(p), "NOPE").query_gene is None
