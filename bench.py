@@ -185,36 +185,13 @@ def main():
     # ------------------------------------------------------------------ our arm
     import spliser_b200
     from spliser_b200.api import Records, pinned_empty
-    dist = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    from spliser_b200.dist import Ranks
+    ranks = Ranks("nccl" if world > 1 else None)
     cfg, desc = workload_config(args.workload, args.reads, rank)
     w = synth.generate(cfg, cache_dir=CACHE)
     ctx = spliser_b200.Context(local)
     n_chrom = len(w.chroms)
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
-
-    def max_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    def sum_over_ranks(x):
-        if dist is None:
-            return x
-        import torch
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
 
     sampler = ClockSampler(local)
     # ---- resident: SoA in HBM -> SSE in HBM
@@ -245,6 +222,7 @@ def main():
         print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "kernel_ms": {"beta1_stab": kern["k_beta1_stab"][1], "spliced": kern["k_spliced"][1], "final": st["ms_final"] / args.steps}}))
         sampler.stop()
         ctx.close()
+        ranks.close()
         return
     # ---- e2e through the C ABI from pinned host arrays
     r = w.records
@@ -302,8 +280,7 @@ def main():
     if rank == 0:
         print(json.dumps(out))
     ctx.close()
-    if dist is not None:
-        dist.destroy_process_group()
+    ranks.close()
 
 
 if __name__ == "__main__":
