@@ -79,6 +79,24 @@ __device__ __forceinline__ int upper_bound_i32(const int32_t* a, int lo, int hi,
     return lo;
 }
 
+// lower_bound(key_lo) and upper_bound(key_hi) over the same sorted range [lo, hi) in one branch-free loop:
+// the two dependent-load chains overlap, and with warp-uniform arguments the trip count is uniform
+__device__ __forceinline__ void bound_pair_i32(const int32_t* a, int lo, int hi, int32_t key_lo, int32_t key_hi, int& i0, int& i1) {
+    int n = hi - lo;
+    if (n <= 0) { i0 = i1 = lo; return; }
+    const int32_t* b0 = a + lo;
+    const int32_t* b1 = a + lo;
+    while (n > 1) {
+        const int half = n >> 1;
+        const int32_t v0 = b0[half - 1], v1 = b1[half - 1];
+        b0 = (v0 < key_lo) ? b0 + half : b0;
+        b1 = (v1 <= key_hi) ? b1 + half : b1;
+        n -= half;
+    }
+    i0 = (int)(b0 - a) + (b0[0] < key_lo ? 1 : 0);
+    i1 = (int)(b1 - a) + (b1[0] <= key_hi ? 1 : 0);
+}
+
 // strand class bit of a read: 0 = '+', 1 = '-' under check_strand (S:374-406); always 0 when unstranded
 __device__ __forceinline__ uint32_t read_class(uint32_t flag, uint32_t mode) {
     if (!(mode & FLAG_STRANDED)) return 0u;
@@ -404,8 +422,8 @@ __device__ __forceinline__ void k3_consume(const K3Stage& stg, const StageMeta& 
         }
         const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
         if (wlo > whi) continue;
-        const int i0 = lower_bound_i32(sp, m.w_lo, m.w_hi, wlo);
-        const int i1 = upper_bound_i32(sp, i0, m.w_hi, whi);
+        int i0, i1;
+        bound_pair_i32(sp, m.w_lo, m.w_hi, wlo, whi, i0, i1);
         if (i0 >= i1) continue;
         if (i1 - i0 <= K3_DENSE) {
             for (int s = i0; s < i1; ++s) {                           // warp-uniform loop
@@ -623,8 +641,8 @@ __device__ __forceinline__ void k4_consume(const K4Stage& stg, const StageMeta& 
         // narrow the window to the positions this warp asks about (broadcast loads)
         const int wlo = __reduce_min_sync(0xffffffffu, l), whi = __reduce_max_sync(0xffffffffu, live ? max(l, r) : INT_MIN);
         if (wlo > whi) continue;                                       // no live lane in this warp
-        const int n0 = lower_bound_i32(sp, m.w_lo, m.w_hi, wlo);
-        const int n1 = upper_bound_i32(sp, n0, m.w_hi, whi);
+        int n0, n1;
+        bound_pair_i32(sp, m.w_lo, m.w_hi, wlo, whi, n0, n1);
         int il = n0, iu = n0, ir = n0;
         if (live) {
             il = lower_bound_i32(sp, n0, n1, l);
