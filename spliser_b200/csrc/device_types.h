@@ -59,6 +59,28 @@ struct DevSoA {
 };
 constexpr uint32_t POS_MASK = 0x7fffffffu;
 
+// Bin-partitioned copy of all M blocks (stream C): blocks grouped by (chromosome, start >> BIN_SHIFT), order
+// inside a bin arbitrary.  K3 streams it in fixed tiles; every warp then sees a tiny genomic window whatever
+// the record order or the intron lengths were.  Each chromosome is padded to a multiple of K3_TILE with
+// never-matching elements so that tiles do not straddle chromosomes.
+constexpr int BIN_SHIFT = 8;            // 256 bp
+constexpr int K3_TILE = 2048;           // blocks per tile / pipeline stage (16 KB)
+struct Tile { uint32_t e0; int32_t w_lo, w_hi; int32_t pad; };   // first element, site index window [w_lo, w_hi)
+struct DevBins {
+    uint32_t* chrom_ext;        // [n_chrom]   largest block start seen (atomicMax)
+    uint32_t* chrom_tot;        // [n_chrom]   blocks on the chromosome
+    uint32_t* chrom_bin_base;   // [n_chrom+1] first bin of each chromosome
+    uint32_t* chrom_tile_base;  // [n_chrom+1] first tile of each chromosome
+    uint32_t* max_len;          // [1]         longest block
+    uint32_t* bin_off;          // [total_bins+1] counts, then exclusive offsets
+    uint32_t* bin_cursor;       // [total_bins]
+    uint32_t* scan_tmp;         // block sums of the scan
+    int32_t*  c_start; uint32_t* c_endk;   // [nC]
+    Tile*     tiles;            // [n_tiles]
+    uint32_t  total_bins, n_tiles, nC;
+    int32_t   n_chrom;
+};
+
 // Per-pass counters, one contiguous u32 buffer (zeroed by one memset per pass).
 struct DevCounters {
     uint32_t* cov;     // [2][S]   reads whose block covers site and site+1, by read strand class
@@ -89,12 +111,14 @@ constexpr uint32_t FLAG_DEBUG_SKIP_EXC = 0x10000u;   // set only by SPLISER_DEBU
 struct KernelTimes { float beta1_ms, spliced_ms, final_ms; };
 
 // launchers (kernels.cu); all asynchronous on `stream`
-void launch_expand_count(const DevRecords& rec, Chunk* chunks, int n_chunks, uint32_t flags, void* stream);
-void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals4, void* stream);
+void launch_expand_count(const DevRecords& rec, Chunk* chunks, int n_chunks, uint32_t flags, DevBins bins, void* stream);
+void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals8, DevBins bins, void* stream);
+void launch_bin_partition(const Chunk* chunks, int n_chunks, DevSoA soa, DevBins bins, void* stream);
+void launch_tile_hints(DevBins bins, DevGraph g, void* stream);
 void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream);
 void launch_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g, void* stream);
 void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream);
-void launch_beta1(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, void* stream);
+void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream);
 void launch_spliced(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t flags, void* stream);
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream);
 int  kernel_launch_count_per_pass();

@@ -124,12 +124,13 @@ struct ReadShape {
     uint32_t nM, nN;        // mapped (M,=,X) ops and N ops
     int32_t  lo, hi;        // min block start, max (block end - 2) over M ops  (lo > hi when none)
     int32_t  qlo, qhi;      // min / max position a site lookup of this read may ask for
+    int32_t  smax, lmax;    // largest block start, longest block
 };
 
 __device__ __forceinline__ ReadShape read_shape(const DevRecords& rec, uint32_t i) {
     ReadShape s;
     s.nM = s.nN = 0;
-    s.lo = INT_MAX; s.hi = INT_MIN; s.qlo = INT_MAX; s.qhi = INT_MIN;
+    s.lo = INT_MAX; s.hi = INT_MIN; s.qlo = INT_MAX; s.qhi = INT_MIN; s.smax = 0; s.lmax = 0;
     int32_t cur = rec.pos[i];
     const uint32_t c0 = rec.cig_off[i], c1 = rec.cig_off[i + 1];
     for (uint32_t k = c0; k < c1; ++k) {
@@ -142,6 +143,7 @@ __device__ __forceinline__ ReadShape read_shape(const DevRecords& rec, uint32_t 
             s.hi = max(s.hi, cur + len - 2);
             s.qlo = min(s.qlo, cur);
             s.qhi = max(s.qhi, cur + len);
+            s.smax = max(s.smax, cur); s.lmax = max(s.lmax, len);
             cur += len;
         } else if (op == 3u) {                            // N : advance, junction (S:480-483)
             s.nN++;
@@ -187,12 +189,13 @@ __device__ __forceinline__ Cnt4 block_exscan4(Cnt4 v, Cnt4& total, Cnt4* warp_to
     return Cnt4{base.a + inc.a - v.a, base.b + inc.b - v.b, base.s + inc.s - v.s, base.j + inc.j - v.j};
 }
 
-__global__ void __launch_bounds__(EXPAND_THREADS) k_expand_count(DevRecords rec, Chunk* chunks, uint32_t mode) {
+__global__ void __launch_bounds__(EXPAND_THREADS) k_expand_count(DevRecords rec, Chunk* chunks, uint32_t mode, DevBins bins) {
     Chunk& ck = chunks[blockIdx.x];
     Cnt4 c{0, 0, 0, 0};
-    int32_t alo = INT_MAX, ahi = INT_MIN, slo = INT_MAX, shi = INT_MIN;
+    int32_t alo = INT_MAX, ahi = INT_MIN, slo = INT_MAX, shi = INT_MIN, smax = 0, lmax = 0;
     for (uint32_t i = ck.rec_lo + threadIdx.x; i < ck.rec_hi; i += EXPAND_THREADS) {
         const ReadShape s = read_shape(rec, i);
+        smax = max(smax, s.smax); lmax = max(lmax, s.lmax);
         if (s.nN == 0) {
             c.a += s.nM;
             alo = min(alo, s.lo); ahi = max(ahi, s.hi);
@@ -202,22 +205,44 @@ __global__ void __launch_bounds__(EXPAND_THREADS) k_expand_count(DevRecords rec,
         }
     }
     __shared__ Cnt4 wt[33];
-    __shared__ int32_t red[4][EXPAND_THREADS / 32];
+    __shared__ int32_t red[6][EXPAND_THREADS / 32];
     Cnt4 total;
     (void)block_exscan4(c, total, wt);
     alo = __reduce_min_sync(0xffffffffu, alo); ahi = __reduce_max_sync(0xffffffffu, ahi);
     slo = __reduce_min_sync(0xffffffffu, slo); shi = __reduce_max_sync(0xffffffffu, shi);
+    smax = __reduce_max_sync(0xffffffffu, smax); lmax = __reduce_max_sync(0xffffffffu, lmax);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) { red[0][warp] = alo; red[1][warp] = ahi; red[2][warp] = slo; red[3][warp] = shi; }
+    if (lane == 0) { red[0][warp] = alo; red[1][warp] = ahi; red[2][warp] = slo; red[3][warp] = shi; red[4][warp] = smax; red[5][warp] = lmax; }
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < EXPAND_THREADS / 32; ++w) {
             alo = min(alo, red[0][w]); ahi = max(ahi, red[1][w]);
             slo = min(slo, red[2][w]); shi = max(shi, red[3][w]);
+            smax = max(smax, red[4][w]); lmax = max(lmax, red[5][w]);
         }
         ck.a_cnt = total.a; ck.b_cnt = total.b; ck.s_cnt = total.s; ck.j_cnt = total.j;
         ck.a_lo = alo; ck.a_hi = ahi; ck.s_lo = slo; ck.s_hi = shi;
+        if (total.a + total.b) {
+            atomicMax(bins.chrom_ext + ck.chrom, (uint32_t)smax);
+            atomicAdd(bins.chrom_tot + ck.chrom, total.a + total.b);
+            atomicMax(bins.max_len, (uint32_t)lmax);
+        }
     }
+}
+
+// bin / tile layout of stream C from the per-chromosome extents and block totals (tiny: one thread)
+__global__ void k_bin_layout(DevBins bins, uint32_t* totals8) {
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t nb = 0, nt = 0;
+    for (int c = 0; c < bins.n_chrom; ++c) {
+        bins.chrom_bin_base[c] = nb; bins.chrom_tile_base[c] = nt;
+        if (bins.chrom_tot[c]) {
+            nb += (bins.chrom_ext[c] >> BIN_SHIFT) + 1;
+            nt += (bins.chrom_tot[c] + K3_TILE - 1) / K3_TILE;
+        }
+    }
+    bins.chrom_bin_base[bins.n_chrom] = nb; bins.chrom_tile_base[bins.n_chrom] = nt;
+    totals8[4] = nb; totals8[5] = nt; totals8[6] = nt * K3_TILE; totals8[7] = bins.max_len[0];
 }
 
 // exclusive scan of the per-chunk totals; single CTA (n_chunks is R / 4096: at most ~1e5)
@@ -320,6 +345,148 @@ __global__ void k_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K0d: bin partition of all M blocks (stream C).  Count and scatter traverse the record-ordered
+// streams chunk by chunk; per-CTA shared-memory histograms (bins relative to the chunk's first
+// bin) keep the global atomics down to one per (chunk, bin).
+// ------------------------------------------------------------------------------------------------
+constexpr int BIN_HIST = 2048;          // 512 kb of chunk span handled in shared memory
+
+__global__ void k_bin_pad(DevBins bins) {        // pad every chromosome to a whole number of tiles
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= bins.n_chrom || !bins.chrom_tot[c]) return;
+    const uint32_t pad = (K3_TILE - bins.chrom_tot[c] % K3_TILE) % K3_TILE;
+    if (pad) atomicAdd(bins.bin_off + bins.chrom_bin_base[c + 1] - 1, pad);
+}
+
+template <bool SCATTER>
+__global__ void __launch_bounds__(256) k_bin_pass(const Chunk* __restrict__ chunks, DevSoA soa, DevBins bins) {
+    const Chunk ck = chunks[blockIdx.x >> 1];
+    const bool bstream = blockIdx.x & 1;
+    const uint32_t n = bstream ? ck.b_cnt : ck.a_cnt;
+    if (n == 0) return;
+    const uint32_t e0 = bstream ? soa.bB + ck.b_base : ck.a_base;
+    const uint32_t gbase = bins.chrom_bin_base[ck.chrom];
+    const int bin0 = max(bstream ? ck.s_lo : ck.a_lo, 0) >> BIN_SHIFT;
+    __shared__ uint32_t hist[BIN_HIST];
+    __shared__ uint32_t base[SCATTER ? BIN_HIST : 1];
+    for (int i = threadIdx.x; i < BIN_HIST; i += 256) hist[i] = 0;
+    __syncthreads();
+    for (uint32_t e = e0 + threadIdx.x; e < e0 + n; e += 256) {
+        const int rel = (max(soa.m_start[e], 0) >> BIN_SHIFT) - bin0;
+        if (rel >= 0 && rel < BIN_HIST) atomicAdd(&hist[rel], 1u);
+        else if (!SCATTER) atomicAdd(bins.bin_off + gbase + bin0 + rel, 1u);
+    }
+    __syncthreads();
+    if (!SCATTER) {
+        for (int i = threadIdx.x; i < BIN_HIST; i += 256)
+            if (hist[i]) atomicAdd(bins.bin_off + gbase + bin0 + i, hist[i]);
+        return;
+    }
+    for (int i = threadIdx.x; i < BIN_HIST; i += 256) {
+        base[i] = hist[i] ? atomicAdd(bins.bin_cursor + gbase + bin0 + i, hist[i]) : 0u;
+        hist[i] = 0;
+    }
+    __syncthreads();
+    for (uint32_t e = e0 + threadIdx.x; e < e0 + n; e += 256) {
+        const int32_t st = soa.m_start[e];
+        const int rel = (max(st, 0) >> BIN_SHIFT) - bin0;
+        uint32_t slot;
+        if (rel >= 0 && rel < BIN_HIST) slot = base[rel] + atomicAdd(&hist[rel], 1u);
+        else slot = atomicAdd(bins.bin_cursor + gbase + bin0 + rel, 1u);
+        bins.c_start[slot] = st;
+        bins.c_endk[slot] = soa.m_endk[e];
+    }
+}
+
+// generic exclusive scan of a u32 array (in place), a[n] receives the total
+constexpr int SCAN_TILE = 4096;
+__global__ void __launch_bounds__(256) k_scan_blocksum(const uint32_t* a, uint32_t n, uint32_t* sums) {
+    __shared__ uint32_t red[8];
+    uint32_t s = 0;
+    const uint32_t b0 = blockIdx.x * SCAN_TILE;
+    for (uint32_t i = b0 + threadIdx.x; i < min(b0 + SCAN_TILE, n); i += 256) s += a[i];
+    s = __reduce_add_sync(0xffffffffu, s);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int w = 1; w < 8; ++w) s += red[w]; sums[blockIdx.x] = s; }
+}
+__global__ void __launch_bounds__(1024) k_scan_sums(uint32_t* sums, uint32_t nblk, uint32_t* total_out) {
+    __shared__ uint32_t wt[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < nblk; base += 1024) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < nblk ? sums[i] : 0;
+        uint32_t a = v;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, a, d); if (lane >= d) a += x; }
+        if (lane == 31) wt[warp] = a;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = wt[lane]; uint32_t b = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, b, d); if (lane >= d) b += x; }
+            wt[lane] = b - w;
+        }
+        __syncthreads();
+        const uint32_t e = carry + wt[warp] + a - v;
+        if (i < nblk) sums[i] = e;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = e + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_out = carry;
+}
+__global__ void __launch_bounds__(256) k_scan_apply(uint32_t* a, uint32_t n, const uint32_t* sums, uint32_t* copy) {
+    __shared__ uint32_t wt[8];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t b0 = blockIdx.x * SCAN_TILE + threadIdx.x * 16;      // 16 consecutive items per thread
+    uint32_t v[16], t = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) { v[q] = (b0 + q < n) ? a[b0 + q] : 0u; t += v[q]; }
+    uint32_t inc = t;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, d); if (lane >= d) inc += x; }
+    if (lane == 31) wt[warp] = inc;
+    __syncthreads();
+    uint32_t run = sums[blockIdx.x] + inc - t;
+    for (int w = 0; w < warp; ++w) run += wt[w];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        if (b0 + q < n) { a[b0 + q] = run; if (copy) copy[b0 + q] = run; }
+        run += v[q];
+    }
+}
+
+// per-tile site windows of stream C
+__global__ void k_tile_hints(DevBins bins, DevGraph g) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= bins.n_tiles) return;
+    int lo = 0, hi = bins.n_chrom;                              // last chromosome with tile_base <= t
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (bins.chrom_tile_base[mid] <= t) lo = mid; else hi = mid; }
+    const int c = lo;
+    const uint32_t cb0 = bins.chrom_bin_base[c], cb1 = bins.chrom_bin_base[c + 1];
+    const uint32_t e0 = bins.bin_off[cb0] + (t - bins.chrom_tile_base[c]) * K3_TILE, e1 = e0 + K3_TILE;
+    auto bin_of = [&](uint32_t e) {                             // last bin of the chromosome with offset <= e
+        uint32_t l = cb0, h = cb1;
+        while (h - l > 1) { const uint32_t mid = (l + h) >> 1; if (bins.bin_off[mid] <= e) l = mid; else h = mid; }
+        return l;
+    };
+    const uint32_t b0 = bin_of(e0), b1 = bin_of(e1 - 1);
+    const int32_t plo = (int32_t)((b0 - cb0) << BIN_SHIFT);
+    const int64_t phi64 = (int64_t)(((uint64_t)(b1 - cb0 + 1)) << BIN_SHIFT) + (int64_t)bins.max_len[0];
+    const int32_t phi = (int32_t)min(phi64, (int64_t)INT_MAX - 1);
+    const int s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
+    const int w_lo = lower_bound_i32(g.site_pos, s0, s1, plo);
+    const int w_hi = upper_bound_i32(g.site_pos, w_lo, s1, phi);
+    Tile tl;
+    tl.e0 = e0; tl.w_lo = max(w_lo, g.own_lo); tl.w_hi = min(w_hi, g.own_hi); tl.pad = 0;
+    bins.tiles[t] = tl;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: alpha and PartnerCounts as segmented reductions of the junction scores
 // ------------------------------------------------------------------------------------------------
 __global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
@@ -349,7 +516,6 @@ __global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
 constexpr int PS_STAGES = 3;
 constexpr int PS_CONSUMERS = 256;                  // 8 consumer warps
 constexpr int PS_THREADS = PS_CONSUMERS + 32;      // + 1 producer warp
-constexpr int K3_TILE = 2048;                      // blocks per stage (16 KB)
 constexpr int K3_SITES = 2048;                     // staged site positions per stage (8 KB)
 constexpr int K4_TILE = 1024;                      // junctions per stage (8 KB)
 constexpr int K4_SITES = 2048;
@@ -460,7 +626,7 @@ __device__ __forceinline__ void k3_consume(const K3Stage& stg, const StageMeta& 
 }
 
 __global__ void __launch_bounds__(PS_THREADS)
-k_beta1_stab(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt) {
+k_beta1_stab(DevBins bins, DevGraph g, DevCounters cnt) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     K3Smem& sm = *reinterpret_cast<K3Smem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -472,37 +638,30 @@ k_beta1_stab(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGrap
         // ===== producer =====
         if (lane != 0) return;
         uint32_t it = 0;
-        // the next item's index and descriptor are fetched while the current item's copies are issued
+        // the next tile's index and descriptor are fetched while the current tile's copies are issued
         uint32_t next = atomicAdd(cnt.work + 0, 1u);
-        Chunk nck = chunks[min(next >> 1, (uint32_t)n_chunks - 1u)];
+        Tile ntl = bins.tiles[min(next, bins.n_tiles - 1u)];
         for (;;) {
             const uint32_t item = next;
-            if (item >= 2u * (uint32_t)n_chunks) break;
-            const Chunk ck = nck;
+            if (item >= bins.n_tiles) break;
+            const Tile tl = ntl;
             next = atomicAdd(cnt.work + 0, 1u);
-            nck = chunks[min(next >> 1, (uint32_t)n_chunks - 1u)];
-            const bool bstream = item & 1u;
-            const uint32_t n = bstream ? ck.b_cnt : ck.a_cnt;
-            const int site_lo = bstream ? ck.s_site_lo : ck.a_site_lo, site_n = bstream ? ck.s_site_n : ck.a_site_n;
-            if (n == 0 || site_n == 0) continue;         // zone-map prune: no site can be stabbed by these blocks
-            const int w_lo = max(site_lo, g.own_lo), w_hi = min(site_lo + site_n, g.own_hi);
-            if (w_lo >= w_hi) continue;
-            const uint32_t e0 = bstream ? soa.bB + ck.b_base : ck.a_base, e1 = e0 + n;
+            ntl = bins.tiles[min(next, bins.n_tiles - 1u)];
+            if (tl.w_lo >= tl.w_hi) continue;            // zone-map prune: no (owned) site near this tile's bins
+            const int site_n = tl.w_hi - tl.w_lo;
             const bool staged = site_n <= K3_SITES;
-            const int al = site_lo & ~3;
-            const uint32_t nst = staged ? (uint32_t)(((site_lo + site_n + 3) & ~3) - al) : 0u;
-            for (uint32_t p = e0 & ~3u; p < e1; p += K3_TILE, ++it) {
-                const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-                mbar_wait(&sm.empty[stage], parity ^ 1u);
-                const uint32_t np = min((uint32_t)K3_TILE, ((e1 + 3u) & ~3u) - p);
-                StageMeta& m = sm.meta[stage];
-                m.e0 = e0; m.e1 = e1; m.p0 = p; m.n = np; m.w_lo = w_lo; m.w_hi = w_hi; m.al = al;
-                m.flags = staged ? 0u : PS_GLOBAL_SITES; m.chunk = (int32_t)(item >> 1);
-                mbar_expect_tx(&sm.full[stage], np * 8u + nst * 4u);
-                bulk_g2s(sm.st[stage].start, soa.m_start + p, np * 4u, &sm.full[stage]);
-                bulk_g2s(sm.st[stage].endk, soa.m_endk + p, np * 4u, &sm.full[stage]);
-                if (nst) bulk_g2s(sm.st[stage].sites, g.site_pos + al, nst * 4u, &sm.full[stage]);
-            }
+            const int al = tl.w_lo & ~3;
+            const uint32_t nst = staged ? (uint32_t)(((tl.w_hi + 3) & ~3) - al) : 0u;
+            const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
+            mbar_wait(&sm.empty[stage], parity ^ 1u);
+            StageMeta& m = sm.meta[stage];
+            m.e0 = tl.e0; m.e1 = tl.e0 + K3_TILE; m.p0 = tl.e0; m.n = K3_TILE; m.w_lo = tl.w_lo; m.w_hi = tl.w_hi; m.al = al;
+            m.flags = staged ? 0u : PS_GLOBAL_SITES; m.chunk = (int32_t)item;
+            mbar_expect_tx(&sm.full[stage], K3_TILE * 8u + nst * 4u);
+            bulk_g2s(sm.st[stage].start, bins.c_start + tl.e0, K3_TILE * 4u, &sm.full[stage]);
+            bulk_g2s(sm.st[stage].endk, bins.c_endk + tl.e0, K3_TILE * 4u, &sm.full[stage]);
+            if (nst) bulk_g2s(sm.st[stage].sites, g.site_pos + al, nst * 4u, &sm.full[stage]);
+            ++it;
         }
         const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
         mbar_wait(&sm.empty[stage], parity ^ 1u);
@@ -900,11 +1059,30 @@ k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
-void launch_expand_count(const DevRecords& rec, Chunk* chunks, int n_chunks, uint32_t flags, void* stream) {
-    if (n_chunks > 0) k_expand_count<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, flags);
+void launch_expand_count(const DevRecords& rec, Chunk* chunks, int n_chunks, uint32_t flags, DevBins bins, void* stream) {
+    if (n_chunks > 0) k_expand_count<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, flags, bins);
 }
-void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals4, void* stream) {
-    k_chunk_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(chunks, n_chunks, totals4);
+void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals8, DevBins bins, void* stream) {
+    k_chunk_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(chunks, n_chunks, totals8);
+    k_bin_layout<<<1, 32, 0, (cudaStream_t)stream>>>(bins, totals8);
+}
+void launch_bin_partition(const Chunk* chunks, int n_chunks, DevSoA soa, DevBins bins, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_chunks <= 0 || bins.total_bins == 0) return;
+    cudaMemsetAsync(bins.bin_off, 0, ((size_t)bins.total_bins + 1) * 4, st);
+    cudaMemsetAsync(bins.c_start, 0x7f, (size_t)bins.nC * 4, st);        // padding never matches: start = 0x7f7f7f7f, end = 0
+    cudaMemsetAsync(bins.c_endk, 0, (size_t)bins.nC * 4, st);
+    k_bin_pad<<<(bins.n_chrom + 127) / 128, 128, 0, st>>>(bins);
+    k_bin_pass<false><<<2 * n_chunks, 256, 0, st>>>(chunks, soa, bins);
+    const uint32_t n = bins.total_bins + 1;                              // the extra slot receives the total
+    const uint32_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_blocksum<<<nblk, 256, 0, st>>>(bins.bin_off, n, bins.scan_tmp);
+    k_scan_sums<<<1, 1024, 0, st>>>(bins.scan_tmp, nblk, bins.scan_tmp + nblk);
+    k_scan_apply<<<nblk, 256, 0, st>>>(bins.bin_off, n, bins.scan_tmp, bins.bin_cursor);
+    k_bin_pass<true><<<2 * n_chunks, 256, 0, st>>>(chunks, soa, bins);
+}
+void launch_tile_hints(DevBins bins, DevGraph g, void* stream) {
+    if (bins.n_tiles) k_tile_hints<<<(bins.n_tiles + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bins, g);
 }
 void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream) {
     if (n_chunks > 0) k_expand_scatter<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, soa, flags);
@@ -929,10 +1107,10 @@ static int persistent_grid(const void* kernel, size_t smem) {
     if (per_sm < 1) per_sm = 1;
     return sms * per_sm;                     // one resident CTA per slot: a multiple of the SM count
 }
-void launch_beta1(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, void* stream) {
-    if (n_chunks <= 0 || g.n_sites <= 0) return;
+void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream) {
+    if (bins.n_tiles == 0 || g.n_sites <= 0) return;
     static const int grid = persistent_grid((const void*)k_beta1_stab, sizeof(K3Smem));
-    k_beta1_stab<<<grid, PS_THREADS, sizeof(K3Smem), (cudaStream_t)stream>>>(chunks, n_chunks, soa, g, cnt);
+    k_beta1_stab<<<grid, PS_THREADS, sizeof(K3Smem), (cudaStream_t)stream>>>(bins, g, cnt);
 }
 void launch_spliced(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
     if (n_chunks <= 0 || g.n_sites <= 0) return;

@@ -76,8 +76,9 @@ struct spl_ctx {
     double stats[SPL_NSTATS] = {0};
 
     // device memory
-    DevBuf d_graph, d_rec, d_chunks, d_soa, d_cnt, d_out, d_tot;
-    uint32_t* h_tot = nullptr;      // pinned, 4 totals
+    DevBuf d_graph, d_rec, d_chunks, d_soa, d_cnt, d_out, d_tot, d_lay, d_bins;
+    uint32_t* h_tot = nullptr;      // pinned, 8 totals
+    DevBins bins{};
     std::vector<cudaEvent_t> events;
 
     // state of the last load
@@ -93,6 +94,7 @@ struct spl_ctx {
     uint32_t flags = 0;
     bool loaded = false;
     int64_t n_aligned = 0;
+    int32_t n_chrom_loaded = 0;
 
     int fail(int code, const char* fmt, ...) {
         char buf[512];
@@ -233,8 +235,9 @@ int check_view(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
 }
 
 // upload records, run the expansion kernels, leave the SoA + chunk table on the device
-int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
+int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, int32_t n_chrom) {
     const double t0 = now_ms();
+    ctx->n_chrom_loaded = n_chrom;
     std::vector<Chunk> hc;
     for (int32_t k = 0; k < v->n_seg; ++k) {
         if (v->seg_chrom[k] < 0) continue;
@@ -267,15 +270,34 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
     ctx->chunks = (Chunk*)ctx->d_chunks.p;
     if (!hc.empty()) CU(cudaMemcpyAsync(ctx->chunks, hc.data(), hc.size() * sizeof(Chunk), cudaMemcpyHostToDevice, ctx->stream));
     CU(ctx->d_tot.reserve(64));
+    // per-chromosome layout arrays of the bin-partitioned stream
+    DevBins& bins = ctx->bins;
+    bins = DevBins{};
+    const size_t nchr = (size_t)std::max(ctx->n_chrom_loaded, 1);
+    {
+        Carver lc;
+        const size_t o_ext = lc.take<uint32_t>(nchr + 1), o_tot = lc.take<uint32_t>(nchr + 1), o_bb = lc.take<uint32_t>(nchr + 2),
+                     o_tb = lc.take<uint32_t>(nchr + 2), o_ml = lc.take<uint32_t>(4);
+        CU(ctx->d_lay.reserve(lc.off + 256));
+        CU(cudaMemsetAsync(ctx->d_lay.p, 0, lc.off + 256, ctx->stream));
+        char* lb = (char*)ctx->d_lay.p;
+        bins.chrom_ext = (uint32_t*)(lb + o_ext); bins.chrom_tot = (uint32_t*)(lb + o_tot);
+        bins.chrom_bin_base = (uint32_t*)(lb + o_bb); bins.chrom_tile_base = (uint32_t*)(lb + o_tb);
+        bins.max_len = (uint32_t*)(lb + o_ml);
+        bins.n_chrom = ctx->n_chrom_loaded;
+    }
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, ctx->stream));
-    launch_expand_count(ctx->rec, ctx->chunks, ctx->n_chunks, flags, ctx->stream);
-    launch_chunk_scan(ctx->chunks, ctx->n_chunks, (uint32_t*)ctx->d_tot.p, ctx->stream);
+    launch_expand_count(ctx->rec, ctx->chunks, ctx->n_chunks, flags, bins, ctx->stream);
+    launch_chunk_scan(ctx->chunks, ctx->n_chunks, (uint32_t*)ctx->d_tot.p, bins, ctx->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->h_tot, ctx->d_tot.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_tot, ctx->d_tot.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // also makes `hc` (pageable) safe to drop
     const size_t nA = ctx->h_tot[0], nB = ctx->h_tot[1], nS = ctx->h_tot[2], nJ = ctx->h_tot[3];
+    const size_t total_bins = ctx->n_chunks ? ctx->h_tot[4] : 0, n_tiles = ctx->n_chunks ? ctx->h_tot[5] : 0;
+    const size_t nC = n_tiles * (size_t)K3_TILE;
+    if (nC >= (size_t)UINT32_MAX - 64) return ctx->fail(SPL_ERR_RANGE, "more than 2^32 mapped blocks in one call");
     Carver s;
     const size_t bB = (nA + 3) & ~(size_t)3;                      // stream B starts on a 128-bit boundary
     if (bB + nB >= (size_t)UINT32_MAX - 64) return ctx->fail(SPL_ERR_RANGE, "more than 2^32 mapped blocks in one call");
@@ -289,7 +311,19 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
     soa.m_start = (int32_t*)(sb + o_ms); soa.m_endk = (uint32_t*)(sb + o_me); soa.bB = (uint32_t)bB;
     soa.sr_boff = (uint32_t*)(sb + o_sb); soa.sr_joff = (uint32_t*)(sb + o_sj);
     soa.jn_l = (uint32_t*)(sb + o_jl); soa.jn_rk = (uint32_t*)(sb + o_jr); soa.jn_read = (uint32_t*)(sb + o_jq);
+    {
+        Carver bc;
+        const size_t nscan = (total_bins + 1 + 4095) / 4096 + 8;
+        const size_t o_bo = bc.take<uint32_t>(total_bins + 8), o_bcur = bc.take<uint32_t>(total_bins + 8), o_tmp = bc.take<uint32_t>(nscan + 8),
+                     o_cs = bc.take<int32_t>(nC + 32), o_ce = bc.take<uint32_t>(nC + 32), o_tl = bc.take<Tile>(n_tiles + 1);
+        CU(ctx->d_bins.reserve(bc.off + 256));
+        char* bb = (char*)ctx->d_bins.p;
+        bins.bin_off = (uint32_t*)(bb + o_bo); bins.bin_cursor = (uint32_t*)(bb + o_bcur); bins.scan_tmp = (uint32_t*)(bb + o_tmp);
+        bins.c_start = (int32_t*)(bb + o_cs); bins.c_endk = (uint32_t*)(bb + o_ce); bins.tiles = (Tile*)(bb + o_tl);
+        bins.total_bins = (uint32_t)total_bins; bins.n_tiles = (uint32_t)n_tiles; bins.nC = (uint32_t)nC;
+    }
     launch_expand_scatter(ctx->rec, ctx->chunks, ctx->n_chunks, soa, flags, ctx->stream);
+    launch_bin_partition(ctx->chunks, ctx->n_chunks, soa, bins, ctx->stream);
     CU(cudaGetLastError());
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -314,7 +348,7 @@ int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     if (ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->d_cnt.p, 0, ctx->cnt_bytes, ctx->stream));
     launch_alpha_reduce(ctx->g, ctx->out, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[1], ctx->stream));
-    launch_beta1(ctx->chunks, ctx->n_chunks, ctx->soa, ctx->g, ctx->cnt, ctx->stream);
+    launch_beta1(ctx->bins, ctx->g, ctx->cnt, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[2], ctx->stream));
     launch_spliced(ctx->chunks, ctx->n_chunks, ctx->soa, ctx->g, ctx->cnt, ctx->flags, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[3], ctx->stream));
@@ -370,7 +404,7 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
         e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, (flags & SPL_FLAG_STRANDED) != 0, ctx->hg);
         graph_ms = now_ms() - tg0;
     });
-    rc = upload_and_expand(ctx, rec, flags);
+    rc = upload_and_expand(ctx, rec, flags, n_chrom);
     ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg0;
     builder.join();
     if (rc) return rc;
@@ -380,6 +414,7 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     if (rc) return rc;
     ctx->stats[SPL_STAT_MS_GRAPH] = graph_ms + (now_ms() - tu0);
     launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
+    launch_tile_hints(ctx->bins, ctx->g, ctx->stream);
     CU(cudaGetLastError());
     ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
     ctx->stats[SPL_STAT_N_EDGES] = (double)ctx->hg.pc_pos.size();
@@ -431,7 +466,7 @@ void spl_destroy(spl_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
         ctx->d_graph.release(); ctx->d_rec.release(); ctx->d_chunks.release(); ctx->d_soa.release();
-        ctx->d_cnt.release(); ctx->d_out.release(); ctx->d_tot.release();
+        ctx->d_cnt.release(); ctx->d_out.release(); ctx->d_tot.release(); ctx->d_lay.release(); ctx->d_bins.release();
         if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
         cudaStreamDestroy(ctx->stream);
     }
@@ -521,9 +556,10 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     rc = upload_graph(ctx, nullptr, 0);
     ctx->tile_index = save_ti; ctx->tile_count = save_tc;
     if (rc) return rc;
-    rc = upload_and_expand(ctx, rec, flags);
+    rc = upload_and_expand(ctx, rec, flags, n_chrom);
     if (rc) return rc;
     launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
+    launch_tile_hints(ctx->bins, ctx->g, ctx->stream);
     rc = count_pass(ctx, nullptr);
     if (rc) return rc;
     const size_t S = (size_t)ctx->hg.n_sites;
