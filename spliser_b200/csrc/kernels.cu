@@ -309,7 +309,7 @@ k_expand_scatter(DevRecords rec, const Chunk* chunks, DevSoA soa, uint32_t mode)
                 } else if (op == 3u) {
                     soa.jn_l[ij] = (uint32_t)(cur - 1) | (seen ? 0u : 0x80000000u);     // S:482; firstN flag (POS <= t filter, S:435)
                     soa.jn_rk[ij] = (uint32_t)(cur + len - 1) | kbit;                   // S:483
-                    soa.jn_read[ij] = run.s + ex.s;                                     // owning spliced read (hot path only)
+                    soa.jn_read[ij] = (run.s + ex.s) | (nN == 1u ? 0x80000000u : 0u);   // owning spliced read | single-junction flag (hot path only)
                     ++ij;
                     cur += len; seen = true;
                 } else if (op == 2u) {
@@ -532,6 +532,23 @@ struct StageMeta {
 };
 constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u;
 
+// producer-side wait: the single producer lane would otherwise spin on the empty barrier for most of the
+// kernel and steal issue slots from the consumers of the co-resident CTAs
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+        if (done) return;
+        __nanosleep(256);
+    }
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
@@ -653,7 +670,7 @@ k_beta1_stab(DevBins bins, DevGraph g, DevCounters cnt) {
             const int al = tl.w_lo & ~3;
             const uint32_t nst = staged ? (uint32_t)(((tl.w_hi + 3) & ~3) - al) : 0u;
             const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-            mbar_wait(&sm.empty[stage], parity ^ 1u);
+            mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
             StageMeta& m = sm.meta[stage];
             m.e0 = tl.e0; m.e1 = tl.e0 + K3_TILE; m.p0 = tl.e0; m.n = K3_TILE; m.w_lo = tl.w_lo; m.w_hi = tl.w_hi; m.al = al;
             m.flags = staged ? 0u : PS_GLOBAL_SITES; m.chunk = (int32_t)item;
@@ -664,7 +681,7 @@ k_beta1_stab(DevBins bins, DevGraph g, DevCounters cnt) {
             ++it;
         }
         const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-        mbar_wait(&sm.empty[stage], parity ^ 1u);
+        mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
         sm.meta[stage].flags = PS_DONE;
         mbar_arrive(&sm.full[stage]);
         return;
@@ -710,19 +727,27 @@ __device__ __forceinline__ bool pc_pair(const DevGraph& g, int t, int32_t l, int
            (in_sorted(g.cp_pos, c0, c1, l) && in_list(g.pc_pos, p0, p1, r));
 }
 
-// exception logic for the read that owns junction j, whose endpoint (side 0 = l, 1 = r) sits on `anchor`
+// Exception logic for the read that owns junction j, whose endpoint (side 0 = l, 1 = r) sits on `anchor`.
+// Every t in the reverse-partner list of the anchor has the anchored endpoint in P_t by construction, so
+// (l, r) is a partner/competitor pair for t (S:494-501) iff the OTHER endpoint is in C_t.
 __device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, uint32_t j,
                                               int anchor, int side, bool combine) {
-    const uint32_t ri = soa.jn_read[j];
-    const uint32_t k = soa.jn_rk[j] >> 31;
-    const uint32_t j0 = soa.sr_joff[ri], j1 = soa.sr_joff[ri + 1];
-    const int32_t l = (int32_t)(soa.jn_l[j] & POS_MASK), r = (int32_t)(soa.jn_rk[j] & POS_MASK);
+    const uint32_t rd = soa.jn_read[j];
+    const uint32_t ri = rd & POS_MASK;
+    const bool single = (rd >> 31) != 0;                               // the read has exactly this one junction
+    const uint32_t rraw = soa.jn_rk[j], lraw_j = soa.jn_l[j];
+    const uint32_t k = rraw >> 31;
+    const int32_t l = (int32_t)(lraw_j & POS_MASK), r = (int32_t)(rraw & POS_MASK);
+    const int32_t other = side == 0 ? r : l;
+    uint32_t j0 = j, j1 = j + 1;
+    if (!single) { j0 = soa.sr_joff[ri]; j1 = soa.sr_joff[ri + 1]; }
     for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
         const int t = g.rp_site[q];
         if (t < g.own_lo || t >= g.own_hi) continue;
-        if (g.cp_off[t + 1] == g.cp_off[t]) continue;                 // no competitors: never a pair
-        if (!pc_pair(g, t, l, r)) continue;
-        if (side == 1 && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) continue;   // already seen at side 0
+        const int c0 = g.cp_off[t], c1 = g.cp_off[t + 1];
+        if (c0 == c1 || !in_sorted(g.cp_pos, c0, c1, other)) continue;
+        // side 1 finds (r in P_t, l in C_t); if (l in P_t, r in C_t) holds as well, side 0 already handled t
+        if (side == 1 && in_sorted(g.cp_pos, c0, c1, r) && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) continue;
         bool earlier = false;
         for (uint32_t jj = j0; jj < j && !earlier; ++jj)
             earlier = pc_pair(g, t, (int32_t)(soa.jn_l[jj] & POS_MASK), (int32_t)(soa.jn_rk[jj] & POS_MASK));
@@ -731,12 +756,18 @@ __device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph&
         const int32_t tp = g.site_pos[t];
         const bool ok = strand_ok(g.site_cls[t], k);
         bool alpha = false; int32_t partner_used = 0; int kstar = -1;
-        for (uint32_t jj = j0; jj < j1; ++jj) {
-            const uint32_t lraw = soa.jn_l[jj];
-            const int32_t ll = (int32_t)(lraw & POS_MASK), rr = (int32_t)(soa.jn_rk[jj] & POS_MASK);
-            if (ll == tp && !(lraw >> 31)) { alpha = true; partner_used = rr; }   // firstN: POS > t, read skipped (S:435)
-            if (rr == tp) { alpha = true; partner_used = ll; }
-            if (ll < tp && tp < rr) kstar = (int)(jj - j0);
+        if (single) {
+            if (l == tp && !(lraw_j >> 31)) { alpha = true; partner_used = r; }
+            if (r == tp) { alpha = true; partner_used = l; }
+            if (l < tp && tp < r) kstar = 0;
+        } else {
+            for (uint32_t jj = j0; jj < j1; ++jj) {
+                const uint32_t lraw = soa.jn_l[jj];
+                const int32_t ll = (int32_t)(lraw & POS_MASK), rr = (int32_t)(soa.jn_rk[jj] & POS_MASK);
+                if (ll == tp && !(lraw >> 31)) { alpha = true; partner_used = rr; }   // firstN: POS > t, read skipped (S:435)
+                if (rr == tp) { alpha = true; partner_used = ll; }
+                if (ll < tp && tp < rr) kstar = (int)(jj - j0);
+            }
         }
         if (alpha) {                                                   // S:519-527
             for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
@@ -874,7 +905,7 @@ k_spliced(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGraph g
             const uint32_t nst = staged ? (uint32_t)(((w_hi + 15) & ~15) - al) : 0u;
             for (uint32_t p = e0 & ~3u; p < e1; p += K4_TILE, ++it) {
                 const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-                mbar_wait(&sm.empty[stage], parity ^ 1u);
+                mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
                 const uint32_t np = min((uint32_t)K4_TILE, ((e1 + 3u) & ~3u) - p);
                 StageMeta& m = sm.meta[stage];
                 m.e0 = e0; m.e1 = e1; m.p0 = p; m.n = np; m.w_lo = w_lo; m.w_hi = w_hi; m.al = al;
@@ -889,7 +920,7 @@ k_spliced(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGraph g
             }
         }
         const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-        mbar_wait(&sm.empty[stage], parity ^ 1u);
+        mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
         sm.meta[stage].flags = PS_DONE;
         mbar_arrive(&sm.full[stage]);
         return;
