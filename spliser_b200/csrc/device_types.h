@@ -4,6 +4,8 @@
 
 namespace spl {
 
+constexpr int BIN_SHIFT = 8;            // 256 bp genomic bins (block partition, site index)
+
 // One work tile = up to CHUNK_READS consecutive records of one chromosome.  The expansion kernels
 // fill the bases/counts; the hint kernel fills the site windows.  K3 streams the chunk's A blocks,
 // K4 its spliced reads.
@@ -25,6 +27,10 @@ struct DevGraph {
     const int32_t* site_pos;            // [n_sites + 8], tail padded with INT32_MAX
     const uint8_t* site_cls;            // [n_sites]
     const uint8_t* site_hot;            // [n_sites + 32] 1 = some site in the reverse-partner list anchored here has competitors
+    // direct-address index of the site table: for chromosome c and bin b = pos >> BIN_SHIFT,
+    // sb_off[sb_base[c] + b] = first global site index with position >= b << BIN_SHIFT (one sentinel per chromosome)
+    const int32_t* sb_base;             // [n_chrom+1]
+    const int32_t* sb_off;              // [sb_base[n_chrom] + 64]
     const int32_t *pt_off, *pt_site;    // Partners (site indices)
     const int32_t *pc_off, *pc_pos;     // PartnerCounts keys
     const int32_t *cp_off, *cp_pos;     // CompetitorPos (sorted)
@@ -63,7 +69,6 @@ constexpr uint32_t POS_MASK = 0x7fffffffu;
 // inside a bin arbitrary.  K3 streams it in fixed tiles; every warp then sees a tiny genomic window whatever
 // the record order or the intron lengths were.  Each chromosome is padded to a multiple of K3_TILE with
 // never-matching elements so that tiles do not straddle chromosomes.
-constexpr int BIN_SHIFT = 8;            // 256 bp
 constexpr int K3_TILE = 2048;           // blocks per tile / pipeline stage (16 KB)
 struct Tile { uint32_t e0; int32_t w_lo, w_hi; int32_t pad; };   // first element, site index window [w_lo, w_hi)
 struct DevBins {

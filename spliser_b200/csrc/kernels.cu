@@ -526,11 +526,13 @@ struct StageMeta {
     uint32_t p0, n;         // global index of staged element 0 (multiple of 4), staged element count
     int32_t  w_lo, w_hi;    // site window (global indices, already clamped to the owned range)
     int32_t  al;            // global site index of staged site 0
-    uint32_t flags;         // PS_DONE | PS_GLOBAL_SITES
+    uint32_t flags;         // PS_DONE | PS_GLOBAL_SITES | PS_GLOBAL_BINS
     int32_t  chunk;
-    int32_t  pad[3];
+    int32_t  sb_g0;         // global sb_off index of the chromosome's bin 0
+    int32_t  sb_nb;         // bins of the chromosome (the sentinel sits at index sb_nb)
+    int32_t  sb_al;         // global sb_off index of staged bin entry 0
 };
-constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u;
+constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u, PS_GLOBAL_BINS = 4u;
 
 // producer-side wait: the single producer lane would otherwise spin on the empty barrier for most of the
 // kernel and steal issue slots from the consumers of the co-resident CTAs
@@ -802,10 +804,12 @@ __device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph&
     }
 }
 
+constexpr int K4_BINS = 1024;                      // staged bin-index entries per stage (256 kb of chunk window)
 struct K4Stage {
     uint32_t l[K4_TILE];
     uint32_t rk[K4_TILE];
     int32_t  sites[K4_SITES + 32];
+    int32_t  sbin[K4_BINS + 8];
     uint8_t  hot[K4_SITES + 32];
 };
 struct K4Smem {
@@ -817,7 +821,7 @@ struct K4Smem {
 };
 
 __device__ __forceinline__ void k4_consume(const K4Stage& stg, const StageMeta& m, const int32_t* __restrict__ sp,
-                                           const uint8_t* __restrict__ hot, const DevSoA& soa, const DevGraph& g,
+                                           const uint8_t* __restrict__ hot, const int32_t* __restrict__ sbp, const DevSoA& soa, const DevGraph& g,
                                            const DevCounters& cnt, bool combine, bool skip_exc, K4Smem& sm) {
     const int S = g.n_sites;
     const int lane = threadIdx.x & 31;
@@ -828,17 +832,21 @@ __device__ __forceinline__ void k4_consume(const K4Stage& stg, const StageMeta& 
         const uint32_t lraw = live ? stg.l[idx] : 0u, rraw = live ? stg.rk[idx] : 0u;
         const int32_t l = live ? (int32_t)(lraw & POS_MASK) : INT_MAX, r = live ? (int32_t)(rraw & POS_MASK) : INT_MIN;
         const uint32_t k = rraw >> 31;
-        // narrow the window to the positions this warp asks about (broadcast loads)
-        const int wlo = __reduce_min_sync(0xffffffffu, l), whi = __reduce_max_sync(0xffffffffu, live ? max(l, r) : INT_MIN);
-        if (wlo > whi) continue;                                       // no live lane in this warp
-        int n0, n1;
-        bound_pair_i32(sp, m.w_lo, m.w_hi, wlo, whi, n0, n1);
-        int il = n0, iu = n0, ir = n0;
+        // site lookups through the direct-address bin index: one load for the bin, then a scan over the 0-2 sites
+        // of the 256 bp bin that precede the position -- no binary search
+        const uint32_t anylive = __ballot_sync(0xffffffffu, live);
+        if (!anylive) continue;
+        const int n1 = m.w_hi;
+        int il = m.w_lo, iu = m.w_lo, ir = m.w_lo;
         if (live) {
-            il = lower_bound_i32(sp, n0, n1, l);
+            il = max(sbp[m.sb_g0 + min(max(l, 0) >> BIN_SHIFT, m.sb_nb)], m.w_lo);
+            while (il < n1 && sp[il] < l) ++il;                        // lower_bound(l)
             iu = il;
             while (iu < n1 && sp[iu] == l) ++iu;                       // upper_bound(l)
-            ir = (r > l) ? lower_bound_i32(sp, iu, n1, r) : il;
+            if (r > l) {
+                ir = max(sbp[m.sb_g0 + min(max(r, 0) >> BIN_SHIFT, m.sb_nb)], iu);
+                while (ir < n1 && sp[ir] < r) ++ir;                    // lower_bound(r)
+            } else ir = il;
         }
         // span range add over sites strictly inside (l, r), aggregated over identical ranges in the warp
         const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);
@@ -903,16 +911,24 @@ k_spliced(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGraph g
             const bool staged = ck.s_site_n <= K4_SITES;
             const int al = ck.s_site_lo & ~15;                         // 16-byte aligned for both element sizes
             const uint32_t nst = staged ? (uint32_t)(((w_hi + 15) & ~15) - al) : 0u;
+            // slice of the bin index covering the chunk's position window
+            const int sb_g0 = g.sb_base[ck.chrom], sb_nb = g.sb_base[ck.chrom + 1] - sb_g0 - 1;
+            const int bl = min(max(ck.s_lo, 0) >> BIN_SHIFT, sb_nb), bh = min(max(ck.s_hi, 0) >> BIN_SHIFT, sb_nb);
+            const int sb_al = (sb_g0 + bl) & ~3;
+            const uint32_t nsb = (uint32_t)(((sb_g0 + bh + 1 + 3) & ~3) - sb_al);
+            const bool bstaged = nsb <= (uint32_t)K4_BINS;
             for (uint32_t p = e0 & ~3u; p < e1; p += K4_TILE, ++it) {
                 const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
                 mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
                 const uint32_t np = min((uint32_t)K4_TILE, ((e1 + 3u) & ~3u) - p);
                 StageMeta& m = sm.meta[stage];
                 m.e0 = e0; m.e1 = e1; m.p0 = p; m.n = np; m.w_lo = w_lo; m.w_hi = w_hi; m.al = al;
-                m.flags = staged ? 0u : PS_GLOBAL_SITES; m.chunk = (int32_t)item;
-                mbar_expect_tx(&sm.full[stage], np * 8u + nst * 5u);
+                m.flags = (staged ? 0u : PS_GLOBAL_SITES) | (bstaged ? 0u : PS_GLOBAL_BINS); m.chunk = (int32_t)item;
+                m.sb_g0 = sb_g0; m.sb_nb = sb_nb; m.sb_al = sb_al;
+                mbar_expect_tx(&sm.full[stage], np * 8u + nst * 5u + (bstaged ? nsb * 4u : 0u));
                 bulk_g2s(sm.st[stage].l, soa.jn_l + p, np * 4u, &sm.full[stage]);
                 bulk_g2s(sm.st[stage].rk, soa.jn_rk + p, np * 4u, &sm.full[stage]);
+                if (bstaged) bulk_g2s(sm.st[stage].sbin, g.sb_off + sb_al, nsb * 4u, &sm.full[stage]);
                 if (nst) {
                     bulk_g2s(sm.st[stage].sites, g.site_pos + al, nst * 4u, &sm.full[stage]);
                     bulk_g2s(sm.st[stage].hot, g.site_hot + al, nst, &sm.full[stage]);
@@ -931,8 +947,9 @@ k_spliced(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGraph g
         mbar_wait(&sm.full[stage], parity);
         const StageMeta m = sm.meta[stage];
         if (m.flags & PS_DONE) break;
-        if (m.flags & PS_GLOBAL_SITES) k4_consume(sm.st[stage], m, g.site_pos, g.site_hot, soa, g, cnt, combine, skip_exc, sm);
-        else k4_consume(sm.st[stage], m, sm.st[stage].sites - m.al, sm.st[stage].hot - m.al, soa, g, cnt, combine, skip_exc, sm);
+        const int32_t* sbp = (m.flags & PS_GLOBAL_BINS) ? g.sb_off : sm.st[stage].sbin - m.sb_al;
+        if (m.flags & PS_GLOBAL_SITES) k4_consume(sm.st[stage], m, g.site_pos, g.site_hot, sbp, soa, g, cnt, combine, skip_exc, sm);
+        else k4_consume(sm.st[stage], m, sm.st[stage].sites - m.al, sm.st[stage].hot - m.al, sbp, soa, g, cnt, combine, skip_exc, sm);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[stage]);                  // the stage can be refilled while the work list drains
         consumer_sync();                                               // work list complete

@@ -130,6 +130,22 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     Carver c;
     const size_t o_cs = c.take<int32_t>((size_t)h.n_chrom + 1), o_pos = c.take<int32_t>(S + 64), o_cls = c.take<uint8_t>(S + 8);
     const size_t o_hot = c.take<uint8_t>(S + 64);
+    // direct-address bin index of the site table
+    std::vector<int32_t> sb_base((size_t)h.n_chrom + 1, 0), sb_off;
+    for (int32_t ch = 0; ch < h.n_chrom; ++ch) {
+        const int64_t s0 = h.cs_off[(size_t)ch], s1 = h.cs_off[(size_t)ch + 1];
+        const int64_t nb = s1 > s0 ? (int64_t)(std::max(h.pos[(size_t)s1 - 1], 0) >> BIN_SHIFT) + 1 : 0;
+        sb_base[(size_t)ch] = (int32_t)sb_off.size();
+        int64_t i = s0;
+        for (int64_t b = 0; b < nb; ++b) {
+            while (i < s1 && h.pos[(size_t)i] < (int32_t)(b << BIN_SHIFT)) ++i;
+            sb_off.push_back((int32_t)i);
+        }
+        sb_off.push_back((int32_t)s1);                                 // sentinel: positions beyond the last bin
+    }
+    sb_base[(size_t)h.n_chrom] = (int32_t)sb_off.size();
+    sb_off.resize(sb_off.size() + 64, (int32_t)S);
+    const size_t o_sbb = c.take<int32_t>(sb_base.size()), o_sbo = c.take<int32_t>(sb_off.size());
     const size_t o_pto = c.take<int32_t>(S + 1), o_pts = c.take<int32_t>(h.pt_site.size() + 1);
     const size_t o_pco = c.take<int32_t>(S + 1), o_pcp = c.take<int32_t>(E + 1);
     const size_t o_cpo = c.take<int32_t>(S + 1), o_cpp = c.take<int32_t>(h.cp_pos.size() + 1);
@@ -153,6 +169,8 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
         put(o_pos, p.data(), p.size() * 4);
     }
     put(o_cls, h.cls.data(), S);
+    put(o_sbb, sb_base.data(), sb_base.size() * 4);
+    put(o_sbo, sb_off.data(), sb_off.size() * 4);
     {   // hot[anchor] = some site of the reverse-partner list anchored here has competitors
         std::vector<uint8_t> hot(S + 64, 0);
         for (size_t a = 0; a < S; ++a)
@@ -179,6 +197,7 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     g.own_lo = (int32_t)((int64_t)S * ti / tc); g.own_hi = (int32_t)((int64_t)S * (ti + 1) / tc);
     g.cs_off = (const int32_t*)(b + o_cs); g.site_pos = (const int32_t*)(b + o_pos); g.site_cls = (const uint8_t*)(b + o_cls);
     g.site_hot = (const uint8_t*)(b + o_hot);
+    g.sb_base = (const int32_t*)(b + o_sbb); g.sb_off = (const int32_t*)(b + o_sbo);
     g.pt_off = (const int32_t*)(b + o_pto); g.pt_site = (const int32_t*)(b + o_pts);
     g.pc_off = (const int32_t*)(b + o_pco); g.pc_pos = (const int32_t*)(b + o_pcp);
     g.cp_off = (const int32_t*)(b + o_cpo); g.cp_pos = (const int32_t*)(b + o_cpp);
