@@ -61,7 +61,8 @@ struct DevSoA {
     uint32_t bB;                                        // first element of stream B (multiple of 4)
     uint32_t* sr_boff; uint32_t* sr_joff;               // [nS+1] per spliced read: offsets into stream B / junctions
     uint32_t* jn_l; uint32_t* jn_rk;                    // [nJ]
-    uint32_t* jn_read;                                  // [nJ] owning spliced read; only touched for hot junctions
+    uint32_t* jn_read;                                  // [nJ] owning spliced read | simple<<31
+    int32_t*  ji_a0; int32_t* ji_end;                   // [nJ] first block start / last block end of the owning read (simple reads)
 };
 constexpr uint32_t POS_MASK = 0x7fffffffu;
 
@@ -70,10 +71,40 @@ constexpr uint32_t POS_MASK = 0x7fffffffu;
 // the record order or the intron lengths were.  Each chromosome is padded to a multiple of K3_TILE with
 // never-matching elements so that tiles do not straddle chromosomes.
 constexpr int K3_TILE = 2048;           // blocks per tile / pipeline stage (16 KB)
+// Junction groups: every distinct (chromosome, l, r, class) junction of the sample with its multiplicity,
+// built once at load time (open-addressing table, one power-of-two sub-table per chromosome, then compacted).
+// A "simple" instance belongs to a read that is exactly block-N-block (no other N, no D, no I-split): for those
+// the exception logic only needs the read's first block start and last block end, kept grouped per junction.
+struct DevJunc {
+    // load-time table
+    uint32_t  n_slots;
+    uint32_t* chrom_jn;           // [n_chrom]   junction instances per chromosome
+    uint32_t* tab_base;           // [n_chrom+1] first slot of each chromosome's sub-table
+    unsigned long long* key;      // [n_slots]   ~(l | rk << 32), 0 = empty
+    uint32_t* s_all; uint32_t* s_simple;        // [n_slots] instance counts
+    uint32_t* s_used; uint32_t* s_off;          // [n_slots+1] scans: dense id, offset of the group's simple instances
+    uint32_t* s_cursor;           // [n_slots]
+    uint32_t* slot_of;            // [nJ] slot of each instance
+    uint32_t* overflow;           // [1] a sub-table filled up (never with the sizes chosen; checked anyway); follows cx_n
+    uint32_t* scan_tmp;           // block sums of the scans
+    // dense distinct-junction table
+    uint32_t  D;
+    uint32_t* dj_l; uint32_t* dj_rk; int32_t* dj_chrom;
+    uint32_t* dj_all; uint32_t* dj_simple; uint32_t* dj_off;
+    int32_t*  gi_a0; int32_t* gi_end;           // simple instances grouped by junction
+    uint32_t  n_complex;
+    uint32_t* cx_j; uint32_t* cx_d; uint32_t* cx_n;   // complex instances: global junction index, dense junction id
+    // per pass
+    uint32_t* hot_l; uint32_t* hot_r;           // [D] anchor + 1 of a hot endpoint, 0 otherwise
+    uint32_t* wl;                 // [2 D] hot (junction << 1 | side) items
+};
+
 struct Tile { uint32_t e0; int32_t w_lo, w_hi; int32_t pad; };   // first element, site index window [w_lo, w_hi)
 struct DevBins {
     uint32_t* chrom_ext;        // [n_chrom]   largest block start seen (atomicMax)
     uint32_t* chrom_tot;        // [n_chrom]   blocks on the chromosome
+    uint32_t* chrom_jn;         // [n_chrom]   junction instances on the chromosome
+    uint32_t* tab_base;         // [n_chrom+1] junction sub-table layout (see DevJunc)
     uint32_t* chrom_bin_base;   // [n_chrom+1] first bin of each chromosome
     uint32_t* chrom_tile_base;  // [n_chrom+1] first tile of each chromosome
     uint32_t* max_len;          // [1]         longest block
@@ -94,7 +125,7 @@ struct DevCounters {
     uint32_t* spanx;   // [S] spanning reads that are flanking (removed from the mutually-exclusive count)
     uint32_t* flank;   // [S] flanking reads (counted as beta2Simple in combine mode only)
     uint32_t* dc;      // [E] PartnerBeta2DoubleCounts increments seen in the BAM
-    uint32_t* work;    // [2] work-item counters of the persistent kernels (K3, K4)
+    uint32_t* work;    // [4] work-item counters: K3 tiles, (unused), junction work-list length, work-list cursor
 };
 
 struct DevOutputs {
@@ -124,7 +155,9 @@ void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chu
 void launch_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g, void* stream);
 void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream);
 void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream);
-void launch_spliced(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t flags, void* stream);
+void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, DevJunc jg, uint32_t* totals4, void* stream);
+void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* totals4, void* stream);
+void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream);
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream);
 int  kernel_launch_count_per_pass();
 

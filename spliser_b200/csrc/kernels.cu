@@ -227,6 +227,7 @@ __global__ void __launch_bounds__(EXPAND_THREADS) k_expand_count(DevRecords rec,
             atomicAdd(bins.chrom_tot + ck.chrom, total.a + total.b);
             atomicMax(bins.max_len, (uint32_t)lmax);
         }
+        if (total.j) atomicAdd(bins.chrom_jn + ck.chrom, total.j);
     }
 }
 
@@ -243,6 +244,18 @@ __global__ void k_bin_layout(DevBins bins, uint32_t* totals8) {
     }
     bins.chrom_bin_base[bins.n_chrom] = nb; bins.chrom_tile_base[bins.n_chrom] = nt;
     totals8[4] = nb; totals8[5] = nt; totals8[6] = nt * K3_TILE; totals8[7] = bins.max_len[0];
+    // junction sub-tables: power of two >= 2 x instances, so a sub-table can never fill up
+    uint32_t ns = 0;
+    for (int c = 0; c < bins.n_chrom; ++c) {
+        bins.tab_base[c] = ns;
+        if (bins.chrom_jn[c]) {
+            uint32_t t = 64;
+            while (t < 2u * bins.chrom_jn[c]) t <<= 1;
+            ns += t;
+        }
+    }
+    bins.tab_base[bins.n_chrom] = ns;
+    totals8[8] = ns;
 }
 
 // exclusive scan of the per-chunk totals; single CTA (n_chunks is R / 4096: at most ~1e5)
@@ -298,23 +311,32 @@ k_expand_scatter(DevRecords rec, const Chunk* chunks, DevSoA soa, uint32_t mode)
             const uint32_t kbit = read_class(rec.flag[i], mode) << 31;
             if (spliced) { soa.sr_boff[run.s + ex.s] = im - soa.bB; soa.sr_joff[run.s + ex.s] = ij; }
             int32_t cur = rec.pos[i];
-            bool seen = false;
+            bool seen = false, last_n = false;
+            int32_t a0 = 0;
+            uint32_t nD = 0, first_m = 1;
+            const uint32_t ij_first = ij;
             for (uint32_t kk = c0; kk < c1; ++kk) {
                 const uint32_t w = rec.cigar[kk];
                 const uint32_t op = w & 15u;
                 const int32_t len = (int32_t)(w >> 4);
                 if (op == 0u || op == 7u || op == 8u) {
+                    if (first_m) { a0 = cur; first_m = 0; }
                     soa.m_start[im] = cur; soa.m_endk[im] = (uint32_t)(cur + len) | kbit; ++im;
-                    cur += len; seen = true;
+                    cur += len; seen = true; last_n = false;
                 } else if (op == 3u) {
                     soa.jn_l[ij] = (uint32_t)(cur - 1) | (seen ? 0u : 0x80000000u);     // S:482; firstN flag (POS <= t filter, S:435)
                     soa.jn_rk[ij] = (uint32_t)(cur + len - 1) | kbit;                   // S:483
-                    soa.jn_read[ij] = (run.s + ex.s) | (nN == 1u ? 0x80000000u : 0u);   // owning spliced read | single-junction flag (hot path only)
                     ++ij;
-                    cur += len; seen = true;
+                    cur += len; seen = true; last_n = true;
                 } else if (op == 2u) {
-                    cur += len; seen = true;
+                    cur += len; seen = true; ++nD;
                 }
+            }
+            if (spliced) {
+                // "simple" read: exactly block - N - block (the aggregated exception path needs only a0 and the end)
+                const bool simple = nN == 1u && nM == 2u && nD == 0u && !last_n && !(soa.jn_l[ij_first] >> 31);
+                const uint32_t tag = (run.s + ex.s) | (simple ? 0x80000000u : 0u);
+                for (uint32_t jj = ij_first; jj < ij; ++jj) { soa.jn_read[jj] = tag; soa.ji_a0[jj] = a0; soa.ji_end[jj] = cur; }
             }
         }
         run.a += total.a; run.b += total.b; run.s += total.s; run.j += total.j;
@@ -487,6 +509,88 @@ __global__ void k_tile_hints(DevBins bins, DevGraph g) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// K0e: junction groups.  Every N operator of the sample is inserted into an open-addressing table
+// (one sub-table per chromosome, keys compared exactly); the table is then compacted into the dense
+// distinct-junction arrays, and the simple instances are grouped per junction.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long jkey(uint32_t lraw, uint32_t rraw) {
+    return ~((unsigned long long)(lraw & POS_MASK) | ((unsigned long long)rraw << 32));    // never 0
+}
+
+__global__ void __launch_bounds__(256) k_jg_insert(const Chunk* __restrict__ chunks, DevSoA soa, DevJunc jg) {
+    const Chunk ck = chunks[blockIdx.x];
+    if (ck.j_cnt == 0) return;
+    const uint32_t t0 = jg.tab_base[ck.chrom], tmask = jg.tab_base[ck.chrom + 1] - t0 - 1;
+    const int lane = threadIdx.x & 31;
+    for (uint32_t jb = ck.j_base; jb < ck.j_base + ck.j_cnt; jb += 256) {
+        const uint32_t j = jb + threadIdx.x;
+        const bool live = j < ck.j_base + ck.j_cnt;
+        const unsigned long long key = live ? jkey(soa.jn_l[j], soa.jn_rk[j]) : 0ull;
+        const bool simple = live && (soa.jn_read[j] >> 31);
+        // neighbouring reads carry the same junction: one table access per distinct key of the warp
+        const uint32_t peers = __match_any_sync(0xffffffffu, key);
+        const uint32_t simple_peers = __ballot_sync(0xffffffffu, simple) & peers;
+        uint32_t slot = 0;
+        if (live && (int)(__ffs(peers) - 1) == lane) {
+            uint32_t h = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & tmask;
+            uint32_t probes = 0;
+            for (;;) {
+                const unsigned long long old = atomicCAS(jg.key + t0 + h, 0ull, key);
+                if (old == 0ull || old == key) break;
+                h = (h + 1) & tmask;
+                if (++probes > tmask) { atomicExch(jg.overflow, 1u); break; }
+            }
+            slot = t0 + h;
+            atomicAdd(jg.s_all + slot, (uint32_t)__popc(peers));
+            if (simple_peers) atomicAdd(jg.s_simple + slot, (uint32_t)__popc(simple_peers));
+        }
+        slot = __shfl_sync(0xffffffffu, slot, live ? (__ffs(peers) - 1) : 0);
+        if (live) jg.slot_of[j] = slot;
+    }
+}
+
+__global__ void k_jg_used(DevJunc jg) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < jg.n_slots) { jg.s_used[s] = jg.key[s] != 0ull; jg.s_off[s] = jg.s_simple[s]; }
+    if (s == jg.n_slots) { jg.s_used[s] = 0; jg.s_off[s] = 0; }
+}
+
+__global__ void k_jg_compact(DevJunc jg, int n_chrom) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= jg.n_slots || jg.key[s] == 0ull) return;
+    const uint32_t d = jg.s_used[s];
+    const unsigned long long key = ~jg.key[s];
+    int lo = 0, hi = n_chrom;                                     // last chromosome with tab_base <= s
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (jg.tab_base[mid] <= s) lo = mid; else hi = mid; }
+    jg.dj_l[d] = (uint32_t)(key & POS_MASK); jg.dj_rk[d] = (uint32_t)(key >> 32); jg.dj_chrom[d] = lo;
+    jg.dj_all[d] = jg.s_all[s]; jg.dj_simple[d] = jg.s_simple[s]; jg.dj_off[d] = jg.s_off[s];
+}
+
+__global__ void __launch_bounds__(256) k_jg_scatter(DevSoA soa, DevJunc jg) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = j < soa.nJ;
+    bool cx = false;
+    uint32_t slot = 0;
+    if (live) {
+        slot = jg.slot_of[j];
+        if (soa.jn_read[j] >> 31) {
+            const uint32_t p = jg.s_off[slot] + atomicAdd(jg.s_cursor + slot, 1u);
+            jg.gi_a0[p] = soa.ji_a0[j]; jg.gi_end[p] = soa.ji_end[j];
+        } else cx = true;
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, cx);
+    if (!bal) return;
+    const int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(jg.cx_n, (uint32_t)__popc(bal));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (cx) {
+        const uint32_t p = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+        jg.cx_j[p] = j; jg.cx_d[p] = jg.s_used[slot];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K1: alpha and PartnerCounts as segmented reductions of the junction scores
 // ------------------------------------------------------------------------------------------------
 __global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
@@ -517,9 +621,6 @@ constexpr int PS_STAGES = 3;
 constexpr int PS_CONSUMERS = 256;                  // 8 consumer warps
 constexpr int PS_THREADS = PS_CONSUMERS + 32;      // + 1 producer warp
 constexpr int K3_SITES = 2048;                     // staged site positions per stage (8 KB)
-constexpr int K4_TILE = 1024;                      // junctions per stage (8 KB)
-constexpr int K4_SITES = 2048;
-constexpr int K4_WORKLIST = 1024;
 
 struct StageMeta {
     uint32_t e0, e1;        // valid global element range of the item
@@ -804,161 +905,119 @@ __device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph&
     }
 }
 
-constexpr int K4_BINS = 1024;                      // staged bin-index entries per stage (256 kb of chunk window)
-struct K4Stage {
-    uint32_t l[K4_TILE];
-    uint32_t rk[K4_TILE];
-    int32_t  sites[K4_SITES + 32];
-    int32_t  sbin[K4_BINS + 8];
-    uint8_t  hot[K4_SITES + 32];
-};
-struct K4Smem {
-    K4Stage st[PS_STAGES];
-    StageMeta meta[PS_STAGES];
-    uint64_t full[PS_STAGES], empty[PS_STAGES];
-    uint32_t wl_j[K4_WORKLIST], wl_a[K4_WORKLIST];
-    uint32_t wl_n;
-};
+// ------------------------------------------------------------------------------------------------
+// K4 per pass: junction kernels over the DISTINCT junctions of the sample.
+//   k_junc_lookup   one thread per distinct junction: site lookups through the bin index, span range add
+//                   weighted by the junction's multiplicity (S:507-512), hot flags of its endpoints, work list
+//   k_junc_simple   one warp per hot (junction, endpoint): the junction's simple instances are classified at
+//                   every exception site in aggregate -- flanking ones by the count alone, covering ones by a
+//                   coalesced pass over the group's (first block start, read end) arrays
+//   k_junc_complex  one thread per complex instance (several N, D or I splits) of a hot junction: the general
+//                   per-read logic (k4_exceptions)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int site_lower(const DevGraph& g, int chrom, int32_t pos) {
+    const int g0 = g.sb_base[chrom], nb = g.sb_base[chrom + 1] - g0 - 1;
+    const int s1 = g.cs_off[chrom + 1];
+    int i = g.sb_off[g0 + min(max(pos, 0) >> BIN_SHIFT, nb)];
+    while (i < s1 && g.site_pos[i] < pos) ++i;
+    return i;
+}
 
-__device__ __forceinline__ void k4_consume(const K4Stage& stg, const StageMeta& m, const int32_t* __restrict__ sp,
-                                           const uint8_t* __restrict__ hot, const int32_t* __restrict__ sbp, const DevSoA& soa, const DevGraph& g,
-                                           const DevCounters& cnt, bool combine, bool skip_exc, K4Smem& sm) {
+__global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = d < jg.D;
     const int S = g.n_sites;
+    uint32_t hl = 0, hr = 0;
+    if (live) {
+        const int32_t l = (int32_t)jg.dj_l[d], r = (int32_t)(jg.dj_rk[d] & POS_MASK);
+        const uint32_t k = jg.dj_rk[d] >> 31;
+        const int c = jg.dj_chrom[d], s1 = g.cs_off[c + 1];
+        const int il = site_lower(g, c, l);
+        int iu = il;
+        while (iu < s1 && g.site_pos[iu] == l) ++iu;                   // upper_bound(l)
+        int ir = il;
+        if (r > l) { ir = max(site_lower(g, c, r), iu); }
+        const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);     // sites strictly inside (l, r)
+        if (x0 < x1) {
+            const uint32_t n = jg.dj_all[d];
+            atomicAdd(cnt.span + k * (S + 1) + x0, n);
+            atomicAdd(cnt.span + k * (S + 1) + x1, 0u - n);
+        }
+        if (!(mode & FLAG_DEBUG_SKIP_EXC)) {
+            if (il < s1 && g.site_pos[il] == l && g.site_hot[il]) hl = (uint32_t)il + 1u;
+            if (ir < s1 && g.site_pos[ir] == r && g.site_hot[ir]) hr = (uint32_t)ir + 1u;
+        }
+        jg.hot_l[d] = hl; jg.hot_r[d] = hr;
+    }
+    // work list of hot (junction, side) items, one atomic per warp
     const int lane = threadIdx.x & 31;
-    for (uint32_t base = 0; base < m.n; base += PS_CONSUMERS) {       // uniform trip count
-        const uint32_t idx = base + threadIdx.x;
-        const uint32_t j = m.p0 + idx;
-        const bool live = idx < m.n && (j - m.e0) < (m.e1 - m.e0);
-        const uint32_t lraw = live ? stg.l[idx] : 0u, rraw = live ? stg.rk[idx] : 0u;
-        const int32_t l = live ? (int32_t)(lraw & POS_MASK) : INT_MAX, r = live ? (int32_t)(rraw & POS_MASK) : INT_MIN;
-        const uint32_t k = rraw >> 31;
-        // site lookups through the direct-address bin index: one load for the bin, then a scan over the 0-2 sites
-        // of the 256 bp bin that precede the position -- no binary search
-        const uint32_t anylive = __ballot_sync(0xffffffffu, live);
-        if (!anylive) continue;
-        const int n1 = m.w_hi;
-        int il = m.w_lo, iu = m.w_lo, ir = m.w_lo;
-        if (live) {
-            il = max(sbp[m.sb_g0 + min(max(l, 0) >> BIN_SHIFT, m.sb_nb)], m.w_lo);
-            while (il < n1 && sp[il] < l) ++il;                        // lower_bound(l)
-            iu = il;
-            while (iu < n1 && sp[iu] == l) ++iu;                       // upper_bound(l)
-            if (r > l) {
-                ir = max(sbp[m.sb_g0 + min(max(r, 0) >> BIN_SHIFT, m.sb_nb)], iu);
-                while (ir < n1 && sp[ir] < r) ++ir;                    // lower_bound(r)
-            } else ir = il;
-        }
-        // span range add over sites strictly inside (l, r), aggregated over identical ranges in the warp
-        const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);
-        const bool add = live && x0 < x1;
-        const uint32_t anyadd = __ballot_sync(0xffffffffu, add);
-        if (anyadd) {
-            const unsigned long long key = add ? (((unsigned long long)(uint32_t)x0 << 32) | ((uint32_t)x1 << 1) | k) : ~0ull;
-            const uint32_t grp = __match_any_sync(0xffffffffu, key);
-            if (add && (int)(__ffs(grp) - 1) == lane) {
-                const uint32_t c = (uint32_t)__popc(grp);
-                atomicAdd(cnt.span + k * (S + 1) + x0, c);
-                atomicAdd(cnt.span + k * (S + 1) + x1, 0u - c);
-            }
-        }
-        const bool hl = live && !skip_exc && il < n1 && sp[il] == l && hot[il];
-        const bool hr = live && !skip_exc && ir < n1 && sp[ir] == r && hot[ir];
 #pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const bool h = side == 0 ? hl : hr;
-            const uint32_t bal = __ballot_sync(0xffffffffu, h);
-            if (!bal) continue;
-            uint32_t slot0 = 0;
-            if (lane == 0) slot0 = atomicAdd(&sm.wl_n, (uint32_t)__popc(bal));
-            slot0 = __shfl_sync(0xffffffffu, slot0, 0);
-            if (h) {
-                const uint32_t slot = slot0 + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-                const int anchor = side == 0 ? il : ir;
-                if (slot < K4_WORKLIST) { sm.wl_j[slot] = j; sm.wl_a[slot] = (uint32_t)anchor | ((uint32_t)side << 31); }
-                else k4_exceptions(soa, g, cnt, j, anchor, side, combine);    // list full: do it now
+    for (int side = 0; side < 2; ++side) {
+        const bool h = (side == 0 ? hl : hr) != 0u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, h);
+        if (!bal) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cnt.work + 2, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (h) jg.wl[base + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (d << 1) | (uint32_t)side;
+    }
+}
+
+__global__ void __launch_bounds__(256) k_junc_simple(DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
+    const bool combine = (mode & FLAG_COMBINE) != 0;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_items = cnt.work[2];
+    for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items; item += gridDim.x * (blockDim.x >> 5)) {
+        const uint32_t w = jg.wl[item];
+        const uint32_t d = w >> 1;
+        const int side = (int)(w & 1u);
+        const uint32_t ns = jg.dj_simple[d];
+        if (ns == 0) continue;                                         // only complex instances carry this junction
+        const int32_t l = (int32_t)jg.dj_l[d], r = (int32_t)(jg.dj_rk[d] & POS_MASK);
+        const uint32_t k = jg.dj_rk[d] >> 31;
+        const int anchor = (int)((side == 0 ? jg.hot_l[d] : jg.hot_r[d]) - 1u);
+        const int32_t other = side == 0 ? r : l;
+        const uint32_t off = jg.dj_off[d];
+        for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {     // warp-uniform loop
+            const int t = g.rp_site[q];
+            if (t < g.own_lo || t >= g.own_hi) continue;
+            const int c0 = g.cp_off[t], c1 = g.cp_off[t + 1];
+            if (c0 == c1 || !in_sorted(g.cp_pos, c0, c1, other)) continue;
+            if (side == 1 && in_sorted(g.cp_pos, c0, c1, r) && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) continue;
+            const int32_t tp = g.site_pos[t];
+            const bool ok = strand_ok(g.site_cls[t], k);
+            if (l < tp && tp < r) {                                    // flanking for every simple instance (S:503-505)
+                if (lane == 0) {
+                    if (ok) atomicAdd(cnt.spanx + t, ns);
+                    if (combine) atomicAdd(cnt.flank + t, ns);
+                }
+            } else if (ok && tp != l && tp != r) {                     // beta1-type for the instances whose block covers t
+                uint32_t c = 0;
+                if (tp < l) { for (uint32_t i = lane; i < ns; i += 32) c += jg.gi_a0[off + i] <= tp; }
+                else        { for (uint32_t i = lane; i < ns; i += 32) c += jg.gi_end[off + i] >= tp + 2; }
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c && lane == 0) {
+                    atomicAdd(cnt.covx + t, c);
+                    for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e)    // S:546-551: partners of t among the read's splice sites
+                        if (g.pc_pos[e] == l || g.pc_pos[e] == r) atomicAdd(cnt.dc + e, c);
+                }
             }
         }
     }
 }
 
-__global__ void __launch_bounds__(PS_THREADS)
-k_spliced(const Chunk* __restrict__ chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t mode) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    K4Smem& sm = *reinterpret_cast<K4Smem*>(smem_raw);
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= jg.n_complex) return;
+    const uint32_t d = jg.cx_d[i];
+    const uint32_t hl = jg.hot_l[d], hr = jg.hot_r[d];
+    if (!(hl | hr)) return;
     const bool combine = (mode & FLAG_COMBINE) != 0;
-    const bool skip_exc = (mode & FLAG_DEBUG_SKIP_EXC) != 0;          // timing experiments only (wrong counts)
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], PS_CONSUMERS / 32); }
-        sm.wl_n = 0;
-    }
-    __syncthreads();
-    if (warp == PS_CONSUMERS / 32) {
-        // ===== producer =====
-        if (lane != 0) return;
-        uint32_t it = 0;
-        uint32_t next = atomicAdd(cnt.work + 1, 1u);
-        Chunk nck = chunks[min(next, (uint32_t)n_chunks - 1u)];
-        for (;;) {
-            const uint32_t item = next;
-            if (item >= (uint32_t)n_chunks) break;
-            const Chunk ck = nck;
-            next = atomicAdd(cnt.work + 1, 1u);
-            nck = chunks[min(next, (uint32_t)n_chunks - 1u)];
-            if (ck.j_cnt == 0 || ck.s_site_n == 0) continue;        // no site inside the chunk's window: nothing to count
-            const int w_lo = ck.s_site_lo, w_hi = ck.s_site_lo + ck.s_site_n;
-            const uint32_t e0 = ck.j_base, e1 = ck.j_base + ck.j_cnt;
-            const bool staged = ck.s_site_n <= K4_SITES;
-            const int al = ck.s_site_lo & ~15;                         // 16-byte aligned for both element sizes
-            const uint32_t nst = staged ? (uint32_t)(((w_hi + 15) & ~15) - al) : 0u;
-            // slice of the bin index covering the chunk's position window
-            const int sb_g0 = g.sb_base[ck.chrom], sb_nb = g.sb_base[ck.chrom + 1] - sb_g0 - 1;
-            const int bl = min(max(ck.s_lo, 0) >> BIN_SHIFT, sb_nb), bh = min(max(ck.s_hi, 0) >> BIN_SHIFT, sb_nb);
-            const int sb_al = (sb_g0 + bl) & ~3;
-            const uint32_t nsb = (uint32_t)(((sb_g0 + bh + 1 + 3) & ~3) - sb_al);
-            const bool bstaged = nsb <= (uint32_t)K4_BINS;
-            for (uint32_t p = e0 & ~3u; p < e1; p += K4_TILE, ++it) {
-                const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-                mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
-                const uint32_t np = min((uint32_t)K4_TILE, ((e1 + 3u) & ~3u) - p);
-                StageMeta& m = sm.meta[stage];
-                m.e0 = e0; m.e1 = e1; m.p0 = p; m.n = np; m.w_lo = w_lo; m.w_hi = w_hi; m.al = al;
-                m.flags = (staged ? 0u : PS_GLOBAL_SITES) | (bstaged ? 0u : PS_GLOBAL_BINS); m.chunk = (int32_t)item;
-                m.sb_g0 = sb_g0; m.sb_nb = sb_nb; m.sb_al = sb_al;
-                mbar_expect_tx(&sm.full[stage], np * 8u + nst * 5u + (bstaged ? nsb * 4u : 0u));
-                bulk_g2s(sm.st[stage].l, soa.jn_l + p, np * 4u, &sm.full[stage]);
-                bulk_g2s(sm.st[stage].rk, soa.jn_rk + p, np * 4u, &sm.full[stage]);
-                if (bstaged) bulk_g2s(sm.st[stage].sbin, g.sb_off + sb_al, nsb * 4u, &sm.full[stage]);
-                if (nst) {
-                    bulk_g2s(sm.st[stage].sites, g.site_pos + al, nst * 4u, &sm.full[stage]);
-                    bulk_g2s(sm.st[stage].hot, g.site_hot + al, nst, &sm.full[stage]);
-                }
-            }
-        }
-        const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-        mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
-        sm.meta[stage].flags = PS_DONE;
-        mbar_arrive(&sm.full[stage]);
-        return;
-    }
-    // ===== consumers =====
-    for (uint32_t it = 0;; ++it) {
-        const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-        mbar_wait(&sm.full[stage], parity);
-        const StageMeta m = sm.meta[stage];
-        if (m.flags & PS_DONE) break;
-        const int32_t* sbp = (m.flags & PS_GLOBAL_BINS) ? g.sb_off : sm.st[stage].sbin - m.sb_al;
-        if (m.flags & PS_GLOBAL_SITES) k4_consume(sm.st[stage], m, g.site_pos, g.site_hot, sbp, soa, g, cnt, combine, skip_exc, sm);
-        else k4_consume(sm.st[stage], m, sm.st[stage].sites - m.al, sm.st[stage].hot - m.al, sbp, soa, g, cnt, combine, skip_exc, sm);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);                  // the stage can be refilled while the work list drains
-        consumer_sync();                                               // work list complete
-        const uint32_t n_items = min(sm.wl_n, (uint32_t)K4_WORKLIST);
-        for (uint32_t i = threadIdx.x; i < n_items; i += PS_CONSUMERS)
-            k4_exceptions(soa, g, cnt, sm.wl_j[i], (int)(sm.wl_a[i] & POS_MASK), (int)(sm.wl_a[i] >> 31), combine);
-        consumer_sync();                                               // everyone has read wl_n / the list
-        if (threadIdx.x == 0) sm.wl_n = 0;
-        consumer_sync();
+    const uint32_t j = jg.cx_j[i];
+#pragma unroll 1
+    for (int side = 0; side < 2; ++side) {
+        const uint32_t a1 = side == 0 ? hl : hr;
+        if (a1) k4_exceptions(soa, g, cnt, j, (int)(a1 - 1u), side, combine);
     }
 }
 
@@ -1160,10 +1219,45 @@ void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream) {
     static const int grid = persistent_grid((const void*)k_beta1_stab, sizeof(K3Smem));
     k_beta1_stab<<<grid, PS_THREADS, sizeof(K3Smem), (cudaStream_t)stream>>>(bins, g, cnt);
 }
-void launch_spliced(const Chunk* chunks, int n_chunks, DevSoA soa, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
-    if (n_chunks <= 0 || g.n_sites <= 0) return;
-    static const int grid = persistent_grid((const void*)k_spliced, sizeof(K4Smem));
-    k_spliced<<<grid, PS_THREADS, sizeof(K4Smem), (cudaStream_t)stream>>>(chunks, n_chunks, soa, g, cnt, flags);
+// phase A: table insert + scans; totals3[0] = distinct junctions, [1] = simple instances (read by the host to size
+// the dense arrays).  phase B: compaction + grouping; totals3[2] = complex instances, [3] = overflow flag.
+void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, DevJunc jg, uint32_t* totals4, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaMemsetAsync(totals4, 0, 16, st);
+    if (n_chunks <= 0 || jg.n_slots == 0 || soa.nJ == 0) return;
+    cudaMemsetAsync(jg.key, 0, (size_t)jg.n_slots * 8, st);
+    cudaMemsetAsync(jg.s_all, 0, (size_t)jg.n_slots * 4, st);
+    cudaMemsetAsync(jg.s_simple, 0, (size_t)jg.n_slots * 4, st);
+    cudaMemsetAsync(jg.s_cursor, 0, (size_t)jg.n_slots * 4, st);
+    cudaMemsetAsync(jg.cx_n, 0, 8, st);                                  // cx_n and overflow are adjacent
+    k_jg_insert<<<n_chunks, 256, 0, st>>>(chunks, soa, jg);
+    const uint32_t n = jg.n_slots + 1;
+    k_jg_used<<<(n + 255) / 256, 256, 0, st>>>(jg);
+    const uint32_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_used, n, jg.scan_tmp);
+    k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk);
+    k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_used, n, jg.scan_tmp, nullptr);
+    k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_off, n, jg.scan_tmp);
+    k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk);
+    k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_off, n, jg.scan_tmp, nullptr);
+    cudaMemcpyAsync(totals4, jg.s_used + jg.n_slots, 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(totals4 + 1, jg.s_off + jg.n_slots, 4, cudaMemcpyDeviceToDevice, st);
+}
+void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* totals4, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (jg.n_slots == 0 || soa.nJ == 0) return;
+    k_jg_compact<<<(jg.n_slots + 255) / 256, 256, 0, st>>>(jg, n_chrom);
+    k_jg_scatter<<<(soa.nJ + 255) / 256, 256, 0, st>>>(soa, jg);
+    cudaMemcpyAsync(totals4 + 2, jg.cx_n, 8, cudaMemcpyDeviceToDevice, st);
+}
+void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (jg.D == 0 || g.n_sites <= 0) return;
+    k_junc_lookup<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, g, cnt, flags);
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    k_junc_simple<<<sms * 8, 256, 0, st>>>(jg, g, cnt, flags);
+    if (jg.n_complex) k_junc_complex<<<(jg.n_complex + 255) / 256, 256, 0, st>>>(soa, jg, g, cnt, flags);
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;
@@ -1172,6 +1266,6 @@ void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags
     k_span_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(out.span_blk, nblk);
     k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags);
 }
-int kernel_launch_count_per_pass() { return 6; }   // alpha_reduce, beta1_stab, spliced, span_blocksum, span_scan, finalize
+int kernel_launch_count_per_pass() { return 8; }   // alpha_reduce, beta1_stab, junc_lookup, junc_simple, junc_complex, span_blocksum, span_scan, finalize
 
 }  // namespace spl

@@ -79,6 +79,8 @@ struct spl_ctx {
     DevBuf d_graph, d_rec, d_chunks, d_soa, d_cnt, d_out, d_tot, d_lay, d_bins;
     uint32_t* h_tot = nullptr;      // pinned, 8 totals
     DevBins bins{};
+    DevJunc jg{};
+    DevBuf d_jtab, d_jdense;
     std::vector<cudaEvent_t> events;
 
     // state of the last load
@@ -288,7 +290,7 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     CU(ctx->d_chunks.reserve((hc.size() + 1) * sizeof(Chunk)));
     ctx->chunks = (Chunk*)ctx->d_chunks.p;
     if (!hc.empty()) CU(cudaMemcpyAsync(ctx->chunks, hc.data(), hc.size() * sizeof(Chunk), cudaMemcpyHostToDevice, ctx->stream));
-    CU(ctx->d_tot.reserve(64));
+    CU(ctx->d_tot.reserve(256));
     // per-chromosome layout arrays of the bin-partitioned stream
     DevBins& bins = ctx->bins;
     bins = DevBins{};
@@ -296,13 +298,15 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     {
         Carver lc;
         const size_t o_ext = lc.take<uint32_t>(nchr + 1), o_tot = lc.take<uint32_t>(nchr + 1), o_bb = lc.take<uint32_t>(nchr + 2),
-                     o_tb = lc.take<uint32_t>(nchr + 2), o_ml = lc.take<uint32_t>(4);
+                     o_tb = lc.take<uint32_t>(nchr + 2), o_ml = lc.take<uint32_t>(4), o_cj = lc.take<uint32_t>(nchr + 1),
+                     o_jt = lc.take<uint32_t>(nchr + 2);
         CU(ctx->d_lay.reserve(lc.off + 256));
         CU(cudaMemsetAsync(ctx->d_lay.p, 0, lc.off + 256, ctx->stream));
         char* lb = (char*)ctx->d_lay.p;
         bins.chrom_ext = (uint32_t*)(lb + o_ext); bins.chrom_tot = (uint32_t*)(lb + o_tot);
         bins.chrom_bin_base = (uint32_t*)(lb + o_bb); bins.chrom_tile_base = (uint32_t*)(lb + o_tb);
         bins.max_len = (uint32_t*)(lb + o_ml);
+        bins.chrom_jn = (uint32_t*)(lb + o_cj); bins.tab_base = (uint32_t*)(lb + o_jt);
         bins.n_chrom = ctx->n_chrom_loaded;
     }
     cudaEvent_t e0, e1;
@@ -311,7 +315,7 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     launch_expand_count(ctx->rec, ctx->chunks, ctx->n_chunks, flags, bins, ctx->stream);
     launch_chunk_scan(ctx->chunks, ctx->n_chunks, (uint32_t*)ctx->d_tot.p, bins, ctx->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->h_tot, ctx->d_tot.p, 32, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(ctx->h_tot, ctx->d_tot.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // also makes `hc` (pageable) safe to drop
     const size_t nA = ctx->h_tot[0], nB = ctx->h_tot[1], nS = ctx->h_tot[2], nJ = ctx->h_tot[3];
     const size_t total_bins = ctx->n_chunks ? ctx->h_tot[4] : 0, n_tiles = ctx->n_chunks ? ctx->h_tot[5] : 0;
@@ -323,6 +327,7 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     const size_t o_ms = s.take<int32_t>(bB + nB + 32), o_me = s.take<uint32_t>(bB + nB + 32);
     const size_t o_sb = s.take<uint32_t>(nS + 16), o_sj = s.take<uint32_t>(nS + 16);
     const size_t o_jl = s.take<uint32_t>(nJ + 16), o_jr = s.take<uint32_t>(nJ + 16), o_jq = s.take<uint32_t>(nJ + 16);
+    const size_t o_ja = s.take<int32_t>(nJ + 16), o_je = s.take<int32_t>(nJ + 16);
     CU(ctx->d_soa.reserve(s.off + 256));
     char* sb = (char*)ctx->d_soa.p;
     DevSoA& soa = ctx->soa;
@@ -330,6 +335,7 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     soa.m_start = (int32_t*)(sb + o_ms); soa.m_endk = (uint32_t*)(sb + o_me); soa.bB = (uint32_t)bB;
     soa.sr_boff = (uint32_t*)(sb + o_sb); soa.sr_joff = (uint32_t*)(sb + o_sj);
     soa.jn_l = (uint32_t*)(sb + o_jl); soa.jn_rk = (uint32_t*)(sb + o_jr); soa.jn_read = (uint32_t*)(sb + o_jq);
+    soa.ji_a0 = (int32_t*)(sb + o_ja); soa.ji_end = (int32_t*)(sb + o_je);
     {
         Carver bc;
         const size_t nscan = (total_bins + 1 + 4095) / 4096 + 8;
@@ -344,8 +350,54 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     launch_expand_scatter(ctx->rec, ctx->chunks, ctx->n_chunks, soa, flags, ctx->stream);
     launch_bin_partition(ctx->chunks, ctx->n_chunks, soa, bins, ctx->stream);
     CU(cudaGetLastError());
+    // ---- junction groups: table -> (sync: distinct count) -> dense arrays + grouped simple instances
+    DevJunc& jg = ctx->jg;
+    jg = DevJunc{};
+    const size_t n_slots = ctx->n_chunks ? ctx->h_tot[8] : 0;
+    {
+        Carver jc;
+        const size_t nscan = (n_slots + 1 + 4095) / 4096 + 8;
+        const size_t o_key = jc.take<unsigned long long>(n_slots + 2), o_sa = jc.take<uint32_t>(n_slots + 2),
+                     o_ss = jc.take<uint32_t>(n_slots + 2), o_su = jc.take<uint32_t>(n_slots + 2), o_so = jc.take<uint32_t>(n_slots + 2),
+                     o_sc = jc.take<uint32_t>(n_slots + 2), o_sl = jc.take<uint32_t>(nJ + 2), o_cn = jc.take<uint32_t>(4),
+                     o_tmp = jc.take<uint32_t>(2 * nscan + 8);
+        CU(ctx->d_jtab.reserve(jc.off + 256));
+        char* jb = (char*)ctx->d_jtab.p;
+        jg.n_slots = (uint32_t)n_slots; jg.chrom_jn = bins.chrom_jn; jg.tab_base = bins.tab_base;
+        jg.key = (unsigned long long*)(jb + o_key); jg.s_all = (uint32_t*)(jb + o_sa); jg.s_simple = (uint32_t*)(jb + o_ss);
+        jg.s_used = (uint32_t*)(jb + o_su); jg.s_off = (uint32_t*)(jb + o_so); jg.s_cursor = (uint32_t*)(jb + o_sc);
+        jg.slot_of = (uint32_t*)(jb + o_sl); jg.cx_n = (uint32_t*)(jb + o_cn); jg.overflow = jg.cx_n + 1;
+        jg.scan_tmp = (uint32_t*)(jb + o_tmp);
+    }
+    uint32_t* d_jtot = (uint32_t*)ctx->d_tot.p + 12;
+    launch_junction_groups_a(ctx->chunks, ctx->n_chunks, soa, jg, d_jtot, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const size_t D = ctx->h_tot[12], n_simple = ctx->h_tot[13];
+    {
+        Carver dc;
+        const size_t o_l = dc.take<uint32_t>(D + 2), o_rk = dc.take<uint32_t>(D + 2), o_ch = dc.take<int32_t>(D + 2),
+                     o_al = dc.take<uint32_t>(D + 2), o_si = dc.take<uint32_t>(D + 2), o_of = dc.take<uint32_t>(D + 2),
+                     o_a0 = dc.take<int32_t>(n_simple + 2), o_en = dc.take<int32_t>(n_simple + 2),
+                     o_cj = dc.take<uint32_t>(nJ - std::min(nJ, n_simple) + 2), o_cd = dc.take<uint32_t>(nJ - std::min(nJ, n_simple) + 2),
+                     o_hl = dc.take<uint32_t>(D + 2), o_hr = dc.take<uint32_t>(D + 2), o_wl = dc.take<uint32_t>(2 * D + 2);
+        CU(ctx->d_jdense.reserve(dc.off + 256));
+        char* db = (char*)ctx->d_jdense.p;
+        jg.D = (uint32_t)D;
+        jg.dj_l = (uint32_t*)(db + o_l); jg.dj_rk = (uint32_t*)(db + o_rk); jg.dj_chrom = (int32_t*)(db + o_ch);
+        jg.dj_all = (uint32_t*)(db + o_al); jg.dj_simple = (uint32_t*)(db + o_si); jg.dj_off = (uint32_t*)(db + o_of);
+        jg.gi_a0 = (int32_t*)(db + o_a0); jg.gi_end = (int32_t*)(db + o_en);
+        jg.cx_j = (uint32_t*)(db + o_cj); jg.cx_d = (uint32_t*)(db + o_cd);
+        jg.hot_l = (uint32_t*)(db + o_hl); jg.hot_r = (uint32_t*)(db + o_hr); jg.wl = (uint32_t*)(db + o_wl);
+    }
+    launch_junction_groups_b(soa, jg, ctx->n_chrom_loaded, d_jtot, ctx->stream);
+    CU(cudaGetLastError());
+    CU(cudaMemcpyAsync(ctx->h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
+    jg.n_complex = ctx->h_tot[14];
+    if (ctx->h_tot[15]) return ctx->fail(SPL_ERR_CUDA, "junction table overflow (internal sizing error)");
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
@@ -369,7 +421,7 @@ int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     if (ev) CU(cudaEventRecord(ev[1], ctx->stream));
     launch_beta1(ctx->bins, ctx->g, ctx->cnt, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[2], ctx->stream));
-    launch_spliced(ctx->chunks, ctx->n_chunks, ctx->soa, ctx->g, ctx->cnt, ctx->flags, ctx->stream);
+    launch_junctions(ctx->soa, ctx->jg, ctx->g, ctx->cnt, ctx->flags, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[3], ctx->stream));
     launch_finalize(ctx->g, ctx->cnt, ctx->out, ctx->flags, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[4], ctx->stream));
@@ -474,7 +526,7 @@ int spl_create(spl_ctx** out, const int* device_ids, int n_devices) {
     if (prop.major != 10)
         return ctx->fail(SPL_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", ctx->device, prop.major, prop.minor);
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
-    CU(cudaHostAlloc((void**)&ctx->h_tot, 64, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&ctx->h_tot, 256, cudaHostAllocDefault));
     return SPL_OK;
 }
 
@@ -485,7 +537,7 @@ void spl_destroy(spl_ctx* ctx) {
         cudaStreamSynchronize(ctx->stream);
         for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
         ctx->d_graph.release(); ctx->d_rec.release(); ctx->d_chunks.release(); ctx->d_soa.release();
-        ctx->d_cnt.release(); ctx->d_out.release(); ctx->d_tot.release(); ctx->d_lay.release(); ctx->d_bins.release();
+        ctx->d_cnt.release(); ctx->d_out.release(); ctx->d_tot.release(); ctx->d_lay.release(); ctx->d_bins.release(); ctx->d_jtab.release(); ctx->d_jdense.release();
         if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
         cudaStreamDestroy(ctx->stream);
     }
