@@ -96,7 +96,7 @@ struct DevJunc {
     uint32_t* cx_j; uint32_t* cx_d; uint32_t* cx_n;   // complex instances: global junction index, dense junction id
     // per pass
     uint32_t* hot_l; uint32_t* hot_r;           // [D] anchor + 1 of a hot endpoint, 0 otherwise
-    uint32_t* wl;                 // [2 D] hot (junction << 1 | side) items
+    unsigned long long* wl;       // hot units: chunk << 32 | junction << 1 | side
 };
 
 struct Tile { uint32_t e0; int32_t w_lo, w_hi; int32_t pad; };   // first element, site index window [w_lo, w_hi)

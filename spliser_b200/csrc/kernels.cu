@@ -637,7 +637,7 @@ constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u, PS_GLOBAL_BINS = 4u;
 
 // producer-side wait: the single producer lane would otherwise spin on the empty barrier for most of the
 // kernel and steal issue slots from the consumers of the co-resident CTAs
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
     const uint32_t addr = smem_u32(bar);
     for (;;) {
         uint32_t done;
@@ -649,7 +649,7 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
             "}\n"
             : "=r"(done) : "r"(addr), "r"(parity) : "memory");
         if (done) return;
-        __nanosleep(256);
+        __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -697,10 +697,9 @@ __device__ __forceinline__ void k3_consume(const K3Stage& stg, const StageMeta& 
             int* s = &st[u].x; int* e = &en[u].x;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const uint32_t idx = m.p0 + gi * 4 + q;
                 const uint32_t ek = (uint32_t)e[q];
                 const int b = (int)(ek & POS_MASK) - 2;                 // last stabbed position
-                const bool valid = gi < ng && (idx - m.e0) < (m.e1 - m.e0) && s[q] <= b;
+                const bool valid = s[q] <= b;                           // padding (start 0x7f7f7f7f, end 0) and 1-base blocks fail
                 inc[u][q] = valid ? ((ek >> 31) ? 0x10000u : 1u) : 0u;    // invalid blocks add 0 whatever they "hit"
                 e[q] = b - s[q];                                        // d = b - a  (>= 0 when valid)
                 if (valid) { lo = min(lo, s[q]); hi = max(hi, b); }
@@ -915,6 +914,8 @@ __device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph&
 //   k_junc_complex  one thread per complex instance (several N, D or I splits) of a hot junction: the general
 //                   per-read logic (k4_exceptions)
 // ------------------------------------------------------------------------------------------------
+constexpr uint32_t JS_CHUNK = 2048;
+
 __device__ __forceinline__ int site_lower(const DevGraph& g, int chrom, int32_t pos) {
     const int g0 = g.sb_base[chrom], nb = g.sb_base[chrom + 1] - g0 - 1;
     const int s1 = g.cs_off[chrom + 1];
@@ -949,35 +950,41 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, Dev
         }
         jg.hot_l[d] = hl; jg.hot_r[d] = hr;
     }
-    // work list of hot (junction, side) items, one atomic per warp
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        const bool h = (side == 0 ? hl : hr) != 0u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, h);
-        if (!bal) continue;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cnt.work + 2, (uint32_t)__popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (h) jg.wl[base + (uint32_t)__popc(bal & ((1u << lane) - 1u))] = (d << 1) | (uint32_t)side;
+    // work list of hot (junction, side, chunk of simple instances) units; big groups are split so that one warp
+    // never walks more than JS_CHUNK instances
+    if (live && (hl | hr)) {
+        const uint32_t ns = jg.dj_simple[d];
+        if (ns) {
+            const uint32_t nch = (ns + JS_CHUNK - 1) / JS_CHUNK;
+            const uint32_t sides = (hl ? 1u : 0u) + (hr ? 1u : 0u);
+            uint32_t p = atomicAdd(cnt.work + 2, nch * sides);
+            for (int side = 0; side < 2; ++side) {
+                if (!(side == 0 ? hl : hr)) continue;
+                for (uint32_t c = 0; c < nch; ++c) jg.wl[p++] = ((unsigned long long)c << 32) | (d << 1) | (uint32_t)side;
+            }
+        }
     }
 }
+
+
 
 __global__ void __launch_bounds__(256) k_junc_simple(DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
     const bool combine = (mode & FLAG_COMBINE) != 0;
     const int lane = threadIdx.x & 31;
     const uint32_t n_items = cnt.work[2];
     for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items; item += gridDim.x * (blockDim.x >> 5)) {
-        const uint32_t w = jg.wl[item];
+        const unsigned long long w64 = jg.wl[item];
+        const uint32_t w = (uint32_t)w64, chunk = (uint32_t)(w64 >> 32);
         const uint32_t d = w >> 1;
         const int side = (int)(w & 1u);
-        const uint32_t ns = jg.dj_simple[d];
-        if (ns == 0) continue;                                         // only complex instances carry this junction
+        const uint32_t ns_all = jg.dj_simple[d];
+        const uint32_t i0 = chunk * JS_CHUNK, i1 = min(ns_all, i0 + JS_CHUNK);
+        const uint32_t ns = i1 - i0;
         const int32_t l = (int32_t)jg.dj_l[d], r = (int32_t)(jg.dj_rk[d] & POS_MASK);
         const uint32_t k = jg.dj_rk[d] >> 31;
         const int anchor = (int)((side == 0 ? jg.hot_l[d] : jg.hot_r[d]) - 1u);
         const int32_t other = side == 0 ? r : l;
-        const uint32_t off = jg.dj_off[d];
+        const uint32_t off = jg.dj_off[d] + i0;
         for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {     // warp-uniform loop
             const int t = g.rp_site[q];
             if (t < g.own_lo || t >= g.own_hi) continue;
