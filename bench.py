@@ -209,17 +209,21 @@ def main():
     value = reads_all * args.steps / (ms_total * 1e-3)
     nA, nB, nJ, nS, S, E = (st[k] for k in ("n_mblocks_a", "n_mblocks_b", "n_junc_ops", "n_spliced", "n_sites", "n_edges"))
     peak, peak_src = measured_peak()
-    # algorithmic bytes of the v2 layout: 8 B per M block (start, end|class), 8 B per junction, 8 B per spliced read
-    kern = {"k_beta1_stab": (8.0 * (nA + nB), st["ms_beta1"] / args.steps), "k_spliced": (8.0 * nJ, st["ms_spliced"] / args.steps)}
+    # algorithmic bytes per pass of the resident layout: 8 B per M block of the bin-partitioned
+    # stream; the junction kernels read the distinct-junction table (24 B), the grouped simple instances (8 B) and
+    # the complex instances (16 B incl. their read's junction list entry)
+    D, n_simple, n_complex = st["n_distinct_junc"], st["n_simple_junc"], st["n_complex_junc"]
+    kern = {"k_beta1_stab": (8.0 * (nA + nB), st["ms_beta1"] / args.steps),
+            "k_junc_*": (24.0 * D + 8.0 * n_simple + 16.0 * n_complex, st["ms_spliced"] / args.steps)}
     dom = max(kern, key=lambda k: kern[k][1])
     k3_bytes, k3_ms = kern[dom]
     k3_gbs = k3_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
-    path_bytes = 8.0 * (nA + nB) + 8.0 * nJ + 8.0 * nS + 25.0 * S + 12.0 * E
+    path_bytes = kern["k_beta1_stab"][0] + kern["k_junc_*"][0] + 25.0 * S + 12.0 * E
     path_ms = st["ms_total"] / args.steps
-    soa_mb = (8.0 * (nA + nB) + 8.0 * nJ + 8.0 * nS) / 1e6
+    soa_mb = path_bytes / 1e6
 
     if args.profile:
-        print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "kernel_ms": {"beta1_stab": kern["k_beta1_stab"][1], "spliced": kern["k_spliced"][1], "final": st["ms_final"] / args.steps}}))
+        print(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "kernel_ms": {"beta1_stab": kern["k_beta1_stab"][1], "junction_kernels": kern["k_junc_*"][1], "final": st["ms_final"] / args.steps}}))
         sampler.stop()
         ctx.close()
         ranks.close()
@@ -264,9 +268,10 @@ def main():
                      "ms_per_launch": k3_ms, "peak_source": peak_src},
         "roofline_path": {"algorithmic_bytes_per_pass": path_bytes, "ms_per_pass": path_ms,
                           "achieved_gbs": path_bytes / (path_ms * 1e-3) / 1e9, "frac": path_bytes / (path_ms * 1e-3) / 1e9 / peak,
-                          "kernel_ms": {"beta1_stab": kern["k_beta1_stab"][1], "spliced": kern["k_spliced"][1], "alpha+scan+finalize": st["ms_final"] / args.steps},
+                          "kernel_ms": {"beta1_stab": kern["k_beta1_stab"][1], "junction_kernels": kern["k_junc_*"][1], "alpha+scan+finalize": st["ms_final"] / args.steps},
                           "kernel_gbs": {k: (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0) for k, v in kern.items()}},
-        "kernel_path": {"n_mblocks_a": int(nA), "n_mblocks_b": int(nB), "n_junction_ops": int(nJ), "n_spliced_reads": int(nS), "n_edges": int(E)},
+        "kernel_path": {"n_mblocks_a": int(nA), "n_mblocks_b": int(nB), "n_junction_ops": int(nJ), "n_spliced_reads": int(nS), "n_edges": int(E),
+                        "n_distinct_junctions": int(D), "n_simple_junction_instances": int(n_simple), "n_complex_junction_instances": int(n_complex)},
         "checksum": {"beta1": int(table.beta1.sum()), "beta2simple": int(table.beta2simple.sum()), "alpha": int(table.alpha.sum())},
     }
     sampler.stop()

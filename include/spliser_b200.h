@@ -185,6 +185,9 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_MS_GRAPH     16   /* host: site table + competing-site graph construction          */
 #define SPL_STAT_MS_UPLOAD    17   /* host wall ms until records are uploaded and expanded           */
 #define SPL_STAT_MS_COUNT     18   /* host wall ms of the counting pass + result download            */
+#define SPL_STAT_N_DISTINCT_J 19   /* distinct (chromosome, l, r, class) junctions of the sample     */
+#define SPL_STAT_N_SIMPLE_J   20   /* junction instances of block-N-block reads (aggregated path)    */
+#define SPL_STAT_N_COMPLEX_J  21   /* junction instances handled per read                            */
 int spl_last_stats(const spl_ctx* ctx, double* stats_out);
 
 /* ---- BAM utilities (used by tests / benchmarks to make synthetic inputs) -------------------- */

@@ -398,6 +398,8 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     jg.n_complex = ctx->h_tot[14];
+    ctx->stats[SPL_STAT_N_DISTINCT_J] = (double)D; ctx->stats[SPL_STAT_N_SIMPLE_J] = (double)n_simple;
+    ctx->stats[SPL_STAT_N_COMPLEX_J] = (double)jg.n_complex;
     if (ctx->h_tot[15]) return ctx->fail(SPL_ERR_CUDA, "junction table overflow (internal sizing error)");
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
