@@ -33,7 +33,8 @@ def is_stale() -> bool:
 def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lz"]
+    extra = os.environ.get("SPLISER_NVCC_FLAGS", "").split()      # tuning experiments only (e.g. -DSPL_K3_DENSE=8)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + SOURCES + ["-lz"]
     res = subprocess.run(cmd, cwd=CSRC, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n%s\n%s" % (res.stdout, res.stderr))

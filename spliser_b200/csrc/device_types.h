@@ -4,7 +4,10 @@
 
 namespace spl {
 
-constexpr int BIN_SHIFT = 8;            // 256 bp genomic bins (block partition, site index)
+#ifndef SPL_BIN_SHIFT
+#define SPL_BIN_SHIFT 8
+#endif
+constexpr int BIN_SHIFT = SPL_BIN_SHIFT;   // 256 bp genomic bins (block partition, site index)
 
 // One work tile = up to CHUNK_READS consecutive records of one chromosome.  The expansion kernels
 // fill the bases/counts; the hint kernel fills the site windows.  K3 streams the chunk's A blocks,

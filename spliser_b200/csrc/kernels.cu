@@ -677,7 +677,10 @@ struct K3Smem {
 // class); long ranges (sparse coverage, displaced blocks of spliced reads) use a per-lane search.
 // ------------------------------------------------------------------------------------------------
 constexpr int K3_GROUPS = 2;     // int4 groups (4 blocks each) per thread and pass
-constexpr int K3_DENSE = 12;     // narrowed ranges longer than this use the per-lane search path
+#ifndef SPL_K3_DENSE
+#define SPL_K3_DENSE 12
+#endif
+constexpr int K3_DENSE = SPL_K3_DENSE;     // narrowed ranges longer than this use the per-lane search path
 
 __device__ __forceinline__ void k3_consume(const K3Stage& stg, const StageMeta& m, const int32_t* __restrict__ sp,
                                            const DevGraph& g, const DevCounters& cnt) {
