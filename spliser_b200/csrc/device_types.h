@@ -5,9 +5,13 @@
 namespace spl {
 
 #ifndef SPL_BIN_SHIFT
-#define SPL_BIN_SHIFT 8
+#define SPL_BIN_SHIFT 7
 #endif
-constexpr int BIN_SHIFT = SPL_BIN_SHIFT;   // 256 bp genomic bins (block partition, site index)
+#ifndef SPL_SB_SHIFT
+#define SPL_SB_SHIFT 6
+#endif
+constexpr int BIN_SHIFT = SPL_BIN_SHIFT;   // 128 bp genomic bins of the block partition (stream C)
+constexpr int SB_SHIFT = SPL_SB_SHIFT;     // 64 bp bins of the direct-address site index
 
 // One work tile = up to CHUNK_READS consecutive records of one chromosome.  The expansion kernels
 // fill the bases/counts; the hint kernel fills the site windows.  K3 streams the chunk's A blocks,
@@ -30,8 +34,8 @@ struct DevGraph {
     const int32_t* site_pos;            // [n_sites + 8], tail padded with INT32_MAX
     const uint8_t* site_cls;            // [n_sites]
     const uint8_t* site_hot;            // [n_sites + 32] 1 = some site in the reverse-partner list anchored here has competitors
-    // direct-address index of the site table: for chromosome c and bin b = pos >> BIN_SHIFT,
-    // sb_off[sb_base[c] + b] = first global site index with position >= b << BIN_SHIFT (one sentinel per chromosome)
+    // direct-address index of the site table: for chromosome c and bin b = pos >> SB_SHIFT,
+    // sb_off[sb_base[c] + b] = first global site index with position >= b << SB_SHIFT (one sentinel per chromosome)
     const int32_t* sb_base;             // [n_chrom+1]
     const int32_t* sb_off;              // [sb_base[n_chrom] + 64]
     const int32_t *pt_off, *pt_site;    // Partners (site indices)

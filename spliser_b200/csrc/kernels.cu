@@ -922,7 +922,7 @@ constexpr uint32_t JS_CHUNK = 2048;
 __device__ __forceinline__ int site_lower(const DevGraph& g, int chrom, int32_t pos) {
     const int g0 = g.sb_base[chrom], nb = g.sb_base[chrom + 1] - g0 - 1;
     const int s1 = g.cs_off[chrom + 1];
-    int i = g.sb_off[g0 + min(max(pos, 0) >> BIN_SHIFT, nb)];
+    int i = g.sb_off[g0 + min(max(pos, 0) >> SB_SHIFT, nb)];
     while (i < s1 && g.site_pos[i] < pos) ++i;
     return i;
 }

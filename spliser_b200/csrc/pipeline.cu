@@ -136,11 +136,11 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     std::vector<int32_t> sb_base((size_t)h.n_chrom + 1, 0), sb_off;
     for (int32_t ch = 0; ch < h.n_chrom; ++ch) {
         const int64_t s0 = h.cs_off[(size_t)ch], s1 = h.cs_off[(size_t)ch + 1];
-        const int64_t nb = s1 > s0 ? (int64_t)(std::max(h.pos[(size_t)s1 - 1], 0) >> BIN_SHIFT) + 1 : 0;
+        const int64_t nb = s1 > s0 ? (int64_t)(std::max(h.pos[(size_t)s1 - 1], 0) >> SB_SHIFT) + 1 : 0;
         sb_base[(size_t)ch] = (int32_t)sb_off.size();
         int64_t i = s0;
         for (int64_t b = 0; b < nb; ++b) {
-            while (i < s1 && h.pos[(size_t)i] < (int32_t)(b << BIN_SHIFT)) ++i;
+            while (i < s1 && h.pos[(size_t)i] < (int32_t)(b << SB_SHIFT)) ++i;
             sb_off.push_back((int32_t)i);
         }
         sb_off.push_back((int32_t)s1);                                 // sentinel: positions beyond the last bin
