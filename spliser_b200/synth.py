@@ -52,6 +52,7 @@ class SynthConfig:
     fragment_mean: int = 300
     min_anchor: int = 8
     organelle_share: float = 0.0      # share of reads on contigs shorter than 1 Mb
+    extra_isoforms: int = 0           # per multi-exon gene: isoforms with random exon skipping / shifted boundaries (dense loci)
 
     def key(self) -> str:
         return hashlib.sha1(repr(sorted(asdict(self).items())).encode()).hexdigest()[:16]
@@ -77,7 +78,7 @@ def config_c3_tile(n_records=25_000_000, tile=0, n_tiles=8) -> SynthConfig:
 def config_c5() -> SynthConfig:
     return SynthConfig(name="c5", seed=20260005, contigs=(("L1", 2_000_000),), n_records=1_000_000, read_len=100,
                        genes_per_mb=1.0, mean_exons=400.0, exon_median=120.0, intron_median=900.0, intron_max=20000,
-                       frac_alt_site=1.0, frac_exon_skip=1.0)
+                       frac_alt_site=1.0, frac_exon_skip=1.0, extra_isoforms=12)
 
 
 def config_small(n_records=20000, seed=1, stranded=False, paired=False) -> SynthConfig:
@@ -202,6 +203,24 @@ def _finish_models(rng, cfg, n_genes, n_ex, ex_len, in_len, g_off, g_start):
         off2 = off - np.arange(len(pick) + 1)
         t_off.append(base + off2)
         base += int(keepm.sum())
+    # dense alternative combinations (configs[4]): several isoforms per gene, each skipping a random subset of the
+    # internal exons and moving some exon boundaries
+    if cfg.extra_isoforms:
+        for gidx in multi:
+            e0, e1 = int(g_off[gidx]), int(g_off[gidx + 1])
+            for _ in range(cfg.extra_isoforms):
+                keep = rng.random(e1 - e0) > 0.3
+                keep[0] = keep[-1] = True
+                st = ex_start[e0:e1][keep].copy()
+                ln = ex_len[e0:e1][keep].copy()
+                sh = rng.integers(0, 40, size=len(st)) * (rng.random(len(st)) < 0.25)
+                sh = np.minimum(sh, ln - 20) * (ln > 40)
+                side = rng.random(len(st)) < 0.5
+                st = st + np.where(side, 0, sh)
+                ln = ln - sh
+                exs.append(st); exl.append(ln); tstr.append(strand[gidx:gidx + 1]); tgene.append(np.array([gidx]))
+                t_off.append(np.array([base, base + len(st)], dtype=np.int64))
+                base += len(st)
     ex_start_all = np.concatenate(exs)
     ex_len_all = np.concatenate(exl)
     offs = [t_off[0]] + [o[1:] for o in t_off[1:]]

@@ -165,3 +165,30 @@ def test_tiles_concatenate_to_the_untiled_result(built_library):
         lo, hi = S * ti // n_tiles, S * (ti + 1) // n_tiles
         b1[lo:hi], b2[lo:hi], sse[lo:hi] = t.beta1[lo:hi], t.beta2simple[lo:hi], t.sse[lo:hi]
     assert np.array_equal(b1, ref.beta1) and np.array_equal(b2, ref.beta2simple) and np.array_equal(sse, ref.sse)
+
+
+@pytest.mark.parametrize("shape", ["c3_tile", "c5_dense_locus", "c2_stranded"])
+def test_config_shaped_workloads_vs_c_oracle(ctx, shape):
+    """The other BASELINE.json configs at depths the C oracle finishes in seconds:
+    configs[2] (one GRCh38-scale tile: long introns up to 500 kb), configs[4] (dense alternative-splicing locus,
+    --beta2Cryptic) and configs[1] (TAIR10 contigs, stranded rf)."""
+    from oracle import c_oracle
+    from spliser_b200 import synth
+    if shape == "c3_tile":
+        cfg = synth.config_c3_tile(300_000, tile=3)
+        flags_extra = 0
+    elif shape == "c5_dense_locus":
+        cfg = synth.config_c5()
+        cfg.n_records = 150_000
+        flags_extra = 4
+    else:
+        cfg = synth.config_c2(500_000)
+        flags_extra = 0
+    w = synth.generate(cfg)
+    flags = w.flags | flags_extra
+    want = c_oracle.process(w.records, len(w.chroms), w.junctions, flags, threads=8)
+    got = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, flags))
+    assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
+    assert int(want["beta1"].sum()) > 0 and int(want["beta2simple"].sum()) > 0
+    if flags_extra:
+        assert int(want["beta2cryptic"].sum()) > 0
