@@ -104,6 +104,7 @@ struct DevJunc {
     // per pass
     uint32_t* hot_l; uint32_t* hot_r;           // [D] anchor + 1 of a hot endpoint, 0 otherwise
     unsigned long long* wl;       // hot units: chunk << 32 | junction << 1 | side
+    uint32_t* cxl_j; uint32_t* cxl_a;           // [2 n_complex] per pass: complex instances of hot junctions (junction index, anchor | side << 31)
 };
 
 struct Tile { uint32_t e0; int32_t w_lo, w_hi; int32_t pad; };   // first element, site index window [w_lo, w_hi)

@@ -1016,18 +1016,38 @@ __global__ void __launch_bounds__(256) k_junc_simple(DevJunc jg, DevGraph g, Dev
     }
 }
 
-__global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
+// complex instances: (1) compact the ones whose junction has a hot endpoint into a dense list (one atomic per
+// warp), (2) run the per-read logic with every lane busy
+__global__ void __launch_bounds__(256) k_junc_complex_filter(DevJunc jg, DevCounters cnt) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= jg.n_complex) return;
-    const uint32_t d = jg.cx_d[i];
-    const uint32_t hl = jg.hot_l[d], hr = jg.hot_r[d];
-    if (!(hl | hr)) return;
-    const bool combine = (mode & FLAG_COMBINE) != 0;
-    const uint32_t j = jg.cx_j[i];
-#pragma unroll 1
+    uint32_t hl = 0, hr = 0, j = 0;
+    if (i < jg.n_complex) {
+        const uint32_t d = jg.cx_d[i];
+        hl = jg.hot_l[d]; hr = jg.hot_r[d];
+        j = jg.cx_j[i];
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
     for (int side = 0; side < 2; ++side) {
         const uint32_t a1 = side == 0 ? hl : hr;
-        if (a1) k4_exceptions(soa, g, cnt, j, (int)(a1 - 1u), side, combine);
+        const uint32_t bal = __ballot_sync(0xffffffffu, a1 != 0u);
+        if (!bal) continue;
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(cnt.work + 3, (uint32_t)__popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (a1) {
+            const uint32_t p = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
+            jg.cxl_j[p] = j; jg.cxl_a[p] = (a1 - 1u) | ((uint32_t)side << 31);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
+    const bool combine = (mode & FLAG_COMBINE) != 0;
+    const uint32_t n = cnt.work[3];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t a = jg.cxl_a[i];
+        k4_exceptions(soa, g, cnt, jg.cxl_j[i], (int)(a & POS_MASK), (int)(a >> 31), combine);
     }
 }
 
@@ -1267,7 +1287,10 @@ void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint3
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     k_junc_simple<<<sms * 8, 256, 0, st>>>(jg, g, cnt, flags);
-    if (jg.n_complex) k_junc_complex<<<(jg.n_complex + 255) / 256, 256, 0, st>>>(soa, jg, g, cnt, flags);
+    if (jg.n_complex) {
+        k_junc_complex_filter<<<(jg.n_complex + 255) / 256, 256, 0, st>>>(jg, cnt);
+        k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags);
+    }
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;
@@ -1276,6 +1299,6 @@ void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags
     k_span_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(out.span_blk, nblk);
     k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags);
 }
-int kernel_launch_count_per_pass() { return 8; }   // alpha_reduce, beta1_stab, junc_lookup, junc_simple, junc_complex, span_blocksum, span_scan, finalize
+int kernel_launch_count_per_pass() { return 9; }   // alpha_reduce, beta1_stab, junc_lookup, junc_simple, junc_complex_filter, junc_complex, span_blocksum, span_scan, finalize
 
 }  // namespace spl

@@ -382,7 +382,8 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
                      o_a0 = dc.take<int32_t>(n_simple + 2), o_en = dc.take<int32_t>(n_simple + 2),
                      o_cj = dc.take<uint32_t>(nJ - std::min(nJ, n_simple) + 2), o_cd = dc.take<uint32_t>(nJ - std::min(nJ, n_simple) + 2),
                      o_hl = dc.take<uint32_t>(D + 2), o_hr = dc.take<uint32_t>(D + 2),
-                     o_wl = dc.take<unsigned long long>(2 * D + 2 * (n_simple / 2048 + 1) + 8);
+                     o_wl = dc.take<unsigned long long>(2 * D + 2 * (n_simple / 2048 + 1) + 8),
+                     o_xj = dc.take<uint32_t>(2 * (nJ - std::min(nJ, n_simple)) + 2), o_xa = dc.take<uint32_t>(2 * (nJ - std::min(nJ, n_simple)) + 2);
         CU(ctx->d_jdense.reserve(dc.off + 256));
         char* db = (char*)ctx->d_jdense.p;
         jg.D = (uint32_t)D;
@@ -391,6 +392,7 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
         jg.gi_a0 = (int32_t*)(db + o_a0); jg.gi_end = (int32_t*)(db + o_en);
         jg.cx_j = (uint32_t*)(db + o_cj); jg.cx_d = (uint32_t*)(db + o_cd);
         jg.hot_l = (uint32_t*)(db + o_hl); jg.hot_r = (uint32_t*)(db + o_hr); jg.wl = (unsigned long long*)(db + o_wl);
+        jg.cxl_j = (uint32_t*)(db + o_xj); jg.cxl_a = (uint32_t*)(db + o_xa);
     }
     launch_junction_groups_b(soa, jg, ctx->n_chrom_loaded, d_jtot, ctx->stream);
     CU(cudaGetLastError());
