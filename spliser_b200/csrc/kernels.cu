@@ -415,8 +415,24 @@ __global__ void __launch_bounds__(256) k_bin_pass(const Chunk* __restrict__ chun
         uint32_t slot;
         if (rel >= 0 && rel < BIN_HIST) slot = base[rel] + atomicAdd(&hist[rel], 1u);
         else slot = atomicAdd(bins.bin_cursor + gbase + bin0 + rel, 1u);
+        const uint32_t ek = soa.m_endk[e];
         bins.c_start[slot] = st;
-        bins.c_endk[slot] = soa.m_endk[e];
+        // stream C carries (start, len1 | class<<31) with len1 = end - 1 - start: site p is covered (S:469) iff
+        // (uint32)(p - start) < len1; blocks of one base have len1 = 0 and never match
+        bins.c_endk[slot] = (uint32_t)max((int32_t)(ek & POS_MASK) - 1 - st, 0) | (ek & 0x80000000u);
+    }
+}
+
+// the slots that pad a chromosome to a whole number of tiles: never-matching elements placed at the chromosome's
+// largest block start, so that they do not widen the site window of the warp that holds them
+__global__ void __launch_bounds__(256) k_bin_fill_pad(DevBins bins) {
+    const int c = blockIdx.x;
+    if (!bins.chrom_tot[c]) return;
+    const uint32_t pad = (K3_TILE - bins.chrom_tot[c] % K3_TILE) % K3_TILE;
+    const uint32_t end = bins.bin_off[bins.chrom_bin_base[c + 1]];
+    for (uint32_t i = threadIdx.x; i < pad; i += 256) {
+        bins.c_start[end - pad + i] = (int32_t)bins.chrom_ext[c];
+        bins.c_endk[end - pad + i] = 0u;
     }
 }
 
@@ -637,17 +653,17 @@ constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u, PS_GLOBAL_BINS = 4u;
 
 // producer-side wait: the single producer lane would otherwise spin on the empty barrier for most of the
 // kernel and steal issue slots from the consumers of the co-resident CTAs
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 128) {
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 512) {
     const uint32_t addr = smem_u32(bar);
     for (;;) {
         uint32_t done;
         asm volatile(
             "{\n"
             ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"     // suspend-time hint: the thread sleeps in hardware
             "selp.u32 %0, 1, 0, P1;\n"
             "}\n"
-            : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+            : "=r"(done) : "r"(addr), "r"(parity), "r"(ns * 4u) : "memory");
         if (done) return;
         __nanosleep(ns);
     }
@@ -676,73 +692,64 @@ struct K3Smem {
 // registers and summed across the warp with one redux.sync per site -> one RED per (warp, site,
 // class); long ranges (sparse coverage, displaced blocks of spliced reads) use a per-lane search.
 // ------------------------------------------------------------------------------------------------
-constexpr int K3_GROUPS = 2;     // int4 groups (4 blocks each) per thread and pass
+constexpr int K3_GROUPS = 2;     // int4 groups (4 blocks each) per thread: a warp owns 256 consecutive elements of the tile
 #ifndef SPL_K3_DENSE
 #define SPL_K3_DENSE 12
 #endif
 constexpr int K3_DENSE = SPL_K3_DENSE;     // narrowed ranges longer than this use the per-lane search path
+static_assert(K3_TILE == PS_CONSUMERS * K3_GROUPS * 4, "one pass of the consumer warps covers a tile");
 
 __device__ __forceinline__ void k3_consume(const K3Stage& stg, const StageMeta& m, const int32_t* __restrict__ sp,
                                            const DevGraph& g, const DevCounters& cnt) {
-    const int lane = threadIdx.x & 31;
-    const uint32_t ng = m.n >> 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int4* gs = reinterpret_cast<const int4*>(stg.start);
-    const int4* ge = reinterpret_cast<const int4*>(stg.endk);
-    for (uint32_t base = 0; base < ng; base += PS_CONSUMERS * K3_GROUPS) {       // uniform trip count
-        int4 st[K3_GROUPS], en[K3_GROUPS];
-        uint32_t inc[K3_GROUPS][4];
-        int lo = INT_MAX, hi = INT_MIN;
+    const uint4* gw = reinterpret_cast<const uint4*>(stg.endk);
+    int a[K3_GROUPS * 4];
+    uint32_t len[K3_GROUPS * 4], inc[K3_GROUPS * 4];
+    int lo = INT_MAX, hi = INT_MIN;
 #pragma unroll
-        for (int u = 0; u < K3_GROUPS; ++u) {
-            const uint32_t gi = base + u * PS_CONSUMERS + threadIdx.x;
-            if (gi < ng) { st[u] = gs[gi]; en[u] = ge[gi]; }
-            else { st[u] = make_int4(INT_MAX, INT_MAX, INT_MAX, INT_MAX); en[u] = make_int4(0, 0, 0, 0); }
-            int* s = &st[u].x; int* e = &en[u].x;
+    for (int u = 0; u < K3_GROUPS; ++u) {
+        const int gi = (warp * K3_GROUPS + u) * 32 + lane;
+        const int4 st = gs[gi];
+        const uint4 w = gw[gi];
+        const int sv[4] = {st.x, st.y, st.z, st.w};
+        const uint32_t wv[4] = {w.x, w.y, w.z, w.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const uint32_t ek = (uint32_t)e[q];
-                const int b = (int)(ek & POS_MASK) - 2;                 // last stabbed position
-                const bool valid = s[q] <= b;                           // padding (start 0x7f7f7f7f, end 0) and 1-base blocks fail
-                inc[u][q] = valid ? ((ek >> 31) ? 0x10000u : 1u) : 0u;    // invalid blocks add 0 whatever they "hit"
-                e[q] = b - s[q];                                        // d = b - a  (>= 0 when valid)
-                if (valid) { lo = min(lo, s[q]); hi = max(hi, b); }
+        for (int q = 0; q < 4; ++q) {
+            const int e = u * 4 + q;
+            a[e] = sv[q];
+            len[e] = wv[q] & POS_MASK;                       // stabbed positions: start <= p < start + len
+            inc[e] = 1u + (wv[q] >> 31) * 0xffffu;           // class 0 counts in the low half-word, class 1 in the high one
+            lo = min(lo, sv[q]);
+            hi = max(hi, sv[q] + (int)len[e]);
+        }
+    }
+    const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi) - 1;
+    if (wlo > whi) return;
+    int i0, i1;
+    bound_pair_i32(sp, m.w_lo, m.w_hi, wlo, whi, i0, i1);
+    if (i0 >= i1) return;
+    if (i1 - i0 <= K3_DENSE) {
+        for (int s = i0; s < i1; ++s) {                           // warp-uniform loop
+            const int p = sp[s];
+            uint32_t c = 0;
+#pragma unroll
+            for (int e = 0; e < K3_GROUPS * 4; ++e)
+                c += ((uint32_t)(p - a[e]) < len[e]) ? inc[e] : 0u;
+            c = __reduce_add_sync(0xffffffffu, c);
+            if (lane == 0 && c) {
+                if (c & 0xffffu) atomicAdd(cnt.cov + s, c & 0xffffu);
+                if (c >> 16) atomicAdd(cnt.cov + g.n_sites + s, c >> 16);
             }
         }
-        const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi);
-        if (wlo > whi) continue;
-        int i0, i1;
-        bound_pair_i32(sp, m.w_lo, m.w_hi, wlo, whi, i0, i1);
-        if (i0 >= i1) continue;
-        if (i1 - i0 <= K3_DENSE) {
-            for (int s = i0; s < i1; ++s) {                           // warp-uniform loop
-                const int p = sp[s];
-                uint32_t c = 0;
+    } else {                                                       // wide window: per-lane search
 #pragma unroll
-                for (int u = 0; u < K3_GROUPS; ++u) {
-                    const int* a = &st[u].x; const int* d = &en[u].x;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q)
-                        c += ((uint32_t)p - (uint32_t)a[q] <= (uint32_t)d[q]) ? inc[u][q] : 0u;
-                }
-                c = __reduce_add_sync(0xffffffffu, c);
-                if (lane == 0 && c) {
-                    if (c & 0xffffu) atomicAdd(cnt.cov + s, c & 0xffffu);
-                    if (c >> 16) atomicAdd(cnt.cov + g.n_sites + s, c >> 16);
-                }
-            }
-        } else {                                                       // wide window: per-lane search
-#pragma unroll
-            for (int u = 0; u < K3_GROUPS; ++u) {
-                const int* a = &st[u].x; const int* d = &en[u].x;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    if (!inc[u][q]) continue;
-                    const uint32_t k = inc[u][q] >> 16;
-                    const int b = a[q] + d[q];
-                    for (int s = lower_bound_i32(sp, i0, i1, a[q]); s < i1 && sp[s] <= b; ++s)
-                        atomicAdd(cnt.cov + k * g.n_sites + s, 1u);
-                }
-            }
+        for (int e = 0; e < K3_GROUPS * 4; ++e) {
+            if (!len[e]) continue;
+            const uint32_t k = inc[e] >> 16;
+            const int b = a[e] + (int)len[e] - 1;
+            for (int s = lower_bound_i32(sp, i0, i1, a[e]); s < i1 && sp[s] <= b; ++s)
+                atomicAdd(cnt.cov + k * g.n_sites + s, 1u);
         }
     }
 }
@@ -1207,8 +1214,6 @@ void launch_bin_partition(const Chunk* chunks, int n_chunks, DevSoA soa, DevBins
     cudaStream_t st = (cudaStream_t)stream;
     if (n_chunks <= 0 || bins.total_bins == 0) return;
     cudaMemsetAsync(bins.bin_off, 0, ((size_t)bins.total_bins + 1) * 4, st);
-    cudaMemsetAsync(bins.c_start, 0x7f, (size_t)bins.nC * 4, st);        // padding never matches: start = 0x7f7f7f7f, end = 0
-    cudaMemsetAsync(bins.c_endk, 0, (size_t)bins.nC * 4, st);
     k_bin_pad<<<(bins.n_chrom + 127) / 128, 128, 0, st>>>(bins);
     k_bin_pass<false><<<2 * n_chunks, 256, 0, st>>>(chunks, soa, bins);
     const uint32_t n = bins.total_bins + 1;                              // the extra slot receives the total
@@ -1217,6 +1222,7 @@ void launch_bin_partition(const Chunk* chunks, int n_chunks, DevSoA soa, DevBins
     k_scan_sums<<<1, 1024, 0, st>>>(bins.scan_tmp, nblk, bins.scan_tmp + nblk);
     k_scan_apply<<<nblk, 256, 0, st>>>(bins.bin_off, n, bins.scan_tmp, bins.bin_cursor);
     k_bin_pass<true><<<2 * n_chunks, 256, 0, st>>>(chunks, soa, bins);
+    k_bin_fill_pad<<<bins.n_chrom, 256, 0, st>>>(bins);
 }
 void launch_tile_hints(DevBins bins, DevGraph g, void* stream) {
     if (bins.n_tiles) k_tile_hints<<<(bins.n_tiles + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bins, g);

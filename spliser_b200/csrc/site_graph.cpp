@@ -13,6 +13,8 @@
 #include "site_graph.h"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -417,6 +419,115 @@ void build_clean_sorted(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
     TICK("csr");
 }
 
+
+// Sites of different chromosomes never interact (the chromosome is the top sort key and partners share the
+// junction's chromosome), so the clean build runs one independent sub-problem per chromosome on a small pool of
+// host threads and concatenates the pieces with shifted indices.
+void build_clean_by_chromosome(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right,
+                               const uint8_t* j_strand, bool stranded, SiteGraph& g) {
+    const size_t J = (size_t)n_junc, NC = (size_t)n_chrom;
+    std::vector<int64_t> roff(NC + 1, 0);
+    for (size_t i = 0; i < J; ++i) roff[(size_t)j_chrom[i] + 1]++;
+    size_t n_used = 0;
+    for (size_t c = 0; c < NC; ++c) { n_used += roff[c + 1] != 0; roff[c + 1] += roff[c]; }
+    unsigned hw = std::thread::hardware_concurrency();
+    if (const char* e = std::getenv("SPLISER_GRAPH_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+    if (n_used <= 1 || J < 4096 || hw <= 1) {
+        build_clean_sorted(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, stranded, g);
+        finish_graph(g);
+        return;
+    }
+    // rows of each chromosome, in table order (keeps first-appearance semantics)
+    std::vector<int32_t> rows(J), lft(J), rgt(J);
+    std::vector<uint8_t> strd(J);
+    {
+        std::vector<int64_t> cur(roff.begin(), roff.end() - 1);
+        for (size_t i = 0; i < J; ++i) {
+            const size_t d = (size_t)cur[(size_t)j_chrom[i]]++;
+            rows[d] = (int32_t)i; lft[d] = j_left[i]; rgt[d] = j_right[i]; strd[d] = j_strand[i];
+        }
+    }
+    std::vector<int32_t> order;                      // chromosomes with rows, biggest first
+    for (size_t c = 0; c < NC; ++c) if (roff[c + 1] > roff[c]) order.push_back((int32_t)c);
+    std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
+        return roff[(size_t)a + 1] - roff[(size_t)a] > roff[(size_t)b + 1] - roff[(size_t)b];
+    });
+    std::vector<SiteGraph> piece(NC);
+    std::atomic<size_t> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const size_t k = next.fetch_add(1);
+            if (k >= order.size()) return;
+            const size_t c = (size_t)order[k];
+            const size_t r0 = (size_t)roff[c], n = (size_t)(roff[c + 1] - roff[c]);
+            std::vector<int32_t> zero(n, 0);
+            build_clean_sorted(1, (int64_t)n, zero.data(), lft.data() + r0, rgt.data() + r0, strd.data() + r0, stranded, piece[c]);
+            finish_graph(piece[c]);
+        }
+    };
+    const size_t nt = std::min<size_t>(std::min<size_t>(hw, 16), order.size());
+    std::vector<std::thread> pool;
+    for (size_t t = 1; t < nt; ++t) pool.emplace_back(worker);
+    worker();
+    for (auto& t : pool) t.join();
+    // ---- concatenate
+    g = SiteGraph();
+    g.n_chrom = n_chrom;
+    g.cs_off.assign(NC + 1, 0);
+    size_t S = 0, E = 0, C = 0, RP = 0;
+    for (size_t c = 0; c < NC; ++c) {
+        const SiteGraph& p = piece[c];
+        g.cs_off[c] = (int64_t)S;
+        S += (size_t)p.n_sites; E += p.pc_pos.size(); C += p.cp_pos.size(); RP += p.rp_site.size();
+    }
+    g.cs_off[NC] = (int64_t)S;
+    g.n_sites = (int64_t)S;
+    g.chrom.resize(S); g.pos.resize(S); g.strand.resize(S); g.cls.resize(S); g.first_line.resize(S);
+    g.pt_off.resize(S + 1); g.pt_site.resize(E); g.pc_pos.resize(E);
+    g.cp_off.resize(S + 1); g.cp_pos.resize(C);
+    g.rp_off.resize(S + 1); g.rp_site.resize(RP);
+    g.inc_off.resize(S + 1); g.inc_line.resize(2 * J);
+    g.einc_off.resize(E + 1); g.einc_line.resize(2 * J);
+    std::vector<size_t> s0(NC + 1, 0), e0(NC + 1, 0), c0(NC + 1, 0), q0(NC + 1, 0), l0(NC + 1, 0);
+    for (size_t c = 0; c < NC; ++c) {
+        const SiteGraph& p = piece[c];
+        s0[c + 1] = s0[c] + (size_t)p.n_sites; e0[c + 1] = e0[c] + p.pc_pos.size(); c0[c + 1] = c0[c] + p.cp_pos.size();
+        q0[c + 1] = q0[c] + p.rp_site.size(); l0[c + 1] = l0[c] + p.inc_line.size();
+    }
+    std::atomic<size_t> nextm{0};
+    auto merger = [&]() {
+        for (;;) {
+            const size_t k = nextm.fetch_add(1);
+            if (k >= order.size()) return;
+            const size_t c = (size_t)order[k];
+            const SiteGraph& p = piece[c];
+            const size_t n = (size_t)p.n_sites, so = s0[c], eo = e0[c], co = c0[c], qo = q0[c], lo = l0[c];
+            const int32_t* rw = rows.data() + roff[c];
+            for (size_t i = 0; i < n; ++i) {
+                g.chrom[so + i] = (int32_t)c; g.pos[so + i] = p.pos[i]; g.strand[so + i] = p.strand[i]; g.cls[so + i] = p.cls[i];
+                g.first_line[so + i] = rw[p.first_line[i]];
+                g.pt_off[so + i] = p.pt_off[i] + (int64_t)eo; g.cp_off[so + i] = p.cp_off[i] + (int64_t)co;
+                g.rp_off[so + i] = p.rp_off[i] + (int64_t)qo; g.inc_off[so + i] = p.inc_off[i] + (int64_t)lo;
+            }
+            for (size_t x = 0; x < p.pc_pos.size(); ++x) {
+                g.pt_site[eo + x] = p.pt_site[x] + (int32_t)so; g.pc_pos[eo + x] = p.pc_pos[x];
+                g.einc_off[eo + x] = p.einc_off[x] + (int64_t)lo;
+            }
+            for (size_t x = 0; x < p.cp_pos.size(); ++x) g.cp_pos[co + x] = p.cp_pos[x];
+            for (size_t x = 0; x < p.rp_site.size(); ++x) g.rp_site[qo + x] = p.rp_site[x] + (int32_t)so;
+            for (size_t x = 0; x < p.inc_line.size(); ++x) g.inc_line[lo + x] = rw[p.inc_line[x]];
+            for (size_t x = 0; x < p.einc_line.size(); ++x) g.einc_line[lo + x] = rw[p.einc_line[x]];
+        }
+    };
+    pool.clear();
+    for (size_t t = 1; t < nt; ++t) pool.emplace_back(merger);
+    merger();
+    for (auto& t : pool) t.join();
+    g.pt_off[S] = (int64_t)E; g.cp_off[S] = (int64_t)C; g.rp_off[S] = (int64_t)RP; g.inc_off[S] = (int64_t)(2 * J);
+    g.einc_off[E] = (int64_t)(2 * J);
+    g.pc_off = g.pt_off;
+}
+
 }  // namespace
 
 std::string build_site_graph(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left,
@@ -435,13 +546,10 @@ std::string build_site_graph(int32_t n_chrom, int64_t n_junc, const int32_t* j_c
     }
     if (!b.emulate) {
         const auto t0 = std::chrono::steady_clock::now();
-        build_clean_sorted(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, stranded, g);
-        const auto t1 = std::chrono::steady_clock::now();
-        finish_graph(g);
+        build_clean_by_chromosome(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, stranded, g);
         if (std::getenv("SPLISER_TIMING")) {
             const auto t2 = std::chrono::steady_clock::now();
-            fprintf(stderr, "site graph: sorted build %.2f ms, competitors+reverse index %.2f ms\n",
-                    std::chrono::duration<double, std::milli>(t1 - t0).count(), std::chrono::duration<double, std::milli>(t2 - t1).count());
+            fprintf(stderr, "site graph: clean build %.2f ms\n", std::chrono::duration<double, std::milli>(t2 - t0).count());
         }
         return "";
     }
