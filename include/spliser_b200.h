@@ -188,6 +188,7 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_N_DISTINCT_J 19   /* distinct (chromosome, l, r, class) junctions of the sample     */
 #define SPL_STAT_N_SIMPLE_J   20   /* junction instances of block-N-block reads (aggregated path)    */
 #define SPL_STAT_N_COMPLEX_J  21   /* junction instances handled per read                            */
+#define SPL_STAT_GRAPH_DEVICE 22   /* 1 = site table + graph built on the device (clean regime), 0 = host emulation */
 int spl_last_stats(const spl_ctx* ctx, double* stats_out);
 
 /* ---- BAM utilities (used by tests / benchmarks to make synthetic inputs) -------------------- */

@@ -198,6 +198,21 @@ class SiteTable:
         return chr(b) if b else ""
 
 
+class _ResultOwner:
+    """Owns one spl_result handle."""
+
+    def __init__(self, lib, h):
+        self._lib, self._h = lib, h
+
+    def __del__(self):
+        h, self._h = self._h, None
+        if h:
+            try:
+                self._lib.spl_result_free(h)
+            except Exception:
+                pass
+
+
 class SpliserError(RuntimeError):
     pass
 
@@ -249,29 +264,31 @@ class Context:
 
     # ---- process -----------------------------------------------------------------------------
     def _take(self, h) -> SiteTable:
+        """SiteTable whose arrays are zero-copy views of the library-owned result; the result is freed
+        (spl_result_free) when the last array that refers to it is garbage-collected."""
         lib = self._lib
-        try:
-            n = lib.spl_result_n_sites(h)
+        owner = _ResultOwner(lib, h)
+        n = lib.spl_result_n_sites(h)
 
-            def arr(fn, cnt, dt):
-                if cnt == 0:
-                    return np.zeros(0, dt)
-                return np.ctypeslib.as_array(fn(h), shape=(cnt,)).astype(dt, copy=True)
-            poff = np.ctypeslib.as_array(lib.spl_result_partner_off(h), shape=(n + 1,)).astype(np.int64, copy=True)
-            coff = np.ctypeslib.as_array(lib.spl_result_comp_off(h), shape=(n + 1,)).astype(np.int64, copy=True)
-            ne, nc = int(poff[-1]), int(coff[-1])
-            return SiteTable(
-                chrom=arr(lib.spl_result_chrom, n, np.int32), pos=arr(lib.spl_result_pos, n, np.int32),
-                strand=arr(lib.spl_result_strand, n, np.uint8), alpha=arr(lib.spl_result_alpha, n, np.int64),
-                beta1=arr(lib.spl_result_beta1, n, np.int64), beta2simple=arr(lib.spl_result_beta2simple, n, np.int64),
-                beta2cryptic=arr(lib.spl_result_beta2cryptic, n, np.int64),
-                beta2weighted=arr(lib.spl_result_beta2weighted, n, np.float64), sse=arr(lib.spl_result_sse, n, np.float64),
-                first_line=arr(lib.spl_result_first_line, n, np.int64),
-                partner_off=poff, partner_pos=arr(lib.spl_result_partner_pos, ne, np.int32),
-                partner_cnt=arr(lib.spl_result_partner_cnt, ne, np.int64),
-                comp_off=coff, comp_pos=arr(lib.spl_result_comp_pos, nc, np.int32))
-        finally:
-            lib.spl_result_free(h)
+        def arr(fn, cnt, ct, dt):
+            if cnt == 0:
+                return np.zeros(0, dt)
+            buf = (ct * cnt).from_address(C.addressof(fn(h).contents))
+            buf._owner = owner                     # numpy keeps `buf` as the base object, `buf` keeps the result alive
+            return np.frombuffer(buf, dtype=dt)
+        poff = arr(lib.spl_result_partner_off, n + 1, C.c_int64, np.int64)
+        coff = arr(lib.spl_result_comp_off, n + 1, C.c_int64, np.int64)
+        ne, nc = int(poff[-1]), int(coff[-1])
+        return SiteTable(
+            chrom=arr(lib.spl_result_chrom, n, C.c_int32, np.int32), pos=arr(lib.spl_result_pos, n, C.c_int32, np.int32),
+            strand=arr(lib.spl_result_strand, n, C.c_uint8, np.uint8), alpha=arr(lib.spl_result_alpha, n, C.c_int64, np.int64),
+            beta1=arr(lib.spl_result_beta1, n, C.c_int64, np.int64), beta2simple=arr(lib.spl_result_beta2simple, n, C.c_int64, np.int64),
+            beta2cryptic=arr(lib.spl_result_beta2cryptic, n, C.c_int64, np.int64),
+            beta2weighted=arr(lib.spl_result_beta2weighted, n, C.c_double, np.float64), sse=arr(lib.spl_result_sse, n, C.c_double, np.float64),
+            first_line=arr(lib.spl_result_first_line, n, C.c_int64, np.int64),
+            partner_off=poff, partner_pos=arr(lib.spl_result_partner_pos, ne, C.c_int32, np.int32),
+            partner_cnt=arr(lib.spl_result_partner_cnt, ne, C.c_int64, np.int64),
+            comp_off=coff, comp_pos=arr(lib.spl_result_comp_pos, nc, C.c_int32, np.int32))
 
     def process_records(self, records: Records, n_chrom: int, junctions: Junctions, flags: int) -> SiteTable:
         v = records.view()

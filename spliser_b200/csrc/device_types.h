@@ -43,7 +43,7 @@ struct DevGraph {
     const int32_t *cp_off, *cp_pos;     // CompetitorPos (sorted)
     const int32_t *rp_off, *rp_site;    // reverse partner index, anchored at first site of a position
     const int32_t *inc_off, *inc_line;  // alpha reduction segments
-    const int32_t *einc_off, *einc_line;// PartnerCounts reduction segments
+    const int32_t *einc_beg, *einc_end, *einc_line;   // PartnerCounts reduction segments [einc_beg[e], einc_end[e])
     const int64_t* j_score;             // junction scores (device copy)
 };
 
@@ -168,5 +168,7 @@ void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* tot
 void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream);
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream);
 int  kernel_launch_count_per_pass();
+void launch_exscan_u32(uint32_t* a, uint32_t n, uint32_t* tmp, uint32_t* total_out, void* stream);
+uint32_t exscan_tmp_words(uint32_t n);
 
 }  // namespace spl

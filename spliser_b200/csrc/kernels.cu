@@ -618,7 +618,7 @@ __global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
     } else if (i < g.n_sites + g.n_edges) {
         const int e = i - g.n_sites;
         int64_t a = 0;
-        for (int k = g.einc_off[e]; k < g.einc_off[e + 1]; ++k) a += g.j_score[g.einc_line[k]];
+        for (int k = g.einc_beg[e]; k < g.einc_end[e]; ++k) a += g.j_score[g.einc_line[k]];
         out.pc_cnt[e] = a;
     }
 }
@@ -1203,6 +1203,16 @@ k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode) {
 // ------------------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------------------
+// in-place exclusive scan of a[0..n); the total goes to *total_out (device).  tmp needs n / SCAN_TILE + 3 words.
+void launch_exscan_u32(uint32_t* a, uint32_t n, uint32_t* tmp, uint32_t* total_out, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) { cudaMemsetAsync(total_out, 0, 4, st); return; }
+    const uint32_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
+    k_scan_blocksum<<<nblk, 256, 0, st>>>(a, n, tmp);
+    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nblk, total_out);
+    k_scan_apply<<<nblk, 256, 0, st>>>(a, n, tmp, nullptr);
+}
+uint32_t exscan_tmp_words(uint32_t n) { return n / SCAN_TILE + 4; }
 void launch_expand_count(const DevRecords& rec, Chunk* chunks, int n_chunks, uint32_t flags, DevBins bins, void* stream) {
     if (n_chunks > 0) k_expand_count<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, flags, bins);
 }

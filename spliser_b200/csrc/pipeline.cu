@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -17,6 +18,7 @@
 #include "../../include/spliser_b200.h"
 #include "bam_io.h"
 #include "device_types.h"
+#include "graph_build.h"
 #include "site_graph.h"
 
 using namespace spl;
@@ -57,15 +59,85 @@ struct Carver {
 
 }  // namespace
 
+// Result arrays live in ONE host allocation (page-locked when a device is present, so the D2H copies run at
+// full PCIe speed); freed arenas are kept in a small pool because pinning tens of MB costs milliseconds.
 struct spl_result {
-    int64_t n = 0;
-    std::vector<int32_t> chrom, pos;
-    std::vector<uint8_t> strand;
-    std::vector<int64_t> alpha, beta1, beta2s, beta2c, first_line;
-    std::vector<double> beta2w, sse;
-    std::vector<int64_t> pc_off, pc_cnt, cp_off;
-    std::vector<int32_t> pc_pos, cp_pos;
+    int64_t n = 0, E = 0, C = 0;
+    void* arena = nullptr;
+    size_t bytes = 0;
+    bool pinned = false;
+    int32_t *chrom = nullptr, *pos = nullptr;
+    uint8_t* strand = nullptr;
+    int64_t *alpha = nullptr, *beta1 = nullptr, *beta2s = nullptr, *beta2c = nullptr, *first_line = nullptr;
+    double *beta2w = nullptr, *sse = nullptr;
+    int64_t *pc_off = nullptr, *pc_cnt = nullptr, *cp_off = nullptr;
+    int32_t *pc_pos = nullptr, *cp_pos = nullptr;
 };
+
+namespace {
+struct Arena { void* p; size_t bytes; bool pinned; };
+std::mutex g_pool_mu;
+std::vector<Arena> g_pool;
+
+Arena arena_get(size_t bytes, bool pinned) {
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        size_t best = g_pool.size();
+        for (size_t i = 0; i < g_pool.size(); ++i)
+            if (g_pool[i].pinned == pinned && g_pool[i].bytes >= bytes && (best == g_pool.size() || g_pool[i].bytes < g_pool[best].bytes)) best = i;
+        if (best < g_pool.size()) { Arena a = g_pool[best]; g_pool.erase(g_pool.begin() + (ptrdiff_t)best); return a; }
+    }
+    Arena a{nullptr, bytes + bytes / 8 + 4096, pinned};
+    if (pinned) {
+        if (cudaHostAlloc(&a.p, a.bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); a.p = nullptr; }
+    } else {
+        a.p = malloc(a.bytes);
+    }
+    return a;
+}
+void arena_put(Arena a) {
+    if (!a.p) return;
+    {
+        std::lock_guard<std::mutex> lk(g_pool_mu);
+        if (g_pool.size() < 4) { g_pool.push_back(a); return; }
+    }
+    if (a.pinned) cudaFreeHost(a.p); else free(a.p);
+}
+
+spl_result* result_alloc(size_t S, size_t E, size_t C, bool pinned) {
+    Carver c;
+    const size_t o_chrom = c.take<int32_t>(S + 1), o_pos = c.take<int32_t>(S + 1), o_strand = c.take<uint8_t>(S + 1);
+    const size_t o_alpha = c.take<int64_t>(S + 1), o_b1 = c.take<int64_t>(S + 1), o_b2s = c.take<int64_t>(S + 1), o_b2c = c.take<int64_t>(S + 1);
+    const size_t o_fl = c.take<int64_t>(S + 1), o_b2w = c.take<double>(S + 1), o_sse = c.take<double>(S + 1);
+    const size_t o_pco = c.take<int64_t>(S + 2), o_pcc = c.take<int64_t>(E + 1), o_cpo = c.take<int64_t>(S + 2);
+    const size_t o_pcp = c.take<int32_t>(E + 1), o_cpp = c.take<int32_t>(C + 1);
+    Arena a = arena_get(c.off + 256, pinned);
+    if (!a.p) return nullptr;
+    spl_result* r = new (std::nothrow) spl_result();
+    if (!r) { arena_put(a); return nullptr; }
+    char* b = (char*)a.p;
+    r->n = (int64_t)S; r->E = (int64_t)E; r->C = (int64_t)C;
+    r->arena = a.p; r->bytes = a.bytes; r->pinned = a.pinned;
+    r->chrom = (int32_t*)(b + o_chrom); r->pos = (int32_t*)(b + o_pos); r->strand = (uint8_t*)(b + o_strand);
+    r->alpha = (int64_t*)(b + o_alpha); r->beta1 = (int64_t*)(b + o_b1); r->beta2s = (int64_t*)(b + o_b2s); r->beta2c = (int64_t*)(b + o_b2c);
+    r->first_line = (int64_t*)(b + o_fl); r->beta2w = (double*)(b + o_b2w); r->sse = (double*)(b + o_sse);
+    r->pc_off = (int64_t*)(b + o_pco); r->pc_cnt = (int64_t*)(b + o_pcc); r->cp_off = (int64_t*)(b + o_cpo);
+    r->pc_pos = (int32_t*)(b + o_pcp); r->cp_pos = (int32_t*)(b + o_cpp);
+    r->pc_off[0] = 0; r->cp_off[0] = 0;
+    if (S == 0) { r->pc_off[1] = 0; r->cp_off[1] = 0; }
+    return r;
+}
+void result_from_host_graph(spl_result* r, const SiteGraph& h) {
+    const size_t S = (size_t)h.n_sites, E = h.pc_pos.size(), Cn = h.cp_pos.size();
+    if (S) {
+        memcpy(r->chrom, h.chrom.data(), S * 4); memcpy(r->pos, h.pos.data(), S * 4); memcpy(r->strand, h.strand.data(), S);
+        memcpy(r->first_line, h.first_line.data(), S * 8);
+        memcpy(r->pc_off, h.pc_off.data(), (S + 1) * 8); memcpy(r->cp_off, h.cp_off.data(), (S + 1) * 8);
+    }
+    if (E) memcpy(r->pc_pos, h.pc_pos.data(), E * 4);
+    if (Cn) memcpy(r->cp_pos, h.cp_pos.data(), Cn * 4);
+}
+}  // namespace
 
 struct spl_ctx {
     int device = 0;
@@ -82,6 +154,15 @@ struct spl_ctx {
     DevJunc jg{};
     DevBuf d_jtab, d_jdense;
     std::vector<cudaEvent_t> events;
+    // device-side graph build (clean regime)
+    cudaStream_t stream2 = nullptr;
+    cudaEvent_t ev_graph = nullptr;
+    GraphBuildMem gbm;
+    GraphDev gdev{};
+    GraphCounts gcnt;
+    bool graph_on_device = false;
+    void* h_stage = nullptr;        // pinned staging of the host-built graph
+    size_t h_stage_bytes = 0;
 
     // state of the last load
     SiteGraph hg;                   // host graph (structure) of the last load
@@ -124,6 +205,8 @@ template <class T> std::vector<int32_t> to_i32(const std::vector<T>& v) {
     return r;
 }
 
+int alloc_counters_outputs(spl_ctx* ctx, size_t S, size_t E);
+
 int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     const SiteGraph& h = ctx->hg;
     const size_t S = (size_t)h.n_sites, E = h.pc_pos.size();
@@ -157,13 +240,20 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     const size_t o_js = c.take<int64_t>((size_t)n_junc + 1);
     const size_t total = c.off + 256;
     CU(ctx->d_graph.reserve(total));
-    std::vector<uint8_t> stage(total, 0);
-    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) memcpy(stage.data() + off, src, bytes); };
+    if (ctx->h_stage_bytes < total) {                                   // pinned staging, kept across calls
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr; ctx->h_stage_bytes = 0;
+        CU(cudaHostAlloc(&ctx->h_stage, total + total / 4, cudaHostAllocDefault));
+        ctx->h_stage_bytes = total + total / 4;
+    }
+    uint8_t* stage = (uint8_t*)ctx->h_stage;
+    auto put = [&](size_t off, const void* src, size_t bytes) { if (bytes) memcpy(stage + off, src, bytes); };
     auto put32 = [&](size_t off, const std::vector<int64_t>& v, size_t expect) {
         std::vector<int32_t> t = to_i32(v);
         t.resize(expect, t.empty() ? 0 : t.back());
         put(off, t.data(), t.size() * 4);
     };
+    memset(stage, 0, total);
     put32(o_cs, h.cs_off, (size_t)h.n_chrom + 1);
     {
         std::vector<int32_t> p(h.pos);
@@ -189,8 +279,8 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     put32(o_ino, h.inc_off, S + 1); put(o_inl, h.inc_line.data(), h.inc_line.size() * 4);
     put32(o_eio, h.einc_off, E + 1); put(o_eil, h.einc_line.data(), h.einc_line.size() * 4);
     if (n_junc) put(o_js, j_score, (size_t)n_junc * 8);
-    CU(cudaMemcpyAsync(ctx->d_graph.p, stage.data(), total, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));   // `stage` is pageable and dies at scope exit
+    CU(cudaMemcpyAsync(ctx->d_graph.p, stage, total, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // the staging buffer is reused by the next call
     ctx->stats[SPL_STAT_H2D_BYTES] += (double)total;
     char* b = (char*)ctx->d_graph.p;
     DevGraph& g = ctx->g;
@@ -205,9 +295,14 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     g.cp_off = (const int32_t*)(b + o_cpo); g.cp_pos = (const int32_t*)(b + o_cpp);
     g.rp_off = (const int32_t*)(b + o_rpo); g.rp_site = (const int32_t*)(b + o_rps);
     g.inc_off = (const int32_t*)(b + o_ino); g.inc_line = (const int32_t*)(b + o_inl);
-    g.einc_off = (const int32_t*)(b + o_eio); g.einc_line = (const int32_t*)(b + o_eil);
+    g.einc_beg = (const int32_t*)(b + o_eio); g.einc_end = g.einc_beg + 1; g.einc_line = (const int32_t*)(b + o_eil);
     g.j_score = (const int64_t*)(b + o_js);
 
+    ctx->graph_on_device = false;
+    return alloc_counters_outputs(ctx, S, E);
+}
+
+int alloc_counters_outputs(spl_ctx* ctx, size_t S, size_t E) {
     // counters + outputs
     Carver cc;
     const size_t c_cov = cc.take<uint32_t>(2 * S + 2), c_span = cc.take<uint32_t>(2 * (S + 1) + 2);
@@ -255,9 +350,8 @@ int check_view(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
     return SPL_OK;
 }
 
-// upload records, run the expansion kernels, leave the SoA + chunk table on the device
-int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, int32_t n_chrom) {
-    const double t0 = now_ms();
+// enqueue the record upload on the context's stream (asynchronous when the caller's arrays are page-locked)
+int upload_records(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
     ctx->n_chrom_loaded = n_chrom;
     std::vector<Chunk> hc;
     for (int32_t k = 0; k < v->n_seg; ++k) {
@@ -277,6 +371,11 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
                  o_cig = c.take<uint32_t>(NC + 4);
     CU(ctx->d_rec.reserve(c.off + 256));
     char* rb = (char*)ctx->d_rec.p;
+    // the chunk table first: it comes from pageable memory, and a pageable copy queued behind the big record
+    // copies would block the host until those are done
+    CU(ctx->d_chunks.reserve((hc.size() + 1) * sizeof(Chunk)));
+    ctx->chunks = (Chunk*)ctx->d_chunks.p;
+    if (!hc.empty()) CU(cudaMemcpyAsync(ctx->chunks, hc.data(), hc.size() * sizeof(Chunk), cudaMemcpyHostToDevice, ctx->stream));
     if (R) {
         CU(cudaMemcpyAsync(rb + o_pos, v->pos, R * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(rb + o_flag, v->flag, R * 2, cudaMemcpyHostToDevice, ctx->stream));
@@ -287,9 +386,11 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     ctx->rec.n_rec = (uint32_t)R;
     ctx->rec.pos = (const int32_t*)(rb + o_pos); ctx->rec.flag = (const uint16_t*)(rb + o_flag);
     ctx->rec.cig_off = (const uint32_t*)(rb + o_off); ctx->rec.cigar = (const uint32_t*)(rb + o_cig);
-    CU(ctx->d_chunks.reserve((hc.size() + 1) * sizeof(Chunk)));
-    ctx->chunks = (Chunk*)ctx->d_chunks.p;
-    if (!hc.empty()) CU(cudaMemcpyAsync(ctx->chunks, hc.data(), hc.size() * sizeof(Chunk), cudaMemcpyHostToDevice, ctx->stream));
+    return SPL_OK;
+}
+
+// run the expansion kernels, leave the SoA + chunk table on the device
+int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
     CU(ctx->d_tot.reserve(256));
     // per-chromosome layout arrays of the bin-partitioned stream
     DevBins& bins = ctx->bins;
@@ -414,8 +515,13 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
         if (v->seg_chrom[k] >= 0) aligned += v->seg_off[k + 1] - v->seg_off[k];
     ctx->n_aligned = aligned;
     ctx->stats[SPL_STAT_N_ALIGNED] = (double)aligned;
-    (void)t0;
     return SPL_OK;
+}
+
+int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, int32_t n_chrom) {
+    int rc = upload_records(ctx, v, n_chrom);
+    if (rc) return rc;
+    return expand_records(ctx, v, flags);
 }
 
 // one counting pass over the resident SoA; events (if given) bracket the three kernel groups
@@ -435,36 +541,70 @@ int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
 }
 
 int fetch(spl_ctx* ctx, spl_result** out_r) {
+    const bool dev = ctx->graph_on_device;
     const SiteGraph& h = ctx->hg;
-    const size_t S = (size_t)h.n_sites, E = h.pc_pos.size();
-    std::unique_ptr<spl_result> r(new spl_result());
-    r->n = (int64_t)S;
-    r->chrom = h.chrom; r->pos = h.pos; r->strand = h.strand; r->first_line = h.first_line;
-    r->pc_off = h.pc_off; r->pc_pos = h.pc_pos; r->cp_off = h.cp_off; r->cp_pos = h.cp_pos;
-    r->alpha.resize(S); r->beta1.resize(S); r->beta2s.resize(S); r->beta2c.resize(S);
-    r->beta2w.resize(S); r->sse.resize(S); r->pc_cnt.resize(E);
+    const size_t S = dev ? ctx->gcnt.S : (size_t)h.n_sites, E = dev ? ctx->gcnt.E : h.pc_pos.size(), Cn = dev ? ctx->gcnt.C : h.cp_pos.size();
+    spl_result* r = result_alloc(S, E, Cn, true);
+    if (!r) return ctx->fail(SPL_ERR_NOMEM, "cannot allocate the result (%zu sites)", S);
+    std::unique_ptr<spl_result, void (*)(spl_result*)> guard(r, spl_result_free);
+    cudaStream_t st = ctx->stream;
+    double bytes = 0;
     if (S) {
-        CU(cudaMemcpyAsync(r->alpha.data(), ctx->out.alpha, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(r->beta1.data(), ctx->out.beta1, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(r->beta2s.data(), ctx->out.beta2s, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(r->beta2c.data(), ctx->out.beta2c, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(r->beta2w.data(), ctx->out.beta2w, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(r->sse.data(), ctx->out.sse, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        if (E) CU(cudaMemcpyAsync(r->pc_cnt.data(), ctx->out.pc_cnt, E * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpyAsync(r->alpha, ctx->out.alpha, S * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(r->beta1, ctx->out.beta1, S * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(r->beta2s, ctx->out.beta2s, S * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(r->beta2c, ctx->out.beta2c, S * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(r->beta2w, ctx->out.beta2w, S * 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaMemcpyAsync(r->sse, ctx->out.sse, S * 8, cudaMemcpyDeviceToHost, st));
+        if (E) CU(cudaMemcpyAsync(r->pc_cnt, ctx->out.pc_cnt, E * 8, cudaMemcpyDeviceToHost, st));
+        bytes += (double)(S * 48 + E * 8);
+        if (dev) {                                                     // the structure lives on the device too
+            const GraphDev& d = ctx->gdev;
+            CU(cudaMemcpyAsync(r->chrom, d.site_chrom, S * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->pos, d.site_pos, S * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->strand, d.site_strand, S, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->first_line, d.first_line, S * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->pc_off, d.pt_off64, (S + 1) * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(r->cp_off, d.cp_off64, (S + 1) * 8, cudaMemcpyDeviceToHost, st));
+            if (E) CU(cudaMemcpyAsync(r->pc_pos, d.pc_pos, E * 4, cudaMemcpyDeviceToHost, st));
+            if (Cn) CU(cudaMemcpyAsync(r->cp_pos, d.cp_pos, Cn * 4, cudaMemcpyDeviceToHost, st));
+            bytes += (double)(S * 33 + 16 + E * 4 + Cn * 4);
+        } else {
+            result_from_host_graph(r, h);
+        }
+        CU(cudaStreamSynchronize(st));
     }
-    ctx->stats[SPL_STAT_D2H_BYTES] += (double)(S * 48 + E * 8);
-    *out_r = r.release();
+    ctx->stats[SPL_STAT_D2H_BYTES] += bytes;
+    *out_r = guard.release();
     return SPL_OK;
 }
 
 void reset_stats(spl_ctx* ctx) { std::fill(ctx->stats, ctx->stats + SPL_NSTATS, 0.0); }
+
+// DevGraph view of a device-built graph
+void adopt_device_graph(spl_ctx* ctx) {
+    const GraphDev& d = ctx->gdev;
+    DevGraph& g = ctx->g;
+    const size_t S = ctx->gcnt.S;
+    g.n_chrom = ctx->n_chrom_loaded; g.n_sites = (int32_t)S; g.n_edges = (int32_t)ctx->gcnt.E;
+    const int64_t tc = std::max(1, ctx->tile_count), ti = std::min<int64_t>(std::max(0, ctx->tile_index), tc - 1);
+    g.own_lo = (int32_t)((int64_t)S * ti / tc); g.own_hi = (int32_t)((int64_t)S * (ti + 1) / tc);
+    g.cs_off = d.cs_off; g.site_pos = d.site_pos; g.site_cls = d.site_cls; g.site_hot = d.site_hot;
+    g.sb_base = d.sb_base; g.sb_off = d.sb_off;
+    g.pt_off = d.pt_off; g.pt_site = d.pt_site; g.pc_off = d.pt_off; g.pc_pos = d.pc_pos;     // clean regime: one PartnerCounts key per partner
+    g.cp_off = d.cp_off; g.cp_pos = d.cp_pos; g.rp_off = d.rp_off; g.rp_site = d.rp_site;
+    g.inc_off = d.inc_off; g.inc_line = d.inc_line;
+    g.einc_beg = d.einc_beg; g.einc_end = d.einc_end; g.einc_line = d.einc_line;
+    g.j_score = d.j_score;
+}
 
 int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
                 const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags) {
     ctx->loaded = false;
     int rc = check_view(ctx, rec, n_chrom);
     if (rc) return rc;
+    if (n_junc < 0) return ctx->fail(SPL_ERR_ARG, "negative size");
+    if (n_junc > 0 && (!j_chrom || !j_left || !j_right || !j_strand)) return ctx->fail(SPL_ERR_ARG, "null junction array");
     if (n_junc > 0 && !j_score) return ctx->fail(SPL_ERR_ARG, "NULL j_score");
     CU(cudaSetDevice(ctx->device));
     reset_stats(ctx);
@@ -472,29 +612,73 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     if (const char* dbg = std::getenv("SPLISER_DEBUG_SKIP_EXC"))
         if (dbg[0] == '1') flags |= FLAG_DEBUG_SKIP_EXC;
     ctx->flags = flags;
-    // the site graph is built on a host thread while the records travel to the GPU and are expanded
+    const bool stranded = (flags & SPL_FLAG_STRANDED) != 0;
     const double tg0 = now_ms();
-    std::string e;
-    double graph_ms = 0;
-    std::thread builder([&]() {
-        e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, (flags & SPL_FLAG_STRANDED) != 0, ctx->hg);
-        graph_ms = now_ms() - tg0;
-    });
-    rc = upload_and_expand(ctx, rec, flags, n_chrom);
-    ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg0;
-    builder.join();
+    // which regime?  (a '?' strand in a stranded run or a degenerate row makes the outcome depend on
+    // the reference's bisection path -> sequential host emulation; everything else is sort/unique on the device)
+    bool clean = n_junc > 0;
+    int32_t max_pos = 1;
+    for (int64_t i = 0; i < n_junc; ++i) {
+        if (j_chrom[i] < 0 || j_chrom[i] >= n_chrom) return ctx->fail(SPL_ERR_ARG, "junction chromosome index out of range");
+        const uint8_t st = j_strand[i];
+        if ((stranded && st != '+' && st != '-') || j_left[i] == j_right[i] || j_left[i] < 0 || j_right[i] < 0) clean = false;
+        max_pos = std::max(max_pos, std::max(j_left[i], j_right[i]));
+    }
+    if (const char* f = std::getenv("SPLISER_FORCE_EMULATION")) if (f[0] == '1') clean = false;
+    if (const char* f = std::getenv("SPLISER_HOST_GRAPH")) if (f[0] == '1') clean = false;
+    if (clean && !graph_build_fits(n_junc, n_chrom, max_pos)) clean = false;
+
+    // the records start travelling first; the graph is built meanwhile (device: second stream, host: a thread)
+    if (clean) {
+        std::string e;
+        if (!graph_build_device(ctx->gbm, j_chrom, j_left, j_right, j_strand, j_score, n_junc, n_chrom, max_pos, stranded, ctx->stream2,
+                                0, ctx->gdev, ctx->gcnt, e))
+            return ctx->fail(SPL_ERR_CUDA, "%s", e.c_str());
+    }
+    rc = upload_records(ctx, rec, n_chrom);
     if (rc) return rc;
-    if (!e.empty()) return ctx->fail(SPL_ERR_ARG, "%s", e.c_str());
-    const double tu0 = now_ms();
-    rc = upload_graph(ctx, j_score, n_junc);
-    if (rc) return rc;
-    ctx->stats[SPL_STAT_MS_GRAPH] = graph_ms + (now_ms() - tu0);
+    if (clean) {
+        std::string e;
+        if (!graph_build_device(ctx->gbm, j_chrom, j_left, j_right, j_strand, j_score, n_junc, n_chrom, max_pos, stranded, ctx->stream2,
+                                1, ctx->gdev, ctx->gcnt, e))
+            return ctx->fail(SPL_ERR_CUDA, "%s", e.c_str());
+        CU(cudaEventRecord(ctx->ev_graph, ctx->stream2));
+        ctx->graph_on_device = true;
+        ctx->stats[SPL_STAT_H2D_BYTES] += ctx->gcnt.h2d_bytes;
+        adopt_device_graph(ctx);
+        rc = alloc_counters_outputs(ctx, ctx->gcnt.S, ctx->gcnt.E);
+        if (rc) return rc;
+        ctx->stats[SPL_STAT_MS_GRAPH] = now_ms() - tg0;
+        rc = expand_records(ctx, rec, flags);
+        ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg0;
+        if (rc) return rc;
+        CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_graph, 0));
+        ctx->stats[SPL_STAT_N_SITES] = (double)ctx->gcnt.S;
+        ctx->stats[SPL_STAT_N_EDGES] = (double)ctx->gcnt.E;
+    } else {
+        std::string e;
+        double graph_ms = 0;
+        std::thread builder([&]() {
+            e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, stranded, ctx->hg);
+            graph_ms = now_ms() - tg0;
+        });
+        rc = expand_records(ctx, rec, flags);
+        ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg0;
+        builder.join();
+        if (rc) return rc;
+        if (!e.empty()) return ctx->fail(SPL_ERR_ARG, "%s", e.c_str());
+        const double tu0 = now_ms();
+        rc = upload_graph(ctx, j_score, n_junc);
+        if (rc) return rc;
+        ctx->stats[SPL_STAT_MS_GRAPH] = graph_ms + (now_ms() - tu0);
+        ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
+        ctx->stats[SPL_STAT_N_EDGES] = (double)ctx->hg.pc_pos.size();
+    }
     launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
     launch_tile_hints(ctx->bins, ctx->g, ctx->stream);
     CU(cudaGetLastError());
-    ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
-    ctx->stats[SPL_STAT_N_EDGES] = (double)ctx->hg.pc_pos.size();
     ctx->stats[SPL_STAT_LAUNCHES] = (double)kernel_launch_count_per_pass();
+    ctx->stats[SPL_STAT_GRAPH_DEVICE] = ctx->graph_on_device ? 1.0 : 0.0;
     ctx->loaded = true;
     return SPL_OK;
 }
@@ -531,7 +715,10 @@ int spl_create(spl_ctx** out, const int* device_ids, int n_devices) {
     if (prop.major != 10)
         return ctx->fail(SPL_ERR_CUDA, "device %d is sm_%d%d; this library carries sm_100a code only", ctx->device, prop.major, prop.minor);
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&ctx->ev_graph, cudaEventDisableTiming));
     CU(cudaHostAlloc((void**)&ctx->h_tot, 256, cudaHostAllocDefault));
+    CU(cudaHostAlloc((void**)&ctx->gbm.h_cnt, 256, cudaHostAllocDefault));
     return SPL_OK;
 }
 
@@ -544,6 +731,11 @@ void spl_destroy(spl_ctx* ctx) {
         ctx->d_graph.release(); ctx->d_rec.release(); ctx->d_chunks.release(); ctx->d_soa.release();
         ctx->d_cnt.release(); ctx->d_out.release(); ctx->d_tot.release(); ctx->d_lay.release(); ctx->d_bins.release(); ctx->d_jtab.release(); ctx->d_jdense.release();
         if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
+        if (ctx->gbm.h_cnt) cudaFreeHost(ctx->gbm.h_cnt);
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->gbm.fin.release(); ctx->gbm.fin2.release(); ctx->gbm.work.release(); ctx->gbm.work2.release();
+        if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
+        if (ctx->ev_graph) cudaEventDestroy(ctx->ev_graph);
         cudaStreamDestroy(ctx->stream);
     }
     delete ctx;
@@ -738,38 +930,46 @@ int spl_build_site_table(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom
         if (err && err_len > 0) snprintf(err, (size_t)err_len, "%s", e.c_str());
         return SPL_ERR_ARG;
     }
-    std::unique_ptr<spl_result> r(new spl_result());
     const size_t S = (size_t)h.n_sites, E = h.pc_pos.size();
-    r->n = (int64_t)S;
-    r->chrom = h.chrom; r->pos = h.pos; r->strand = h.strand; r->first_line = h.first_line;
-    r->pc_off = h.pc_off; r->pc_pos = h.pc_pos; r->cp_off = h.cp_off; r->cp_pos = h.cp_pos;
-    r->alpha.assign(S, 0); r->beta1.assign(S, 0); r->beta2s.assign(S, 0); r->beta2c.assign(S, 0);
-    r->beta2w.assign(S, 0.0); r->sse.assign(S, 0.0); r->pc_cnt.assign(E, 0);
-    for (size_t t = 0; t < S; ++t)
+    spl_result* r = result_alloc(S, E, h.cp_pos.size(), false);
+    if (!r) {
+        if (err && err_len > 0) snprintf(err, (size_t)err_len, "out of memory");
+        return SPL_ERR_NOMEM;
+    }
+    result_from_host_graph(r, h);
+    for (size_t t = 0; t < S; ++t) {
+        r->alpha[t] = 0; r->beta1[t] = 0; r->beta2s[t] = 0; r->beta2c[t] = 0; r->beta2w[t] = 0.0; r->sse[t] = 0.0;
         for (int64_t k = h.inc_off[t]; k < h.inc_off[t + 1]; ++k) r->alpha[t] += j_score[h.inc_line[(size_t)k]];
-    for (size_t x = 0; x < E; ++x)
+    }
+    for (size_t x = 0; x < E; ++x) {
+        r->pc_cnt[x] = 0;
         for (int64_t k = h.einc_off[x]; k < h.einc_off[x + 1]; ++k) r->pc_cnt[x] += j_score[h.einc_line[(size_t)k]];
-    *out = r.release();
+    }
+    *out = r;
     return SPL_OK;
 }
 
 int64_t spl_result_n_sites(const spl_result* r) { return r ? r->n : 0; }
-const int32_t* spl_result_chrom(const spl_result* r) { return r->chrom.data(); }
-const int32_t* spl_result_pos(const spl_result* r) { return r->pos.data(); }
-const uint8_t* spl_result_strand(const spl_result* r) { return r->strand.data(); }
-const int64_t* spl_result_alpha(const spl_result* r) { return r->alpha.data(); }
-const int64_t* spl_result_beta1(const spl_result* r) { return r->beta1.data(); }
-const int64_t* spl_result_beta2simple(const spl_result* r) { return r->beta2s.data(); }
-const int64_t* spl_result_beta2cryptic(const spl_result* r) { return r->beta2c.data(); }
-const double* spl_result_beta2weighted(const spl_result* r) { return r->beta2w.data(); }
-const double* spl_result_sse(const spl_result* r) { return r->sse.data(); }
-const int64_t* spl_result_first_line(const spl_result* r) { return r->first_line.data(); }
-const int64_t* spl_result_partner_off(const spl_result* r) { return r->pc_off.data(); }
-const int32_t* spl_result_partner_pos(const spl_result* r) { return r->pc_pos.data(); }
-const int64_t* spl_result_partner_cnt(const spl_result* r) { return r->pc_cnt.data(); }
-const int64_t* spl_result_comp_off(const spl_result* r) { return r->cp_off.data(); }
-const int32_t* spl_result_comp_pos(const spl_result* r) { return r->cp_pos.data(); }
-void spl_result_free(spl_result* r) { delete r; }
+const int32_t* spl_result_chrom(const spl_result* r) { return r->chrom; }
+const int32_t* spl_result_pos(const spl_result* r) { return r->pos; }
+const uint8_t* spl_result_strand(const spl_result* r) { return r->strand; }
+const int64_t* spl_result_alpha(const spl_result* r) { return r->alpha; }
+const int64_t* spl_result_beta1(const spl_result* r) { return r->beta1; }
+const int64_t* spl_result_beta2simple(const spl_result* r) { return r->beta2s; }
+const int64_t* spl_result_beta2cryptic(const spl_result* r) { return r->beta2c; }
+const double* spl_result_beta2weighted(const spl_result* r) { return r->beta2w; }
+const double* spl_result_sse(const spl_result* r) { return r->sse; }
+const int64_t* spl_result_first_line(const spl_result* r) { return r->first_line; }
+const int64_t* spl_result_partner_off(const spl_result* r) { return r->pc_off; }
+const int32_t* spl_result_partner_pos(const spl_result* r) { return r->pc_pos; }
+const int64_t* spl_result_partner_cnt(const spl_result* r) { return r->pc_cnt; }
+const int64_t* spl_result_comp_off(const spl_result* r) { return r->cp_off; }
+const int32_t* spl_result_comp_pos(const spl_result* r) { return r->cp_pos; }
+void spl_result_free(spl_result* r) {
+    if (!r) return;
+    arena_put(Arena{r->arena, r->bytes, r->pinned});
+    delete r;
+}
 
 void* spl_host_alloc(size_t bytes) {
     void* p = nullptr;

@@ -305,7 +305,8 @@ void build_clean_sorted(int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
     const size_t J = (size_t)n_junc;
     g = SiteGraph();
     g.n_chrom = n_chrom;
-    const bool timing = std::getenv("SPLISER_TIMING") != nullptr;
+    const char* tenv = std::getenv("SPLISER_TIMING");
+    const bool timing = tenv && tenv[0] == '2';
     auto tprev = std::chrono::steady_clock::now();
 #define TICK(name) do { if (timing) { auto tn = std::chrono::steady_clock::now(); fprintf(stderr, "  %-16s %.2f ms\n", name, std::chrono::duration<double, std::milli>(tn - tprev).count()); tprev = tn; } } while (0)
     // ---- endpoints -> sites
@@ -452,6 +453,14 @@ void build_clean_by_chromosome(int32_t n_chrom, int64_t n_junc, const int32_t* j
     std::sort(order.begin(), order.end(), [&](int32_t a, int32_t b) {
         return roff[(size_t)a + 1] - roff[(size_t)a] > roff[(size_t)b + 1] - roff[(size_t)b];
     });
+    const bool timing = std::getenv("SPLISER_TIMING") != nullptr;
+    auto tp = std::chrono::steady_clock::now();
+    auto lap = [&](const char* name) {
+        if (!timing) return;
+        const auto tn = std::chrono::steady_clock::now();
+        fprintf(stderr, "  [by-chrom] %-10s %.2f ms\n", name, std::chrono::duration<double, std::milli>(tn - tp).count());
+        tp = tn;
+    };
     std::vector<SiteGraph> piece(NC);
     std::atomic<size_t> next{0};
     auto worker = [&]() {
@@ -461,8 +470,15 @@ void build_clean_by_chromosome(int32_t n_chrom, int64_t n_junc, const int32_t* j
             const size_t c = (size_t)order[k];
             const size_t r0 = (size_t)roff[c], n = (size_t)(roff[c + 1] - roff[c]);
             std::vector<int32_t> zero(n, 0);
+            const auto w0 = std::chrono::steady_clock::now();
             build_clean_sorted(1, (int64_t)n, zero.data(), lft.data() + r0, rgt.data() + r0, strd.data() + r0, stranded, piece[c]);
+            const auto w1 = std::chrono::steady_clock::now();
             finish_graph(piece[c]);
+            if (timing) {
+                const auto w2 = std::chrono::steady_clock::now();
+                fprintf(stderr, "    chrom %zu rows %zu: start +%.2f sorted %.2f finish %.2f ms\n", c, n, std::chrono::duration<double, std::milli>(w0 - tp).count(),
+                        std::chrono::duration<double, std::milli>(w1 - w0).count(), std::chrono::duration<double, std::milli>(w2 - w1).count());
+            }
         }
     };
     const size_t nt = std::min<size_t>(std::min<size_t>(hw, 16), order.size());
@@ -470,6 +486,7 @@ void build_clean_by_chromosome(int32_t n_chrom, int64_t n_junc, const int32_t* j
     for (size_t t = 1; t < nt; ++t) pool.emplace_back(worker);
     worker();
     for (auto& t : pool) t.join();
+    lap("pieces");
     // ---- concatenate
     g = SiteGraph();
     g.n_chrom = n_chrom;
@@ -523,6 +540,7 @@ void build_clean_by_chromosome(int32_t n_chrom, int64_t n_junc, const int32_t* j
     for (size_t t = 1; t < nt; ++t) pool.emplace_back(merger);
     merger();
     for (auto& t : pool) t.join();
+    lap("merge");
     g.pt_off[S] = (int64_t)E; g.cp_off[S] = (int64_t)C; g.rp_off[S] = (int64_t)RP; g.inc_off[S] = (int64_t)(2 * J);
     g.einc_off[E] = (int64_t)(2 * J);
     g.pc_off = g.pt_off;

@@ -192,3 +192,22 @@ def test_config_shaped_workloads_vs_c_oracle(ctx, shape):
     assert int(want["beta1"].sum()) > 0 and int(want["beta2simple"].sum()) > 0
     if flags_extra:
         assert int(want["beta2cryptic"].sum()) > 0
+
+
+def test_host_and_device_graph_builders_agree(ctx, monkeypatch):
+    """Clean regime: the site table / competing-site graph is built on the device (sort / unique / group-by,
+    graph_build.cu); SPLISER_HOST_GRAPH=1 forces the host builder (site_graph.cpp).  Every output column and
+    both CSR structures must be identical, stranded and unstranded."""
+    from oracle import c_oracle
+    from spliser_b200 import synth
+    for stranded in (True, False):
+        w = synth.generate(synth.config_small(100_000, seed=77 + stranded, stranded=stranded, paired=stranded))
+        monkeypatch.delenv("SPLISER_HOST_GRAPH", raising=False)
+        dev = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags | 4))
+        assert ctx.stats()["graph_on_device"] == 1.0
+        monkeypatch.setenv("SPLISER_HOST_GRAPH", "1")
+        host = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags | 4))
+        assert ctx.stats()["graph_on_device"] == 0.0
+        monkeypatch.delenv("SPLISER_HOST_GRAPH", raising=False)
+        assert c_oracle.diff_tables(dev, host) is None, c_oracle.diff_tables(dev, host)
+        assert len(dev["pos"]) > 1000 and len(dev["comp_pos"]) > 0
