@@ -90,7 +90,8 @@ struct DevJunc {
     unsigned long long* key;      // [n_slots]   ~(l | rk << 32), 0 = empty
     uint32_t* s_all; uint32_t* s_simple;        // [n_slots] instance counts
     uint32_t* s_used; uint32_t* s_off;          // [n_slots+1] scans: dense id, offset of the group's simple instances
-    uint32_t* s_cursor;           // [n_slots]
+    uint32_t* s_coff;             // [n_slots+1] scan: offset of the group's complex instances
+    uint32_t* s_cursor; uint32_t* s_ccur;       // [n_slots] scatter cursors (simple / complex)
     uint32_t* slot_of;            // [nJ] slot of each instance
     uint32_t* overflow;           // [1] a sub-table filled up (never with the sizes chosen; checked anyway); follows cx_n
     uint32_t* scan_tmp;           // block sums of the scans
@@ -100,11 +101,12 @@ struct DevJunc {
     uint32_t* dj_all; uint32_t* dj_simple; uint32_t* dj_off;
     int32_t*  gi_a0; int32_t* gi_end;           // simple instances grouped by junction
     uint32_t  n_complex;
-    uint32_t* cx_j; uint32_t* cx_d; uint32_t* cx_n;   // complex instances: global junction index, dense junction id
+    uint32_t* dj_coff;            // [D] offset of the junction's complex instances in cx_j
+    uint32_t* cx_j; uint32_t* cx_n;             // complex instances grouped by junction: global junction index; cx_n: scratch word before `overflow`
     // per pass
     uint32_t* hot_l; uint32_t* hot_r;           // [D] anchor + 1 of a hot endpoint, 0 otherwise
     unsigned long long* wl;       // hot units: chunk << 32 | junction << 1 | side
-    uint32_t* cxl_j; uint32_t* cxl_a;           // [2 n_complex] per pass: complex instances of hot junctions (junction index, anchor | side << 31)
+    uint32_t* cxd_base; uint32_t* cxd_ds;       // [2 D] per pass: descriptors of hot (junction, side) with complex instances: first flat index, d << 1 | side
 };
 
 struct Tile { uint32_t e0; int32_t w_lo, w_hi; int32_t pad; };   // first element, site index window [w_lo, w_hi)
@@ -133,7 +135,7 @@ struct DevCounters {
     uint32_t* spanx;   // [S] spanning reads that are flanking (removed from the mutually-exclusive count)
     uint32_t* flank;   // [S] flanking reads (counted as beta2Simple in combine mode only)
     uint32_t* dc;      // [E] PartnerBeta2DoubleCounts increments seen in the BAM
-    uint32_t* work;    // [4] work-item counters: K3 tiles, (unused), junction work-list length, work-list cursor
+    uint32_t* work;    // [8] work-item counters: [0] K3 tiles, [2] junction work-list length, [4..5] one u64: complex descriptors << 40 | flat instances
 };
 
 struct DevOutputs {
@@ -163,6 +165,7 @@ void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chu
 void launch_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g, void* stream);
 void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream);
 void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream);
+void launch_jtab_layout(DevBins bins, int attempt, uint32_t* totals8, void* stream);
 void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, DevJunc jg, uint32_t* totals4, void* stream);
 void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* totals4, void* stream);
 void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream);

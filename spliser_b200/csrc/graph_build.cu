@@ -119,7 +119,7 @@ __global__ void k_gb_heads(const uint64_t* __restrict__ k, uint32_t n, int low, 
 }
 
 __global__ void k_gb_sites(const uint64_t* __restrict__ k, const uint32_t* __restrict__ ex, uint32_t n, int vb, int pb, int stranded,
-                           const uint8_t* __restrict__ js, GraphDev g, uint32_t* __restrict__ site_of, uint32_t* __restrict__ cs_cnt) {
+                           const uint8_t* __restrict__ js, GraphDev g, uint32_t* __restrict__ site_of) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const uint64_t key = k[e] >> vb;
@@ -138,23 +138,27 @@ __global__ void k_gb_sites(const uint64_t* __restrict__ k, const uint32_t* __res
         g.first_line[idx] = (int64_t)line;
         g.site_cls[idx] = !stranded ? 0 : st == '+' ? 1 : st == '-' ? 2 : 3;
         g.inc_off[idx] = (int32_t)e;
-        atomicAdd(cs_cnt + chrom, 1u);
     }
     if (e == n - 1) g.inc_off[idx + 1] = (int32_t)n;
 }
 
-// per-chromosome site ranges and the layout of the direct-address bin index (one thread: n_chrom is small)
-__global__ void k_gb_chrom_layout(const uint32_t* __restrict__ cs_cnt, int n_chrom, GraphDev g, uint32_t* __restrict__ counts) {
+// per-chromosome site ranges: the table is sorted by chromosome, so cs_off[c] is a lower bound (one thread per chromosome)
+__global__ void k_gb_cs_off(GraphDev g, int n_chrom, const uint32_t* __restrict__ counts) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n_chrom) return;
+    int lo = 0, hi = (int)counts[0];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.site_chrom[mid] < c) lo = mid + 1; else hi = mid; }
+    g.cs_off[c] = lo;
+}
+// layout of the direct-address bin index (one thread: a running sum over the chromosomes)
+__global__ void k_gb_chrom_layout(int n_chrom, GraphDev g, uint32_t* __restrict__ counts) {
     if (blockIdx.x || threadIdx.x) return;
-    int32_t s = 0, nb = 0;
+    int32_t nb = 0;
     for (int c = 0; c < n_chrom; ++c) {
-        g.cs_off[c] = s;
-        const int32_t s1 = s + (int32_t)cs_cnt[c];
+        const int32_t s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
         g.sb_base[c] = nb;
-        nb += (s1 > s ? (max(g.site_pos[s1 - 1], 0) >> SB_SHIFT) + 1 : 0) + 1;     // + sentinel
-        s = s1;
+        nb += (s1 > s0 ? (max(g.site_pos[s1 - 1], 0) >> SB_SHIFT) + 1 : 0) + 1;     // + sentinel
     }
-    g.cs_off[n_chrom] = s;
     g.sb_base[n_chrom] = nb;
     counts[1] = (uint32_t)nb;
 }
@@ -362,7 +366,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     Carve w;
     const size_t w_ka = w.take<uint64_t>(n2 + 2), w_kb = w.take<uint64_t>(n2 + 2), w_flag = w.take<uint32_t>(n2 + 2);
     const size_t w_hist = w.take<uint32_t>(256 * (size_t)max_tiles + 2), w_tmp = w.take<uint32_t>(exscan_tmp_words(256u * max_tiles) + exscan_tmp_words(n2 + 2) + 8);
-    const size_t w_cnt = w.take<uint32_t>(16), w_site_of = w.take<uint32_t>(n2 + 2), w_cs = w.take<uint32_t>((size_t)n_chrom + 1);
+    const size_t w_cnt = w.take<uint32_t>(16), w_site_of = w.take<uint32_t>(n2 + 2);
     const size_t w_usrc = w.take<uint32_t>(n2 + 2), w_udst = w.take<uint32_t>(n2 + 2), w_ufirst = w.take<uint32_t>(n2 + 2), w_ulo = w.take<uint32_t>(n2 + 2);
     const size_t w_esrc = w.take<uint32_t>(n2 + 2), w_nc = w.take<uint32_t>(n2 + 2), w_c1 = w.take<uint32_t>(n2 + 2), w_c2 = w.take<uint32_t>(n2 + 2);
     GB_CU(m.work.reserve(w.off + 256));
@@ -370,7 +374,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     uint64_t* ka = (uint64_t*)(wb + w_ka); uint64_t* kb = (uint64_t*)(wb + w_kb);
     uint32_t* flag = (uint32_t*)(wb + w_flag);
     uint32_t* d_cnt = (uint32_t*)(wb + w_cnt);                            // [0] S, [1] bin entries, [2] E, [3] candidates, [4] C, [5] scratch
-    uint32_t* site_of = (uint32_t*)(wb + w_site_of); uint32_t* cs_cnt = (uint32_t*)(wb + w_cs);
+    uint32_t* site_of = (uint32_t*)(wb + w_site_of);
     uint32_t* u_src = (uint32_t*)(wb + w_usrc); uint32_t* u_dst = (uint32_t*)(wb + w_udst); uint32_t* u_first = (uint32_t*)(wb + w_ufirst);
     uint32_t* u_lo = (uint32_t*)(wb + w_ulo); uint32_t* e_src = (uint32_t*)(wb + w_esrc);
     uint32_t* ncand = (uint32_t*)(wb + w_nc); uint32_t* c1 = (uint32_t*)(wb + w_c1); uint32_t* c2 = (uint32_t*)(wb + w_c2);
@@ -387,7 +391,6 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     GB_CU(cudaMemcpyAsync((void*)g.j_score, j_score, (size_t)J * 8, cudaMemcpyHostToDevice, st));
     counts.h2d_bytes = (double)J * 21.0;
     GB_CU(cudaMemsetAsync(d_cnt, 0, 64, st));
-    GB_CU(cudaMemsetAsync(cs_cnt, 0, ((size_t)n_chrom + 1) * 4, st));
     return true;
     }
 
@@ -397,8 +400,9 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     uint64_t* other = sa == ka ? kb : ka;
     k_gb_heads<<<cdiv(n2, 256), 256, 0, st>>>(sa, n2, vb, flag);
     launch_exscan_u32(flag, n2, stmp, d_cnt + 0, st);
-    k_gb_sites<<<cdiv(n2, 256), 256, 0, st>>>(sa, flag, n2, vb, pb, stranded ? 1 : 0, d_js, g, site_of, cs_cnt);
-    k_gb_chrom_layout<<<1, 32, 0, st>>>(cs_cnt, n_chrom, g, d_cnt);
+    k_gb_sites<<<cdiv(n2, 256), 256, 0, st>>>(sa, flag, n2, vb, pb, stranded ? 1 : 0, d_js, g, site_of);
+    k_gb_cs_off<<<cdiv((uint32_t)n_chrom + 1, 128), 128, 0, st>>>(g, n_chrom, d_cnt);
+    k_gb_chrom_layout<<<1, 32, 0, st>>>(n_chrom, g, d_cnt);
     GB_CU(cudaGetLastError());
     GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
     GB_CU(cudaStreamSynchronize(st));

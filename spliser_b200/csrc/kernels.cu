@@ -244,13 +244,21 @@ __global__ void k_bin_layout(DevBins bins, uint32_t* totals8) {
     }
     bins.chrom_bin_base[bins.n_chrom] = nb; bins.chrom_tile_base[bins.n_chrom] = nt;
     totals8[4] = nb; totals8[5] = nt; totals8[6] = nt * K3_TILE; totals8[7] = bins.max_len[0];
-    // junction sub-tables: power of two >= 2 x instances, so a sub-table can never fill up
+}
+
+// junction sub-tables, one power-of-two table per chromosome.  attempt 0 sizes them for the usual case (distinct
+// junctions are a tiny fraction of the N operators: instances / 8, at least 1024 slots); if a probe sequence gets long
+// the insert kernel raises the overflow flag and the host retries with attempt 1: >= 2 x instances, which cannot fill.
+__global__ void k_jtab_layout(DevBins bins, int attempt, uint32_t* totals8) {
+    if (blockIdx.x || threadIdx.x) return;
     uint32_t ns = 0;
     for (int c = 0; c < bins.n_chrom; ++c) {
         bins.tab_base[c] = ns;
         if (bins.chrom_jn[c]) {
+            const uint32_t jn = bins.chrom_jn[c];
+            const uint32_t want = (attempt > 0 || jn <= 4096u) ? 2u * jn : max(8192u, jn >> 3);
             uint32_t t = 64;
-            while (t < 2u * bins.chrom_jn[c]) t <<= 1;
+            while (t < want) t <<= 1;
             ns += t;
         }
     }
@@ -554,7 +562,7 @@ __global__ void __launch_bounds__(256) k_jg_insert(const Chunk* __restrict__ chu
                 const unsigned long long old = atomicCAS(jg.key + t0 + h, 0ull, key);
                 if (old == 0ull || old == key) break;
                 h = (h + 1) & tmask;
-                if (++probes > tmask) { atomicExch(jg.overflow, 1u); break; }
+                if (++probes > min(tmask, 512u)) { atomicExch(jg.overflow, 1u); break; }      // the host re-sizes the table and retries
             }
             slot = t0 + h;
             atomicAdd(jg.s_all + slot, (uint32_t)__popc(peers));
@@ -567,8 +575,8 @@ __global__ void __launch_bounds__(256) k_jg_insert(const Chunk* __restrict__ chu
 
 __global__ void k_jg_used(DevJunc jg) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s < jg.n_slots) { jg.s_used[s] = jg.key[s] != 0ull; jg.s_off[s] = jg.s_simple[s]; }
-    if (s == jg.n_slots) { jg.s_used[s] = 0; jg.s_off[s] = 0; }
+    if (s < jg.n_slots) { jg.s_used[s] = jg.key[s] != 0ull; jg.s_off[s] = jg.s_simple[s]; jg.s_coff[s] = jg.s_all[s] - jg.s_simple[s]; }
+    if (s == jg.n_slots) { jg.s_used[s] = 0; jg.s_off[s] = 0; jg.s_coff[s] = 0; }
 }
 
 __global__ void k_jg_compact(DevJunc jg, int n_chrom) {
@@ -579,7 +587,7 @@ __global__ void k_jg_compact(DevJunc jg, int n_chrom) {
     int lo = 0, hi = n_chrom;                                     // last chromosome with tab_base <= s
     while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (jg.tab_base[mid] <= s) lo = mid; else hi = mid; }
     jg.dj_l[d] = (uint32_t)(key & POS_MASK); jg.dj_rk[d] = (uint32_t)(key >> 32); jg.dj_chrom[d] = lo;
-    jg.dj_all[d] = jg.s_all[s]; jg.dj_simple[d] = jg.s_simple[s]; jg.dj_off[d] = jg.s_off[s];
+    jg.dj_all[d] = jg.s_all[s]; jg.dj_simple[d] = jg.s_simple[s]; jg.dj_off[d] = jg.s_off[s]; jg.dj_coff[d] = jg.s_coff[s];
 }
 
 __global__ void __launch_bounds__(256) k_jg_scatter(DevSoA soa, DevJunc jg) {
@@ -589,20 +597,19 @@ __global__ void __launch_bounds__(256) k_jg_scatter(DevSoA soa, DevJunc jg) {
     uint32_t slot = 0;
     if (live) {
         slot = jg.slot_of[j];
-        if (soa.jn_read[j] >> 31) {
-            const uint32_t p = jg.s_off[slot] + atomicAdd(jg.s_cursor + slot, 1u);
-            jg.gi_a0[p] = soa.ji_a0[j]; jg.gi_end[p] = soa.ji_end[j];
-        } else cx = true;
+        cx = !(soa.jn_read[j] >> 31);
     }
-    const uint32_t bal = __ballot_sync(0xffffffffu, cx);
-    if (!bal) return;
+    // neighbouring reads carry the same junction: one cursor atomic per distinct (slot, kind) of the warp
+    const uint32_t peers = __match_any_sync(0xffffffffu, live ? ((slot << 1) | (cx ? 1u : 0u)) : 0xffffffffu);
     const int lane = threadIdx.x & 31;
+    const int leader = __ffs(peers) - 1;
     uint32_t base = 0;
-    if (lane == 0) base = atomicAdd(jg.cx_n, (uint32_t)__popc(bal));
-    base = __shfl_sync(0xffffffffu, base, 0);
-    if (cx) {
-        const uint32_t p = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-        jg.cx_j[p] = j; jg.cx_d[p] = jg.s_used[slot];
+    if (live && lane == leader) base = atomicAdd((cx ? jg.s_ccur : jg.s_cursor) + slot, (uint32_t)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live) {
+        const uint32_t rank = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        if (cx) jg.cx_j[jg.s_coff[slot] + rank] = j;
+        else { const uint32_t p = jg.s_off[slot] + rank; jg.gi_a0[p] = soa.ji_a0[j]; jg.gi_end[p] = soa.ji_end[j]; }
     }
 }
 
@@ -960,6 +967,22 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, Dev
         }
         jg.hot_l[d] = hl; jg.hot_r[d] = hr;
     }
+    // complex instances of a hot (junction, side): one descriptor reserves a range of the flat per-pass index space;
+    // the 64-bit counter carries (descriptors << 40 | instances), so descriptor order == flat index order
+    if (live && (hl | hr)) {
+        const uint32_t nc = jg.dj_all[d] - jg.dj_simple[d];
+        if (nc) {
+            const uint32_t sides = (hl ? 1u : 0u) + (hr ? 1u : 0u);
+            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(cnt.work + 4),
+                                                     ((unsigned long long)sides << 40) | ((unsigned long long)nc * sides));
+            uint32_t slot = (uint32_t)(old >> 40), base = (uint32_t)(old & ((1ull << 40) - 1ull));
+            for (int side = 0; side < 2; ++side) {
+                if (!(side == 0 ? hl : hr)) continue;
+                jg.cxd_base[slot] = base; jg.cxd_ds[slot] = (d << 1) | (uint32_t)side;
+                ++slot; base += nc;
+            }
+        }
+    }
     // work list of hot (junction, side, chunk of simple instances) units; big groups are split so that one warp
     // never walks more than JS_CHUNK instances
     if (live && (hl | hr)) {
@@ -1023,38 +1046,19 @@ __global__ void __launch_bounds__(256) k_junc_simple(DevJunc jg, DevGraph g, Dev
     }
 }
 
-// complex instances: (1) compact the ones whose junction has a hot endpoint into a dense list (one atomic per
-// warp), (2) run the per-read logic with every lane busy
-__global__ void __launch_bounds__(256) k_junc_complex_filter(DevJunc jg, DevCounters cnt) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    uint32_t hl = 0, hr = 0, j = 0;
-    if (i < jg.n_complex) {
-        const uint32_t d = jg.cx_d[i];
-        hl = jg.hot_l[d]; hr = jg.hot_r[d];
-        j = jg.cx_j[i];
-    }
-    const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int side = 0; side < 2; ++side) {
-        const uint32_t a1 = side == 0 ? hl : hr;
-        const uint32_t bal = __ballot_sync(0xffffffffu, a1 != 0u);
-        if (!bal) continue;
-        uint32_t base = 0;
-        if (lane == 0) base = atomicAdd(cnt.work + 3, (uint32_t)__popc(bal));
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (a1) {
-            const uint32_t p = base + (uint32_t)__popc(bal & ((1u << lane) - 1u));
-            jg.cxl_j[p] = j; jg.cxl_a[p] = (a1 - 1u) | ((uint32_t)side << 31);
-        }
-    }
-}
-
+// complex instances of hot junctions: flat index -> descriptor (binary search over the descriptor bases) -> instance
 __global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
     const bool combine = (mode & FLAG_COMBINE) != 0;
-    const uint32_t n = cnt.work[3];
+    const unsigned long long w = *reinterpret_cast<const unsigned long long*>(cnt.work + 4);
+    const uint32_t n_desc = (uint32_t)(w >> 40), n = (uint32_t)(w & ((1ull << 40) - 1ull));
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        const uint32_t a = jg.cxl_a[i];
-        k4_exceptions(soa, g, cnt, jg.cxl_j[i], (int)(a & POS_MASK), (int)(a >> 31), combine);
+        uint32_t lo = 0, hi = n_desc;                                  // last descriptor with base <= i
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (jg.cxd_base[mid] <= i) lo = mid; else hi = mid; }
+        const uint32_t ds = jg.cxd_ds[lo], d = ds >> 1;
+        const int side = (int)(ds & 1u);
+        const uint32_t j = jg.cx_j[jg.dj_coff[d] + (i - jg.cxd_base[lo])];
+        const int anchor = (int)((side == 0 ? jg.hot_l[d] : jg.hot_r[d]) - 1u);
+        k4_exceptions(soa, g, cnt, j, anchor, side, combine);
     }
 }
 
@@ -1275,6 +1279,7 @@ void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, Dev
     cudaMemsetAsync(jg.s_all, 0, (size_t)jg.n_slots * 4, st);
     cudaMemsetAsync(jg.s_simple, 0, (size_t)jg.n_slots * 4, st);
     cudaMemsetAsync(jg.s_cursor, 0, (size_t)jg.n_slots * 4, st);
+    cudaMemsetAsync(jg.s_ccur, 0, (size_t)jg.n_slots * 4, st);
     cudaMemsetAsync(jg.cx_n, 0, 8, st);                                  // cx_n and overflow are adjacent
     k_jg_insert<<<n_chunks, 256, 0, st>>>(chunks, soa, jg);
     const uint32_t n = jg.n_slots + 1;
@@ -1286,15 +1291,23 @@ void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, Dev
     k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_off, n, jg.scan_tmp);
     k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk);
     k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_off, n, jg.scan_tmp, nullptr);
+    k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_coff, n, jg.scan_tmp);
+    k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk);
+    k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_coff, n, jg.scan_tmp, nullptr);
+    cudaMemcpyAsync(totals4 + 2, jg.s_coff + jg.n_slots, 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(totals4, jg.s_used + jg.n_slots, 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(totals4 + 1, jg.s_off + jg.n_slots, 4, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(totals4 + 3, jg.overflow, 4, cudaMemcpyDeviceToDevice, st);
+}
+void launch_jtab_layout(DevBins bins, int attempt, uint32_t* totals8, void* stream) {
+    k_jtab_layout<<<1, 32, 0, (cudaStream_t)stream>>>(bins, attempt, totals8);
 }
 void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* totals4, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (jg.n_slots == 0 || soa.nJ == 0) return;
     k_jg_compact<<<(jg.n_slots + 255) / 256, 256, 0, st>>>(jg, n_chrom);
     k_jg_scatter<<<(soa.nJ + 255) / 256, 256, 0, st>>>(soa, jg);
-    cudaMemcpyAsync(totals4 + 2, jg.cx_n, 8, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(totals4 + 3, jg.overflow, 4, cudaMemcpyDeviceToDevice, st);
 }
 void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
@@ -1303,10 +1316,7 @@ void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint3
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     k_junc_simple<<<sms * 8, 256, 0, st>>>(jg, g, cnt, flags);
-    if (jg.n_complex) {
-        k_junc_complex_filter<<<(jg.n_complex + 255) / 256, 256, 0, st>>>(jg, cnt);
-        k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags);
-    }
+    if (jg.n_complex) k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags);
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;
@@ -1315,6 +1325,6 @@ void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags
     k_span_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(out.span_blk, nblk);
     k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags);
 }
-int kernel_launch_count_per_pass() { return 9; }   // alpha_reduce, beta1_stab, junc_lookup, junc_simple, junc_complex_filter, junc_complex, span_blocksum, span_scan, finalize
+int kernel_launch_count_per_pass() { return 8; }   // alpha_reduce, beta1_stab, junc_lookup, junc_simple, junc_complex, span_blocksum, span_scan, finalize
 
 }  // namespace spl

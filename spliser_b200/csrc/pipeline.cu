@@ -307,7 +307,7 @@ int alloc_counters_outputs(spl_ctx* ctx, size_t S, size_t E) {
     Carver cc;
     const size_t c_cov = cc.take<uint32_t>(2 * S + 2), c_span = cc.take<uint32_t>(2 * (S + 1) + 2);
     const size_t c_covx = cc.take<uint32_t>(S + 1), c_spanx = cc.take<uint32_t>(S + 1), c_flank = cc.take<uint32_t>(S + 1);
-    const size_t c_dc = cc.take<uint32_t>(E + 1), c_work = cc.take<uint32_t>(4);
+    const size_t c_dc = cc.take<uint32_t>(E + 1), c_work = cc.take<uint32_t>(8);
     ctx->cnt_bytes = cc.off + 256;
     CU(ctx->d_cnt.reserve(ctx->cnt_bytes));
     char* cb = (char*)ctx->d_cnt.p;
@@ -454,13 +454,21 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
     // ---- junction groups: table -> (sync: distinct count) -> dense arrays + grouped simple instances
     DevJunc& jg = ctx->jg;
     jg = DevJunc{};
-    const size_t n_slots = ctx->n_chunks ? ctx->h_tot[8] : 0;
-    {
+    uint32_t* d_jtot = (uint32_t*)ctx->d_tot.p + 12;
+    for (int attempt = 0;; ++attempt) {
+        size_t n_slots = 0;
+        if (ctx->n_chunks) {
+            launch_jtab_layout(bins, attempt, (uint32_t*)ctx->d_tot.p, ctx->stream);
+            CU(cudaMemcpyAsync(ctx->h_tot + 8, (uint32_t*)ctx->d_tot.p + 8, 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaStreamSynchronize(ctx->stream));
+            n_slots = ctx->h_tot[8];
+        }
         Carver jc;
         const size_t nscan = (n_slots + 1 + 4095) / 4096 + 8;
         const size_t o_key = jc.take<unsigned long long>(n_slots + 2), o_sa = jc.take<uint32_t>(n_slots + 2),
                      o_ss = jc.take<uint32_t>(n_slots + 2), o_su = jc.take<uint32_t>(n_slots + 2), o_so = jc.take<uint32_t>(n_slots + 2),
                      o_sc = jc.take<uint32_t>(n_slots + 2), o_sl = jc.take<uint32_t>(nJ + 2), o_cn = jc.take<uint32_t>(4),
+                     o_co = jc.take<uint32_t>(n_slots + 2), o_cc = jc.take<uint32_t>(n_slots + 2),
                      o_tmp = jc.take<uint32_t>(2 * nscan + 8);
         CU(ctx->d_jtab.reserve(jc.off + 256));
         char* jb = (char*)ctx->d_jtab.p;
@@ -469,38 +477,41 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
         jg.s_used = (uint32_t*)(jb + o_su); jg.s_off = (uint32_t*)(jb + o_so); jg.s_cursor = (uint32_t*)(jb + o_sc);
         jg.slot_of = (uint32_t*)(jb + o_sl); jg.cx_n = (uint32_t*)(jb + o_cn); jg.overflow = jg.cx_n + 1;
         jg.scan_tmp = (uint32_t*)(jb + o_tmp);
+        jg.s_coff = (uint32_t*)(jb + o_co); jg.s_ccur = (uint32_t*)(jb + o_cc);
+        launch_junction_groups_a(ctx->chunks, ctx->n_chunks, soa, jg, d_jtot, ctx->stream);
+        CU(cudaGetLastError());
+        CU(cudaMemcpyAsync(ctx->h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        if (!ctx->h_tot[15]) break;                                    // no sub-table got crowded
+        if (attempt >= 1) return ctx->fail(SPL_ERR_CUDA, "junction table overflow (internal sizing error)");
     }
-    uint32_t* d_jtot = (uint32_t*)ctx->d_tot.p + 12;
-    launch_junction_groups_a(ctx->chunks, ctx->n_chunks, soa, jg, d_jtot, ctx->stream);
-    CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    const size_t D = ctx->h_tot[12], n_simple = ctx->h_tot[13];
+    const size_t D = ctx->h_tot[12], n_simple = ctx->h_tot[13], n_complex = ctx->h_tot[14];
     {
         Carver dc;
         const size_t o_l = dc.take<uint32_t>(D + 2), o_rk = dc.take<uint32_t>(D + 2), o_ch = dc.take<int32_t>(D + 2),
-                     o_al = dc.take<uint32_t>(D + 2), o_si = dc.take<uint32_t>(D + 2), o_of = dc.take<uint32_t>(D + 2),
+                     o_al = dc.take<uint32_t>(D + 2), o_si = dc.take<uint32_t>(D + 2), o_of = dc.take<uint32_t>(D + 2), o_cf = dc.take<uint32_t>(D + 2),
                      o_a0 = dc.take<int32_t>(n_simple + 2), o_en = dc.take<int32_t>(n_simple + 2),
-                     o_cj = dc.take<uint32_t>(nJ - std::min(nJ, n_simple) + 2), o_cd = dc.take<uint32_t>(nJ - std::min(nJ, n_simple) + 2),
+                     o_cj = dc.take<uint32_t>(n_complex + 2),
                      o_hl = dc.take<uint32_t>(D + 2), o_hr = dc.take<uint32_t>(D + 2),
                      o_wl = dc.take<unsigned long long>(2 * D + 2 * (n_simple / 2048 + 1) + 8),
-                     o_xj = dc.take<uint32_t>(2 * (nJ - std::min(nJ, n_simple)) + 2), o_xa = dc.take<uint32_t>(2 * (nJ - std::min(nJ, n_simple)) + 2);
+                     o_xb = dc.take<uint32_t>(2 * D + 2), o_xd = dc.take<uint32_t>(2 * D + 2);
         CU(ctx->d_jdense.reserve(dc.off + 256));
         char* db = (char*)ctx->d_jdense.p;
         jg.D = (uint32_t)D;
         jg.dj_l = (uint32_t*)(db + o_l); jg.dj_rk = (uint32_t*)(db + o_rk); jg.dj_chrom = (int32_t*)(db + o_ch);
         jg.dj_all = (uint32_t*)(db + o_al); jg.dj_simple = (uint32_t*)(db + o_si); jg.dj_off = (uint32_t*)(db + o_of);
+        jg.dj_coff = (uint32_t*)(db + o_cf);
         jg.gi_a0 = (int32_t*)(db + o_a0); jg.gi_end = (int32_t*)(db + o_en);
-        jg.cx_j = (uint32_t*)(db + o_cj); jg.cx_d = (uint32_t*)(db + o_cd);
+        jg.cx_j = (uint32_t*)(db + o_cj);
         jg.hot_l = (uint32_t*)(db + o_hl); jg.hot_r = (uint32_t*)(db + o_hr); jg.wl = (unsigned long long*)(db + o_wl);
-        jg.cxl_j = (uint32_t*)(db + o_xj); jg.cxl_a = (uint32_t*)(db + o_xa);
+        jg.cxd_base = (uint32_t*)(db + o_xb); jg.cxd_ds = (uint32_t*)(db + o_xd);
+        jg.n_complex = (uint32_t)n_complex;
     }
     launch_junction_groups_b(soa, jg, ctx->n_chrom_loaded, d_jtot, ctx->stream);
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(ctx->h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    jg.n_complex = ctx->h_tot[14];
     ctx->stats[SPL_STAT_N_DISTINCT_J] = (double)D; ctx->stats[SPL_STAT_N_SIMPLE_J] = (double)n_simple;
     ctx->stats[SPL_STAT_N_COMPLEX_J] = (double)jg.n_complex;
     if (ctx->h_tot[15]) return ctx->fail(SPL_ERR_CUDA, "junction table overflow (internal sizing error)");
