@@ -149,7 +149,10 @@ struct DevOutputs {
 constexpr int CHUNK_READS = 4096;       // records per chunk
 constexpr int EXPAND_THREADS = 512;     // one record per thread and round
 constexpr int FIN_THREADS = 256;
-constexpr int FIN_ITEMS = 4;            // sites per thread in the span scan
+#ifndef SPL_FIN_ITEMS
+#define SPL_FIN_ITEMS 1
+#endif
+constexpr int FIN_ITEMS = SPL_FIN_ITEMS; // sites per thread in the span scan (1: the beta2 gather wants every site on its own thread)
 
 constexpr uint32_t FLAG_STRANDED = 1u, FLAG_RF = 2u, FLAG_CRYPTIC = 4u, FLAG_COMBINE = 8u;
 constexpr uint32_t FLAG_DEBUG_SKIP_EXC = 0x10000u;   // set only by SPLISER_DEBUG_SKIP_EXC=1 (kernel timing experiments)

@@ -643,7 +643,10 @@ __global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
 constexpr int PS_STAGES = 3;
 constexpr int PS_CONSUMERS = 256;                  // 8 consumer warps
 constexpr int PS_THREADS = PS_CONSUMERS + 32;      // + 1 producer warp
-constexpr int K3_SITES = 2048;                     // staged site positions per stage (8 KB)
+#ifndef SPL_K3_SITES
+#define SPL_K3_SITES 504
+#endif
+constexpr int K3_SITES = SPL_K3_SITES;             // staged site positions per stage (2 KB; a tile's window is a few dozen sites)
 
 struct StageMeta {
     uint32_t e0, e1;        // valid global element range of the item
@@ -734,7 +737,14 @@ __device__ __forceinline__ void k3_consume(const K3Stage& stg, const StageMeta& 
     const int wlo = __reduce_min_sync(0xffffffffu, lo), whi = __reduce_max_sync(0xffffffffu, hi) - 1;
     if (wlo > whi) return;
     int i0, i1;
-    bound_pair_i32(sp, m.w_lo, m.w_hi, wlo, whi, i0, i1);
+    if (m.w_hi - m.w_lo <= 32) {                                     // usual case: one site per lane, two ballots
+        const int sidx = m.w_lo + lane;
+        const int sv = sidx < m.w_hi ? sp[sidx] : INT_MAX;
+        i0 = m.w_lo + __popc(__ballot_sync(0xffffffffu, sv < wlo));
+        i1 = m.w_lo + __popc(__ballot_sync(0xffffffffu, sv <= whi));
+    } else {
+        bound_pair_i32(sp, m.w_lo, m.w_hi, wlo, whi, i0, i1);
+    }
     if (i0 >= i1) return;
     if (i1 - i0 <= K3_DENSE) {
         for (int s = i0; s < i1; ++s) {                           // warp-uniform loop
@@ -967,36 +977,60 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, Dev
         }
         jg.hot_l[d] = hl; jg.hot_r[d] = hr;
     }
+    // Reservations are aggregated per warp (one atomic per warp and list instead of one per hot junction).
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const uint32_t sides = (hl ? 1u : 0u) + (hr ? 1u : 0u);
     // complex instances of a hot (junction, side): one descriptor reserves a range of the flat per-pass index space;
     // the 64-bit counter carries (descriptors << 40 | instances), so descriptor order == flat index order
-    if (live && (hl | hr)) {
-        const uint32_t nc = jg.dj_all[d] - jg.dj_simple[d];
-        if (nc) {
-            const uint32_t sides = (hl ? 1u : 0u) + (hr ? 1u : 0u);
-            const unsigned long long old = atomicAdd(reinterpret_cast<unsigned long long*>(cnt.work + 4),
-                                                     ((unsigned long long)sides << 40) | ((unsigned long long)nc * sides));
-            uint32_t slot = (uint32_t)(old >> 40), base = (uint32_t)(old & ((1ull << 40) - 1ull));
-            for (int side = 0; side < 2; ++side) {
-                if (!(side == 0 ? hl : hr)) continue;
-                jg.cxd_base[slot] = base; jg.cxd_ds[slot] = (d << 1) | (uint32_t)side;
-                ++slot; base += nc;
+    {
+        const uint32_t nc = (live && sides) ? jg.dj_all[d] - jg.dj_simple[d] : 0u;
+        const uint32_t nd = nc ? sides : 0u, ni = nc * sides;
+        uint32_t pd = nd, pi = ni;                                     // inclusive warp scans
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, pd, o), b = __shfl_up_sync(0xffffffffu, pi, o);
+            if (lane >= o) { pd += a; pi += b; }
+        }
+        const uint32_t td = __shfl_sync(0xffffffffu, pd, 31), ti = __shfl_sync(0xffffffffu, pi, 31);
+        if (td) {                                                      // warp-uniform
+            unsigned long long old = 0;
+            if (lane == 0) old = atomicAdd(reinterpret_cast<unsigned long long*>(cnt.work + 4), ((unsigned long long)td << 40) | ti);
+            old = __shfl_sync(0xffffffffu, old, 0);
+            uint32_t slot = (uint32_t)(old >> 40) + pd - nd, base = (uint32_t)(old & ((1ull << 40) - 1ull)) + pi - ni;
+            if (nc) {
+                for (int side = 0; side < 2; ++side) {
+                    if (!(side == 0 ? hl : hr)) continue;
+                    jg.cxd_base[slot] = base; jg.cxd_ds[slot] = (d << 1) | (uint32_t)side;
+                    ++slot; base += nc;
+                }
             }
         }
     }
     // work list of hot (junction, side, chunk of simple instances) units; big groups are split so that one warp
     // never walks more than JS_CHUNK instances
-    if (live && (hl | hr)) {
-        const uint32_t ns = jg.dj_simple[d];
-        if (ns) {
-            const uint32_t nch = (ns + JS_CHUNK - 1) / JS_CHUNK;
-            const uint32_t sides = (hl ? 1u : 0u) + (hr ? 1u : 0u);
-            uint32_t p = atomicAdd(cnt.work + 2, nch * sides);
-            for (int side = 0; side < 2; ++side) {
-                if (!(side == 0 ? hl : hr)) continue;
-                for (uint32_t c = 0; c < nch; ++c) jg.wl[p++] = ((unsigned long long)c << 32) | (d << 1) | (uint32_t)side;
+    {
+        const uint32_t ns = (live && sides) ? jg.dj_simple[d] : 0u;
+        const uint32_t nch = (ns + JS_CHUNK - 1) / JS_CHUNK;
+        const uint32_t nu = nch * sides;
+        uint32_t pu = nu;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t a = __shfl_up_sync(0xffffffffu, pu, o); if (lane >= o) pu += a; }
+        const uint32_t tu = __shfl_sync(0xffffffffu, pu, 31);
+        if (tu) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(cnt.work + 2, tu);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            uint32_t p = base + pu - nu;
+            if (nu) {
+                for (int side = 0; side < 2; ++side) {
+                    if (!(side == 0 ? hl : hr)) continue;
+                    for (uint32_t c = 0; c < nch; ++c) jg.wl[p++] = ((unsigned long long)c << 32) | (d << 1) | (uint32_t)side;
+                }
             }
         }
     }
+    (void)lt;
 }
 
 
@@ -1051,9 +1085,16 @@ __global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, De
     const bool combine = (mode & FLAG_COMBINE) != 0;
     const unsigned long long w = *reinterpret_cast<const unsigned long long*>(cnt.work + 4);
     const uint32_t n_desc = (uint32_t)(w >> 40), n = (uint32_t)(w & ((1ull << 40) - 1ull));
+    const int lane = threadIdx.x & 31;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        uint32_t lo = 0, hi = n_desc;                                  // last descriptor with base <= i
-        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (jg.cxd_base[mid] <= i) lo = mid; else hi = mid; }
+        // the warp's 32 consecutive flat indices mostly share a descriptor: lane 0 searches, the others step forward
+        uint32_t lo = 0;
+        if (lane == 0) {
+            uint32_t hi = n_desc;                                      // last descriptor with base <= i
+            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (jg.cxd_base[mid] <= i) lo = mid; else hi = mid; }
+        }
+        lo = __shfl_sync(__activemask(), lo, 0);
+        while (lo + 1 < n_desc && jg.cxd_base[lo + 1] <= i) ++lo;
         const uint32_t ds = jg.cxd_ds[lo], d = ds >> 1;
         const int side = (int)(ds & 1u);
         const uint32_t j = jg.cx_j[jg.dj_coff[d] + (i - jg.cxd_base[lo])];
