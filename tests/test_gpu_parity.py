@@ -211,3 +211,54 @@ def test_host_and_device_graph_builders_agree(ctx, monkeypatch):
         monkeypatch.delenv("SPLISER_HOST_GRAPH", raising=False)
         assert c_oracle.diff_tables(dev, host) is None, c_oracle.diff_tables(dev, host)
         assert len(dev["pos"]) > 1000 and len(dev["comp_pos"]) > 0
+
+
+def test_c4_shaped_recount_vs_c_oracle(ctx):
+    """BASELINE configs[3] shape at reduced size: K samples of one genome (own reads, own junction subset); every site
+    of the merged table that a sample lacks is re-counted in that sample's reads with the partner / competitor
+    positions accumulated from the lower-indexed samples (S:869-904), strand '' when no earlier sample had it."""
+    import numpy as np
+    from oracle import c_oracle
+    from spliser_b200 import Junctions, Records, api, synth
+    K = 4
+    w = synth.generate(synth.config_small(240_000, seed=91, stranded=True, paired=True))
+    rng = np.random.default_rng(5)
+    r, j = w.records, w.junctions
+    n_chrom = len(w.chroms)
+    samples = []
+    for k in range(K):
+        keep_j = rng.random(len(j)) < 0.85
+        jk = Junctions(j.chrom[keep_j], j.left[keep_j], j.right[keep_j], j.score[keep_j], j.strand[keep_j])
+        pos, flag, ops, off, seg_off = [], [], [], [0], [0]
+        for s in range(len(r.seg_chrom)):
+            for i in range(int(r.seg_off[s]) + k, int(r.seg_off[s + 1]), K):
+                pos.append(r.pos[i]); flag.append(r.flag[i])
+                ops.extend(r.cigar[int(r.cig_off[i]):int(r.cig_off[i + 1])])
+                off.append(len(ops))
+            seg_off.append(len(pos))
+        rk = Records(pos, flag, off, ops, r.seg_chrom, seg_off)
+        tk = api.build_site_table(n_chrom, jk, w.flags)
+        table = {}
+        for i in range(len(tk)):
+            table[(int(tk.chrom[i]), int(tk.pos[i]), tk.strand_str(i))] = (sorted(tk.partners(i)), tk.competitors(i))
+        samples.append((rk, table))
+    union = sorted(set().union(*[set(t) for _, t in samples]))
+    total = 0
+    for k in range(K):
+        rk, tab = samples[k]
+        gaps = []
+        for key in union:
+            if key in tab:
+                continue
+            P, C, strand = set(), set(), ""
+            for jx in range(k):
+                if key in samples[jx][1]:
+                    p, c = samples[jx][1][key]
+                    P |= set(p); C |= set(c); strand = key[2]
+            gaps.append((key[0], key[1], strand, sorted(P), sorted(C)))
+        assert gaps
+        want1, want2 = c_oracle.recount(rk, n_chrom, gaps, w.flags | 8, threads=8)
+        got1, got2 = ctx.recount_records(rk, n_chrom, gaps, w.flags | 8)
+        assert np.array_equal(got1, want1) and np.array_equal(got2, want2), (k, int(np.sum(got1 != want1)), int(np.sum(got2 != want2)))
+        total += int(want1.sum()) + int(want2.sum())
+    assert total > 0
