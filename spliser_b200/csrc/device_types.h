@@ -103,11 +103,15 @@ struct DevJunc {
     uint32_t  n_complex;
     uint32_t* dj_coff;            // [D] offset of the junction's complex instances in cx_j
     uint32_t* cx_j; uint32_t* cx_n;             // complex instances grouped by junction: global junction index; cx_n: scratch word before `overflow`
+    uint4*    cx_rng;             // [n_complex] the owning read of each complex instance: junctions [x, y), blocks [z, w) (absolute indices)
     // per pass
     uint32_t* hot_l; uint32_t* hot_r;           // [D] anchor + 1 of a hot endpoint, 0 otherwise
     unsigned long long* wl;       // hot units: chunk << 32 | junction << 1 | side
     uint32_t* cxd_base; uint32_t* cxd_ds;       // [2 D] per pass: descriptors of hot (junction, side) with complex instances: first flat index, d << 1 | side
+    uint32_t* cxd_nt; int32_t* cxd_t;           // [2 D], [2 D * CXD_T] sites the (junction, side) is a partner/competitor pair for
 };
+
+constexpr int CXD_T = 4;          // pair sites kept inline per descriptor
 
 struct Tile { uint32_t e0; int32_t w_lo, w_hi; int32_t pad; };   // first element, site index window [w_lo, w_hi)
 struct DevBins {

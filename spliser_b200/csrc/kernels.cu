@@ -608,7 +608,11 @@ __global__ void __launch_bounds__(256) k_jg_scatter(DevSoA soa, DevJunc jg) {
     base = __shfl_sync(0xffffffffu, base, leader);
     if (live) {
         const uint32_t rank = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
-        if (cx) jg.cx_j[jg.s_coff[slot] + rank] = j;
+        if (cx) {
+            const uint32_t ri = soa.jn_read[j] & POS_MASK;
+            jg.cx_j[jg.s_coff[slot] + rank] = j;
+            jg.cx_rng[jg.s_coff[slot] + rank] = make_uint4(soa.sr_joff[ri], soa.sr_joff[ri + 1], soa.bB + soa.sr_boff[ri], soa.bB + soa.sr_boff[ri + 1]);
+        }
         else { const uint32_t p = jg.s_off[slot] + rank; jg.gi_a0[p] = soa.ji_a0[j]; jg.gi_end[p] = soa.ji_end[j]; }
     }
 }
@@ -856,79 +860,66 @@ __device__ __forceinline__ bool pc_pair(const DevGraph& g, int t, int32_t l, int
            (in_sorted(g.cp_pos, c0, c1, l) && in_list(g.pc_pos, p0, p1, r));
 }
 
-// Exception logic for the read that owns junction j, whose endpoint (side 0 = l, 1 = r) sits on `anchor`.
-// Every t in the reverse-partner list of the anchor has the anchored endpoint in P_t by construction, so
-// (l, r) is a partner/competitor pair for t (S:494-501) iff the OTHER endpoint is in C_t.
-__device__ __forceinline__ void k4_exceptions(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, uint32_t j,
-                                              int anchor, int side, bool combine) {
-    const uint32_t rd = soa.jn_read[j];
-    const uint32_t ri = rd & POS_MASK;
-    const bool single = (rd >> 31) != 0;                               // the read has exactly this one junction
-    const uint32_t rraw = soa.jn_rk[j], lraw_j = soa.jn_l[j];
-    const uint32_t k = rraw >> 31;
-    const int32_t l = (int32_t)(lraw_j & POS_MASK), r = (int32_t)(rraw & POS_MASK);
-    const int32_t other = side == 0 ? r : l;
-    uint32_t j0 = j, j1 = j + 1;
-    if (!single) { j0 = soa.sr_joff[ri]; j1 = soa.sr_joff[ri + 1]; }
-    for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
-        const int t = g.rp_site[q];
-        if (t < g.own_lo || t >= g.own_hi) continue;
-        const int c0 = g.cp_off[t], c1 = g.cp_off[t + 1];
-        if (c0 == c1 || !in_sorted(g.cp_pos, c0, c1, other)) continue;
-        // side 1 finds (r in P_t, l in C_t); if (l in P_t, r in C_t) holds as well, side 0 already handled t
-        if (side == 1 && in_sorted(g.cp_pos, c0, c1, r) && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) continue;
-        bool earlier = false;
-        for (uint32_t jj = j0; jj < j && !earlier; ++jj)
-            earlier = pc_pair(g, t, (int32_t)(soa.jn_l[jj] & POS_MASK), (int32_t)(soa.jn_rk[jj] & POS_MASK));
-        if (earlier) continue;
-        // j is the first junction of this read that makes compSplicing true for t: classify the read at t
-        const int32_t tp = g.site_pos[t];
-        const bool ok = strand_ok(g.site_cls[t], k);
-        bool alpha = false; int32_t partner_used = 0; int kstar = -1;
-        if (single) {
-            if (l == tp && !(lraw_j >> 31)) { alpha = true; partner_used = r; }
-            if (r == tp) { alpha = true; partner_used = l; }
-            if (l < tp && tp < r) kstar = 0;
-        } else {
-            for (uint32_t jj = j0; jj < j1; ++jj) {
-                const uint32_t lraw = soa.jn_l[jj];
-                const int32_t ll = (int32_t)(lraw & POS_MASK), rr = (int32_t)(soa.jn_rk[jj] & POS_MASK);
-                if (ll == tp && !(lraw >> 31)) { alpha = true; partner_used = rr; }   // firstN: POS > t, read skipped (S:435)
-                if (rr == tp) { alpha = true; partner_used = ll; }
-                if (ll < tp && tp < rr) kstar = (int)(jj - j0);
-            }
+// The read that owns junction j (its junctions are [j0, j1), its blocks [b0, b1)) makes compSplicing true for site t
+// through j, unless an earlier junction of the read already did: classify the read at t (S:503-557, first match wins).
+__device__ __forceinline__ void k4_classify(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, int t, uint32_t j,
+                                            uint32_t j0, uint32_t j1, uint32_t b0, uint32_t b1, uint32_t k, bool combine) {
+    bool earlier = false;
+    for (uint32_t jj = j0; jj < j && !earlier; ++jj)
+        earlier = pc_pair(g, t, (int32_t)(soa.jn_l[jj] & POS_MASK), (int32_t)(soa.jn_rk[jj] & POS_MASK));
+    if (earlier) return;
+    const int32_t tp = g.site_pos[t];
+    const bool ok = strand_ok(g.site_cls[t], k);
+    bool alpha = false; int32_t partner_used = 0; int kstar = -1;
+    for (uint32_t jj = j0; jj < j1; ++jj) {
+        const uint32_t lraw = soa.jn_l[jj];
+        const int32_t ll = (int32_t)(lraw & POS_MASK), rr = (int32_t)(soa.jn_rk[jj] & POS_MASK);
+        if (ll == tp && !(lraw >> 31)) { alpha = true; partner_used = rr; }   // firstN: POS > t, read skipped (S:435)
+        if (rr == tp) { alpha = true; partner_used = ll; }
+        if (ll < tp && tp < rr) kstar = (int)(jj - j0);
+    }
+    if (alpha) {                                                   // S:519-527
+        for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
+            const int32_t pp = g.pc_pos[e];
+            if (pp == partner_used) continue;
+            bool in_read = false;
+            for (uint32_t jj = j0; jj < j1 && !in_read; ++jj)
+                in_read = (int32_t)(soa.jn_l[jj] & POS_MASK) == pp || (int32_t)(soa.jn_rk[jj] & POS_MASK) == pp;
+            if (in_read) atomicAdd(cnt.dc + e, 1u);
         }
-        if (alpha) {                                                   // S:519-527
+    } else if (kstar >= 0) {
+        if (kstar >= (int)(j - j0)) {                              // compSplicing already true at k*: flanking (S:503-505)
+            if (ok) atomicAdd(cnt.spanx + t, 1u);
+            if (combine) atomicAdd(cnt.flank + t, 1u);
+        }
+    } else if (ok) {
+        bool covers = false;
+        for (uint32_t b = b0; b < b1 && !covers; ++b)
+            covers = soa.m_start[b] <= tp && (int32_t)(soa.m_endk[b] & POS_MASK) >= tp + 2;
+        if (covers) {                                              // beta1-type, S:544-552
+            atomicAdd(cnt.covx + t, 1u);
             for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
                 const int32_t pp = g.pc_pos[e];
-                if (pp == partner_used) continue;
                 bool in_read = false;
                 for (uint32_t jj = j0; jj < j1 && !in_read; ++jj)
                     in_read = (int32_t)(soa.jn_l[jj] & POS_MASK) == pp || (int32_t)(soa.jn_rk[jj] & POS_MASK) == pp;
                 if (in_read) atomicAdd(cnt.dc + e, 1u);
             }
-        } else if (kstar >= 0) {
-            if (kstar >= (int)(j - j0)) {                              // compSplicing already true at k*: flanking (S:503-505)
-                if (ok) atomicAdd(cnt.spanx + t, 1u);
-                if (combine) atomicAdd(cnt.flank + t, 1u);
-            }
-        } else if (ok) {
-            const uint32_t b0 = soa.bB + soa.sr_boff[ri], b1 = soa.bB + soa.sr_boff[ri + 1];
-            bool covers = false;
-            for (uint32_t b = b0; b < b1 && !covers; ++b)
-                covers = soa.m_start[b] <= tp && (int32_t)(soa.m_endk[b] & POS_MASK) >= tp + 2;
-            if (covers) {                                              // beta1-type, S:544-552
-                atomicAdd(cnt.covx + t, 1u);
-                for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
-                    const int32_t pp = g.pc_pos[e];
-                    bool in_read = false;
-                    for (uint32_t jj = j0; jj < j1 && !in_read; ++jj)
-                        in_read = (int32_t)(soa.jn_l[jj] & POS_MASK) == pp || (int32_t)(soa.jn_rk[jj] & POS_MASK) == pp;
-                    if (in_read) atomicAdd(cnt.dc + e, 1u);
-                }
-            }
         }
     }
+}
+
+// Is junction (l, r), whose endpoint (side 0 = l, 1 = r) sits on `anchor`, a partner/competitor pair for the q-th site
+// of the anchor's reverse-partner list?  Every t of that list has the anchored endpoint in P_t by construction, so
+// (l, r) is a pair for t (S:494-501) iff the OTHER endpoint is in C_t.  Returns t or -1.
+__device__ __forceinline__ int k4_pair_site(const DevGraph& g, int q, int side, int32_t l, int32_t r) {
+    const int t = g.rp_site[q];
+    if (t < g.own_lo || t >= g.own_hi) return -1;
+    const int c0 = g.cp_off[t], c1 = g.cp_off[t + 1];
+    if (c0 == c1 || !in_sorted(g.cp_pos, c0, c1, side == 0 ? r : l)) return -1;
+    // side 1 finds (r in P_t, l in C_t); if (l in P_t, r in C_t) holds as well, side 0 already handled t
+    if (side == 1 && in_sorted(g.cp_pos, c0, c1, r) && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) return -1;
+    return t;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1002,6 +993,18 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, Dev
                 for (int side = 0; side < 2; ++side) {
                     if (!(side == 0 ? hl : hr)) continue;
                     jg.cxd_base[slot] = base; jg.cxd_ds[slot] = (d << 1) | (uint32_t)side;
+                    // the sites this (junction, side) is a partner/competitor pair for depend on the junction alone:
+                    // found once here, not once per instance (CXD_T inline slots; more -> the instances walk the list)
+                    const int anchor = (int)((side == 0 ? hl : hr) - 1u);
+                    const int32_t jl = (int32_t)jg.dj_l[d], jr = (int32_t)(jg.dj_rk[d] & POS_MASK);
+                    uint32_t nt = 0;
+                    for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
+                        const int t = k4_pair_site(g, q, side, jl, jr);
+                        if (t < 0) continue;
+                        if (nt < (uint32_t)CXD_T) jg.cxd_t[slot * CXD_T + nt] = t;
+                        ++nt;
+                    }
+                    jg.cxd_nt[slot] = nt;
                     ++slot; base += nc;
                 }
             }
@@ -1097,9 +1100,22 @@ __global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, De
         while (lo + 1 < n_desc && jg.cxd_base[lo + 1] <= i) ++lo;
         const uint32_t ds = jg.cxd_ds[lo], d = ds >> 1;
         const int side = (int)(ds & 1u);
-        const uint32_t j = jg.cx_j[jg.dj_coff[d] + (i - jg.cxd_base[lo])];
-        const int anchor = (int)((side == 0 ? jg.hot_l[d] : jg.hot_r[d]) - 1u);
-        k4_exceptions(soa, g, cnt, j, anchor, side, combine);
+        const uint32_t nt = jg.cxd_nt[lo];
+        if (nt == 0) continue;
+        const uint32_t p = jg.dj_coff[d] + (i - jg.cxd_base[lo]);
+        const uint32_t j = jg.cx_j[p];
+        const uint4 rr = jg.cx_rng[p];                                 // the owning read: junctions [x, y), blocks [z, w)
+        const uint32_t k = jg.dj_rk[d] >> 31;
+        if (nt <= (uint32_t)CXD_T) {
+            for (uint32_t x = 0; x < nt; ++x) k4_classify(soa, g, cnt, jg.cxd_t[lo * CXD_T + x], j, rr.x, rr.y, rr.z, rr.w, k, combine);
+        } else {
+            const int anchor = (int)((side == 0 ? jg.hot_l[d] : jg.hot_r[d]) - 1u);
+            const int32_t jl = (int32_t)jg.dj_l[d], jr = (int32_t)(jg.dj_rk[d] & POS_MASK);
+            for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
+                const int t = k4_pair_site(g, q, side, jl, jr);
+                if (t >= 0) k4_classify(soa, g, cnt, t, j, rr.x, rr.y, rr.z, rr.w, k, combine);
+            }
+        }
     }
 }
 

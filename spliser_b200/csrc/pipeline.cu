@@ -494,7 +494,8 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
                      o_cj = dc.take<uint32_t>(n_complex + 2),
                      o_hl = dc.take<uint32_t>(D + 2), o_hr = dc.take<uint32_t>(D + 2),
                      o_wl = dc.take<unsigned long long>(2 * D + 2 * (n_simple / 2048 + 1) + 8),
-                     o_xb = dc.take<uint32_t>(2 * D + 2), o_xd = dc.take<uint32_t>(2 * D + 2);
+                     o_xb = dc.take<uint32_t>(2 * D + 2), o_xd = dc.take<uint32_t>(2 * D + 2),
+                     o_xn = dc.take<uint32_t>(2 * D + 2), o_xt = dc.take<int32_t>((2 * D + 2) * CXD_T), o_cr = dc.take<uint4>(n_complex + 2);
         CU(ctx->d_jdense.reserve(dc.off + 256));
         char* db = (char*)ctx->d_jdense.p;
         jg.D = (uint32_t)D;
@@ -505,6 +506,7 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
         jg.cx_j = (uint32_t*)(db + o_cj);
         jg.hot_l = (uint32_t*)(db + o_hl); jg.hot_r = (uint32_t*)(db + o_hr); jg.wl = (unsigned long long*)(db + o_wl);
         jg.cxd_base = (uint32_t*)(db + o_xb); jg.cxd_ds = (uint32_t*)(db + o_xd);
+        jg.cxd_nt = (uint32_t*)(db + o_xn); jg.cxd_t = (int32_t*)(db + o_xt); jg.cx_rng = (uint4*)(db + o_cr);
         jg.n_complex = (uint32_t)n_complex;
     }
     launch_junction_groups_b(soa, jg, ctx->n_chrom_loaded, d_jtot, ctx->stream);
