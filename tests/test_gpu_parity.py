@@ -262,3 +262,64 @@ def test_c4_shaped_recount_vs_c_oracle(ctx):
         assert np.array_equal(got1, want1) and np.array_equal(got2, want2), (k, int(np.sum(got1 != want1)), int(np.sum(got2 != want2)))
         total += int(want1.sum()) + int(want2.sum())
     assert total > 0
+
+
+def _subset(r, keep):
+    """Records restricted to a boolean mask (vectorised; segments keep their chromosome)."""
+    import numpy as np
+    from spliser_b200 import Records
+    ncig = np.diff(r.cig_off.astype(np.int64))
+    op_keep = np.repeat(keep, ncig)
+    off = np.zeros(int(keep.sum()) + 1, np.uint32)
+    np.cumsum(ncig[keep], out=off[1:])
+    csum = np.concatenate([[0], np.cumsum(keep)])
+    seg_off = csum[r.seg_off]
+    return Records(r.pos[keep], r.flag[keep], off, r.cigar[op_keep], r.seg_chrom, seg_off)
+
+
+def test_full_size_configs1_properties(ctx):
+    """BASELINE configs[1] at its full size (40M records, stranded rf) through size-independent properties:
+    (1) counts are additive over any split of the reads once the junction-table-only part is removed,
+    (2) genomic tiles concatenate to the untiled result, (3) passes over the resident layout are idempotent,
+    (4) alpha equals the junction scores summed per site."""
+    import os
+    import tempfile
+    import numpy as np
+    import spliser_b200
+    from spliser_b200 import Records, synth
+    n = int(os.environ.get("SPLISER_FULLSIZE_READS", "40000000"))
+    cache = os.environ.get("SPLISER_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "spliser_bench_cache"))
+    w = synth.generate(synth.config_c2(n), cache_dir=cache)
+    r, j, nc = w.records, w.junctions, len(w.chroms)
+    full = ctx.process_records(r, nc, j, w.flags)
+    S = len(full)
+    assert S > 100_000 and int(full.beta1.sum()) > 0 and int(full.beta2simple.sum()) > 0
+    # (4)
+    assert int(full.alpha.sum()) == 2 * int(j.score.sum())
+    # (1) linearity
+    rng = np.random.default_rng(11)
+    keep = rng.random(len(r)) < 0.5
+    a = ctx.process_records(_subset(r, keep), nc, j, w.flags)
+    b = ctx.process_records(_subset(r, ~keep), nc, j, w.flags)
+    none = ctx.process_records(Records(np.zeros(0, np.int32), np.zeros(0, np.uint16), np.zeros(1, np.uint32), np.zeros(0, np.uint32),
+                                       np.zeros(0, np.int32), np.zeros(1, np.int64)), nc, j, w.flags)
+    assert np.array_equal(a.pos, full.pos) and np.array_equal(none.pos, full.pos)
+    assert int(none.beta1.sum()) == 0
+    assert np.array_equal(a.beta1 + b.beta1, full.beta1)
+    assert np.array_equal(a.beta2simple + b.beta2simple - none.beta2simple, full.beta2simple)
+    assert np.array_equal(a.alpha, full.alpha) and np.array_equal(a.partner_cnt, full.partner_cnt)
+    # (3) idempotence of the resident passes
+    ctx.resident_load(r, nc, j, w.flags)
+    ctx.resident_count(3)
+    res = ctx.resident_fetch()
+    for k in ("beta1", "beta2simple", "sse", "alpha", "beta2cryptic"):
+        assert np.array_equal(getattr(res, k), getattr(full, k)), k
+    # (2) tiles
+    n_tiles = 4
+    b1 = np.zeros(S, np.int64); b2 = np.zeros(S, np.int64)
+    for ti in range(n_tiles):
+        with spliser_b200.Context(0, tile=(ti, n_tiles)) as c:
+            t = c.process_records(r, nc, j, w.flags)
+            lo, hi = S * ti // n_tiles, S * (ti + 1) // n_tiles
+            b1[lo:hi], b2[lo:hi] = t.beta1[lo:hi], t.beta2simple[lo:hi]
+    assert np.array_equal(b1, full.beta1) and np.array_equal(b2, full.beta2simple)
