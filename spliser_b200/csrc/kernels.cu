@@ -127,40 +127,14 @@ struct ReadShape {
     int32_t  smax, lmax;    // largest block start, longest block
 };
 
-// Warp-cooperative CIGAR staging: the 32 records a warp handles in one round own one contiguous range of the cigar array
-// (records are stored back to back), so the lanes copy that range into a warp-private shared-memory slice with coalesced,
-// independent loads and then parse their own record from shared memory.  Ranges longer than the slice (a round of very
-// fragmented reads) are parsed from global memory instead.
-constexpr int CIG_SLICE = 320;          // words per warp
-struct CigSrc {
-    const uint32_t* p;                  // ops of this lane's record: p[0 .. n)
-    uint32_t n;
-};
-__device__ __forceinline__ CigSrc stage_cigar(const DevRecords& rec, uint32_t i, bool live, uint32_t* slice /* [CIG_SLICE] of this warp */) {
-    const int lane = threadIdx.x & 31;
-    uint32_t c0 = 0, c1 = 0;
-    if (live) { c0 = rec.cig_off[i]; c1 = rec.cig_off[i + 1]; }
-    const uint32_t live_mask = __ballot_sync(0xffffffffu, live);
-    CigSrc src{rec.cigar + c0, c1 - c0};
-    if (!live_mask) return src;
-    const int first = __ffs(live_mask) - 1, last = 31 - __clz(live_mask);
-    const uint32_t w0 = __shfl_sync(0xffffffffu, c0, first), w1 = __shfl_sync(0xffffffffu, c1, last);
-    __syncwarp();                       // the previous round's parse is over
-    if (w1 - w0 <= (uint32_t)CIG_SLICE) {
-        for (uint32_t k = lane; k < w1 - w0; k += 32) slice[k] = rec.cigar[w0 + k];
-        src.p = slice + (c0 - w0);
-    }
-    __syncwarp();
-    return src;
-}
-
-__device__ __forceinline__ ReadShape read_shape(const CigSrc& cg, int32_t pos) {
+__device__ __forceinline__ ReadShape read_shape(const DevRecords& rec, uint32_t i) {
     ReadShape s;
     s.nM = s.nN = 0;
     s.lo = INT_MAX; s.hi = INT_MIN; s.qlo = INT_MAX; s.qhi = INT_MIN; s.smax = 0; s.lmax = 0;
-    int32_t cur = pos;
-    for (uint32_t k = 0; k < cg.n; ++k) {
-        const uint32_t v = cg.p[k];
+    int32_t cur = rec.pos[i];
+    const uint32_t c0 = rec.cig_off[i], c1 = rec.cig_off[i + 1];
+    for (uint32_t k = c0; k < c1; ++k) {
+        const uint32_t v = rec.cigar[k];
         const uint32_t op = v & 15u;
         const int32_t len = (int32_t)(v >> 4);
         if (op == 0u || op == 7u || op == 8u) {           // M = X : mapped + advance (S:457-459)
@@ -219,13 +193,8 @@ __global__ void __launch_bounds__(EXPAND_THREADS) k_expand_count(DevRecords rec,
     Chunk& ck = chunks[blockIdx.x];
     Cnt4 c{0, 0, 0, 0};
     int32_t alo = INT_MAX, ahi = INT_MIN, slo = INT_MAX, shi = INT_MIN, smax = 0, lmax = 0;
-    __shared__ uint32_t cig_slice[EXPAND_THREADS / 32][CIG_SLICE];
-    for (uint32_t base = ck.rec_lo; base < ck.rec_hi; base += EXPAND_THREADS) {      // uniform trip count
-        const uint32_t i = base + threadIdx.x;
-        const bool live = i < ck.rec_hi;
-        const CigSrc cg = stage_cigar(rec, i, live, cig_slice[threadIdx.x >> 5]);
-        if (!live) continue;
-        const ReadShape s = read_shape(cg, rec.pos[i]);
+    for (uint32_t i = ck.rec_lo + threadIdx.x; i < ck.rec_hi; i += EXPAND_THREADS) {
+        const ReadShape s = read_shape(rec, i);
         smax = max(smax, s.smax); lmax = max(lmax, s.lmax);
         if (s.nN == 0) {
             c.a += s.nM;
@@ -327,16 +296,15 @@ __global__ void __launch_bounds__(EXPAND_THREADS)
 k_expand_scatter(DevRecords rec, const Chunk* chunks, DevSoA soa, uint32_t mode) {
     const Chunk ck = chunks[blockIdx.x];
     __shared__ Cnt4 wt[33];
-    __shared__ uint32_t cig_slice[EXPAND_THREADS / 32][CIG_SLICE];
     Cnt4 run{ck.a_base, soa.bB + ck.b_base, ck.s_base, ck.j_base};       // running output cursors of the chunk
     for (uint32_t base = ck.rec_lo; base < ck.rec_hi; base += EXPAND_THREADS) {   // uniform trip count
         const uint32_t i = base + threadIdx.x;
         const bool live = i < ck.rec_hi;
-        uint32_t nM = 0, nN = 0;
-        const CigSrc cg = stage_cigar(rec, i, live, cig_slice[threadIdx.x >> 5]);
+        uint32_t nM = 0, nN = 0, c0 = 0, c1 = 0;
         if (live) {
-            for (uint32_t k = 0; k < cg.n; ++k) {
-                const uint32_t op = cg.p[k] & 15u;
+            c0 = rec.cig_off[i]; c1 = rec.cig_off[i + 1];
+            for (uint32_t k = c0; k < c1; ++k) {
+                const uint32_t op = rec.cigar[k] & 15u;
                 nM += (op == 0u || op == 7u || op == 8u);
                 nN += (op == 3u);
             }
@@ -355,8 +323,8 @@ k_expand_scatter(DevRecords rec, const Chunk* chunks, DevSoA soa, uint32_t mode)
             int32_t a0 = 0;
             uint32_t nD = 0, first_m = 1;
             const uint32_t ij_first = ij;
-            for (uint32_t kk = 0; kk < cg.n; ++kk) {
-                const uint32_t w = cg.p[kk];
+            for (uint32_t kk = c0; kk < c1; ++kk) {
+                const uint32_t w = rec.cigar[kk];
                 const uint32_t op = w & 15u;
                 const int32_t len = (int32_t)(w >> 4);
                 if (op == 0u || op == 7u || op == 8u) {
