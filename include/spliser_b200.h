@@ -188,6 +188,7 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_N_DISTINCT_J 19   /* distinct (chromosome, l, r, class) junctions of the sample     */
 #define SPL_STAT_N_SIMPLE_J   20   /* junction instances of block-N-block reads (aggregated path)    */
 #define SPL_STAT_N_COMPLEX_J  21   /* junction instances handled per read                            */
+#define SPL_STAT_BAM_DEVICE   23   /* 1 = BGZF inflate + BAM record parse ran on the device, 0 = host reader (fallback)  */
 #define SPL_STAT_GRAPH_DEVICE 22   /* 1 = site table + graph built on the device (clean regime), 0 = host emulation */
 int spl_last_stats(const spl_ctx* ctx, double* stats_out);
 
@@ -203,6 +204,10 @@ int spl_read_bam(const char* path, int32_t n_chrom, const char* const* chrom_nam
                  spl_records** out, char* err, int err_len);
 const spl_records_view* spl_records_get(const spl_records* r);
 void spl_records_free(spl_records* r);
+
+/* Test hook: the raw-DEFLATE decoder the device runs on every BGZF member (csrc/inflate.h), compiled for the host.
+ * Returns 0 and *out_len on success, a positive decoder error code on corrupt input, -1 on NULL arguments. */
+int spl_debug_inflate(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, uint32_t* out_len);
 
 /* Page-locked host memory for callers that want full-speed host->device copies of their record
  * arrays (numpy arrays can be built over it).  Needs a CUDA device. */

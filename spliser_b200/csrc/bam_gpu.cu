@@ -1,0 +1,258 @@
+// BAM ingest on the device: BGZF members are inflated by the GPU and the BAM records are parsed
+// straight into the record arrays the expansion kernels read -- the decoded records never exist on the host.
+//
+//   k_bgzf_inflate     one warp per BGZF member (<= 64 KiB each, independent DEFLATE streams): lane 0 runs the decoder of
+//                      inflate.h with its Huffman tables in shared memory; tens of thousands of members decode concurrently
+//   k_bam_first        per member: the first offset at which a plausible chain of BAM records starts (records are NOT
+//                      aligned to members in general: htsjdk and this library's own writer cut members every 0xff00 bytes)
+//   k_bam_walk<false>  per member: walks the record chain from that offset to the member's end, counting records and
+//                      CIGAR operators and reporting where the walk lands
+//   (host)             the landing offsets are chained from the header's end: member s is accepted iff the walk of the
+//                      previous accepted member lands exactly on its candidate.  If every link holds, the chain is the
+//                      true record chain by induction -- the speculation in k_bam_first is verified, never trusted.
+//                      Any broken link (or a feature this path does not parse: CG-tag long CIGARs) -> the caller falls
+//                      back to the host reader (bam_io.cpp).
+//   k_bam_walk<true>   per accepted member: second walk writing POS, FLAG, chromosome and CIGAR of every kept record
+//   k_bam_segments     chromosome boundaries of the record arrays (a coordinate-sorted BAM has one segment per reference)
+// Kept records follow the host reader: mapped to a caller chromosome and with at least one CIGAR operator (bam_io.cpp).
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bam_gpu.h"
+#include "inflate.h"
+
+namespace spl {
+
+namespace {
+
+constexpr int INF_WARPS = 8;
+
+__global__ void __launch_bounds__(INF_WARPS * 32)
+k_bgzf_inflate(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ mem, uint32_t n_mem, uint8_t* __restrict__ out, uint32_t* __restrict__ err) {
+    __shared__ InflateTables tabs[INF_WARPS];
+    const uint32_t m = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
+    if (m >= n_mem || (threadIdx.x & 31) != 0) return;
+    const BgzfMember b = mem[m];
+    uint32_t produced = 0;
+    const int rc = inflate_member(comp + b.coff, b.clen, out + b.uoff, b.isize, &produced, tabs[threadIdx.x >> 5]);
+    if (rc != INF_OK || produced != b.isize) atomicMax(err, 1u + m);
+}
+
+__device__ __forceinline__ uint32_t ld32(const uint8_t* p) {
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+}
+__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
+
+// Could a BAM record start at offset o?  Necessary conditions only: a true record always passes.
+__device__ __forceinline__ bool plausible(const uint8_t* __restrict__ u, uint64_t o, uint64_t total, int32_t n_ref, uint64_t* next) {
+    if (o + 36 > total) return false;
+    const uint8_t* r = u + o;
+    const uint32_t bs = ld32(r);
+    if (bs < 32u || bs > (1u << 30)) return false;
+    const int32_t refid = (int32_t)ld32(r + 4), pos = (int32_t)ld32(r + 8);
+    const uint32_t l_name = r[12], n_cig = ld16(r + 16);
+    const int32_t l_seq = (int32_t)ld32(r + 20), next_ref = (int32_t)ld32(r + 24), next_pos = (int32_t)ld32(r + 28);
+    if (refid < -1 || refid >= n_ref || next_ref < -1 || next_ref >= n_ref) return false;
+    if (pos < -1 || next_pos < -1 || l_name < 1u || l_seq < 0) return false;
+    const uint64_t need = 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
+    if (need > bs || o + 4 + bs > total) return false;
+    if (r[36 + l_name - 1] != 0) return false;                        // read name is NUL-terminated
+    *next = o + 4 + bs;
+    return true;
+}
+
+// first[m] = smallest offset in member m's byte range from which three plausible records chain (or the stream ends)
+__global__ void __launch_bounds__(256) k_bam_first(const uint8_t* __restrict__ u, const BgzfMember* __restrict__ mem, uint32_t n_mem,
+                                                   uint64_t total, int32_t n_ref, uint64_t first0, uint64_t* __restrict__ first) {
+    const uint32_t m = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= n_mem) return;
+    const uint64_t lo = mem[m].uoff, hi = lo + mem[m].isize;
+    if (first0 >= hi) { if (lane == 0) first[m] = ~0ull; return; }      // header-only member
+    if (first0 >= lo) { if (lane == 0) first[m] = first0; return; }     // the member holding the header's end: known exactly
+    uint64_t found = ~0ull;
+    for (uint64_t base = lo; base < hi && found == ~0ull; base += 32) {
+        const uint64_t o = base + lane;
+        bool ok = false;
+        if (o < hi) {
+            uint64_t a, b, c;
+            ok = plausible(u, o, total, n_ref, &a) && (a == total || (plausible(u, a, total, n_ref, &b) && (b == total || plausible(u, b, total, n_ref, &c))));
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, ok);
+        if (bal) found = base + (uint64_t)(__ffs(bal) - 1);
+    }
+    if (lane == 0) first[m] = found;
+}
+
+struct WalkOut { uint64_t land; uint32_t n_rec, n_cig, flags, pad; };
+constexpr uint32_t WALK_BAD = 1u, WALK_LONG_CIGAR = 2u;
+
+template <bool FILL>
+__global__ void __launch_bounds__(128) k_bam_walk(const uint8_t* __restrict__ u, const BgzfMember* __restrict__ mem, uint32_t n_mem, uint64_t total,
+                                                  int32_t n_ref, const int32_t* __restrict__ refmap, const uint64_t* __restrict__ first,
+                                                  WalkOut* __restrict__ wo, const uint64_t* __restrict__ rec_base, const uint64_t* __restrict__ cig_base,
+                                                  DevRecordArrays out) {
+    const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= n_mem) return;
+    uint64_t o = first[m];
+    if (FILL) { if (rec_base[m] == ~0ull) return; }                      // member not on the verified chain
+    if (o == ~0ull) { if (!FILL) wo[m] = WalkOut{~0ull, 0, 0, 0, 0}; return; }
+    const uint64_t limit = mem[m].uoff + mem[m].isize;
+    uint32_t n_rec = 0, n_cig_tot = 0, flags = 0;
+    uint64_t ri = FILL ? rec_base[m] : 0, ci = FILL ? cig_base[m] : 0;
+    while (o < limit) {
+        uint64_t nx;
+        if (!plausible(u, o, total, n_ref, &nx)) { flags |= WALK_BAD; break; }
+        const uint8_t* r = u + o + 4;
+        const int32_t refid = (int32_t)ld32(r);
+        const uint32_t l_name = r[8], n_cig = ld16(r + 12), flag = ld16(r + 14);
+        const int32_t l_seq = (int32_t)ld32(r + 16);
+        const uint8_t* cig = r + 32 + l_name;
+        // CIGARs of more than 65535 operators live in a CG tag (SAM spec 4.2.2): left to the host reader
+        if (n_cig == 2 && ld32(cig) == (((uint32_t)l_seq << 4) | 4u) && (ld32(cig + 4) & 15u) == 3u) flags |= WALK_LONG_CIGAR;
+        const int32_t chrom = refid >= 0 ? refmap[refid] : -1;
+        if (chrom >= 0 && n_cig > 0) {
+            if (FILL) {
+                out.pos[ri] = (int32_t)ld32(r + 4) + 1;
+                out.flag[ri] = (uint16_t)flag;
+                out.chrom[ri] = chrom;
+                out.cig_off[ri] = (uint32_t)ci;
+                for (uint32_t k = 0; k < n_cig; ++k) out.cigar[ci + k] = ld32(cig + 4 * k);
+            }
+            ++n_rec; n_cig_tot += n_cig; ++ri; ci += n_cig;
+        }
+        o = nx;
+    }
+    if (!FILL) wo[m] = WalkOut{o, n_rec, n_cig_tot, flags, 0};
+}
+
+// boundaries of the chromosome segments: seg[k] = (first record, chromosome)
+__global__ void k_bam_segments(const int32_t* __restrict__ chrom, uint64_t n, uint32_t* __restrict__ n_seg, uint64_t* __restrict__ seg_first,
+                               int32_t* __restrict__ seg_chrom, uint32_t cap) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (i == 0 || chrom[i] != chrom[i - 1]) {
+        const uint32_t k = atomicAdd(n_seg, 1u);
+        if (k < cap) { seg_first[k] = i; seg_chrom[k] = chrom[i]; }
+    }
+}
+
+__global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
+
+}  // namespace
+
+#define BG_CU(call)                                                                     \
+    do {                                                                                \
+        cudaError_t _e = (call);                                                        \
+        if (_e != cudaSuccess) { err = std::string(#call) + ": " + cudaGetErrorString(_e); return BAMGPU_ERROR; } \
+    } while (0)
+
+int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const std::vector<BgzfMember>& members, uint64_t total_u,
+                   uint64_t first_record, int32_t n_ref, const std::vector<int32_t>& refmap, void* stream,
+                   DevRecordArrays& out, BamGpuCounts& cnt, std::string& err) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const uint32_t n_mem = (uint32_t)members.size();
+    cnt = BamGpuCounts{};
+    if (n_mem == 0 || first_record >= total_u) { out = DevRecordArrays{}; return BAMGPU_OK; }
+    // ---- compressed file + member table to the device, inflate
+    BG_CU(mem.comp.reserve(fsz + 64));
+    BG_CU(mem.unc.reserve(total_u + 64));
+    BG_CU(mem.tab.reserve((size_t)n_mem * (sizeof(BgzfMember) + 8 + sizeof(WalkOut) + 16) + ((size_t)n_ref + 1) * 4 + 4096));
+    char* tb = (char*)mem.tab.p;
+    BgzfMember* d_mem = (BgzfMember*)tb; tb += (size_t)n_mem * sizeof(BgzfMember);
+    uint64_t* d_first = (uint64_t*)tb; tb += (size_t)n_mem * 8;
+    WalkOut* d_wo = (WalkOut*)tb; tb += (size_t)n_mem * sizeof(WalkOut);
+    uint64_t* d_rbase = (uint64_t*)tb; tb += (size_t)n_mem * 8;
+    uint64_t* d_cbase = (uint64_t*)tb; tb += (size_t)n_mem * 8;
+    int32_t* d_refmap = (int32_t*)tb; tb += ((size_t)n_ref + 1) * 4;
+    uint32_t* d_err = (uint32_t*)(((uintptr_t)tb + 15) & ~(uintptr_t)15);
+    BG_CU(cudaMemcpyAsync(mem.comp.p, file_pinned, fsz, cudaMemcpyHostToDevice, st));
+    BG_CU(cudaMemcpyAsync(d_mem, members.data(), (size_t)n_mem * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
+    if (n_ref > 0) BG_CU(cudaMemcpyAsync(d_refmap, refmap.data(), (size_t)n_ref * 4, cudaMemcpyHostToDevice, st));
+    BG_CU(cudaMemsetAsync(d_err, 0, 16, st));
+    cnt.h2d_bytes = (double)fsz + (double)n_mem * sizeof(BgzfMember);
+    const uint8_t* d_u = (const uint8_t*)mem.unc.p;
+    k_bgzf_inflate<<<(n_mem + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t*)mem.comp.p, d_mem, n_mem, (uint8_t*)mem.unc.p, d_err);
+    // ---- speculative record starts + counting walk
+    k_bam_first<<<(n_mem + 7) / 8, 256, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, first_record, d_first);
+    k_bam_walk<false><<<(n_mem + 127) / 128, 128, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, d_refmap, d_first, d_wo, nullptr, nullptr, DevRecordArrays{});
+    BG_CU(cudaGetLastError());
+    std::vector<uint64_t> h_first(n_mem);
+    std::vector<WalkOut> h_wo(n_mem);
+    uint32_t h_err[4] = {0, 0, 0, 0};
+    BG_CU(cudaMemcpyAsync(h_first.data(), d_first, (size_t)n_mem * 8, cudaMemcpyDeviceToHost, st));
+    BG_CU(cudaMemcpyAsync(h_wo.data(), d_wo, (size_t)n_mem * sizeof(WalkOut), cudaMemcpyDeviceToHost, st));
+    BG_CU(cudaMemcpyAsync(h_err, d_err, 16, cudaMemcpyDeviceToHost, st));
+    BG_CU(cudaStreamSynchronize(st));
+    if (h_err[0]) { err = "BGZF inflate failed on the device (member " + std::to_string(h_err[0] - 1) + ")"; return BAMGPU_FALLBACK; }
+    // ---- verify the chain: each accepted member's walk must land exactly on the next accepted member's candidate
+    std::vector<uint64_t> rbase(n_mem, ~0ull), cbase(n_mem, ~0ull);
+    uint64_t expect = first_record, nrec = 0, ncig = 0;
+    uint32_t m = 0;
+    while (expect < total_u) {
+        while (m < n_mem && members[m].uoff + members[m].isize <= expect) ++m;      // member that holds `expect`
+        if (m >= n_mem) { err = "record chain leaves the file"; return BAMGPU_FALLBACK; }
+        if (h_first[m] != expect) { err = "record boundary speculation failed"; return BAMGPU_FALLBACK; }
+        if (h_wo[m].flags & WALK_BAD) { err = "implausible BAM record"; return BAMGPU_FALLBACK; }
+        if (h_wo[m].flags & WALK_LONG_CIGAR) { err = "CG-tag CIGAR"; return BAMGPU_FALLBACK; }
+        rbase[m] = nrec; cbase[m] = ncig;
+        nrec += h_wo[m].n_rec; ncig += h_wo[m].n_cig;
+        expect = h_wo[m].land;
+        ++m;
+    }
+    if (expect != total_u) { err = "truncated BAM (partial record at end of file)"; return BAMGPU_FALLBACK; }
+    if (nrec >= (uint64_t)UINT32_MAX - 16 || ncig >= (uint64_t)UINT32_MAX - 16) { err = "more than 2^32 records or CIGAR operators"; return BAMGPU_FALLBACK; }
+    cnt.n_rec = nrec; cnt.n_cigar = ncig;
+    // ---- record arrays
+    {
+        size_t off = 0;
+        auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; const size_t o = off; off += bytes; return o; };
+        const size_t o_pos = take((nrec + 4) * 4), o_flag = take((nrec + 4) * 2), o_off = take((nrec + 4) * 4), o_cig = take((ncig + 4) * 4),
+                     o_chr = take((nrec + 4) * 4), o_sf = take(BAMGPU_MAX_SEG * 8), o_sc = take(BAMGPU_MAX_SEG * 4), o_ns = take(16);
+        BG_CU(mem.rec.reserve(off + 256));
+        char* rb = (char*)mem.rec.p;
+        out.pos = (int32_t*)(rb + o_pos); out.flag = (uint16_t*)(rb + o_flag); out.cig_off = (uint32_t*)(rb + o_off);
+        out.cigar = (uint32_t*)(rb + o_cig); out.chrom = (int32_t*)(rb + o_chr);
+        uint64_t* d_sf = (uint64_t*)(rb + o_sf); int32_t* d_sc = (int32_t*)(rb + o_sc); uint32_t* d_ns = (uint32_t*)(rb + o_ns);
+        BG_CU(cudaMemcpyAsync(d_rbase, rbase.data(), (size_t)n_mem * 8, cudaMemcpyHostToDevice, st));
+        BG_CU(cudaMemcpyAsync(d_cbase, cbase.data(), (size_t)n_mem * 8, cudaMemcpyHostToDevice, st));
+        BG_CU(cudaMemsetAsync(d_ns, 0, 16, st));
+        k_bam_walk<true><<<(n_mem + 127) / 128, 128, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, d_refmap, d_first, nullptr, d_rbase, d_cbase, out);
+        k_set_u32<<<1, 1, 0, st>>>(out.cig_off + nrec, (uint32_t)ncig);
+        if (nrec) k_bam_segments<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(out.chrom, nrec, d_ns, d_sf, d_sc, BAMGPU_MAX_SEG);
+        BG_CU(cudaGetLastError());
+        uint32_t h_ns = 0;
+        BG_CU(cudaMemcpyAsync(&h_ns, d_ns, 4, cudaMemcpyDeviceToHost, st));
+        BG_CU(cudaStreamSynchronize(st));
+        if (h_ns > BAMGPU_MAX_SEG) { err = "too many chromosome segments (unsorted BAM?)"; return BAMGPU_FALLBACK; }
+        std::vector<uint64_t> sf(h_ns);
+        std::vector<int32_t> sc(h_ns);
+        if (h_ns) {
+            BG_CU(cudaMemcpyAsync(sf.data(), d_sf, (size_t)h_ns * 8, cudaMemcpyDeviceToHost, st));
+            BG_CU(cudaMemcpyAsync(sc.data(), d_sc, (size_t)h_ns * 4, cudaMemcpyDeviceToHost, st));
+            BG_CU(cudaStreamSynchronize(st));
+        }
+        std::vector<uint32_t> order(h_ns);
+        for (uint32_t k = 0; k < h_ns; ++k) order[k] = k;
+        std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return sf[a] < sf[b]; });
+        cnt.seg_chrom.clear(); cnt.seg_off.clear();
+        for (uint32_t k : order) { cnt.seg_chrom.push_back(sc[k]); cnt.seg_off.push_back((int64_t)sf[k]); }
+        cnt.seg_off.push_back((int64_t)nrec);
+        if (cnt.seg_chrom.empty()) cnt.seg_off.assign(1, 0);
+    }
+    return BAMGPU_OK;
+}
+
+}  // namespace spl
+
+// host build of the same decoder the device runs (unit tests compare it with zlib without a GPU)
+extern "C" int spl_debug_inflate(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, uint32_t* out_len) {
+    if (!src || !dst || !out_len) return -1;
+    static thread_local spl::InflateTables t;
+    return spl::inflate_member(src, n, dst, cap, out_len, t);
+}

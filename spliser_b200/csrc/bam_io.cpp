@@ -1,6 +1,7 @@
 // BGZF / BAM reader and writer over zlib.  Replaces, for this path, the `samtools view` subprocess
 // of SpliSER_v0_1_8.py:422 (one fork per splice site) by one streaming pass over the file.
 #include "bam_io.h"
+#include "bam_gpu.h"
 
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -231,6 +232,76 @@ std::string read_bam(const char* path, int32_t n_chrom, const char* const* chrom
     if (carry) return "truncated BAM (partial record at end of file)";
     out.seg_off.push_back((int64_t)out.pos.size());
     if (out.seg_chrom.empty()) out.seg_off.assign(1, 0);
+    return "";
+}
+
+// ---- scan for the device ingest path (bam_gpu.cu) -----------------------------------------------
+std::string bam_scan(const uint8_t* file, size_t fsz, int32_t n_chrom, const char* const* chrom_names, std::vector<BgzfMember>& members,
+                     uint64_t& total_u, uint64_t& first_record, int32_t& n_ref, std::vector<int32_t>& refmap) {
+    members.clear();
+    size_t off = 0;
+    uint64_t utotal = 0;
+    while (off + 18 <= fsz) {
+        const uint8_t* h = file + off;
+        if (h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) return "not a BGZF file (bad gzip member header)";
+        const uint32_t xlen = rd16(h + 10);
+        if (off + 12 + xlen > fsz) return "truncated BGZF header";
+        uint32_t bsize = 0;
+        bool have = false;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const uint8_t* e = h + 12 + x;
+            const uint32_t slen = rd16(e + 2);
+            if (e[0] == 'B' && e[1] == 'C' && slen == 2 && x + 6 <= xlen) { bsize = rd16(e + 4); have = true; }
+            x += 4 + slen;
+        }
+        if (!have) return "BGZF member without BC subfield";
+        const size_t total = (size_t)bsize + 1;
+        if (off + total > fsz || total < 12 + xlen + 8) return "truncated BGZF block";
+        BgzfMember b;
+        b.coff = off + 12 + xlen;
+        b.clen = (uint32_t)(total - 12 - xlen - 8);
+        b.isize = rd32(file + off + total - 4);
+        b.uoff = utotal;
+        if (b.isize > 65536) return "BGZF member larger than 64 KiB";
+        utotal += b.isize;
+        if (b.isize) members.push_back(b);
+        off += total;
+    }
+    if (off != fsz) return "trailing garbage after last BGZF block";
+    total_u = utotal;
+    // ---- header: inflate leading members on the host until it is complete
+    std::vector<uint8_t> hb;
+    size_t mi = 0;
+    auto need = [&](size_t bytes) -> bool {
+        while (hb.size() < bytes && mi < members.size()) {
+            const BgzfMember& b = members[mi++];
+            const size_t o = hb.size();
+            hb.resize(o + b.isize);
+            if (!inflate_block(file + b.coff, b.clen, hb.data() + o, b.isize)) return false;
+        }
+        return hb.size() >= bytes;
+    };
+    if (!need(12) || memcmp(hb.data(), "BAM\1", 4) != 0) return "not a BAM file (bad magic)";
+    const int64_t l_text = rdi32(hb.data() + 4);
+    if (l_text < 0 || !need(8 + (size_t)l_text + 4)) return "truncated BAM header";
+    size_t q = 8 + (size_t)l_text;
+    n_ref = rdi32(hb.data() + q);
+    q += 4;
+    if (n_ref < 0) return "corrupt BAM header (n_ref < 0)";
+    std::unordered_map<std::string, int32_t> names;
+    for (int32_t c = 0; c < n_chrom; ++c)
+        if (chrom_names && chrom_names[c]) names.emplace(chrom_names[c], c);
+    refmap.assign((size_t)n_ref, -1);
+    for (int32_t r = 0; r < n_ref; ++r) {
+        if (!need(q + 4)) return "truncated BAM reference list";
+        const int32_t l_name = rdi32(hb.data() + q);
+        if (l_name < 1 || !need(q + 4 + (size_t)l_name + 4)) return "truncated BAM reference list";
+        std::string nm((const char*)hb.data() + q + 4, (size_t)l_name - 1);
+        auto it = names.find(nm);
+        if (it != names.end()) refmap[(size_t)r] = it->second;
+        q += 4 + (size_t)l_name + 4;
+    }
+    first_record = q;
     return "";
 }
 

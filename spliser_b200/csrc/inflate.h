@@ -1,0 +1,226 @@
+// Raw DEFLATE (RFC 1951) decoder for one BGZF member, written to run as one GPU thread per member (lane 0 of a warp,
+// tables in shared memory) and, unchanged, on the host (unit-tested against zlib in tests/test_host.py through
+// spl_debug_inflate).  A BGZF member inflates to at most 64 KiB, so the whole LZ77 window is the output buffer itself.
+//
+// Decoding uses one-level lookup tables of FAST_BITS bits for the literal/length and distance codes; codes longer than
+// FAST_BITS fall back to the canonical count/first-code walk (RFC 1951 3.2.2).  Everything is bounds-checked: a corrupt
+// member yields an error code, never an out-of-range access.
+#pragma once
+#include <cstdint>
+
+#if defined(__CUDACC__)
+#define SPL_HD __host__ __device__ __forceinline__
+#else
+#define SPL_HD inline
+#endif
+
+namespace spl {
+
+constexpr int INF_FAST_BITS = 10;
+constexpr int INF_MAXBITS = 15;
+
+// per-decoder scratch (shared memory on the device: one per warp)
+struct InflateTables {
+    uint16_t lit_fast[1 << INF_FAST_BITS];    // (symbol << 4) | length, 0 = not a short code
+    uint16_t dist_fast[1 << INF_FAST_BITS];
+    uint16_t lit_count[INF_MAXBITS + 1], dist_count[INF_MAXBITS + 1];
+    uint16_t lit_sym[288], dist_sym[32];      // symbols ordered by (length, symbol)
+    uint8_t  lens[320];                       // code lengths while a dynamic header is read
+};
+
+enum : int { INF_OK = 0, INF_ERR_INPUT = 1, INF_ERR_OUTPUT = 2, INF_ERR_CODE = 3, INF_ERR_DIST = 4, INF_ERR_STORED = 5 };
+
+struct BitReader {
+    const uint8_t* src;
+    uint32_t n, pos;
+    uint64_t buf;
+    int bits;
+    SPL_HD void init(const uint8_t* s, uint32_t len) { src = s; n = len; pos = 0; buf = 0; bits = 0; }
+    SPL_HD void refill() {
+        while (bits <= 56 && pos < n) { buf |= (uint64_t)src[pos++] << bits; bits += 8; }
+    }
+    SPL_HD uint32_t peek(int k) const { return (uint32_t)(buf & ((1ull << k) - 1ull)); }
+    SPL_HD void drop(int k) { buf >>= k; bits -= k; }
+    SPL_HD uint32_t take(int k) { const uint32_t v = peek(k); drop(k); return v; }
+};
+
+SPL_HD uint32_t inf_reverse(uint32_t code, int len) {
+    uint32_t r = 0;
+    for (int i = 0; i < len; ++i) { r = (r << 1) | (code & 1u); code >>= 1; }
+    return r;
+}
+
+// canonical Huffman tables from code lengths; returns false for an over-subscribed set
+SPL_HD bool inf_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* sym, uint16_t* fast) {
+    for (int l = 0; l <= INF_MAXBITS; ++l) count[l] = 0;
+    for (int s = 0; s < n; ++s) count[lens[s]]++;
+    for (int i = 0; i < (1 << INF_FAST_BITS); ++i) fast[i] = 0;
+    int left = 1;
+    for (int l = 1; l <= INF_MAXBITS; ++l) {
+        left <<= 1;
+        left -= (int)count[l];
+        if (left < 0) return false;
+    }
+    uint16_t offs[INF_MAXBITS + 2];
+    offs[1] = 0;
+    for (int l = 1; l <= INF_MAXBITS; ++l) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
+    for (int s = 0; s < n; ++s)
+        if (lens[s]) sym[offs[lens[s]]++] = (uint16_t)s;
+    // fast table: canonical codes in increasing (length, symbol) order
+    uint32_t code = 0;
+    int idx = 0;
+    for (int l = 1; l <= INF_FAST_BITS; ++l) {
+        for (int k = 0; k < (int)count[l]; ++k, ++idx, ++code) {
+            const uint32_t rev = inf_reverse(code, l);
+            const uint16_t e = (uint16_t)((sym[idx] << 4) | l);
+            for (uint32_t f = rev; f < (1u << INF_FAST_BITS); f += (1u << l)) fast[f] = e;
+        }
+        code <<= 1;
+    }
+    return true;
+}
+
+// decode one symbol; -1 on an invalid code
+SPL_HD int inf_decode(BitReader& br, const uint16_t* count, const uint16_t* sym, const uint16_t* fast) {
+    const uint16_t e = fast[br.peek(INF_FAST_BITS)];
+    if (e) {
+        if ((e & 15) > br.bits) return -1;
+        br.drop(e & 15);
+        return e >> 4;
+    }
+    // long code: canonical walk, one bit at a time (RFC 1951 3.2.2 / zlib's puff.c)
+    int code = 0, first = 0, index = 0;
+    uint64_t b = br.buf;
+    for (int len = 1; len <= INF_MAXBITS; ++len) {
+        if (len > br.bits) return -1;
+        code |= (int)(b & 1u);
+        b >>= 1;
+        const int cnt = count[len];
+        if (code - cnt < first) { br.drop(len); return sym[index + (code - first)]; }
+        index += cnt; first += cnt; first <<= 1; code <<= 1;
+    }
+    return -1;
+}
+
+// inflate `src[0..n)` into `dst[0..cap)`; *out_len receives the bytes produced
+SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, uint32_t* out_len, InflateTables& t) {
+    const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+    BitReader br;
+    br.init(src, n);
+    uint32_t out = 0;
+    int last = 0;
+    while (!last) {
+        br.refill();
+        if (br.bits < 3) return INF_ERR_INPUT;
+        last = (int)br.take(1);
+        const uint32_t type = br.take(2);
+        if (type == 0) {                                   // stored
+            br.drop(br.bits & 7);
+            br.refill();
+            if (br.bits < 32) return INF_ERR_INPUT;
+            const uint32_t len = br.take(16), nlen = br.take(16);
+            if ((len ^ 0xffffu) != nlen) return INF_ERR_STORED;
+            // bytes still in the bit buffer come first
+            uint32_t left = len;
+            while (left && br.bits >= 8) {
+                if (out >= cap) return INF_ERR_OUTPUT;
+                dst[out++] = (uint8_t)br.take(8);
+                --left;
+            }
+            if (left) {
+                if (br.bits != 0) return INF_ERR_INPUT;
+                if (br.pos + left > br.n) return INF_ERR_INPUT;
+                if (out + left > cap) return INF_ERR_OUTPUT;
+                for (uint32_t i = 0; i < left; ++i) dst[out + i] = br.src[br.pos + i];
+                out += left; br.pos += left;
+            }
+            continue;
+        }
+        if (type == 3) return INF_ERR_CODE;
+        if (type == 1) {                                   // fixed codes
+            for (int s = 0; s < 144; ++s) t.lens[s] = 8;
+            for (int s = 144; s < 256; ++s) t.lens[s] = 9;
+            for (int s = 256; s < 280; ++s) t.lens[s] = 7;
+            for (int s = 280; s < 288; ++s) t.lens[s] = 8;
+            inf_build(t.lens, 288, t.lit_count, t.lit_sym, t.lit_fast);
+            for (int s = 0; s < 30; ++s) t.lens[s] = 5;
+            inf_build(t.lens, 30, t.dist_count, t.dist_sym, t.dist_fast);
+        } else {                                           // dynamic codes
+            br.refill();
+            if (br.bits < 14) return INF_ERR_INPUT;
+            const int nlen = (int)br.take(5) + 257, ndist = (int)br.take(5) + 1, ncode = (int)br.take(4) + 4;
+            if (nlen > 286 || ndist > 30) return INF_ERR_CODE;
+            uint8_t cl[19];
+            for (int i = 0; i < 19; ++i) cl[i] = 0;
+            for (int i = 0; i < ncode; ++i) {
+                br.refill();
+                if (br.bits < 3) return INF_ERR_INPUT;
+                cl[ORDER[i]] = (uint8_t)br.take(3);
+            }
+            // the code-length code reuses the distance tables as scratch
+            if (!inf_build(cl, 19, t.dist_count, t.dist_sym, t.dist_fast)) return INF_ERR_CODE;
+            int idx = 0;
+            while (idx < nlen + ndist) {
+                br.refill();
+                const int s = inf_decode(br, t.dist_count, t.dist_sym, t.dist_fast);
+                if (s < 0) return INF_ERR_CODE;
+                if (s < 16) { t.lens[idx++] = (uint8_t)s; continue; }
+                int rep, val = 0;
+                if (s == 16) {
+                    if (idx == 0) return INF_ERR_CODE;
+                    val = t.lens[idx - 1];
+                    if (br.bits < 2) return INF_ERR_INPUT;
+                    rep = 3 + (int)br.take(2);
+                } else if (s == 17) {
+                    if (br.bits < 3) return INF_ERR_INPUT;
+                    rep = 3 + (int)br.take(3);
+                } else {
+                    if (br.bits < 7) return INF_ERR_INPUT;
+                    rep = 11 + (int)br.take(7);
+                }
+                if (idx + rep > nlen + ndist) return INF_ERR_CODE;
+                while (rep--) t.lens[idx++] = (uint8_t)val;
+            }
+            if (t.lens[256] == 0) return INF_ERR_CODE;
+            // distance lengths first (they sit behind the literal lengths), then the literal/length code
+            uint8_t dl[32];
+            for (int s = 0; s < ndist; ++s) dl[s] = t.lens[nlen + s];
+            if (!inf_build(t.lens, nlen, t.lit_count, t.lit_sym, t.lit_fast)) return INF_ERR_CODE;
+            if (!inf_build(dl, ndist, t.dist_count, t.dist_sym, t.dist_fast)) return INF_ERR_CODE;
+        }
+        // ---- symbols
+        for (;;) {
+            br.refill();
+            const int s = inf_decode(br, t.lit_count, t.lit_sym, t.lit_fast);
+            if (s < 0) return INF_ERR_CODE;
+            if (s < 256) {
+                if (out >= cap) return INF_ERR_OUTPUT;
+                dst[out++] = (uint8_t)s;
+                continue;
+            }
+            if (s == 256) break;
+            if (s > 285) return INF_ERR_CODE;
+            // length / distance bases and extra bits in closed form (RFC 1951 3.2.5)
+            const int li = s - 257;
+            const int lext = (li < 8 || li == 28) ? 0 : ((li - 4) >> 2);
+            const uint32_t lbase = li < 8 ? 3u + (uint32_t)li : li == 28 ? 258u : 3u + ((4u + (uint32_t)(li & 3)) << lext);
+            if (lext > br.bits) return INF_ERR_INPUT;
+            const uint32_t len = lbase + br.take(lext);
+            br.refill();
+            const int ds = inf_decode(br, t.dist_count, t.dist_sym, t.dist_fast);
+            if (ds < 0 || ds > 29) return INF_ERR_CODE;
+            const int dext = ds < 4 ? 0 : ((ds - 2) >> 1);
+            const uint32_t dbase = ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + (uint32_t)(ds & 1)) << dext);
+            if (dext > br.bits) return INF_ERR_INPUT;
+            const uint32_t dist = dbase + br.take(dext);
+            if (dist > out) return INF_ERR_DIST;
+            if (out + len > cap) return INF_ERR_OUTPUT;
+            for (uint32_t i = 0; i < len; ++i) dst[out + i] = dst[out - dist + i];     // overlapping copies repeat the pattern
+            out += len;
+        }
+    }
+    *out_len = out;
+    return INF_OK;
+}
+
+}  // namespace spl

@@ -9,6 +9,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <atomic>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -16,6 +20,7 @@
 #include <vector>
 
 #include "../../include/spliser_b200.h"
+#include "bam_gpu.h"
 #include "bam_io.h"
 #include "device_types.h"
 #include "graph_build.h"
@@ -163,6 +168,12 @@ struct spl_ctx {
     bool graph_on_device = false;
     void* h_stage = nullptr;        // pinned staging of the host-built graph
     size_t h_stage_bytes = 0;
+    // device-side BAM ingest
+    BamGpuMem bgm;
+    DevRecordArrays dev_rec{};
+    bool rec_on_device = false;     // the next load takes its records from dev_rec (no host arrays, no upload)
+    void* h_file = nullptr;         // pinned image of the BAM file
+    size_t h_file_bytes = 0;
 
     // state of the last load
     SiteGraph hg;                   // host graph (structure) of the last load
@@ -333,8 +344,9 @@ int alloc_counters_outputs(spl_ctx* ctx, size_t S, size_t E) {
 int check_view(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
     if (!v) return ctx->fail(SPL_ERR_ARG, "records view is NULL");
     if (v->n_rec < 0 || v->n_cigar < 0 || v->n_seg < 0) return ctx->fail(SPL_ERR_ARG, "negative size in records view");
-    if (v->n_rec > 0 && (!v->pos || !v->flag || !v->cig_off)) return ctx->fail(SPL_ERR_ARG, "NULL record array");
-    if (v->n_cigar > 0 && !v->cigar) return ctx->fail(SPL_ERR_ARG, "NULL cigar array");
+    const bool dev = ctx->rec_on_device;
+    if (!dev && v->n_rec > 0 && (!v->pos || !v->flag || !v->cig_off)) return ctx->fail(SPL_ERR_ARG, "NULL record array");
+    if (!dev && v->n_cigar > 0 && !v->cigar) return ctx->fail(SPL_ERR_ARG, "NULL cigar array");
     if (v->n_seg > 0 && (!v->seg_chrom || !v->seg_off)) return ctx->fail(SPL_ERR_ARG, "NULL segment array");
     if (v->n_rec >= (int64_t)UINT32_MAX - 16 || v->n_cigar >= (int64_t)UINT32_MAX - 16)
         return ctx->fail(SPL_ERR_RANGE, "more than 2^32 records or CIGAR operators in one call");
@@ -346,7 +358,7 @@ int check_view(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
     }
     if (v->n_seg > 0 && prev != v->n_rec) return ctx->fail(SPL_ERR_ARG, "segments do not cover all records");
     if (v->n_seg == 0 && v->n_rec != 0) return ctx->fail(SPL_ERR_ARG, "records without segments");
-    if (v->n_rec > 0 && (int64_t)v->cig_off[v->n_rec] != v->n_cigar) return ctx->fail(SPL_ERR_ARG, "cig_off[n_rec] != n_cigar");
+    if (!dev && v->n_rec > 0 && (int64_t)v->cig_off[v->n_rec] != v->n_cigar) return ctx->fail(SPL_ERR_ARG, "cig_off[n_rec] != n_cigar");
     return SPL_OK;
 }
 
@@ -369,13 +381,19 @@ int upload_records(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
     Carver c;
     const size_t o_pos = c.take<int32_t>(R + 4), o_flag = c.take<uint16_t>(R + 4), o_off = c.take<uint32_t>(R + 4),
                  o_cig = c.take<uint32_t>(NC + 4);
-    CU(ctx->d_rec.reserve(c.off + 256));
+    if (!ctx->rec_on_device) CU(ctx->d_rec.reserve(c.off + 256));
     char* rb = (char*)ctx->d_rec.p;
     // the chunk table first: it comes from pageable memory, and a pageable copy queued behind the big record
     // copies would block the host until those are done
     CU(ctx->d_chunks.reserve((hc.size() + 1) * sizeof(Chunk)));
     ctx->chunks = (Chunk*)ctx->d_chunks.p;
     if (!hc.empty()) CU(cudaMemcpyAsync(ctx->chunks, hc.data(), hc.size() * sizeof(Chunk), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->rec_on_device) {                                          // parsed on the device from the BAM (bam_gpu.cu)
+        ctx->rec.n_rec = (uint32_t)R;
+        ctx->rec.pos = ctx->dev_rec.pos; ctx->rec.flag = ctx->dev_rec.flag;
+        ctx->rec.cig_off = ctx->dev_rec.cig_off; ctx->rec.cigar = ctx->dev_rec.cigar;
+        return SPL_OK;
+    }
     if (R) {
         CU(cudaMemcpyAsync(rb + o_pos, v->pos, R * 4, cudaMemcpyHostToDevice, ctx->stream));
         CU(cudaMemcpyAsync(rb + o_flag, v->flag, R * 2, cudaMemcpyHostToDevice, ctx->stream));
@@ -696,6 +714,63 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     return SPL_OK;
 }
 
+// BAM file -> record arrays on the device.  SPL_OK: ctx->dev_rec / `cnt` are filled and `view` describes them
+// (array pointers NULL, ctx->rec_on_device must be set by the caller around the load).  *fallback = true: use the host reader.
+int ingest_bam_device(spl_ctx* ctx, const char* path, int32_t n_chrom, const char* const* chrom_names, BamGpuCounts& cnt,
+                      spl_records_view& view, bool* fallback) {
+    *fallback = false;
+    if (const char* f = std::getenv("SPLISER_HOST_BAM")) if (f[0] == '1') { *fallback = true; return SPL_OK; }
+    const int fd = open(path, O_RDONLY);
+    if (fd < 0) return ctx->fail(SPL_ERR_IO, "cannot open BAM file %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 28) { close(fd); return ctx->fail(SPL_ERR_IO, "BAM file too small: %s", path); }
+    const size_t fsz = (size_t)st.st_size;
+    if (ctx->h_file_bytes < fsz) {
+        if (ctx->h_file) cudaFreeHost(ctx->h_file);
+        ctx->h_file = nullptr; ctx->h_file_bytes = 0;
+        if (cudaHostAlloc(&ctx->h_file, fsz + fsz / 8 + 4096, cudaHostAllocDefault) != cudaSuccess) {
+            cudaGetLastError(); close(fd);
+            *fallback = true;                                           // not enough page-locked memory: the host reader streams
+            return SPL_OK;
+        }
+        ctx->h_file_bytes = fsz + fsz / 8 + 4096;
+    }
+    {   // page cache -> page-locked image, a few threads
+        const int nt = (int)std::min<size_t>(8, std::max<size_t>(1, fsz >> 24));
+        std::atomic<bool> bad(false);
+        auto rd = [&](int t) {
+            size_t lo = fsz * (size_t)t / (size_t)nt;
+            const size_t hi = fsz * (size_t)(t + 1) / (size_t)nt;
+            while (lo < hi) {
+                const ssize_t k = pread(fd, (char*)ctx->h_file + lo, hi - lo, (off_t)lo);
+                if (k <= 0) { bad = true; return; }
+                lo += (size_t)k;
+            }
+        };
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(rd, t);
+        rd(0);
+        for (auto& t : pool) t.join();
+        close(fd);
+        if (bad) return ctx->fail(SPL_ERR_IO, "read error on %s", path);
+    }
+    std::vector<BgzfMember> members;
+    std::vector<int32_t> refmap;
+    uint64_t total_u = 0, first_record = 0;
+    int32_t n_ref = 0;
+    std::string e = bam_scan((const uint8_t*)ctx->h_file, fsz, n_chrom, chrom_names, members, total_u, first_record, n_ref, refmap);
+    if (!e.empty()) return ctx->fail(SPL_ERR_IO, "%s", e.c_str());
+    const int rc = bam_gpu_ingest(ctx->bgm, (const uint8_t*)ctx->h_file, fsz, members, total_u, first_record, n_ref, refmap, ctx->stream,
+                                  ctx->dev_rec, cnt, e);
+    if (rc == BAMGPU_ERROR) return ctx->fail(SPL_ERR_CUDA, "%s", e.c_str());
+    if (rc == BAMGPU_FALLBACK) { *fallback = true; return SPL_OK; }
+    view = spl_records_view{};
+    view.n_rec = (int64_t)cnt.n_rec; view.n_cigar = (int64_t)cnt.n_cigar;
+    view.n_seg = (int32_t)cnt.seg_chrom.size();
+    view.seg_chrom = cnt.seg_chrom.data(); view.seg_off = cnt.seg_off.data();
+    return SPL_OK;
+}
+
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
@@ -746,6 +821,8 @@ void spl_destroy(spl_ctx* ctx) {
         if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
         if (ctx->gbm.h_cnt) cudaFreeHost(ctx->gbm.h_cnt);
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        if (ctx->h_file) cudaFreeHost(ctx->h_file);
+        ctx->bgm.comp.release(); ctx->bgm.unc.release(); ctx->bgm.tab.release(); ctx->bgm.rec.release();
         ctx->gbm.fin.release(); ctx->gbm.fin2.release(); ctx->gbm.work.release(); ctx->gbm.work2.release();
         if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
         if (ctx->ev_graph) cudaEventDestroy(ctx->ev_graph);
@@ -803,6 +880,25 @@ int spl_process(spl_ctx* ctx, const char* bam_path, int32_t n_chrom, const char*
     if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
     if (!bam_path) return ctx->fail(SPL_ERR_ARG, "bam_path is NULL");
     const double t0 = now_ms();
+    CU(cudaSetDevice(ctx->device));
+    {   // BGZF inflate + record parse on the device; the host reader is the fallback for what that path does not cover
+        BamGpuCounts cnt;
+        spl_records_view dv{};
+        bool fallback = false;
+        int rc = ingest_bam_device(ctx, bam_path, n_chrom, chrom_names, cnt, dv, &fallback);
+        if (rc) return rc;
+        if (!fallback) {
+            const double t1 = now_ms();
+            ctx->rec_on_device = true;
+            rc = spl_process_records(ctx, &dv, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, out);
+            ctx->rec_on_device = false;
+            ctx->stats[SPL_STAT_MS_DECODE] = t1 - t0;
+            ctx->stats[SPL_STAT_H2D_BYTES] += cnt.h2d_bytes;
+            ctx->stats[SPL_STAT_BAM_DEVICE] = 1.0;
+            ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
+            return rc;
+        }
+    }
     BamRecords recs;
     std::string e = read_bam(bam_path, n_chrom, chrom_names, ctx->n_threads, recs);
     if (!e.empty()) return ctx->fail(SPL_ERR_IO, "%s", e.c_str());
@@ -868,6 +964,25 @@ int spl_recount(spl_ctx* ctx, const char* bam_path, int32_t n_chrom, const char*
     if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
     if (!bam_path) return ctx->fail(SPL_ERR_ARG, "bam_path is NULL");
     const double t0 = now_ms();
+    CU(cudaSetDevice(ctx->device));
+    {
+        BamGpuCounts cnt;
+        spl_records_view dv{};
+        bool fallback = false;
+        int rc = ingest_bam_device(ctx, bam_path, n_chrom, chrom_names, cnt, dv, &fallback);
+        if (rc) return rc;
+        if (!fallback) {
+            const double t1 = now_ms();
+            ctx->rec_on_device = true;
+            rc = spl_recount_records(ctx, &dv, n_chrom, n_sites, s_chrom, s_pos, s_strand, p_off, p_pos, c_off, c_pos, flags,
+                                     beta1_out, beta2simple_out);
+            ctx->rec_on_device = false;
+            ctx->stats[SPL_STAT_MS_DECODE] = t1 - t0;
+            ctx->stats[SPL_STAT_BAM_DEVICE] = 1.0;
+            ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
+            return rc;
+        }
+    }
     BamRecords recs;
     std::string e = read_bam(bam_path, n_chrom, chrom_names, ctx->n_threads, recs);
     if (!e.empty()) return ctx->fail(SPL_ERR_IO, "%s", e.c_str());

@@ -323,3 +323,46 @@ def test_full_size_configs1_properties(ctx):
             lo, hi = S * ti // n_tiles, S * (ti + 1) // n_tiles
             b1[lo:hi], b2[lo:hi] = t.beta1[lo:hi], t.beta2simple[lo:hi]
     assert np.array_equal(b1, full.beta1) and np.array_equal(b2, full.beta2simple)
+
+
+def test_bam_ingest_on_the_device(ctx, tmp_path, monkeypatch):
+    """spl_process / spl_recount from a BAM file: BGZF inflate and BAM record parsing run on the GPU (bam_gpu.cu; record
+    boundaries are speculated per BGZF member and verified as one chain).  Results must equal the records path and the
+    host reader, with references in a different order than the caller's chromosome index and an unknown reference."""
+    import numpy as np
+    from oracle import c_oracle
+    from spliser_b200 import Junctions, Records, synth
+    w = synth.generate(synth.config_small(150_000, seed=61, stranded=True, paired=True))
+    r, j = w.records, w.junctions
+    # BAM reference order: [ZZ (unknown to the caller), T1, T2]; caller chrom_index: [T2, T1]
+    bam = str(tmp_path / "s.bam")
+    extra = Records.from_reads(["ZZ"], [("ZZ", 100 + 3 * i, 0, "20M100N20M") for i in range(500)])
+    pos = np.concatenate([extra.pos, r.pos]); flag = np.concatenate([extra.flag, r.flag])
+    cig = np.concatenate([extra.cigar, r.cigar])
+    off = np.concatenate([extra.cig_off, r.cig_off[1:] + extra.cig_off[-1]])
+    seg_chrom = np.concatenate([[0], r.seg_chrom + 1]); seg_off = np.concatenate([[0], r.seg_off + len(extra)])
+    Records(pos, flag, off, cig, seg_chrom, seg_off).write_bam(bam, ["ZZ"] + list(w.chroms))
+    caller = [w.chroms[1], w.chroms[0]]
+    remap = np.array([1, 0], np.int32)
+    jj = Junctions(remap[j.chrom], j.left, j.right, j.score, j.strand)
+    order = [int(np.nonzero(r.seg_chrom == c)[0][0]) for c in (0, 1)]     # records path input in BAM order, caller indices
+    rec_caller = Records(r.pos, r.flag, r.cig_off, r.cigar, remap[r.seg_chrom], r.seg_off)
+    want = c_oracle.table_dict(ctx.process_records(rec_caller, 2, jj, w.flags | 4))
+    monkeypatch.delenv("SPLISER_HOST_BAM", raising=False)
+    got = c_oracle.table_dict(ctx.process_bam(bam, caller, jj, w.flags | 4))
+    st = ctx.stats()
+    assert st["bam_on_device"] == 1.0 and st["n_aligned"] == len(r), st
+    assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
+    monkeypatch.setenv("SPLISER_HOST_BAM", "1")
+    host = c_oracle.table_dict(ctx.process_bam(bam, caller, jj, w.flags | 4))
+    assert ctx.stats()["bam_on_device"] == 0.0
+    assert c_oracle.diff_tables(host, want) is None
+    monkeypatch.delenv("SPLISER_HOST_BAM", raising=False)
+    # the re-count entry point takes the same route
+    t = ctx.process_records(rec_caller, 2, jj, w.flags)
+    gaps = [(int(t.chrom[i]), int(t.pos[i]), t.strand_str(i), sorted(t.partners(i)), t.competitors(i)) for i in range(0, len(t), 7)]
+    a1, a2 = ctx.recount_records(rec_caller, 2, gaps, w.flags | 8)
+    b1, b2 = ctx.recount_bam(bam, caller, gaps, w.flags | 8)
+    assert ctx.stats()["bam_on_device"] == 1.0
+    assert np.array_equal(a1, b1) and np.array_equal(a2, b2) and int(a1.sum()) > 0
+    assert len(order) == 2

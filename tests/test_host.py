@@ -154,3 +154,49 @@ def test_gene_assignment_matches_reference_golden(tmp_path):
     q = load_annotation(str(p), "G2")
     assert q.query_gene.name == "G2" and len(q.genes[0]) == 1
     assert load_annotation(str(p), "NOPE").query_gene is None
+
+
+def test_device_inflate_decoder_matches_zlib_on_the_host():
+    """csrc/inflate.h is the raw-DEFLATE decoder every GPU warp runs on a BGZF member; the same source compiled for
+    the host must reproduce zlib byte for byte (stored, fixed and dynamic blocks, long codes) and reject corrupt input."""
+    import ctypes as C
+    import zlib
+    import numpy as np
+    from spliser_b200 import _lib
+    lib = _lib.load()
+    rng = np.random.default_rng(3)
+
+    def inflate(comp, cap):
+        src = np.frombuffer(comp, np.uint8).copy() if len(comp) else np.zeros(1, np.uint8)
+        dst = np.full(cap + 8, 0xEE, np.uint8)
+        n = C.c_uint32(0)
+        rc = lib.spl_debug_inflate(src.ctypes.data_as(_lib.c_u8p), len(comp), dst.ctypes.data_as(_lib.c_u8p), cap, C.byref(n))
+        return rc, dst[:n.value].tobytes(), dst
+    n_cases = 0
+    for level in (0, 1, 6, 9):
+        for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE, zlib.Z_FILTERED):
+            for kind in range(6):
+                n = int(rng.integers(0, 65281)) if kind else kind
+                if kind == 1:
+                    raw = rng.integers(0, 256, n, dtype=np.uint8).tobytes()
+                elif kind == 2:
+                    raw = rng.choice(np.frombuffer(b"ACGT", np.uint8), n).tobytes()
+                elif kind == 3:
+                    raw = bytes(n)
+                elif kind == 4:      # BAM-like: small little-endian integers
+                    raw = rng.integers(0, 40, n // 4 + 1, dtype=np.int32).tobytes()[:n]
+                else:
+                    raw = (rng.integers(0, 256, 97, dtype=np.uint8).tobytes() * (n // 97 + 1))[:n]
+                co = zlib.compressobj(level, zlib.DEFLATED, -15, 8, strategy)
+                comp = co.compress(raw) + co.flush()
+                rc, out, dst = inflate(comp, len(raw))
+                assert rc == 0 and out == raw and dst[len(raw)] == 0xEE, (level, strategy, kind, n, rc)
+                n_cases += 1
+                if len(comp) > 8:    # truncated and corrupted members fail cleanly
+                    rc, _, _ = inflate(comp[:len(comp) // 2], len(raw))
+                    assert rc != 0
+                    inflate(comp[:len(comp) // 3] + bytes([comp[len(comp) // 3] ^ 0x5A]) + comp[len(comp) // 3 + 1:], len(raw))
+                if len(raw) > 1:     # output capacity is respected
+                    rc, _, dst = inflate(comp, len(raw) - 1)
+                    assert rc != 0 and dst[len(raw) - 1] == 0xEE
+    assert n_cases == 120
