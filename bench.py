@@ -158,6 +158,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="records in the CPU baseline's genomic sub-region")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-bam", action="store_true", help="skip the from-a-BAM-file measurement")
     ap.add_argument("--profile", action="store_true", help="resident passes only (for ncu): no e2e, no CPU baseline")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -295,6 +296,39 @@ def main():
                         "n_distinct_junctions": int(D), "n_simple_junction_instances": int(n_simple), "n_complex_junction_instances": int(n_complex)},
         "checksum": {"beta1": int(table.beta1.sum()), "beta2simple": int(table.beta2simple.sum()), "alpha": int(table.alpha.sum())},
     }
+    # ---- the same call from a BAM FILE (spl_process): BGZF inflate + record parse on the device vs the host reader
+    if world == 1 and not args.no_bam:
+        try:
+            bam = os.path.join(CACHE, "bench_%s_%d.bam" % (args.workload, len(r)))
+            if not os.path.exists(bam):
+                os.makedirs(CACHE, exist_ok=True)
+                r.write_bam(bam + ".tmp", w.chroms, w.chrom_len)
+                os.replace(bam + ".tmp", bam)
+            table = None
+            ctx.process_bam(bam, w.chroms, w.junctions, w.flags)       # warm-up (allocations, page cache)
+            tb = []
+            for _ in range(max(1, args.e2e_steps)):
+                a = time.perf_counter()
+                tbam = ctx.process_bam(bam, w.chroms, w.junctions, w.flags)
+                tb.append(time.perf_counter() - a)
+                sb = ctx.stats()
+                same = bool(np.array_equal(tbam.beta1, table.beta1) and np.array_equal(tbam.sse, table.sse)) if table is not None else None
+                table_b = tbam
+            os.environ["SPLISER_HOST_BAM"] = "1"
+            a = time.perf_counter()
+            th = ctx.process_bam(bam, w.chroms, w.junctions, w.flags)
+            host_s = time.perf_counter() - a
+            sh = ctx.stats()
+            del os.environ["SPLISER_HOST_BAM"]
+            out["bam_e2e"] = {"value": reads_rank / float(np.mean(tb)), "unit": "reads/s", "ms_per_step": 1e3 * float(np.mean(tb)),
+                              "bam_bytes": os.path.getsize(bam), "bam_on_device": bool(sb["bam_on_device"]), "ms_ingest": round(sb["ms_decode"], 3),
+                              "host_reader": {"ms_per_step": 1e3 * host_s, "ms_decode": round(sh["ms_decode"], 3), "threads": ncores},
+                              "identical_to_host_reader": bool(np.array_equal(th.beta1, table_b.beta1) and np.array_equal(th.beta2simple, table_b.beta2simple)
+                                                                and np.array_equal(th.sse, table_b.sse)),
+                              "note": "spl_process(bam_path): file image -> pinned -> H2D, BGZF inflate + BAM parse on the device, then the same path as e2e; "
+                                      "synthetic BAM without SEQ/QUAL (records only), so the file is much smaller than a sequencer's"}
+        except Exception as ex:                                      # never lose the main line over the extra measurement
+            out["bam_e2e"] = {"error": repr(ex)}
     sampler.stop()
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         rec_s, junc_s = region_sample(w, args.cpu_sample)

@@ -1,8 +1,9 @@
 // BAM ingest on the device: BGZF members are inflated by the GPU and the BAM records are parsed
 // straight into the record arrays the expansion kernels read -- the decoded records never exist on the host.
 //
-//   k_bgzf_inflate     one warp per BGZF member (<= 64 KiB each, independent DEFLATE streams): lane 0 runs the decoder of
-//                      inflate.h with its Huffman tables in shared memory; tens of thousands of members decode concurrently
+//   k_bgzf_inflate     one warp per BGZF member (<= 64 KiB each, independent DEFLATE streams): the warp runs the decoder of
+//                      inflate.h (Huffman tables in shared memory, symbol decode uniform across the lanes, LZ77 match bytes
+//                      split between the lanes); tens of thousands of members decode concurrently
 //   k_bam_first        per member: the first offset at which a plausible chain of BAM records starts (records are NOT
 //                      aligned to members in general: htsjdk and this library's own writer cut members every 0xff00 bytes)
 //   k_bam_walk<false>  per member: walks the record chain from that offset to the member's end, counting records and
@@ -36,11 +37,11 @@ __global__ void __launch_bounds__(INF_WARPS * 32)
 k_bgzf_inflate(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ mem, uint32_t n_mem, uint8_t* __restrict__ out, uint32_t* __restrict__ err) {
     __shared__ InflateTables tabs[INF_WARPS];
     const uint32_t m = blockIdx.x * INF_WARPS + (threadIdx.x >> 5);
-    if (m >= n_mem || (threadIdx.x & 31) != 0) return;
+    if (m >= n_mem) return;                                              // whole warps leave together
     const BgzfMember b = mem[m];
     uint32_t produced = 0;
-    const int rc = inflate_member(comp + b.coff, b.clen, out + b.uoff, b.isize, &produced, tabs[threadIdx.x >> 5]);
-    if (rc != INF_OK || produced != b.isize) atomicMax(err, 1u + m);
+    const int rc = inflate_member(comp + b.coff, b.clen, out + b.uoff, b.isize, &produced, tabs[threadIdx.x >> 5], WarpLanes());
+    if ((threadIdx.x & 31) == 0 && (rc != INF_OK || produced != b.isize)) atomicMax(err, 1u + m);
 }
 
 __device__ __forceinline__ uint32_t ld32(const uint8_t* p) {
@@ -48,21 +49,45 @@ __device__ __forceinline__ uint32_t ld32(const uint8_t* p) {
 }
 __device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
 
+// unaligned little-endian 32-bit load from two aligned words (the inflated stream is 256-byte aligned and padded)
+__device__ __forceinline__ uint32_t ld32u(const uint8_t* __restrict__ u, uint64_t o) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(u + (o & ~3ull));
+    return __funnelshift_r(w[0], w[1], (uint32_t)(o & 3ull) * 8u);
+}
+
+// fixed part of a BAM record at offset o, read as 9 aligned words
+struct RecHdr { uint32_t bs, l_name, n_cig, flag; int32_t refid, pos, l_seq, next_ref, next_pos; };
+__device__ __forceinline__ RecHdr read_hdr(const uint8_t* __restrict__ u, uint64_t o) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(u + (o & ~3ull));
+    const uint32_t sh = (uint32_t)(o & 3ull) * 8u;
+    uint32_t a[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] = w[i];
+    RecHdr h;
+    h.bs = __funnelshift_r(a[0], a[1], sh);
+    h.refid = (int32_t)__funnelshift_r(a[1], a[2], sh);
+    h.pos = (int32_t)__funnelshift_r(a[2], a[3], sh);
+    h.l_name = __funnelshift_r(a[3], a[4], sh) & 0xffu;
+    const uint32_t cf = __funnelshift_r(a[4], a[5], sh);
+    h.n_cig = cf & 0xffffu; h.flag = cf >> 16;
+    h.l_seq = (int32_t)__funnelshift_r(a[5], a[6], sh);
+    h.next_ref = (int32_t)__funnelshift_r(a[6], a[7], sh);
+    h.next_pos = (int32_t)__funnelshift_r(a[7], a[8], sh);
+    return h;
+}
+
 // Could a BAM record start at offset o?  Necessary conditions only: a true record always passes.
-__device__ __forceinline__ bool plausible(const uint8_t* __restrict__ u, uint64_t o, uint64_t total, int32_t n_ref, uint64_t* next) {
+__device__ __forceinline__ bool plausible(const uint8_t* __restrict__ u, uint64_t o, uint64_t total, int32_t n_ref, uint64_t* next, RecHdr* out = nullptr) {
     if (o + 36 > total) return false;
-    const uint8_t* r = u + o;
-    const uint32_t bs = ld32(r);
-    if (bs < 32u || bs > (1u << 30)) return false;
-    const int32_t refid = (int32_t)ld32(r + 4), pos = (int32_t)ld32(r + 8);
-    const uint32_t l_name = r[12], n_cig = ld16(r + 16);
-    const int32_t l_seq = (int32_t)ld32(r + 20), next_ref = (int32_t)ld32(r + 24), next_pos = (int32_t)ld32(r + 28);
-    if (refid < -1 || refid >= n_ref || next_ref < -1 || next_ref >= n_ref) return false;
-    if (pos < -1 || next_pos < -1 || l_name < 1u || l_seq < 0) return false;
-    const uint64_t need = 32ull + l_name + 4ull * n_cig + ((uint64_t)l_seq + 1) / 2 + (uint64_t)l_seq;
-    if (need > bs || o + 4 + bs > total) return false;
-    if (r[36 + l_name - 1] != 0) return false;                        // read name is NUL-terminated
-    *next = o + 4 + bs;
+    const RecHdr h = read_hdr(u, o);
+    if (h.bs < 32u || h.bs > (1u << 30)) return false;
+    if (h.refid < -1 || h.refid >= n_ref || h.next_ref < -1 || h.next_ref >= n_ref) return false;
+    if (h.pos < -1 || h.next_pos < -1 || h.l_name < 1u || h.l_seq < 0) return false;
+    const uint64_t need = 32ull + h.l_name + 4ull * h.n_cig + ((uint64_t)h.l_seq + 1) / 2 + (uint64_t)h.l_seq;
+    if (need > h.bs || o + 4 + h.bs > total) return false;
+    if (u[o + 36 + h.l_name - 1] != 0) return false;                   // read name is NUL-terminated
+    *next = o + 4 + h.bs;
+    if (out) *out = h;
     return true;
 }
 
@@ -107,24 +132,21 @@ __global__ void __launch_bounds__(128) k_bam_walk(const uint8_t* __restrict__ u,
     uint64_t ri = FILL ? rec_base[m] : 0, ci = FILL ? cig_base[m] : 0;
     while (o < limit) {
         uint64_t nx;
-        if (!plausible(u, o, total, n_ref, &nx)) { flags |= WALK_BAD; break; }
-        const uint8_t* r = u + o + 4;
-        const int32_t refid = (int32_t)ld32(r);
-        const uint32_t l_name = r[8], n_cig = ld16(r + 12), flag = ld16(r + 14);
-        const int32_t l_seq = (int32_t)ld32(r + 16);
-        const uint8_t* cig = r + 32 + l_name;
+        RecHdr h;
+        if (!plausible(u, o, total, n_ref, &nx, &h)) { flags |= WALK_BAD; break; }
+        const uint64_t cig = o + 36 + h.l_name;
         // CIGARs of more than 65535 operators live in a CG tag (SAM spec 4.2.2): left to the host reader
-        if (n_cig == 2 && ld32(cig) == (((uint32_t)l_seq << 4) | 4u) && (ld32(cig + 4) & 15u) == 3u) flags |= WALK_LONG_CIGAR;
-        const int32_t chrom = refid >= 0 ? refmap[refid] : -1;
-        if (chrom >= 0 && n_cig > 0) {
+        if (h.n_cig == 2 && ld32u(u, cig) == (((uint32_t)h.l_seq << 4) | 4u) && (ld32u(u, cig + 4) & 15u) == 3u) flags |= WALK_LONG_CIGAR;
+        const int32_t chrom = h.refid >= 0 ? refmap[h.refid] : -1;
+        if (chrom >= 0 && h.n_cig > 0) {
             if (FILL) {
-                out.pos[ri] = (int32_t)ld32(r + 4) + 1;
-                out.flag[ri] = (uint16_t)flag;
+                out.pos[ri] = h.pos + 1;
+                out.flag[ri] = (uint16_t)h.flag;
                 out.chrom[ri] = chrom;
                 out.cig_off[ri] = (uint32_t)ci;
-                for (uint32_t k = 0; k < n_cig; ++k) out.cigar[ci + k] = ld32(cig + 4 * k);
+                for (uint32_t k = 0; k < h.n_cig; ++k) out.cigar[ci + k] = ld32u(u, cig + 4ull * k);
             }
-            ++n_rec; n_cig_tot += n_cig; ++ri; ci += n_cig;
+            ++n_rec; n_cig_tot += h.n_cig; ++ri; ci += h.n_cig;
         }
         o = nx;
     }
@@ -161,7 +183,7 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
     if (n_mem == 0 || first_record >= total_u) { out = DevRecordArrays{}; return BAMGPU_OK; }
     // ---- compressed file + member table to the device, inflate
     BG_CU(mem.comp.reserve(fsz + 64));
-    BG_CU(mem.unc.reserve(total_u + 64));
+    BG_CU(mem.unc.reserve(total_u + 256));                              // the aligned-word reads of the parser run a few bytes past the end
     BG_CU(mem.tab.reserve((size_t)n_mem * (sizeof(BgzfMember) + 8 + sizeof(WalkOut) + 16) + ((size_t)n_ref + 1) * 4 + 4096));
     char* tb = (char*)mem.tab.p;
     BgzfMember* d_mem = (BgzfMember*)tb; tb += (size_t)n_mem * sizeof(BgzfMember);
@@ -254,5 +276,5 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
 extern "C" int spl_debug_inflate(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, uint32_t* out_len) {
     if (!src || !dst || !out_len) return -1;
     static thread_local spl::InflateTables t;
-    return spl::inflate_member(src, n, dst, cap, out_len, t);
+    return spl::inflate_member(src, n, dst, cap, out_len, t, spl::OneLane());
 }

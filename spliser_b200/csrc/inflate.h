@@ -37,6 +37,17 @@ struct BitReader {
     int bits;
     SPL_HD void init(const uint8_t* s, uint32_t len) { src = s; n = len; pos = 0; buf = 0; bits = 0; }
     SPL_HD void refill() {
+        if (bits <= 32 && pos + 4 <= n) {                   // 4 bytes at once while a whole word of input is left
+            uint32_t w;
+#if defined(__CUDA_ARCH__)
+            const uint32_t* a = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src + pos) & ~(uintptr_t)3);
+            w = __funnelshift_r(a[0], a[1], (uint32_t)(reinterpret_cast<uintptr_t>(src + pos) & 3u) * 8u);   // a[1] stays inside the file image (+ padding)
+#else
+            w = (uint32_t)src[pos] | ((uint32_t)src[pos + 1] << 8) | ((uint32_t)src[pos + 2] << 16) | ((uint32_t)src[pos + 3] << 24);
+#endif
+            buf |= (uint64_t)w << bits;
+            bits += 32; pos += 4;
+        }
         while (bits <= 56 && pos < n) { buf |= (uint64_t)src[pos++] << bits; bits += 8; }
     }
     SPL_HD uint32_t peek(int k) const { return (uint32_t)(buf & ((1ull << k) - 1ull)); }
@@ -102,8 +113,28 @@ SPL_HD int inf_decode(BitReader& br, const uint16_t* count, const uint16_t* sym,
     return -1;
 }
 
+// How many cooperating lanes run the decoder.  On the device all 32 lanes of a warp execute the (uniform) decode loop
+// redundantly -- same bit buffer, broadcast table reads -- and split the byte copies of LZ77 matches and stored blocks
+// between them: a serial copy through global memory pays one load latency PER BYTE, the split copy one per 32 bytes.
+// Tables are built by lane 0 alone (the build has read-modify-write steps); everything else the lanes write in common
+// is the same value from every lane.
+struct OneLane {
+    SPL_HD int lane() const { return 0; }
+    SPL_HD int count() const { return 1; }
+    SPL_HD void sync() const {}
+};
+#if defined(__CUDACC__)
+struct WarpLanes {
+    __device__ __forceinline__ int lane() const { return (int)(threadIdx.x & 31u); }
+    __device__ __forceinline__ int count() const { return 32; }
+    __device__ __forceinline__ void sync() const { __syncwarp(); }
+};
+#endif
+
 // inflate `src[0..n)` into `dst[0..cap)`; *out_len receives the bytes produced
-SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, uint32_t* out_len, InflateTables& t) {
+template <class Lanes>
+SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t cap, uint32_t* out_len, InflateTables& t, const Lanes& ln) {
+    const int lane = ln.lane(), nl = ln.count();
     const uint8_t ORDER[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
     BitReader br;
     br.init(src, n);
@@ -124,14 +155,15 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             uint32_t left = len;
             while (left && br.bits >= 8) {
                 if (out >= cap) return INF_ERR_OUTPUT;
-                dst[out++] = (uint8_t)br.take(8);
-                --left;
+                const uint8_t v = (uint8_t)br.take(8);
+                if (lane == 0) dst[out] = v;
+                ++out; --left;
             }
             if (left) {
                 if (br.bits != 0) return INF_ERR_INPUT;
                 if (br.pos + left > br.n) return INF_ERR_INPUT;
                 if (out + left > cap) return INF_ERR_OUTPUT;
-                for (uint32_t i = 0; i < left; ++i) dst[out + i] = br.src[br.pos + i];
+                for (uint32_t i = (uint32_t)lane; i < left; i += (uint32_t)nl) dst[out + i] = br.src[br.pos + i];
                 out += left; br.pos += left;
             }
             continue;
@@ -142,9 +174,14 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             for (int s = 144; s < 256; ++s) t.lens[s] = 9;
             for (int s = 256; s < 280; ++s) t.lens[s] = 7;
             for (int s = 280; s < 288; ++s) t.lens[s] = 8;
-            inf_build(t.lens, 288, t.lit_count, t.lit_sym, t.lit_fast);
-            for (int s = 0; s < 30; ++s) t.lens[s] = 5;
-            inf_build(t.lens, 30, t.dist_count, t.dist_sym, t.dist_fast);
+            uint8_t dl[32];
+            for (int s = 0; s < 30; ++s) dl[s] = 5;
+            ln.sync();
+            if (lane == 0) {
+                inf_build(t.lens, 288, t.lit_count, t.lit_sym, t.lit_fast);
+                inf_build(dl, 30, t.dist_count, t.dist_sym, t.dist_fast);
+            }
+            ln.sync();
         } else {                                           // dynamic codes
             br.refill();
             if (br.bits < 14) return INF_ERR_INPUT;
@@ -158,7 +195,10 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
                 cl[ORDER[i]] = (uint8_t)br.take(3);
             }
             // the code-length code reuses the distance tables as scratch
-            if (!inf_build(cl, 19, t.dist_count, t.dist_sym, t.dist_fast)) return INF_ERR_CODE;
+            ln.sync();                                                  // nobody still decodes with the previous block's tables
+            if (lane == 0) t.lens[318] = inf_build(cl, 19, t.dist_count, t.dist_sym, t.dist_fast) ? 1 : 0;   // verdict for every lane:
+            ln.sync();                                                  // error exits must be uniform across the warp
+            if (!t.lens[318]) return INF_ERR_CODE;
             int idx = 0;
             while (idx < nlen + ndist) {
                 br.refill();
@@ -185,8 +225,14 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             // distance lengths first (they sit behind the literal lengths), then the literal/length code
             uint8_t dl[32];
             for (int s = 0; s < ndist; ++s) dl[s] = t.lens[nlen + s];
-            if (!inf_build(t.lens, nlen, t.lit_count, t.lit_sym, t.lit_fast)) return INF_ERR_CODE;
-            if (!inf_build(dl, ndist, t.dist_count, t.dist_sym, t.dist_fast)) return INF_ERR_CODE;
+            ln.sync();
+            if (lane == 0) {
+                const bool ok = inf_build(t.lens, nlen, t.lit_count, t.lit_sym, t.lit_fast) &&
+                                inf_build(dl, ndist, t.dist_count, t.dist_sym, t.dist_fast);
+                t.lens[319] = ok ? 1 : 0;                               // slots 318 / 319 are never code lengths (at most 286 + 30)
+            }
+            ln.sync();
+            if (!t.lens[319]) return INF_ERR_CODE;
         }
         // ---- symbols
         for (;;) {
@@ -195,7 +241,8 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             if (s < 0) return INF_ERR_CODE;
             if (s < 256) {
                 if (out >= cap) return INF_ERR_OUTPUT;
-                dst[out++] = (uint8_t)s;
+                if (lane == 0) dst[out] = (uint8_t)s;
+                ++out;
                 continue;
             }
             if (s == 256) break;
@@ -215,7 +262,12 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             const uint32_t dist = dbase + br.take(dext);
             if (dist > out) return INF_ERR_DIST;
             if (out + len > cap) return INF_ERR_OUTPUT;
-            for (uint32_t i = 0; i < len; ++i) dst[out + i] = dst[out - dist + i];     // overlapping copies repeat the pattern
+            // every source byte of the match is already written (overlapping matches repeat the last `dist` bytes), so
+            // the lanes copy independent bytes; the syncs order them against lane 0's literal stores
+            ln.sync();
+            if (dist >= len) { for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) dst[out + i] = dst[out - dist + i]; }
+            else { for (uint32_t i = (uint32_t)lane; i < len; i += (uint32_t)nl) dst[out + i] = dst[out - dist + (i % dist)]; }
+            ln.sync();
             out += len;
         }
     }
