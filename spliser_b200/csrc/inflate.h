@@ -16,13 +16,15 @@
 
 namespace spl {
 
-constexpr int INF_FAST_BITS = 10;
+constexpr int INF_FAST_BITS = 9;
 constexpr int INF_MAXBITS = 15;
 
 // per-decoder scratch (shared memory on the device: one per warp)
 struct InflateTables {
-    uint16_t lit_fast[1 << INF_FAST_BITS];    // (symbol << 4) | length, 0 = not a short code
-    uint16_t dist_fast[1 << INF_FAST_BITS];
+    // fast entries: value << 16 | op << 8 | code length; 0 = not a short code.  op: 0 literal / plain symbol (value = symbol),
+    // 16 | extra bits = length or distance (value = base), 32 = end of block, 64 = invalid symbol
+    uint32_t lit_fast[1 << INF_FAST_BITS];
+    uint32_t dist_fast[1 << INF_FAST_BITS];
     uint16_t lit_count[INF_MAXBITS + 1], dist_count[INF_MAXBITS + 1];
     uint16_t lit_sym[288], dist_sym[32];      // symbols ordered by (length, symbol)
     uint8_t  lens[320];                       // code lengths while a dynamic header is read
@@ -61,8 +63,28 @@ SPL_HD uint32_t inf_reverse(uint32_t code, int len) {
     return r;
 }
 
+enum : int { INF_KIND_LITLEN = 0, INF_KIND_DIST = 1, INF_KIND_PLAIN = 2 };
+
+// (value << 16 | op << 8) of a symbol: literals and plain symbols carry themselves, length / distance symbols their base
+// and extra-bit count in closed form (RFC 1951 3.2.5)
+SPL_HD uint32_t inf_entry(int kind, int sym) {
+    if (kind == INF_KIND_PLAIN || (kind == INF_KIND_LITLEN && sym < 256)) return (uint32_t)sym << 16;
+    if (kind == INF_KIND_LITLEN) {
+        if (sym == 256) return 32u << 8;
+        if (sym > 285) return 64u << 8;
+        const int li = sym - 257;
+        const int ext = (li < 8 || li == 28) ? 0 : ((li - 4) >> 2);
+        const uint32_t base = li < 8 ? 3u + (uint32_t)li : li == 28 ? 258u : 3u + ((4u + (uint32_t)(li & 3)) << ext);
+        return (base << 16) | ((16u | (uint32_t)ext) << 8);
+    }
+    if (sym > 29) return 64u << 8;
+    const int ext = sym < 4 ? 0 : ((sym - 2) >> 1);
+    const uint32_t base = sym < 4 ? 1u + (uint32_t)sym : 1u + ((2u + (uint32_t)(sym & 1)) << ext);
+    return (base << 16) | ((16u | (uint32_t)ext) << 8);
+}
+
 // canonical Huffman tables from code lengths; returns false for an over-subscribed set
-SPL_HD bool inf_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* sym, uint16_t* fast) {
+SPL_HD bool inf_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* sym, uint32_t* fast, int kind) {
     for (int l = 0; l <= INF_MAXBITS; ++l) count[l] = 0;
     for (int s = 0; s < n; ++s) count[lens[s]]++;
     for (int i = 0; i < (1 << INF_FAST_BITS); ++i) fast[i] = 0;
@@ -83,7 +105,7 @@ SPL_HD bool inf_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* sym
     for (int l = 1; l <= INF_FAST_BITS; ++l) {
         for (int k = 0; k < (int)count[l]; ++k, ++idx, ++code) {
             const uint32_t rev = inf_reverse(code, l);
-            const uint16_t e = (uint16_t)((sym[idx] << 4) | l);
+            const uint32_t e = inf_entry(kind, sym[idx]) | (uint32_t)l;
             for (uint32_t f = rev; f < (1u << INF_FAST_BITS); f += (1u << l)) fast[f] = e;
         }
         code <<= 1;
@@ -91,26 +113,26 @@ SPL_HD bool inf_build(const uint8_t* lens, int n, uint16_t* count, uint16_t* sym
     return true;
 }
 
-// decode one symbol; -1 on an invalid code
-SPL_HD int inf_decode(BitReader& br, const uint16_t* count, const uint16_t* sym, const uint16_t* fast) {
-    const uint16_t e = fast[br.peek(INF_FAST_BITS)];
+// decode one symbol and consume its code; returns its entry (value << 16 | op << 8), or 64 << 8 on an invalid code
+SPL_HD uint32_t inf_decode(BitReader& br, const uint16_t* count, const uint16_t* sym, const uint32_t* fast, int kind) {
+    const uint32_t e = fast[br.peek(INF_FAST_BITS)];
     if (e) {
-        if ((e & 15) > br.bits) return -1;
-        br.drop(e & 15);
-        return e >> 4;
+        if ((int)(e & 0xffu) > br.bits) return 64u << 8;
+        br.drop((int)(e & 0xffu));
+        return e;
     }
     // long code: canonical walk, one bit at a time (RFC 1951 3.2.2 / zlib's puff.c)
     int code = 0, first = 0, index = 0;
     uint64_t b = br.buf;
     for (int len = 1; len <= INF_MAXBITS; ++len) {
-        if (len > br.bits) return -1;
+        if (len > br.bits) return 64u << 8;
         code |= (int)(b & 1u);
         b >>= 1;
         const int cnt = count[len];
-        if (code - cnt < first) { br.drop(len); return sym[index + (code - first)]; }
+        if (code - cnt < first) { br.drop(len); return inf_entry(kind, sym[index + (code - first)]); }
         index += cnt; first += cnt; first <<= 1; code <<= 1;
     }
-    return -1;
+    return 64u << 8;
 }
 
 // How many cooperating lanes run the decoder.  On the device all 32 lanes of a warp execute the (uniform) decode loop
@@ -178,8 +200,8 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             for (int s = 0; s < 30; ++s) dl[s] = 5;
             ln.sync();
             if (lane == 0) {
-                inf_build(t.lens, 288, t.lit_count, t.lit_sym, t.lit_fast);
-                inf_build(dl, 30, t.dist_count, t.dist_sym, t.dist_fast);
+                inf_build(t.lens, 288, t.lit_count, t.lit_sym, t.lit_fast, INF_KIND_LITLEN);
+                inf_build(dl, 30, t.dist_count, t.dist_sym, t.dist_fast, INF_KIND_DIST);
             }
             ln.sync();
         } else {                                           // dynamic codes
@@ -196,14 +218,15 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             }
             // the code-length code reuses the distance tables as scratch
             ln.sync();                                                  // nobody still decodes with the previous block's tables
-            if (lane == 0) t.lens[318] = inf_build(cl, 19, t.dist_count, t.dist_sym, t.dist_fast) ? 1 : 0;   // verdict for every lane:
+            if (lane == 0) t.lens[318] = inf_build(cl, 19, t.dist_count, t.dist_sym, t.dist_fast, INF_KIND_PLAIN) ? 1 : 0;   // verdict for every lane:
             ln.sync();                                                  // error exits must be uniform across the warp
             if (!t.lens[318]) return INF_ERR_CODE;
             int idx = 0;
             while (idx < nlen + ndist) {
                 br.refill();
-                const int s = inf_decode(br, t.dist_count, t.dist_sym, t.dist_fast);
-                if (s < 0) return INF_ERR_CODE;
+                const uint32_t ce = inf_decode(br, t.dist_count, t.dist_sym, t.dist_fast, INF_KIND_PLAIN);
+                if (ce & (64u << 8)) return INF_ERR_CODE;
+                const int s = (int)(ce >> 16);
                 if (s < 16) { t.lens[idx++] = (uint8_t)s; continue; }
                 int rep, val = 0;
                 if (s == 16) {
@@ -227,39 +250,35 @@ SPL_HD int inflate_member(const uint8_t* src, uint32_t n, uint8_t* dst, uint32_t
             for (int s = 0; s < ndist; ++s) dl[s] = t.lens[nlen + s];
             ln.sync();
             if (lane == 0) {
-                const bool ok = inf_build(t.lens, nlen, t.lit_count, t.lit_sym, t.lit_fast) &&
-                                inf_build(dl, ndist, t.dist_count, t.dist_sym, t.dist_fast);
+                const bool ok = inf_build(t.lens, nlen, t.lit_count, t.lit_sym, t.lit_fast, INF_KIND_LITLEN) &&
+                                inf_build(dl, ndist, t.dist_count, t.dist_sym, t.dist_fast, INF_KIND_DIST);
                 t.lens[319] = ok ? 1 : 0;                               // slots 318 / 319 are never code lengths (at most 286 + 30)
             }
             ln.sync();
             if (!t.lens[319]) return INF_ERR_CODE;
         }
-        // ---- symbols
+        // ---- symbols: one table entry gives (literal | length base + extra bits | end of block), a second one the distance
         for (;;) {
             br.refill();
-            const int s = inf_decode(br, t.lit_count, t.lit_sym, t.lit_fast);
-            if (s < 0) return INF_ERR_CODE;
-            if (s < 256) {
+            const uint32_t e = inf_decode(br, t.lit_count, t.lit_sym, t.lit_fast, INF_KIND_LITLEN);
+            const uint32_t op = (e >> 8) & 0xffu;
+            if (op == 0) {
                 if (out >= cap) return INF_ERR_OUTPUT;
-                if (lane == 0) dst[out] = (uint8_t)s;
+                if (lane == 0) dst[out] = (uint8_t)(e >> 16);
                 ++out;
                 continue;
             }
-            if (s == 256) break;
-            if (s > 285) return INF_ERR_CODE;
-            // length / distance bases and extra bits in closed form (RFC 1951 3.2.5)
-            const int li = s - 257;
-            const int lext = (li < 8 || li == 28) ? 0 : ((li - 4) >> 2);
-            const uint32_t lbase = li < 8 ? 3u + (uint32_t)li : li == 28 ? 258u : 3u + ((4u + (uint32_t)(li & 3)) << lext);
+            if (op & 32u) break;
+            if (op & 64u) return INF_ERR_CODE;
+            const int lext = (int)(op & 15u);
             if (lext > br.bits) return INF_ERR_INPUT;
-            const uint32_t len = lbase + br.take(lext);
-            br.refill();
-            const int ds = inf_decode(br, t.dist_count, t.dist_sym, t.dist_fast);
-            if (ds < 0 || ds > 29) return INF_ERR_CODE;
-            const int dext = ds < 4 ? 0 : ((ds - 2) >> 1);
-            const uint32_t dbase = ds < 4 ? 1u + (uint32_t)ds : 1u + ((2u + (uint32_t)(ds & 1)) << dext);
+            const uint32_t len = (e >> 16) + br.take(lext);
+            if (br.bits < 28) br.refill();                     // a distance needs at most 15 + 13 bits
+            const uint32_t de = inf_decode(br, t.dist_count, t.dist_sym, t.dist_fast, INF_KIND_DIST);
+            if (de & (64u << 8)) return INF_ERR_CODE;
+            const int dext = (int)((de >> 8) & 15u);
             if (dext > br.bits) return INF_ERR_INPUT;
-            const uint32_t dist = dbase + br.take(dext);
+            const uint32_t dist = (de >> 16) + br.take(dext);
             if (dist > out) return INF_ERR_DIST;
             if (out + len > cap) return INF_ERR_OUTPUT;
             // every source byte of the match is already written (overlapping matches repeat the last `dist` bytes), so
