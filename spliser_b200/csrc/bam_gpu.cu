@@ -44,11 +44,6 @@ k_bgzf_inflate(const uint8_t* __restrict__ comp, const BgzfMember* __restrict__ 
     if ((threadIdx.x & 31) == 0 && (rc != INF_OK || produced != b.isize)) atomicMax(err, 1u + m);
 }
 
-__device__ __forceinline__ uint32_t ld32(const uint8_t* p) {
-    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
-}
-__device__ __forceinline__ uint32_t ld16(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8); }
-
 // unaligned little-endian 32-bit load from two aligned words (the inflated stream is 256-byte aligned and padded)
 __device__ __forceinline__ uint32_t ld32u(const uint8_t* __restrict__ u, uint64_t o) {
     const uint32_t* w = reinterpret_cast<const uint32_t*>(u + (o & ~3ull));
@@ -182,9 +177,15 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
     cnt = BamGpuCounts{};
     if (n_mem == 0 || first_record >= total_u) { out = DevRecordArrays{}; return BAMGPU_OK; }
     // ---- compressed file + member table to the device, inflate
-    BG_CU(mem.comp.reserve(fsz + 64));
-    BG_CU(mem.unc.reserve(total_u + 256));                              // the aligned-word reads of the parser run a few bytes past the end
-    BG_CU(mem.tab.reserve((size_t)n_mem * (sizeof(BgzfMember) + 8 + sizeof(WalkOut) + 16) + ((size_t)n_ref + 1) * 4 + 4096));
+    // not enough device memory for the file image + the inflated stream: the host reader streams the file instead
+    if (mem.comp.reserve(fsz + 64) != cudaSuccess ||
+        mem.unc.reserve(total_u + 256) != cudaSuccess ||                // the aligned-word reads of the parser run a few bytes past the end
+        mem.tab.reserve((size_t)n_mem * (sizeof(BgzfMember) + 8 + sizeof(WalkOut) + 16) + ((size_t)n_ref + 1) * 4 + 4096) != cudaSuccess) {
+        cudaGetLastError();
+        mem.comp.release(); mem.unc.release();
+        err = "not enough device memory for the inflated BAM";
+        return BAMGPU_FALLBACK;
+    }
     char* tb = (char*)mem.tab.p;
     BgzfMember* d_mem = (BgzfMember*)tb; tb += (size_t)n_mem * sizeof(BgzfMember);
     uint64_t* d_first = (uint64_t*)tb; tb += (size_t)n_mem * 8;
@@ -236,7 +237,7 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
         auto take = [&](size_t bytes) { off = (off + 255) & ~(size_t)255; const size_t o = off; off += bytes; return o; };
         const size_t o_pos = take((nrec + 4) * 4), o_flag = take((nrec + 4) * 2), o_off = take((nrec + 4) * 4), o_cig = take((ncig + 4) * 4),
                      o_chr = take((nrec + 4) * 4), o_sf = take(BAMGPU_MAX_SEG * 8), o_sc = take(BAMGPU_MAX_SEG * 4), o_ns = take(16);
-        BG_CU(mem.rec.reserve(off + 256));
+        if (mem.rec.reserve(off + 256) != cudaSuccess) { cudaGetLastError(); err = "not enough device memory for the record arrays"; return BAMGPU_FALLBACK; }
         char* rb = (char*)mem.rec.p;
         out.pos = (int32_t*)(rb + o_pos); out.flag = (uint16_t*)(rb + o_flag); out.cig_off = (uint32_t*)(rb + o_off);
         out.cigar = (uint32_t*)(rb + o_cig); out.chrom = (int32_t*)(rb + o_chr);

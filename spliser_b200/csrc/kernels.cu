@@ -37,17 +37,19 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                  "l"(src), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
 }
+// consumer-side wait: try_wait with a suspend-time hint parks the warp in hardware until the phase flips (or the hint
+// expires), instead of spinning through issue slots the other resident warps need
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra DONE;\n"
         "bra LAB_WAIT;\n"
         "DONE:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(20000u)
         : "memory");
 }
 
@@ -667,7 +669,7 @@ constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u, PS_GLOBAL_BINS = 4u;
 
 // producer-side wait: the single producer lane would otherwise spin on the empty barrier for most of the
 // kernel and steal issue slots from the consumers of the co-resident CTAs
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 512) {
+__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 5000) {
     const uint32_t addr = smem_u32(bar);
     for (;;) {
         uint32_t done;
@@ -679,7 +681,6 @@ __device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity
             "}\n"
             : "=r"(done) : "r"(addr), "r"(parity), "r"(ns * 4u) : "memory");
         if (done) return;
-        __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
@@ -706,6 +707,10 @@ struct K3Smem {
 // registers and summed across the warp with one redux.sync per site -> one RED per (warp, site,
 // class); long ranges (sparse coverage, displaced blocks of spliced reads) use a per-lane search.
 // ------------------------------------------------------------------------------------------------
+#ifndef SPL_K3_BATCH
+#define SPL_K3_BATCH 4
+#endif
+constexpr int K3_BATCH = SPL_K3_BATCH;     // tiles a producer claims per atomic
 constexpr int K3_GROUPS = 2;     // int4 groups (4 blocks each) per thread: a warp owns 256 consecutive elements of the tile
 #ifndef SPL_K3_DENSE
 #define SPL_K3_DENSE 12
@@ -788,30 +793,40 @@ k_beta1_stab(DevBins bins, DevGraph g, DevCounters cnt) {
         // ===== producer =====
         if (lane != 0) return;
         uint32_t it = 0;
-        // the next tile's index and descriptor are fetched while the current tile's copies are issued
-        uint32_t next = atomicAdd(cnt.work + 0, 1u);
-        Tile ntl = bins.tiles[min(next, bins.n_tiles - 1u)];
+        // tiles are claimed K3_BATCH at a time: the round trips of the claim (atomic) and of the descriptor loads are paid once
+        // per batch, after the copies of the current batch are in flight
+        uint32_t nbase = atomicAdd(cnt.work + 0, (uint32_t)K3_BATCH);
+        Tile ntl[K3_BATCH];
+#pragma unroll
+        for (int b = 0; b < K3_BATCH; ++b) ntl[b] = bins.tiles[min(nbase + b, bins.n_tiles - 1u)];
         for (;;) {
-            const uint32_t item = next;
-            if (item >= bins.n_tiles) break;
-            const Tile tl = ntl;
-            next = atomicAdd(cnt.work + 0, 1u);
-            ntl = bins.tiles[min(next, bins.n_tiles - 1u)];
-            if (tl.w_lo >= tl.w_hi) continue;            // zone-map prune: no (owned) site near this tile's bins
-            const int site_n = tl.w_hi - tl.w_lo;
-            const bool staged = site_n <= K3_SITES;
-            const int al = tl.w_lo & ~3;
-            const uint32_t nst = staged ? (uint32_t)(((tl.w_hi + 3) & ~3) - al) : 0u;
-            const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
-            mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
-            StageMeta& m = sm.meta[stage];
-            m.e0 = tl.e0; m.e1 = tl.e0 + K3_TILE; m.p0 = tl.e0; m.n = K3_TILE; m.w_lo = tl.w_lo; m.w_hi = tl.w_hi; m.al = al;
-            m.flags = staged ? 0u : PS_GLOBAL_SITES; m.chunk = (int32_t)item;
-            mbar_expect_tx(&sm.full[stage], K3_TILE * 8u + nst * 4u);
-            bulk_g2s(sm.st[stage].start, bins.c_start + tl.e0, K3_TILE * 4u, &sm.full[stage]);
-            bulk_g2s(sm.st[stage].endk, bins.c_endk + tl.e0, K3_TILE * 4u, &sm.full[stage]);
-            if (nst) bulk_g2s(sm.st[stage].sites, g.site_pos + al, nst * 4u, &sm.full[stage]);
-            ++it;
+            const uint32_t base = nbase;
+            if (base >= bins.n_tiles) break;
+            Tile tls[K3_BATCH];
+#pragma unroll
+            for (int b = 0; b < K3_BATCH; ++b) tls[b] = ntl[b];
+#pragma unroll
+            for (int b = 0; b < K3_BATCH; ++b) {
+                const Tile tl = tls[b];
+                if (base + b >= bins.n_tiles || tl.w_lo >= tl.w_hi) continue;     // past the end / zone-map prune: no (owned) site near this tile's bins
+                const int site_n = tl.w_hi - tl.w_lo;
+                const bool staged = site_n <= K3_SITES;
+                const int al = tl.w_lo & ~3;
+                const uint32_t nst = staged ? (uint32_t)(((tl.w_hi + 3) & ~3) - al) : 0u;
+                const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
+                mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
+                StageMeta& m = sm.meta[stage];
+                m.e0 = tl.e0; m.e1 = tl.e0 + K3_TILE; m.p0 = tl.e0; m.n = K3_TILE; m.w_lo = tl.w_lo; m.w_hi = tl.w_hi; m.al = al;
+                m.flags = staged ? 0u : PS_GLOBAL_SITES; m.chunk = (int32_t)(base + b);
+                mbar_expect_tx(&sm.full[stage], K3_TILE * 8u + nst * 4u);
+                bulk_g2s(sm.st[stage].start, bins.c_start + tl.e0, K3_TILE * 4u, &sm.full[stage]);
+                bulk_g2s(sm.st[stage].endk, bins.c_endk + tl.e0, K3_TILE * 4u, &sm.full[stage]);
+                if (nst) bulk_g2s(sm.st[stage].sites, g.site_pos + al, nst * 4u, &sm.full[stage]);
+                ++it;
+            }
+            nbase = atomicAdd(cnt.work + 0, (uint32_t)K3_BATCH);
+#pragma unroll
+            for (int b = 0; b < K3_BATCH; ++b) ntl[b] = bins.tiles[min(nbase + b, bins.n_tiles - 1u)];
         }
         const uint32_t stage = it % PS_STAGES, parity = (it / PS_STAGES) & 1u;
         mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
