@@ -175,7 +175,7 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_N_ALIGNED    10   /* records with >= 1 CIGAR op ("aligned reads")              */
 #define SPL_STAT_LAUNCHES     11   /* kernels launched per pass                                 */
 #define SPL_STAT_MS_EXPAND    12   /* ms of the record -> SoA expansion at load time            */
-#define SPL_NSTATS            24
+#define SPL_NSTATS            32
 
 /* per-call statistics of the last spl_process* / spl_recount* call (same indices; MS_* are
  * host wall-clock of the stages; extra indices below) */
@@ -189,6 +189,7 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_N_SIMPLE_J   20   /* junction instances of block-N-block reads (aggregated path)    */
 #define SPL_STAT_N_COMPLEX_J  21   /* junction instances handled per read                            */
 #define SPL_STAT_BAM_DEVICE   23   /* 1 = BGZF inflate + BAM record parse ran on the device, 0 = host reader (fallback)  */
+#define SPL_STAT_N_PARTS      24   /* parts the record upload was cut into (1 or 2; 2 = expansion overlapped with the copy)  */
 #define SPL_STAT_GRAPH_DEVICE 22   /* 1 = site table + graph built on the device (clean regime), 0 = host emulation */
 int spl_last_stats(const spl_ctx* ctx, double* stats_out);
 

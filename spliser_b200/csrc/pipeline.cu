@@ -144,6 +144,28 @@ void result_from_host_graph(spl_result* r, const SiteGraph& h) {
 }
 }  // namespace
 
+// Everything derived from one contiguous run of record segments (whole chromosomes).  A big upload is cut into two
+// parts so that the expansion of the first overlaps the host->device copy of the second; the counting kernels then run
+// once per part into the same counters (chromosomes, hence bins / tiles / junction tables, are disjoint between parts).
+constexpr int MAX_PARTS = 2;
+struct Part {
+    DevBuf d_rec, d_chunks, d_soa, d_tot, d_lay, d_bins, d_jtab, d_jdense;
+    uint32_t* h_tot = nullptr;      // pinned totals read back during the expansion
+    void* h_chunks = nullptr;       // pinned staging of the chunk table
+    size_t h_chunks_bytes = 0;
+    cudaEvent_t ev_up = nullptr;    // the part's records (and chunk table) have arrived
+    DevBins bins{};
+    DevJunc jg{};
+    DevRecords rec{};
+    DevSoA soa{};
+    Chunk* chunks = nullptr;
+    int n_chunks = 0;
+    void release() {
+        d_rec.release(); d_chunks.release(); d_soa.release(); d_tot.release(); d_lay.release(); d_bins.release();
+        d_jtab.release(); d_jdense.release();
+    }
+};
+
 struct spl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -153,11 +175,10 @@ struct spl_ctx {
     double stats[SPL_NSTATS] = {0};
 
     // device memory
-    DevBuf d_graph, d_rec, d_chunks, d_soa, d_cnt, d_out, d_tot, d_lay, d_bins;
-    uint32_t* h_tot = nullptr;      // pinned, 8 totals
-    DevBins bins{};
-    DevJunc jg{};
-    DevBuf d_jtab, d_jdense;
+    DevBuf d_graph, d_cnt, d_out;
+    Part part[MAX_PARTS];           // record-derived state (see Part)
+    int n_parts = 1;
+    cudaStream_t copy_stream = nullptr;   // record uploads (so that a part's expansion overlaps the next part's copy)
     std::vector<cudaEvent_t> events;
     // device-side graph build (clean regime)
     cudaStream_t stream2 = nullptr;
@@ -178,12 +199,8 @@ struct spl_ctx {
     // state of the last load
     SiteGraph hg;                   // host graph (structure) of the last load
     DevGraph g{};
-    DevRecords rec{};
-    DevSoA soa{};
     DevCounters cnt{};
     DevOutputs out{};
-    Chunk* chunks = nullptr;
-    int n_chunks = 0;
     size_t cnt_bytes = 0;
     uint32_t flags = 0;
     bool loaded = false;
@@ -362,56 +379,76 @@ int check_view(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
     return SPL_OK;
 }
 
-// enqueue the record upload on the context's stream (asynchronous when the caller's arrays are page-locked)
-int upload_records(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
+// enqueue the upload of the records of segments [s0, s1) on the copy stream (asynchronous when the caller's arrays are
+// page-locked); record / CIGAR indices inside the part are relative to its first record, CIGAR offsets stay absolute
+int upload_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0, int32_t s1, int32_t n_chrom) {
     ctx->n_chrom_loaded = n_chrom;
+    const bool dev = ctx->rec_on_device;
+    const int64_t r0 = s1 > s0 ? v->seg_off[s0] : 0, r1 = s1 > s0 ? v->seg_off[s1] : 0;
     std::vector<Chunk> hc;
-    for (int32_t k = 0; k < v->n_seg; ++k) {
+    for (int32_t k = s0; k < s1; ++k) {
         if (v->seg_chrom[k] < 0) continue;
         for (int64_t lo = v->seg_off[k]; lo < v->seg_off[k + 1]; lo += CHUNK_READS) {
             Chunk c{};
             c.chrom = v->seg_chrom[k];
-            c.rec_lo = (uint32_t)lo;
-            c.rec_hi = (uint32_t)std::min<int64_t>(lo + CHUNK_READS, v->seg_off[k + 1]);
+            c.rec_lo = (uint32_t)(lo - r0);
+            c.rec_hi = (uint32_t)(std::min<int64_t>(lo + CHUNK_READS, v->seg_off[k + 1]) - r0);
             hc.push_back(c);
         }
     }
-    ctx->n_chunks = (int)hc.size();
-    const size_t R = (size_t)v->n_rec, NC = (size_t)v->n_cigar;
+    P.n_chunks = (int)hc.size();
+    const size_t R = (size_t)(r1 - r0);
+    const size_t c0 = (dev || R == 0) ? 0 : (size_t)v->cig_off[r0], c1 = dev ? (size_t)v->n_cigar : (R == 0 ? 0 : (size_t)v->cig_off[r1]);
+    const size_t NC = c1 - c0;
     Carver c;
     const size_t o_pos = c.take<int32_t>(R + 4), o_flag = c.take<uint16_t>(R + 4), o_off = c.take<uint32_t>(R + 4),
                  o_cig = c.take<uint32_t>(NC + 4);
-    if (!ctx->rec_on_device) CU(ctx->d_rec.reserve(c.off + 256));
-    char* rb = (char*)ctx->d_rec.p;
-    // the chunk table first: it comes from pageable memory, and a pageable copy queued behind the big record
-    // copies would block the host until those are done
-    CU(ctx->d_chunks.reserve((hc.size() + 1) * sizeof(Chunk)));
-    ctx->chunks = (Chunk*)ctx->d_chunks.p;
-    if (!hc.empty()) CU(cudaMemcpyAsync(ctx->chunks, hc.data(), hc.size() * sizeof(Chunk), cudaMemcpyHostToDevice, ctx->stream));
-    if (ctx->rec_on_device) {                                          // parsed on the device from the BAM (bam_gpu.cu)
-        ctx->rec.n_rec = (uint32_t)R;
-        ctx->rec.pos = ctx->dev_rec.pos; ctx->rec.flag = ctx->dev_rec.flag;
-        ctx->rec.cig_off = ctx->dev_rec.cig_off; ctx->rec.cigar = ctx->dev_rec.cigar;
+    if (!dev) CU(P.d_rec.reserve(c.off + 256));
+    char* rb = (char*)P.d_rec.p;
+    // the chunk table travels from a page-locked staging buffer on the same stream as the records, in front of them (a
+    // pageable copy on the compute stream would queue behind every big copy already submitted and hold the kernels back)
+    CU(P.d_chunks.reserve((hc.size() + 1) * sizeof(Chunk)));
+    P.chunks = (Chunk*)P.d_chunks.p;
+    cudaStream_t cs = dev ? ctx->stream : ctx->copy_stream;
+    if (!hc.empty()) {
+        const size_t bytes = hc.size() * sizeof(Chunk);
+        if (P.h_chunks_bytes < bytes) {
+            if (P.h_chunks) cudaFreeHost(P.h_chunks);
+            P.h_chunks = nullptr; P.h_chunks_bytes = 0;
+            CU(cudaHostAlloc(&P.h_chunks, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
+            P.h_chunks_bytes = bytes + bytes / 4 + 4096;
+        }
+        memcpy(P.h_chunks, hc.data(), bytes);
+        CU(cudaMemcpyAsync(P.chunks, P.h_chunks, bytes, cudaMemcpyHostToDevice, cs));
+    }
+    if (dev) {                                                         // parsed on the device from the BAM (bam_gpu.cu)
+        P.rec.n_rec = (uint32_t)R;
+        P.rec.pos = ctx->dev_rec.pos; P.rec.flag = ctx->dev_rec.flag;
+        P.rec.cig_off = ctx->dev_rec.cig_off; P.rec.cigar = ctx->dev_rec.cigar;
+        CU(cudaEventRecord(P.ev_up, ctx->stream));
         return SPL_OK;
     }
     if (R) {
-        CU(cudaMemcpyAsync(rb + o_pos, v->pos, R * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(rb + o_flag, v->flag, R * 2, cudaMemcpyHostToDevice, ctx->stream));
-        CU(cudaMemcpyAsync(rb + o_off, v->cig_off, (R + 1) * 4, cudaMemcpyHostToDevice, ctx->stream));
-        if (NC) CU(cudaMemcpyAsync(rb + o_cig, v->cigar, NC * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaMemcpyAsync(rb + o_pos, v->pos + r0, R * 4, cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(rb + o_flag, v->flag + r0, R * 2, cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(rb + o_off, v->cig_off + r0, (R + 1) * 4, cudaMemcpyHostToDevice, cs));
+        if (NC) CU(cudaMemcpyAsync(rb + o_cig, v->cigar + c0, NC * 4, cudaMemcpyHostToDevice, cs));
     }
+    CU(cudaEventRecord(P.ev_up, cs));
     ctx->stats[SPL_STAT_H2D_BYTES] += (double)(R * 10 + 4 + NC * 4 + hc.size() * sizeof(Chunk));
-    ctx->rec.n_rec = (uint32_t)R;
-    ctx->rec.pos = (const int32_t*)(rb + o_pos); ctx->rec.flag = (const uint16_t*)(rb + o_flag);
-    ctx->rec.cig_off = (const uint32_t*)(rb + o_off); ctx->rec.cigar = (const uint32_t*)(rb + o_cig);
+    P.rec.n_rec = (uint32_t)R;
+    P.rec.pos = (const int32_t*)(rb + o_pos); P.rec.flag = (const uint16_t*)(rb + o_flag);
+    P.rec.cig_off = (const uint32_t*)(rb + o_off);
+    P.rec.cigar = (const uint32_t*)(rb + o_cig) - c0;                  // indexed with the absolute offsets of cig_off
     return SPL_OK;
 }
 
 // run the expansion kernels, leave the SoA + chunk table on the device
-int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
-    CU(ctx->d_tot.reserve(256));
+int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0, int32_t s1, uint32_t flags) {
+    CU(cudaStreamWaitEvent(ctx->stream, P.ev_up, 0));
+    CU(P.d_tot.reserve(256));
     // per-chromosome layout arrays of the bin-partitioned stream
-    DevBins& bins = ctx->bins;
+    DevBins& bins = P.bins;
     bins = DevBins{};
     const size_t nchr = (size_t)std::max(ctx->n_chrom_loaded, 1);
     {
@@ -419,9 +456,9 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
         const size_t o_ext = lc.take<uint32_t>(nchr + 1), o_tot = lc.take<uint32_t>(nchr + 1), o_bb = lc.take<uint32_t>(nchr + 2),
                      o_tb = lc.take<uint32_t>(nchr + 2), o_ml = lc.take<uint32_t>(4), o_cj = lc.take<uint32_t>(nchr + 1),
                      o_jt = lc.take<uint32_t>(nchr + 2);
-        CU(ctx->d_lay.reserve(lc.off + 256));
-        CU(cudaMemsetAsync(ctx->d_lay.p, 0, lc.off + 256, ctx->stream));
-        char* lb = (char*)ctx->d_lay.p;
+        CU(P.d_lay.reserve(lc.off + 256));
+        CU(cudaMemsetAsync(P.d_lay.p, 0, lc.off + 256, ctx->stream));
+        char* lb = (char*)P.d_lay.p;
         bins.chrom_ext = (uint32_t*)(lb + o_ext); bins.chrom_tot = (uint32_t*)(lb + o_tot);
         bins.chrom_bin_base = (uint32_t*)(lb + o_bb); bins.chrom_tile_base = (uint32_t*)(lb + o_tb);
         bins.max_len = (uint32_t*)(lb + o_ml);
@@ -431,13 +468,13 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
     CU(cudaEventRecord(e0, ctx->stream));
-    launch_expand_count(ctx->rec, ctx->chunks, ctx->n_chunks, flags, bins, ctx->stream);
-    launch_chunk_scan(ctx->chunks, ctx->n_chunks, (uint32_t*)ctx->d_tot.p, bins, ctx->stream);
+    launch_expand_count(P.rec, P.chunks, P.n_chunks, flags, bins, ctx->stream);
+    launch_chunk_scan(P.chunks, P.n_chunks, (uint32_t*)P.d_tot.p, bins, ctx->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->h_tot, ctx->d_tot.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(P.h_tot, P.d_tot.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // also makes `hc` (pageable) safe to drop
-    const size_t nA = ctx->h_tot[0], nB = ctx->h_tot[1], nS = ctx->h_tot[2], nJ = ctx->h_tot[3];
-    const size_t total_bins = ctx->n_chunks ? ctx->h_tot[4] : 0, n_tiles = ctx->n_chunks ? ctx->h_tot[5] : 0;
+    const size_t nA = P.h_tot[0], nB = P.h_tot[1], nS = P.h_tot[2], nJ = P.h_tot[3];
+    const size_t total_bins = P.n_chunks ? P.h_tot[4] : 0, n_tiles = P.n_chunks ? P.h_tot[5] : 0;
     const size_t nC = n_tiles * (size_t)K3_TILE;
     if (nC >= (size_t)UINT32_MAX - 64) return ctx->fail(SPL_ERR_RANGE, "more than 2^32 mapped blocks in one call");
     Carver s;
@@ -447,9 +484,9 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
     const size_t o_sb = s.take<uint32_t>(nS + 16), o_sj = s.take<uint32_t>(nS + 16);
     const size_t o_jl = s.take<uint32_t>(nJ + 16), o_jr = s.take<uint32_t>(nJ + 16), o_jq = s.take<uint32_t>(nJ + 16);
     const size_t o_ja = s.take<int32_t>(nJ + 16), o_je = s.take<int32_t>(nJ + 16);
-    CU(ctx->d_soa.reserve(s.off + 256));
-    char* sb = (char*)ctx->d_soa.p;
-    DevSoA& soa = ctx->soa;
+    CU(P.d_soa.reserve(s.off + 256));
+    char* sb = (char*)P.d_soa.p;
+    DevSoA& soa = P.soa;
     soa.nA = (uint32_t)nA; soa.nB = (uint32_t)nB; soa.nS = (uint32_t)nS; soa.nJ = (uint32_t)nJ;
     soa.m_start = (int32_t*)(sb + o_ms); soa.m_endk = (uint32_t*)(sb + o_me); soa.bB = (uint32_t)bB;
     soa.sr_boff = (uint32_t*)(sb + o_sb); soa.sr_joff = (uint32_t*)(sb + o_sj);
@@ -460,26 +497,26 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
         const size_t nscan = (total_bins + 1 + 4095) / 4096 + 8;
         const size_t o_bo = bc.take<uint32_t>(total_bins + 8), o_bcur = bc.take<uint32_t>(total_bins + 8), o_tmp = bc.take<uint32_t>(nscan + 8),
                      o_cs = bc.take<int32_t>(nC + 32), o_ce = bc.take<uint32_t>(nC + 32), o_tl = bc.take<Tile>(n_tiles + 1);
-        CU(ctx->d_bins.reserve(bc.off + 256));
-        char* bb = (char*)ctx->d_bins.p;
+        CU(P.d_bins.reserve(bc.off + 256));
+        char* bb = (char*)P.d_bins.p;
         bins.bin_off = (uint32_t*)(bb + o_bo); bins.bin_cursor = (uint32_t*)(bb + o_bcur); bins.scan_tmp = (uint32_t*)(bb + o_tmp);
         bins.c_start = (int32_t*)(bb + o_cs); bins.c_endk = (uint32_t*)(bb + o_ce); bins.tiles = (Tile*)(bb + o_tl);
         bins.total_bins = (uint32_t)total_bins; bins.n_tiles = (uint32_t)n_tiles; bins.nC = (uint32_t)nC;
     }
-    launch_expand_scatter(ctx->rec, ctx->chunks, ctx->n_chunks, soa, flags, ctx->stream);
-    launch_bin_partition(ctx->chunks, ctx->n_chunks, soa, bins, ctx->stream);
+    launch_expand_scatter(P.rec, P.chunks, P.n_chunks, soa, flags, ctx->stream);
+    launch_bin_partition(P.chunks, P.n_chunks, soa, bins, ctx->stream);
     CU(cudaGetLastError());
     // ---- junction groups: table -> (sync: distinct count) -> dense arrays + grouped simple instances
-    DevJunc& jg = ctx->jg;
+    DevJunc& jg = P.jg;
     jg = DevJunc{};
-    uint32_t* d_jtot = (uint32_t*)ctx->d_tot.p + 12;
+    uint32_t* d_jtot = (uint32_t*)P.d_tot.p + 12;
     for (int attempt = 0;; ++attempt) {
         size_t n_slots = 0;
-        if (ctx->n_chunks) {
-            launch_jtab_layout(bins, attempt, (uint32_t*)ctx->d_tot.p, ctx->stream);
-            CU(cudaMemcpyAsync(ctx->h_tot + 8, (uint32_t*)ctx->d_tot.p + 8, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (P.n_chunks) {
+            launch_jtab_layout(bins, attempt, (uint32_t*)P.d_tot.p, ctx->stream);
+            CU(cudaMemcpyAsync(P.h_tot + 8, (uint32_t*)P.d_tot.p + 8, 4, cudaMemcpyDeviceToHost, ctx->stream));
             CU(cudaStreamSynchronize(ctx->stream));
-            n_slots = ctx->h_tot[8];
+            n_slots = P.h_tot[8];
         }
         Carver jc;
         const size_t nscan = (n_slots + 1 + 4095) / 4096 + 8;
@@ -488,22 +525,22 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
                      o_sc = jc.take<uint32_t>(n_slots + 2), o_sl = jc.take<uint32_t>(nJ + 2), o_cn = jc.take<uint32_t>(4),
                      o_co = jc.take<uint32_t>(n_slots + 2), o_cc = jc.take<uint32_t>(n_slots + 2),
                      o_tmp = jc.take<uint32_t>(2 * nscan + 8);
-        CU(ctx->d_jtab.reserve(jc.off + 256));
-        char* jb = (char*)ctx->d_jtab.p;
+        CU(P.d_jtab.reserve(jc.off + 256));
+        char* jb = (char*)P.d_jtab.p;
         jg.n_slots = (uint32_t)n_slots; jg.chrom_jn = bins.chrom_jn; jg.tab_base = bins.tab_base;
         jg.key = (unsigned long long*)(jb + o_key); jg.s_all = (uint32_t*)(jb + o_sa); jg.s_simple = (uint32_t*)(jb + o_ss);
         jg.s_used = (uint32_t*)(jb + o_su); jg.s_off = (uint32_t*)(jb + o_so); jg.s_cursor = (uint32_t*)(jb + o_sc);
         jg.slot_of = (uint32_t*)(jb + o_sl); jg.cx_n = (uint32_t*)(jb + o_cn); jg.overflow = jg.cx_n + 1;
         jg.scan_tmp = (uint32_t*)(jb + o_tmp);
         jg.s_coff = (uint32_t*)(jb + o_co); jg.s_ccur = (uint32_t*)(jb + o_cc);
-        launch_junction_groups_a(ctx->chunks, ctx->n_chunks, soa, jg, d_jtot, ctx->stream);
+        launch_junction_groups_a(P.chunks, P.n_chunks, soa, jg, d_jtot, ctx->stream);
         CU(cudaGetLastError());
-        CU(cudaMemcpyAsync(ctx->h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CU(cudaMemcpyAsync(P.h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
         CU(cudaStreamSynchronize(ctx->stream));
-        if (!ctx->h_tot[15]) break;                                    // no sub-table got crowded
+        if (!P.h_tot[15]) break;                                    // no sub-table got crowded
         if (attempt >= 1) return ctx->fail(SPL_ERR_CUDA, "junction table overflow (internal sizing error)");
     }
-    const size_t D = ctx->h_tot[12], n_simple = ctx->h_tot[13], n_complex = ctx->h_tot[14];
+    const size_t D = P.h_tot[12], n_simple = P.h_tot[13], n_complex = P.h_tot[14];
     {
         Carver dc;
         const size_t o_l = dc.take<uint32_t>(D + 2), o_rk = dc.take<uint32_t>(D + 2), o_ch = dc.take<int32_t>(D + 2),
@@ -514,8 +551,8 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
                      o_wl = dc.take<unsigned long long>(2 * D + 2 * (n_simple / 2048 + 1) + 8),
                      o_xb = dc.take<uint32_t>(2 * D + 2), o_xd = dc.take<uint32_t>(2 * D + 2),
                      o_xn = dc.take<uint32_t>(2 * D + 2), o_xt = dc.take<int32_t>((2 * D + 2) * CXD_T), o_cr = dc.take<uint4>(n_complex + 2);
-        CU(ctx->d_jdense.reserve(dc.off + 256));
-        char* db = (char*)ctx->d_jdense.p;
+        CU(P.d_jdense.reserve(dc.off + 256));
+        char* db = (char*)P.d_jdense.p;
         jg.D = (uint32_t)D;
         jg.dj_l = (uint32_t*)(db + o_l); jg.dj_rk = (uint32_t*)(db + o_rk); jg.dj_chrom = (int32_t*)(db + o_ch);
         jg.dj_all = (uint32_t*)(db + o_al); jg.dj_simple = (uint32_t*)(db + o_si); jg.dj_off = (uint32_t*)(db + o_of);
@@ -529,30 +566,32 @@ int expand_records(spl_ctx* ctx, const spl_records_view* v, uint32_t flags) {
     }
     launch_junction_groups_b(soa, jg, ctx->n_chrom_loaded, d_jtot, ctx->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(ctx->h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaMemcpyAsync(P.h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaEventRecord(e1, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
-    ctx->stats[SPL_STAT_N_DISTINCT_J] = (double)D; ctx->stats[SPL_STAT_N_SIMPLE_J] = (double)n_simple;
-    ctx->stats[SPL_STAT_N_COMPLEX_J] = (double)jg.n_complex;
-    if (ctx->h_tot[15]) return ctx->fail(SPL_ERR_CUDA, "junction table overflow (internal sizing error)");
+    ctx->stats[SPL_STAT_N_DISTINCT_J] += (double)D; ctx->stats[SPL_STAT_N_SIMPLE_J] += (double)n_simple;
+    ctx->stats[SPL_STAT_N_COMPLEX_J] += (double)jg.n_complex;
+    if (P.h_tot[15]) return ctx->fail(SPL_ERR_CUDA, "junction table overflow (internal sizing error)");
     float ms = 0;
     CU(cudaEventElapsedTime(&ms, e0, e1));
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    ctx->stats[SPL_STAT_MS_EXPAND] = ms;
-    ctx->stats[SPL_STAT_N_MBLOCKS_A] = (double)nA; ctx->stats[SPL_STAT_N_MBLOCKS_B] = (double)nB;
-    ctx->stats[SPL_STAT_N_SPLICED] = (double)nS; ctx->stats[SPL_STAT_N_JUNC_OPS] = (double)nJ;
+    ctx->stats[SPL_STAT_MS_EXPAND] += ms;
+    ctx->stats[SPL_STAT_N_MBLOCKS_A] += (double)nA; ctx->stats[SPL_STAT_N_MBLOCKS_B] += (double)nB;
+    ctx->stats[SPL_STAT_N_SPLICED] += (double)nS; ctx->stats[SPL_STAT_N_JUNC_OPS] += (double)nJ;
     int64_t aligned = 0;
-    for (int32_t k = 0; k < v->n_seg; ++k)
+    for (int32_t k = s0; k < s1; ++k)
         if (v->seg_chrom[k] >= 0) aligned += v->seg_off[k + 1] - v->seg_off[k];
-    ctx->n_aligned = aligned;
-    ctx->stats[SPL_STAT_N_ALIGNED] = (double)aligned;
+    ctx->n_aligned += aligned;
+    ctx->stats[SPL_STAT_N_ALIGNED] += (double)aligned;
     return SPL_OK;
 }
 
 int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, int32_t n_chrom) {
-    int rc = upload_records(ctx, v, n_chrom);
+    ctx->n_parts = 1;
+    ctx->n_aligned = 0;
+    int rc = upload_records(ctx, ctx->part[0], v, 0, v->n_seg, n_chrom);
     if (rc) return rc;
-    return expand_records(ctx, v, flags);
+    return expand_records(ctx, ctx->part[0], v, 0, v->n_seg, flags);
 }
 
 // one counting pass over the resident SoA; events (if given) bracket the three kernel groups
@@ -561,9 +600,15 @@ int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     if (ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->d_cnt.p, 0, ctx->cnt_bytes, ctx->stream));
     launch_alpha_reduce(ctx->g, ctx->out, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[1], ctx->stream));
-    launch_beta1(ctx->bins, ctx->g, ctx->cnt, ctx->stream);
+    for (int p = 0; p < ctx->n_parts; ++p) {
+        if (p && ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->cnt.work, 0, 32, ctx->stream));      // tile counter of the previous part
+        launch_beta1(ctx->part[p].bins, ctx->g, ctx->cnt, ctx->stream);
+    }
     if (ev) CU(cudaEventRecord(ev[2], ctx->stream));
-    launch_junctions(ctx->soa, ctx->jg, ctx->g, ctx->cnt, ctx->flags, ctx->stream);
+    for (int p = 0; p < ctx->n_parts; ++p) {
+        if (p && ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->cnt.work, 0, 32, ctx->stream));      // work lists of the previous part
+        launch_junctions(ctx->part[p].soa, ctx->part[p].jg, ctx->g, ctx->cnt, ctx->flags, ctx->stream);
+    }
     if (ev) CU(cudaEventRecord(ev[3], ctx->stream));
     launch_finalize(ctx->g, ctx->cnt, ctx->out, ctx->flags, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[4], ctx->stream));
@@ -630,7 +675,8 @@ void adopt_device_graph(spl_ctx* ctx) {
 }
 
 int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
-                const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags) {
+                const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags,
+                bool split_ok) {
     ctx->loaded = false;
     int rc = check_view(ctx, rec, n_chrom);
     if (rc) return rc;
@@ -666,8 +712,55 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
                                 0, ctx->gdev, ctx->gcnt, e))
             return ctx->fail(SPL_ERR_CUDA, "%s", e.c_str());
     }
-    rc = upload_records(ctx, rec, n_chrom);
+    // A big host upload is cut in two at a chromosome boundary: the first part's expansion runs while the second part is
+    // still on the wire.  The second part is the smaller one (its expansion is the only one left exposed): ~20 % of the records.
+    int32_t cut = rec->n_seg;
+    {
+        int64_t min_rec = 4000000;
+        if (const char* f = std::getenv("SPLISER_SPLIT_MIN_RECORDS")) min_rec = atoll(f);
+        if (split_ok && !ctx->rec_on_device && rec->n_seg >= 2 && rec->n_rec >= min_rec) {
+            const int64_t want = rec->n_rec - rec->n_rec / 5;
+            int64_t best = -1;
+            for (int32_t k = 1; k < rec->n_seg; ++k) {
+                const int64_t d = rec->seg_off[k] > want ? rec->seg_off[k] - want : want - rec->seg_off[k];
+                if (rec->seg_off[k] > 0 && rec->seg_off[k] < rec->n_rec && (best < 0 || d < best)) { best = d; cut = k; }
+            }
+        }
+    }
+    ctx->n_parts = cut < rec->n_seg ? 2 : 1;
+    ctx->n_aligned = 0;
+    cudaEvent_t dbg[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const bool dbg_on = std::getenv("SPLISER_TIMING") != nullptr;
+    if (dbg_on) { for (auto& e : dbg) cudaEventCreate(&e); cudaEventRecord(dbg[0], ctx->copy_stream); }
+    rc = upload_records(ctx, ctx->part[0], rec, 0, cut, n_chrom);
+    if (dbg_on) cudaEventRecord(dbg[1], ctx->copy_stream);
     if (rc) return rc;
+    if (ctx->n_parts == 2) {
+        rc = upload_records(ctx, ctx->part[1], rec, cut, rec->n_seg, n_chrom);
+        if (rc) return rc;
+    }
+    if (dbg_on) cudaEventRecord(dbg[2], ctx->copy_stream);
+    const bool timing = std::getenv("SPLISER_TIMING") != nullptr;
+    if (timing) fprintf(stderr, "[load] +%.2f ms uploads queued (%d part(s), cut at segment %d of %d)\n", now_ms() - tg0, ctx->n_parts, cut, rec->n_seg);
+    auto expand_all = [&]() -> int {
+        for (int p = 0; p < ctx->n_parts; ++p) {
+            if (timing) fprintf(stderr, "[load] +%.2f ms expand part %d starts\n", now_ms() - tg0, p);
+            if (dbg_on && p == 0) { cudaStreamWaitEvent(ctx->stream, ctx->part[0].ev_up, 0); cudaEventRecord(dbg[3], ctx->stream); }
+            const int r = expand_records(ctx, ctx->part[p], rec, p == 0 ? 0 : cut, p == 0 ? cut : rec->n_seg, flags);
+            if (r) return r;
+            if (dbg_on && p == 0) cudaEventRecord(dbg[4], ctx->stream);
+            if (timing) fprintf(stderr, "[load] +%.2f ms expand part %d done\n", now_ms() - tg0, p);
+            if (dbg_on && p == ctx->n_parts - 1) {
+                cudaDeviceSynchronize();
+                float a = 0, b = 0, c = 0, d = 0;
+                cudaEventElapsedTime(&a, dbg[0], dbg[1]); cudaEventElapsedTime(&b, dbg[0], dbg[2]);
+                cudaEventElapsedTime(&c, dbg[0], dbg[3]); cudaEventElapsedTime(&d, dbg[0], dbg[4]);
+                fprintf(stderr, "[load] device timeline: copies A done %.2f, copies B done %.2f, kernels A start %.2f, kernels A end %.2f ms\n", a, b, c, d);
+                for (auto& e : dbg) cudaEventDestroy(e);
+            }
+        }
+        return SPL_OK;
+    };
     if (clean) {
         std::string e;
         if (!graph_build_device(ctx->gbm, j_chrom, j_left, j_right, j_strand, j_score, n_junc, n_chrom, max_pos, stranded, ctx->stream2,
@@ -680,7 +773,7 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
         rc = alloc_counters_outputs(ctx, ctx->gcnt.S, ctx->gcnt.E);
         if (rc) return rc;
         ctx->stats[SPL_STAT_MS_GRAPH] = now_ms() - tg0;
-        rc = expand_records(ctx, rec, flags);
+        rc = expand_all();
         ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg0;
         if (rc) return rc;
         CU(cudaStreamWaitEvent(ctx->stream, ctx->ev_graph, 0));
@@ -693,7 +786,7 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
             e = build_site_graph(n_chrom, n_junc, j_chrom, j_left, j_right, j_strand, stranded, ctx->hg);
             graph_ms = now_ms() - tg0;
         });
-        rc = expand_records(ctx, rec, flags);
+        rc = expand_all();
         ctx->stats[SPL_STAT_MS_UPLOAD] = now_ms() - tg0;
         builder.join();
         if (rc) return rc;
@@ -705,11 +798,14 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
         ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
         ctx->stats[SPL_STAT_N_EDGES] = (double)ctx->hg.pc_pos.size();
     }
-    launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
-    launch_tile_hints(ctx->bins, ctx->g, ctx->stream);
+    for (int p = 0; p < ctx->n_parts; ++p) {
+        launch_chunk_hints(ctx->part[p].chunks, ctx->part[p].n_chunks, ctx->g, ctx->stream);
+        launch_tile_hints(ctx->part[p].bins, ctx->g, ctx->stream);
+    }
     CU(cudaGetLastError());
     ctx->stats[SPL_STAT_LAUNCHES] = (double)kernel_launch_count_per_pass();
     ctx->stats[SPL_STAT_GRAPH_DEVICE] = ctx->graph_on_device ? 1.0 : 0.0;
+    ctx->stats[SPL_STAT_N_PARTS] = (double)ctx->n_parts;
     ctx->loaded = true;
     return SPL_OK;
 }
@@ -805,7 +901,11 @@ int spl_create(spl_ctx** out, const int* device_ids, int n_devices) {
     CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking));
     CU(cudaEventCreateWithFlags(&ctx->ev_graph, cudaEventDisableTiming));
-    CU(cudaHostAlloc((void**)&ctx->h_tot, 256, cudaHostAllocDefault));
+    CU(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (int p = 0; p < MAX_PARTS; ++p) {
+        CU(cudaHostAlloc((void**)&ctx->part[p].h_tot, 256, cudaHostAllocDefault));
+        CU(cudaEventCreateWithFlags(&ctx->part[p].ev_up, cudaEventDisableTiming));
+    }
     CU(cudaHostAlloc((void**)&ctx->gbm.h_cnt, 256, cudaHostAllocDefault));
     return SPL_OK;
 }
@@ -816,9 +916,14 @@ void spl_destroy(spl_ctx* ctx) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
         for (cudaEvent_t e : ctx->events) cudaEventDestroy(e);
-        ctx->d_graph.release(); ctx->d_rec.release(); ctx->d_chunks.release(); ctx->d_soa.release();
-        ctx->d_cnt.release(); ctx->d_out.release(); ctx->d_tot.release(); ctx->d_lay.release(); ctx->d_bins.release(); ctx->d_jtab.release(); ctx->d_jdense.release();
-        if (ctx->h_tot) cudaFreeHost(ctx->h_tot);
+        ctx->d_graph.release(); ctx->d_cnt.release(); ctx->d_out.release();
+        for (int p = 0; p < MAX_PARTS; ++p) {
+            ctx->part[p].release();
+            if (ctx->part[p].h_tot) cudaFreeHost(ctx->part[p].h_tot);
+            if (ctx->part[p].h_chunks) cudaFreeHost(ctx->part[p].h_chunks);
+            if (ctx->part[p].ev_up) cudaEventDestroy(ctx->part[p].ev_up);
+        }
+        if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
         if (ctx->gbm.h_cnt) cudaFreeHost(ctx->gbm.h_cnt);
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         if (ctx->h_file) cudaFreeHost(ctx->h_file);
@@ -860,7 +965,7 @@ int spl_process_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     *out = nullptr;
     if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
     const double t0 = now_ms();
-    int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags);
+    int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, true);
     if (rc) return rc;
     const double tc0 = now_ms();
     rc = count_pass(ctx, nullptr);
@@ -935,8 +1040,10 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     if (rc) return rc;
     rc = upload_and_expand(ctx, rec, flags, n_chrom);
     if (rc) return rc;
-    launch_chunk_hints(ctx->chunks, ctx->n_chunks, ctx->g, ctx->stream);
-    launch_tile_hints(ctx->bins, ctx->g, ctx->stream);
+    for (int p = 0; p < ctx->n_parts; ++p) {
+        launch_chunk_hints(ctx->part[p].chunks, ctx->part[p].n_chunks, ctx->g, ctx->stream);
+        launch_tile_hints(ctx->part[p].bins, ctx->g, ctx->stream);
+    }
     rc = count_pass(ctx, nullptr);
     if (rc) return rc;
     const size_t S = (size_t)ctx->hg.n_sites;
@@ -999,11 +1106,11 @@ int spl_resident_load(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom
                       const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags) {
     if (!ctx) return SPL_ERR_ARG;
     if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
-    int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags);
+    int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, false);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
     // the raw records are not needed once expanded
-    ctx->d_rec.release();
+    for (int p = 0; p < MAX_PARTS; ++p) ctx->part[p].d_rec.release();
     return SPL_OK;
 }
 

@@ -366,3 +366,23 @@ def test_bam_ingest_on_the_device(ctx, tmp_path, monkeypatch):
     assert ctx.stats()["bam_on_device"] == 1.0
     assert np.array_equal(a1, b1) and np.array_equal(a2, b2) and int(a1.sum()) > 0
     assert len(order) == 2
+
+
+@pytest.mark.parametrize("shape", ["small", "c2"])
+def test_split_upload_equals_single_upload(ctx, monkeypatch, shape):
+    """A big host upload is cut in two at a chromosome boundary so that the first part's expansion overlaps the second
+    part's copy; the counting kernels then run once per part.  SPLISER_SPLIT_MIN_RECORDS forces / forbids the cut."""
+    from oracle import c_oracle
+    from spliser_b200 import synth
+    w = synth.generate(synth.config_small(150_000, seed=71, stranded=True, paired=True) if shape == "small" else synth.config_c2(400_000))
+    monkeypatch.setenv("SPLISER_SPLIT_MIN_RECORDS", "1000000000")
+    one = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags | 4))
+    assert ctx.stats()["n_parts"] == 1.0
+    monkeypatch.setenv("SPLISER_SPLIT_MIN_RECORDS", "1000")
+    two = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags | 4))
+    st = ctx.stats()
+    assert st["n_parts"] == 2.0 and st["n_aligned"] == len(w.records)
+    monkeypatch.delenv("SPLISER_SPLIT_MIN_RECORDS", raising=False)
+    assert c_oracle.diff_tables(one, two) is None, c_oracle.diff_tables(one, two)
+    want = c_oracle.process(w.records, len(w.chroms), w.junctions, w.flags | 4, threads=8)
+    assert c_oracle.diff_tables(two, want) is None
