@@ -5,12 +5,12 @@
 namespace spl {
 
 #ifndef SPL_BIN_SHIFT
-#define SPL_BIN_SHIFT 7
+#define SPL_BIN_SHIFT 6
 #endif
 #ifndef SPL_SB_SHIFT
 #define SPL_SB_SHIFT 6
 #endif
-constexpr int BIN_SHIFT = SPL_BIN_SHIFT;   // 128 bp genomic bins of the block partition (stream C)
+constexpr int BIN_SHIFT = SPL_BIN_SHIFT;   // 64 bp genomic bins of the block partition (stream C)
 constexpr int SB_SHIFT = SPL_SB_SHIFT;     // 64 bp bins of the direct-address site index
 
 // One work tile = up to CHUNK_READS consecutive records of one chromosome.  The expansion kernels
