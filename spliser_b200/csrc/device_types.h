@@ -104,8 +104,10 @@ struct DevJunc {
     uint32_t* dj_coff;            // [D] offset of the junction's complex instances in cx_j
     uint32_t* cx_j; uint32_t* cx_n;             // complex instances grouped by junction: global junction index; cx_n: scratch word before `overflow`
     uint4*    cx_rng;             // [n_complex] the owning read of each complex instance: junctions [x, y), blocks [z, w) (absolute indices)
-    // per pass
+    // per (sample, site table): filled by k_junc_lookup after the graph is on the device
     uint32_t* hot_l; uint32_t* hot_r;           // [D] anchor + 1 of a hot endpoint, 0 otherwise
+    uint32_t* sp_x0; uint32_t* sp_x1;           // [D] offsets into cnt.span of the junction's +n / -n (sp_x1 = ~0: no site strictly inside)
+    uint32_t* prep;                             // [8] [2] simple work-list length, [4..5] one u64: complex descriptors << 40 | flat instances
     unsigned long long* wl;       // hot units: chunk << 32 | junction << 1 | side
     uint32_t* cxd_base; uint32_t* cxd_ds;       // [2 D] per pass: descriptors of hot (junction, side) with complex instances: first flat index, d << 1 | side
     uint32_t* cxd_nt; int32_t* cxd_t;           // [2 D], [2 D * CXD_T] sites the (junction, side) is a partner/competitor pair for
@@ -139,7 +141,7 @@ struct DevCounters {
     uint32_t* spanx;   // [S] spanning reads that are flanking (removed from the mutually-exclusive count)
     uint32_t* flank;   // [S] flanking reads (counted as beta2Simple in combine mode only)
     uint32_t* dc;      // [E] PartnerBeta2DoubleCounts increments seen in the BAM
-    uint32_t* work;    // [8] work-item counters: [0] K3 tiles, [2] junction work-list length, [4..5] one u64: complex descriptors << 40 | flat instances
+    uint32_t* work;    // [8] work-item counters: [0] K3 tiles
 };
 
 struct DevOutputs {
@@ -175,6 +177,7 @@ void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream);
 void launch_jtab_layout(DevBins bins, int attempt, uint32_t* totals8, void* stream);
 void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, DevJunc jg, uint32_t* totals4, void* stream);
 void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* totals4, void* stream);
+void launch_junction_prepare(DevJunc jg, DevGraph g, uint32_t flags, void* stream);
 void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream);
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream);
 int  kernel_launch_count_per_pass();

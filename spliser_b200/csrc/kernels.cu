@@ -938,9 +938,10 @@ __device__ __forceinline__ int k4_pair_site(const DevGraph& g, int q, int side, 
 }
 
 // ------------------------------------------------------------------------------------------------
-// K4 per pass: junction kernels over the DISTINCT junctions of the sample.
-//   k_junc_lookup   one thread per distinct junction: site lookups through the bin index, span range add
-//                   weighted by the junction's multiplicity (S:507-512), hot flags of its endpoints, work list
+// K4: junction kernels over the DISTINCT junctions of the sample.
+//   k_junc_lookup   (load time) one thread per distinct junction: site lookups through the bin index, offsets of its
+//                   span range add, hot flags of its endpoints, pair sites, work lists
+//   k_junc_span     span range add weighted by the junction's multiplicity (S:507-512)
 //   k_junc_simple   one warp per hot (junction, endpoint): the junction's simple instances are classified at
 //                   every exception site in aggregate -- flanking ones by the count alone, covering ones by a
 //                   coalesced pass over the group's (first block start, read end) arrays
@@ -957,7 +958,7 @@ __device__ __forceinline__ int site_lower(const DevGraph& g, int chrom, int32_t 
     return i;
 }
 
-__global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
+__global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, uint32_t mode) {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = d < jg.D;
     const int S = g.n_sites;
@@ -972,11 +973,8 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, Dev
         int ir = il;
         if (r > l) { ir = max(site_lower(g, c, r), iu); }
         const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);     // sites strictly inside (l, r)
-        if (x0 < x1) {
-            const uint32_t n = jg.dj_all[d];
-            atomicAdd(cnt.span + k * (S + 1) + x0, n);
-            atomicAdd(cnt.span + k * (S + 1) + x1, 0u - n);
-        }
+        jg.sp_x0[d] = (uint32_t)(k * (uint32_t)(S + 1) + (uint32_t)max(x0, 0));   // where k_junc_span adds +n / -n (S:507-512)
+        jg.sp_x1[d] = x0 < x1 ? (uint32_t)(k * (uint32_t)(S + 1) + (uint32_t)x1) : 0xffffffffu;
         if (!(mode & FLAG_DEBUG_SKIP_EXC)) {
             if (il < s1 && g.site_pos[il] == l && g.site_hot[il]) hl = (uint32_t)il + 1u;
             if (ir < s1 && g.site_pos[ir] == r && g.site_hot[ir]) hr = (uint32_t)ir + 1u;
@@ -1001,7 +999,7 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, Dev
         const uint32_t td = __shfl_sync(0xffffffffu, pd, 31), ti = __shfl_sync(0xffffffffu, pi, 31);
         if (td) {                                                      // warp-uniform
             unsigned long long old = 0;
-            if (lane == 0) old = atomicAdd(reinterpret_cast<unsigned long long*>(cnt.work + 4), ((unsigned long long)td << 40) | ti);
+            if (lane == 0) old = atomicAdd(reinterpret_cast<unsigned long long*>(jg.prep + 4), ((unsigned long long)td << 40) | ti);
             old = __shfl_sync(0xffffffffu, old, 0);
             uint32_t slot = (uint32_t)(old >> 40) + pd - nd, base = (uint32_t)(old & ((1ull << 40) - 1ull)) + pi - ni;
             if (nc) {
@@ -1037,7 +1035,7 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, Dev
         const uint32_t tu = __shfl_sync(0xffffffffu, pu, 31);
         if (tu) {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(cnt.work + 2, tu);
+            if (lane == 0) base = atomicAdd(jg.prep + 2, tu);
             base = __shfl_sync(0xffffffffu, base, 0);
             uint32_t p = base + pu - nu;
             if (nu) {
@@ -1053,10 +1051,21 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, Dev
 
 
 
+// per pass: the span difference array gets +-multiplicity of every distinct junction at the offsets found at load time
+__global__ void __launch_bounds__(256) k_junc_span(DevJunc jg, DevCounters cnt) {
+    const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= jg.D) return;
+    const uint32_t x1 = jg.sp_x1[d];
+    if (x1 == 0xffffffffu) return;
+    const uint32_t n = jg.dj_all[d];
+    atomicAdd(cnt.span + jg.sp_x0[d], n);
+    atomicAdd(cnt.span + x1, 0u - n);
+}
+
 __global__ void __launch_bounds__(256) k_junc_simple(DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
     const bool combine = (mode & FLAG_COMBINE) != 0;
     const int lane = threadIdx.x & 31;
-    const uint32_t n_items = cnt.work[2];
+    const uint32_t n_items = jg.prep[2];
     for (uint32_t item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); item < n_items; item += gridDim.x * (blockDim.x >> 5)) {
         const unsigned long long w64 = jg.wl[item];
         const uint32_t w = (uint32_t)w64, chunk = (uint32_t)(w64 >> 32);
@@ -1101,7 +1110,7 @@ __global__ void __launch_bounds__(256) k_junc_simple(DevJunc jg, DevGraph g, Dev
 // complex instances of hot junctions: flat index -> descriptor (binary search over the descriptor bases) -> instance
 __global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
     const bool combine = (mode & FLAG_COMBINE) != 0;
-    const unsigned long long w = *reinterpret_cast<const unsigned long long*>(cnt.work + 4);
+    const unsigned long long w = *reinterpret_cast<const unsigned long long*>(jg.prep + 4);
     const uint32_t n_desc = (uint32_t)(w >> 40), n = (uint32_t)(w & ((1ull << 40) - 1ull));
     const int lane = threadIdx.x & 31;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -1384,11 +1393,19 @@ void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* tot
 void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (jg.D == 0 || g.n_sites <= 0) return;
-    k_junc_lookup<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, g, cnt, flags);
+    k_junc_span<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, cnt);
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     k_junc_simple<<<sms * 8, 256, 0, st>>>(jg, g, cnt, flags);
     if (jg.n_complex) k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags);
+}
+// load time (after the site table is on the device): per distinct junction, the site lookups, hot flags, pair sites and the
+// work lists of the exception kernels -- all functions of (sample junctions x site table), like the tile hints
+void launch_junction_prepare(DevJunc jg, DevGraph g, uint32_t flags, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (jg.D == 0 || g.n_sites <= 0) return;
+    cudaMemsetAsync(jg.prep, 0, 32, st);
+    k_junc_lookup<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, g, flags);
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;
@@ -1397,6 +1414,6 @@ void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags
     k_span_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(out.span_blk, nblk);
     k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags);
 }
-int kernel_launch_count_per_pass() { return 8; }   // alpha_reduce, beta1_stab, junc_lookup, junc_simple, junc_complex, span_blocksum, span_scan, finalize
+int kernel_launch_count_per_pass() { return 8; }   // alpha_reduce, beta1_stab, junc_span, junc_simple, junc_complex, span_blocksum, span_scan, finalize
 
 }  // namespace spl

@@ -550,7 +550,8 @@ int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0,
                      o_hl = dc.take<uint32_t>(D + 2), o_hr = dc.take<uint32_t>(D + 2),
                      o_wl = dc.take<unsigned long long>(2 * D + 2 * (n_simple / 2048 + 1) + 8),
                      o_xb = dc.take<uint32_t>(2 * D + 2), o_xd = dc.take<uint32_t>(2 * D + 2),
-                     o_xn = dc.take<uint32_t>(2 * D + 2), o_xt = dc.take<int32_t>((2 * D + 2) * CXD_T), o_cr = dc.take<uint4>(n_complex + 2);
+                     o_xn = dc.take<uint32_t>(2 * D + 2), o_xt = dc.take<int32_t>((2 * D + 2) * CXD_T), o_cr = dc.take<uint4>(n_complex + 2),
+                     o_s0 = dc.take<uint32_t>(D + 2), o_s1 = dc.take<uint32_t>(D + 2), o_pr = dc.take<uint32_t>(8);
         CU(P.d_jdense.reserve(dc.off + 256));
         char* db = (char*)P.d_jdense.p;
         jg.D = (uint32_t)D;
@@ -562,6 +563,7 @@ int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0,
         jg.hot_l = (uint32_t*)(db + o_hl); jg.hot_r = (uint32_t*)(db + o_hr); jg.wl = (unsigned long long*)(db + o_wl);
         jg.cxd_base = (uint32_t*)(db + o_xb); jg.cxd_ds = (uint32_t*)(db + o_xd);
         jg.cxd_nt = (uint32_t*)(db + o_xn); jg.cxd_t = (int32_t*)(db + o_xt); jg.cx_rng = (uint4*)(db + o_cr);
+        jg.sp_x0 = (uint32_t*)(db + o_s0); jg.sp_x1 = (uint32_t*)(db + o_s1); jg.prep = (uint32_t*)(db + o_pr);
         jg.n_complex = (uint32_t)n_complex;
     }
     launch_junction_groups_b(soa, jg, ctx->n_chrom_loaded, d_jtot, ctx->stream);
@@ -606,7 +608,6 @@ int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     }
     if (ev) CU(cudaEventRecord(ev[2], ctx->stream));
     for (int p = 0; p < ctx->n_parts; ++p) {
-        if (p && ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->cnt.work, 0, 32, ctx->stream));      // work lists of the previous part
         launch_junctions(ctx->part[p].soa, ctx->part[p].jg, ctx->g, ctx->cnt, ctx->flags, ctx->stream);
     }
     if (ev) CU(cudaEventRecord(ev[3], ctx->stream));
@@ -801,6 +802,7 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     for (int p = 0; p < ctx->n_parts; ++p) {
         launch_chunk_hints(ctx->part[p].chunks, ctx->part[p].n_chunks, ctx->g, ctx->stream);
         launch_tile_hints(ctx->part[p].bins, ctx->g, ctx->stream);
+        launch_junction_prepare(ctx->part[p].jg, ctx->g, ctx->flags, ctx->stream);
     }
     CU(cudaGetLastError());
     ctx->stats[SPL_STAT_LAUNCHES] = (double)kernel_launch_count_per_pass();
@@ -1043,6 +1045,7 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     for (int p = 0; p < ctx->n_parts; ++p) {
         launch_chunk_hints(ctx->part[p].chunks, ctx->part[p].n_chunks, ctx->g, ctx->stream);
         launch_tile_hints(ctx->part[p].bins, ctx->g, ctx->stream);
+        launch_junction_prepare(ctx->part[p].jg, ctx->g, ctx->flags, ctx->stream);
     }
     rc = count_pass(ctx, nullptr);
     if (rc) return rc;
