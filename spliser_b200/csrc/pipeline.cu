@@ -154,6 +154,8 @@ struct Part {
     void* h_chunks = nullptr;       // pinned staging of the chunk table
     size_t h_chunks_bytes = 0;
     cudaEvent_t ev_up = nullptr;    // the part's records (and chunk table) have arrived
+    cudaEvent_t ev_e0 = nullptr, ev_e1 = nullptr;   // bracket the part's load-time kernels (read after the call's final sync)
+    bool timed = false;
     DevBins bins{};
     DevJunc jg{};
     DevRecords rec{};
@@ -193,6 +195,7 @@ struct spl_ctx {
     BamGpuMem bgm;
     DevRecordArrays dev_rec{};
     bool rec_on_device = false;     // the next load takes its records from dev_rec (no host arrays, no upload)
+    spl_result* pending = nullptr;  // result whose structure arrays are already on their way to the host (device-built graph)
     void* h_file = nullptr;         // pinned image of the BAM file
     size_t h_file_bytes = 0;
 
@@ -465,11 +468,10 @@ int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0,
         bins.chrom_jn = (uint32_t*)(lb + o_cj); bins.tab_base = (uint32_t*)(lb + o_jt);
         bins.n_chrom = ctx->n_chrom_loaded;
     }
-    cudaEvent_t e0, e1;
-    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
-    CU(cudaEventRecord(e0, ctx->stream));
+    CU(cudaEventRecord(P.ev_e0, ctx->stream));
     launch_expand_count(P.rec, P.chunks, P.n_chunks, flags, bins, ctx->stream);
     launch_chunk_scan(P.chunks, P.n_chunks, (uint32_t*)P.d_tot.p, bins, ctx->stream);
+    if (P.n_chunks) launch_jtab_layout(bins, 0, (uint32_t*)P.d_tot.p, ctx->stream);       // sizes of the junction sub-tables ride on the same read-back
     CU(cudaGetLastError());
     CU(cudaMemcpyAsync(P.h_tot, P.d_tot.p, 40, cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));   // also makes `hc` (pageable) safe to drop
@@ -513,9 +515,11 @@ int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0,
     for (int attempt = 0;; ++attempt) {
         size_t n_slots = 0;
         if (P.n_chunks) {
-            launch_jtab_layout(bins, attempt, (uint32_t*)P.d_tot.p, ctx->stream);
-            CU(cudaMemcpyAsync(P.h_tot + 8, (uint32_t*)P.d_tot.p + 8, 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CU(cudaStreamSynchronize(ctx->stream));
+            if (attempt > 0) {                                          // a crowded sub-table: re-size for the worst case
+                launch_jtab_layout(bins, attempt, (uint32_t*)P.d_tot.p, ctx->stream);
+                CU(cudaMemcpyAsync(P.h_tot + 8, (uint32_t*)P.d_tot.p + 8, 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CU(cudaStreamSynchronize(ctx->stream));
+            }
             n_slots = P.h_tot[8];
         }
         Carver jc;
@@ -568,16 +572,10 @@ int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0,
     }
     launch_junction_groups_b(soa, jg, ctx->n_chrom_loaded, d_jtot, ctx->stream);
     CU(cudaGetLastError());
-    CU(cudaMemcpyAsync(P.h_tot + 12, d_jtot, 16, cudaMemcpyDeviceToHost, ctx->stream));
-    CU(cudaEventRecord(e1, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    CU(cudaEventRecord(P.ev_e1, ctx->stream));                         // no host sync here: the caller's next sync covers it
+    P.timed = true;
     ctx->stats[SPL_STAT_N_DISTINCT_J] += (double)D; ctx->stats[SPL_STAT_N_SIMPLE_J] += (double)n_simple;
     ctx->stats[SPL_STAT_N_COMPLEX_J] += (double)jg.n_complex;
-    if (P.h_tot[15]) return ctx->fail(SPL_ERR_CUDA, "junction table overflow (internal sizing error)");
-    float ms = 0;
-    CU(cudaEventElapsedTime(&ms, e0, e1));
-    cudaEventDestroy(e0); cudaEventDestroy(e1);
-    ctx->stats[SPL_STAT_MS_EXPAND] += ms;
     ctx->stats[SPL_STAT_N_MBLOCKS_A] += (double)nA; ctx->stats[SPL_STAT_N_MBLOCKS_B] += (double)nB;
     ctx->stats[SPL_STAT_N_SPLICED] += (double)nS; ctx->stats[SPL_STAT_N_JUNC_OPS] += (double)nJ;
     int64_t aligned = 0;
@@ -621,7 +619,9 @@ int fetch(spl_ctx* ctx, spl_result** out_r) {
     const bool dev = ctx->graph_on_device;
     const SiteGraph& h = ctx->hg;
     const size_t S = dev ? ctx->gcnt.S : (size_t)h.n_sites, E = dev ? ctx->gcnt.E : h.pc_pos.size(), Cn = dev ? ctx->gcnt.C : h.cp_pos.size();
-    spl_result* r = result_alloc(S, E, Cn, true);
+    const bool pre = dev && ctx->pending && (size_t)ctx->pending->n == S && (size_t)ctx->pending->E == E && (size_t)ctx->pending->C == Cn;
+    spl_result* r = pre ? ctx->pending : result_alloc(S, E, Cn, true);
+    if (pre) ctx->pending = nullptr;
     if (!r) return ctx->fail(SPL_ERR_NOMEM, "cannot allocate the result (%zu sites)", S);
     std::unique_ptr<spl_result, void (*)(spl_result*)> guard(r, spl_result_free);
     cudaStream_t st = ctx->stream;
@@ -635,7 +635,9 @@ int fetch(spl_ctx* ctx, spl_result** out_r) {
         CU(cudaMemcpyAsync(r->sse, ctx->out.sse, S * 8, cudaMemcpyDeviceToHost, st));
         if (E) CU(cudaMemcpyAsync(r->pc_cnt, ctx->out.pc_cnt, E * 8, cudaMemcpyDeviceToHost, st));
         bytes += (double)(S * 48 + E * 8);
-        if (dev) {                                                     // the structure lives on the device too
+        if (pre) {                                                     // structure arrays were sent during the load
+            CU(cudaStreamSynchronize(ctx->stream2));
+        } else if (dev) {                                              // the structure lives on the device too
             const GraphDev& d = ctx->gdev;
             CU(cudaMemcpyAsync(r->chrom, d.site_chrom, S * 4, cudaMemcpyDeviceToHost, st));
             CU(cudaMemcpyAsync(r->pos, d.site_pos, S * 4, cudaMemcpyDeviceToHost, st));
@@ -658,6 +660,18 @@ int fetch(spl_ctx* ctx, spl_result** out_r) {
 
 void reset_stats(spl_ctx* ctx) { std::fill(ctx->stats, ctx->stats + SPL_NSTATS, 0.0); }
 
+// CUDA-event time of the load-time kernels; call after a stream sync that follows the load
+void collect_expand_ms(spl_ctx* ctx) {
+    for (int p = 0; p < MAX_PARTS; ++p) {
+        Part& P = ctx->part[p];
+        if (!P.timed) continue;
+        P.timed = false;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, P.ev_e0, P.ev_e1) == cudaSuccess) ctx->stats[SPL_STAT_MS_EXPAND] += ms;
+        else cudaGetLastError();
+    }
+}
+
 // DevGraph view of a device-built graph
 void adopt_device_graph(spl_ctx* ctx) {
     const GraphDev& d = ctx->gdev;
@@ -679,6 +693,7 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
                 const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags,
                 bool split_ok) {
     ctx->loaded = false;
+    if (ctx->pending) { cudaStreamSynchronize(ctx->stream2); spl_result_free(ctx->pending); ctx->pending = nullptr; }
     int rc = check_view(ctx, rec, n_chrom);
     if (rc) return rc;
     if (n_junc < 0) return ctx->fail(SPL_ERR_ARG, "negative size");
@@ -769,6 +784,26 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
             return ctx->fail(SPL_ERR_CUDA, "%s", e.c_str());
         CU(cudaEventRecord(ctx->ev_graph, ctx->stream2));
         ctx->graph_on_device = true;
+        if (split_ok) {
+            // one-shot call: the site table / CSR structure goes back to the host now, under the record upload (PCIe is
+            // full duplex), so that the final fetch only moves the per-site results
+            const GraphDev& d = ctx->gdev;
+            const size_t S = ctx->gcnt.S, E = ctx->gcnt.E, Cn = ctx->gcnt.C;
+            spl_result* r = result_alloc(S, E, Cn, true);
+            if (r) {
+                cudaStream_t s2 = ctx->stream2;
+                ctx->pending = r;
+                CU(cudaMemcpyAsync(r->chrom, d.site_chrom, S * 4, cudaMemcpyDeviceToHost, s2));
+                CU(cudaMemcpyAsync(r->pos, d.site_pos, S * 4, cudaMemcpyDeviceToHost, s2));
+                CU(cudaMemcpyAsync(r->strand, d.site_strand, S, cudaMemcpyDeviceToHost, s2));
+                CU(cudaMemcpyAsync(r->first_line, d.first_line, S * 8, cudaMemcpyDeviceToHost, s2));
+                CU(cudaMemcpyAsync(r->pc_off, d.pt_off64, (S + 1) * 8, cudaMemcpyDeviceToHost, s2));
+                CU(cudaMemcpyAsync(r->cp_off, d.cp_off64, (S + 1) * 8, cudaMemcpyDeviceToHost, s2));
+                if (E) CU(cudaMemcpyAsync(r->pc_pos, d.pc_pos, E * 4, cudaMemcpyDeviceToHost, s2));
+                if (Cn) CU(cudaMemcpyAsync(r->cp_pos, d.cp_pos, Cn * 4, cudaMemcpyDeviceToHost, s2));
+                ctx->stats[SPL_STAT_D2H_BYTES] += (double)(S * 33 + 16 + E * 4 + Cn * 4);
+            }
+        }
         ctx->stats[SPL_STAT_H2D_BYTES] += ctx->gcnt.h2d_bytes;
         adopt_device_graph(ctx);
         rc = alloc_counters_outputs(ctx, ctx->gcnt.S, ctx->gcnt.E);
@@ -907,6 +942,7 @@ int spl_create(spl_ctx** out, const int* device_ids, int n_devices) {
     for (int p = 0; p < MAX_PARTS; ++p) {
         CU(cudaHostAlloc((void**)&ctx->part[p].h_tot, 256, cudaHostAllocDefault));
         CU(cudaEventCreateWithFlags(&ctx->part[p].ev_up, cudaEventDisableTiming));
+        CU(cudaEventCreate(&ctx->part[p].ev_e0)); CU(cudaEventCreate(&ctx->part[p].ev_e1));
     }
     CU(cudaHostAlloc((void**)&ctx->gbm.h_cnt, 256, cudaHostAllocDefault));
     return SPL_OK;
@@ -924,9 +960,12 @@ void spl_destroy(spl_ctx* ctx) {
             if (ctx->part[p].h_tot) cudaFreeHost(ctx->part[p].h_tot);
             if (ctx->part[p].h_chunks) cudaFreeHost(ctx->part[p].h_chunks);
             if (ctx->part[p].ev_up) cudaEventDestroy(ctx->part[p].ev_up);
+            if (ctx->part[p].ev_e0) cudaEventDestroy(ctx->part[p].ev_e0);
+            if (ctx->part[p].ev_e1) cudaEventDestroy(ctx->part[p].ev_e1);
         }
         if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
         if (ctx->gbm.h_cnt) cudaFreeHost(ctx->gbm.h_cnt);
+        if (ctx->pending) { spl_result_free(ctx->pending); ctx->pending = nullptr; }
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         if (ctx->h_file) cudaFreeHost(ctx->h_file);
         ctx->bgm.comp.release(); ctx->bgm.unc.release(); ctx->bgm.tab.release(); ctx->bgm.rec.release();
@@ -973,6 +1012,7 @@ int spl_process_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     rc = count_pass(ctx, nullptr);
     if (rc) return rc;
     rc = fetch(ctx, out);
+    collect_expand_ms(ctx);
     ctx->stats[SPL_STAT_MS_COUNT] = now_ms() - tc0;
     ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
     return rc;
@@ -1056,6 +1096,7 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
         CU(cudaMemcpyAsync(b2.data(), ctx->out.beta2s, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
     }
     CU(cudaStreamSynchronize(ctx->stream));
+    collect_expand_ms(ctx);
     for (int64_t i = 0; i < n_sites; ++i) { beta1_out[i] = 0; beta2simple_out[i] = 0; }
     for (size_t k = 0; k < S; ++k) {
         const int64_t gi = ctx->hg.gap_index[k];
@@ -1112,6 +1153,7 @@ int spl_resident_load(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom
     int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, false);
     if (rc) return rc;
     CU(cudaStreamSynchronize(ctx->stream));
+    collect_expand_ms(ctx);
     // the raw records are not needed once expanded
     for (int p = 0; p < MAX_PARTS; ++p) ctx->part[p].d_rec.release();
     return SPL_OK;
