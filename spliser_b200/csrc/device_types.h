@@ -107,6 +107,7 @@ struct DevJunc {
     // per (sample, site table): filled by k_junc_lookup after the graph is on the device
     uint32_t* hot_l; uint32_t* hot_r;           // [D] anchor + 1 of a hot endpoint, 0 otherwise
     uint32_t* sp_x0; uint32_t* sp_x1;           // [D] offsets into cnt.span of the junction's +n / -n (sp_x1 = ~0: no site strictly inside)
+    uint32_t* cx_pack;                          // [flat hot complex instances * 24] packed reads (k_junc_pack), sized after k_junc_lookup
     uint32_t* prep;                             // [8] [2] simple work-list length, [4..5] one u64: complex descriptors << 40 | flat instances
     unsigned long long* wl;       // hot units: chunk << 32 | junction << 1 | side
     uint32_t* cxd_base; uint32_t* cxd_ds;       // [2 D] per pass: descriptors of hot (junction, side) with complex instances: first flat index, d << 1 | side
@@ -178,6 +179,7 @@ void launch_jtab_layout(DevBins bins, int attempt, uint32_t* totals8, void* stre
 void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, DevJunc jg, uint32_t* totals4, void* stream);
 void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* totals4, void* stream);
 void launch_junction_prepare(DevJunc jg, DevGraph g, uint32_t flags, void* stream);
+void launch_junction_pack(DevSoA soa, DevJunc jg, void* stream);
 void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream);
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream);
 int  kernel_launch_count_per_pass();

@@ -875,50 +875,78 @@ __device__ __forceinline__ bool pc_pair(const DevGraph& g, int t, int32_t l, int
            (in_sorted(g.cp_pos, c0, c1, l) && in_list(g.pc_pos, p0, p1, r));
 }
 
-// The read that owns junction j (its junctions are [j0, j1), its blocks [b0, b1)) makes compSplicing true for site t
-// through j, unless an earlier junction of the read already did: classify the read at t (S:503-557, first match wins).
-__device__ __forceinline__ void k4_classify(const DevSoA& soa, const DevGraph& g, const DevCounters& cnt, int t, uint32_t j,
-                                            uint32_t j0, uint32_t j1, uint32_t b0, uint32_t b1, uint32_t k, bool combine) {
+// Two views of the read that owns a complex junction instance: straight from the record-ordered SoA (three dependent
+// DRAM round trips per item) or from the packed record k_junc_pack wrote at load time (one coalesced 96-byte load).
+struct ReadGlobal {
+    const DevSoA& soa;
+    uint32_t j0, b0, nj, nb, jrel;
+    __device__ __forceinline__ uint32_t jl(uint32_t x) const { return soa.jn_l[j0 + x]; }
+    __device__ __forceinline__ uint32_t jr(uint32_t x) const { return soa.jn_rk[j0 + x]; }
+    __device__ __forceinline__ int32_t bs(uint32_t x) const { return soa.m_start[b0 + x]; }
+    __device__ __forceinline__ uint32_t be(uint32_t x) const { return soa.m_endk[b0 + x]; }
+};
+constexpr int CXP_WORDS = 24, CXP_MAXJ = 4, CXP_MAXB = 6;     // packed record: header, 4 junctions, 6 blocks, descriptor, class
+struct ReadPacked {
+    const uint32_t* w;
+    uint32_t nj, nb, jrel;
+    __device__ __forceinline__ uint32_t jl(uint32_t x) const { return w[1 + 2 * x]; }
+    __device__ __forceinline__ uint32_t jr(uint32_t x) const { return w[2 + 2 * x]; }
+    __device__ __forceinline__ int32_t bs(uint32_t x) const { return (int32_t)w[9 + 2 * x]; }
+    __device__ __forceinline__ uint32_t be(uint32_t x) const { return w[10 + 2 * x]; }
+};
+
+// The read makes compSplicing true for site t through its junction number rd.jrel, unless an earlier junction of the read
+// already did: classify the read at t (S:503-557, first match wins).
+// +1 on a counter, aggregated over the lanes of the warp that are here with the same address (the instances a warp handles
+// mostly belong to one junction, so they hit the same few sites: one RED per warp and address instead of one per read)
+__device__ __forceinline__ void agg_inc(uint32_t* p) {
+    const unsigned active = __activemask();
+    const unsigned peers = __match_any_sync(active, (unsigned long long)(uintptr_t)p);
+    if ((int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(p, (uint32_t)__popc(peers));
+}
+
+template <class Rd>
+__device__ __forceinline__ void k4_classify(const Rd& rd, const DevGraph& g, const DevCounters& cnt, int t, uint32_t k, bool combine) {
     bool earlier = false;
-    for (uint32_t jj = j0; jj < j && !earlier; ++jj)
-        earlier = pc_pair(g, t, (int32_t)(soa.jn_l[jj] & POS_MASK), (int32_t)(soa.jn_rk[jj] & POS_MASK));
+    for (uint32_t x = 0; x < rd.jrel && !earlier; ++x)
+        earlier = pc_pair(g, t, (int32_t)(rd.jl(x) & POS_MASK), (int32_t)(rd.jr(x) & POS_MASK));
     if (earlier) return;
     const int32_t tp = g.site_pos[t];
     const bool ok = strand_ok(g.site_cls[t], k);
     bool alpha = false; int32_t partner_used = 0; int kstar = -1;
-    for (uint32_t jj = j0; jj < j1; ++jj) {
-        const uint32_t lraw = soa.jn_l[jj];
-        const int32_t ll = (int32_t)(lraw & POS_MASK), rr = (int32_t)(soa.jn_rk[jj] & POS_MASK);
+    for (uint32_t x = 0; x < rd.nj; ++x) {
+        const uint32_t lraw = rd.jl(x);
+        const int32_t ll = (int32_t)(lraw & POS_MASK), rr = (int32_t)(rd.jr(x) & POS_MASK);
         if (ll == tp && !(lraw >> 31)) { alpha = true; partner_used = rr; }   // firstN: POS > t, read skipped (S:435)
         if (rr == tp) { alpha = true; partner_used = ll; }
-        if (ll < tp && tp < rr) kstar = (int)(jj - j0);
+        if (ll < tp && tp < rr) kstar = (int)x;
     }
     if (alpha) {                                                   // S:519-527
         for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
             const int32_t pp = g.pc_pos[e];
             if (pp == partner_used) continue;
             bool in_read = false;
-            for (uint32_t jj = j0; jj < j1 && !in_read; ++jj)
-                in_read = (int32_t)(soa.jn_l[jj] & POS_MASK) == pp || (int32_t)(soa.jn_rk[jj] & POS_MASK) == pp;
-            if (in_read) atomicAdd(cnt.dc + e, 1u);
+            for (uint32_t x = 0; x < rd.nj && !in_read; ++x)
+                in_read = (int32_t)(rd.jl(x) & POS_MASK) == pp || (int32_t)(rd.jr(x) & POS_MASK) == pp;
+            if (in_read) agg_inc(cnt.dc + e);
         }
     } else if (kstar >= 0) {
-        if (kstar >= (int)(j - j0)) {                              // compSplicing already true at k*: flanking (S:503-505)
-            if (ok) atomicAdd(cnt.spanx + t, 1u);
-            if (combine) atomicAdd(cnt.flank + t, 1u);
+        if (kstar >= (int)rd.jrel) {                               // compSplicing already true at k*: flanking (S:503-505)
+            if (ok) agg_inc(cnt.spanx + t);
+            if (combine) agg_inc(cnt.flank + t);
         }
     } else if (ok) {
         bool covers = false;
-        for (uint32_t b = b0; b < b1 && !covers; ++b)
-            covers = soa.m_start[b] <= tp && (int32_t)(soa.m_endk[b] & POS_MASK) >= tp + 2;
+        for (uint32_t b = 0; b < rd.nb && !covers; ++b)
+            covers = rd.bs(b) <= tp && (int32_t)(rd.be(b) & POS_MASK) >= tp + 2;
         if (covers) {                                              // beta1-type, S:544-552
-            atomicAdd(cnt.covx + t, 1u);
+            agg_inc(cnt.covx + t);
             for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
                 const int32_t pp = g.pc_pos[e];
                 bool in_read = false;
-                for (uint32_t jj = j0; jj < j1 && !in_read; ++jj)
-                    in_read = (int32_t)(soa.jn_l[jj] & POS_MASK) == pp || (int32_t)(soa.jn_rk[jj] & POS_MASK) == pp;
-                if (in_read) atomicAdd(cnt.dc + e, 1u);
+                for (uint32_t x = 0; x < rd.nj && !in_read; ++x)
+                    in_read = (int32_t)(rd.jl(x) & POS_MASK) == pp || (int32_t)(rd.jr(x) & POS_MASK) == pp;
+                if (in_read) agg_inc(cnt.dc + e);
             }
         }
     }
@@ -1107,37 +1135,79 @@ __global__ void __launch_bounds__(256) k_junc_simple(DevJunc jg, DevGraph g, Dev
     }
 }
 
-// complex instances of hot junctions: flat index -> descriptor (binary search over the descriptor bases) -> instance
-__global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
-    const bool combine = (mode & FLAG_COMBINE) != 0;
-    const unsigned long long w = *reinterpret_cast<const unsigned long long*>(jg.prep + 4);
-    const uint32_t n_desc = (uint32_t)(w >> 40), n = (uint32_t)(w & ((1ull << 40) - 1ull));
+// flat index of a hot complex instance -> its descriptor: lane 0 of the warp searches, the others step forward (the warp's 32
+// consecutive flat indices mostly share a descriptor)
+__device__ __forceinline__ uint32_t cx_descriptor(const DevJunc& jg, uint32_t n_desc, uint32_t i) {
     const int lane = threadIdx.x & 31;
+    uint32_t lo = 0;
+    if (lane == 0) {
+        uint32_t hi = n_desc;                                          // last descriptor with base <= i
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (jg.cxd_base[mid] <= i) lo = mid; else hi = mid; }
+    }
+    lo = __shfl_sync(__activemask(), lo, 0);
+    while (lo + 1 < n_desc && jg.cxd_base[lo + 1] <= i) ++lo;
+    return lo;
+}
+
+// load time: one packed record per hot complex instance, in flat-index order, so that the per-pass kernel reads its
+// read's junctions and blocks with one coalesced load instead of chasing them through the SoA
+__global__ void __launch_bounds__(256) k_junc_pack(DevSoA soa, DevJunc jg) {
+    const unsigned long long w64 = *reinterpret_cast<const unsigned long long*>(jg.prep + 4);
+    const uint32_t n_desc = (uint32_t)(w64 >> 40), n = (uint32_t)(w64 & ((1ull << 40) - 1ull));
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-        // the warp's 32 consecutive flat indices mostly share a descriptor: lane 0 searches, the others step forward
-        uint32_t lo = 0;
-        if (lane == 0) {
-            uint32_t hi = n_desc;                                      // last descriptor with base <= i
-            while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (jg.cxd_base[mid] <= i) lo = mid; else hi = mid; }
-        }
-        lo = __shfl_sync(__activemask(), lo, 0);
-        while (lo + 1 < n_desc && jg.cxd_base[lo + 1] <= i) ++lo;
-        const uint32_t ds = jg.cxd_ds[lo], d = ds >> 1;
-        const int side = (int)(ds & 1u);
-        const uint32_t nt = jg.cxd_nt[lo];
-        if (nt == 0) continue;
+        const uint32_t lo = cx_descriptor(jg, n_desc, i);
+        const uint32_t d = jg.cxd_ds[lo] >> 1;
         const uint32_t p = jg.dj_coff[d] + (i - jg.cxd_base[lo]);
         const uint32_t j = jg.cx_j[p];
         const uint4 rr = jg.cx_rng[p];                                 // the owning read: junctions [x, y), blocks [z, w)
+        const uint32_t nj = rr.y - rr.x, nb = rr.w - rr.z;
+        uint32_t* o = jg.cx_pack + (size_t)i * CXP_WORDS;
+        if (nj > (uint32_t)CXP_MAXJ || nb > (uint32_t)CXP_MAXB) { o[0] = 0xffffffffu; o[21] = lo; continue; }    // walked through the SoA instead
+        o[0] = nj | (nb << 8) | ((j - rr.x) << 16);
+        for (uint32_t x = 0; x < nj; ++x) { o[1 + 2 * x] = soa.jn_l[rr.x + x]; o[2 + 2 * x] = soa.jn_rk[rr.x + x]; }
+        for (uint32_t b = 0; b < nb; ++b) { o[9 + 2 * b] = (uint32_t)soa.m_start[rr.z + b]; o[10 + 2 * b] = soa.m_endk[rr.z + b]; }
+        o[21] = lo;
+    }
+}
+
+// per pass: the general per-read state machine for the complex instances of hot junctions
+__global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
+    const bool combine = (mode & FLAG_COMBINE) != 0;
+    const unsigned long long w64 = *reinterpret_cast<const unsigned long long*>(jg.prep + 4);
+    const uint32_t n = (uint32_t)(w64 & ((1ull << 40) - 1ull));
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        uint32_t w[CXP_WORDS];
+        const uint4* src = reinterpret_cast<const uint4*>(jg.cx_pack + (size_t)i * CXP_WORDS);
+#pragma unroll
+        for (int q = 0; q < CXP_WORDS / 4; ++q) { const uint4 v = src[q]; w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w; }
+        const uint32_t lo = w[21];
+        const uint32_t nt = jg.cxd_nt[lo];
+        if (nt == 0) continue;
+        const uint32_t ds = jg.cxd_ds[lo], d = ds >> 1;
+        const int side = (int)(ds & 1u);
         const uint32_t k = jg.dj_rk[d] >> 31;
-        if (nt <= (uint32_t)CXD_T) {
-            for (uint32_t x = 0; x < nt; ++x) k4_classify(soa, g, cnt, jg.cxd_t[lo * CXD_T + x], j, rr.x, rr.y, rr.z, rr.w, k, combine);
-        } else {
+        if (w[0] != 0xffffffffu) {
+            const ReadPacked rd{w, w[0] & 0xffu, (w[0] >> 8) & 0xffu, w[0] >> 16};
+            if (nt <= (uint32_t)CXD_T) {
+                for (uint32_t x = 0; x < nt; ++x) k4_classify(rd, g, cnt, jg.cxd_t[lo * CXD_T + x], k, combine);
+            } else {
+                const int anchor = (int)((side == 0 ? jg.hot_l[d] : jg.hot_r[d]) - 1u);
+                const int32_t jl = (int32_t)jg.dj_l[d], jr = (int32_t)(jg.dj_rk[d] & POS_MASK);
+                for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
+                    const int t = k4_pair_site(g, q, side, jl, jr);
+                    if (t >= 0) k4_classify(rd, g, cnt, t, k, combine);
+                }
+            }
+        } else {                                                       // long read: more junctions / blocks than a packed record holds
+            const uint32_t p = jg.dj_coff[d] + (i - jg.cxd_base[lo]);
+            const uint32_t j = jg.cx_j[p];
+            const uint4 rr = jg.cx_rng[p];
+            const ReadGlobal rd{soa, rr.x, rr.z, rr.y - rr.x, rr.w - rr.z, j - rr.x};
             const int anchor = (int)((side == 0 ? jg.hot_l[d] : jg.hot_r[d]) - 1u);
             const int32_t jl = (int32_t)jg.dj_l[d], jr = (int32_t)(jg.dj_rk[d] & POS_MASK);
             for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
                 const int t = k4_pair_site(g, q, side, jl, jr);
-                if (t >= 0) k4_classify(soa, g, cnt, t, j, rr.x, rr.y, rr.z, rr.w, k, combine);
+                if (t >= 0) k4_classify(rd, g, cnt, t, k, combine);
             }
         }
     }
@@ -1397,7 +1467,7 @@ void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint3
     static int sms = 0;
     if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
     k_junc_simple<<<sms * 8, 256, 0, st>>>(jg, g, cnt, flags);
-    if (jg.n_complex) k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags);
+    if (jg.n_complex && jg.cx_pack) k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags);
 }
 // load time (after the site table is on the device): per distinct junction, the site lookups, hot flags, pair sites and the
 // work lists of the exception kernels -- all functions of (sample junctions x site table), like the tile hints
@@ -1406,6 +1476,12 @@ void launch_junction_prepare(DevJunc jg, DevGraph g, uint32_t flags, void* strea
     if (jg.D == 0 || g.n_sites <= 0) return;
     cudaMemsetAsync(jg.prep, 0, 32, st);
     k_junc_lookup<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, g, flags);
+}
+void launch_junction_pack(DevSoA soa, DevJunc jg, void* stream) {
+    if (jg.D == 0 || jg.n_complex == 0 || !jg.cx_pack) return;
+    static int sms = 0;
+    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    k_junc_pack<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(soa, jg);
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;

@@ -149,7 +149,7 @@ void result_from_host_graph(spl_result* r, const SiteGraph& h) {
 // once per part into the same counters (chromosomes, hence bins / tiles / junction tables, are disjoint between parts).
 constexpr int MAX_PARTS = 2;
 struct Part {
-    DevBuf d_rec, d_chunks, d_soa, d_tot, d_lay, d_bins, d_jtab, d_jdense;
+    DevBuf d_rec, d_chunks, d_soa, d_tot, d_lay, d_bins, d_jtab, d_jdense, d_cxpack;
     uint32_t* h_tot = nullptr;      // pinned totals read back during the expansion
     void* h_chunks = nullptr;       // pinned staging of the chunk table
     size_t h_chunks_bytes = 0;
@@ -164,7 +164,7 @@ struct Part {
     int n_chunks = 0;
     void release() {
         d_rec.release(); d_chunks.release(); d_soa.release(); d_tot.release(); d_lay.release(); d_bins.release();
-        d_jtab.release(); d_jdense.release();
+        d_jtab.release(); d_jdense.release(); d_cxpack.release();
     }
 };
 
@@ -672,6 +672,35 @@ void collect_expand_ms(spl_ctx* ctx) {
     }
 }
 
+// Everything that depends on (sample x site table): site windows of the chunks / tiles, and per distinct junction the site
+// lookups, hot flags, pair sites and exception work lists; then one packed record per hot complex instance (its count is
+// only known now, hence the one read-back).
+int prepare_parts(spl_ctx* ctx) {
+    for (int p = 0; p < ctx->n_parts; ++p) {
+        Part& P = ctx->part[p];
+        launch_chunk_hints(P.chunks, P.n_chunks, ctx->g, ctx->stream);
+        launch_tile_hints(P.bins, ctx->g, ctx->stream);
+        P.jg.cx_pack = nullptr;
+        launch_junction_prepare(P.jg, ctx->g, ctx->flags, ctx->stream);
+        P.h_tot[20] = P.h_tot[21] = 0;
+        if (P.jg.D && P.jg.n_complex && ctx->g.n_sites > 0)
+            CU(cudaMemcpyAsync(P.h_tot + 20, P.jg.prep + 4, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < ctx->n_parts; ++p) {
+        Part& P = ctx->part[p];
+        const unsigned long long w = (unsigned long long)P.h_tot[20] | ((unsigned long long)P.h_tot[21] << 32);
+        const size_t n_flat = (size_t)(w & ((1ull << 40) - 1ull));
+        if (!n_flat) continue;
+        CU(P.d_cxpack.reserve(n_flat * 24 * sizeof(uint32_t) + 256));
+        P.jg.cx_pack = (uint32_t*)P.d_cxpack.p;
+        launch_junction_pack(P.soa, P.jg, ctx->stream);
+    }
+    CU(cudaGetLastError());
+    return SPL_OK;
+}
+
 // DevGraph view of a device-built graph
 void adopt_device_graph(spl_ctx* ctx) {
     const GraphDev& d = ctx->gdev;
@@ -834,11 +863,7 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
         ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
         ctx->stats[SPL_STAT_N_EDGES] = (double)ctx->hg.pc_pos.size();
     }
-    for (int p = 0; p < ctx->n_parts; ++p) {
-        launch_chunk_hints(ctx->part[p].chunks, ctx->part[p].n_chunks, ctx->g, ctx->stream);
-        launch_tile_hints(ctx->part[p].bins, ctx->g, ctx->stream);
-        launch_junction_prepare(ctx->part[p].jg, ctx->g, ctx->flags, ctx->stream);
-    }
+    { const int prc = prepare_parts(ctx); if (prc) return prc; }
     CU(cudaGetLastError());
     ctx->stats[SPL_STAT_LAUNCHES] = (double)kernel_launch_count_per_pass();
     ctx->stats[SPL_STAT_GRAPH_DEVICE] = ctx->graph_on_device ? 1.0 : 0.0;
@@ -1082,11 +1107,7 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     if (rc) return rc;
     rc = upload_and_expand(ctx, rec, flags, n_chrom);
     if (rc) return rc;
-    for (int p = 0; p < ctx->n_parts; ++p) {
-        launch_chunk_hints(ctx->part[p].chunks, ctx->part[p].n_chunks, ctx->g, ctx->stream);
-        launch_tile_hints(ctx->part[p].bins, ctx->g, ctx->stream);
-        launch_junction_prepare(ctx->part[p].jg, ctx->g, ctx->flags, ctx->stream);
-    }
+    { const int prc = prepare_parts(ctx); if (prc) return prc; }
     rc = count_pass(ctx, nullptr);
     if (rc) return rc;
     const size_t S = (size_t)ctx->hg.n_sites;
