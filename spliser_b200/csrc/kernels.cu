@@ -1,10 +1,10 @@
 // Hand-written sm_100a kernels for the SpliSER counting path.
 //
 //   K0  expand_count / chunk_scan / expand_scatter / chunk_hints : BAM-style records -> SoA
-//   K1  alpha_reduce   : junction scores -> alpha[site], PartnerCounts[edge]   (SpliSER_v0_1_8.py:341,:353-355)
+//   K1  alpha reduce (extra blocks of k_span_blocksum): junction scores -> alpha[site], PartnerCounts[edge]   (SpliSER_v0_1_8.py:341,:353-355)
 //   K3  beta1_stab     : M-block vs site stabbing count                        (S:454-477)
 //   K4  spliced        : N-span range adds + compSplicing exceptions           (S:480-557)
-//   K5  span_blocksum / span_scan / finalize : prefix scan, beta2 gather (S:581-623), SSE (S:626-639)
+//   K5  span_blocksum / finalize : prefix scan, beta2 gather (S:581-623), SSE (S:626-639)
 //
 // Nothing here is a dense contraction, so no tensor-core path: the kernels are HBM streaming
 // (K3) or L2/latency bound graph lookups (K4, K5).  Site tiles are staged into shared memory with
@@ -622,8 +622,7 @@ __global__ void __launch_bounds__(256) k_jg_scatter(DevSoA soa, DevJunc jg) {
 // ------------------------------------------------------------------------------------------------
 // K1: alpha and PartnerCounts as segmented reductions of the junction scores
 // ------------------------------------------------------------------------------------------------
-__global__ void k_alpha_reduce(DevGraph g, DevOutputs out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void alpha_reduce_item(const DevGraph& g, const DevOutputs& out, int i) {
     if (i < g.n_sites) {
         int64_t a = 0;
         for (int k = g.inc_off[i]; k < g.inc_off[i + 1]; ++k) a += g.j_score[g.inc_line[k]];
@@ -1218,7 +1217,13 @@ __global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, De
 // ------------------------------------------------------------------------------------------------
 constexpr int FIN_TILE = FIN_THREADS * FIN_ITEMS;
 
-__global__ void __launch_bounds__(FIN_THREADS) k_span_blocksum(DevCounters cnt, int S, uint32_t* blk) {
+// blocks [0, nblk): per-block sums of the span difference array; blocks beyond: alpha / PartnerCounts reduction (K1), which
+// only has to be done before k_finalize and shares this launch
+__global__ void __launch_bounds__(FIN_THREADS) k_span_blocksum(DevCounters cnt, int S, uint32_t* blk, int nblk, DevGraph g, DevOutputs out) {
+    if ((int)blockIdx.x >= nblk) {
+        alpha_reduce_item(g, out, ((int)blockIdx.x - nblk) * FIN_THREADS + (int)threadIdx.x);
+        return;
+    }
     __shared__ uint32_t red[2][FIN_THREADS / 32];
     uint32_t s0 = 0, s1 = 0;
     const int base = blockIdx.x * FIN_TILE;
@@ -1232,42 +1237,6 @@ __global__ void __launch_bounds__(FIN_THREADS) k_span_blocksum(DevCounters cnt, 
     if (threadIdx.x == 0) {
         for (int w = 1; w < FIN_THREADS / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
         blk[2 * blockIdx.x] = s0; blk[2 * blockIdx.x + 1] = s1;
-    }
-}
-
-__global__ void __launch_bounds__(1024) k_span_scan(uint32_t* blk, int nblk) {   // exclusive scan, single CTA
-    __shared__ uint32_t wt[2][32];
-    __shared__ uint32_t carry[2];
-    if (threadIdx.x < 2) carry[threadIdx.x] = 0;
-    __syncthreads();
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < nblk; base += 1024) {
-        const int i = base + (int)threadIdx.x;
-        const uint32_t v0 = i < nblk ? blk[2 * i] : 0, v1 = i < nblk ? blk[2 * i + 1] : 0;
-        uint32_t a0 = v0, a1 = v1;                                  // inclusive scan inside the warp
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t x0 = __shfl_up_sync(0xffffffffu, a0, d), x1 = __shfl_up_sync(0xffffffffu, a1, d);
-            if (lane >= d) { a0 += x0; a1 += x1; }
-        }
-        if (lane == 31) { wt[0][warp] = a0; wt[1][warp] = a1; }
-        __syncthreads();
-        if (warp == 0) {                                            // exclusive scan of the 32 warp totals
-            const uint32_t w0 = wt[0][lane], w1 = wt[1][lane];
-            uint32_t b0 = w0, b1 = w1;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const uint32_t x0 = __shfl_up_sync(0xffffffffu, b0, d), x1 = __shfl_up_sync(0xffffffffu, b1, d);
-                if (lane >= d) { b0 += x0; b1 += x1; }
-            }
-            wt[0][lane] = b0 - w0; wt[1][lane] = b1 - w1;
-        }
-        __syncthreads();
-        const uint32_t e0 = carry[0] + wt[0][warp] + a0 - v0, e1 = carry[1] + wt[1][warp] + a1 - v1;
-        if (i < nblk) { blk[2 * i] = e0; blk[2 * i + 1] = e1; }
-        __syncthreads();
-        if (threadIdx.x == 1023) { carry[0] = e0 + v0; carry[1] = e1 + v1; }
-        __syncthreads();
     }
 }
 
@@ -1294,7 +1263,15 @@ k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode) {
     }
     if (lane == 31) { wt[0][warp] = a0; wt[1][warp] = a1; }
     __syncthreads();
-    uint32_t run0 = out.span_blk[2 * blockIdx.x] + a0 - t0, run1 = out.span_blk[2 * blockIdx.x + 1] + a1 - t1;
+    // prefix over the preceding blocks' sums (k_span_blocksum): a few thousand values, summed by the block itself
+    __shared__ uint32_t pre[2][FIN_THREADS / 32];
+    uint32_t p0 = 0, p1 = 0;
+    for (int b = threadIdx.x; b < (int)blockIdx.x; b += FIN_THREADS) { p0 += out.span_blk[2 * b]; p1 += out.span_blk[2 * b + 1]; }
+    p0 = __reduce_add_sync(0xffffffffu, p0); p1 = __reduce_add_sync(0xffffffffu, p1);
+    if (lane == 0) { pre[0][warp] = p0; pre[1][warp] = p1; }
+    __syncthreads();
+    uint32_t run0 = a0 - t0, run1 = a1 - t1;
+    for (int w = 0; w < FIN_THREADS / 32; ++w) { run0 += pre[0][w]; run1 += pre[1][w]; }
     for (int w = 0; w < warp; ++w) { run0 += wt[0][w]; run1 += wt[1][w]; }
 
     const bool stranded = (mode & FLAG_STRANDED) != 0, cryptic = (mode & FLAG_CRYPTIC) != 0, combine = (mode & FLAG_COMBINE) != 0;
@@ -1398,9 +1375,8 @@ void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chu
 void launch_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g, void* stream) {
     if (n_chunks > 0) k_chunk_hints<<<(n_chunks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(chunks, n_chunks, g);
 }
-void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream) {
-    const int n = g.n_sites + g.n_edges;
-    if (n > 0) k_alpha_reduce<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(g, out);
+void launch_alpha_reduce(DevGraph, DevOutputs, void*) {
+    // alpha / PartnerCounts are reduced by the extra blocks of k_span_blocksum (launch_finalize)
 }
 static int persistent_grid(const void* kernel, size_t smem) {
     static int sms = 0;
@@ -1486,10 +1462,10 @@ void launch_junction_pack(DevSoA soa, DevJunc jg, void* stream) {
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;
     const int nblk = (g.n_sites + FIN_TILE - 1) / FIN_TILE;
-    k_span_blocksum<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(cnt, g.n_sites, out.span_blk);
-    k_span_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(out.span_blk, nblk);
+    const int nalpha = (g.n_sites + g.n_edges + FIN_THREADS - 1) / FIN_THREADS;
+    k_span_blocksum<<<nblk + nalpha, FIN_THREADS, 0, (cudaStream_t)stream>>>(cnt, g.n_sites, out.span_blk, nblk, g, out);
     k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags);
 }
-int kernel_launch_count_per_pass() { return 8; }   // alpha_reduce, beta1_stab, junc_span, junc_simple, junc_complex, span_blocksum, span_scan, finalize
+int kernel_launch_count_per_pass() { return 6; }   // beta1_stab, junc_span, junc_simple, junc_complex, span_blocksum (+ alpha reduce), finalize
 
 }  // namespace spl
