@@ -81,7 +81,7 @@ class ClockSampler:
         self.rows, self.proc = [], None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
@@ -210,6 +210,7 @@ def main():
     sampler = ClockSampler(local)
     # ---- resident: SoA in HBM -> SSE in HBM
     ctx.resident_load(w.records, n_chrom, w.junctions, w.flags)
+    t_load = time.time()
     ctx.resident_count(args.warmup)
     barrier()
     t0 = time.time()
@@ -217,7 +218,6 @@ def main():
     t1 = time.time()
     barrier()
     ms_total = max_over_ranks(st["ms_total"])
-    clocks = sampler.window(t0, t1)
     reads_rank = st["n_aligned"]
     reads_all = sum_over_ranks(reads_rank)
     value = reads_all * args.steps / (ms_total * 1e-3)
@@ -265,6 +265,10 @@ def main():
         stats = ctx.stats()
     e2e_step = max_over_ranks(float(np.mean(e2e_t)))
     e2e_val = reads_all / e2e_step
+    # the timed passes last a few ms, shorter than nvidia-smi's sampling period: the clock record covers the whole GPU-active
+    # stretch around them (warm-up passes, timed passes, end-to-end calls)
+    clocks = sampler.window(t_load, time.time())
+    clocks["window"] = "warm-up + timed passes + e2e calls"
 
     out = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

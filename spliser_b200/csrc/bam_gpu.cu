@@ -13,7 +13,8 @@
 //                      true record chain by induction -- the speculation in k_bam_first is verified, never trusted.
 //                      Any broken link (or a feature this path does not parse: CG-tag long CIGARs) -> the caller falls
 //                      back to the host reader (bam_io.cpp).
-//   k_bam_walk<true>   per accepted member: second walk writing POS, FLAG, chromosome and CIGAR of every kept record
+//   k_bam_fill         one warp per accepted member: the kept records (offsets listed by the counting walk) are written out
+//                      round-robin by the lanes: POS, FLAG, chromosome and CIGAR
 //   k_bam_segments     chromosome boundaries of the record arrays (a coordinate-sorted BAM has one segment per reference)
 // Kept records follow the host reader: mapped to a caller chromosome and with at least one CIGAR operator (bam_io.cpp).
 #include <cuda_runtime.h>
@@ -112,11 +113,15 @@ __global__ void __launch_bounds__(256) k_bam_first(const uint8_t* __restrict__ u
 struct WalkOut { uint64_t land; uint32_t n_rec, n_cig, flags, pad; };
 constexpr uint32_t WALK_BAD = 1u, WALK_LONG_CIGAR = 2u;
 
+// slot of member m's first kept-record offset in the scratch list: a record is at least 36 bytes, so the records that
+// START inside a member of isize bytes number at most isize / 32 + 1
+__device__ __forceinline__ uint64_t list_base(const BgzfMember& b, uint32_t m) { return (b.uoff >> 5) + m; }
+
 template <bool FILL>
 __global__ void __launch_bounds__(128) k_bam_walk(const uint8_t* __restrict__ u, const BgzfMember* __restrict__ mem, uint32_t n_mem, uint64_t total,
                                                   int32_t n_ref, const int32_t* __restrict__ refmap, const uint64_t* __restrict__ first,
                                                   WalkOut* __restrict__ wo, const uint64_t* __restrict__ rec_base, const uint64_t* __restrict__ cig_base,
-                                                  DevRecordArrays out) {
+                                                  DevRecordArrays out, uint32_t* __restrict__ kept) {
     const uint32_t m = blockIdx.x * blockDim.x + threadIdx.x;
     if (m >= n_mem) return;
     uint64_t o = first[m];
@@ -134,6 +139,7 @@ __global__ void __launch_bounds__(128) k_bam_walk(const uint8_t* __restrict__ u,
         if (h.n_cig == 2 && ld32u(u, cig) == (((uint32_t)h.l_seq << 4) | 4u) && (ld32u(u, cig + 4) & 15u) == 3u) flags |= WALK_LONG_CIGAR;
         const int32_t chrom = h.refid >= 0 ? refmap[h.refid] : -1;
         if (chrom >= 0 && h.n_cig > 0) {
+            if (!FILL && kept) kept[list_base(mem[m], m) + n_rec] = (uint32_t)(o - mem[m].uoff);   // may exceed isize-1 never: o < limit
             if (FILL) {
                 out.pos[ri] = h.pos + 1;
                 out.flag[ri] = (uint16_t)h.flag;
@@ -146,6 +152,44 @@ __global__ void __launch_bounds__(128) k_bam_walk(const uint8_t* __restrict__ u,
         o = nx;
     }
     if (!FILL) wo[m] = WalkOut{o, n_rec, n_cig_tot, flags, 0};
+}
+
+// second pass, one WARP per accepted member: the lanes take the kept records of the member round-robin from the offset list
+// the counting walk left, so neighbouring lanes write neighbouring records (the per-thread walk wrote with a stride of
+// ~1,000 records between lanes)
+__global__ void __launch_bounds__(256) k_bam_fill(const uint8_t* __restrict__ u, const BgzfMember* __restrict__ mem, uint32_t n_mem,
+                                                  const int32_t* __restrict__ refmap, const WalkOut* __restrict__ wo,
+                                                  const uint64_t* __restrict__ rec_base, const uint64_t* __restrict__ cig_base,
+                                                  const uint32_t* __restrict__ kept, DevRecordArrays out) {
+    const uint32_t m = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (m >= n_mem || rec_base[m] == ~0ull) return;
+    const BgzfMember b = mem[m];
+    const uint32_t n = wo[m].n_rec;
+    const uint64_t lb = list_base(b, m), r0 = rec_base[m];
+    uint64_t ci = cig_base[m];
+    for (uint32_t k0 = 0; k0 < n; k0 += 32) {                           // warp-uniform
+        const uint32_t k = k0 + lane;
+        const bool live = k < n;
+        uint64_t o = 0;
+        RecHdr h{};
+        if (live) { o = b.uoff + kept[lb + k]; h = read_hdr(u, o); }
+        const uint32_t nc = live ? h.n_cig : 0u;
+        uint32_t pre = nc;                                             // inclusive scan of the CIGAR lengths
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, pre, d); if (lane >= d) pre += x; }
+        const uint32_t tot = __shfl_sync(0xffffffffu, pre, 31);
+        if (live) {
+            const uint64_t c0 = ci + pre - nc, ri = r0 + k;
+            out.pos[ri] = h.pos + 1;
+            out.flag[ri] = (uint16_t)h.flag;
+            out.chrom[ri] = refmap[h.refid];
+            out.cig_off[ri] = (uint32_t)c0;
+            const uint64_t cig = o + 36 + h.l_name;
+            for (uint32_t q = 0; q < nc; ++q) out.cigar[c0 + q] = ld32u(u, cig + 4ull * q);
+        }
+        ci += tot;
+    }
 }
 
 // boundaries of the chromosome segments: seg[k] = (first record, chromosome)
@@ -170,7 +214,7 @@ __global__ void k_set_u32(uint32_t* p, uint32_t v) { *p = v; }
     } while (0)
 
 int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const std::vector<BgzfMember>& members, uint64_t total_u,
-                   uint64_t first_record, int32_t n_ref, const std::vector<int32_t>& refmap, void* stream,
+                   uint64_t first_record, int32_t n_ref, const std::vector<int32_t>& refmap, void* stream, bool comp_uploaded,
                    DevRecordArrays& out, BamGpuCounts& cnt, std::string& err) {
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t n_mem = (uint32_t)members.size();
@@ -180,7 +224,8 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
     // not enough device memory for the file image + the inflated stream: the host reader streams the file instead
     if (mem.comp.reserve(fsz + 64) != cudaSuccess ||
         mem.unc.reserve(total_u + 256) != cudaSuccess ||                // the aligned-word reads of the parser run a few bytes past the end
-        mem.tab.reserve((size_t)n_mem * (sizeof(BgzfMember) + 8 + sizeof(WalkOut) + 16) + ((size_t)n_ref + 1) * 4 + 4096) != cudaSuccess) {
+        mem.tab.reserve((size_t)n_mem * (sizeof(BgzfMember) + 8 + sizeof(WalkOut) + 16) + ((size_t)n_ref + 1) * 4 + 4096) != cudaSuccess ||
+        mem.list.reserve(((size_t)(total_u >> 5) + n_mem + 8) * 4) != cudaSuccess) {
         cudaGetLastError();
         mem.comp.release(); mem.unc.release();
         err = "not enough device memory for the inflated BAM";
@@ -194,16 +239,17 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
     uint64_t* d_cbase = (uint64_t*)tb; tb += (size_t)n_mem * 8;
     int32_t* d_refmap = (int32_t*)tb; tb += ((size_t)n_ref + 1) * 4;
     uint32_t* d_err = (uint32_t*)(((uintptr_t)tb + 15) & ~(uintptr_t)15);
-    BG_CU(cudaMemcpyAsync(mem.comp.p, file_pinned, fsz, cudaMemcpyHostToDevice, st));
+    if (!comp_uploaded) BG_CU(cudaMemcpyAsync(mem.comp.p, file_pinned, fsz, cudaMemcpyHostToDevice, st));
     BG_CU(cudaMemcpyAsync(d_mem, members.data(), (size_t)n_mem * sizeof(BgzfMember), cudaMemcpyHostToDevice, st));
     if (n_ref > 0) BG_CU(cudaMemcpyAsync(d_refmap, refmap.data(), (size_t)n_ref * 4, cudaMemcpyHostToDevice, st));
     BG_CU(cudaMemsetAsync(d_err, 0, 16, st));
     cnt.h2d_bytes = (double)fsz + (double)n_mem * sizeof(BgzfMember);
     const uint8_t* d_u = (const uint8_t*)mem.unc.p;
+    uint32_t* d_kept = (uint32_t*)mem.list.p;
     k_bgzf_inflate<<<(n_mem + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t*)mem.comp.p, d_mem, n_mem, (uint8_t*)mem.unc.p, d_err);
     // ---- speculative record starts + counting walk
     k_bam_first<<<(n_mem + 7) / 8, 256, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, first_record, d_first);
-    k_bam_walk<false><<<(n_mem + 127) / 128, 128, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, d_refmap, d_first, d_wo, nullptr, nullptr, DevRecordArrays{});
+    k_bam_walk<false><<<(n_mem + 127) / 128, 128, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, d_refmap, d_first, d_wo, nullptr, nullptr, DevRecordArrays{}, d_kept);
     BG_CU(cudaGetLastError());
     std::vector<uint64_t> h_first(n_mem);
     std::vector<WalkOut> h_wo(n_mem);
@@ -245,7 +291,7 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
         BG_CU(cudaMemcpyAsync(d_rbase, rbase.data(), (size_t)n_mem * 8, cudaMemcpyHostToDevice, st));
         BG_CU(cudaMemcpyAsync(d_cbase, cbase.data(), (size_t)n_mem * 8, cudaMemcpyHostToDevice, st));
         BG_CU(cudaMemsetAsync(d_ns, 0, 16, st));
-        k_bam_walk<true><<<(n_mem + 127) / 128, 128, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, d_refmap, d_first, nullptr, d_rbase, d_cbase, out);
+        k_bam_fill<<<(n_mem + 7) / 8, 256, 0, st>>>(d_u, d_mem, n_mem, d_refmap, d_wo, d_rbase, d_cbase, d_kept, out);
         k_set_u32<<<1, 1, 0, st>>>(out.cig_off + nrec, (uint32_t)ncig);
         if (nrec) k_bam_segments<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(out.chrom, nrec, d_ns, d_sf, d_sc, BAMGPU_MAX_SEG);
         BG_CU(cudaGetLastError());

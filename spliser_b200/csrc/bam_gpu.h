@@ -24,7 +24,7 @@ struct DevRecordArrays {     // what DevRecords points at, plus the chromosome o
     int32_t* chrom = nullptr;
 };
 
-struct BamGpuMem { GbBuf comp, unc, tab, rec; };
+struct BamGpuMem { GbBuf comp, unc, tab, rec, list; };
 
 struct BamGpuCounts {
     uint64_t n_rec = 0, n_cigar = 0;
@@ -44,6 +44,7 @@ std::string bam_scan(const uint8_t* file, size_t fsz, int32_t n_chrom, const cha
 // Device: inflate + parse.  BAMGPU_FALLBACK (err says why) = use the host reader instead; nothing was counted yet.
 int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const std::vector<BgzfMember>& members, uint64_t total_u,
                    uint64_t first_record, int32_t n_ref, const std::vector<int32_t>& refmap, void* stream,
+                   bool comp_uploaded /* mem.comp already holds the file image (copy queued on `stream`) */,
                    DevRecordArrays& out, BamGpuCounts& cnt, std::string& err);
 
 }  // namespace spl

@@ -912,14 +912,23 @@ int ingest_bam_device(spl_ctx* ctx, const char* path, int32_t n_chrom, const cha
         close(fd);
         if (bad) return ctx->fail(SPL_ERR_IO, "read error on %s", path);
     }
+    // the file image starts travelling now; the host walks the BGZF member headers meanwhile
+    bool uploaded = false;
+    if (ctx->bgm.comp.reserve(fsz + 64) == cudaSuccess) {
+        CU(cudaMemcpyAsync(ctx->bgm.comp.p, ctx->h_file, fsz, cudaMemcpyHostToDevice, ctx->stream));
+        uploaded = true;
+    } else {
+        cudaGetLastError();
+    }
     std::vector<BgzfMember> members;
     std::vector<int32_t> refmap;
     uint64_t total_u = 0, first_record = 0;
     int32_t n_ref = 0;
     std::string e = bam_scan((const uint8_t*)ctx->h_file, fsz, n_chrom, chrom_names, members, total_u, first_record, n_ref, refmap);
-    if (!e.empty()) return ctx->fail(SPL_ERR_IO, "%s", e.c_str());
+    if (!e.empty()) { cudaStreamSynchronize(ctx->stream); return ctx->fail(SPL_ERR_IO, "%s", e.c_str()); }
     const int rc = bam_gpu_ingest(ctx->bgm, (const uint8_t*)ctx->h_file, fsz, members, total_u, first_record, n_ref, refmap, ctx->stream,
-                                  ctx->dev_rec, cnt, e);
+                                  uploaded, ctx->dev_rec, cnt, e);
+    if (rc != BAMGPU_OK) cudaStreamSynchronize(ctx->stream);           // the pinned image may be re-used by the fallback / next call
     if (rc == BAMGPU_ERROR) return ctx->fail(SPL_ERR_CUDA, "%s", e.c_str());
     if (rc == BAMGPU_FALLBACK) { *fallback = true; return SPL_OK; }
     view = spl_records_view{};
@@ -993,7 +1002,7 @@ void spl_destroy(spl_ctx* ctx) {
         if (ctx->pending) { spl_result_free(ctx->pending); ctx->pending = nullptr; }
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         if (ctx->h_file) cudaFreeHost(ctx->h_file);
-        ctx->bgm.comp.release(); ctx->bgm.unc.release(); ctx->bgm.tab.release(); ctx->bgm.rec.release();
+        ctx->bgm.comp.release(); ctx->bgm.unc.release(); ctx->bgm.tab.release(); ctx->bgm.rec.release(); ctx->bgm.list.release();
         ctx->gbm.fin.release(); ctx->gbm.fin2.release(); ctx->gbm.work.release(); ctx->gbm.work2.release();
         if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
         if (ctx->ev_graph) cudaEventDestroy(ctx->ev_graph);
