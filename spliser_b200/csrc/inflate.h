@@ -39,7 +39,8 @@ struct BitReader {
     int bits;
     SPL_HD void init(const uint8_t* s, uint32_t len) { src = s; n = len; pos = 0; buf = 0; bits = 0; }
     SPL_HD void refill() {
-        if (bits <= 32 && pos + 4 <= n) {                   // 4 bytes at once while a whole word of input is left
+        if (pos + 4 <= n) {                                 // 4 bytes at once while a whole word of input is left: >= 33 bits
+            if (bits > 32) return;                          // afterwards, which covers one literal/length or one distance symbol
             uint32_t w;
 #if defined(__CUDA_ARCH__)
             const uint32_t* a = reinterpret_cast<const uint32_t*>(reinterpret_cast<uintptr_t>(src + pos) & ~(uintptr_t)3);
@@ -49,8 +50,9 @@ struct BitReader {
 #endif
             buf |= (uint64_t)w << bits;
             bits += 32; pos += 4;
+            return;
         }
-        while (bits <= 56 && pos < n) { buf |= (uint64_t)src[pos++] << bits; bits += 8; }
+        while (bits <= 56 && pos < n) { buf |= (uint64_t)src[pos++] << bits; bits += 8; }     // tail of the member
     }
     SPL_HD uint32_t peek(int k) const { return (uint32_t)(buf & ((1ull << k) - 1ull)); }
     SPL_HD void drop(int k) { buf >>= k; bits -= k; }
