@@ -276,7 +276,10 @@ def main():
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": desc, "records_per_gpu": int(reads_rank), "sites_per_gpu": int(S), "junction_rows": len(w.junctions),
                    "l2": "no flush needed: the streamed SoA is %.0f MB per pass, larger than the 126 MB L2" % soa_mb,
-                   "timing": "CUDA events on the library's stream around %d passes; max over ranks" % args.steps},
+                   "timing": "CUDA events on the library's stream around %d passes; max over ranks" % args.steps,
+                   "value_scope": "one counting pass (alpha reduce, beta1 stabbing, junction span + exceptions, beta2 gather, SSE) over the "
+                                  "counting layout resident in HBM; building that layout from the raw records is load-time work: see from_records "
+                                  "(device time incl. it) and e2e (host arrays -> host table, everything included)"},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": int(stats["d2h_bytes"]),
                 "ms_per_step": 1e3 * e2e_step,
