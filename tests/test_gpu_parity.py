@@ -413,3 +413,33 @@ def test_bam_ingest_records_longer_than_a_bgzf_member(ctx, tmp_path):
     assert ctx.stats()["bam_on_device"] == 1.0
     assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
     assert int(want["beta1"].sum()) > 0
+
+
+def test_tile_sharded_process_with_record_slices(built_library):
+    """One sample sharded by genomic tile the way N GPUs would do it (here sequentially on one): every tile context gets
+    only the records spliser_b200.dist.tile_records cuts for it and counts only the sites it owns; the owned slices
+    concatenate to the single-context result (no exchange step)."""
+    import numpy as np
+    import spliser_b200
+    from spliser_b200 import api, dist, synth
+    w = synth.generate(synth.config_c3_tile(200_000, tile=1))
+    nc = len(w.chroms)
+    with spliser_b200.Context(0) as full_ctx:
+        ref = full_ctx.process_records(w.records, nc, w.junctions, w.flags | 4)
+        ref = {k: np.array(getattr(ref, k)) for k in ("beta1", "beta2simple", "beta2cryptic", "sse", "alpha", "pos")}
+    table = api.build_site_table(nc, w.junctions, w.flags)
+    S = len(table)
+    assert np.array_equal(table.pos, ref["pos"])
+    span = dist.max_reference_span(w.records)
+    n_tiles = 4
+    got = {k: np.zeros(S, ref[k].dtype) for k in ("beta1", "beta2simple", "beta2cryptic", "sse")}
+    for t in range(n_tiles):
+        rec_t = dist.tile_records(w.records, table, nc, t, n_tiles, max_span=span)
+        assert 0 < len(rec_t) < len(w.records)
+        with spliser_b200.Context(0, tile=(t, n_tiles)) as c:
+            part = c.process_records(rec_t, nc, w.junctions, w.flags | 4)
+            lo, hi = dist.tile_of(t, n_tiles, S)
+            for k in got:
+                got[k][lo:hi] = getattr(part, k)[lo:hi]
+    for k in got:
+        assert np.array_equal(got[k], ref[k]), k

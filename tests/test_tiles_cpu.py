@@ -1,0 +1,51 @@
+"""Genomic-tile sharding of ONE sample, host logic on the CPU: the record slices spliser_b200.dist cuts
+for each tile must give, for the sites the tile owns, exactly the counts of the unsharded run -- checked with the oracle,
+which (like the reference) counts site by site and so notices any missing alignment."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from spliser_b200 import api, dist, synth
+
+
+@pytest.mark.parametrize("shape,n_tiles", [("small", 3), ("c3_tile", 4)])
+def test_tile_record_slices_reproduce_the_unsharded_counts(shape, n_tiles):
+    if shape == "small":
+        w = synth.generate(synth.config_small(60_000, seed=101, stranded=True, paired=True))
+    else:
+        w = synth.generate(synth.config_c3_tile(80_000, tile=2))      # long introns: reads reach far across tile edges
+    nc = len(w.chroms)
+    full = c_oracle.process(w.records, nc, w.junctions, w.flags | 4, threads=8)
+    table = api.build_site_table(nc, w.junctions, w.flags)
+    S = len(table)
+    assert S == len(full["pos"]) and np.array_equal(table.pos, full["pos"])
+    span = dist.max_reference_span(w.records)
+    assert span >= 75
+    got = {k: np.zeros(S, full[k].dtype) for k in ("beta1", "beta2simple", "beta2cryptic", "sse", "alpha")}
+    n_sent = 0
+    for t in range(n_tiles):
+        rec_t = dist.tile_records(w.records, table, nc, t, n_tiles, max_span=span)
+        n_sent += len(rec_t)
+        assert len(rec_t) < len(w.records)                              # a tile gets a slice, not the sample
+        part = c_oracle.process(rec_t, nc, w.junctions, w.flags | 4, threads=8)
+        lo, hi = dist.tile_of(t, n_tiles, S)
+        for k in got:
+            got[k][lo:hi] = part[k][lo:hi]
+    for k in got:
+        assert np.array_equal(got[k], full[k]), k
+    assert n_sent < 1.5 * len(w.records)                                # edge duplication stays a small fraction
+
+
+def test_tile_slices_edge_cases():
+    from spliser_b200 import Junctions, Records
+    rec = Records.from_reads(["A", "B"], [("A", 100, 0, "50M"), ("A", 120, 0, "20M500N20M"), ("B", 10, 0, "30M")])
+    j = Junctions([0, 0], [139, 139], [640, 700], [1, 2], [ord("+"), ord("+")])
+    table = api.build_site_table(2, j, 0)
+    assert dist.max_reference_span(rec) == 540
+    # more tiles than sites: the empty tiles get no records at all
+    sent = [len(dist.tile_records(rec, table, 2, t, 8)) for t in range(8)]
+    assert sum(1 for n in sent if n == 0) >= 5 and max(sent) == 2
+    # chromosome B has no site: its read is never sent
+    assert all(int(c) == 0 for t in range(8) for c in dist.tile_records(rec, table, 2, t, 8).seg_chrom)
+    empty = Records.from_reads(["A"], [])
+    assert dist.max_reference_span(empty) == 0 and len(dist.tile_records(empty, table, 2, 0, 2)) == 0
