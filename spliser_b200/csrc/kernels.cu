@@ -1219,14 +1219,15 @@ constexpr int FIN_TILE = FIN_THREADS * FIN_ITEMS;
 
 // blocks [0, nblk): per-block sums of the span difference array; blocks beyond: alpha / PartnerCounts reduction (K1), which
 // only has to be done before k_finalize and shares this launch
-__global__ void __launch_bounds__(FIN_THREADS) k_span_blocksum(DevCounters cnt, int S, uint32_t* blk, int nblk, DevGraph g, DevOutputs out) {
+__global__ void __launch_bounds__(FIN_THREADS) k_span_blocksum(DevCounters cnt, int S, uint32_t* blk, int nblk, int blk0, DevGraph g, DevOutputs out) {
     if ((int)blockIdx.x >= nblk) {
         alpha_reduce_item(g, out, ((int)blockIdx.x - nblk) * FIN_THREADS + (int)threadIdx.x);
         return;
     }
     __shared__ uint32_t red[2][FIN_THREADS / 32];
     uint32_t s0 = 0, s1 = 0;
-    const int base = blockIdx.x * FIN_TILE;
+    const int bx = (int)blockIdx.x + blk0;                 // only the blocks that hold owned sites (tile sharding)
+    const int base = bx * FIN_TILE;
     for (int q = 0; q < FIN_ITEMS; ++q) {
         const int i = base + q * FIN_THREADS + threadIdx.x;
         if (i < S) { s0 += cnt.span[i]; s1 += cnt.span[(S + 1) + i]; }
@@ -1236,17 +1237,18 @@ __global__ void __launch_bounds__(FIN_THREADS) k_span_blocksum(DevCounters cnt, 
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < FIN_THREADS / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
-        blk[2 * blockIdx.x] = s0; blk[2 * blockIdx.x + 1] = s1;
+        blk[2 * bx] = s0; blk[2 * bx + 1] = s1;
     }
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
-k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode) {
+k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode, int blk0) {
     const int S = g.n_sites;
     __shared__ uint32_t wt[2][FIN_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int bx = (int)blockIdx.x + blk0;                 // blocks before blk0 hold no owned site: their span sums are zero
     // each thread owns FIN_ITEMS consecutive sites so that the in-thread running sum is in order
-    const int first = blockIdx.x * FIN_TILE + threadIdx.x * FIN_ITEMS;
+    const int first = bx * FIN_TILE + threadIdx.x * FIN_ITEMS;
     uint32_t d0[FIN_ITEMS], d1[FIN_ITEMS];
     uint32_t t0 = 0, t1 = 0;
 #pragma unroll
@@ -1266,7 +1268,7 @@ k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode) {
     // prefix over the preceding blocks' sums (k_span_blocksum): a few thousand values, summed by the block itself
     __shared__ uint32_t pre[2][FIN_THREADS / 32];
     uint32_t p0 = 0, p1 = 0;
-    for (int b = threadIdx.x; b < (int)blockIdx.x; b += FIN_THREADS) { p0 += out.span_blk[2 * b]; p1 += out.span_blk[2 * b + 1]; }
+    for (int b = blk0 + (int)threadIdx.x; b < bx; b += FIN_THREADS) { p0 += out.span_blk[2 * b]; p1 += out.span_blk[2 * b + 1]; }
     p0 = __reduce_add_sync(0xffffffffu, p0); p1 = __reduce_add_sync(0xffffffffu, p1);
     if (lane == 0) { pre[0][warp] = p0; pre[1][warp] = p1; }
     __syncthreads();
@@ -1328,6 +1330,7 @@ k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode) {
             const int64_t den = alpha_t + b1 + b2;
             if (den > 0) sse = __ddiv_rn((double)alpha_t, (double)den);
         }
+        if (!owned) { b1 = 0; b2 = 0; b2c = 0; b2w = 0.0; sse = 0.0; }     // another tile's site: zero-filled (include/spliser_b200.h)
         out.beta1[t] = b1; out.beta2s[t] = b2; out.beta2c[t] = b2c; out.beta2w[t] = b2w; out.sse[t] = sse;
     }
 }
@@ -1461,10 +1464,12 @@ void launch_junction_pack(DevSoA soa, DevJunc jg, void* stream) {
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;
-    const int nblk = (g.n_sites + FIN_TILE - 1) / FIN_TILE;
+    // only the blocks of FIN_TILE sites that hold sites this context owns (all of them without tile sharding)
+    const int lo = min(max(g.own_lo, 0), g.n_sites), hi = min(max(g.own_hi, lo), g.n_sites);
+    const int blk0 = lo / FIN_TILE, nblk = hi > lo ? (hi - 1) / FIN_TILE - blk0 + 1 : 0;
     const int nalpha = (g.n_sites + g.n_edges + FIN_THREADS - 1) / FIN_THREADS;
-    k_span_blocksum<<<nblk + nalpha, FIN_THREADS, 0, (cudaStream_t)stream>>>(cnt, g.n_sites, out.span_blk, nblk, g, out);
-    k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags);
+    k_span_blocksum<<<nblk + nalpha, FIN_THREADS, 0, (cudaStream_t)stream>>>(cnt, g.n_sites, out.span_blk, nblk, blk0, g, out);
+    if (nblk) k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags, blk0);
 }
 int kernel_launch_count_per_pass() { return 6; }   // beta1_stab, junc_span, junc_simple, junc_complex, span_blocksum (+ alpha reduce), finalize
 

@@ -358,6 +358,8 @@ int alloc_counters_outputs(spl_ctx* ctx, size_t S, size_t E) {
     o.beta2s = (int64_t*)(ob + o_b2); o.beta2c = (int64_t*)(ob + o_b2c); o.beta2w = (double*)(ob + o_b2w);
     o.sse = (double*)(ob + o_sse); o.dc_tot = (int64_t*)(ob + o_dct); o.dc_present = (uint8_t*)(ob + o_dcp);
     o.span_blk = (uint32_t*)(ob + o_blk);
+    // a tile context finalizes only the sites it owns; the others read back as zeros
+    if (ctx->tile_count > 1) CU(cudaMemsetAsync(ctx->d_out.p, 0, oc.off + 256, ctx->stream));
     return SPL_OK;
 }
 
