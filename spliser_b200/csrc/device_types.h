@@ -30,6 +30,7 @@ struct Chunk {
 struct DevGraph {
     int32_t n_chrom, n_sites, n_edges;
     int32_t own_lo, own_hi;             // site index range this context owns (tile sharding)
+    int32_t pt_is_pc;                   // 1: Partners entry a <-> PartnerCounts entry a (clean regime; pt_off == pc_off)
     const int32_t* cs_off;              // [n_chrom+1]
     const int32_t* site_pos;            // [n_sites + 8], tail padded with INT32_MAX
     const uint8_t* site_cls;            // [n_sites]

@@ -1296,9 +1296,30 @@ k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode, int blk0)
         const int32_t tp = g.site_pos[t];
         const int64_t alpha_t = out.alpha[t];
         const int e_lo = g.pc_off[t], e_hi = g.pc_off[t + 1];
-        for (int e = e_lo; e < e_hi; ++e) { out.dc_tot[e] = cnt.dc[e]; out.dc_present[e] = cnt.dc[e] != 0; }
         int64_t b2c = 0;
         double b2w = 0.0;
+        if (g.pt_is_pc) {
+            // clean regime: Partners and PartnerCounts entries correspond one to one (a partner object per position), so the
+            // double-count bookkeeping of S:592-611 stays in registers
+            for (int a = g.pt_off[t]; a < g.pt_off[t + 1]; ++a) {
+                const int p = g.pt_site[a];
+                const int32_t pp = g.pc_pos[a];
+                int64_t tab = 0; bool hit = false;
+                for (int x = g.pc_off[p]; x < g.pc_off[p + 1]; ++x) {      // S:592-599
+                    const int32_t cpos = g.pc_pos[x];
+                    if ((pp > tp && cpos < tp) || (pp < tp && cpos > tp)) { tab += out.pc_cnt[x]; hit = true; }
+                }
+                b2 += tab;
+                const uint32_t dcv = cnt.dc[a];
+                const int64_t pcount = out.pc_cnt[a];
+                int64_t v = out.alpha[p] - pcount;                         // S:606
+                if (hit || dcv) { v -= (int64_t)dcv + tab; if (v < 0) v = 0; }       // subIntNoNeg, S:608-611
+                b2c += v;
+                const double wgt = alpha_t > 0 ? __ddiv_rn((double)pcount, (double)alpha_t) : 0.0;   // S:615
+                b2w = __dadd_rn(b2w, __dmul_rn((double)v, wgt));           // mul then add, no FMA (S:617-619)
+            }
+        } else {
+        for (int e = e_lo; e < e_hi; ++e) { out.dc_tot[e] = cnt.dc[e]; out.dc_present[e] = cnt.dc[e] != 0; }
         for (int a = g.pt_off[t]; a < g.pt_off[t + 1]; ++a) {
             const int p = g.pt_site[a];
             const int32_t pp = g.site_pos[p];
@@ -1319,6 +1340,7 @@ k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode, int blk0)
                 const double wgt = alpha_t > 0 ? __ddiv_rn((double)pcount, (double)alpha_t) : 0.0;   // S:615
                 b2w = __dadd_rn(b2w, __dmul_rn((double)v, wgt));           // mul then add, no FMA (S:617-619)
             }
+        }
         }
         // ---- calculateSSE, S:626-639
         double sse = 0.0;

@@ -318,6 +318,7 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
     g.n_chrom = h.n_chrom; g.n_sites = (int32_t)S; g.n_edges = (int32_t)E;
     const int64_t tc = std::max(1, ctx->tile_count), ti = std::min<int64_t>(std::max(0, ctx->tile_index), tc - 1);
     g.own_lo = (int32_t)((int64_t)S * ti / tc); g.own_hi = (int32_t)((int64_t)S * (ti + 1) / tc);
+    g.pt_is_pc = (!h.dirty_regime && h.gap_index.empty() && h.pt_site.size() == h.pc_pos.size() && h.pt_off == h.pc_off) ? 1 : 0;
     g.cs_off = (const int32_t*)(b + o_cs); g.site_pos = (const int32_t*)(b + o_pos); g.site_cls = (const uint8_t*)(b + o_cls);
     g.site_hot = (const uint8_t*)(b + o_hot);
     g.sb_base = (const int32_t*)(b + o_sbb); g.sb_off = (const int32_t*)(b + o_sbo);
@@ -711,6 +712,7 @@ void adopt_device_graph(spl_ctx* ctx) {
     g.n_chrom = ctx->n_chrom_loaded; g.n_sites = (int32_t)S; g.n_edges = (int32_t)ctx->gcnt.E;
     const int64_t tc = std::max(1, ctx->tile_count), ti = std::min<int64_t>(std::max(0, ctx->tile_index), tc - 1);
     g.own_lo = (int32_t)((int64_t)S * ti / tc); g.own_hi = (int32_t)((int64_t)S * (ti + 1) / tc);
+    g.pt_is_pc = 1;
     g.cs_off = d.cs_off; g.site_pos = d.site_pos; g.site_cls = d.site_cls; g.site_hot = d.site_hot;
     g.sb_base = d.sb_base; g.sb_off = d.sb_off;
     g.pt_off = d.pt_off; g.pt_site = d.pt_site; g.pc_off = d.pt_off; g.pc_pos = d.pc_pos;     // clean regime: one PartnerCounts key per partner
