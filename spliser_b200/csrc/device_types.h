@@ -14,8 +14,7 @@ constexpr int BIN_SHIFT = SPL_BIN_SHIFT;   // 64 bp genomic bins of the block pa
 constexpr int SB_SHIFT = SPL_SB_SHIFT;     // 64 bp bins of the direct-address site index
 
 // One work tile = up to CHUNK_READS consecutive records of one chromosome.  The expansion kernels
-// fill the bases/counts; the hint kernel fills the site windows.  K3 streams the chunk's A blocks,
-// K4 its spliced reads.
+// fill the bases/counts; the bin partition and the junction grouping walk the SoA chunk by chunk.
 struct Chunk {
     int32_t  chrom;
     uint32_t rec_lo, rec_hi;            // [rec_lo, rec_hi) records (host-filled)
@@ -23,8 +22,7 @@ struct Chunk {
     uint32_t a_base, b_base, s_base, j_base; // exclusive scan of the totals
     int32_t  a_lo, a_hi;                // min block start / max (block end - 2) over A blocks (empty: lo > hi)
     int32_t  s_lo, s_hi;                // min / max position any lookup of the chunk's spliced reads can ask for
-    int32_t  a_site_lo, a_site_n;       // global site index range with a_lo <= pos <= a_hi
-    int32_t  s_site_lo, s_site_n;       // global site index range with s_lo <= pos <= s_hi
+    int32_t  reserved[4];               // (site windows of an earlier design; the tiles of stream C carry them now)
 };
 
 struct DevGraph {
@@ -173,7 +171,6 @@ void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals8, DevBins b
 void launch_bin_partition(const Chunk* chunks, int n_chunks, DevSoA soa, DevBins bins, void* stream);
 void launch_tile_hints(DevBins bins, DevGraph g, void* stream);
 void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream);
-void launch_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g, void* stream);
 void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream);
 void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream);
 void launch_jtab_layout(DevBins bins, int attempt, uint32_t* totals8, void* stream);

@@ -1,6 +1,6 @@
 // Hand-written sm_100a kernels for the SpliSER counting path.
 //
-//   K0  expand_count / chunk_scan / expand_scatter / chunk_hints : BAM-style records -> SoA
+//   K0  expand_count / chunk_scan / expand_scatter : BAM-style records -> SoA
 //   K1  alpha reduce (extra blocks of k_span_blocksum): junction scores -> alpha[site], PartnerCounts[edge]   (SpliSER_v0_1_8.py:341,:353-355)
 //   K3  beta1_stab     : M-block vs site stabbing count                        (S:454-477)
 //   K4  spliced        : N-span range adds + compSplicing exceptions           (S:480-557)
@@ -355,25 +355,6 @@ k_expand_scatter(DevRecords rec, const Chunk* chunks, DevSoA soa, uint32_t mode)
         soa.sr_boff[ck.s_base + ck.s_cnt] = ck.b_base + ck.b_cnt;
         soa.sr_joff[ck.s_base + ck.s_cnt] = ck.j_base + ck.j_cnt;
     }
-}
-
-// per-chunk site windows: global index range of the chromosome's sites inside [lo, hi]
-__global__ void k_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_chunks) return;
-    Chunk& ck = chunks[i];
-    const int c = ck.chrom;
-    const int s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
-    if (ck.a_cnt && ck.a_lo <= ck.a_hi) {
-        const int lo = lower_bound_i32(g.site_pos, s0, s1, ck.a_lo);
-        const int hi = upper_bound_i32(g.site_pos, lo, s1, ck.a_hi);
-        ck.a_site_lo = lo; ck.a_site_n = hi - lo;
-    } else { ck.a_site_lo = s0; ck.a_site_n = 0; }
-    if (ck.s_cnt && ck.s_lo <= ck.s_hi) {
-        const int lo = lower_bound_i32(g.site_pos, s0, s1, ck.s_lo);
-        const int hi = upper_bound_i32(g.site_pos, lo, s1, ck.s_hi);
-        ck.s_site_lo = lo; ck.s_site_n = hi - lo;
-    } else { ck.s_site_lo = s0; ck.s_site_n = 0; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1396,9 +1377,6 @@ void launch_tile_hints(DevBins bins, DevGraph g, void* stream) {
 }
 void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream) {
     if (n_chunks > 0) k_expand_scatter<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, soa, flags);
-}
-void launch_chunk_hints(Chunk* chunks, int n_chunks, DevGraph g, void* stream) {
-    if (n_chunks > 0) k_chunk_hints<<<(n_chunks + 127) / 128, 128, 0, (cudaStream_t)stream>>>(chunks, n_chunks, g);
 }
 void launch_alpha_reduce(DevGraph, DevOutputs, void*) {
     // alpha / PartnerCounts are reduced by the extra blocks of k_span_blocksum (launch_finalize)

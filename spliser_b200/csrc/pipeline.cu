@@ -681,7 +681,6 @@ void collect_expand_ms(spl_ctx* ctx) {
 int prepare_parts(spl_ctx* ctx) {
     for (int p = 0; p < ctx->n_parts; ++p) {
         Part& P = ctx->part[p];
-        launch_chunk_hints(P.chunks, P.n_chunks, ctx->g, ctx->stream);
         launch_tile_hints(P.bins, ctx->g, ctx->stream);
         P.jg.cx_pack = nullptr;
         launch_junction_prepare(P.jg, ctx->g, ctx->flags, ctx->stream);
