@@ -1,0 +1,93 @@
+"""The host layer of the SpliSER-compatible CLI on the CPU: BED parsing, locus filters, gene assignment, TSV writers and the
+`combine` merge driver (order dependence, gap collection) run for real; only the counting calls behind the C ABI are
+replaced by a stand-in context that answers them with the oracle (test infrastructure -- the product never does this).
+Outputs must be byte-identical to what the unmodified reference wrote (golden fixtures).  The same tests with the CUDA
+path behind the ABI are in test_cli_gpu.py."""
+import os
+
+import pytest
+
+from common import load_golden
+from oracle import c_oracle
+from spliser_b200 import Records, api
+
+
+class OracleContext:
+    """Answers process_bam / recount_bam like spliser_b200.Context, with the C oracle instead of the GPU."""
+
+    def process_bam(self, bam_path, chrom_names, junctions, flags):
+        rec = Records.from_bam(bam_path, chrom_names)
+        return api.SiteTable(**c_oracle.process(rec, len(chrom_names), junctions, flags))
+
+    def process_records(self, records, n_chrom, junctions, flags):
+        return api.SiteTable(**c_oracle.process(records, n_chrom, junctions, flags))
+
+    def recount_bam(self, bam_path, chrom_names, gaps, flags):
+        rec = Records.from_bam(bam_path, chrom_names)
+        return c_oracle.recount(rec, len(chrom_names), gaps, flags)
+
+    def recount_records(self, records, n_chrom, gaps, flags):
+        return c_oracle.recount(records, n_chrom, gaps, flags)
+
+    def close(self):
+        pass
+
+
+def _write_inputs(tmp, case):
+    bed = os.path.join(tmp, "j.bed")
+    open(bed, "w").write(case["bed"])
+    reads = [tuple(r) for r in case["reads"]]
+    refs = sorted({r[0] for r in reads}) or ["C"]
+    bam = os.path.join(tmp, "x.bam")
+    Records.from_reads(refs, reads).write_bam(bam, refs)
+    gff = None
+    if case.get("gff"):
+        gff = os.path.join(tmp, "a.gff")
+        open(gff, "w").write(case["gff"])
+    return bam, bed, gff
+
+
+def test_process_cli_text_on_cpu(tmp_path, built_library):
+    from spliser_b200 import cli
+    cases = load_golden("appendix_a.json.gz")["process"] + load_golden("process_fuzz.json.gz")[::9]
+    ctx = OracleContext()
+    for k, case in enumerate(cases):
+        d = tmp_path / ("p%d" % k)
+        d.mkdir()
+        bam, bed, gff = _write_inputs(str(d), case)
+        out = str(d / "out")
+        cli.process(bam, bed, out, qGene=case.get("qgene", "All"), qChrom=case.get("qchrom", "All"),
+                    maxIntronSize=case.get("max_intron", 0), annotationFile=gff, isStranded=case["stranded"],
+                    strandedType=case["stype"], isbeta2Cryptic=case["cryptic"], ctx=ctx)
+        assert open(out + ".SpliSER.tsv").read() == case["tsv"], case.get("name", case.get("seed"))
+
+
+def test_combine_merge_driver_on_cpu(tmp_path, built_library):
+    from spliser_b200 import cli
+    cases = load_golden("appendix_a.json.gz")["combine"] + load_golden("combine_fuzz.json.gz")
+    ctx = OracleContext()
+    for k, case in enumerate(cases):
+        d = tmp_path / ("c%d" % k)
+        d.mkdir()
+        lines = []
+        for i, s in enumerate(case["samples"]):
+            p = str(d / ("s%d.SpliSER.tsv" % i))
+            open(p, "w").write(s["tsv"])
+            bam = str(d / ("s%d.bam" % i))
+            Records.from_reads(["C"], [tuple(r) for r in s["reads"]]).write_bam(bam, ["C"])
+            lines.append("%s\t%s\t%s\n" % (s["title"], p, bam))
+        sf = str(d / "samples.tsv")
+        open(sf, "w").writelines(lines)
+        out = str(d / "out")
+        cli.combine(sf, out, isStranded=case["stranded"], strandedType=case["stype"], ctx=ctx)
+        assert open(out + ".combined.tsv").read() == case["combined"], case.get("name", case.get("seed"))
+
+
+def test_cli_errors_mirror_the_reference(tmp_path, built_library):
+    from spliser_b200 import cli
+    case = [c for c in load_golden("appendix_a.json.gz")["process"] if c["name"] == "A.4-locus"][0]
+    bam, bed, gff = _write_inputs(str(tmp_path), case)
+    with pytest.raises(AttributeError):                       # -g gene absent from the annotation (S:283)
+        cli.process(bam, bed, str(tmp_path / "o"), qGene="NOPE", qChrom="C", maxIntronSize=50, annotationFile=gff, ctx=OracleContext())
+    with pytest.raises(UnboundLocalError):                    # --isStranded with a type other than fr / rf (S:378-406)
+        cli.process(bam, bed, str(tmp_path / "o"), isStranded=True, strandedType="xx", ctx=OracleContext())
