@@ -144,10 +144,11 @@ void result_from_host_graph(spl_result* r, const SiteGraph& h) {
 }
 }  // namespace
 
-// Everything derived from one contiguous run of record segments (whole chromosomes).  A big upload is cut into two
-// parts so that the expansion of the first overlaps the host->device copy of the second; the counting kernels then run
-// once per part into the same counters (chromosomes, hence bins / tiles / junction tables, are disjoint between parts).
-constexpr int MAX_PARTS = 2;
+// Everything derived from one contiguous run of records.  A big upload is cut into up to three parts so that the expansion
+// of one part overlaps the host->device copy of the next; the counting kernels then run once per part into the same
+// counters (every part has its own bins / tiles / junction tables; a chromosome or a junction may appear in several
+// parts -- counts are additive).
+constexpr int MAX_PARTS = 3;
 struct Part {
     DevBuf d_rec, d_chunks, d_soa, d_tot, d_lay, d_bins, d_jtab, d_jdense, d_cxpack;
     uint32_t* h_tot = nullptr;      // pinned totals read back during the expansion
@@ -385,20 +386,20 @@ int check_view(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom) {
     return SPL_OK;
 }
 
-// enqueue the upload of the records of segments [s0, s1) on the copy stream (asynchronous when the caller's arrays are
+// enqueue the upload of records [r0, r1) on the copy stream (asynchronous when the caller's arrays are
 // page-locked); record / CIGAR indices inside the part are relative to its first record, CIGAR offsets stay absolute
-int upload_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0, int32_t s1, int32_t n_chrom) {
+int upload_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int64_t r0, int64_t r1, int32_t n_chrom) {
     ctx->n_chrom_loaded = n_chrom;
     const bool dev = ctx->rec_on_device;
-    const int64_t r0 = s1 > s0 ? v->seg_off[s0] : 0, r1 = s1 > s0 ? v->seg_off[s1] : 0;
     std::vector<Chunk> hc;
-    for (int32_t k = s0; k < s1; ++k) {
+    for (int32_t k = 0; k < v->n_seg; ++k) {                            // the part's share of every chromosome segment
         if (v->seg_chrom[k] < 0) continue;
-        for (int64_t lo = v->seg_off[k]; lo < v->seg_off[k + 1]; lo += CHUNK_READS) {
+        const int64_t a = std::max(v->seg_off[k], r0), b = std::min(v->seg_off[k + 1], r1);
+        for (int64_t lo = a; lo < b; lo += CHUNK_READS) {
             Chunk c{};
             c.chrom = v->seg_chrom[k];
             c.rec_lo = (uint32_t)(lo - r0);
-            c.rec_hi = (uint32_t)(std::min<int64_t>(lo + CHUNK_READS, v->seg_off[k + 1]) - r0);
+            c.rec_hi = (uint32_t)(std::min<int64_t>(lo + CHUNK_READS, b) - r0);
             hc.push_back(c);
         }
     }
@@ -450,7 +451,7 @@ int upload_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0,
 }
 
 // run the expansion kernels, leave the SoA + chunk table on the device
-int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0, int32_t s1, uint32_t flags) {
+int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int64_t r0, int64_t r1, uint32_t flags) {
     CU(cudaStreamWaitEvent(ctx->stream, P.ev_up, 0));
     CU(P.d_tot.reserve(256));
     // per-chromosome layout arrays of the bin-partitioned stream
@@ -582,8 +583,8 @@ int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0,
     ctx->stats[SPL_STAT_N_MBLOCKS_A] += (double)nA; ctx->stats[SPL_STAT_N_MBLOCKS_B] += (double)nB;
     ctx->stats[SPL_STAT_N_SPLICED] += (double)nS; ctx->stats[SPL_STAT_N_JUNC_OPS] += (double)nJ;
     int64_t aligned = 0;
-    for (int32_t k = s0; k < s1; ++k)
-        if (v->seg_chrom[k] >= 0) aligned += v->seg_off[k + 1] - v->seg_off[k];
+    for (int32_t k = 0; k < v->n_seg; ++k)
+        if (v->seg_chrom[k] >= 0) aligned += std::max<int64_t>(0, std::min(v->seg_off[k + 1], r1) - std::max(v->seg_off[k], r0));
     ctx->n_aligned += aligned;
     ctx->stats[SPL_STAT_N_ALIGNED] += (double)aligned;
     return SPL_OK;
@@ -592,9 +593,9 @@ int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int32_t s0,
 int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, int32_t n_chrom) {
     ctx->n_parts = 1;
     ctx->n_aligned = 0;
-    int rc = upload_records(ctx, ctx->part[0], v, 0, v->n_seg, n_chrom);
+    int rc = upload_records(ctx, ctx->part[0], v, 0, v->n_rec, n_chrom);
     if (rc) return rc;
-    return expand_records(ctx, ctx->part[0], v, 0, v->n_seg, flags);
+    return expand_records(ctx, ctx->part[0], v, 0, v->n_rec, flags);
 }
 
 // one counting pass over the resident SoA; events (if given) bracket the three kernel groups
@@ -760,41 +761,44 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
                                 0, ctx->gdev, ctx->gcnt, e))
             return ctx->fail(SPL_ERR_CUDA, "%s", e.c_str());
     }
-    // A big host upload is cut in two at a chromosome boundary: the first part's expansion runs while the second part is
-    // still on the wire.  The second part is the smaller one (its expansion is the only one left exposed): ~20 % of the records.
-    int32_t cut = rec->n_seg;
+    // A big host upload is cut into up to three parts of decreasing size (55 / 30 / 15 % of the records, at chunk
+    // granularity, inside a chromosome if need be): the expansion of each part runs while the next one is still on the
+    // wire, and only the last, smallest part's expansion stays exposed.
+    int64_t cuts[MAX_PARTS + 1] = {0, rec->n_rec, rec->n_rec, rec->n_rec};
+    ctx->n_parts = 1;
     {
         int64_t min_rec = 4000000;
+        int want_parts = MAX_PARTS;
         if (const char* f = std::getenv("SPLISER_SPLIT_MIN_RECORDS")) min_rec = atoll(f);
-        if (split_ok && !ctx->rec_on_device && rec->n_seg >= 2 && rec->n_rec >= min_rec) {
-            const int64_t want = rec->n_rec - rec->n_rec / 5;
-            int64_t best = -1;
-            for (int32_t k = 1; k < rec->n_seg; ++k) {
-                const int64_t d = rec->seg_off[k] > want ? rec->seg_off[k] - want : want - rec->seg_off[k];
-                if (rec->seg_off[k] > 0 && rec->seg_off[k] < rec->n_rec && (best < 0 || d < best)) { best = d; cut = k; }
+        if (const char* f = std::getenv("SPLISER_SPLIT_PARTS")) want_parts = std::max(1, std::min(MAX_PARTS, atoi(f)));
+        if (split_ok && !ctx->rec_on_device && want_parts > 1 && rec->n_rec >= min_rec && rec->n_rec >= 4 * (int64_t)CHUNK_READS) {
+            const double frac2[] = {0.80}, frac3[] = {0.55, 0.85};
+            const double* fr = want_parts == 2 ? frac2 : frac3;
+            ctx->n_parts = want_parts;
+            for (int p = 1; p < want_parts; ++p) {
+                int64_t c = (int64_t)(fr[p - 1] * (double)rec->n_rec) / CHUNK_READS * CHUNK_READS;
+                cuts[p] = std::max(cuts[p - 1] + CHUNK_READS, std::min(c, rec->n_rec - CHUNK_READS));
             }
+            cuts[want_parts] = rec->n_rec;
         }
     }
-    ctx->n_parts = cut < rec->n_seg ? 2 : 1;
     ctx->n_aligned = 0;
     cudaEvent_t dbg[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const bool dbg_on = std::getenv("SPLISER_TIMING") != nullptr;
     if (dbg_on) { for (auto& e : dbg) cudaEventCreate(&e); cudaEventRecord(dbg[0], ctx->copy_stream); }
-    rc = upload_records(ctx, ctx->part[0], rec, 0, cut, n_chrom);
-    if (dbg_on) cudaEventRecord(dbg[1], ctx->copy_stream);
-    if (rc) return rc;
-    if (ctx->n_parts == 2) {
-        rc = upload_records(ctx, ctx->part[1], rec, cut, rec->n_seg, n_chrom);
+    for (int p = 0; p < ctx->n_parts; ++p) {
+        rc = upload_records(ctx, ctx->part[p], rec, cuts[p], cuts[p + 1], n_chrom);
         if (rc) return rc;
+        if (dbg_on && p == 0) cudaEventRecord(dbg[1], ctx->copy_stream);
     }
     if (dbg_on) cudaEventRecord(dbg[2], ctx->copy_stream);
     const bool timing = std::getenv("SPLISER_TIMING") != nullptr;
-    if (timing) fprintf(stderr, "[load] +%.2f ms uploads queued (%d part(s), cut at segment %d of %d)\n", now_ms() - tg0, ctx->n_parts, cut, rec->n_seg);
+    if (timing) fprintf(stderr, "[load] +%.2f ms uploads queued (%d part(s))\n", now_ms() - tg0, ctx->n_parts);
     auto expand_all = [&]() -> int {
         for (int p = 0; p < ctx->n_parts; ++p) {
             if (timing) fprintf(stderr, "[load] +%.2f ms expand part %d starts\n", now_ms() - tg0, p);
             if (dbg_on && p == 0) { cudaStreamWaitEvent(ctx->stream, ctx->part[0].ev_up, 0); cudaEventRecord(dbg[3], ctx->stream); }
-            const int r = expand_records(ctx, ctx->part[p], rec, p == 0 ? 0 : cut, p == 0 ? cut : rec->n_seg, flags);
+            const int r = expand_records(ctx, ctx->part[p], rec, cuts[p], cuts[p + 1], flags);
             if (r) return r;
             if (dbg_on && p == 0) cudaEventRecord(dbg[4], ctx->stream);
             if (timing) fprintf(stderr, "[load] +%.2f ms expand part %d done\n", now_ms() - tg0, p);

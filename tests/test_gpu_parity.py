@@ -368,10 +368,11 @@ def test_bam_ingest_on_the_device(ctx, tmp_path, monkeypatch):
     assert len(order) == 2
 
 
-@pytest.mark.parametrize("shape", ["small", "c2"])
-def test_split_upload_equals_single_upload(ctx, monkeypatch, shape):
-    """A big host upload is cut in two at a chromosome boundary so that the first part's expansion overlaps the second
-    part's copy; the counting kernels then run once per part.  SPLISER_SPLIT_MIN_RECORDS forces / forbids the cut."""
+@pytest.mark.parametrize("shape,parts", [("small", 2), ("small", 3), ("c2", 3)])
+def test_split_upload_equals_single_upload(ctx, monkeypatch, shape, parts):
+    """A big host upload is cut into up to three parts (at chunk granularity, inside a chromosome if need be) so that the
+    expansion of one part overlaps the copy of the next; the counting kernels then run once per part into the same
+    counters.  SPLISER_SPLIT_MIN_RECORDS forces / forbids the cut, SPLISER_SPLIT_PARTS picks the number of parts."""
     from oracle import c_oracle
     from spliser_b200 import synth
     w = synth.generate(synth.config_small(150_000, seed=71, stranded=True, paired=True) if shape == "small" else synth.config_c2(400_000))
@@ -379,10 +380,12 @@ def test_split_upload_equals_single_upload(ctx, monkeypatch, shape):
     one = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags | 4))
     assert ctx.stats()["n_parts"] == 1.0
     monkeypatch.setenv("SPLISER_SPLIT_MIN_RECORDS", "1000")
+    monkeypatch.setenv("SPLISER_SPLIT_PARTS", str(parts))
     two = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags | 4))
     st = ctx.stats()
-    assert st["n_parts"] == 2.0 and st["n_aligned"] == len(w.records)
+    assert st["n_parts"] == float(parts) and st["n_aligned"] == len(w.records)
     monkeypatch.delenv("SPLISER_SPLIT_MIN_RECORDS", raising=False)
+    monkeypatch.delenv("SPLISER_SPLIT_PARTS", raising=False)
     assert c_oracle.diff_tables(one, two) is None, c_oracle.diff_tables(one, two)
     want = c_oracle.process(w.records, len(w.chroms), w.junctions, w.flags | 4, threads=8)
     assert c_oracle.diff_tables(two, want) is None
