@@ -664,6 +664,17 @@ int fetch(spl_ctx* ctx, spl_result** out_r) {
 
 void reset_stats(spl_ctx* ctx) { std::fill(ctx->stats, ctx->stats + SPL_NSTATS, 0.0); }
 
+// an entry point is about to return an error: nothing may still be reading the caller's (borrowed) arrays
+int drain_on_error(spl_ctx* ctx, int rc) {
+    if (rc && ctx->stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamSynchronize(ctx->stream2);
+        cudaStreamSynchronize(ctx->stream);
+        cudaGetLastError();
+    }
+    return rc;
+}
+
 // CUDA-event time of the load-time kernels; call after a stream sync that follows the load
 void collect_expand_ms(spl_ctx* ctx) {
     for (int p = 0; p < MAX_PARTS; ++p) {
@@ -1048,11 +1059,11 @@ int spl_process_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
     const double t0 = now_ms();
     int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, true);
-    if (rc) return rc;
+    if (rc) return drain_on_error(ctx, rc);
     const double tc0 = now_ms();
     rc = count_pass(ctx, nullptr);
-    if (rc) return rc;
-    rc = fetch(ctx, out);
+    if (rc) return drain_on_error(ctx, rc);
+    rc = drain_on_error(ctx, fetch(ctx, out));
     collect_expand_ms(ctx);
     ctx->stats[SPL_STAT_MS_COUNT] = now_ms() - tc0;
     ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
@@ -1122,10 +1133,10 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     ctx->tile_index = save_ti; ctx->tile_count = save_tc;
     if (rc) return rc;
     rc = upload_and_expand(ctx, rec, flags, n_chrom);
-    if (rc) return rc;
-    { const int prc = prepare_parts(ctx); if (prc) return prc; }
+    if (rc) return drain_on_error(ctx, rc);
+    { const int prc = prepare_parts(ctx); if (prc) return drain_on_error(ctx, prc); }
     rc = count_pass(ctx, nullptr);
-    if (rc) return rc;
+    if (rc) return drain_on_error(ctx, rc);
     const size_t S = (size_t)ctx->hg.n_sites;
     std::vector<int64_t> b1(S), b2(S);
     if (S) {
@@ -1188,7 +1199,7 @@ int spl_resident_load(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom
     if (!ctx) return SPL_ERR_ARG;
     if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
     int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, false);
-    if (rc) return rc;
+    if (rc) return drain_on_error(ctx, rc);
     CU(cudaStreamSynchronize(ctx->stream));
     collect_expand_ms(ctx);
     // the raw records are not needed once expanded
