@@ -22,6 +22,37 @@ from .bed import parse_bed12
 from .genes import NA_NAME, gene_name, load_annotation
 
 VERSION = "v0.1.8 (spliser_b200)"
+
+
+def _eval_partners(text):
+    """The Partners column (`str(dict)` of int -> int, S:662) without ast: `combine` evaluates it three times per row and
+    ast.literal_eval was two thirds of its run time.  Anything that is not the plain form goes to literal_eval."""
+    t = text.strip()
+    if t == "{}":
+        return {}
+    if t.startswith("{") and t.endswith("}"):
+        try:
+            out = {}
+            for item in t[1:-1].split(","):
+                k, v = item.split(":")
+                out[int(k)] = int(v)
+            return out
+        except ValueError:
+            pass
+    return literal_eval(text)
+
+
+def _eval_competitors(text):
+    """The Competitors column (`str(list)` of int, S:663); same fast path / fallback as _eval_partners."""
+    t = text.strip()
+    if t == "[]":
+        return []
+    if t.startswith("[") and t.endswith("]"):
+        try:
+            return [int(x) for x in t[1:-1].split(",")]
+        except ValueError:
+            pass
+    return literal_eval(text)
 PROCESS_HEADER = ("Region\tSite\tStrand\tGene\tSSE\talpha_count\tbeta1_count\tbeta2Simple_count\tbeta2Cryptic_count\t"
                   "beta2Cryptic_weighted\tPartners\tCompetitors\n")
 COMBINE_HEADER = ("Sample\tRegion\tSite\tStrand\tGene\tSSE\talpha_count\tbeta1_count\tbeta2Simple_count\tbeta2Cryptic_count\t"
@@ -205,10 +236,10 @@ def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType
                         iter_go[idx] = True
                         strand_now = str(vals[2])
                         site.rows[idx] = ("has", vals, strand_now)
-                        for key in literal_eval(str(vals[10])):                                           # S:889-892
+                        for key in _eval_partners(str(vals[10])):                                           # S:889-892
                             if key not in site.partners:
                                 site.partners.append(key)
-                        for c in literal_eval(str(vals[11])):                                             # S:894-897
+                        for c in _eval_competitors(str(vals[11])):                                             # S:894-897
                             if c not in site.competitors:
                                 site.competitors.append(c)
                                 site.competitors.sort()
@@ -269,7 +300,7 @@ def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType
                     alpha, beta1, beta2s = int(vals[5]), int(vals[6]), int(vals[7])
                     if vals[8] != "NA":
                         beta2c, beta2w = int(vals[8]), float(vals[9])
-                    pcounts = literal_eval(str(vals[10]))
+                    pcounts = _eval_partners(str(vals[10]))
                 elif row is not None and row[0] == "gap":
                     b1, b2 = recount[idx]
                     beta1, beta2s = int(b1[row[1]]), int(b2[row[1]])
