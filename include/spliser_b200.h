@@ -193,6 +193,92 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_GRAPH_DEVICE 22   /* 1 = site table + graph built on the device (clean regime), 0 = host emulation */
 int spl_last_stats(const spl_ctx* ctx, double* stats_out);
 
+/* ---- host text layer (no GPU): Gene column, .SpliSER.tsv writer, combine merge driver ------------
+ * What surrounds the counting call in the reference's CLI, done natively because per-row Python
+ * string work costs seconds where the counting costs milliseconds.  Byte-identical output. */
+typedef struct spl_strtab {          /* n strings: string i = blob[off[i] .. off[i+1]) (no terminators) */
+    int64_t n;
+    const char* blob;
+    const int64_t* off;              /* [n+1] */
+} spl_strtab;
+
+typedef struct spl_site_columns {    /* the arrays of an spl_result (or any table in the same layout) */
+    int64_t n_sites;
+    const int32_t* chrom;  const int32_t* pos;  const int64_t* first_line;
+    const int64_t* alpha;  const int64_t* beta1;  const int64_t* beta2simple;  const int64_t* beta2cryptic;
+    const double* beta2weighted;  const double* sse;
+    const int64_t* partner_off;  const int32_t* partner_pos;  const int64_t* partner_cnt;
+    const int64_t* comp_off;  const int32_t* comp_pos;
+} spl_site_columns;
+
+/* The text half of findAlphaCounts (S:255-288) for a whole BED12 file image: lines with exactly 12
+ * tab-separated fields (S:259), chromosome index in first-appearance order appended to chrom_index
+ * (what the annotation registered, S:90-92, S:265-268; may be NULL), -c filter (qchrom, NULL = "All",
+ * S:269), site positions and score (S:274-277), -g window (S:279-288) when use_gene_window != 0.
+ * The result carries the junction table in the layout of spl_process, the id of every kept row's
+ * column-6 text (for spl_write_process_tsv) and the two string lists.  A field int() would reject
+ * fails the call (SPL_ERR_ARG; the reference raises ValueError). */
+typedef struct spl_bed spl_bed;
+int spl_bed_parse(const char* text, int64_t len, const spl_strtab* chrom_index, const char* qchrom,
+                  int use_gene_window, int64_t gene_left, int64_t gene_right, int64_t max_intron,
+                  spl_bed** out, char* err, int err_len);
+void spl_bed_free(spl_bed* b);
+int64_t spl_bed_n_junctions(const spl_bed* b);
+const int32_t* spl_bed_chrom(const spl_bed* b);
+const int32_t* spl_bed_left(const spl_bed* b);
+const int32_t* spl_bed_right(const spl_bed* b);
+const int64_t* spl_bed_score(const spl_bed* b);
+const uint8_t* spl_bed_strand(const spl_bed* b);
+const int32_t* spl_bed_strand_id(const spl_bed* b);
+int64_t spl_bed_n_chrom(const spl_bed* b);
+const char* spl_bed_chrom_name(const spl_bed* b, int64_t i, int64_t* len);
+int64_t spl_bed_n_strand_texts(const spl_bed* b);
+const char* spl_bed_strand_text(const spl_bed* b, int64_t i, int64_t* len);
+
+/* binary_gene_search (S:118-173) for n positions against the genes of ONE chromosome in list order
+ * (insort by leftPos, S:95), control flow kept: overlapping genes make the bisection order-dependent
+ * and the last-ditch window (S:162-169) never looks at the last gene.  Strands are compared as ids
+ * of the caller's string table (equal id <=> equal text); plus_id / minus_id are the ids of "+" / "-".
+ * out_idx[i] = index into the gene list, or -1 ("NA"). */
+int spl_gene_search(int64_t n_genes, const int32_t* g_left, const int32_t* g_right, const int32_t* g_strand,
+                    int64_t n, const int32_t* pos, const int32_t* strand, int32_t plus_id, int32_t minus_id,
+                    int is_stranded, int32_t* out_idx);
+
+/* outputBedFile (S:641-664).  strand_texts = the distinct BED column-6 texts, line_strand[j] = id of
+ * junction row j's text (the Strand column prints the text of the row that created the site:
+ * first_line); site_gene[i] indexes gene_names, < 0 (or site_gene == NULL) prints "NA". */
+int spl_write_process_tsv(const char* path, const spl_site_columns* table, const spl_strtab* chrom_names,
+                          const spl_strtab* strand_texts, const int32_t* line_strand,
+                          const spl_strtab* gene_names, const int32_t* site_gene, int cryptic,
+                          char* err, int err_len);
+
+/* combine (S:742-917) around the re-count: parse every sample's .SpliSER.tsv, replay the lock-step
+ * merge (S:791-917; a gap of sample k sees the partners / competitors / strand gathered from the
+ * samples before k only), hand out each sample's gap list in the argument layout of spl_recount
+ * (s_chrom = region ids of spl_combine_region_name), take the counts back, write the .combined.tsv
+ * (outputCombinedLines, S:722-740).  The region order (S:761-789) is the caller's: it gets the run
+ * of consecutive distinct regions of every file from spl_combine_sample_runs. */
+typedef struct spl_combine spl_combine;
+int  spl_combine_create(spl_combine** out);
+void spl_combine_destroy(spl_combine* c);
+const char* spl_combine_last_error(const spl_combine* c);
+int  spl_combine_add_sample(spl_combine* c, const char* title, const char* tsv_path);
+int64_t spl_combine_n_samples(const spl_combine* c);
+int64_t spl_combine_n_regions(const spl_combine* c);
+const char* spl_combine_region_name(const spl_combine* c, int64_t region);
+int64_t spl_combine_sample_rows(const spl_combine* c, int64_t sample);
+int64_t spl_combine_sample_runs(const spl_combine* c, int64_t sample, const int32_t** runs);
+int  spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t* region_order,
+                       const char* qgene /* NULL = "All" */, int is_stranded);
+int64_t spl_combine_n_sites(const spl_combine* c);     /* merged sites that will be written */
+int64_t spl_combine_n_filled(const spl_combine* c);    /* "Filled in Beta read counts for N Sites" (S:917) */
+int64_t spl_combine_gaps(const spl_combine* c, int64_t sample, const int32_t** s_region, const int32_t** s_pos,
+                         const uint8_t** s_strand, const int64_t** p_off, const int32_t** p_pos,
+                         const int64_t** c_off, const int32_t** c_pos);
+int  spl_combine_set_recount(spl_combine* c, int64_t sample, int64_t n_gaps, const int64_t* beta1,
+                             const int64_t* beta2simple);
+int  spl_combine_write(spl_combine* c, const char* path, int cryptic);
+
 /* ---- BAM utilities (used by tests / benchmarks to make synthetic inputs) -------------------- */
 /* Writes a coordinate-sorted BAM (BGZF, no index needed by this library) from record arrays;
  * ref_len may be NULL (lengths written as 2^29).  SEQ/QUAL are omitted ('*'). */

@@ -133,3 +133,44 @@ def gen_combine_case(seed):
                        key=lambda x: x[1])
         samples.append(dict(title="S%d" % s, bed=bed, reads=reads))
     return dict(seed=seed, samples=samples, stranded=stranded, stype=stype)
+
+
+def gen_combine_wide_case(seed):
+    """`combine` beyond the single-region cases: 2-5 samples over 1-3 regions (a sample may lack a whole region, which
+    exercises the region order of S:761-789), a GFF so that the Gene column is filled and `-g` can filter the merged
+    rows (S:908), `--beta2Cryptic` on about half the cases (beta2_weighted goes through str(float), S:734), overlapping
+    genes on both strands."""
+    rng = random.Random(seed)
+    stranded = rng.random() < 0.5
+    stype = rng.choice(["fr", "rf"])
+    cryptic = rng.random() < 0.5
+    chroms = ["K%d" % i for i in range(rng.randint(1, 3))]
+    gff, grids, universe, genes = [], {}, {}, []
+    for c in chroms:
+        nsite = rng.randint(5, 9)
+        grids[c] = sorted(rng.sample(range(100, 1000, 10), nsite))
+        universe[c] = []
+        for _ in range(rng.randint(4, 9)):
+            l, r = sorted(rng.sample(grids[c], 2))
+            universe[c].append((l, r, rng.choice(["+", "-"])))
+        cut = rng.randrange(300, 800, 10)
+        spans = [(90, cut + rng.choice([0, 0, 60])), (cut, 1010)]
+        if rng.random() < 0.3:
+            spans.append((rng.randrange(100, 500, 10), rng.randrange(510, 1000, 10)))
+        for k, (a, b) in enumerate(spans):
+            name = "%s_g%d" % (c, k)
+            genes.append(name)
+            gff.append("%s\tx\tgene\t%d\t%d\t.\t%s\t.\tID=%s;Name=n%d\n" % (c, a, b, rng.choice(["+", "-"]), name, k))
+    samples = []
+    for s in range(rng.randint(2, 5)):
+        present = [c for c in chroms if rng.random() < 0.8] or [chroms[0]]
+        bed, reads = [], []
+        for c in present:
+            keep = [j for j in universe[c] if rng.random() < 0.6] or [universe[c][0]]
+            bed.extend(bed_line(c, l, r, rng.randint(1, 8), st) for l, r, st in keep)
+        for c in chroms:
+            reads.extend(sorted(((c,) + _gen_read(rng, grids[c]) for _ in range(rng.randint(5, 30))), key=lambda x: x[1]))
+        samples.append(dict(title="W%d" % s, bed="".join(bed), reads=reads))
+    qgene = rng.choice(genes) if rng.random() < 0.3 else "All"
+    return dict(seed=seed, chroms=chroms, samples=samples, stranded=stranded, stype=stype, cryptic=cryptic,
+                gff="".join(gff), qgene=qgene)

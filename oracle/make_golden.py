@@ -8,6 +8,7 @@ Fixtures:
   appendix_a.json.gz   SURVEY.md Appendix A scenarios A.1-A.4 (known-answer, incl. TSV text)
   process_fuzz.json.gz seeded fuzz cases (oracle/fuzzgen.py) with the reference's per-site rows
   combine_fuzz.json.gz seeded combine cases: per-sample TSVs, combined TSV, every gap re-count
+  combine_wide.json.gz same over several regions, with annotation / -g / --beta2Cryptic (fuzzgen.gen_combine_wide_case)
 """
 from __future__ import annotations
 
@@ -22,6 +23,7 @@ OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 
 
 N_PROCESS = 360
 N_COMBINE = 80
+N_COMBINE_WIDE = 60
 
 
 def _dump(name, obj):
@@ -120,12 +122,32 @@ def combine_fuzz(n=N_COMBINE):
     return cases
 
 
+def combine_wide(n=N_COMBINE_WIDE):
+    cases = []
+    for seed in range(n):
+        case = fuzzgen.gen_combine_wide_case(20262000 + seed)
+        samples = []
+        for s in case["samples"]:
+            tsv, _ = R.run_process(s["bed"], s["reads"], stranded=case["stranded"],
+                                   stype=case["stype"] if case["stranded"] else None, cryptic=case["cryptic"],
+                                   gff_text=case["gff"])
+            s["tsv"] = tsv
+            samples.append((s["title"], tsv, s["reads"]))
+        ctsv, gaps = R.run_combine(samples, stranded=case["stranded"], stype=case["stype"], cryptic=case["cryptic"],
+                                   qgene=case["qgene"])
+        case["combined"] = ctsv
+        case["gaps"] = gaps
+        cases.append(case)
+    return cases
+
+
 def main():
     if not R.reference_available():
         sys.exit("reference not mounted; golden vectors can only be regenerated in the authoring container")
     _dump("appendix_a.json.gz", appendix_a())
     _dump("process_fuzz.json.gz", process_fuzz())
     _dump("combine_fuzz.json.gz", combine_fuzz())
+    _dump("combine_wide.json.gz", combine_wide())
 
 
 if __name__ == "__main__":

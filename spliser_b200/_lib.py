@@ -33,6 +33,17 @@ class RecordsView(C.Structure):
                 ("seg_off", c_i64p)]
 
 
+class StrTab(C.Structure):
+    _fields_ = [("n", C.c_int64), ("blob", C.c_char_p), ("off", c_i64p)]
+
+
+class SiteColumns(C.Structure):
+    _fields_ = [("n_sites", C.c_int64), ("chrom", c_i32p), ("pos", c_i32p), ("first_line", c_i64p),
+                ("alpha", c_i64p), ("beta1", c_i64p), ("beta2simple", c_i64p), ("beta2cryptic", c_i64p),
+                ("beta2weighted", c_f64p), ("sse", c_f64p), ("partner_off", c_i64p), ("partner_pos", c_i32p),
+                ("partner_cnt", c_i64p), ("comp_off", c_i64p), ("comp_pos", c_i32p)]
+
+
 _JUNC = [C.c_int64, c_i32p, c_i32p, c_i32p, c_i64p, c_u8p]
 _GAPS = [C.c_int64, c_i32p, c_i32p, c_u8p, c_i64p, c_i32p, c_i64p, c_i32p]
 
@@ -75,6 +86,39 @@ SIGNATURES = {
     "spl_records_get": (C.POINTER(RecordsView), [C.c_void_p]),
     "spl_records_free": (None, [C.c_void_p]),
     "spl_debug_inflate": (C.c_int, [c_u8p, C.c_uint32, c_u8p, C.c_uint32, c_u32p]),
+    "spl_bed_parse": (C.c_int, [C.c_char_p, C.c_int64, C.POINTER(StrTab), C.c_char_p, C.c_int, C.c_int64, C.c_int64, C.c_int64,
+                                C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
+    "spl_bed_free": (None, [C.c_void_p]),
+    "spl_bed_n_junctions": (C.c_int64, [C.c_void_p]),
+    "spl_bed_chrom": (c_i32p, [C.c_void_p]),
+    "spl_bed_left": (c_i32p, [C.c_void_p]),
+    "spl_bed_right": (c_i32p, [C.c_void_p]),
+    "spl_bed_score": (c_i64p, [C.c_void_p]),
+    "spl_bed_strand": (c_u8p, [C.c_void_p]),
+    "spl_bed_strand_id": (c_i32p, [C.c_void_p]),
+    "spl_bed_n_chrom": (C.c_int64, [C.c_void_p]),
+    "spl_bed_chrom_name": (C.c_void_p, [C.c_void_p, C.c_int64, c_i64p]),
+    "spl_bed_n_strand_texts": (C.c_int64, [C.c_void_p]),
+    "spl_bed_strand_text": (C.c_void_p, [C.c_void_p, C.c_int64, c_i64p]),
+    "spl_gene_search": (C.c_int, [C.c_int64, c_i32p, c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int, c_i32p]),
+    "spl_write_process_tsv": (C.c_int, [C.c_char_p, C.POINTER(SiteColumns), C.POINTER(StrTab), C.POINTER(StrTab), c_i32p,
+                                        C.POINTER(StrTab), c_i32p, C.c_int, C.c_char_p, C.c_int]),
+    "spl_combine_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "spl_combine_destroy": (None, [C.c_void_p]),
+    "spl_combine_last_error": (C.c_char_p, [C.c_void_p]),
+    "spl_combine_add_sample": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "spl_combine_n_samples": (C.c_int64, [C.c_void_p]),
+    "spl_combine_n_regions": (C.c_int64, [C.c_void_p]),
+    "spl_combine_region_name": (C.c_char_p, [C.c_void_p, C.c_int64]),
+    "spl_combine_sample_rows": (C.c_int64, [C.c_void_p, C.c_int64]),
+    "spl_combine_sample_runs": (C.c_int64, [C.c_void_p, C.c_int64, C.POINTER(c_i32p)]),
+    "spl_combine_merge": (C.c_int, [C.c_void_p, C.c_int64, c_i32p, C.c_char_p, C.c_int]),
+    "spl_combine_n_sites": (C.c_int64, [C.c_void_p]),
+    "spl_combine_n_filled": (C.c_int64, [C.c_void_p]),
+    "spl_combine_gaps": (C.c_int64, [C.c_void_p, C.c_int64, C.POINTER(c_i32p), C.POINTER(c_i32p), C.POINTER(c_u8p),
+                                     C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i64p), C.POINTER(c_i32p)]),
+    "spl_combine_set_recount": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, c_i64p, c_i64p]),
+    "spl_combine_write": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int]),
     "spl_host_alloc": (C.c_void_p, [C.c_size_t]),
     "spl_host_free": (None, [C.c_void_p]),
 }

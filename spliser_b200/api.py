@@ -164,6 +164,57 @@ class Records:
 
 
 @dataclass
+class GapTable:
+    """The (site, sample) gaps of one sample for `combine`'s re-count (S:899-904) in the argument layout of
+    spl_recount: position, chromosome index, strand byte (0 = ''), partner / competitor positions as CSR.
+    Iterating yields the tuples (chrom_idx, pos, strand_str, partners, competitors)."""
+    chrom: np.ndarray
+    pos: np.ndarray
+    strand: np.ndarray
+    p_off: np.ndarray
+    p_pos: np.ndarray
+    c_off: np.ndarray
+    c_pos: np.ndarray
+
+    def __post_init__(self):
+        self.chrom = np.ascontiguousarray(self.chrom, dtype=np.int32)
+        self.pos = np.ascontiguousarray(self.pos, dtype=np.int32)
+        self.strand = np.ascontiguousarray(self.strand, dtype=np.uint8)
+        self.p_off = np.ascontiguousarray(self.p_off, dtype=np.int64)
+        self.p_pos = np.ascontiguousarray(self.p_pos, dtype=np.int32)
+        self.c_off = np.ascontiguousarray(self.c_off, dtype=np.int64)
+        self.c_pos = np.ascontiguousarray(self.c_pos, dtype=np.int32)
+        n = len(self.pos)
+        if not (len(self.chrom) == len(self.strand) == n and len(self.p_off) == len(self.c_off) == n + 1):
+            raise ValueError("gap arrays differ in length")
+
+    def __len__(self):
+        return len(self.pos)
+
+    def __iter__(self):
+        for i in range(len(self.pos)):
+            b = int(self.strand[i])
+            yield (int(self.chrom[i]), int(self.pos[i]), chr(b) if b else "",
+                   [int(x) for x in self.p_pos[self.p_off[i]:self.p_off[i + 1]]],
+                   [int(x) for x in self.c_pos[self.c_off[i]:self.c_off[i + 1]]])
+
+    @classmethod
+    def from_tuples(cls, gaps):
+        n = len(gaps)
+        p_off = np.zeros(n + 1, dtype=np.int64)
+        c_off = np.zeros(n + 1, dtype=np.int64)
+        pp, cp = [], []
+        for i, g in enumerate(gaps):
+            pp.extend(g[3])
+            cp.extend(g[4])
+            p_off[i + 1] = len(pp)
+            c_off[i + 1] = len(cp)
+        return cls(np.array([g[0] for g in gaps], dtype=np.int32), np.array([g[1] for g in gaps], dtype=np.int32),
+                   np.array([(ord(g[2][0]) if g[2] else 0) for g in gaps], dtype=np.uint8),
+                   p_off, np.array(pp, dtype=np.int32), c_off, np.array(cp, dtype=np.int32))
+
+
+@dataclass
 class SiteTable:
     """Per-site results in the reference's output order (outputBedFile, S:645-663)."""
     chrom: np.ndarray
@@ -307,25 +358,11 @@ class Context:
     # ---- combine re-count ----------------------------------------------------------------------
     @staticmethod
     def _gap_args(gaps):
-        """gaps: list of (chrom_idx, pos, strand_str, partner_positions, competitor_positions)."""
-        n = len(gaps)
-        s_chrom = np.array([g[0] for g in gaps], dtype=np.int32)
-        s_pos = np.array([g[1] for g in gaps], dtype=np.int32)
-        s_strand = np.array([(ord(g[2][0]) if g[2] else 0) for g in gaps], dtype=np.uint8)
-        p_off = np.zeros(n + 1, dtype=np.int64)
-        c_off = np.zeros(n + 1, dtype=np.int64)
-        pp, cp = [], []
-        for i, g in enumerate(gaps):
-            pp.extend(g[3])
-            cp.extend(g[4])
-            p_off[i + 1] = len(pp)
-            c_off[i + 1] = len(cp)
-        p_pos = np.array(pp, dtype=np.int32)
-        c_pos = np.array(cp, dtype=np.int32)
-        keep = (s_chrom, s_pos, s_strand, p_off, p_pos, c_off, c_pos)
-        args = (C.c_int64(n), _ptr(s_chrom, L.c_i32p), _ptr(s_pos, L.c_i32p), _ptr(s_strand, L.c_u8p),
-                _ptr(p_off, L.c_i64p), _ptr(p_pos, L.c_i32p), _ptr(c_off, L.c_i64p), _ptr(c_pos, L.c_i32p))
-        return keep, args
+        """gaps: GapTable, or a list of (chrom_idx, pos, strand_str, partner_positions, competitor_positions)."""
+        g = gaps if isinstance(gaps, GapTable) else GapTable.from_tuples(gaps)
+        args = (C.c_int64(len(g)), _ptr(g.chrom, L.c_i32p), _ptr(g.pos, L.c_i32p), _ptr(g.strand, L.c_u8p),
+                _ptr(g.p_off, L.c_i64p), _ptr(g.p_pos, L.c_i32p), _ptr(g.c_off, L.c_i64p), _ptr(g.c_pos, L.c_i32p))
+        return g, args
 
     def recount_records(self, records: Records, n_chrom: int, gaps, flags: int):
         keep, args = self._gap_args(gaps)

@@ -15,48 +15,15 @@ from __future__ import annotations
 import argparse
 import sys
 import timeit
-from ast import literal_eval
+
+import numpy as np
 
 from . import api
 from .bed import parse_bed12
-from .genes import NA_NAME, gene_name, load_annotation
+from .genes import load_annotation
+from .hosttext import CombineMerge, write_process_tsv as _native_write_process_tsv
 
 VERSION = "v0.1.8 (spliser_b200)"
-
-
-def _eval_partners(text):
-    """The Partners column (`str(dict)` of int -> int, S:662) without ast: `combine` evaluates it three times per row and
-    ast.literal_eval was two thirds of its run time.  Anything that is not the plain form goes to literal_eval."""
-    t = text.strip()
-    if t == "{}":
-        return {}
-    if t.startswith("{") and t.endswith("}"):
-        try:
-            out = {}
-            for item in t[1:-1].split(","):
-                k, v = item.split(":")
-                out[int(k)] = int(v)
-            return out
-        except ValueError:
-            pass
-    return literal_eval(text)
-
-
-def _eval_competitors(text):
-    """The Competitors column (`str(list)` of int, S:663); same fast path / fallback as _eval_partners."""
-    t = text.strip()
-    if t == "[]":
-        return []
-    if t.startswith("[") and t.endswith("]"):
-        try:
-            return [int(x) for x in t[1:-1].split(",")]
-        except ValueError:
-            pass
-    return literal_eval(text)
-PROCESS_HEADER = ("Region\tSite\tStrand\tGene\tSSE\talpha_count\tbeta1_count\tbeta2Simple_count\tbeta2Cryptic_count\t"
-                  "beta2Cryptic_weighted\tPartners\tCompetitors\n")
-COMBINE_HEADER = ("Sample\tRegion\tSite\tStrand\tGene\tSSE\talpha_count\tbeta1_count\tbeta2Simple_count\tbeta2Cryptic_count\t"
-                  "beta2_weighted\tPartners\tCompetitors\n")
 
 
 # ------------------------------------------------------------------------------------------------ process
@@ -80,21 +47,9 @@ def process_table(ctx, bam_path, bed_lines, *, annotation=None, qchrom="All", qg
 
 
 def write_process_tsv(path, chroms, table, sstr, *, annotation=None, is_stranded=False, beta2_cryptic=False):
-    """outputBedFile (S:641-664)."""
-    with open(path, "w") as out:
-        out.write(PROCESS_HEADER)
-        for i in range(len(table)):
-            ci, pos = int(table.chrom[i]), int(table.pos[i])
-            strand = sstr[int(table.first_line[i])]              # full column-6 text of the row that created the site
-            gene = gene_name(annotation, ci, pos, strand, is_stranded) if annotation is not None else NA_NAME
-            cols = [chroms[ci], str(pos), strand, gene, "{0:.3f}".format(float(table.sse[i])), str(int(table.alpha[i])),
-                    str(int(table.beta1[i])), str(int(table.beta2simple[i]))]
-            if beta2_cryptic:
-                cols += [str(int(table.beta2cryptic[i])), "{0:.5f}".format(float(table.beta2weighted[i]))]
-            else:
-                cols += ["NA", "NA"]
-            cols += [str(table.partners(i)), str(table.competitors(i))]
-            out.write("\t".join(cols) + "\n")
+    """outputBedFile (S:641-664) with the Gene column of S:313-329: native (csrc/host_text.cpp), one call for the table."""
+    _native_write_process_tsv(path, chroms, table, sstr, annotation=annotation, is_stranded=is_stranded,
+                              beta2_cryptic=beta2_cryptic)
 
 
 def process(inBAM, inBed, outputPath, qGene="All", qChrom="All", maxIntronSize=0, annotationFile=None, aType="gene",
@@ -118,23 +73,20 @@ def process(inBAM, inBed, outputPath, qGene="All", qChrom="All", maxIntronSize=0
 
 
 # ------------------------------------------------------------------------------------------------ combine
-def _chrom_order(paths):
+def _chrom_order(runs_per_file):
     """Region order across files: the reference builds a before/after graph and sorts it topologically
-    (S:761-789, Graph in Gene_Site_Iter_Graph_v0_1_8.py:358-396)."""
+    (S:761-789, Graph in Gene_Site_Iter_Graph_v0_1_8.py:358-396).  runs_per_file: for every sample file the consecutive
+    distinct regions of its rows (all the reference's scan looks at)."""
     all_chroms, before_list, after_list = [], [], []
-    for p in paths:
+    for runs in runs_per_file:
         before = "-1"
-        with open(p) as fh:
-            for idx, line in enumerate(fh):
-                if idx == 0:
-                    continue
-                chrom = line.split("\t")[0]
-                if chrom != before:
-                    before_list.append(before)
-                    after_list.append(chrom)
-                    before = chrom
-                    if chrom not in all_chroms:
-                        all_chroms.insert(0, chrom)
+        for chrom in runs:
+            if chrom != before:
+                before_list.append(before)
+                after_list.append(chrom)
+                before = chrom
+                if chrom not in all_chroms:
+                    all_chroms.insert(0, chrom)
     if not all_chroms:
         print("No genomic regions found - EXITING")
         sys.exit()
@@ -161,23 +113,12 @@ def _chrom_order(paths):
     return stack[1:]
 
 
-class _MergedSite:
-    __slots__ = ("chrom", "pos", "gene", "rows", "partners", "competitors", "emit")
-
-    def __init__(self, chrom, pos, gene, n):
-        self.chrom, self.pos, self.gene = chrom, pos, gene
-        self.rows = [None] * n           # per sample: ("has", vals) or ("gap", gap_id) or None (filtered out)
-        self.partners = []               # PartnerCounts keys in insertion order (S:889-892)
-        self.competitors = []            # sorted unique (S:894-897)
-        self.emit = True
-
-
 def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType="fr", isbeta2Cryptic=False, ctx=None,
             records_by_bam=None):
-    """combine (S:742-917).  Pass 1 replays the lock-step merge and collects, per sample, the sites it lacks
-    together with the partner / competitor / strand context accumulated from lower-indexed samples only
-    (the reference's order dependence); one spl_recount call per sample fills them; pass 2
-    writes the rows."""
+    """combine (S:742-917).  The native merge driver (csrc/host_text.cpp) parses the sample tables and replays the
+    lock-step merge, collecting per sample the sites it lacks together with the partner / competitor / strand context
+    gathered from lower-indexed samples only (the reference's order dependence); one spl_recount call
+    per sample fills them; the driver then writes the rows."""
     print("Combining samples...")
     titles, bed_paths, bam_paths = [], [], []
     with open(samplesFile) as fh:
@@ -189,139 +130,37 @@ def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType
                 print(str(titles), str(bed_paths), str(bam_paths))
                 raise Exception("Samples File contains lines that do not have exactly 3 tab-separated columns")
     n = len(titles)
-    chroms_in_order = _chrom_order(bed_paths)
-    iters = [open(p) for p in bed_paths]
-    for it in iters:
-        next(it, None)
-    current_vals = [[""] * 11 for _ in range(n)]
-    chroms = [""] * n
-    iter_go, iter_done = [True] * n, [False] * n
-    pos_idx, max_idx = 0, len(chroms_in_order) - 1
-    current_chrom = chroms_in_order[pos_idx]
-    lowest, lowest_strand = -1, "?"
-    merged = []
-    gaps = [[] for _ in range(n)]        # per sample: (chrom_name, pos, strand, partners, competitors)
-    filled = 0
-    while not all(iter_done):
-        assoc_gene = ""
-        for idx, it in enumerate(iters):
-            if not iter_done[idx]:
-                if iter_go[idx]:
-                    nxt = next(it, None)
-                    if nxt is not None:
-                        current_vals[idx] = nxt.rstrip().split("\t")
-                        chroms[idx] = current_vals[idx][0]
-                        iter_go[idx] = False
-                    else:
-                        iter_done[idx] = True
-                        chroms[idx] = None
-                if chroms[idx] == current_chrom:
-                    pos = int(current_vals[idx][1])
-                    strand = current_vals[idx][2]
-                    if pos < lowest or lowest == -1 or (isStranded and pos == lowest and strand == "+"):     # S:847
-                        lowest, lowest_strand = int(pos), strand
-                        assoc_gene = current_vals[idx][3]
-        if not all(iter_done):
-            if not any(c == current_chrom for c in chroms):                                              # S:857-866
-                pos_idx += 1
-                current_chrom = chroms_in_order[pos_idx] if pos_idx <= max_idx else None
-            else:
-                site = _MergedSite(current_chrom, lowest, assoc_gene, n)
-                site.emit = (qGene == "All" or qGene == assoc_gene)
-                strand_now = ""
-                filled_gap = False
-                for idx, vals in enumerate(current_vals):
-                    if (vals[0] == current_chrom and int(vals[1]) == lowest and not iter_done[idx]
-                            and (not isStranded or vals[2] == lowest_strand)):                            # S:870
-                        iter_go[idx] = True
-                        strand_now = str(vals[2])
-                        site.rows[idx] = ("has", vals, strand_now)
-                        for key in _eval_partners(str(vals[10])):                                           # S:889-892
-                            if key not in site.partners:
-                                site.partners.append(key)
-                        for c in _eval_competitors(str(vals[11])):                                             # S:894-897
-                            if c not in site.competitors:
-                                site.competitors.append(c)
-                                site.competitors.sort()
-                    elif site.emit:                                                                       # S:899-904
-                        filled_gap = True
-                        site.rows[idx] = ("gap", len(gaps[idx]), strand_now)
-                        gaps[idx].append((current_chrom, lowest, strand_now, list(site.partners), list(site.competitors)))
-                merged.append(site)
-                if filled_gap:
-                    filled += 1
-            lowest = -1
-    for it in iters:
-        it.close()
-
-    # ---- one batched re-count per sample
     flags = api.mode_flags(isStranded, strandedType, False, combine=True)
     own = ctx is None
-    recount = [None] * n
-    if any(gaps):
-        ctx = ctx or api.Context(0)
-    try:
-        for idx in range(n):
-            if not gaps[idx]:
-                continue
-            names = []
-            for g in gaps[idx]:
-                if g[0] not in names:
-                    names.append(g[0])
-            arg = [(names.index(g[0]), g[1], g[2], g[3], g[4]) for g in gaps[idx]]
-            if records_by_bam is not None:
-                recount[idx] = ctx.recount_records(records_by_bam(bam_paths[idx], names), len(names), arg, flags)
-            else:
-                recount[idx] = ctx.recount_bam(bam_paths[idx], names, arg, flags)
-    finally:
-        if own and ctx is not None:
-            ctx.close()
-
-    # ---- pass 2: rows (outputCombinedLines, S:722-740)
-    with open(outputPath + ".combined.tsv", "w") as out:
-        out.write(COMBINE_HEADER)
-        for site in merged:
-            if not site.emit:
-                continue
-            strand_final = ""
-            per = []
-            for idx in range(n):
-                row = site.rows[idx]
-                if row is not None:
-                    strand_final = row[2] if row[0] == "has" else strand_final
-            # the strand printed for every sample row is the site's final strand (setStrand of the last sample that has it)
-            for idx in range(n):
-                row = site.rows[idx]
-                alpha = beta1 = beta2s = beta2c = 0
-                beta2w = 0.0
-                pcounts = {}
-                if row is not None and row[0] == "has":
-                    vals = row[1]
-                    alpha, beta1, beta2s = int(vals[5]), int(vals[6]), int(vals[7])
-                    if vals[8] != "NA":
-                        beta2c, beta2w = int(vals[8]), float(vals[9])
-                    pcounts = _eval_partners(str(vals[10]))
-                elif row is not None and row[0] == "gap":
-                    b1, b2 = recount[idx]
-                    beta1, beta2s = int(b1[row[1]]), int(b2[row[1]])
-                per.append((alpha, beta1, beta2s, beta2c, beta2w, pcounts, row))
-            for idx in range(n):
-                alpha, beta1, beta2s, beta2c, beta2w, pcounts, row = per[idx]
-                sse = 0.0
-                if row is not None and row[0] == "has":                      # calculateSSE, S:626-639 (gap rows: setSSE(0.0))
-                    betas = beta1 + beta2s
-                    if isbeta2Cryptic:
-                        betas = betas + beta2w
-                    den = alpha + betas
-                    sse = (alpha / den) if den > 0.0 else 0.0
-                cols = [titles[idx], site.chrom, str(site.pos), strand_final, site.gene, "{0:.3f}".format(sse), str(alpha),
-                        str(beta1), str(beta2s)]
-                if isbeta2Cryptic:
-                    cols += [str(beta2c), str(beta2w if (row is not None and row[0] == "has" and row[1][8] != "NA") else 0.0)]
+    with CombineMerge() as cm:
+        for title, path in zip(titles, bed_paths):
+            cm.add_sample(title, path)
+        regions = cm.region_names()
+        order = _chrom_order([[regions[r] for r in cm.sample_runs(k)] for k in range(n)])
+        region_id = {name: i for i, name in enumerate(regions)}
+        cm.merge([region_id[name] for name in order], qGene, isStranded)
+        try:
+            for k in range(n):                      # one batched re-count per sample (every S:903 call of that sample)
+                gaps = cm.gaps(k)
+                if not len(gaps):
+                    continue
+                uniq, first = np.unique(gaps.chrom, return_index=True)
+                local = uniq[np.argsort(first)]     # the sample's gap regions in first-appearance order
+                names = [regions[r] for r in local]
+                remap = np.full(len(regions), -1, dtype=np.int32)
+                remap[local] = np.arange(len(local), dtype=np.int32)
+                gaps.chrom = np.ascontiguousarray(remap[gaps.chrom])
+                ctx = ctx or api.Context(0)
+                if records_by_bam is not None:
+                    b1, b2 = ctx.recount_records(records_by_bam(bam_paths[k], names), len(names), gaps, flags)
                 else:
-                    cols += ["NA", "NA"]
-                cols += [str({k: int(pcounts.get(k, 0)) for k in site.partners}), str(site.competitors)]
-                out.write("\t".join(cols) + "\n")
+                    b1, b2 = ctx.recount_bam(bam_paths[k], names, gaps, flags)
+                cm.set_recount(k, b1, b2)
+        finally:
+            if own and ctx is not None:
+                ctx.close()
+        cm.write(outputPath + ".combined.tsv", isbeta2Cryptic)
+        filled = cm.n_filled()
     print("Filled in Beta read counts for {} Sites not detected in some samples".format(filled))
 
 

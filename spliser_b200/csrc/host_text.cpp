@@ -1,0 +1,780 @@
+// host_text.cpp -- the text side of the CLI, native: Gene column lookup, the .SpliSER.tsv writer and the `combine`
+// merge driver.  Host only, no CUDA: once the counting takes tens of milliseconds the
+// per-row Python string work around it (seconds) is what a user waits for.
+//
+// Restates, inside /root/reference/SpliSER_v0_1_8.py ("S:"): binary_gene_search (S:118-173), outputBedFile (S:641-664),
+// outputCombinedLines (S:722-740) and the lock-step merge of combine (S:791-917) with its order dependence (a gap of
+// sample k sees the partners / competitors / strand collected from the samples before k only).  Output is
+// byte-identical to the reference's: Python's str(int), "{:.3f}" / "{:.5f}" (correctly rounded, like glibc printf),
+// str(float) (shortest round-trip digits, exponent form outside 1e-4 <= |v| < 1e16), str(dict), str(list).
+#include <charconv>
+#include <cerrno>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <string_view>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/spliser_b200.h"
+
+namespace {
+
+void set_err(char* err, int err_len, const char* fmt, ...) {
+    if (!err || err_len <= 0) return;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, (size_t)err_len, fmt, ap);
+    va_end(ap);
+}
+
+// ---- buffered text output -----------------------------------------------------------------------------------------
+struct Out {
+    FILE* f = nullptr;
+    std::vector<char> buf;
+    size_t n = 0;
+    bool bad = false;
+    explicit Out(FILE* fp) : f(fp), buf(1 << 20) {}
+    void flush() {
+        if (n && fwrite(buf.data(), 1, n, f) != n) bad = true;
+        n = 0;
+    }
+    char* room(size_t need) {
+        if (n + need > buf.size()) flush();
+        if (need > buf.size()) buf.resize(need);
+        return buf.data() + n;
+    }
+    void put(const char* s, size_t len) {
+        memcpy(room(len), s, len);
+        n += len;
+    }
+    void put(std::string_view s) { put(s.data(), s.size()); }
+    void ch(char c) { *room(1) = c; n += 1; }
+    void i64(long long v) {                                   // str(int)
+        char* p = room(24);
+        auto r = std::to_chars(p, p + 24, v);
+        n += (size_t)(r.ptr - p);
+    }
+    void fixed(double v, int prec) {                          // "{0:.<prec>f}".format(v)
+        char* p = room(400);
+        n += (size_t)snprintf(p, 400, "%.*f", prec, v);
+    }
+    void pyfloat(double v) {                                  // str(float)
+        char* p = room(40);
+        if (v != v) { memcpy(p, "nan", 3); n += 3; return; }
+        if (v == 0.0) { size_t k = std::signbit(v) ? 4 : 3; memcpy(p, std::signbit(v) ? "-0.0" : "0.0", k); n += k; return; }
+        if (v - v != 0.0) { size_t k = v < 0 ? 4 : 3; memcpy(p, v < 0 ? "-inf" : "inf", k); n += k; return; }
+        char t[40];
+        auto r = std::to_chars(t, t + 40, v, std::chars_format::scientific);   // shortest round trip: [-]d[.ddd]e[+-]XX
+        size_t len = (size_t)(r.ptr - t);
+        size_t epos = 0;
+        while (epos < len && t[epos] != 'e') ++epos;
+        int e10 = atoi(std::string(t + epos + 1, len - epos - 1).c_str());
+        if (e10 < -4 || e10 >= 16) { memcpy(p, t, len); n += len; return; }    // float_repr_style 'r': exponent form
+        char* q = p;
+        size_t i = 0;
+        if (t[0] == '-') { *q++ = '-'; i = 1; }
+        char dig[24];
+        int nd = 0;
+        for (; i < epos; ++i) if (t[i] != '.') dig[nd++] = t[i];
+        int decpt = e10 + 1;
+        if (decpt <= 0) {
+            *q++ = '0'; *q++ = '.';
+            for (int z = 0; z < -decpt; ++z) *q++ = '0';
+            memcpy(q, dig, (size_t)nd); q += nd;
+        } else if (decpt >= nd) {
+            memcpy(q, dig, (size_t)nd); q += nd;
+            for (int z = 0; z < decpt - nd; ++z) *q++ = '0';
+            *q++ = '.'; *q++ = '0';
+        } else {
+            memcpy(q, dig, (size_t)decpt); q += decpt;
+            *q++ = '.';
+            memcpy(q, dig + decpt, (size_t)(nd - decpt)); q += nd - decpt;
+        }
+        n += (size_t)(q - p);
+    }
+};
+
+inline std::string_view tab_get(const spl_strtab* t, int64_t i) {
+    return std::string_view(t->blob + t->off[i], (size_t)(t->off[i + 1] - t->off[i]));
+}
+
+inline long long floordiv2(long long a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
+
+}  // namespace
+
+// ======================================================================================================= gene lookup
+extern "C" int spl_gene_search(int64_t n_genes, const int32_t* g_left, const int32_t* g_right, const int32_t* g_strand,
+                               int64_t n, const int32_t* pos, const int32_t* strand, int32_t plus_id, int32_t minus_id,
+                               int is_stranded, int32_t* out_idx) {
+    if (n_genes < 0 || n < 0 || (n_genes && (!g_left || !g_right || !g_strand)) || (n && (!pos || !strand || !out_idx)))
+        return SPL_ERR_ARG;
+    const long long length = n_genes;
+    for (int64_t s = 0; s < n; ++s) {
+        if (length == 0) { out_idx[s] = -1; continue; }
+        const long long p = pos[s];
+        const int32_t st = strand[s];
+        const bool any_strand = !is_stranded || (st != plus_id && st != minus_id);
+        auto strand_ok = [&](long long k) { return st == g_strand[k] || any_strand; };
+        long long idx = length / 2, past_max = length, past_min = 0, last_idx = -1, new_idx = idx;
+        bool stuck = false, found = false;
+        while (!stuck && !found) {                                          // S:142-160
+            const long long gl = g_left[idx], gr = g_right[idx];
+            if (p >= gl && p <= gr && strand_ok(idx)) { found = true; break; }
+            else if (p >= gr) { new_idx = idx + floordiv2(past_max - idx); past_min = idx; }
+            else if (p <= gl) { new_idx = idx - floordiv2(idx - past_min); past_max = idx; if (idx == 1) new_idx = 0; }
+            if (idx != last_idx) { last_idx = idx; idx = new_idx; }
+            else stuck = true;
+        }
+        if (!found && stuck) {                                              // S:162-169: the window moves with idx
+            for (int i = -3; i < 3; ++i) {
+                const long long k = idx + i;
+                if (k >= 0 && k < length - 1 && p >= g_left[k] && p <= g_right[k] && strand_ok(k)) {
+                    found = true; stuck = false; idx = k;
+                }
+            }
+        }
+        out_idx[s] = (found && !stuck) ? (int32_t)idx : -1;
+    }
+    return SPL_OK;
+}
+
+// ================================================================================================== .SpliSER.tsv writer
+namespace {
+const char PROCESS_HEADER[] =
+    "Region\tSite\tStrand\tGene\tSSE\talpha_count\tbeta1_count\tbeta2Simple_count\tbeta2Cryptic_count\t"
+    "beta2Cryptic_weighted\tPartners\tCompetitors\n";
+const char COMBINE_HEADER[] =
+    "Sample\tRegion\tSite\tStrand\tGene\tSSE\talpha_count\tbeta1_count\tbeta2Simple_count\tbeta2Cryptic_count\t"
+    "beta2_weighted\tPartners\tCompetitors\n";
+}
+
+extern "C" int spl_write_process_tsv(const char* path, const spl_site_columns* t, const spl_strtab* chrom_names,
+                                     const spl_strtab* strand_texts, const int32_t* line_strand,
+                                     const spl_strtab* gene_names, const int32_t* site_gene, int cryptic,
+                                     char* err, int err_len) {
+    if (!path || !t || !chrom_names || !strand_texts || (t->n_sites && !line_strand)) {
+        set_err(err, err_len, "spl_write_process_tsv: null argument");
+        return SPL_ERR_ARG;
+    }
+    FILE* f = fopen(path, "w");
+    if (!f) { set_err(err, err_len, "cannot open %s: %s", path, strerror(errno)); return SPL_ERR_IO; }
+    Out o(f);
+    o.put(PROCESS_HEADER, sizeof(PROCESS_HEADER) - 1);
+    for (int64_t i = 0; i < t->n_sites; ++i) {
+        const int32_t ci = t->chrom[i];
+        const int32_t sid = line_strand[t->first_line[i]];
+        if (ci < 0 || ci >= chrom_names->n || sid < 0 || sid >= strand_texts->n ||
+            (site_gene && gene_names && site_gene[i] >= gene_names->n)) {
+            fclose(f);
+            set_err(err, err_len, "spl_write_process_tsv: site %lld refers to a name outside its table", (long long)i);
+            return SPL_ERR_ARG;
+        }
+        o.put(tab_get(chrom_names, ci)); o.ch('\t');
+        o.i64(t->pos[i]); o.ch('\t');
+        o.put(tab_get(strand_texts, sid)); o.ch('\t');
+        if (site_gene && gene_names && site_gene[i] >= 0) o.put(tab_get(gene_names, site_gene[i]));
+        else o.put("NA", 2);
+        o.ch('\t');
+        o.fixed(t->sse[i], 3); o.ch('\t');
+        o.i64(t->alpha[i]); o.ch('\t');
+        o.i64(t->beta1[i]); o.ch('\t');
+        o.i64(t->beta2simple[i]); o.ch('\t');
+        if (cryptic) {
+            o.i64(t->beta2cryptic[i]); o.ch('\t');
+            o.fixed(t->beta2weighted[i], 5); o.ch('\t');
+        } else {
+            o.put("NA\tNA\t", 6);
+        }
+        o.ch('{');                                                           // str(dict): PartnerCounts, S:662
+        for (int64_t e = t->partner_off[i]; e < t->partner_off[i + 1]; ++e) {
+            if (e > t->partner_off[i]) o.put(", ", 2);
+            o.i64(t->partner_pos[e]); o.put(": ", 2); o.i64(t->partner_cnt[e]);
+        }
+        o.put("}\t[", 3);                                                    // str(list): CompetitorPos, S:663
+        for (int64_t e = t->comp_off[i]; e < t->comp_off[i + 1]; ++e) {
+            if (e > t->comp_off[i]) o.put(", ", 2);
+            o.i64(t->comp_pos[e]);
+        }
+        o.put("]\n", 2);
+    }
+    o.flush();
+    const bool bad = o.bad;
+    if (fclose(f) != 0 || bad) { set_err(err, err_len, "write to %s failed", path); return SPL_ERR_IO; }
+    return SPL_OK;
+}
+
+// ======================================================================================================= combine merge
+namespace {
+
+struct Interner {
+    std::unordered_map<std::string, int32_t> map;
+    std::vector<std::string> names;
+    int32_t id(std::string_view s) {
+        auto it = map.find(std::string(s));
+        if (it != map.end()) return it->second;
+        int32_t k = (int32_t)names.size();
+        names.emplace_back(s);
+        map.emplace(names.back(), k);
+        return k;
+    }
+};
+
+struct Sample {
+    std::string title;
+    // one entry per data row of the .SpliSER.tsv, file order
+    std::vector<int32_t> region, pos, strand, gene;
+    std::vector<int64_t> alpha, beta1, beta2s, beta2c;
+    std::vector<double> beta2w;
+    std::vector<uint8_t> has_cryptic;                  // column 8 != "NA"
+    std::vector<int64_t> p_off, c_off;                 // CSR of the Partners / Competitors columns
+    std::vector<int32_t> p_key, c_key;
+    std::vector<int64_t> p_cnt;
+    std::vector<int32_t> runs;                         // consecutive distinct regions (for the region order, S:761-789)
+    // gaps of this sample in the argument layout of spl_recount
+    std::vector<int32_t> g_region, g_pos;
+    std::vector<uint8_t> g_strand;
+    std::vector<int64_t> gp_off{0}, gc_off{0};
+    std::vector<int32_t> gp_pos, gc_pos;
+    std::vector<int64_t> r_beta1, r_beta2s;            // re-count results handed back by the caller
+    bool have_recount = false;
+};
+
+struct Merged {
+    int32_t region, pos, gene;
+    int64_t cell;                                      // first of n_samples entries in `cells`
+    int64_t part_off, comp_off;                        // final unions in `u_part` / `u_comp`
+};
+
+}  // namespace
+
+struct spl_combine {
+    Interner regions, strands, genes;
+    std::vector<Sample> samples;
+    std::vector<Merged> merged;
+    std::vector<int64_t> cells;                        // per (merged site, sample): row index, or -(gap id)-2, or -1 = not emitted
+    std::vector<int32_t> u_part, u_comp;
+    std::vector<int64_t> u_part_end, u_comp_end;
+    int64_t n_filled = 0;
+    bool merged_done = false;
+    std::string err;
+};
+
+namespace {
+
+// int(text) for the plain decimal forms a .SpliSER.tsv holds
+bool parse_i64(std::string_view s, int64_t* out) {
+    while (!s.empty() && (s.front() == ' ')) s.remove_prefix(1);
+    while (!s.empty() && (s.back() == ' ')) s.remove_suffix(1);
+    if (!s.empty() && s.front() == '+') s.remove_prefix(1);
+    if (s.empty()) return false;
+    long long v = 0;
+    auto r = std::from_chars(s.data(), s.data() + s.size(), v);
+    if (r.ec != std::errc() || r.ptr != s.data() + s.size()) return false;
+    *out = v;
+    return true;
+}
+
+bool parse_f64(std::string_view s, double* out) {
+    std::string z(s);
+    char* end = nullptr;
+    errno = 0;
+    double v = strtod(z.c_str(), &end);
+    if (end == z.c_str()) return false;
+    while (*end == ' ') ++end;
+    if (*end) return false;
+    *out = v;
+    return true;
+}
+
+// "{200: 5, 300: 3}" -> keys / counts;  "[200, 300]" -> keys
+bool parse_partners(std::string_view s, std::vector<int32_t>& key, std::vector<int64_t>& cnt) {
+    while (!s.empty() && s.front() == ' ') s.remove_prefix(1);
+    while (!s.empty() && s.back() == ' ') s.remove_suffix(1);
+    if (s.size() < 2 || s.front() != '{' || s.back() != '}') return false;
+    s = s.substr(1, s.size() - 2);
+    if (s.find_first_not_of(' ') == std::string_view::npos) return true;
+    size_t first = key.size();
+    while (true) {
+        size_t comma = s.find(',');
+        std::string_view item = s.substr(0, comma);
+        size_t colon = item.find(':');
+        if (colon == std::string_view::npos) return false;
+        int64_t k, c;
+        if (!parse_i64(item.substr(0, colon), &k) || !parse_i64(item.substr(colon + 1), &c)) return false;
+        bool dup = false;                                  // a dict keeps the first position of a repeated key, the last value
+        for (size_t e = first; e < key.size(); ++e) if (key[e] == (int32_t)k) { cnt[e] = c; dup = true; }
+        if (!dup) { key.push_back((int32_t)k); cnt.push_back(c); }
+        if (comma == std::string_view::npos) break;
+        s.remove_prefix(comma + 1);
+    }
+    return true;
+}
+
+bool parse_competitors(std::string_view s, std::vector<int32_t>& key) {
+    while (!s.empty() && s.front() == ' ') s.remove_prefix(1);
+    while (!s.empty() && s.back() == ' ') s.remove_suffix(1);
+    if (s.size() < 2 || s.front() != '[' || s.back() != ']') return false;
+    s = s.substr(1, s.size() - 2);
+    if (s.find_first_not_of(' ') == std::string_view::npos) return true;
+    while (true) {
+        size_t comma = s.find(',');
+        int64_t k;
+        if (!parse_i64(s.substr(0, comma), &k)) return false;
+        key.push_back((int32_t)k);
+        if (comma == std::string_view::npos) break;
+        s.remove_prefix(comma + 1);
+    }
+    return true;
+}
+
+bool read_file(const char* path, std::string& data) {
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    char chunk[1 << 16];
+    size_t k;
+    while ((k = fread(chunk, 1, sizeof chunk, f)) > 0) data.append(chunk, k);
+    bool ok = !ferror(f);
+    fclose(f);
+    return ok;
+}
+
+inline bool is_py_space(char c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r' || c == '\v' || c == '\f'; }
+
+}  // namespace
+
+extern "C" int spl_combine_create(spl_combine** out) {
+    if (!out) return SPL_ERR_ARG;
+    *out = new (std::nothrow) spl_combine();
+    return *out ? SPL_OK : SPL_ERR_NOMEM;
+}
+
+extern "C" void spl_combine_destroy(spl_combine* c) { delete c; }
+
+extern "C" const char* spl_combine_last_error(const spl_combine* c) { return c ? c->err.c_str() : "null spl_combine"; }
+
+// One sample = one row of the samples file (S:750-759): its title and its .SpliSER.tsv.  The header line is skipped
+// (S:799-800); every other line is rstrip()ped and split on tabs (S:836) and must have the twelve columns of S:643.
+extern "C" int spl_combine_add_sample(spl_combine* c, const char* title, const char* tsv_path) {
+    if (!c || !title || !tsv_path) return SPL_ERR_ARG;
+    if (c->merged_done) { c->err = "spl_combine_add_sample after spl_combine_merge"; return SPL_ERR_ARG; }
+    std::string data;
+    if (!read_file(tsv_path, data)) { c->err = std::string("cannot read ") + tsv_path; return SPL_ERR_IO; }
+    Sample s;
+    s.title = title;
+    s.p_off.push_back(0);
+    s.c_off.push_back(0);
+    size_t at = 0, line_no = 0;
+    int32_t last_region = -1;
+    try {
+        while (at < data.size()) {
+            size_t nl = data.find('\n', at);
+            size_t end = nl == std::string::npos ? data.size() : nl;
+            std::string_view line(data.data() + at, end - at);
+            at = nl == std::string::npos ? data.size() : nl + 1;
+            if (line_no++ == 0) continue;
+            while (!line.empty() && is_py_space(line.back())) line.remove_suffix(1);
+            std::string_view col[12];
+            int nc = 0;
+            size_t p = 0;
+            while (nc < 12) {
+                size_t tab = line.find('\t', p);
+                col[nc++] = line.substr(p, tab == std::string_view::npos ? std::string_view::npos : tab - p);
+                if (tab == std::string_view::npos) break;
+                p = tab + 1;
+            }
+            if (nc < 12) {
+                c->err = std::string(tsv_path) + ": line " + std::to_string(line_no) + " has fewer than 12 tab-separated columns";
+                return SPL_ERR_ARG;
+            }
+            size_t extra = col[11].find('\t');                      // further columns are ignored (vals[11] is the 12th)
+            if (extra != std::string_view::npos) col[11] = col[11].substr(0, extra);
+            int64_t pos, a, b1, b2, bc = 0;
+            double bw = 0.0;
+            bool ok = parse_i64(col[1], &pos) && parse_i64(col[5], &a) && parse_i64(col[6], &b1) && parse_i64(col[7], &b2);
+            const bool has_c = col[8] != "NA";
+            if (ok && has_c) ok = parse_i64(col[8], &bc) && parse_f64(col[9], &bw);
+            ok = ok && parse_partners(col[10], s.p_key, s.p_cnt) && parse_competitors(col[11], s.c_key);
+            if (!ok) {
+                c->err = std::string(tsv_path) + ": line " + std::to_string(line_no) + " is not a .SpliSER.tsv row";
+                return SPL_ERR_ARG;
+            }
+            const int32_t rid = c->regions.id(col[0]);
+            if (rid != last_region) { s.runs.push_back(rid); last_region = rid; }
+            s.region.push_back(rid);
+            s.pos.push_back((int32_t)pos);
+            s.strand.push_back(c->strands.id(col[2]));
+            s.gene.push_back(c->genes.id(col[3]));
+            s.alpha.push_back(a); s.beta1.push_back(b1); s.beta2s.push_back(b2); s.beta2c.push_back(bc);
+            s.beta2w.push_back(bw);
+            s.has_cryptic.push_back(has_c ? 1 : 0);
+            s.p_off.push_back((int64_t)s.p_key.size());
+            s.c_off.push_back((int64_t)s.c_key.size());
+        }
+    } catch (const std::bad_alloc&) {
+        c->err = "out of memory";
+        return SPL_ERR_NOMEM;
+    }
+    c->samples.push_back(std::move(s));
+    return SPL_OK;
+}
+
+extern "C" int64_t spl_combine_n_samples(const spl_combine* c) { return c ? (int64_t)c->samples.size() : 0; }
+extern "C" int64_t spl_combine_n_regions(const spl_combine* c) { return c ? (int64_t)c->regions.names.size() : 0; }
+extern "C" const char* spl_combine_region_name(const spl_combine* c, int64_t i) {
+    return (c && i >= 0 && i < (int64_t)c->regions.names.size()) ? c->regions.names[(size_t)i].c_str() : nullptr;
+}
+extern "C" int64_t spl_combine_sample_rows(const spl_combine* c, int64_t sample) {
+    return (c && sample >= 0 && sample < (int64_t)c->samples.size()) ? (int64_t)c->samples[(size_t)sample].pos.size() : -1;
+}
+extern "C" int64_t spl_combine_sample_runs(const spl_combine* c, int64_t sample, const int32_t** runs) {
+    if (!c || sample < 0 || sample >= (int64_t)c->samples.size()) return -1;
+    const Sample& s = c->samples[(size_t)sample];
+    if (runs) *runs = s.runs.data();
+    return (int64_t)s.runs.size();
+}
+
+// The lock-step merge (S:791-917).  region_order = chromsInOrder (S:761-789) as region ids; qgene NULL = "All".
+extern "C" int spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t* region_order, const char* qgene,
+                                 int is_stranded) {
+    if (!c || n_order <= 0 || !region_order) { if (c) c->err = "spl_combine_merge: empty region order"; return SPL_ERR_ARG; }
+    if (c->merged_done) { c->err = "spl_combine_merge called twice"; return SPL_ERR_ARG; }
+    const size_t n = c->samples.size();
+    if (n == 0) { c->err = "spl_combine_merge: no samples"; return SPL_ERR_ARG; }
+    const int32_t NONE = -2, INITIAL = -3;                 // chroms[idx] = None (iterator done) / '' (nothing read yet)
+    const int32_t plus_id = c->strands.map.count("+") ? c->strands.map["+"] : -9;
+    int32_t qgene_id = -1;
+    bool all_genes = (qgene == nullptr);
+    if (!all_genes) { auto it = c->genes.map.find(qgene); qgene_id = it == c->genes.map.end() ? -9 : it->second; }
+    std::vector<int64_t> cur(n, -1), nrows(n);
+    std::vector<int32_t> chroms(n, INITIAL);
+    std::vector<char> go(n, 1), done(n, 0);
+    for (size_t k = 0; k < n; ++k) nrows[k] = (int64_t)c->samples[k].pos.size();
+    int64_t order_at = 0;
+    int32_t current = region_order[0];
+    int64_t lowest = -1;
+    int32_t lowest_strand = -1;
+    size_t n_done = 0;
+    std::vector<int32_t> part, comp;
+    try {
+        while (n_done < n) {
+            int32_t assoc_gene = -1;                                              // ""
+            for (size_t k = 0; k < n; ++k) {                                      // S:827-855
+                if (done[k]) continue;
+                Sample& s = c->samples[k];
+                if (go[k]) {
+                    if (cur[k] + 1 < nrows[k]) { ++cur[k]; chroms[k] = s.region[(size_t)cur[k]]; go[k] = 0; }
+                    else { done[k] = 1; ++n_done; chroms[k] = NONE; }
+                }
+                if (chroms[k] == current && chroms[k] >= 0) {
+                    const int64_t p = s.pos[(size_t)cur[k]];
+                    const int32_t st = s.strand[(size_t)cur[k]];
+                    if (p < lowest || lowest == -1 || (is_stranded && p == lowest && st == plus_id)) {   // S:847
+                        lowest = p; lowest_strand = st; assoc_gene = s.gene[(size_t)cur[k]];
+                    }
+                }
+            }
+            if (n_done < n) {
+                bool any_here = false;
+                for (size_t k = 0; k < n; ++k) if (chroms[k] == current && chroms[k] >= 0) any_here = true;
+                if (!any_here) {                                                  // S:857-866
+                    if (++order_at >= n_order) {
+                        c->err = "spl_combine_merge: rows remain on a region that is not in the region order";
+                        return SPL_ERR_ARG;
+                    }
+                    current = region_order[order_at];
+                } else {
+                    const bool emit = all_genes || (assoc_gene == qgene_id);
+                    Merged m;
+                    m.region = current; m.pos = (int32_t)lowest; m.gene = assoc_gene;
+                    m.cell = emit ? (int64_t)c->cells.size() : -1;
+                    if (emit) c->cells.resize(c->cells.size() + n, -1);
+                    part.clear(); comp.clear();
+                    int32_t strand_now = -1;                                      // ''
+                    bool filled_gap = false;
+                    for (size_t k = 0; k < n; ++k) {                              // S:868-904
+                        Sample& s = c->samples[k];
+                        const int64_t r = cur[k];
+                        const bool has = !done[k] && r >= 0 && s.region[(size_t)r] == current && s.pos[(size_t)r] == lowest &&
+                                         (!is_stranded || s.strand[(size_t)r] == lowest_strand);
+                        if (has) {
+                            go[k] = 1;
+                            strand_now = s.strand[(size_t)r];
+                            if (emit) c->cells[(size_t)m.cell + k] = r;
+                            for (int64_t e = s.p_off[(size_t)r]; e < s.p_off[(size_t)r + 1]; ++e) {          // S:889-892
+                                bool seen = false;
+                                for (int32_t q : part) if (q == s.p_key[(size_t)e]) { seen = true; break; }
+                                if (!seen) part.push_back(s.p_key[(size_t)e]);
+                            }
+                            for (int64_t e = s.c_off[(size_t)r]; e < s.c_off[(size_t)r + 1]; ++e) {          // S:894-897
+                                const int32_t v = s.c_key[(size_t)e];
+                                size_t at = 0;
+                                while (at < comp.size() && comp[at] < v) ++at;
+                                if (at == comp.size() || comp[at] != v) comp.insert(comp.begin() + (long)at, v);
+                            }
+                        } else if (emit) {                                        // S:899-904: a gap of sample k
+                            filled_gap = true;
+                            c->cells[(size_t)m.cell + k] = -(int64_t)s.g_pos.size() - 2;
+                            s.g_region.push_back(current);
+                            s.g_pos.push_back((int32_t)lowest);
+                            const std::string* sn = strand_now >= 0 ? &c->strands.names[(size_t)strand_now] : nullptr;
+                            s.g_strand.push_back((sn && !sn->empty()) ? (uint8_t)(*sn)[0] : 0);
+                            s.gp_pos.insert(s.gp_pos.end(), part.begin(), part.end());
+                            s.gc_pos.insert(s.gc_pos.end(), comp.begin(), comp.end());
+                            s.gp_off.push_back((int64_t)s.gp_pos.size());
+                            s.gc_off.push_back((int64_t)s.gc_pos.size());
+                        }
+                    }
+                    if (emit) {
+                        m.part_off = (int64_t)c->u_part.size();
+                        m.comp_off = (int64_t)c->u_comp.size();
+                        c->u_part.insert(c->u_part.end(), part.begin(), part.end());
+                        c->u_comp.insert(c->u_comp.end(), comp.begin(), comp.end());
+                        c->u_part_end.push_back((int64_t)c->u_part.size());
+                        c->u_comp_end.push_back((int64_t)c->u_comp.size());
+                        c->merged.push_back(m);
+                        if (filled_gap) ++c->n_filled;
+                    }
+                }
+            }
+            lowest = -1;
+        }
+    } catch (const std::bad_alloc&) {
+        c->err = "out of memory";
+        return SPL_ERR_NOMEM;
+    }
+    c->merged_done = true;
+    return SPL_OK;
+}
+
+extern "C" int64_t spl_combine_n_sites(const spl_combine* c) { return c ? (int64_t)c->merged.size() : 0; }
+extern "C" int64_t spl_combine_n_filled(const spl_combine* c) { return c ? c->n_filled : 0; }
+
+extern "C" int64_t spl_combine_gaps(const spl_combine* c, int64_t sample, const int32_t** s_region, const int32_t** s_pos,
+                                    const uint8_t** s_strand, const int64_t** p_off, const int32_t** p_pos,
+                                    const int64_t** c_off, const int32_t** c_pos) {
+    if (!c || !c->merged_done || sample < 0 || sample >= (int64_t)c->samples.size()) return -1;
+    const Sample& s = c->samples[(size_t)sample];
+    if (s_region) *s_region = s.g_region.data();
+    if (s_pos) *s_pos = s.g_pos.data();
+    if (s_strand) *s_strand = s.g_strand.data();
+    if (p_off) *p_off = s.gp_off.data();
+    if (p_pos) *p_pos = s.gp_pos.data();
+    if (c_off) *c_off = s.gc_off.data();
+    if (c_pos) *c_pos = s.gc_pos.data();
+    return (int64_t)s.g_pos.size();
+}
+
+extern "C" int spl_combine_set_recount(spl_combine* c, int64_t sample, int64_t n_gaps, const int64_t* beta1,
+                                       const int64_t* beta2simple) {
+    if (!c || !c->merged_done || sample < 0 || sample >= (int64_t)c->samples.size()) return SPL_ERR_ARG;
+    Sample& s = c->samples[(size_t)sample];
+    if (n_gaps != (int64_t)s.g_pos.size() || (n_gaps && (!beta1 || !beta2simple))) {
+        c->err = "spl_combine_set_recount: gap count differs from spl_combine_gaps";
+        return SPL_ERR_ARG;
+    }
+    s.r_beta1.assign(beta1, beta1 + n_gaps);
+    s.r_beta2s.assign(beta2simple, beta2simple + n_gaps);
+    s.have_recount = true;
+    return SPL_OK;
+}
+
+// outputCombinedLines for every merged site (S:722-740, called at S:912-915)
+extern "C" int spl_combine_write(spl_combine* c, const char* path, int cryptic) {
+    if (!c || !path) return SPL_ERR_ARG;
+    if (!c->merged_done) { c->err = "spl_combine_write before spl_combine_merge"; return SPL_ERR_ARG; }
+    const size_t n = c->samples.size();
+    for (size_t k = 0; k < n; ++k)
+        if (!c->samples[k].g_pos.empty() && !c->samples[k].have_recount) {
+            c->err = "spl_combine_write: sample " + std::to_string(k) + " has gaps without re-count results";
+            return SPL_ERR_ARG;
+        }
+    FILE* f = fopen(path, "w");
+    if (!f) { c->err = std::string("cannot open ") + path + ": " + strerror(errno); return SPL_ERR_IO; }
+    Out o(f);
+    o.put(COMBINE_HEADER, sizeof(COMBINE_HEADER) - 1);
+    for (size_t mi = 0; mi < c->merged.size(); ++mi) {
+        const Merged& m = c->merged[mi];
+        const int64_t* cell = &c->cells[(size_t)m.cell];
+        int32_t strand_final = -1;                          // Site.setStrand by every sample that has the site (S:873)
+        for (size_t k = 0; k < n; ++k)
+            if (cell[k] >= 0) strand_final = c->samples[k].strand[(size_t)cell[k]];
+        const int32_t* part = c->u_part.data() + m.part_off;
+        const size_t n_part = (size_t)(c->u_part_end[mi] - m.part_off);
+        const int32_t* comp = c->u_comp.data() + m.comp_off;
+        const size_t n_comp = (size_t)(c->u_comp_end[mi] - m.comp_off);
+        for (size_t k = 0; k < n; ++k) {
+            const Sample& s = c->samples[k];
+            long long alpha = 0, beta1 = 0, beta2s = 0, beta2c = 0;
+            double beta2w = 0.0, sse = 0.0;
+            const int64_t r = cell[k];
+            bool cryptic_row = false;
+            if (r >= 0) {
+                alpha = s.alpha[(size_t)r]; beta1 = s.beta1[(size_t)r]; beta2s = s.beta2s[(size_t)r];
+                if (s.has_cryptic[(size_t)r]) { beta2c = s.beta2c[(size_t)r]; beta2w = s.beta2w[(size_t)r]; cryptic_row = true; }
+                if (cryptic) {                              // calculateSSE (S:626-639)
+                    double betas = (double)(beta1 + beta2s) + beta2w;
+                    double den = (double)alpha + betas;
+                    sse = den > 0.0 ? (double)alpha / den : 0.0;
+                } else {
+                    long long den = alpha + beta1 + beta2s;
+                    sse = den > 0 ? (double)alpha / (double)den : 0.0;
+                }
+            } else if (r <= -2) {
+                const size_t g = (size_t)(-r - 2);
+                beta1 = s.r_beta1[g]; beta2s = s.r_beta2s[g];
+            }
+            o.put(s.title); o.ch('\t');
+            o.put(c->regions.names[(size_t)m.region]); o.ch('\t');
+            o.i64(m.pos); o.ch('\t');
+            if (strand_final >= 0) o.put(c->strands.names[(size_t)strand_final]);
+            o.ch('\t');
+            if (m.gene >= 0) o.put(c->genes.names[(size_t)m.gene]);
+            o.ch('\t');
+            o.fixed(sse, 3); o.ch('\t');
+            o.i64(alpha); o.ch('\t'); o.i64(beta1); o.ch('\t'); o.i64(beta2s); o.ch('\t');
+            if (cryptic) { o.i64(beta2c); o.ch('\t'); o.pyfloat(cryptic_row ? beta2w : 0.0); o.ch('\t'); }
+            else o.put("NA\tNA\t", 6);
+            o.ch('{');
+            for (size_t e = 0; e < n_part; ++e) {
+                long long cnt = 0;
+                if (r >= 0)
+                    for (int64_t q = s.p_off[(size_t)r]; q < s.p_off[(size_t)r + 1]; ++q)
+                        if (s.p_key[(size_t)q] == part[e]) { cnt = s.p_cnt[(size_t)q]; break; }
+                if (e) o.put(", ", 2);
+                o.i64(part[e]); o.put(": ", 2); o.i64(cnt);
+            }
+            o.put("}\t[", 3);
+            for (size_t e = 0; e < n_comp; ++e) {
+                if (e) o.put(", ", 2);
+                o.i64(comp[e]);
+            }
+            o.put("]\n", 2);
+        }
+    }
+    o.flush();
+    const bool bad = o.bad;
+    if (fclose(f) != 0 || bad) { c->err = std::string("write to ") + path + " failed"; return SPL_ERR_IO; }
+    return SPL_OK;
+}
+
+// ===================================================================================================== BED12 junctions
+// The text half of findAlphaCounts (S:255-288): lines with exactly 12 tab-separated fields (S:259), chromosome index in
+// first-appearance order appended to what the annotation registered (S:90-92, S:265-268), -c filter (S:269), left /
+// right site positions and score (S:274-277), -g window (S:279-288).
+struct spl_bed {
+    std::vector<int32_t> chrom, left, right, strand_id;
+    std::vector<int64_t> score;
+    std::vector<uint8_t> strand;
+    Interner chroms, strand_texts;
+};
+
+namespace {
+// int(text): optional surrounding blanks, optional sign, decimal digits
+bool bed_int(std::string_view s, long long* out) {
+    while (!s.empty() && is_py_space(s.front())) s.remove_prefix(1);
+    while (!s.empty() && is_py_space(s.back())) s.remove_suffix(1);
+    if (!s.empty() && s.front() == '+') { s.remove_prefix(1); if (!s.empty() && s.front() == '-') return false; }
+    if (s.empty()) return false;
+    auto r = std::from_chars(s.data(), s.data() + s.size(), *out);
+    return r.ec == std::errc() && r.ptr == s.data() + s.size();
+}
+}  // namespace
+
+extern "C" int spl_bed_parse(const char* text, int64_t len, const spl_strtab* chrom_index, const char* qchrom,
+                             int use_gene_window, int64_t gene_left, int64_t gene_right, int64_t max_intron,
+                             spl_bed** out, char* err, int err_len) {
+    if (!out || len < 0 || (len && !text)) { set_err(err, err_len, "spl_bed_parse: null argument"); return SPL_ERR_ARG; }
+    spl_bed* b = new (std::nothrow) spl_bed();
+    if (!b) return SPL_ERR_NOMEM;
+    try {
+        if (chrom_index)
+            for (int64_t i = 0; i < chrom_index->n; ++i) b->chroms.id(tab_get(chrom_index, i));
+        const std::string_view q = qchrom ? std::string_view(qchrom) : std::string_view();
+        int64_t at = 0, line_no = 0;
+        while (at < len) {
+            const char* nl = (const char*)memchr(text + at, '\n', (size_t)(len - at));
+            const int64_t end = nl ? (nl - text) : len;
+            std::string_view line(text + at, (size_t)(end - at));
+            at = nl ? end + 1 : len;
+            ++line_no;
+            std::string_view col[12];
+            int nc = 0;
+            size_t p = 0;
+            bool more = false;
+            while (true) {
+                size_t tab = line.find('\t', p);
+                if (nc == 12) { more = true; break; }
+                col[nc++] = line.substr(p, tab == std::string_view::npos ? std::string_view::npos : tab - p);
+                if (tab == std::string_view::npos) break;
+                p = tab + 1;
+            }
+            if (nc != 12 || more) continue;                                  // S:259
+            const int32_t ci = b->chroms.id(col[0]);                         // registered before the -c test (S:265-269)
+            if (qchrom && col[0] != q) continue;
+            std::string_view sizes = col[10];
+            size_t comma = sizes.find(',');
+            if (comma == std::string_view::npos) {
+                set_err(err, err_len, "BED line %lld: blockSizes needs two values", (long long)line_no);
+                delete b;
+                return SPL_ERR_ARG;
+            }
+            std::string_view second = sizes.substr(comma + 1);
+            second = second.substr(0, second.find(','));
+            long long start, stop, a0, a1, score;
+            if (!bed_int(col[1], &start) || !bed_int(col[2], &stop) || !bed_int(sizes.substr(0, comma), &a0) ||
+                !bed_int(second, &a1) || !bed_int(col[4], &score)) {
+                set_err(err, err_len, "BED line %lld: invalid literal for int()", (long long)line_no);
+                delete b;
+                return SPL_ERR_ARG;
+            }
+            const long long left = start + a0, right = stop - a1;            // S:275-276
+            if (use_gene_window) {                                           // S:279-288
+                const bool lin = (left + max_intron >= gene_left) && (left <= gene_right);
+                const bool rin = (right - max_intron <= gene_right) && (right >= gene_left);
+                if (!(lin || rin)) continue;
+            }
+            if (left < INT32_MIN || left > INT32_MAX || right < INT32_MIN || right > INT32_MAX) {
+                set_err(err, err_len, "BED line %lld: position outside 32 bits", (long long)line_no);
+                delete b;
+                return SPL_ERR_RANGE;
+            }
+            b->chrom.push_back(ci);
+            b->left.push_back((int32_t)left);
+            b->right.push_back((int32_t)right);
+            b->score.push_back(score);
+            b->strand.push_back(col[5].empty() ? 0 : (uint8_t)col[5][0]);
+            b->strand_id.push_back(b->strand_texts.id(col[5]));
+        }
+    } catch (const std::bad_alloc&) {
+        delete b;
+        set_err(err, err_len, "out of memory");
+        return SPL_ERR_NOMEM;
+    }
+    *out = b;
+    return SPL_OK;
+}
+
+extern "C" void spl_bed_free(spl_bed* b) { delete b; }
+extern "C" int64_t spl_bed_n_junctions(const spl_bed* b) { return b ? (int64_t)b->chrom.size() : 0; }
+extern "C" const int32_t* spl_bed_chrom(const spl_bed* b) { return b->chrom.data(); }
+extern "C" const int32_t* spl_bed_left(const spl_bed* b) { return b->left.data(); }
+extern "C" const int32_t* spl_bed_right(const spl_bed* b) { return b->right.data(); }
+extern "C" const int64_t* spl_bed_score(const spl_bed* b) { return b->score.data(); }
+extern "C" const uint8_t* spl_bed_strand(const spl_bed* b) { return b->strand.data(); }
+extern "C" const int32_t* spl_bed_strand_id(const spl_bed* b) { return b->strand_id.data(); }
+extern "C" int64_t spl_bed_n_chrom(const spl_bed* b) { return b ? (int64_t)b->chroms.names.size() : 0; }
+extern "C" const char* spl_bed_chrom_name(const spl_bed* b, int64_t i, int64_t* len) {
+    if (!b || i < 0 || i >= (int64_t)b->chroms.names.size()) return nullptr;
+    if (len) *len = (int64_t)b->chroms.names[(size_t)i].size();
+    return b->chroms.names[(size_t)i].data();
+}
+extern "C" int64_t spl_bed_n_strand_texts(const spl_bed* b) { return b ? (int64_t)b->strand_texts.names.size() : 0; }
+extern "C" const char* spl_bed_strand_text(const spl_bed* b, int64_t i, int64_t* len) {
+    if (!b || i < 0 || i >= (int64_t)b->strand_texts.names.size()) return nullptr;
+    if (len) *len = (int64_t)b->strand_texts.names[(size_t)i].size();
+    return b->strand_texts.names[(size_t)i].data();
+}

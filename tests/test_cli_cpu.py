@@ -83,6 +83,40 @@ def test_combine_merge_driver_on_cpu(tmp_path, built_library):
         assert open(out + ".combined.tsv").read() == case["combined"], case.get("name", case.get("seed"))
 
 
+def _run_wide_combine(cli, ctx, case, d):
+    """One combine_wide golden case through cli.process (per sample, with the annotation) and cli.combine."""
+    lines = []
+    gff = str(d / "a.gff")
+    open(gff, "w").write(case["gff"])
+    for i, s in enumerate(case["samples"]):
+        reads = [tuple(r) for r in s["reads"]]
+        bam = str(d / ("s%d.bam" % i))
+        Records.from_reads(case["chroms"], reads).write_bam(bam, case["chroms"])
+        bed = str(d / ("s%d.bed" % i))
+        open(bed, "w").write(s["bed"])
+        out = str(d / ("s%d" % i))
+        cli.process(bam, bed, out, annotationFile=gff, isStranded=case["stranded"],
+                    strandedType=case["stype"] if case["stranded"] else None, isbeta2Cryptic=case["cryptic"], ctx=ctx)
+        assert open(out + ".SpliSER.tsv").read() == s["tsv"], (case["seed"], i)
+        lines.append("%s\t%s\t%s\n" % (s["title"], out + ".SpliSER.tsv", bam))
+    sf = str(d / "samples.tsv")
+    open(sf, "w").writelines(lines)
+    out = str(d / "out")
+    cli.combine(sf, out, qGene=case["qgene"], isStranded=case["stranded"], strandedType=case["stype"],
+                isbeta2Cryptic=case["cryptic"], ctx=ctx)
+    assert open(out + ".combined.tsv").read() == case["combined"], case["seed"]
+
+
+def test_combine_over_regions_genes_and_cryptic_on_cpu(tmp_path, built_library):
+    """Several regions (some absent from a sample), annotation + -g filter, --beta2Cryptic (str(float) column)."""
+    from spliser_b200 import cli
+    ctx = OracleContext()
+    for k, case in enumerate(load_golden("combine_wide.json.gz")):
+        d = tmp_path / ("w%d" % k)
+        d.mkdir()
+        _run_wide_combine(cli, ctx, case, d)
+
+
 def test_cli_errors_mirror_the_reference(tmp_path, built_library):
     from spliser_b200 import cli
     case = [c for c in load_golden("appendix_a.json.gz")["process"] if c["name"] == "A.4-locus"][0]

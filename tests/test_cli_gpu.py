@@ -84,3 +84,14 @@ def test_combine_cli_matches_reference(ctx, tmp_path):
         d.mkdir()
         got = _run_combine(ctx, str(d), case)
         assert got == case["combined"], case.get("name", case.get("seed"))
+
+
+def test_combine_over_regions_genes_and_cryptic(ctx, tmp_path):
+    """combine_wide golden cases (several regions, annotation + -g, --beta2Cryptic): cli.process per sample and
+    cli.combine, both byte-identical to the reference's files."""
+    from spliser_b200 import cli
+    from test_cli_cpu import _run_wide_combine
+    for k, case in enumerate(load_golden("combine_wide.json.gz")):
+        d = tmp_path / ("w%d" % k)
+        d.mkdir()
+        _run_wide_combine(cli, ctx, case, d)

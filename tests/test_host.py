@@ -200,3 +200,83 @@ def test_device_inflate_decoder_matches_zlib_on_the_host():
                     rc, _, dst = inflate(comp, len(raw) - 1)
                     assert rc != 0 and dst[len(raw) - 1] == 0xEE
     assert n_cases == 120
+
+
+def test_native_gene_search_equals_the_python_restatement(built_library):
+    """spl_gene_search (csrc/host_text.cpp) against genes.binary_gene_search (the restatement pinned on the reference's
+    golden rows above): overlapping / nested genes, both strands, '?' site strands, positions on the gene bounds, lists
+    of 0-40 genes (the last-ditch window of S:162-169 and its skipped last gene matter for the short ones)."""
+    import bisect
+    import random
+    from spliser_b200 import api, hosttext
+    from spliser_b200.genes import Annotation, Gene, binary_gene_search
+    rng = random.Random(11)
+    n_checked = n_found = 0
+    for trial in range(300):
+        genes = []
+        for k in range(rng.randint(0, 40)):
+            left = rng.randrange(0, 3000, 10)
+            g = Gene("C", "g%d_%d" % (trial, k), left, left + rng.choice([5, 40, 200, 900, 2500]), rng.choice("+-"))
+            bisect.insort(genes, g)
+        ann = Annotation(chrom_index=["C"], genes=[genes])
+        n = 200
+        edges = [g.left for g in genes] + [g.right for g in genes] or [0]
+        pos = [rng.choice(edges) + rng.choice([-1, 0, 0, 1]) if rng.random() < 0.4 else rng.randrange(0, 6000) for _ in range(n)]
+        pos = [max(p, 0) for p in pos]
+        strands = [rng.choice(["+", "-", "?", ".", ""]) for _ in range(n)]
+        for stranded in (False, True):
+            vocab, sid = hosttext.strand_ids(strands)
+            z = np.zeros(n, np.int64)
+            table = api.SiteTable(chrom=np.zeros(n, np.int32), pos=np.array(pos, np.int32), strand=np.zeros(n, np.uint8),
+                                  alpha=z, beta1=z, beta2simple=z, beta2cryptic=z, beta2weighted=np.zeros(n), sse=np.zeros(n),
+                                  first_line=np.arange(n, dtype=np.int64), partner_off=np.zeros(n + 1, np.int64),
+                                  partner_pos=np.zeros(0, np.int32), partner_cnt=np.zeros(0, np.int64),
+                                  comp_off=np.zeros(n + 1, np.int64), comp_pos=np.zeros(0, np.int32))
+            names, got = hosttext.assign_genes(ann, table, sid, vocab, stranded)
+            want = [binary_gene_search(genes, p, s, stranded) for p, s in zip(pos, strands)]
+            assert got.tolist() == want, (trial, stranded)
+            n_checked += n
+            n_found += sum(w >= 0 for w in want)
+    assert n_checked == 300 * 2 * 200 and n_found > n_checked // 4
+
+
+def test_combined_tsv_prints_floats_like_python(tmp_path, built_library):
+    """beta2_weighted of a .combined.tsv is str(float(text)) (S:734): shortest round-trip digits, exponent form below 1e-4
+    and from 1e16.  One sample, no gaps, so nothing needs the GPU."""
+    from spliser_b200 import cli
+    texts = ["0.00000", "0.00001", "0.00010", "0.00123", "0.10000", "0.33333", "1.00000", "2.50000", "123456.78901",
+             "1e-7", "5e-324", "1.7976931348623157e308", "1e15", "1e16", "12345678901234567890", "0.1", "3", "1e22", "1.5e-5"]
+    rows = ["Region\tSite\tStrand\tGene\tSSE\talpha_count\tbeta1_count\tbeta2Simple_count\tbeta2Cryptic_count\t"
+            "beta2Cryptic_weighted\tPartners\tCompetitors\n"]
+    for i, t in enumerate(texts):
+        rows.append("C\t%d\t+\tNA\t0.500\t%d\t2\t1\t7\t%s\t{%d: 3, 5000: 1}\t[%d, 7000]\n" % (100 + i, i, t, 900 + i, 800 + i))
+    p = tmp_path / "a.SpliSER.tsv"
+    p.write_text("".join(rows))
+    sf = tmp_path / "samples.tsv"
+    sf.write_text("A\t%s\tnone.bam\n" % p)
+    cli.combine(str(sf), str(tmp_path / "out"), isbeta2Cryptic=True)
+    got = open(str(tmp_path / "out") + ".combined.tsv").read().splitlines()[1:]
+    assert len(got) == len(texts)
+    for i, (line, t) in enumerate(zip(got, texts)):
+        v = line.split("\t")
+        w = float(t)
+        den = i + (2 + 1 + w)
+        assert v[10] == str(w), (t, v[10])
+        assert v[5] == "{0:.3f}".format(i / den if den > 0.0 else 0.0)
+        assert v[11] == str({900 + i: 3, 5000: 1}) and v[12] == str([800 + i, 7000])
+
+
+def test_combine_rejects_malformed_tables(tmp_path, built_library):
+    from spliser_b200 import SpliserError, cli
+    p = tmp_path / "bad.SpliSER.tsv"
+    p.write_text("header\nC\t100\t+\tNA\t0.5\t1\t2\n")
+    sf = tmp_path / "samples.tsv"
+    sf.write_text("A\t%s\tnone.bam\n" % p)
+    with pytest.raises(SpliserError, match="fewer than 12"):
+        cli.combine(str(sf), str(tmp_path / "out"))
+    sf.write_text("A\t%s\tnone.bam\n" % (tmp_path / "absent.tsv"))
+    with pytest.raises(IOError):
+        cli.combine(str(sf), str(tmp_path / "out"))
+    sf.write_text("A\tonly-two-columns\n")
+    with pytest.raises(Exception, match="exactly 3"):
+        cli.combine(str(sf), str(tmp_path / "out"))
