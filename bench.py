@@ -134,6 +134,58 @@ def cpu_port_run(rec, junc, n_chrom, flags, threads):
     return time.perf_counter() - t0
 
 
+def synthetic_gff(w, path):
+    """A gene every ~4 kb on both strands (seeded): only the Gene column of the TSV depends on it."""
+    rng = np.random.default_rng(20260099)
+    with open(path, "w") as fh:
+        for c, n in zip(w.chroms, w.chrom_len):
+            k = max(1, int(n) // 4000)
+            starts = np.sort(rng.integers(1, max(2, int(n) - 6000), size=k))
+            lens = rng.integers(500, 6000, size=k)
+            strand = rng.integers(0, 2, size=k)
+            fh.writelines("%s\tsynthetic\tgene\t%d\t%d\t.\t%s\t.\tID=%s_G%06d;Name=n%d\n" % (c, a, a + b, "+-"[d], c, i, i)
+                          for i, (a, b, d) in enumerate(zip(starts.tolist(), lens.tolist(), strand.tolist())))
+
+
+def cli_process_run(ctx, w, bam, args, reads):
+    """`spliser_b200.cli.process` on files, timed as a whole and per stage (host wall clock)."""
+    from spliser_b200 import cli
+    from spliser_b200.genes import load_annotation
+    stem = os.path.join(CACHE, "bench_%s_%d" % (args.workload, len(w.records)))
+    bed, gff, outp = stem + ".bed", stem + ".gff", stem + ".out"
+    if not os.path.exists(bed):
+        open(bed + ".tmp", "w").write(w.bed12_text())
+        os.replace(bed + ".tmp", bed)
+    if not os.path.exists(gff):
+        synthetic_gff(w, gff + ".tmp")
+        os.replace(gff + ".tmp", gff)
+    stranded = bool(w.flags & 1)
+    kw = dict(annotationFile=gff, isStranded=stranded, strandedType="rf" if stranded else None, ctx=ctx)
+    cli.process(bam, bed, outp, **kw)                               # warm-up (page cache, allocations)
+    ts = []
+    for _ in range(max(1, args.e2e_steps)):
+        a = time.perf_counter()
+        cli.process(bam, bed, outp, **kw)
+        ts.append(time.perf_counter() - a)
+    a = time.perf_counter()
+    ann = load_annotation(gff)
+    b = time.perf_counter()
+    with open(bed) as fh:
+        chroms, table, sstr = cli.process_table(ctx, bam, fh, annotation=ann, is_stranded=stranded, stranded_type=kw["strandedType"])
+    c = time.perf_counter()
+    ms_count = ctx.stats()["ms_total"]
+    cli.write_process_tsv(outp + ".SpliSER.tsv", chroms, table, sstr, annotation=ann, is_stranded=stranded)
+    d = time.perf_counter()
+    n_rows = sum(1 for _ in open(outp + ".SpliSER.tsv")) - 1
+    step = float(np.mean(ts))
+    return {"value": reads / step, "unit": "reads/s", "ms_per_step": 1e3 * step, "rows_written": n_rows, "tsv_bytes": os.path.getsize(outp + ".SpliSER.tsv"),
+            "genes": sum(len(g) for g in ann.genes),
+            "breakdown_ms": {"annotation": round(1e3 * (b - a), 2), "bed_parse+spl_process": round(1e3 * (c - b), 2), "of_which_spl_process": round(ms_count, 2),
+                             "gene_column+tsv_writer": round(1e3 * (d - c), 2)},
+            "note": "cli.process(BAM, BED12, GFF) -> .SpliSER.tsv: annotation load (Python), BED12 parse (native), spl_process(bam) on the device, "
+                    "Gene column + TSV writer (native); byte-identical output is pinned by tests/test_cli_*.py"}
+
+
 def emit(line):
     """The ONE JSON line goes to the real stdout; everything else a library prints (NCCL banner, warnings) was
     redirected to stderr at start-up."""
@@ -349,6 +401,11 @@ def main():
                                       "synthetic BAM without SEQ/QUAL (records only), so the file is much smaller than a sequencer's"}
         except Exception as ex:                                      # never lose the main line over the extra measurement
             out["bam_e2e"] = {"error": repr(ex)}
+        # ---- the whole `process` command: BAM + BED12 + GFF files -> .SpliSER.tsv on disk (what a SpliSER user runs)
+        try:
+            out["cli_e2e"] = cli_process_run(ctx, w, bam, args, reads_rank)
+        except Exception as ex:
+            out["cli_e2e"] = {"error": repr(ex)}
     sampler.stop()
     if rank == 0 and not args.no_cpu_baseline and world == 1:
         rec_s, junc_s = region_sample(w, args.cpu_sample)

@@ -262,7 +262,11 @@ typedef struct spl_combine spl_combine;
 int  spl_combine_create(spl_combine** out);
 void spl_combine_destroy(spl_combine* c);
 const char* spl_combine_last_error(const spl_combine* c);
+int  spl_combine_set_threads(spl_combine* c, int n_threads);    /* parsing / formatting workers; 0 = all hardware threads */
 int  spl_combine_add_sample(spl_combine* c, const char* title, const char* tsv_path);
+/* n samples in samples-file order, parsed concurrently (n_threads 0 = the context's setting) */
+int  spl_combine_add_samples(spl_combine* c, int64_t n, const char* const* titles, const char* const* tsv_paths,
+                             int n_threads);
 int64_t spl_combine_n_samples(const spl_combine* c);
 int64_t spl_combine_n_regions(const spl_combine* c);
 const char* spl_combine_region_name(const spl_combine* c, int64_t region);

@@ -106,7 +106,9 @@ SIGNATURES = {
     "spl_combine_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "spl_combine_destroy": (None, [C.c_void_p]),
     "spl_combine_last_error": (C.c_char_p, [C.c_void_p]),
+    "spl_combine_set_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "spl_combine_add_sample": (C.c_int, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "spl_combine_add_samples": (C.c_int, [C.c_void_p, C.c_int64, c_strp, c_strp, C.c_int]),
     "spl_combine_n_samples": (C.c_int64, [C.c_void_p]),
     "spl_combine_n_regions": (C.c_int64, [C.c_void_p]),
     "spl_combine_region_name": (C.c_char_p, [C.c_void_p, C.c_int64]),

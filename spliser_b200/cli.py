@@ -133,8 +133,7 @@ def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType
     flags = api.mode_flags(isStranded, strandedType, False, combine=True)
     own = ctx is None
     with CombineMerge() as cm:
-        for title, path in zip(titles, bed_paths):
-            cm.add_sample(title, path)
+        cm.add_samples(titles, bed_paths)
         regions = cm.region_names()
         order = _chrom_order([[regions[r] for r in cm.sample_runs(k)] for k in range(n)])
         region_id = {name: i for i, name in enumerate(regions)}

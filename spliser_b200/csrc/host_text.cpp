@@ -7,6 +7,8 @@
 // sample k sees the partners / competitors / strand collected from the samples before k only).  Output is
 // byte-identical to the reference's: Python's str(int), "{:.3f}" / "{:.5f}" (correctly rounded, like glibc printf),
 // str(float) (shortest round-trip digits, exponent form outside 1e-4 <= |v| < 1e16), str(dict), str(list).
+#include <algorithm>
+#include <atomic>
 #include <charconv>
 #include <cerrno>
 #include <cmath>
@@ -16,6 +18,8 @@
 #include <cstring>
 #include <string>
 #include <string_view>
+#include <system_error>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -33,13 +37,16 @@ void set_err(char* err, int err_len, const char* fmt, ...) {
 
 // ---- buffered text output -----------------------------------------------------------------------------------------
 struct Out {
-    FILE* f = nullptr;
+    FILE* f = nullptr;                 // sink: a file ...
+    std::string* mem = nullptr;        // ... or a string (the parallel formatters of spl_combine_write)
     std::vector<char> buf;
     size_t n = 0;
     bool bad = false;
     explicit Out(FILE* fp) : f(fp), buf(1 << 20) {}
+    explicit Out(std::string* m) : mem(m), buf(1 << 16) {}
     void flush() {
-        if (n && fwrite(buf.data(), 1, n, f) != n) bad = true;
+        if (n && f && fwrite(buf.data(), 1, n, f) != n) bad = true;
+        if (n && mem) mem->append(buf.data(), n);
         n = 0;
     }
     char* room(size_t need) {
@@ -213,13 +220,15 @@ namespace {
 struct Interner {
     std::unordered_map<std::string, int32_t> map;
     std::vector<std::string> names;
+    int32_t last = -1;                                 // consecutive rows mostly repeat the region / strand / gene
     int32_t id(std::string_view s) {
+        if (last >= 0 && names[(size_t)last] == s) return last;
         auto it = map.find(std::string(s));
-        if (it != map.end()) return it->second;
+        if (it != map.end()) return last = it->second;
         int32_t k = (int32_t)names.size();
         names.emplace_back(s);
         map.emplace(names.back(), k);
-        return k;
+        return last = k;
     }
 };
 
@@ -259,6 +268,7 @@ struct spl_combine {
     std::vector<int32_t> u_part, u_comp;
     std::vector<int64_t> u_part_end, u_comp_end;
     int64_t n_filled = 0;
+    int n_threads = 0;                                 // 0 = every hardware thread
     bool merged_done = false;
     std::string err;
 };
@@ -354,16 +364,24 @@ extern "C" int spl_combine_create(spl_combine** out) {
 
 extern "C" void spl_combine_destroy(spl_combine* c) { delete c; }
 
+extern "C" int spl_combine_set_threads(spl_combine* c, int n_threads) {
+    if (!c || n_threads < 0) return SPL_ERR_ARG;
+    c->n_threads = n_threads;
+    return SPL_OK;
+}
+
 extern "C" const char* spl_combine_last_error(const spl_combine* c) { return c ? c->err.c_str() : "null spl_combine"; }
 
 // One sample = one row of the samples file (S:750-759): its title and its .SpliSER.tsv.  The header line is skipped
 // (S:799-800); every other line is rstrip()ped and split on tabs (S:836) and must have the twelve columns of S:643.
-extern "C" int spl_combine_add_sample(spl_combine* c, const char* title, const char* tsv_path) {
-    if (!c || !title || !tsv_path) return SPL_ERR_ARG;
-    if (c->merged_done) { c->err = "spl_combine_add_sample after spl_combine_merge"; return SPL_ERR_ARG; }
+// Region / strand / gene ids are local to the sample here (samples parse concurrently); spl_combine_add_samples
+// renumbers them into the shared tables in sample order.
+namespace {
+struct LocalTables { Interner regions, strands, genes; };
+
+int parse_sample(const char* title, const char* tsv_path, Sample& s, LocalTables& lt, std::string& err) {
     std::string data;
-    if (!read_file(tsv_path, data)) { c->err = std::string("cannot read ") + tsv_path; return SPL_ERR_IO; }
-    Sample s;
+    if (!read_file(tsv_path, data)) { err = std::string("cannot read ") + tsv_path; return SPL_ERR_IO; }
     s.title = title;
     s.p_off.push_back(0);
     s.c_off.push_back(0);
@@ -371,27 +389,25 @@ extern "C" int spl_combine_add_sample(spl_combine* c, const char* title, const c
     int32_t last_region = -1;
     try {
         while (at < data.size()) {
-            size_t nl = data.find('\n', at);
-            size_t end = nl == std::string::npos ? data.size() : nl;
+            const char* nlp = (const char*)memchr(data.data() + at, '\n', data.size() - at);
+            size_t end = nlp ? (size_t)(nlp - data.data()) : data.size();
             std::string_view line(data.data() + at, end - at);
-            at = nl == std::string::npos ? data.size() : nl + 1;
+            at = nlp ? end + 1 : data.size();
             if (line_no++ == 0) continue;
             while (!line.empty() && is_py_space(line.back())) line.remove_suffix(1);
             std::string_view col[12];
             int nc = 0;
             size_t p = 0;
-            while (nc < 12) {
+            while (nc < 12) {                                       // further columns are ignored (vals[11] is the 12th)
                 size_t tab = line.find('\t', p);
                 col[nc++] = line.substr(p, tab == std::string_view::npos ? std::string_view::npos : tab - p);
                 if (tab == std::string_view::npos) break;
                 p = tab + 1;
             }
             if (nc < 12) {
-                c->err = std::string(tsv_path) + ": line " + std::to_string(line_no) + " has fewer than 12 tab-separated columns";
+                err = std::string(tsv_path) + ": line " + std::to_string(line_no) + " has fewer than 12 tab-separated columns";
                 return SPL_ERR_ARG;
             }
-            size_t extra = col[11].find('\t');                      // further columns are ignored (vals[11] is the 12th)
-            if (extra != std::string_view::npos) col[11] = col[11].substr(0, extra);
             int64_t pos, a, b1, b2, bc = 0;
             double bw = 0.0;
             bool ok = parse_i64(col[1], &pos) && parse_i64(col[5], &a) && parse_i64(col[6], &b1) && parse_i64(col[7], &b2);
@@ -399,15 +415,15 @@ extern "C" int spl_combine_add_sample(spl_combine* c, const char* title, const c
             if (ok && has_c) ok = parse_i64(col[8], &bc) && parse_f64(col[9], &bw);
             ok = ok && parse_partners(col[10], s.p_key, s.p_cnt) && parse_competitors(col[11], s.c_key);
             if (!ok) {
-                c->err = std::string(tsv_path) + ": line " + std::to_string(line_no) + " is not a .SpliSER.tsv row";
+                err = std::string(tsv_path) + ": line " + std::to_string(line_no) + " is not a .SpliSER.tsv row";
                 return SPL_ERR_ARG;
             }
-            const int32_t rid = c->regions.id(col[0]);
+            const int32_t rid = lt.regions.id(col[0]);
             if (rid != last_region) { s.runs.push_back(rid); last_region = rid; }
             s.region.push_back(rid);
             s.pos.push_back((int32_t)pos);
-            s.strand.push_back(c->strands.id(col[2]));
-            s.gene.push_back(c->genes.id(col[3]));
+            s.strand.push_back(lt.strands.id(col[2]));
+            s.gene.push_back(lt.genes.id(col[3]));
             s.alpha.push_back(a); s.beta1.push_back(b1); s.beta2s.push_back(b2); s.beta2c.push_back(bc);
             s.beta2w.push_back(bw);
             s.has_cryptic.push_back(has_c ? 1 : 0);
@@ -415,11 +431,72 @@ extern "C" int spl_combine_add_sample(spl_combine* c, const char* title, const c
             s.c_off.push_back((int64_t)s.c_key.size());
         }
     } catch (const std::bad_alloc&) {
-        c->err = "out of memory";
+        err = "out of memory";
         return SPL_ERR_NOMEM;
     }
-    c->samples.push_back(std::move(s));
     return SPL_OK;
+}
+
+// runs `work` on nt threads (the caller's included); a thread that cannot be started just means fewer workers
+template <class F> void run_parallel(int nt, F& work) {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) {
+        try { pool.emplace_back([&work]() { work(); }); } catch (const std::system_error&) { break; }
+    }
+    work();
+    for (auto& th : pool) th.join();
+}
+
+int worker_count(int requested, size_t jobs) {
+    int n = requested > 0 ? requested : (int)std::thread::hardware_concurrency();
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    return (int)std::min<size_t>((size_t)n, std::max<size_t>(jobs, 1));
+}
+}  // namespace
+
+extern "C" int spl_combine_add_samples(spl_combine* c, int64_t n, const char* const* titles, const char* const* tsv_paths,
+                                       int n_threads) {
+    if (!c || n < 0 || (n && (!titles || !tsv_paths))) return SPL_ERR_ARG;
+    if (c->merged_done) { c->err = "spl_combine_add_samples after spl_combine_merge"; return SPL_ERR_ARG; }
+    for (int64_t k = 0; k < n; ++k)
+        if (!titles[k] || !tsv_paths[k]) { c->err = "spl_combine_add_samples: null title or path"; return SPL_ERR_ARG; }
+    std::vector<Sample> parsed((size_t)n);
+    std::vector<LocalTables> local((size_t)n);
+    std::vector<std::string> errs((size_t)n);
+    std::vector<int> rcs((size_t)n, SPL_OK);
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (int64_t k; (k = next.fetch_add(1)) < n;)
+            rcs[(size_t)k] = parse_sample(titles[k], tsv_paths[k], parsed[(size_t)k], local[(size_t)k], errs[(size_t)k]);
+    };
+    const int nt = worker_count(n_threads > 0 ? n_threads : c->n_threads, (size_t)n);
+    try {
+        run_parallel(nt, work);
+        for (int64_t k = 0; k < n; ++k)
+            if (rcs[(size_t)k] != SPL_OK) { c->err = errs[(size_t)k]; return rcs[(size_t)k]; }   // the first failing sample, in file order
+        for (int64_t k = 0; k < n; ++k) {                       // local ids -> shared ids, first appearance in sample order
+            Sample& s = parsed[(size_t)k];
+            LocalTables& lt = local[(size_t)k];
+            std::vector<int32_t> rmap, smap, gmap;
+            for (auto& nm : lt.regions.names) rmap.push_back(c->regions.id(nm));
+            for (auto& nm : lt.strands.names) smap.push_back(c->strands.id(nm));
+            for (auto& nm : lt.genes.names) gmap.push_back(c->genes.id(nm));
+            for (auto& v : s.region) v = rmap[(size_t)v];
+            for (auto& v : s.runs) v = rmap[(size_t)v];
+            for (auto& v : s.strand) v = smap[(size_t)v];
+            for (auto& v : s.gene) v = gmap[(size_t)v];
+            c->samples.push_back(std::move(s));
+        }
+    } catch (const std::exception& e) {
+        c->err = std::string("spl_combine_add_samples: ") + e.what();
+        return SPL_ERR_NOMEM;
+    }
+    return SPL_OK;
+}
+
+extern "C" int spl_combine_add_sample(spl_combine* c, const char* title, const char* tsv_path) {
+    return spl_combine_add_samples(c, 1, &title, &tsv_path, 1);
 }
 
 extern "C" int64_t spl_combine_n_samples(const spl_combine* c) { return c ? (int64_t)c->samples.size() : 0; }
@@ -582,7 +659,71 @@ extern "C" int spl_combine_set_recount(spl_combine* c, int64_t sample, int64_t n
     return SPL_OK;
 }
 
-// outputCombinedLines for every merged site (S:722-740, called at S:912-915)
+// outputCombinedLines for every merged site (S:722-740, called at S:912-915).  Blocks of merged sites are formatted
+// concurrently into memory and written in order.
+namespace {
+void format_merged_site(const spl_combine* c, size_t mi, int cryptic, Out& o) {
+    const size_t n = c->samples.size();
+    const Merged& m = c->merged[mi];
+    const int64_t* cell = &c->cells[(size_t)m.cell];
+    int32_t strand_final = -1;                          // Site.setStrand by every sample that has the site (S:873)
+    for (size_t k = 0; k < n; ++k)
+        if (cell[k] >= 0) strand_final = c->samples[k].strand[(size_t)cell[k]];
+    const int32_t* part = c->u_part.data() + m.part_off;
+    const size_t n_part = (size_t)(c->u_part_end[mi] - m.part_off);
+    const int32_t* comp = c->u_comp.data() + m.comp_off;
+    const size_t n_comp = (size_t)(c->u_comp_end[mi] - m.comp_off);
+    for (size_t k = 0; k < n; ++k) {
+        const Sample& s = c->samples[k];
+        long long alpha = 0, beta1 = 0, beta2s = 0, beta2c = 0;
+        double beta2w = 0.0, sse = 0.0;
+        const int64_t r = cell[k];
+        bool cryptic_row = false;
+        if (r >= 0) {
+            alpha = s.alpha[(size_t)r]; beta1 = s.beta1[(size_t)r]; beta2s = s.beta2s[(size_t)r];
+            if (s.has_cryptic[(size_t)r]) { beta2c = s.beta2c[(size_t)r]; beta2w = s.beta2w[(size_t)r]; cryptic_row = true; }
+            if (cryptic) {                              // calculateSSE (S:626-639)
+                double betas = (double)(beta1 + beta2s) + beta2w;
+                double den = (double)alpha + betas;
+                sse = den > 0.0 ? (double)alpha / den : 0.0;
+            } else {
+                long long den = alpha + beta1 + beta2s;
+                sse = den > 0 ? (double)alpha / (double)den : 0.0;
+            }
+        } else if (r <= -2) {
+            const size_t g = (size_t)(-r - 2);
+            beta1 = s.r_beta1[g]; beta2s = s.r_beta2s[g];
+        }
+        o.put(s.title); o.ch('\t');
+        o.put(c->regions.names[(size_t)m.region]); o.ch('\t');
+        o.i64(m.pos); o.ch('\t');
+        if (strand_final >= 0) o.put(c->strands.names[(size_t)strand_final]);
+        o.ch('\t');
+        if (m.gene >= 0) o.put(c->genes.names[(size_t)m.gene]);
+        o.ch('\t');
+        o.fixed(sse, 3); o.ch('\t');
+        o.i64(alpha); o.ch('\t'); o.i64(beta1); o.ch('\t'); o.i64(beta2s); o.ch('\t');
+        if (cryptic) { o.i64(beta2c); o.ch('\t'); o.pyfloat(cryptic_row ? beta2w : 0.0); o.ch('\t'); }
+        else o.put("NA\tNA\t", 6);
+        o.ch('{');
+        for (size_t e = 0; e < n_part; ++e) {
+            long long cnt = 0;
+            if (r >= 0)
+                for (int64_t q = s.p_off[(size_t)r]; q < s.p_off[(size_t)r + 1]; ++q)
+                    if (s.p_key[(size_t)q] == part[e]) { cnt = s.p_cnt[(size_t)q]; break; }
+            if (e) o.put(", ", 2);
+            o.i64(part[e]); o.put(": ", 2); o.i64(cnt);
+        }
+        o.put("}\t[", 3);
+        for (size_t e = 0; e < n_comp; ++e) {
+            if (e) o.put(", ", 2);
+            o.i64(comp[e]);
+        }
+        o.put("]\n", 2);
+    }
+}
+}  // namespace
+
 extern "C" int spl_combine_write(spl_combine* c, const char* path, int cryptic) {
     if (!c || !path) return SPL_ERR_ARG;
     if (!c->merged_done) { c->err = "spl_combine_write before spl_combine_merge"; return SPL_ERR_ARG; }
@@ -594,69 +735,34 @@ extern "C" int spl_combine_write(spl_combine* c, const char* path, int cryptic) 
         }
     FILE* f = fopen(path, "w");
     if (!f) { c->err = std::string("cannot open ") + path + ": " + strerror(errno); return SPL_ERR_IO; }
-    Out o(f);
-    o.put(COMBINE_HEADER, sizeof(COMBINE_HEADER) - 1);
-    for (size_t mi = 0; mi < c->merged.size(); ++mi) {
-        const Merged& m = c->merged[mi];
-        const int64_t* cell = &c->cells[(size_t)m.cell];
-        int32_t strand_final = -1;                          // Site.setStrand by every sample that has the site (S:873)
-        for (size_t k = 0; k < n; ++k)
-            if (cell[k] >= 0) strand_final = c->samples[k].strand[(size_t)cell[k]];
-        const int32_t* part = c->u_part.data() + m.part_off;
-        const size_t n_part = (size_t)(c->u_part_end[mi] - m.part_off);
-        const int32_t* comp = c->u_comp.data() + m.comp_off;
-        const size_t n_comp = (size_t)(c->u_comp_end[mi] - m.comp_off);
-        for (size_t k = 0; k < n; ++k) {
-            const Sample& s = c->samples[k];
-            long long alpha = 0, beta1 = 0, beta2s = 0, beta2c = 0;
-            double beta2w = 0.0, sse = 0.0;
-            const int64_t r = cell[k];
-            bool cryptic_row = false;
-            if (r >= 0) {
-                alpha = s.alpha[(size_t)r]; beta1 = s.beta1[(size_t)r]; beta2s = s.beta2s[(size_t)r];
-                if (s.has_cryptic[(size_t)r]) { beta2c = s.beta2c[(size_t)r]; beta2w = s.beta2w[(size_t)r]; cryptic_row = true; }
-                if (cryptic) {                              // calculateSSE (S:626-639)
-                    double betas = (double)(beta1 + beta2s) + beta2w;
-                    double den = (double)alpha + betas;
-                    sse = den > 0.0 ? (double)alpha / den : 0.0;
-                } else {
-                    long long den = alpha + beta1 + beta2s;
-                    sse = den > 0 ? (double)alpha / (double)den : 0.0;
+    bool bad = fwrite(COMBINE_HEADER, 1, sizeof(COMBINE_HEADER) - 1, f) != sizeof(COMBINE_HEADER) - 1;
+    const size_t total = c->merged.size();
+    const size_t block = std::max<size_t>(64, 65536 / std::max<size_t>(n, 1));        // merged sites per formatting job
+    const size_t n_blocks = (total + block - 1) / block;
+    const int nt = worker_count(c->n_threads, n_blocks);
+    try {
+        std::vector<std::string> text((size_t)nt);
+        for (size_t wave = 0; wave < n_blocks && !bad; wave += (size_t)nt) {
+            const size_t in_wave = std::min<size_t>((size_t)nt, n_blocks - wave);
+            std::atomic<size_t> next{0};
+            auto work = [&]() {
+                for (size_t j; (j = next.fetch_add(1)) < in_wave;) {
+                    text[j].clear();
+                    Out o(&text[j]);
+                    const size_t lo = (wave + j) * block, hi = std::min(total, lo + block);
+                    for (size_t mi = lo; mi < hi; ++mi) format_merged_site(c, mi, cryptic, o);
+                    o.flush();
                 }
-            } else if (r <= -2) {
-                const size_t g = (size_t)(-r - 2);
-                beta1 = s.r_beta1[g]; beta2s = s.r_beta2s[g];
-            }
-            o.put(s.title); o.ch('\t');
-            o.put(c->regions.names[(size_t)m.region]); o.ch('\t');
-            o.i64(m.pos); o.ch('\t');
-            if (strand_final >= 0) o.put(c->strands.names[(size_t)strand_final]);
-            o.ch('\t');
-            if (m.gene >= 0) o.put(c->genes.names[(size_t)m.gene]);
-            o.ch('\t');
-            o.fixed(sse, 3); o.ch('\t');
-            o.i64(alpha); o.ch('\t'); o.i64(beta1); o.ch('\t'); o.i64(beta2s); o.ch('\t');
-            if (cryptic) { o.i64(beta2c); o.ch('\t'); o.pyfloat(cryptic_row ? beta2w : 0.0); o.ch('\t'); }
-            else o.put("NA\tNA\t", 6);
-            o.ch('{');
-            for (size_t e = 0; e < n_part; ++e) {
-                long long cnt = 0;
-                if (r >= 0)
-                    for (int64_t q = s.p_off[(size_t)r]; q < s.p_off[(size_t)r + 1]; ++q)
-                        if (s.p_key[(size_t)q] == part[e]) { cnt = s.p_cnt[(size_t)q]; break; }
-                if (e) o.put(", ", 2);
-                o.i64(part[e]); o.put(": ", 2); o.i64(cnt);
-            }
-            o.put("}\t[", 3);
-            for (size_t e = 0; e < n_comp; ++e) {
-                if (e) o.put(", ", 2);
-                o.i64(comp[e]);
-            }
-            o.put("]\n", 2);
+            };
+            run_parallel((int)in_wave, work);
+            for (size_t j = 0; j < in_wave && !bad; ++j)
+                if (fwrite(text[j].data(), 1, text[j].size(), f) != text[j].size()) bad = true;
         }
+    } catch (const std::exception& e) {
+        fclose(f);
+        c->err = std::string("spl_combine_write: ") + e.what();
+        return SPL_ERR_NOMEM;
     }
-    o.flush();
-    const bool bad = o.bad;
     if (fclose(f) != 0 || bad) { c->err = std::string("write to ") + path + " failed"; return SPL_ERR_IO; }
     return SPL_OK;
 }

@@ -141,6 +141,16 @@ class CombineMerge:
     def add_sample(self, title, tsv_path):
         self._check(self._lib.spl_combine_add_sample(self._h, str(title).encode(), str(tsv_path).encode()), "spl_combine_add_sample")
 
+    def add_samples(self, titles, tsv_paths, threads=0):
+        """All samples of the samples file, in its order; the tables are parsed concurrently."""
+        n = len(titles)
+        t = (C.c_char_p * max(1, n))(*[str(x).encode() for x in titles])
+        p = (C.c_char_p * max(1, n))(*[str(x).encode() for x in tsv_paths])
+        self._check(self._lib.spl_combine_add_samples(self._h, n, t, p, int(threads)), "spl_combine_add_samples")
+
+    def set_threads(self, n):
+        self._check(self._lib.spl_combine_set_threads(self._h, int(n)), "spl_combine_set_threads")
+
     def region_names(self):
         return [self._lib.spl_combine_region_name(self._h, i).decode() for i in range(self._lib.spl_combine_n_regions(self._h))]
 
