@@ -111,6 +111,48 @@ inline std::string_view tab_get(const spl_strtab* t, int64_t i) {
 
 inline long long floordiv2(long long a) { return a >= 0 ? a / 2 : -((-a + 1) / 2); }
 
+// runs `work` on nt threads (the caller's included); a thread that cannot be started just means fewer workers
+template <class F> void run_parallel(int nt, F& work) {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nt; ++t) {
+        try { pool.emplace_back([&work]() { work(); }); } catch (const std::system_error&) { break; }
+    }
+    work();
+    for (auto& th : pool) th.join();
+}
+
+int worker_count(int requested, size_t jobs) {
+    int n = requested > 0 ? requested : (int)std::thread::hardware_concurrency();
+    if (n < 1) n = 1;
+    if (n > 64) n = 64;
+    return (int)std::min<size_t>((size_t)n, std::max<size_t>(jobs, 1));
+}
+
+// Formats [0, total) in blocks of `block` items on up to `threads` workers (0 = every hardware thread) and writes the
+// blocks to `f` in order.  fmt(lo, hi, out) appends the text of items [lo, hi).
+template <class F> bool write_blocks(FILE* f, size_t total, size_t block, int threads, F fmt) {
+    const size_t n_blocks = (total + block - 1) / block;
+    const int nt = worker_count(threads, n_blocks);
+    std::vector<std::string> text((size_t)nt);
+    for (size_t wave = 0; wave < n_blocks; wave += (size_t)nt) {
+        const size_t in_wave = std::min<size_t>((size_t)nt, n_blocks - wave);
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t j; (j = next.fetch_add(1)) < in_wave;) {
+                text[j].clear();
+                Out o(&text[j]);
+                const size_t lo = (wave + j) * block;
+                fmt(lo, std::min(total, lo + block), o);
+                o.flush();
+            }
+        };
+        run_parallel((int)in_wave, work);
+        for (size_t j = 0; j < in_wave; ++j)
+            if (fwrite(text[j].data(), 1, text[j].size(), f) != text[j].size()) return false;
+    }
+    return true;
+}
+
 }  // namespace
 
 // ======================================================================================================= gene lookup
@@ -167,50 +209,57 @@ extern "C" int spl_write_process_tsv(const char* path, const spl_site_columns* t
         set_err(err, err_len, "spl_write_process_tsv: null argument");
         return SPL_ERR_ARG;
     }
-    FILE* f = fopen(path, "w");
-    if (!f) { set_err(err, err_len, "cannot open %s: %s", path, strerror(errno)); return SPL_ERR_IO; }
-    Out o(f);
-    o.put(PROCESS_HEADER, sizeof(PROCESS_HEADER) - 1);
     for (int64_t i = 0; i < t->n_sites; ++i) {
         const int32_t ci = t->chrom[i];
         const int32_t sid = line_strand[t->first_line[i]];
         if (ci < 0 || ci >= chrom_names->n || sid < 0 || sid >= strand_texts->n ||
             (site_gene && gene_names && site_gene[i] >= gene_names->n)) {
-            fclose(f);
             set_err(err, err_len, "spl_write_process_tsv: site %lld refers to a name outside its table", (long long)i);
             return SPL_ERR_ARG;
         }
-        o.put(tab_get(chrom_names, ci)); o.ch('\t');
-        o.i64(t->pos[i]); o.ch('\t');
-        o.put(tab_get(strand_texts, sid)); o.ch('\t');
-        if (site_gene && gene_names && site_gene[i] >= 0) o.put(tab_get(gene_names, site_gene[i]));
-        else o.put("NA", 2);
-        o.ch('\t');
-        o.fixed(t->sse[i], 3); o.ch('\t');
-        o.i64(t->alpha[i]); o.ch('\t');
-        o.i64(t->beta1[i]); o.ch('\t');
-        o.i64(t->beta2simple[i]); o.ch('\t');
-        if (cryptic) {
-            o.i64(t->beta2cryptic[i]); o.ch('\t');
-            o.fixed(t->beta2weighted[i], 5); o.ch('\t');
-        } else {
-            o.put("NA\tNA\t", 6);
-        }
-        o.ch('{');                                                           // str(dict): PartnerCounts, S:662
-        for (int64_t e = t->partner_off[i]; e < t->partner_off[i + 1]; ++e) {
-            if (e > t->partner_off[i]) o.put(", ", 2);
-            o.i64(t->partner_pos[e]); o.put(": ", 2); o.i64(t->partner_cnt[e]);
-        }
-        o.put("}\t[", 3);                                                    // str(list): CompetitorPos, S:663
-        for (int64_t e = t->comp_off[i]; e < t->comp_off[i + 1]; ++e) {
-            if (e > t->comp_off[i]) o.put(", ", 2);
-            o.i64(t->comp_pos[e]);
-        }
-        o.put("]\n", 2);
     }
-    o.flush();
-    const bool bad = o.bad;
-    if (fclose(f) != 0 || bad) { set_err(err, err_len, "write to %s failed", path); return SPL_ERR_IO; }
+    FILE* f = fopen(path, "w");
+    if (!f) { set_err(err, err_len, "cannot open %s: %s", path, strerror(errno)); return SPL_ERR_IO; }
+    bool ok = fwrite(PROCESS_HEADER, 1, sizeof(PROCESS_HEADER) - 1, f) == sizeof(PROCESS_HEADER) - 1;
+    auto rows = [&](size_t lo, size_t hi, Out& o) {
+        for (size_t i = lo; i < hi; ++i) {
+            o.put(tab_get(chrom_names, t->chrom[i])); o.ch('\t');
+            o.i64(t->pos[i]); o.ch('\t');
+            o.put(tab_get(strand_texts, line_strand[t->first_line[i]])); o.ch('\t');
+            if (site_gene && gene_names && site_gene[i] >= 0) o.put(tab_get(gene_names, site_gene[i]));
+            else o.put("NA", 2);
+            o.ch('\t');
+            o.fixed(t->sse[i], 3); o.ch('\t');
+            o.i64(t->alpha[i]); o.ch('\t');
+            o.i64(t->beta1[i]); o.ch('\t');
+            o.i64(t->beta2simple[i]); o.ch('\t');
+            if (cryptic) {
+                o.i64(t->beta2cryptic[i]); o.ch('\t');
+                o.fixed(t->beta2weighted[i], 5); o.ch('\t');
+            } else {
+                o.put("NA\tNA\t", 6);
+            }
+            o.ch('{');                                                       // str(dict): PartnerCounts, S:662
+            for (int64_t e = t->partner_off[i]; e < t->partner_off[i + 1]; ++e) {
+                if (e > t->partner_off[i]) o.put(", ", 2);
+                o.i64(t->partner_pos[e]); o.put(": ", 2); o.i64(t->partner_cnt[e]);
+            }
+            o.put("}\t[", 3);                                                // str(list): CompetitorPos, S:663
+            for (int64_t e = t->comp_off[i]; e < t->comp_off[i + 1]; ++e) {
+                if (e > t->comp_off[i]) o.put(", ", 2);
+                o.i64(t->comp_pos[e]);
+            }
+            o.put("]\n", 2);
+        }
+    };
+    try {
+        ok = ok && write_blocks(f, (size_t)t->n_sites, 16384, 0, rows);
+    } catch (const std::exception& e) {
+        fclose(f);
+        set_err(err, err_len, "spl_write_process_tsv: %s", e.what());
+        return SPL_ERR_NOMEM;
+    }
+    if (fclose(f) != 0 || !ok) { set_err(err, err_len, "write to %s failed", path); return SPL_ERR_IO; }
     return SPL_OK;
 }
 
@@ -437,22 +486,6 @@ int parse_sample(const char* title, const char* tsv_path, Sample& s, LocalTables
     return SPL_OK;
 }
 
-// runs `work` on nt threads (the caller's included); a thread that cannot be started just means fewer workers
-template <class F> void run_parallel(int nt, F& work) {
-    std::vector<std::thread> pool;
-    for (int t = 1; t < nt; ++t) {
-        try { pool.emplace_back([&work]() { work(); }); } catch (const std::system_error&) { break; }
-    }
-    work();
-    for (auto& th : pool) th.join();
-}
-
-int worker_count(int requested, size_t jobs) {
-    int n = requested > 0 ? requested : (int)std::thread::hardware_concurrency();
-    if (n < 1) n = 1;
-    if (n > 64) n = 64;
-    return (int)std::min<size_t>((size_t)n, std::max<size_t>(jobs, 1));
-}
 }  // namespace
 
 extern "C" int spl_combine_add_samples(spl_combine* c, int64_t n, const char* const* titles, const char* const* tsv_paths,
@@ -736,28 +769,11 @@ extern "C" int spl_combine_write(spl_combine* c, const char* path, int cryptic) 
     FILE* f = fopen(path, "w");
     if (!f) { c->err = std::string("cannot open ") + path + ": " + strerror(errno); return SPL_ERR_IO; }
     bool bad = fwrite(COMBINE_HEADER, 1, sizeof(COMBINE_HEADER) - 1, f) != sizeof(COMBINE_HEADER) - 1;
-    const size_t total = c->merged.size();
     const size_t block = std::max<size_t>(64, 65536 / std::max<size_t>(n, 1));        // merged sites per formatting job
-    const size_t n_blocks = (total + block - 1) / block;
-    const int nt = worker_count(c->n_threads, n_blocks);
     try {
-        std::vector<std::string> text((size_t)nt);
-        for (size_t wave = 0; wave < n_blocks && !bad; wave += (size_t)nt) {
-            const size_t in_wave = std::min<size_t>((size_t)nt, n_blocks - wave);
-            std::atomic<size_t> next{0};
-            auto work = [&]() {
-                for (size_t j; (j = next.fetch_add(1)) < in_wave;) {
-                    text[j].clear();
-                    Out o(&text[j]);
-                    const size_t lo = (wave + j) * block, hi = std::min(total, lo + block);
-                    for (size_t mi = lo; mi < hi; ++mi) format_merged_site(c, mi, cryptic, o);
-                    o.flush();
-                }
-            };
-            run_parallel((int)in_wave, work);
-            for (size_t j = 0; j < in_wave && !bad; ++j)
-                if (fwrite(text[j].data(), 1, text[j].size(), f) != text[j].size()) bad = true;
-        }
+        bad = bad || !write_blocks(f, c->merged.size(), block, c->n_threads, [&](size_t lo, size_t hi, Out& o) {
+            for (size_t mi = lo; mi < hi; ++mi) format_merged_site(c, mi, cryptic, o);
+        });
     } catch (const std::exception& e) {
         fclose(f);
         c->err = std::string("spl_combine_write: ") + e.what();

@@ -53,34 +53,52 @@ def strand_ids(strand_strings, vocab=None):
     return vocab, ids
 
 
+def _gene_columns(annotation, vocab):
+    """Per chromosome (left, right, strand id) arrays + the flat name list, built once per annotation and strand vocabulary."""
+    key = tuple(sorted(vocab.items()))
+    cached = getattr(annotation, "_columns", None)
+    if cached is not None and cached[0] == key:
+        return cached[1]
+    names, base, cols = [], [], []
+    for genes in annotation.genes:
+        base.append(len(names))
+        names.extend(g.name for g in genes)
+        cols.append((np.array([g.left for g in genes], dtype=np.int32), np.array([g.right for g in genes], dtype=np.int32),
+                     np.array([vocab.setdefault(g.strand, len(vocab)) for g in genes], dtype=np.int32)))
+    out = (names, base, cols, StrTable(names))
+    try:
+        annotation._columns = (tuple(sorted(vocab.items())), out)
+    except AttributeError:
+        pass
+    return out
+
+
 def assign_genes(annotation, table: SiteTable, site_strand, vocab, is_stranded):
     """Gene column of every site: binary_gene_search over the site's chromosome with the strand text of the BED row that
     created the site (S:313-329).  Returns (gene name list, int32 index per site, -1 = NA)."""
     lib = L.load()
-    names, base = [], []
-    for genes in annotation.genes:
-        base.append(len(names))
-        names.extend(g.name for g in genes)
-    out = np.full(len(table), -1, dtype=np.int32)
     plus, minus = vocab.setdefault("+", len(vocab)), vocab.setdefault("-", len(vocab))
+    names, base, cols, _ = _gene_columns(annotation, vocab)
+    out = np.full(len(table), -1, dtype=np.int32)
     chrom = np.asarray(table.chrom)
     pos = np.ascontiguousarray(table.pos, dtype=np.int32)
-    for ci in np.unique(chrom):
-        genes = annotation.genes_of(int(ci))
-        if not genes:
+    site_strand = np.ascontiguousarray(site_strand, dtype=np.int32)
+    # sites come grouped by chromosome (output order); fall back to a mask per chromosome when they do not
+    change = np.flatnonzero(np.diff(chrom)) + 1 if len(chrom) else np.zeros(0, np.int64)
+    starts = np.concatenate(([0], change)).astype(np.int64) if len(chrom) else np.zeros(0, np.int64)
+    ends = np.concatenate((change, [len(chrom)])).astype(np.int64) if len(chrom) else np.zeros(0, np.int64)
+    for a, b in zip(starts.tolist(), ends.tolist()):
+        ci = int(chrom[a])
+        if ci < 0 or ci >= len(cols) or not len(cols[ci][0]):
             continue
-        sel = np.nonzero(chrom == ci)[0]
-        gl = np.array([g.left for g in genes], dtype=np.int32)
-        gr = np.array([g.right for g in genes], dtype=np.int32)
-        gs = np.array([vocab.setdefault(g.strand, len(vocab)) for g in genes], dtype=np.int32)
-        p = np.ascontiguousarray(pos[sel])
-        st = np.ascontiguousarray(site_strand[sel], dtype=np.int32)
-        idx = np.empty(len(sel), dtype=np.int32)
-        rc = lib.spl_gene_search(len(genes), _ptr(gl, L.c_i32p), _ptr(gr, L.c_i32p), _ptr(gs, L.c_i32p), len(sel),
+        gl, gr, gs = cols[ci]
+        p, st = pos[a:b], site_strand[a:b]
+        idx = np.empty(b - a, dtype=np.int32)
+        rc = lib.spl_gene_search(len(gl), _ptr(gl, L.c_i32p), _ptr(gr, L.c_i32p), _ptr(gs, L.c_i32p), b - a,
                                  _ptr(p, L.c_i32p), _ptr(st, L.c_i32p), plus, minus, int(bool(is_stranded)), _ptr(idx, L.c_i32p))
         if rc != 0:
             raise SpliserError("spl_gene_search failed (code %d)" % rc)
-        out[sel] = np.where(idx >= 0, idx + base[int(ci)], -1)
+        out[a:b] = np.where(idx >= 0, idx + base[ci], -1)
     return names, out
 
 
@@ -92,7 +110,7 @@ def write_process_tsv(path, chroms, table: SiteTable, strand_strings, *, annotat
     if annotation is not None and len(table):
         site_strand = line_strand[np.asarray(table.first_line)]
         names, site_gene = assign_genes(annotation, table, site_strand, vocab, is_stranded)
-        gene_tab = StrTable(names)
+        gene_tab = _gene_columns(annotation, vocab)[3]
     texts = [None] * len(vocab)
     for s, i in vocab.items():
         texts[i] = s
