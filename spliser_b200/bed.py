@@ -39,16 +39,22 @@ class StrandColumn:
         return list(self) == list(other)
 
 
-def _text_of(lines) -> str:
+def _bytes_of(lines) -> bytes:
+    """File image as the reference's text-mode iteration sees it (universal newlines)."""
     if isinstance(lines, str):
-        return lines
-    if isinstance(lines, bytes):
-        return lines.decode()
-    read = getattr(lines, "read", None)
-    if read is not None:
-        data = read()
-        return data.decode() if isinstance(data, bytes) else data
-    return "".join((x if x.endswith("\n") else x + "\n") for x in map(str, lines))
+        return lines.encode()
+    if not isinstance(lines, bytes):
+        raw = getattr(lines, "buffer", None)         # open text file: take the bytes underneath, no decode + encode
+        if raw is not None and hasattr(raw, "read") and lines.tell() == 0:
+            lines = raw.read()
+        elif hasattr(lines, "read"):
+            data = lines.read()
+            return data if isinstance(data, bytes) else data.encode()
+        else:
+            return "".join((x if x.endswith("\n") else x + "\n") for x in map(str, lines)).encode()
+    if b"\r" in lines:
+        lines = lines.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+    return lines
 
 
 def parse_bed12(lines, chrom_index=None, qchrom="All", qgene_bounds=None, max_intron=0):
@@ -59,7 +65,7 @@ def parse_bed12(lines, chrom_index=None, qchrom="All", qgene_bounds=None, max_in
     qgene_bounds: (leftPos, rightPos) of the query gene when -g is used, else None."""
     from .hosttext import StrTable
     lib = L.load()
-    raw = _text_of(lines).encode()
+    raw = _bytes_of(lines)
     tab = StrTable(list(chrom_index)) if chrom_index else None
     gl, gr = (int(qgene_bounds[0]), int(qgene_bounds[1])) if qgene_bounds is not None else (0, 0)
     h = C.c_void_p()

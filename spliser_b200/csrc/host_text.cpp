@@ -272,6 +272,10 @@ struct Interner {
     int32_t last = -1;                                 // consecutive rows mostly repeat the region / strand / gene
     int32_t id(std::string_view s) {
         if (last >= 0 && names[(size_t)last] == s) return last;
+        if (names.size() <= 8) {                       // a handful of strands / regions: no hashing
+            for (size_t k = 0; k < names.size(); ++k)
+                if (names[k] == s) return last = (int32_t)k;
+        }
         auto it = map.find(std::string(s));
         if (it != map.end()) return last = it->second;
         int32_t k = (int32_t)names.size();
@@ -446,12 +450,13 @@ int parse_sample(const char* title, const char* tsv_path, Sample& s, LocalTables
             while (!line.empty() && is_py_space(line.back())) line.remove_suffix(1);
             std::string_view col[12];
             int nc = 0;
-            size_t p = 0;
-            while (nc < 12) {                                       // further columns are ignored (vals[11] is the 12th)
-                size_t tab = line.find('\t', p);
-                col[nc++] = line.substr(p, tab == std::string_view::npos ? std::string_view::npos : tab - p);
-                if (tab == std::string_view::npos) break;
-                p = tab + 1;
+            {                                                       // further columns are ignored (vals[11] is the 12th)
+                const char* q = line.data();
+                const char* const e = q + line.size();
+                const char* field = q;
+                for (; q < e && nc < 12; ++q)
+                    if (*q == '\t') { col[nc++] = std::string_view(field, (size_t)(q - field)); field = q + 1; }
+                if (nc < 12) col[nc++] = std::string_view(field, (size_t)(e - field));
             }
             if (nc < 12) {
                 err = std::string(tsv_path) + ": line " + std::to_string(line_no) + " has fewer than 12 tab-separated columns";
@@ -818,22 +823,24 @@ extern "C" int spl_bed_parse(const char* text, int64_t len, const spl_strtab* ch
         const std::string_view q = qchrom ? std::string_view(qchrom) : std::string_view();
         int64_t at = 0, line_no = 0;
         while (at < len) {
-            const char* nl = (const char*)memchr(text + at, '\n', (size_t)(len - at));
-            const int64_t end = nl ? (nl - text) : len;
-            std::string_view line(text + at, (size_t)(end - at));
-            at = nl ? end + 1 : len;
-            ++line_no;
+            // one pass over the line: fields end at tabs, the line at '\n' (its text stays out of the last field)
+            const char* p = text + at;
+            const char* const e = text + len;
+            const char* field = p;
             std::string_view col[12];
             int nc = 0;
-            size_t p = 0;
-            bool more = false;
-            while (true) {
-                size_t tab = line.find('\t', p);
-                if (nc == 12) { more = true; break; }
-                col[nc++] = line.substr(p, tab == std::string_view::npos ? std::string_view::npos : tab - p);
-                if (tab == std::string_view::npos) break;
-                p = tab + 1;
+            for (; p < e && *p != '\n'; ++p) {
+                if (*p == '\t') {
+                    if (nc < 12) col[nc] = std::string_view(field, (size_t)(p - field));
+                    ++nc;
+                    field = p + 1;
+                }
             }
+            if (nc < 12) col[nc] = std::string_view(field, (size_t)(p - field));
+            ++nc;
+            at = p < e ? (p - text) + 1 : len;
+            ++line_no;
+            const bool more = false;
             if (nc != 12 || more) continue;                                  // S:259
             const int32_t ci = b->chroms.id(col[0]);                         // registered before the -c test (S:265-269)
             if (qchrom && col[0] != q) continue;

@@ -8,7 +8,6 @@ value of the first attribute (README.md:64).
 """
 from __future__ import annotations
 
-import bisect
 from dataclasses import dataclass, field
 
 
@@ -49,25 +48,35 @@ def load_annotation(path, qgene="All") -> Annotation:
     """createGenes (S:50-116).  The -t/--annotationType argument is ignored by the reference (S:82 tests
     the literal 'gene'), so it is not a parameter here."""
     ann = Annotation()
+    index = {}
     with open(path) as fh:
         for line in fh:
-            if not line.strip() or line.startswith("#"):
+            if line.startswith("#") or "\tgene\t" not in line:      # cheap pre-filter; the column test below decides
                 continue
             f = line.rstrip("\n").split("\t")
             if len(f) < 9 or f[2] != "gene":
                 continue
-            chrom, left, right, strand = f[0], int(f[3]) - 1, int(f[4]), f[6]
+            chrom = f[0]
             name = _first_attribute(f[8])
-            if chrom not in ann.chrom_index:
+            ci = index.get(chrom)
+            if ci is None:
+                ci = index[chrom] = len(ann.chrom_index)
                 ann.chrom_index.append(chrom)
                 ann.genes.append([])
-            g = Gene(chrom, name, left, right, strand)
+            g = Gene(chrom, name, int(f[3]) - 1, int(f[4]), f[6])
             if qgene == "All":
-                bisect.insort(ann.genes[ann.chrom_index.index(chrom)], g)
+                ann.genes[ci].append(g)
             elif name == qgene:
                 ann.query_gene = g
-                ann.genes[ann.chrom_index.index(chrom)].append(g)
+                ann.genes[ci].append(g)
+    if qgene == "All":
+        for genes in ann.genes:          # insort_right by leftPos in file order (S:95) == stable sort by leftPos
+            genes.sort(key=_left_of)
     return ann
+
+
+def _left_of(g):
+    return g.left
 
 
 def binary_gene_search(array, pos, strand, is_stranded) -> int:
