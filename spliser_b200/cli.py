@@ -20,6 +20,7 @@ import numpy as np
 
 from . import api
 from .bed import parse_bed12
+from .dist import samples_of
 from .genes import load_annotation
 from .hosttext import CombineMerge, write_process_tsv as _native_write_process_tsv
 
@@ -113,12 +114,36 @@ def _chrom_order(runs_per_file):
     return stack[1:]
 
 
+def _recount_sample(ctx, cm, k, regions, bam_path, flags, records_by_bam):
+    """Every S:903 call of sample k in one spl_recount call; returns False when the sample has no gaps."""
+    gaps = cm.gaps(k)
+    if not len(gaps):
+        return False
+    uniq, first = np.unique(gaps.chrom, return_index=True)
+    local = uniq[np.argsort(first)]                 # the sample's gap regions in first-appearance order
+    names = [regions[r] for r in local]
+    remap = np.full(len(regions), -1, dtype=np.int32)
+    remap[local] = np.arange(len(local), dtype=np.int32)
+    gaps.chrom = np.ascontiguousarray(remap[gaps.chrom])
+    if records_by_bam is not None:
+        b1, b2 = ctx.recount_records(records_by_bam(bam_path, names), len(names), gaps, flags)
+    else:
+        b1, b2 = ctx.recount_bam(bam_path, names, gaps, flags)
+    cm.set_recount(k, b1, b2)
+    return True
+
+
 def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType="fr", isbeta2Cryptic=False, ctx=None,
-            records_by_bam=None):
+            records_by_bam=None, devices=None, context_factory=None):
     """combine (S:742-917).  The native merge driver (csrc/host_text.cpp) parses the sample tables and replays the
     lock-step merge, collecting per sample the sites it lacks together with the partner / competitor / strand context
     gathered from lower-indexed samples only (the reference's order dependence); one spl_recount call
-    per sample fills them; the driver then writes the rows."""
+    per sample fills them; the driver then writes the rows.
+
+    The re-count shards by sample: with `devices` = several CUDA ordinals, one context per device runs on
+    its own host thread and takes the samples dist.samples_of(rank, n_devices, n_samples); a sample's result depends on
+    nothing but its own BAM and gap list, so the host only collects the count arrays.  `ctx` (one existing context) takes
+    precedence; `context_factory(device)` replaces api.Context (tests)."""
     print("Combining samples...")
     titles, bed_paths, bam_paths = [], [], []
     with open(samplesFile) as fh:
@@ -131,33 +156,41 @@ def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType
                 raise Exception("Samples File contains lines that do not have exactly 3 tab-separated columns")
     n = len(titles)
     flags = api.mode_flags(isStranded, strandedType, False, combine=True)
-    own = ctx is None
     with CombineMerge() as cm:
         cm.add_samples(titles, bed_paths)
         regions = cm.region_names()
         order = _chrom_order([[regions[r] for r in cm.sample_runs(k)] for k in range(n)])
         region_id = {name: i for i, name in enumerate(regions)}
         cm.merge([region_id[name] for name in order], qGene, isStranded)
-        try:
-            for k in range(n):                      # one batched re-count per sample (every S:903 call of that sample)
-                gaps = cm.gaps(k)
-                if not len(gaps):
-                    continue
-                uniq, first = np.unique(gaps.chrom, return_index=True)
-                local = uniq[np.argsort(first)]     # the sample's gap regions in first-appearance order
-                names = [regions[r] for r in local]
-                remap = np.full(len(regions), -1, dtype=np.int32)
-                remap[local] = np.arange(len(local), dtype=np.int32)
-                gaps.chrom = np.ascontiguousarray(remap[gaps.chrom])
-                ctx = ctx or api.Context(0)
-                if records_by_bam is not None:
-                    b1, b2 = ctx.recount_records(records_by_bam(bam_paths[k], names), len(names), gaps, flags)
-                else:
-                    b1, b2 = ctx.recount_bam(bam_paths[k], names, gaps, flags)
-                cm.set_recount(k, b1, b2)
-        finally:
-            if own and ctx is not None:
-                ctx.close()
+        make = context_factory or api.Context
+        devs = [0] if not devices else list(devices)
+        if ctx is not None or len(devs) == 1:
+            own = None
+            try:
+                for k in range(n):
+                    if ctx is None and cm.n_gaps(k):
+                        ctx = own = make(devs[0])
+                    if cm.n_gaps(k):
+                        _recount_sample(ctx, cm, k, regions, bam_paths[k], flags, records_by_bam)
+            finally:
+                if own is not None:
+                    own.close()
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+
+            def rank_work(rank):                    # one context per device, samples dealt round-robin
+                mine = [k for k in samples_of(rank, len(devs), n) if cm.n_gaps(k)]
+                if not mine:
+                    return 0
+                c = make(devs[rank])
+                try:
+                    for k in mine:
+                        _recount_sample(c, cm, k, regions, bam_paths[k], flags, records_by_bam)
+                finally:
+                    c.close()
+                return len(mine)
+            with ThreadPoolExecutor(max_workers=len(devs)) as pool:
+                list(pool.map(rank_work, range(len(devs))))
         cm.write(outputPath + ".combined.tsv", isbeta2Cryptic)
         filled = cm.n_filled()
     print("Filled in Beta read counts for {} Sites not detected in some samples".format(filled))
@@ -188,8 +221,12 @@ def main(argv=None):
     c.add_argument("--isStranded", dest="isStranded", default=False, action="store_true")
     c.add_argument("-s", "--strandedType", dest="strandedType", nargs="?", default="fr", type=str)
     c.add_argument("--beta2Cryptic", dest="isbeta2Cryptic", default=False, action="store_true")
+    c.add_argument("--gpus", dest="n_gpus", nargs="?", default=1, type=int,
+                   help="re-count the samples on this many GPUs (sharded by sample; not a reference option)")
     kwargs = vars(parser.parse_args(argv))
     command = kwargs.pop("command")
+    if command == "combine":
+        kwargs["devices"] = list(range(max(1, kwargs.pop("n_gpus") or 1)))
     if command == "process" and kwargs.get("qGene") != "All" and (kwargs.get("annotationFile") is None or kwargs.get("maxIntronSize") is None):
         parser.error("--gene requires --annotationFile and --maxIntronSize")                      # S:1350-1353
     elif command in ("process", "combine") and kwargs.get("isStranded") and kwargs.get("strandedType") is None:

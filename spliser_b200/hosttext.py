@@ -182,6 +182,9 @@ class CombineMerge:
         q = None if qgene == "All" else str(qgene).encode()
         self._check(self._lib.spl_combine_merge(self._h, len(order), _ptr(order, L.c_i32p), q, int(bool(is_stranded))), "spl_combine_merge")
 
+    def n_gaps(self, k):
+        return int(self._lib.spl_combine_gaps(self._h, k, None, None, None, None, None, None, None))
+
     def gaps(self, k) -> GapTable:
         """Gap list of sample k; chromosome indices are region ids (region_names())."""
         ps = [L.c_i32p(), L.c_i32p(), L.c_u8p(), L.c_i64p(), L.c_i32p(), L.c_i64p(), L.c_i32p()]

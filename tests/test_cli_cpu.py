@@ -83,7 +83,7 @@ def test_combine_merge_driver_on_cpu(tmp_path, built_library):
         assert open(out + ".combined.tsv").read() == case["combined"], case.get("name", case.get("seed"))
 
 
-def _run_wide_combine(cli, ctx, case, d):
+def _run_wide_combine(cli, ctx, case, d, **combine_kw):
     """One combine_wide golden case through cli.process (per sample, with the annotation) and cli.combine."""
     lines = []
     gff = str(d / "a.gff")
@@ -102,8 +102,10 @@ def _run_wide_combine(cli, ctx, case, d):
     sf = str(d / "samples.tsv")
     open(sf, "w").writelines(lines)
     out = str(d / "out")
+    if combine_kw:
+        ctx = None
     cli.combine(sf, out, qGene=case["qgene"], isStranded=case["stranded"], strandedType=case["stype"],
-                isbeta2Cryptic=case["cryptic"], ctx=ctx)
+                isbeta2Cryptic=case["cryptic"], ctx=ctx, **combine_kw)
     assert open(out + ".combined.tsv").read() == case["combined"], case["seed"]
 
 
@@ -115,6 +117,24 @@ def test_combine_over_regions_genes_and_cryptic_on_cpu(tmp_path, built_library):
         d = tmp_path / ("w%d" % k)
         d.mkdir()
         _run_wide_combine(cli, ctx, case, d)
+
+
+def test_combine_sharded_by_sample_over_contexts_on_cpu(tmp_path, built_library):
+    """The re-count of `combine` sharded by sample: three stand-in contexts on three host threads, samples dealt
+    round-robin (dist.samples_of); the combined table does not depend on who re-counted which sample."""
+    from spliser_b200 import cli
+    made = []
+
+    def factory(device):
+        made.append(device)
+        return OracleContext()
+    cases = [c for c in load_golden("combine_wide.json.gz") if len(c["samples"]) >= 3][:12]
+    assert cases
+    for k, case in enumerate(cases):
+        d = tmp_path / ("m%d" % k)
+        d.mkdir()
+        _run_wide_combine(cli, OracleContext(), case, d, devices=[0, 1, 2], context_factory=factory)
+    assert set(made) <= {0, 1, 2} and len(set(made)) >= 2
 
 
 def test_cli_errors_mirror_the_reference(tmp_path, built_library):

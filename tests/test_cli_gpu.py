@@ -95,3 +95,19 @@ def test_combine_over_regions_genes_and_cryptic(ctx, tmp_path):
         d = tmp_path / ("w%d" % k)
         d.mkdir()
         _run_wide_combine(cli, ctx, case, d)
+
+
+def test_combine_sharded_by_sample_over_contexts(ctx, tmp_path):
+    """Sample-sharded re-count with one context per host thread.  On a one-GPU box both contexts sit on device 0 (what is
+    exercised is the concurrency of independent contexts); on a multi-GPU box they sit on devices 0 and 1."""
+    import ctypes
+    from spliser_b200 import cli
+    from test_cli_cpu import _run_wide_combine
+    n_dev = ctypes.c_int(0)
+    ctypes.CDLL("libcuda.so.1").cuDeviceGetCount(ctypes.byref(n_dev))       # the driver is initialised (ctx fixture)
+    devices = [0, 1] if n_dev.value >= 2 else [0, 0]
+    cases = [c for c in load_golden("combine_wide.json.gz") if len(c["samples"]) >= 3][:10]
+    for k, case in enumerate(cases):
+        d = tmp_path / ("m%d" % k)
+        d.mkdir()
+        _run_wide_combine(cli, ctx, case, d, devices=devices)
