@@ -10,6 +10,7 @@
 // (K3) or L2/latency bound graph lookups (K4, K5).  Site tiles are staged into shared memory with
 // a 1-D TMA bulk copy (cp.async.bulk + mbarrier), blocks are loaded 128 bits at a time, matches
 // are aggregated per warp with redux.sync before a single RED per (warp, site).
+#include <mutex>
 #include <cuda_runtime.h>
 #include <climits>
 #include <cstdint>
@@ -1381,23 +1382,28 @@ void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chu
 void launch_alpha_reduce(DevGraph, DevOutputs, void*) {
     // alpha / PartnerCounts are reduced by the extra blocks of k_span_blocksum (launch_finalize)
 }
-static int persistent_grid(const void* kernel, size_t smem) {
-    static int sms = 0;
-    if (!sms) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    }
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+// Grid of the persistent K3 kernel on the CURRENT device: the dynamic shared-memory attribute and the SM count belong to a
+// device, and one process may drive several (one context per device, e.g. the sample-sharded re-count of `combine`).
+static int beta1_grid() {
+    static std::mutex mu;
+    static int grid_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && grid_of[dev]) return grid_of[dev];
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute((const void*)k_beta1_stab, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K3Smem));
     int per_sm = 1;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, PS_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_beta1_stab, PS_THREADS, sizeof(K3Smem));
     if (per_sm < 1) per_sm = 1;
-    return sms * per_sm;                     // one resident CTA per slot: a multiple of the SM count
+    const int grid = sms * per_sm;           // one resident CTA per slot: a multiple of the SM count
+    if (dev >= 0 && dev < 64) grid_of[dev] = grid;
+    return grid;
 }
 void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream) {
     if (bins.n_tiles == 0 || g.n_sites <= 0) return;
-    static const int grid = persistent_grid((const void*)k_beta1_stab, sizeof(K3Smem));
-    k_beta1_stab<<<grid, PS_THREADS, sizeof(K3Smem), (cudaStream_t)stream>>>(bins, g, cnt);
+    k_beta1_stab<<<beta1_grid(), PS_THREADS, sizeof(K3Smem), (cudaStream_t)stream>>>(bins, g, cnt);
 }
 // phase A: table insert + scans; totals3[0] = distinct junctions, [1] = simple instances (read by the host to size
 // the dense arrays).  phase B: compaction + grouping; totals3[2] = complex instances, [3] = overflow flag.
