@@ -280,3 +280,91 @@ def test_combine_rejects_malformed_tables(tmp_path, built_library):
     sf.write_text("A\tonly-two-columns\n")
     with pytest.raises(Exception, match="exactly 3"):
         cli.combine(str(sf), str(tmp_path / "out"))
+
+
+def _bed_reference_semantics(lines, chrom_index=(), qchrom="All", bounds=None, max_intron=0):
+    """findAlphaCounts' text half (S:255-288) line by line, as plain Python: the checker for spl_bed_parse."""
+    chroms, out = list(chrom_index), []
+    for line in lines:
+        v = str(line).split("\t")
+        if len(v) != 12:
+            continue
+        if v[0] not in chroms:
+            chroms.append(v[0])
+        if not (qchrom == v[0] or qchrom == "All"):
+            continue
+        flank = v[10].split(",")
+        left, right, score = int(v[1]) + int(flank[0]), int(v[2]) - int(flank[1]), int(v[4])
+        if bounds is not None:
+            lin = (left + max_intron >= bounds[0]) and (left <= bounds[1])
+            rin = (right - max_intron <= bounds[1]) and (right >= bounds[0])
+            if not (lin or rin):
+                continue
+        out.append((chroms.index(v[0]), left, right, score, v[5]))
+    return chroms, out
+
+
+def test_native_bed_parser_edge_cases(tmp_path, built_library):
+    from spliser_b200.bed import parse_bed12
+
+    def row(chrom, start, end, score, strand, sizes="10,10", tail="0,90"):
+        return "\t".join([chrom, str(start), str(end), "J", str(score), strand, str(start), str(end), "255,0,0", "2", sizes, tail]) + "\n"
+    lines = [
+        "track name=junctions description=\"x\"\n",                       # not 12 fields
+        row("chrB", 90, 310, 5, "+"),
+        row("chrA", 90, 210, 3, "-"),
+        row("chrB", 190, 410, " 7 ", "?", sizes=" 12 , 8 ,"),               # int() strips blanks; regtools' trailing comma
+        row("chrC", 5, 60, "+4", ""),                                      # explicit sign, empty strand column
+        row("chrB", 90, 310, 2, "+-odd"),                                  # multi-character strand text is kept verbatim
+        row("chrA", 1000, 1300, 1, ".").rstrip("\n") + "\textra\n",        # 13 fields: skipped
+        "chrD\t1\t2\n",                                                    # short line
+        row("chrD", 400, 900, 9, "+", tail="0,490").rstrip("\n"),          # last line without a newline
+    ]
+    for kw in (dict(), dict(qchrom="chrB"), dict(qchrom="chrZ"), dict(chrom_index=["chrA", "chrQ"]),
+               dict(qchrom="chrB", bounds=(250, 320), max_intron=0), dict(bounds=(250, 320), max_intron=100)):
+        want_chroms, want = _bed_reference_semantics(lines, kw.get("chrom_index", ()), kw.get("qchrom", "All"), kw.get("bounds"), kw.get("max_intron", 0))
+        chroms, j, sstr = parse_bed12(lines, kw.get("chrom_index"), kw.get("qchrom", "All"), kw.get("bounds"), kw.get("max_intron", 0))
+        got = [(int(j.chrom[i]), int(j.left[i]), int(j.right[i]), int(j.score[i]), sstr[i]) for i in range(len(j))]
+        assert chroms == want_chroms and got == want, kw
+        assert [int(b) for b in j.strand] == [(ord(s[0]) if s else 0) for *_, s in want]
+    # the same bytes through a file handle, with CRLF line ends (text mode translates them before the reference sees them)
+    p = tmp_path / "crlf.bed"
+    p.write_bytes("".join(lines).replace("\n", "\r\n").encode())
+    with open(p) as fh:
+        chroms, j, sstr = parse_bed12(fh)
+    assert (chroms, len(j)) == (_bed_reference_semantics(lines)[0], len(_bed_reference_semantics(lines)[1]))
+    with pytest.raises(ValueError):
+        parse_bed12([row("c", "x1", 60, 1, "+")])                          # int('x1') raises in the reference too
+    with pytest.raises(ValueError):
+        parse_bed12([row("c", 5, 60, 1, "+", sizes="10")])                 # flankSize[1] does not exist
+    with pytest.raises(OverflowError):
+        parse_bed12([row("c", 2 ** 31, 2 ** 31 + 50, 1, "+")])
+    assert len(parse_bed12([])[1]) == 0 and parse_bed12("")[0] == []
+
+
+def test_native_combine_parser_edge_cases(tmp_path, built_library):
+    """Rows as the merge loop reads them (S:836: rstrip() then split on tabs): CRLF line ends, trailing blanks, extra
+    columns, a dict text with a repeated key, NA cryptic columns; two samples with and without the site."""
+    from spliser_b200 import cli
+    hdr = "Region\tSite\tStrand\tGene\tSSE\talpha_count\tbeta1_count\tbeta2Simple_count\tbeta2Cryptic_count\tbeta2Cryptic_weighted\tPartners\tCompetitors"
+    a = [hdr, "C\t100\t+\tg1\t0.500\t4\t3\t1\tNA\tNA\t{300: 4, 300: 5}\t[250]\textra\tcolumns   ",
+         "C\t300\t+\tg1\t1.000\t4\t0\t0\tNA\tNA\t{100: 4}\t[]"]
+    b = [hdr, "C\t100\t+\tg1\t0.250\t1\t3\t0\tNA\tNA\t{ 250 : 1 }\t[ 300 ]\t"]
+    (tmp_path / "a.tsv").write_bytes(("\r\n".join(a) + "\r\n").encode())
+    (tmp_path / "b.tsv").write_bytes(("\n".join(b)).encode())                 # no final newline
+
+    class NoReads:
+        def recount_bam(self, bam, names, gaps, flags):
+            assert names == ["C"] and [g[1] for g in gaps] == [300] and [g[3] for g in gaps] == [[100]]
+            return np.array([7]), np.array([2])
+
+        def close(self):
+            pass
+    sf = tmp_path / "samples.tsv"
+    sf.write_text("A\t%s\tx.bam\nB\t%s\ty.bam\n" % (tmp_path / "a.tsv", tmp_path / "b.tsv"))
+    cli.combine(str(sf), str(tmp_path / "out"), ctx=NoReads())
+    got = open(str(tmp_path / "out") + ".combined.tsv").read().splitlines()[1:]
+    assert got == ["A\tC\t100\t+\tg1\t0.500\t4\t3\t1\tNA\tNA\t{300: 5, 250: 0}\t[250, 300]",
+                   "B\tC\t100\t+\tg1\t0.250\t1\t3\t0\tNA\tNA\t{300: 0, 250: 1}\t[250, 300]",
+                   "A\tC\t300\t+\tg1\t1.000\t4\t0\t0\tNA\tNA\t{100: 4}\t[]",
+                   "B\tC\t300\t+\tg1\t0.000\t0\t7\t2\tNA\tNA\t{100: 0}\t[]"]
