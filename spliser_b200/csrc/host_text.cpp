@@ -811,74 +811,133 @@ bool bed_int(std::string_view s, long long* out) {
 }
 }  // namespace
 
+namespace {
+struct BedFilter {
+    const char* qchrom;
+    bool window;
+    long long gene_left, gene_right, max_intron;
+};
+
+// Parses the lines of text[lo, hi) (hi at a line boundary) into `b` with ids local to `b`; returns SPL_OK or the error
+// of the first bad line (err_line = its 1-based number inside the piece).  n_lines = lines seen.
+int bed_parse_piece(const char* text, int64_t lo, int64_t hi, const BedFilter& f, spl_bed* b, int64_t* n_lines,
+                    int64_t* err_line, const char** err_msg) {
+    const std::string_view q = f.qchrom ? std::string_view(f.qchrom) : std::string_view();
+    int64_t at = lo, line_no = 0;
+    *n_lines = 0;
+    while (at < hi) {
+        // one pass over the line: fields end at tabs, the line at '\n' (its text stays out of the last field)
+        const char* p = text + at;
+        const char* const e = text + hi;
+        const char* field = p;
+        std::string_view col[12];
+        int nc = 0;
+        for (; p < e && *p != '\n'; ++p) {
+            if (*p == '\t') {
+                if (nc < 12) col[nc] = std::string_view(field, (size_t)(p - field));
+                ++nc;
+                field = p + 1;
+            }
+        }
+        if (nc < 12) col[nc] = std::string_view(field, (size_t)(p - field));
+        ++nc;
+        at = p < e ? (p - text) + 1 : hi;
+        *n_lines = ++line_no;
+        if (nc != 12) continue;                                          // S:259
+        const int32_t ci = b->chroms.id(col[0]);                         // registered before the -c test (S:265-269)
+        if (f.qchrom && col[0] != q) continue;
+        std::string_view sizes = col[10];
+        size_t comma = sizes.find(',');
+        if (comma == std::string_view::npos) { *err_line = line_no; *err_msg = "blockSizes needs two values"; return SPL_ERR_ARG; }
+        std::string_view second = sizes.substr(comma + 1);
+        second = second.substr(0, second.find(','));
+        long long start, stop, a0, a1, score;
+        if (!bed_int(col[1], &start) || !bed_int(col[2], &stop) || !bed_int(sizes.substr(0, comma), &a0) ||
+            !bed_int(second, &a1) || !bed_int(col[4], &score)) {
+            *err_line = line_no; *err_msg = "invalid literal for int()";
+            return SPL_ERR_ARG;
+        }
+        const long long left = start + a0, right = stop - a1;            // S:275-276
+        if (f.window) {                                                  // S:279-288
+            const bool lin = (left + f.max_intron >= f.gene_left) && (left <= f.gene_right);
+            const bool rin = (right - f.max_intron <= f.gene_right) && (right >= f.gene_left);
+            if (!(lin || rin)) continue;
+        }
+        if (left < INT32_MIN || left > INT32_MAX || right < INT32_MIN || right > INT32_MAX) {
+            *err_line = line_no; *err_msg = "position outside 32 bits";
+            return SPL_ERR_RANGE;
+        }
+        b->chrom.push_back(ci);
+        b->left.push_back((int32_t)left);
+        b->right.push_back((int32_t)right);
+        b->score.push_back(score);
+        b->strand.push_back(col[5].empty() ? 0 : (uint8_t)col[5][0]);
+        b->strand_id.push_back(b->strand_texts.id(col[5]));
+    }
+    return SPL_OK;
+}
+}  // namespace
+
+// The file image is cut into pieces at line ends; the pieces parse concurrently with ids local to the piece and are
+// appended in file order, which renumbers chromosomes and strand texts by first appearance exactly as one pass would.
 extern "C" int spl_bed_parse(const char* text, int64_t len, const spl_strtab* chrom_index, const char* qchrom,
                              int use_gene_window, int64_t gene_left, int64_t gene_right, int64_t max_intron,
                              spl_bed** out, char* err, int err_len) {
     if (!out || len < 0 || (len && !text)) { set_err(err, err_len, "spl_bed_parse: null argument"); return SPL_ERR_ARG; }
     spl_bed* b = new (std::nothrow) spl_bed();
     if (!b) return SPL_ERR_NOMEM;
+    const BedFilter f{qchrom, use_gene_window != 0, gene_left, gene_right, max_intron};
     try {
         if (chrom_index)
             for (int64_t i = 0; i < chrom_index->n; ++i) b->chroms.id(tab_get(chrom_index, i));
-        const std::string_view q = qchrom ? std::string_view(qchrom) : std::string_view();
-        int64_t at = 0, line_no = 0;
-        while (at < len) {
-            // one pass over the line: fields end at tabs, the line at '\n' (its text stays out of the last field)
-            const char* p = text + at;
-            const char* const e = text + len;
-            const char* field = p;
-            std::string_view col[12];
-            int nc = 0;
-            for (; p < e && *p != '\n'; ++p) {
-                if (*p == '\t') {
-                    if (nc < 12) col[nc] = std::string_view(field, (size_t)(p - field));
-                    ++nc;
-                    field = p + 1;
-                }
-            }
-            if (nc < 12) col[nc] = std::string_view(field, (size_t)(p - field));
-            ++nc;
-            at = p < e ? (p - text) + 1 : len;
-            ++line_no;
-            const bool more = false;
-            if (nc != 12 || more) continue;                                  // S:259
-            const int32_t ci = b->chroms.id(col[0]);                         // registered before the -c test (S:265-269)
-            if (qchrom && col[0] != q) continue;
-            std::string_view sizes = col[10];
-            size_t comma = sizes.find(',');
-            if (comma == std::string_view::npos) {
-                set_err(err, err_len, "BED line %lld: blockSizes needs two values", (long long)line_no);
-                delete b;
-                return SPL_ERR_ARG;
-            }
-            std::string_view second = sizes.substr(comma + 1);
-            second = second.substr(0, second.find(','));
-            long long start, stop, a0, a1, score;
-            if (!bed_int(col[1], &start) || !bed_int(col[2], &stop) || !bed_int(sizes.substr(0, comma), &a0) ||
-                !bed_int(second, &a1) || !bed_int(col[4], &score)) {
-                set_err(err, err_len, "BED line %lld: invalid literal for int()", (long long)line_no);
-                delete b;
-                return SPL_ERR_ARG;
-            }
-            const long long left = start + a0, right = stop - a1;            // S:275-276
-            if (use_gene_window) {                                           // S:279-288
-                const bool lin = (left + max_intron >= gene_left) && (left <= gene_right);
-                const bool rin = (right - max_intron <= gene_right) && (right >= gene_left);
-                if (!(lin || rin)) continue;
-            }
-            if (left < INT32_MIN || left > INT32_MAX || right < INT32_MIN || right > INT32_MAX) {
-                set_err(err, err_len, "BED line %lld: position outside 32 bits", (long long)line_no);
-                delete b;
-                return SPL_ERR_RANGE;
-            }
-            b->chrom.push_back(ci);
-            b->left.push_back((int32_t)left);
-            b->right.push_back((int32_t)right);
-            b->score.push_back(score);
-            b->strand.push_back(col[5].empty() ? 0 : (uint8_t)col[5][0]);
-            b->strand_id.push_back(b->strand_texts.id(col[5]));
+        const int nt = worker_count(0, (size_t)(len / (1 << 20)) + 1);       // about 1 MB of text per piece and worker
+        std::vector<int64_t> cut{0};
+        for (int k = 1; k < nt; ++k) {
+            int64_t c = std::max(cut.back(), len * k / nt);
+            const char* nl = c < len ? (const char*)memchr(text + c, '\n', (size_t)(len - c)) : nullptr;
+            cut.push_back(nl ? (nl - text) + 1 : len);
         }
-    } catch (const std::bad_alloc&) {
+        cut.push_back(len);
+        const size_t np = cut.size() - 1;
+        std::vector<spl_bed> piece(np);
+        std::vector<int> rc(np, SPL_OK);
+        std::vector<int64_t> lines(np, 0), bad_line(np, 0);
+        std::vector<const char*> msg(np, "");
+        std::atomic<size_t> next{0};
+        auto work = [&]() {
+            for (size_t k; (k = next.fetch_add(1)) < np;) {
+                try { rc[k] = bed_parse_piece(text, cut[k], cut[k + 1], f, &piece[k], &lines[k], &bad_line[k], &msg[k]); }
+                catch (const std::bad_alloc&) { rc[k] = SPL_ERR_NOMEM; msg[k] = "out of memory"; }
+            }
+        };
+        run_parallel((int)std::min<size_t>((size_t)nt, np), work);
+        int64_t line0 = 0;
+        for (size_t k = 0; k < np; ++k) {                                    // the first bad line in file order decides
+            if (rc[k] != SPL_OK) {
+                if (rc[k] == SPL_ERR_NOMEM) set_err(err, err_len, "out of memory");
+                else set_err(err, err_len, "BED line %lld: %s", (long long)(line0 + bad_line[k]), msg[k]);
+                const int code = rc[k];
+                delete b;
+                return code;
+            }
+            line0 += lines[k];
+        }
+        size_t total = 0;
+        for (auto& pc : piece) total += pc.chrom.size();
+        b->chrom.reserve(total); b->left.reserve(total); b->right.reserve(total);
+        b->score.reserve(total); b->strand.reserve(total); b->strand_id.reserve(total);
+        for (auto& pc : piece) {
+            std::vector<int32_t> cmap, smap;
+            for (auto& nm : pc.chroms.names) cmap.push_back(b->chroms.id(nm));
+            for (auto& nm : pc.strand_texts.names) smap.push_back(b->strand_texts.id(nm));
+            for (int32_t v : pc.chrom) b->chrom.push_back(cmap[(size_t)v]);
+            for (int32_t v : pc.strand_id) b->strand_id.push_back(smap[(size_t)v]);
+            b->left.insert(b->left.end(), pc.left.begin(), pc.left.end());
+            b->right.insert(b->right.end(), pc.right.begin(), pc.right.end());
+            b->score.insert(b->score.end(), pc.score.begin(), pc.score.end());
+            b->strand.insert(b->strand.end(), pc.strand.begin(), pc.strand.end());
+        }
+    } catch (const std::exception&) {
         delete b;
         set_err(err, err_len, "out of memory");
         return SPL_ERR_NOMEM;

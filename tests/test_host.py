@@ -368,3 +368,36 @@ def test_native_combine_parser_edge_cases(tmp_path, built_library):
                    "B\tC\t100\t+\tg1\t0.250\t1\t3\t0\tNA\tNA\t{300: 0, 250: 1}\t[250, 300]",
                    "A\tC\t300\t+\tg1\t1.000\t4\t0\t0\tNA\tNA\t{100: 4}\t[]",
                    "B\tC\t300\t+\tg1\t0.000\t0\t7\t2\tNA\tNA\t{100: 0}\t[]"]
+
+
+def test_native_bed_parser_in_pieces(built_library):
+    """A BED12 image of several MB is cut at line ends and parsed concurrently; the merged result (chromosome index and
+    strand-text ids by first appearance, row order, the line number of the first bad line) equals one sequential pass."""
+    import random
+    from spliser_b200.bed import parse_bed12
+    rng = random.Random(4)
+    chrom_pool = ["chr%d" % i for i in range(1, 40)]
+    lines = []
+    for i in range(70000):
+        c = chrom_pool[min(len(chrom_pool) - 1, (i * len(chrom_pool)) // 70000 + rng.choice([0, 0, 0, 1]))]
+        s = rng.randrange(1, 10 ** 8)
+        e = s + rng.randrange(60, 5000)
+        strand = rng.choice(["+", "-", "?", ".", "+x", "st%d" % (i // 9000)])
+        lines.append("%s\t%d\t%d\tJUNC%08d\t%d\t%s\t%d\t%d\t255,0,0\t2\t%d,%d\t0,%d\n"
+                     % (c, s, e, i, rng.randrange(1, 999), strand, s, e, rng.randrange(8, 30), rng.randrange(8, 30), e - s - 8))
+        if i % 5000 == 17:
+            lines.append("# comment line %d\n" % i)
+    text = "".join(lines)
+    assert len(text) > 4 * (1 << 20)
+    for kw in (dict(), dict(qchrom="chr7"), dict(chrom_index=["chr30", "zz"], bounds=(10 ** 7, 2 * 10 ** 7), max_intron=50000)):
+        want_chroms, want = _bed_reference_semantics(lines, kw.get("chrom_index", ()), kw.get("qchrom", "All"), kw.get("bounds"), kw.get("max_intron", 0))
+        chroms, j, sstr = parse_bed12(text, kw.get("chrom_index"), kw.get("qchrom", "All"), kw.get("bounds"), kw.get("max_intron", 0))
+        assert chroms == want_chroms and len(j) == len(want)
+        assert list(zip(j.chrom.tolist(), j.left.tolist(), j.right.tolist(), j.score.tolist(), list(sstr))) == want
+    bad = list(lines)
+    bad[61234] = bad[61234].replace("JUNC", "J").replace("\t255,0,0", "\t255,0,0", 1).split("\t")
+    bad[61234][1] = "12x"
+    bad[61234] = "\t".join(bad[61234])
+    bad[69000] = bad[69000].replace("\t2\t", "\t2\tq", 1)
+    with pytest.raises(ValueError, match="BED line 61235:"):
+        parse_bed12("".join(bad))
