@@ -235,6 +235,27 @@ const char* spl_bed_chrom_name(const spl_bed* b, int64_t i, int64_t* len);
 int64_t spl_bed_n_strand_texts(const spl_bed* b);
 const char* spl_bed_strand_text(const spl_bed* b, int64_t i, int64_t* len);
 
+/* createGenes (S:50-116) for a whole GFF / GTF file image, without HTSeq: feature lines of type "gene" give
+ * leftPos = start - 1, rightPos = end, the strand column and, as name, the value of the first attribute
+ * (README.md:64).  Chromosomes in first-appearance order among the gene lines (S:90-92); genes grouped by
+ * chromosome (spl_genes_chrom_off), each list in insort order by leftPos (S:95).  With qgene != NULL only
+ * the genes of that name are kept (file order) and spl_genes_query is the last of them (QUERY_gene). */
+typedef struct spl_genes spl_genes;
+int spl_genes_parse(const char* text, int64_t len, const char* qgene, spl_genes** out, char* err, int err_len);
+void spl_genes_free(spl_genes* g);
+int64_t spl_genes_n(const spl_genes* g);
+int64_t spl_genes_n_chrom(const spl_genes* g);
+const char* spl_genes_chrom_name(const spl_genes* g, int64_t i, int64_t* len);
+const int64_t* spl_genes_chrom_off(const spl_genes* g);
+const int32_t* spl_genes_left(const spl_genes* g);
+const int32_t* spl_genes_right(const spl_genes* g);
+const int32_t* spl_genes_strand_id(const spl_genes* g);
+int64_t spl_genes_n_strand_texts(const spl_genes* g);
+const char* spl_genes_strand_text(const spl_genes* g, int64_t i, int64_t* len);
+const char* spl_genes_names(const spl_genes* g);          /* blob of all names, see spl_genes_name_off */
+const int64_t* spl_genes_name_off(const spl_genes* g);    /* [n + 1] */
+int64_t spl_genes_query(const spl_genes* g);              /* flat index of QUERY_gene, -1 = none */
+
 /* binary_gene_search (S:118-173) for n positions against the genes of ONE chromosome in list order
  * (insort by leftPos, S:95), control flow kept: overlapping genes make the bisection order-dependent
  * and the last-ditch window (S:162-169) never looks at the last gene.  Strands are compared as ids

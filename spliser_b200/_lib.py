@@ -100,6 +100,20 @@ SIGNATURES = {
     "spl_bed_chrom_name": (C.c_void_p, [C.c_void_p, C.c_int64, c_i64p]),
     "spl_bed_n_strand_texts": (C.c_int64, [C.c_void_p]),
     "spl_bed_strand_text": (C.c_void_p, [C.c_void_p, C.c_int64, c_i64p]),
+    "spl_genes_parse": (C.c_int, [C.c_char_p, C.c_int64, C.c_char_p, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
+    "spl_genes_free": (None, [C.c_void_p]),
+    "spl_genes_n": (C.c_int64, [C.c_void_p]),
+    "spl_genes_n_chrom": (C.c_int64, [C.c_void_p]),
+    "spl_genes_chrom_name": (C.c_void_p, [C.c_void_p, C.c_int64, c_i64p]),
+    "spl_genes_chrom_off": (c_i64p, [C.c_void_p]),
+    "spl_genes_left": (c_i32p, [C.c_void_p]),
+    "spl_genes_right": (c_i32p, [C.c_void_p]),
+    "spl_genes_strand_id": (c_i32p, [C.c_void_p]),
+    "spl_genes_n_strand_texts": (C.c_int64, [C.c_void_p]),
+    "spl_genes_strand_text": (C.c_void_p, [C.c_void_p, C.c_int64, c_i64p]),
+    "spl_genes_names": (C.c_void_p, [C.c_void_p]),
+    "spl_genes_name_off": (c_i64p, [C.c_void_p]),
+    "spl_genes_query": (C.c_int64, [C.c_void_p]),
     "spl_gene_search": (C.c_int, [C.c_int64, c_i32p, c_i32p, c_i32p, C.c_int64, c_i32p, c_i32p, C.c_int32, C.c_int32, C.c_int, c_i32p]),
     "spl_write_process_tsv": (C.c_int, [C.c_char_p, C.POINTER(SiteColumns), C.POINTER(StrTab), C.POINTER(StrTab), c_i32p,
                                         C.POINTER(StrTab), c_i32p, C.c_int, C.c_char_p, C.c_int]),

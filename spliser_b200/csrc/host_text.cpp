@@ -966,3 +966,134 @@ extern "C" const char* spl_bed_strand_text(const spl_bed* b, int64_t i, int64_t*
     if (len) *len = (int64_t)b->strand_texts.names[(size_t)i].size();
     return b->strand_texts.names[(size_t)i].data();
 }
+
+// ========================================================================================================== annotation
+// createGenes (S:50-116) without HTSeq: every feature line whose type column is "gene" becomes a Gene with
+// leftPos = GFF start - 1, rightPos = GFF end (HTSeq's iv.start / iv.end), its strand column and, as name, the value of
+// its first attribute (README.md:64).  Chromosomes are indexed by first appearance among the gene lines (S:90-92).
+// Without a query gene every chromosome's list is in insort order (S:95: bisect.insort by leftPos = stable sort by
+// leftPos); with one, only the genes of that name are kept, in file order, and the last of them is QUERY_gene (S:97-101).
+struct spl_genes {
+    Interner chroms, strand_texts;
+    std::vector<int64_t> chrom_off;                    // [n_chrom + 1] into the arrays below (grouped by chromosome)
+    std::vector<int32_t> left, right, strand_id;
+    std::vector<int64_t> name_off{0};
+    std::string names;
+    int64_t query = -1;                                // flat index of QUERY_gene, -1 = none
+};
+
+namespace {
+struct GeneRow { int32_t chrom, left, right, strand; int64_t name_at, name_len, order; };
+
+std::string_view py_strip(std::string_view s) {
+    while (!s.empty() && is_py_space(s.front())) s.remove_prefix(1);
+    while (!s.empty() && is_py_space(s.back())) s.remove_suffix(1);
+    return s;
+}
+
+// value of the first attribute: "ID=AT1G01010;..." -> AT1G01010 (GFF3), 'gene_id "X"; ...' -> X (GTF)
+std::string_view first_attribute(std::string_view col9) {
+    std::string_view first = py_strip(col9.substr(0, col9.find(';')));
+    const size_t eq = first.find('=');
+    if (eq != std::string_view::npos) return first.substr(eq + 1);
+    size_t ws = 0;
+    while (ws < first.size() && !is_py_space(first[ws])) ++ws;
+    if (ws == first.size()) return first;
+    std::string_view rest = first.substr(ws);
+    while (!rest.empty() && is_py_space(rest.front())) rest.remove_prefix(1);
+    while (!rest.empty() && rest.front() == '"') rest.remove_prefix(1);
+    while (!rest.empty() && rest.back() == '"') rest.remove_suffix(1);
+    return rest;
+}
+}  // namespace
+
+extern "C" int spl_genes_parse(const char* text, int64_t len, const char* qgene, spl_genes** out, char* err, int err_len) {
+    if (!out || len < 0 || (len && !text)) { set_err(err, err_len, "spl_genes_parse: null argument"); return SPL_ERR_ARG; }
+    spl_genes* g = new (std::nothrow) spl_genes();
+    if (!g) return SPL_ERR_NOMEM;
+    try {
+        const std::string_view q = qgene ? std::string_view(qgene) : std::string_view();
+        std::vector<GeneRow> rows;
+        int64_t at = 0, line_no = 0, last_match = -1;
+        while (at < len) {
+            const char* nl = (const char*)memchr(text + at, '\n', (size_t)(len - at));
+            const int64_t end = nl ? (nl - text) : len;
+            std::string_view line(text + at, (size_t)(end - at));
+            at = nl ? end + 1 : len;
+            ++line_no;
+            if (line.empty() || line.front() == '#') continue;
+            std::string_view col[9];
+            int nc = 0;
+            {
+                const char* p = line.data();
+                const char* const e = p + line.size();
+                const char* field = p;
+                for (; p < e && nc < 9; ++p)
+                    if (*p == '\t') { col[nc++] = std::string_view(field, (size_t)(p - field)); field = p + 1; }
+                if (nc < 9) col[nc++] = std::string_view(field, (size_t)(e - field));
+            }
+            if (nc < 9 || col[2] != "gene") continue;
+            long long start, stop;
+            if (!bed_int(col[3], &start) || !bed_int(col[4], &stop)) {
+                set_err(err, err_len, "annotation line %lld: invalid literal for int()", (long long)line_no);
+                delete g;
+                return SPL_ERR_ARG;
+            }
+            if (start - 1 < INT32_MIN || start - 1 > INT32_MAX || stop < INT32_MIN || stop > INT32_MAX) {
+                set_err(err, err_len, "annotation line %lld: position outside 32 bits", (long long)line_no);
+                delete g;
+                return SPL_ERR_RANGE;
+            }
+            const std::string_view name = first_attribute(col[8]);
+            const int32_t ci = g->chroms.id(col[0]);             // registered for every gene line, kept or not (S:90-92)
+            if (qgene && name != q) continue;
+            if (qgene) last_match = (int64_t)rows.size();
+            rows.push_back(GeneRow{ci, (int32_t)(start - 1), (int32_t)stop, g->strand_texts.id(col[6]),
+                                   (int64_t)(name.data() - text), (int64_t)name.size(), (int64_t)rows.size()});
+        }
+        // group by chromosome; inside one: insort order (stable by leftPos) without a query gene, file order with one
+        std::stable_sort(rows.begin(), rows.end(), [&](const GeneRow& a, const GeneRow& b) {
+            if (a.chrom != b.chrom) return a.chrom < b.chrom;
+            return !qgene && a.left < b.left;
+        });
+        const size_t nc = g->chroms.names.size();
+        g->chrom_off.assign(nc + 1, 0);
+        for (const GeneRow& r : rows) g->chrom_off[(size_t)r.chrom + 1]++;
+        for (size_t c = 0; c < nc; ++c) g->chrom_off[c + 1] += g->chrom_off[c];
+        for (size_t i = 0; i < rows.size(); ++i) {
+            const GeneRow& r = rows[i];
+            g->left.push_back(r.left); g->right.push_back(r.right); g->strand_id.push_back(r.strand);
+            g->names.append(text + r.name_at, (size_t)r.name_len);
+            g->name_off.push_back((int64_t)g->names.size());
+            if (r.order == last_match) g->query = (int64_t)i;
+        }
+    } catch (const std::exception&) {
+        delete g;
+        set_err(err, err_len, "out of memory");
+        return SPL_ERR_NOMEM;
+    }
+    *out = g;
+    return SPL_OK;
+}
+
+extern "C" void spl_genes_free(spl_genes* g) { delete g; }
+extern "C" int64_t spl_genes_n(const spl_genes* g) { return g ? (int64_t)g->left.size() : 0; }
+extern "C" int64_t spl_genes_n_chrom(const spl_genes* g) { return g ? (int64_t)g->chroms.names.size() : 0; }
+extern "C" const char* spl_genes_chrom_name(const spl_genes* g, int64_t i, int64_t* len) {
+    if (!g || i < 0 || i >= (int64_t)g->chroms.names.size()) return nullptr;
+    if (len) *len = (int64_t)g->chroms.names[(size_t)i].size();
+    return g->chroms.names[(size_t)i].data();
+}
+extern "C" const int64_t* spl_genes_chrom_off(const spl_genes* g) { return g->chrom_off.data(); }
+extern "C" const int32_t* spl_genes_left(const spl_genes* g) { return g->left.data(); }
+extern "C" const int32_t* spl_genes_right(const spl_genes* g) { return g->right.data(); }
+extern "C" const int32_t* spl_genes_strand_id(const spl_genes* g) { return g->strand_id.data(); }
+extern "C" int64_t spl_genes_n_strand_texts(const spl_genes* g) { return g ? (int64_t)g->strand_texts.names.size() : 0; }
+extern "C" const char* spl_genes_strand_text(const spl_genes* g, int64_t i, int64_t* len) {
+    if (!g || i < 0 || i >= (int64_t)g->strand_texts.names.size()) return nullptr;
+    if (len) *len = (int64_t)g->strand_texts.names[(size_t)i].size();
+    return g->strand_texts.names[(size_t)i].data();
+}
+extern "C" const char* spl_genes_names(const spl_genes* g) { return g->names.data(); }
+extern "C" const int64_t* spl_genes_name_off(const spl_genes* g) { return g->name_off.data(); }
+extern "C" int64_t spl_genes_query(const spl_genes* g) { return g ? g->query : -1; }

@@ -1,14 +1,15 @@
-"""Annotation loading and gene assignment -- host-side Python, outside the accelerated path.
+"""Annotation loading and gene assignment -- host side, outside the counting path.
 
-Restates createGenes (SpliSER_v0_1_8.py:50-116) without HTSeq (not installable here) and
-binary_gene_search (S:118-173) with its quirks, because the Gene column of the .SpliSER.tsv is a
+Restates createGenes (SpliSER_v0_1_8.py:50-116) without HTSeq (not installable here; the file is parsed natively by
+spl_genes_parse) and binary_gene_search (S:118-173) with its quirks (the product runs the native spl_gene_search; the
+Python version below is the readable restatement the tests compare it with), because the Gene column of the .SpliSER.tsv is a
 pure function of (chromosome, position, strand of the BED row that created the site) and must not
 change.  HTSeq.GFF_Reader semantics relied upon: iv.start = GFF start - 1, iv.end = GFF end, name =
 value of the first attribute (README.md:64).
 """
 from __future__ import annotations
 
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 
 
 @dataclass(order=False)
@@ -26,57 +27,79 @@ class Gene:
 NA_NAME = "NA"
 
 
-@dataclass
+class GeneColumns:
+    """The genes of an annotation as flat arrays grouped by chromosome (what spl_genes_parse returns):
+    genes of chromosome c are rows chrom_off[c] .. chrom_off[c + 1] in list order (S:95)."""
+
+    def __init__(self, chrom_off, left, right, strand_id, strand_texts, names):
+        self.chrom_off, self.left, self.right, self.strand_id = chrom_off, left, right, strand_id
+        self.strand_texts, self.names = strand_texts, names
+
+
 class Annotation:
-    chrom_index: list = field(default_factory=list)       # first-appearance order (S:90-92)
-    genes: list = field(default_factory=list)             # per chromosome, insort by leftPos (S:95)
-    query_gene: Gene | None = None
+    """chrom_index: first-appearance order (S:90-92); genes: per chromosome, insort by leftPos (S:95), as Gene objects
+    (built on first use when the annotation came from the native parser, which keeps them as GeneColumns)."""
+
+    def __init__(self, chrom_index=None, genes=None, query_gene=None, columns=None):
+        self.chrom_index = list(chrom_index) if chrom_index is not None else []
+        self._genes = genes if genes is not None or columns is not None else []
+        self.query_gene = query_gene
+        self.columns = columns
+
+    @property
+    def genes(self):
+        if self._genes is None:
+            c = self.columns
+            self._genes = [[Gene(self.chrom_index[ci], c.names[k], int(c.left[k]), int(c.right[k]), c.strand_texts[int(c.strand_id[k])])
+                            for k in range(int(c.chrom_off[ci]), int(c.chrom_off[ci + 1]))] for ci in range(len(self.chrom_index))]
+        return self._genes
 
     def genes_of(self, chrom_idx):
         return self.genes[chrom_idx] if chrom_idx < len(self.genes) else []
 
 
-def _first_attribute(col9: str) -> str:
-    first = col9.split(";")[0].strip()
-    if "=" in first:
-        return first.split("=", 1)[1]
-    parts = first.split(None, 1)             # GTF: key "value"
-    return parts[1].strip('"') if len(parts) > 1 else first
-
-
 def load_annotation(path, qgene="All") -> Annotation:
-    """createGenes (S:50-116).  The -t/--annotationType argument is ignored by the reference (S:82 tests
-    the literal 'gene'), so it is not a parameter here."""
-    ann = Annotation()
-    index = {}
-    with open(path) as fh:
-        for line in fh:
-            if line.startswith("#") or "\tgene\t" not in line:      # cheap pre-filter; the column test below decides
-                continue
-            f = line.rstrip("\n").split("\t")
-            if len(f) < 9 or f[2] != "gene":
-                continue
-            chrom = f[0]
-            name = _first_attribute(f[8])
-            ci = index.get(chrom)
-            if ci is None:
-                ci = index[chrom] = len(ann.chrom_index)
-                ann.chrom_index.append(chrom)
-                ann.genes.append([])
-            g = Gene(chrom, name, int(f[3]) - 1, int(f[4]), f[6])
-            if qgene == "All":
-                ann.genes[ci].append(g)
-            elif name == qgene:
-                ann.query_gene = g
-                ann.genes[ci].append(g)
-    if qgene == "All":
-        for genes in ann.genes:          # insort_right by leftPos in file order (S:95) == stable sort by leftPos
-            genes.sort(key=_left_of)
+    """createGenes (S:50-116), parsed natively (spl_genes_parse).  The -t/--annotationType argument is ignored by the
+    reference (S:82 tests the literal 'gene'), so it is not a parameter here."""
+    import ctypes as C
+
+    import numpy as np
+
+    from . import _lib as L
+    lib = L.load()
+    with open(path, "rb") as fh:
+        raw = fh.read()
+    if b"\r" in raw:                                   # the reference reads in text mode (universal newlines)
+        raw = raw.replace(b"\r\n", b"\n").replace(b"\r", b"\n")
+    h = C.c_void_p()
+    err = C.create_string_buffer(256)
+    rc = lib.spl_genes_parse(raw, len(raw), None if qgene == "All" else str(qgene).encode(), C.byref(h), err, 256)
+    if rc != 0:
+        raise (OverflowError if rc == -5 else ValueError)(err.value.decode())
+    try:
+        n, nc = lib.spl_genes_n(h), lib.spl_genes_n_chrom(h)
+
+        def arr(p, cnt, dt):
+            return np.ctypeslib.as_array(p, shape=(cnt,)).astype(dt, copy=True) if cnt else np.zeros(0, dt)
+
+        def texts(count, get):
+            ln = C.c_int64()
+            return [C.string_at(get(h, i, C.byref(ln)), ln.value).decode() for i in range(count)]
+        name_off = arr(lib.spl_genes_name_off(h), n + 1, np.int64)
+        blob = C.string_at(lib.spl_genes_names(h), int(name_off[-1])) if n else b""
+        off = name_off.tolist()
+        names = [blob[off[k]:off[k + 1]].decode() for k in range(n)]
+        cols = GeneColumns(arr(lib.spl_genes_chrom_off(h), nc + 1, np.int64), arr(lib.spl_genes_left(h), n, np.int32),
+                           arr(lib.spl_genes_right(h), n, np.int32), arr(lib.spl_genes_strand_id(h), n, np.int32),
+                           texts(lib.spl_genes_n_strand_texts(h), lib.spl_genes_strand_text), names)
+        ann = Annotation(texts(nc, lib.spl_genes_chrom_name), None, None, cols)
+        k = lib.spl_genes_query(h)
+        if k >= 0:
+            ci = int(np.searchsorted(cols.chrom_off, k, side="right")) - 1
+            ann.query_gene = Gene(ann.chrom_index[ci], names[k], int(cols.left[k]), int(cols.right[k]), cols.strand_texts[int(cols.strand_id[k])])
+    finally:
+        lib.spl_genes_free(h)
     return ann
-
-
-def _left_of(g):
-    return g.left
 
 
 def binary_gene_search(array, pos, strand, is_stranded) -> int:

@@ -59,12 +59,21 @@ def _gene_columns(annotation, vocab):
     cached = getattr(annotation, "_columns", None)
     if cached is not None and cached[0] == key:
         return cached[1]
-    names, base, cols = [], [], []
-    for genes in annotation.genes:
-        base.append(len(names))
-        names.extend(g.name for g in genes)
-        cols.append((np.array([g.left for g in genes], dtype=np.int32), np.array([g.right for g in genes], dtype=np.int32),
-                     np.array([vocab.setdefault(g.strand, len(vocab)) for g in genes], dtype=np.int32)))
+    gc = getattr(annotation, "columns", None)
+    if gc is not None:                                   # native parser: arrays already there, strand ids -> this vocabulary
+        smap = np.array([vocab.setdefault(t, len(vocab)) for t in gc.strand_texts] or [0], dtype=np.int32)
+        names, base, cols = gc.names, gc.chrom_off[:-1].tolist(), []
+        for ci in range(len(gc.chrom_off) - 1):
+            a, b = int(gc.chrom_off[ci]), int(gc.chrom_off[ci + 1])
+            cols.append((np.ascontiguousarray(gc.left[a:b]), np.ascontiguousarray(gc.right[a:b]),
+                         np.ascontiguousarray(smap[gc.strand_id[a:b]])))
+    else:
+        names, base, cols = [], [], []
+        for genes in annotation.genes:
+            base.append(len(names))
+            names.extend(g.name for g in genes)
+            cols.append((np.array([g.left for g in genes], dtype=np.int32), np.array([g.right for g in genes], dtype=np.int32),
+                         np.array([vocab.setdefault(g.strand, len(vocab)) for g in genes], dtype=np.int32)))
     out = (names, base, cols, StrTable(names))
     try:
         annotation._columns = (tuple(sorted(vocab.items())), out)

@@ -401,3 +401,74 @@ def test_native_bed_parser_in_pieces(built_library):
     bad[69000] = bad[69000].replace("\t2\t", "\t2\tq", 1)
     with pytest.raises(ValueError, match="BED line 61235:"):
         parse_bed12("".join(bad))
+
+
+def _create_genes_reference_semantics(text, qgene="All"):
+    """createGenes (S:50-116) with HTSeq's GFF_Reader conventions restated in plain Python (iv.start = start - 1, iv.end = end,
+    name = value of the first attribute): the checker for spl_genes_parse."""
+    import bisect
+    from spliser_b200.genes import Gene
+
+    def _first_attribute(col9):
+        first = col9.split(";")[0].strip()
+        if "=" in first:
+            return first.split("=", 1)[1]
+        parts = first.split(None, 1)             # GTF: key "value"
+        return parts[1].strip('"') if len(parts) > 1 else first
+    chrom_index, genes, query = [], [], None
+    for line in text.splitlines():
+        if not line.strip() or line.startswith("#"):
+            continue
+        f = line.split("\t")
+        if len(f) < 9 or f[2] != "gene":
+            continue
+        g = Gene(f[0], _first_attribute(f[8]), int(f[3]) - 1, int(f[4]), f[6])
+        if f[0] not in chrom_index:
+            chrom_index.append(f[0])
+            genes.append([])
+        if qgene == "All":
+            bisect.insort(genes[chrom_index.index(f[0])], g)
+        elif g.name == qgene:
+            query = g
+            genes[chrom_index.index(f[0])].append(g)
+    return chrom_index, genes, query
+
+
+def test_native_annotation_parser_equals_the_python_restatement(tmp_path, built_library):
+    import random
+    from spliser_b200.genes import load_annotation
+    rng = random.Random(21)
+    for trial in range(40):
+        lines = ["##gff-version 3\n", "#!comment\n"]
+        chroms = ["c%d" % i for i in range(rng.randint(1, 4))]
+        for k in range(rng.randint(0, 120)):
+            c = rng.choice(chroms)
+            start = rng.choice([10, 50, 50, 200, rng.randrange(1, 5000)])
+            end = start + rng.randrange(0, 900)
+            kind = rng.choice(["gene", "gene", "gene", "mRNA", "exon", "Gene", "gene "])
+            name = rng.choice(["G%d" % rng.randrange(12), "AT%dG%05d" % (rng.randint(1, 5), k)])
+            attr = rng.choice(["ID=%s;Name=x%d" % (name, k), "ID=%s" % name, " ID=%s ;Note=a=b" % name, 'gene_id "%s"; transcript_id "t%d";' % (name, k),
+                               'gene_id  "%s"' % name, name, "Parent=p;ID=%s" % name, "ID=%s=tail;x" % name, ""])
+            cols = [c, "src", kind, str(start) if rng.random() > 0.05 else " %d " % start, str(end), ".", rng.choice(["+", "-", ".", "?"]), ".", attr]
+            if rng.random() < 0.1:
+                cols.append("tenth column")
+            if rng.random() < 0.05:
+                cols = cols[:rng.randint(1, 8)]
+            lines.append("\t".join(cols) + "\n")
+            if rng.random() < 0.03:
+                lines.append("\n")
+        text = "".join(lines)
+        if trial % 5 == 0:
+            text = text.rstrip("\n")                                     # no newline at the end of the file
+        p = tmp_path / ("a%d.gff" % trial)
+        p.write_bytes((text.replace("\n", "\r\n") if trial % 7 == 3 else text).encode())
+        for q in ("All", "G3", "G7", "absent"):
+            want_idx, want_genes, want_q = _create_genes_reference_semantics(text, q)
+            ann = load_annotation(str(p), q)
+            assert ann.chrom_index == want_idx, (trial, q)
+            assert ann.genes == want_genes, (trial, q)
+            assert ann.query_gene == want_q, (trial, q)
+    bad = tmp_path / "bad.gff"
+    bad.write_text("c\ts\tgene\tten\t20\t.\t+\t.\tID=g\n")
+    with pytest.raises(ValueError):
+        load_annotation(str(bad))
