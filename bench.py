@@ -182,7 +182,7 @@ def cli_process_run(ctx, w, bam, args, reads):
             "genes": sum(len(g) for g in ann.genes),
             "breakdown_ms": {"annotation": round(1e3 * (b - a), 2), "bed_parse+spl_process": round(1e3 * (c - b), 2), "of_which_spl_process": round(ms_count, 2),
                              "gene_column+tsv_writer": round(1e3 * (d - c), 2)},
-            "note": "cli.process(BAM, BED12, GFF) -> .SpliSER.tsv: annotation load (Python), BED12 parse (native), spl_process(bam) on the device, "
+            "note": "cli.process(BAM, BED12, GFF) -> .SpliSER.tsv: annotation and BED12 parse (native), spl_process(bam) on the device, "
                     "Gene column + TSV writer (native); byte-identical output is pinned by tests/test_cli_*.py"}
 
 
