@@ -65,9 +65,11 @@ struct Out {
         auto r = std::to_chars(p, p + 24, v);
         n += (size_t)(r.ptr - p);
     }
-    void fixed(double v, int prec) {                          // "{0:.<prec>f}".format(v)
+    void fixed(double v, int prec) {                          // "{0:.<prec>f}".format(v): correctly rounded like printf
         char* p = room(400);
-        n += (size_t)snprintf(p, 400, "%.*f", prec, v);
+        if (v - v != 0.0) { n += (size_t)snprintf(p, 400, "%.*f", prec, v); return; }     // inf / nan spelled by printf
+        auto r = std::to_chars(p, p + 400, v, std::chars_format::fixed, prec);
+        n += (size_t)(r.ptr - p);
     }
     void pyfloat(double v) {                                  // str(float)
         char* p = room(40);
@@ -122,6 +124,10 @@ template <class F> void run_parallel(int nt, F& work) {
 }
 
 int worker_count(int requested, size_t jobs) {
+    if (requested <= 0) {                              // SPLISER_HOST_THREADS bounds the text layer's workers (default: all cores)
+        const char* env = getenv("SPLISER_HOST_THREADS");
+        if (env && atoi(env) > 0) requested = atoi(env);
+    }
     int n = requested > 0 ? requested : (int)std::thread::hardware_concurrency();
     if (n < 1) n = 1;
     if (n > 64) n = 64;
@@ -162,7 +168,8 @@ extern "C" int spl_gene_search(int64_t n_genes, const int32_t* g_left, const int
     if (n_genes < 0 || n < 0 || (n_genes && (!g_left || !g_right || !g_strand)) || (n && (!pos || !strand || !out_idx)))
         return SPL_ERR_ARG;
     const long long length = n_genes;
-    for (int64_t s = 0; s < n; ++s) {
+    auto search = [&](int64_t lo, int64_t hi) {
+    for (int64_t s = lo; s < hi; ++s) {
         if (length == 0) { out_idx[s] = -1; continue; }
         const long long p = pos[s];
         const int32_t st = strand[s];
@@ -187,6 +194,20 @@ extern "C" int spl_gene_search(int64_t n_genes, const int32_t* g_left, const int
             }
         }
         out_idx[s] = (found && !stuck) ? (int32_t)idx : -1;
+    }
+    };
+    // the sites are independent: blocks of them on every core
+    const int64_t block = 8192;
+    const int64_t n_blocks = (n + block - 1) / block;
+    if (n_blocks <= 1) { search(0, n); return SPL_OK; }
+    std::atomic<int64_t> next{0};
+    auto work = [&]() {
+        for (int64_t b; (b = next.fetch_add(1)) < n_blocks;) search(b * block, std::min(n, (b + 1) * block));
+    };
+    try {
+        run_parallel(worker_count(0, (size_t)n_blocks), work);
+    } catch (const std::exception&) {
+        return SPL_ERR_NOMEM;
     }
     return SPL_OK;
 }

@@ -472,3 +472,27 @@ def test_native_annotation_parser_equals_the_python_restatement(tmp_path, built_
     bad.write_text("c\ts\tgene\tten\t20\t.\t+\t.\tID=g\n")
     with pytest.raises(ValueError):
         load_annotation(str(bad))
+
+
+def test_process_tsv_numbers_print_like_python(tmp_path, built_library):
+    """SSE ('{:.3f}') and beta2Cryptic_weighted ('{:.5f}') of the native writer against Python's own formatting: random values,
+    exact ties of the binary value (0.0625 -> '0.062', 0.5 ulp cases), large magnitudes, negative zero."""
+    from spliser_b200 import api, hosttext
+    rng = np.random.default_rng(8)
+    vals = np.concatenate([rng.random(20000), rng.random(5000) * 1e6, rng.integers(0, 2 ** 20, 5000) / 2.0 ** 14,
+                           np.array([0.0625, 0.0005, 0.0015, 0.5, 2.5, 1.0005, 0.1235, 1e15 + 0.5, 123456789.987654321, -0.0, 0.0,
+                                     0.00049999999999999999, 0.9995, 0.99949999999999994, 1e-300, 7e22])])
+    n = len(vals)
+    z = np.zeros(n, np.int64)
+    w = vals[::-1].copy()
+    t = api.SiteTable(chrom=np.zeros(n, np.int32), pos=np.arange(1, n + 1, dtype=np.int32), strand=np.zeros(n, np.uint8), alpha=z, beta1=z,
+                      beta2simple=z, beta2cryptic=z, beta2weighted=w, sse=vals, first_line=z, partner_off=np.zeros(n + 1, np.int64),
+                      partner_pos=np.zeros(0, np.int32), partner_cnt=np.zeros(0, np.int64), comp_off=np.zeros(n + 1, np.int64),
+                      comp_pos=np.zeros(0, np.int32))
+    p = str(tmp_path / "n.tsv")
+    hosttext.write_process_tsv(p, ["C"], t, ["+"], beta2_cryptic=True)
+    rows = open(p).read().splitlines()[1:]
+    assert len(rows) == n
+    for i, line in enumerate(rows):
+        f = line.split("\t")
+        assert f[4] == "{0:.3f}".format(float(vals[i])) and f[9] == "{0:.5f}".format(float(w[i])), (i, vals[i], f[4], f[9])
