@@ -127,6 +127,18 @@ def traffic_from_profile():
     return None
 
 
+def python_reference_note():
+    """The unmodified (Python) reference cannot run on the GPU box; oracle/time_reference.py timed it in the authoring
+    container on configs[0] and recorded how much faster the C port timed here is (profiles/r1_reference_python_c1.json)."""
+    p = os.path.join(ROOT, "profiles", "r1_reference_python_c1.json")
+    try:
+        d = json.load(open(p))
+        return {"reads_per_s": d["reference_reads_per_s"], "cores": 1, "workload": "configs[0], authoring container, samtools fork replaced by an in-process indexed store (its time excluded)",
+                "c_port_over_python_reference_1_thread": d["c_port_over_reference"]["threads_1"], "source": "profiles/r1_reference_python_c1.json"}
+    except (OSError, ValueError, KeyError):
+        return None
+
+
 def cpu_port_run(rec, junc, n_chrom, flags, threads):
     from oracle import c_oracle
     t0 = time.perf_counter()
@@ -246,7 +258,8 @@ def main():
             "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int64", "data": "synthetic",
             "config": {"workload": desc, "note": "reference is single-threaded Python + one samtools fork per site; this arm times the oracle's C port of its algorithm (per-site read fetch + per-CIGAR-op state machine) with OpenMP over sites"},
-            "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "port", "sample": sample,
+                             "python_reference": python_reference_note()},
             "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
         return
@@ -411,7 +424,8 @@ def main():
         rec_s, junc_s = region_sample(w, args.cpu_sample)
         dt = min(cpu_port_run(rec_s, junc_s, n_chrom, w.flags, ncores) for _ in range(2))
         out["cpu_baseline"] = {"value": len(rec_s) / dt, "unit": "reads/s", "cores": ncores, "kind": "port",
-                               "sample": "first %d records of %s (genomic sub-region, same coverage) + its %d junctions; C port of the reference algorithm, OpenMP over sites" % (len(rec_s), w.chroms[int(rec_s.seg_chrom[0])], len(junc_s))}
+                               "sample": "first %d records of %s (genomic sub-region, same coverage) + its %d junctions; C port of the reference algorithm, OpenMP over sites" % (len(rec_s), w.chroms[int(rec_s.seg_chrom[0])], len(junc_s)),
+                               "python_reference": python_reference_note()}
     elif rank == 0:
         out["cpu_baseline"] = None
     if rank == 0:

@@ -112,6 +112,27 @@ def test_c1_shaped_workload_vs_c_oracle(ctx):
     assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
 
 
+def test_full_configs0_equals_the_unmodified_reference(ctx, tmp_path):
+    """BASELINE configs[0] at its full size (2M records, 28.6k junctions, 56k sites, unstranded): the unmodified reference
+    ran this workload in the authoring container (oracle/time_reference.py) and left a digest of its own per-site result
+    (tests/golden/c1_full_reference.json).  The CUDA path must reproduce it from the record arrays and from a BAM file."""
+    import json
+    import os
+    from common import GOLDEN
+    from oracle import c_oracle, time_reference
+    from spliser_b200 import synth
+    gold = json.load(open(os.path.join(GOLDEN, "c1_full_reference.json")))
+    w = synth.generate(synth.config_c1())
+    got = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags))
+    assert len(got["pos"]) == gold["sites"]
+    assert {k: int(got[k].sum()) for k in ("alpha", "beta1", "beta2simple")} == gold["sums"]
+    assert time_reference.digest_of_table(got) == gold["digest"]
+    bam = str(tmp_path / "c1.bam")
+    w.records.write_bam(bam, w.chroms, w.chrom_len)
+    via_bam = c_oracle.table_dict(ctx.process_bam(bam, w.chroms, w.junctions, w.flags))
+    assert time_reference.digest_of_table(via_bam) == gold["digest"]
+
+
 def test_resident_path_equals_process_path(ctx):
     from oracle import c_oracle
     from spliser_b200 import synth
