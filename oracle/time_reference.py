@@ -17,7 +17,11 @@ Outputs (committed, with this script as their recipe):
                                          `tests/test_oracle.py` holds the C oracle to it on the CPU and
                                          `tests/test_gpu_parity.py` the CUDA path on the B200
 
+  tests/golden/reference_digests.json    (--shapes) full-table digests (every column, Partners / Competitors included) of the
+                                         reference on the config-shaped workloads of the GPU parity tests
+
     python oracle/time_reference.py [--records N]
+    python oracle/time_reference.py --shapes
 """
 from __future__ import annotations
 
@@ -102,7 +106,7 @@ class _Popen:
         self.stdout = store.view(args[3])
 
 
-def run_reference(w):
+def run_reference(w, cryptic=False):
     """-> (site rows of the reference, seconds total, seconds inside the samtools stand-in, SAM lines, sites)."""
     store = IndexedStore(w)
     mod = ref_runner.load_reference(ref_runner.ReadStore())
@@ -117,7 +121,7 @@ def run_reference(w):
         stranded = bool(w.flags & 1)
         t0 = time.perf_counter()
         try:
-            mod.process("x.bam", bed, os.path.join(td, "out"), "All", "All", 0, None, "gene", stranded, "rf" if stranded else None, False)
+            mod.process("x.bam", bed, os.path.join(td, "out"), "All", "All", 0, None, "gene", stranded, "rf" if stranded else None, bool(cryptic))
         finally:
             sys.argv, sys.stdout = old_argv, old_out
         total = time.perf_counter() - t0
@@ -146,8 +150,89 @@ def digest_of_rows(chrom_names, rows):
                           [float.fromhex(r["sse"]) for r in rows])
 
 
+FULL_FIELDS = (("chrom", np.int32), ("pos", np.int32), ("strand", np.uint8), ("alpha", np.int64), ("beta1", np.int64),
+               ("beta2simple", np.int64), ("beta2cryptic", np.int64), ("beta2weighted", np.float64), ("sse", np.float64),
+               ("partner_off", np.int64), ("partner_pos", np.int32), ("partner_cnt", np.int64), ("comp_off", np.int64), ("comp_pos", np.int32))
+
+
+def full_digest_of_table(t):
+    """Every column of the per-site result incl. the Partners / Competitors CSR (floats bit for bit), order-sensitive."""
+    h = hashlib.sha256()
+    for k, dt in FULL_FIELDS:
+        h.update(np.ascontiguousarray(np.asarray(t[k]), dtype=dt).tobytes())
+    return h.hexdigest()
+
+
+def table_of_rows(chrom_names, rows):
+    """Rows dumped from the reference's Site objects (ref_runner._site_dump) -> the column layout of the oracle / product table."""
+    ci = {c: i for i, c in enumerate(chrom_names)}
+    p_off, c_off = [0], [0]
+    pp, pc, cp = [], [], []
+    for r in rows:
+        for pos, cnt in r["partners"]:
+            pp.append(pos); pc.append(cnt)
+        cp.extend(r["competitors"])
+        p_off.append(len(pp)); c_off.append(len(cp))
+    return dict(chrom=[ci[r["chrom"]] for r in rows], pos=[r["pos"] for r in rows],
+                strand=[ord(r["strand"][0]) if r["strand"] else 0 for r in rows], alpha=[r["alpha"] for r in rows],
+                beta1=[r["beta1"] for r in rows], beta2simple=[r["beta2s"] for r in rows], beta2cryptic=[r["beta2c"] for r in rows],
+                beta2weighted=[float.fromhex(r["beta2w"]) for r in rows], sse=[float.fromhex(r["sse"]) for r in rows],
+                partner_off=p_off, partner_pos=pp, partner_cnt=pc, comp_off=c_off, comp_pos=cp)
+
+
+def shape(name):
+    """The config-shaped workloads of tests/test_gpu_parity.py::test_config_shaped_workloads_vs_c_oracle -> (SynthConfig, extra flags)."""
+    from spliser_b200 import synth
+    if name == "c1_full":
+        return synth.config_c1(), 0
+    if name == "c3_tile":
+        return synth.config_c3_tile(300_000, tile=3), 0
+    if name == "c5_dense_locus":
+        cfg = synth.config_c5()
+        cfg.n_records = 150_000
+        return cfg, 4
+    if name == "c2_stranded":
+        return synth.config_c2(500_000), 0
+    raise KeyError(name)
+
+
+SHAPES = ("c1_full", "c3_tile", "c5_dense_locus", "c2_stranded")
+
+
+def make_shape_digests():
+    """tests/golden/reference_digests.json: full-table digests of the unmodified reference on the config-shaped workloads."""
+    from spliser_b200 import synth
+    out = {}
+    for name in SHAPES:
+        cfg, extra = shape(name)
+        w = synth.generate(cfg)
+        flags = w.flags | extra
+        rows, total, in_store, lines, calls = run_reference(w, cryptic=bool(extra & 4))
+        ref = table_of_rows(w.chroms, rows)
+        port = c_oracle.process(w.records, len(w.chroms), w.junctions, flags, threads=0)
+        d_ref, d_port = full_digest_of_table(ref), full_digest_of_table(port)
+        print("%-16s %8d records %7d sites  reference %.1f s (%.1f s in the read store)  C port == reference: %s" %
+              (name, len(w.records), len(rows), total, in_store, d_ref == d_port), flush=True)
+        if d_ref != d_port:
+            raise SystemExit("C port differs from the reference on %s: %s" % (name, c_oracle.diff_tables(
+                {k: np.asarray(v) for k, v in dict(ref, first_line=port["first_line"]).items()}, port)))
+        out[name] = {"records": len(w.records), "junction_rows": len(w.junctions), "sites": len(rows), "flags": int(flags), "digest": d_ref,
+                     "sums": {k: int(np.sum(ref[k])) for k in ("alpha", "beta1", "beta2simple", "beta2cryptic")},
+                     "reference_seconds_own_python": round(total - in_store, 2)}
+    doc = {"made_by": "oracle/time_reference.py --shapes (unmodified reference, authoring container)",
+           "digest_of": "sha256 over " + " ".join("%s(%s)" % (k, np.dtype(dt).name) for k, dt in FULL_FIELDS) + "; floats by their bits; site order of the reference",
+           "shapes": out}
+    with open(os.path.join(ROOT, "tests", "golden", "reference_digests.json"), "w") as fh:
+        json.dump(doc, fh, indent=1)
+        fh.write("\n")
+
+
 def main():
     from spliser_b200 import synth
+    if "--shapes" in sys.argv:
+        if not ref_runner.reference_available():
+            raise SystemExit("reference not mounted at %s" % ref_runner.REF_DIR)
+        return make_shape_digests()
     ap = argparse.ArgumentParser()
     ap.add_argument("--records", type=int, default=0, help="records of the configs[0] shape (default: its full 2M)")
     ap.add_argument("--no-write", action="store_true")

@@ -127,6 +127,8 @@ def test_full_configs0_equals_the_unmodified_reference(ctx, tmp_path):
     assert len(got["pos"]) == gold["sites"]
     assert {k: int(got[k].sum()) for k in ("alpha", "beta1", "beta2simple")} == gold["sums"]
     assert time_reference.digest_of_table(got) == gold["digest"]
+    full = json.load(open(os.path.join(GOLDEN, "reference_digests.json")))["shapes"]["c1_full"]["digest"]
+    assert time_reference.full_digest_of_table(got) == full                # every column, Partners / Competitors included
     bam = str(tmp_path / "c1.bam")
     w.records.write_bam(bam, w.chroms, w.chrom_len)
     via_bam = c_oracle.table_dict(ctx.process_bam(bam, w.chroms, w.junctions, w.flags))
@@ -192,19 +194,15 @@ def test_tiles_concatenate_to_the_untiled_result(built_library):
 def test_config_shaped_workloads_vs_c_oracle(ctx, shape):
     """The other BASELINE.json configs at depths the C oracle finishes in seconds:
     configs[2] (one GRCh38-scale tile: long introns up to 500 kb), configs[4] (dense alternative-splicing locus,
-    --beta2Cryptic) and configs[1] (TAIR10 contigs, stranded rf)."""
-    from oracle import c_oracle
+    --beta2Cryptic) and configs[1] (TAIR10 contigs, stranded rf).  The unmodified reference ran the same three workloads in
+    the authoring container (oracle/time_reference.py --shapes): the digest of its whole table (every column, Partners and
+    Competitors included, floats by their bits) is in tests/golden/reference_digests.json and must be reproduced too."""
+    import json
+    import os
+    from common import GOLDEN
+    from oracle import c_oracle, time_reference
     from spliser_b200 import synth
-    if shape == "c3_tile":
-        cfg = synth.config_c3_tile(300_000, tile=3)
-        flags_extra = 0
-    elif shape == "c5_dense_locus":
-        cfg = synth.config_c5()
-        cfg.n_records = 150_000
-        flags_extra = 4
-    else:
-        cfg = synth.config_c2(500_000)
-        flags_extra = 0
+    cfg, flags_extra = time_reference.shape(shape)
     w = synth.generate(cfg)
     flags = w.flags | flags_extra
     want = c_oracle.process(w.records, len(w.chroms), w.junctions, flags, threads=8)
@@ -213,6 +211,9 @@ def test_config_shaped_workloads_vs_c_oracle(ctx, shape):
     assert int(want["beta1"].sum()) > 0 and int(want["beta2simple"].sum()) > 0
     if flags_extra:
         assert int(want["beta2cryptic"].sum()) > 0
+    gold = json.load(open(os.path.join(GOLDEN, "reference_digests.json")))["shapes"][shape]
+    assert gold["records"] == len(w.records) and gold["sites"] == len(got["pos"])
+    assert time_reference.full_digest_of_table(got) == gold["digest"]
 
 
 def test_host_and_device_graph_builders_agree(ctx, monkeypatch):
