@@ -137,6 +137,19 @@ def test_combine_sharded_by_sample_over_contexts_on_cpu(tmp_path, built_library)
     assert set(made) <= {0, 1, 2} and len(set(made)) >= 2
 
 
+def test_c4_shaped_process_and_combine_equal_the_reference_files_on_cpu(tmp_path, built_library):
+    """configs[3] shape at reduced size (6 samples of one genome, 1.2M records, 14k sites each, 11k re-counted gaps): the
+    unmodified reference wrote the six .SpliSER.tsv and the .combined.tsv in the authoring container (oracle/c4_shape.py);
+    the CLI must write the same bytes from BAM / BED12 files."""
+    import json
+    from oracle import c4_shape
+    from spliser_b200 import cli
+    gold = json.load(open(c4_shape.GOLDEN))
+    per_sample, combined = c4_shape.run_cli(cli, OracleContext(), str(tmp_path))
+    assert per_sample == gold["process_sha256"]
+    assert combined == gold["combined_sha256"]
+
+
 def test_cli_errors_mirror_the_reference(tmp_path, built_library):
     from spliser_b200 import cli
     case = [c for c in load_golden("appendix_a.json.gz")["process"] if c["name"] == "A.4-locus"][0]

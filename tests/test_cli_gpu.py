@@ -97,6 +97,18 @@ def test_combine_over_regions_genes_and_cryptic(ctx, tmp_path):
         _run_wide_combine(cli, ctx, case, d)
 
 
+def test_c4_shaped_process_and_combine_equal_the_reference_files(ctx, tmp_path):
+    """configs[3] shape at reduced size (6 samples of one genome, 1.2M records, 14k sites each, 11k re-counted gaps): the CLI
+    on BAM / BED12 files with the CUDA path must write the bytes the unmodified reference wrote (oracle/c4_shape.py)."""
+    import json
+    from oracle import c4_shape
+    from spliser_b200 import cli
+    gold = json.load(open(c4_shape.GOLDEN))
+    per_sample, combined = c4_shape.run_cli(cli, ctx, str(tmp_path))
+    assert per_sample == gold["process_sha256"]
+    assert combined == gold["combined_sha256"]
+
+
 def test_combine_sharded_by_sample_over_contexts(ctx, tmp_path):
     """Sample-sharded re-count with one context per host thread.  On a one-GPU box both contexts sit on device 0 (what is
     exercised is the concurrency of independent contexts); on a multi-GPU box they sit on devices 0 and 1."""
