@@ -620,7 +620,7 @@ __device__ __forceinline__ void alpha_reduce_item(const DevGraph& g, const DevOu
 // ------------------------------------------------------------------------------------------------
 // Persistent, warp-specialised streaming kernels (K3, K4).
 //
-// grid = SMs x resident CTAs; every CTA has one producer warp and four consumer warps.  The producer
+// grid = SMs x resident CTAs; every CTA has one producer warp and eight consumer warps.  The producer
 // (one elected lane) pulls work items from a global atomic counter (dynamic scheduling: chunks differ
 // a lot in cost), and for each piece of an item issues 1-D TMA bulk copies (cp.async.bulk) of the
 // SoA slices and of the chunk's site window into a ring of shared-memory stages, completion tracked
