@@ -191,12 +191,27 @@ def shape(name):
         cfg = synth.config_c5()
         cfg.n_records = 150_000
         return cfg, 4
-    if name == "c2_stranded":
+    if name in ("c2_stranded", "c2_dirty_strands"):
         return synth.config_c2(500_000), 0
     raise KeyError(name)
 
 
-SHAPES = ("c1_full", "c3_tile", "c5_dense_locus", "c2_stranded")
+def shape_workload(name):
+    """-> (Workload, flags).  c2_dirty_strands: the stranded configs[1] shape with every 12th BED row's strand replaced by '?'
+    (what regtools writes for junctions without an XS tag): the dirty regime of SURVEY.md 8(a), where a '?' row joins whichever
+    same-position site the reference's bisection lands on."""
+    from spliser_b200 import Junctions, synth
+    cfg, extra = shape(name)
+    w = synth.generate(cfg)
+    if name == "c2_dirty_strands":
+        j = w.junctions
+        strand = j.strand.copy()
+        strand[np.random.default_rng(12).permutation(len(j))[:len(j) // 12]] = ord("?")
+        w.junctions = Junctions(j.chrom, j.left, j.right, j.score, strand)
+    return w, w.flags | extra
+
+
+SHAPES = ("c1_full", "c3_tile", "c5_dense_locus", "c2_stranded", "c2_dirty_strands")
 
 
 def make_shape_digests():
@@ -204,10 +219,8 @@ def make_shape_digests():
     from spliser_b200 import synth
     out = {}
     for name in SHAPES:
-        cfg, extra = shape(name)
-        w = synth.generate(cfg)
-        flags = w.flags | extra
-        rows, total, in_store, lines, calls = run_reference(w, cryptic=bool(extra & 4))
+        w, flags = shape_workload(name)
+        rows, total, in_store, lines, calls = run_reference(w, cryptic=bool(flags & 4))
         ref = table_of_rows(w.chroms, rows)
         port = c_oracle.process(w.records, len(w.chroms), w.junctions, flags, threads=0)
         d_ref, d_port = full_digest_of_table(ref), full_digest_of_table(port)

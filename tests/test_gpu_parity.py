@@ -190,7 +190,7 @@ def test_tiles_concatenate_to_the_untiled_result(built_library):
     assert np.array_equal(b1, ref.beta1) and np.array_equal(b2, ref.beta2simple) and np.array_equal(sse, ref.sse)
 
 
-@pytest.mark.parametrize("shape", ["c3_tile", "c5_dense_locus", "c2_stranded"])
+@pytest.mark.parametrize("shape", ["c3_tile", "c5_dense_locus", "c2_stranded", "c2_dirty_strands"])
 def test_config_shaped_workloads_vs_c_oracle(ctx, shape):
     """The other BASELINE.json configs at depths the C oracle finishes in seconds:
     configs[2] (one GRCh38-scale tile: long introns up to 500 kb), configs[4] (dense alternative-splicing locus,
@@ -202,9 +202,8 @@ def test_config_shaped_workloads_vs_c_oracle(ctx, shape):
     from common import GOLDEN
     from oracle import c_oracle, time_reference
     from spliser_b200 import synth
-    cfg, flags_extra = time_reference.shape(shape)
-    w = synth.generate(cfg)
-    flags = w.flags | flags_extra
+    w, flags = time_reference.shape_workload(shape)
+    flags_extra = flags & 4
     want = c_oracle.process(w.records, len(w.chroms), w.junctions, flags, threads=8)
     got = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, flags))
     assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
