@@ -268,6 +268,10 @@ def main():
     import spliser_b200
     from spliser_b200.api import Records, pinned_empty
     from spliser_b200.dist import Ranks
+    from spliser_b200.dist import bind_to_device_node, host_topology
+    topo = host_topology(local)
+    topo["bound_to_gpu_node"] = bind_to_device_node(topo) if os.environ.get("SPLISER_NUMA_BIND") == "1" else False
+    topo.pop("_bind", None)
     ranks = Ranks("nccl" if world > 1 else None)
     strong = args.scaling == "strong" and world > 1
     cfg, desc = workload_config(args.workload, args.reads, 0 if strong else rank)
@@ -354,6 +358,7 @@ def main():
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": desc, "records_per_gpu": int(reads_rank), "sites_per_gpu": int(S), "junction_rows": len(w.junctions),
                    "l2": "no flush needed: the streamed SoA is %.0f MB per pass, larger than the 126 MB L2" % soa_mb,
+                   "host": topo,
                    "timing": "CUDA events on the library's stream around %d passes; max over ranks" % args.steps,
                    "value_scope": "one counting pass (alpha reduce, beta1 stabbing, junction span + exceptions, beta2 gather, SSE) over the "
                                   "counting layout resident in HBM; building that layout from the raw records is load-time work: see from_records "

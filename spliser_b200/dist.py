@@ -49,6 +49,86 @@ class Ranks:
             self.dist = None
 
 
+# ------------------------------------------------------------------------------------------------
+# Host topology of a rank: which NUMA node its GPU hangs off and which CPUs the process may run on.  Page-locked
+# staging memory is placed on the node of the thread that allocates it, so a rank running on the other socket uploads its
+# records across the socket interconnect.  host_topology() only reports (bench.py prints it with every line);
+# bind_to_device_node() restricts the calling process to the GPU's node -- opt-in (SPLISER_NUMA_BIND=1 in bench.py)
+# until its effect on the end-to-end number has been measured on the target box.
+# ------------------------------------------------------------------------------------------------
+def parse_cpulist(text):
+    """'0-3,8,10-11' (sysfs cpulist) -> sorted list of CPU numbers; malformed pieces are skipped."""
+    cpus = set()
+    for part in str(text).strip().split(","):
+        part = part.strip()
+        if not part:
+            continue
+        try:
+            if "-" in part:
+                a, b = part.split("-", 1)
+                cpus.update(range(int(a), int(b) + 1))
+            else:
+                cpus.add(int(part))
+        except ValueError:
+            continue
+    return sorted(cpus)
+
+
+def _read(path):
+    try:
+        with open(path) as fh:
+            return fh.read().strip()
+    except OSError:
+        return None
+
+
+def host_topology(device, sysfs="/sys", bus_id=None):
+    """-> dict(gpu_bus_id, gpu_numa_node, numa_nodes, node_cpus (of the GPU's node), cpus_allowed, cpus_allowed_on_gpu_node).
+    Unknown pieces are None; never raises."""
+    import subprocess
+    info = dict(gpu_bus_id=None, gpu_numa_node=None, numa_nodes=None, node_cpus=None, cpus_allowed=None, cpus_allowed_on_gpu_node=None)
+    try:
+        allowed = sorted(os.sched_getaffinity(0))
+        info["cpus_allowed"] = len(allowed)
+        nodes = [d for d in os.listdir(os.path.join(sysfs, "devices/system/node")) if d.startswith("node") and d[4:].isdigit()]
+        info["numa_nodes"] = len(nodes)
+        if bus_id is None:
+            res = subprocess.run(["nvidia-smi", "-i", str(device), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True, timeout=20)
+            bus_id = res.stdout.strip().splitlines()[0].strip() if res.returncode == 0 and res.stdout.strip() else None
+        if bus_id:
+            info["gpu_bus_id"] = bus_id
+            short = bus_id.lower()
+            if len(short.split(":")[0]) == 8:                # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+                short = short[4:]
+            node = _read(os.path.join(sysfs, "bus/pci/devices", short, "numa_node"))
+            if node is not None and node.lstrip("-").isdigit():
+                info["gpu_numa_node"] = int(node)
+                if int(node) >= 0:
+                    cl = _read(os.path.join(sysfs, "devices/system/node/node%d/cpulist" % int(node)))
+                    if cl is not None:
+                        cpus = parse_cpulist(cl)
+                        info["node_cpus"] = len(cpus)
+                        info["cpus_allowed_on_gpu_node"] = len(set(cpus) & set(allowed))
+                        info["_bind"] = sorted(set(cpus) & set(allowed))
+    except Exception:                                        # noqa: BLE001 -- reporting only
+        pass
+    return info
+
+
+def bind_to_device_node(info):
+    """Restricts the calling process to the allowed CPUs of its GPU's NUMA node (host_topology(...) result).  Returns True if
+    the affinity was changed.  No-op when the node is unknown, the box has one node, or no allowed CPU sits on that node."""
+    cpus = info.get("_bind") or []
+    if not cpus or (info.get("numa_nodes") or 1) < 2 or len(cpus) == (info.get("cpus_allowed") or 0):
+        return False
+    try:
+        os.sched_setaffinity(0, cpus)
+        return True
+    except OSError:
+        return False
+
+
 def tile_of(rank, world, n_sites):
     """Owned site slice [lo, hi) of a rank when one sample is sharded by genomic tile (spl_set_tile)."""
     return n_sites * rank // world, n_sites * (rank + 1) // world

@@ -64,3 +64,33 @@ def test_bench_reference_arm_prints_the_contract_line(tmp_path):
     assert two.returncode == 0, two.stderr[-2000:]
     lines = [ln for ln in two.stdout.splitlines() if ln.startswith("{")]
     assert len(lines) == 1 and json.loads(lines[0])["n_gpus"] == 2
+
+
+def test_host_topology_against_a_fake_sysfs(tmp_path):
+    """The NUMA report bench.py attaches to every line (and the opt-in binding) reads sysfs only: a fake tree with two
+    nodes, the GPU on node 1."""
+    from spliser_b200.dist import bind_to_device_node, host_topology, parse_cpulist
+    assert parse_cpulist("0-3,8,10-11") == [0, 1, 2, 3, 8, 10, 11] and parse_cpulist("") == [] and parse_cpulist("a,2") == [2]
+    allowed = sorted(os.sched_getaffinity(0))
+    half = allowed[len(allowed) // 2:] or allowed
+    for n, cl in ((0, "900-903"), (1, ",".join(map(str, half)))):
+        d = tmp_path / "devices/system/node" / ("node%d" % n)
+        d.mkdir(parents=True)
+        (d / "cpulist").write_text(cl + "\n")
+    dev = tmp_path / "bus/pci/devices/0000:1b:00.0"
+    dev.mkdir(parents=True)
+    (dev / "numa_node").write_text("1\n")
+    t = host_topology(0, sysfs=str(tmp_path), bus_id="00000000:1B:00.0")
+    assert t["gpu_numa_node"] == 1 and t["numa_nodes"] == 2 and t["node_cpus"] == len(half)
+    assert t["cpus_allowed"] == len(allowed) and t["cpus_allowed_on_gpu_node"] == len(half)
+    if len(half) < len(allowed):
+        try:
+            assert bind_to_device_node(t) and sorted(os.sched_getaffinity(0)) == half
+        finally:
+            os.sched_setaffinity(0, allowed)
+    # unknown GPU / single node / virtualised numa_node = -1: report only, never bind
+    (dev / "numa_node").write_text("-1\n")
+    t = host_topology(0, sysfs=str(tmp_path), bus_id="00000000:1B:00.0")
+    assert t["gpu_numa_node"] == -1 and not bind_to_device_node(t)
+    t = host_topology(0, sysfs=str(tmp_path / "absent"), bus_id="00000000:1B:00.0")
+    assert t["gpu_numa_node"] is None and not bind_to_device_node(t)
