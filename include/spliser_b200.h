@@ -295,6 +295,12 @@ int64_t spl_combine_sample_rows(const spl_combine* c, int64_t sample);
 int64_t spl_combine_sample_runs(const spl_combine* c, int64_t sample, const int32_t** runs);
 int  spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t* region_order,
                        const char* qgene /* NULL = "All" */, int is_stranded);
+/* combineShallow (SpliSER_v0_1_8.py:920-1167): the same merge with the -m/--minSamples, -r/--minReads, -e/--minSSE filters
+ * (S:1066-1084, S:1108, S:1154-1160) and, with -g, only that gene's rows loaded (S:947-956); everything after the merge
+ * (spl_combine_gaps, spl_recount, spl_combine_set_recount, spl_combine_write) is shared with combine */
+int  spl_combine_merge_shallow(spl_combine* c, int64_t n_order, const int32_t* region_order,
+                               const char* qgene /* NULL = "All" */, int is_stranded,
+                               int64_t min_samples, int64_t min_reads, double min_sse);
 int64_t spl_combine_n_sites(const spl_combine* c);     /* merged sites that will be written */
 int64_t spl_combine_n_filled(const spl_combine* c);    /* "Filled in Beta read counts for N Sites" (S:917) */
 int64_t spl_combine_gaps(const spl_combine* c, int64_t sample, const int32_t** s_region, const int32_t** s_pos,

@@ -179,8 +179,9 @@ def run_process(bed_text: str, reads, *, stranded=False, stype=None, cryptic=Fal
     return tsv, _site_dump(mod)
 
 
-def run_combine(samples, *, stranded=False, stype="fr", cryptic=False, qgene="All"):
+def run_combine(samples, *, stranded=False, stype="fr", cryptic=False, qgene="All", shallow=None):
     """samples: list of (title, spliser_tsv_text, reads) in samples-file order.
+    shallow: None = `combine`; (minSamples, minReads, minSSE) = `combineShallow` (SpliSER_v0_1_8.py:920).
     Returns (.combined.tsv text, log of every checkBam gap call with its inputs and results)."""
     store = ReadStore()
     mod_store_names = []
@@ -214,10 +215,13 @@ def run_combine(samples, *, stranded=False, stype="fr", cryptic=False, qgene="Al
         mod.checkBam = logged_check
         out = os.path.join(td, "out")
         old_argv, old_out = sys.argv, sys.stdout
-        sys.argv = ["SpliSER", "combine"]
+        sys.argv = ["SpliSER", "combine" if shallow is None else "combineShallow"]
         sys.stdout = io.StringIO()
         try:
-            mod.combine(sf, out, qgene, stranded, stype, cryptic)
+            if shallow is None:
+                mod.combine(sf, out, qgene, stranded, stype, cryptic)
+            else:
+                mod.combineShallow(sf, out, qgene, stranded, shallow[0], shallow[1], shallow[2], stype, cryptic)
         finally:
             sys.argv, sys.stdout = old_argv, old_out
         with open(out + ".combined.tsv") as fh:

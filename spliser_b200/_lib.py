@@ -129,6 +129,7 @@ SIGNATURES = {
     "spl_combine_sample_rows": (C.c_int64, [C.c_void_p, C.c_int64]),
     "spl_combine_sample_runs": (C.c_int64, [C.c_void_p, C.c_int64, C.POINTER(c_i32p)]),
     "spl_combine_merge": (C.c_int, [C.c_void_p, C.c_int64, c_i32p, C.c_char_p, C.c_int]),
+    "spl_combine_merge_shallow": (C.c_int, [C.c_void_p, C.c_int64, c_i32p, C.c_char_p, C.c_int, C.c_int64, C.c_int64, C.c_double]),
     "spl_combine_n_sites": (C.c_int64, [C.c_void_p]),
     "spl_combine_n_filled": (C.c_int64, [C.c_void_p]),
     "spl_combine_gaps": (C.c_int64, [C.c_void_p, C.c_int64, C.POINTER(c_i32p), C.POINTER(c_i32p), C.POINTER(c_u8p),

@@ -133,8 +133,22 @@ def _recount_sample(ctx, cm, k, regions, bam_path, flags, records_by_bam):
     return True
 
 
+def combineShallow(samplesFile, outputPath, qGene="All", isStranded=False, minSamples=0, minReads=10, minSSE=0.0, strandedType=None,
+                   isbeta2Cryptic=False, ctx=None, records_by_bam=None, devices=None, context_factory=None):
+    """combineShallow (S:920-1167): `combine` for many shallow samples.  The same lock-step merge and the same re-count of the
+    sites a sample lacks (checkBam at S:1145 -> one spl_recount call per sample), with three filters on which positions are
+    kept at all -- a position needs at least `minSamples` samples showing it with alpha + beta1 + beta2Simple >= `minReads`
+    and SSE >= `minSSE` (S:1066-1084, S:1108) -- and, with -g, only the rows of that gene loaded from every table
+    (S:947-956).  The quirks of the reference's loop are kept (csrc/host_text.cpp, merge_impl): the count runs over the rows
+    of both strands of a position, and a dropped position moves every sample on whose current row has that position number,
+    whatever its region or strand (S:1158-1160).  Unlike `combine`, a samples-file line without exactly three columns is
+    skipped silently (S:930-935)."""
+    return combine(samplesFile, outputPath, qGene, isStranded, strandedType, isbeta2Cryptic, ctx, records_by_bam, devices,
+                   context_factory, _shallow=(minSamples, minReads, minSSE))
+
+
 def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType="fr", isbeta2Cryptic=False, ctx=None,
-            records_by_bam=None, devices=None, context_factory=None):
+            records_by_bam=None, devices=None, context_factory=None, _shallow=None):
     """combine (S:742-917).  The native merge driver (csrc/host_text.cpp) parses the sample tables and replays the
     lock-step merge, collecting per sample the sites it lacks together with the partner / competitor / strand context
     gathered from lower-indexed samples only (the reference's order dependence); one spl_recount call
@@ -151,7 +165,7 @@ def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType
             values = line.split("\t")
             if len(values) == 3:
                 titles.append(values[0]); bed_paths.append(values[1]); bam_paths.append(values[2].rstrip())
-            else:
+            elif _shallow is None:
                 print(str(titles), str(bed_paths), str(bam_paths))
                 raise Exception("Samples File contains lines that do not have exactly 3 tab-separated columns")
     n = len(titles)
@@ -161,7 +175,10 @@ def combine(samplesFile, outputPath, qGene="All", isStranded=False, strandedType
         regions = cm.region_names()
         order = _chrom_order([[regions[r] for r in cm.sample_runs(k)] for k in range(n)])
         region_id = {name: i for i, name in enumerate(regions)}
-        cm.merge([region_id[name] for name in order], qGene, isStranded)
+        if _shallow is None:
+            cm.merge([region_id[name] for name in order], qGene, isStranded)
+        else:
+            cm.merge_shallow([region_id[name] for name in order], qGene, isStranded, *_shallow)
         make = context_factory or api.Context
         devs = [0] if not devices else list(devices)
         if ctx is not None or len(devs) == 1:
@@ -223,20 +240,34 @@ def main(argv=None):
     c.add_argument("--beta2Cryptic", dest="isbeta2Cryptic", default=False, action="store_true")
     c.add_argument("--gpus", dest="n_gpus", nargs="?", default=1, type=int,
                    help="re-count the samples on this many GPUs (sharded by sample; not a reference option)")
+    cs = sub.add_parser("combineShallow")
+    cs.add_argument("-S", "--samplesFile", dest="samplesFile", required=True)
+    cs.add_argument("-g", "--gene", dest="qGene", nargs="?", default="All", type=str)
+    cs.add_argument("-o", "--outputPath", dest="outputPath", required=True)
+    cs.add_argument("--isStranded", dest="isStranded", default=False, action="store_true")
+    cs.add_argument("-m", "--minSamples", dest="minSamples", nargs="?", default=0, type=int)
+    cs.add_argument("-r", "--minReads", dest="minReads", nargs="?", default=10, type=int)
+    cs.add_argument("-e", "--minSSE", dest="minSSE", nargs="?", default=0.00, type=float)
+    cs.add_argument("-s", "--strandedType", dest="strandedType", nargs="?", type=str)
+    cs.add_argument("--beta2Cryptic", dest="isbeta2Cryptic", default=False, action="store_true")
+    cs.add_argument("--gpus", dest="n_gpus", nargs="?", default=1, type=int,
+                    help="re-count the samples on this many GPUs (sharded by sample; not a reference option)")
     kwargs = vars(parser.parse_args(argv))
     command = kwargs.pop("command")
-    if command == "combine":
+    if command in ("combine", "combineShallow"):
         kwargs["devices"] = list(range(max(1, kwargs.pop("n_gpus") or 1)))
     if command == "process" and kwargs.get("qGene") != "All" and (kwargs.get("annotationFile") is None or kwargs.get("maxIntronSize") is None):
         parser.error("--gene requires --annotationFile and --maxIntronSize")                      # S:1350-1353
-    elif command in ("process", "combine") and kwargs.get("isStranded") and kwargs.get("strandedType") is None:
+    elif command in ("process", "combine", "combineShallow") and kwargs.get("isStranded") and kwargs.get("strandedType") is None:
         parser.error("--isStranded requires parameter --strandedType/-s as fr or rf")            # S:1354-1355
     elif command == "process":
         process(**kwargs)
     elif command == "combine":
         combine(**kwargs)
+    elif command == "combineShallow":
+        combineShallow(**kwargs)
     else:
-        parser.error("command must be process or combine (combineShallow / output are unchanged Python in the reference)")
+        parser.error("command must be process, combine or combineShallow (output is unchanged Python in the reference)")
     print("Total runtime (s): \t" + str(timeit.default_timer() - start))
 
 

@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <string>
 #include <string_view>
 #include <system_error>
@@ -312,6 +313,7 @@ struct Sample {
     std::vector<int32_t> region, pos, strand, gene;
     std::vector<int64_t> alpha, beta1, beta2s, beta2c;
     std::vector<double> beta2w;
+    std::vector<double> sse;                           // column 4 as float(text); NaN when it is not a number (only combineShallow reads it)
     std::vector<uint8_t> has_cryptic;                  // column 8 != "NA"
     std::vector<int64_t> p_off, c_off;                 // CSR of the Partners / Competitors columns
     std::vector<int32_t> p_key, c_key;
@@ -501,6 +503,10 @@ int parse_sample(const char* title, const char* tsv_path, Sample& s, LocalTables
             s.gene.push_back(lt.genes.id(col[3]));
             s.alpha.push_back(a); s.beta1.push_back(b1); s.beta2s.push_back(b2); s.beta2c.push_back(bc);
             s.beta2w.push_back(bw);
+            {
+                double sse = 0.0;
+                s.sse.push_back(parse_f64(col[4], &sse) ? sse : std::numeric_limits<double>::quiet_NaN());
+            }
             s.has_cryptic.push_back(has_c ? 1 : 0);
             s.p_off.push_back((int64_t)s.p_key.size());
             s.c_off.push_back((int64_t)s.c_key.size());
@@ -573,9 +579,18 @@ extern "C" int64_t spl_combine_sample_runs(const spl_combine* c, int64_t sample,
     return (int64_t)s.runs.size();
 }
 
-// The lock-step merge (S:791-917).  region_order = chromsInOrder (S:761-789) as region ids; qgene NULL = "All".
-extern "C" int spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t* region_order, const char* qgene,
-                                 int is_stranded) {
+// The lock-step merge of `combine` (S:791-917) and, with `sh`, of `combineShallow` (S:977-1167).
+// region_order = chromsInOrder (S:761-789 / S:960-988) as region ids; qgene NULL = "All".
+// combineShallow differs in four places, each marked SHALLOW below: with -g only the rows of that gene are loaded at all
+// (S:947-956), a '+' row takes over a tied position only from a row of another strand (S:1066), a position is kept only
+// if at least minSamples samples show it with >= minReads reads and SSE >= minSSE -- counted over the rows of BOTH strands
+// at that position, in sample order, restarting whenever the lowest position changes hands (S:1066-1084, S:1108) -- and a
+// position that fails makes every sample whose current row has that position NUMBER move on, whatever the row's region or
+// strand (S:1158-1160).
+namespace {
+struct ShallowOpts { int64_t min_samples, min_reads; double min_sse; };
+
+int merge_impl(spl_combine* c, int64_t n_order, const int32_t* region_order, const char* qgene, int is_stranded, const ShallowOpts* sh) {
     if (!c || n_order <= 0 || !region_order) { if (c) c->err = "spl_combine_merge: empty region order"; return SPL_ERR_ARG; }
     if (c->merged_done) { c->err = "spl_combine_merge called twice"; return SPL_ERR_ARG; }
     const size_t n = c->samples.size();
@@ -585,10 +600,27 @@ extern "C" int spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t*
     int32_t qgene_id = -1;
     bool all_genes = (qgene == nullptr);
     if (!all_genes) { auto it = c->genes.map.find(qgene); qgene_id = it == c->genes.map.end() ? -9 : it->second; }
-    std::vector<int64_t> cur(n, -1), nrows(n);
+    std::vector<int64_t> cur(n, -1), nrows(n), fpos(n, -1);          // fpos: position in rows[k] when filtered
     std::vector<int32_t> chroms(n, INITIAL);
     std::vector<char> go(n, 1), done(n, 0);
     for (size_t k = 0; k < n; ++k) nrows[k] = (int64_t)c->samples[k].pos.size();
+    // SHALLOW with -g: the merge only ever sees the rows of that gene (S:947-956)
+    const bool filtered = sh && !all_genes;
+    std::vector<std::vector<int64_t>> rows;
+    if (filtered) {
+        rows.resize(n);
+        for (size_t k = 0; k < n; ++k)
+            for (int64_t r = 0; r < nrows[k]; ++r)
+                if (c->samples[k].gene[(size_t)r] == qgene_id) rows[k].push_back(r);
+    }
+    if (sh)
+        for (size_t k = 0; k < n; ++k)
+            for (size_t r = 0; r < c->samples[k].sse.size(); ++r)
+                if (c->samples[k].sse[r] != c->samples[k].sse[r] && (!filtered || c->samples[k].gene[r] == qgene_id)) {
+                    c->err = "combineShallow: sample " + c->samples[k].title + ", data row " + std::to_string(r + 1) + ": the SSE column is not a number";
+                    return SPL_ERR_ARG;
+                }
+    int64_t pos_counter = 0;
     int64_t order_at = 0;
     int32_t current = region_order[0];
     int64_t lowest = -1;
@@ -598,18 +630,29 @@ extern "C" int spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t*
     try {
         while (n_done < n) {
             int32_t assoc_gene = -1;                                              // ""
-            for (size_t k = 0; k < n; ++k) {                                      // S:827-855
+            pos_counter = 0;                                                      // S:1014
+            for (size_t k = 0; k < n; ++k) {                                      // S:827-855 / S:1016-1084
                 if (done[k]) continue;
                 Sample& s = c->samples[k];
                 if (go[k]) {
-                    if (cur[k] + 1 < nrows[k]) { ++cur[k]; chroms[k] = s.region[(size_t)cur[k]]; go[k] = 0; }
+                    bool got;
+                    if (filtered) { got = fpos[k] + 1 < (int64_t)rows[k].size(); if (got) cur[k] = rows[k][(size_t)++fpos[k]]; }
+                    else { got = cur[k] + 1 < nrows[k]; if (got) ++cur[k]; }
+                    if (got) { chroms[k] = s.region[(size_t)cur[k]]; go[k] = 0; }
                     else { done[k] = 1; ++n_done; chroms[k] = NONE; }
                 }
                 if (chroms[k] == current && chroms[k] >= 0) {
                     const int64_t p = s.pos[(size_t)cur[k]];
                     const int32_t st = s.strand[(size_t)cur[k]];
-                    if (p < lowest || lowest == -1 || (is_stranded && p == lowest && st == plus_id)) {   // S:847
+                    // S:847; SHALLOW (S:1066): only a '+' row of ANOTHER strand than the current holder takes a tie
+                    const bool tie = is_stranded && p == lowest && st == plus_id && (!sh || st != lowest_strand);
+                    const bool pass = sh && (s.alpha[(size_t)cur[k]] + s.beta1[(size_t)cur[k]] + s.beta2s[(size_t)cur[k]] >= sh->min_reads) &&
+                                      (s.sse[(size_t)cur[k]] >= sh->min_sse);
+                    if (p < lowest || lowest == -1 || tie) {
                         lowest = p; lowest_strand = st; assoc_gene = s.gene[(size_t)cur[k]];
+                        pos_counter = pass ? 1 : 0;                                       // S:1071-1077
+                    } else if (p == lowest && pass) {
+                        ++pos_counter;                                                    // S:1079-1084
                     }
                 }
             }
@@ -622,6 +665,9 @@ extern "C" int spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t*
                         return SPL_ERR_ARG;
                     }
                     current = region_order[order_at];
+                } else if (sh && pos_counter < sh->min_samples) {                // SHALLOW, S:1154-1160: the position is dropped
+                    for (size_t k = 0; k < n; ++k)
+                        if (!done[k] && cur[k] >= 0 && c->samples[k].pos[(size_t)cur[k]] == lowest) go[k] = 1;
                 } else {
                     const bool emit = all_genes || (assoc_gene == qgene_id);
                     Merged m;
@@ -684,6 +730,17 @@ extern "C" int spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t*
     }
     c->merged_done = true;
     return SPL_OK;
+}
+}  // namespace
+
+extern "C" int spl_combine_merge(spl_combine* c, int64_t n_order, const int32_t* region_order, const char* qgene, int is_stranded) {
+    return merge_impl(c, n_order, region_order, qgene, is_stranded, nullptr);
+}
+
+extern "C" int spl_combine_merge_shallow(spl_combine* c, int64_t n_order, const int32_t* region_order, const char* qgene, int is_stranded,
+                                         int64_t min_samples, int64_t min_reads, double min_sse) {
+    const ShallowOpts sh{min_samples, min_reads, min_sse};
+    return merge_impl(c, n_order, region_order, qgene, is_stranded, &sh);
 }
 
 extern "C" int64_t spl_combine_n_sites(const spl_combine* c) { return c ? (int64_t)c->merged.size() : 0; }

@@ -191,6 +191,13 @@ class CombineMerge:
         q = None if qgene == "All" else str(qgene).encode()
         self._check(self._lib.spl_combine_merge(self._h, len(order), _ptr(order, L.c_i32p), q, int(bool(is_stranded))), "spl_combine_merge")
 
+    def merge_shallow(self, region_order, qgene="All", is_stranded=False, min_samples=0, min_reads=10, min_sse=0.0):
+        """combineShallow's merge (S:977-1167): minSamples / minReads / minSSE filters, -g as a row pre-filter."""
+        order = np.ascontiguousarray(region_order, dtype=np.int32)
+        q = None if qgene == "All" else str(qgene).encode()
+        self._check(self._lib.spl_combine_merge_shallow(self._h, len(order), _ptr(order, L.c_i32p), q, int(bool(is_stranded)),
+                                                        int(min_samples), int(min_reads), float(min_sse)), "spl_combine_merge_shallow")
+
     def n_gaps(self, k):
         return int(self._lib.spl_combine_gaps(self._h, k, None, None, None, None, None, None, None))
 

@@ -137,6 +137,49 @@ def test_combine_sharded_by_sample_over_contexts_on_cpu(tmp_path, built_library)
     assert set(made) <= {0, 1, 2} and len(set(made)) >= 2
 
 
+def run_shallow_cases(cli, ctx, tmp_path, stride=1):
+    """combine_shallow golden cases (oracle/make_golden.py --shallow): cli.combineShallow on the samples of the referenced
+    combine_wide / combine_fuzz case -> list of (case id, got text, wanted text) that differ."""
+    cases = load_golden("combine_shallow.json.gz")[::stride]
+    bases, dirs, bad = {}, {}, []
+    for n, g in enumerate(cases):
+        if g["base"] is None:                                 # crafted known-answer case: samples stored inline
+            base, key = g, ("crafted", g["name"])
+            g = dict(g, index=g["name"])
+        else:
+            base, key = bases.setdefault(g["base"], load_golden(g["base"]))[g["index"]], (g["base"], g["index"])
+        if key not in dirs:                                   # the sample files of a base case are written once
+            d = tmp_path / ("b%d" % len(dirs))
+            d.mkdir()
+            chroms = base.get("chroms", ["C"])
+            lines = []
+            for i, smp in enumerate(base["samples"]):
+                p = str(d / ("s%d.SpliSER.tsv" % i))
+                open(p, "w").write(smp["tsv"])
+                bam = str(d / ("s%d.bam" % i))
+                Records.from_reads(chroms, [tuple(r) for r in smp["reads"]]).write_bam(bam, chroms)
+                lines.append("%s\t%s\t%s\n" % (smp["title"], p, bam))
+            open(str(d / "samples.tsv"), "w").writelines(lines)
+            dirs[key] = d
+        d = dirs[key]
+        out = str(d / ("out%d" % n))
+        cli.combineShallow(str(d / "samples.tsv"), out, qGene=g["qgene"], isStranded=base["stranded"], minSamples=g["min_samples"],
+                           minReads=g["min_reads"], minSSE=g["min_sse"], strandedType=base["stype"], isbeta2Cryptic=g["cryptic"], ctx=ctx)
+        got = open(out + ".combined.tsv").read()
+        if got != g["combined"]:
+            bad.append(((g["base"], g["index"], g["min_samples"], g["min_reads"], g["min_sse"], g["qgene"]), got, g["combined"]))
+    return len(cases), bad
+
+
+def test_combine_shallow_equals_the_reference_files_on_cpu(tmp_path, built_library):
+    """combineShallow (S:920-1167): 400 runs of the unmodified reference over a grid of -m / -r / -e settings, with and without
+    -g and --beta2Cryptic, on the samples of the combine goldens; the merge driver's shallow mode must write the same bytes."""
+    from spliser_b200 import cli
+    n, bad = run_shallow_cases(cli, OracleContext(), tmp_path)
+    assert n >= 400
+    assert not bad, "%d/%d differ; first: %r\n--- got\n%s\n--- want\n%s" % (len(bad), n, bad[0][0], bad[0][1][:1500], bad[0][2][:1500])
+
+
 def test_c4_shaped_process_and_combine_equal_the_reference_files_on_cpu(tmp_path, built_library):
     """configs[3] shape at reduced size (6 samples of one genome, 1.2M records, 14k sites each, 11k re-counted gaps): the
     unmodified reference wrote the six .SpliSER.tsv and the .combined.tsv in the authoring container (oracle/c4_shape.py);

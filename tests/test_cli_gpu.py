@@ -123,3 +123,13 @@ def test_combine_sharded_by_sample_over_contexts(ctx, tmp_path):
         d = tmp_path / ("m%d" % k)
         d.mkdir()
         _run_wide_combine(cli, ctx, case, d, devices=devices)
+
+
+def test_combine_shallow_matches_reference(ctx, tmp_path):
+    """combineShallow (S:920-1167) with the CUDA re-count behind it: the crafted quirk cases and every second run of the
+    -m / -r / -e grid the unmodified reference wrote (tests/golden/combine_shallow.json.gz), byte for byte."""
+    from spliser_b200 import cli
+    from test_cli_cpu import run_shallow_cases
+    n, bad = run_shallow_cases(cli, ctx, tmp_path, stride=2)
+    assert n >= 200
+    assert not bad, "%d/%d differ; first: %r" % (len(bad), n, bad[0][0])
