@@ -176,7 +176,11 @@ def fuzz_combine(rng, seconds, tmp):
                 names = m.region_names()
                 order = list(range(len(names)))
                 rng.shuffle(order)
-                m.merge(order, qgene="All", is_stranded=bool(rng.random() < 0.5))
+                if n % 3 == 2:
+                    m.merge_shallow(order, qgene="All" if rng.random() < 0.7 else "NA", is_stranded=bool(rng.random() < 0.5),
+                                    min_samples=int(rng.integers(0, 4)), min_reads=int(rng.integers(0, 40)), min_sse=float(rng.random()))
+                else:
+                    m.merge(order, qgene="All", is_stranded=bool(rng.random() < 0.5))
                 for k in range(3):
                     g = m.gaps(k)
                     m.set_recount(k, np.arange(len(g), dtype=np.int64), np.arange(len(g), dtype=np.int64))
