@@ -201,3 +201,23 @@ def test_cli_errors_mirror_the_reference(tmp_path, built_library):
         cli.process(bam, bed, str(tmp_path / "o"), qGene="NOPE", qChrom="C", maxIntronSize=50, annotationFile=gff, ctx=OracleContext())
     with pytest.raises(UnboundLocalError):                    # --isStranded with a type other than fr / rf (S:378-406)
         cli.process(bam, bed, str(tmp_path / "o"), isStranded=True, strandedType="xx", ctx=OracleContext())
+
+
+def test_command_line_mirrors_the_reference_options(tmp_path, built_library, monkeypatch):
+    """Sub-commands and option names of S:1300-1361 (process / combine / combineShallow), the two argument checks of S:1349-1355,
+    and the dispatch with the parsed values."""
+    from spliser_b200 import cli
+    with pytest.raises(SystemExit):                           # --isStranded requires -s (S:1354-1355)
+        cli.main(["combineShallow", "-S", "s.tsv", "-o", "out", "--isStranded"])
+    with pytest.raises(SystemExit):                           # --gene requires --annotationFile (S:1350-1353)
+        cli.main(["process", "-B", "x.bam", "-b", "x.bed", "-o", "out", "-g", "G1"])
+    seen = {}
+    monkeypatch.setattr(cli, "combineShallow", lambda **kw: seen.update(kw))
+    cli.main(["combineShallow", "-S", "s.tsv", "-o", "out", "-g", "G7", "-m", "3", "-r", "12", "-e", "0.25", "--isStranded", "-s", "rf",
+              "--beta2Cryptic", "--gpus", "2"])
+    assert seen == dict(samplesFile="s.tsv", outputPath="out", qGene="G7", isStranded=True, minSamples=3, minReads=12, minSSE=0.25,
+                        strandedType="rf", isbeta2Cryptic=True, devices=[0, 1])
+    seen.clear()
+    cli.main(["combineShallow", "-S", "s.tsv", "-o", "out"])  # the reference's defaults: -m 0, -r 10, -e 0.0
+    assert (seen["minSamples"], seen["minReads"], seen["minSSE"], seen["qGene"], seen["strandedType"]) == (0, 10, 0.0, "All", None)
+
