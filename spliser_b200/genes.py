@@ -31,9 +31,23 @@ class GeneColumns:
     """The genes of an annotation as flat arrays grouped by chromosome (what spl_genes_parse returns):
     genes of chromosome c are rows chrom_off[c] .. chrom_off[c + 1] in list order (S:95)."""
 
-    def __init__(self, chrom_off, left, right, strand_id, strand_texts, names):
+    def __init__(self, chrom_off, left, right, strand_id, strand_texts, names=None, names_blob=None, name_off=None):
         self.chrom_off, self.left, self.right, self.strand_id = chrom_off, left, right, strand_id
-        self.strand_texts, self.names = strand_texts, names
+        self.strand_texts, self._names = strand_texts, names
+        self.names_blob, self.name_off = names_blob, name_off       # UTF-8 blob + offsets as the native parser returns them
+
+    @property
+    def names(self):
+        """Gene names as a list of str: decoded on first use (the TSV writer takes the blob as it is)."""
+        if self._names is None:
+            blob, off = self.names_blob, self.name_off.tolist()
+            self._names = [blob[off[k]:off[k + 1]].decode() for k in range(len(off) - 1)]
+        return self._names
+
+    def name(self, k):
+        if self._names is not None:
+            return self._names[k]
+        return self.names_blob[int(self.name_off[k]):int(self.name_off[k + 1])].decode()
 
 
 class Annotation:
@@ -87,16 +101,14 @@ def load_annotation(path, qgene="All") -> Annotation:
             return [C.string_at(get(h, i, C.byref(ln)), ln.value).decode() for i in range(count)]
         name_off = arr(lib.spl_genes_name_off(h), n + 1, np.int64)
         blob = C.string_at(lib.spl_genes_names(h), int(name_off[-1])) if n else b""
-        off = name_off.tolist()
-        names = [blob[off[k]:off[k + 1]].decode() for k in range(n)]
         cols = GeneColumns(arr(lib.spl_genes_chrom_off(h), nc + 1, np.int64), arr(lib.spl_genes_left(h), n, np.int32),
                            arr(lib.spl_genes_right(h), n, np.int32), arr(lib.spl_genes_strand_id(h), n, np.int32),
-                           texts(lib.spl_genes_n_strand_texts(h), lib.spl_genes_strand_text), names)
+                           texts(lib.spl_genes_n_strand_texts(h), lib.spl_genes_strand_text), names_blob=blob, name_off=name_off)
         ann = Annotation(texts(nc, lib.spl_genes_chrom_name), None, None, cols)
         k = lib.spl_genes_query(h)
         if k >= 0:
             ci = int(np.searchsorted(cols.chrom_off, k, side="right")) - 1
-            ann.query_gene = Gene(ann.chrom_index[ci], names[k], int(cols.left[k]), int(cols.right[k]), cols.strand_texts[int(cols.strand_id[k])])
+            ann.query_gene = Gene(ann.chrom_index[ci], cols.name(k), int(cols.left[k]), int(cols.right[k]), cols.strand_texts[int(cols.strand_id[k])])
     finally:
         lib.spl_genes_free(h)
     return ann

@@ -24,6 +24,15 @@ class StrTable:
             np.cumsum([len(e) for e in enc], out=self.off[1:])
         self.c = L.StrTab(len(enc), self.blob, _ptr(self.off, L.c_i64p))
 
+    @classmethod
+    def from_blob(cls, blob, off):
+        """UTF-8 blob + int64 offsets (n + 1) as they are, without a round trip through str."""
+        t = cls.__new__(cls)
+        t.blob = bytes(blob)
+        t.off = np.ascontiguousarray(off, dtype=np.int64)
+        t.c = L.StrTab(len(t.off) - 1, t.blob, _ptr(t.off, L.c_i64p))
+        return t
+
     def ref(self):
         return C.byref(self.c)
 
@@ -53,6 +62,22 @@ def strand_ids(strand_strings, vocab=None):
     return vocab, ids
 
 
+class _LazyNames:
+    """The flat gene name list of a natively parsed annotation: decoded only if somebody indexes it."""
+
+    def __init__(self, gc):
+        self._gc = gc
+
+    def __len__(self):
+        return len(self._gc.name_off) - 1
+
+    def __getitem__(self, k):
+        return self._gc.names[k]
+
+    def __iter__(self):
+        return iter(self._gc.names)
+
+
 def _gene_columns(annotation, vocab):
     """Per chromosome (left, right, strand id) arrays + the flat name list, built once per annotation and strand vocabulary."""
     key = tuple(sorted(vocab.items()))
@@ -62,7 +87,8 @@ def _gene_columns(annotation, vocab):
     gc = getattr(annotation, "columns", None)
     if gc is not None:                                   # native parser: arrays already there, strand ids -> this vocabulary
         smap = np.array([vocab.setdefault(t, len(vocab)) for t in gc.strand_texts] or [0], dtype=np.int32)
-        names, base, cols = gc.names, gc.chrom_off[:-1].tolist(), []
+        blob_tab = StrTable.from_blob(gc.names_blob, gc.name_off) if getattr(gc, "names_blob", None) is not None else None
+        names, base, cols = (gc if blob_tab is not None else gc.names), gc.chrom_off[:-1].tolist(), []
         for ci in range(len(gc.chrom_off) - 1):
             a, b = int(gc.chrom_off[ci]), int(gc.chrom_off[ci + 1])
             cols.append((np.ascontiguousarray(gc.left[a:b]), np.ascontiguousarray(gc.right[a:b]),
@@ -74,7 +100,10 @@ def _gene_columns(annotation, vocab):
             names.extend(g.name for g in genes)
             cols.append((np.array([g.left for g in genes], dtype=np.int32), np.array([g.right for g in genes], dtype=np.int32),
                          np.array([vocab.setdefault(g.strand, len(vocab)) for g in genes], dtype=np.int32)))
-    out = (names, base, cols, StrTable(names))
+    if gc is not None and blob_tab is not None:
+        out = (_LazyNames(gc), base, cols, blob_tab)
+    else:
+        out = (names, base, cols, StrTable(names))
     try:
         annotation._columns = (tuple(sorted(vocab.items())), out)
     except AttributeError:
