@@ -17,6 +17,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
+#include <condition_variable>
+#include <exception>
 #include <string>
 #include <string_view>
 #include <system_error>
@@ -139,25 +142,104 @@ int worker_count(int requested, size_t jobs) {
 // blocks to `f` in order.  fmt(lo, hi, out) appends the text of items [lo, hi).
 template <class F> bool write_blocks(FILE* f, size_t total, size_t block, int threads, F fmt) {
     const size_t n_blocks = (total + block - 1) / block;
+    if (n_blocks == 0) return true;
     const int nt = worker_count(threads, n_blocks);
-    std::vector<std::string> text((size_t)nt);
-    for (size_t wave = 0; wave < n_blocks; wave += (size_t)nt) {
-        const size_t in_wave = std::min<size_t>((size_t)nt, n_blocks - wave);
-        std::atomic<size_t> next{0};
-        auto work = [&]() {
-            for (size_t j; (j = next.fetch_add(1)) < in_wave;) {
-                text[j].clear();
-                Out o(&text[j]);
-                const size_t lo = (wave + j) * block;
-                fmt(lo, std::min(total, lo + block), o);
-                o.flush();
-            }
-        };
-        run_parallel((int)in_wave, work);
-        for (size_t j = 0; j < in_wave; ++j)
-            if (fwrite(text[j].data(), 1, text[j].size(), f) != text[j].size()) return false;
+    if (nt <= 1 || n_blocks == 1) {                                       // nothing to overlap
+        std::string text;
+        for (size_t j = 0; j < n_blocks; ++j) {
+            text.clear();
+            Out o(&text);
+            fmt(j * block, std::min(total, (j + 1) * block), o);
+            o.flush();
+            if (fwrite(text.data(), 1, text.size(), f) != text.size()) return false;
+        }
+        return true;
     }
-    return true;
+    // The workers format blocks in index order of claim; the calling thread writes block j as soon as it is ready, while the
+    // later blocks are still being formatted.  A worker does not start block j before block j - window has been written,
+    // which bounds the text held in memory to `window` blocks whatever the size of the table.
+    const size_t window = (size_t)nt * 3;
+    std::vector<std::string> slot(window);
+    std::vector<char> ready(n_blocks, 0);
+    std::mutex mu;
+    std::condition_variable cv_ready, cv_room;
+    size_t written = 0, next = 0;
+    bool failed = false;
+    std::exception_ptr worker_error;
+    auto work = [&]() {
+        for (;;) {
+            size_t j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                if (failed || next >= n_blocks) return;
+                j = next++;
+                cv_room.wait(lk, [&] { return failed || j < written + window; });
+                if (failed) return;
+            }
+            std::string& text = slot[j % window];
+            try {
+                text.clear();
+                Out o(&text);
+                fmt(j * block, std::min(total, (j + 1) * block), o);
+                o.flush();
+            } catch (...) {
+                std::lock_guard<std::mutex> lk(mu);
+                if (!worker_error) worker_error = std::current_exception();
+                failed = true;
+                cv_ready.notify_all(); cv_room.notify_all();
+                return;
+            }
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                ready[j] = 1;
+            }
+            cv_ready.notify_all();
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < nt; ++t) {
+        try { pool.emplace_back(work); } catch (const std::system_error&) { break; }
+    }
+    bool ok = true;
+    if (pool.empty()) {                                                   // no thread could be started: format here
+        std::lock_guard<std::mutex> lk(mu);
+        failed = true;
+        ok = false;
+    }
+    for (size_t j = 0; ok && j < n_blocks; ++j) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv_ready.wait(lk, [&] { return failed || ready[j]; });
+            if (failed) { ok = false; break; }
+        }
+        const std::string& text = slot[j % window];
+        if (fwrite(text.data(), 1, text.size(), f) != text.size()) ok = false;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            written = j + 1;
+            if (!ok) failed = true;
+        }
+        cv_room.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (!ok) failed = true;
+    }
+    cv_room.notify_all(); cv_ready.notify_all();
+    for (auto& th : pool) th.join();
+    if (worker_error) std::rethrow_exception(worker_error);
+    if (pool.empty()) {                                                   // sequential fallback, from the start
+        std::string text;
+        for (size_t j = 0; j < n_blocks; ++j) {
+            text.clear();
+            Out o(&text);
+            fmt(j * block, std::min(total, (j + 1) * block), o);
+            o.flush();
+            if (fwrite(text.data(), 1, text.size(), f) != text.size()) return false;
+        }
+        return true;
+    }
+    return ok;
 }
 
 }  // namespace
