@@ -983,6 +983,8 @@ struct BedFilter {
 int bed_parse_piece(const char* text, int64_t lo, int64_t hi, const BedFilter& f, spl_bed* b, int64_t* n_lines,
                     int64_t* err_line, const char** err_msg) {
     const std::string_view q = f.qchrom ? std::string_view(f.qchrom) : std::string_view();
+    // the line count is kept in a local and stored once per return path: the pieces' counters sit next to each other in
+    // one cache line, so a store per line from every worker would bounce that line between the cores
     int64_t at = lo, line_no = 0;
     *n_lines = 0;
     while (at < hi) {
@@ -1002,19 +1004,19 @@ int bed_parse_piece(const char* text, int64_t lo, int64_t hi, const BedFilter& f
         if (nc < 12) col[nc] = std::string_view(field, (size_t)(p - field));
         ++nc;
         at = p < e ? (p - text) + 1 : hi;
-        *n_lines = ++line_no;
+        ++line_no;
         if (nc != 12) continue;                                          // S:259
         const int32_t ci = b->chroms.id(col[0]);                         // registered before the -c test (S:265-269)
         if (f.qchrom && col[0] != q) continue;
         std::string_view sizes = col[10];
         size_t comma = sizes.find(',');
-        if (comma == std::string_view::npos) { *err_line = line_no; *err_msg = "blockSizes needs two values"; return SPL_ERR_ARG; }
+        if (comma == std::string_view::npos) { *n_lines = line_no; *err_line = line_no; *err_msg = "blockSizes needs two values"; return SPL_ERR_ARG; }
         std::string_view second = sizes.substr(comma + 1);
         second = second.substr(0, second.find(','));
         long long start, stop, a0, a1, score;
         if (!bed_int(col[1], &start) || !bed_int(col[2], &stop) || !bed_int(sizes.substr(0, comma), &a0) ||
             !bed_int(second, &a1) || !bed_int(col[4], &score)) {
-            *err_line = line_no; *err_msg = "invalid literal for int()";
+            *n_lines = line_no; *err_line = line_no; *err_msg = "invalid literal for int()";
             return SPL_ERR_ARG;
         }
         const long long left = start + a0, right = stop - a1;            // S:275-276
@@ -1024,7 +1026,7 @@ int bed_parse_piece(const char* text, int64_t lo, int64_t hi, const BedFilter& f
             if (!(lin || rin)) continue;
         }
         if (left < INT32_MIN || left > INT32_MAX || right < INT32_MIN || right > INT32_MAX) {
-            *err_line = line_no; *err_msg = "position outside 32 bits";
+            *n_lines = line_no; *err_line = line_no; *err_msg = "position outside 32 bits";
             return SPL_ERR_RANGE;
         }
         b->chrom.push_back(ci);
@@ -1034,6 +1036,7 @@ int bed_parse_piece(const char* text, int64_t lo, int64_t hi, const BedFilter& f
         b->strand.push_back(col[5].empty() ? 0 : (uint8_t)col[5][0]);
         b->strand_id.push_back(b->strand_texts.id(col[5]));
     }
+    *n_lines = line_no;
     return SPL_OK;
 }
 }  // namespace
