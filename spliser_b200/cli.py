@@ -28,9 +28,25 @@ VERSION = "v0.1.8 (spliser_b200)"
 
 
 # ------------------------------------------------------------------------------------------------ process
+def _append_bed_chroms(annotation, bed_chroms, junc):
+    """Chromosome index of a BED12 parsed on its own -> the reference's index: the annotation's names first (S:90-92), then
+    the BED's names not among them in their order of first appearance (S:265-268); the junction table is renumbered."""
+    chroms = list(annotation.chrom_index)
+    at = {c: i for i, c in enumerate(chroms)}
+    remap = np.zeros(max(1, len(bed_chroms)), dtype=np.int32)
+    for i, c in enumerate(bed_chroms):
+        if c not in at:
+            at[c] = len(chroms)
+            chroms.append(c)
+        remap[i] = at[c]
+    return chroms, api.Junctions(remap[junc.chrom], junc.left, junc.right, junc.score, junc.strand)
+
+
 def process_table(ctx, bam_path, bed_lines, *, annotation=None, qchrom="All", qgene="All", max_intron=0,
-                  is_stranded=False, stranded_type=None, beta2_cryptic=False, records=None):
-    """Steps 1-3 of process() (S:710-717).  Returns (chrom_index, SiteTable, strand strings per junction row)."""
+                  is_stranded=False, stranded_type=None, beta2_cryptic=False, records=None, parsed_bed=None):
+    """Steps 1-3 of process() (S:710-717).  Returns (chrom_index, SiteTable, strand strings per junction row).
+    parsed_bed: (chroms, Junctions, strand column) of the same BED12 already parsed WITHOUT an annotation (process() does
+    that while the annotation loads); only valid without -g, whose window needs the gene first."""
     chrom_index = list(annotation.chrom_index) if annotation is not None else []
     bounds = None
     if qgene != "All":
@@ -38,7 +54,12 @@ def process_table(ctx, bam_path, bed_lines, *, annotation=None, qchrom="All", qg
         if q is None:                           # S:283: QUERY_gene is None -> AttributeError in the reference
             raise AttributeError("'NoneType' object has no attribute 'getLeftPos'")
         bounds = (q.left, q.right)
-    chroms, junc, sstr = parse_bed12(bed_lines, chrom_index, qchrom, bounds, int(max_intron))
+    if parsed_bed is not None and bounds is None:
+        chroms, junc, sstr = parsed_bed
+        if annotation is not None:
+            chroms, junc = _append_bed_chroms(annotation, chroms, junc)
+    else:
+        chroms, junc, sstr = parse_bed12(bed_lines, chrom_index, qchrom, bounds, int(max_intron))
     flags = api.mode_flags(is_stranded, stranded_type, beta2_cryptic)
     if records is not None:
         table = ctx.process_records(records, len(chroms), junc, flags)
@@ -57,14 +78,29 @@ def process(inBAM, inBed, outputPath, qGene="All", qChrom="All", maxIntronSize=0
             isStranded=False, strandedType=None, isbeta2Cryptic=False, ctx=None):
     print("Processing")
     print("Stranded Analysis {}".format(strandedType) if isStranded else "Unstranded Analysis")
-    annotation = load_annotation(annotationFile, qGene) if annotationFile is not None else None
+    parsed_bed = None
+    if annotationFile is not None and qGene == "All":
+        # without -g the annotation and the BED12 do not depend on each other: both parse at the same time (native code,
+        # the GIL is released) and the BED's chromosome numbers are appended to the annotation's afterwards.  The
+        # annotation is loaded on this thread, so its errors still come first, as in the reference (S:703-711).
+        from concurrent.futures import ThreadPoolExecutor
+
+        def bed_alone():
+            with open(inBed) as fh:
+                return parse_bed12(fh, None, qChrom, None, 0)
+        with ThreadPoolExecutor(max_workers=1) as pool:
+            fut = pool.submit(bed_alone)
+            annotation = load_annotation(annotationFile, qGene)
+            parsed_bed = fut.result()
+    else:
+        annotation = load_annotation(annotationFile, qGene) if annotationFile is not None else None
     own = ctx is None
     ctx = ctx or api.Context(0)
     try:
         with open(inBed) as fh:
             chroms, table, sstr = process_table(ctx, inBAM, fh, annotation=annotation, qchrom=qChrom, qgene=qGene,
                                                 max_intron=maxIntronSize, is_stranded=isStranded, stranded_type=strandedType,
-                                                beta2_cryptic=isbeta2Cryptic)
+                                                beta2_cryptic=isbeta2Cryptic, parsed_bed=parsed_bed)
     finally:
         if own:
             ctx.close()

@@ -496,3 +496,31 @@ def test_process_tsv_numbers_print_like_python(tmp_path, built_library):
     for i, line in enumerate(rows):
         f = line.split("\t")
         assert f[4] == "{0:.3f}".format(float(vals[i])) and f[9] == "{0:.5f}".format(float(w[i])), (i, vals[i], f[4], f[9])
+
+
+def test_bed_parsed_alone_then_appended_equals_parse_after_the_annotation(built_library):
+    """cli.process parses the BED12 while the annotation loads and appends the BED's chromosome numbers to the annotation's
+    afterwards: same chromosome index (S:90-92 then S:265-268) and junction table as parsing with the annotation's index."""
+    import types
+    from spliser_b200.bed import parse_bed12
+    from spliser_b200.cli import _append_bed_chroms
+    rng = np.random.default_rng(8)
+    names = ["Chr%d" % i for i in range(1, 9)] + ["ChrC", "scaffold_12"]
+    for trial in range(60):
+        ann = [names[i] for i in rng.permutation(len(names))[:int(rng.integers(0, 7))]]
+        rows = []
+        for i in range(int(rng.integers(0, 40))):
+            c = names[int(rng.integers(0, len(names)))]
+            s = int(rng.integers(0, 100000))
+            rows.append("%s\t%d\t%d\tJ\t%d\t%s\t0\t0\t0\t2\t10,12\t0,90" % (c, s, s + 200, int(rng.integers(1, 99)), "+-?"[int(rng.integers(0, 3))]))
+            if rng.random() < 0.1:
+                rows.append("%s\t1\t2\tshort line" % c)                       # not 12 columns: ignored, registers nothing
+        text = "\n".join(rows) + ("\n" if rows else "")
+        qchrom = "All" if trial % 3 else names[trial % len(names)]
+        want_chroms, want_j, want_s = parse_bed12(text, ann, qchrom, None, 0)
+        alone_chroms, alone_j, alone_s = parse_bed12(text, None, qchrom, None, 0)
+        got_chroms, got_j = _append_bed_chroms(types.SimpleNamespace(chrom_index=ann), alone_chroms, alone_j)
+        assert got_chroms == want_chroms, trial
+        for k in ("chrom", "left", "right", "score", "strand"):
+            assert np.array_equal(getattr(got_j, k), getattr(want_j, k)), (trial, k)
+        assert list(alone_s) == list(want_s)
