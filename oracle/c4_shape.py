@@ -29,6 +29,7 @@ sys.path.insert(0, ROOT)
 N_COND, N_REP = 3, 2
 N_RECORDS = 1_200_000
 SEED = 20260004
+SHALLOW = (4, 6, 0.05)            # combineShallow -m / -r / -e of the second merge
 GOLDEN = os.path.join(ROOT, "tests", "golden", "c4_shape_reference.json")
 
 
@@ -85,7 +86,9 @@ def run_cli(cli, ctx, tmp):
         fh.writelines(lines)
     out = os.path.join(tmp, "combined")
     cli.combine(sf, out, isStranded=True, strandedType="rf", ctx=ctx)
-    return digests, sha(open(out + ".combined.tsv", "rb").read())
+    out2 = os.path.join(tmp, "shallow")
+    cli.combineShallow(sf, out2, isStranded=True, minSamples=SHALLOW[0], minReads=SHALLOW[1], minSSE=SHALLOW[2], strandedType="rf", ctx=ctx)
+    return digests, sha(open(out + ".combined.tsv", "rb").read()), sha(open(out2 + ".combined.tsv", "rb").read())
 
 
 def main():
@@ -140,14 +143,36 @@ def main():
             sys.argv, sys.stdout = old_argv, old_out
         t_comb = time.perf_counter() - t0
         combined = open(out + ".combined.tsv").read()
-    print("combine: %d rows, %d re-counted gaps, %.1f s" % (combined.count("\n") - 1, n_gap[0], t_comb))
+        n_comb_gaps = n_gap[0]
+        mod = ref_runner.load_reference(ref_runner.ReadStore())              # module state is global: a fresh copy for the second merge
+        mod.subprocess.Popen = lambda args, stdout=None, **kw: _Popen(stores[args[2]], args)
+        orig2 = mod.checkBam
+        n_gap2 = [0]
+
+        def counted2(*a, **kw):
+            n_gap2[0] += 1
+            return orig2(*a, **kw)
+        mod.checkBam = counted2
+        out2 = os.path.join(td, "shallow")
+        sys.argv, sys.stdout = ["SpliSER", "combineShallow"], io.StringIO()
+        t0 = time.perf_counter()
+        try:
+            mod.combineShallow(sf, out2, "All", True, SHALLOW[0], SHALLOW[1], SHALLOW[2], "rf", False)
+        finally:
+            sys.argv, sys.stdout = old_argv, old_out
+        t_shallow = time.perf_counter() - t0
+        shallow = open(out2 + ".combined.tsv").read()
+    print("combine: %d rows, %d re-counted gaps, %.1f s" % (combined.count("\n") - 1, n_comb_gaps, t_comb))
+    print("combineShallow -m %d -r %d -e %g: %d rows, %d re-counted gaps, %.1f s" % (SHALLOW + (shallow.count("\n") - 1, n_gap2[0], t_shallow)))
     doc = {"made_by": "oracle/c4_shape.py (unmodified reference, authoring container)",
            "workload": "configs[3] shape at reduced size: %d samples (%d conditions x %d replicates) of one synthetic genome (%s), %d records in all, stranded rf"
                        % (len(samples), N_COND, N_REP, ", ".join(chroms), N_RECORDS),
            "titles": [s[0] for s in samples], "records": [len(s[1]) for s in samples],
            "process_rows": [t.count("\n") - 1 for t in tsvs], "process_sha256": [sha(t) for t in tsvs],
-           "combined_rows": combined.count("\n") - 1, "recounted_gaps": n_gap[0], "combined_sha256": sha(combined),
-           "reference_seconds": {"process_per_sample": [round(x, 2) for x in secs], "combine": round(t_comb, 2)}}
+           "combined_rows": combined.count("\n") - 1, "recounted_gaps": n_comb_gaps, "combined_sha256": sha(combined),
+           "shallow_settings": {"minSamples": SHALLOW[0], "minReads": SHALLOW[1], "minSSE": SHALLOW[2]},
+           "shallow_rows": shallow.count("\n") - 1, "shallow_recounted_gaps": n_gap2[0], "shallow_sha256": sha(shallow),
+           "reference_seconds": {"process_per_sample": [round(x, 2) for x in secs], "combine": round(t_comb, 2), "combineShallow": round(t_shallow, 2)}}
     with open(GOLDEN, "w") as fh:
         json.dump(doc, fh, indent=1)
         fh.write("\n")

@@ -188,9 +188,10 @@ def test_c4_shaped_process_and_combine_equal_the_reference_files_on_cpu(tmp_path
     from oracle import c4_shape
     from spliser_b200 import cli
     gold = json.load(open(c4_shape.GOLDEN))
-    per_sample, combined = c4_shape.run_cli(cli, OracleContext(), str(tmp_path))
+    per_sample, combined, shallow = c4_shape.run_cli(cli, OracleContext(), str(tmp_path))
     assert per_sample == gold["process_sha256"]
     assert combined == gold["combined_sha256"]
+    assert shallow == gold["shallow_sha256"]                  # combineShallow -m 4 -r 6 -e 0.05 over the same samples
 
 
 def test_cli_errors_mirror_the_reference(tmp_path, built_library):

@@ -104,9 +104,10 @@ def test_c4_shaped_process_and_combine_equal_the_reference_files(ctx, tmp_path):
     from oracle import c4_shape
     from spliser_b200 import cli
     gold = json.load(open(c4_shape.GOLDEN))
-    per_sample, combined = c4_shape.run_cli(cli, ctx, str(tmp_path))
+    per_sample, combined, shallow = c4_shape.run_cli(cli, ctx, str(tmp_path))
     assert per_sample == gold["process_sha256"]
     assert combined == gold["combined_sha256"]
+    assert shallow == gold["shallow_sha256"]                  # combineShallow -m 4 -r 6 -e 0.05 over the same samples
 
 
 def test_combine_sharded_by_sample_over_contexts(ctx, tmp_path):
