@@ -191,6 +191,8 @@ def combine_shallow_crafted():
         samples = []
         for title, bed, reads in specs:
             tsv, _ = R.run_process(bed, reads, stranded=stranded, stype=stype if stranded else None)
+            if not bed:                                   # a sample without junctions: its table is the header line alone
+                assert tsv.count("\n") == 1
             samples.append(dict(title=title, tsv=tsv, reads=reads))
         for ms, mr, me in settings:
             ctsv, gaps = R.run_combine([(x["title"], x["tsv"], x["reads"]) for x in samples], stranded=stranded, stype=stype,
@@ -206,6 +208,10 @@ def combine_shallow_crafted():
     case("Y-both-strands-counted", ["C"], [ap, bm], True, [(1, 5, 0.0), (2, 5, 0.0), (1, 1, 0.0)])
     case("Z-plus-takes-the-tie", ["C"], [bm, ap], True, [(1, 5, 0.0), (2, 5, 0.0), (1, 1, 0.0), (1, 5, 0.5)])
     case("YZ-unstranded", ["C"], [bm, ap], False, [(1, 5, 0.0), (2, 5, 0.0)])
+    # E  a sample whose table holds the header line only (no junction reached the BED12): every site of the others is a gap in it
+    empty = ("E", "", [("C", 81, 0, j1)] * 3 + [("C", 90, 0, "30M")])
+    case("E-empty-table-last", ["C"], [ap, empty], False, [(0, 10, 0.0), (1, 3, 0.0), (2, 3, 0.0)])
+    case("E-empty-table-first", ["C"], [empty, ap], True, [(0, 10, 0.0), (1, 3, 0.0)])
     return out
 
 
