@@ -191,6 +191,8 @@ def shape(name):
         cfg = synth.config_c5()
         cfg.n_records = 150_000
         return cfg, 4
+    if name == "c5_full":                                  # configs[4] at its full size: 1M records on the dense locus, --beta2Cryptic
+        return synth.config_c5(), 4
     if name in ("c2_stranded", "c2_dirty_strands"):
         return synth.config_c2(500_000), 0
     raise KeyError(name)
@@ -211,7 +213,7 @@ def shape_workload(name):
     return w, w.flags | extra
 
 
-SHAPES = ("c1_full", "c3_tile", "c5_dense_locus", "c2_stranded", "c2_dirty_strands")
+SHAPES = ("c1_full", "c3_tile", "c5_dense_locus", "c2_stranded", "c2_dirty_strands", "c5_full")
 
 
 def make_shape_digests():

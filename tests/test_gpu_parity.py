@@ -476,3 +476,10 @@ def test_dirty_strand_regime_at_scale_equals_the_unmodified_reference(ctx):
     unmodified reference (tests/golden/reference_digests.json) and the C oracle."""
     test_config_shaped_workloads_vs_c_oracle(ctx, "c2_dirty_strands")
 
+
+def test_full_configs4_equals_the_unmodified_reference(ctx):
+    """BASELINE configs[4] at its full size (1M records on the dense alternative-splicing locus, 7.7k sites, --beta2Cryptic: the
+    legacy weighted competing-site mode): whole-table digest of the unmodified reference (34 s of its Python for this
+    workload; tests/golden/reference_digests.json) and the C oracle."""
+    test_config_shaped_workloads_vs_c_oracle(ctx, "c5_full")
+
