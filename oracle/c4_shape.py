@@ -6,6 +6,8 @@ a replicate a few more), so the merged table has gaps in every sample -- are eac
 `combine` (re-count of the sites a sample lacks, SpliSER_v0_1_8.py:742-917), stranded rf.
 
     python oracle/c4_shape.py        # authoring container: runs the reference, writes tests/golden/c4_shape_reference.json
+    python oracle/c4_shape.py c4x48  # the same with configs[3]'s own sample count, 48 = 6 conditions x 8 replicates, on a smaller
+                                     # genome -> tests/golden/c4_48_samples_reference.json
 
 The golden holds the sha256 of every `.SpliSER.tsv` and of the `.combined.tsv` the reference wrote; the CLI tests rebuild the
 same inputs (`build_samples`, deterministic), run spliser_b200.cli on BAM / BED12 files and compare the bytes' digests
@@ -31,6 +33,23 @@ N_RECORDS = 1_200_000
 SEED = 20260004
 SHALLOW = (4, 6, 0.05)            # combineShallow -m / -r / -e of the second merge
 GOLDEN = os.path.join(ROOT, "tests", "golden", "c4_shape_reference.json")
+CONTIGS = (("R1", 4_000_000), ("R2", 2_500_000), ("R3", 1_200_000))
+
+
+class Shape:
+    """One configs[3]-shaped workload: conditions x replicates samples of one synthetic genome."""
+
+    def __init__(self, name, n_cond, n_rep, n_records, seed, shallow, contigs, golden):
+        self.name, self.n_cond, self.n_rep, self.n_records, self.seed = name, n_cond, n_rep, n_records, seed
+        self.shallow, self.contigs, self.golden = shallow, contigs, golden
+
+
+SIX = Shape("c4", N_COND, N_REP, N_RECORDS, SEED, SHALLOW, CONTIGS, GOLDEN)
+# the sample count configs[3] names (6 conditions x 8 replicates = 48 samples), on a smaller genome so that the reference's
+# merge (literal_eval of every cell of 48 tables) and the CPU test stay in the tens of seconds
+FORTY_EIGHT = Shape("c4x48", 6, 8, 1_440_000, 20260048, (24, 4, 0.05), (("R1", 1_500_000), ("R2", 900_000)),
+                    os.path.join(ROOT, "tests", "golden", "c4_48_samples_reference.json"))
+SHAPES = {s.name: s for s in (SIX, FORTY_EIGHT)}
 
 
 def _subset(r, keep):
@@ -42,14 +61,15 @@ def _subset(r, keep):
     return Records(r.pos[keep], r.flag[keep], off, r.cigar[np.repeat(keep, ncig)], r.seg_chrom, csum[r.seg_off])
 
 
-def build_samples():
+def build_samples(shape=SIX):
     """-> (chromosome names, chromosome lengths, [(title, Records, BED12 text)] in samples-file order)."""
     from spliser_b200 import Junctions, synth
     from spliser_b200.synth import Workload
-    w = synth.generate(synth.SynthConfig(name="c4", seed=SEED, contigs=(("R1", 4_000_000), ("R2", 2_500_000), ("R3", 1_200_000)), n_records=N_RECORDS,
+    w = synth.generate(synth.SynthConfig(name="c4", seed=shape.seed, contigs=shape.contigs, n_records=shape.n_records,
                                          read_len=100, paired=True, stranded=True, genes_per_mb=165.0))
-    rng = np.random.default_rng(SEED)
+    rng = np.random.default_rng(shape.seed)
     r, j = w.records, w.junctions
+    N_COND, N_REP = shape.n_cond, shape.n_rep
     n_s = N_COND * N_REP
     owner = rng.integers(0, n_s, len(r))                       # every record belongs to one sample
     cond_drop = rng.random((N_COND, len(j))) < 0.08
@@ -69,9 +89,10 @@ def sha(text) -> str:
     return hashlib.sha256(text.encode() if isinstance(text, str) else text).hexdigest()
 
 
-def run_cli(cli, ctx, tmp):
+def run_cli(cli, ctx, tmp, shape=SIX):
     """The product CLI on files: `process` per sample, then `combine` -> ([digest of each .SpliSER.tsv], digest of .combined.tsv)."""
-    chroms, chrom_len, samples = build_samples()
+    chroms, chrom_len, samples = build_samples(shape)
+    SHALLOW = shape.shallow
     lines, digests = [], []
     for i, (title, rec, bed_text) in enumerate(samples):
         bam, bed, out = os.path.join(tmp, "s%d.bam" % i), os.path.join(tmp, "s%d.bed" % i), os.path.join(tmp, "s%d" % i)
@@ -91,13 +112,14 @@ def run_cli(cli, ctx, tmp):
     return digests, sha(open(out + ".combined.tsv", "rb").read()), sha(open(out2 + ".combined.tsv", "rb").read())
 
 
-def main():
+def main(shape=SIX):
     from oracle import ref_runner
     from oracle.time_reference import IndexedStore, _Popen
     from spliser_b200.synth import Workload
     if not ref_runner.reference_available():
         raise SystemExit("reference not mounted at %s" % ref_runner.REF_DIR)
-    chroms, chrom_len, samples = build_samples()
+    chroms, chrom_len, samples = build_samples(shape)
+    SHALLOW, N_COND, N_REP, N_RECORDS, GOLDEN = shape.shallow, shape.n_cond, shape.n_rep, shape.n_records, shape.golden
     stores, tsvs, secs = {}, [], []
     old_argv, old_out = sys.argv, sys.stdout
     with tempfile.TemporaryDirectory() as td:
@@ -164,7 +186,7 @@ def main():
         shallow = open(out2 + ".combined.tsv").read()
     print("combine: %d rows, %d re-counted gaps, %.1f s" % (combined.count("\n") - 1, n_comb_gaps, t_comb))
     print("combineShallow -m %d -r %d -e %g: %d rows, %d re-counted gaps, %.1f s" % (SHALLOW + (shallow.count("\n") - 1, n_gap2[0], t_shallow)))
-    doc = {"made_by": "oracle/c4_shape.py (unmodified reference, authoring container)",
+    doc = {"made_by": "oracle/c4_shape.py%s (unmodified reference, authoring container)" % ("" if shape is SIX else " " + shape.name),
            "workload": "configs[3] shape at reduced size: %d samples (%d conditions x %d replicates) of one synthetic genome (%s), %d records in all, stranded rf"
                        % (len(samples), N_COND, N_REP, ", ".join(chroms), N_RECORDS),
            "titles": [s[0] for s in samples], "records": [len(s[1]) for s in samples],
@@ -179,4 +201,4 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    main(SHAPES[sys.argv[1]] if len(sys.argv) > 1 else SIX)

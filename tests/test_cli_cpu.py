@@ -194,6 +194,22 @@ def test_c4_shaped_process_and_combine_equal_the_reference_files_on_cpu(tmp_path
     assert shallow == gold["shallow_sha256"]                  # combineShallow -m 4 -r 6 -e 0.05 over the same samples
 
 
+def test_c4_with_48_samples_equals_the_reference_files_on_cpu(tmp_path, built_library):
+    """configs[3]'s own sample count: 48 samples (6 conditions x 8 replicates) of one genome, 1.44M records in all; the
+    unmodified reference wrote 48 .SpliSER.tsv, the 210,576-row .combined.tsv (24,131 re-counted gaps) and the
+    combineShallow -m 24 -r 4 -e 0.05 table (oracle/c4_shape.py c4x48); the CLI must write the same bytes."""
+    import json
+    from oracle import c4_shape
+    from spliser_b200 import cli
+    shape = c4_shape.FORTY_EIGHT
+    gold = json.load(open(shape.golden))
+    assert len(gold["titles"]) == 48
+    per_sample, combined, shallow = c4_shape.run_cli(cli, OracleContext(), str(tmp_path), shape)
+    assert per_sample == gold["process_sha256"]
+    assert combined == gold["combined_sha256"]
+    assert shallow == gold["shallow_sha256"]
+
+
 def test_cli_errors_mirror_the_reference(tmp_path, built_library):
     from spliser_b200 import cli
     case = [c for c in load_golden("appendix_a.json.gz")["process"] if c["name"] == "A.4-locus"][0]
