@@ -208,6 +208,17 @@ def test_c4_with_48_samples_equals_the_reference_files_on_cpu(tmp_path, built_li
     assert per_sample == gold["process_sha256"]
     assert combined == gold["combined_sha256"]
     assert shallow == gold["shallow_sha256"]
+    # the same merge with the re-count sharded by sample over 8 devices: one context per device on its own host
+    # thread, six samples each; the bytes do not depend on the sharding
+    made = []
+
+    def factory(device):
+        made.append(device)
+        return OracleContext()
+    out = str(tmp_path / "sharded")
+    cli.combine(str(tmp_path / "samples.tsv"), out, isStranded=True, strandedType="rf", devices=list(range(8)), context_factory=factory)
+    assert sorted(made) == list(range(8))
+    assert c4_shape.sha(open(out + ".combined.tsv", "rb").read()) == gold["combined_sha256"]
 
 
 def test_cli_errors_mirror_the_reference(tmp_path, built_library):
