@@ -221,6 +221,20 @@ def test_c4_with_48_samples_equals_the_reference_files_on_cpu(tmp_path, built_li
     assert c4_shape.sha(open(out + ".combined.tsv", "rb").read()) == gold["combined_sha256"]
 
 
+def test_annotated_process_equals_the_reference_files_on_cpu(tmp_path, built_library):
+    """configs[1]'s flow with the GFF annotation at reduced size (400k records, 10k sites, ~1.8k overlapping / nested genes on
+    both strands): stranded, unstranded, the annotation with its lines shuffled, and -g / -c / -m; the unmodified reference
+    wrote the four .SpliSER.tsv (oracle/c2_annotated.py), the CLI must write the same bytes -- Gene column included."""
+    import json
+    from oracle import c2_annotated
+    from spliser_b200 import cli
+    gold = json.load(open(c2_annotated.GOLDEN))["variants"]
+    got = c2_annotated.run_cli(cli, OracleContext(), str(tmp_path))
+    assert sorted(got) == sorted(gold)
+    for name, digest in got.items():
+        assert digest == gold[name]["sha256"], name
+
+
 def test_cli_errors_mirror_the_reference(tmp_path, built_library):
     from spliser_b200 import cli
     case = [c for c in load_golden("appendix_a.json.gz")["process"] if c["name"] == "A.4-locus"][0]
