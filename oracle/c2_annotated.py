@@ -3,8 +3,8 @@
 BASELINE configs[1]'s flow at reduced size, WITH the GFF annotation (gene assignment, SpliSER_v0_1_8.py:76-173 and S:313-329),
 driven through the unmodified reference: one stranded-rf sample of a three-contig synthetic genome and a dense annotation
 (a gene every ~3 kb on either strand, lengths up to 7 kb, so genes overlap and nest -- the cases where the reference's
-bisection over gene starts has its quirks).  Four runs: all genes stranded; all genes unstranded; the same annotation with
-its lines shuffled (createGenes inserts by bisection, S:93-110); and `-g GENE -c CHROM -m 20000` (the window filter).
+bisection over gene starts has its quirks).  Five runs: all genes stranded; all genes unstranded; the same annotation with
+its lines shuffled (createGenes inserts by bisection, S:93-110); `-g GENE -c CHROM -m 20000` (the window filter); and `-t mRNA` (no effect in the reference, S:82).
 
     python oracle/c2_annotated.py        # authoring container: runs the reference, writes tests/golden/c2_annotated_reference.json
 
@@ -71,6 +71,7 @@ def build_inputs():
         "unstranded": (text, dict(isStranded=False, strandedType=None)),
         "shuffled_annotation": ("".join(shuffled), dict(isStranded=True, strandedType="rf")),
         "query_gene": (text, dict(isStranded=True, strandedType="rf", qGene=qgene, qChrom=qchrom, maxIntronSize=20000)),
+        "atype_mRNA": (text, dict(isStranded=True, strandedType="rf", aType="mRNA")),         # -t mRNA: the reference tests line.type == 'gene' whatever -t says (S:82)
     }
     return w, variants
 
@@ -122,7 +123,7 @@ def main():
             sys.argv, sys.stdout = ["SpliSER", "process"], io.StringIO()
             t0 = time.perf_counter()
             try:
-                mod.process("s.bam", bed, o, kw.get("qGene", "All"), kw.get("qChrom", "All"), kw.get("maxIntronSize", 0), gff, "gene",
+                mod.process("s.bam", bed, o, kw.get("qGene", "All"), kw.get("qChrom", "All"), kw.get("maxIntronSize", 0), gff, kw.get("aType", "gene"),
                             kw["isStranded"], kw["strandedType"], False)
             finally:
                 sys.argv, sys.stdout = old_argv, old_out

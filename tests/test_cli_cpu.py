@@ -223,8 +223,8 @@ def test_c4_with_48_samples_equals_the_reference_files_on_cpu(tmp_path, built_li
 
 def test_annotated_process_equals_the_reference_files_on_cpu(tmp_path, built_library):
     """configs[1]'s flow with the GFF annotation at reduced size (400k records, 10k sites, ~1.8k overlapping / nested genes on
-    both strands): stranded, unstranded, the annotation with its lines shuffled, and -g / -c / -m; the unmodified reference
-    wrote the four .SpliSER.tsv (oracle/c2_annotated.py), the CLI must write the same bytes -- Gene column included."""
+    both strands): stranded, unstranded, the annotation with its lines shuffled, -g / -c / -m, and -t mRNA; the unmodified
+    reference wrote the five .SpliSER.tsv (oracle/c2_annotated.py), the CLI must write the same bytes -- Gene column included."""
     import json
     from oracle import c2_annotated
     from spliser_b200 import cli
