@@ -63,6 +63,15 @@ void spl_destroy(spl_ctx* ctx);
 const char* spl_last_error(const spl_ctx* ctx);   /* NUL-terminated, valid until next call on ctx */
 int  spl_set_tile(spl_ctx* ctx, int tile_index, int tile_count);
 int  spl_set_threads(spl_ctx* ctx, int n_host_threads);   /* BGZF inflate / record parse workers */
+/* Counting variant of the following calls on this context.  Both give identical results (tests hold them to each other
+ * and to the reference); FUSED is the product path, STAB the cross-check north_star asks for:
+ *   SPL_VARIANT_FUSED  one kernel walks the records' CIGARs and range-adds into difference arrays over the site
+ *                      table (S:469, S:507 as +1/-1 at two lower_bound indices), prefix scan in the finalize kernel
+ *   SPL_VARIANT_STAB   records are first expanded into a bin-partitioned block stream; a block-vs-site stabbing
+ *                      kernel with TMA-staged site tiles counts coverage, junctions are handled per distinct junction */
+#define SPL_VARIANT_FUSED 0
+#define SPL_VARIANT_STAB  1
+int  spl_set_variant(spl_ctx* ctx, int variant);
 const char* spl_version(void);
 
 /* ---- process (S:710-717) ------------------------------------------------------------------- */

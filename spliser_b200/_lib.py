@@ -55,6 +55,7 @@ SIGNATURES = {
     "spl_last_error": (C.c_char_p, [C.c_void_p]),
     "spl_set_tile": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "spl_set_threads": (C.c_int, [C.c_void_p, C.c_int]),
+    "spl_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "spl_last_stats": (C.c_int, [C.c_void_p, c_f64p]),
     "spl_process": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, c_strp] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),
     "spl_process_records": (C.c_int, [C.c_void_p, C.POINTER(RecordsView), C.c_int32] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),

@@ -308,6 +308,12 @@ class Context:
         if rc != 0:
             raise SpliserError("%s: %s (code %d)" % (what, self._lib.spl_last_error(self._h).decode(), rc))
 
+    def set_variant(self, variant):
+        """'fused' (product path: difference arrays straight from the records) or 'stab' (block-vs-site stabbing over a
+        bin-partitioned block stream; the cross-check)."""
+        v = {"fused": 0, "stab": 1}[variant] if isinstance(variant, str) else int(variant)
+        self._check(self._lib.spl_set_variant(self._h, v), "spl_set_variant")
+
     def stats(self):
         buf = (C.c_double * L.SPL_NSTATS)()
         self._lib.spl_last_stats(self._h, buf)

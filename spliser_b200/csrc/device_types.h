@@ -22,8 +22,20 @@ struct Chunk {
     uint32_t a_base, b_base, s_base, j_base; // exclusive scan of the totals
     int32_t  a_lo, a_hi;                // min block start / max (block end - 2) over A blocks (empty: lo > hi)
     int32_t  s_lo, s_hi;                // min / max position any lookup of the chunk's spliced reads can ask for
-    int32_t  reserved[4];               // (site windows of an earlier design; the tiles of stream C carry them now)
 };
+
+// Work item of the fused counting kernel (count_fused.cu): up to FC_RECS consecutive records of one chromosome.
+// The host fills chrom / rec_lo / rec_hi; k_chunk_bounds adds the CIGAR range and the chromosome's site / bin ranges.
+constexpr int FC_RECS = 1024;
+struct FChunk {
+    int32_t  chrom;
+    uint32_t rec_lo, rec_hi;            // records [rec_lo, rec_hi)
+    uint32_t c_lo, c_hi;                // their CIGAR words [c_lo, c_hi)
+    int32_t  s0, s1;                    // site index range of the chromosome
+    int32_t  sb_g0, sb_nb;              // direct-address bin index of the chromosome: first entry, number of bins (sentinel at sb_nb)
+    int32_t  pad[3];
+};
+static_assert(sizeof(FChunk) == 48, "FChunk is loaded as three 128-bit words");
 
 struct DevGraph {
     int32_t n_chrom, n_sites, n_edges;
@@ -134,14 +146,18 @@ struct DevBins {
 };
 
 // Per-pass counters, one contiguous u32 buffer (zeroed by one memset per pass).
+// diff: four difference arrays in site-index space, interleaved per site (one 16-byte element per site):
+//   word 4*s + k      reads of strand class k whose M/=/X block covers site s and s+1 (S:469)
+//   word 4*s + 2 + k  reads of strand class k whose N strictly spans site s (S:507-512)
+// An operator that stabs the site index range [lo, hi) adds +1 at lo and -1 at hi; k_finalize takes the prefix sums.
 struct DevCounters {
-    uint32_t* cov;     // [2][S]   reads whose block covers site and site+1, by read strand class
-    uint32_t* span;    // [2][S+1] difference array: reads whose N strictly spans the site
+    uint32_t* diff;    // [(S+1) * 4]
+    uint32_t* cov;     // [2][S]   direct coverage counts by read strand class (stabbing variant K3 only; zero otherwise)
     uint32_t* covx;    // [S] covering reads that are beta1-type (moved from beta1 to beta2Simple)
     uint32_t* spanx;   // [S] spanning reads that are flanking (removed from the mutually-exclusive count)
     uint32_t* flank;   // [S] flanking reads (counted as beta2Simple in combine mode only)
     uint32_t* dc;      // [E] PartnerBeta2DoubleCounts increments seen in the BAM
-    uint32_t* work;    // [8] work-item counters: [0] K3 tiles
+    uint32_t* work;    // [16] work-item counters: [0] K3 tiles, [8 + p] chunks of upload part p (fused kernel)
 };
 
 struct DevOutputs {
@@ -149,19 +165,19 @@ struct DevOutputs {
     int64_t* beta1; int64_t* beta2s; int64_t* beta2c;
     double* beta2w; double* sse;
     int64_t* dc_tot; uint8_t* dc_present;   // [E] scratch of the beta2 gather
-    uint32_t* span_blk;                 // block sums for the span scan
+    uint32_t* span_blk;                 // [4 per block] block sums of the four difference arrays
 };
 
 constexpr int CHUNK_READS = 4096;       // records per chunk
 constexpr int EXPAND_THREADS = 512;     // one record per thread and round
-constexpr int FIN_THREADS = 256;
-#ifndef SPL_FIN_ITEMS
-#define SPL_FIN_ITEMS 1
-#endif
-constexpr int FIN_ITEMS = SPL_FIN_ITEMS; // sites per thread in the span scan (1: the beta2 gather wants every site on its own thread)
+constexpr int FIN_THREADS = 256;        // sites per block of the difference-array scan (one site per thread: the beta2 gather wants that)
 
 constexpr uint32_t FLAG_STRANDED = 1u, FLAG_RF = 2u, FLAG_CRYPTIC = 4u, FLAG_COMBINE = 8u;
-constexpr uint32_t FLAG_DEBUG_SKIP_EXC = 0x10000u;   // set only by SPLISER_DEBUG_SKIP_EXC=1 (kernel timing experiments)
+#ifdef SPL_DEBUG_HOOKS
+constexpr uint32_t FLAG_DEBUG_SKIP_EXC = 0x10000u;   // kernel timing experiments only: compiled in with -DSPL_DEBUG_HOOKS, never in the shipped library
+#else
+constexpr uint32_t FLAG_DEBUG_SKIP_EXC = 0u;
+#endif
 
 struct KernelTimes { float beta1_ms, spliced_ms, final_ms; };
 
@@ -171,7 +187,6 @@ void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals8, DevBins b
 void launch_bin_partition(const Chunk* chunks, int n_chunks, DevSoA soa, DevBins bins, void* stream);
 void launch_tile_hints(DevBins bins, DevGraph g, void* stream);
 void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream);
-void launch_alpha_reduce(DevGraph g, DevOutputs out, void* stream);
 void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream);
 void launch_jtab_layout(DevBins bins, int attempt, uint32_t* totals8, void* stream);
 void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, DevJunc jg, uint32_t* totals4, void* stream);
@@ -183,5 +198,10 @@ void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags
 int  kernel_launch_count_per_pass();
 void launch_exscan_u32(uint32_t* a, uint32_t n, uint32_t* tmp, uint32_t* total_out, void* stream);
 uint32_t exscan_tmp_words(uint32_t n);
+// fused difference-array variant (count_fused.cu)
+void launch_chunk_bounds(FChunk* chunks, uint32_t lo, uint32_t hi, const uint32_t* cig_off, DevGraph g, void* stream);
+void launch_count_fused(const DevRecords& rec, const FChunk* chunks, uint32_t lo, uint32_t hi, DevGraph g, DevCounters cnt,
+                        uint32_t* work, uint32_t flags, void* stream);
+int  sm_count_current_device();
 
 }  // namespace spl

@@ -16,105 +16,9 @@
 #include <cstdint>
 
 #include "device_types.h"
+#include "dev_helpers.cuh"
 
 namespace spl {
-
-// ------------------------------------------------------------------------------------------------
-// small device helpers
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-// 1-D TMA bulk copy global -> shared, completion signalled on the mbarrier (SASS: UBLKCP)
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-// consumer-side wait: try_wait with a suspend-time hint parks the warp in hardware until the phase flips (or the hint
-// expires), instead of spinning through issue slots the other resident warps need
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile(
-        "{\n"
-        ".reg .pred P1;\n"
-        "LAB_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
-        "@P1 bra DONE;\n"
-        "bra LAB_WAIT;\n"
-        "DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(20000u)
-        : "memory");
-}
-
-__device__ __forceinline__ int4 ldg_stream(const int4* p) {   // streaming 128-bit load, no L1 allocation
-    int4 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
-    return r;
-}
-__device__ __forceinline__ uint32_t ldg_stream_u32(const uint32_t* p) {
-    uint32_t r;
-    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
-    return r;
-}
-
-// first index in [lo, hi) with a[idx] >= key
-__device__ __forceinline__ int lower_bound_i32(const int32_t* a, int lo, int hi, int32_t key) {
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-// first index in [lo, hi) with a[idx] > key
-__device__ __forceinline__ int upper_bound_i32(const int32_t* a, int lo, int hi, int32_t key) {
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a[mid] <= key) lo = mid + 1; else hi = mid;
-    }
-    return lo;
-}
-
-// lower_bound(key_lo) and upper_bound(key_hi) over the same sorted range [lo, hi) in one branch-free loop:
-// the two dependent-load chains overlap, and with warp-uniform arguments the trip count is uniform
-__device__ __forceinline__ void bound_pair_i32(const int32_t* a, int lo, int hi, int32_t key_lo, int32_t key_hi, int& i0, int& i1) {
-    int n = hi - lo;
-    if (n <= 0) { i0 = i1 = lo; return; }
-    const int32_t* b0 = a + lo;
-    const int32_t* b1 = a + lo;
-    while (n > 1) {
-        const int half = n >> 1;
-        const int32_t v0 = b0[half - 1], v1 = b1[half - 1];
-        b0 = (v0 < key_lo) ? b0 + half : b0;
-        b1 = (v1 <= key_hi) ? b1 + half : b1;
-        n -= half;
-    }
-    i0 = (int)(b0 - a) + (b0[0] < key_lo ? 1 : 0);
-    i1 = (int)(b1 - a) + (b1[0] <= key_hi ? 1 : 0);
-}
-
-// strand class bit of a read: 0 = '+', 1 = '-' under check_strand (S:374-406); always 0 when unstranded
-__device__ __forceinline__ uint32_t read_class(uint32_t flag, uint32_t mode) {
-    if (!(mode & FLAG_STRANDED)) return 0u;
-    const bool first = (flag & 64u) || !(flag & 1u);
-    const bool rev = (flag & 16u) != 0;
-    bool plus = first != rev;               // fr
-    if (mode & FLAG_RF) plus = !plus;
-    return plus ? 0u : 1u;
-}
-
-// does a read of class k match a site of class c?  (CLS_ANY matches class 0 only because every
-// read of an unstranded run is class 0)
-__device__ __forceinline__ bool strand_ok(uint32_t site_cls, uint32_t k) {
-    return (site_cls == 0u && k == 0u) || (site_cls == 1u && k == 0u) || (site_cls == 2u && k == 1u);
-}
 
 struct Cnt4 { uint32_t a, b, s, j; };
 
@@ -648,25 +552,6 @@ struct StageMeta {
 };
 constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u, PS_GLOBAL_BINS = 4u;
 
-// producer-side wait: the single producer lane would otherwise spin on the empty barrier for most of the
-// kernel and steal issue slots from the consumers of the co-resident CTAs
-__device__ __forceinline__ void mbar_wait_backoff(uint64_t* bar, uint32_t parity, uint32_t ns = 5000) {
-    const uint32_t addr = smem_u32(bar);
-    for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred P1;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n"     // suspend-time hint: the thread sleeps in hardware
-            "selp.u32 %0, 1, 0, P1;\n"
-            "}\n"
-            : "=r"(done) : "r"(addr), "r"(parity), "r"(ns * 4u) : "memory");
-        if (done) return;
-    }
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PS_CONSUMERS) : "memory"); }
 
 struct K3Stage {
@@ -828,34 +713,6 @@ k_beta1_stab(DevBins bins, DevGraph g, DevCounters cnt) {
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// K4: junctions of spliced reads.  One consumer thread per N operator; junction slices, the chunk's
-// site window and its "hot" flags are staged by the producer.  Per junction (l, r):
-//   * range add of +1 over the sites strictly inside (l, r) into the span difference array
-//     (mutually-exclusive reads, S:507-512), aggregated across the warp with match.any because
-//     neighbouring reads usually carry the same junction;
-//   * if a site at l or r anchors a reverse-partner list with competitors ("hot"), the read may make
-//     compSplicing true for some site t (S:494-501): the (junction, endpoint) item is parked in a
-//     shared-memory work list and processed after the streaming loop of the stage with every lane
-//     busy (the exception logic is a chain of dependent graph lookups).
-// ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool in_list(const int32_t* a, int lo, int hi, int32_t key) {
-    for (int i = lo; i < hi; ++i)
-        if (a[i] == key) return true;
-    return false;
-}
-__device__ __forceinline__ bool in_sorted(const int32_t* a, int lo, int hi, int32_t key) {
-    const int i = lower_bound_i32(a, lo, hi, key);
-    return i < hi && a[i] == key;
-}
-
-// is junction (l, r) a partner/competitor pair for site t?  (S:494-501)
-__device__ __forceinline__ bool pc_pair(const DevGraph& g, int t, int32_t l, int32_t r) {
-    const int p0 = g.pc_off[t], p1 = g.pc_off[t + 1], c0 = g.cp_off[t], c1 = g.cp_off[t + 1];
-    return (in_list(g.pc_pos, p0, p1, l) && in_sorted(g.cp_pos, c0, c1, r)) ||
-           (in_sorted(g.cp_pos, c0, c1, l) && in_list(g.pc_pos, p0, p1, r));
-}
-
 // Two views of the read that owns a complex junction instance: straight from the record-ordered SoA (three dependent
 // DRAM round trips per item) or from the packed record k_junc_pack wrote at load time (one coalesced 96-byte load).
 struct ReadGlobal {
@@ -876,76 +733,6 @@ struct ReadPacked {
     __device__ __forceinline__ uint32_t be(uint32_t x) const { return w[10 + 2 * x]; }
 };
 
-// The read makes compSplicing true for site t through its junction number rd.jrel, unless an earlier junction of the read
-// already did: classify the read at t (S:503-557, first match wins).
-// +1 on a counter, aggregated over the lanes of the warp that are here with the same address (the instances a warp handles
-// mostly belong to one junction, so they hit the same few sites: one RED per warp and address instead of one per read)
-__device__ __forceinline__ void agg_inc(uint32_t* p) {
-    const unsigned active = __activemask();
-    const unsigned peers = __match_any_sync(active, (unsigned long long)(uintptr_t)p);
-    if ((int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(p, (uint32_t)__popc(peers));
-}
-
-template <class Rd>
-__device__ __forceinline__ void k4_classify(const Rd& rd, const DevGraph& g, const DevCounters& cnt, int t, uint32_t k, bool combine) {
-    bool earlier = false;
-    for (uint32_t x = 0; x < rd.jrel && !earlier; ++x)
-        earlier = pc_pair(g, t, (int32_t)(rd.jl(x) & POS_MASK), (int32_t)(rd.jr(x) & POS_MASK));
-    if (earlier) return;
-    const int32_t tp = g.site_pos[t];
-    const bool ok = strand_ok(g.site_cls[t], k);
-    bool alpha = false; int32_t partner_used = 0; int kstar = -1;
-    for (uint32_t x = 0; x < rd.nj; ++x) {
-        const uint32_t lraw = rd.jl(x);
-        const int32_t ll = (int32_t)(lraw & POS_MASK), rr = (int32_t)(rd.jr(x) & POS_MASK);
-        if (ll == tp && !(lraw >> 31)) { alpha = true; partner_used = rr; }   // firstN: POS > t, read skipped (S:435)
-        if (rr == tp) { alpha = true; partner_used = ll; }
-        if (ll < tp && tp < rr) kstar = (int)x;
-    }
-    if (alpha) {                                                   // S:519-527
-        for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
-            const int32_t pp = g.pc_pos[e];
-            if (pp == partner_used) continue;
-            bool in_read = false;
-            for (uint32_t x = 0; x < rd.nj && !in_read; ++x)
-                in_read = (int32_t)(rd.jl(x) & POS_MASK) == pp || (int32_t)(rd.jr(x) & POS_MASK) == pp;
-            if (in_read) agg_inc(cnt.dc + e);
-        }
-    } else if (kstar >= 0) {
-        if (kstar >= (int)rd.jrel) {                               // compSplicing already true at k*: flanking (S:503-505)
-            if (ok) agg_inc(cnt.spanx + t);
-            if (combine) agg_inc(cnt.flank + t);
-        }
-    } else if (ok) {
-        bool covers = false;
-        for (uint32_t b = 0; b < rd.nb && !covers; ++b)
-            covers = rd.bs(b) <= tp && (int32_t)(rd.be(b) & POS_MASK) >= tp + 2;
-        if (covers) {                                              // beta1-type, S:544-552
-            agg_inc(cnt.covx + t);
-            for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
-                const int32_t pp = g.pc_pos[e];
-                bool in_read = false;
-                for (uint32_t x = 0; x < rd.nj && !in_read; ++x)
-                    in_read = (int32_t)(rd.jl(x) & POS_MASK) == pp || (int32_t)(rd.jr(x) & POS_MASK) == pp;
-                if (in_read) agg_inc(cnt.dc + e);
-            }
-        }
-    }
-}
-
-// Is junction (l, r), whose endpoint (side 0 = l, 1 = r) sits on `anchor`, a partner/competitor pair for the q-th site
-// of the anchor's reverse-partner list?  Every t of that list has the anchored endpoint in P_t by construction, so
-// (l, r) is a pair for t (S:494-501) iff the OTHER endpoint is in C_t.  Returns t or -1.
-__device__ __forceinline__ int k4_pair_site(const DevGraph& g, int q, int side, int32_t l, int32_t r) {
-    const int t = g.rp_site[q];
-    if (t < g.own_lo || t >= g.own_hi) return -1;
-    const int c0 = g.cp_off[t], c1 = g.cp_off[t + 1];
-    if (c0 == c1 || !in_sorted(g.cp_pos, c0, c1, side == 0 ? r : l)) return -1;
-    // side 1 finds (r in P_t, l in C_t); if (l in P_t, r in C_t) holds as well, side 0 already handled t
-    if (side == 1 && in_sorted(g.cp_pos, c0, c1, r) && in_list(g.pc_pos, g.pc_off[t], g.pc_off[t + 1], l)) return -1;
-    return t;
-}
-
 // ------------------------------------------------------------------------------------------------
 // K4: junction kernels over the DISTINCT junctions of the sample.
 //   k_junc_lookup   (load time) one thread per distinct junction: site lookups through the bin index, offsets of its
@@ -959,18 +746,9 @@ __device__ __forceinline__ int k4_pair_site(const DevGraph& g, int q, int side, 
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t JS_CHUNK = 2048;
 
-__device__ __forceinline__ int site_lower(const DevGraph& g, int chrom, int32_t pos) {
-    const int g0 = g.sb_base[chrom], nb = g.sb_base[chrom + 1] - g0 - 1;
-    const int s1 = g.cs_off[chrom + 1];
-    int i = g.sb_off[g0 + min(max(pos, 0) >> SB_SHIFT, nb)];
-    while (i < s1 && g.site_pos[i] < pos) ++i;
-    return i;
-}
-
 __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, uint32_t mode) {
     const uint32_t d = blockIdx.x * blockDim.x + threadIdx.x;
     const bool live = d < jg.D;
-    const int S = g.n_sites;
     uint32_t hl = 0, hr = 0;
     if (live) {
         const int32_t l = (int32_t)jg.dj_l[d], r = (int32_t)(jg.dj_rk[d] & POS_MASK);
@@ -982,8 +760,8 @@ __global__ void __launch_bounds__(256) k_junc_lookup(DevJunc jg, DevGraph g, uin
         int ir = il;
         if (r > l) { ir = max(site_lower(g, c, r), iu); }
         const int x0 = max(iu, g.own_lo), x1 = min(ir, g.own_hi);     // sites strictly inside (l, r)
-        jg.sp_x0[d] = (uint32_t)(k * (uint32_t)(S + 1) + (uint32_t)max(x0, 0));   // where k_junc_span adds +n / -n (S:507-512)
-        jg.sp_x1[d] = x0 < x1 ? (uint32_t)(k * (uint32_t)(S + 1) + (uint32_t)x1) : 0xffffffffu;
+        jg.sp_x0[d] = 4u * (uint32_t)max(x0, 0) + 2u + k;                  // word of cnt.diff where k_junc_span adds +n / -n (S:507-512)
+        jg.sp_x1[d] = x0 < x1 ? 4u * (uint32_t)x1 + 2u + k : 0xffffffffu;
         if (!(mode & FLAG_DEBUG_SKIP_EXC)) {
             if (il < s1 && g.site_pos[il] == l && g.site_hot[il]) hl = (uint32_t)il + 1u;
             if (ir < s1 && g.site_pos[ir] == r && g.site_hot[ir]) hr = (uint32_t)ir + 1u;
@@ -1067,8 +845,8 @@ __global__ void __launch_bounds__(256) k_junc_span(DevJunc jg, DevCounters cnt) 
     const uint32_t x1 = jg.sp_x1[d];
     if (x1 == 0xffffffffu) return;
     const uint32_t n = jg.dj_all[d];
-    atomicAdd(cnt.span + jg.sp_x0[d], n);
-    atomicAdd(cnt.span + x1, 0u - n);
+    atomicAdd(cnt.diff + jg.sp_x0[d], n);
+    atomicAdd(cnt.diff + x1, 0u - n);
 }
 
 __global__ void __launch_bounds__(256) k_junc_simple(DevJunc jg, DevGraph g, DevCounters cnt, uint32_t mode) {
@@ -1195,148 +973,140 @@ __global__ void __launch_bounds__(256) k_junc_complex(DevSoA soa, DevJunc jg, De
 }
 
 // ------------------------------------------------------------------------------------------------
-// K5: span prefix scan + beta2 gather + SSE
+// K5: prefix scan of the four difference arrays + beta2 gather + SSE
 // ------------------------------------------------------------------------------------------------
-constexpr int FIN_TILE = FIN_THREADS * FIN_ITEMS;
-
-// blocks [0, nblk): per-block sums of the span difference array; blocks beyond: alpha / PartnerCounts reduction (K1), which
+// blocks [0, nblk): per-block sums of the difference arrays; blocks beyond: alpha / PartnerCounts reduction (K1), which
 // only has to be done before k_finalize and shares this launch
 __global__ void __launch_bounds__(FIN_THREADS) k_span_blocksum(DevCounters cnt, int S, uint32_t* blk, int nblk, int blk0, DevGraph g, DevOutputs out) {
     if ((int)blockIdx.x >= nblk) {
         alpha_reduce_item(g, out, ((int)blockIdx.x - nblk) * FIN_THREADS + (int)threadIdx.x);
         return;
     }
-    __shared__ uint32_t red[2][FIN_THREADS / 32];
-    uint32_t s0 = 0, s1 = 0;
+    __shared__ uint32_t red[4][FIN_THREADS / 32];
     const int bx = (int)blockIdx.x + blk0;                 // only the blocks that hold owned sites (tile sharding)
-    const int base = bx * FIN_TILE;
-    for (int q = 0; q < FIN_ITEMS; ++q) {
-        const int i = base + q * FIN_THREADS + threadIdx.x;
-        if (i < S) { s0 += cnt.span[i]; s1 += cnt.span[(S + 1) + i]; }
-    }
-    s0 = __reduce_add_sync(0xffffffffu, s0); s1 = __reduce_add_sync(0xffffffffu, s1);
-    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s0; red[1][threadIdx.x >> 5] = s1; }
+    const int i = bx * FIN_THREADS + (int)threadIdx.x;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (i < S) v = reinterpret_cast<const uint4*>(cnt.diff)[i];
+    v.x = __reduce_add_sync(0xffffffffu, v.x); v.y = __reduce_add_sync(0xffffffffu, v.y);
+    v.z = __reduce_add_sync(0xffffffffu, v.z); v.w = __reduce_add_sync(0xffffffffu, v.w);
+    if ((threadIdx.x & 31) == 0) { const int w = threadIdx.x >> 5; red[0][w] = v.x; red[1][w] = v.y; red[2][w] = v.z; red[3][w] = v.w; }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int w = 1; w < FIN_THREADS / 32; ++w) { s0 += red[0][w]; s1 += red[1][w]; }
-        blk[2 * bx] = s0; blk[2 * bx + 1] = s1;
+    if (threadIdx.x < 4) {
+        uint32_t s = 0;
+        for (int w = 0; w < FIN_THREADS / 32; ++w) s += red[threadIdx.x][w];
+        blk[4 * bx + threadIdx.x] = s;
     }
 }
 
 __global__ void __launch_bounds__(FIN_THREADS)
 k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode, int blk0) {
     const int S = g.n_sites;
-    __shared__ uint32_t wt[2][FIN_THREADS / 32];
+    __shared__ uint32_t wt[4][FIN_THREADS / 32];
+    __shared__ uint32_t pre[4][FIN_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int bx = (int)blockIdx.x + blk0;                 // blocks before blk0 hold no owned site: their span sums are zero
-    // each thread owns FIN_ITEMS consecutive sites so that the in-thread running sum is in order
-    const int first = bx * FIN_TILE + threadIdx.x * FIN_ITEMS;
-    uint32_t d0[FIN_ITEMS], d1[FIN_ITEMS];
-    uint32_t t0 = 0, t1 = 0;
+    const int bx = (int)blockIdx.x + blk0;                 // blocks before blk0 hold no owned site: their sums are zero
+    const int t = bx * FIN_THREADS + (int)threadIdx.x;     // one site per thread
+    uint4 d = make_uint4(0, 0, 0, 0);
+    if (t < S) d = reinterpret_cast<const uint4*>(cnt.diff)[t];
+    uint32_t a[4] = {d.x, d.y, d.z, d.w};
 #pragma unroll
-    for (int q = 0; q < FIN_ITEMS; ++q) {
-        const int i = first + q;
-        d0[q] = i < S ? cnt.span[i] : 0; d1[q] = i < S ? cnt.span[(S + 1) + i] : 0;
-        t0 += d0[q]; t1 += d1[q];
-    }
-    uint32_t a0 = t0, a1 = t1;
+    for (int o = 1; o < 32; o <<= 1) {
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t x0 = __shfl_up_sync(0xffffffffu, a0, d), x1 = __shfl_up_sync(0xffffffffu, a1, d);
-        if (lane >= d) { a0 += x0; a1 += x1; }
+        for (int c = 0; c < 4; ++c) { const uint32_t x = __shfl_up_sync(0xffffffffu, a[c], o); if (lane >= o) a[c] += x; }
     }
-    if (lane == 31) { wt[0][warp] = a0; wt[1][warp] = a1; }
-    __syncthreads();
+    if (lane == 31) { wt[0][warp] = a[0]; wt[1][warp] = a[1]; wt[2][warp] = a[2]; wt[3][warp] = a[3]; }
     // prefix over the preceding blocks' sums (k_span_blocksum): a few thousand values, summed by the block itself
-    __shared__ uint32_t pre[2][FIN_THREADS / 32];
-    uint32_t p0 = 0, p1 = 0;
-    for (int b = blk0 + (int)threadIdx.x; b < bx; b += FIN_THREADS) { p0 += out.span_blk[2 * b]; p1 += out.span_blk[2 * b + 1]; }
-    p0 = __reduce_add_sync(0xffffffffu, p0); p1 = __reduce_add_sync(0xffffffffu, p1);
-    if (lane == 0) { pre[0][warp] = p0; pre[1][warp] = p1; }
+    uint32_t p[4] = {0, 0, 0, 0};
+    for (int b = blk0 + (int)threadIdx.x; b < bx; b += FIN_THREADS) {
+        const uint4 s = reinterpret_cast<const uint4*>(out.span_blk)[b];
+        p[0] += s.x; p[1] += s.y; p[2] += s.z; p[3] += s.w;
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) p[c] = __reduce_add_sync(0xffffffffu, p[c]);
+    if (lane == 0) { pre[0][warp] = p[0]; pre[1][warp] = p[1]; pre[2][warp] = p[2]; pre[3][warp] = p[3]; }
     __syncthreads();
-    uint32_t run0 = a0 - t0, run1 = a1 - t1;
-    for (int w = 0; w < FIN_THREADS / 32; ++w) { run0 += pre[0][w]; run1 += pre[1][w]; }
-    for (int w = 0; w < warp; ++w) { run0 += wt[0][w]; run1 += wt[1][w]; }
+    uint32_t run[4];                                        // inclusive prefix at site t
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        uint32_t r = a[c];
+        for (int w = 0; w < FIN_THREADS / 32; ++w) r += pre[c][w];
+        for (int w = 0; w < warp; ++w) r += wt[c][w];
+        run[c] = r;
+    }
+    if (t >= S) return;
 
     const bool stranded = (mode & FLAG_STRANDED) != 0, cryptic = (mode & FLAG_CRYPTIC) != 0, combine = (mode & FLAG_COMBINE) != 0;
-#pragma unroll 1
-    for (int q = 0; q < FIN_ITEMS; ++q) {
-        const int t = first + q;
-        if (t >= S) break;
-        run0 += d0[q]; run1 += d1[q];                       // inclusive prefix = reads whose N spans site t
-        const bool owned = t >= g.own_lo && t < g.own_hi;
-        const uint32_t c = g.site_cls[t];
-        uint32_t cov = 0, span = 0;
-        if (!stranded) { cov = cnt.cov[t]; span = run0; }
-        else if (c == 1u) { cov = cnt.cov[t]; span = run0; }
-        else if (c == 2u) { cov = cnt.cov[S + t]; span = run1; }
-        const uint32_t covx = cnt.covx[t], spanx = cnt.spanx[t];
-        int64_t b1 = (int64_t)cov - (int64_t)covx;
-        int64_t b2 = (int64_t)covx + (int64_t)span - (int64_t)spanx + (combine ? (int64_t)cnt.flank[t] : 0);
-        if (!owned || c == 4u) { b1 = 0; b2 = 0; }
-        // ---- findBeta2Counts, S:581-623
-        const int32_t tp = g.site_pos[t];
-        const int64_t alpha_t = out.alpha[t];
-        const int e_lo = g.pc_off[t], e_hi = g.pc_off[t + 1];
-        int64_t b2c = 0;
-        double b2w = 0.0;
-        if (g.pt_is_pc) {
-            // clean regime: Partners and PartnerCounts entries correspond one to one (a partner object per position), so the
-            // double-count bookkeeping of S:592-611 stays in registers
-            for (int a = g.pt_off[t]; a < g.pt_off[t + 1]; ++a) {
-                const int p = g.pt_site[a];
-                const int32_t pp = g.pc_pos[a];
-                int64_t tab = 0; bool hit = false;
-                for (int x = g.pc_off[p]; x < g.pc_off[p + 1]; ++x) {      // S:592-599
-                    const int32_t cpos = g.pc_pos[x];
-                    if ((pp > tp && cpos < tp) || (pp < tp && cpos > tp)) { tab += out.pc_cnt[x]; hit = true; }
-                }
-                b2 += tab;
-                const uint32_t dcv = cnt.dc[a];
-                const int64_t pcount = out.pc_cnt[a];
-                int64_t v = out.alpha[p] - pcount;                         // S:606
-                if (hit || dcv) { v -= (int64_t)dcv + tab; if (v < 0) v = 0; }       // subIntNoNeg, S:608-611
-                b2c += v;
-                const double wgt = alpha_t > 0 ? __ddiv_rn((double)pcount, (double)alpha_t) : 0.0;   // S:615
-                b2w = __dadd_rn(b2w, __dmul_rn((double)v, wgt));           // mul then add, no FMA (S:617-619)
+    const bool owned = t >= g.own_lo && t < g.own_hi;
+    const uint32_t c = g.site_cls[t];
+    uint32_t cov = 0, span = 0;
+    if (!stranded || c == 1u) { cov = run[0] + cnt.cov[t]; span = run[2]; }
+    else if (c == 2u) { cov = run[1] + cnt.cov[S + t]; span = run[3]; }
+    const uint32_t covx = cnt.covx[t], spanx = cnt.spanx[t];
+    int64_t b1 = (int64_t)cov - (int64_t)covx;
+    int64_t b2 = (int64_t)covx + (int64_t)span - (int64_t)spanx + (combine ? (int64_t)cnt.flank[t] : 0);
+    if (!owned || c == 4u) { b1 = 0; b2 = 0; }
+    // ---- findBeta2Counts, S:581-623
+    const int32_t tp = g.site_pos[t];
+    const int64_t alpha_t = out.alpha[t];
+    const int e_lo = g.pc_off[t], e_hi = g.pc_off[t + 1];
+    int64_t b2c = 0;
+    double b2w = 0.0;
+    if (g.pt_is_pc) {
+        // clean regime: Partners and PartnerCounts entries correspond one to one (a partner object per position), so the
+        // double-count bookkeeping of S:592-611 stays in registers
+        for (int x = g.pt_off[t]; x < g.pt_off[t + 1]; ++x) {
+            const int pp_site = g.pt_site[x];
+            const int32_t pp = g.pc_pos[x];
+            int64_t tab = 0; bool hit = false;
+            for (int y = g.pc_off[pp_site]; y < g.pc_off[pp_site + 1]; ++y) {      // S:592-599
+                const int32_t cpos = g.pc_pos[y];
+                if ((pp > tp && cpos < tp) || (pp < tp && cpos > tp)) { tab += out.pc_cnt[y]; hit = true; }
             }
-        } else {
+            b2 += tab;
+            const uint32_t dcv = cnt.dc[x];
+            const int64_t pcount = out.pc_cnt[x];
+            int64_t v = out.alpha[pp_site] - pcount;                       // S:606
+            if (hit || dcv) { v -= (int64_t)dcv + tab; if (v < 0) v = 0; }       // subIntNoNeg, S:608-611
+            b2c += v;
+            const double wgt = alpha_t > 0 ? __ddiv_rn((double)pcount, (double)alpha_t) : 0.0;   // S:615
+            b2w = __dadd_rn(b2w, __dmul_rn((double)v, wgt));               // mul then add, no FMA (S:617-619)
+        }
+    } else {
         for (int e = e_lo; e < e_hi; ++e) { out.dc_tot[e] = cnt.dc[e]; out.dc_present[e] = cnt.dc[e] != 0; }
-        for (int a = g.pt_off[t]; a < g.pt_off[t + 1]; ++a) {
-            const int p = g.pt_site[a];
-            const int32_t pp = g.site_pos[p];
+        for (int x = g.pt_off[t]; x < g.pt_off[t + 1]; ++x) {
+            const int pp_site = g.pt_site[x];
+            const int32_t pp = g.site_pos[pp_site];
             int et = e_lo;
             while (et < e_hi && g.pc_pos[et] != pp) ++et;                  // PartnerCounts[pSite.getPos()], S:604
             int64_t tab = 0; bool hit = false;
-            for (int x = g.pc_off[p]; x < g.pc_off[p + 1]; ++x) {          // S:592-599
-                const int32_t cpos = g.pc_pos[x];
-                if ((pp > tp && cpos < tp) || (pp < tp && cpos > tp)) { tab += out.pc_cnt[x]; hit = true; }
+            for (int y = g.pc_off[pp_site]; y < g.pc_off[pp_site + 1]; ++y) {  // S:592-599
+                const int32_t cpos = g.pc_pos[y];
+                if ((pp > tp && cpos < tp) || (pp < tp && cpos > tp)) { tab += out.pc_cnt[y]; hit = true; }
             }
             b2 += tab;
             if (et < e_hi) {
                 if (hit) { out.dc_tot[et] += tab; out.dc_present[et] = 1; }
                 const int64_t pcount = out.pc_cnt[et];
-                int64_t v = out.alpha[p] - pcount;                         // S:606
+                int64_t v = out.alpha[pp_site] - pcount;                   // S:606
                 if (out.dc_present[et]) { v -= out.dc_tot[et]; if (v < 0) v = 0; }   // subIntNoNeg, S:608-611
                 b2c += v;
                 const double wgt = alpha_t > 0 ? __ddiv_rn((double)pcount, (double)alpha_t) : 0.0;   // S:615
                 b2w = __dadd_rn(b2w, __dmul_rn((double)v, wgt));           // mul then add, no FMA (S:617-619)
             }
         }
-        }
-        // ---- calculateSSE, S:626-639
-        double sse = 0.0;
-        if (cryptic) {
-            const double betas = __dadd_rn((double)(b1 + b2), b2w);
-            const double den = __dadd_rn((double)alpha_t, betas);
-            if (den > 0.0) sse = __ddiv_rn((double)alpha_t, den);
-        } else {
-            const int64_t den = alpha_t + b1 + b2;
-            if (den > 0) sse = __ddiv_rn((double)alpha_t, (double)den);
-        }
-        if (!owned) { b1 = 0; b2 = 0; b2c = 0; b2w = 0.0; sse = 0.0; }     // another tile's site: zero-filled (include/spliser_b200.h)
-        out.beta1[t] = b1; out.beta2s[t] = b2; out.beta2c[t] = b2c; out.beta2w[t] = b2w; out.sse[t] = sse;
     }
+    // ---- calculateSSE, S:626-639
+    double sse = 0.0;
+    if (cryptic) {
+        const double betas = __dadd_rn((double)(b1 + b2), b2w);
+        const double den = __dadd_rn((double)alpha_t, betas);
+        if (den > 0.0) sse = __ddiv_rn((double)alpha_t, den);
+    } else {
+        const int64_t den = alpha_t + b1 + b2;
+        if (den > 0) sse = __ddiv_rn((double)alpha_t, (double)den);
+    }
+    if (!owned) { b1 = 0; b2 = 0; b2c = 0; b2w = 0.0; sse = 0.0; }     // another tile's site: zero-filled (include/spliser_b200.h)
+    out.beta1[t] = b1; out.beta2s[t] = b2; out.beta2c[t] = b2c; out.beta2w[t] = b2w; out.sse[t] = sse;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1379,8 +1149,19 @@ void launch_tile_hints(DevBins bins, DevGraph g, void* stream) {
 void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream) {
     if (n_chunks > 0) k_expand_scatter<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, soa, flags);
 }
-void launch_alpha_reduce(DevGraph, DevOutputs, void*) {
-    // alpha / PartnerCounts are reduced by the extra blocks of k_span_blocksum (launch_finalize)
+// SM count of the CURRENT device (one process may drive several devices, one context each)
+int sm_count_current_device() {
+    static std::mutex mu;
+    static int sms_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lock(mu);
+    if (dev >= 0 && dev < 64 && sms_of[dev]) return sms_of[dev];
+    int sms = 0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms < 1) sms = 1;
+    if (dev >= 0 && dev < 64) sms_of[dev] = sms;
+    return sms;
 }
 // Grid of the persistent K3 kernel on the CURRENT device: the dynamic shared-memory attribute and the SM count belong to a
 // device, and one process may drive several (one context per device, e.g. the sample-sharded re-count of `combine`).
@@ -1449,8 +1230,7 @@ void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint3
     cudaStream_t st = (cudaStream_t)stream;
     if (jg.D == 0 || g.n_sites <= 0) return;
     k_junc_span<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, cnt);
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int sms = sm_count_current_device();
     k_junc_simple<<<sms * 8, 256, 0, st>>>(jg, g, cnt, flags);
     if (jg.n_complex && jg.cx_pack) k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags);
 }
@@ -1464,19 +1244,18 @@ void launch_junction_prepare(DevJunc jg, DevGraph g, uint32_t flags, void* strea
 }
 void launch_junction_pack(DevSoA soa, DevJunc jg, void* stream) {
     if (jg.D == 0 || jg.n_complex == 0 || !jg.cx_pack) return;
-    static int sms = 0;
-    if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    const int sms = sm_count_current_device();
     k_junc_pack<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(soa, jg);
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;
-    // only the blocks of FIN_TILE sites that hold sites this context owns (all of them without tile sharding)
+    // only the blocks of FIN_THREADS sites that hold sites this context owns (all of them without tile sharding)
     const int lo = min(max(g.own_lo, 0), g.n_sites), hi = min(max(g.own_hi, lo), g.n_sites);
-    const int blk0 = lo / FIN_TILE, nblk = hi > lo ? (hi - 1) / FIN_TILE - blk0 + 1 : 0;
+    const int blk0 = lo / FIN_THREADS, nblk = hi > lo ? (hi - 1) / FIN_THREADS - blk0 + 1 : 0;
     const int nalpha = (g.n_sites + g.n_edges + FIN_THREADS - 1) / FIN_THREADS;
     k_span_blocksum<<<nblk + nalpha, FIN_THREADS, 0, (cudaStream_t)stream>>>(cnt, g.n_sites, out.span_blk, nblk, blk0, g, out);
     if (nblk) k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags, blk0);
 }
-int kernel_launch_count_per_pass() { return 6; }   // beta1_stab, junc_span, junc_simple, junc_complex, span_blocksum (+ alpha reduce), finalize
+int kernel_launch_count_per_pass() { return 6; }   // stabbing variant: beta1_stab, junc_span, junc_simple, junc_complex, span_blocksum (+ alpha reduce), finalize
 
 }  // namespace spl

@@ -169,13 +169,30 @@ struct Part {
     }
 };
 
+// Fused variant: the records of a call live in ONE device allocation (absolute record / CIGAR indices); the upload is cut
+// into slabs so that the counting kernel of one slab runs under the copy of the next.
+constexpr int MAX_FPARTS = 8;
+struct FPart { uint32_t chunk_lo = 0, chunk_hi = 0; cudaEvent_t ev_up = nullptr; };
+
 struct spl_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
     std::string err;
     int n_threads = 0;
     int tile_index = 0, tile_count = 1;
+    int variant = SPL_VARIANT_FUSED;
+    int loaded_variant = SPL_VARIANT_FUSED;
     double stats[SPL_NSTATS] = {0};
+
+    // fused variant (count_fused.cu)
+    DevBuf d_frec, d_fchunks;
+    void* h_fchunks = nullptr;
+    size_t h_fchunks_bytes = 0;
+    DevRecords frec{};
+    FChunk* fchunks = nullptr;
+    uint32_t n_fchunks = 0;
+    FPart fpart[MAX_FPARTS];
+    int n_fparts = 0;
 
     // device memory
     DevBuf d_graph, d_cnt, d_out;
@@ -338,21 +355,21 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
 int alloc_counters_outputs(spl_ctx* ctx, size_t S, size_t E) {
     // counters + outputs
     Carver cc;
-    const size_t c_cov = cc.take<uint32_t>(2 * S + 2), c_span = cc.take<uint32_t>(2 * (S + 1) + 2);
+    const size_t c_diff = cc.take<uint32_t>(4 * (S + 1) + 4), c_cov = cc.take<uint32_t>(2 * S + 2);
     const size_t c_covx = cc.take<uint32_t>(S + 1), c_spanx = cc.take<uint32_t>(S + 1), c_flank = cc.take<uint32_t>(S + 1);
-    const size_t c_dc = cc.take<uint32_t>(E + 1), c_work = cc.take<uint32_t>(8);
+    const size_t c_dc = cc.take<uint32_t>(E + 1), c_work = cc.take<uint32_t>(16);
     ctx->cnt_bytes = cc.off + 256;
     CU(ctx->d_cnt.reserve(ctx->cnt_bytes));
     char* cb = (char*)ctx->d_cnt.p;
-    ctx->cnt.cov = (uint32_t*)(cb + c_cov); ctx->cnt.span = (uint32_t*)(cb + c_span);
+    ctx->cnt.diff = (uint32_t*)(cb + c_diff); ctx->cnt.cov = (uint32_t*)(cb + c_cov);
     ctx->cnt.covx = (uint32_t*)(cb + c_covx); ctx->cnt.spanx = (uint32_t*)(cb + c_spanx);
     ctx->cnt.flank = (uint32_t*)(cb + c_flank); ctx->cnt.dc = (uint32_t*)(cb + c_dc); ctx->cnt.work = (uint32_t*)(cb + c_work);
     Carver oc;
-    const size_t nblk = (S + FIN_THREADS * FIN_ITEMS - 1) / (FIN_THREADS * FIN_ITEMS) + 1;
+    const size_t nblk = (S + FIN_THREADS - 1) / FIN_THREADS + 1;
     const size_t o_al = oc.take<int64_t>(S + 1), o_pc = oc.take<int64_t>(E + 1), o_b1 = oc.take<int64_t>(S + 1),
                  o_b2 = oc.take<int64_t>(S + 1), o_b2c = oc.take<int64_t>(S + 1), o_b2w = oc.take<double>(S + 1),
                  o_sse = oc.take<double>(S + 1), o_dct = oc.take<int64_t>(E + 1), o_dcp = oc.take<uint8_t>(E + 1),
-                 o_blk = oc.take<uint32_t>(2 * nblk + 2);
+                 o_blk = oc.take<uint32_t>(4 * nblk + 4);
     CU(ctx->d_out.reserve(oc.off + 256));
     char* ob = (char*)ctx->d_out.p;
     DevOutputs& o = ctx->out;
@@ -598,11 +615,116 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
     return expand_records(ctx, ctx->part[0], v, 0, v->n_rec, flags);
 }
 
-// one counting pass over the resident SoA; events (if given) bracket the three kernel groups
-int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
+// Fused variant: chunk table + records to the device.  The records of the call go into one allocation; a big host upload is
+// cut into up to MAX_FPARTS slabs (at chunk granularity) on the copy stream, each followed by an event: the counting
+// kernel of a slab runs while the next one is still on the wire.  Records parsed on the device (bam_gpu.cu) are adopted.
+int fused_upload(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom, bool split_ok) {
+    ctx->n_chrom_loaded = n_chrom;
+    const bool dev = ctx->rec_on_device;
+    std::vector<FChunk> hc;
+    int64_t aligned = 0;
+    for (int32_t k = 0; k < v->n_seg; ++k) {
+        if (v->seg_chrom[k] < 0) continue;
+        const int64_t a = v->seg_off[k], b = v->seg_off[k + 1];
+        aligned += b - a;
+        for (int64_t lo = a; lo < b; lo += FC_RECS) {
+            FChunk c{};
+            c.chrom = v->seg_chrom[k];
+            c.rec_lo = (uint32_t)lo;
+            c.rec_hi = (uint32_t)std::min<int64_t>(lo + FC_RECS, b);
+            hc.push_back(c);
+        }
+    }
+    ctx->n_aligned = aligned;
+    ctx->stats[SPL_STAT_N_ALIGNED] = (double)aligned;
+    ctx->n_fchunks = (uint32_t)hc.size();
+    const size_t R = (size_t)v->n_rec, NC = (size_t)v->n_cigar;
+    cudaStream_t cs = dev ? ctx->stream : ctx->copy_stream;
+    // the chunk table travels from a page-locked staging buffer on the same stream as the records, in front of them
+    CU(ctx->d_fchunks.reserve((hc.size() + 1) * sizeof(FChunk)));
+    ctx->fchunks = (FChunk*)ctx->d_fchunks.p;
+    if (!hc.empty()) {
+        const size_t bytes = hc.size() * sizeof(FChunk);
+        if (ctx->h_fchunks_bytes < bytes) {
+            if (ctx->h_fchunks) cudaFreeHost(ctx->h_fchunks);
+            ctx->h_fchunks = nullptr; ctx->h_fchunks_bytes = 0;
+            CU(cudaHostAlloc(&ctx->h_fchunks, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
+            ctx->h_fchunks_bytes = bytes + bytes / 4 + 4096;
+        }
+        memcpy(ctx->h_fchunks, hc.data(), bytes);
+        CU(cudaMemcpyAsync(ctx->fchunks, ctx->h_fchunks, bytes, cudaMemcpyHostToDevice, cs));
+        ctx->stats[SPL_STAT_H2D_BYTES] += (double)bytes;
+    }
+    ctx->n_fparts = 1;
+    ctx->fpart[0].chunk_lo = 0; ctx->fpart[0].chunk_hi = ctx->n_fchunks;
+    if (dev) {
+        ctx->frec.n_rec = (uint32_t)R;
+        ctx->frec.pos = ctx->dev_rec.pos; ctx->frec.flag = ctx->dev_rec.flag;
+        ctx->frec.cig_off = ctx->dev_rec.cig_off; ctx->frec.cigar = ctx->dev_rec.cigar;
+        CU(cudaEventRecord(ctx->fpart[0].ev_up, ctx->stream));
+        return SPL_OK;
+    }
+    Carver c;
+    const size_t o_pos = c.take<int32_t>(R + 32), o_flag = c.take<uint16_t>(R + 32), o_off = c.take<uint32_t>(R + 40),
+                 o_cig = c.take<uint32_t>(NC + 32);
+    CU(ctx->d_frec.reserve(c.off + 256));
+    char* rb = (char*)ctx->d_frec.p;
+    ctx->frec.n_rec = (uint32_t)R;
+    ctx->frec.pos = (const int32_t*)(rb + o_pos); ctx->frec.flag = (const uint16_t*)(rb + o_flag);
+    ctx->frec.cig_off = (const uint32_t*)(rb + o_off); ctx->frec.cigar = (const uint32_t*)(rb + o_cig);
+    // slabs
+    int want = 1;
+    {
+        int64_t min_rec = 2000000;
+        int max_parts = MAX_FPARTS;
+        if (const char* f = std::getenv("SPLISER_SPLIT_MIN_RECORDS")) min_rec = std::max<int64_t>(1, atoll(f));
+        if (const char* f = std::getenv("SPLISER_SPLIT_PARTS")) max_parts = std::max(1, std::min(MAX_FPARTS, atoi(f)));
+        if (split_ok) want = (int)std::max<int64_t>(1, std::min<int64_t>(max_parts, (int64_t)R / min_rec));
+        want = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, hc.size()));
+    }
+    ctx->n_fparts = want;
+    size_t r_prev = 0;
+    for (int p = 0; p < want; ++p) {
+        const uint32_t k0 = (uint32_t)(hc.size() * (size_t)p / (size_t)want), k1 = (uint32_t)(hc.size() * (size_t)(p + 1) / (size_t)want);
+        ctx->fpart[p].chunk_lo = k0; ctx->fpart[p].chunk_hi = k1;
+        const size_t r0 = r_prev, r1 = (p == want - 1 || k1 >= hc.size()) ? R : (size_t)hc[k1].rec_lo;
+        r_prev = r1;
+        if (r1 > r0) {
+            const size_t c0 = (size_t)v->cig_off[r0], c1 = (size_t)v->cig_off[r1];
+            CU(cudaMemcpyAsync(rb + o_pos + r0 * 4, v->pos + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(rb + o_flag + r0 * 2, v->flag + r0, (r1 - r0) * 2, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(rb + o_off + r0 * 4, v->cig_off + r0, (r1 - r0 + 1) * 4, cudaMemcpyHostToDevice, cs));
+            if (c1 > c0) CU(cudaMemcpyAsync(rb + o_cig + c0 * 4, v->cigar + c0, (c1 - c0) * 4, cudaMemcpyHostToDevice, cs));
+            ctx->stats[SPL_STAT_H2D_BYTES] += (double)((r1 - r0) * 10 + 4 + (c1 - c0) * 4);
+        }
+        CU(cudaEventRecord(ctx->fpart[p].ev_up, cs));
+    }
+    return SPL_OK;
+}
+
+// fused variant: one pass = counters zeroed, one counting kernel per slab (as soon as the slab has arrived), finalize
+int fused_count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     if (ev) CU(cudaEventRecord(ev[0], ctx->stream));
     if (ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->d_cnt.p, 0, ctx->cnt_bytes, ctx->stream));
-    launch_alpha_reduce(ctx->g, ctx->out, ctx->stream);
+    if (ev) CU(cudaEventRecord(ev[1], ctx->stream));
+    for (int p = 0; p < ctx->n_fparts; ++p) {
+        const FPart& P = ctx->fpart[p];
+        CU(cudaStreamWaitEvent(ctx->stream, P.ev_up, 0));
+        launch_chunk_bounds(ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->frec.cig_off, ctx->g, ctx->stream);
+        launch_count_fused(ctx->frec, ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->g, ctx->cnt, ctx->cnt.work + 8 + p, ctx->flags, ctx->stream);
+    }
+    if (ev) { CU(cudaEventRecord(ev[2], ctx->stream)); CU(cudaEventRecord(ev[3], ctx->stream)); }
+    launch_finalize(ctx->g, ctx->cnt, ctx->out, ctx->flags, ctx->stream);
+    if (ev) CU(cudaEventRecord(ev[4], ctx->stream));
+    CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+// one counting pass over the resident SoA; events (if given) bracket the three kernel groups
+int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
+    if (ctx->loaded_variant == SPL_VARIANT_FUSED) return fused_count_pass(ctx, ev);
+    if (ev) CU(cudaEventRecord(ev[0], ctx->stream));
+    if (ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->d_cnt.p, 0, ctx->cnt_bytes, ctx->stream));
     if (ev) CU(cudaEventRecord(ev[1], ctx->stream));
     for (int p = 0; p < ctx->n_parts; ++p) {
         if (p && ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->cnt.work, 0, 32, ctx->stream));      // tile counter of the previous part
@@ -746,9 +868,13 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     CU(cudaSetDevice(ctx->device));
     reset_stats(ctx);
     flags &= 0xfu;
+#ifdef SPL_DEBUG_HOOKS
     if (const char* dbg = std::getenv("SPLISER_DEBUG_SKIP_EXC"))
         if (dbg[0] == '1') flags |= FLAG_DEBUG_SKIP_EXC;
+#endif
     ctx->flags = flags;
+    const bool fused = ctx->variant == SPL_VARIANT_FUSED;
+    ctx->loaded_variant = ctx->variant;
     const bool stranded = (flags & SPL_FLAG_STRANDED) != 0;
     const double tg0 = now_ms();
     // which regime?  (a '?' strand in a stranded run or a degenerate row makes the outcome depend on
@@ -797,6 +923,11 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     cudaEvent_t dbg[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     const bool dbg_on = std::getenv("SPLISER_TIMING") != nullptr;
     if (dbg_on) { for (auto& e : dbg) cudaEventCreate(&e); cudaEventRecord(dbg[0], ctx->copy_stream); }
+    if (fused) {
+        ctx->n_parts = 0;
+        rc = fused_upload(ctx, rec, n_chrom, split_ok);
+        if (rc) return rc;
+    }
     for (int p = 0; p < ctx->n_parts; ++p) {
         rc = upload_records(ctx, ctx->part[p], rec, cuts[p], cuts[p + 1], n_chrom);
         if (rc) return rc;
@@ -881,11 +1012,11 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
         ctx->stats[SPL_STAT_N_SITES] = (double)ctx->hg.n_sites;
         ctx->stats[SPL_STAT_N_EDGES] = (double)ctx->hg.pc_pos.size();
     }
-    { const int prc = prepare_parts(ctx); if (prc) return prc; }
+    if (!fused) { const int prc = prepare_parts(ctx); if (prc) return prc; }
     CU(cudaGetLastError());
-    ctx->stats[SPL_STAT_LAUNCHES] = (double)kernel_launch_count_per_pass();
+    ctx->stats[SPL_STAT_LAUNCHES] = fused ? (double)(2 * ctx->n_fparts + 2) : (double)kernel_launch_count_per_pass();
     ctx->stats[SPL_STAT_GRAPH_DEVICE] = ctx->graph_on_device ? 1.0 : 0.0;
-    ctx->stats[SPL_STAT_N_PARTS] = (double)ctx->n_parts;
+    ctx->stats[SPL_STAT_N_PARTS] = (double)(fused ? ctx->n_fparts : ctx->n_parts);
     ctx->loaded = true;
     return SPL_OK;
 }
@@ -996,6 +1127,7 @@ int spl_create(spl_ctx** out, const int* device_ids, int n_devices) {
         CU(cudaEventCreateWithFlags(&ctx->part[p].ev_up, cudaEventDisableTiming));
         CU(cudaEventCreate(&ctx->part[p].ev_e0)); CU(cudaEventCreate(&ctx->part[p].ev_e1));
     }
+    for (int p = 0; p < MAX_FPARTS; ++p) CU(cudaEventCreateWithFlags(&ctx->fpart[p].ev_up, cudaEventDisableTiming));
     CU(cudaHostAlloc((void**)&ctx->gbm.h_cnt, 256, cudaHostAllocDefault));
     return SPL_OK;
 }
@@ -1016,6 +1148,9 @@ void spl_destroy(spl_ctx* ctx) {
             if (ctx->part[p].ev_e1) cudaEventDestroy(ctx->part[p].ev_e1);
         }
         if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
+        ctx->d_frec.release(); ctx->d_fchunks.release();
+        if (ctx->h_fchunks) cudaFreeHost(ctx->h_fchunks);
+        for (int p = 0; p < MAX_FPARTS; ++p) if (ctx->fpart[p].ev_up) cudaEventDestroy(ctx->fpart[p].ev_up);
         if (ctx->gbm.h_cnt) cudaFreeHost(ctx->gbm.h_cnt);
         if (ctx->pending) { spl_result_free(ctx->pending); ctx->pending = nullptr; }
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -1035,6 +1170,14 @@ int spl_set_tile(spl_ctx* ctx, int tile_index, int tile_count) {
     if (!ctx) return SPL_ERR_ARG;
     if (tile_count < 1 || tile_index < 0 || tile_index >= tile_count) return ctx->fail(SPL_ERR_ARG, "bad tile %d/%d", tile_index, tile_count);
     ctx->tile_index = tile_index; ctx->tile_count = tile_count;
+    return SPL_OK;
+}
+
+int spl_set_variant(spl_ctx* ctx, int variant) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (variant != SPL_VARIANT_FUSED && variant != SPL_VARIANT_STAB) return ctx->fail(SPL_ERR_ARG, "unknown variant %d", variant);
+    ctx->variant = variant;
+    ctx->loaded = false;
     return SPL_OK;
 }
 
@@ -1132,9 +1275,16 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     rc = upload_graph(ctx, nullptr, 0);
     ctx->tile_index = save_ti; ctx->tile_count = save_tc;
     if (rc) return rc;
-    rc = upload_and_expand(ctx, rec, flags, n_chrom);
-    if (rc) return drain_on_error(ctx, rc);
-    { const int prc = prepare_parts(ctx); if (prc) return drain_on_error(ctx, prc); }
+    ctx->loaded_variant = ctx->variant;
+    if (ctx->variant == SPL_VARIANT_FUSED) {
+        rc = fused_upload(ctx, rec, n_chrom, false);
+        if (rc) return drain_on_error(ctx, rc);
+    } else {
+        rc = upload_and_expand(ctx, rec, flags, n_chrom);
+        if (rc) return drain_on_error(ctx, rc);
+        const int prc = prepare_parts(ctx);
+        if (prc) return drain_on_error(ctx, prc);
+    }
     rc = count_pass(ctx, nullptr);
     if (rc) return drain_on_error(ctx, rc);
     const size_t S = (size_t)ctx->hg.n_sites;
@@ -1202,7 +1352,7 @@ int spl_resident_load(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom
     if (rc) return drain_on_error(ctx, rc);
     CU(cudaStreamSynchronize(ctx->stream));
     collect_expand_ms(ctx);
-    // the raw records are not needed once expanded
+    // stabbing variant: the raw records are not needed once expanded
     for (int p = 0; p < MAX_PARTS; ++p) ctx->part[p].d_rec.release();
     return SPL_OK;
 }

@@ -147,6 +147,31 @@ def test_resident_path_equals_process_path(ctx):
     assert st["n_aligned"] == len(w.records) and st["ms_total"] > 0
 
 
+def test_stabbing_variant_equals_difference_array_variant(ctx):
+    """north_star: the stabbing count (block-vs-site, TMA-staged site tiles) is checked against the difference-array /
+    prefix-scan formulation.  Both variants must give the oracle's table: fuzz cases (every branch), a stranded synthetic
+    sample through process, the resident path and a combine re-count."""
+    from oracle import c_oracle, fuzzgen
+    from spliser_b200 import synth
+    w = synth.generate(synth.config_small(150_000, seed=35, stranded=True, paired=True))
+    want = c_oracle.process(w.records, len(w.chroms), w.junctions, w.flags | 4, threads=8)
+    cases = [fuzzgen.gen_case(seed, n_chrom=1 + (seed % 2), dirty=(seed % 4 == 1), max_reads=60) for seed in range(930000, 930040)]
+    try:
+        for variant in ("stab", "fused"):
+            ctx.set_variant(variant)
+            for case in cases:
+                d = first_diff(gpu_process_rows(ctx, case), oracle_process_rows(case))
+                assert d is None, (variant, case["seed"], d)
+            got = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), w.junctions, w.flags | 4))
+            assert c_oracle.diff_tables(got, want) is None, (variant, c_oracle.diff_tables(got, want))
+            ctx.resident_load(w.records, len(w.chroms), w.junctions, w.flags | 4)
+            ctx.resident_count(2)
+            got = c_oracle.table_dict(ctx.resident_fetch())
+            assert c_oracle.diff_tables(got, want) is None, (variant, "resident", c_oracle.diff_tables(got, want))
+    finally:
+        ctx.set_variant("fused")
+
+
 def test_shuffled_records_give_identical_counts(ctx):
     """Any record order inside a chromosome segment is exact (the sorted-input fast paths have fallbacks)."""
     import numpy as np
