@@ -32,12 +32,15 @@ namespace spl {
 namespace {
 
 constexpr int FC_STAGES = 3;
-constexpr int FC_CWARPS = 16;
+#ifndef SPL_FC_CWARPS
+#define SPL_FC_CWARPS 12
+#endif
+constexpr int FC_CWARPS = SPL_FC_CWARPS;
 constexpr int FC_CONSUMERS = FC_CWARPS * 32;
 constexpr int FC_THREADS = FC_CONSUMERS + 32;
 constexpr int FC_RPAD = 16;                 // slack for the 16-byte alignment of the staged record slices
 constexpr int FC_CIG = 4096;                // staged CIGAR words per stage (a chunk with more reads them from global memory)
-constexpr int FC_LIST = 128;                // hot items per warp list
+constexpr int FC_LIST = 192;                // hot items per warp list
 constexpr int FC_BATCH = 2;                 // chunks a producer claims per atomic
 constexpr int FC_WALK = 256;                // operators longer than this jump through the bin index instead of walking
 constexpr int FC_MAXJ = 4, FC_MAXB = 6;     // junctions / blocks of a read kept in registers by the exception path
@@ -61,6 +64,7 @@ struct FSmem {
     FStage st[FC_STAGES];
     unsigned long long list[FC_CWARPS][FC_LIST];
     FMeta meta[FC_STAGES];
+    uint32_t next_group[FC_STAGES];     // next group of 32 records of the staged chunk (claimed by the consumer warps)
     uint64_t full[FC_STAGES], empty[FC_STAGES];
 };
 
@@ -184,45 +188,149 @@ __device__ __noinline__ void hot_item(unsigned long long item, const FStage& st,
 }
 
 template <bool STAGED>
-__device__ __forceinline__ void flush_list(unsigned long long* list, uint32_t& list_n, const FStage& st, const FMeta& m,
-                                           const CigSrc<STAGED>& cw, const FArgs& A, int lane) {
+__device__ __noinline__ void flush_list(const unsigned long long* list, uint32_t list_n, const FStage& st, const FMeta& m,
+                                        const CigSrc<STAGED>& cw, const FArgs& A) {
     __syncwarp();
-    for (uint32_t x = (uint32_t)lane; x < list_n; x += 32) hot_item<STAGED>(list[x], st, m, cw, A);
+    for (uint32_t x = threadIdx.x & 31u; x < list_n; x += 32) hot_item<STAGED>(list[x], st, m, cw, A);
     __syncwarp();
-    list_n = 0;
+}
+
+// hot endpoints of this step go to the warp's list: hl / hr = anchor + 1 of the junction's left / right end (0: not hot)
+__device__ __forceinline__ void push_hot(unsigned long long* list, uint32_t& list_n, uint32_t hl, uint32_t hr, uint32_t i, uint32_t j, int lane) {
+    const uint32_t pm_l = __ballot_sync(0xffffffffu, hl != 0u), pm_r = __ballot_sync(0xffffffffu, hr != 0u);
+    if (pm_l | pm_r) {
+        const uint32_t lt = (1u << lane) - 1u;
+        const uint32_t tag = (i << 21) | (j & 0xfffffu);
+        if (hl) list[list_n + __popc(pm_l & lt)] = ((unsigned long long)(hl - 1u) << 32) | tag;
+        if (hr) list[list_n + __popc(pm_l) + __popc(pm_r & lt)] = ((unsigned long long)(hr - 1u) << 32) | tag | (1u << 20);
+        list_n += (uint32_t)(__popc(pm_l) + __popc(pm_r));
+    }
 }
 
 // ---- the records of one staged chunk ---------------------------------------------------------------
+// Groups of 32 consecutive records are handed out dynamically (shared-memory counter of the stage): a warp that is held up
+// does not hold the stage.  Per group, two ways to the same counts:
+//   stab   the group's reads are coordinate-sorted neighbours, so their first FC_SLOTS operators cover a window of a few
+//          sites.  The window's site range is found once per warp; every site is then tested against each lane's operators
+//          from registers ((uint32)(p - start) < len - 1, S:469 / S:507) and the per-kind, per-class hits of the warp are
+//          summed with one redux.sync -> direct counts (cnt.dir), one RED per (warp, site, kind).  A hot site also checks
+//          the lanes' junction ends against its position.
+//   chain  wide windows (long introns next to dense sites, unsorted input) and operators beyond the first FC_SLOTS: the lane
+//          carries the site index of its reference position along its CIGAR and adds +1 / -1 at the two ends of the stabbed
+//          index range in the difference arrays (cnt.diff), runs of equal targets in neighbouring lanes merged.
+constexpr int FC_SLOTS = 5;
+#ifndef SPL_FC_STAB_MAX
+#define SPL_FC_STAB_MAX 16
+#endif
+constexpr int FC_STAB_MAX = SPL_FC_STAB_MAX;
+
 template <bool STAGED>
-__device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsigned long long* list, const FArgs& A) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+__device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsigned long long* list, uint32_t* next_group, const FArgs& A) {
+    const int lane = threadIdx.x & 31;
     const DevGraph& g = A.g;
     const CigSrc<STAGED> cw{STAGED ? st.cig : A.rec.cigar, STAGED ? m.cig_base : 0u};
     const int32_t* __restrict__ sp = g.site_pos;
     const uint8_t* __restrict__ hot = g.site_hot;
     const int s0 = m.s0, s1 = m.s1, own_lo = g.own_lo, own_hi = g.own_hi;
     uint32_t list_n = 0;                                             // warp-uniform
-    for (uint32_t base = (uint32_t)warp * 32u; base < m.n_rec; base += FC_CONSUMERS) {
-        const uint32_t i = base + (uint32_t)lane;
+    for (;;) {
+        // a group pushes at most 4 entries per lane on the stab path (two junctions in FC_SLOTS operators)
+        if (list_n > (uint32_t)(FC_LIST - 128)) { flush_list<STAGED>(list, list_n, st, m, cw, A); list_n = 0; }
+        uint32_t gi = 0;
+        if (lane == 0) gi = atomicAdd(next_group, 1u);
+        gi = __shfl_sync(0xffffffffu, gi, 0);
+        if (gi * 32u >= m.n_rec) break;
+        const uint32_t i = gi * 32u + (uint32_t)lane;
         const bool live = i < m.n_rec;
-        int32_t cur = 0;
-        uint32_t c0 = 0, nop = 0, k = 0;
-        if (live) {
-            cur = st.pos[m.skip + i];
-            c0 = st.off[m.skip + i];
-            nop = st.off[m.skip + i + 1] - c0;
-            k = read_class(st.flag[m.skip + i], A.mode);
+        int32_t pos = 0;
+        uint32_t nop = 0, k = 0;
+        // ---- the first FC_SLOTS operators as boundaries in registers: operator j covers [b[j], b[j+1])
+        int32_t b[FC_SLOTS + 1];
+        uint32_t tM = 0, tN = 0;                                     // bit j: operator j is M/=/X (S:457-459) / N (S:480-483)
+        bool odd = false;                                            // zero-length M / N, more than two N: left to the chain path
+        {
+            uint32_t c0 = 0;
+            if (live) {
+                pos = st.pos[m.skip + i];
+                c0 = st.off[m.skip + i];
+                nop = st.off[m.skip + i + 1] - c0;
+                k = read_class(st.flag[m.skip + i], A.mode);
+            }
+            b[0] = pos;
+#pragma unroll
+            for (int j = 0; j < FC_SLOTS; ++j) {
+                const uint32_t w = (uint32_t)j < nop ? cw(c0 + j) : 5u;  // filler: a zero-length H (no progression)
+                const uint32_t op = w & 15u;
+                const int32_t len = (int32_t)(w >> 4);
+                const uint32_t isM = (0x181u >> op) & 1u, isN = (0x008u >> op) & 1u, adv = (0x18du >> op) & 1u;   // + D: advance only (S:460-462)
+                tM |= isM << j; tN |= isN << j;
+                odd |= ((isM | isN) != 0u) && len == 0;
+                b[j + 1] = b[j] + (adv ? len : 0);
+            }
+            odd |= __popc(tN) > 2;
         }
-        const uint32_t maxop = __reduce_max_sync(0xffffffffu, nop);
-        int idx = (live && nop) ? bin_lower(g, m, cur, s0) : s0;      // first site with position >= cur, carried along the read
-        for (uint32_t j = 0; j < maxop; ++j) {
-            if (list_n > (uint32_t)(FC_LIST - 64)) flush_list<STAGED>(list, list_n, st, m, cw, A, lane);
-            const uint32_t w = j < nop ? cw(c0 + j) : 5u;             // filler: a zero-length H (no progression)
+        const bool has = live && nop != 0u;
+        const int32_t wlo = __reduce_min_sync(0xffffffffu, has ? pos - 1 : INT_MAX);
+        const int32_t whi = __reduce_max_sync(0xffffffffu, has ? b[FC_SLOTS] - 1 : INT_MIN);
+        if (wlo > whi) continue;                                     // nothing aligned in this group
+        // ---- the window's sites: one coalesced load of the 32 sites from the window's bin on, the rest by ballot
+        const int ib = max(__ldg(g.sb_off + m.sb_g0 + min(max(wlo, 0) >> SB_SHIFT, m.sb_nb)), s0);
+        const int32_t v = ib + lane < s1 ? __ldg(sp + ib + lane) : INT_MAX;
+        const uint32_t hotv = ib + lane < s1 ? (uint32_t)__ldg(hot + ib + lane) : 0u;
+        const int d = __popc(__ballot_sync(0xffffffffu, v < wlo));   // loaded sites in front of the window
+        const int nw = __popc(__ballot_sync(0xffffffffu, v >= wlo && v <= whi));
+        const uint32_t hotmask = __ballot_sync(0xffffffffu, hotv != 0u);
+        const bool wide = __any_sync(0xffffffffu, odd) || d + nw >= 32 || nw > FC_STAB_MAX;
+        uint32_t j0 = 0;                                             // first operator left to the chain path
+        bool act = has;
+        int32_t cur = pos;
+        if (!wide) {
+            for (int q = 0; q < nw; ++q) {                           // warp-uniform
+                const int32_t p = __shfl_sync(0xffffffffu, v, d + q);
+                const int32_t p1 = p + 1;
+                const int s = ib + d + q;
+                uint32_t hm = 0;                                     // operator that stabs p: b[j] <= p <= b[j+1] - 2 (S:469 / S:507)
+#pragma unroll
+                for (int j = 0; j < FC_SLOTS; ++j) hm |= (p >= b[j] && p1 < b[j + 1]) ? (1u << j) : 0u;
+                uint32_t c = (((hm & tM) ? 1u : 0u) | ((hm & tN) ? 0x10000u : 0u)) << (8u * k);   // byte fields: cov class 0 / 1, span class 0 / 1
+                c = __reduce_add_sync(0xffffffffu, c);
+                if (c && s >= own_lo && s < own_hi && lane < 4) {
+                    const uint32_t f = (c >> (8 * lane)) & 0xffu;
+                    if (f) atomicAdd(A.cnt.dir + 4 * s + lane, f);
+                }
+                if ((hotmask >> (d + q)) & 1u) {                     // an anchor: junction ends of the lanes that sit on it (S:494-501)
+                    uint32_t hl = 0, hr = 0, jl = 0, jr = 0;
+#pragma unroll
+                    for (int j = 0; j < FC_SLOTS; ++j) {
+                        if ((tN >> j) & 1u) {
+                            if (p1 == b[j]) { hl = (uint32_t)s + 1u; jl = (uint32_t)j; }            // l = start - 1 (S:482)
+                            if (p1 == b[j + 1]) { hr = (uint32_t)s + 1u; jr = (uint32_t)j; }        // r = end - 1 (S:483)
+                        }
+                    }
+                    // one list entry carries one operator index: the two ends of a lane at this site belong to different operators
+                    push_hot(list, list_n, hl, 0u, i, jl, lane);
+                    push_hot(list, list_n, 0u, hr, i, jr, lane);
+                }
+            }
+            j0 = FC_SLOTS;
+            act = live && nop > (uint32_t)FC_SLOTS;
+            cur = b[FC_SLOTS];
+        }
+        if (!__any_sync(0xffffffffu, act)) continue;
+        // ---- chain path: operators [j0, nop) of the active lanes in lock step
+        const uint32_t c0 = live ? st.off[m.skip + i] : 0u;
+        const uint32_t rem = act ? nop - j0 : 0u;
+        const uint32_t maxrem = __reduce_max_sync(0xffffffffu, rem);
+        int idx = act ? bin_lower(g, m, cur, s0) : s0;               // first site with position >= cur, carried along the read
+        for (uint32_t t = 0; t < maxrem; ++t) {
+            if (list_n > (uint32_t)(FC_LIST - 64)) { flush_list<STAGED>(list, list_n, st, m, cw, A); list_n = 0; }   // rare path
+            const uint32_t j = j0 + t;
+            const uint32_t w = t < rem ? cw(c0 + j) : 5u;
             const uint32_t op = w & 15u;
             const int32_t len = (int32_t)(w >> 4);
-            const bool isM = op == 0u || op == 7u || op == 8u;        // M = X: mapped + advance (S:457-459)
-            const bool isN = op == 3u;                                // N: advance, junction (S:480-483)
-            const bool adv = isM || isN || op == 2u;                  // D: advance only (S:460-462); I S H P: no progression
+            const bool isM = (0x181u >> op) & 1u;
+            const bool isN = op == 3u;
+            const bool adv = (0x18du >> op) & 1u;
             int ie = idx, inx = idx;
             bool v = false;
             uint32_t key_lo = 0, key_hi = 0, hl = 0, hr = 0;
@@ -253,18 +361,11 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                 run_add(A.cnt.diff, key_lo, v, false, lane);
                 run_add(A.cnt.diff, key_hi, v, true, lane);
             }
-            const uint32_t pm_l = __ballot_sync(0xffffffffu, hl != 0u), pm_r = __ballot_sync(0xffffffffu, hr != 0u);
-            if (pm_l | pm_r) {
-                const uint32_t lt = (1u << lane) - 1u;
-                const uint32_t tag = (i << 21) | (j & 0xfffffu);
-                if (hl) list[list_n + __popc(pm_l & lt)] = ((unsigned long long)(hl - 1u) << 32) | tag;
-                if (hr) list[list_n + __popc(pm_l) + __popc(pm_r & lt)] = ((unsigned long long)(hr - 1u) << 32) | tag | (1u << 20);
-                list_n += (uint32_t)(__popc(pm_l) + __popc(pm_r));
-            }
+            push_hot(list, list_n, hl, hr, i, j, lane);
             if (adv) { cur += len; idx = inx; }
         }
     }
-    if (list_n) flush_list<STAGED>(list, list_n, st, m, cw, A, lane);
+    if (list_n) flush_list<STAGED>(list, list_n, st, m, cw, A);
 }
 
 __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_constant__ FArgs A) {
@@ -321,6 +422,7 @@ __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_cons
                 FMeta& m = sm.meta[stage];
                 m.flags = staged ? 0u : FM_GLOBAL_CIG; m.n_rec = rec_hi - rec_lo; m.skip = rec_lo - a0; m.cig_base = ca;
                 m.chrom = chrom; m.s0 = s0; m.s1 = s1; m.sb_g0 = sb_g0; m.sb_nb = sb_nb;
+                sm.next_group[stage] = 0u;
                 FStage& st = sm.st[stage];
                 mbar_expect_tx(&sm.full[stage], nr * 4u + noff * 4u + nr * 2u + (staged ? nw * 4u : 0u));
                 bulk_g2s(st.pos, A.rec.pos + a0, nr * 4u, &sm.full[stage]);
@@ -342,8 +444,8 @@ __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_cons
         mbar_wait(&sm.full[stage], parity);
         const FMeta m = sm.meta[stage];
         if (m.flags & FM_DONE) break;
-        if (m.flags & FM_GLOBAL_CIG) consume<false>(sm.st[stage], m, sm.list[warp], A);
-        else consume<true>(sm.st[stage], m, sm.list[warp], A);
+        if (m.flags & FM_GLOBAL_CIG) consume<false>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], A);
+        else consume<true>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], A);
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.empty[stage]);
     }

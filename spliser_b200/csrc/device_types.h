@@ -152,6 +152,7 @@ struct DevBins {
 // An operator that stabs the site index range [lo, hi) adds +1 at lo and -1 at hi; k_finalize takes the prefix sums.
 struct DevCounters {
     uint32_t* diff;    // [(S+1) * 4]
+    uint32_t* dir;     // [S * 4]   same four kinds, counted directly per site (fused kernel, groups with a narrow site window)
     uint32_t* cov;     // [2][S]   direct coverage counts by read strand class (stabbing variant K3 only; zero otherwise)
     uint32_t* covx;    // [S] covering reads that are beta1-type (moved from beta1 to beta2Simple)
     uint32_t* spanx;   // [S] spanning reads that are flanking (removed from the mutually-exclusive count)

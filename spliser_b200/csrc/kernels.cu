@@ -1034,6 +1034,10 @@ k_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t mode, int blk0)
         run[c] = r;
     }
     if (t >= S) return;
+    {   // + the direct counts of the same four kinds
+        const uint4 dd = reinterpret_cast<const uint4*>(cnt.dir)[t];
+        run[0] += dd.x; run[1] += dd.y; run[2] += dd.z; run[3] += dd.w;
+    }
 
     const bool stranded = (mode & FLAG_STRANDED) != 0, cryptic = (mode & FLAG_CRYPTIC) != 0, combine = (mode & FLAG_COMBINE) != 0;
     const bool owned = t >= g.own_lo && t < g.own_hi;

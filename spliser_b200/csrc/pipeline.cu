@@ -355,13 +355,13 @@ int upload_graph(spl_ctx* ctx, const int64_t* j_score, int64_t n_junc) {
 int alloc_counters_outputs(spl_ctx* ctx, size_t S, size_t E) {
     // counters + outputs
     Carver cc;
-    const size_t c_diff = cc.take<uint32_t>(4 * (S + 1) + 4), c_cov = cc.take<uint32_t>(2 * S + 2);
+    const size_t c_diff = cc.take<uint32_t>(4 * (S + 1) + 4), c_dir = cc.take<uint32_t>(4 * (S + 1) + 4), c_cov = cc.take<uint32_t>(2 * S + 2);
     const size_t c_covx = cc.take<uint32_t>(S + 1), c_spanx = cc.take<uint32_t>(S + 1), c_flank = cc.take<uint32_t>(S + 1);
     const size_t c_dc = cc.take<uint32_t>(E + 1), c_work = cc.take<uint32_t>(16);
     ctx->cnt_bytes = cc.off + 256;
     CU(ctx->d_cnt.reserve(ctx->cnt_bytes));
     char* cb = (char*)ctx->d_cnt.p;
-    ctx->cnt.diff = (uint32_t*)(cb + c_diff); ctx->cnt.cov = (uint32_t*)(cb + c_cov);
+    ctx->cnt.diff = (uint32_t*)(cb + c_diff); ctx->cnt.dir = (uint32_t*)(cb + c_dir); ctx->cnt.cov = (uint32_t*)(cb + c_cov);
     ctx->cnt.covx = (uint32_t*)(cb + c_covx); ctx->cnt.spanx = (uint32_t*)(cb + c_spanx);
     ctx->cnt.flank = (uint32_t*)(cb + c_flank); ctx->cnt.dc = (uint32_t*)(cb + c_dc); ctx->cnt.work = (uint32_t*)(cb + c_work);
     Carver oc;
