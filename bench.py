@@ -1,23 +1,32 @@
 #!/usr/bin/env python
 """Benchmark of the SpliSER counting path (BASELINE.json metric: aligned reads/s to per-site SSE).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c1|c3|small]
-    torchrun --nproc-per-node N ... bench.py --gpus N ...          (one rank per GPU, weak scaling)
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c3|c1|small|c4]
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          (one rank per GPU)
 
-One "step" = one pass of the hot path over one sample: read SoA -> per-site alpha, beta1, beta2Simple,
-beta2Cryptic, SSE.  Per rank the workload is BASELINE.json configs[1] (full A. thaliana genome, 40M
-150 bp PE records, --isStranded -s rf) generated synthetically with a per-rank seed.
+One "step" = one pass of the hot path over one sample: alignment records + junction table -> per-site alpha, beta1,
+beta2Simple, beta2Cryptic, SSE (what `process` does per sample, SpliSER_v0_1_8.py:710-717).
 
-  value     reads/s with the SoA already resident in HBM (CUDA events on the library's stream)
-  e2e       reads/s through the C ABI from (pinned) host record arrays: junction table -> site graph,
-            H2D copies, record expansion, counting, D2H of the per-site results, all inside the timed region
-  roofline  dominant kernel (k_beta1_stab): algorithmic bytes / its CUDA-event time vs measured HBM peak
-  cpu_baseline / --impl reference: the oracle's C port of the reference algorithm on the host cores,
-            on a bounded genomic sub-region of the same workload (same coverage density)
+  N = 1   workload = BASELINE.json configs[1] (full A. thaliana genome, 40M 150 bp PE records, --isStranded -s rf).
+  N > 1   ONE sample sharded over the GPUs by genomic tile (north_star): workload = configs[2] (GRCh38
+          contig lengths, 200M 150 bp PE records); every rank receives the records of its read-balanced tile (reads that
+          reach across a tile edge go to both tiles) and counts the sites it owns; no data-path collective.  `--scaling weak`
+          runs one sample per GPU instead (replicas).
+
+  value     reads/s of the WHOLE per-sample path with the record arrays and the junction table resident in HBM: site table
+            + competing-site graph (K1), counters zeroed, fused counting kernel, prefix scan + beta2 gather + SSE.  CUDA events
+            on the library's stream around K passes, every kernel of the path inside; max over ranks.
+  e2e       the same through the C ABI from pinned host arrays (spl_process_records): H2D of records and junction table, the
+            path above, D2H of the result table, host wall clock.
+  roofline  the slowest kernel of the timed path (k_count_fused): SURVEY 8(d) algorithmic bytes of the read SoA / its
+            CUDA-event time vs the measured HBM peak.
+  parity    the table e2e returned is compared with the oracle's C port of the reference on the SAME full workload
+            (every column, floats bit for bit); that oracle run is also the cpu_baseline.
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
 import subprocess
@@ -35,40 +44,47 @@ METRIC = "aligned reads/s to per-site SSE"
 CACHE = os.environ.get("SPLISER_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "spliser_bench_cache"))
 
 
-def workload_config(name, reads, rank):
+def workload_config(name, reads, rank=0):
     from spliser_b200 import synth
     if name == "c2":
         cfg = synth.config_c2(reads or 40_000_000)
         desc = "configs[1]: full A. thaliana genome (TAIR10 contig lengths), %d 150 bp PE records, --isStranded -s rf" % cfg.n_records
+    elif name == "c3":
+        cfg = synth.config_c3_full(reads or 200_000_000)
+        desc = "configs[2]: GRCh38 primary contig lengths, %d 150 bp PE records, introns up to 500 kb, --isStranded -s rf" % cfg.n_records
     elif name == "c1":
         cfg = synth.config_c1()
         if reads:
             cfg.n_records = reads
         desc = "configs[0]: Chr1-sized contig, %d 100 bp SE records, unstranded" % cfg.n_records
-    elif name == "c3":
-        cfg = synth.config_c3_tile(reads or 25_000_000, tile=rank % 8)
-        desc = "configs[2]: one genomic tile (3 contigs) of a GRCh38-scale sample, %d 150 bp PE records, stranded rf" % cfg.n_records
     elif name == "small":
         cfg = synth.config_small(reads or 200_000, seed=3, stranded=True, paired=True)
         desc = "small test workload, %d records" % cfg.n_records
     else:
         raise SystemExit("unknown workload %s" % name)
-    cfg.seed += 7919 * rank          # every rank counts its own sample (weak scaling)
+    cfg.seed += 7919 * rank
     return cfg, desc
 
 
-def region_sample(w, max_reads):
-    """First `max_reads` records of the first chromosome segment + the junctions inside that region:
-    a genomic sub-region with the workload's own coverage density."""
+def generate_once(cfg, ranks):
+    """Rank 0 builds the workload into the cache; the other ranks of the node load it from there."""
+    from spliser_b200 import synth
+    if ranks.rank == 0:
+        w = synth.generate(cfg, cache_dir=CACHE)
+    ranks.barrier()
+    if ranks.rank != 0:
+        w = synth.generate(cfg, cache_dir=CACHE)
+    return w
+
+
+def first_segment(w):
+    """Records of the first chromosome segment + its junctions (the bounded sample of the reference arm on big workloads)."""
     from spliser_b200 import Junctions, Records
     r, j = w.records, w.junctions
-    n = int(min(max_reads, r.seg_off[1] - r.seg_off[0])) if len(r.seg_chrom) else 0
-    if n == 0:
-        return r, j
-    cut = int(r.pos[n - 1])
+    n = int(r.seg_off[1] - r.seg_off[0]) if len(r.seg_chrom) else 0
     c0 = int(r.seg_chrom[0])
     rec = Records(r.pos[:n], r.flag[:n], r.cig_off[:n + 1], r.cigar[:int(r.cig_off[n])], [c0], [0, n])
-    keep = (j.chrom == c0) & (j.right <= cut)
+    keep = j.chrom == c0
     return rec, Junctions(j.chrom[keep], j.left[keep], j.right[keep], j.score[keep], j.strand[keep])
 
 
@@ -117,14 +133,12 @@ def measured_peak():
     return 6650.0, "B200_PROFILING.md fallback 6.65 TB/s (of fallback)"
 
 
-def traffic_from_profile():
+def traffic_from_profile(kernel):
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
-        try:
-            return json.load(open(p)).get("k_beta1_stab_dram_bytes_per_launch")
-        except (ValueError, OSError):
-            return None
-    return None
+    try:
+        return json.load(open(p)).get(kernel + "_dram_bytes_per_launch")
+    except (ValueError, OSError):
+        return None
 
 
 def python_reference_note():
@@ -139,11 +153,25 @@ def python_reference_note():
         return None
 
 
-def cpu_port_run(rec, junc, n_chrom, flags, threads):
+def soa_counts(r):
+    """What SURVEY 8(d) counts in the read SoA: M/=/X blocks, N operators, spliced reads."""
+    op = r.cigar & 15
+    is_m = (op == 0) | (op == 7) | (op == 8)
+    is_n = op == 3
+    b_m, b_n = int(is_m.sum()), int(is_n.sum())
+    csum = np.concatenate([[0], np.cumsum(is_n, dtype=np.int64)])
+    per_rec = csum[r.cig_off[1:].astype(np.int64)] - csum[r.cig_off[:-1].astype(np.int64)]
+    return b_m, b_n, int((per_rec > 0).sum())
+
+
+def table_digest(t):
+    """sha256 over every column of a result table (dict of arrays or SiteTable), floats bit for bit."""
     from oracle import c_oracle
-    t0 = time.perf_counter()
-    c_oracle.process(rec, n_chrom, junc, flags, threads=threads)
-    return time.perf_counter() - t0
+    d = t if isinstance(t, dict) else c_oracle.table_dict(t)
+    h = hashlib.sha256()
+    for k in c_oracle.TABLE_FIELDS:
+        h.update(np.ascontiguousarray(d[k]).tobytes())
+    return h.hexdigest()[:32]
 
 
 def synthetic_gff(w, path):
@@ -207,6 +235,41 @@ def emit(line):
 _REAL_STDOUT = 1
 
 
+def reference_arm(args, ncores):
+    """The reference's algorithm on the host cores: oracle/spliser_oracle.c (C port, OpenMP over sites).  configs[1] runs in
+    full every step; configs[2] is bounded to its first chromosome so that K + W steps end within minutes."""
+    from oracle import c_oracle
+    from spliser_b200 import synth
+    strong = args.gpus > 1 and args.scaling == "strong"
+    cfg, desc = workload_config(args.workload, args.reads)
+    w = synth.generate(cfg, cache_dir=CACHE)
+    if args.workload == "c3" and not args.reference_full:
+        rec, junc = first_segment(w)
+        sample = "first chromosome of the workload (%s: %d records, %d junctions) per step" % (w.chroms[int(rec.seg_chrom[0])], len(rec), len(junc))
+    else:
+        rec, junc = w.records, w.junctions
+        sample = "the full workload (%d records, %d junctions) per step" % (len(rec), len(junc))
+    times = []
+    for i in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        c_oracle.process(rec, len(w.chroms), junc, w.flags, threads=ncores)
+        if i >= args.warmup:
+            times.append(time.perf_counter() - t0)
+    tot = float(sum(times))
+    val = len(rec) * len(times) / tot
+    if strong:
+        desc += " -- ONE sample sharded by genomic tile over %d GPUs" % args.gpus
+    emit(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "strong" if strong else "weak",
+        "vs_baseline": None, "dtype": "int64", "data": "synthetic",
+        "config": {"workload": desc, "note": "the reference is single-threaded Python + one samtools fork per site and cannot run on this box (no samtools / HTSeq); this arm times the "
+                                             "oracle's C port of its algorithm (per-site read fetch + per-CIGAR-op state machine, S:408-639) with OpenMP over sites on every host core"},
+        "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "port", "sample": sample, "python_reference": python_reference_note()},
+        "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}))
+
+
 def main():
     global _REAL_STDOUT
     sys.stdout.flush()
@@ -217,16 +280,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2")
-    ap.add_argument("--reads", type=int, default=0, help="records per GPU (default: the named config's size)")
+    ap.add_argument("--workload", default=None, help="c2 (default at N = 1), c3 (default at N > 1), c1, small, c4 (combine of 48 samples)")
+    ap.add_argument("--reads", type=int, default=0, help="records of the sample (default: the named config's size)")
     ap.add_argument("--e2e-steps", type=int, default=3)
-    ap.add_argument("--cpu-sample", type=int, default=2_000_000, help="records in the CPU baseline's genomic sub-region")
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-bam", action="store_true", help="skip the from-a-BAM-file measurement")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the oracle run (parity check + cpu_baseline)")
+    ap.add_argument("--no-bam", action="store_true", help="skip the from-a-BAM-file and CLI measurements")
+    ap.add_argument("--no-variants", action="store_true", help="skip the stabbing-variant comparison pass")
+    ap.add_argument("--reference-full", action="store_true", help="reference arm: the full workload every step even on configs[2]")
     ap.add_argument("--profile", action="store_true", help="resident passes only (for ncu): no e2e, no CPU baseline")
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
-                    help="weak: one sample per GPU (default); strong: ONE sample sharded over the GPUs by genomic tile "
-                         "(each rank gets the records of its tile, edge-spanning reads duplicated, and counts the sites it owns)")
+    ap.add_argument("--scaling", default="strong", choices=["weak", "strong"],
+                    help="N > 1: strong (default) = ONE sample sharded over the GPUs by genomic tile; weak = one sample per GPU (replicas)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -235,95 +298,98 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = os.cpu_count() or 1
+    if args.workload is None:
+        args.workload = "c2" if max(world, args.gpus) == 1 else "c3"
+    if args.workload == "c4":
+        import bench_combine
+        return bench_combine.run(args, rank, world, local, emit)
 
-    from spliser_b200 import synth
-
-    # ------------------------------------------------------------------ reference arm: CPU port
     if args.impl == "reference":
-        if rank != 0:
-            return
-        cfg, desc = workload_config(args.workload, args.reads, 0)
-        w = synth.generate(cfg, cache_dir=CACHE)
-        rec, junc = region_sample(w, args.cpu_sample)
-        times = []
-        for i in range(args.warmup + args.steps):
-            dt = cpu_port_run(rec, junc, len(w.chroms), w.flags, ncores)
-            if i >= args.warmup:
-                times.append(dt)
-        tot = float(sum(times))
-        val = len(rec) * len(times) / tot
-        sample = "first %d records of %s (one genomic sub-region, same coverage) + its %d junctions, per step" % (len(rec), w.chroms[int(rec.seg_chrom[0])], len(junc))
-        emit(json.dumps({
-            "impl": "reference", "metric": METRIC, "value": val, "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * tot / len(times), "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "int64", "data": "synthetic",
-            "config": {"workload": desc, "note": "reference is single-threaded Python + one samtools fork per site; this arm times the oracle's C port of its algorithm (per-site read fetch + per-CIGAR-op state machine) with OpenMP over sites"},
-            "cpu_baseline": {"value": val, "unit": "reads/s", "cores": ncores, "kind": "port", "sample": sample,
-                             "python_reference": python_reference_note()},
-            "e2e": {"value": val, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}))
+        if rank == 0:
+            reference_arm(args, ncores)
         return
 
     # ------------------------------------------------------------------ our arm
     import spliser_b200
+    from spliser_b200 import api, dist, synth
     from spliser_b200.api import Records, pinned_empty
-    from spliser_b200.dist import Ranks
-    from spliser_b200.dist import bind_to_device_node, host_topology
+    from spliser_b200.dist import Ranks, bind_to_device_node, host_topology
     topo = host_topology(local)
-    topo["bound_to_gpu_node"] = bind_to_device_node(topo) if os.environ.get("SPLISER_NUMA_BIND") == "1" else False
+    topo["bound_to_gpu_node"] = bind_to_device_node(topo) if os.environ.get("SPLISER_NUMA_BIND", "1") == "1" else False
     topo.pop("_bind", None)
     ranks = Ranks("nccl" if world > 1 else None)
     strong = args.scaling == "strong" and world > 1
-    cfg, desc = workload_config(args.workload, args.reads, 0 if strong else rank)
-    w = synth.generate(cfg, cache_dir=CACHE)
+    cfg, desc = workload_config(args.workload, args.reads, 0 if (strong or world == 1) else rank)
+    w = generate_once(cfg, ranks) if (strong or world == 1) else synth.generate(cfg, cache_dir=CACHE)
     n_chrom = len(w.chroms)
     n_sample = len(w.records)
+    full_records = w.records
+    tile = None
     if strong:
-        # the same sample on every rank; rank r keeps the records of genomic tile r and owns the r-th slice of the site table
-        from spliser_b200 import api, dist
+        # the same sample on every rank; rank r keeps the records of its read-balanced genomic tile and owns that slice of the site table
         table0 = api.build_site_table(n_chrom, w.junctions, w.flags)
-        w.records = dist.tile_records(w.records, table0, n_chrom, rank, world)
+        cuts = dist.balanced_tiles(full_records, table0, n_chrom, world)
+        tile = (cuts[rank], cuts[rank + 1])
+        w.records = dist.tile_records(full_records, table0, n_chrom, rank, world, site_range=tile, seg_spans=dist.segment_max_spans(full_records))
         desc += " -- ONE sample sharded by genomic tile over %d GPUs" % world
-        ctx = spliser_b200.Context(local, tile=(rank, world))
+        ctx = spliser_b200.Context(local)
+        ctx.set_tile_sites(*tile)
     else:
         ctx = spliser_b200.Context(local)
     barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
 
     sampler = ClockSampler(local)
-    # ---- resident: SoA in HBM -> SSE in HBM
+    # ---- resident: records + junction table in HBM -> SSE in HBM, the whole per-sample path timed
     ctx.resident_load(w.records, n_chrom, w.junctions, w.flags)
     t_load = time.time()
     ctx.resident_count(args.warmup)
     barrier()
-    t0 = time.time()
     st = ctx.resident_count(args.steps)
-    t1 = time.time()
     barrier()
     ms_total = max_over_ranks(st["ms_total"])
     reads_rank = st["n_aligned"]
-    reads_all = float(n_sample) if strong else sum_over_ranks(reads_rank)      # strong: the sample counts once, duplicates do not
+    reads_all = float(n_sample) if strong else sum_over_ranks(reads_rank)      # strong: the sample counts once, edge duplicates do not
     value = reads_all * args.steps / (ms_total * 1e-3)
-    nA, nB, nJ, nS, S, E = (st[k] for k in ("n_mblocks_a", "n_mblocks_b", "n_junc_ops", "n_spliced", "n_sites", "n_edges"))
+    S, E = st["n_sites"], st["n_edges"]
     peak, peak_src = measured_peak()
-    # algorithmic bytes per pass of the resident layout: 8 B per M block of the bin-partitioned
-    # stream; the junction kernels read the distinct-junction table (24 B), the grouped simple instances (8 B) and
-    # the complex instances (16 B incl. their read's junction list entry)
-    D, n_simple, n_complex = st["n_distinct_junc"], st["n_simple_junc"], st["n_complex_junc"]
-    kern = {"k_beta1_stab": (8.0 * (nA + nB), st["ms_beta1"] / args.steps),
-            "k_junc_*": (24.0 * D + 8.0 * n_simple + 16.0 * n_complex, st["ms_spliced"] / args.steps)}
-    dom = max(kern, key=lambda k: kern[k][1])
-    k3_bytes, k3_ms = kern[dom]
-    k3_gbs = k3_bytes / (k3_ms * 1e-3) / 1e9 if k3_ms > 0 else 0.0
-    path_bytes = kern["k_beta1_stab"][0] + kern["k_junc_*"][0] + 25.0 * S + 12.0 * E
+    kernel_ms = {"site_table+graph (K1)": st["ms_graph_dev"] / args.steps, "k_count_fused": st["ms_beta1"] / args.steps,
+                 "memset+scan+beta2+SSE (K5)": st["ms_final"] / args.steps}
+    b_m, b_n, r_spl = soa_counts(w.records)
+    # bytes = 9 B_M + 8 B_N + 8 R_spl + 5 S (site table) for the counting kernel; + 12 E + 20 S for the whole path
+    k_bytes = 9.0 * b_m + 8.0 * b_n + 8.0 * r_spl + 5.0 * S
+    path_bytes = k_bytes + 12.0 * E + 20.0 * S
+    rec_bytes = 10.0 * len(w.records) + 4.0 * len(w.records.cigar)
+    k_ms = kernel_ms["k_count_fused"]
+    k_gbs = k_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0
     path_ms = st["ms_total"] / args.steps
-    soa_mb = path_bytes / 1e6
 
     if args.profile:
-        emit(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "kernel_ms": {"beta1_stab": kern["k_beta1_stab"][1], "junction_kernels": kern["k_junc_*"][1], "final": st["ms_final"] / args.steps}}))
+        emit(json.dumps({"profile_run": True, "ms_per_step": ms_total / args.steps, "kernel_ms": kernel_ms, "launches_per_step": st["launches"]}))
         sampler.stop()
         ctx.close()
         ranks.close()
         return
+
+    # ---- the north_star cross-check: the stabbing variant's counting pass over its pre-digested layout (N = 1 only)
+    variants = None
+    if world == 1 and not args.no_variants:
+        try:
+            ctx.set_variant("stab")
+            ctx.resident_load(w.records, n_chrom, w.junctions, w.flags)
+            ctx.resident_count(args.warmup)
+            sv = ctx.resident_count(args.steps)
+            load_ms = ctx.stats()["ms_expand"]
+            stab_table = ctx.resident_fetch()
+            variants = {"stab": {"ms_count_pass": sv["ms_total"] / args.steps, "ms_layout_kernels_at_load": load_ms,
+                                 "ms_k_beta1_stab": sv["ms_beta1"] / args.steps, "ms_junction_kernels": sv["ms_spliced"] / args.steps,
+                                 "digest": table_digest(stab_table),
+                                 "note": "block-vs-site stabbing over a bin-partitioned block stream (TMA-staged site tiles): its counting pass needs the layout "
+                                         "kernels first (expansion, bin partition, junction grouping), so the per-sample path is their sum"},
+                        "fused": {"ms_per_sample_path": path_ms}}
+            del stab_table
+        finally:
+            ctx.set_variant("fused")
+
     # ---- e2e through the C ABI from pinned host arrays
     r = w.records
     pinned = {}
@@ -347,45 +413,102 @@ def main():
         stats = ctx.stats()
     e2e_step = max_over_ranks(float(np.mean(e2e_t)))
     e2e_val = reads_all / e2e_step
-    # the timed passes last a few ms, shorter than nvidia-smi's sampling period: the clock record covers the whole GPU-active
-    # stretch around them (warm-up passes, timed passes, end-to-end calls)
     clocks = sampler.window(t_load, time.time())
     clocks["window"] = "warm-up + timed passes + e2e calls"
+    if variants is not None:
+        variants["fused"]["digest"] = table_digest(table)
+        variants["identical"] = variants["fused"]["digest"] == variants["stab"]["digest"]
 
     out = {
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": desc, "records_per_gpu": int(reads_rank), "sites_per_gpu": int(S), "junction_rows": len(w.junctions),
-                   "l2": "no flush needed: the streamed SoA is %.0f MB per pass, larger than the 126 MB L2" % soa_mb,
+        "config": {"workload": desc, "records_per_gpu": int(reads_rank), "sites": int(S), "junction_rows": len(w.junctions),
+                   "tile_sites": list(tile) if tile else None,
+                   "l2": "no flush needed: every pass streams %.0f MB of records, larger than the 126 MB L2" % (rec_bytes / 1e6),
                    "host": topo,
                    "timing": "CUDA events on the library's stream around %d passes; max over ranks" % args.steps,
-                   "value_scope": "one counting pass (alpha reduce, beta1 stabbing, junction span + exceptions, beta2 gather, SSE) over the "
-                                  "counting layout resident in HBM; building that layout from the raw records is load-time work: see from_records "
-                                  "(device time incl. it) and e2e (host arrays -> host table, everything included)"},
+                   "value_scope": "records + junction table resident in HBM -> per-site table in HBM, every per-sample kernel inside the timed region: site table + "
+                                  "competing-site graph build (K1, %s), counter memset, fused counting kernel, prefix scan + beta2 gather + SSE; only the copies "
+                                  "are outside (they are inside e2e)" % ("rebuilt every pass" if st.get("graph_timed") else "NOT rebuilt: host-built graph")},
         "clocks": clocks,
         "e2e": {"value": e2e_val, "unit": "reads/s", "h2d_bytes_per_step": int(stats["h2d_bytes"]), "d2h_bytes_per_step": int(stats["d2h_bytes"]),
-                "ms_per_step": 1e3 * e2e_step,
-                "breakdown_ms": {k: round(stats[k], 3) for k in ("ms_total", "ms_graph", "ms_upload", "ms_expand", "ms_count")},
+                "ms_per_step": 1e3 * e2e_step, "parts": int(stats["n_parts"]),
+                "breakdown_ms": {k: round(stats[k], 3) for k in ("ms_total", "ms_graph", "ms_upload", "ms_count")},
                 "graph_on_device": bool(stats["graph_on_device"]),
-                "note": "host wall clock around spl_process_records: junction table -> site table + graph (device sort/unique in the clean regime), pinned H2D of the records, expansion, counting, D2H"},
-        "from_records": {"note": "same metric with the RAW record arrays resident in HBM instead of the counting layout: adds the load-time kernels "
-                                 "(record expansion, bin partition, junction grouping; CUDA events) to one counting pass; the site table + graph build "
-                                 "(about 1 ms of small sort kernels) runs on a second stream under the record upload and is not included",
-                         "ms_load_kernels": round(stats["ms_expand"], 3), "ms_count_pass": round(ms_total / args.steps, 4),
-                         "value": reads_rank / ((stats["ms_expand"] + ms_total / args.steps) * 1e-3) * world, "unit": "reads/s"},
-        "gpu_launches": int(st["launches"]) * args.steps,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": k3_gbs, "peak": peak, "unit": "GB/s",
-                     "frac": k3_gbs / peak, "traffic": traffic_from_profile(), "algorithmic_bytes_per_launch": k3_bytes,
-                     "ms_per_launch": k3_ms, "peak_source": peak_src},
-        "roofline_path": {"algorithmic_bytes_per_pass": path_bytes, "ms_per_pass": path_ms,
+                "note": "host wall clock around spl_process_records: junction table -> site table + graph (device), pinned H2D of the records in slabs with the counting "
+                        "kernel of a slab under the copy of the next, finalize, D2H of the table"},
+        "gpu_launches": int(round(st["launches"] * args.steps)),
+        "launches_per_step": st["launches"],
+        "roofline": {"bound": "hbm", "kernel": "k_count_fused", "achieved": k_gbs, "peak": peak, "unit": "GB/s",
+                     "frac": k_gbs / peak, "traffic": traffic_from_profile("k_count_fused"), "algorithmic_bytes_per_launch": k_bytes,
+                     "ms_per_launch": k_ms, "peak_source": peak_src,
+                     "bytes_definition": "SURVEY 8(d): 9 B per M/=/X block + 8 B per N + 8 B per spliced read + 5 B per site; the kernel streams the more compact "
+                                         "record layout (10 B per record + 4 B per CIGAR operator = %.0f MB per launch)" % (rec_bytes / 1e6),
+                     "record_bytes_per_launch": rec_bytes, "achieved_on_record_bytes_gbs": rec_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0},
+        "roofline_path": {"algorithmic_bytes_per_step": path_bytes, "ms_per_step": path_ms,
                           "achieved_gbs": path_bytes / (path_ms * 1e-3) / 1e9, "frac": path_bytes / (path_ms * 1e-3) / 1e9 / peak,
-                          "kernel_ms": {"beta1_stab": kern["k_beta1_stab"][1], "junction_kernels": kern["k_junc_*"][1], "alpha+scan+finalize": st["ms_final"] / args.steps},
-                          "kernel_gbs": {k: (v[0] / (v[1] * 1e-3) / 1e9 if v[1] > 0 else 0.0) for k, v in kern.items()}},
-        "kernel_path": {"n_mblocks_a": int(nA), "n_mblocks_b": int(nB), "n_junction_ops": int(nJ), "n_spliced_reads": int(nS), "n_edges": int(E),
-                        "n_distinct_junctions": int(D), "n_simple_junction_instances": int(n_simple), "n_complex_junction_instances": int(n_complex)},
+                          "kernel_ms": kernel_ms},
+        "kernel_path": {"n_mblocks": b_m, "n_junction_ops": b_n, "n_spliced_reads": r_spl, "n_edges": int(E), "n_cigar_ops": int(len(w.records.cigar))},
+        "variants": variants,
         "checksum": {"beta1": int(table.beta1.sum()), "beta2simple": int(table.beta2simple.sum()), "alpha": int(table.alpha.sum())},
     }
+
+    # ---- parity inside the measurement + CPU baseline on the SAME workload
+    if strong:
+        # the owned slices of every rank concatenate to the table one GPU computes for the whole sample
+        lo, hi = tile
+        np.savez(os.path.join(CACHE, "tile_%d_of_%d.npz" % (rank, world)), beta1=table.beta1[lo:hi], beta2simple=table.beta2simple[lo:hi],
+                 beta2cryptic=table.beta2cryptic[lo:hi], sse=table.sse[lo:hi], beta2weighted=table.beta2weighted[lo:hi])
+        barrier()
+        if rank == 0:
+            from oracle import c_oracle
+            parts = [np.load(os.path.join(CACHE, "tile_%d_of_%d.npz" % (q, world))) for q in range(world)]
+            ctx.set_tile_sites(-1, -1)
+            whole = ctx.process_records(full_records, n_chrom, w.junctions, w.flags)
+            cat = dict(c_oracle.table_dict(whole))
+            for k in ("beta1", "beta2simple", "beta2cryptic", "sse", "beta2weighted"):
+                cat[k] = np.concatenate([p[k] for p in parts])
+            d = c_oracle.diff_tables(cat, c_oracle.table_dict(whole))
+            out["parity_checked"] = d is None
+            out["parity"] = {"against": "the untiled single-GPU table of the same sample (rank 0): the owned slices of the %d tiles, concatenated, every column" % world,
+                             "tiles_digest": table_digest(cat), "single_gpu_digest": table_digest(whole), "first_difference": d}
+            table = whole
+        sent = sum_over_ranks(float(len(w.records)))
+        if rank == 0:
+            out["parity"]["records_sent"] = int(sent)
+            out["parity"]["edge_duplication"] = sent / n_sample - 1.0
+    if rank == 0 and not args.no_cpu_baseline:
+        from oracle import c_oracle
+        if args.workload == "c3":
+            # bounded: the first chromosome of the sample (its sites are the first rows of the table)
+            rec_s, junc_s = first_segment(Workload_like(full_records, w.junctions))
+            sample = "first chromosome of the sample (%d records, %d junctions)" % (len(rec_s), len(junc_s))
+            t0 = time.perf_counter()
+            want = c_oracle.process(rec_s, n_chrom, junc_s, w.flags, threads=ncores)
+            dt = time.perf_counter() - t0
+            ns = len(want["pos"])
+            got = c_oracle.table_dict(table)
+            sub_ok = all(np.array_equal(np.asarray(got[k][:ns]).view(np.int64) if np.asarray(got[k]).dtype.kind == "f" else np.asarray(got[k][:ns]),
+                                        np.asarray(want[k]).view(np.int64) if np.asarray(want[k]).dtype.kind == "f" else np.asarray(want[k]))
+                         for k in ("pos", "alpha", "beta1", "beta2simple", "beta2cryptic", "sse"))
+            out.setdefault("parity", {})["oracle_subset"] = {"against": "oracle/spliser_oracle.c on " + sample + ": the first %d rows of the table" % ns, "identical": bool(sub_ok)}
+            out["parity_checked"] = bool(out.get("parity_checked", True) and sub_ok)
+            out["cpu_baseline"] = {"value": len(rec_s) / dt, "unit": "reads/s", "cores": ncores, "kind": "port", "sample": sample, "python_reference": python_reference_note()}
+        else:
+            t0 = time.perf_counter()
+            want = c_oracle.process(full_records, n_chrom, w.junctions, w.flags, threads=ncores)
+            dt = time.perf_counter() - t0
+            diff = c_oracle.diff_tables(c_oracle.table_dict(table), want)
+            out["parity_checked"] = diff is None
+            out["parity"] = {"against": "oracle/spliser_oracle.c (C port of the reference, pinned to the reference's golden vectors) on the same full workload, every column, floats bit for bit",
+                             "table_digest": table_digest(table), "oracle_digest": table_digest(want), "first_difference": diff}
+            out["cpu_baseline"] = {"value": n_sample / dt, "unit": "reads/s", "cores": ncores, "kind": "port",
+                                   "sample": "the full workload, once (%d records, %d junctions, %.1f s): C port of the reference algorithm, OpenMP over sites" % (n_sample, len(w.junctions), dt),
+                                   "python_reference": python_reference_note()}
+    elif rank == 0:
+        out["cpu_baseline"] = None
+
     # ---- the same call from a BAM FILE (spl_process): BGZF inflate + record parse on the device vs the host reader
     if world == 1 and not args.no_bam:
         try:
@@ -425,18 +548,15 @@ def main():
         except Exception as ex:
             out["cli_e2e"] = {"error": repr(ex)}
     sampler.stop()
-    if rank == 0 and not args.no_cpu_baseline and world == 1:
-        rec_s, junc_s = region_sample(w, args.cpu_sample)
-        dt = min(cpu_port_run(rec_s, junc_s, n_chrom, w.flags, ncores) for _ in range(2))
-        out["cpu_baseline"] = {"value": len(rec_s) / dt, "unit": "reads/s", "cores": ncores, "kind": "port",
-                               "sample": "first %d records of %s (genomic sub-region, same coverage) + its %d junctions; C port of the reference algorithm, OpenMP over sites" % (len(rec_s), w.chroms[int(rec_s.seg_chrom[0])], len(junc_s)),
-                               "python_reference": python_reference_note()}
-    elif rank == 0:
-        out["cpu_baseline"] = None
     if rank == 0:
         emit(json.dumps(out))
     ctx.close()
     ranks.close()
+
+
+class Workload_like:
+    def __init__(self, records, junctions):
+        self.records, self.junctions = records, junctions
 
 
 if __name__ == "__main__":

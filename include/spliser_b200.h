@@ -62,6 +62,9 @@ int  spl_create(spl_ctx** out, const int* device_ids, int n_devices);
 void spl_destroy(spl_ctx* ctx);
 const char* spl_last_error(const spl_ctx* ctx);   /* NUL-terminated, valid until next call on ctx */
 int  spl_set_tile(spl_ctx* ctx, int tile_index, int tile_count);
+/* The same with an explicit owned range [site_lo, site_hi) of global site indices (reference list order), for tiles
+ * balanced by read count rather than by site count; (-1, -1) returns to spl_set_tile's equal slices. */
+int  spl_set_tile_sites(spl_ctx* ctx, int64_t site_lo, int64_t site_hi);
 int  spl_set_threads(spl_ctx* ctx, int n_host_threads);   /* BGZF inflate / record parse workers */
 /* Counting variant of the following calls on this context.  Both give identical results (tests hold them to each other
  * and to the reference); FUSED is the product path, STAB the cross-check north_star asks for:
@@ -73,6 +76,7 @@ int  spl_set_threads(spl_ctx* ctx, int n_host_threads);   /* BGZF inflate / reco
 #define SPL_VARIANT_STAB  1
 int  spl_set_variant(spl_ctx* ctx, int variant);
 const char* spl_version(void);
+unsigned long long spl_kernel_launches(void);   /* kernels this library has launched in this process so far (every launch is counted) */
 
 /* ---- process (S:710-717) ------------------------------------------------------------------- */
 /* Junction table = BED12 lines in file order AFTER the 12-column / -c / -g filters (S:259-288):
@@ -159,9 +163,12 @@ void spl_result_free(spl_result* r);
  * Roofline measurements need the read SoA already in HBM when the timed region starts:
  *   spl_resident_load   uploads records + junction table, builds the site graph and expands
  *                       the records into the structure-of-arrays the counting kernels stream
- *   spl_resident_count  runs the counting kernels (alpha reduce, beta1 stabbing, spliced-read
- *                       corrections, beta2 gather, SSE) `iters` times on the context's stream,
- *                       timed with CUDA events on that stream; results stay in HBM
+ *   spl_resident_count  runs the per-sample path `iters` times on the context's stream, timed with CUDA
+ *                       events on that stream; results stay in HBM.  Fused variant: site table + graph from
+ *                       the resident junction table, counters zeroed, counting kernel over the resident
+ *                       records, prefix scan + beta2 gather + SSE -- everything spl_process_records
+ *                       launches for a sample except the copies.  Stabbing variant: the counting pass
+ *                       over the layout spl_resident_load prepared.
  *   spl_resident_fetch  copies the last results to the host as an spl_result
  * stats_out (may be NULL) receives SPL_NSTATS doubles, see SPL_STAT_* below. */
 int spl_resident_load(spl_ctx* ctx, const spl_records_view* rec,
@@ -182,7 +189,7 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_N_SITES       8
 #define SPL_STAT_N_EDGES       9   /* directed site->partner entries                            */
 #define SPL_STAT_N_ALIGNED    10   /* records with >= 1 CIGAR op ("aligned reads")              */
-#define SPL_STAT_LAUNCHES     11   /* kernels launched per pass                                 */
+#define SPL_STAT_LAUNCHES     11   /* kernels launched per pass (counted at the launch sites)   */
 #define SPL_STAT_MS_EXPAND    12   /* ms of the record -> SoA expansion at load time            */
 #define SPL_NSTATS            32
 
@@ -200,6 +207,8 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_BAM_DEVICE   23   /* 1 = BGZF inflate + BAM record parse ran on the device, 0 = host reader (fallback)  */
 #define SPL_STAT_N_PARTS      24   /* parts the record upload was cut into (1 or 2; 2 = expansion overlapped with the copy)  */
 #define SPL_STAT_GRAPH_DEVICE 22   /* 1 = site table + graph built on the device (clean regime), 0 = host emulation */
+#define SPL_STAT_MS_GRAPH_DEV 25   /* spl_resident_count: summed CUDA-event ms of the site table + graph build inside the timed passes */
+#define SPL_STAT_GRAPH_TIMED  26   /* spl_resident_count: 1 = every pass rebuilt the site table + graph (fused variant, clean regime) */
 int spl_last_stats(const spl_ctx* ctx, double* stats_out);
 
 /* ---- host text layer (no GPU): Gene column, .SpliSER.tsv writer, combine merge driver ------------

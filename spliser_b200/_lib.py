@@ -16,7 +16,7 @@ SPL_FLAG_COMBINE = 8
 SPL_NSTATS = 32
 STAT_NAMES = ("ms_total", "ms_beta1", "ms_spliced", "ms_final", "n_mblocks_a", "n_mblocks_b", "n_junc_ops",
               "n_spliced", "n_sites", "n_edges", "n_aligned", "launches", "ms_expand", "ms_decode",
-              "h2d_bytes", "d2h_bytes", "ms_graph", "ms_upload", "ms_count", "n_distinct_junc", "n_simple_junc", "n_complex_junc", "graph_on_device", "bam_on_device", "n_parts", "r25", "r26", "r27", "r28", "r29", "r30", "r31")
+              "h2d_bytes", "d2h_bytes", "ms_graph", "ms_upload", "ms_count", "n_distinct_junc", "n_simple_junc", "n_complex_junc", "graph_on_device", "bam_on_device", "n_parts", "ms_graph_dev", "graph_timed", "r27", "r28", "r29", "r30", "r31")
 
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
@@ -50,10 +50,12 @@ _GAPS = [C.c_int64, c_i32p, c_i32p, c_u8p, c_i64p, c_i32p, c_i64p, c_i32p]
 # every symbol declared in include/spliser_b200.h: name -> (restype, argtypes)
 SIGNATURES = {
     "spl_version": (C.c_char_p, []),
+    "spl_kernel_launches": (C.c_ulonglong, []),
     "spl_create": (C.c_int, [C.POINTER(C.c_void_p), c_i32p, C.c_int]),
     "spl_destroy": (None, [C.c_void_p]),
     "spl_last_error": (C.c_char_p, [C.c_void_p]),
     "spl_set_tile": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "spl_set_tile_sites": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64]),
     "spl_set_threads": (C.c_int, [C.c_void_p, C.c_int]),
     "spl_set_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "spl_last_stats": (C.c_int, [C.c_void_p, c_f64p]),

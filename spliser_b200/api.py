@@ -308,6 +308,11 @@ class Context:
         if rc != 0:
             raise SpliserError("%s: %s (code %d)" % (what, self._lib.spl_last_error(self._h).decode(), rc))
 
+    def set_tile_sites(self, site_lo, site_hi):
+        """Owned range [site_lo, site_hi) of global site indices for the following calls (tiles balanced by read count,
+        spliser_b200.dist.balanced_tiles); (-1, -1) = no tiling."""
+        self._check(self._lib.spl_set_tile_sites(self._h, int(site_lo), int(site_hi)), "spl_set_tile_sites")
+
     def set_variant(self, variant):
         """'fused' (product path: difference arrays straight from the records) or 'stab' (block-vs-site stabbing over a
         bin-partitioned block stream; the cross-check)."""

@@ -26,6 +26,7 @@
 #include <vector>
 
 #include "bam_gpu.h"
+#include "device_types.h"
 #include "inflate.h"
 
 namespace spl {
@@ -246,10 +247,10 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
     cnt.h2d_bytes = (double)fsz + (double)n_mem * sizeof(BgzfMember);
     const uint8_t* d_u = (const uint8_t*)mem.unc.p;
     uint32_t* d_kept = (uint32_t*)mem.list.p;
-    k_bgzf_inflate<<<(n_mem + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t*)mem.comp.p, d_mem, n_mem, (uint8_t*)mem.unc.p, d_err);
+    { SPL_LAUNCH; k_bgzf_inflate<<<(n_mem + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t*)mem.comp.p, d_mem, n_mem, (uint8_t*)mem.unc.p, d_err); }
     // ---- speculative record starts + counting walk
-    k_bam_first<<<(n_mem + 7) / 8, 256, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, first_record, d_first);
-    k_bam_walk<false><<<(n_mem + 127) / 128, 128, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, d_refmap, d_first, d_wo, nullptr, nullptr, DevRecordArrays{}, d_kept);
+    { SPL_LAUNCH; k_bam_first<<<(n_mem + 7) / 8, 256, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, first_record, d_first); }
+    { SPL_LAUNCH; k_bam_walk<false><<<(n_mem + 127) / 128, 128, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, d_refmap, d_first, d_wo, nullptr, nullptr, DevRecordArrays{}, d_kept); }
     BG_CU(cudaGetLastError());
     std::vector<uint64_t> h_first(n_mem);
     std::vector<WalkOut> h_wo(n_mem);
@@ -291,9 +292,9 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
         BG_CU(cudaMemcpyAsync(d_rbase, rbase.data(), (size_t)n_mem * 8, cudaMemcpyHostToDevice, st));
         BG_CU(cudaMemcpyAsync(d_cbase, cbase.data(), (size_t)n_mem * 8, cudaMemcpyHostToDevice, st));
         BG_CU(cudaMemsetAsync(d_ns, 0, 16, st));
-        k_bam_fill<<<(n_mem + 7) / 8, 256, 0, st>>>(d_u, d_mem, n_mem, d_refmap, d_wo, d_rbase, d_cbase, d_kept, out);
-        k_set_u32<<<1, 1, 0, st>>>(out.cig_off + nrec, (uint32_t)ncig);
-        if (nrec) k_bam_segments<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(out.chrom, nrec, d_ns, d_sf, d_sc, BAMGPU_MAX_SEG);
+        { SPL_LAUNCH; k_bam_fill<<<(n_mem + 7) / 8, 256, 0, st>>>(d_u, d_mem, n_mem, d_refmap, d_wo, d_rbase, d_cbase, d_kept, out); }
+        { SPL_LAUNCH; k_set_u32<<<1, 1, 0, st>>>(out.cig_off + nrec, (uint32_t)ncig); }
+        if (nrec) { SPL_LAUNCH; k_bam_segments<<<(unsigned)((nrec + 255) / 256), 256, 0, st>>>(out.chrom, nrec, d_ns, d_sf, d_sc, BAMGPU_MAX_SEG); }
         BG_CU(cudaGetLastError());
         uint32_t h_ns = 0;
         BG_CU(cudaMemcpyAsync(&h_ns, d_ns, 4, cudaMemcpyDeviceToHost, st));

@@ -485,7 +485,7 @@ int fused_grid() {
 }  // namespace
 
 void launch_chunk_bounds(FChunk* chunks, uint32_t lo, uint32_t hi, const uint32_t* cig_off, DevGraph g, void* stream) {
-    if (hi > lo) k_chunk_bounds<<<(hi - lo + 255) / 256, 256, 0, (cudaStream_t)stream>>>(chunks, lo, hi, cig_off, g);
+    if (hi > lo) { SPL_LAUNCH; k_chunk_bounds<<<(hi - lo + 255) / 256, 256, 0, (cudaStream_t)stream>>>(chunks, lo, hi, cig_off, g); }
 }
 
 // `work` points at a zeroed u32 (the chunk counter of this launch)
@@ -494,7 +494,7 @@ void launch_count_fused(const DevRecords& rec, const FChunk* chunks, uint32_t lo
     if (hi <= lo || g.n_sites <= 0) return;
     FArgs a{rec, chunks, lo, hi, g, cnt, work, flags};
     const int grid = (int)min((uint32_t)fused_grid(), (hi - lo + (uint32_t)FC_BATCH - 1u) / (uint32_t)FC_BATCH);
-    k_count_fused<<<grid, FC_THREADS, sizeof(FSmem), (cudaStream_t)stream>>>(a);
+    { SPL_LAUNCH; k_count_fused<<<grid, FC_THREADS, sizeof(FSmem), (cudaStream_t)stream>>>(a); }
 }
 
 }  // namespace spl

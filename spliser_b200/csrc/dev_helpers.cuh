@@ -162,19 +162,21 @@ __device__ __forceinline__ bool pc_pair(const DevGraph& g, int t, int32_t l, int
            (in_sorted(g.cp_pos, c0, c1, l) && in_list(g.pc_pos, p0, p1, r));
 }
 
-// +1 on a counter, aggregated over the lanes of the warp that are here with the same address (the instances a warp handles
+// +w on a counter, aggregated over the lanes of the warp that are here with the same address (the instances a warp handles
 // mostly belong to one junction, so they hit the same few sites: one RED per warp and address instead of one per read)
-__device__ __forceinline__ void agg_inc(uint32_t* p) {
+__device__ __forceinline__ void agg_add(uint32_t* p, uint32_t w) {
     const unsigned active = __activemask();
     const unsigned peers = __match_any_sync(active, (unsigned long long)(uintptr_t)p);
-    if ((int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(p, (uint32_t)__popc(peers));
+    const uint32_t total = __reduce_add_sync(peers, w);
+    if ((int)(threadIdx.x & 31u) == __ffs(peers) - 1) atomicAdd(p, total);
 }
 
 // The read makes compSplicing true for site t through its junction number rd.jrel, unless an earlier junction of the read
-// already did: classify the read at t (S:503-557, first match wins).  Rd: nj, nb, jrel, jl(x) (bit 31: the N is the read's
+// already did: classify the read at t (S:503-557, first match wins); every counter moves by w.  Rd: nj, nb, jrel, jl(x) (bit 31: the N is the read's
 // first advancing operator -> POS > l, S:435), jr(x), bs(x), be(x) (block start / end; callers may leave flag bits in bit 31).
 template <class Rd>
-__device__ __forceinline__ void k4_classify(const Rd& rd, const DevGraph& g, const DevCounters& cnt, int t, uint32_t k, bool combine) {
+__device__ __forceinline__ void k4_classify(const Rd& rd, const DevGraph& g, const DevCounters& cnt, int t, uint32_t k, bool combine,
+                                            uint32_t w = 1u /* identical reads this one stands for */) {
     bool earlier = false;
     for (uint32_t x = 0; x < rd.jrel && !earlier; ++x)
         earlier = pc_pair(g, t, (int32_t)(rd.jl(x) & POS_MASK), (int32_t)(rd.jr(x) & POS_MASK));
@@ -196,25 +198,25 @@ __device__ __forceinline__ void k4_classify(const Rd& rd, const DevGraph& g, con
             bool in_read = false;
             for (uint32_t x = 0; x < rd.nj && !in_read; ++x)
                 in_read = (int32_t)(rd.jl(x) & POS_MASK) == pp || (int32_t)(rd.jr(x) & POS_MASK) == pp;
-            if (in_read) agg_inc(cnt.dc + e);
+            if (in_read) agg_add(cnt.dc + e, w);
         }
     } else if (kstar >= 0) {
         if (kstar >= (int)rd.jrel) {                               // compSplicing already true at k*: flanking (S:503-505)
-            if (ok) agg_inc(cnt.spanx + t);
-            if (combine) agg_inc(cnt.flank + t);
+            if (ok) agg_add(cnt.spanx + t, w);
+            if (combine) agg_add(cnt.flank + t, w);
         }
     } else if (ok) {
         bool covers = false;
         for (uint32_t b = 0; b < rd.nb && !covers; ++b)
             covers = rd.bs(b) <= tp && (int32_t)(rd.be(b) & POS_MASK) >= tp + 2;
         if (covers) {                                              // beta1-type, S:544-552
-            agg_inc(cnt.covx + t);
+            agg_add(cnt.covx + t, w);
             for (int e = g.pc_off[t]; e < g.pc_off[t + 1]; ++e) {
                 const int32_t pp = g.pc_pos[e];
                 bool in_read = false;
                 for (uint32_t x = 0; x < rd.nj && !in_read; ++x)
                     in_read = (int32_t)(rd.jl(x) & POS_MASK) == pp || (int32_t)(rd.jr(x) & POS_MASK) == pp;
-                if (in_read) agg_inc(cnt.dc + e);
+                if (in_read) agg_add(cnt.dc + e, w);
             }
         }
     }

@@ -1,8 +1,13 @@
 // Device-side data layout shared by kernels.cu and pipeline.cu.  See DESIGN.md "Data layout in HBM".
 #pragma once
+#include <atomic>
 #include <cstdint>
 
 namespace spl {
+
+// every kernel launch of the library is counted (bench.py reports the launches inside its timed region)
+extern std::atomic<unsigned long long> g_kernel_launches;
+#define SPL_LAUNCH (++::spl::g_kernel_launches)
 
 #ifndef SPL_BIN_SHIFT
 #define SPL_BIN_SHIFT 6

@@ -89,9 +89,9 @@ struct Sorter {
         for (int shift = lo; shift < hi; shift += 8) {
             const int width = hi - shift < 8 ? hi - shift : 8;
             const uint32_t mask = (1u << width) - 1u;
-            k_rs_hist<<<n_tiles, RS_THREADS, 0, st>>>(a, n, shift, mask, hist, n_tiles);
+            { SPL_LAUNCH; k_rs_hist<<<n_tiles, RS_THREADS, 0, st>>>(a, n, shift, mask, hist, n_tiles); }
             launch_exscan_u32(hist, 256u * n_tiles, tmp, total, st);
-            k_rs_scatter<<<n_tiles, RS_THREADS, 0, st>>>(a, b, n, shift, mask, hist, n_tiles);
+            { SPL_LAUNCH; k_rs_scatter<<<n_tiles, RS_THREADS, 0, st>>>(a, b, n, shift, mask, hist, n_tiles); }
             uint64_t* t = a; a = b; b = t;
         }
         return a;
@@ -395,30 +395,30 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     }
 
     // ---- A: sites
-    k_gb_keys_a<<<cdiv(J, 256), 256, 0, st>>>(d_jc, d_jl, d_jr, d_js, J, stranded ? 1 : 0, pb, vb, ka);
+    { SPL_LAUNCH; k_gb_keys_a<<<cdiv(J, 256), 256, 0, st>>>(d_jc, d_jl, d_jr, d_js, J, stranded ? 1 : 0, pb, vb, ka); }
     uint64_t* sa = sorter.sort(ka, kb, n2, vb, vb + 1 + pb + cb);
     uint64_t* other = sa == ka ? kb : ka;
-    k_gb_heads<<<cdiv(n2, 256), 256, 0, st>>>(sa, n2, vb, flag);
+    { SPL_LAUNCH; k_gb_heads<<<cdiv(n2, 256), 256, 0, st>>>(sa, n2, vb, flag); }
     launch_exscan_u32(flag, n2, stmp, d_cnt + 0, st);
-    k_gb_sites<<<cdiv(n2, 256), 256, 0, st>>>(sa, flag, n2, vb, pb, stranded ? 1 : 0, d_js, g, site_of);
-    k_gb_cs_off<<<cdiv((uint32_t)n_chrom + 1, 128), 128, 0, st>>>(g, n_chrom, d_cnt);
-    k_gb_chrom_layout<<<1, 32, 0, st>>>(n_chrom, g, d_cnt);
+    { SPL_LAUNCH; k_gb_sites<<<cdiv(n2, 256), 256, 0, st>>>(sa, flag, n2, vb, pb, stranded ? 1 : 0, d_js, g, site_of); }
+    { SPL_LAUNCH; k_gb_cs_off<<<cdiv((uint32_t)n_chrom + 1, 128), 128, 0, st>>>(g, n_chrom, d_cnt); }
+    { SPL_LAUNCH; k_gb_chrom_layout<<<1, 32, 0, st>>>(n_chrom, g, d_cnt); }
     GB_CU(cudaGetLastError());
     GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
     GB_CU(cudaStreamSynchronize(st));
     const uint32_t S = m.h_cnt[0], NB = m.h_cnt[1];
     if (S == 0 || S > n2) { err = "graph build: bad site count"; return false; }
     const int sbits = bits_for_u64((uint64_t)S);                          // S itself is used as a sentinel in phase D
-    k_gb_fill_i32<<<1, 64, 0, st>>>(g.site_pos + S, 64, INT_MAX);        // tail padding (never matches)
+    { SPL_LAUNCH; k_gb_fill_i32<<<1, 64, 0, st>>>(g.site_pos + S, 64, INT_MAX); }        // tail padding (never matches)
     GB_CU(cudaMemsetAsync(g.site_hot, 0, (size_t)S + 64, st));
 
     // ---- B: PartnerCounts entries
-    k_gb_keys_b<<<cdiv(J, 256), 256, 0, st>>>(site_of, J, sbits, lb, other);
+    { SPL_LAUNCH; k_gb_keys_b<<<cdiv(J, 256), 256, 0, st>>>(site_of, J, sbits, lb, other); }
     uint64_t* sbk = sorter.sort(other, sa, n2, lb, lb + 2 * sbits);
     other = sbk == ka ? kb : ka;
-    k_gb_heads<<<cdiv(n2, 256), 256, 0, st>>>(sbk, n2, lb, flag);
+    { SPL_LAUNCH; k_gb_heads<<<cdiv(n2, 256), 256, 0, st>>>(sbk, n2, lb, flag); }
     launch_exscan_u32(flag, n2, stmp, d_cnt + 2, st);
-    k_gb_edges<<<cdiv(n2, 256), 256, 0, st>>>(sbk, flag, n2, lb, sbits, g, u_src, u_dst, u_first, u_lo);
+    { SPL_LAUNCH; k_gb_edges<<<cdiv(n2, 256), 256, 0, st>>>(sbk, flag, n2, lb, sbits, g, u_src, u_dst, u_first, u_lo); }
     GB_CU(cudaGetLastError());
     GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
     GB_CU(cudaStreamSynchronize(st));
@@ -427,12 +427,12 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     const int eb = bits_for_u64((uint64_t)(E - 1));
 
     // ---- C: first-appearance order inside a site
-    k_gb_keys_c<<<cdiv(E, 256), 256, 0, st>>>(u_src, u_first, E, lb, eb, other);
+    { SPL_LAUNCH; k_gb_keys_c<<<cdiv(E, 256), 256, 0, st>>>(u_src, u_first, E, lb, eb, other); }
     uint64_t* sc = sorter.sort(other, other == ka ? kb : ka, E, eb, eb + lb + sbits);
-    k_gb_csr<<<cdiv(E, 256), 256, 0, st>>>(sc, E, S, eb, lb, u_dst, u_lo, g, e_src);
+    { SPL_LAUNCH; k_gb_csr<<<cdiv(E, 256), 256, 0, st>>>(sc, E, S, eb, lb, u_dst, u_lo, g, e_src); }
 
     // ---- D: competitors
-    k_gb_cand_count<<<cdiv(S, 256), 256, 0, st>>>(g, S, ncand);
+    { SPL_LAUNCH; k_gb_cand_count<<<cdiv(S, 256), 256, 0, st>>>(g, S, ncand); }
     launch_exscan_u32(ncand, S, stmp, d_cnt + 3, st);
     GB_CU(cudaGetLastError());
     GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
@@ -450,9 +450,9 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
         uint32_t* dflag = (uint32_t*)(cbp + c_f);
         uint32_t* dtmp = (uint32_t*)(cbp + c_t) + exscan_tmp_words(256u * tiles) + 4;
         Sorter ds{(uint32_t*)(cbp + c_h), (uint32_t*)(cbp + c_t), d_cnt + 5, st};
-        k_gb_cand_fill<<<cdiv(S, 256), 256, 0, st>>>(g, S, ncand, pb, da);
+        { SPL_LAUNCH; k_gb_cand_fill<<<cdiv(S, 256), 256, 0, st>>>(g, S, ncand, pb, da); }
         uint64_t* sd = ds.sort(da, db, NCAND, 0, pb + sbits);
-        k_gb_cand_heads<<<cdiv(NCAND, 256), 256, 0, st>>>(sd, NCAND, pb, S, dflag);
+        { SPL_LAUNCH; k_gb_cand_heads<<<cdiv(NCAND, 256), 256, 0, st>>>(sd, NCAND, pb, S, dflag); }
         launch_exscan_u32(dflag, NCAND, dtmp, d_cnt + 4, st);
         GB_CU(cudaGetLastError());
         GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
@@ -463,7 +463,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
         GB_CU(m.fin2.reserve(x.off + 256));
         g.cp_pos = (int32_t*)((char*)m.fin2.p + x_cp); g.sb_off = (int32_t*)((char*)m.fin2.p + x_sb);
         GB_CU(cudaMemsetAsync(c1, 0, ((size_t)S + 1) * 4, st));           // cp_cnt
-        k_gb_comp<<<cdiv(NCAND, 256), 256, 0, st>>>(sd, dflag, NCAND, pb, S, g, c1);
+        { SPL_LAUNCH; k_gb_comp<<<cdiv(NCAND, 256), 256, 0, st>>>(sd, dflag, NCAND, pb, S, g, c1); }
         GB_CU(cudaMemcpyAsync(g.cp_off, c1, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
         launch_exscan_u32((uint32_t*)g.cp_off, S, stmp, (uint32_t*)g.cp_off + S, st);
         counts.C = C;
@@ -472,13 +472,13 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     // ---- E: reverse partners, hot flags, bin index
     GB_CU(cudaMemsetAsync(c1, 0, ((size_t)S + 1) * 4, st));               // rp_cnt
     GB_CU(cudaMemsetAsync(c2, 0, ((size_t)S + 1) * 4, st));               // rp_cur
-    k_gb_rp_count<<<cdiv(E, 256), 256, 0, st>>>(g, E, c1);
+    { SPL_LAUNCH; k_gb_rp_count<<<cdiv(E, 256), 256, 0, st>>>(g, E, c1); }
     GB_CU(cudaMemcpyAsync(g.rp_off, c1, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
     launch_exscan_u32((uint32_t*)g.rp_off, S, stmp, (uint32_t*)g.rp_off + S, st);
-    k_gb_rp_fill<<<cdiv(E, 256), 256, 0, st>>>(g, E, e_src, c2);
-    k_gb_sb_fill<<<cdiv(NB + 64, 256), 256, 0, st>>>(g, n_chrom, S, NB);
-    k_gb_widen<<<cdiv(S + 1, 256), 256, 0, st>>>(g.pt_off, g.pt_off64, S + 1);
-    k_gb_widen<<<cdiv(S + 1, 256), 256, 0, st>>>(g.cp_off, g.cp_off64, S + 1);
+    { SPL_LAUNCH; k_gb_rp_fill<<<cdiv(E, 256), 256, 0, st>>>(g, E, e_src, c2); }
+    { SPL_LAUNCH; k_gb_sb_fill<<<cdiv(NB + 64, 256), 256, 0, st>>>(g, n_chrom, S, NB); }
+    { SPL_LAUNCH; k_gb_widen<<<cdiv(S + 1, 256), 256, 0, st>>>(g.pt_off, g.pt_off64, S + 1); }
+    { SPL_LAUNCH; k_gb_widen<<<cdiv(S + 1, 256), 256, 0, st>>>(g.cp_off, g.cp_off64, S + 1); }
     GB_CU(cudaGetLastError());
     counts.S = S; counts.E = E; counts.NB = NB;
     return true;

@@ -20,6 +20,8 @@
 
 namespace spl {
 
+std::atomic<unsigned long long> g_kernel_launches{0};
+
 struct Cnt4 { uint32_t a, b, s, j; };
 
 // ------------------------------------------------------------------------------------------------
@@ -1121,37 +1123,37 @@ void launch_exscan_u32(uint32_t* a, uint32_t n, uint32_t* tmp, uint32_t* total_o
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) { cudaMemsetAsync(total_out, 0, 4, st); return; }
     const uint32_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_blocksum<<<nblk, 256, 0, st>>>(a, n, tmp);
-    k_scan_sums<<<1, 1024, 0, st>>>(tmp, nblk, total_out);
-    k_scan_apply<<<nblk, 256, 0, st>>>(a, n, tmp, nullptr);
+    { SPL_LAUNCH; k_scan_blocksum<<<nblk, 256, 0, st>>>(a, n, tmp); }
+    { SPL_LAUNCH; k_scan_sums<<<1, 1024, 0, st>>>(tmp, nblk, total_out); }
+    { SPL_LAUNCH; k_scan_apply<<<nblk, 256, 0, st>>>(a, n, tmp, nullptr); }
 }
 uint32_t exscan_tmp_words(uint32_t n) { return n / SCAN_TILE + 4; }
 void launch_expand_count(const DevRecords& rec, Chunk* chunks, int n_chunks, uint32_t flags, DevBins bins, void* stream) {
-    if (n_chunks > 0) k_expand_count<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, flags, bins);
+    if (n_chunks > 0) { SPL_LAUNCH; k_expand_count<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, flags, bins); }
 }
 void launch_chunk_scan(Chunk* chunks, int n_chunks, uint32_t* totals8, DevBins bins, void* stream) {
-    k_chunk_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(chunks, n_chunks, totals8);
-    k_bin_layout<<<1, 32, 0, (cudaStream_t)stream>>>(bins, totals8);
+    { SPL_LAUNCH; k_chunk_scan<<<1, 1024, 0, (cudaStream_t)stream>>>(chunks, n_chunks, totals8); }
+    { SPL_LAUNCH; k_bin_layout<<<1, 32, 0, (cudaStream_t)stream>>>(bins, totals8); }
 }
 void launch_bin_partition(const Chunk* chunks, int n_chunks, DevSoA soa, DevBins bins, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n_chunks <= 0 || bins.total_bins == 0) return;
     cudaMemsetAsync(bins.bin_off, 0, ((size_t)bins.total_bins + 1) * 4, st);
-    k_bin_pad<<<(bins.n_chrom + 127) / 128, 128, 0, st>>>(bins);
-    k_bin_pass<false><<<2 * n_chunks, 256, 0, st>>>(chunks, soa, bins);
+    { SPL_LAUNCH; k_bin_pad<<<(bins.n_chrom + 127) / 128, 128, 0, st>>>(bins); }
+    { SPL_LAUNCH; k_bin_pass<false><<<2 * n_chunks, 256, 0, st>>>(chunks, soa, bins); }
     const uint32_t n = bins.total_bins + 1;                              // the extra slot receives the total
     const uint32_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_blocksum<<<nblk, 256, 0, st>>>(bins.bin_off, n, bins.scan_tmp);
-    k_scan_sums<<<1, 1024, 0, st>>>(bins.scan_tmp, nblk, bins.scan_tmp + nblk);
-    k_scan_apply<<<nblk, 256, 0, st>>>(bins.bin_off, n, bins.scan_tmp, bins.bin_cursor);
-    k_bin_pass<true><<<2 * n_chunks, 256, 0, st>>>(chunks, soa, bins);
-    k_bin_fill_pad<<<bins.n_chrom, 256, 0, st>>>(bins);
+    { SPL_LAUNCH; k_scan_blocksum<<<nblk, 256, 0, st>>>(bins.bin_off, n, bins.scan_tmp); }
+    { SPL_LAUNCH; k_scan_sums<<<1, 1024, 0, st>>>(bins.scan_tmp, nblk, bins.scan_tmp + nblk); }
+    { SPL_LAUNCH; k_scan_apply<<<nblk, 256, 0, st>>>(bins.bin_off, n, bins.scan_tmp, bins.bin_cursor); }
+    { SPL_LAUNCH; k_bin_pass<true><<<2 * n_chunks, 256, 0, st>>>(chunks, soa, bins); }
+    { SPL_LAUNCH; k_bin_fill_pad<<<bins.n_chrom, 256, 0, st>>>(bins); }
 }
 void launch_tile_hints(DevBins bins, DevGraph g, void* stream) {
-    if (bins.n_tiles) k_tile_hints<<<(bins.n_tiles + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bins, g);
+    if (bins.n_tiles) { SPL_LAUNCH; k_tile_hints<<<(bins.n_tiles + 127) / 128, 128, 0, (cudaStream_t)stream>>>(bins, g); }
 }
 void launch_expand_scatter(const DevRecords& rec, const Chunk* chunks, int n_chunks, DevSoA soa, uint32_t flags, void* stream) {
-    if (n_chunks > 0) k_expand_scatter<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, soa, flags);
+    if (n_chunks > 0) { SPL_LAUNCH; k_expand_scatter<<<n_chunks, EXPAND_THREADS, 0, (cudaStream_t)stream>>>(rec, chunks, soa, flags); }
 }
 // SM count of the CURRENT device (one process may drive several devices, one context each)
 int sm_count_current_device() {
@@ -1188,7 +1190,7 @@ static int beta1_grid() {
 }
 void launch_beta1(DevBins bins, DevGraph g, DevCounters cnt, void* stream) {
     if (bins.n_tiles == 0 || g.n_sites <= 0) return;
-    k_beta1_stab<<<beta1_grid(), PS_THREADS, sizeof(K3Smem), (cudaStream_t)stream>>>(bins, g, cnt);
+    { SPL_LAUNCH; k_beta1_stab<<<beta1_grid(), PS_THREADS, sizeof(K3Smem), (cudaStream_t)stream>>>(bins, g, cnt); }
 }
 // phase A: table insert + scans; totals3[0] = distinct junctions, [1] = simple instances (read by the host to size
 // the dense arrays).  phase B: compaction + grouping; totals3[2] = complex instances, [3] = overflow flag.
@@ -1202,41 +1204,41 @@ void launch_junction_groups_a(const Chunk* chunks, int n_chunks, DevSoA soa, Dev
     cudaMemsetAsync(jg.s_cursor, 0, (size_t)jg.n_slots * 4, st);
     cudaMemsetAsync(jg.s_ccur, 0, (size_t)jg.n_slots * 4, st);
     cudaMemsetAsync(jg.cx_n, 0, 8, st);                                  // cx_n and overflow are adjacent
-    k_jg_insert<<<n_chunks, 256, 0, st>>>(chunks, soa, jg);
+    { SPL_LAUNCH; k_jg_insert<<<n_chunks, 256, 0, st>>>(chunks, soa, jg); }
     const uint32_t n = jg.n_slots + 1;
-    k_jg_used<<<(n + 255) / 256, 256, 0, st>>>(jg);
+    { SPL_LAUNCH; k_jg_used<<<(n + 255) / 256, 256, 0, st>>>(jg); }
     const uint32_t nblk = (n + SCAN_TILE - 1) / SCAN_TILE;
-    k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_used, n, jg.scan_tmp);
-    k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk);
-    k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_used, n, jg.scan_tmp, nullptr);
-    k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_off, n, jg.scan_tmp);
-    k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk);
-    k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_off, n, jg.scan_tmp, nullptr);
-    k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_coff, n, jg.scan_tmp);
-    k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk);
-    k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_coff, n, jg.scan_tmp, nullptr);
+    { SPL_LAUNCH; k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_used, n, jg.scan_tmp); }
+    { SPL_LAUNCH; k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk); }
+    { SPL_LAUNCH; k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_used, n, jg.scan_tmp, nullptr); }
+    { SPL_LAUNCH; k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_off, n, jg.scan_tmp); }
+    { SPL_LAUNCH; k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk); }
+    { SPL_LAUNCH; k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_off, n, jg.scan_tmp, nullptr); }
+    { SPL_LAUNCH; k_scan_blocksum<<<nblk, 256, 0, st>>>(jg.s_coff, n, jg.scan_tmp); }
+    { SPL_LAUNCH; k_scan_sums<<<1, 1024, 0, st>>>(jg.scan_tmp, nblk, jg.scan_tmp + nblk); }
+    { SPL_LAUNCH; k_scan_apply<<<nblk, 256, 0, st>>>(jg.s_coff, n, jg.scan_tmp, nullptr); }
     cudaMemcpyAsync(totals4 + 2, jg.s_coff + jg.n_slots, 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(totals4, jg.s_used + jg.n_slots, 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(totals4 + 1, jg.s_off + jg.n_slots, 4, cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(totals4 + 3, jg.overflow, 4, cudaMemcpyDeviceToDevice, st);
 }
 void launch_jtab_layout(DevBins bins, int attempt, uint32_t* totals8, void* stream) {
-    k_jtab_layout<<<1, 32, 0, (cudaStream_t)stream>>>(bins, attempt, totals8);
+    { SPL_LAUNCH; k_jtab_layout<<<1, 32, 0, (cudaStream_t)stream>>>(bins, attempt, totals8); }
 }
 void launch_junction_groups_b(DevSoA soa, DevJunc jg, int n_chrom, uint32_t* totals4, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (jg.n_slots == 0 || soa.nJ == 0) return;
-    k_jg_compact<<<(jg.n_slots + 255) / 256, 256, 0, st>>>(jg, n_chrom);
-    k_jg_scatter<<<(soa.nJ + 255) / 256, 256, 0, st>>>(soa, jg);
+    { SPL_LAUNCH; k_jg_compact<<<(jg.n_slots + 255) / 256, 256, 0, st>>>(jg, n_chrom); }
+    { SPL_LAUNCH; k_jg_scatter<<<(soa.nJ + 255) / 256, 256, 0, st>>>(soa, jg); }
     cudaMemcpyAsync(totals4 + 3, jg.overflow, 4, cudaMemcpyDeviceToDevice, st);
 }
 void launch_junctions(DevSoA soa, DevJunc jg, DevGraph g, DevCounters cnt, uint32_t flags, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (jg.D == 0 || g.n_sites <= 0) return;
-    k_junc_span<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, cnt);
+    { SPL_LAUNCH; k_junc_span<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, cnt); }
     const int sms = sm_count_current_device();
-    k_junc_simple<<<sms * 8, 256, 0, st>>>(jg, g, cnt, flags);
-    if (jg.n_complex && jg.cx_pack) k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags);
+    { SPL_LAUNCH; k_junc_simple<<<sms * 8, 256, 0, st>>>(jg, g, cnt, flags); }
+    if (jg.n_complex && jg.cx_pack) { SPL_LAUNCH; k_junc_complex<<<sms * 8, 256, 0, st>>>(soa, jg, g, cnt, flags); }
 }
 // load time (after the site table is on the device): per distinct junction, the site lookups, hot flags, pair sites and the
 // work lists of the exception kernels -- all functions of (sample junctions x site table), like the tile hints
@@ -1244,12 +1246,12 @@ void launch_junction_prepare(DevJunc jg, DevGraph g, uint32_t flags, void* strea
     cudaStream_t st = (cudaStream_t)stream;
     if (jg.D == 0 || g.n_sites <= 0) return;
     cudaMemsetAsync(jg.prep, 0, 32, st);
-    k_junc_lookup<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, g, flags);
+    { SPL_LAUNCH; k_junc_lookup<<<(jg.D + 255) / 256, 256, 0, st>>>(jg, g, flags); }
 }
 void launch_junction_pack(DevSoA soa, DevJunc jg, void* stream) {
     if (jg.D == 0 || jg.n_complex == 0 || !jg.cx_pack) return;
     const int sms = sm_count_current_device();
-    k_junc_pack<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(soa, jg);
+    { SPL_LAUNCH; k_junc_pack<<<sms * 8, 256, 0, (cudaStream_t)stream>>>(soa, jg); }
 }
 void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags, void* stream) {
     if (g.n_sites <= 0) return;
@@ -1257,8 +1259,8 @@ void launch_finalize(DevGraph g, DevCounters cnt, DevOutputs out, uint32_t flags
     const int lo = min(max(g.own_lo, 0), g.n_sites), hi = min(max(g.own_hi, lo), g.n_sites);
     const int blk0 = lo / FIN_THREADS, nblk = hi > lo ? (hi - 1) / FIN_THREADS - blk0 + 1 : 0;
     const int nalpha = (g.n_sites + g.n_edges + FIN_THREADS - 1) / FIN_THREADS;
-    k_span_blocksum<<<nblk + nalpha, FIN_THREADS, 0, (cudaStream_t)stream>>>(cnt, g.n_sites, out.span_blk, nblk, blk0, g, out);
-    if (nblk) k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags, blk0);
+    { SPL_LAUNCH; k_span_blocksum<<<nblk + nalpha, FIN_THREADS, 0, (cudaStream_t)stream>>>(cnt, g.n_sites, out.span_blk, nblk, blk0, g, out); }
+    if (nblk) { SPL_LAUNCH; k_finalize<<<nblk, FIN_THREADS, 0, (cudaStream_t)stream>>>(g, cnt, out, flags, blk0); }
 }
 int kernel_launch_count_per_pass() { return 6; }   // stabbing variant: beta1_stab, junc_span, junc_simple, junc_complex, span_blocksum (+ alpha reduce), finalize
 

@@ -145,24 +145,71 @@ def samples_of(rank, world, n_samples):
 # a tile edge go to both tiles, whole (compSplicing looks at all junctions of a read).  No exchange step: the owned
 # slices of the per-tile results concatenate to the single-context result.
 # ------------------------------------------------------------------------------------------------
-def max_reference_span(records):
-    """Longest reference span (M/D/N/=/X lengths) of any record: how far to the left of a tile a read that still
-    reaches it can start."""
+def _reference_spans(records):
+    """Reference span (sum of M/D/N/=/X lengths) of every record."""
     import numpy as np
-    if len(records) == 0 or len(records.cigar) == 0:
-        return 0
+    if len(records) == 0:
+        return np.zeros(0, np.int64)
     op = records.cigar & 15
     adv = np.where((op == 0) | (op == 2) | (op == 3) | (op == 7) | (op == 8), records.cigar >> 4, 0).astype(np.int64)
     csum = np.concatenate([[0], np.cumsum(adv)])
-    span = csum[records.cig_off[1:].astype(np.int64)] - csum[records.cig_off[:-1].astype(np.int64)]
+    return csum[records.cig_off[1:].astype(np.int64)] - csum[records.cig_off[:-1].astype(np.int64)]
+
+
+def max_reference_span(records):
+    """Longest reference span of any record: how far to the left of a tile a read that still reaches it can start."""
+    span = _reference_spans(records)
     return int(span.max()) if len(span) else 0
 
 
-def tile_position_ranges(table, n_chrom, tile, n_tiles):
-    """Per chromosome, the [lowest, highest] position of the sites tile `tile` of `n_tiles` owns (None: owns nothing there).
+def segment_max_spans(records):
+    """Longest reference span per chromosome segment: one 500 kb intron on one chromosome must not widen the left edge of
+    every tile on every other chromosome."""
+    import numpy as np
+    span = _reference_spans(records)
+    return [int(span[int(records.seg_off[s]):int(records.seg_off[s + 1])].max()) if records.seg_off[s + 1] > records.seg_off[s] else 0
+            for s in range(len(records.seg_chrom))]
+
+
+def balanced_tiles(records, table, n_chrom, n_tiles):
+    """Site-index cut points [0 = c_0 <= c_1 <= ... <= c_n = S] that give every tile about the same number of records
+    (SURVEY 8(e)): the number of records starting at or before each site is a prefix sum over the per-chromosome record
+    positions; tile k ends at the first site where that count reaches k/n of the sample."""
+    import numpy as np
+    S = len(table)
+    if S == 0 or n_tiles <= 1:
+        return [0] + [S] * max(1, n_tiles)
+    per_chrom = [[] for _ in range(n_chrom)]
+    for s in range(len(records.seg_chrom)):
+        c = int(records.seg_chrom[s])
+        if 0 <= c < n_chrom:
+            per_chrom[c].append(np.asarray(records.pos[int(records.seg_off[s]):int(records.seg_off[s + 1])]))
+    cum = np.zeros(S, np.int64)
+    base = 0
+    chrom, pos = np.asarray(table.chrom), np.asarray(table.pos)
+    for c in range(n_chrom):
+        sel = np.nonzero(chrom == c)[0]
+        p = np.concatenate(per_chrom[c]) if per_chrom[c] else np.zeros(0, np.int32)
+        if len(p) > 1 and np.any(p[1:] < p[:-1]):
+            p = np.sort(p)
+        if len(sel):
+            cum[sel] = base + np.searchsorted(p, pos[sel], side="right")
+        base += len(p)
+    cum = np.maximum.accumulate(cum)
+    total = max(base, 1)
+    cuts = [0]
+    for k in range(1, n_tiles):
+        cuts.append(max(cuts[-1], int(np.searchsorted(cum, total * k // n_tiles, side="left"))))
+    cuts.append(S)
+    return cuts
+
+
+def tile_position_ranges(table, n_chrom, tile, n_tiles, site_range=None):
+    """Per chromosome, the [lowest, highest] position of the sites a tile owns (None: owns nothing there).  The tile is the
+    `tile`-th equal slice of the site table, or the explicit site index range `site_range`.
     `table` is the site table in library order (api.build_site_table: exact in every strand regime)."""
     import numpy as np
-    lo, hi = tile_of(tile, n_tiles, len(table))
+    lo, hi = site_range if site_range is not None else tile_of(tile, n_tiles, len(table))
     out = [None] * n_chrom
     if hi > lo:
         chrom, pos = np.asarray(table.chrom[lo:hi]), np.asarray(table.pos[lo:hi])
@@ -172,14 +219,18 @@ def tile_position_ranges(table, n_chrom, tile, n_tiles):
     return out
 
 
-def tile_records(records, table, n_chrom, tile, n_tiles, max_span=None):
-    """The records tile `tile` needs: per chromosome segment, the contiguous run of (coordinate-sorted) records that start
-    no later than the tile's last site + 1 and no earlier than its first site - max_span.  Returns a Records."""
+def tile_records(records, table, n_chrom, tile, n_tiles, max_span=None, site_range=None, seg_spans=None):
+    """The records a tile needs: per chromosome segment, the contiguous run of (coordinate-sorted) records that start
+    no later than the tile's last site + 1 and no earlier than its first site - the segment's longest reference span
+    (seg_spans, from segment_max_spans; or one global max_span).  Returns a Records."""
     import numpy as np
     from .api import Records
-    if max_span is None:
-        max_span = max_reference_span(records)
-    ranges = tile_position_ranges(table, n_chrom, tile, n_tiles)
+    if seg_spans is None:
+        if max_span is None:
+            seg_spans = segment_max_spans(records)
+        else:
+            seg_spans = [max_span] * len(records.seg_chrom)
+    ranges = tile_position_ranges(table, n_chrom, tile, n_tiles, site_range)
     pos_l, flag_l, cig_l, ncig_l, seg_chrom, seg_off = [], [], [], [], [], [0]
     total = 0
     for s in range(len(records.seg_chrom)):
@@ -191,7 +242,7 @@ def tile_records(records, table, n_chrom, tile, n_tiles, max_span=None):
         if np.any(p[1:] < p[:-1]):                      # not coordinate-sorted: keep the whole segment
             a, b = 0, r1 - r0
         else:
-            a = int(np.searchsorted(p, ranges[c][0] - max_span - 1, side="left"))
+            a = int(np.searchsorted(p, ranges[c][0] - seg_spans[s] - 1, side="left"))
             b = int(np.searchsorted(p, ranges[c][1] + 1, side="right"))
         if b <= a:
             continue

@@ -53,6 +53,7 @@ class SynthConfig:
     min_anchor: int = 8
     organelle_share: float = 0.0      # share of reads on contigs shorter than 1 Mb
     extra_isoforms: int = 0           # per multi-exon gene: isoforms with random exon skipping / shifted boundaries (dense loci)
+    per_contig_rng: bool = False      # every contig draws from its own generator (seed, contig index): contigs can be built in parallel
 
     def key(self) -> str:
         return hashlib.sha1(repr(sorted(asdict(self).items())).encode()).hexdigest()[:16]
@@ -73,6 +74,13 @@ def config_c3_tile(n_records=25_000_000, tile=0, n_tiles=8) -> SynthConfig:
     return SynthConfig(name="c3t%d" % tile, seed=20260003 + 100 * tile, contigs=contigs, n_records=n_records, read_len=150,
                        paired=True, stranded=True, genes_per_mb=9.0, exon_median=140.0, intron_median=1500.0,
                        intron_min=70, intron_max=500_000, mean_exons=9.0)
+
+
+def config_c3_full(n_records=200_000_000) -> SynthConfig:
+    """BASELINE configs[2]: GRCh38 primary contig lengths, 150 bp PE records, ~400k junctions, introns up to 500 kb."""
+    return SynthConfig(name="c3full", seed=20260003, contigs=GRCH38, n_records=n_records, read_len=150, paired=True,
+                       stranded=True, genes_per_mb=9.0, exon_median=140.0, intron_median=1500.0, intron_min=70,
+                       intron_max=500_000, mean_exons=9.0, per_contig_rng=True)
 
 
 def config_c5() -> SynthConfig:
@@ -349,8 +357,66 @@ def _add_indels_softclips(rng, cfg, pos, ops):
     return pos, full
 
 
-def generate(cfg: SynthConfig, cache_dir=None) -> Workload:
-    """Builds (or loads from the .npz cache) the workload for `cfg`."""
+def _contig(cfg, rng, clen, n_rec):
+    """Records + junction table of one contig."""
+    m = _gene_models(rng, cfg, int(clen))
+    pos, flag, ops, strand = _reads_for_contig(rng, cfg, m, int(n_rec))
+    pos, ops = _add_indels_softclips(rng, cfg, pos, ops)
+    order = np.argsort(pos, kind="stable")
+    pos, flag, ops, strand = pos[order], flag[order], ops[order], strand[order]
+    out = dict(jl=None, jr=None, js=None, jst=None)
+    # junction table from the reads themselves (regtools-style anchors)
+    w = ops.shape[1]
+    is_n = (ops & 15) == OP_N
+    is_n &= ops > 0
+    adv = np.where(np.isin(ops & 15, (OP_M, OP_D, OP_N)) & (ops > 0), ops >> 4, 0).astype(np.int64)
+    start_of_op = pos[:, None] + np.cumsum(adv, axis=1) - adv
+    rr, cc = np.nonzero(is_n)
+    if len(rr):
+        left = start_of_op[rr, cc] - 1
+        right = left + (ops[rr, cc] >> 4).astype(np.int64)
+        pc = np.maximum(cc - 1, 0)
+        nc = np.minimum(cc + 1, w - 1)
+        # nearest non-empty op on each side is an M block by construction
+        prev_m = (ops[rr, pc] >> 4) * ((ops[rr, pc] & 15) == OP_M)
+        for back in (2, 3):
+            pc2 = np.maximum(cc - back, 0)
+            prev_m = np.where(prev_m == 0, (ops[rr, pc2] >> 4) * ((ops[rr, pc2] & 15) == OP_M) * (ops[rr, pc2] > 0), prev_m)
+        next_m = (ops[rr, nc] >> 4) * ((ops[rr, nc] & 15) == OP_M)
+        good = (prev_m >= cfg.min_anchor) & (next_m >= cfg.min_anchor)
+        key = left[good] * (1 << 31) + right[good]
+        uk, first_idx, cnt = np.unique(key, return_index=True, return_counts=True)
+        out["jl"] = (uk >> 31).astype(np.int32); out["jr"] = (uk & ((1 << 31) - 1)).astype(np.int32)
+        out["js"] = cnt.astype(np.int64)
+        st = strand[rr][good][first_idx]
+        out["jst"] = np.where(st == 0, ord("+"), ord("-")).astype(np.uint8) if cfg.stranded else np.full(len(uk), ord("?"), np.uint8)
+    out["pos"] = pos.astype(np.int32); out["flag"] = flag
+    out["ncig"] = (ops > 0).sum(axis=1).astype(np.int64)
+    out["flat"] = ops[ops > 0]                                  # row-major: per-read op order is preserved
+    return out
+
+
+def _contig_job(args):
+    cfg, ci, clen, n = args
+    return _contig(cfg, np.random.default_rng([cfg.seed, ci]), clen, n)
+
+
+def _contigs_parallel(cfg, todo, workers):
+    """Contigs of a per_contig_rng config, built by a pool of processes (the result does not depend on the pool size)."""
+    jobs = [(cfg, ci, clen, n) for ci, clen, n in todo]
+    workers = max(1, min(int(workers or 1), len(jobs)))
+    if workers == 1:
+        return [_contig_job(j) for j in jobs]
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(workers) as pool:
+        return pool.map(_contig_job, jobs, chunksize=1)
+
+
+def generate(cfg: SynthConfig, cache_dir=None, workers=None) -> Workload:
+    """Builds (or loads from the .npz cache) the workload for `cfg`.  workers: processes for per_contig_rng configs
+    (default: half the cores)."""
+    if workers is None:
+        workers = max(1, (os.cpu_count() or 2) // 2)
     if cache_dir:
         path = os.path.join(cache_dir, "spliser_synth_%s_%s.npz" % (cfg.name, cfg.key()))
         if os.path.exists(path):
@@ -373,46 +439,18 @@ def generate(cfg: SynthConfig, cache_dir=None) -> Workload:
     seg_chrom, seg_off = [], [0]
     jc, jl, jr, js, jst = [], [], [], [], []
     total = 0
-    for ci, (cname, clen) in enumerate(cfg.contigs):
-        if n_per[ci] <= 0:
-            continue
-        m = _gene_models(rng, cfg, int(clen))
-        pos, flag, ops, strand = _reads_for_contig(rng, cfg, m, int(n_per[ci]))
-        pos, ops = _add_indels_softclips(rng, cfg, pos, ops)
-        order = np.argsort(pos, kind="stable")
-        pos, flag, ops, strand = pos[order], flag[order], ops[order], strand[order]
-        # junction table from the reads themselves (regtools-style anchors)
-        w = ops.shape[1]
-        is_n = (ops & 15) == OP_N
-        is_n &= ops > 0
-        adv = np.where(np.isin(ops & 15, (OP_M, OP_D, OP_N)) & (ops > 0), ops >> 4, 0).astype(np.int64)
-        start_of_op = pos[:, None] + np.cumsum(adv, axis=1) - adv
-        rr, cc = np.nonzero(is_n)
-        if len(rr):
-            left = start_of_op[rr, cc] - 1
-            right = left + (ops[rr, cc] >> 4).astype(np.int64)
-            prev_m = np.zeros(len(rr), np.int64)
-            next_m = np.zeros(len(rr), np.int64)
-            pc = np.maximum(cc - 1, 0)
-            nc = np.minimum(cc + 1, w - 1)
-            # nearest non-empty op on each side is an M block by construction
-            prev_m = (ops[rr, pc] >> 4) * ((ops[rr, pc] & 15) == OP_M)
-            for back in (2, 3):
-                pc2 = np.maximum(cc - back, 0)
-                prev_m = np.where(prev_m == 0, (ops[rr, pc2] >> 4) * ((ops[rr, pc2] & 15) == OP_M) * (ops[rr, pc2] > 0), prev_m)
-            next_m = (ops[rr, nc] >> 4) * ((ops[rr, nc] & 15) == OP_M)
-            good = (prev_m >= cfg.min_anchor) & (next_m >= cfg.min_anchor)
-            key = left[good] * (1 << 31) + right[good]
-            uk, first_idx, cnt = np.unique(key, return_index=True, return_counts=True)
-            jl.append((uk >> 31).astype(np.int32)); jr.append((uk & ((1 << 31) - 1)).astype(np.int32))
-            js.append(cnt.astype(np.int64)); jc.append(np.full(len(uk), len(seg_chrom), np.int32))
-            st = strand[rr][good][first_idx]
-            jst.append(np.where(st == 0, ord("+"), ord("-")).astype(np.uint8) if cfg.stranded else np.full(len(uk), ord("?"), np.uint8))
-        ncig = (ops > 0).sum(axis=1)
-        flat = ops[ops > 0]                                  # row-major: per-read op order is preserved
-        P.append(pos.astype(np.int32)); F.append(flag); O.append(ncig.astype(np.int64)); C.append(flat)
+    todo = [(ci, int(clen), int(n_per[ci])) for ci, (cname, clen) in enumerate(cfg.contigs) if n_per[ci] > 0]
+    if cfg.per_contig_rng:
+        results = _contigs_parallel(cfg, todo, workers)
+    else:
+        results = (_contig(cfg, rng, clen, n) for ci, clen, n in todo)
+    for (ci, clen, n), res in zip(todo, results):
+        if res["jl"] is not None:
+            jl.append(res["jl"]); jr.append(res["jr"]); js.append(res["js"]); jst.append(res["jst"])
+            jc.append(np.full(len(res["jl"]), len(seg_chrom), np.int32))
+        P.append(res["pos"]); F.append(res["flag"]); O.append(res["ncig"]); C.append(res["flat"])
         seg_chrom.append(ci)
-        total += len(pos)
+        total += len(res["pos"])
         seg_off.append(total)
     pos = np.concatenate(P) if P else np.zeros(0, np.int32)
     flag = np.concatenate(F) if F else np.zeros(0, np.uint16)

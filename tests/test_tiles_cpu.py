@@ -49,3 +49,30 @@ def test_tile_slices_edge_cases():
     assert all(int(c) == 0 for t in range(8) for c in dist.tile_records(rec, table, 2, t, 8).seg_chrom)
     empty = Records.from_reads(["A"], [])
     assert dist.max_reference_span(empty) == 0 and len(dist.tile_records(empty, table, 2, 0, 2)) == 0
+
+
+def test_read_balanced_tiles_reproduce_the_unsharded_counts():
+    """Tiles cut by read count (dist.balanced_tiles) with per-segment span bounds: the owned slices still concatenate to the
+    unsharded result, and no tile receives much more than its share of the records."""
+    w = synth.generate(synth.config_c3_tile(80_000, tile=2))
+    nc = len(w.chroms)
+    full = c_oracle.process(w.records, nc, w.junctions, w.flags | 4, threads=8)
+    table = api.build_site_table(nc, w.junctions, w.flags)
+    S = len(table)
+    n_tiles = 4
+    cuts = dist.balanced_tiles(w.records, table, nc, n_tiles)
+    assert cuts[0] == 0 and cuts[-1] == S and all(a <= b for a, b in zip(cuts, cuts[1:]))
+    spans = dist.segment_max_spans(w.records)
+    assert len(spans) == len(w.records.seg_chrom) and max(spans) == dist.max_reference_span(w.records)
+    got = {k: np.zeros(S, full[k].dtype) for k in ("beta1", "beta2simple", "beta2cryptic", "sse", "alpha")}
+    sent = []
+    for t in range(n_tiles):
+        lo, hi = cuts[t], cuts[t + 1]
+        rec_t = dist.tile_records(w.records, table, nc, t, n_tiles, site_range=(lo, hi), seg_spans=spans)
+        sent.append(len(rec_t))
+        part = c_oracle.process(rec_t, nc, w.junctions, w.flags | 4, threads=8)
+        for k in got:
+            got[k][lo:hi] = part[k][lo:hi]
+    for k in got:
+        assert np.array_equal(got[k], full[k]), k
+    assert max(sent) < 1.6 * len(w.records) / n_tiles, sent            # balanced by reads, edge duplicates included
