@@ -247,6 +247,7 @@ int bam_gpu_ingest(BamGpuMem& mem, const uint8_t* file_pinned, size_t fsz, const
     cnt.h2d_bytes = (double)fsz + (double)n_mem * sizeof(BgzfMember);
     const uint8_t* d_u = (const uint8_t*)mem.unc.p;
     uint32_t* d_kept = (uint32_t*)mem.list.p;
+    BG_CU(cudaMemsetAsync((uint8_t*)mem.unc.p + total_u, 0, 256, st));     // the parser's aligned-word reads run a few bytes past the end
     { SPL_LAUNCH; k_bgzf_inflate<<<(n_mem + INF_WARPS - 1) / INF_WARPS, INF_WARPS * 32, 0, st>>>((const uint8_t*)mem.comp.p, d_mem, n_mem, (uint8_t*)mem.unc.p, d_err); }
     // ---- speculative record starts + counting walk
     { SPL_LAUNCH; k_bam_first<<<(n_mem + 7) / 8, 256, 0, st>>>(d_u, d_mem, n_mem, total_u, n_ref, first_record, d_first); }

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_cons
     FSmem& sm = *reinterpret_cast<FSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], FC_CWARPS); }
+        for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], FC_CONSUMERS); }
     }
     __syncthreads();
     if (warp == FC_CWARPS) {
@@ -446,8 +446,9 @@ __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_cons
         if (m.flags & FM_DONE) break;
         if (m.flags & FM_GLOBAL_CIG) consume<false>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], A);
         else consume<true>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], A);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        // every consumer thread releases the stage itself: its reads of the stage (and of the stage's meta data) are ordered
+        // before the producer's next copy by its own arrive (release) / the producer's wait (acquire)
+        mbar_arrive(&sm.empty[stage]);
     }
 }
 

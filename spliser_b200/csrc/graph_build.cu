@@ -16,7 +16,9 @@
 
 #include <climits>
 #include <cstdint>
+#include <algorithm>
 #include <string>
+#include <vector>
 
 #include "device_types.h"
 #include "graph_build.h"
@@ -77,9 +79,81 @@ k_rs_scatter(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32
     }
 }
 
+// ---- single-pass exclusive scan (decoupled look-back): one launch, no host-known length needed ------------------
+// Tiles take tickets from a counter (so every predecessor of a running tile is running or done) and publish
+// (epoch | flag | value) in one 64-bit word; a new epoch per call makes the words of earlier calls read as "not yet".
+constexpr int LB_THREADS = 256, LB_ITEMS = 8, LB_TILE = LB_THREADS * LB_ITEMS;
+constexpr unsigned long long LB_AGG = 1ull, LB_PREFIX = 2ull;
+
+__global__ void __launch_bounds__(LB_THREADS)
+k_scan_lb(uint32_t* __restrict__ a, uint32_t n_host, const uint32_t* __restrict__ n_dev, unsigned long long* __restrict__ desc,
+          uint32_t* __restrict__ ticket, uint32_t epoch, uint32_t* __restrict__ total_out, uint32_t* __restrict__ total_out2) {
+    __shared__ uint32_t s_tile, s_prev, wsum[LB_THREADS / 32];
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t t = s_tile;
+    const uint32_t base = t * LB_TILE + threadIdx.x * LB_ITEMS;
+    uint32_t v[LB_ITEMS], sum = 0;
+#pragma unroll
+    for (int q = 0; q < LB_ITEMS; ++q) { v[q] = base + q < n ? a[base + q] : 0u; sum += v[q]; }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < LB_THREADS / 32; ++w) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
+    if (threadIdx.x == 0) {
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        volatile unsigned long long* d = desc;
+        uint32_t prev = 0;
+        if (t == 0) {
+            d[0] = tag | (LB_PREFIX << 32) | total;
+        } else {
+            d[t] = tag | (LB_AGG << 32) | total;
+            for (uint32_t p = t - 1;; ) {
+                const unsigned long long w = d[p];
+                if ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0ull) continue;          // not published yet
+                prev += (uint32_t)w;
+                if (((w >> 32) & 3ull) == LB_PREFIX) break;
+                --p;
+            }
+            d[t] = tag | (LB_PREFIX << 32) | (prev + total);
+        }
+        s_prev = prev;
+        if (t == gridDim.x - 1) {                                       // every ticket of this launch has been handed out
+            *ticket = 0u;
+            if (total_out) *total_out = prev + total;
+            if (total_out2) *total_out2 = prev + total;
+        }
+    }
+    __syncthreads();
+    uint32_t run = s_prev + wbase + inc - sum;
+#pragma unroll
+    for (int q = 0; q < LB_ITEMS; ++q) { if (base + q < n) a[base + q] = run; run += v[q]; }
+}
+
+struct Scanner {
+    unsigned long long* desc;     // [max tiles], zeroed once
+    uint32_t* ticket;             // [1], zero between launches
+    uint32_t* epoch;              // host counter
+    cudaStream_t st;
+    // exclusive scan of a[0..n) in place; n = min(n_host, *n_dev) when n_dev is given; the total goes to total_out (and total_out2)
+    void scan(uint32_t* a, uint32_t n_host, const uint32_t* n_dev, uint32_t* total_out, uint32_t* total_out2 = nullptr) const {
+        const uint32_t tiles = (n_host + LB_TILE - 1) / LB_TILE;
+        if (tiles == 0) { if (total_out) cudaMemsetAsync(total_out, 0, 4, st); if (total_out2) cudaMemsetAsync(total_out2, 0, 4, st); return; }
+        *epoch = (*epoch + 1u) & 0x3fffffffu;
+        if (*epoch == 0u) *epoch = 1u;
+        { SPL_LAUNCH; k_scan_lb<<<tiles, LB_THREADS, 0, st>>>(a, n_host, n_dev, desc, ticket, *epoch, total_out, total_out2); }
+    }
+};
+
 struct Sorter {
     uint32_t* hist;      // [256 * max_tiles + 1]
-    uint32_t* tmp;       // scan scratch
+    Scanner sc;
     uint32_t* total;     // [1] scratch
     cudaStream_t st;
     // stable sort of a[0..n) on bits [lo, hi); b is the ping-pong buffer; returns the buffer that holds the result
@@ -90,7 +164,7 @@ struct Sorter {
             const int width = hi - shift < 8 ? hi - shift : 8;
             const uint32_t mask = (1u << width) - 1u;
             { SPL_LAUNCH; k_rs_hist<<<n_tiles, RS_THREADS, 0, st>>>(a, n, shift, mask, hist, n_tiles); }
-            launch_exscan_u32(hist, 256u * n_tiles, tmp, total, st);
+            sc.scan(hist, 256u * n_tiles, nullptr, total);
             { SPL_LAUNCH; k_rs_scatter<<<n_tiles, RS_THREADS, 0, st>>>(a, b, n, shift, mask, hist, n_tiles); }
             uint64_t* t = a; a = b; b = t;
         }
@@ -119,7 +193,8 @@ __global__ void k_gb_heads(const uint64_t* __restrict__ k, uint32_t n, int low, 
 }
 
 __global__ void k_gb_sites(const uint64_t* __restrict__ k, const uint32_t* __restrict__ ex, uint32_t n, int vb, int pb, int stranded,
-                           const uint8_t* __restrict__ js, GraphDev g, uint32_t* __restrict__ site_of) {
+                           const uint8_t* __restrict__ js, GraphDev g, uint32_t* __restrict__ site_of, uint32_t* __restrict__ inc_eid,
+                           uint32_t* __restrict__ counts) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n) return;
     const uint64_t key = k[e] >> vb;
@@ -127,6 +202,7 @@ __global__ void k_gb_sites(const uint64_t* __restrict__ k, const uint32_t* __res
     const uint32_t idx = ex[e] - (head ? 0u : 1u);
     const uint32_t eid = (uint32_t)(k[e] & ((1ull << vb) - 1ull));
     site_of[eid] = idx;
+    inc_eid[e] = eid;                                                  // endpoint 2 * row + side; its junction partner is eid ^ 1
     g.inc_line[e] = (int32_t)(eid >> 1);
     if (head) {
         const uint32_t line = eid >> 1;
@@ -139,7 +215,11 @@ __global__ void k_gb_sites(const uint64_t* __restrict__ k, const uint32_t* __res
         g.site_cls[idx] = !stranded ? 0 : st == '+' ? 1 : st == '-' ? 2 : 3;
         g.inc_off[idx] = (int32_t)e;
     }
-    if (e == n - 1) g.inc_off[idx + 1] = (int32_t)n;
+    if (e == n - 1) {
+        g.inc_off[idx + 1] = (int32_t)n;
+        counts[7] = idx + 2u;                                          // S + 1: length of the per-site scans that also want their total
+        for (int q = 0; q < 64; ++q) g.site_pos[idx + 1 + q] = INT_MAX;   // tail padding (never matches)
+    }
 }
 
 // per-chromosome site ranges: the table is sorted by chromosome, so cs_off[c] is a lower bound (one thread per chromosome)
@@ -163,112 +243,110 @@ __global__ void k_gb_chrom_layout(int n_chrom, GraphDev g, uint32_t* __restrict_
     counts[1] = (uint32_t)nb;
 }
 
-__global__ void k_gb_sb_fill(GraphDev g, int n_chrom, uint32_t S, uint32_t n_entries) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_entries + 64u) return;
-    if (i >= n_entries) { g.sb_off[i] = (int32_t)S; return; }
-    int lo = 0, hi = n_chrom;                                           // last chromosome with sb_base <= i
-    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((uint32_t)g.sb_base[mid] <= i) lo = mid; else hi = mid; }
-    const int c = lo;
-    const int32_t b = (int32_t)i - g.sb_base[c], nb = g.sb_base[c + 1] - g.sb_base[c] - 1;
-    int s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
-    if (b >= nb) { g.sb_off[i] = s1; return; }
-    const int32_t key = b << SB_SHIFT;
-    while (s0 < s1) { const int mid = (s0 + s1) >> 1; if (g.site_pos[mid] < key) s0 = mid + 1; else s1 = mid; }
-    g.sb_off[i] = s0;
-}
-
-// ---- phase B: directed edges -> PartnerCounts entries -------------------------------------------
-__global__ void k_gb_keys_b(const uint32_t* __restrict__ site_of, uint32_t J, int sbits, int lb, uint64_t* __restrict__ keys) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= J) return;
-    const uint64_t a = site_of[2 * i], b = site_of[2 * i + 1];
-    keys[2 * i] = (((a << sbits) | b) << lb) | i;                        // row order == first-appearance order
-    keys[2 * i + 1] = (((b << sbits) | a) << lb) | i;
-}
-
-__global__ void k_gb_edges(const uint64_t* __restrict__ k, const uint32_t* __restrict__ ex, uint32_t n, int lb, int sbits, GraphDev g,
-                           uint32_t* __restrict__ u_src, uint32_t* __restrict__ u_dst, uint32_t* __restrict__ u_first, uint32_t* __restrict__ u_lo) {
-    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= n) return;
-    const uint64_t pair = k[e] >> lb;
-    const bool head = e == 0 || pair != (k[e - 1] >> lb);
-    const uint32_t u = ex[e] - (head ? 0u : 1u);
-    const uint32_t line = (uint32_t)(k[e] & ((1ull << lb) - 1ull));
-    g.einc_line[e] = (int32_t)line;
-    if (head) {
-        u_dst[u] = (uint32_t)(pair & ((1ull << sbits) - 1ull));
-        u_src[u] = (uint32_t)(pair >> sbits);
-        u_first[u] = line;
-        u_lo[u] = e;
+__global__ void k_gb_sb_fill(GraphDev g, int n_chrom, const uint32_t* __restrict__ counts) {
+    const uint32_t S = counts[0], n_entries = counts[1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_entries + 64u; i += gridDim.x * blockDim.x) {
+        if (i >= n_entries) { g.sb_off[i] = (int32_t)S; continue; }
+        int lo = 0, hi = n_chrom;                                       // last chromosome with sb_base <= i
+        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((uint32_t)g.sb_base[mid] <= i) lo = mid; else hi = mid; }
+        const int c = lo;
+        const int32_t b = (int32_t)i - g.sb_base[c], nb = g.sb_base[c + 1] - g.sb_base[c] - 1;
+        int s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
+        if (b >= nb) { g.sb_off[i] = s1; continue; }
+        const int32_t key = b << SB_SHIFT;
+        while (s0 < s1) { const int mid = (s0 + s1) >> 1; if (g.site_pos[mid] < key) s0 = mid + 1; else s1 = mid; }
+        g.sb_off[i] = s0;
     }
-    if (e == n - 1) u_lo[u + 1] = n;
 }
 
-// ---- phase C: entries of a site in first-appearance order ---------------------------------------
-__global__ void k_gb_keys_c(const uint32_t* __restrict__ u_src, const uint32_t* __restrict__ u_first, uint32_t E, int lb, int eb,
-                            uint64_t* __restrict__ keys) {
-    const uint32_t u = blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= E) return;
-    keys[u] = ((((uint64_t)u_src[u] << lb) | u_first[u]) << eb) | u;
+// ---- phase B: Partners / PartnerCounts of every site, straight from its incident endpoints ----------------
+// The endpoints of a site are already grouped and in row order (phase A); the junction partner of endpoint e is e ^ 1.
+// A site's distinct partners in first-appearance order (G:243-262) are found by one thread per site: degrees are small
+// (a splice site has a handful of partners), so the quadratic scan over the incident list stays in L1.
+__device__ __forceinline__ uint32_t partner_of(const uint32_t* __restrict__ site_of, const uint32_t* __restrict__ inc_eid, uint32_t k) {
+    return site_of[inc_eid[k] ^ 1u];
 }
-
-__global__ void k_gb_csr(const uint64_t* __restrict__ k, uint32_t E, uint32_t S, int eb, int lb, const uint32_t* __restrict__ u_dst,
-                         const uint32_t* __restrict__ u_lo, GraphDev g, uint32_t* __restrict__ e_src) {
-    const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= E) return;
-    const uint32_t u = (uint32_t)(k[x] & ((1ull << eb) - 1ull));
-    const uint32_t src = (uint32_t)(k[x] >> (eb + lb));
-    const uint32_t dst = u_dst[u];
-    g.pt_site[x] = (int32_t)dst;
-    g.pc_pos[x] = g.site_pos[dst];
-    g.einc_beg[x] = (int32_t)u_lo[u];
-    g.einc_end[x] = (int32_t)u_lo[u + 1];
-    e_src[x] = src;
-    if (x == 0 || src != (uint32_t)(k[x - 1] >> (eb + lb))) g.pt_off[src] = (int32_t)x;      // every site has >= 1 entry
-    if (x == E - 1) g.pt_off[S] = (int32_t)E;
-}
-
-// ---- phase D: competitors (S:364-372) ------------------------------------------------------------
-__global__ void k_gb_cand_count(GraphDev g, uint32_t S, uint32_t* __restrict__ ncand) {
+__global__ void k_gb_pt_count(GraphDev g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ site_of,
+                              const uint32_t* __restrict__ inc_eid, uint32_t* __restrict__ npt) {
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= S) return;
-    uint32_t n = 0;
-    for (int a = g.pt_off[t]; a < g.pt_off[t + 1]; ++a) {
-        const int p = g.pt_site[a];
-        n += (uint32_t)(g.pt_off[p + 1] - g.pt_off[p]);
+    if (t >= counts[0]) return;
+    const uint32_t o = (uint32_t)g.inc_off[t], d = (uint32_t)g.inc_off[t + 1] - o;
+    uint32_t u = 0;
+    for (uint32_t i = 0; i < d; ++i) {
+        const uint32_t p = partner_of(site_of, inc_eid, o + i);
+        bool first = true;
+        for (uint32_t q = 0; q < i && first; ++q) first = partner_of(site_of, inc_eid, o + q) != p;
+        u += first;
     }
-    ncand[t] = n;
+    npt[t] = u;
+}
+// entries of site t: partner site, partner position, and the rows whose score adds to the entry (S:353-355), grouped
+__global__ void k_gb_pt_fill(GraphDev g, uint32_t* __restrict__ counts, const uint32_t* __restrict__ site_of,
+                             const uint32_t* __restrict__ inc_eid, const uint32_t* __restrict__ pt_off_u, uint32_t* __restrict__ e_src) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t S = counts[0];
+    if (t > S) return;
+    g.pt_off[t] = (int32_t)pt_off_u[t];
+    g.pt_off64[t] = (int64_t)pt_off_u[t];
+    if (t == S) return;
+    const uint32_t o = (uint32_t)g.inc_off[t], d = (uint32_t)g.inc_off[t + 1] - o;
+    uint32_t x = pt_off_u[t], w = o;
+    for (uint32_t i = 0; i < d; ++i) {
+        const uint32_t p = partner_of(site_of, inc_eid, o + i);
+        bool first = true;
+        for (uint32_t q = 0; q < i && first; ++q) first = partner_of(site_of, inc_eid, o + q) != p;
+        if (!first) continue;
+        g.pt_site[x] = (int32_t)p;
+        g.pc_pos[x] = g.site_pos[p];
+        g.einc_beg[x] = (int32_t)w;
+        for (uint32_t q = i; q < d; ++q)
+            if (partner_of(site_of, inc_eid, o + q) == p) g.einc_line[w++] = (int32_t)(inc_eid[o + q] >> 1);
+        g.einc_end[x] = (int32_t)w;
+        e_src[x] = t;
+        ++x;
+    }
 }
 
-__global__ void k_gb_cand_fill(GraphDev g, uint32_t S, const uint32_t* __restrict__ cand_off, int pb, uint64_t* __restrict__ keys) {
-    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= S) return;
-    uint32_t w = cand_off[t];
-    const int32_t tp = g.site_pos[t];
-    for (int a = g.pt_off[t]; a < g.pt_off[t + 1]; ++a) {
+// ---- phase D: competitors (S:364-372): sorted distinct positions of the partners' partners, own position excluded ---
+// One thread per site, selection by repeated minimum: every round finds the smallest candidate above the last one written.
+__device__ __forceinline__ int32_t next_competitor(const GraphDev& g, const int32_t* __restrict__ pt_off, uint32_t t, int32_t tp, int32_t last) {
+    int32_t best = INT_MAX;
+    for (int a = pt_off[t]; a < pt_off[t + 1]; ++a) {
         const int p = g.pt_site[a];
-        for (int q = g.pt_off[p]; q < g.pt_off[p + 1]; ++q) {
-            const int32_t cpos = g.pc_pos[q];                            // position of the partner's partner
-            keys[w++] = cpos != tp ? (((uint64_t)t << pb) | (uint32_t)cpos) : ((uint64_t)S << pb);   // own position: parked behind every site
+        for (int q = pt_off[p]; q < pt_off[p + 1]; ++q) {
+            const int32_t c = g.pc_pos[q];                                // position of the partner's partner
+            if (c != tp && c > last && c < best) best = c;
         }
     }
+    return best;
 }
-
-__global__ void k_gb_cand_heads(const uint64_t* __restrict__ k, uint32_t n, int pb, uint32_t S, uint32_t* __restrict__ flag) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    flag[i] = ((uint32_t)(k[i] >> pb) != S && (i == 0 || k[i] != k[i - 1])) ? 1u : 0u;
+__global__ void k_gb_cp_count(GraphDev g, const uint32_t* __restrict__ counts, uint32_t* __restrict__ ncp) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= counts[0]) return;
+    const int32_t tp = g.site_pos[t];
+    uint32_t u = 0;
+    for (int32_t last = INT_MIN;;) {
+        last = next_competitor(g, g.pt_off, t, tp, last);
+        if (last == INT_MAX) break;
+        ++u;
+    }
+    ncp[t] = u;
 }
-
-__global__ void k_gb_comp(const uint64_t* __restrict__ k, const uint32_t* __restrict__ ex, uint32_t n, int pb, uint32_t S, GraphDev g,
-                          uint32_t* __restrict__ cp_cnt) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const uint32_t t = (uint32_t)(k[i] >> pb);
-    if (t == S || !(i == 0 || k[i] != k[i - 1])) return;
-    g.cp_pos[ex[i]] = (int32_t)(k[i] & ((1ull << pb) - 1ull));          // sorted by (site, position): compaction keeps the order
-    atomicAdd(cp_cnt + t, 1u);
+__global__ void k_gb_cp_fill(GraphDev g, uint32_t* __restrict__ counts, const uint32_t* __restrict__ cp_off_u, uint32_t cap) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t S = counts[0];
+    if (t > S) return;
+    g.cp_off[t] = (int32_t)cp_off_u[t];
+    g.cp_off64[t] = (int64_t)cp_off_u[t];
+    if (t == S) { if (cp_off_u[S] > cap) counts[6] = 1u; return; }          // the competitor array is too small: the host re-runs with room
+    const int32_t tp = g.site_pos[t];
+    uint32_t x = cp_off_u[t];
+    for (int32_t last = INT_MIN;;) {
+        last = next_competitor(g, g.pt_off, t, tp, last);
+        if (last == INT_MAX) break;
+        if (x < cap) g.cp_pos[x] = last;
+        ++x;
+    }
 }
 
 // ---- phase E: reverse-partner index ---------------------------------------------------------------
@@ -277,27 +355,20 @@ __global__ void k_gb_comp(const uint64_t* __restrict__ k, const uint32_t* __rest
 __device__ __forceinline__ uint32_t anchor_of(const GraphDev& g, uint32_t p) {
     return (p > 0 && g.site_pos[p - 1] == g.site_pos[p] && g.site_chrom[p - 1] == g.site_chrom[p]) ? p - 1 : p;
 }
-__global__ void k_gb_rp_count(GraphDev g, uint32_t E, uint32_t* __restrict__ rp_cnt) {
+__global__ void k_gb_rp_count(GraphDev g, const uint32_t* __restrict__ counts, uint32_t* __restrict__ rp_cnt) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= E) return;
+    if (x >= counts[2]) return;
     atomicAdd(rp_cnt + anchor_of(g, (uint32_t)g.pt_site[x]), 1u);
 }
-__global__ void k_gb_rp_fill(GraphDev g, uint32_t E, const uint32_t* __restrict__ e_src, uint32_t* __restrict__ rp_cur) {
+__global__ void k_gb_rp_fill(GraphDev g, const uint32_t* __restrict__ counts, const uint32_t* __restrict__ e_src, const uint32_t* __restrict__ rp_off_u,
+                             uint32_t* __restrict__ rp_cur) {
     const uint32_t x = blockIdx.x * blockDim.x + threadIdx.x;
-    if (x >= E) return;
+    if (x <= counts[0]) g.rp_off[x] = (int32_t)rp_off_u[x];
+    if (x >= counts[2]) return;
     const uint32_t a = anchor_of(g, (uint32_t)g.pt_site[x]);
     const uint32_t t = e_src[x];
-    g.rp_site[(uint32_t)g.rp_off[a] + atomicAdd(rp_cur + a, 1u)] = (int32_t)t;      // order inside a list does not matter: only counted
+    g.rp_site[rp_off_u[a] + atomicAdd(rp_cur + a, 1u)] = (int32_t)t;      // order inside a list does not matter: only counted
     if (g.cp_off[t + 1] > g.cp_off[t]) g.site_hot[a] = 1;
-}
-
-__global__ void k_gb_widen(const int32_t* __restrict__ a, int64_t* __restrict__ o, uint32_t n) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) o[i] = a[i];
-}
-__global__ void k_gb_fill_i32(int32_t* a, uint32_t n, int32_t v) {
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) a[i] = v;
 }
 
 inline uint32_t cdiv(uint32_t a, uint32_t b) { return (a + b - 1) / b; }
@@ -334,13 +405,27 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     cudaStream_t st = (cudaStream_t)stream;
     const uint32_t J = (uint32_t)n_junc, n2 = 2 * J;
     const int pb = bits_for_u64((uint64_t)(max_pos > 0 ? max_pos : 1)), cb = bits_for_u64((uint64_t)(n_chrom > 1 ? n_chrom - 1 : 1));
-    const int vb = bits_for_u64((uint64_t)(n2 - 1)), lb = bits_for_u64((uint64_t)(J - 1));
+    const int vb = bits_for_u64((uint64_t)(n2 - 1));
 
-    // ---- allocations bounded by J (final arrays + workspace); cp_pos / sb_off follow once their sizes are known
+    if (phase == 0) {
+        // exact size of the direct-address bin index: per chromosome, bins up to its highest site position + a sentinel
+        std::vector<int32_t> cmax((size_t)n_chrom, -1);
+        for (int64_t i = 0; i < n_junc; ++i) {
+            int32_t& v = cmax[(size_t)j_chrom[i]];
+            v = std::max(v, std::max(j_left[i], j_right[i]));
+        }
+        uint64_t nb = 0;
+        for (int32_t c = 0; c < n_chrom; ++c) nb += (cmax[(size_t)c] >= 0 ? (uint64_t)(cmax[(size_t)c] >> SB_SHIFT) + 1u : 0u) + 1u;
+        if (nb >= ((uint64_t)1 << 31)) { err = "graph build: bin index exceeds 2^31 entries"; return false; }
+        m.nb_host = (uint32_t)nb;
+        if (m.cap_c < 8u * (size_t)n2 + 1024u) m.cap_c = 8u * (size_t)n2 + 1024u;
+    }
+
+    // ---- final arrays (bounded by J), competitor array (capacity, checked on the device) and bin index
     Carve f;
     const size_t o_cs = f.take<int32_t>((size_t)n_chrom + 1), o_sbb = f.take<int32_t>((size_t)n_chrom + 1);
-    const size_t o_chrom = f.take<int32_t>(n2 + 1), o_pos = f.take<int32_t>(n2 + 64), o_strand = f.take<uint8_t>(n2 + 8), o_cls = f.take<uint8_t>(n2 + 8);
-    const size_t o_hot = f.take<uint8_t>(n2 + 64), o_fl = f.take<int64_t>(n2 + 1);
+    const size_t o_chrom = f.take<int32_t>(n2 + 1), o_pos = f.take<int32_t>(n2 + 72), o_strand = f.take<uint8_t>(n2 + 8), o_cls = f.take<uint8_t>(n2 + 8);
+    const size_t o_hot = f.take<uint8_t>(n2 + 72), o_fl = f.take<int64_t>(n2 + 1);
     const size_t o_pto = f.take<int32_t>(n2 + 2), o_pts = f.take<int32_t>(n2 + 1), o_pcp = f.take<int32_t>(n2 + 1);
     const size_t o_cpo = f.take<int32_t>(n2 + 2), o_rpo = f.take<int32_t>(n2 + 2), o_rps = f.take<int32_t>(n2 + 1);
     const size_t o_ino = f.take<int32_t>(n2 + 2), o_inl = f.take<int32_t>(n2 + 1);
@@ -349,6 +434,9 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     const size_t o_pto64 = f.take<int64_t>(n2 + 2), o_cpo64 = f.take<int64_t>(n2 + 2);
     const size_t o_jc = f.take<int32_t>(J), o_jl = f.take<int32_t>(J), o_jr = f.take<int32_t>(J), o_jst = f.take<uint8_t>((size_t)J + 8);
     GB_CU(m.fin.reserve(f.off + 256));
+    Carve x;
+    const size_t x_cp = x.take<int32_t>(m.cap_c + 1), x_sb = x.take<int32_t>((size_t)m.nb_host + 64);
+    GB_CU(m.fin2.reserve(x.off + 256));
     char* fb = (char*)m.fin.p;
     g = GraphDev{};
     g.cs_off = (int32_t*)(fb + o_cs); g.sb_base = (int32_t*)(fb + o_sbb);
@@ -359,128 +447,95 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     g.inc_off = (int32_t*)(fb + o_ino); g.inc_line = (int32_t*)(fb + o_inl);
     g.einc_beg = (int32_t*)(fb + o_eib); g.einc_end = (int32_t*)(fb + o_eie); g.einc_line = (int32_t*)(fb + o_eil);
     g.j_score = (int64_t*)(fb + o_js); g.pt_off64 = (int64_t*)(fb + o_pto64); g.cp_off64 = (int64_t*)(fb + o_cpo64);
+    g.cp_pos = (int32_t*)((char*)m.fin2.p + x_cp); g.sb_off = (int32_t*)((char*)m.fin2.p + x_sb);
     int32_t* d_jc = (int32_t*)(fb + o_jc); int32_t* d_jl = (int32_t*)(fb + o_jl); int32_t* d_jr = (int32_t*)(fb + o_jr);
     uint8_t* d_js = (uint8_t*)(fb + o_jst);
 
     const uint32_t max_tiles = cdiv(n2, RS_TILE) + 1;
+    const uint32_t lb_tiles = cdiv(std::max(256u * max_tiles, n2 + 2u), LB_TILE) + 2;
     Carve w;
     const size_t w_ka = w.take<uint64_t>(n2 + 2), w_kb = w.take<uint64_t>(n2 + 2), w_flag = w.take<uint32_t>(n2 + 2);
-    const size_t w_hist = w.take<uint32_t>(256 * (size_t)max_tiles + 2), w_tmp = w.take<uint32_t>(exscan_tmp_words(256u * max_tiles) + exscan_tmp_words(n2 + 2) + 8);
-    const size_t w_cnt = w.take<uint32_t>(16), w_site_of = w.take<uint32_t>(n2 + 2);
-    const size_t w_usrc = w.take<uint32_t>(n2 + 2), w_udst = w.take<uint32_t>(n2 + 2), w_ufirst = w.take<uint32_t>(n2 + 2), w_ulo = w.take<uint32_t>(n2 + 2);
-    const size_t w_esrc = w.take<uint32_t>(n2 + 2), w_nc = w.take<uint32_t>(n2 + 2), w_c1 = w.take<uint32_t>(n2 + 2), w_c2 = w.take<uint32_t>(n2 + 2);
+    const size_t w_hist = w.take<uint32_t>(256 * (size_t)max_tiles + 2);
+    const size_t w_cnt = w.take<uint32_t>(16), w_site_of = w.take<uint32_t>(n2 + 2), w_eid = w.take<uint32_t>(n2 + 2);
+    const size_t w_esrc = w.take<uint32_t>(n2 + 2), w_npt = w.take<uint32_t>(n2 + 4), w_ncp = w.take<uint32_t>(n2 + 4);
+    const size_t w_c1 = w.take<uint32_t>(n2 + 4), w_c2 = w.take<uint32_t>(n2 + 4);
+    const size_t w_desc = w.take<unsigned long long>(lb_tiles + 32);       // descriptors, then the ticket word
+    const bool fresh = m.work.cap < w.off + 256;
     GB_CU(m.work.reserve(w.off + 256));
     char* wb = (char*)m.work.p;
     uint64_t* ka = (uint64_t*)(wb + w_ka); uint64_t* kb = (uint64_t*)(wb + w_kb);
     uint32_t* flag = (uint32_t*)(wb + w_flag);
-    uint32_t* d_cnt = (uint32_t*)(wb + w_cnt);                            // [0] S, [1] bin entries, [2] E, [3] candidates, [4] C, [5] scratch
-    uint32_t* site_of = (uint32_t*)(wb + w_site_of);
-    uint32_t* u_src = (uint32_t*)(wb + w_usrc); uint32_t* u_dst = (uint32_t*)(wb + w_udst); uint32_t* u_first = (uint32_t*)(wb + w_ufirst);
-    uint32_t* u_lo = (uint32_t*)(wb + w_ulo); uint32_t* e_src = (uint32_t*)(wb + w_esrc);
-    uint32_t* ncand = (uint32_t*)(wb + w_nc); uint32_t* c1 = (uint32_t*)(wb + w_c1); uint32_t* c2 = (uint32_t*)(wb + w_c2);
-    uint32_t* stmp = (uint32_t*)(wb + w_tmp) + exscan_tmp_words(256u * max_tiles) + 4;      // scan scratch of the phase kernels
-    Sorter sorter{(uint32_t*)(wb + w_hist), (uint32_t*)(wb + w_tmp), d_cnt + 5, st};
+    uint32_t* d_cnt = (uint32_t*)(wb + w_cnt);     // [0] S, [1] bin entries, [2] E, [4] C, [5] scratch, [6] competitor overflow, [7] S + 1
+    uint32_t* site_of = (uint32_t*)(wb + w_site_of); uint32_t* inc_eid = (uint32_t*)(wb + w_eid);
+    uint32_t* e_src = (uint32_t*)(wb + w_esrc);
+    uint32_t* npt = (uint32_t*)(wb + w_npt); uint32_t* ncp = (uint32_t*)(wb + w_ncp);
+    uint32_t* c1 = (uint32_t*)(wb + w_c1); uint32_t* c2 = (uint32_t*)(wb + w_c2);
+    unsigned long long* desc = (unsigned long long*)(wb + w_desc);
+    const Scanner sc{desc, (uint32_t*)(desc + lb_tiles + 8), &m.scan_epoch, st};
+    const Sorter sorter{(uint32_t*)(wb + w_hist), sc, d_cnt + 5, st};
 
     // ---- junction table to the device (phase 0: queued before the caller starts the big record upload, which
     // would otherwise sit in front of it on the host->device copy engine)
     if (phase == 0) {
-    GB_CU(cudaMemcpyAsync(d_jc, j_chrom, (size_t)J * 4, cudaMemcpyHostToDevice, st));
-    GB_CU(cudaMemcpyAsync(d_jl, j_left, (size_t)J * 4, cudaMemcpyHostToDevice, st));
-    GB_CU(cudaMemcpyAsync(d_jr, j_right, (size_t)J * 4, cudaMemcpyHostToDevice, st));
-    GB_CU(cudaMemcpyAsync(d_js, j_strand, (size_t)J, cudaMemcpyHostToDevice, st));
-    GB_CU(cudaMemcpyAsync((void*)g.j_score, j_score, (size_t)J * 8, cudaMemcpyHostToDevice, st));
-    counts.h2d_bytes = (double)J * 21.0;
-    GB_CU(cudaMemsetAsync(d_cnt, 0, 64, st));
-    return true;
+        GB_CU(cudaMemcpyAsync(d_jc, j_chrom, (size_t)J * 4, cudaMemcpyHostToDevice, st));
+        GB_CU(cudaMemcpyAsync(d_jl, j_left, (size_t)J * 4, cudaMemcpyHostToDevice, st));
+        GB_CU(cudaMemcpyAsync(d_jr, j_right, (size_t)J * 4, cudaMemcpyHostToDevice, st));
+        GB_CU(cudaMemcpyAsync(d_js, j_strand, (size_t)J, cudaMemcpyHostToDevice, st));
+        GB_CU(cudaMemcpyAsync((void*)g.j_score, j_score, (size_t)J * 8, cudaMemcpyHostToDevice, st));
+        counts.h2d_bytes = (double)J * 21.0;
+        GB_CU(cudaMemsetAsync(d_cnt, 0, 64, st));
+        m.scan_epoch = 0;
+        GB_CU(cudaMemsetAsync(desc, 0, ((size_t)lb_tiles + 32) * sizeof(unsigned long long), st));     // descriptors + ticket
+        m.ready = true;
+        return true;
     }
+    if (fresh || !m.ready) { err = "graph build: phase 1 without phase 0"; return false; }
 
     // ---- A: sites
+    GB_CU(cudaMemsetAsync(d_cnt + 6, 0, 4, st));
     { SPL_LAUNCH; k_gb_keys_a<<<cdiv(J, 256), 256, 0, st>>>(d_jc, d_jl, d_jr, d_js, J, stranded ? 1 : 0, pb, vb, ka); }
     uint64_t* sa = sorter.sort(ka, kb, n2, vb, vb + 1 + pb + cb);
-    uint64_t* other = sa == ka ? kb : ka;
     { SPL_LAUNCH; k_gb_heads<<<cdiv(n2, 256), 256, 0, st>>>(sa, n2, vb, flag); }
-    launch_exscan_u32(flag, n2, stmp, d_cnt + 0, st);
-    { SPL_LAUNCH; k_gb_sites<<<cdiv(n2, 256), 256, 0, st>>>(sa, flag, n2, vb, pb, stranded ? 1 : 0, d_js, g, site_of); }
+    sc.scan(flag, n2, nullptr, d_cnt + 0);
+    GB_CU(cudaMemsetAsync(g.site_hot, 0, (size_t)n2 + 64, st));
+    { SPL_LAUNCH; k_gb_sites<<<cdiv(n2, 256), 256, 0, st>>>(sa, flag, n2, vb, pb, stranded ? 1 : 0, d_js, g, site_of, inc_eid, d_cnt); }
     { SPL_LAUNCH; k_gb_cs_off<<<cdiv((uint32_t)n_chrom + 1, 128), 128, 0, st>>>(g, n_chrom, d_cnt); }
     { SPL_LAUNCH; k_gb_chrom_layout<<<1, 32, 0, st>>>(n_chrom, g, d_cnt); }
-    GB_CU(cudaGetLastError());
-    GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
-    GB_CU(cudaStreamSynchronize(st));
-    const uint32_t S = m.h_cnt[0], NB = m.h_cnt[1];
-    if (S == 0 || S > n2) { err = "graph build: bad site count"; return false; }
-    const int sbits = bits_for_u64((uint64_t)S);                          // S itself is used as a sentinel in phase D
-    { SPL_LAUNCH; k_gb_fill_i32<<<1, 64, 0, st>>>(g.site_pos + S, 64, INT_MAX); }        // tail padding (never matches)
-    GB_CU(cudaMemsetAsync(g.site_hot, 0, (size_t)S + 64, st));
 
-    // ---- B: PartnerCounts entries
-    { SPL_LAUNCH; k_gb_keys_b<<<cdiv(J, 256), 256, 0, st>>>(site_of, J, sbits, lb, other); }
-    uint64_t* sbk = sorter.sort(other, sa, n2, lb, lb + 2 * sbits);
-    other = sbk == ka ? kb : ka;
-    { SPL_LAUNCH; k_gb_heads<<<cdiv(n2, 256), 256, 0, st>>>(sbk, n2, lb, flag); }
-    launch_exscan_u32(flag, n2, stmp, d_cnt + 2, st);
-    { SPL_LAUNCH; k_gb_edges<<<cdiv(n2, 256), 256, 0, st>>>(sbk, flag, n2, lb, sbits, g, u_src, u_dst, u_first, u_lo); }
-    GB_CU(cudaGetLastError());
-    GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
-    GB_CU(cudaStreamSynchronize(st));
-    const uint32_t E = m.h_cnt[2];
-    if (E == 0 || E > n2) { err = "graph build: bad edge count"; return false; }
-    const int eb = bits_for_u64((uint64_t)(E - 1));
-
-    // ---- C: first-appearance order inside a site
-    { SPL_LAUNCH; k_gb_keys_c<<<cdiv(E, 256), 256, 0, st>>>(u_src, u_first, E, lb, eb, other); }
-    uint64_t* sc = sorter.sort(other, other == ka ? kb : ka, E, eb, eb + lb + sbits);
-    { SPL_LAUNCH; k_gb_csr<<<cdiv(E, 256), 256, 0, st>>>(sc, E, S, eb, lb, u_dst, u_lo, g, e_src); }
+    // ---- B: Partners / PartnerCounts entries per site
+    GB_CU(cudaMemsetAsync(npt, 0, ((size_t)n2 + 4) * 4, st));
+    { SPL_LAUNCH; k_gb_pt_count<<<cdiv(n2, 128), 128, 0, st>>>(g, d_cnt, site_of, inc_eid, npt); }
+    sc.scan(npt, n2 + 2, d_cnt + 7, d_cnt + 2);
+    { SPL_LAUNCH; k_gb_pt_fill<<<cdiv(n2 + 1, 128), 128, 0, st>>>(g, d_cnt, site_of, inc_eid, npt, e_src); }
 
     // ---- D: competitors
-    { SPL_LAUNCH; k_gb_cand_count<<<cdiv(S, 256), 256, 0, st>>>(g, S, ncand); }
-    launch_exscan_u32(ncand, S, stmp, d_cnt + 3, st);
-    GB_CU(cudaGetLastError());
-    GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
-    GB_CU(cudaStreamSynchronize(st));
-    const uint32_t NCAND = m.h_cnt[3];
-    if ((uint64_t)NCAND >= ((uint64_t)1 << 31)) { err = "graph build: competitor candidate list exceeds 2^31"; return false; }
-    {
-        const uint32_t tiles = cdiv(NCAND, RS_TILE) + 1;
-        Carve c;
-        const size_t c_a = c.take<uint64_t>((size_t)NCAND + 2), c_b = c.take<uint64_t>((size_t)NCAND + 2), c_f = c.take<uint32_t>((size_t)NCAND + 2);
-        const size_t c_h = c.take<uint32_t>(256 * (size_t)tiles + 2), c_t = c.take<uint32_t>(exscan_tmp_words(256u * tiles) + exscan_tmp_words(NCAND + 2) + 8);
-        GB_CU(m.work2.reserve(c.off + 256));
-        char* cbp = (char*)m.work2.p;
-        uint64_t* da = (uint64_t*)(cbp + c_a); uint64_t* db = (uint64_t*)(cbp + c_b);
-        uint32_t* dflag = (uint32_t*)(cbp + c_f);
-        uint32_t* dtmp = (uint32_t*)(cbp + c_t) + exscan_tmp_words(256u * tiles) + 4;
-        Sorter ds{(uint32_t*)(cbp + c_h), (uint32_t*)(cbp + c_t), d_cnt + 5, st};
-        { SPL_LAUNCH; k_gb_cand_fill<<<cdiv(S, 256), 256, 0, st>>>(g, S, ncand, pb, da); }
-        uint64_t* sd = ds.sort(da, db, NCAND, 0, pb + sbits);
-        { SPL_LAUNCH; k_gb_cand_heads<<<cdiv(NCAND, 256), 256, 0, st>>>(sd, NCAND, pb, S, dflag); }
-        launch_exscan_u32(dflag, NCAND, dtmp, d_cnt + 4, st);
-        GB_CU(cudaGetLastError());
-        GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
-        GB_CU(cudaStreamSynchronize(st));
-        const uint32_t C = m.h_cnt[4];
-        Carve x;
-        const size_t x_cp = x.take<int32_t>((size_t)C + 1), x_sb = x.take<int32_t>((size_t)NB + 64);
-        GB_CU(m.fin2.reserve(x.off + 256));
-        g.cp_pos = (int32_t*)((char*)m.fin2.p + x_cp); g.sb_off = (int32_t*)((char*)m.fin2.p + x_sb);
-        GB_CU(cudaMemsetAsync(c1, 0, ((size_t)S + 1) * 4, st));           // cp_cnt
-        { SPL_LAUNCH; k_gb_comp<<<cdiv(NCAND, 256), 256, 0, st>>>(sd, dflag, NCAND, pb, S, g, c1); }
-        GB_CU(cudaMemcpyAsync(g.cp_off, c1, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
-        launch_exscan_u32((uint32_t*)g.cp_off, S, stmp, (uint32_t*)g.cp_off + S, st);
-        counts.C = C;
-    }
+    GB_CU(cudaMemsetAsync(ncp, 0, ((size_t)n2 + 4) * 4, st));
+    { SPL_LAUNCH; k_gb_cp_count<<<cdiv(n2, 128), 128, 0, st>>>(g, d_cnt, ncp); }
+    sc.scan(ncp, n2 + 2, d_cnt + 7, d_cnt + 4);
+    { SPL_LAUNCH; k_gb_cp_fill<<<cdiv(n2 + 1, 128), 128, 0, st>>>(g, d_cnt, ncp, (uint32_t)std::min<size_t>(m.cap_c, 0xffffffffu)); }
 
     // ---- E: reverse partners, hot flags, bin index
-    GB_CU(cudaMemsetAsync(c1, 0, ((size_t)S + 1) * 4, st));               // rp_cnt
-    GB_CU(cudaMemsetAsync(c2, 0, ((size_t)S + 1) * 4, st));               // rp_cur
-    { SPL_LAUNCH; k_gb_rp_count<<<cdiv(E, 256), 256, 0, st>>>(g, E, c1); }
-    GB_CU(cudaMemcpyAsync(g.rp_off, c1, (size_t)S * 4, cudaMemcpyDeviceToDevice, st));
-    launch_exscan_u32((uint32_t*)g.rp_off, S, stmp, (uint32_t*)g.rp_off + S, st);
-    { SPL_LAUNCH; k_gb_rp_fill<<<cdiv(E, 256), 256, 0, st>>>(g, E, e_src, c2); }
-    { SPL_LAUNCH; k_gb_sb_fill<<<cdiv(NB + 64, 256), 256, 0, st>>>(g, n_chrom, S, NB); }
-    { SPL_LAUNCH; k_gb_widen<<<cdiv(S + 1, 256), 256, 0, st>>>(g.pt_off, g.pt_off64, S + 1); }
-    { SPL_LAUNCH; k_gb_widen<<<cdiv(S + 1, 256), 256, 0, st>>>(g.cp_off, g.cp_off64, S + 1); }
+    GB_CU(cudaMemsetAsync(c1, 0, ((size_t)n2 + 4) * 4, st));               // rp_cnt
+    GB_CU(cudaMemsetAsync(c2, 0, ((size_t)n2 + 4) * 4, st));               // rp_cur
+    { SPL_LAUNCH; k_gb_rp_count<<<cdiv(n2, 256), 256, 0, st>>>(g, d_cnt, c1); }
+    sc.scan(c1, n2 + 2, d_cnt + 7, d_cnt + 5);
+    { SPL_LAUNCH; k_gb_rp_fill<<<cdiv(n2 + 2, 256), 256, 0, st>>>(g, d_cnt, e_src, c1, c2); }
+    { SPL_LAUNCH; k_gb_sb_fill<<<296, 256, 0, st>>>(g, n_chrom, d_cnt); }
     GB_CU(cudaGetLastError());
-    counts.S = S; counts.E = E; counts.NB = NB;
+    if (phase == 2) return true;                                           // timed rebuild of a table whose sizes are known
+
+    GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
+    GB_CU(cudaStreamSynchronize(st));
+    const uint32_t S = m.h_cnt[0], NB = m.h_cnt[1], E = m.h_cnt[2], C = m.h_cnt[4];
+    if (S == 0 || S > n2) { err = "graph build: bad site count"; return false; }
+    if (E == 0 || E > n2) { err = "graph build: bad edge count"; return false; }
+    if (NB != m.nb_host) { err = "graph build: bin index size mismatch"; return false; }
+    if (m.h_cnt[6]) {                                                      // more competitors than the array holds: once more with room
+        if ((size_t)C <= m.cap_c) { err = "graph build: inconsistent competitor overflow"; return false; }
+        m.cap_c = (size_t)C + 1024;
+        return graph_build_device(m, j_chrom, j_left, j_right, j_strand, j_score, n_junc, n_chrom, max_pos, stranded, stream, phase, g, counts, err);
+    }
+    counts.S = S; counts.E = E; counts.NB = NB; counts.C = C;
     return true;
 }
 

@@ -25,6 +25,10 @@ struct GbBuf {                       // grow-only device allocation
 struct GraphBuildMem {
     GbBuf fin, fin2, work, work2;    // final arrays (sized by J / by C and the bin count), workspaces
     uint32_t* h_cnt = nullptr;       // pinned, 16 words
+    uint32_t scan_epoch = 0;         // look-back scans: a new epoch per launch
+    uint32_t nb_host = 0;            // entries of the direct-address bin index (exact, from the junction table)
+    size_t cap_c = 0;                // capacity of the competitor array (checked on the device; grown and re-run when too small)
+    bool ready = false;              // phase 0 has run on these buffers
 };
 
 // writable view of the arrays DevGraph points at, plus what only the host-facing result needs
@@ -47,9 +51,10 @@ struct GraphCounts { uint32_t S = 0, E = 0, C = 0, NB = 0; double h2d_bytes = 0;
 // do the packed sort keys fit in 64 bits for a table of J rows?
 bool graph_build_fits(int64_t J, int32_t n_chrom, int32_t max_pos);
 
-// clean-regime build on `stream`; synchronises the stream a few times (array sizes).  false + err on failure.
+// clean-regime build on `stream`.  Phase 1 synchronises the stream ONCE, at the end, to read the table sizes; phase 2 runs
+// the same kernels without any host synchronisation (timed rebuild of a table whose sizes are known).  false + err on failure.
 bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right, const uint8_t* j_strand,
                         const int64_t* j_score, int64_t n_junc, int32_t n_chrom, int32_t max_pos, bool stranded, void* stream,
-                        int phase /* 0: allocate + upload the junction table, 1: build */, GraphDev& g, GraphCounts& counts, std::string& err);
+                        int phase /* 0: allocate + upload the junction table, 1: build + read sizes, 2: build only */, GraphDev& g, GraphCounts& counts, std::string& err);
 
 }  // namespace spl

@@ -654,7 +654,7 @@ k_beta1_stab(DevBins bins, DevGraph g, DevCounters cnt) {
     K3Smem& sm = *reinterpret_cast<K3Smem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
-        for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], PS_CONSUMERS / 32); }
+        for (int s = 0; s < PS_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], PS_CONSUMERS); }
     }
     __syncthreads();
     if (warp == PS_CONSUMERS / 32) {
@@ -710,8 +710,7 @@ k_beta1_stab(DevBins bins, DevGraph g, DevCounters cnt) {
         if (m.flags & PS_DONE) break;
         if (m.flags & PS_GLOBAL_SITES) k3_consume(sm.st[stage], m, g.site_pos, g, cnt);
         else k3_consume(sm.st[stage], m, sm.st[stage].sites - m.al, g, cnt);
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.empty[stage]);
+        mbar_arrive(&sm.empty[stage]);       // every consumer thread releases the stage itself (release / acquire with the producer's wait)
     }
 }
 
@@ -923,6 +922,7 @@ __global__ void __launch_bounds__(256) k_junc_pack(DevSoA soa, DevJunc jg) {
         const uint4 rr = jg.cx_rng[p];                                 // the owning read: junctions [x, y), blocks [z, w)
         const uint32_t nj = rr.y - rr.x, nb = rr.w - rr.z;
         uint32_t* o = jg.cx_pack + (size_t)i * CXP_WORDS;
+        for (int q = 0; q < CXP_WORDS; ++q) o[q] = 0u;                // the reader loads whole records
         if (nj > (uint32_t)CXP_MAXJ || nb > (uint32_t)CXP_MAXB) { o[0] = 0xffffffffu; o[21] = lo; continue; }    // walked through the SoA instead
         o[0] = nj | (nb << 8) | ((j - rr.x) << 16);
         for (uint32_t x = 0; x < nj; ++x) { o[1 + 2 * x] = soa.jn_l[rr.x + x]; o[2 + 2 * x] = soa.jn_rk[rr.x + x]; }

@@ -487,6 +487,7 @@ int upload_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int64_t r0,
 int expand_records(spl_ctx* ctx, Part& P, const spl_records_view* v, int64_t r0, int64_t r1, uint32_t flags) {
     CU(cudaStreamWaitEvent(ctx->stream, P.ev_up, 0));
     CU(P.d_tot.reserve(256));
+    CU(cudaMemsetAsync(P.d_tot.p, 0, 256, ctx->stream));
     // per-chromosome layout arrays of the bin-partitioned stream
     DevBins& bins = P.bins;
     bins = DevBins{};
@@ -1406,7 +1407,7 @@ int spl_resident_count(spl_ctx* ctx, int iters, double* stats_out) {
         if (regraph) {
             std::string e;
             if (!graph_build_device(ctx->gbm, nullptr, nullptr, nullptr, nullptr, nullptr, ctx->res_n_junc, ctx->res_n_chrom, ctx->res_max_pos,
-                                    ctx->res_stranded, ctx->stream, 1, ctx->gdev, ctx->gcnt, e))
+                                    ctx->res_stranded, ctx->stream, 2, ctx->gdev, ctx->gcnt, e))
                 return ctx->fail(SPL_ERR_CUDA, "%s", e.c_str());
             adopt_device_graph(ctx);
             int rc = alloc_counters_outputs(ctx, ctx->gcnt.S, ctx->gcnt.E);
