@@ -208,6 +208,7 @@ int spl_resident_fetch(spl_ctx* ctx, spl_result** out);
 #define SPL_STAT_N_PARTS      24   /* parts the record upload was cut into (1 or 2; 2 = expansion overlapped with the copy)  */
 #define SPL_STAT_GRAPH_DEVICE 22   /* 1 = site table + graph built on the device (clean regime), 0 = host emulation */
 #define SPL_STAT_MS_GRAPH_DEV 25   /* spl_resident_count: summed CUDA-event ms of the site table + graph build inside the timed passes */
+#define SPL_STAT_N_HOT_ITEMS  27   /* junction ends on hot sites queued for the exception kernel in the last pass (fused variant) */
 #define SPL_STAT_GRAPH_TIMED  26   /* spl_resident_count: 1 = every pass rebuilt the site table + graph (fused variant, clean regime) */
 int spl_last_stats(const spl_ctx* ctx, double* stats_out);
 

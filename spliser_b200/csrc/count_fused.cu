@@ -33,7 +33,7 @@ namespace {
 
 constexpr int FC_STAGES = 3;
 #ifndef SPL_FC_CWARPS
-#define SPL_FC_CWARPS 12
+#define SPL_FC_CWARPS 14
 #endif
 constexpr int FC_CWARPS = SPL_FC_CWARPS;
 constexpr int FC_CONSUMERS = FC_CWARPS * 32;
@@ -57,6 +57,7 @@ static_assert(sizeof(FStage) % 16 == 0 && ((FC_RECS + FC_RPAD) * 4) % 16 == 0 &&
 
 struct FMeta {
     uint32_t flags, n_rec, skip, cig_base;  // skip: staged index of the chunk's first record; cig_base: absolute index of staged word 0
+    uint32_t rec_lo;                        // absolute index of the chunk's first record
     int32_t  chrom, s0, s1, sb_g0, sb_nb;
 };
 
@@ -76,6 +77,10 @@ struct FArgs {
     DevCounters cnt;
     uint32_t* work;
     uint32_t mode;
+    uint4* hotq;             // global queue of hot (record, operator, side) items: {anchor, record, operator | side << 31, weight}
+    uint32_t* hot_n;         // [0] items written (may exceed hot_cap: the excess was dropped and the pass must be repeated with room)
+    uint32_t hot_cap;
+    uint32_t rec_base;       // (unused by the kernel; kept for symmetry with the item layout: records are absolute indices)
 };
 
 // +n on word `key` of the difference arrays for every run of neighbouring lanes with the same key (v: the lane takes part)
@@ -145,15 +150,15 @@ struct ReadWalk {            // any read: every access walks the CIGAR again (lo
 };
 
 // one hot (record, operator, side): find the sites the junction is a partner/competitor pair for and classify the read there
-template <bool STAGED>
-__device__ __noinline__ void hot_item(unsigned long long item, const FStage& st, const FMeta& m, const CigSrc<STAGED>& cw, const FArgs& A) {
-    const int anchor = (int)(uint32_t)(item >> 32);
-    const uint32_t lo = (uint32_t)item;
-    const uint32_t ri = lo >> 21, side = (lo >> 20) & 1u, j = lo & 0xfffffu;
-    const int32_t pos = st.pos[m.skip + ri];
-    const uint32_t c0 = st.off[m.skip + ri], nop = st.off[m.skip + ri + 1] - c0;
-    const uint32_t k = read_class(st.flag[m.skip + ri], A.mode);
-    const bool combine = (A.mode & FLAG_COMBINE) != 0;
+// (S:494-557).  Runs in k_hot_items, one thread per queued item, from the record arrays in global memory.
+__device__ __forceinline__ void hot_item(const DevRecords& rec, const DevGraph& g, const DevCounters& cnt, uint32_t mode, uint4 it) {
+    const int anchor = (int)it.x;
+    const uint32_t ri = it.y, side = it.z >> 31, j = it.z & 0x7fffffffu, wgt = it.w;
+    const int32_t pos = __ldg(rec.pos + ri);
+    const uint32_t c0 = __ldg(rec.cig_off + ri), nop = __ldg(rec.cig_off + ri + 1) - c0;
+    const uint32_t k = read_class(__ldg(rec.flag + ri), mode);
+    const bool combine = (mode & FLAG_COMBINE) != 0;
+    const CigSrc<false> cw{rec.cigar, 0u};
     ReadRegs rr;
     rr.nj = rr.nb = rr.jrel = 0;
     int32_t cur = pos, jl = 0, jr = 0;
@@ -172,26 +177,37 @@ __device__ __noinline__ void hot_item(unsigned long long item, const FStage& st,
             cur += len; seen = true;
         }
     }
-    const DevGraph& g = A.g;
     if (rr.nj <= (uint32_t)FC_MAXJ && rr.nb <= (uint32_t)FC_MAXB) {
         for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
             const int t = k4_pair_site(g, q, (int)side, jl, jr);
-            if (t >= 0) k4_classify(rr, g, A.cnt, t, k, combine);
+            if (t >= 0) k4_classify(rr, g, cnt, t, k, combine, wgt);
         }
     } else {
-        const ReadWalk<STAGED> rw{cw, c0, nop, pos, rr.nj, rr.nb, rr.jrel};
+        const ReadWalk<false> rw{cw, c0, nop, pos, rr.nj, rr.nb, rr.jrel};
         for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
             const int t = k4_pair_site(g, q, (int)side, jl, jr);
-            if (t >= 0) k4_classify(rw, g, A.cnt, t, k, combine);
+            if (t >= 0) k4_classify(rw, g, cnt, t, k, combine, wgt);
         }
     }
 }
 
-template <bool STAGED>
-__device__ __noinline__ void flush_list(const unsigned long long* list, uint32_t list_n, const FStage& st, const FMeta& m,
-                                        const CigSrc<STAGED>& cw, const FArgs& A) {
+__global__ void __launch_bounds__(256) k_hot_items(DevRecords rec, DevGraph g, DevCounters cnt, uint32_t mode, const uint4* __restrict__ hotq,
+                                                   const uint32_t* __restrict__ hot_n, uint32_t hot_cap) {
+    const uint32_t n = min(*hot_n, hot_cap);
+    for (uint32_t x = blockIdx.x * blockDim.x + threadIdx.x; x < n; x += gridDim.x * blockDim.x) hot_item(rec, g, cnt, mode, hotq[x]);
+}
+
+// the warp's list goes to the global queue: one reservation per flush
+__device__ __forceinline__ void flush_list(const unsigned long long* list, uint32_t list_n, uint32_t rec_lo, const FArgs& A, int lane) {
     __syncwarp();
-    for (uint32_t x = threadIdx.x & 31u; x < list_n; x += 32) hot_item<STAGED>(list[x], st, m, cw, A);
+    uint32_t base = 0;
+    if (lane == 0) base = atomicAdd(A.hot_n, list_n);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    for (uint32_t x = (uint32_t)lane; x < list_n; x += 32) {
+        const unsigned long long it = list[x];
+        const uint32_t lo = (uint32_t)it;
+        if (base + x < A.hot_cap) A.hotq[base + x] = make_uint4((uint32_t)(it >> 32), rec_lo + (lo >> 21), (lo & 0xfffffu) | (((lo >> 20) & 1u) << 31), 1u);
+    }
     __syncwarp();
 }
 
@@ -235,7 +251,7 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
     uint32_t list_n = 0;                                             // warp-uniform
     for (;;) {
         // a group pushes at most 4 entries per lane on the stab path (two junctions in FC_SLOTS operators)
-        if (list_n > (uint32_t)(FC_LIST - 128)) { flush_list<STAGED>(list, list_n, st, m, cw, A); list_n = 0; }
+        if (list_n > (uint32_t)(FC_LIST - 128)) { flush_list(list, list_n, m.rec_lo, A, lane); list_n = 0; }
         uint32_t gi = 0;
         if (lane == 0) gi = atomicAdd(next_group, 1u);
         gi = __shfl_sync(0xffffffffu, gi, 0);
@@ -308,8 +324,10 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                         }
                     }
                     // one list entry carries one operator index: the two ends of a lane at this site belong to different operators
-                    push_hot(list, list_n, hl, 0u, i, jl, lane);
-                    push_hot(list, list_n, 0u, hr, i, jr, lane);
+                    if (__any_sync(0xffffffffu, (hl | hr) != 0u)) {
+                        push_hot(list, list_n, hl, 0u, i, jl, lane);
+                        push_hot(list, list_n, 0u, hr, i, jr, lane);
+                    }
                 }
             }
             j0 = FC_SLOTS;
@@ -323,7 +341,7 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
         const uint32_t maxrem = __reduce_max_sync(0xffffffffu, rem);
         int idx = act ? bin_lower(g, m, cur, s0) : s0;               // first site with position >= cur, carried along the read
         for (uint32_t t = 0; t < maxrem; ++t) {
-            if (list_n > (uint32_t)(FC_LIST - 64)) { flush_list<STAGED>(list, list_n, st, m, cw, A); list_n = 0; }   // rare path
+            if (list_n > (uint32_t)(FC_LIST - 64)) { flush_list(list, list_n, m.rec_lo, A, lane); list_n = 0; }
             const uint32_t j = j0 + t;
             const uint32_t w = t < rem ? cw(c0 + j) : 5u;
             const uint32_t op = w & 15u;
@@ -365,7 +383,7 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
             if (adv) { cur += len; idx = inx; }
         }
     }
-    if (list_n) flush_list<STAGED>(list, list_n, st, m, cw, A);
+    if (list_n) flush_list(list, list_n, m.rec_lo, A, lane);
 }
 
 __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_constant__ FArgs A) {
@@ -421,7 +439,7 @@ __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_cons
                 mbar_wait_backoff(&sm.empty[stage], parity ^ 1u);
                 FMeta& m = sm.meta[stage];
                 m.flags = staged ? 0u : FM_GLOBAL_CIG; m.n_rec = rec_hi - rec_lo; m.skip = rec_lo - a0; m.cig_base = ca;
-                m.chrom = chrom; m.s0 = s0; m.s1 = s1; m.sb_g0 = sb_g0; m.sb_nb = sb_nb;
+                m.rec_lo = rec_lo; m.chrom = chrom; m.s0 = s0; m.s1 = s1; m.sb_g0 = sb_g0; m.sb_nb = sb_nb;
                 sm.next_group[stage] = 0u;
                 FStage& st = sm.st[stage];
                 mbar_expect_tx(&sm.full[stage], nr * 4u + noff * 4u + nr * 2u + (staged ? nw * 4u : 0u));
@@ -489,13 +507,20 @@ void launch_chunk_bounds(FChunk* chunks, uint32_t lo, uint32_t hi, const uint32_
     if (hi > lo) { SPL_LAUNCH; k_chunk_bounds<<<(hi - lo + 255) / 256, 256, 0, (cudaStream_t)stream>>>(chunks, lo, hi, cig_off, g); }
 }
 
-// `work` points at a zeroed u32 (the chunk counter of this launch)
+// `work` points at a zeroed u32 (the chunk counter of this launch); hot items are appended to hotq (hot_n counts them)
 void launch_count_fused(const DevRecords& rec, const FChunk* chunks, uint32_t lo, uint32_t hi, DevGraph g, DevCounters cnt,
-                        uint32_t* work, uint32_t flags, void* stream) {
+                        uint32_t* work, uint32_t flags, uint4* hotq, uint32_t* hot_n, uint32_t hot_cap, void* stream) {
     if (hi <= lo || g.n_sites <= 0) return;
-    FArgs a{rec, chunks, lo, hi, g, cnt, work, flags};
+    FArgs a{rec, chunks, lo, hi, g, cnt, work, flags, hotq, hot_n, hot_cap, 0u};
     const int grid = (int)min((uint32_t)fused_grid(), (hi - lo + (uint32_t)FC_BATCH - 1u) / (uint32_t)FC_BATCH);
     { SPL_LAUNCH; k_count_fused<<<grid, FC_THREADS, sizeof(FSmem), (cudaStream_t)stream>>>(a); }
+}
+
+// the queued hot items of every slab, after the counting kernels: one thread per item
+void launch_hot_items(const DevRecords& rec, DevGraph g, DevCounters cnt, uint32_t flags, const uint4* hotq, const uint32_t* hot_n,
+                      uint32_t hot_cap, void* stream) {
+    if (g.n_sites <= 0 || hot_cap == 0) return;
+    { SPL_LAUNCH; k_hot_items<<<sm_count_current_device() * 8, 256, 0, (cudaStream_t)stream>>>(rec, g, cnt, flags, hotq, hot_n, hot_cap); }
 }
 
 }  // namespace spl

@@ -3,6 +3,8 @@
 #include <atomic>
 #include <cstdint>
 
+#include <vector_types.h>
+
 namespace spl {
 
 // every kernel launch of the library is counted (bench.py reports the launches inside its timed region)
@@ -207,7 +209,9 @@ uint32_t exscan_tmp_words(uint32_t n);
 // fused difference-array variant (count_fused.cu)
 void launch_chunk_bounds(FChunk* chunks, uint32_t lo, uint32_t hi, const uint32_t* cig_off, DevGraph g, void* stream);
 void launch_count_fused(const DevRecords& rec, const FChunk* chunks, uint32_t lo, uint32_t hi, DevGraph g, DevCounters cnt,
-                        uint32_t* work, uint32_t flags, void* stream);
+                        uint32_t* work, uint32_t flags, uint4* hotq, uint32_t* hot_n, uint32_t hot_cap, void* stream);
+void launch_hot_items(const DevRecords& rec, DevGraph g, DevCounters cnt, uint32_t flags, const uint4* hotq, const uint32_t* hot_n,
+                      uint32_t hot_cap, void* stream);
 int  sm_count_current_device();
 
 }  // namespace spl

@@ -186,7 +186,9 @@ struct spl_ctx {
     double stats[SPL_NSTATS] = {0};
 
     // fused variant (count_fused.cu)
-    DevBuf d_frec, d_fchunks;
+    DevBuf d_frec, d_fchunks, d_hotq;
+    uint32_t hot_cap = 0;           // items the global hot queue holds; a pass that needs more is repeated with room
+    uint32_t* h_hot = nullptr;      // pinned: hot item count of the last pass
     void* h_fchunks = nullptr;
     size_t h_fchunks_bytes = 0;
     DevRecords frec{};
@@ -373,7 +375,7 @@ int alloc_counters_outputs(spl_ctx* ctx, size_t S, size_t E) {
     Carver cc;
     const size_t c_diff = cc.take<uint32_t>(4 * (S + 1) + 4), c_dir = cc.take<uint32_t>(4 * (S + 1) + 4), c_cov = cc.take<uint32_t>(2 * S + 2);
     const size_t c_covx = cc.take<uint32_t>(S + 1), c_spanx = cc.take<uint32_t>(S + 1), c_flank = cc.take<uint32_t>(S + 1);
-    const size_t c_dc = cc.take<uint32_t>(E + 1), c_work = cc.take<uint32_t>(16);
+    const size_t c_dc = cc.take<uint32_t>(E + 1), c_work = cc.take<uint32_t>(32);
     ctx->cnt_bytes = cc.off + 256;
     CU(ctx->d_cnt.reserve(ctx->cnt_bytes));
     char* cb = (char*)ctx->d_cnt.p;
@@ -672,6 +674,14 @@ int fused_upload(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom, bool 
         CU(cudaMemcpyAsync(ctx->fchunks, ctx->h_fchunks, bytes, cudaMemcpyHostToDevice, cs));
         ctx->stats[SPL_STAT_H2D_BYTES] += (double)bytes;
     }
+    {   // global queue of hot items (count_fused.cu): sized for the usual share, grown when a pass overflows it
+        const uint64_t want = std::max<uint64_t>(1u << 18, (uint64_t)v->n_cigar / 16 + (1u << 16));
+        if (ctx->hot_cap < want) {
+            CU(ctx->d_hotq.reserve((size_t)want * 16));
+            ctx->hot_cap = (uint32_t)std::min<uint64_t>(want, 0xfffffff0u);
+        }
+        *ctx->h_hot = 0;
+    }
     ctx->n_fparts = 1;
     ctx->fpart[0].chunk_lo = 0; ctx->fpart[0].chunk_hi = ctx->n_fchunks;
     if (dev) {
@@ -724,13 +734,18 @@ int fused_count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     if (ev) CU(cudaEventRecord(ev[0], ctx->stream));
     if (ctx->g.n_sites > 0) CU(cudaMemsetAsync(ctx->d_cnt.p, 0, ctx->cnt_bytes, ctx->stream));
     if (ev) CU(cudaEventRecord(ev[1], ctx->stream));
+    uint32_t* hot_n = ctx->cnt.work + 24;
     for (int p = 0; p < ctx->n_fparts; ++p) {
         const FPart& P = ctx->fpart[p];
         CU(cudaStreamWaitEvent(ctx->stream, P.ev_up, 0));
         launch_chunk_bounds(ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->frec.cig_off, ctx->g, ctx->stream);
-        launch_count_fused(ctx->frec, ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->g, ctx->cnt, ctx->cnt.work + 8 + p, ctx->flags, ctx->stream);
+        launch_count_fused(ctx->frec, ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->g, ctx->cnt, ctx->cnt.work + 8 + p, ctx->flags,
+                           (uint4*)ctx->d_hotq.p, hot_n, ctx->hot_cap, ctx->stream);
     }
-    if (ev) { CU(cudaEventRecord(ev[2], ctx->stream)); CU(cudaEventRecord(ev[3], ctx->stream)); }
+    if (ev) CU(cudaEventRecord(ev[2], ctx->stream));
+    if (ctx->n_fchunks) launch_hot_items(ctx->frec, ctx->g, ctx->cnt, ctx->flags, (const uint4*)ctx->d_hotq.p, hot_n, ctx->hot_cap, ctx->stream);
+    if (ctx->g.n_sites > 0) CU(cudaMemcpyAsync(ctx->h_hot, hot_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ev) CU(cudaEventRecord(ev[3], ctx->stream));
     launch_finalize(ctx->g, ctx->cnt, ctx->out, ctx->flags, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[4], ctx->stream));
     CU(cudaGetLastError());
@@ -755,6 +770,22 @@ int count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     launch_finalize(ctx->g, ctx->cnt, ctx->out, ctx->flags, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[4], ctx->stream));
     CU(cudaGetLastError());
+    return SPL_OK;
+}
+
+// after a stream sync that follows a fused pass: did the hot queue hold every item?  If not, it is grown and the caller
+// repeats the pass (counters are re-zeroed by the pass itself).
+int hot_queue_overflow(spl_ctx* ctx, bool* again) {
+    *again = false;
+    if (ctx->loaded_variant != SPL_VARIANT_FUSED || ctx->g.n_sites <= 0) return SPL_OK;
+    const uint32_t n = *ctx->h_hot;
+    ctx->stats[SPL_STAT_N_HOT_ITEMS] = (double)n;
+    if (n <= ctx->hot_cap) return SPL_OK;
+    const uint64_t want = (uint64_t)n + (n >> 3) + 1024;
+    if (want >= 0xfffffff0ull) return ctx->fail(SPL_ERR_RANGE, "more than 2^32 hot junction items in one call");
+    CU(ctx->d_hotq.reserve((size_t)want * 16));
+    ctx->hot_cap = (uint32_t)want;
+    *again = true;
     return SPL_OK;
 }
 
@@ -1145,6 +1176,8 @@ int spl_create(spl_ctx** out, const int* device_ids, int n_devices) {
         CU(cudaEventCreate(&ctx->part[p].ev_e0)); CU(cudaEventCreate(&ctx->part[p].ev_e1));
     }
     for (int p = 0; p < MAX_FPARTS; ++p) CU(cudaEventCreateWithFlags(&ctx->fpart[p].ev_up, cudaEventDisableTiming));
+    CU(cudaHostAlloc((void**)&ctx->h_hot, 64, cudaHostAllocDefault));
+    *ctx->h_hot = 0;
     CU(cudaHostAlloc((void**)&ctx->gbm.h_cnt, 256, cudaHostAllocDefault));
     return SPL_OK;
 }
@@ -1165,7 +1198,8 @@ void spl_destroy(spl_ctx* ctx) {
             if (ctx->part[p].ev_e1) cudaEventDestroy(ctx->part[p].ev_e1);
         }
         if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-        ctx->d_frec.release(); ctx->d_fchunks.release();
+        ctx->d_frec.release(); ctx->d_fchunks.release(); ctx->d_hotq.release();
+        if (ctx->h_hot) cudaFreeHost(ctx->h_hot);
         if (ctx->h_fchunks) cudaFreeHost(ctx->h_fchunks);
         for (int p = 0; p < MAX_FPARTS; ++p) if (ctx->fpart[p].ev_up) cudaEventDestroy(ctx->fpart[p].ev_up);
         if (ctx->gbm.h_cnt) cudaFreeHost(ctx->gbm.h_cnt);
@@ -1232,9 +1266,17 @@ int spl_process_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
     int rc = load_common(ctx, rec, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, true);
     if (rc) return drain_on_error(ctx, rc);
     const double tc0 = now_ms();
-    rc = count_pass(ctx, nullptr);
-    if (rc) return drain_on_error(ctx, rc);
-    rc = drain_on_error(ctx, fetch(ctx, out));
+    for (;;) {
+        rc = count_pass(ctx, nullptr);
+        if (rc) return drain_on_error(ctx, rc);
+        rc = drain_on_error(ctx, fetch(ctx, out));
+        if (rc) return rc;
+        bool again = false;
+        rc = hot_queue_overflow(ctx, &again);
+        if (rc) { spl_result_free(*out); *out = nullptr; return rc; }
+        if (!again) break;
+        spl_result_free(*out); *out = nullptr;
+    }
     collect_expand_ms(ctx);
     ctx->stats[SPL_STAT_MS_COUNT] = now_ms() - tc0;
     ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
@@ -1314,15 +1356,21 @@ int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
         const int prc = prepare_parts(ctx);
         if (prc) return drain_on_error(ctx, prc);
     }
-    rc = count_pass(ctx, nullptr);
-    if (rc) return drain_on_error(ctx, rc);
     const size_t S = (size_t)ctx->hg.n_sites;
     std::vector<int64_t> b1(S), b2(S);
-    if (S) {
-        CU(cudaMemcpyAsync(b1.data(), ctx->out.beta1, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
-        CU(cudaMemcpyAsync(b2.data(), ctx->out.beta2s, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    for (;;) {
+        rc = count_pass(ctx, nullptr);
+        if (rc) return drain_on_error(ctx, rc);
+        if (S) {
+            CU(cudaMemcpyAsync(b1.data(), ctx->out.beta1, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+            CU(cudaMemcpyAsync(b2.data(), ctx->out.beta2s, S * 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+        CU(cudaStreamSynchronize(ctx->stream));
+        bool again = false;
+        rc = hot_queue_overflow(ctx, &again);
+        if (rc) return rc;
+        if (!again) break;
     }
-    CU(cudaStreamSynchronize(ctx->stream));
     collect_expand_ms(ctx);
     for (int64_t i = 0; i < n_sites; ++i) { beta1_out[i] = 0; beta2simple_out[i] = 0; }
     for (size_t k = 0; k < S; ++k) {
@@ -1400,6 +1448,7 @@ int spl_resident_count(spl_ctx* ctx, int iters, double* stats_out) {
     // resident junction table (K1), counters zeroed, counting kernel, prefix scan + beta2 gather + SSE.  (The stabbing
     // variant times its counting pass over the layout prepared at load time; the dirty regime keeps its host-built graph.)
     const bool regraph = ctx->loaded_variant == SPL_VARIANT_FUSED && ctx->res_clean && ctx->graph_on_device;
+    for (int attempt = 0;; ++attempt) {
     const unsigned long long launches0 = g_kernel_launches.load();
     for (int it = 0; it < iters; ++it) {
         cudaEvent_t* ev = ctx->events.data() + (size_t)it * 6;
@@ -1417,6 +1466,12 @@ int spl_resident_count(spl_ctx* ctx, int iters, double* stats_out) {
         if (rc) return rc;
     }
     CU(cudaStreamSynchronize(ctx->stream));
+    {
+        bool again = false;
+        const int orc = hot_queue_overflow(ctx, &again);
+        if (orc) return orc;
+        if (again && attempt < 4) continue;
+    }
     float total = 0, b1 = 0, sp = 0, fin = 0, gr = 0;
     CU(cudaEventElapsedTime(&total, ctx->events[5], ctx->events[(size_t)(iters - 1) * 6 + 4]));
     for (int it = 0; it < iters; ++it) {
@@ -1432,6 +1487,8 @@ int spl_resident_count(spl_ctx* ctx, int iters, double* stats_out) {
     ctx->stats[SPL_STAT_MS_GRAPH_DEV] = gr;
     ctx->stats[SPL_STAT_GRAPH_TIMED] = regraph ? 1.0 : 0.0;
     ctx->stats[SPL_STAT_LAUNCHES] = (double)(g_kernel_launches.load() - launches0) / (double)iters;   // kernels launched per timed pass (counted)
+    break;
+    }
     if (stats_out) memcpy(stats_out, ctx->stats, sizeof ctx->stats);
     return SPL_OK;
 }
