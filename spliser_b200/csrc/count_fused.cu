@@ -264,6 +264,7 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
         int32_t b[FC_SLOTS + 1];
         uint32_t tM = 0, tN = 0;                                     // bit j: operator j is M/=/X (S:457-459) / N (S:480-483)
         bool odd = false;                                            // zero-length M / N, more than two N: left to the chain path
+        uint32_t nslot = 0;
         {
             uint32_t c0 = 0;
             if (live) {
@@ -273,15 +274,19 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                 k = read_class(st.flag[m.skip + i], A.mode);
             }
             b[0] = pos;
+            nslot = min(__reduce_max_sync(0xffffffffu, nop), (uint32_t)FC_SLOTS);   // warp-uniform: operators anybody in the group has
 #pragma unroll
             for (int j = 0; j < FC_SLOTS; ++j) {
-                const uint32_t w = (uint32_t)j < nop ? cw(c0 + j) : 5u;  // filler: a zero-length H (no progression)
-                const uint32_t op = w & 15u;
-                const int32_t len = (int32_t)(w >> 4);
-                const uint32_t isM = (0x181u >> op) & 1u, isN = (0x008u >> op) & 1u, adv = (0x18du >> op) & 1u;   // + D: advance only (S:460-462)
-                tM |= isM << j; tN |= isN << j;
-                odd |= ((isM | isN) != 0u) && len == 0;
-                b[j + 1] = b[j] + (adv ? len : 0);
+                b[j + 1] = b[j];
+                if ((uint32_t)j < nslot) {                           // uniform
+                    const uint32_t w = (uint32_t)j < nop ? cw(c0 + j) : 5u;  // filler: a zero-length H (no progression)
+                    const uint32_t op = w & 15u;
+                    const int32_t len = (int32_t)(w >> 4);
+                    const uint32_t isM = (0x181u >> op) & 1u, isN = (0x008u >> op) & 1u, adv = (0x18du >> op) & 1u;   // + D: advance only (S:460-462)
+                    tM |= isM << j; tN |= isN << j;
+                    odd |= ((isM | isN) != 0u) && len == 0;
+                    if (adv) b[j + 1] += len;
+                }
             }
             odd |= __popc(tN) > 2;
         }
@@ -301,20 +306,21 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
         bool act = has;
         int32_t cur = pos;
         if (!wide) {
-            for (int q = 0; q < nw; ++q) {                           // warp-uniform
+            const uint32_t incM = 1u << (8u * k), incN = 0x10000u << (8u * k);   // byte fields of the redux word: cov class 0 / 1, span class 0 / 1
+            uint32_t mine = 0;                                       // lane q keeps the warp's sums for the q-th site of the window
+            uint32_t hot_run = hotmask >> d;
+            for (int q = 0; q < nw; ++q, hot_run >>= 1) {            // warp-uniform
                 const int32_t p = __shfl_sync(0xffffffffu, v, d + q);
                 const int32_t p1 = p + 1;
-                const int s = ib + d + q;
                 uint32_t hm = 0;                                     // operator that stabs p: b[j] <= p <= b[j+1] - 2 (S:469 / S:507)
 #pragma unroll
-                for (int j = 0; j < FC_SLOTS; ++j) hm |= (p >= b[j] && p1 < b[j + 1]) ? (1u << j) : 0u;
-                uint32_t c = (((hm & tM) ? 1u : 0u) | ((hm & tN) ? 0x10000u : 0u)) << (8u * k);   // byte fields: cov class 0 / 1, span class 0 / 1
+                for (int j = 0; j < FC_SLOTS; ++j)
+                    if ((uint32_t)j < nslot) { if (p >= b[j] && p1 < b[j + 1]) hm |= 1u << j; }
+                uint32_t c = ((hm & tM) ? incM : 0u) + ((hm & tN) ? incN : 0u);
                 c = __reduce_add_sync(0xffffffffu, c);
-                if (c && s >= own_lo && s < own_hi && lane < 4) {
-                    const uint32_t f = (c >> (8 * lane)) & 0xffu;
-                    if (f) atomicAdd(A.cnt.dir + 4 * s + lane, f);
-                }
-                if ((hotmask >> (d + q)) & 1u) {                     // an anchor: junction ends of the lanes that sit on it (S:494-501)
+                if (lane == q) mine = c;
+                if (hot_run & 1u) {                                  // an anchor: junction ends of the lanes that sit on it (S:494-501)
+                    const int s = ib + d + q;
                     uint32_t hl = 0, hr = 0, jl = 0, jr = 0;
 #pragma unroll
                     for (int j = 0; j < FC_SLOTS; ++j) {
@@ -329,6 +335,15 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                         push_hot(list, list_n, 0u, hr, i, jr, lane);
                     }
                 }
+            }
+            // one lane per site of the window adds the warp's sums to the direct counters (up to four kinds)
+            const int sm_ = ib + d + lane;
+            if (mine && lane < nw && sm_ >= own_lo && sm_ < own_hi) {
+                uint32_t* dst = A.cnt.dir + 4 * sm_;
+                if (mine & 0xffu) atomicAdd(dst, mine & 0xffu);
+                if (mine & 0xff00u) atomicAdd(dst + 1, (mine >> 8) & 0xffu);
+                if (mine & 0xff0000u) atomicAdd(dst + 2, (mine >> 16) & 0xffu);
+                if (mine >> 24) atomicAdd(dst + 3, mine >> 24);
             }
             j0 = FC_SLOTS;
             act = live && nop > (uint32_t)FC_SLOTS;
