@@ -399,19 +399,26 @@ def main():
         b[:] = a
         pinned[k] = b
     pr = Records(pinned["pos"], pinned["flag"], pinned["cig_off"], pinned["cigar"], r.seg_chrom, r.seg_off)
-    ctx.process_records(pr, n_chrom, w.junctions, w.flags)       # warm-up (allocations)
-    barrier()
-    e2e_t = []
-    stats = None
-    table = None
-    for _ in range(max(1, args.e2e_steps)):
-        table = None                     # the previous sample's result is released before the next call (its pinned arena is reused)
+    pk = api.PackedRecords.from_records(pr, alloc=pinned_empty)      # the packed host layout (17 B per record), page-locked; shares nothing with pr but the segments
+    pk.cigar = pr.cigar                                              # (the CIGAR array is the same in both layouts)
+
+    def timed_calls(fn):
+        fn()                                                         # warm-up (allocations)
         barrier()
-        a = time.perf_counter()
-        table = ctx.process_records(pr, n_chrom, w.junctions, w.flags)
-        e2e_t.append(time.perf_counter() - a)
-        stats = ctx.stats()
-    e2e_step = max_over_ranks(float(np.mean(e2e_t)))
+        ts, st_, tab = [], None, None
+        for _ in range(max(1, args.e2e_steps)):
+            tab = None                   # the previous sample's result is released before the next call (its pinned arena is reused)
+            barrier()
+            a = time.perf_counter()
+            tab = fn()
+            ts.append(time.perf_counter() - a)
+            st_ = ctx.stats()
+        return max_over_ranks(float(np.mean(ts))), st_, tab
+
+    plain_step, plain_stats, table = timed_calls(lambda: ctx.process_records(pr, n_chrom, w.junctions, w.flags))
+    plain_digest = table_digest(table)
+    table = None
+    e2e_step, stats, table = timed_calls(lambda: ctx.process_packed(pk, n_chrom, w.junctions, w.flags))
     e2e_val = reads_all / e2e_step
     clocks = sampler.window(t_load, time.time())
     clocks["window"] = "warm-up + timed passes + e2e calls"
@@ -436,8 +443,10 @@ def main():
                 "ms_per_step": 1e3 * e2e_step, "parts": int(stats["n_parts"]),
                 "breakdown_ms": {k: round(stats[k], 3) for k in ("ms_total", "ms_graph", "ms_upload", "ms_count")},
                 "graph_on_device": bool(stats["graph_on_device"]),
-                "note": "host wall clock around spl_process_records: junction table -> site table + graph (device), pinned H2D of the records in slabs with the counting "
-                        "kernel of a slab under the copy of the next, finalize, D2H of the table"},
+                "note": "host wall clock around spl_process_packed (17 B per record on the wire): junction table -> site table + graph (device), pinned H2D of the records in "
+                        "slabs with the unpack + counting kernels of a slab under the copy of the next, finalize, D2H of the table",
+                "plain_view": {"ms_per_step": 1e3 * plain_step, "h2d_bytes_per_step": int(plain_stats["h2d_bytes"]), "identical_table": plain_digest == table_digest(table),
+                               "note": "the same through spl_process_records (20 B per record: POS i32, FLAG u16, cig_off u32, CIGAR words)"}},
         "gpu_launches": int(round(st["launches"] * args.steps)),
         "launches_per_step": st["launches"],
         "roofline": {"bound": "hbm", "kernel": "k_count_fused", "achieved": k_gbs, "peak": peak, "unit": "GB/s",

@@ -33,6 +33,11 @@ class RecordsView(C.Structure):
                 ("seg_off", c_i64p)]
 
 
+class PackedView(C.Structure):
+    _fields_ = [("n_rec", C.c_int64), ("n_cigar", C.c_int64), ("pos", c_i32p), ("flag8", c_u8p), ("n_op", c_u16p),
+                ("cigar", c_u32p), ("cig_index", c_u32p), ("n_seg", C.c_int32), ("seg_chrom", c_i32p), ("seg_off", c_i64p)]
+
+
 class StrTab(C.Structure):
     _fields_ = [("n", C.c_int64), ("blob", C.c_char_p), ("off", c_i64p)]
 
@@ -61,6 +66,7 @@ SIGNATURES = {
     "spl_last_stats": (C.c_int, [C.c_void_p, c_f64p]),
     "spl_process": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, c_strp] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),
     "spl_process_records": (C.c_int, [C.c_void_p, C.POINTER(RecordsView), C.c_int32] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),
+    "spl_process_packed": (C.c_int, [C.c_void_p, C.POINTER(PackedView), C.c_int32] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),
     "spl_recount": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, c_strp] + _GAPS + [C.c_uint32, c_i64p, c_i64p]),
     "spl_recount_records": (C.c_int, [C.c_void_p, C.POINTER(RecordsView), C.c_int32] + _GAPS + [C.c_uint32, c_i64p, c_i64p]),
     "spl_build_site_table": (C.c_int, [C.c_int32] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),

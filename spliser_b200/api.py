@@ -163,6 +163,57 @@ class Records:
             raise IOError("spl_write_bam(%s) failed with %d" % (path, rc))
 
 
+PACKED_INDEX_STRIDE = 1024
+
+
+class PackedRecords:
+    """The packed host layout of spl_process_packed (spl_packed_view): POS, three flag bits, operator count and a sparse
+    CIGAR index -- 17 bytes per record on the wire instead of 20.  `alloc` = a function (n, dtype) -> array, e.g.
+    api.pinned_empty for page-locked columns."""
+
+    def __init__(self, pos, flag8, n_op, cigar, cig_index, seg_chrom, seg_off):
+        self.pos = np.ascontiguousarray(pos, dtype=np.int32)
+        self.flag8 = np.ascontiguousarray(flag8, dtype=np.uint8)
+        self.n_op = np.ascontiguousarray(n_op, dtype=np.uint16)
+        self.cigar = np.ascontiguousarray(cigar, dtype=np.uint32)
+        self.cig_index = np.ascontiguousarray(cig_index, dtype=np.uint32)
+        self.seg_chrom = np.ascontiguousarray(seg_chrom, dtype=np.int32)
+        self.seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.pos)
+
+    @classmethod
+    def from_records(cls, r: "Records", alloc=None):
+        nop = np.diff(r.cig_off.astype(np.int64))
+        if len(nop) and int(nop.max()) > 65535:
+            raise ValueError("a record has more than 65535 CIGAR operators: use the plain Records view")
+        f = r.flag
+        flag8 = ((f & 1) | (((f >> 4) & 1) << 1) | (((f >> 6) & 1) << 2)).astype(np.uint8)
+        index = np.concatenate([r.cig_off[::PACKED_INDEX_STRIDE], r.cig_off[-1:]]).astype(np.uint32)
+        cols = dict(pos=r.pos, flag8=flag8, n_op=nop.astype(np.uint16), cigar=r.cigar, cig_index=index)
+        if alloc is not None:
+            for k, a in list(cols.items()):
+                b = alloc(len(a), a.dtype)
+                b[:] = a
+                cols[k] = b
+        return cls(cols["pos"], cols["flag8"], cols["n_op"], cols["cigar"], cols["cig_index"], r.seg_chrom, r.seg_off)
+
+    def view(self) -> L.PackedView:
+        v = L.PackedView()
+        v.n_rec = len(self.pos)
+        v.n_cigar = len(self.cigar)
+        v.pos = _ptr(self.pos, L.c_i32p)
+        v.flag8 = _ptr(self.flag8, L.c_u8p)
+        v.n_op = _ptr(self.n_op, L.c_u16p)
+        v.cigar = _ptr(self.cigar, L.c_u32p)
+        v.cig_index = _ptr(self.cig_index, L.c_u32p)
+        v.n_seg = len(self.seg_chrom)
+        v.seg_chrom = _ptr(self.seg_chrom, L.c_i32p)
+        v.seg_off = _ptr(self.seg_off, L.c_i64p)
+        return v
+
+
 @dataclass
 class GapTable:
     """The (site, sample) gaps of one sample for `combine`'s re-count (S:899-904) in the argument layout of
@@ -357,6 +408,13 @@ class Context:
         h = C.c_void_p()
         rc = self._lib.spl_process_records(self._h, C.byref(v), n_chrom, *junctions.args(), flags, C.byref(h))
         self._check(rc, "spl_process_records")
+        return self._take(h)
+
+    def process_packed(self, records: "PackedRecords", n_chrom: int, junctions: Junctions, flags: int) -> SiteTable:
+        v = records.view()
+        h = C.c_void_p()
+        rc = self._lib.spl_process_packed(self._h, C.byref(v), n_chrom, *junctions.args(), flags, C.byref(h))
+        self._check(rc, "spl_process_packed")
         return self._take(h)
 
     def process_bam(self, bam_path, chrom_names, junctions: Junctions, flags: int) -> SiteTable:

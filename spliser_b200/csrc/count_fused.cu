@@ -500,6 +500,70 @@ __global__ void k_chunk_bounds(FChunk* chunks, uint32_t lo, uint32_t hi, const u
     chunks[i] = c;
 }
 
+// ---- packed host layout -> the arrays the counting kernel stages (spl_process_packed) -------------------------------
+// Per record the packed view carries POS, three flag bits and the operator count; the CIGAR offsets are rebuilt here by a
+// single-pass exclusive scan (decoupled look-back: tiles take tickets, publish epoch | flag | value in one 64-bit word), and
+// the flag bits are put back where check_strand expects them (S:374-406).
+constexpr int UP_THREADS = 256, UP_ITEMS = 8, UP_TILE = UP_THREADS * UP_ITEMS;
+__global__ void __launch_bounds__(UP_THREADS)
+k_unpack_records(const uint16_t* __restrict__ n_op, const uint8_t* __restrict__ flag8, uint32_t r0, uint32_t r1, uint32_t cig_base,
+                 uint32_t* __restrict__ cig_off, uint16_t* __restrict__ flag16, unsigned long long* __restrict__ desc,
+                 uint32_t* __restrict__ ticket, uint32_t epoch) {
+    __shared__ uint32_t s_tile, s_prev, wsum[UP_THREADS / 32];
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t t = s_tile;
+    const uint32_t base = r0 + t * UP_TILE + threadIdx.x * UP_ITEMS;
+    uint32_t v[UP_ITEMS], sum = 0;
+#pragma unroll
+    for (int q = 0; q < UP_ITEMS; ++q) {
+        v[q] = 0;
+        if (base + q < r1) {
+            v[q] = n_op[base + q];
+            const uint32_t f = flag8[base + q];
+            flag16[base + q] = (uint16_t)((f & 1u) | ((f & 2u) << 3) | ((f & 4u) << 4));      // 0x1 paired, 0x10 reverse, 0x40 first in pair
+        }
+        sum += v[q];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < UP_THREADS / 32; ++w) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
+    if (threadIdx.x == 0) {
+        const unsigned long long tag = (unsigned long long)epoch << 34;
+        volatile unsigned long long* d = desc;
+        uint32_t prev = 0;
+        if (t == 0) {
+            d[0] = tag | (2ull << 32) | total;
+        } else {
+            d[t] = tag | (1ull << 32) | total;
+            for (uint32_t p = t - 1;;) {
+                const unsigned long long w = d[p];
+                if ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0ull) continue;          // not published yet
+                prev += (uint32_t)w;
+                if (((w >> 32) & 3ull) == 2ull) break;
+                --p;
+            }
+            d[t] = tag | (2ull << 32) | (prev + total);
+        }
+        s_prev = prev;
+        if (t == gridDim.x - 1) *ticket = 0u;                           // every ticket of this launch has been handed out
+    }
+    __syncthreads();
+    uint32_t run = cig_base + s_prev + wbase + inc - sum;
+#pragma unroll
+    for (int q = 0; q < UP_ITEMS; ++q) {
+        if (base + q < r1) cig_off[base + q] = run;
+        run += v[q];
+        if (base + q + 1 == r1) cig_off[r1] = run;                      // the slab's end offset (the next slab writes the same value)
+    }
+}
+
 int fused_grid() {
     static std::mutex mu;
     static int grid_of[64] = {0};
@@ -529,6 +593,14 @@ void launch_count_fused(const DevRecords& rec, const FChunk* chunks, uint32_t lo
     FArgs a{rec, chunks, lo, hi, g, cnt, work, flags, hotq, hot_n, hot_cap, 0u};
     const int grid = (int)min((uint32_t)fused_grid(), (hi - lo + (uint32_t)FC_BATCH - 1u) / (uint32_t)FC_BATCH);
     { SPL_LAUNCH; k_count_fused<<<grid, FC_THREADS, sizeof(FSmem), (cudaStream_t)stream>>>(a); }
+}
+
+// records [r0, r1) of a packed upload: cig_off[r0 .. r1] (cig_base = offset of record r0) and flag[r0 .. r1)
+uint32_t unpack_desc_words(uint32_t n_rec) { return (n_rec + UP_TILE - 1) / UP_TILE + 8; }
+void launch_unpack_records(const uint16_t* n_op, const uint8_t* flag8, uint32_t r0, uint32_t r1, uint32_t cig_base, uint32_t* cig_off,
+                           uint16_t* flag16, unsigned long long* desc, uint32_t* ticket, uint32_t epoch, void* stream) {
+    if (r1 <= r0) return;
+    { SPL_LAUNCH; k_unpack_records<<<(r1 - r0 + UP_TILE - 1) / UP_TILE, UP_THREADS, 0, (cudaStream_t)stream>>>(n_op, flag8, r0, r1, cig_base, cig_off, flag16, desc, ticket, epoch); }
 }
 
 // the queued hot items of every slab, after the counting kernels: one thread per item

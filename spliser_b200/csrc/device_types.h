@@ -212,6 +212,9 @@ void launch_count_fused(const DevRecords& rec, const FChunk* chunks, uint32_t lo
                         uint32_t* work, uint32_t flags, uint4* hotq, uint32_t* hot_n, uint32_t hot_cap, void* stream);
 void launch_hot_items(const DevRecords& rec, DevGraph g, DevCounters cnt, uint32_t flags, const uint4* hotq, const uint32_t* hot_n,
                       uint32_t hot_cap, void* stream);
+uint32_t unpack_desc_words(uint32_t n_rec);
+void launch_unpack_records(const uint16_t* n_op, const uint8_t* flag8, uint32_t r0, uint32_t r1, uint32_t cig_base, uint32_t* cig_off,
+                           uint16_t* flag16, unsigned long long* desc, uint32_t* ticket, uint32_t epoch, void* stream);
 int  sm_count_current_device();
 
 }  // namespace spl

@@ -186,7 +186,8 @@ struct spl_ctx {
     double stats[SPL_NSTATS] = {0};
 
     // fused variant (count_fused.cu)
-    DevBuf d_frec, d_fchunks, d_hotq;
+    DevBuf d_frec, d_fchunks, d_hotq, d_fpk, d_unpack;   // d_fpk: packed columns (n_op, flag8) of spl_process_packed; d_unpack: scan descriptors + ticket
+    uint32_t unpack_epoch = 0;
     uint32_t hot_cap = 0;           // items the global hot queue holds; a pass that needs more is repeated with room
     uint32_t* h_hot = nullptr;      // pinned: hot item count of the last pass
     void* h_fchunks = nullptr;
@@ -729,6 +730,115 @@ int fused_upload(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom, bool 
     return SPL_OK;
 }
 
+// The same for the packed host layout (spl_packed_view: POS, three flag bits, operator count; 17 B per record instead of 20):
+// slabs are cut at multiples of SPL_PACKED_INDEX_STRIDE records, where the view's sparse CIGAR index gives the offsets; the
+// CIGAR offsets of every record and the SAM flag bits are rebuilt on the device (k_unpack_records) as each slab arrives.
+int fused_upload_packed(spl_ctx* ctx, const spl_packed_view* v, int32_t n_chrom, bool split_ok) {
+    ctx->n_chrom_loaded = n_chrom;
+    std::vector<FChunk> hc;
+    int64_t aligned = 0;
+    for (int32_t k = 0; k < v->n_seg; ++k) {
+        if (v->seg_chrom[k] < 0) continue;
+        const int64_t a = v->seg_off[k], b = v->seg_off[k + 1];
+        aligned += b - a;
+        for (int64_t lo = a; lo < b; lo += FC_RECS) {
+            FChunk c{};
+            c.chrom = v->seg_chrom[k];
+            c.rec_lo = (uint32_t)lo;
+            c.rec_hi = (uint32_t)std::min<int64_t>(lo + FC_RECS, b);
+            hc.push_back(c);
+        }
+    }
+    ctx->n_aligned = aligned;
+    ctx->stats[SPL_STAT_N_ALIGNED] = (double)aligned;
+    ctx->n_fchunks = (uint32_t)hc.size();
+    const size_t R = (size_t)v->n_rec, NC = (size_t)v->n_cigar;
+    cudaStream_t cs = ctx->copy_stream;
+    CU(ctx->d_fchunks.reserve((hc.size() + 1) * sizeof(FChunk)));
+    ctx->fchunks = (FChunk*)ctx->d_fchunks.p;
+    if (!hc.empty()) {
+        const size_t bytes = hc.size() * sizeof(FChunk);
+        if (ctx->h_fchunks_bytes < bytes) {
+            if (ctx->h_fchunks) cudaFreeHost(ctx->h_fchunks);
+            ctx->h_fchunks = nullptr; ctx->h_fchunks_bytes = 0;
+            CU(cudaHostAlloc(&ctx->h_fchunks, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
+            ctx->h_fchunks_bytes = bytes + bytes / 4 + 4096;
+        }
+        memcpy(ctx->h_fchunks, hc.data(), bytes);
+        CU(cudaMemcpyAsync(ctx->fchunks, ctx->h_fchunks, bytes, cudaMemcpyHostToDevice, cs));
+        ctx->stats[SPL_STAT_H2D_BYTES] += (double)bytes;
+    }
+    {
+        const uint64_t want = std::max<uint64_t>(1u << 18, (uint64_t)v->n_cigar / 16 + (1u << 16));
+        if (ctx->hot_cap < want) {
+            CU(ctx->d_hotq.reserve((size_t)want * 16));
+            ctx->hot_cap = (uint32_t)std::min<uint64_t>(want, 0xfffffff0u);
+        }
+        *ctx->h_hot = 0;
+    }
+    Carver c;
+    const size_t o_pos = c.take<int32_t>(R + 32), o_flag = c.take<uint16_t>(R + 32), o_off = c.take<uint32_t>(R + 40),
+                 o_cig = c.take<uint32_t>(NC + 32);
+    CU(ctx->d_frec.reserve(c.off + 256));
+    char* rb = (char*)ctx->d_frec.p;
+    ctx->frec.n_rec = (uint32_t)R;
+    ctx->frec.pos = (const int32_t*)(rb + o_pos); ctx->frec.flag = (const uint16_t*)(rb + o_flag);
+    ctx->frec.cig_off = (const uint32_t*)(rb + o_off); ctx->frec.cigar = (const uint32_t*)(rb + o_cig);
+    Carver pc;
+    const size_t p_nop = pc.take<uint16_t>(R + 32), p_f8 = pc.take<uint8_t>(R + 32);
+    CU(ctx->d_fpk.reserve(pc.off + 256));
+    char* pb = (char*)ctx->d_fpk.p;
+    const size_t dwords = unpack_desc_words((uint32_t)R);
+    if (ctx->d_unpack.cap < (dwords + 8) * 8) {
+        CU(ctx->d_unpack.reserve((dwords + 8) * 8));
+        CU(cudaMemsetAsync(ctx->d_unpack.p, 0, ctx->d_unpack.cap, ctx->stream));
+        ctx->unpack_epoch = 0;
+    }
+    uint32_t* ticket = (uint32_t*)ctx->d_unpack.p;                    // fixed place: calls of different sizes share it (it is zero between launches)
+    unsigned long long* desc = (unsigned long long*)ctx->d_unpack.p + 2;
+    // slabs: cut at multiples of the index stride; a chunk belongs to the slab that holds its last record
+    const size_t K = SPL_PACKED_INDEX_STRIDE;
+    int want = 1;
+    {
+        int64_t min_rec = 2000000;
+        int max_parts = MAX_FPARTS;
+        if (const char* f = std::getenv("SPLISER_SPLIT_MIN_RECORDS")) min_rec = std::max<int64_t>(1, atoll(f));
+        if (const char* f = std::getenv("SPLISER_SPLIT_PARTS")) max_parts = std::max(1, std::min(MAX_FPARTS, atoi(f)));
+        if (split_ok) want = (int)std::max<int64_t>(1, std::min<int64_t>(max_parts, (int64_t)R / min_rec));
+        want = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, R / K));
+    }
+    ctx->n_fparts = want;
+    size_t r0 = 0;
+    uint32_t k0 = 0;
+    for (int p = 0; p < want; ++p) {
+        size_t r1 = (p == want - 1) ? R : (R * (size_t)(p + 1) / (size_t)want) / K * K;
+        if (r1 < r0) r1 = r0;
+        uint32_t k1 = k0;
+        while (k1 < hc.size() && hc[k1].rec_hi <= r1) ++k1;
+        ctx->fpart[p].chunk_lo = k0; ctx->fpart[p].chunk_hi = k1;
+        k0 = k1;
+        const size_t c0 = (size_t)v->cig_index[r0 / K], c1 = r1 == R ? NC : (size_t)v->cig_index[r1 / K];
+        if (r1 > r0) {
+            CU(cudaMemcpyAsync(rb + o_pos + r0 * 4, v->pos + r0, (r1 - r0) * 4, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(pb + p_nop + r0 * 2, v->n_op + r0, (r1 - r0) * 2, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(pb + p_f8 + r0, v->flag8 + r0, (r1 - r0), cudaMemcpyHostToDevice, cs));
+            if (c1 > c0) CU(cudaMemcpyAsync(rb + o_cig + c0 * 4, v->cigar + c0, (c1 - c0) * 4, cudaMemcpyHostToDevice, cs));
+            ctx->stats[SPL_STAT_H2D_BYTES] += (double)((r1 - r0) * 7 + (c1 - c0) * 4);
+        }
+        CU(cudaEventRecord(ctx->fpart[p].ev_up, cs));
+        if (r1 > r0) {
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->fpart[p].ev_up, 0));
+            ctx->unpack_epoch = (ctx->unpack_epoch + 1u) & 0x3fffffffu;
+            if (ctx->unpack_epoch == 0u) ctx->unpack_epoch = 1u;
+            launch_unpack_records((const uint16_t*)(pb + p_nop), (const uint8_t*)(pb + p_f8), (uint32_t)r0, (uint32_t)r1, (uint32_t)c0,
+                                  (uint32_t*)(rb + o_off), (uint16_t*)(rb + o_flag), desc, ticket, ctx->unpack_epoch, ctx->stream);
+        }
+        r0 = r1;
+    }
+    ctx->fpart[want - 1].chunk_hi = (uint32_t)hc.size();
+    return SPL_OK;
+}
+
 // fused variant: one pass = counters zeroed, one counting kernel per slab (as soon as the slab has arrived), finalize
 int fused_count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     if (ev) CU(cudaEventRecord(ev[0], ctx->stream));
@@ -904,7 +1014,7 @@ void adopt_device_graph(spl_ctx* ctx) {
 
 int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
                 const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags,
-                bool split_ok) {
+                bool split_ok, const spl_packed_view* packed = nullptr) {
     ctx->loaded = false;
     if (ctx->pending) { cudaStreamSynchronize(ctx->stream2); spl_result_free(ctx->pending); ctx->pending = nullptr; }
     int rc = check_view(ctx, rec, n_chrom);
@@ -973,7 +1083,7 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     if (dbg_on) { for (auto& e : dbg) cudaEventCreate(&e); cudaEventRecord(dbg[0], ctx->copy_stream); }
     if (fused) {
         ctx->n_parts = 0;
-        rc = fused_upload(ctx, rec, n_chrom, split_ok);
+        rc = packed ? fused_upload_packed(ctx, packed, n_chrom, split_ok) : fused_upload(ctx, rec, n_chrom, split_ok);
         if (rc) return rc;
     }
     for (int p = 0; p < ctx->n_parts; ++p) {
@@ -1278,6 +1388,42 @@ int spl_process_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chr
         spl_result_free(*out); *out = nullptr;
     }
     collect_expand_ms(ctx);
+    ctx->stats[SPL_STAT_MS_COUNT] = now_ms() - tc0;
+    ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
+    return rc;
+}
+
+int spl_process_packed(spl_ctx* ctx, const spl_packed_view* pv, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
+                       const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand,
+                       uint32_t flags, spl_result** out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!out) return ctx->fail(SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    if (!pv) return ctx->fail(SPL_ERR_ARG, "packed view is NULL");
+    if (ctx->variant != SPL_VARIANT_FUSED) return ctx->fail(SPL_ERR_ARG, "the packed view is read by the fused variant only");
+    if (pv->n_rec > 0 && (!pv->pos || !pv->flag8 || !pv->n_op || !pv->cig_index)) return ctx->fail(SPL_ERR_ARG, "NULL packed array");
+    if (pv->n_cigar > 0 && !pv->cigar) return ctx->fail(SPL_ERR_ARG, "NULL cigar array");
+    // the segment / size checks are those of the plain view (arrays are not dereferenced there for device-resident records)
+    spl_records_view shell{};
+    shell.n_rec = pv->n_rec; shell.n_cigar = pv->n_cigar; shell.n_seg = pv->n_seg; shell.seg_chrom = pv->seg_chrom; shell.seg_off = pv->seg_off;
+    const double t0 = now_ms();
+    ctx->rec_on_device = true;                                         // check_view: no host record arrays to look at
+    int rc = load_common(ctx, &shell, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, true, pv);
+    ctx->rec_on_device = false;
+    if (rc) return drain_on_error(ctx, rc);
+    const double tc0 = now_ms();
+    for (;;) {
+        rc = count_pass(ctx, nullptr);
+        if (rc) return drain_on_error(ctx, rc);
+        rc = drain_on_error(ctx, fetch(ctx, out));
+        if (rc) return rc;
+        bool again = false;
+        rc = hot_queue_overflow(ctx, &again);
+        if (rc) { spl_result_free(*out); *out = nullptr; return rc; }
+        if (!again) break;
+        spl_result_free(*out); *out = nullptr;
+    }
     ctx->stats[SPL_STAT_MS_COUNT] = now_ms() - tc0;
     ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
     return rc;

@@ -174,6 +174,31 @@ def test_stabbing_variant_equals_difference_array_variant(ctx):
         ctx.set_variant("fused")
 
 
+@pytest.mark.parametrize("parts", [1, 3])
+def test_packed_view_equals_plain_view(ctx, monkeypatch, parts):
+    """spl_process_packed (POS, three flag bits, operator count, sparse CIGAR index; offsets and SAM flag bits rebuilt on the
+    device) gives the table of spl_process_records: a stranded paired synthetic sample incl. odd flags, one slab and three."""
+    from oracle import c_oracle, fuzzgen
+    from spliser_b200 import PackedRecords, Records, synth
+    from spliser_b200.bed import parse_bed12
+    w = synth.generate(synth.config_small(150_000, seed=77, stranded=True, paired=True))
+    want = c_oracle.process(w.records, len(w.chroms), w.junctions, w.flags | 4, threads=8)
+    monkeypatch.setenv("SPLISER_SPLIT_MIN_RECORDS", "1000" if parts > 1 else "1000000000")
+    monkeypatch.setenv("SPLISER_SPLIT_PARTS", str(parts))
+    pk = PackedRecords.from_records(w.records)
+    got = c_oracle.table_dict(ctx.process_packed(pk, len(w.chroms), w.junctions, w.flags | 4))
+    assert ctx.stats()["n_parts"] == float(parts)
+    assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
+    monkeypatch.delenv("SPLISER_SPLIT_MIN_RECORDS"); monkeypatch.delenv("SPLISER_SPLIT_PARTS")
+    for seed in range(940000, 940030):                       # every flag combination / CIGAR shape of the fuzz generator
+        case = fuzzgen.gen_case(seed, n_chrom=1 + (seed % 2), dirty=(seed % 4 == 1), max_reads=60)
+        chroms, junc, _ = parse_bed12(case["bed"].splitlines(True))
+        rec = Records.from_reads(chroms, [tuple(r) for r in case["reads"]])
+        a = c_oracle.table_dict(ctx.process_records(rec, len(chroms), junc, case_flags(case)))
+        b = c_oracle.table_dict(ctx.process_packed(PackedRecords.from_records(rec), len(chroms), junc, case_flags(case)))
+        assert c_oracle.diff_tables(a, b) is None, (seed, c_oracle.diff_tables(a, b))
+
+
 def test_shuffled_records_give_identical_counts(ctx):
     """Any record order inside a chromosome segment is exact (the sorted-input fast paths have fallbacks)."""
     import numpy as np
