@@ -353,7 +353,7 @@ def main():
     S, E = st["n_sites"], st["n_edges"]
     peak, peak_src = measured_peak()
     kernel_ms = {"site_table+graph (K1)": st["ms_graph_dev"] / args.steps, "k_count_fused": st["ms_beta1"] / args.steps,
-                 "memset+scan+beta2+SSE (K5)": st["ms_final"] / args.steps}
+                 "k_hot_items": st["ms_spliced"] / args.steps, "memset+scan+beta2+SSE (K5)": st["ms_final"] / args.steps}
     b_m, b_n, r_spl = soa_counts(w.records)
     # bytes = 9 B_M + 8 B_N + 8 R_spl + 5 S (site table) for the counting kernel; + 12 E + 20 S for the whole path
     k_bytes = 9.0 * b_m + 8.0 * b_n + 8.0 * r_spl + 5.0 * S
@@ -483,6 +483,17 @@ def main():
             out["parity"] = {"against": "the untiled single-GPU table of the same sample (rank 0): the owned slices of the %d tiles, concatenated, every column" % world,
                              "tiles_digest": table_digest(cat), "single_gpu_digest": table_digest(whole), "first_difference": d}
             table = whole
+            # the same sample, untiled, on ONE GPU through the same timed path: the denominator of the strong-scaling efficiency
+            ctx.resident_load(full_records, n_chrom, w.junctions, w.flags)
+            ctx.resident_count(args.warmup)
+            s1 = ctx.resident_count(args.steps)
+            v1 = n_sample * args.steps / (s1["ms_total"] * 1e-3)
+            out["strong_scaling"] = {"value_1gpu_same_workload": v1, "ms_per_step_1gpu": s1["ms_total"] / args.steps, "speedup": value / v1,
+                                     "efficiency": value / v1 / world,
+                                     "kernel_ms_1gpu": {"site_table+graph (K1)": s1["ms_graph_dev"] / args.steps, "k_count_fused": s1["ms_beta1"] / args.steps,
+                                                        "k_hot_items": s1["ms_spliced"] / args.steps, "memset+scan+beta2+SSE (K5)": s1["ms_final"] / args.steps},
+                                     "note": "rank 0 times the untiled sample on its GPU after the tiled measurement; the site table + graph is built in full by every rank "
+                                             "(it is not sharded), which bounds the speed-up"}
         sent = sum_over_ranks(float(len(w.records)))
         if rank == 0:
             out["parity"]["records_sent"] = int(sent)

@@ -106,28 +106,40 @@ k_scan_lb(uint32_t* __restrict__ a, uint32_t n_host, const uint32_t* __restrict_
     uint32_t wbase = 0, total = 0;
 #pragma unroll
     for (int w = 0; w < LB_THREADS / 32; ++w) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
-    if (threadIdx.x == 0) {
+    if (warp == 0) {
+        // look-back by one warp: 32 predecessors per round; the nearest one that already knows its inclusive prefix ends the walk
         const unsigned long long tag = (unsigned long long)epoch << 34;
         volatile unsigned long long* d = desc;
         uint32_t prev = 0;
         if (t == 0) {
-            d[0] = tag | (LB_PREFIX << 32) | total;
+            if (lane == 0) d[0] = tag | (LB_PREFIX << 32) | total;
         } else {
-            d[t] = tag | (LB_AGG << 32) | total;
-            for (uint32_t p = t - 1;; ) {
-                const unsigned long long w = d[p];
-                if ((w >> 34) != epoch || ((w >> 32) & 3ull) == 0ull) continue;          // not published yet
-                prev += (uint32_t)w;
-                if (((w >> 32) & 3ull) == LB_PREFIX) break;
-                --p;
+            if (lane == 0) d[t] = tag | (LB_AGG << 32) | total;
+            int64_t hi = (int64_t)t - 1;                                // lane 0 looks at tile hi, lane 1 at hi - 1, ...
+            for (;;) {
+                const int64_t p = hi - lane;
+                unsigned long long w = 0;
+                bool ready = true;
+                if (p >= 0) {
+                    w = d[p];
+                    ready = (w >> 34) == epoch && ((w >> 32) & 3ull) != 0ull;
+                }
+                if (!__all_sync(0xffffffffu, ready)) continue;          // somebody has not published yet: look again
+                const uint32_t is_prefix = __ballot_sync(0xffffffffu, p >= 0 && ((w >> 32) & 3ull) == LB_PREFIX);
+                const int stop = is_prefix ? __ffs(is_prefix) - 1 : 31; // nearest tile with an inclusive prefix
+                prev += __reduce_add_sync(0xffffffffu, (p >= 0 && lane <= stop) ? (uint32_t)w : 0u);
+                if (is_prefix || hi - 32 < 0) break;
+                hi -= 32;
             }
-            d[t] = tag | (LB_PREFIX << 32) | (prev + total);
+            if (lane == 0) d[t] = tag | (LB_PREFIX << 32) | (prev + total);
         }
-        s_prev = prev;
-        if (t == gridDim.x - 1) {                                       // every ticket of this launch has been handed out
-            *ticket = 0u;
-            if (total_out) *total_out = prev + total;
-            if (total_out2) *total_out2 = prev + total;
+        if (lane == 0) {
+            s_prev = prev;
+            if (t == gridDim.x - 1) {                                   // every ticket of this launch has been handed out
+                *ticket = 0u;
+                if (total_out) *total_out = prev + total;
+                if (total_out2) *total_out2 = prev + total;
+            }
         }
     }
     __syncthreads();
@@ -222,40 +234,64 @@ __global__ void k_gb_sites(const uint64_t* __restrict__ k, const uint32_t* __res
     }
 }
 
-// per-chromosome site ranges: the table is sorted by chromosome, so cs_off[c] is a lower bound (one thread per chromosome)
-__global__ void k_gb_cs_off(GraphDev g, int n_chrom, const uint32_t* __restrict__ counts) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c > n_chrom) return;
-    int lo = 0, hi = (int)counts[0];
-    while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.site_chrom[mid] < c) lo = mid + 1; else hi = mid; }
-    g.cs_off[c] = lo;
-}
-// layout of the direct-address bin index (one thread: a running sum over the chromosomes)
-__global__ void k_gb_chrom_layout(int n_chrom, GraphDev g, uint32_t* __restrict__ counts) {
-    if (blockIdx.x || threadIdx.x) return;
-    int32_t nb = 0;
-    for (int c = 0; c < n_chrom; ++c) {
-        const int32_t s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
-        g.sb_base[c] = nb;
-        nb += (s1 > s0 ? (max(g.site_pos[s1 - 1], 0) >> SB_SHIFT) + 1 : 0) + 1;     // + sentinel
+// per-chromosome site ranges (the table is sorted by chromosome, so cs_off[c] is a lower bound) and the layout of the
+// direct-address bin index, one CTA: the searches run side by side, only the running sum over the chromosomes is serial
+__global__ void __launch_bounds__(256) k_gb_chroms(GraphDev g, int n_chrom, uint32_t* __restrict__ counts) {
+    const int S = (int)counts[0];
+    for (int c = threadIdx.x; c <= n_chrom; c += blockDim.x) {
+        int lo = 0, hi = S;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.site_chrom[mid] < c) lo = mid + 1; else hi = mid; }
+        g.cs_off[c] = lo;
     }
-    g.sb_base[n_chrom] = nb;
-    counts[1] = (uint32_t)nb;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) {
+        const int32_t s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
+        g.sb_base[c] = (s1 > s0 ? (max(g.site_pos[s1 - 1], 0) >> SB_SHIFT) + 1 : 0) + 1;     // bins + sentinel (turned into offsets below)
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t nb = 0;
+        for (int c = 0; c < n_chrom; ++c) { const int32_t v = g.sb_base[c]; g.sb_base[c] = nb; nb += v; }
+        g.sb_base[n_chrom] = nb;
+        counts[1] = (uint32_t)nb;
+    }
 }
 
-__global__ void k_gb_sb_fill(GraphDev g, int n_chrom, const uint32_t* __restrict__ counts) {
+// direct-address bin index: sb_off[sb_base[c] + b] = first site of chromosome c with position >= b << SB_SHIFT.  A thread owns
+// eight consecutive entries (one 32-byte store): one binary search for the first, a forward walk over the site table for the
+// rest -- consecutive bins mostly share their site, and a GRCh38-scale index has 5e7 entries.
+constexpr int SBF_RUN = 8;
+__global__ void __launch_bounds__(256) k_gb_sb_fill(GraphDev g, int n_chrom, const uint32_t* __restrict__ counts) {
     const uint32_t S = counts[0], n_entries = counts[1];
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_entries + 64u; i += gridDim.x * blockDim.x) {
-        if (i >= n_entries) { g.sb_off[i] = (int32_t)S; continue; }
-        int lo = 0, hi = n_chrom;                                       // last chromosome with sb_base <= i
-        while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((uint32_t)g.sb_base[mid] <= i) lo = mid; else hi = mid; }
-        const int c = lo;
-        const int32_t b = (int32_t)i - g.sb_base[c], nb = g.sb_base[c + 1] - g.sb_base[c] - 1;
-        int s0 = g.cs_off[c], s1 = g.cs_off[c + 1];
-        if (b >= nb) { g.sb_off[i] = s1; continue; }
-        const int32_t key = b << SB_SHIFT;
-        while (s0 < s1) { const int mid = (s0 + s1) >> 1; if (g.site_pos[mid] < key) s0 = mid + 1; else s1 = mid; }
-        g.sb_off[i] = s0;
+    const uint32_t n_runs = (n_entries + 64u + SBF_RUN - 1) / SBF_RUN;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n_runs; r += gridDim.x * blockDim.x) {
+        const uint32_t i0 = r * SBF_RUN;
+        int32_t out[SBF_RUN];
+        int c = -1, s0 = 0, s1 = 0, cur = 0;
+        int32_t nb = 0, cb = 0;
+#pragma unroll
+        for (int q = 0; q < SBF_RUN; ++q) {
+            const uint32_t i = i0 + q;
+            if (i >= n_entries) { out[q] = (int32_t)S; continue; }
+            if (c < 0 || (int32_t)i >= g.sb_base[c + 1]) {              // (re)locate the chromosome of this entry
+                int lo = 0, hi = n_chrom;                               // last chromosome with sb_base <= i
+                while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if ((uint32_t)g.sb_base[mid] <= i) lo = mid; else hi = mid; }
+                c = lo; cb = g.sb_base[c]; nb = g.sb_base[c + 1] - cb - 1;
+                s0 = g.cs_off[c]; s1 = g.cs_off[c + 1];
+                const int32_t key = ((int32_t)i - cb) << SB_SHIFT;
+                int a = s0, e = s1;
+                while (a < e) { const int mid = (a + e) >> 1; if (g.site_pos[mid] < key) a = mid + 1; else e = mid; }
+                cur = a;
+            }
+            const int32_t bq = (int32_t)i - cb;
+            if (bq >= nb) { out[q] = s1; continue; }                    // the chromosome's sentinel
+            const int32_t key = bq << SB_SHIFT;
+            while (cur < s1 && g.site_pos[cur] < key) ++cur;
+            out[q] = cur;
+        }
+        int4* dst = reinterpret_cast<int4*>(g.sb_off + i0);            // the array is allocated in whole runs
+        dst[0] = make_int4(out[0], out[1], out[2], out[3]);
+        dst[1] = make_int4(out[4], out[5], out[6], out[7]);
     }
 }
 
@@ -435,7 +471,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     const size_t o_jc = f.take<int32_t>(J), o_jl = f.take<int32_t>(J), o_jr = f.take<int32_t>(J), o_jst = f.take<uint8_t>((size_t)J + 8);
     GB_CU(m.fin.reserve(f.off + 256));
     Carve x;
-    const size_t x_cp = x.take<int32_t>(m.cap_c + 1), x_sb = x.take<int32_t>((size_t)m.nb_host + 64);
+    const size_t x_cp = x.take<int32_t>(m.cap_c + 1), x_sb = x.take<int32_t>((size_t)m.nb_host + 64 + 16);
     GB_CU(m.fin2.reserve(x.off + 256));
     char* fb = (char*)m.fin.p;
     g = GraphDev{};
@@ -499,8 +535,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     sc.scan(flag, n2, nullptr, d_cnt + 0);
     GB_CU(cudaMemsetAsync(g.site_hot, 0, (size_t)n2 + 64, st));
     { SPL_LAUNCH; k_gb_sites<<<cdiv(n2, 256), 256, 0, st>>>(sa, flag, n2, vb, pb, stranded ? 1 : 0, d_js, g, site_of, inc_eid, d_cnt); }
-    { SPL_LAUNCH; k_gb_cs_off<<<cdiv((uint32_t)n_chrom + 1, 128), 128, 0, st>>>(g, n_chrom, d_cnt); }
-    { SPL_LAUNCH; k_gb_chrom_layout<<<1, 32, 0, st>>>(n_chrom, g, d_cnt); }
+    { SPL_LAUNCH; k_gb_chroms<<<1, 256, 0, st>>>(g, n_chrom, d_cnt); }
 
     // ---- B: Partners / PartnerCounts entries per site
     GB_CU(cudaMemsetAsync(npt, 0, ((size_t)n2 + 4) * 4, st));
@@ -520,7 +555,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     { SPL_LAUNCH; k_gb_rp_count<<<cdiv(n2, 256), 256, 0, st>>>(g, d_cnt, c1); }
     sc.scan(c1, n2 + 2, d_cnt + 7, d_cnt + 5);
     { SPL_LAUNCH; k_gb_rp_fill<<<cdiv(n2 + 2, 256), 256, 0, st>>>(g, d_cnt, e_src, c1, c2); }
-    { SPL_LAUNCH; k_gb_sb_fill<<<296, 256, 0, st>>>(g, n_chrom, d_cnt); }
+    { SPL_LAUNCH; k_gb_sb_fill<<<148 * 8, 256, 0, st>>>(g, n_chrom, d_cnt); }
     GB_CU(cudaGetLastError());
     if (phase == 2) return true;                                           // timed rebuild of a table whose sizes are known
 
