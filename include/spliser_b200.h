@@ -158,6 +158,28 @@ int spl_build_site_table(int32_t n_chrom,
                          const int64_t* j_score, const uint8_t* j_strand,
                          uint32_t flags, spl_result** out, char* err, int err_len);
 
+/* ---- junction extraction -------------------------------------------------
+ * The junction table `process` needs, from the alignments themselves: replaces the `regtools junctions extract` pre-step
+ * of the reference's workflow (README.md:41) -- alpha is then the count of the same records the beta terms are counted
+ * from (S:274-277 reads it from the BED12 score column).  A record supports the junction (l, r) of one of its N operators
+ * when min_intron <= length(N) <= max_intron and the aligned stretches on both sides of the N (M/=/X/D operators up to the
+ * neighbouring N or the end of the read) are at least min_anchor long; regtools' defaults are 8 / 70 / 500000.  regtools is
+ * not part of the reference tree: these rules are restated from its documentation (parity unpinned; the tests pin the
+ * kernel to synthetic samples whose generator knows the table).  Strand: with SPL_FLAG_STRANDED the strand check_strand
+ * derives from the FLAG ('+' / '-'), else '?'.  Rows are sorted by (chromosome, l, r, strand). */
+typedef struct spl_junctions spl_junctions;
+int spl_extract_junctions(spl_ctx* ctx, const char* bam_path, int32_t n_chrom, const char* const* chrom_names,
+                          int32_t min_anchor, int32_t min_intron, int32_t max_intron, uint32_t flags, spl_junctions** out);
+int spl_extract_junctions_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom,
+                                  int32_t min_anchor, int32_t min_intron, int32_t max_intron, uint32_t flags, spl_junctions** out);
+int64_t        spl_junctions_n(const spl_junctions* j);
+const int32_t* spl_junctions_chrom(const spl_junctions* j);
+const int32_t* spl_junctions_left(const spl_junctions* j);      /* j_left / j_right / j_score / j_strand of spl_process */
+const int32_t* spl_junctions_right(const spl_junctions* j);
+const int64_t* spl_junctions_score(const spl_junctions* j);
+const uint8_t* spl_junctions_strand(const spl_junctions* j);
+void spl_junctions_free(spl_junctions* j);
+
 /* ---- result accessors ---------------------------------------------------------------------- */
 /* Sites are in the reference's output order: chrom_index order, then the per-chromosome list
  * order of site2D_array (position ascending; '+' before '-' in a stranded run, G:123-136). */

@@ -424,6 +424,35 @@ class Context:
         self._check(rc, "spl_process")
         return self._take(h)
 
+    # ---- junction extraction (the regtools pre-step, README.md:41) ---------------------------------
+    def _take_junctions(self, h) -> Junctions:
+        lib = self._lib
+        try:
+            n = lib.spl_junctions_n(h)
+
+            def arr(fn, dt):
+                return np.ctypeslib.as_array(fn(h), shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+            return Junctions(arr(lib.spl_junctions_chrom, np.int32), arr(lib.spl_junctions_left, np.int32), arr(lib.spl_junctions_right, np.int32),
+                             arr(lib.spl_junctions_score, np.int64), arr(lib.spl_junctions_strand, np.uint8))
+        finally:
+            lib.spl_junctions_free(h)
+
+    def extract_junctions_records(self, records: Records, n_chrom: int, flags: int = 0, min_anchor=8, min_intron=70, max_intron=500000) -> Junctions:
+        """Junction table (left, right, score, strand) from the alignments: what `regtools junctions extract -a 8 -m 70 -M 500000`
+        feeds the reference with.  flags: FLAG_STRANDED (| FLAG_RF) gives '+' / '-' strands, else '?'."""
+        v = records.view()
+        h = C.c_void_p()
+        rc = self._lib.spl_extract_junctions_records(self._h, C.byref(v), n_chrom, min_anchor, min_intron, max_intron, flags, C.byref(h))
+        self._check(rc, "spl_extract_junctions_records")
+        return self._take_junctions(h)
+
+    def extract_junctions_bam(self, bam_path, chrom_names, flags: int = 0, min_anchor=8, min_intron=70, max_intron=500000) -> Junctions:
+        names = (C.c_char_p * max(1, len(chrom_names)))(*[c.encode() for c in chrom_names])
+        h = C.c_void_p()
+        rc = self._lib.spl_extract_junctions(self._h, str(bam_path).encode(), len(chrom_names), names, min_anchor, min_intron, max_intron, flags, C.byref(h))
+        self._check(rc, "spl_extract_junctions")
+        return self._take_junctions(h)
+
     # ---- combine re-count ----------------------------------------------------------------------
     @staticmethod
     def _gap_args(gaps):

@@ -419,6 +419,82 @@ struct Carve {
     }
 };
 
+// ---- junction extraction from the alignments (replaces the `regtools junctions extract` pre-step,
+// README.md:41): every N operator with min_intron <= length <= max_intron whose two flanking aligned stretches (M/=/X/D up to
+// the neighbouring N or the end of the read) are >= min_anchor long supports the junction (chromosome, l, r, strand); the
+// score of a junction is the number of supporting records (what findAlphaCounts reads as alpha, S:274-277).  regtools is
+// neither in the reference tree nor in this image: its defaults (-a 8 -m 70 -M 500000) are restated from its documentation.
+struct JeSeg { const int64_t* seg_off; const int32_t* seg_chrom; int32_t n_seg; };
+
+__device__ __forceinline__ int je_chrom_of(const JeSeg& sg, uint32_t r) {
+    int lo = 0, hi = sg.n_seg;                                          // last segment with seg_off <= r
+    while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (sg.seg_off[mid] <= (int64_t)r) lo = mid; else hi = mid; }
+    return sg.seg_chrom[lo];
+}
+
+// EMIT = false: count the supporting N operators of every record; true: write their keys at the scanned offsets
+template <bool EMIT>
+__global__ void __launch_bounds__(256) k_je_walk(DevRecords rec, JeSeg sg, uint32_t mode, int32_t min_anchor, int32_t min_intron, int32_t max_intron,
+                                                 int pb, uint32_t* __restrict__ cnt, uint64_t* __restrict__ keys) {
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rec.n_rec) return;
+    const int chrom = je_chrom_of(sg, r);
+    uint32_t n = 0, w = EMIT ? cnt[r] : 0u;
+    if (chrom >= 0) {
+        const uint32_t c0 = rec.cig_off[r], c1 = rec.cig_off[r + 1];
+        const uint32_t flag = rec.flag[r];
+        uint32_t strand = 0;                                            // 0 '?', 1 '+', 2 '-'
+        if (mode & FLAG_STRANDED) {
+            const bool first = (flag & 64u) || !(flag & 1u), rev = (flag & 16u) != 0;
+            bool plus = first != rev;
+            if (mode & FLAG_RF) plus = !plus;
+            strand = plus ? 1u : 2u;
+        }
+        int32_t cur = rec.pos[r];
+        int32_t left = 0;                                               // aligned stretch in front of the pending N
+        int32_t pl = 0, plen = -1;                                      // pending junction: l, length (-1: none)
+        int32_t pleft = 0;
+        for (uint32_t k = c0; k <= c1; ++k) {
+            const uint32_t v = k < c1 ? rec.cigar[k] : 3u;              // a virtual N closes the last stretch
+            const uint32_t op = v & 15u;
+            const int32_t len = (int32_t)(v >> 4);
+            if (op == 3u) {
+                if (plen >= 0 && plen >= min_intron && plen <= max_intron && pleft >= min_anchor && left >= min_anchor) {
+                    if (EMIT) keys[w] = ((((uint64_t)(uint32_t)chrom << pb | (uint64_t)(uint32_t)pl) << 20 | (uint64_t)(uint32_t)plen) << 2) | strand;
+                    ++w; ++n;
+                }
+                pl = cur - 1; plen = k < c1 ? len : -1; pleft = left; left = 0;
+                cur += len;
+            } else if (op == 0u || op == 7u || op == 8u || op == 2u) {
+                left += len; cur += len;
+            }
+        }
+    }
+    if (!EMIT) cnt[r] = n;
+}
+
+__global__ void k_je_heads(const uint64_t* __restrict__ k, uint32_t n, uint32_t* __restrict__ flag) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e < n) flag[e] = (e == 0 || k[e] != k[e - 1]) ? 1u : 0u;
+}
+__global__ void k_je_out(const uint64_t* __restrict__ k, const uint32_t* __restrict__ ex, uint32_t n, int pb, int32_t* __restrict__ o_chrom,
+                         int32_t* __restrict__ o_left, int32_t* __restrict__ o_right, uint8_t* __restrict__ o_strand, unsigned long long* __restrict__ o_score) {
+    const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n) return;
+    const bool head = e == 0 || k[e] != k[e - 1];
+    const uint32_t idx = ex[e] - (head ? 0u : 1u);
+    atomicAdd(o_score + idx, 1ull);
+    if (head) {
+        const uint64_t key = k[e];
+        const uint32_t st = (uint32_t)(key & 3u);
+        const int32_t plen = (int32_t)((key >> 2) & 0xfffffu);
+        const int32_t l = (int32_t)((key >> 22) & ((1ull << pb) - 1ull));
+        o_chrom[idx] = (int32_t)(key >> (22 + pb));
+        o_left[idx] = l; o_right[idx] = l + plen;
+        o_strand[idx] = st == 1u ? (uint8_t)'+' : st == 2u ? (uint8_t)'-' : (uint8_t)'?';
+    }
+}
+
 }  // namespace
 
 bool graph_build_fits(int64_t J, int32_t n_chrom, int32_t max_pos) {
@@ -571,6 +647,79 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
         return graph_build_device(m, j_chrom, j_left, j_right, j_strand, j_score, n_junc, n_chrom, max_pos, stranded, stream, phase, g, counts, err);
     }
     counts.S = S; counts.E = E; counts.NB = NB; counts.C = C;
+    return true;
+}
+
+// Junction table of the device-resident records, sorted by (chromosome, l, r, strand).  Synchronises the stream (sizes).
+bool junction_extract_device(JuncExtractMem& m, const DevRecords& rec, const int64_t* h_seg_off, const int32_t* h_seg_chrom, int32_t n_seg,
+                             int32_t n_chrom, uint32_t mode, int32_t min_anchor, int32_t min_intron, int32_t max_intron, void* stream,
+                             std::vector<int32_t>& chrom, std::vector<int32_t>& left, std::vector<int32_t>& right, std::vector<int64_t>& score,
+                             std::vector<uint8_t>& strand, std::string& err) {
+    cudaStream_t st = (cudaStream_t)stream;
+    chrom.clear(); left.clear(); right.clear(); score.clear(); strand.clear();
+    const uint32_t R = rec.n_rec;
+    if (R == 0 || n_seg == 0) return true;
+    if (max_intron >= (1 << 20)) { err = "junction extraction: max_intron must be below 2^20"; return false; }
+    const int pb = 31, cb = bits_for_u64((uint64_t)(n_chrom > 1 ? n_chrom - 1 : 1));
+    if (cb + pb + 22 > 64) { err = "junction extraction: too many chromosomes for the packed key"; return false; }
+    Carve a;
+    const size_t a_so = a.take<int64_t>((size_t)n_seg + 1), a_sc = a.take<int32_t>((size_t)n_seg + 1), a_cnt = a.take<uint32_t>((size_t)R + 4);
+    const uint32_t lb_tiles0 = cdiv(R + 2u, LB_TILE) + 2;
+    const size_t a_desc = a.take<unsigned long long>(lb_tiles0 + 32), a_tot = a.take<uint32_t>(16);
+    GB_CU(m.a.reserve(a.off + 256));
+    char* ab = (char*)m.a.p;
+    GB_CU(cudaMemcpyAsync(ab + a_so, h_seg_off, ((size_t)n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
+    GB_CU(cudaMemcpyAsync(ab + a_sc, h_seg_chrom, (size_t)n_seg * 4, cudaMemcpyHostToDevice, st));
+    GB_CU(cudaMemsetAsync(ab + a_desc, 0, ((size_t)lb_tiles0 + 32) * 8, st));
+    GB_CU(cudaMemsetAsync(ab + a_tot, 0, 64, st));
+    const JeSeg sg{(const int64_t*)(ab + a_so), (const int32_t*)(ab + a_sc), n_seg};
+    uint32_t* cnt = (uint32_t*)(ab + a_cnt);
+    uint32_t* d_tot = (uint32_t*)(ab + a_tot);
+    uint32_t epoch = 0;
+    unsigned long long* desc0 = (unsigned long long*)(ab + a_desc);
+    const Scanner sc0{desc0, (uint32_t*)(desc0 + lb_tiles0 + 8), &epoch, st};
+    { SPL_LAUNCH; k_je_walk<false><<<cdiv(R, 256), 256, 0, st>>>(rec, sg, mode, min_anchor, min_intron, max_intron, pb, cnt, nullptr); }
+    sc0.scan(cnt, R, nullptr, d_tot);
+    uint32_t h_n = 0;
+    GB_CU(cudaMemcpyAsync(&h_n, d_tot, 4, cudaMemcpyDeviceToHost, st));
+    GB_CU(cudaStreamSynchronize(st));
+    const uint32_t n = h_n;
+    if (n == 0) return true;
+    const uint32_t max_tiles = cdiv(n, RS_TILE) + 1;
+    const uint32_t lb_tiles = cdiv(std::max(256u * max_tiles, n + 2u), LB_TILE) + 2;
+    Carve b;
+    const size_t b_ka = b.take<uint64_t>((size_t)n + 2), b_kb = b.take<uint64_t>((size_t)n + 2), b_flag = b.take<uint32_t>((size_t)n + 2);
+    const size_t b_hist = b.take<uint32_t>(256 * (size_t)max_tiles + 2), b_desc = b.take<unsigned long long>(lb_tiles + 32);
+    const size_t b_oc = b.take<int32_t>((size_t)n + 1), b_ol = b.take<int32_t>((size_t)n + 1), b_or = b.take<int32_t>((size_t)n + 1),
+                 b_os = b.take<uint8_t>((size_t)n + 8), b_sc = b.take<unsigned long long>((size_t)n + 1);
+    GB_CU(m.b.reserve(b.off + 256));
+    char* bb = (char*)m.b.p;
+    uint64_t* ka = (uint64_t*)(bb + b_ka); uint64_t* kb = (uint64_t*)(bb + b_kb);
+    uint32_t* flag = (uint32_t*)(bb + b_flag);
+    unsigned long long* desc = (unsigned long long*)(bb + b_desc);
+    GB_CU(cudaMemsetAsync(desc, 0, ((size_t)lb_tiles + 32) * 8, st));
+    GB_CU(cudaMemsetAsync(bb + b_sc, 0, ((size_t)n + 1) * 8, st));
+    uint32_t epoch2 = 0;
+    const Scanner sc{desc, (uint32_t*)(desc + lb_tiles + 8), &epoch2, st};
+    const Sorter sorter{(uint32_t*)(bb + b_hist), sc, d_tot + 5, st};
+    { SPL_LAUNCH; k_je_walk<true><<<cdiv(R, 256), 256, 0, st>>>(rec, sg, mode, min_anchor, min_intron, max_intron, pb, cnt, ka); }
+    uint64_t* sk = sorter.sort(ka, kb, n, 0, 22 + pb + cb);
+    { SPL_LAUNCH; k_je_heads<<<cdiv(n, 256), 256, 0, st>>>(sk, n, flag); }
+    sc.scan(flag, n, nullptr, d_tot + 1);
+    { SPL_LAUNCH; k_je_out<<<cdiv(n, 256), 256, 0, st>>>(sk, flag, n, pb, (int32_t*)(bb + b_oc), (int32_t*)(bb + b_ol), (int32_t*)(bb + b_or),
+                                                       (uint8_t*)(bb + b_os), (unsigned long long*)(bb + b_sc)); }
+    GB_CU(cudaGetLastError());
+    uint32_t h_u = 0;
+    GB_CU(cudaMemcpyAsync(&h_u, d_tot + 1, 4, cudaMemcpyDeviceToHost, st));
+    GB_CU(cudaStreamSynchronize(st));
+    const size_t U = h_u;
+    chrom.resize(U); left.resize(U); right.resize(U); strand.resize(U); score.resize(U);
+    GB_CU(cudaMemcpyAsync(chrom.data(), bb + b_oc, U * 4, cudaMemcpyDeviceToHost, st));
+    GB_CU(cudaMemcpyAsync(left.data(), bb + b_ol, U * 4, cudaMemcpyDeviceToHost, st));
+    GB_CU(cudaMemcpyAsync(right.data(), bb + b_or, U * 4, cudaMemcpyDeviceToHost, st));
+    GB_CU(cudaMemcpyAsync(strand.data(), bb + b_os, U, cudaMemcpyDeviceToHost, st));
+    GB_CU(cudaMemcpyAsync(score.data(), bb + b_sc, U * 8, cudaMemcpyDeviceToHost, st));
+    GB_CU(cudaStreamSynchronize(st));
     return true;
 }
 

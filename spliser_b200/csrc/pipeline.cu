@@ -208,6 +208,7 @@ struct spl_ctx {
     cudaStream_t stream2 = nullptr;
     cudaEvent_t ev_graph = nullptr;
     GraphBuildMem gbm;
+    JuncExtractMem jem;
     GraphDev gdev{};
     GraphCounts gcnt;
     bool graph_on_device = false;
@@ -1318,6 +1319,7 @@ void spl_destroy(spl_ctx* ctx) {
         if (ctx->h_file) cudaFreeHost(ctx->h_file);
         ctx->bgm.comp.release(); ctx->bgm.unc.release(); ctx->bgm.tab.release(); ctx->bgm.rec.release(); ctx->bgm.list.release();
         ctx->gbm.fin.release(); ctx->gbm.fin2.release(); ctx->gbm.work.release(); ctx->gbm.work2.release();
+        ctx->jem.a.release(); ctx->jem.b.release();
         if (ctx->stream2) { cudaStreamSynchronize(ctx->stream2); cudaStreamDestroy(ctx->stream2); }
         if (ctx->ev_graph) cudaEventDestroy(ctx->ev_graph);
         cudaStreamDestroy(ctx->stream);
@@ -1467,6 +1469,80 @@ int spl_process(spl_ctx* ctx, const char* bam_path, int32_t n_chrom, const char*
     ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
     return rc;
 }
+
+struct spl_junctions {
+    std::vector<int32_t> chrom, left, right;
+    std::vector<int64_t> score;
+    std::vector<uint8_t> strand;
+};
+
+namespace {
+int extract_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int32_t min_anchor, int32_t min_intron, int32_t max_intron,
+                   uint32_t flags, spl_junctions** out) {
+    if (min_anchor < 0 || min_intron < 0 || max_intron < min_intron) return ctx->fail(SPL_ERR_ARG, "bad anchor / intron bounds");
+    ctx->loaded = false;
+    int rc = check_view(ctx, rec, n_chrom);
+    if (rc) return rc;
+    CU(cudaSetDevice(ctx->device));
+    reset_stats(ctx);
+    rc = fused_upload(ctx, rec, n_chrom, false);
+    if (rc) return drain_on_error(ctx, rc);
+    CU(cudaStreamWaitEvent(ctx->stream, ctx->fpart[0].ev_up, 0));
+    std::unique_ptr<spl_junctions> j(new (std::nothrow) spl_junctions());
+    if (!j) return ctx->fail(SPL_ERR_NOMEM, "out of memory");
+    std::string e;
+    if (!junction_extract_device(ctx->jem, ctx->frec, rec->seg_off, rec->seg_chrom, rec->n_seg, n_chrom, flags & 3u, min_anchor, min_intron,
+                                 max_intron, ctx->stream, j->chrom, j->left, j->right, j->score, j->strand, e))
+        return drain_on_error(ctx, ctx->fail(SPL_ERR_CUDA, "%s", e.c_str()));
+    *out = j.release();
+    return SPL_OK;
+}
+}  // namespace
+
+int spl_extract_junctions_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int32_t min_anchor, int32_t min_intron,
+                                  int32_t max_intron, uint32_t flags, spl_junctions** out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!out) return ctx->fail(SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    return extract_common(ctx, rec, n_chrom, min_anchor, min_intron, max_intron, flags, out);
+}
+
+int spl_extract_junctions(spl_ctx* ctx, const char* bam_path, int32_t n_chrom, const char* const* chrom_names, int32_t min_anchor,
+                          int32_t min_intron, int32_t max_intron, uint32_t flags, spl_junctions** out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!out) return ctx->fail(SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    if (!bam_path) return ctx->fail(SPL_ERR_ARG, "bam_path is NULL");
+    CU(cudaSetDevice(ctx->device));
+    {
+        BamGpuCounts cnt;
+        spl_records_view dv{};
+        bool fallback = false;
+        int rc = ingest_bam_device(ctx, bam_path, n_chrom, chrom_names, cnt, dv, &fallback);
+        if (rc) return rc;
+        if (!fallback) {
+            ctx->rec_on_device = true;
+            rc = extract_common(ctx, &dv, n_chrom, min_anchor, min_intron, max_intron, flags, out);
+            ctx->rec_on_device = false;
+            return rc;
+        }
+    }
+    BamRecords recs;
+    std::string e = read_bam(bam_path, n_chrom, chrom_names, ctx->n_threads, recs);
+    if (!e.empty()) return ctx->fail(SPL_ERR_IO, "%s", e.c_str());
+    spl_records_view v = recs.view();
+    return extract_common(ctx, &v, n_chrom, min_anchor, min_intron, max_intron, flags, out);
+}
+
+int64_t spl_junctions_n(const spl_junctions* j) { return j ? (int64_t)j->chrom.size() : 0; }
+const int32_t* spl_junctions_chrom(const spl_junctions* j) { return j->chrom.data(); }
+const int32_t* spl_junctions_left(const spl_junctions* j) { return j->left.data(); }
+const int32_t* spl_junctions_right(const spl_junctions* j) { return j->right.data(); }
+const int64_t* spl_junctions_score(const spl_junctions* j) { return j->score.data(); }
+const uint8_t* spl_junctions_strand(const spl_junctions* j) { return j->strand.data(); }
+void spl_junctions_free(spl_junctions* j) { delete j; }
 
 int spl_recount_records(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_sites, const int32_t* s_chrom,
                         const int32_t* s_pos, const uint8_t* s_strand, const int64_t* p_off, const int32_t* p_pos,

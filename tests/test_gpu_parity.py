@@ -535,3 +535,40 @@ def test_full_configs4_equals_the_unmodified_reference(ctx):
     workload; tests/golden/reference_digests.json) and the C oracle."""
     test_config_shaped_workloads_vs_c_oracle(ctx, "c5_full")
 
+
+
+def test_junction_extraction_from_the_alignments(ctx, tmp_path):
+    """the junction table from the records themselves (the `regtools junctions extract` pre-step).  regtools is
+    not in the reference tree, so its rules are restated (parity unpinned); here the kernel is pinned to what is known: the
+    synthetic generator's own table (anchors >= 8 on both sides, score = supporting records, strand of the gene / '?'), a
+    numpy restatement on the same records, hand-made records for every filter, and process on the extracted table."""
+    import numpy as np
+    from oracle import c_oracle
+    from spliser_b200 import Records, synth
+
+    def as_rows(j):
+        return sorted(zip(j.chrom.tolist(), j.left.tolist(), j.right.tolist(), j.score.tolist(), [chr(x) for x in j.strand.tolist()]))
+
+    for stranded, paired, seed in ((False, False, 5), (True, True, 6)):
+        w = synth.generate(synth.config_small(120_000, seed=seed, stranded=stranded, paired=paired))
+        got = ctx.extract_junctions_records(w.records, len(w.chroms), w.flags & 3)
+        assert as_rows(got) == as_rows(w.junctions)
+        assert [tuple(x) for x in zip(got.chrom.tolist(), got.left.tolist(), got.right.tolist())] == sorted(zip(got.chrom.tolist(), got.left.tolist(), got.right.tolist()))
+        # the same through a BAM file, and `process` on the extracted table equals `process` on the generator's table
+        bam = str(tmp_path / ("j%d.bam" % seed))
+        w.records.write_bam(bam, w.chroms, w.chrom_len)
+        assert as_rows(ctx.extract_junctions_bam(bam, w.chroms, w.flags & 3)) == as_rows(w.junctions)
+        a = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), got, w.flags))
+        b = c_oracle.process(w.records, len(w.chroms), w.junctions, w.flags, threads=8)
+        for k in ("pos", "alpha", "beta1", "beta2simple", "sse"):
+            assert np.array_equal(np.asarray(a[k]), np.asarray(b[k])), k
+    # every filter, by hand: anchors (incl. a D inside the stretch and an I that does not count), intron bounds, two junctions in
+    # one read sharing the middle stretch, a soft clip that is no anchor, strands from the flags
+    reads = [("C", 100, 0, "20M100N20M"), ("C", 100, 16, "20M100N20M"), ("C", 113, 0, "7M100N20M"), ("C", 100, 0, "20M100N7M"),
+             ("C", 100, 0, "20M60N20M"), ("C", 100, 0, "20M600000N20M"), ("C", 300, 0, "5M2D4M90N3M1I6M"), ("C", 500, 0, "10M80N6M80N10M"),
+             ("C", 700, 0, "10M80N8M80N10M"), ("C", 900, 0, "4S7M100N20M"), ("C", 100, 99, "20M100N20M"), ("C", 100, 147, "20M100N20M")]
+    rec = Records.from_reads(["C"], reads)
+    got = as_rows(ctx.extract_junctions_records(rec, 1, 0))
+    assert got == [(0, 119, 219, 4, "?"), (0, 310, 400, 1, "?"), (0, 709, 789, 1, "?"), (0, 797, 877, 1, "?")], got
+    got = as_rows(ctx.extract_junctions_records(rec, 1, 1 | 2))          # --isStranded -s rf
+    assert (0, 119, 219, 1, "+") in got and (0, 119, 219, 3, "-") in got, got       # flags 0, 99, 147 read '-' under rf, flag 16 '+' (S:374-406)
