@@ -331,9 +331,12 @@ def main():
         cuts = dist.balanced_tiles(full_records, table0, n_chrom, world)
         tile = (cuts[rank], cuts[rank + 1])
         w.records = dist.tile_records(full_records, table0, n_chrom, rank, world, site_range=tile, seg_spans=dist.segment_max_spans(full_records))
+        # ... and builds its own site table + graph from the junction rows its sites and their partners touch (BED order kept)
+        full_junctions = w.junctions
+        rows_kept, w.junctions, tile_local = dist.tile_junctions(full_junctions, table0, n_chrom, tile, w.flags)
         desc += " -- ONE sample sharded by genomic tile over %d GPUs" % world
         ctx = spliser_b200.Context(local)
-        ctx.set_tile_sites(*tile)
+        ctx.set_tile_sites(*tile_local)
     else:
         ctx = spliser_b200.Context(local)
     barrier, max_over_ranks, sum_over_ranks = ranks.barrier, ranks.max, ranks.sum
@@ -430,8 +433,13 @@ def main():
         "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "config": {"workload": desc, "records_per_gpu": int(reads_rank), "sites": int(S), "junction_rows": len(w.junctions),
+        "config": {"workload": desc, "records_per_gpu": int(reads_rank), "sites": len(table0) if strong else int(S),
+                   "junction_rows": len(full_junctions) if strong else len(w.junctions),
                    "tile_sites": list(tile) if tile else None,
+                   "tile_graph": {"junction_rows_of_the_sample": len(full_junctions), "junction_rows_of_this_tile": len(w.junctions),
+                                  "sites_of_this_tile_table": int(S), "owned_slice_of_it": list(tile_local),
+                                  "note": "every rank builds the site table + competing-site graph of ITS tile from the junction rows that touch "
+                                          "its sites or their partners (dist.tile_junctions); owned rows are identical to the full table's"} if tile else None,
                    "l2": "no flush needed: every pass streams %.0f MB of records, larger than the 126 MB L2" % (rec_bytes / 1e6),
                    "host": topo,
                    "timing": "CUDA events on the library's stream around %d passes; max over ranks" % args.steps,
@@ -460,31 +468,29 @@ def main():
                           "kernel_ms": kernel_ms},
         "kernel_path": {"n_mblocks": b_m, "n_junction_ops": b_n, "n_spliced_reads": r_spl, "n_edges": int(E), "n_cigar_ops": int(len(w.records.cigar))},
         "variants": variants,
-        "checksum": {"beta1": int(table.beta1.sum()), "beta2simple": int(table.beta2simple.sum()), "alpha": int(table.alpha.sum())},
+        "checksum": {k: int(getattr(table, k)[slice(*tile_local) if strong else slice(None)].sum()) for k in ("beta1", "beta2simple", "alpha")},
     }
 
     # ---- parity inside the measurement + CPU baseline on the SAME workload
     if strong:
         # the owned slices of every rank concatenate to the table one GPU computes for the whole sample
-        lo, hi = tile
-        np.savez(os.path.join(CACHE, "tile_%d_of_%d.npz" % (rank, world)), beta1=table.beta1[lo:hi], beta2simple=table.beta2simple[lo:hi],
-                 beta2cryptic=table.beta2cryptic[lo:hi], sse=table.sse[lo:hi], beta2weighted=table.beta2weighted[lo:hi])
+        part = dist.owned_part(table, tile_local, rows_kept)
+        np.savez(os.path.join(CACHE, "tile_%d_of_%d.npz" % (rank, world)), **part)
         barrier()
         if rank == 0:
             from oracle import c_oracle
-            parts = [np.load(os.path.join(CACHE, "tile_%d_of_%d.npz" % (q, world))) for q in range(world)]
+            parts = [dict(np.load(os.path.join(CACHE, "tile_%d_of_%d.npz" % (q, world)))) for q in range(world)]
             ctx.set_tile_sites(-1, -1)
-            whole = ctx.process_records(full_records, n_chrom, w.junctions, w.flags)
-            cat = dict(c_oracle.table_dict(whole))
-            for k in ("beta1", "beta2simple", "beta2cryptic", "sse", "beta2weighted"):
-                cat[k] = np.concatenate([p[k] for p in parts])
+            whole = ctx.process_records(full_records, n_chrom, full_junctions, w.flags)
+            cat = dist.concat_parts(parts, c_oracle.table_dict(whole))
             d = c_oracle.diff_tables(cat, c_oracle.table_dict(whole))
             out["parity_checked"] = d is None
-            out["parity"] = {"against": "the untiled single-GPU table of the same sample (rank 0): the owned slices of the %d tiles, concatenated, every column" % world,
+            out["parity"] = {"against": "the untiled single-GPU table of the same sample (rank 0): the owned rows of the %d per-tile tables (each built from the tile's own "
+                                        "junction rows), concatenated, every column incl. Partners / PartnerCounts / CompetitorPos" % world,
                              "tiles_digest": table_digest(cat), "single_gpu_digest": table_digest(whole), "first_difference": d}
             table = whole
             # the same sample, untiled, on ONE GPU through the same timed path: the denominator of the strong-scaling efficiency
-            ctx.resident_load(full_records, n_chrom, w.junctions, w.flags)
+            ctx.resident_load(full_records, n_chrom, full_junctions, w.flags)
             ctx.resident_count(args.warmup)
             s1 = ctx.resident_count(args.steps)
             v1 = n_sample * args.steps / (s1["ms_total"] * 1e-3)
@@ -492,8 +498,7 @@ def main():
                                      "efficiency": value / v1 / world,
                                      "kernel_ms_1gpu": {"site_table+graph (K1)": s1["ms_graph_dev"] / args.steps, "k_count_fused": s1["ms_beta1"] / args.steps,
                                                         "k_hot_items": s1["ms_spliced"] / args.steps, "memset+scan+beta2+SSE (K5)": s1["ms_final"] / args.steps},
-                                     "note": "rank 0 times the untiled sample on its GPU after the tiled measurement; the site table + graph is built in full by every rank "
-                                             "(it is not sharded), which bounds the speed-up"}
+                                     "note": "rank 0 times the untiled sample (all records, all junction rows) on its GPU after the tiled measurement"}
         sent = sum_over_ranks(float(len(w.records)))
         if rank == 0:
             out["parity"]["records_sent"] = int(sent)
@@ -502,7 +507,7 @@ def main():
         from oracle import c_oracle
         if args.workload == "c3":
             # bounded: the first chromosome of the sample (its sites are the first rows of the table)
-            rec_s, junc_s = first_segment(Workload_like(full_records, w.junctions))
+            rec_s, junc_s = first_segment(Workload_like(full_records, full_junctions if strong else w.junctions))
             sample = "first chromosome of the sample (%d records, %d junctions)" % (len(rec_s), len(junc_s))
             t0 = time.perf_counter()
             want = c_oracle.process(rec_s, n_chrom, junc_s, w.flags, threads=ncores)

@@ -258,3 +258,103 @@ def tile_records(records, table, n_chrom, tile, n_tiles, max_span=None, site_ran
     off = np.zeros(total + 1, np.uint32)
     np.cumsum(np.concatenate(ncig_l), out=off[1:])
     return Records(np.concatenate(pos_l), np.concatenate(flag_l), off, np.concatenate(cig_l), seg_chrom, seg_off)
+
+
+# ------------------------------------------------------------------------------------------------
+# The junction rows a tile needs (the site table + competing-site graph are then built per tile, not replicated).
+# An owned site t needs: every row touching t (alpha, Partners in insertion order, PartnerCounts: S:341-355) and every
+# row touching a partner p of t (p's PartnerCounts and alpha for findBeta2Counts, S:590-613; the partners of p are t's
+# competitors, S:364-372).  A partner lies within the chromosome's longest junction of t, so the rows with an endpoint
+# inside [first owned position - H, last owned position + H] are a superset.  The rows keep their BED order, so the
+# sub-table's owned rows equal the full table's in every column.
+# ------------------------------------------------------------------------------------------------
+def is_dirty_regime(junctions, flags):
+    """Stranded run with a strand byte other than + / - (or a zero-length row): the reference's site identity then depends
+    on the path of its bisection through the WHOLE list, so the table is not cut."""
+    import numpy as np
+    if len(junctions) == 0:
+        return False
+    if np.any(junctions.left == junctions.right):
+        return True
+    return bool(flags & 1) and bool(np.any((junctions.strand != 43) & (junctions.strand != 45)))
+
+
+def tile_junctions(junctions, table, n_chrom, site_range, flags):
+    """(rows kept as indices into `junctions`, sub-table Junctions, owned slice [lo', hi') of the sub-table's site table).
+    `table`: the full site table in library order (api.build_site_table)."""
+    import numpy as np
+    from .api import Junctions
+    lo, hi = site_range
+    J = len(junctions)
+    if is_dirty_regime(junctions, flags) or hi <= lo:
+        return np.arange(J, dtype=np.int64), junctions, (lo, hi)
+    ranges = tile_position_ranges(table, n_chrom, 0, 1, site_range=(lo, hi))
+    keep = np.zeros(J, bool)
+    jc, jl, jr = junctions.chrom, junctions.left.astype(np.int64), junctions.right.astype(np.int64)
+    # sites sit at both ends of a row; the alpha of a site counts rows by position, whatever the orientation of the row
+    a, b = np.minimum(jl, jr), np.maximum(jl, jr)
+    for c in range(n_chrom):
+        if ranges[c] is None:
+            continue
+        on = jc == c
+        if not on.any():
+            continue
+        H = int((b[on] - a[on]).max()) + 1
+        w0, w1 = ranges[c][0] - H, ranges[c][1] + H
+        keep |= on & (((a >= w0) & (a <= w1)) | ((b >= w0) & (b <= w1)))
+    idx = np.nonzero(keep)[0].astype(np.int64)
+    sub = Junctions(junctions.chrom[idx], junctions.left[idx], junctions.right[idx], junctions.score[idx], junctions.strand[idx])
+    # the owned sites keep their order in the sub-table and every site at an owned position is present: the slice starts
+    # after the sub-table sites that sort before the first owned (chromosome, position), plus the same-position sites before it
+    chrom, pos = np.asarray(table.chrom), np.asarray(table.pos)
+    c0, p0 = int(chrom[lo]), int(pos[lo])
+    first_same = lo
+    while first_same > 0 and int(chrom[first_same - 1]) == c0 and int(pos[first_same - 1]) == p0:
+        first_same -= 1
+    ends_c = np.concatenate([sub.chrom, sub.chrom]).astype(np.int64)
+    ends_p = np.concatenate([sub.left, sub.right]).astype(np.int64)
+    stranded = bool(flags & 1)
+    if stranded:
+        ends_s = np.concatenate([sub.strand, sub.strand]).astype(np.int64)
+        key = (ends_c << 40) | (ends_p << 8) | ends_s
+    else:
+        key = (ends_c << 40) | (ends_p << 8)
+    before = (ends_c < c0) | ((ends_c == c0) & (ends_p < p0))
+    n_before = len(np.unique(key[before]))
+    lo2 = n_before + (lo - first_same)
+    return idx, sub, (lo2, lo2 + (hi - lo))
+
+
+_PART_COLS = ("chrom", "pos", "strand", "first_line", "alpha", "beta1", "beta2simple", "beta2cryptic", "beta2weighted", "sse")
+
+
+def owned_part(table, local_range, rows_kept=None):
+    """The owned rows of a tile's result as a dict of arrays (every column; CSR columns as lengths + values).
+    rows_kept maps the sub-table's BED row numbers (first_line) back to the full junction table's."""
+    import numpy as np
+    lo, hi = local_range
+    out = {k: np.asarray(getattr(table, k))[lo:hi].copy() for k in _PART_COLS}
+    if rows_kept is not None and hi > lo:
+        out["first_line"] = np.asarray(rows_kept)[out["first_line"].astype(np.int64)].astype(out["first_line"].dtype)
+    po, co = np.asarray(table.partner_off).astype(np.int64), np.asarray(table.comp_off).astype(np.int64)
+    out["partner_len"] = np.diff(po[lo:hi + 1])
+    out["partner_pos"] = np.asarray(table.partner_pos)[po[lo]:po[hi]].copy()
+    out["partner_cnt"] = np.asarray(table.partner_cnt)[po[lo]:po[hi]].copy()
+    out["comp_len"] = np.diff(co[lo:hi + 1])
+    out["comp_pos"] = np.asarray(table.comp_pos)[co[lo]:co[hi]].copy()
+    return out
+
+
+def concat_parts(parts, like):
+    """Table dict (the SiteTable column names as keys) from the owned parts of every tile, in tile order; dtypes as in `like`."""
+    import numpy as np
+    out = {k: np.concatenate([p[k] for p in parts]).astype(np.asarray(like[k]).dtype) for k in _PART_COLS}
+    for name, ln in (("partner", "partner_len"), ("comp", "comp_len")):
+        lens = np.concatenate([p[ln] for p in parts]).astype(np.int64)
+        off = np.zeros(len(lens) + 1, np.asarray(like[name + "_off"]).dtype)
+        np.cumsum(lens, out=off[1:])
+        out[name + "_off"] = off
+    out["partner_pos"] = np.concatenate([p["partner_pos"] for p in parts]).astype(np.asarray(like["partner_pos"]).dtype)
+    out["partner_cnt"] = np.concatenate([p["partner_cnt"] for p in parts]).astype(np.asarray(like["partner_cnt"]).dtype)
+    out["comp_pos"] = np.concatenate([p["comp_pos"] for p in parts]).astype(np.asarray(like["comp_pos"]).dtype)
+    return out

@@ -47,7 +47,7 @@ def test_bench_reference_arm_prints_the_contract_line(tmp_path):
     keys of the bench contract; under torchrun (N > 1) rank 0 alone prints it and the other rank exits 0 without work."""
     import json
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", SPLISER_BENCH_CACHE=str(tmp_path))
-    tail = ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--reads", "120000", "--cpu-sample", "40000"]
+    tail = ["bench.py", "--impl", "reference", "--steps", "1", "--warmup", "1", "--reads", "120000"]
     one = subprocess.run([sys.executable] + tail, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)
     assert one.returncode == 0, one.stderr[-2000:]
     lines = [ln for ln in one.stdout.splitlines() if ln.startswith("{")]

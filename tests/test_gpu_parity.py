@@ -521,6 +521,38 @@ def test_tile_sharded_process_with_record_slices(built_library):
         assert np.array_equal(got[k], ref[k]), k
 
 
+@pytest.mark.parametrize("shape,n_tiles", [("c3_tile", 4), ("c2", 3)])
+def test_tiles_with_their_own_graph_concatenate_to_the_untiled_table(built_library, shape, n_tiles):
+    """Tile sharding with the site table + competing-site graph built per tile from the junction rows dist.tile_junctions keeps
+    (what bench.py --gpus N runs): read-balanced cuts, per-segment span bounds, every column of the concatenated owned rows
+    equal to the single-context table AND to the C oracle's."""
+    import numpy as np
+    import spliser_b200
+    from oracle import c_oracle
+    from spliser_b200 import api, dist, synth
+    w = synth.generate(synth.config_c3_tile(300_000, tile=1) if shape == "c3_tile" else synth.config_c2(400_000))
+    nc = len(w.chroms)
+    flags = w.flags | 4
+    with spliser_b200.Context(0) as full_ctx:
+        whole = c_oracle.table_dict(full_ctx.process_records(w.records, nc, w.junctions, flags))
+        whole = {k: np.array(v) for k, v in whole.items()}
+    table = api.build_site_table(nc, w.junctions, w.flags)
+    cuts = dist.balanced_tiles(w.records, table, nc, n_tiles)
+    spans = dist.segment_max_spans(w.records)
+    parts = []
+    for t in range(n_tiles):
+        lo, hi = cuts[t], cuts[t + 1]
+        rows, junc_t, local = dist.tile_junctions(w.junctions, table, nc, (lo, hi), w.flags)
+        rec_t = dist.tile_records(w.records, table, nc, t, n_tiles, site_range=(lo, hi), seg_spans=spans)
+        with spliser_b200.Context(0) as c:
+            c.set_tile_sites(*local)
+            parts.append(dist.owned_part(c.process_records(rec_t, nc, junc_t, flags), local, rows))
+    cat = dist.concat_parts(parts, whole)
+    assert c_oracle.diff_tables(cat, whole) is None, c_oracle.diff_tables(cat, whole)
+    want = c_oracle.process(w.records, nc, w.junctions, flags, threads=8)
+    assert c_oracle.diff_tables(cat, want) is None, c_oracle.diff_tables(cat, want)
+
+
 def test_dirty_strand_regime_at_scale_equals_the_unmodified_reference(ctx):
     """configs[1] shape (500k records, stranded rf) with '?' in every 12th BED row (regtools writes '?' for junctions without an
     XS tag): SURVEY.md 8(a)'s dirty regime -- a '?' row joins whichever same-position site the reference's bisection lands on,

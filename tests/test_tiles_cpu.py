@@ -76,3 +76,53 @@ def test_read_balanced_tiles_reproduce_the_unsharded_counts():
     for k in got:
         assert np.array_equal(got[k], full[k]), k
     assert max(sent) < 1.6 * len(w.records) / n_tiles, sent            # balanced by reads, edge duplicates included
+
+
+@pytest.mark.parametrize("shape,n_tiles,stranded", [("small", 3, True), ("small", 5, False), ("c3_tile", 4, True)])
+def test_tile_junction_rows_give_the_owned_rows_of_the_full_table(shape, n_tiles, stranded):
+    """Each tile builds its OWN site table + graph from the junction rows dist.tile_junctions keeps (SURVEY 8(e) has the
+    graph replicated; cutting it removes the one per-sample stage that did not shrink with the number of GPUs): the owned
+    rows of the per-tile tables, concatenated, equal the unsharded table in every column -- Partners in insertion order,
+    PartnerCounts, CompetitorPos, first BED line, beta2Cryptic (which reads the partners' own PartnerCounts) included."""
+    if shape == "small":
+        w = synth.generate(synth.config_small(60_000, seed=103, stranded=stranded, paired=True))
+    else:
+        w = synth.generate(synth.config_c3_tile(80_000, tile=2))
+    nc = len(w.chroms)
+    flags = w.flags | 4
+    full = c_oracle.process(w.records, nc, w.junctions, flags, threads=8)
+    table = api.build_site_table(nc, w.junctions, w.flags)
+    cuts = dist.balanced_tiles(w.records, table, nc, n_tiles)
+    spans = dist.segment_max_spans(w.records)
+    parts, kept = [], []
+    for t in range(n_tiles):
+        lo, hi = cuts[t], cuts[t + 1]
+        rows, junc_t, (lo2, hi2) = dist.tile_junctions(w.junctions, table, nc, (lo, hi), w.flags)
+        kept.append(len(rows))
+        rec_t = dist.tile_records(w.records, table, nc, t, n_tiles, site_range=(lo, hi), seg_spans=spans)
+        part = c_oracle.process(rec_t, nc, junc_t, flags, threads=8)
+        assert hi2 - lo2 == hi - lo and hi2 <= len(part["pos"])
+        assert np.array_equal(part["pos"][lo2:hi2], full["pos"][lo:hi]) and np.array_equal(part["strand"][lo2:hi2], full["strand"][lo:hi])
+
+        class T:                                                       # the dict as attributes, like a SiteTable
+            pass
+        tt = T()
+        for k, v in part.items():
+            setattr(tt, k, v)
+        parts.append(dist.owned_part(tt, (lo2, hi2), rows))
+    cat = dist.concat_parts(parts, full)
+    assert c_oracle.diff_tables(cat, full) is None
+    if n_tiles >= 4 and shape == "c3_tile":
+        assert max(kept) < 0.8 * len(w.junctions), kept                # a tile builds a part of the graph, not all of it
+
+
+def test_tile_junctions_dirty_regime_is_not_cut():
+    from spliser_b200 import Junctions
+    j = Junctions([0, 0, 0], [100, 100, 900], [300, 300, 1200], [1, 2, 3], [ord("?"), ord("+"), ord("-")])
+    table = api.build_site_table(1, j, 1)
+    rows, sub, rng = dist.tile_junctions(j, table, 1, (0, 2), 1)
+    assert len(rows) == 3 and sub is j and rng == (0, 2)
+    # the same rows in an unstranded run are a clean table: the far row is dropped for a tile that owns the first two sites
+    table = api.build_site_table(1, j, 0)
+    rows, sub, rng = dist.tile_junctions(j, table, 1, (0, 2), 0)
+    assert list(rows) == [0, 1] and rng == (0, 2)
