@@ -239,6 +239,7 @@ constexpr int FC_SLOTS = 5;
 #define SPL_FC_STAB_MAX 16
 #endif
 constexpr int FC_STAB_MAX = SPL_FC_STAB_MAX;
+static_assert(FC_STAB_MAX < 32, "the anchor loop masks the window's sites with (1 << nw) - 1");
 
 template <bool STAGED>
 __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsigned long long* list, uint32_t* next_group, const FArgs& A) {
@@ -260,11 +261,13 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
         const bool live = i < m.n_rec;
         int32_t pos = 0;
         uint32_t nop = 0, k = 0;
-        // ---- the first FC_SLOTS operators as boundaries in registers: operator j covers [b[j], b[j+1])
+        // ---- the first FC_SLOTS operators in registers: operator j covers [b[j], b[j+1]); a site at p is stabbed by it
+        // (covered, S:469 / strictly inside the junction, S:507) iff (uint32)(p - b[j]) < len1[j] with len1 = length - 1 for
+        // M/=/X/N operators and 0 otherwise; wf[j] is the operator's field of the warp's sum (cov / span x strand class)
         int32_t b[FC_SLOTS + 1];
-        uint32_t tM = 0, tN = 0;                                     // bit j: operator j is M/=/X (S:457-459) / N (S:480-483)
-        bool odd = false;                                            // zero-length M / N, more than two N: left to the chain path
-        uint32_t nslot = 0;
+        uint32_t len1[FC_SLOTS], wf[FC_SLOTS];
+        uint32_t tN = 0;                                             // bit j: operator j is N (S:480-483)
+        uint32_t zl = 0;                                             // bit 31: a zero-length M / N (left to the chain path, like more than two N)
         {
             uint32_t c0 = 0;
             if (live) {
@@ -274,22 +277,25 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                 k = read_class(st.flag[m.skip + i], A.mode);
             }
             b[0] = pos;
-            nslot = min(__reduce_max_sync(0xffffffffu, nop), (uint32_t)FC_SLOTS);   // warp-uniform: operators anybody in the group has
+            const uint32_t incM = 1u << (8u * k), dN = 0xffffu << (8u * k);          // byte fields of the redux word: cov class 0 / 1, span class 0 / 1 (incN = incM + dN)
 #pragma unroll
             for (int j = 0; j < FC_SLOTS; ++j) {
-                b[j + 1] = b[j];
-                if ((uint32_t)j < nslot) {                           // uniform
-                    const uint32_t w = (uint32_t)j < nop ? cw(c0 + j) : 5u;  // filler: a zero-length H (no progression)
-                    const uint32_t op = w & 15u;
-                    const int32_t len = (int32_t)(w >> 4);
-                    const uint32_t isM = (0x181u >> op) & 1u, isN = (0x008u >> op) & 1u, adv = (0x18du >> op) & 1u;   // + D: advance only (S:460-462)
-                    tM |= isM << j; tN |= isN << j;
-                    odd |= ((isM | isN) != 0u) && len == 0;
-                    if (adv) b[j + 1] += len;
+                {                                                    // (no test against nslot: nearly every group has a read with FC_SLOTS operators)
+                    const uint32_t cwd = (uint32_t)j < nop ? cw(c0 + j) : 5u;  // filler: a zero-length H (no progression)
+                    const uint32_t op = cwd & 15u, len = cwd >> 4;
+                    // 0 / 1 factors instead of selects: the multiplies run on the FMA pipe, the ALU pipe is the busy one here
+                    const uint32_t adv = (0x18du >> op) & 1u;        // M D N = X advance (S:457-464)
+                    const uint32_t cnt_op = (0x189u >> op) & 1u;     // M = X (S:457-459) and N (S:480-483) stab sites
+                    const uint32_t isN = (0x008u >> op) & 1u;
+                    b[j + 1] = b[j] + (int32_t)(len * adv);
+                    len1[j] = (len - 1u) * cnt_op;                   // length 1 stabs nothing; length 0 sets bit 31 (-> chain path)
+                    zl |= len1[j];
+                    wf[j] = cnt_op * incM + isN * dN;
+                    tN += isN << j;
                 }
             }
-            odd |= __popc(tN) > 2;
         }
+        const bool odd = (zl >> 31) != 0u || __popc(tN) > 2;
         const bool has = live && nop != 0u;
         const int32_t wlo = __reduce_min_sync(0xffffffffu, has ? pos - 1 : INT_MAX);
         const int32_t whi = __reduce_max_sync(0xffffffffu, has ? b[FC_SLOTS] - 1 : INT_MIN);
@@ -306,44 +312,43 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
         bool act = has;
         int32_t cur = pos;
         if (!wide) {
-            const uint32_t incM = 1u << (8u * k), incN = 0x10000u << (8u * k);   // byte fields of the redux word: cov class 0 / 1, span class 0 / 1
             uint32_t mine = 0;                                       // lane q keeps the warp's sums for the q-th site of the window
-            uint32_t hot_run = hotmask >> d;
-            for (int q = 0; q < nw; ++q, hot_run >>= 1) {            // warp-uniform
+#pragma unroll 2
+            for (int q = 0; q < nw; ++q) {                           // warp-uniform
                 const int32_t p = __shfl_sync(0xffffffffu, v, d + q);
-                const int32_t p1 = p + 1;
-                uint32_t hm = 0;                                     // operator that stabs p: b[j] <= p <= b[j+1] - 2 (S:469 / S:507)
+                uint32_t c = 0;                                      // the operators are disjoint: at most one of them is hit
 #pragma unroll
                 for (int j = 0; j < FC_SLOTS; ++j)
-                    if ((uint32_t)j < nslot) { if (p >= b[j] && p1 < b[j + 1]) hm |= 1u << j; }
-                uint32_t c = ((hm & tM) ? incM : 0u) + ((hm & tN) ? incN : 0u);
+                    asm("{\n\t.reg .pred hit;\n\tsetp.lt.u32 hit, %1, %2;\n\t@hit add.u32 %0, %0, %3;\n\t}" : "+r"(c) : "r"((uint32_t)(p - b[j])), "r"(len1[j]), "r"(wf[j]));
                 c = __reduce_add_sync(0xffffffffu, c);
                 if (lane == q) mine = c;
-                if (hot_run & 1u) {                                  // an anchor: junction ends of the lanes that sit on it (S:494-501)
-                    const int s = ib + d + q;
-                    uint32_t hl = 0, hr = 0, jl = 0, jr = 0;
+            }
+            // anchors in the window: junction ends of the lanes that sit on them (S:494-501)
+            for (uint32_t hs = (hotmask >> d) & ((1u << nw) - 1u); hs; hs &= hs - 1u) {      // warp-uniform; nw <= FC_STAB_MAX < 32
+                const int q = __ffs(hs) - 1;
+                const int32_t p1 = __shfl_sync(0xffffffffu, v, d + q) + 1;
+                const int s = ib + d + q;
+                uint32_t hl = 0, hr = 0, jl = 0, jr = 0;
 #pragma unroll
-                    for (int j = 0; j < FC_SLOTS; ++j) {
-                        if ((tN >> j) & 1u) {
-                            if (p1 == b[j]) { hl = (uint32_t)s + 1u; jl = (uint32_t)j; }            // l = start - 1 (S:482)
-                            if (p1 == b[j + 1]) { hr = (uint32_t)s + 1u; jr = (uint32_t)j; }        // r = end - 1 (S:483)
-                        }
-                    }
-                    // one list entry carries one operator index: the two ends of a lane at this site belong to different operators
-                    if (__any_sync(0xffffffffu, (hl | hr) != 0u)) {
-                        push_hot(list, list_n, hl, 0u, i, jl, lane);
-                        push_hot(list, list_n, 0u, hr, i, jr, lane);
+                for (int j = 0; j < FC_SLOTS; ++j) {
+                    if ((tN >> j) & 1u) {
+                        if (p1 == b[j]) { hl = (uint32_t)s + 1u; jl = (uint32_t)j; }            // l = start - 1 (S:482)
+                        if (p1 == b[j + 1]) { hr = (uint32_t)s + 1u; jr = (uint32_t)j; }        // r = end - 1 (S:483)
                     }
                 }
+                // one list entry carries one operator index: the two ends of a lane at this site belong to different operators
+                if (__any_sync(0xffffffffu, (hl | hr) != 0u)) {
+                    push_hot(list, list_n, hl, 0u, i, jl, lane);
+                    push_hot(list, list_n, 0u, hr, i, jr, lane);
+                }
             }
-            // one lane per site of the window adds the warp's sums to the direct counters (up to four kinds)
+            // one lane per site of the window adds the warp's sums to the direct counters: two 64-bit REDs, each the two strand
+            // classes of a kind (the 32-bit halves cannot carry into each other: a counter never exceeds the record count)
             const int sm_ = ib + d + lane;
             if (mine && lane < nw && sm_ >= own_lo && sm_ < own_hi) {
-                uint32_t* dst = A.cnt.dir + 4 * sm_;
-                if (mine & 0xffu) atomicAdd(dst, mine & 0xffu);
-                if (mine & 0xff00u) atomicAdd(dst + 1, (mine >> 8) & 0xffu);
-                if (mine & 0xff0000u) atomicAdd(dst + 2, (mine >> 16) & 0xffu);
-                if (mine >> 24) atomicAdd(dst + 3, mine >> 24);
+                unsigned long long* dst = reinterpret_cast<unsigned long long*>(A.cnt.dir + 4 * sm_);
+                if (mine & 0xffffu) atomicAdd(dst, (unsigned long long)(mine & 0xffu) | ((unsigned long long)((mine >> 8) & 0xffu) << 32));
+                if (mine >> 16) atomicAdd(dst + 1, (unsigned long long)((mine >> 16) & 0xffu) | ((unsigned long long)(mine >> 24) << 32));
             }
             j0 = FC_SLOTS;
             act = live && nop > (uint32_t)FC_SLOTS;
