@@ -63,6 +63,7 @@ struct FMeta {
 
 struct FSmem {
     FStage st[FC_STAGES];
+    uint4 lut[32];                      // operator table, entry 2 * code + strand class: {advance mask, field of the warp's sum, counted mask, is N}
     unsigned long long list[FC_CWARPS][FC_LIST];
     FMeta meta[FC_STAGES];
     uint32_t next_group[FC_STAGES];     // next group of 32 records of the staged chunk (claimed by the consumer warps)
@@ -94,6 +95,17 @@ __device__ __forceinline__ void run_add(uint32_t* base, uint32_t key, bool v, bo
         const uint32_t n = (uint32_t)((after ? __ffs(after) - 1 : 32) - lane);
         atomicAdd(base + key, neg ? 0u - n : n);
     }
+}
+
+// plain atomics (the compiler wraps atomicAdd in a warp-aggregation sequence of a dozen instructions, which a single
+// elected lane or lanes with distinct addresses do not need)
+__device__ __forceinline__ uint32_t atoms_inc(uint32_t* smem_word) {
+    uint32_t old;
+    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(smem_word)) : "memory");
+    return old;
+}
+__device__ __forceinline__ void red_add64(unsigned long long* p, unsigned long long v) {
+    asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
 // the staged (or, for oversized chunks, global) CIGAR words of a chunk
@@ -242,7 +254,7 @@ constexpr int FC_STAB_MAX = SPL_FC_STAB_MAX;
 static_assert(FC_STAB_MAX < 32, "the anchor loop masks the window's sites with (1 << nw) - 1");
 
 template <bool STAGED>
-__device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsigned long long* list, uint32_t* next_group, const FArgs& A) {
+__device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsigned long long* list, uint32_t* next_group, uint32_t lut_base, const FArgs& A) {
     const int lane = threadIdx.x & 31;
     const DevGraph& g = A.g;
     const CigSrc<STAGED> cw{STAGED ? st.cig : A.rec.cigar, STAGED ? m.cig_base : 0u};
@@ -254,7 +266,7 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
         // a group pushes at most 4 entries per lane on the stab path (two junctions in FC_SLOTS operators)
         if (list_n > (uint32_t)(FC_LIST - 128)) { flush_list(list, list_n, m.rec_lo, A, lane); list_n = 0; }
         uint32_t gi = 0;
-        if (lane == 0) gi = atomicAdd(next_group, 1u);
+        if (lane == 0) gi = atoms_inc(next_group);
         gi = __shfl_sync(0xffffffffu, gi, 0);
         if (gi * 32u >= m.n_rec) break;
         const uint32_t i = gi * 32u + (uint32_t)lane;
@@ -277,22 +289,18 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                 k = read_class(st.flag[m.skip + i], A.mode);
             }
             b[0] = pos;
-            const uint32_t incM = 1u << (8u * k), dN = 0xffffu << (8u * k);          // byte fields of the redux word: cov class 0 / 1, span class 0 / 1 (incN = incM + dN)
+            const uint32_t lut_k = lut_base + (k << 4);             // shared-memory address of this strand class's entries
 #pragma unroll
-            for (int j = 0; j < FC_SLOTS; ++j) {
-                {                                                    // (no test against nslot: nearly every group has a read with FC_SLOTS operators)
-                    const uint32_t cwd = (uint32_t)j < nop ? cw(c0 + j) : 5u;  // filler: a zero-length H (no progression)
-                    const uint32_t op = cwd & 15u, len = cwd >> 4;
-                    // 0 / 1 factors instead of selects: the multiplies run on the FMA pipe, the ALU pipe is the busy one here
-                    const uint32_t adv = (0x18du >> op) & 1u;        // M D N = X advance (S:457-464)
-                    const uint32_t cnt_op = (0x189u >> op) & 1u;     // M = X (S:457-459) and N (S:480-483) stab sites
-                    const uint32_t isN = (0x008u >> op) & 1u;
-                    b[j + 1] = b[j] + (int32_t)(len * adv);
-                    len1[j] = (len - 1u) * cnt_op;                   // length 1 stabs nothing; length 0 sets bit 31 (-> chain path)
-                    zl |= len1[j];
-                    wf[j] = cnt_op * incM + isN * dN;
-                    tN += isN << j;
-                }
+            for (int j = 0; j < FC_SLOTS; ++j) {                     // (no test against the group's longest read: nearly every group has one with FC_SLOTS operators)
+                const uint32_t cwd = (uint32_t)j < nop ? cw(c0 + j) : 5u;      // filler: a zero-length H (no progression)
+                uint4 e;                                             // what the operator code means (S:457-464, :480-483), looked up instead of computed
+                asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(lut_k + ((cwd & 15u) << 5)));
+                const uint32_t len = cwd >> 4;
+                b[j + 1] = b[j] + (int32_t)(len & e.x);
+                len1[j] = (len - 1u) & e.z;                          // length 1 stabs nothing; length 0 sets bit 31 (-> chain path)
+                zl |= len1[j];
+                wf[j] = e.y;
+                tN += e.w << j;
             }
         }
         const bool odd = (zl >> 31) != 0u || __popc(tN) > 2;
@@ -347,8 +355,8 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
             const int sm_ = ib + d + lane;
             if (mine && lane < nw && sm_ >= own_lo && sm_ < own_hi) {
                 unsigned long long* dst = reinterpret_cast<unsigned long long*>(A.cnt.dir + 4 * sm_);
-                if (mine & 0xffffu) atomicAdd(dst, (unsigned long long)(mine & 0xffu) | ((unsigned long long)((mine >> 8) & 0xffu) << 32));
-                if (mine >> 16) atomicAdd(dst + 1, (unsigned long long)((mine >> 16) & 0xffu) | ((unsigned long long)(mine >> 24) << 32));
+                if (mine & 0xffffu) red_add64(dst, (unsigned long long)(mine & 0xffu) | ((unsigned long long)((mine >> 8) & 0xffu) << 32));
+                if (mine >> 16) red_add64(dst + 1, (unsigned long long)((mine >> 16) & 0xffu) | ((unsigned long long)(mine >> 24) << 32));
             }
             j0 = FC_SLOTS;
             act = live && nop > (uint32_t)FC_SLOTS;
@@ -413,6 +421,15 @@ __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_cons
     if (threadIdx.x == 0) {
         for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], FC_CONSUMERS); }
     }
+    if (threadIdx.x < 32) {
+        // entry 2 * code + class: M = X stab sites with the coverage field of the class (S:457-459, :469), N with the span field
+        // (S:480-483, :507), D only advances (S:460-462), I S H P (and the unassigned codes) do nothing
+        const uint32_t op = threadIdx.x >> 1, k = threadIdx.x & 1u;
+        const bool isM = op == 0u || op == 7u || op == 8u, isN = op == 3u, adv = isM || isN || op == 2u;
+        const uint32_t incM = 1u << (8u * k);                        // byte fields of the redux word: cov class 0 / 1, span class 0 / 1
+        sm.lut[threadIdx.x] = make_uint4(adv ? 0xffffffffu : 0u, isM ? incM : (isN ? incM << 16 : 0u), (isM || isN) ? 0xffffffffu : 0u, isN ? 1u : 0u);
+    }
+    const uint32_t lut_base = smem_u32(sm.lut);
     __syncthreads();
     if (warp == FC_CWARPS) {
         // ===== producer =====
@@ -482,8 +499,8 @@ __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_cons
         mbar_wait(&sm.full[stage], parity);
         const FMeta m = sm.meta[stage];
         if (m.flags & FM_DONE) break;
-        if (m.flags & FM_GLOBAL_CIG) consume<false>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], A);
-        else consume<true>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], A);
+        if (m.flags & FM_GLOBAL_CIG) consume<false>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], lut_base, A);
+        else consume<true>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], lut_base, A);
         // every consumer thread releases the stage itself: its reads of the stage (and of the stage's meta data) are ordered
         // before the producer's next copy by its own arrive (release) / the producer's wait (acquire)
         mbar_arrive(&sm.empty[stage]);
