@@ -404,6 +404,10 @@ def main():
     pr = Records(pinned["pos"], pinned["flag"], pinned["cig_off"], pinned["cigar"], r.seg_chrom, r.seg_off)
     pk = api.PackedRecords.from_records(pr, alloc=pinned_empty)      # the packed host layout (17 B per record), page-locked; shares nothing with pr but the segments
     pk.cigar = pr.cigar                                              # (the CIGAR array is the same in both layouts)
+    try:
+        ck = api.CompactRecords.from_records(pr, alloc=pinned_empty)  # the compact host layout (about 9 B per record), page-locked
+    except ValueError:                                               # a record with more than 255 operators: the packed view is the fallback
+        ck = None
 
     def timed_calls(fn):
         fn()                                                         # warm-up (allocations)
@@ -421,7 +425,13 @@ def main():
     plain_step, plain_stats, table = timed_calls(lambda: ctx.process_records(pr, n_chrom, w.junctions, w.flags))
     plain_digest = table_digest(table)
     table = None
-    e2e_step, stats, table = timed_calls(lambda: ctx.process_packed(pk, n_chrom, w.junctions, w.flags))
+    packed_step, packed_stats, table = timed_calls(lambda: ctx.process_packed(pk, n_chrom, w.junctions, w.flags))
+    packed_digest = table_digest(table)
+    if ck is not None:
+        table = None
+        e2e_step, stats, table = timed_calls(lambda: ctx.process_compact(ck, n_chrom, w.junctions, w.flags))
+    else:
+        e2e_step, stats = packed_step, packed_stats
     e2e_val = reads_all / e2e_step
     clocks = sampler.window(t_load, time.time())
     clocks["window"] = "warm-up + timed passes + e2e calls"
@@ -451,8 +461,13 @@ def main():
                 "ms_per_step": 1e3 * e2e_step, "parts": int(stats["n_parts"]),
                 "breakdown_ms": {k: round(stats[k], 3) for k in ("ms_total", "ms_graph", "ms_upload", "ms_count")},
                 "graph_on_device": bool(stats["graph_on_device"]),
-                "note": "host wall clock around spl_process_packed (17 B per record on the wire): junction table -> site table + graph (device), pinned H2D of the records in "
-                        "slabs with the unpack + counting kernels of a slab under the copy of the next, finalize, D2H of the table",
+                "entry_point": "spl_process_compact" if ck is not None else "spl_process_packed",
+                "bytes_per_record_on_the_wire": round(float(stats["h2d_bytes"]) / max(1, len(r)), 2),
+                "note": "host wall clock around spl_process_compact (POS as 16-bit offsets per stride of 1024 records, operator count in a byte, 16-bit CIGAR operators "
+                        "with a 32-bit stream for records with a long one): junction table -> site table + graph (device), pinned H2D of the records in slabs with the "
+                        "unpack + counting kernels of a slab under the copy of the next, finalize, D2H of the table",
+                "packed_view": {"ms_per_step": 1e3 * packed_step, "h2d_bytes_per_step": int(packed_stats["h2d_bytes"]), "identical_table": packed_digest == table_digest(table),
+                                "note": "the same through spl_process_packed (17 B per record: POS i32, three flag bits, operator count u16, CIGAR words)"},
                 "plain_view": {"ms_per_step": 1e3 * plain_step, "h2d_bytes_per_step": int(plain_stats["h2d_bytes"]), "identical_table": plain_digest == table_digest(table),
                                "note": "the same through spl_process_records (20 B per record: POS i32, FLAG u16, cig_off u32, CIGAR words)"}},
         "gpu_launches": int(round(st["launches"] * args.steps)),

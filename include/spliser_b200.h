@@ -134,6 +134,38 @@ int spl_process_packed(spl_ctx* ctx, const spl_packed_view* rec,
                        const int64_t* j_score, const uint8_t* j_strand,
                        uint32_t flags, spl_result** out);
 
+/* The same from a compact host layout: about 9 bytes per record cross PCIe.  Records are taken in strides of
+ * SPL_PACKED_INDEX_STRIDE (the last one may be short).  POS travels as a 16-bit offset from pos_base[stride] (the lowest POS of
+ * the stride); a stride whose positions span more than 65535 has pos_base = -(w + 1) and its POS values, 32-bit, in
+ * pos_wide[w * STRIDE ..].  A record's operators are 16-bit words (op | len << 4) in cigar16 when every length is below 4096,
+ * else BAM-encoded 32-bit words in cigar32 (flag8 bit 3 says which); idx16 / idx32 give the offset of every stride's first
+ * record in the two streams, so that a decoder appends to both as it goes and the device unpacks every stride on its own.
+ * Records with more than 255 operators need the plain or the packed view. */
+typedef struct spl_compact_view {
+    int64_t n_rec;
+    int64_t n_cigar;              /* operators of all records (n16 + n32); must be < 2^32 */
+    int64_t n16, n32;             /* words in cigar16 / cigar32 */
+    int64_t n_wide;               /* strides listed in pos_wide */
+    const uint16_t* pos16;        /* [n_rec]   POS - pos_base[r / STRIDE] (anything for records of a wide stride) */
+    const uint8_t*  flag8;        /* [n_rec]   bits 0-2 as in spl_packed_view; bit 3: the operators are in cigar32 */
+    const uint8_t*  n_op8;        /* [n_rec]   CIGAR operators of the record */
+    const uint16_t* cigar16;      /* [n16] */
+    const uint32_t* cigar32;      /* [n32] */
+    const int32_t*  pos_base;     /* [ceil(n_rec / STRIDE)] */
+    const int32_t*  pos_wide;     /* [n_wide * STRIDE] */
+    const uint32_t* idx16;        /* [ceil(n_rec / STRIDE) + 1] */
+    const uint32_t* idx32;        /* [ceil(n_rec / STRIDE) + 1] */
+    int32_t n_seg;
+    const int32_t*  seg_chrom;    /* as in spl_records_view */
+    const int64_t*  seg_off;
+} spl_compact_view;
+
+int spl_process_compact(spl_ctx* ctx, const spl_compact_view* rec,
+                        int32_t n_chrom,
+                        int64_t n_junc, const int32_t* j_chrom, const int32_t* j_left, const int32_t* j_right,
+                        const int64_t* j_score, const uint8_t* j_strand,
+                        uint32_t flags, spl_result** out);
+
 /* ---- combine re-count (S:899-904) ---------------------------------------------------------- */
 /* One call per sample.  For gap site i: position s_pos[i] on chromosome s_chrom[i] with strand
  * byte s_strand[i] (0 = ''), partner positions p_pos[p_off[i] .. p_off[i+1]) (keys of

@@ -5,7 +5,7 @@ package is its Python host side: ctypes binding, numpy API, BED12 parsing, gene 
 SpliSER-compatible CLI and TSV writers.  Importing the package does not need a GPU; creating a
 Context does, and there is no CPU fallback.
 """
-from .api import (Context, Junctions, PackedRecords, Records, SiteTable, SpliserError, mode_flags,  # noqa: F401
+from .api import (CompactRecords, Context, Junctions, PackedRecords, Records, SiteTable, SpliserError, mode_flags,  # noqa: F401
                   FLAG_COMBINE, FLAG_CRYPTIC, FLAG_RF, FLAG_STRANDED)
 
 __version__ = "0.1.0"

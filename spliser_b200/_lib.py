@@ -38,6 +38,13 @@ class PackedView(C.Structure):
                 ("cigar", c_u32p), ("cig_index", c_u32p), ("n_seg", C.c_int32), ("seg_chrom", c_i32p), ("seg_off", c_i64p)]
 
 
+class CompactView(C.Structure):
+    _fields_ = [("n_rec", C.c_int64), ("n_cigar", C.c_int64), ("n16", C.c_int64), ("n32", C.c_int64), ("n_wide", C.c_int64),
+                ("pos16", c_u16p), ("flag8", c_u8p), ("n_op8", c_u8p), ("cigar16", c_u16p), ("cigar32", c_u32p),
+                ("pos_base", c_i32p), ("pos_wide", c_i32p), ("idx16", c_u32p), ("idx32", c_u32p),
+                ("n_seg", C.c_int32), ("seg_chrom", c_i32p), ("seg_off", c_i64p)]
+
+
 class StrTab(C.Structure):
     _fields_ = [("n", C.c_int64), ("blob", C.c_char_p), ("off", c_i64p)]
 
@@ -67,6 +74,7 @@ SIGNATURES = {
     "spl_process": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, c_strp] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),
     "spl_process_records": (C.c_int, [C.c_void_p, C.POINTER(RecordsView), C.c_int32] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),
     "spl_process_packed": (C.c_int, [C.c_void_p, C.POINTER(PackedView), C.c_int32] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),
+    "spl_process_compact": (C.c_int, [C.c_void_p, C.POINTER(CompactView), C.c_int32] + _JUNC + [C.c_uint32, C.POINTER(C.c_void_p)]),
     "spl_extract_junctions": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int32, c_strp, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "spl_extract_junctions_records": (C.c_int, [C.c_void_p, C.POINTER(RecordsView), C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(C.c_void_p)]),
     "spl_junctions_n": (C.c_int64, [C.c_void_p]),

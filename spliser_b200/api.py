@@ -214,6 +214,112 @@ class PackedRecords:
         return v
 
 
+class CompactRecords:
+    """The compact host layout of spl_process_compact (spl_compact_view), about 9 bytes per record on the wire: POS as a 16-bit
+    offset from the lowest POS of the record's stride of PACKED_INDEX_STRIDE records (strides spanning more than 65535 bp keep
+    their 32-bit positions in pos_wide), operator count in a byte, operators in 16 bits unless the record has one of length
+    >= 4096 (then all of its operators are BAM-encoded in the 32-bit stream).  `alloc` as in PackedRecords."""
+    COLS = (("pos16", np.uint16), ("flag8", np.uint8), ("n_op8", np.uint8), ("cigar16", np.uint16), ("cigar32", np.uint32),
+            ("pos_base", np.int32), ("pos_wide", np.int32), ("idx16", np.uint32), ("idx32", np.uint32))
+
+    def __init__(self, cols, seg_chrom, seg_off):
+        for k, dt in self.COLS:
+            setattr(self, k, np.ascontiguousarray(cols[k], dtype=dt))
+        self.seg_chrom = np.ascontiguousarray(seg_chrom, dtype=np.int32)
+        self.seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+
+    def __len__(self):
+        return len(self.pos16)
+
+    @property
+    def wire_bytes(self):
+        return sum(getattr(self, k).nbytes for k, _ in self.COLS)
+
+    @classmethod
+    def from_records(cls, r: "Records", alloc=None):
+        K = PACKED_INDEX_STRIDE
+        R = len(r)
+        off = r.cig_off.astype(np.int64)
+        nop = np.diff(off)
+        if R and int(nop.max()) > 255:
+            raise ValueError("a record has more than 255 CIGAR operators: use the packed or the plain Records view")
+        # records with an operator of 4096 bases or more keep 32-bit operators
+        long_op = (r.cigar >> 4) >= 4096
+        csum = np.concatenate([[0], np.cumsum(long_op, dtype=np.int64)])
+        rec_long = (csum[off[1:]] - csum[off[:-1]]) > 0
+        op_long = np.repeat(rec_long, nop)
+        c32 = r.cigar[op_long]
+        c16 = r.cigar[~op_long].astype(np.uint16)
+        f = r.flag
+        flag8 = ((f & 1) | (((f >> 4) & 1) << 1) | (((f >> 6) & 1) << 2) | (rec_long.astype(np.uint16) << 3)).astype(np.uint8)
+        nS = np.concatenate([[0], np.cumsum(np.where(rec_long, 0, nop), dtype=np.int64)])
+        nL = np.concatenate([[0], np.cumsum(np.where(rec_long, nop, 0), dtype=np.int64)])
+        NS = (R + K - 1) // K
+        starts = np.minimum(np.arange(NS + 1, dtype=np.int64) * K, R)
+        idx16, idx32 = nS[starts].astype(np.uint32), nL[starts].astype(np.uint32)
+        # positions: per stride the lowest POS and 16-bit offsets, or the stride's 32-bit positions when it spans too much
+        pos = r.pos.astype(np.int64)
+        pad = NS * K - R
+        if NS:
+            lo = np.minimum.reduceat(pos, starts[:-1]) if R else np.zeros(0, np.int64)
+            hi = np.maximum.reduceat(pos, starts[:-1]) if R else np.zeros(0, np.int64)
+        else:
+            lo = hi = np.zeros(0, np.int64)
+        wide = ((hi - lo) > 65535) | (lo < 0)
+        w_id = np.cumsum(wide) - 1
+        pos_base = np.where(wide, -(w_id + 1), lo).astype(np.int32)
+        stride_of = np.arange(R, dtype=np.int64) // K
+        pos16 = np.where(wide[stride_of], 0, pos - lo[stride_of]).astype(np.uint16) if R else np.zeros(0, np.uint16)
+        pos_wide = np.zeros(int(wide.sum()) * K, np.int32)
+        if wide.any():
+            padded = np.concatenate([r.pos, np.zeros(pad, np.int32)]).reshape(NS, K)
+            pos_wide = np.ascontiguousarray(padded[wide]).reshape(-1)
+        cols = dict(pos16=pos16, flag8=flag8, n_op8=nop.astype(np.uint8), cigar16=c16, cigar32=c32, pos_base=pos_base, pos_wide=pos_wide,
+                    idx16=idx16, idx32=idx32)
+        if alloc is not None:
+            for k, a in list(cols.items()):
+                b = alloc(len(a), a.dtype)
+                b[:] = a
+                cols[k] = b
+        return cls(cols, r.seg_chrom, r.seg_off)
+
+    def to_records(self) -> "Records":
+        """The plain view again (numpy restatement of what k_unpack_compact does on the device; used by the CPU tests)."""
+        K = PACKED_INDEX_STRIDE
+        R = len(self)
+        nop = self.n_op8.astype(np.int64)
+        rec_long = (self.flag8 & 8) != 0
+        off = np.concatenate([[0], np.cumsum(nop)])
+        op_long = np.repeat(rec_long, nop)
+        cigar = np.zeros(int(off[-1]), np.uint32)
+        cigar[op_long] = self.cigar32
+        cigar[~op_long] = self.cigar16.astype(np.uint32)
+        stride_of = np.arange(R, dtype=np.int64) // K
+        base = self.pos_base.astype(np.int64)[stride_of] if R else np.zeros(0, np.int64)
+        pos = base + self.pos16.astype(np.int64)
+        w = base < 0
+        if w.any():
+            pos[w] = self.pos_wide[(-(base[w] + 1)) * K + (np.arange(R)[w] % K)]
+        f = self.flag8.astype(np.uint16)
+        flag = ((f & 1) | ((f & 2) << 3) | ((f & 4) << 4)).astype(np.uint16)
+        return Records(pos.astype(np.int32), flag, off.astype(np.uint32), cigar, self.seg_chrom, self.seg_off)
+
+    def view(self) -> L.CompactView:
+        v = L.CompactView()
+        v.n_rec = len(self.pos16)
+        v.n16, v.n32 = len(self.cigar16), len(self.cigar32)
+        v.n_cigar = v.n16 + v.n32
+        v.n_wide = len(self.pos_wide) // PACKED_INDEX_STRIDE
+        v.pos16 = _ptr(self.pos16, L.c_u16p); v.flag8 = _ptr(self.flag8, L.c_u8p); v.n_op8 = _ptr(self.n_op8, L.c_u8p)
+        v.cigar16 = _ptr(self.cigar16, L.c_u16p); v.cigar32 = _ptr(self.cigar32, L.c_u32p)
+        v.pos_base = _ptr(self.pos_base, L.c_i32p); v.pos_wide = _ptr(self.pos_wide, L.c_i32p)
+        v.idx16 = _ptr(self.idx16, L.c_u32p); v.idx32 = _ptr(self.idx32, L.c_u32p)
+        v.n_seg = len(self.seg_chrom)
+        v.seg_chrom = _ptr(self.seg_chrom, L.c_i32p)
+        v.seg_off = _ptr(self.seg_off, L.c_i64p)
+        return v
+
+
 @dataclass
 class GapTable:
     """The (site, sample) gaps of one sample for `combine`'s re-count (S:899-904) in the argument layout of
@@ -415,6 +521,13 @@ class Context:
         h = C.c_void_p()
         rc = self._lib.spl_process_packed(self._h, C.byref(v), n_chrom, *junctions.args(), flags, C.byref(h))
         self._check(rc, "spl_process_packed")
+        return self._take(h)
+
+    def process_compact(self, records: "CompactRecords", n_chrom: int, junctions: Junctions, flags: int) -> SiteTable:
+        v = records.view()
+        h = C.c_void_p()
+        rc = self._lib.spl_process_compact(self._h, C.byref(v), n_chrom, *junctions.args(), flags, C.byref(h))
+        self._check(rc, "spl_process_compact")
         return self._take(h)
 
     def process_bam(self, bam_path, chrom_names, junctions: Junctions, flags: int) -> SiteTable:

@@ -24,6 +24,7 @@
 #include <cstdint>
 #include <mutex>
 
+#include "../../include/spliser_b200.h"
 #include "dev_helpers.cuh"
 #include "device_types.h"
 
@@ -62,8 +63,9 @@ struct FMeta {
 };
 
 struct FSmem {
-    FStage st[FC_STAGES];
     uint4 lut[32];                      // operator table, entry 2 * code + strand class: {advance mask, field of the warp's sum, counted mask, is N}
+                                        // (first member: 512-byte aligned, so that an entry's address is base | code << 5 | class << 4)
+    FStage st[FC_STAGES];
     unsigned long long list[FC_CWARPS][FC_LIST];
     FMeta meta[FC_STAGES];
     uint32_t next_group[FC_STAGES];     // next group of 32 records of the staged chunk (claimed by the consumer warps)
@@ -289,12 +291,12 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                 k = read_class(st.flag[m.skip + i], A.mode);
             }
             b[0] = pos;
-            const uint32_t lut_k = lut_base + (k << 4);             // shared-memory address of this strand class's entries
+            const uint32_t lut_k = lut_base | (k << 4);             // shared-memory address of this strand class's entries
 #pragma unroll
             for (int j = 0; j < FC_SLOTS; ++j) {                     // (no test against the group's longest read: nearly every group has one with FC_SLOTS operators)
                 const uint32_t cwd = (uint32_t)j < nop ? cw(c0 + j) : 5u;      // filler: a zero-length H (no progression)
                 uint4 e;                                             // what the operator code means (S:457-464, :480-483), looked up instead of computed
-                asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(lut_k + ((cwd & 15u) << 5)));
+                asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(lut_k | ((cwd << 5) & 0x1e0u)));
                 const uint32_t len = cwd >> 4;
                 b[j + 1] = b[j] + (int32_t)(len & e.x);
                 len1[j] = (len - 1u) & e.z;                          // length 1 stabs nothing; length 0 sets bit 31 (-> chain path)
@@ -415,10 +417,11 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
 }
 
 __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_constant__ FArgs A) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     FSmem& sm = *reinterpret_cast<FSmem*>(smem_raw);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
+        if (smem_u32(sm.lut) & 511u) __trap();                       // the table's addressing relies on it
         for (int s = 0; s < FC_STAGES; ++s) { mbar_init(&sm.full[s], 1); mbar_init(&sm.empty[s], FC_CONSUMERS); }
     }
     if (threadIdx.x < 32) {
@@ -586,6 +589,61 @@ k_unpack_records(const uint16_t* __restrict__ n_op, const uint8_t* __restrict__ 
     }
 }
 
+// ---- compact host layout -> the same arrays (spl_process_compact) ----------------------------------------------------
+// 9 B per record on the wire instead of 17: POS as a 16-bit offset from the lowest POS of the record's stride of
+// SPL_PACKED_INDEX_STRIDE records (strides wider than 65535 bp keep 32-bit positions in a side array), operator count in a byte,
+// CIGAR operators in 16 bits (op | len << 4, len < 4096) unless the record has a longer operator (then its operators are in the
+// 32-bit stream, BAM-encoded).  Per stride the view carries the offsets of its first record in both operator streams, so every
+// stride unpacks on its own: one CTA per stride, four consecutive records per thread, block-local scans of the two operator
+// counts.  A 16-bit operator zero-extends to the BAM encoding.
+constexpr int UC_THREADS = 256, UC_PER = 4;
+static_assert(UC_THREADS * UC_PER == SPL_PACKED_INDEX_STRIDE, "one CTA unpacks one stride");
+struct CompactDev {
+    const uint16_t* pos16; const uint8_t* flag8; const uint8_t* n_op8;
+    const uint16_t* c16; const uint32_t* c32;
+    const int32_t* pos_base; const int32_t* pos_wide; const uint32_t* idx16; const uint32_t* idx32;
+};
+__global__ void __launch_bounds__(UC_THREADS)
+k_unpack_compact(CompactDev v, uint32_t stride0, uint32_t r_end, int32_t* __restrict__ pos, uint16_t* __restrict__ flag16,
+                 uint32_t* __restrict__ cig_off, uint32_t* __restrict__ cigar) {
+    __shared__ uint32_t wS[UC_THREADS / 32], wL[UC_THREADS / 32];
+    const uint32_t k = stride0 + blockIdx.x;
+    const uint32_t rb = k * (uint32_t)SPL_PACKED_INDEX_STRIDE + threadIdx.x * UC_PER;
+    uint32_t n[UC_PER], f[UC_PER], sS = 0, sL = 0;
+#pragma unroll
+    for (int q = 0; q < UC_PER; ++q) {
+        n[q] = 0; f[q] = 0;
+        if (rb + q < r_end) { n[q] = v.n_op8[rb + q]; f[q] = v.flag8[rb + q]; }
+        if (f[q] & 8u) sL += n[q]; else sS += n[q];
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t iS = sS, iL = sL;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, iS, o), b = __shfl_up_sync(0xffffffffu, iL, o);
+        if (lane >= o) { iS += a; iL += b; }
+    }
+    if (lane == 31) { wS[warp] = iS; wL[warp] = iL; }
+    __syncthreads();
+    uint32_t bS = v.idx16[k] + iS - sS, bL = v.idx32[k] + iL - sL;       // this thread's first operator in either stream
+#pragma unroll
+    for (int w = 0; w < UC_THREADS / 32; ++w) if (w < warp) { bS += wS[w]; bL += wL[w]; }
+    uint32_t out = bS + bL;                                                // operators of all records before this one
+    const int32_t base = v.pos_base[k];
+#pragma unroll
+    for (int q = 0; q < UC_PER; ++q) {
+        const uint32_t r = rb + q;
+        if (r >= r_end) break;
+        cig_off[r] = out;
+        pos[r] = base >= 0 ? base + (int32_t)v.pos16[r] : v.pos_wide[(size_t)(-(base + 1)) * SPL_PACKED_INDEX_STRIDE + (r - k * (uint32_t)SPL_PACKED_INDEX_STRIDE)];
+        flag16[r] = (uint16_t)((f[q] & 1u) | ((f[q] & 2u) << 3) | ((f[q] & 4u) << 4));          // 0x1 paired, 0x10 reverse, 0x40 first in pair
+        if (f[q] & 8u) { for (uint32_t j = 0; j < n[q]; ++j) cigar[out + j] = v.c32[bL + j]; bL += n[q]; }
+        else           { for (uint32_t j = 0; j < n[q]; ++j) cigar[out + j] = (uint32_t)v.c16[bS + j]; bS += n[q]; }
+        out += n[q];
+        if (r + 1 == r_end) cig_off[r_end] = out;                           // the slab's end offset (the next slab writes the same value)
+    }
+}
+
 int fused_grid() {
     static std::mutex mu;
     static int grid_of[64] = {0};
@@ -623,6 +681,16 @@ void launch_unpack_records(const uint16_t* n_op, const uint8_t* flag8, uint32_t 
                            uint16_t* flag16, unsigned long long* desc, uint32_t* ticket, uint32_t epoch, void* stream) {
     if (r1 <= r0) return;
     { SPL_LAUNCH; k_unpack_records<<<(r1 - r0 + UP_TILE - 1) / UP_TILE, UP_THREADS, 0, (cudaStream_t)stream>>>(n_op, flag8, r0, r1, cig_base, cig_off, flag16, desc, ticket, epoch); }
+}
+
+// strides [stride0, ...) up to record r_end of a compact upload: pos / flag / cig_off[.. r_end] / cigar of those records
+void launch_unpack_compact(const uint16_t* pos16, const uint8_t* flag8, const uint8_t* n_op8, const uint16_t* c16, const uint32_t* c32,
+                           const int32_t* pos_base, const int32_t* pos_wide, const uint32_t* idx16, const uint32_t* idx32, uint32_t r0,
+                           uint32_t r1, int32_t* pos, uint16_t* flag16, uint32_t* cig_off, uint32_t* cigar, void* stream) {
+    if (r1 <= r0) return;
+    const CompactDev v{pos16, flag8, n_op8, c16, c32, pos_base, pos_wide, idx16, idx32};
+    const uint32_t s0 = r0 / SPL_PACKED_INDEX_STRIDE, s1 = (r1 + SPL_PACKED_INDEX_STRIDE - 1) / SPL_PACKED_INDEX_STRIDE;
+    { SPL_LAUNCH; k_unpack_compact<<<s1 - s0, UC_THREADS, 0, (cudaStream_t)stream>>>(v, s0, r1, pos, flag16, cig_off, cigar); }
 }
 
 // the queued hot items of every slab, after the counting kernels: one thread per item

@@ -186,6 +186,7 @@ struct spl_ctx {
     double stats[SPL_NSTATS] = {0};
 
     // fused variant (count_fused.cu)
+    DevBuf d_cpk;                                        // the columns of a compact upload (spl_process_compact)
     DevBuf d_frec, d_fchunks, d_hotq, d_fpk, d_unpack;   // d_fpk: packed columns (n_op, flag8) of spl_process_packed; d_unpack: scan descriptors + ticket
     uint32_t unpack_epoch = 0;
     uint32_t hot_cap = 0;           // items the global hot queue holds; a pass that needs more is repeated with room
@@ -840,6 +841,119 @@ int fused_upload_packed(spl_ctx* ctx, const spl_packed_view* v, int32_t n_chrom,
     return SPL_OK;
 }
 
+// The same for the compact host layout (spl_compact_view, about 9 B per record): every stride of SPL_PACKED_INDEX_STRIDE records
+// carries its own anchors (lowest POS, offsets into the 16-bit and the 32-bit operator streams), so a slab is unpacked by one
+// kernel (k_unpack_compact, one CTA per stride) as soon as it has arrived, under the copy of the next slab.
+int fused_upload_compact(spl_ctx* ctx, const spl_compact_view* v, int32_t n_chrom, bool split_ok) {
+    ctx->n_chrom_loaded = n_chrom;
+    std::vector<FChunk> hc;
+    int64_t aligned = 0;
+    for (int32_t k = 0; k < v->n_seg; ++k) {
+        if (v->seg_chrom[k] < 0) continue;
+        const int64_t a = v->seg_off[k], b = v->seg_off[k + 1];
+        aligned += b - a;
+        for (int64_t lo = a; lo < b; lo += FC_RECS) {
+            FChunk c{};
+            c.chrom = v->seg_chrom[k];
+            c.rec_lo = (uint32_t)lo;
+            c.rec_hi = (uint32_t)std::min<int64_t>(lo + FC_RECS, b);
+            hc.push_back(c);
+        }
+    }
+    ctx->n_aligned = aligned;
+    ctx->stats[SPL_STAT_N_ALIGNED] = (double)aligned;
+    ctx->n_fchunks = (uint32_t)hc.size();
+    const size_t R = (size_t)v->n_rec, NC = (size_t)v->n_cigar, K = SPL_PACKED_INDEX_STRIDE;
+    const size_t NS = (R + K - 1) / K, N16 = (size_t)v->n16, N32 = (size_t)v->n32, NW = (size_t)v->n_wide;
+    cudaStream_t cs = ctx->copy_stream;
+    CU(ctx->d_fchunks.reserve((hc.size() + 1) * sizeof(FChunk)));
+    ctx->fchunks = (FChunk*)ctx->d_fchunks.p;
+    if (!hc.empty()) {
+        const size_t bytes = hc.size() * sizeof(FChunk);
+        if (ctx->h_fchunks_bytes < bytes) {
+            if (ctx->h_fchunks) cudaFreeHost(ctx->h_fchunks);
+            ctx->h_fchunks = nullptr; ctx->h_fchunks_bytes = 0;
+            CU(cudaHostAlloc(&ctx->h_fchunks, bytes + bytes / 4 + 4096, cudaHostAllocDefault));
+            ctx->h_fchunks_bytes = bytes + bytes / 4 + 4096;
+        }
+        memcpy(ctx->h_fchunks, hc.data(), bytes);
+        CU(cudaMemcpyAsync(ctx->fchunks, ctx->h_fchunks, bytes, cudaMemcpyHostToDevice, cs));
+        ctx->stats[SPL_STAT_H2D_BYTES] += (double)bytes;
+    }
+    {
+        const uint64_t want = std::max<uint64_t>(1u << 18, (uint64_t)v->n_cigar / 16 + (1u << 16));
+        if (ctx->hot_cap < want) {
+            CU(ctx->d_hotq.reserve((size_t)want * 16));
+            ctx->hot_cap = (uint32_t)std::min<uint64_t>(want, 0xfffffff0u);
+        }
+        *ctx->h_hot = 0;
+    }
+    Carver c;
+    const size_t o_pos = c.take<int32_t>(R + 32), o_flag = c.take<uint16_t>(R + 32), o_off = c.take<uint32_t>(R + 40),
+                 o_cig = c.take<uint32_t>(NC + 32);
+    CU(ctx->d_frec.reserve(c.off + 256));
+    char* rb = (char*)ctx->d_frec.p;
+    ctx->frec.n_rec = (uint32_t)R;
+    ctx->frec.pos = (const int32_t*)(rb + o_pos); ctx->frec.flag = (const uint16_t*)(rb + o_flag);
+    ctx->frec.cig_off = (const uint32_t*)(rb + o_off); ctx->frec.cigar = (const uint32_t*)(rb + o_cig);
+    Carver pc;
+    const size_t p_p16 = pc.take<uint16_t>(R + 32), p_f8 = pc.take<uint8_t>(R + 32), p_n8 = pc.take<uint8_t>(R + 32),
+                 p_c16 = pc.take<uint16_t>(N16 + 32), p_c32 = pc.take<uint32_t>(N32 + 32), p_base = pc.take<int32_t>(NS + 8),
+                 p_i16 = pc.take<uint32_t>(NS + 8), p_i32 = pc.take<uint32_t>(NS + 8), p_wide = pc.take<int32_t>(NW * K + 32);
+    CU(ctx->d_cpk.reserve(pc.off + 256));
+    char* pb = (char*)ctx->d_cpk.p;
+    if (R > 0) {
+        // the per-stride anchors (12 B per 1024 records) and the wide strides' positions go first
+        CU(cudaMemcpyAsync(pb + p_base, v->pos_base, NS * 4, cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(pb + p_i16, v->idx16, (NS + 1) * 4, cudaMemcpyHostToDevice, cs));
+        CU(cudaMemcpyAsync(pb + p_i32, v->idx32, (NS + 1) * 4, cudaMemcpyHostToDevice, cs));
+        if (NW) CU(cudaMemcpyAsync(pb + p_wide, v->pos_wide, NW * K * 4, cudaMemcpyHostToDevice, cs));
+        ctx->stats[SPL_STAT_H2D_BYTES] += (double)(NS * 12 + 8 + NW * K * 4);
+    }
+    int want = 1;
+    {
+        int64_t min_rec = 2000000;
+        int max_parts = MAX_FPARTS;
+        if (const char* f = std::getenv("SPLISER_SPLIT_MIN_RECORDS")) min_rec = std::max<int64_t>(1, atoll(f));
+        if (const char* f = std::getenv("SPLISER_SPLIT_PARTS")) max_parts = std::max(1, std::min(MAX_FPARTS, atoi(f)));
+        if (split_ok) want = (int)std::max<int64_t>(1, std::min<int64_t>(max_parts, (int64_t)R / min_rec));
+        want = (int)std::min<size_t>((size_t)want, std::max<size_t>(1, R / K));
+    }
+    ctx->n_fparts = want;
+    size_t r0 = 0;
+    uint32_t k0 = 0;
+    for (int p = 0; p < want; ++p) {
+        size_t r1 = (p == want - 1) ? R : (R * (size_t)(p + 1) / (size_t)want) / K * K;
+        if (r1 < r0) r1 = r0;
+        uint32_t k1 = k0;
+        while (k1 < hc.size() && hc[k1].rec_hi <= r1) ++k1;
+        ctx->fpart[p].chunk_lo = k0; ctx->fpart[p].chunk_hi = k1;
+        k0 = k1;
+        if (r1 > r0) {
+            const size_t s0 = r0 / K, s1 = (r1 + K - 1) / K;
+            const size_t a16 = v->idx16[s0], b16 = v->idx16[s1], a32 = v->idx32[s0], b32 = v->idx32[s1];
+            CU(cudaMemcpyAsync(pb + p_p16 + r0 * 2, v->pos16 + r0, (r1 - r0) * 2, cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(pb + p_f8 + r0, v->flag8 + r0, (r1 - r0), cudaMemcpyHostToDevice, cs));
+            CU(cudaMemcpyAsync(pb + p_n8 + r0, v->n_op8 + r0, (r1 - r0), cudaMemcpyHostToDevice, cs));
+            if (b16 > a16) CU(cudaMemcpyAsync(pb + p_c16 + a16 * 2, v->cigar16 + a16, (b16 - a16) * 2, cudaMemcpyHostToDevice, cs));
+            if (b32 > a32) CU(cudaMemcpyAsync(pb + p_c32 + a32 * 4, v->cigar32 + a32, (b32 - a32) * 4, cudaMemcpyHostToDevice, cs));
+            ctx->stats[SPL_STAT_H2D_BYTES] += (double)((r1 - r0) * 4 + (b16 - a16) * 2 + (b32 - a32) * 4);
+        }
+        CU(cudaEventRecord(ctx->fpart[p].ev_up, cs));
+        if (r1 > r0) {
+            CU(cudaStreamWaitEvent(ctx->stream, ctx->fpart[p].ev_up, 0));
+            launch_unpack_compact((const uint16_t*)(pb + p_p16), (const uint8_t*)(pb + p_f8), (const uint8_t*)(pb + p_n8),
+                                  (const uint16_t*)(pb + p_c16), (const uint32_t*)(pb + p_c32), (const int32_t*)(pb + p_base),
+                                  (const int32_t*)(pb + p_wide), (const uint32_t*)(pb + p_i16), (const uint32_t*)(pb + p_i32),
+                                  (uint32_t)r0, (uint32_t)r1, (int32_t*)(rb + o_pos), (uint16_t*)(rb + o_flag), (uint32_t*)(rb + o_off),
+                                  (uint32_t*)(rb + o_cig), ctx->stream);
+        }
+        r0 = r1;
+    }
+    ctx->fpart[want - 1].chunk_hi = (uint32_t)hc.size();
+    return SPL_OK;
+}
+
 // fused variant: one pass = counters zeroed, one counting kernel per slab (as soon as the slab has arrived), finalize
 int fused_count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     if (ev) CU(cudaEventRecord(ev[0], ctx->stream));
@@ -1015,7 +1129,7 @@ void adopt_device_graph(spl_ctx* ctx) {
 
 int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
                 const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand, uint32_t flags,
-                bool split_ok, const spl_packed_view* packed = nullptr) {
+                bool split_ok, const spl_packed_view* packed = nullptr, const spl_compact_view* compact = nullptr) {
     ctx->loaded = false;
     if (ctx->pending) { cudaStreamSynchronize(ctx->stream2); spl_result_free(ctx->pending); ctx->pending = nullptr; }
     int rc = check_view(ctx, rec, n_chrom);
@@ -1084,7 +1198,8 @@ int load_common(spl_ctx* ctx, const spl_records_view* rec, int32_t n_chrom, int6
     if (dbg_on) { for (auto& e : dbg) cudaEventCreate(&e); cudaEventRecord(dbg[0], ctx->copy_stream); }
     if (fused) {
         ctx->n_parts = 0;
-        rc = packed ? fused_upload_packed(ctx, packed, n_chrom, split_ok) : fused_upload(ctx, rec, n_chrom, split_ok);
+        rc = compact ? fused_upload_compact(ctx, compact, n_chrom, split_ok)
+                     : packed ? fused_upload_packed(ctx, packed, n_chrom, split_ok) : fused_upload(ctx, rec, n_chrom, split_ok);
         if (rc) return rc;
     }
     for (int p = 0; p < ctx->n_parts; ++p) {
@@ -1309,7 +1424,7 @@ void spl_destroy(spl_ctx* ctx) {
             if (ctx->part[p].ev_e1) cudaEventDestroy(ctx->part[p].ev_e1);
         }
         if (ctx->copy_stream) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamDestroy(ctx->copy_stream); }
-        ctx->d_frec.release(); ctx->d_fchunks.release(); ctx->d_hotq.release();
+        ctx->d_frec.release(); ctx->d_fchunks.release(); ctx->d_hotq.release(); ctx->d_fpk.release(); ctx->d_unpack.release(); ctx->d_cpk.release();
         if (ctx->h_hot) cudaFreeHost(ctx->h_hot);
         if (ctx->h_fchunks) cudaFreeHost(ctx->h_fchunks);
         for (int p = 0; p < MAX_FPARTS; ++p) if (ctx->fpart[p].ev_up) cudaEventDestroy(ctx->fpart[p].ev_up);
@@ -1412,6 +1527,56 @@ int spl_process_packed(spl_ctx* ctx, const spl_packed_view* pv, int32_t n_chrom,
     const double t0 = now_ms();
     ctx->rec_on_device = true;                                         // check_view: no host record arrays to look at
     int rc = load_common(ctx, &shell, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, true, pv);
+    ctx->rec_on_device = false;
+    if (rc) return drain_on_error(ctx, rc);
+    const double tc0 = now_ms();
+    for (;;) {
+        rc = count_pass(ctx, nullptr);
+        if (rc) return drain_on_error(ctx, rc);
+        rc = drain_on_error(ctx, fetch(ctx, out));
+        if (rc) return rc;
+        bool again = false;
+        rc = hot_queue_overflow(ctx, &again);
+        if (rc) { spl_result_free(*out); *out = nullptr; return rc; }
+        if (!again) break;
+        spl_result_free(*out); *out = nullptr;
+    }
+    ctx->stats[SPL_STAT_MS_COUNT] = now_ms() - tc0;
+    ctx->stats[SPL_STAT_MS_TOTAL] = now_ms() - t0;
+    return rc;
+}
+
+int spl_process_compact(spl_ctx* ctx, const spl_compact_view* cv, int32_t n_chrom, int64_t n_junc, const int32_t* j_chrom,
+                        const int32_t* j_left, const int32_t* j_right, const int64_t* j_score, const uint8_t* j_strand,
+                        uint32_t flags, spl_result** out) {
+    if (!ctx) return SPL_ERR_ARG;
+    if (!out) return ctx->fail(SPL_ERR_ARG, "out is NULL");
+    *out = nullptr;
+    if (!ctx->stream) return ctx->fail(SPL_ERR_CUDA, "context has no CUDA device; libspliser_b200 has no CPU fallback");
+    if (!cv) return ctx->fail(SPL_ERR_ARG, "compact view is NULL");
+    if (ctx->variant != SPL_VARIANT_FUSED) return ctx->fail(SPL_ERR_ARG, "the compact view is read by the fused variant only");
+    if (cv->n_rec < 0 || cv->n16 < 0 || cv->n32 < 0 || cv->n_wide < 0 || cv->n16 + cv->n32 != cv->n_cigar)
+        return ctx->fail(SPL_ERR_ARG, "compact view: inconsistent sizes");
+    if (cv->n_rec > 0 && (!cv->pos16 || !cv->flag8 || !cv->n_op8 || !cv->pos_base || !cv->idx16 || !cv->idx32))
+        return ctx->fail(SPL_ERR_ARG, "NULL compact array");
+    if ((cv->n16 > 0 && !cv->cigar16) || (cv->n32 > 0 && !cv->cigar32) || (cv->n_wide > 0 && !cv->pos_wide))
+        return ctx->fail(SPL_ERR_ARG, "NULL compact array");
+    {   // the anchors are what the device trusts: check them here (12 B per 1024 records)
+        const int64_t K = SPL_PACKED_INDEX_STRIDE, NS = (cv->n_rec + K - 1) / K;
+        if (cv->n_rec > 0 && (cv->idx16[0] != 0 || cv->idx32[0] != 0 || (int64_t)cv->idx16[NS] != cv->n16 || (int64_t)cv->idx32[NS] != cv->n32))
+            return ctx->fail(SPL_ERR_ARG, "compact view: operator index does not span the streams");
+        for (int64_t k = 0; k < NS; ++k) {
+            if (cv->idx16[k + 1] < cv->idx16[k] || cv->idx32[k + 1] < cv->idx32[k]) return ctx->fail(SPL_ERR_ARG, "compact view: operator index not monotonic");
+            if ((uint64_t)(cv->idx16[k + 1] - cv->idx16[k]) + (cv->idx32[k + 1] - cv->idx32[k]) > 255u * (uint64_t)K)
+                return ctx->fail(SPL_ERR_ARG, "compact view: a stride claims more operators than its records can hold");
+            if (cv->pos_base[k] < 0 && -(int64_t)cv->pos_base[k] - 1 >= cv->n_wide) return ctx->fail(SPL_ERR_ARG, "compact view: wide stride out of range");
+        }
+    }
+    spl_records_view shell{};
+    shell.n_rec = cv->n_rec; shell.n_cigar = cv->n_cigar; shell.n_seg = cv->n_seg; shell.seg_chrom = cv->seg_chrom; shell.seg_off = cv->seg_off;
+    const double t0 = now_ms();
+    ctx->rec_on_device = true;                                         // check_view: no host record arrays to look at
+    int rc = load_common(ctx, &shell, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, true, nullptr, cv);
     ctx->rec_on_device = false;
     if (rc) return drain_on_error(ctx, rc);
     const double tc0 = now_ms();

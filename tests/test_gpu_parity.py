@@ -199,6 +199,54 @@ def test_packed_view_equals_plain_view(ctx, monkeypatch, parts):
         assert c_oracle.diff_tables(a, b) is None, (seed, c_oracle.diff_tables(a, b))
 
 
+@pytest.mark.parametrize("parts", [1, 3])
+def test_compact_view_equals_plain_view(ctx, monkeypatch, parts):
+    """spl_process_compact (16-bit POS offsets per stride, operator count in a byte, 16-bit operators with a 32-bit stream for
+    records with a long one; every stride unpacked on the device from its own anchors) gives the table of spl_process_records:
+    a stranded paired sample in one slab and three, a GRCh38-shaped tile (wide strides, introns of 4096 bases and more),
+    shuffled records (every stride wide) and the fuzz generator's flag / CIGAR shapes incl. empty inputs."""
+    import numpy as np
+    from oracle import c_oracle, fuzzgen
+    from spliser_b200 import CompactRecords, Records, synth
+    from spliser_b200.bed import parse_bed12
+    w = synth.generate(synth.config_small(150_000, seed=77, stranded=True, paired=True))
+    want = c_oracle.process(w.records, len(w.chroms), w.junctions, w.flags | 4, threads=8)
+    monkeypatch.setenv("SPLISER_SPLIT_MIN_RECORDS", "1000" if parts > 1 else "1000000000")
+    monkeypatch.setenv("SPLISER_SPLIT_PARTS", str(parts))
+    ck = CompactRecords.from_records(w.records)
+    assert ck.wire_bytes < 10 * len(w.records)
+    got = c_oracle.table_dict(ctx.process_compact(ck, len(w.chroms), w.junctions, w.flags | 4))
+    assert ctx.stats()["n_parts"] == float(parts)
+    assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
+    w3 = synth.generate(synth.config_c3_tile(200_000, tile=1))
+    ck3 = CompactRecords.from_records(w3.records)
+    assert len(ck3.cigar32) > 0 and len(ck3.pos_wide) > 0 and len(ck3.cigar16) > 0
+    a = c_oracle.table_dict(ctx.process_records(w3.records, len(w3.chroms), w3.junctions, w3.flags | 4))
+    b = c_oracle.table_dict(ctx.process_compact(ck3, len(w3.chroms), w3.junctions, w3.flags | 4))
+    assert c_oracle.diff_tables(a, b) is None, c_oracle.diff_tables(a, b)
+    monkeypatch.delenv("SPLISER_SPLIT_MIN_RECORDS"); monkeypatch.delenv("SPLISER_SPLIT_PARTS")
+    # shuffled inside the segments: positions of a stride span the chromosome
+    r = w.records
+    rng = np.random.default_rng(3)
+    order = np.concatenate([int(r.seg_off[s]) + rng.permutation(int(r.seg_off[s + 1] - r.seg_off[s])) for s in range(len(r.seg_chrom))])
+    nop = np.diff(r.cig_off.astype(np.int64))[order]
+    off = np.concatenate([[0], np.cumsum(nop)])
+    src = np.repeat(r.cig_off[:-1].astype(np.int64)[order], nop) + (np.arange(int(off[-1])) - np.repeat(off[:-1], nop))
+    sh = Records(r.pos[order], r.flag[order], off, r.cigar[src], r.seg_chrom, r.seg_off)
+    b = c_oracle.table_dict(ctx.process_compact(CompactRecords.from_records(sh), len(w.chroms), w.junctions, w.flags | 4))
+    assert c_oracle.diff_tables(b, want) is None, c_oracle.diff_tables(b, want)
+    for seed in range(940000, 940030):                       # every flag combination / CIGAR shape of the fuzz generator
+        case = fuzzgen.gen_case(seed, n_chrom=1 + (seed % 2), dirty=(seed % 4 == 1), max_reads=60)
+        chroms, junc, _ = parse_bed12(case["bed"].splitlines(True))
+        rec = Records.from_reads(chroms, [tuple(r) for r in case["reads"]])
+        a = c_oracle.table_dict(ctx.process_records(rec, len(chroms), junc, case_flags(case)))
+        b = c_oracle.table_dict(ctx.process_compact(CompactRecords.from_records(rec), len(chroms), junc, case_flags(case)))
+        assert c_oracle.diff_tables(a, b) is None, (seed, c_oracle.diff_tables(a, b))
+    empty = Records.from_reads(["A"], [])
+    t = ctx.process_compact(CompactRecords.from_records(empty), len(w.chroms), w.junctions, w.flags)
+    assert int(t.beta1.sum()) == 0 and np.array_equal(t.alpha, got["alpha"])
+
+
 def test_shuffled_records_give_identical_counts(ctx):
     """Any record order inside a chromosome segment is exact (the sorted-input fast paths have fallbacks)."""
     import numpy as np

@@ -524,3 +524,33 @@ def test_bed_parsed_alone_then_appended_equals_parse_after_the_annotation(built_
         for k in ("chrom", "left", "right", "score", "strand"):
             assert np.array_equal(getattr(got_j, k), getattr(want_j, k)), (trial, k)
         assert list(alone_s) == list(want_s)
+
+
+def test_compact_records_round_trip():
+    """api.CompactRecords (the host layout of spl_process_compact): packing and the numpy restatement of the device's unpack
+    give the plain view back -- sorted and shuffled records, a GRCh38-shaped tile (wide strides, long introns in the 32-bit
+    stream), empty input; records with more than 255 operators are refused."""
+    import numpy as np
+    import pytest
+    from spliser_b200 import CompactRecords, Records, synth
+    for cfg in (synth.config_small(30_000, seed=5, stranded=True, paired=True), synth.config_c3_tile(40_000, tile=2)):
+        r = synth.generate(cfg).records
+        for shuffled in (False, True):
+            if shuffled:
+                order = np.random.default_rng(2).permutation(len(r))
+                nop = np.diff(r.cig_off.astype(np.int64))[order]
+                off = np.concatenate([[0], np.cumsum(nop)])
+                src = np.repeat(r.cig_off[:-1].astype(np.int64)[order], nop) + (np.arange(int(off[-1])) - np.repeat(off[:-1], nop))
+                r = Records(r.pos[order], r.flag[order], off, r.cigar[src], [0], [0, len(r)])
+            c = CompactRecords.from_records(r)
+            back = c.to_records()
+            assert np.array_equal(back.pos, r.pos) and np.array_equal(back.cig_off, r.cig_off) and np.array_equal(back.cigar, r.cigar)
+            assert np.array_equal(back.flag, r.flag & (1 | 16 | 64))
+            v = c.view()
+            assert v.n16 + v.n32 == v.n_cigar == len(r.cigar) and int(c.idx16[-1]) == v.n16 and int(c.idx32[-1]) == v.n32
+            assert np.all((r.cigar[np.repeat((c.flag8 & 8) == 0, c.n_op8)] >> 4) < 4096)
+    e = CompactRecords.from_records(Records.from_reads(["A"], []))
+    assert len(e) == 0 and len(e.idx16) == 1 and len(e.to_records()) == 0
+    big = Records.from_reads(["A"], [("A", 10, 0, "1M1I" * 130)])
+    with pytest.raises(ValueError):
+        CompactRecords.from_records(big)
