@@ -82,7 +82,8 @@ k_rs_scatter(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32
 // ---- single-pass exclusive scan (decoupled look-back): one launch, no host-known length needed ------------------
 // Tiles take tickets from a counter (so every predecessor of a running tile is running or done) and publish
 // (epoch | flag | value) in one 64-bit word; a new epoch per call makes the words of earlier calls read as "not yet".
-constexpr int LB_THREADS = 256, LB_ITEMS = 8, LB_TILE = LB_THREADS * LB_ITEMS;
+constexpr int LB_THREADS = 512, LB_ITEMS = 16, LB_TILE = LB_THREADS * LB_ITEMS;   // big tiles: the tables are 10^5 - 10^6 elements, and a
+                                                                               // tile's look-back costs one L2 round trip per 32 predecessors
 constexpr unsigned long long LB_AGG = 1ull, LB_PREFIX = 2ull;
 
 __global__ void __launch_bounds__(LB_THREADS)
@@ -614,20 +615,17 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     { SPL_LAUNCH; k_gb_chroms<<<1, 256, 0, st>>>(g, n_chrom, d_cnt); }
 
     // ---- B: Partners / PartnerCounts entries per site
-    GB_CU(cudaMemsetAsync(npt, 0, ((size_t)n2 + 4) * 4, st));
+    GB_CU(cudaMemsetAsync(npt, 0, (size_t)((char*)(c2 + n2 + 4) - (char*)npt), st));   // npt, ncp, rp_cnt, rp_cur: adjacent in the carve
     { SPL_LAUNCH; k_gb_pt_count<<<cdiv(n2, 128), 128, 0, st>>>(g, d_cnt, site_of, inc_eid, npt); }
     sc.scan(npt, n2 + 2, d_cnt + 7, d_cnt + 2);
     { SPL_LAUNCH; k_gb_pt_fill<<<cdiv(n2 + 1, 128), 128, 0, st>>>(g, d_cnt, site_of, inc_eid, npt, e_src); }
 
     // ---- D: competitors
-    GB_CU(cudaMemsetAsync(ncp, 0, ((size_t)n2 + 4) * 4, st));
     { SPL_LAUNCH; k_gb_cp_count<<<cdiv(n2, 128), 128, 0, st>>>(g, d_cnt, ncp); }
     sc.scan(ncp, n2 + 2, d_cnt + 7, d_cnt + 4);
     { SPL_LAUNCH; k_gb_cp_fill<<<cdiv(n2 + 1, 128), 128, 0, st>>>(g, d_cnt, ncp, (uint32_t)std::min<size_t>(m.cap_c, 0xffffffffu)); }
 
     // ---- E: reverse partners, hot flags, bin index
-    GB_CU(cudaMemsetAsync(c1, 0, ((size_t)n2 + 4) * 4, st));               // rp_cnt
-    GB_CU(cudaMemsetAsync(c2, 0, ((size_t)n2 + 4) * 4, st));               // rp_cur
     { SPL_LAUNCH; k_gb_rp_count<<<cdiv(n2, 256), 256, 0, st>>>(g, d_cnt, c1); }
     sc.scan(c1, n2 + 2, d_cnt + 7, d_cnt + 5);
     { SPL_LAUNCH; k_gb_rp_fill<<<cdiv(n2 + 2, 256), 256, 0, st>>>(g, d_cnt, e_src, c1, c2); }

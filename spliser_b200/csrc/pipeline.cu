@@ -1576,15 +1576,28 @@ int spl_process_compact(spl_ctx* ctx, const spl_compact_view* cv, int32_t n_chro
     shell.n_rec = cv->n_rec; shell.n_cigar = cv->n_cigar; shell.n_seg = cv->n_seg; shell.seg_chrom = cv->seg_chrom; shell.seg_off = cv->seg_off;
     const double t0 = now_ms();
     ctx->rec_on_device = true;                                         // check_view: no host record arrays to look at
+    bool timeline = std::getenv("SPLISER_TIMING") != nullptr;
+    cudaEvent_t te[3] = {nullptr, nullptr, nullptr};
+    if (timeline) { for (auto& e : te) cudaEventCreate(&e); cudaEventRecord(te[0], ctx->copy_stream); }
     int rc = load_common(ctx, &shell, n_chrom, n_junc, j_chrom, j_left, j_right, j_score, j_strand, flags, true, nullptr, cv);
     ctx->rec_on_device = false;
     if (rc) return drain_on_error(ctx, rc);
+    if (timeline) cudaEventRecord(te[2], ctx->copy_stream);            // behind the last slab's copy
     const double tc0 = now_ms();
     for (;;) {
         rc = count_pass(ctx, nullptr);
         if (rc) return drain_on_error(ctx, rc);
+        if (timeline) cudaEventRecord(te[1], ctx->stream);
         rc = drain_on_error(ctx, fetch(ctx, out));
         if (rc) return rc;
+        if (timeline) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, te[0], te[2]); cudaEventElapsedTime(&b, te[0], te[1]);
+            fprintf(stderr, "[compact] host: load returned +%.2f ms, fetch done +%.2f ms; device: last slab arrived +%.2f ms, finalize done +%.2f ms\n",
+                    tc0 - t0, now_ms() - t0, a, b);
+            for (auto& e : te) cudaEventDestroy(e);
+            timeline = false;
+        }
         bool again = false;
         rc = hot_queue_overflow(ctx, &again);
         if (rc) { spl_result_free(*out); *out = nullptr; return rc; }
