@@ -41,7 +41,7 @@ constexpr int FC_CONSUMERS = FC_CWARPS * 32;
 constexpr int FC_THREADS = FC_CONSUMERS + 32;
 constexpr int FC_RPAD = 16;                 // slack for the 16-byte alignment of the staged record slices
 constexpr int FC_CIG = 4096;                // staged CIGAR words per stage (a chunk with more reads them from global memory)
-constexpr int FC_LIST = 192;                // hot items per warp list
+constexpr int FC_LIST = 160;                // hot items per warp list
 constexpr int FC_BATCH = 2;                 // chunks a producer claims per atomic
 constexpr int FC_WALK = 256;                // operators longer than this jump through the bin index instead of walking
 constexpr int FC_MAXJ = 4, FC_MAXB = 6;     // junctions / blocks of a read kept in registers by the exception path
@@ -67,6 +67,7 @@ struct FSmem {
                                         // (first member: 512-byte aligned, so that an entry's address is base | code << 5 | class << 4)
     FStage st[FC_STAGES];
     unsigned long long list[FC_CWARPS][FC_LIST];
+    uint32_t lother[FC_CWARPS][FC_LIST];  // the junction's other end (position) of every list entry
     FMeta meta[FC_STAGES];
     uint32_t next_group[FC_STAGES];     // next group of 32 records of the staged chunk (claimed by the consumer warps)
     uint64_t full[FC_STAGES], empty[FC_STAGES];
@@ -80,7 +81,7 @@ struct FArgs {
     DevCounters cnt;
     uint32_t* work;
     uint32_t mode;
-    uint4* hotq;             // global queue of hot (record, operator, side) items: {anchor, record, operator | side << 31, weight}
+    uint4* hotq;             // global queue of hot (record, operator, side) items: {anchor, record, operator | side << 31, position of the junction's other end}
     uint32_t* hot_n;         // [0] items written (may exceed hot_cap: the excess was dropped and the pass must be repeated with room)
     uint32_t hot_cap;
     uint32_t rec_base;       // (unused by the kernel; kept for symmetry with the item layout: records are absolute indices)
@@ -167,7 +168,17 @@ struct ReadWalk {            // any read: every access walks the CIGAR again (lo
 // (S:494-557).  Runs in k_hot_items, one thread per queued item, from the record arrays in global memory.
 __device__ __forceinline__ void hot_item(const DevRecords& rec, const DevGraph& g, const DevCounters& cnt, uint32_t mode, uint4 it) {
     const int anchor = (int)it.x;
-    const uint32_t ri = it.y, side = it.z >> 31, j = it.z & 0x7fffffffu, wgt = it.w;
+    const uint32_t ri = it.y, side = it.z >> 31, j = it.z & 0x7fffffffu;
+    // the junction: the anchored end sits on the anchor's position, the item carries the other one.  Most items end here: the
+    // anchor is hot because SOME junction through it is a partner/competitor pair for a site -- this one only if its other end
+    // is a competitor of a site of the anchor's reverse-partner list (graph lookups only, no record is touched)
+    const int32_t ap = __ldg(g.site_pos + anchor), other = (int32_t)it.w;
+    const int32_t jl = side == 0u ? ap : other, jr = side == 0u ? other : ap;
+    const int q0 = g.rp_off[anchor], q1 = g.rp_off[anchor + 1];
+    int first = -1;
+    for (int q = q0; q < q1 && first < 0; ++q)
+        if (k4_pair_site(g, q, (int)side, jl, jr) >= 0) first = q;
+    if (first < 0) return;
     const int32_t pos = __ldg(rec.pos + ri);
     const uint32_t c0 = __ldg(rec.cig_off + ri), nop = __ldg(rec.cig_off + ri + 1) - c0;
     const uint32_t k = read_class(__ldg(rec.flag + ri), mode);
@@ -175,7 +186,7 @@ __device__ __forceinline__ void hot_item(const DevRecords& rec, const DevGraph& 
     const CigSrc<false> cw{rec.cigar, 0u};
     ReadRegs rr;
     rr.nj = rr.nb = rr.jrel = 0;
-    int32_t cur = pos, jl = 0, jr = 0;
+    int32_t cur = pos;
     bool seen = false;
     for (uint32_t q = 0; q < nop; ++q) {
         const uint32_t w = cw(c0 + q), op = w & 15u;
@@ -184,7 +195,7 @@ __device__ __forceinline__ void hot_item(const DevRecords& rec, const DevGraph& 
             if (rr.nb < (uint32_t)FC_MAXB) { rr.bsv[rr.nb] = cur; rr.bev[rr.nb] = (uint32_t)(cur + len); }
             ++rr.nb; cur += len; seen = true;
         } else if (op == 3u) {
-            if (q == j) { rr.jrel = rr.nj; jl = cur - 1; jr = cur + len - 1; }
+            if (q == j) rr.jrel = rr.nj;
             if (rr.nj < (uint32_t)FC_MAXJ) { rr.jlv[rr.nj] = (uint32_t)(cur - 1) | (seen ? 0u : 0x80000000u); rr.jrv[rr.nj] = (uint32_t)(cur + len - 1); }
             ++rr.nj; cur += len; seen = true;
         } else if (op == 2u) {
@@ -192,15 +203,15 @@ __device__ __forceinline__ void hot_item(const DevRecords& rec, const DevGraph& 
         }
     }
     if (rr.nj <= (uint32_t)FC_MAXJ && rr.nb <= (uint32_t)FC_MAXB) {
-        for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
+        for (int q = first; q < q1; ++q) {
             const int t = k4_pair_site(g, q, (int)side, jl, jr);
-            if (t >= 0) k4_classify(rr, g, cnt, t, k, combine, wgt);
+            if (t >= 0) k4_classify(rr, g, cnt, t, k, combine, 1u);
         }
     } else {
         const ReadWalk<false> rw{cw, c0, nop, pos, rr.nj, rr.nb, rr.jrel};
-        for (int q = g.rp_off[anchor]; q < g.rp_off[anchor + 1]; ++q) {
+        for (int q = first; q < q1; ++q) {
             const int t = k4_pair_site(g, q, (int)side, jl, jr);
-            if (t >= 0) k4_classify(rw, g, cnt, t, k, combine, wgt);
+            if (t >= 0) k4_classify(rw, g, cnt, t, k, combine, 1u);
         }
     }
 }
@@ -212,7 +223,7 @@ __global__ void __launch_bounds__(256) k_hot_items(DevRecords rec, DevGraph g, D
 }
 
 // the warp's list goes to the global queue: one reservation per flush
-__device__ __forceinline__ void flush_list(const unsigned long long* list, uint32_t list_n, uint32_t rec_lo, const FArgs& A, int lane) {
+__device__ __forceinline__ void flush_list(const unsigned long long* list, const uint32_t* lother, uint32_t list_n, uint32_t rec_lo, const FArgs& A, int lane) {
     __syncwarp();
     uint32_t base = 0;
     if (lane == 0) base = atomicAdd(A.hot_n, list_n);
@@ -220,19 +231,21 @@ __device__ __forceinline__ void flush_list(const unsigned long long* list, uint3
     for (uint32_t x = (uint32_t)lane; x < list_n; x += 32) {
         const unsigned long long it = list[x];
         const uint32_t lo = (uint32_t)it;
-        if (base + x < A.hot_cap) A.hotq[base + x] = make_uint4((uint32_t)(it >> 32), rec_lo + (lo >> 21), (lo & 0xfffffu) | (((lo >> 20) & 1u) << 31), 1u);
+        if (base + x < A.hot_cap) A.hotq[base + x] = make_uint4((uint32_t)(it >> 32), rec_lo + (lo >> 21), (lo & 0xfffffu) | (((lo >> 20) & 1u) << 31), lother[x]);
     }
     __syncwarp();
 }
 
-// hot endpoints of this step go to the warp's list: hl / hr = anchor + 1 of the junction's left / right end (0: not hot)
-__device__ __forceinline__ void push_hot(unsigned long long* list, uint32_t& list_n, uint32_t hl, uint32_t hr, uint32_t i, uint32_t j, int lane) {
+// hot endpoints of this step go to the warp's list: hl / hr = anchor + 1 of the junction's left / right end (0: not hot);
+// pl / pr = the junction's l / r (each entry carries the end that is NOT on its anchor)
+__device__ __forceinline__ void push_hot(unsigned long long* list, uint32_t* lother, uint32_t& list_n, uint32_t hl, uint32_t hr, int32_t pl, int32_t pr,
+                                         uint32_t i, uint32_t j, int lane) {
     const uint32_t pm_l = __ballot_sync(0xffffffffu, hl != 0u), pm_r = __ballot_sync(0xffffffffu, hr != 0u);
     if (pm_l | pm_r) {
         const uint32_t lt = (1u << lane) - 1u;
         const uint32_t tag = (i << 21) | (j & 0xfffffu);
-        if (hl) list[list_n + __popc(pm_l & lt)] = ((unsigned long long)(hl - 1u) << 32) | tag;
-        if (hr) list[list_n + __popc(pm_l) + __popc(pm_r & lt)] = ((unsigned long long)(hr - 1u) << 32) | tag | (1u << 20);
+        if (hl) { const uint32_t x = list_n + __popc(pm_l & lt); list[x] = ((unsigned long long)(hl - 1u) << 32) | tag; lother[x] = (uint32_t)pr; }
+        if (hr) { const uint32_t x = list_n + __popc(pm_l) + __popc(pm_r & lt); list[x] = ((unsigned long long)(hr - 1u) << 32) | tag | (1u << 20); lother[x] = (uint32_t)pl; }
         list_n += (uint32_t)(__popc(pm_l) + __popc(pm_r));
     }
 }
@@ -256,7 +269,7 @@ constexpr int FC_STAB_MAX = SPL_FC_STAB_MAX;
 static_assert(FC_STAB_MAX < 32, "the anchor loop masks the window's sites with (1 << nw) - 1");
 
 template <bool STAGED>
-__device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsigned long long* list, uint32_t* next_group, uint32_t lut_base, const FArgs& A) {
+__device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsigned long long* list, uint32_t* lother, uint32_t* next_group, uint32_t lut_base, const FArgs& A) {
     const int lane = threadIdx.x & 31;
     const DevGraph& g = A.g;
     const CigSrc<STAGED> cw{STAGED ? st.cig : A.rec.cigar, STAGED ? m.cig_base : 0u};
@@ -266,7 +279,7 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
     uint32_t list_n = 0;                                             // warp-uniform
     for (;;) {
         // a group pushes at most 4 entries per lane on the stab path (two junctions in FC_SLOTS operators)
-        if (list_n > (uint32_t)(FC_LIST - 128)) { flush_list(list, list_n, m.rec_lo, A, lane); list_n = 0; }
+        if (list_n > (uint32_t)(FC_LIST - 128)) { flush_list(list, lother, list_n, m.rec_lo, A, lane); list_n = 0; }
         uint32_t gi = 0;
         if (lane == 0) gi = atoms_inc(next_group);
         gi = __shfl_sync(0xffffffffu, gi, 0);
@@ -339,17 +352,18 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                 const int32_t p1 = __shfl_sync(0xffffffffu, v, d + q) + 1;
                 const int s = ib + d + q;
                 uint32_t hl = 0, hr = 0, jl = 0, jr = 0;
+                int32_t ol = 0, orr = 0;                              // the other end of the junction whose left / right end sits here
 #pragma unroll
                 for (int j = 0; j < FC_SLOTS; ++j) {
                     if ((tN >> j) & 1u) {
-                        if (p1 == b[j]) { hl = (uint32_t)s + 1u; jl = (uint32_t)j; }            // l = start - 1 (S:482)
-                        if (p1 == b[j + 1]) { hr = (uint32_t)s + 1u; jr = (uint32_t)j; }        // r = end - 1 (S:483)
+                        if (p1 == b[j]) { hl = (uint32_t)s + 1u; jl = (uint32_t)j; ol = b[j + 1] - 1; }        // l = start - 1 (S:482)
+                        if (p1 == b[j + 1]) { hr = (uint32_t)s + 1u; jr = (uint32_t)j; orr = b[j] - 1; }       // r = end - 1 (S:483)
                     }
                 }
                 // one list entry carries one operator index: the two ends of a lane at this site belong to different operators
                 if (__any_sync(0xffffffffu, (hl | hr) != 0u)) {
-                    push_hot(list, list_n, hl, 0u, i, jl, lane);
-                    push_hot(list, list_n, 0u, hr, i, jr, lane);
+                    push_hot(list, lother, list_n, hl, 0u, 0, ol, i, jl, lane);
+                    push_hot(list, lother, list_n, 0u, hr, orr, 0, i, jr, lane);
                 }
             }
             // one lane per site of the window adds the warp's sums to the direct counters: two 64-bit REDs, each the two strand
@@ -371,7 +385,7 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
         const uint32_t maxrem = __reduce_max_sync(0xffffffffu, rem);
         int idx = act ? bin_lower(g, m, cur, s0) : s0;               // first site with position >= cur, carried along the read
         for (uint32_t t = 0; t < maxrem; ++t) {
-            if (list_n > (uint32_t)(FC_LIST - 64)) { flush_list(list, list_n, m.rec_lo, A, lane); list_n = 0; }
+            if (list_n > (uint32_t)(FC_LIST - 64)) { flush_list(list, lother, list_n, m.rec_lo, A, lane); list_n = 0; }
             const uint32_t j = j0 + t;
             const uint32_t w = t < rem ? cw(c0 + j) : 5u;
             const uint32_t op = w & 15u;
@@ -409,11 +423,11 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
                 run_add(A.cnt.diff, key_lo, v, false, lane);
                 run_add(A.cnt.diff, key_hi, v, true, lane);
             }
-            push_hot(list, list_n, hl, hr, i, j, lane);
+            push_hot(list, lother, list_n, hl, hr, cur - 1, cur + len - 1, i, j, lane);
             if (adv) { cur += len; idx = inx; }
         }
     }
-    if (list_n) flush_list(list, list_n, m.rec_lo, A, lane);
+    if (list_n) flush_list(list, lother, list_n, m.rec_lo, A, lane);
 }
 
 __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_constant__ FArgs A) {
@@ -502,8 +516,8 @@ __global__ void __launch_bounds__(FC_THREADS, 2) k_count_fused(const __grid_cons
         mbar_wait(&sm.full[stage], parity);
         const FMeta m = sm.meta[stage];
         if (m.flags & FM_DONE) break;
-        if (m.flags & FM_GLOBAL_CIG) consume<false>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], lut_base, A);
-        else consume<true>(sm.st[stage], m, sm.list[warp], &sm.next_group[stage], lut_base, A);
+        if (m.flags & FM_GLOBAL_CIG) consume<false>(sm.st[stage], m, sm.list[warp], sm.lother[warp], &sm.next_group[stage], lut_base, A);
+        else consume<true>(sm.st[stage], m, sm.list[warp], sm.lother[warp], &sm.next_group[stage], lut_base, A);
         // every consumer thread releases the stage itself: its reads of the stage (and of the stage's meta data) are ordered
         // before the producer's next copy by its own arrive (release) / the producer's wait (acquire)
         mbar_arrive(&sm.empty[stage]);

@@ -923,7 +923,10 @@ int fused_upload_compact(spl_ctx* ctx, const spl_compact_view* v, int32_t n_chro
     size_t r0 = 0;
     uint32_t k0 = 0;
     for (int p = 0; p < want; ++p) {
-        size_t r1 = (p == want - 1) ? R : (R * (size_t)(p + 1) / (size_t)want) / K * K;
+        // slabs of decreasing size (cumulative share 1 - (1 - (p + 1) / n)^2): what stays exposed after the last copy is the unpack
+        // and the counting of the last slab, so that one is small
+        const double rest = 1.0 - (double)(p + 1) / (double)want;
+        size_t r1 = (p == want - 1) ? R : (size_t)((double)R * (1.0 - rest * rest)) / K * K;
         if (r1 < r0) r1 = r0;
         uint32_t k1 = k0;
         while (k1 < hc.size() && hc[k1].rec_hi <= r1) ++k1;
