@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <fcntl.h>
 #include <sys/stat.h>
 #include <unistd.h>
@@ -172,7 +173,14 @@ struct Part {
 // Fused variant: the records of a call live in ONE device allocation (absolute record / CIGAR indices); the upload is cut
 // into slabs so that the counting kernel of one slab runs under the copy of the next.
 constexpr int MAX_FPARTS = 8;
-struct FPart { uint32_t chunk_lo = 0, chunk_hi = 0; cudaEvent_t ev_up = nullptr; };
+struct FPart {
+    uint32_t chunk_lo = 0, chunk_hi = 0;
+    cudaEvent_t ev_up = nullptr;
+    // packed / compact uploads: the slab's unpack kernel.  It is launched by the first counting pass, right in front of the slab's
+    // counting kernel -- queued at upload time it would sit in the stream behind the LAST slab's copy together with everything
+    // that follows it, and no counting would overlap the upload
+    std::function<void(cudaStream_t)> unpack;
+};
 
 struct spl_ctx {
     int device = 0;
@@ -642,6 +650,7 @@ int upload_and_expand(spl_ctx* ctx, const spl_records_view* v, uint32_t flags, i
 // kernel of a slab runs while the next one is still on the wire.  Records parsed on the device (bam_gpu.cu) are adopted.
 int fused_upload(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom, bool split_ok) {
     ctx->n_chrom_loaded = n_chrom;
+    for (auto& P : ctx->fpart) P.unpack = nullptr;                    // nothing left over from an earlier call
     const bool dev = ctx->rec_on_device;
     std::vector<FChunk> hc;
     int64_t aligned = 0;
@@ -737,6 +746,7 @@ int fused_upload(spl_ctx* ctx, const spl_records_view* v, int32_t n_chrom, bool 
 // CIGAR offsets of every record and the SAM flag bits are rebuilt on the device (k_unpack_records) as each slab arrives.
 int fused_upload_packed(spl_ctx* ctx, const spl_packed_view* v, int32_t n_chrom, bool split_ok) {
     ctx->n_chrom_loaded = n_chrom;
+    for (auto& P : ctx->fpart) P.unpack = nullptr;                    // nothing left over from an earlier call
     std::vector<FChunk> hc;
     int64_t aligned = 0;
     for (int32_t k = 0; k < v->n_seg; ++k) {
@@ -828,12 +838,15 @@ int fused_upload_packed(spl_ctx* ctx, const spl_packed_view* v, int32_t n_chrom,
             ctx->stats[SPL_STAT_H2D_BYTES] += (double)((r1 - r0) * 7 + (c1 - c0) * 4);
         }
         CU(cudaEventRecord(ctx->fpart[p].ev_up, cs));
+        ctx->fpart[p].unpack = nullptr;
         if (r1 > r0) {
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->fpart[p].ev_up, 0));
             ctx->unpack_epoch = (ctx->unpack_epoch + 1u) & 0x3fffffffu;
             if (ctx->unpack_epoch == 0u) ctx->unpack_epoch = 1u;
-            launch_unpack_records((const uint16_t*)(pb + p_nop), (const uint8_t*)(pb + p_f8), (uint32_t)r0, (uint32_t)r1, (uint32_t)c0,
-                                  (uint32_t*)(rb + o_off), (uint16_t*)(rb + o_flag), desc, ticket, ctx->unpack_epoch, ctx->stream);
+            const uint32_t epoch = ctx->unpack_epoch;
+            ctx->fpart[p].unpack = [=](cudaStream_t st) {
+                launch_unpack_records((const uint16_t*)(pb + p_nop), (const uint8_t*)(pb + p_f8), (uint32_t)r0, (uint32_t)r1, (uint32_t)c0,
+                                      (uint32_t*)(rb + o_off), (uint16_t*)(rb + o_flag), desc, ticket, epoch, st);
+            };
         }
         r0 = r1;
     }
@@ -846,6 +859,7 @@ int fused_upload_packed(spl_ctx* ctx, const spl_packed_view* v, int32_t n_chrom,
 // kernel (k_unpack_compact, one CTA per stride) as soon as it has arrived, under the copy of the next slab.
 int fused_upload_compact(spl_ctx* ctx, const spl_compact_view* v, int32_t n_chrom, bool split_ok) {
     ctx->n_chrom_loaded = n_chrom;
+    for (auto& P : ctx->fpart) P.unpack = nullptr;                    // nothing left over from an earlier call
     std::vector<FChunk> hc;
     int64_t aligned = 0;
     for (int32_t k = 0; k < v->n_seg; ++k) {
@@ -943,13 +957,15 @@ int fused_upload_compact(spl_ctx* ctx, const spl_compact_view* v, int32_t n_chro
             ctx->stats[SPL_STAT_H2D_BYTES] += (double)((r1 - r0) * 4 + (b16 - a16) * 2 + (b32 - a32) * 4);
         }
         CU(cudaEventRecord(ctx->fpart[p].ev_up, cs));
+        ctx->fpart[p].unpack = nullptr;
         if (r1 > r0) {
-            CU(cudaStreamWaitEvent(ctx->stream, ctx->fpart[p].ev_up, 0));
-            launch_unpack_compact((const uint16_t*)(pb + p_p16), (const uint8_t*)(pb + p_f8), (const uint8_t*)(pb + p_n8),
-                                  (const uint16_t*)(pb + p_c16), (const uint32_t*)(pb + p_c32), (const int32_t*)(pb + p_base),
-                                  (const int32_t*)(pb + p_wide), (const uint32_t*)(pb + p_i16), (const uint32_t*)(pb + p_i32),
-                                  (uint32_t)r0, (uint32_t)r1, (int32_t*)(rb + o_pos), (uint16_t*)(rb + o_flag), (uint32_t*)(rb + o_off),
-                                  (uint32_t*)(rb + o_cig), ctx->stream);
+            ctx->fpart[p].unpack = [=](cudaStream_t st) {
+                launch_unpack_compact((const uint16_t*)(pb + p_p16), (const uint8_t*)(pb + p_f8), (const uint8_t*)(pb + p_n8),
+                                      (const uint16_t*)(pb + p_c16), (const uint32_t*)(pb + p_c32), (const int32_t*)(pb + p_base),
+                                      (const int32_t*)(pb + p_wide), (const uint32_t*)(pb + p_i16), (const uint32_t*)(pb + p_i32),
+                                      (uint32_t)r0, (uint32_t)r1, (int32_t*)(rb + o_pos), (uint16_t*)(rb + o_flag), (uint32_t*)(rb + o_off),
+                                      (uint32_t*)(rb + o_cig), st);
+            };
         }
         r0 = r1;
     }
@@ -964,8 +980,9 @@ int fused_count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     if (ev) CU(cudaEventRecord(ev[1], ctx->stream));
     uint32_t* hot_n = ctx->cnt.work + 24;
     for (int p = 0; p < ctx->n_fparts; ++p) {
-        const FPart& P = ctx->fpart[p];
+        FPart& P = ctx->fpart[p];
         CU(cudaStreamWaitEvent(ctx->stream, P.ev_up, 0));
+        if (P.unpack) { P.unpack(ctx->stream); P.unpack = nullptr; }      // once: a repeated pass finds the arrays in place
         launch_chunk_bounds(ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->frec.cig_off, ctx->g, ctx->stream);
         launch_count_fused(ctx->frec, ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->g, ctx->cnt, ctx->cnt.work + 8 + p, ctx->flags,
                            (uint4*)ctx->d_hotq.p, hot_n, ctx->hot_cap, ctx->stream);
