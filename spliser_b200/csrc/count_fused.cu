@@ -69,7 +69,7 @@ struct FSmem {
     unsigned long long list[FC_CWARPS][FC_LIST];
     uint32_t lother[FC_CWARPS][FC_LIST];  // the junction's other end (position) of every list entry
     FMeta meta[FC_STAGES];
-    uint32_t next_group[FC_STAGES];     // next group of 32 records of the staged chunk (claimed by the consumer warps)
+    uint32_t next_group[FC_STAGES];     // next record of the staged chunk (the consumer warps take 32 at a time)
     uint64_t full[FC_STAGES], empty[FC_STAGES];
 };
 
@@ -100,13 +100,7 @@ __device__ __forceinline__ void run_add(uint32_t* base, uint32_t key, bool v, bo
     }
 }
 
-// plain atomics (the compiler wraps atomicAdd in a warp-aggregation sequence of a dozen instructions, which a single
-// elected lane or lanes with distinct addresses do not need)
-__device__ __forceinline__ uint32_t atoms_inc(uint32_t* smem_word) {
-    uint32_t old;
-    asm volatile("atom.shared.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(smem_word)) : "memory");
-    return old;
-}
+// plain RED for lanes with distinct addresses (the compiler wraps atomicAdd in a warp-aggregation sequence of a dozen instructions)
 __device__ __forceinline__ void red_add64(unsigned long long* p, unsigned long long v) {
     asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -280,12 +274,11 @@ __device__ __forceinline__ void consume(const FStage& st, const FMeta& m, unsign
     for (;;) {
         // a group pushes at most 4 entries per lane on the stab path (two junctions in FC_SLOTS operators)
         if (list_n > (uint32_t)(FC_LIST - 128)) { flush_list(list, lother, list_n, m.rec_lo, A, lane); list_n = 0; }
-        uint32_t gi = 0;
-        if (lane == 0) gi = atoms_inc(next_group);
-        gi = __shfl_sync(0xffffffffu, gi, 0);
-        if (gi * 32u >= m.n_rec) break;
-        const uint32_t i = gi * 32u + (uint32_t)lane;
+        // every lane takes a record number from the stage's counter: ptxas turns the warp's 32 increments of one address into a single
+        // ATOMS of +32 and hands the lanes consecutive numbers (nothing below needs more than "each record exactly once")
+        const uint32_t i = atomicAdd(next_group, 1u);
         const bool live = i < m.n_rec;
+        if (!__any_sync(0xffffffffu, live)) break;
         int32_t pos = 0;
         uint32_t nop = 0, k = 0;
         // ---- the first FC_SLOTS operators in registers: operator j covers [b[j], b[j+1]); a site at p is stabbed by it
