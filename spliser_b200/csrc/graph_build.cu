@@ -27,12 +27,16 @@ namespace spl {
 
 namespace {
 
+// Stable LSD radix sort, RS_BITS-bit digits: the site keys of a 30 Mb genome are 29 bits wide (3 passes of 10 instead of 4 of 8),
+// GRCh38's 34 bits (4 instead of 5); every pass is three small launches, so the pass count is the cost.
 constexpr int RS_THREADS = 256, RS_ITEMS = 8, RS_TILE = RS_THREADS * RS_ITEMS;
+constexpr int RS_BITS = 10, RS_BINS = 1 << RS_BITS, RS_BPT = RS_BINS / RS_THREADS;      // digits a thread looks after
 
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_hist(const uint64_t* __restrict__ in, uint32_t n, int shift, uint32_t mask, uint32_t* __restrict__ hist, uint32_t n_tiles) {
-    __shared__ uint32_t h[256];
-    h[threadIdx.x] = 0;
+    __shared__ uint32_t h[RS_BINS];
+#pragma unroll
+    for (int q = 0; q < RS_BPT; ++q) h[q * RS_THREADS + threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = blockIdx.x * RS_TILE;
 #pragma unroll
@@ -41,40 +45,47 @@ k_rs_hist(const uint64_t* __restrict__ in, uint32_t n, int shift, uint32_t mask,
         if (i < n) atomicAdd(&h[(uint32_t)(in[i] >> shift) & mask], 1u);
     }
     __syncthreads();
-    hist[threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];      // digit-major: one scan gives every (digit, tile) offset
+#pragma unroll
+    for (int q = 0; q < RS_BPT; ++q) {                               // digit-major: one scan gives every (digit, tile) offset
+        const uint32_t d = q * RS_THREADS + threadIdx.x;
+        hist[d * n_tiles + blockIdx.x] = h[d];
+    }
 }
 
 // stable ranked scatter: element order inside a tile is (round, warp, lane) = index order
 __global__ void __launch_bounds__(RS_THREADS)
 k_rs_scatter(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, uint32_t n, int shift, uint32_t mask,
              const uint32_t* __restrict__ offs, uint32_t n_tiles) {
-    __shared__ uint32_t wc[RS_THREADS / 32][256];
-    __shared__ uint32_t base[256];
+    __shared__ uint32_t wc[RS_THREADS / 32][RS_BINS];
+    __shared__ uint32_t base[RS_BINS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    base[threadIdx.x] = offs[threadIdx.x * n_tiles + blockIdx.x];
 #pragma unroll
-    for (int w = 0; w < RS_THREADS / 32; ++w) wc[w][threadIdx.x] = 0;
+    for (int q = 0; q < RS_BPT; ++q) {
+        const uint32_t d = q * RS_THREADS + threadIdx.x;
+        base[d] = offs[d * n_tiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) wc[w][d] = 0;
+    }
     __syncthreads();
     const uint32_t t0 = blockIdx.x * RS_TILE;
     for (int r = 0; r < RS_ITEMS; ++r) {
         const uint32_t i = t0 + r * RS_THREADS + threadIdx.x;
         const bool live = i < n;
         const uint64_t key = live ? in[i] : 0ull;
-        const uint32_t d = live ? ((uint32_t)(key >> shift) & mask) : 256u;       // dead lanes form their own group
+        const uint32_t d = live ? ((uint32_t)(key >> shift) & mask) : (uint32_t)RS_BINS;   // dead lanes form their own group
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const uint32_t below = __popc(peers & ((1u << lane) - 1u));
         if (live && below == 0) wc[warp][d] = (uint32_t)__popc(peers);
         __syncthreads();
+        uint32_t pre = 0;
         if (live) {
-            uint32_t pre = 0;
             for (int w = 0; w < warp; ++w) pre += wc[w][d];
             out[base[d] + pre + below] = key;
         }
         __syncthreads();
-        uint32_t tot = 0;
-#pragma unroll
-        for (int w = 0; w < RS_THREADS / 32; ++w) { tot += wc[w][threadIdx.x]; wc[w][threadIdx.x] = 0; }
-        base[threadIdx.x] += tot;
+        // only the digits this round touched have counts: the thread that wrote a count (first lane of its group in its warp)
+        // adds it to the digit's base and clears it -- no sweep over all RS_BINS digits per round
+        if (live && below == 0) { atomicAdd(&base[d], wc[warp][d]); wc[warp][d] = 0; }
         __syncthreads();
     }
 }
@@ -165,7 +176,7 @@ struct Scanner {
 };
 
 struct Sorter {
-    uint32_t* hist;      // [256 * max_tiles + 1]
+    uint32_t* hist;      // [RS_BINS * max_tiles + 1]
     Scanner sc;
     uint32_t* total;     // [1] scratch
     cudaStream_t st;
@@ -173,11 +184,13 @@ struct Sorter {
     uint64_t* sort(uint64_t* a, uint64_t* b, uint32_t n, int lo, int hi) const {
         if (n < 2) return a;
         const uint32_t n_tiles = (n + RS_TILE - 1) / RS_TILE;
-        for (int shift = lo; shift < hi; shift += 8) {
-            const int width = hi - shift < 8 ? hi - shift : 8;
+        // equal digit widths (34 bits = 4 x 9 rather than 10 + 10 + 10 + 4): the histogram of a narrow digit is cheaper to scan
+        const int passes = (hi - lo + RS_BITS - 1) / RS_BITS, step = (hi - lo + passes - 1) / passes;
+        for (int shift = lo; shift < hi; shift += step) {
+            const int width = hi - shift < step ? hi - shift : step;
             const uint32_t mask = (1u << width) - 1u;
             { SPL_LAUNCH; k_rs_hist<<<n_tiles, RS_THREADS, 0, st>>>(a, n, shift, mask, hist, n_tiles); }
-            sc.scan(hist, 256u * n_tiles, nullptr, total);
+            sc.scan(hist, (mask + 1u) * n_tiles, nullptr, total);
             { SPL_LAUNCH; k_rs_scatter<<<n_tiles, RS_THREADS, 0, st>>>(a, b, n, shift, mask, hist, n_tiles); }
             uint64_t* t = a; a = b; b = t;
         }
@@ -565,10 +578,10 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     uint8_t* d_js = (uint8_t*)(fb + o_jst);
 
     const uint32_t max_tiles = cdiv(n2, RS_TILE) + 1;
-    const uint32_t lb_tiles = cdiv(std::max(256u * max_tiles, n2 + 2u), LB_TILE) + 2;
+    const uint32_t lb_tiles = cdiv(std::max((uint32_t)RS_BINS * max_tiles, n2 + 2u), LB_TILE) + 2;
     Carve w;
     const size_t w_ka = w.take<uint64_t>(n2 + 2), w_kb = w.take<uint64_t>(n2 + 2), w_flag = w.take<uint32_t>(n2 + 2);
-    const size_t w_hist = w.take<uint32_t>(256 * (size_t)max_tiles + 2);
+    const size_t w_hist = w.take<uint32_t>((size_t)RS_BINS * (size_t)max_tiles + 2);
     const size_t w_cnt = w.take<uint32_t>(16), w_site_of = w.take<uint32_t>(n2 + 2), w_eid = w.take<uint32_t>(n2 + 2);
     const size_t w_esrc = w.take<uint32_t>(n2 + 2), w_npt = w.take<uint32_t>(n2 + 4), w_ncp = w.take<uint32_t>(n2 + 4);
     const size_t w_c1 = w.take<uint32_t>(n2 + 4), w_c2 = w.take<uint32_t>(n2 + 4);
@@ -684,10 +697,10 @@ bool junction_extract_device(JuncExtractMem& m, const DevRecords& rec, const int
     const uint32_t n = h_n;
     if (n == 0) return true;
     const uint32_t max_tiles = cdiv(n, RS_TILE) + 1;
-    const uint32_t lb_tiles = cdiv(std::max(256u * max_tiles, n + 2u), LB_TILE) + 2;
+    const uint32_t lb_tiles = cdiv(std::max((uint32_t)RS_BINS * max_tiles, n + 2u), LB_TILE) + 2;
     Carve b;
     const size_t b_ka = b.take<uint64_t>((size_t)n + 2), b_kb = b.take<uint64_t>((size_t)n + 2), b_flag = b.take<uint32_t>((size_t)n + 2);
-    const size_t b_hist = b.take<uint32_t>(256 * (size_t)max_tiles + 2), b_desc = b.take<unsigned long long>(lb_tiles + 32);
+    const size_t b_hist = b.take<uint32_t>((size_t)RS_BINS * (size_t)max_tiles + 2), b_desc = b.take<unsigned long long>(lb_tiles + 32);
     const size_t b_oc = b.take<int32_t>((size_t)n + 1), b_ol = b.take<int32_t>((size_t)n + 1), b_or = b.take<int32_t>((size_t)n + 1),
                  b_os = b.take<uint8_t>((size_t)n + 8), b_sc = b.take<unsigned long long>((size_t)n + 1);
     GB_CU(m.b.reserve(b.off + 256));
