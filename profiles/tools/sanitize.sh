@@ -6,7 +6,7 @@
 # initcheck (reads of uninitialised device memory).  The selected tests cover every kernel: golden fuzz (all modes, dirty
 # regime), a synthetic sample through the records path and through the device BAM ingest, the re-count entry point.
 set -u
-SEL='test_appendix_a_known_answers or test_empty_and_ragged_inputs or test_bam_ingest_on_the_device or test_golden_combine_recount or test_stabbing_variant_equals_difference_array_variant'
+SEL='test_appendix_a_known_answers or test_empty_and_ragged_inputs or test_bam_ingest_on_the_device or test_golden_combine_recount or test_stabbing_variant_equals_difference_array_variant or test_compact_view_equals_plain_view or test_junction_extraction'
 export SPLISER_SANITIZE_SMALL=1
 for tool in memcheck racecheck synccheck initcheck; do
     echo "=== compute-sanitizer --tool $tool"

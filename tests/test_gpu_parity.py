@@ -209,16 +209,18 @@ def test_compact_view_equals_plain_view(ctx, monkeypatch, parts):
     from oracle import c_oracle, fuzzgen
     from spliser_b200 import CompactRecords, Records, synth
     from spliser_b200.bed import parse_bed12
-    w = synth.generate(synth.config_small(150_000, seed=77, stranded=True, paired=True))
+    import os
+    small = os.environ.get("SPLISER_SANITIZE_SMALL") == "1"           # under compute-sanitizer: the same kernels on less data
+    w = synth.generate(synth.config_small(8_000 if small else 150_000, seed=77, stranded=True, paired=True))
     want = c_oracle.process(w.records, len(w.chroms), w.junctions, w.flags | 4, threads=8)
     monkeypatch.setenv("SPLISER_SPLIT_MIN_RECORDS", "1000" if parts > 1 else "1000000000")
     monkeypatch.setenv("SPLISER_SPLIT_PARTS", str(parts))
     ck = CompactRecords.from_records(w.records)
-    assert ck.wire_bytes < 10 * len(w.records)
+    assert small or ck.wire_bytes < 10 * len(w.records)
     got = c_oracle.table_dict(ctx.process_compact(ck, len(w.chroms), w.junctions, w.flags | 4))
     assert ctx.stats()["n_parts"] == float(parts)
     assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
-    w3 = synth.generate(synth.config_c3_tile(200_000, tile=1))
+    w3 = synth.generate(synth.config_c3_tile(20_000 if small else 200_000, tile=1))
     ck3 = CompactRecords.from_records(w3.records)
     assert len(ck3.cigar32) > 0 and len(ck3.pos_wide) > 0 and len(ck3.cigar16) > 0
     a = c_oracle.table_dict(ctx.process_records(w3.records, len(w3.chroms), w3.junctions, w3.flags | 4))
@@ -235,7 +237,7 @@ def test_compact_view_equals_plain_view(ctx, monkeypatch, parts):
     sh = Records(r.pos[order], r.flag[order], off, r.cigar[src], r.seg_chrom, r.seg_off)
     b = c_oracle.table_dict(ctx.process_compact(CompactRecords.from_records(sh), len(w.chroms), w.junctions, w.flags | 4))
     assert c_oracle.diff_tables(b, want) is None, c_oracle.diff_tables(b, want)
-    for seed in range(940000, 940030):                       # every flag combination / CIGAR shape of the fuzz generator
+    for seed in range(940000, 940006 if small else 940030):   # every flag combination / CIGAR shape of the fuzz generator
         case = fuzzgen.gen_case(seed, n_chrom=1 + (seed % 2), dirty=(seed % 4 == 1), max_reads=60)
         chroms, junc, _ = parse_bed12(case["bed"].splitlines(True))
         rec = Records.from_reads(chroms, [tuple(r) for r in case["reads"]])
@@ -399,7 +401,8 @@ def _subset(r, keep):
 
 
 def test_full_size_configs1_properties(ctx):
-    """BASELINE configs[1] at its full size (40M records, stranded rf) through size-independent properties:
+    """BASELINE configs[1] at its full size (40M records, stranded rf): (0) the whole table equals the C oracle's, and
+    size-independent properties:
     (1) counts are additive over any split of the reads once the junction-table-only part is removed,
     (2) genomic tiles concatenate to the untiled result, (3) passes over the resident layout are idempotent,
     (4) alpha equals the junction scores summed per site."""
@@ -415,6 +418,16 @@ def test_full_size_configs1_properties(ctx):
     full = ctx.process_records(r, nc, j, w.flags)
     S = len(full)
     assert S > 100_000 and int(full.beta1.sum()) > 0 and int(full.beta2simple.sum()) > 0
+    # (0) the whole table against the C oracle (the reference's algorithm, pinned to its golden vectors) at the full size, every
+    # column, floats bit for bit -- through the plain view and through the compact view
+    from oracle import c_oracle
+    from spliser_b200 import CompactRecords
+    want = c_oracle.process(r, nc, j, w.flags, threads=os.cpu_count() or 8)
+    d = c_oracle.diff_tables(c_oracle.table_dict(full), want)
+    assert d is None, d
+    d = c_oracle.diff_tables(c_oracle.table_dict(ctx.process_compact(CompactRecords.from_records(r), nc, j, w.flags)), want)
+    assert d is None, d
+    del want
     # (4)
     assert int(full.alpha.sum()) == 2 * int(j.score.sum())
     # (1) linearity
@@ -444,6 +457,35 @@ def test_full_size_configs1_properties(ctx):
             lo, hi = S * ti // n_tiles, S * (ti + 1) // n_tiles
             b1[lo:hi], b2[lo:hi] = t.beta1[lo:hi], t.beta2simple[lo:hi]
     assert np.array_equal(b1, full.beta1) and np.array_equal(b2, full.beta2simple)
+
+
+def test_configs2_tile_at_scale_vs_c_oracle(ctx):
+    """A GRCh38-scale tile of BASELINE configs[2] with 25M records (introns up to 500 kb): the rows of the first chromosome
+    segment against the C oracle run on that segment's records and junction rows (every column a read can change), and the
+    whole table's alpha against the junction scores."""
+    import os
+    import tempfile
+    import numpy as np
+    from oracle import c_oracle
+    from spliser_b200 import Junctions, Records, synth
+    n = int(os.environ.get("SPLISER_C3_TILE_READS", "25000000"))
+    cache = os.environ.get("SPLISER_BENCH_CACHE", os.path.join(tempfile.gettempdir(), "spliser_bench_cache"))
+    w = synth.generate(synth.config_c3_tile(n, tile=0), cache_dir=cache)
+    r, j, nc = w.records, w.junctions, len(w.chroms)
+    t = ctx.process_records(r, nc, j, w.flags)
+    assert int(t.alpha.sum()) == 2 * int(j.score.sum()) and int(t.beta1.sum()) > 0
+    k = int(r.seg_off[1] - r.seg_off[0])
+    c0 = int(r.seg_chrom[0])
+    rec = Records(r.pos[:k], r.flag[:k], r.cig_off[:k + 1], r.cigar[:int(r.cig_off[k])], [c0], [0, k])
+    keep = j.chrom == c0
+    sub = Junctions(j.chrom[keep], j.left[keep], j.right[keep], j.score[keep], j.strand[keep])
+    want = c_oracle.process(rec, nc, sub, w.flags, threads=os.cpu_count() or 8)
+    rows = np.nonzero(np.asarray(t.chrom) == c0)[0]
+    assert len(rows) == len(want["pos"]) > 1000
+    got = c_oracle.table_dict(t)
+    for col in ("pos", "strand", "alpha", "beta1", "beta2simple", "beta2cryptic"):
+        assert np.array_equal(np.asarray(got[col])[rows], np.asarray(want[col])), col
+    assert np.array_equal(np.asarray(got["sse"])[rows].view(np.int64), np.asarray(want["sse"]).view(np.int64))
 
 
 def test_bam_ingest_on_the_device(ctx, tmp_path, monkeypatch):
