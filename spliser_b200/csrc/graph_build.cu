@@ -160,15 +160,113 @@ k_scan_lb(uint32_t* __restrict__ a, uint32_t n_host, const uint32_t* __restrict_
     for (int q = 0; q < LB_ITEMS; ++q) { if (base + q < n) a[base + q] = run; run += v[q]; }
 }
 
+// ---- the same scan with ONE grid-wide rendezvous instead of a look-back chain ------------------------------------------
+// The tables of this path are 10^5 - 10^6 elements: a few hundred tiles, all resident at once.  Every tile publishes its sum,
+// waits until all have (arrive counter), and adds up the sums of the tiles in front of it -- the latency of one global
+// round trip instead of one per 32 predecessors.  Only launched when the grid fits the device (the launcher checks); the
+// look-back kernel above takes the larger inputs.  gb[0] = arrive, gb[1] = depart (the last tile to leave zeroes both),
+// gb[8 + t] = sum of tile t.
+constexpr int GS_THREADS = 512, GS_ITEMS = 8, GS_TILE = GS_THREADS * GS_ITEMS, GS_MAX_TILES = 1024;
+constexpr int SC_EXTRA = 16 + (8 + GS_MAX_TILES) / 2 + 8;              // 64-bit words behind the descriptors: ticket at +8, gb at +16
+
+__global__ void __launch_bounds__(GS_THREADS)
+k_scan_gb(uint32_t* __restrict__ a, uint32_t n_host, const uint32_t* __restrict__ n_dev, uint32_t* __restrict__ gb,
+          uint32_t* __restrict__ total_out, uint32_t* __restrict__ total_out2) {
+    __shared__ uint32_t wsum[GS_THREADS / 32], wpre[GS_THREADS / 32], s_prev;
+    const uint32_t n = n_dev ? min(*n_dev, n_host) : n_host;
+    const uint32_t t = blockIdx.x, tiles = gridDim.x;
+    const uint32_t base = t * GS_TILE + threadIdx.x * GS_ITEMS;
+    uint32_t v[GS_ITEMS], sum = 0;
+    if (base + GS_ITEMS <= n) {                                         // two 16-byte loads (the arrays are 256-byte aligned)
+        const uint4 x = *reinterpret_cast<const uint4*>(a + base), y = *reinterpret_cast<const uint4*>(a + base + 4);
+        v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w; v[4] = y.x; v[5] = y.y; v[6] = y.z; v[7] = y.w;
+    } else {
+#pragma unroll
+        for (int q = 0; q < GS_ITEMS; ++q) v[q] = base + q < n ? a[base + q] : 0u;
+    }
+#pragma unroll
+    for (int q = 0; q < GS_ITEMS; ++q) sum += v[q];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < GS_THREADS / 32; ++w) { if (w < warp) wbase += wsum[w]; total += wsum[w]; }
+    volatile uint32_t* vg = gb;
+    if (threadIdx.x == 0) {
+        vg[8 + t] = total;
+        __threadfence();
+        atomicAdd(gb, 1u);
+        while (vg[0] < tiles) { }                                       // every tile of the grid is resident (launcher), so this ends
+        __threadfence();
+    }
+    __syncthreads();
+    // sums of the tiles in front: GS_THREADS threads, at most GS_MAX_TILES / GS_THREADS values each
+    uint32_t part = 0;
+    for (uint32_t x = threadIdx.x; x < t; x += GS_THREADS) part += vg[8 + x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_down_sync(0xffffffffu, part, o);
+    if (lane == 0) wpre[warp] = part;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t prev = 0;
+#pragma unroll
+        for (int w = 0; w < GS_THREADS / 32; ++w) prev += wpre[w];
+        s_prev = prev;
+        if (t == tiles - 1) {
+            if (total_out) *total_out = prev + total;
+            if (total_out2) *total_out2 = prev + total;
+        }
+        __threadfence();
+        if (atomicAdd(gb + 1, 1u) == tiles - 1) { vg[0] = 0u; vg[1] = 0u; }   // the last one out: nobody reads the sums any more
+    }
+    __syncthreads();
+    uint32_t run = s_prev + wbase + inc - sum;
+    if (base + GS_ITEMS <= n) {
+        uint4 x, y;
+        x.x = run; run += v[0]; x.y = run; run += v[1]; x.z = run; run += v[2]; x.w = run; run += v[3];
+        y.x = run; run += v[4]; y.y = run; run += v[5]; y.z = run; run += v[6]; y.w = run;
+        *reinterpret_cast<uint4*>(a + base) = x; *reinterpret_cast<uint4*>(a + base + 4) = y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < GS_ITEMS; ++q) { if (base + q < n) a[base + q] = run; run += v[q]; }
+    }
+}
+
+// tiles of k_scan_gb that are resident at once on the current device (the rendezvous needs all of them)
+int scan_gb_capacity() {
+    static std::atomic<int> cap_of[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 0;
+    int c = cap_of[dev].load();
+    if (c) return c;
+    int per_sm = 0, sms = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_scan_gb, GS_THREADS, 0);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    c = std::max(1, std::min(GS_MAX_TILES, per_sm * sms / 2));          // half of it: other streams may hold SMs (upload-time kernels)
+    cap_of[dev].store(c);
+    return c;
+}
+
 struct Scanner {
     unsigned long long* desc;     // [max tiles], zeroed once
     uint32_t* ticket;             // [1], zero between launches
     uint32_t* epoch;              // host counter
     cudaStream_t st;
+    uint32_t* gb;                 // [8 + GS_MAX_TILES] rendezvous words + tile sums of k_scan_gb, zeroed once
     // exclusive scan of a[0..n) in place; n = min(n_host, *n_dev) when n_dev is given; the total goes to total_out (and total_out2)
     void scan(uint32_t* a, uint32_t n_host, const uint32_t* n_dev, uint32_t* total_out, uint32_t* total_out2 = nullptr) const {
         const uint32_t tiles = (n_host + LB_TILE - 1) / LB_TILE;
         if (tiles == 0) { if (total_out) cudaMemsetAsync(total_out, 0, 4, st); if (total_out2) cudaMemsetAsync(total_out2, 0, 4, st); return; }
+        const uint32_t gtiles = (n_host + GS_TILE - 1) / GS_TILE;
+        if (gb && (int)gtiles <= scan_gb_capacity()) {
+            { SPL_LAUNCH; k_scan_gb<<<gtiles, GS_THREADS, 0, st>>>(a, n_host, n_dev, gb, total_out, total_out2); }
+            return;
+        }
         *epoch = (*epoch + 1u) & 0x3fffffffu;
         if (*epoch == 0u) *epoch = 1u;
         { SPL_LAUNCH; k_scan_lb<<<tiles, LB_THREADS, 0, st>>>(a, n_host, n_dev, desc, ticket, *epoch, total_out, total_out2); }
@@ -585,7 +683,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     const size_t w_cnt = w.take<uint32_t>(16), w_site_of = w.take<uint32_t>(n2 + 2), w_eid = w.take<uint32_t>(n2 + 2);
     const size_t w_esrc = w.take<uint32_t>(n2 + 2), w_npt = w.take<uint32_t>(n2 + 4), w_ncp = w.take<uint32_t>(n2 + 4);
     const size_t w_c1 = w.take<uint32_t>(n2 + 4), w_c2 = w.take<uint32_t>(n2 + 4);
-    const size_t w_desc = w.take<unsigned long long>(lb_tiles + 32);       // descriptors, then the ticket word
+    const size_t w_desc = w.take<unsigned long long>(lb_tiles + SC_EXTRA);  // descriptors, then the ticket word and the rendezvous words
     const bool fresh = m.work.cap < w.off + 256;
     GB_CU(m.work.reserve(w.off + 256));
     char* wb = (char*)m.work.p;
@@ -597,7 +695,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     uint32_t* npt = (uint32_t*)(wb + w_npt); uint32_t* ncp = (uint32_t*)(wb + w_ncp);
     uint32_t* c1 = (uint32_t*)(wb + w_c1); uint32_t* c2 = (uint32_t*)(wb + w_c2);
     unsigned long long* desc = (unsigned long long*)(wb + w_desc);
-    const Scanner sc{desc, (uint32_t*)(desc + lb_tiles + 8), &m.scan_epoch, st};
+    const Scanner sc{desc, (uint32_t*)(desc + lb_tiles + 8), &m.scan_epoch, st, (uint32_t*)(desc + lb_tiles + 16)};
     const Sorter sorter{(uint32_t*)(wb + w_hist), sc, d_cnt + 5, st};
 
     // ---- junction table to the device (phase 0: queued before the caller starts the big record upload, which
@@ -611,7 +709,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
         counts.h2d_bytes = (double)J * 21.0;
         GB_CU(cudaMemsetAsync(d_cnt, 0, 64, st));
         m.scan_epoch = 0;
-        GB_CU(cudaMemsetAsync(desc, 0, ((size_t)lb_tiles + 32) * sizeof(unsigned long long), st));     // descriptors + ticket
+        GB_CU(cudaMemsetAsync(desc, 0, ((size_t)lb_tiles + SC_EXTRA) * sizeof(unsigned long long), st));     // descriptors + ticket + rendezvous words
         m.ready = true;
         return true;
     }
@@ -676,19 +774,19 @@ bool junction_extract_device(JuncExtractMem& m, const DevRecords& rec, const int
     Carve a;
     const size_t a_so = a.take<int64_t>((size_t)n_seg + 1), a_sc = a.take<int32_t>((size_t)n_seg + 1), a_cnt = a.take<uint32_t>((size_t)R + 4);
     const uint32_t lb_tiles0 = cdiv(R + 2u, LB_TILE) + 2;
-    const size_t a_desc = a.take<unsigned long long>(lb_tiles0 + 32), a_tot = a.take<uint32_t>(16);
+    const size_t a_desc = a.take<unsigned long long>(lb_tiles0 + SC_EXTRA), a_tot = a.take<uint32_t>(16);
     GB_CU(m.a.reserve(a.off + 256));
     char* ab = (char*)m.a.p;
     GB_CU(cudaMemcpyAsync(ab + a_so, h_seg_off, ((size_t)n_seg + 1) * 8, cudaMemcpyHostToDevice, st));
     GB_CU(cudaMemcpyAsync(ab + a_sc, h_seg_chrom, (size_t)n_seg * 4, cudaMemcpyHostToDevice, st));
-    GB_CU(cudaMemsetAsync(ab + a_desc, 0, ((size_t)lb_tiles0 + 32) * 8, st));
+    GB_CU(cudaMemsetAsync(ab + a_desc, 0, ((size_t)lb_tiles0 + SC_EXTRA) * 8, st));
     GB_CU(cudaMemsetAsync(ab + a_tot, 0, 64, st));
     const JeSeg sg{(const int64_t*)(ab + a_so), (const int32_t*)(ab + a_sc), n_seg};
     uint32_t* cnt = (uint32_t*)(ab + a_cnt);
     uint32_t* d_tot = (uint32_t*)(ab + a_tot);
     uint32_t epoch = 0;
     unsigned long long* desc0 = (unsigned long long*)(ab + a_desc);
-    const Scanner sc0{desc0, (uint32_t*)(desc0 + lb_tiles0 + 8), &epoch, st};
+    const Scanner sc0{desc0, (uint32_t*)(desc0 + lb_tiles0 + 8), &epoch, st, (uint32_t*)(desc0 + lb_tiles0 + 16)};
     { SPL_LAUNCH; k_je_walk<false><<<cdiv(R, 256), 256, 0, st>>>(rec, sg, mode, min_anchor, min_intron, max_intron, pb, cnt, nullptr); }
     sc0.scan(cnt, R, nullptr, d_tot);
     uint32_t h_n = 0;
@@ -700,7 +798,7 @@ bool junction_extract_device(JuncExtractMem& m, const DevRecords& rec, const int
     const uint32_t lb_tiles = cdiv(std::max((uint32_t)RS_BINS * max_tiles, n + 2u), LB_TILE) + 2;
     Carve b;
     const size_t b_ka = b.take<uint64_t>((size_t)n + 2), b_kb = b.take<uint64_t>((size_t)n + 2), b_flag = b.take<uint32_t>((size_t)n + 2);
-    const size_t b_hist = b.take<uint32_t>((size_t)RS_BINS * (size_t)max_tiles + 2), b_desc = b.take<unsigned long long>(lb_tiles + 32);
+    const size_t b_hist = b.take<uint32_t>((size_t)RS_BINS * (size_t)max_tiles + 2), b_desc = b.take<unsigned long long>(lb_tiles + SC_EXTRA);
     const size_t b_oc = b.take<int32_t>((size_t)n + 1), b_ol = b.take<int32_t>((size_t)n + 1), b_or = b.take<int32_t>((size_t)n + 1),
                  b_os = b.take<uint8_t>((size_t)n + 8), b_sc = b.take<unsigned long long>((size_t)n + 1);
     GB_CU(m.b.reserve(b.off + 256));
@@ -708,10 +806,10 @@ bool junction_extract_device(JuncExtractMem& m, const DevRecords& rec, const int
     uint64_t* ka = (uint64_t*)(bb + b_ka); uint64_t* kb = (uint64_t*)(bb + b_kb);
     uint32_t* flag = (uint32_t*)(bb + b_flag);
     unsigned long long* desc = (unsigned long long*)(bb + b_desc);
-    GB_CU(cudaMemsetAsync(desc, 0, ((size_t)lb_tiles + 32) * 8, st));
+    GB_CU(cudaMemsetAsync(desc, 0, ((size_t)lb_tiles + SC_EXTRA) * 8, st));
     GB_CU(cudaMemsetAsync(bb + b_sc, 0, ((size_t)n + 1) * 8, st));
     uint32_t epoch2 = 0;
-    const Scanner sc{desc, (uint32_t*)(desc + lb_tiles + 8), &epoch2, st};
+    const Scanner sc{desc, (uint32_t*)(desc + lb_tiles + 8), &epoch2, st, (uint32_t*)(desc + lb_tiles + 16)};
     const Sorter sorter{(uint32_t*)(bb + b_hist), sc, d_tot + 5, st};
     { SPL_LAUNCH; k_je_walk<true><<<cdiv(R, 256), 256, 0, st>>>(rec, sg, mode, min_anchor, min_intron, max_intron, pb, cnt, ka); }
     uint64_t* sk = sorter.sort(ka, kb, n, 0, 22 + pb + cb);
