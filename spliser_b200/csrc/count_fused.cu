@@ -612,7 +612,7 @@ struct CompactDev {
 };
 __global__ void __launch_bounds__(UC_THREADS)
 k_unpack_compact(CompactDev v, uint32_t stride0, uint32_t r_end, int32_t* __restrict__ pos, uint16_t* __restrict__ flag16,
-                 uint32_t* __restrict__ cig_off, uint32_t* __restrict__ cigar) {
+                 uint32_t* __restrict__ cig_off, uint32_t* __restrict__ cigar, uint32_t* __restrict__ bad) {
     __shared__ uint32_t wS[UC_THREADS / 32], wL[UC_THREADS / 32];
     const uint32_t k = stride0 + blockIdx.x;
     const uint32_t rb = k * (uint32_t)SPL_PACKED_INDEX_STRIDE + threadIdx.x * UC_PER;
@@ -633,8 +633,23 @@ k_unpack_compact(CompactDev v, uint32_t stride0, uint32_t r_end, int32_t* __rest
     if (lane == 31) { wS[warp] = iS; wL[warp] = iL; }
     __syncthreads();
     uint32_t bS = v.idx16[k] + iS - sS, bL = v.idx32[k] + iL - sL;       // this thread's first operator in either stream
+    uint32_t tS = 0, tL = 0;
 #pragma unroll
-    for (int w = 0; w < UC_THREADS / 32; ++w) if (w < warp) { bS += wS[w]; bL += wL[w]; }
+    for (int w = 0; w < UC_THREADS / 32; ++w) { if (w < warp) { bS += wS[w]; bL += wL[w]; } tS += wS[w]; tL += wL[w]; }
+    // the per-record counts must add up to what the stride's anchors say, or the offsets below would leave the streams: such a
+    // stride is unpacked as records without operators and the call fails (the host reads the flag after the pass)
+    if (tS != v.idx16[k + 1] - v.idx16[k] || tL != v.idx32[k + 1] - v.idx32[k]) {
+        if (threadIdx.x == 0) atomicOr(bad, 1u);
+        const uint32_t o = v.idx16[k] + v.idx32[k];
+#pragma unroll
+        for (int q = 0; q < UC_PER; ++q) {
+            const uint32_t r = rb + q;
+            if (r >= r_end) break;
+            cig_off[r] = o; pos[r] = 0; flag16[r] = 0;
+            if (r + 1 == r_end) cig_off[r_end] = o;
+        }
+        return;
+    }
     uint32_t out = bS + bL;                                                // operators of all records before this one
     const int32_t base = v.pos_base[k];
 #pragma unroll
@@ -693,11 +708,11 @@ void launch_unpack_records(const uint16_t* n_op, const uint8_t* flag8, uint32_t 
 // strides [stride0, ...) up to record r_end of a compact upload: pos / flag / cig_off[.. r_end] / cigar of those records
 void launch_unpack_compact(const uint16_t* pos16, const uint8_t* flag8, const uint8_t* n_op8, const uint16_t* c16, const uint32_t* c32,
                            const int32_t* pos_base, const int32_t* pos_wide, const uint32_t* idx16, const uint32_t* idx32, uint32_t r0,
-                           uint32_t r1, int32_t* pos, uint16_t* flag16, uint32_t* cig_off, uint32_t* cigar, void* stream) {
+                           uint32_t r1, int32_t* pos, uint16_t* flag16, uint32_t* cig_off, uint32_t* cigar, uint32_t* bad, void* stream) {
     if (r1 <= r0) return;
     const CompactDev v{pos16, flag8, n_op8, c16, c32, pos_base, pos_wide, idx16, idx32};
     const uint32_t s0 = r0 / SPL_PACKED_INDEX_STRIDE, s1 = (r1 + SPL_PACKED_INDEX_STRIDE - 1) / SPL_PACKED_INDEX_STRIDE;
-    { SPL_LAUNCH; k_unpack_compact<<<s1 - s0, UC_THREADS, 0, (cudaStream_t)stream>>>(v, s0, r1, pos, flag16, cig_off, cigar); }
+    { SPL_LAUNCH; k_unpack_compact<<<s1 - s0, UC_THREADS, 0, (cudaStream_t)stream>>>(v, s0, r1, pos, flag16, cig_off, cigar, bad); }
 }
 
 // the queued hot items of every slab, after the counting kernels: one thread per item

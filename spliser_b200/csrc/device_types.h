@@ -217,7 +217,7 @@ void launch_unpack_records(const uint16_t* n_op, const uint8_t* flag8, uint32_t 
                            uint16_t* flag16, unsigned long long* desc, uint32_t* ticket, uint32_t epoch, void* stream);
 void launch_unpack_compact(const uint16_t* pos16, const uint8_t* flag8, const uint8_t* n_op8, const uint16_t* c16, const uint32_t* c32,
                            const int32_t* pos_base, const int32_t* pos_wide, const uint32_t* idx16, const uint32_t* idx32, uint32_t r0,
-                           uint32_t r1, int32_t* pos, uint16_t* flag16, uint32_t* cig_off, uint32_t* cigar, void* stream);
+                           uint32_t r1, int32_t* pos, uint16_t* flag16, uint32_t* cig_off, uint32_t* cigar, uint32_t* bad, void* stream);
 int  sm_count_current_device();
 
 }  // namespace spl

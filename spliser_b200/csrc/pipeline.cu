@@ -964,7 +964,7 @@ int fused_upload_compact(spl_ctx* ctx, const spl_compact_view* v, int32_t n_chro
                                       (const uint16_t*)(pb + p_c16), (const uint32_t*)(pb + p_c32), (const int32_t*)(pb + p_base),
                                       (const int32_t*)(pb + p_wide), (const uint32_t*)(pb + p_i16), (const uint32_t*)(pb + p_i32),
                                       (uint32_t)r0, (uint32_t)r1, (int32_t*)(rb + o_pos), (uint16_t*)(rb + o_flag), (uint32_t*)(rb + o_off),
-                                      (uint32_t*)(rb + o_cig), st);
+                                      (uint32_t*)(rb + o_cig), ctx->cnt.work + 25, st);
             };
         }
         r0 = r1;
@@ -982,14 +982,14 @@ int fused_count_pass(spl_ctx* ctx, cudaEvent_t* ev /* 5 or NULL */) {
     for (int p = 0; p < ctx->n_fparts; ++p) {
         FPart& P = ctx->fpart[p];
         CU(cudaStreamWaitEvent(ctx->stream, P.ev_up, 0));
-        if (P.unpack) { P.unpack(ctx->stream); P.unpack = nullptr; }      // once: a repeated pass finds the arrays in place
+        if (P.unpack) { if (ctx->g.n_sites > 0) P.unpack(ctx->stream); P.unpack = nullptr; }   // once: a repeated pass finds the arrays in place (no sites: nothing reads them)
         launch_chunk_bounds(ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->frec.cig_off, ctx->g, ctx->stream);
         launch_count_fused(ctx->frec, ctx->fchunks, P.chunk_lo, P.chunk_hi, ctx->g, ctx->cnt, ctx->cnt.work + 8 + p, ctx->flags,
                            (uint4*)ctx->d_hotq.p, hot_n, ctx->hot_cap, ctx->stream);
     }
     if (ev) CU(cudaEventRecord(ev[2], ctx->stream));
     if (ctx->n_fchunks) launch_hot_items(ctx->frec, ctx->g, ctx->cnt, ctx->flags, (const uint4*)ctx->d_hotq.p, hot_n, ctx->hot_cap, ctx->stream);
-    if (ctx->g.n_sites > 0) CU(cudaMemcpyAsync(ctx->h_hot, hot_n, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->g.n_sites > 0) CU(cudaMemcpyAsync(ctx->h_hot, hot_n, 8, cudaMemcpyDeviceToHost, ctx->stream));   // + the unpack kernels' verdict
     if (ev) CU(cudaEventRecord(ev[3], ctx->stream));
     launch_finalize(ctx->g, ctx->cnt, ctx->out, ctx->flags, ctx->stream);
     if (ev) CU(cudaEventRecord(ev[4], ctx->stream));
@@ -1025,6 +1025,7 @@ int hot_queue_overflow(spl_ctx* ctx, bool* again) {
     if (ctx->loaded_variant != SPL_VARIANT_FUSED || ctx->g.n_sites <= 0) return SPL_OK;
     const uint32_t n = *ctx->h_hot;
     ctx->stats[SPL_STAT_N_HOT_ITEMS] = (double)n;
+    if (ctx->h_hot[1]) { ctx->h_hot[1] = 0; return ctx->fail(SPL_ERR_ARG, "compact view: the operator counts of a stride disagree with its index"); }
     if (n <= ctx->hot_cap) return SPL_OK;
     const uint64_t want = (uint64_t)n + (n >> 3) + 1024;
     if (want >= 0xfffffff0ull) return ctx->fail(SPL_ERR_RANGE, "more than 2^32 hot junction items in one call");

@@ -247,6 +247,19 @@ def test_compact_view_equals_plain_view(ctx, monkeypatch, parts):
     empty = Records.from_reads(["A"], [])
     t = ctx.process_compact(CompactRecords.from_records(empty), len(w.chroms), w.junctions, w.flags)
     assert int(t.beta1.sum()) == 0 and np.array_equal(t.alpha, got["alpha"])
+    from spliser_b200 import Junctions
+    none = ctx.process_compact(ck, len(w.chroms), Junctions([], [], [], [], []), w.flags)
+    assert len(none) == 0
+    # a view whose per-record operator counts disagree with a stride's index is refused (by the device, which is what trusts
+    # them), and the context works afterwards
+    from spliser_b200 import SpliserError
+    bad = CompactRecords.from_records(w.records)
+    bad.n_op8 = bad.n_op8.copy()
+    bad.n_op8[len(bad) // 2] += 3
+    with pytest.raises(SpliserError):
+        ctx.process_compact(bad, len(w.chroms), w.junctions, w.flags | 4)
+    again = c_oracle.table_dict(ctx.process_compact(ck, len(w.chroms), w.junctions, w.flags | 4))
+    assert c_oracle.diff_tables(again, want) is None
 
 
 def test_shuffled_records_give_identical_counts(ctx):
