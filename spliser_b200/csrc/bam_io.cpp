@@ -34,7 +34,7 @@ inline uint16_t rd16(const uint8_t* p) { return (uint16_t)(p[0] | (p[1] << 8)); 
 inline uint32_t rd32(const uint8_t* p) { return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24); }
 inline int32_t rdi32(const uint8_t* p) { return (int32_t)rd32(p); }
 
-struct BgzfBlock { size_t coff; uint32_t clen; uint32_t isize; size_t uoff; };
+struct BgzfBlock { size_t coff; uint32_t clen; uint32_t isize; size_t uoff; uint32_t crc = 0; };
 
 int worker_count(int n) {
     if (n > 0) return n;
@@ -124,6 +124,8 @@ std::string read_bam(const char* path, int32_t n_chrom, const char* const* chrom
         b.coff = off + 12 + xlen;
         b.clen = (uint32_t)(total - 12 - xlen - 8);
         b.isize = rd32(file + off + total - 4);
+        if (b.isize > 65536u) return "BGZF member claims more than 64 KiB of data (ISIZE)";     // the format's bound; bam_scan enforces the same
+        b.crc = rd32(file + off + total - 8);
         b.uoff = utotal;
         utotal += b.isize;
         if (b.isize) blocks.push_back(b);
@@ -153,7 +155,9 @@ std::string read_bam(const char* path, int32_t n_chrom, const char* const* chrom
                 const size_t k = next.fetch_add(1);
                 if (k >= bj) break;
                 const BgzfBlock& b = blocks[k];
-                if (!inflate_block(file + b.coff, b.clen, buf.data() + carry + (b.uoff - ubase), b.isize)) bad = true;
+                uint8_t* dst = buf.data() + carry + (b.uoff - ubase);
+                if (!inflate_block(file + b.coff, b.clen, dst, b.isize)) bad = true;
+                else if ((uint32_t)crc32(crc32(0L, Z_NULL, 0), dst, b.isize) != b.crc) bad = true;     // htslib checks it too: a damaged member that still inflates to ISIZE bytes must not be counted
             }
         };
         std::vector<std::thread> pool;
@@ -161,7 +165,7 @@ std::string read_bam(const char* path, int32_t n_chrom, const char* const* chrom
         for (int t = 1; t < nt; ++t) pool.emplace_back(work);
         work();
         for (auto& t : pool) t.join();
-        if (bad) return "BGZF inflate failed (corrupt block)";
+        if (bad) return "BGZF inflate failed (corrupt block or CRC32 mismatch)";
         bi = bj;
 
         const uint8_t* p = buf.data();

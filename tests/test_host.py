@@ -74,6 +74,19 @@ def test_bam_roundtrip(tmp_path, built_library):
     open(str(tmp_path / "bad.bam"), "wb").write(b"not a bam file at all, just bytes" * 4)
     with pytest.raises(IOError):
         Records.from_bam(str(tmp_path / "bad.bam"), w.chroms)
+    # a member whose CRC32 field does not match its data is refused (as htslib does), and so is an ISIZE above the format's 64 KiB
+    raw = bytearray(open(path, "rb").read())
+    bsize = int.from_bytes(raw[16:18], "little") + 1                    # first member: BC subfield right behind the fixed header
+    crc_at = bsize - 8
+    raw[crc_at] ^= 0x5a
+    open(str(tmp_path / "crc.bam"), "wb").write(raw)
+    with pytest.raises(IOError):
+        Records.from_bam(str(tmp_path / "crc.bam"), w.chroms)
+    raw[crc_at] ^= 0x5a
+    raw[bsize - 4:bsize] = (70000).to_bytes(4, "little")
+    open(str(tmp_path / "isize.bam"), "wb").write(raw)
+    with pytest.raises(IOError):
+        Records.from_bam(str(tmp_path / "isize.bam"), w.chroms)
 
 
 def test_records_from_reads_segments():
