@@ -582,6 +582,41 @@ def main():
                                       "synthetic BAM without SEQ/QUAL (records only), so the file is much smaller than a sequencer's"}
         except Exception as ex:                                      # never lose the main line over the extra measurement
             out["bam_e2e"] = {"error": repr(ex)}
+        # ---- the same from a sequencer-shaped BAM (read names, SEQ, QUAL): the first 8M records of the sample
+        try:
+            n_seq = min(len(r), 8_000_000)
+            sub = Records(r.pos[:n_seq], r.flag[:n_seq], r.cig_off[:n_seq + 1], r.cigar[:int(r.cig_off[n_seq])],
+                          *_cut_segments(r, n_seq))
+            seq_bam = os.path.join(CACHE, "bench_%s_%d_seq.bam" % (args.workload, n_seq))
+            if not os.path.exists(seq_bam):
+                sub.write_bam(seq_bam + ".tmp", w.chroms, w.chrom_len, with_seq=True)
+                os.replace(seq_bam + ".tmp", seq_bam)
+            op = sub.cigar & 15
+            qop = np.where((op == 0) | (op == 1) | (op == 4) | (op == 7) | (op == 8), sub.cigar >> 4, 0).astype(np.int64)
+            qs = np.concatenate([[0], np.cumsum(qop)])
+            qlen = qs[sub.cig_off[1:].astype(np.int64)] - qs[sub.cig_off[:-1].astype(np.int64)]
+            inflated = int((36 + 11 + 4 * np.diff(sub.cig_off.astype(np.int64)) + (qlen + 1) // 2 + qlen).sum())
+            ctx.process_bam(seq_bam, w.chroms, w.junctions, w.flags)
+            ts = []
+            for _ in range(max(1, args.e2e_steps)):
+                a = time.perf_counter()
+                ts_table = ctx.process_bam(seq_bam, w.chroms, w.junctions, w.flags)
+                ts.append(time.perf_counter() - a)
+                ss = ctx.stats()
+                del ts_table
+            want_seq = ctx.process_records(sub, n_chrom, w.junctions, w.flags)
+            got_seq = ctx.process_bam(seq_bam, w.chroms, w.junctions, w.flags)
+            out["bam_e2e_seq"] = {"records": n_seq, "value": n_seq / float(np.mean(ts)), "unit": "reads/s", "ms_per_step": 1e3 * float(np.mean(ts)),
+                                  "bam_bytes": os.path.getsize(seq_bam), "inflated_bytes": inflated, "ms_ingest": round(ss["ms_decode"], 3),
+                                  "bam_on_device": bool(ss["bam_on_device"]),
+                                  "inflated_gb_per_s_of_ingest": inflated / (ss["ms_decode"] * 1e-3) / 1e9 if ss["ms_decode"] > 0 else None,
+                                  "identical_to_records_path": bool(np.array_equal(want_seq.beta1, got_seq.beta1) and np.array_equal(want_seq.beta2simple, got_seq.beta2simple)
+                                                                    and np.array_equal(want_seq.sse, got_seq.sse)),
+                                  "note": "a sequencer-shaped file: read names, SEQ and QUAL of the CIGAR's query length (seeded pseudo-random bases, slowly changing "
+                                          "qualities), so the BGZF members are mostly literals and the inflated stream is ~8 x the records-only file's per record"}
+            del want_seq, got_seq
+        except Exception as ex:
+            out["bam_e2e_seq"] = {"error": repr(ex)}
         # ---- the whole `process` command: BAM + BED12 + GFF files -> .SpliSER.tsv on disk (what a SpliSER user runs)
         try:
             out["cli_e2e"] = cli_process_run(ctx, w, bam, args, reads_rank)
@@ -592,6 +627,13 @@ def main():
         emit(json.dumps(out))
     ctx.close()
     ranks.close()
+
+
+def _cut_segments(r, n):
+    """(seg_chrom, seg_off) of the first n records of r."""
+    k = int(np.searchsorted(np.asarray(r.seg_off), n, side="left"))
+    off = [int(x) for x in r.seg_off[:k]] + [n]
+    return [int(c) for c in r.seg_chrom[:len(off) - 1]], off
 
 
 class Workload_like:

@@ -412,6 +412,10 @@ int  spl_combine_write(spl_combine* c, const char* path, int cryptic);
  * ref_len may be NULL (lengths written as 2^29).  SEQ/QUAL are omitted ('*'). */
 int spl_write_bam(const char* path, int32_t n_ref, const char* const* ref_names, const int32_t* ref_len,
                   const spl_records_view* rec /* seg_chrom indexes ref_names */, int n_threads);
+/* The same with read names, SEQ and QUAL of the CIGAR's query length (seeded pseudo-random bases, quality strings that change
+ * slowly): a sequencer-shaped file -- members of mostly literals, about 10 x the inflated bytes -- for the ingest benchmark. */
+int spl_write_bam_seq(const char* path, int32_t n_ref, const char* const* ref_names, const int32_t* ref_len,
+                      const spl_records_view* rec, int n_threads);
 /* Decodes a BAM into library-owned record arrays (host only; no GPU needed).  chrom_names maps
  * BAM reference names to caller chromosome indices; records on other references are dropped. */
 typedef struct spl_records spl_records;

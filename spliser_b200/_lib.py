@@ -108,6 +108,7 @@ SIGNATURES = {
     "spl_resident_count": (C.c_int, [C.c_void_p, C.c_int, c_f64p]),
     "spl_resident_fetch": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p)]),
     "spl_write_bam": (C.c_int, [C.c_char_p, C.c_int32, c_strp, c_i32p, C.POINTER(RecordsView), C.c_int]),
+    "spl_write_bam_seq": (C.c_int, [C.c_char_p, C.c_int32, c_strp, c_i32p, C.POINTER(RecordsView), C.c_int]),
     "spl_read_bam": (C.c_int, [C.c_char_p, C.c_int32, c_strp, C.c_int, C.POINTER(C.c_void_p), C.c_char_p, C.c_int]),
     "spl_records_get": (C.POINTER(RecordsView), [C.c_void_p]),
     "spl_records_free": (None, [C.c_void_p]),

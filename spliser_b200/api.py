@@ -150,15 +150,16 @@ class Records:
             lib.spl_records_free(h)
         return out
 
-    def write_bam(self, path, ref_names, ref_len=None, threads=0):
+    def write_bam(self, path, ref_names, ref_len=None, threads=0, with_seq=False):
+        """with_seq: read names, SEQ and QUAL of the CIGAR's query length are written too (a sequencer-shaped file)."""
         lib = L.load()
         names = (C.c_char_p * max(1, len(ref_names)))(*[c.encode() for c in ref_names])
         rl = None
         if ref_len is not None:
             rl = np.ascontiguousarray(ref_len, dtype=np.int32)
         v = self.view()
-        rc = lib.spl_write_bam(str(path).encode(), len(ref_names), names,
-                               _ptr(rl, L.c_i32p) if rl is not None else None, C.byref(v), threads)
+        rc = (lib.spl_write_bam_seq if with_seq else lib.spl_write_bam)(str(path).encode(), len(ref_names), names,
+                                                                        _ptr(rl, L.c_i32p) if rl is not None else None, C.byref(v), threads)
         if rc != 0:
             raise IOError("spl_write_bam(%s) failed with %d" % (path, rc))
 

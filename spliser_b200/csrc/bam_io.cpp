@@ -353,10 +353,10 @@ bool deflate_block(const uint8_t* src, uint32_t n, std::vector<uint8_t>& dst) {
 }  // namespace
 
 std::string write_bam(const char* path, int32_t n_ref, const char* const* ref_names, const int32_t* ref_len,
-                      const spl_records_view* rec, int n_threads) {
+                      const spl_records_view* rec, int n_threads, bool with_seq) {
     if (!path || !rec || n_ref < 0) return "bad argument";
     std::vector<uint8_t> u;
-    u.reserve((size_t)rec->n_rec * 40 + (size_t)rec->n_cigar * 4 + 4096);
+    u.reserve((size_t)rec->n_rec * (with_seq ? 300 : 40) + (size_t)rec->n_cigar * 4 + 4096);
     u.insert(u.end(), {'B', 'A', 'M', 1});
     std::string text = "@HD\tVN:1.6\tSO:coordinate\n";
     for (int32_t r = 0; r < n_ref; ++r)
@@ -383,18 +383,52 @@ std::string write_bam(const char* path, int32_t n_ref, const char* const* ref_na
                 if (op == 0 || op == 2 || op == 3 || op == 7 || op == 8) reflen += rec->cigar[k] >> 4;
             }
             const int32_t pos0 = rec->pos[i] - 1;
-            wr32(u, 32 + 2 + n_cig * 4);
+            if (!with_seq) {
+                wr32(u, 32 + 2 + n_cig * 4);
+                wr32(u, (uint32_t)ref);
+                wr32(u, (uint32_t)pos0);
+                u.push_back(2);                       // l_read_name
+                u.push_back(255);                     // mapq
+                wr16(u, (uint16_t)reg2bin(pos0, pos0 + (reflen ? reflen : 1)));
+                wr16(u, (uint16_t)n_cig);
+                wr16(u, rec->flag[i]);
+                wr32(u, 0);                           // l_seq
+                wr32(u, (uint32_t)-1); wr32(u, (uint32_t)-1); wr32(u, 0);   // next_refID, next_pos, tlen
+                u.push_back('r'); u.push_back(0);
+                for (uint32_t k = c0; k < c1; ++k) wr32(u, rec->cigar[k]);
+                continue;
+            }
+            // a sequencer-shaped record: read name, SEQ and QUAL of the CIGAR's query length (seeded pseudo-random bases and
+            // qualities: the member then consists mostly of literals, like a real file; the counting path reads none of it)
+            uint32_t qlen = 0;
+            for (uint32_t k = c0; k < c1; ++k) {
+                const uint32_t op = rec->cigar[k] & 15u;
+                if (op == 0 || op == 1 || op == 4 || op == 7 || op == 8) qlen += rec->cigar[k] >> 4;
+            }
+            char name[16];
+            const int ln = snprintf(name, sizeof name, "r%09lld", (long long)(i % 1000000000LL)) + 1;
+            wr32(u, 32 + (uint32_t)ln + n_cig * 4 + (qlen + 1) / 2 + qlen);
             wr32(u, (uint32_t)ref);
             wr32(u, (uint32_t)pos0);
-            u.push_back(2);                       // l_read_name
-            u.push_back(255);                     // mapq
+            u.push_back((uint8_t)ln);
+            u.push_back(255);
             wr16(u, (uint16_t)reg2bin(pos0, pos0 + (reflen ? reflen : 1)));
             wr16(u, (uint16_t)n_cig);
             wr16(u, rec->flag[i]);
-            wr32(u, 0);                           // l_seq
-            wr32(u, (uint32_t)-1); wr32(u, (uint32_t)-1); wr32(u, 0);   // next_refID, next_pos, tlen
-            u.push_back('r'); u.push_back(0);
+            wr32(u, qlen);
+            wr32(u, (uint32_t)-1); wr32(u, (uint32_t)-1); wr32(u, 0);
+            u.insert(u.end(), name, name + ln);
             for (uint32_t k = c0; k < c1; ++k) wr32(u, rec->cigar[k]);
+            uint64_t x = 0x9e3779b97f4a7c15ull * (uint64_t)(i + 1);
+            auto rnd = [&x]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+            static const uint8_t base4[4] = {1, 2, 4, 8};          // A C G T in the 4-bit encoding
+            for (uint32_t q = 0; q < (qlen + 1) / 2; ++q) { const uint64_t v = rnd(); u.push_back((uint8_t)((base4[v & 3] << 4) | base4[(v >> 2) & 3])); }
+            uint32_t ql = 30;
+            for (uint32_t q = 0; q < qlen; ++q) {                   // a slow random walk around Q30, like a quality string
+                const uint64_t v = rnd();
+                if ((v & 7) == 0) ql = 2 + (uint32_t)((v >> 8) % 39);
+                u.push_back((uint8_t)ql);
+            }
         }
     }
     const size_t PIECE = 0xff00;
@@ -435,6 +469,13 @@ struct spl_records {
 };
 
 extern "C" {
+
+int spl_write_bam_seq(const char* path, int32_t n_ref, const char* const* ref_names, const int32_t* ref_len,
+                      const spl_records_view* rec, int n_threads) {
+    const std::string e = spl::write_bam(path, n_ref, ref_names, ref_len, rec, n_threads, true);
+    if (!e.empty()) { fprintf(stderr, "spl_write_bam_seq: %s\n", e.c_str()); return SPL_ERR_IO; }
+    return SPL_OK;
+}
 
 int spl_write_bam(const char* path, int32_t n_ref, const char* const* ref_names, const int32_t* ref_len,
                   const spl_records_view* rec, int n_threads) {

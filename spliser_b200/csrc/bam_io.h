@@ -26,6 +26,6 @@ struct BamRecords {
 std::string read_bam(const char* path, int32_t n_chrom, const char* const* chrom_names, int n_threads, BamRecords& out);
 
 std::string write_bam(const char* path, int32_t n_ref, const char* const* ref_names, const int32_t* ref_len,
-                      const spl_records_view* rec, int n_threads);
+                      const spl_records_view* rec, int n_threads, bool with_seq = false);
 
 }  // namespace spl

@@ -542,6 +542,14 @@ def test_bam_ingest_on_the_device(ctx, tmp_path, monkeypatch):
     assert ctx.stats()["bam_on_device"] == 1.0
     assert np.array_equal(a1, b1) and np.array_equal(a2, b2) and int(a1.sum()) > 0
     assert len(order) == 2
+    # a sequencer-shaped file (read names, SEQ, QUAL: members of mostly literals, records far longer than their CIGAR)
+    seq_bam = str(tmp_path / "seq.bam")
+    rec_caller.write_bam(seq_bam, caller, with_seq=True)
+    import os
+    assert os.path.getsize(seq_bam) > 5 * os.path.getsize(bam)
+    got = c_oracle.table_dict(ctx.process_bam(seq_bam, caller, jj, w.flags | 4))
+    assert ctx.stats()["bam_on_device"] == 1.0
+    assert c_oracle.diff_tables(got, want) is None, c_oracle.diff_tables(got, want)
 
 
 @pytest.mark.parametrize("shape,parts", [("small", 2), ("small", 3), ("c2", 3)])
