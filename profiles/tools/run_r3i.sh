@@ -1,0 +1,7 @@
+set -x
+cd $GRAFT_REPO_ROOT
+mkdir -p gpurun_out
+timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 300 -k "bam or configs0" 2>&1 | tail -6 > gpurun_out/r3i_pytest.log
+cat gpurun_out/r3i_pytest.log
+timeout 600 python profiles/tools/bam_ingest_profile.py 8000000 seq 2>&1 | tail -3
+timeout 600 python profiles/tools/bam_ingest_profile.py 40000000 2>&1 | tail -3
