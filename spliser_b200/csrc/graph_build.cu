@@ -350,10 +350,23 @@ __global__ void k_gb_sites(const uint64_t* __restrict__ k, const uint32_t* __res
 // direct-address bin index, one CTA: the searches run side by side, only the running sum over the chromosomes is serial
 __global__ void __launch_bounds__(256) k_gb_chroms(GraphDev g, int n_chrom, uint32_t* __restrict__ counts) {
     const int S = (int)counts[0];
-    for (int c = threadIdx.x; c <= n_chrom; c += blockDim.x) {
-        int lo = 0, hi = S;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (g.site_chrom[mid] < c) lo = mid + 1; else hi = mid; }
-        g.cs_off[c] = lo;
+    // one warp per chromosome: 32 probes per round narrow [lo, hi) by a factor of 33 (four dependent loads for a million sites
+    // instead of twenty)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int c = warp; c <= n_chrom; c += n_warps) {
+        int lo = 0, hi = S;                                             // first site with chromosome >= c lies in [lo, hi]
+        while (hi - lo > 0) {
+            const int step = (hi - lo + 32) / 33;                       // probes at lo + (lane + 1) * step - 1
+            const int at = min(lo + (lane + 1) * step - 1, hi - 1);
+            const bool ge = g.site_chrom[at] >= c;
+            const uint32_t bal = __ballot_sync(0xffffffffu, ge);
+            if (bal == 0u) { lo = min(lo + 32 * step, hi); if (lo + 0 >= hi) break; continue; }
+            const int first = __ffs(bal) - 1;                           // first probe that is already >= c
+            hi = min(lo + (first + 1) * step - 1, hi - 1);
+            lo = first ? min(lo + first * step, hi) : lo;
+            if (step == 1) { lo = hi; break; }
+        }
+        if (lane == 0) g.cs_off[c] = lo;
     }
     __syncthreads();
     for (int c = threadIdx.x; c < n_chrom; c += blockDim.x) {

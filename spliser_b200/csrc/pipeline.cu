@@ -1337,32 +1337,38 @@ int ingest_bam_device(spl_ctx* ctx, const char* path, int32_t n_chrom, const cha
         }
         ctx->h_file_bytes = fsz + fsz / 8 + 4096;
     }
-    {   // page cache -> page-locked image, a few threads
-        const int nt = (int)std::min<size_t>(8, std::max<size_t>(1, fsz >> 24));
+    // page cache -> page-locked image in slabs (a few threads per slab); a slab starts travelling to the device as soon as it is
+    // in place, under the read of the next one; the host walks the BGZF member headers after the last slab
+    bool uploaded = ctx->bgm.comp.reserve(fsz + 64) == cudaSuccess;
+    if (!uploaded) cudaGetLastError();
+    {
+        const size_t SLAB = (size_t)64 << 20;
+        const int nt = (int)std::min<size_t>(8, std::max<size_t>(1, std::min(fsz, SLAB) >> 23));
         std::atomic<bool> bad(false);
-        auto rd = [&](int t) {
-            size_t lo = fsz * (size_t)t / (size_t)nt;
-            const size_t hi = fsz * (size_t)(t + 1) / (size_t)nt;
-            while (lo < hi) {
-                const ssize_t k = pread(fd, (char*)ctx->h_file + lo, hi - lo, (off_t)lo);
-                if (k <= 0) { bad = true; return; }
-                lo += (size_t)k;
+        for (size_t s0 = 0; s0 < fsz; s0 += SLAB) {
+            const size_t s1 = std::min(fsz, s0 + SLAB), len = s1 - s0;
+            auto rd = [&](int t) {
+                size_t lo = s0 + len * (size_t)t / (size_t)nt;
+                const size_t hi = s0 + len * (size_t)(t + 1) / (size_t)nt;
+                while (lo < hi) {
+                    const ssize_t k = pread(fd, (char*)ctx->h_file + lo, hi - lo, (off_t)lo);
+                    if (k <= 0) { bad = true; return; }
+                    lo += (size_t)k;
+                }
+            };
+            std::vector<std::thread> pool;
+            for (int t = 1; t < nt; ++t) pool.emplace_back(rd, t);
+            rd(0);
+            for (auto& t : pool) t.join();
+            if (bad) break;
+            if (uploaded && cudaMemcpyAsync((char*)ctx->bgm.comp.p + s0, (const char*)ctx->h_file + s0, len, cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) {
+                close(fd);
+                cudaStreamSynchronize(ctx->stream);
+                return ctx->fail(SPL_ERR_CUDA, "copy of the BAM image failed: %s", cudaGetErrorString(cudaGetLastError()));
             }
-        };
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back(rd, t);
-        rd(0);
-        for (auto& t : pool) t.join();
+        }
         close(fd);
-        if (bad) return ctx->fail(SPL_ERR_IO, "read error on %s", path);
-    }
-    // the file image starts travelling now; the host walks the BGZF member headers meanwhile
-    bool uploaded = false;
-    if (ctx->bgm.comp.reserve(fsz + 64) == cudaSuccess) {
-        CU(cudaMemcpyAsync(ctx->bgm.comp.p, ctx->h_file, fsz, cudaMemcpyHostToDevice, ctx->stream));
-        uploaded = true;
-    } else {
-        cudaGetLastError();
+        if (bad) { cudaStreamSynchronize(ctx->stream); return ctx->fail(SPL_ERR_IO, "read error on %s", path); }
     }
     std::vector<BgzfMember> members;
     std::vector<int32_t> refmap;
