@@ -7,7 +7,7 @@
 // difference array (cnt.diff, cov words for M, span words for N); k_finalize takes the prefix sums.  The stabbing
 // variant (k_beta1_stab in kernels.cu, streaming a bin-partitioned copy of the blocks) is kept for the cross-check.
 //
-// Layout of the kernel: persistent CTAs (2 per SM), one producer warp + 16 consumer warps.
+// Layout of the kernel: persistent CTAs (2 per SM), one producer warp + 15 consumer warps (512 threads: with 64 registers each, two CTAs fill the register file).
 //   producer  claims chunks of <= FC_RECS records from a global counter and stages their pos / flag / cig_off / CIGAR
 //             slices into a 3-stage shared-memory ring with 1-D TMA bulk copies (cp.async.bulk + mbarrier);
 //   consumers one record per lane.  A lane walks its CIGAR from shared memory and carries the site index of its
@@ -34,7 +34,7 @@ namespace {
 
 constexpr int FC_STAGES = 3;
 #ifndef SPL_FC_CWARPS
-#define SPL_FC_CWARPS 14
+#define SPL_FC_CWARPS 15
 #endif
 constexpr int FC_CWARPS = SPL_FC_CWARPS;
 constexpr int FC_CONSUMERS = FC_CWARPS * 32;
@@ -84,7 +84,6 @@ struct FArgs {
     uint4* hotq;             // global queue of hot (record, operator, side) items: {anchor, record, operator | side << 31, position of the junction's other end}
     uint32_t* hot_n;         // [0] items written (may exceed hot_cap: the excess was dropped and the pass must be repeated with room)
     uint32_t hot_cap;
-    uint32_t rec_base;       // (unused by the kernel; kept for symmetry with the item layout: records are absolute indices)
 };
 
 // +n on word `key` of the difference arrays for every run of neighbouring lanes with the same key (v: the lane takes part)
@@ -692,7 +691,7 @@ void launch_chunk_bounds(FChunk* chunks, uint32_t lo, uint32_t hi, const uint32_
 void launch_count_fused(const DevRecords& rec, const FChunk* chunks, uint32_t lo, uint32_t hi, DevGraph g, DevCounters cnt,
                         uint32_t* work, uint32_t flags, uint4* hotq, uint32_t* hot_n, uint32_t hot_cap, void* stream) {
     if (hi <= lo || g.n_sites <= 0) return;
-    FArgs a{rec, chunks, lo, hi, g, cnt, work, flags, hotq, hot_n, hot_cap, 0u};
+    FArgs a{rec, chunks, lo, hi, g, cnt, work, flags, hotq, hot_n, hot_cap};
     const int grid = (int)min((uint32_t)fused_grid(), (hi - lo + (uint32_t)FC_BATCH - 1u) / (uint32_t)FC_BATCH);
     { SPL_LAUNCH; k_count_fused<<<grid, FC_THREADS, sizeof(FSmem), (cudaStream_t)stream>>>(a); }
 }

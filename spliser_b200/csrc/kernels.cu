@@ -297,27 +297,28 @@ __global__ void __launch_bounds__(256) k_bin_pass(const Chunk* __restrict__ chun
         else if (!SCATTER) atomicAdd(bins.bin_off + gbase + bin0 + rel, 1u);
     }
     __syncthreads();
-    if (!SCATTER) {
+    if constexpr (!SCATTER) {
         for (int i = threadIdx.x; i < BIN_HIST; i += 256)
             if (hist[i]) atomicAdd(bins.bin_off + gbase + bin0 + i, hist[i]);
         return;
-    }
-    for (int i = threadIdx.x; i < BIN_HIST; i += 256) {
-        base[i] = hist[i] ? atomicAdd(bins.bin_cursor + gbase + bin0 + i, hist[i]) : 0u;
-        hist[i] = 0;
-    }
-    __syncthreads();
-    for (uint32_t e = e0 + threadIdx.x; e < e0 + n; e += 256) {
-        const int32_t st = soa.m_start[e];
-        const int rel = (max(st, 0) >> BIN_SHIFT) - bin0;
-        uint32_t slot;
-        if (rel >= 0 && rel < BIN_HIST) slot = base[rel] + atomicAdd(&hist[rel], 1u);
-        else slot = atomicAdd(bins.bin_cursor + gbase + bin0 + rel, 1u);
-        const uint32_t ek = soa.m_endk[e];
-        bins.c_start[slot] = st;
-        // stream C carries (start, len1 | class<<31) with len1 = end - 1 - start: site p is covered (S:469) iff
-        // (uint32)(p - start) < len1; blocks of one base have len1 = 0 and never match
-        bins.c_endk[slot] = (uint32_t)max((int32_t)(ek & POS_MASK) - 1 - st, 0) | (ek & 0x80000000u);
+    } else {
+        for (int i = threadIdx.x; i < BIN_HIST; i += 256) {
+            base[i] = hist[i] ? atomicAdd(bins.bin_cursor + gbase + bin0 + i, hist[i]) : 0u;
+            hist[i] = 0;
+        }
+        __syncthreads();
+        for (uint32_t e = e0 + threadIdx.x; e < e0 + n; e += 256) {
+            const int32_t st = soa.m_start[e];
+            const int rel = (max(st, 0) >> BIN_SHIFT) - bin0;
+            uint32_t slot;
+            if (rel >= 0 && rel < BIN_HIST) slot = base[rel] + atomicAdd(&hist[rel], 1u);
+            else slot = atomicAdd(bins.bin_cursor + gbase + bin0 + rel, 1u);
+            const uint32_t ek = soa.m_endk[e];
+            bins.c_start[slot] = st;
+            // stream C carries (start, len1 | class<<31) with len1 = end - 1 - start: site p is covered (S:469) iff
+            // (uint32)(p - start) < len1; blocks of one base have len1 = 0 and never match
+            bins.c_endk[slot] = (uint32_t)max((int32_t)(ek & POS_MASK) - 1 - st, 0) | (ek & 0x80000000u);
+        }
     }
 }
 
@@ -546,13 +547,13 @@ struct StageMeta {
     uint32_t p0, n;         // global index of staged element 0 (multiple of 4), staged element count
     int32_t  w_lo, w_hi;    // site window (global indices, already clamped to the owned range)
     int32_t  al;            // global site index of staged site 0
-    uint32_t flags;         // PS_DONE | PS_GLOBAL_SITES | PS_GLOBAL_BINS
+    uint32_t flags;         // PS_DONE | PS_GLOBAL_SITES
     int32_t  chunk;
     int32_t  sb_g0;         // global sb_off index of the chromosome's bin 0
     int32_t  sb_nb;         // bins of the chromosome (the sentinel sits at index sb_nb)
     int32_t  sb_al;         // global sb_off index of staged bin entry 0
 };
-constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u, PS_GLOBAL_BINS = 4u;
+constexpr uint32_t PS_DONE = 1u, PS_GLOBAL_SITES = 2u;
 
 __device__ __forceinline__ void consumer_sync() { asm volatile("bar.sync 1, %0;" ::"n"(PS_CONSUMERS) : "memory"); }
 
