@@ -136,7 +136,8 @@ def measured_peak():
 def traffic_from_profile(kernel):
     p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
-        return json.load(open(p)).get(kernel + "_dram_bytes_per_launch")
+        d = json.load(open(p))
+        return d.get("step_dram_bytes") if kernel == "step" else d.get(kernel + "_dram_bytes_per_launch")
     except (ValueError, OSError):
         return None
 
@@ -478,7 +479,7 @@ def main():
                      "bytes_definition": "SURVEY 8(d): 9 B per M/=/X block + 8 B per N + 8 B per spliced read + 5 B per site; the kernel streams the more compact "
                                          "record layout (10 B per record + 4 B per CIGAR operator = %.0f MB per launch)" % (rec_bytes / 1e6),
                      "record_bytes_per_launch": rec_bytes, "achieved_on_record_bytes_gbs": rec_bytes / (k_ms * 1e-3) / 1e9 if k_ms > 0 else 0.0},
-        "roofline_path": {"algorithmic_bytes_per_step": path_bytes, "ms_per_step": path_ms,
+        "roofline_path": {"algorithmic_bytes_per_step": path_bytes, "ms_per_step": path_ms, "traffic": traffic_from_profile("step") if world == 1 and args.workload == "c2" else None,
                           "achieved_gbs": path_bytes / (path_ms * 1e-3) / 1e9, "frac": path_bytes / (path_ms * 1e-3) / 1e9 / peak,
                           "kernel_ms": kernel_ms},
         "kernel_path": {"n_mblocks": b_m, "n_junction_ops": b_n, "n_spliced_reads": r_spl, "n_edges": int(E), "n_cigar_ops": int(len(w.records.cigar))},
