@@ -98,12 +98,23 @@ def _htseq_shim() -> types.ModuleType:
                 iv = _IV()
                 iv.chrom, iv.start, iv.end, iv.strand = f[0], int(f[3]) - 1, int(f[4]), f[6]
                 feat.iv = iv
-                first = f[8].split(";")[0].strip()
-                if "=" in first:
-                    feat.name = first.split("=", 1)[1]
-                else:  # GTF: key "value"
-                    parts = first.split(None, 1)
-                    feat.name = parts[1].strip('"') if len(parts) > 1 else first
+                # HTSeq.parse_GFF_attribute_string(..., extra_return_first_value=True), restated from its published source:
+                # quote-safe split at ';', \s*([^\s=]+)[\s=]+(.*) on the first piece, one pair of enclosing quotes removed
+                piece, in_quote = f[8], False
+                for i, ch in enumerate(f[8]):
+                    if ch == '"':
+                        in_quote = not in_quote
+                    elif ch == ";" and not in_quote:
+                        piece = f[8][:i]
+                        break
+                if not piece.strip():
+                    feat.name = "_unnamed_"
+                else:
+                    mo = re.match(r"\s*([^\s=]+)[\s=]+(.*)", piece, re.S)
+                    val = mo.group(2) if mo else piece.strip()
+                    if mo and len(val) >= 2 and val.startswith('"') and val.endswith('"'):
+                        val = val[1:-1]
+                    feat.name = val
                 yield feat
 
     mod.GFF_Reader = GFF_Reader

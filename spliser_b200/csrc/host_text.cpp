@@ -1154,19 +1154,32 @@ std::string_view py_strip(std::string_view s) {
     return s;
 }
 
-// value of the first attribute: "ID=AT1G01010;..." -> AT1G01010 (GFF3), 'gene_id "X"; ...' -> X (GTF)
+// Value of the first attribute, the way HTSeq.GFF_Reader names a feature (parse_GFF_attribute_string, restated from its
+// published source; HTSeq is not in this image, so: parity unpinned): the attribute column is cut at the first ';' that is
+// not inside double quotes; the piece must look like  \s* key [\s=]+ value  with a key free of blanks and '='; the value runs to
+// the end of the piece (trailing blanks included) and loses one pair of enclosing double quotes.  "ID=AT1G01010;..." ->
+// AT1G01010 (GFF3), 'gene_id "X"; ...' -> X (GTF), 'gene_id "A=B"' -> A=B, "ID= X" -> X.  An empty first piece names the
+// feature "_unnamed_"; a piece without a separator (HTSeq raises there) keeps the whole piece.
 std::string_view first_attribute(std::string_view col9) {
-    std::string_view first = py_strip(col9.substr(0, col9.find(';')));
-    const size_t eq = first.find('=');
-    if (eq != std::string_view::npos) return first.substr(eq + 1);
-    size_t ws = 0;
-    while (ws < first.size() && !is_py_space(first[ws])) ++ws;
-    if (ws == first.size()) return first;
-    std::string_view rest = first.substr(ws);
-    while (!rest.empty() && is_py_space(rest.front())) rest.remove_prefix(1);
-    while (!rest.empty() && rest.front() == '"') rest.remove_prefix(1);
-    while (!rest.empty() && rest.back() == '"') rest.remove_suffix(1);
-    return rest;
+    static const char unnamed[] = "_unnamed_";
+    size_t cut = col9.size();
+    bool in_quote = false;
+    for (size_t i = 0; i < col9.size(); ++i) {
+        if (col9[i] == '"') in_quote = !in_quote;
+        else if (!in_quote && col9[i] == ';') { cut = i; break; }
+    }
+    std::string_view piece = col9.substr(0, cut);
+    size_t a = 0;
+    while (a < piece.size() && is_py_space(piece[a])) ++a;
+    if (a == piece.size()) return std::string_view(unnamed, 9);
+    size_t k = a;
+    while (k < piece.size() && !is_py_space(piece[k]) && piece[k] != '=') ++k;          // the key
+    size_t v = k;
+    while (v < piece.size() && (is_py_space(piece[v]) || piece[v] == '=')) ++v;          // [\s=]+
+    if (k == a || v == k) return py_strip(piece);                                        // no key or no separator
+    std::string_view val = piece.substr(v);
+    if (val.size() >= 2 && val.front() == '"' && val.back() == '"') { val.remove_prefix(1); val.remove_suffix(1); }
+    return val;
 }
 }  // namespace
 
@@ -1184,6 +1197,7 @@ extern "C" int spl_genes_parse(const char* text, int64_t len, const char* qgene,
             std::string_view line(text + at, (size_t)(end - at));
             at = nl ? end + 1 : len;
             ++line_no;
+            if (!line.empty() && line.back() == '\r') line.remove_suffix(1);   // universal newlines, as Python's text mode reads the file
             if (line.empty() || line.front() == '#') continue;
             std::string_view col[9];
             int nc = 0;

@@ -423,11 +423,25 @@ def _create_genes_reference_semantics(text, qgene="All"):
     from spliser_b200.genes import Gene
 
     def _first_attribute(col9):
-        first = col9.split(";")[0].strip()
-        if "=" in first:
-            return first.split("=", 1)[1]
-        parts = first.split(None, 1)             # GTF: key "value"
-        return parts[1].strip('"') if len(parts) > 1 else first
+        # HTSeq.parse_GFF_attribute_string(..., extra_return_first_value=True), restated: quote-safe split at ';', then
+        # \\s*([^\\s=]+)[\\s=]+(.*) on the first piece, one pair of enclosing quotes removed
+        import re
+        piece, in_quote = col9, False
+        for i, ch in enumerate(col9):
+            if ch == '"':
+                in_quote = not in_quote
+            elif ch == ";" and not in_quote:
+                piece = col9[:i]
+                break
+        if not piece.strip():
+            return "_unnamed_"
+        mo = re.match(r"\s*([^\s=]+)[\s=]+(.*)", piece, re.S)
+        if not mo:
+            return piece.strip()
+        val = mo.group(2)
+        if len(val) >= 2 and val.startswith('"') and val.endswith('"'):
+            val = val[1:-1]
+        return val
     chrom_index, genes, query = [], [], None
     for line in text.splitlines():
         if not line.strip() or line.startswith("#"):
@@ -567,3 +581,20 @@ def test_compact_records_round_trip():
     big = Records.from_reads(["A"], [("A", 10, 0, "1M1I" * 130)])
     with pytest.raises(ValueError):
         CompactRecords.from_records(big)
+
+
+def test_first_attribute_follows_htseq(tmp_path, built_library):
+    """Gene names as HTSeq.GFF_Reader gives them (first attribute value; parse_GFF_attribute_string restated, parity unpinned):
+    quote-safe split at ';', key and value separated by blanks and / or '=', one pair of enclosing quotes removed."""
+    from spliser_b200.genes import load_annotation
+    cases = [("ID=AT1G01010;Name=x", "AT1G01010"), ('gene_id "G1"; transcript_id "t"', "G1"), ('gene_id "A=B"; x "y"', "A=B"),
+             ("ID= X;Name=n", "X"), ('gene_id "a;b"; x', "a;b"), ("ID=g=tail;x", "g=tail"), ('Name "q" ', '"q" '), ("", "_unnamed_"),
+             (" ;ID=late", "_unnamed_"), ("lonely", "lonely"), ("ID=", "")]
+    text = "".join("c\ts\tgene\t%d\t%d\t.\t+\t.\t%s\n" % (10 * (i + 1), 10 * (i + 1) + 5, a) for i, (a, _) in enumerate(cases))
+    p = tmp_path / "a.gff"
+    p.write_text(text)
+    ann = load_annotation(str(p))
+    got = [g.name for g in ann.genes[0]]
+    assert got == [w for _, w in cases]
+    want_idx, want_genes, _ = _create_genes_reference_semantics(text)
+    assert [g.name for g in want_genes[0]] == got
