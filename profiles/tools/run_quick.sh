@@ -1,3 +1,4 @@
+# development loop on one B200 under gpurun: a slice of the parity tests, then the resident timing of the fused path
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
