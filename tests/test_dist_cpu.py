@@ -42,6 +42,54 @@ def test_two_gloo_ranks(tmp_path):
     assert res.stdout.count("ok") == 2
 
 
+def test_one_sample_tiled_over_two_gloo_ranks(tmp_path):
+    """The N > 1 path of bench.py on the CPU: ONE sample sharded over two ranks by genomic tile -- read-balanced cuts, the tile's
+    records, the tile's own junction rows (every rank builds its own site table), counting by the oracle standing in for the
+    device, owned rows written out, rank 0 concatenates: the table equals the unsharded one in every column.  No data-path
+    collective: the ranks only meet at barriers."""
+    script = tmp_path / "t.py"
+    script.write_text(textwrap.dedent('''
+        import os, sys
+        sys.path.insert(0, %r)
+        import numpy as np
+        from oracle import c_oracle
+        from spliser_b200 import api, dist, synth
+        from spliser_b200.dist import Ranks
+        r = Ranks("gloo")
+        out = %r
+        w = synth.generate(synth.config_small(40000, seed=7, stranded=True, paired=True))     # the same sample on every rank
+        nc = len(w.chroms)
+        table = api.build_site_table(nc, w.junctions, w.flags)
+        cuts = dist.balanced_tiles(w.records, table, nc, r.world)
+        lo, hi = cuts[r.rank], cuts[r.rank + 1]
+        rec_t = dist.tile_records(w.records, table, nc, r.rank, r.world, site_range=(lo, hi), seg_spans=dist.segment_max_spans(w.records))
+        rows, junc_t, local = dist.tile_junctions(w.junctions, table, nc, (lo, hi), w.flags)
+        assert len(rec_t) < len(w.records) and len(junc_t) <= len(w.junctions)
+        part = c_oracle.process(rec_t, nc, junc_t, w.flags | 4, threads=2)
+        class T: pass
+        t = T()
+        for k, v in part.items(): setattr(t, k, v)
+        np.savez(os.path.join(out, "part_%%d.npz" %% r.rank), **dist.owned_part(t, local, rows))
+        sent = r.sum(len(rec_t))
+        r.barrier()
+        if r.rank == 0:
+            full = c_oracle.process(w.records, nc, w.junctions, w.flags | 4, threads=2)
+            parts = [dict(np.load(os.path.join(out, "part_%%d.npz" %% q))) for q in range(r.world)]
+            d = c_oracle.diff_tables(dist.concat_parts(parts, full), full)
+            assert d is None, d
+            assert 0.9 * len(w.records) <= sent < 1.2 * len(w.records)     # edge reads go to both tiles; reads that can touch no site go to none
+        r.barrier()
+        r.close()
+        print("rank", r.rank, "ok")
+    ''' % (ROOT, str(tmp_path))))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+           "--master-port", "29521", str(script)]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count("ok") == 2
+
+
 def test_bench_reference_arm_prints_the_contract_line(tmp_path):
     """`bench.py --impl reference` (the CPU arm the driver runs beside ours) on a small workload: ONE JSON line with the
     keys of the bench contract; under torchrun (N > 1) rank 0 alone prints it and the other rank exits 0 without work."""
