@@ -24,7 +24,7 @@ with spliser_b200.Context(0) as ctx:
         ctx.resident_load(w.records, len(w.chroms), w.junctions, w.flags)
         ctx.resident_count(3)
         st = ctx.resident_count(10)
-        out[v] = {k: st[k] / 10 for k in ("ms_total", "ms_beta1", "ms_spliced", "ms_final")}
+        out[v] = {k: st[k] / 10 for k in ("ms_total", "ms_graph_dev", "ms_beta1", "ms_spliced", "ms_final")}
         out[v]["reads_per_s"] = len(w.records) / (st["ms_total"] / 10 * 1e-3)
         t = ctx.resident_fetch()
         tables[v] = (int(t.beta1.sum()), int(t.beta2simple.sum()), int(t.alpha.sum()), float(t.sse.sum()))

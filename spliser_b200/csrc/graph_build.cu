@@ -17,6 +17,9 @@
 #include <climits>
 #include <cstdint>
 #include <algorithm>
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -544,6 +547,549 @@ struct Carve {
     }
 };
 
+// ---- K1 as ONE persistent cooperative kernel -----------------------------------------------------------------------
+// The launches above are 3 - 17 us each for tables of 10^5 - 10^6 keys: two dozen of them have a floor of ~0.2 ms whatever the
+// size of the table.  Here two CTAs per SM walk through the same phases, separated by grid-wide barriers
+// (14 of them) instead of kernel boundaries; every CTA owns one contiguous slice of the keys and, later, of the sites (a warp
+// one run of the slice's keys in the sort, a thread one run of the slice's sites in the per-site phases: no block-wide
+// synchronisation inside the loops, the warps hide each other's latency):
+//   keys -> 3 x [histogram | B | per-digit scan over the CTAs | B | digit bases, ranked scatter | B]
+//        -> heads counted | B | site indices, site columns | B | (last CTA: chromosome ranges + bin layout)
+//        -> Partners counted | B | Partners filled, reverse-partner counts | B | competitors counted | B
+//        -> competitors filled, reverse partners filled, hot flags.
+// The bin index (up to 5e7 entries on GRCh38) keeps its own wide launch behind it.  Launched with
+// cudaLaunchCooperativeKernel (co-residency guaranteed by the driver); the launch-per-phase path above stays as the fallback
+// (SPLISER_K1_LAUNCHES=1, or a device without cooperative launch) and the two are held to the same table by the tests.
+constexpr int CO_THREADS = 512, CO_WARPS = CO_THREADS / 32, CO_MAX_G = CO_THREADS, CO_STAMPS = 24, CO_KB = 4;
+static_assert(RS_BINS == 2 * CO_THREADS, "digit prefix: two digits per thread");
+constexpr size_t CO_SMEM = ((size_t)CO_WARPS * RS_BINS + 32 + 2 * CO_MAX_G) * sizeof(uint32_t);
+
+struct CoopArgs {
+    const int32_t *jc, *jl, *jr;
+    const uint8_t* js;
+    uint32_t J;
+    int stranded, pb, vb, lo, hi, n_chrom;
+    uint64_t *ka, *kb;
+    uint32_t *hist;                  // [RS_BINS * G], digit-major
+    uint32_t *dtot;                  // [RS_BINS]
+    uint32_t *parts;                 // [4][CO_MAX_G] per-CTA sums: heads, Partners entries, competitors, reverse partners
+    uint32_t *bar;                   // [0] arrive (monotonic inside a launch), [1] depart; zero between launches
+    uint32_t *cnt;                   // the d_cnt words of the launch-per-phase path
+    uint32_t *stamps;                // [CO_STAMPS] globaltimer (ns, low word) of CTA 0 after every barrier, or null
+    uint32_t *site_of, *inc_eid, *e_src, *ncp, *rp_cnt, *rp_cur, *loc_rp;
+    uint32_t cap;
+    GraphDev g;
+};
+
+__device__ __forceinline__ void co_grid_sync(uint32_t* bar, uint32_t& target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        while (*(volatile uint32_t*)bar < target) { }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void co_stamp(const uint32_t* /*unused*/, uint32_t* stamps, int k) {
+    if (stamps && k < CO_STAMPS && blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        stamps[k] = (uint32_t)t;
+    }
+}
+
+// exclusive prefix of one value per thread over the CTA; total = sum over the CTA (two __syncthreads: s_w is free again after it)
+__device__ __forceinline__ uint32_t co_block_excl(uint32_t v, uint32_t* s_w, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    if (lane == 31) s_w[warp] = inc;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < CO_WARPS; ++w) { const uint32_t x = s_w[w]; if (w < warp) wbase += x; tot += x; }
+    __syncthreads();
+    total = tot;
+    return wbase + inc - v;
+}
+
+// after a barrier: s_pre[c] = sum of part[0..c) for every CTA c, total = sum of all; returns this CTA's prefix
+__device__ __forceinline__ uint32_t co_parts_prefix(const uint32_t* part, uint32_t* s_pre, uint32_t* s_w, uint32_t& total) {
+    const uint32_t v = threadIdx.x < gridDim.x ? __ldcg(part + threadIdx.x) : 0u;
+    const uint32_t ex = co_block_excl(v, s_w, total);
+    if (threadIdx.x < gridDim.x) s_pre[threadIdx.x] = ex;
+    __syncthreads();
+    return s_pre[blockIdx.x];
+}
+
+__device__ __forceinline__ uint32_t co_partner(const CoopArgs& a, uint32_t k) { return a.site_of[a.inc_eid[k] ^ 1u]; }
+
+// the general per-site loops (any degree), as in k_gb_pt_count / k_gb_pt_fill / k_gb_cp_count
+__device__ __forceinline__ uint32_t co_pt_count_site(const CoopArgs& a, uint32_t o, uint32_t d) {
+    uint32_t u = 0;
+    for (uint32_t i = 0; i < d; ++i) {
+        const uint32_t p = co_partner(a, o + i);
+        bool first = true;
+        for (uint32_t q = 0; q < i && first; ++q) first = co_partner(a, o + q) != p;
+        u += first;
+    }
+    return u;
+}
+__device__ __forceinline__ uint32_t co_pt_fill_site(const CoopArgs& a, const GraphDev& g, uint32_t t, uint32_t o, uint32_t d, uint32_t x) {
+    uint32_t w = o;
+    for (uint32_t i = 0; i < d; ++i) {
+        const uint32_t p = co_partner(a, o + i);
+        bool first = true;
+        for (uint32_t q = 0; q < i && first; ++q) first = co_partner(a, o + q) != p;
+        if (!first) continue;
+        g.pt_site[x] = (int32_t)p;
+        g.pc_pos[x] = g.site_pos[p];
+        g.einc_beg[x] = (int32_t)w;
+        for (uint32_t q = i; q < d; ++q)
+            if (co_partner(a, o + q) == p) g.einc_line[w++] = (int32_t)(a.inc_eid[o + q] >> 1);
+        g.einc_end[x] = (int32_t)w;
+        a.e_src[x] = t;
+        atomicAdd(a.rp_cnt + anchor_of(g, p), 1u);
+        ++x;
+    }
+    return x;
+}
+__device__ __forceinline__ uint32_t co_cp_count_site(const GraphDev& g, uint32_t t) {
+    const int32_t tp = g.site_pos[t];
+    uint32_t u = 0;
+    for (int32_t last = INT_MIN;;) {
+        last = next_competitor(g, g.pt_off, t, tp, last);
+        if (last == INT_MAX) break;
+        ++u;
+    }
+    return u;
+}
+
+__global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
+    extern __shared__ __align__(16) uint32_t co_sm[];
+    uint32_t (*wc)[RS_BINS] = reinterpret_cast<uint32_t (*)[RS_BINS]>(co_sm);      // [CO_WARPS][RS_BINS]: counts, then bases, per warp
+    uint32_t* s_w = co_sm + CO_WARPS * RS_BINS;                                    // [32]
+    uint32_t* s_pre = s_w + 32;                                                    // [CO_MAX_G]
+    uint32_t* s_pre2 = s_pre + CO_MAX_G;                                           // [CO_MAX_G]
+    const uint32_t G = gridDim.x, c = blockIdx.x, tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    const uint32_t J = a.J, n2 = 2u * J;
+    const GraphDev& g = a.g;
+    const int vb = a.vb, pb = a.pb;
+    uint32_t target = 0;
+    int stamp = 0;
+    co_stamp(nullptr, a.stamps, stamp++);
+
+    // ---- scratch that the later phases add into; endpoint keys of this CTA's slice
+    for (uint32_t i = c * CO_THREADS + tid; i < n2 + 64u; i += G * CO_THREADS) g.site_hot[i] = 0;
+    for (uint32_t i = c * CO_THREADS + tid; i < n2 + 4u; i += G * CO_THREADS) { a.rp_cnt[i] = 0u; a.rp_cur[i] = 0u; }
+    if (c == 0 && tid == 0) a.cnt[6] = 0u;
+    const uint32_t K = (n2 + G - 1) / G;                                           // keys per CTA
+    const uint32_t k0 = min(c * K, n2), k1 = min(k0 + K, n2);
+    const uint32_t Kw = (K + CO_WARPS - 1) / CO_WARPS;                             // ... per warp: [w0, w1), in index order over the warps
+    const uint32_t w0 = min(k0 + (uint32_t)warp * Kw, k1), w1 = min(w0 + Kw, k1);
+    for (uint32_t e = w0 + lane; e < w1; e += 32) {
+        const uint32_t i = e >> 1;
+        const uint64_t sb = (a.stranded && a.js[i] == '-') ? 1u : 0u;
+        const uint64_t ch = (uint64_t)(uint32_t)a.jc[i] << (pb + 1);
+        const uint32_t pos = (uint32_t)((e & 1u) ? a.jr[i] : a.jl[i]);
+        a.ka[e] = ((ch | ((uint64_t)pos << 1) | sb) << vb) | (uint64_t)e;
+    }
+    __syncwarp();
+
+    // ---- stable LSD radix sort.  Every warp ranks its own run of keys: counts per (warp, digit) in shared memory, the CTA's
+    // sums go through the grid-wide digit scan, come back as the CTA's bases, and are turned into per-warp bases in place.
+    uint64_t* in = a.ka;
+    uint64_t* out = a.kb;
+    {
+        const int passes = (a.hi - a.lo + RS_BITS - 1) / RS_BITS, step = (a.hi - a.lo + passes - 1) / passes;
+        for (int shift = a.lo; shift < a.hi; shift += step) {
+            const int width = a.hi - shift < step ? a.hi - shift : step;
+            const uint32_t nb = 1u << width, mask = nb - 1u;
+            for (uint32_t i = tid; i < (uint32_t)(CO_WARPS * RS_BINS); i += CO_THREADS) co_sm[i] = 0u;
+            __syncthreads();
+            for (uint32_t eb = w0; eb < w1; eb += 32 * CO_KB) {                    // CO_KB loads in flight per lane, then the counts
+                uint64_t kr[CO_KB];
+#pragma unroll
+                for (int q = 0; q < CO_KB; ++q) { const uint32_t e = eb + q * 32 + lane; kr[q] = e < w1 ? in[e] : 0ull; }
+#pragma unroll
+                for (int q = 0; q < CO_KB; ++q) if (eb + q * 32 + lane < w1) atomicAdd(&wc[warp][(uint32_t)(kr[q] >> shift) & mask], 1u);
+            }
+            __syncthreads();
+            for (uint32_t d = tid; d < nb; d += CO_THREADS) {
+                uint32_t h = 0;
+#pragma unroll
+                for (int w = 0; w < CO_WARPS; ++w) h += wc[w][d];
+                a.hist[d * G + c] = h;
+            }
+            co_grid_sync(a.bar, target);
+            co_stamp(nullptr, a.stamps, stamp++);
+            // one warp per digit: exclusive scan of the digit's counts over the CTAs, digit total
+            for (uint32_t d = c + G * (uint32_t)warp; d < nb; d += G * CO_WARPS) {
+                uint32_t v[CO_MAX_G / 32];
+#pragma unroll
+                for (int q = 0; q < CO_MAX_G / 32; ++q) { const uint32_t x = q * 32 + lane; v[q] = x < G ? a.hist[d * G + x] : 0u; }
+                uint32_t run = 0;
+#pragma unroll
+                for (int q = 0; q < CO_MAX_G / 32; ++q) {
+                    if ((uint32_t)(q * 32) >= G) break;
+                    const uint32_t x = q * 32 + lane;
+                    uint32_t inc = v[q];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += y; }
+                    if (x < G) a.hist[d * G + x] = run + inc - v[q];
+                    run += __shfl_sync(0xffffffffu, inc, 31);
+                }
+                if (lane == 0) a.dtot[d] = run;
+            }
+            co_grid_sync(a.bar, target);
+            co_stamp(nullptr, a.stamps, stamp++);
+            {   // base of digit d for this CTA = keys with a smaller digit + keys with digit d in the CTAs in front; then per warp
+                const uint32_t d0 = 2u * tid;
+                const uint32_t v0 = d0 < nb ? a.dtot[d0] : 0u, v1 = d0 + 1u < nb ? a.dtot[d0 + 1u] : 0u;
+                const uint32_t h0 = d0 < nb ? a.hist[d0 * G + c] : 0u, h1 = d0 + 1u < nb ? a.hist[(d0 + 1u) * G + c] : 0u;
+                uint32_t tot;
+                const uint32_t ex = co_block_excl(v0 + v1, s_w, tot);
+                if (d0 < nb) {
+                    uint32_t b = ex + h0;
+#pragma unroll
+                    for (int w = 0; w < CO_WARPS; ++w) { const uint32_t t = wc[w][d0]; wc[w][d0] = b; b += t; }
+                }
+                if (d0 + 1u < nb) {
+                    uint32_t b = ex + v0 + h1;
+#pragma unroll
+                    for (int w = 0; w < CO_WARPS; ++w) { const uint32_t t = wc[w][d0 + 1u]; wc[w][d0 + 1u] = b; b += t; }
+                }
+            }
+            __syncthreads();
+            for (uint32_t eb = w0; eb < w1; eb += 32 * CO_KB) {                    // element order = (warp, round, lane) = index order
+                uint64_t kr[CO_KB];
+#pragma unroll
+                for (int q = 0; q < CO_KB; ++q) { const uint32_t e = eb + q * 32 + lane; kr[q] = e < w1 ? in[e] : 0ull; }
+#pragma unroll
+                for (int q = 0; q < CO_KB; ++q) {
+                    if (eb + q * 32 >= w1) break;                                   // warp-uniform
+                    const bool live = eb + q * 32 + lane < w1;
+                    const uint64_t key = kr[q];
+                    const uint32_t d = live ? ((uint32_t)(key >> shift) & mask) : (uint32_t)RS_BINS;   // dead lanes form their own group
+                    const uint32_t peers = __match_any_sync(0xffffffffu, d);
+                    const uint32_t below = __popc(peers & ((1u << lane) - 1u));
+                    uint32_t at = 0;
+                    if (live) at = wc[warp][d];
+                    __syncwarp();
+                    if (live) {
+                        out[at + below] = key;
+                        if (below == 0) wc[warp][d] = at + (uint32_t)__popc(peers);
+                    }
+                    __syncwarp();
+                }
+            }
+            co_grid_sync(a.bar, target);
+            co_stamp(nullptr, a.stamps, stamp++);
+            uint64_t* t = in; in = out; out = t;
+        }
+    }
+    const uint64_t* sk = in;
+
+    // ---- sites: heads of the runs of equal (chromosome, position, strand bit); thread tid owns the keys [e0, e1) of the CTA's slice
+    const uint32_t kq = (K + CO_THREADS - 1) / CO_THREADS;
+    const uint32_t e0 = min(k0 + tid * kq, k1), e1 = min(e0 + kq, k1);
+    uint32_t heads_in_front;                                                        // ... of this thread's first key, inside the CTA
+    {
+        uint32_t h = 0;
+        uint64_t prev = (e0 > 0 && e0 < e1) ? (sk[e0 - 1] >> vb) : 0ull;
+        for (uint32_t eb = e0; eb < e1; eb += CO_KB) {
+            uint64_t kr[CO_KB];
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) kr[q] = eb + q < e1 ? sk[eb + q] : 0ull;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (eb + q >= e1) break;
+                const uint64_t cur = kr[q] >> vb;
+                h += (eb + q == 0 || cur != prev) ? 1u : 0u;
+                prev = cur;
+            }
+        }
+        uint32_t tot;
+        heads_in_front = co_block_excl(h, s_w, tot);
+        if (tid == 0) a.parts[0 * CO_MAX_G + c] = tot;
+    }
+    co_grid_sync(a.bar, target);
+    co_stamp(nullptr, a.stamps, stamp++);
+    uint32_t S;
+    {
+        uint32_t run = co_parts_prefix(a.parts + 0 * CO_MAX_G, s_pre, s_w, S) + heads_in_front;   // heads in front of key e
+        uint64_t prev = (e0 > 0 && e0 < e1) ? (sk[e0 - 1] >> vb) : 0ull;
+        for (uint32_t eb = e0; eb < e1; eb += CO_KB) {
+            uint64_t kr[CO_KB];
+            uint8_t sr[CO_KB];
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) kr[q] = eb + q < e1 ? sk[eb + q] : 0ull;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) sr[q] = eb + q < e1 ? a.js[(uint32_t)(kr[q] & ((1ull << vb) - 1ull)) >> 1] : (uint8_t)0;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (eb + q >= e1) break;
+                const uint32_t e = eb + q;
+                const uint64_t kk = kr[q];
+                const uint64_t key = kk >> vb;
+                const bool head = e == 0 || key != prev;
+                prev = key;
+                run += head ? 1u : 0u;
+                const uint32_t idx = run - 1u;
+                const uint32_t eid = (uint32_t)(kk & ((1ull << vb) - 1ull));
+                a.site_of[eid] = idx;
+                a.inc_eid[e] = eid;                                                 // endpoint 2 * row + side; its junction partner is eid ^ 1
+                g.inc_line[e] = (int32_t)(eid >> 1);
+                if (head) {
+                    const uint32_t line = eid >> 1;
+                    const uint8_t st = sr[q];
+                    g.site_chrom[idx] = (int32_t)(key >> (pb + 1));
+                    g.site_pos[idx] = (int32_t)((key >> 1) & ((1ull << pb) - 1ull));
+                    g.site_strand[idx] = st;                                        // first-seen strand (stable sort keeps row order)
+                    g.first_line[idx] = (int64_t)line;
+                    g.site_cls[idx] = !a.stranded ? 0 : st == '+' ? 1 : st == '-' ? 2 : 3;
+                    g.inc_off[idx] = (int32_t)e;
+                }
+            }
+        }
+        if (c == 0 && tid < 64) g.site_pos[S + tid] = INT_MAX;                     // tail padding (never matches)
+        if (c == 0 && tid == 0) { g.inc_off[S] = (int32_t)n2; a.cnt[0] = S; a.cnt[7] = S + 1u; }
+    }
+    co_grid_sync(a.bar, target);
+    co_stamp(nullptr, a.stamps, stamp++);
+
+    // ---- chromosome ranges + layout of the bin index: the last CTA, the others go on (only k_gb_sb_fill reads these)
+    if (c == G - 1) {
+        const int n_chrom = a.n_chrom;
+        for (int ch = warp; ch <= n_chrom; ch += CO_WARPS) {
+            int lo = 0, hi = (int)S;                                                // first site with chromosome >= ch lies in [lo, hi]
+            while (hi - lo > 0) {
+                const int step = (hi - lo + 32) / 33;
+                const int at = min(lo + (lane + 1) * step - 1, hi - 1);
+                const bool ge = g.site_chrom[at] >= ch;
+                const uint32_t bal = __ballot_sync(0xffffffffu, ge);
+                if (bal == 0u) { lo = min(lo + 32 * step, hi); if (lo >= hi) break; continue; }
+                const int first = __ffs(bal) - 1;
+                hi = min(lo + (first + 1) * step - 1, hi - 1);
+                lo = first ? min(lo + first * step, hi) : lo;
+                if (step == 1) { lo = hi; break; }
+            }
+            if (lane == 0) g.cs_off[ch] = lo;
+        }
+        __syncthreads();
+        for (int ch = tid; ch < n_chrom; ch += CO_THREADS) {
+            const int32_t q0 = g.cs_off[ch], q1 = g.cs_off[ch + 1];
+            g.sb_base[ch] = (q1 > q0 ? (max(g.site_pos[q1 - 1], 0) >> SB_SHIFT) + 1 : 0) + 1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int32_t nbins = 0;
+            for (int ch = 0; ch < n_chrom; ++ch) { const int32_t v = g.sb_base[ch]; g.sb_base[ch] = nbins; nbins += v; }
+            g.sb_base[n_chrom] = nbins;
+            a.cnt[1] = (uint32_t)nbins;
+        }
+    }
+
+    // ---- per-site phases: CTA c owns the sites [s0, s1), thread tid the run [t0, t1) of them
+    const uint32_t Ks = max((S + G - 1) / G, 1u);
+    const uint32_t s0 = min(c * Ks, S), s1 = min(s0 + Ks, S);
+    const uint32_t sq = (Ks + CO_THREADS - 1) / CO_THREADS;
+    const uint32_t t0 = min(s0 + tid * sq, s1), t1 = min(t0 + sq, s1);
+    // Every loop below takes CO_KB sites (or entries) at a time and loads level by level -- all of a level's loads are in flight
+    // together, so a batch costs one memory round trip per level instead of one per site and level.  Sites of degree one (nearly
+    // all of them) take the short way, the others the general loops of the launch-per-phase kernels.
+    uint32_t pt_front;                                                              // Partners entries in front of site t0, inside the CTA
+    {
+        uint32_t run = 0;
+        for (uint32_t tb = t0; tb < t1; tb += CO_KB) {
+            uint32_t io[CO_KB + 1];
+#pragma unroll
+            for (int q = 0; q <= CO_KB; ++q) io[q] = tb + q <= t1 ? (uint32_t)g.inc_off[tb + q] : 0u;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (tb + q >= t1) break;
+                const uint32_t d = io[q + 1] - io[q];
+                run += d == 1u ? 1u : co_pt_count_site(a, io[q], d);
+            }
+        }
+        uint32_t tot;
+        pt_front = co_block_excl(run, s_w, tot);
+        if (tid == 0) a.parts[1 * CO_MAX_G + c] = tot;
+    }
+    co_grid_sync(a.bar, target);
+    co_stamp(nullptr, a.stamps, stamp++);
+    uint32_t E;
+    {
+        uint32_t x = co_parts_prefix(a.parts + 1 * CO_MAX_G, s_pre, s_w, E) + pt_front;
+        for (uint32_t tb = t0; tb < t1; tb += CO_KB) {
+            uint32_t io[CO_KB + 1], eid[CO_KB], pp[CO_KB];
+            int32_t pos[CO_KB], posm[CO_KB], chr[CO_KB], chrm[CO_KB];
+#pragma unroll
+            for (int q = 0; q <= CO_KB; ++q) io[q] = tb + q <= t1 ? (uint32_t)g.inc_off[tb + q] : 0u;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) eid[q] = tb + q < t1 ? a.inc_eid[io[q]] : 0u;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) pp[q] = tb + q < t1 ? a.site_of[eid[q] ^ 1u] : 0u;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                const bool lv = tb + q < t1;
+                pos[q] = lv ? g.site_pos[pp[q]] : 0; chr[q] = lv ? g.site_chrom[pp[q]] : 0;
+                posm[q] = lv && pp[q] > 0 ? g.site_pos[pp[q] - 1] : -1; chrm[q] = lv && pp[q] > 0 ? g.site_chrom[pp[q] - 1] : -1;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (tb + q >= t1) break;
+                const uint32_t t = tb + q, o = io[q], d = io[q + 1] - o;
+                g.pt_off[t] = (int32_t)x;
+                g.pt_off64[t] = (int64_t)x;
+                if (d == 1u) {
+                    g.pt_site[x] = (int32_t)pp[q];
+                    g.pc_pos[x] = pos[q];
+                    g.einc_beg[x] = (int32_t)o;
+                    g.einc_line[o] = (int32_t)(eid[q] >> 1);
+                    g.einc_end[x] = (int32_t)(o + 1u);
+                    a.e_src[x] = t;
+                    atomicAdd(a.rp_cnt + ((pp[q] > 0 && posm[q] == pos[q] && chrm[q] == chr[q]) ? pp[q] - 1u : pp[q]), 1u);
+                    ++x;
+                } else {
+                    x = co_pt_fill_site(a, g, t, o, d, x);
+                }
+            }
+        }
+        if (c == 0 && tid == 0) { g.pt_off[S] = (int32_t)E; g.pt_off64[S] = (int64_t)E; a.cnt[2] = E; }
+    }
+    co_grid_sync(a.bar, target);
+    co_stamp(nullptr, a.stamps, stamp++);
+    uint32_t cp_front;
+    {   // competitors counted; the reverse-partner counts of the own sites are final since the barrier
+        uint32_t run = 0, run2 = 0;
+        for (uint32_t tb = t0; tb < t1; tb += CO_KB) {
+            uint32_t xo[CO_KB + 1], pp[CO_KB], po0[CO_KB], po1[CO_KB], rc[CO_KB];
+#pragma unroll
+            for (int q = 0; q <= CO_KB; ++q) xo[q] = tb + q <= t1 ? (uint32_t)g.pt_off[tb + q] : 0u;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) { rc[q] = tb + q < t1 ? a.rp_cnt[tb + q] : 0u; pp[q] = tb + q < t1 ? (uint32_t)g.pt_site[xo[q]] : 0u; }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) { po0[q] = tb + q < t1 ? (uint32_t)g.pt_off[pp[q]] : 0u; po1[q] = tb + q < t1 ? (uint32_t)g.pt_off[pp[q] + 1u] : 0u; }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (tb + q >= t1) break;
+                const uint32_t t = tb + q;
+                // one partner whose only partner is this site: nobody competes
+                const uint32_t u = (xo[q + 1] - xo[q] == 1u && po1[q] - po0[q] == 1u) ? 0u : co_cp_count_site(g, t);
+                a.ncp[t] = u;
+                a.loc_rp[t] = run2;                                                 // inside the thread for now
+                run += u;
+                run2 += rc[q];
+            }
+        }
+        uint32_t tot, tot2;
+        cp_front = co_block_excl(run, s_w, tot);
+        const uint32_t rp_front = co_block_excl(run2, s_w, tot2);
+        for (uint32_t t = t0; t < t1; ++t) a.loc_rp[t] += rp_front;                 // read by other CTAs after the barrier
+        if (tid == 0) { a.parts[2 * CO_MAX_G + c] = tot; a.parts[3 * CO_MAX_G + c] = tot2; }
+    }
+    co_grid_sync(a.bar, target);
+    co_stamp(nullptr, a.stamps, stamp++);
+    {
+        uint32_t C, RP;
+        uint32_t x = co_parts_prefix(a.parts + 2 * CO_MAX_G, s_pre, s_w, C) + cp_front;
+        const uint32_t rpb = co_parts_prefix(a.parts + 3 * CO_MAX_G, s_pre2, s_w, RP);
+        for (uint32_t tb = t0; tb < t1; tb += CO_KB) {
+            uint32_t nc[CO_KB], lr[CO_KB];
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) { nc[q] = tb + q < t1 ? a.ncp[tb + q] : 0u; lr[q] = tb + q < t1 ? a.loc_rp[tb + q] : 0u; }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (tb + q >= t1) break;
+                const uint32_t t = tb + q;
+                g.cp_off[t] = (int32_t)x;
+                g.cp_off64[t] = (int64_t)x;
+                g.rp_off[t] = (int32_t)(rpb + lr[q]);
+                if (nc[q] == 0u) continue;
+                const int32_t tp = g.site_pos[t];
+                for (int32_t last = INT_MIN;;) {
+                    last = next_competitor(g, g.pt_off, t, tp, last);
+                    if (last == INT_MAX) break;
+                    if (x < a.cap) g.cp_pos[x] = last;
+                    ++x;
+                }
+            }
+        }
+        if (c == 0 && tid == 0) {
+            g.cp_off[S] = (int32_t)C; g.cp_off64[S] = (int64_t)C; g.rp_off[S] = (int32_t)RP;
+            a.cnt[4] = C; a.cnt[5] = RP;
+            if (C > a.cap) a.cnt[6] = 1u;                                          // the host re-runs with room
+        }
+        // reverse-partner lists + hot flags, one thread per Partners entry; the offset of a site owned by another CTA is its
+        // prefix inside that CTA (written before the barrier) + that CTA's base
+        const uint32_t stride = G * CO_THREADS;
+        for (uint32_t eb = c * CO_THREADS + tid; eb < E; eb += CO_KB * stride) {
+            uint32_t pp[CO_KB], ts[CO_KB], an[CO_KB], nc[CO_KB], lr[CO_KB], at[CO_KB];
+            int32_t pos[CO_KB], posm[CO_KB], chr[CO_KB], chrm[CO_KB];
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                const uint32_t e = eb + q * stride;
+                pp[q] = e < E ? (uint32_t)g.pt_site[e] : 0u; ts[q] = e < E ? a.e_src[e] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                const bool lv = eb + q * stride < E;
+                pos[q] = lv ? g.site_pos[pp[q]] : 0; chr[q] = lv ? g.site_chrom[pp[q]] : 0;
+                posm[q] = lv && pp[q] > 0 ? g.site_pos[pp[q] - 1] : -1; chrm[q] = lv && pp[q] > 0 ? g.site_chrom[pp[q] - 1] : -1;
+                nc[q] = lv ? a.ncp[ts[q]] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                const bool lv = eb + q * stride < E;
+                an[q] = (pp[q] > 0 && posm[q] == pos[q] && chrm[q] == chr[q]) ? pp[q] - 1u : pp[q];
+                lr[q] = lv ? a.loc_rp[an[q]] : 0u;
+                at[q] = lv ? atomicAdd(a.rp_cur + an[q], 1u) : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (eb + q * stride >= E) break;
+                g.rp_site[s_pre2[an[q] / Ks] + lr[q] + at[q]] = (int32_t)ts[q];     // order inside a list does not matter: only counted
+                if (nc[q] > 0u) g.site_hot[an[q]] = 1;
+            }
+        }
+    }
+    co_stamp(nullptr, a.stamps, stamp++);
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        if (atomicAdd(a.bar + 1, 1u) == G - 1) { a.bar[0] = 0u; a.bar[1] = 0u; }  // the last CTA out: nobody waits on the words any more
+    }
+}
+
+// CTAs of k_gb_coop on the current device (two per SM), 0 when the device cannot run it
+int coop_grid() {
+    static std::atomic<int> grid_of[64];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return 0;
+    int gsz = grid_of[dev].load();
+    if (gsz) return gsz > 0 ? gsz : 0;
+    int coop = 0, sms = 0, per_sm = 0;
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (coop && cudaFuncSetAttribute((const void*)k_gb_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CO_SMEM) == cudaSuccess)
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_gb_coop, CO_THREADS, CO_SMEM);
+    cudaGetLastError();
+    int want = 2;                                                                  // CTAs per SM (the phases are latency-bound: more warps per SM)
+    if (const char* f = std::getenv("SPLISER_K1_CTAS_PER_SM")) want = std::max(1, atoi(f));
+    gsz = (coop && per_sm >= 1 && sms >= 1) ? std::min(sms * std::min(per_sm, want), CO_MAX_G) : -1;
+    if (const char* f = std::getenv("SPLISER_K1_LAUNCHES")) if (f[0] == '1') gsz = -1;
+    grid_of[dev].store(gsz);
+    return gsz > 0 ? gsz : 0;
+}
+
+
 // ---- junction extraction from the alignments (replaces the `regtools junctions extract` pre-step,
 // README.md:41): every N operator with min_intron <= length <= max_intron whose two flanking aligned stretches (M/=/X/D up to
 // the neighbouring N or the end of the read) are >= min_anchor long supports the junction (chromosome, l, r, strand); the
@@ -697,6 +1243,10 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     const size_t w_esrc = w.take<uint32_t>(n2 + 2), w_npt = w.take<uint32_t>(n2 + 4), w_ncp = w.take<uint32_t>(n2 + 4);
     const size_t w_c1 = w.take<uint32_t>(n2 + 4), w_c2 = w.take<uint32_t>(n2 + 4);
     const size_t w_desc = w.take<unsigned long long>(lb_tiles + SC_EXTRA);  // descriptors, then the ticket word and the rendezvous words
+    const int coop_g = coop_grid();                                         // scratch of the one-kernel build (k_gb_coop)
+    const size_t w_chist = w.take<uint32_t>((size_t)RS_BINS * (size_t)std::max(coop_g, 1)), w_dtot = w.take<uint32_t>(RS_BINS);
+    const size_t w_parts = w.take<uint32_t>(4 * CO_MAX_G), w_bar = w.take<uint32_t>(16);
+    const size_t w_l3 = w.take<uint32_t>(n2 + 4), w_stamps = w.take<uint32_t>(CO_STAMPS);
     const bool fresh = m.work.cap < w.off + 256;
     GB_CU(m.work.reserve(w.off + 256));
     char* wb = (char*)m.work.p;
@@ -723,11 +1273,42 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
         GB_CU(cudaMemsetAsync(d_cnt, 0, 64, st));
         m.scan_epoch = 0;
         GB_CU(cudaMemsetAsync(desc, 0, ((size_t)lb_tiles + SC_EXTRA) * sizeof(unsigned long long), st));     // descriptors + ticket + rendezvous words
+        GB_CU(cudaMemsetAsync(wb + w_bar, 0, 64, st));                     // barrier words of k_gb_coop (it leaves them zero)
         m.ready = true;
         return true;
     }
     if (fresh || !m.ready) { err = "graph build: phase 1 without phase 0"; return false; }
 
+    if (coop_g > 0) {
+        CoopArgs ca{};
+        ca.jc = d_jc; ca.jl = d_jl; ca.jr = d_jr; ca.js = d_js;
+        ca.J = J; ca.stranded = stranded ? 1 : 0; ca.pb = pb; ca.vb = vb; ca.lo = vb; ca.hi = vb + 1 + pb + cb; ca.n_chrom = n_chrom;
+        ca.ka = ka; ca.kb = kb;
+        ca.hist = (uint32_t*)(wb + w_chist); ca.dtot = (uint32_t*)(wb + w_dtot); ca.parts = (uint32_t*)(wb + w_parts);
+        ca.bar = (uint32_t*)(wb + w_bar); ca.cnt = d_cnt;
+        ca.site_of = site_of; ca.inc_eid = inc_eid; ca.e_src = e_src; ca.ncp = ncp; ca.rp_cnt = c1; ca.rp_cur = c2;
+        ca.loc_rp = (uint32_t*)(wb + w_l3);
+        static const bool want_stamps = std::getenv("SPLISER_K1_STAMPS") != nullptr;      // phase timeline of CTA 0 (diagnostics)
+        ca.stamps = want_stamps ? (uint32_t*)(wb + w_stamps) : nullptr;
+        ca.cap = (uint32_t)std::min<size_t>(m.cap_c, 0xffffffffu);
+        ca.g = g;
+        void* params[] = {(void*)&ca};
+        SPL_LAUNCH;
+        GB_CU(cudaLaunchCooperativeKernel((const void*)k_gb_coop, dim3((unsigned)coop_g), dim3(CO_THREADS), params, CO_SMEM, st));
+        { SPL_LAUNCH; k_gb_sb_fill<<<148 * 8, 256, 0, st>>>(g, n_chrom, d_cnt); }
+        GB_CU(cudaGetLastError());
+        if (want_stamps && phase == 1) {
+            uint32_t h[CO_STAMPS] = {0};
+            GB_CU(cudaMemsetAsync(wb + w_stamps, 0, sizeof(h), st));
+            SPL_LAUNCH;
+            GB_CU(cudaLaunchCooperativeKernel((const void*)k_gb_coop, dim3((unsigned)coop_g), dim3(CO_THREADS), params, CO_SMEM, st));
+            GB_CU(cudaMemcpyAsync(h, wb + w_stamps, sizeof(h), cudaMemcpyDeviceToHost, st));
+            GB_CU(cudaStreamSynchronize(st));
+            fprintf(stderr, "[k1 stamps, us since kernel start, grid %d]", coop_g);
+            for (int q = 1; q < CO_STAMPS && h[q]; ++q) fprintf(stderr, " %.1f", (double)(uint32_t)(h[q] - h[0]) * 1e-3);
+            fprintf(stderr, "\n");
+        }
+    } else {
     // ---- A: sites
     GB_CU(cudaMemsetAsync(d_cnt + 6, 0, 4, st));
     { SPL_LAUNCH; k_gb_keys_a<<<cdiv(J, 256), 256, 0, st>>>(d_jc, d_jl, d_jr, d_js, J, stranded ? 1 : 0, pb, vb, ka); }
@@ -755,6 +1336,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     { SPL_LAUNCH; k_gb_rp_fill<<<cdiv(n2 + 2, 256), 256, 0, st>>>(g, d_cnt, e_src, c1, c2); }
     { SPL_LAUNCH; k_gb_sb_fill<<<148 * 8, 256, 0, st>>>(g, n_chrom, d_cnt); }
     GB_CU(cudaGetLastError());
+    }
     if (phase == 2) return true;                                           // timed rebuild of a table whose sizes are known
 
     GB_CU(cudaMemcpyAsync(m.h_cnt, d_cnt, 64, cudaMemcpyDeviceToHost, st));
