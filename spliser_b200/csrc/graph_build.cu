@@ -549,7 +549,7 @@ struct Carve {
 
 // ---- K1 as ONE persistent cooperative kernel -----------------------------------------------------------------------
 // The launches above are 3 - 17 us each for tables of 10^5 - 10^6 keys: two dozen of them have a floor of ~0.2 ms whatever the
-// size of the table.  Here two CTAs per SM walk through the same phases, separated by grid-wide barriers
+// size of the table.  Here one CTA per SM walks through the same phases, separated by grid-wide barriers
 // (14 of them) instead of kernel boundaries; every CTA owns one contiguous slice of the keys and, later, of the sites (a warp
 // one run of the slice's keys in the sort, a thread one run of the slice's sites in the per-site phases: no block-wide
 // synchronisation inside the loops, the warps hide each other's latency):
@@ -560,7 +560,7 @@ struct Carve {
 // The bin index (up to 5e7 entries on GRCh38) keeps its own wide launch behind it.  Launched with
 // cudaLaunchCooperativeKernel (co-residency guaranteed by the driver); the launch-per-phase path above stays as the fallback
 // (SPLISER_K1_LAUNCHES=1, or a device without cooperative launch) and the two are held to the same table by the tests.
-constexpr int CO_THREADS = 512, CO_WARPS = CO_THREADS / 32, CO_MAX_G = CO_THREADS, CO_STAMPS = 24, CO_KB = 4;
+constexpr int CO_THREADS = 512, CO_WARPS = CO_THREADS / 32, CO_MAX_G = CO_THREADS, CO_STAMPS = 24, CO_KB = 4, CO_WL = RS_BINS / 2;
 static_assert(RS_BINS == 2 * CO_THREADS, "digit prefix: two digits per thread");
 constexpr size_t CO_SMEM = ((size_t)CO_WARPS * RS_BINS + 32 + 2 * CO_MAX_G) * sizeof(uint32_t);
 
@@ -615,6 +615,28 @@ __device__ __forceinline__ uint32_t co_block_excl(uint32_t v, uint32_t* s_w, uin
     __syncthreads();
     total = tot;
     return wbase + inc - v;
+}
+
+// exclusive prefix of v over the lanes of the warp; total = the warp's sum
+__device__ __forceinline__ uint32_t co_warp_excl(uint32_t v, uint32_t& total) {
+    const int lane = threadIdx.x & 31;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+    total = __shfl_sync(0xffffffffu, inc, 31);
+    return inc - v;
+}
+// exclusive prefix of one (warp-uniform) value per warp over the warps of the CTA; total = the CTA's sum
+__device__ __forceinline__ uint32_t co_warps_excl(uint32_t wtotal, uint32_t* s_w, uint32_t& total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) s_w[warp] = wtotal;
+    __syncthreads();
+    uint32_t wbase = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < CO_WARPS; ++w) { const uint32_t x = s_w[w]; if (w < warp) wbase += x; tot += x; }
+    __syncthreads();
+    total = tot;
+    return wbase;
 }
 
 // after a barrier: s_pre[c] = sum of part[0..c) for every CTA c, total = sum of all; returns this CTA's prefix
@@ -688,6 +710,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
     for (uint32_t i = c * CO_THREADS + tid; i < n2 + 64u; i += G * CO_THREADS) g.site_hot[i] = 0;
     for (uint32_t i = c * CO_THREADS + tid; i < n2 + 4u; i += G * CO_THREADS) { a.rp_cnt[i] = 0u; a.rp_cur[i] = 0u; }
     if (c == 0 && tid == 0) a.cnt[6] = 0u;
+    if (c == 0) for (int ch = tid; ch <= a.n_chrom; ch += CO_THREADS) g.sb_base[ch] = 1;      // a chromosome without sites: its sentinel bin
     const uint32_t K = (n2 + G - 1) / G;                                           // keys per CTA
     const uint32_t k0 = min(c * K, n2), k1 = min(k0 + K, n2);
     const uint32_t Kw = (K + CO_WARPS - 1) / CO_WARPS;                             // ... per warp: [w0, w1), in index order over the warps
@@ -795,66 +818,82 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
     }
     const uint64_t* sk = in;
 
-    // ---- sites: heads of the runs of equal (chromosome, position, strand bit); thread tid owns the keys [e0, e1) of the CTA's slice
-    const uint32_t kq = (K + CO_THREADS - 1) / CO_THREADS;
-    const uint32_t e0 = min(k0 + tid * kq, k1), e1 = min(e0 + kq, k1);
-    uint32_t heads_in_front;                                                        // ... of this thread's first key, inside the CTA
+    // ---- sites: heads of the runs of equal (chromosome, position, strand bit).  The warp keeps its run [w0, w1) of the sorted keys,
+    // lane-consecutive (coalesced loads and stores); heads are ranked by ballot inside the warp, over the warps by their totals
+    const uint32_t full = 0xffffffffu, lt_mask = (1u << lane) - 1u;
+    uint32_t heads_in_front;                                                        // ... of this warp's first key, inside the CTA
     {
         uint32_t h = 0;
-        uint64_t prev = (e0 > 0 && e0 < e1) ? (sk[e0 - 1] >> vb) : 0ull;
-        for (uint32_t eb = e0; eb < e1; eb += CO_KB) {
-            uint64_t kr[CO_KB];
-#pragma unroll
-            for (int q = 0; q < CO_KB; ++q) kr[q] = eb + q < e1 ? sk[eb + q] : 0ull;
+        for (uint32_t eb = w0; eb < w1; eb += 32 * CO_KB) {
+            uint64_t kr[CO_KB], kp[CO_KB];
 #pragma unroll
             for (int q = 0; q < CO_KB; ++q) {
-                if (eb + q >= e1) break;
-                const uint64_t cur = kr[q] >> vb;
-                h += (eb + q == 0 || cur != prev) ? 1u : 0u;
-                prev = cur;
+                const uint32_t e = eb + q * 32 + lane;
+                kr[q] = e < w1 ? sk[e] : 0ull; kp[q] = (e < w1 && e > 0) ? sk[e - 1] : 0ull;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                const uint32_t e = eb + q * 32 + lane;
+                h += __popc(__ballot_sync(full, e < w1 && (e == 0 || (kr[q] >> vb) != (kp[q] >> vb))));
             }
         }
         uint32_t tot;
-        heads_in_front = co_block_excl(h, s_w, tot);
+        heads_in_front = co_warps_excl(h, s_w, tot);
         if (tid == 0) a.parts[0 * CO_MAX_G + c] = tot;
     }
     co_grid_sync(a.bar, target);
     co_stamp(nullptr, a.stamps, stamp++);
     uint32_t S;
     {
-        uint32_t run = co_parts_prefix(a.parts + 0 * CO_MAX_G, s_pre, s_w, S) + heads_in_front;   // heads in front of key e
-        uint64_t prev = (e0 > 0 && e0 < e1) ? (sk[e0 - 1] >> vb) : 0ull;
-        for (uint32_t eb = e0; eb < e1; eb += CO_KB) {
-            uint64_t kr[CO_KB];
+        uint32_t run = co_parts_prefix(a.parts + 0 * CO_MAX_G, s_pre, s_w, S) + heads_in_front;   // heads in front of the round
+        for (uint32_t eb = w0; eb < w1; eb += 32 * CO_KB) {
+            uint64_t kr[CO_KB], kp[CO_KB];
             uint8_t sr[CO_KB];
 #pragma unroll
-            for (int q = 0; q < CO_KB; ++q) kr[q] = eb + q < e1 ? sk[eb + q] : 0ull;
+            for (int q = 0; q < CO_KB; ++q) {
+                const uint32_t e = eb + q * 32 + lane;
+                kr[q] = e < w1 ? sk[e] : 0ull; kp[q] = (e < w1 && e > 0) ? sk[e - 1] : 0ull;
+            }
 #pragma unroll
-            for (int q = 0; q < CO_KB; ++q) sr[q] = eb + q < e1 ? a.js[(uint32_t)(kr[q] & ((1ull << vb) - 1ull)) >> 1] : (uint8_t)0;
+            for (int q = 0; q < CO_KB; ++q) sr[q] = eb + q * 32 + lane < w1 ? a.js[(uint32_t)(kr[q] & ((1ull << vb) - 1ull)) >> 1] : (uint8_t)0;
 #pragma unroll
             for (int q = 0; q < CO_KB; ++q) {
-                if (eb + q >= e1) break;
-                const uint32_t e = eb + q;
+                if (eb + q * 32 >= w1) break;                                       // warp-uniform
+                const uint32_t e = eb + q * 32 + lane;
+                const bool live = e < w1;
                 const uint64_t kk = kr[q];
                 const uint64_t key = kk >> vb;
-                const bool head = e == 0 || key != prev;
-                prev = key;
-                run += head ? 1u : 0u;
-                const uint32_t idx = run - 1u;
-                const uint32_t eid = (uint32_t)(kk & ((1ull << vb) - 1ull));
-                a.site_of[eid] = idx;
-                a.inc_eid[e] = eid;                                                 // endpoint 2 * row + side; its junction partner is eid ^ 1
-                g.inc_line[e] = (int32_t)(eid >> 1);
-                if (head) {
-                    const uint32_t line = eid >> 1;
-                    const uint8_t st = sr[q];
-                    g.site_chrom[idx] = (int32_t)(key >> (pb + 1));
-                    g.site_pos[idx] = (int32_t)((key >> 1) & ((1ull << pb) - 1ull));
-                    g.site_strand[idx] = st;                                        // first-seen strand (stable sort keeps row order)
-                    g.first_line[idx] = (int64_t)line;
-                    g.site_cls[idx] = !a.stranded ? 0 : st == '+' ? 1 : st == '-' ? 2 : 3;
-                    g.inc_off[idx] = (int32_t)e;
+                const bool head = live && (e == 0 || key != (kp[q] >> vb));
+                const uint32_t hb = __ballot_sync(full, head);
+                if (live) {
+                    const uint32_t idx = run + __popc(hb & lt_mask) + (head ? 1u : 0u) - 1u;
+                    const uint32_t eid = (uint32_t)(kk & ((1ull << vb) - 1ull));
+                    a.site_of[eid] = idx;
+                    a.inc_eid[e] = eid;                                             // endpoint 2 * row + side; its junction partner is eid ^ 1
+                    g.inc_line[e] = (int32_t)(eid >> 1);
+                    if (head) {
+                        const uint32_t line = eid >> 1;
+                        const uint8_t st = sr[q];
+                        // chromosome ranges of the table and the bin count of every chromosome, where the chromosome changes
+                        const int ccur = (int)(key >> (pb + 1)), cprev = e == 0 ? -1 : (int)((kp[q] >> vb) >> (pb + 1));
+                        if (ccur != cprev) {
+                            for (int ch = cprev + 1; ch <= ccur; ++ch) g.cs_off[ch] = (int32_t)idx;
+                            if (cprev >= 0) g.sb_base[cprev] = (int32_t)((((kp[q] >> vb) >> 1) & ((1ull << pb) - 1ull)) >> SB_SHIFT) + 2;   // bins + sentinel
+                        }
+                        g.site_chrom[idx] = (int32_t)(key >> (pb + 1));
+                        g.site_pos[idx] = (int32_t)((key >> 1) & ((1ull << pb) - 1ull));
+                        g.site_strand[idx] = st;                                    // first-seen strand (stable sort keeps row order)
+                        g.first_line[idx] = (int64_t)line;
+                        g.site_cls[idx] = !a.stranded ? 0 : st == '+' ? 1 : st == '-' ? 2 : 3;
+                        g.inc_off[idx] = (int32_t)e;
+                    }
+                    if (e == n2 - 1u) {                                             // the last key closes the last chromosome with sites
+                        const int ccur = (int)(key >> (pb + 1));
+                        for (int ch = ccur + 1; ch <= a.n_chrom; ++ch) g.cs_off[ch] = (int32_t)S;
+                        g.sb_base[ccur] = (int32_t)(((key >> 1) & ((1ull << pb) - 1ull)) >> SB_SHIFT) + 2;
+                    }
                 }
+                run += __popc(hb);
             }
         }
         if (c == 0 && tid < 64) g.site_pos[S + tid] = INT_MAX;                     // tail padding (never matches)
@@ -863,91 +902,121 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
     co_grid_sync(a.bar, target);
     co_stamp(nullptr, a.stamps, stamp++);
 
-    // ---- chromosome ranges + layout of the bin index: the last CTA, the others go on (only k_gb_sb_fill reads these)
-    if (c == G - 1) {
-        const int n_chrom = a.n_chrom;
-        for (int ch = warp; ch <= n_chrom; ch += CO_WARPS) {
-            int lo = 0, hi = (int)S;                                                // first site with chromosome >= ch lies in [lo, hi]
-            while (hi - lo > 0) {
-                const int step = (hi - lo + 32) / 33;
-                const int at = min(lo + (lane + 1) * step - 1, hi - 1);
-                const bool ge = g.site_chrom[at] >= ch;
-                const uint32_t bal = __ballot_sync(0xffffffffu, ge);
-                if (bal == 0u) { lo = min(lo + 32 * step, hi); if (lo >= hi) break; continue; }
-                const int first = __ffs(bal) - 1;
-                hi = min(lo + (first + 1) * step - 1, hi - 1);
-                lo = first ? min(lo + first * step, hi) : lo;
-                if (step == 1) { lo = hi; break; }
-            }
-            if (lane == 0) g.cs_off[ch] = lo;
+    // ---- layout of the bin index: running sum of the chromosomes' bin counts, one warp of the last CTA (only k_gb_sb_fill reads it)
+    if (c == G - 1 && warp == 0) {
+        uint32_t nbins = 0;
+        for (int cb0 = 0; cb0 < a.n_chrom; cb0 += 32) {
+            const int ch = cb0 + lane;
+            const uint32_t v = ch < a.n_chrom ? (uint32_t)g.sb_base[ch] : 0u;
+            uint32_t wt;
+            const uint32_t ex = co_warp_excl(v, wt);
+            if (ch < a.n_chrom) g.sb_base[ch] = (int32_t)(nbins + ex);
+            nbins += wt;
         }
-        __syncthreads();
-        for (int ch = tid; ch < n_chrom; ch += CO_THREADS) {
-            const int32_t q0 = g.cs_off[ch], q1 = g.cs_off[ch + 1];
-            g.sb_base[ch] = (q1 > q0 ? (max(g.site_pos[q1 - 1], 0) >> SB_SHIFT) + 1 : 0) + 1;
-        }
-        __syncthreads();
-        if (tid == 0) {
-            int32_t nbins = 0;
-            for (int ch = 0; ch < n_chrom; ++ch) { const int32_t v = g.sb_base[ch]; g.sb_base[ch] = nbins; nbins += v; }
-            g.sb_base[n_chrom] = nbins;
-            a.cnt[1] = (uint32_t)nbins;
-        }
+        if (lane == 0) { g.sb_base[a.n_chrom] = (int32_t)nbins; a.cnt[1] = nbins; }
     }
 
-    // ---- per-site phases: CTA c owns the sites [s0, s1), thread tid the run [t0, t1) of them
+    // ---- per-site phases: CTA c owns the sites [s0, s1), warp w the run [t0, t1) of them, lane-consecutive
+    // Every loop below takes CO_KB rounds of 32 sites (or entries) at a time and loads level by level -- all of a level's loads are in
+    // flight together.  Sites of degree one (nearly all of them) take the short way, the others the general loops of the
+    // launch-per-phase kernels.
     const uint32_t Ks = max((S + G - 1) / G, 1u);
     const uint32_t s0 = min(c * Ks, S), s1 = min(s0 + Ks, S);
-    const uint32_t sq = (Ks + CO_THREADS - 1) / CO_THREADS;
-    const uint32_t t0 = min(s0 + tid * sq, s1), t1 = min(t0 + sq, s1);
-    // Every loop below takes CO_KB sites (or entries) at a time and loads level by level -- all of a level's loads are in flight
-    // together, so a batch costs one memory round trip per level instead of one per site and level.  Sites of degree one (nearly
-    // all of them) take the short way, the others the general loops of the launch-per-phase kernels.
+    const uint32_t Kws = (Ks + CO_WARPS - 1) / CO_WARPS;
+    const uint32_t t0 = min(s0 + (uint32_t)warp * Kws, s1), t1 = min(t0 + Kws, s1);
+    // sites that need the general loops go to the warp's list (the sort's counters are free now) and are taken 32 at a time: a warp
+    // pays the long dependent chains once per 32 such sites, not once per round that holds one
+    uint32_t* wl = co_sm + (uint32_t)warp * RS_BINS;                                // [CO_WL] (site, offset) pairs
+    uint32_t ln = 0;                                                                // entries in the list (warp-uniform)
     uint32_t pt_front;                                                              // Partners entries in front of site t0, inside the CTA
     {
         uint32_t run = 0;
-        for (uint32_t tb = t0; tb < t1; tb += CO_KB) {
-            uint32_t io[CO_KB + 1];
-#pragma unroll
-            for (int q = 0; q <= CO_KB; ++q) io[q] = tb + q <= t1 ? (uint32_t)g.inc_off[tb + q] : 0u;
+        auto drain = [&]() {
+            __syncwarp();
+            for (uint32_t i0 = 0; i0 < ln; i0 += 32) {
+                uint32_t u = 0;
+                if (i0 + lane < ln) {
+                    const uint32_t t = wl[2u * (i0 + lane)];
+                    const uint32_t o = (uint32_t)g.inc_off[t];
+                    u = co_pt_count_site(a, o, (uint32_t)g.inc_off[t + 1] - o);
+                    a.ncp[t] = u;
+                }
+                run += __reduce_add_sync(full, u);
+            }
+            __syncwarp();
+            ln = 0;
+        };
+        for (uint32_t tb = t0; tb < t1; tb += 32 * CO_KB) {
+            uint32_t io[CO_KB], io1[CO_KB];
 #pragma unroll
             for (int q = 0; q < CO_KB; ++q) {
-                if (tb + q >= t1) break;
-                const uint32_t d = io[q + 1] - io[q];
-                run += d == 1u ? 1u : co_pt_count_site(a, io[q], d);
+                const uint32_t t = tb + q * 32 + lane;
+                io[q] = t < t1 ? (uint32_t)g.inc_off[t] : 0u; io1[q] = t < t1 ? (uint32_t)g.inc_off[t + 1] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                const uint32_t t = tb + q * 32 + lane;
+                const uint32_t d = io1[q] - io[q];
+                const bool one = t < t1 && d == 1u, gen = t < t1 && d != 1u;
+                if (one) a.ncp[t] = 1u;                                             // ncp: scratch until the competitors
+                run += __popc(__ballot_sync(full, one));
+                const uint32_t gm = __ballot_sync(full, gen);
+                if (gm) {
+                    if (ln + 32u > (uint32_t)CO_WL) drain();
+                    if (gen) wl[2u * (ln + __popc(gm & lt_mask))] = t;
+                    ln += __popc(gm);
+                }
             }
         }
+        drain();
         uint32_t tot;
-        pt_front = co_block_excl(run, s_w, tot);
+        pt_front = co_warps_excl(run, s_w, tot);
         if (tid == 0) a.parts[1 * CO_MAX_G + c] = tot;
     }
     co_grid_sync(a.bar, target);
     co_stamp(nullptr, a.stamps, stamp++);
     uint32_t E;
     {
-        uint32_t x = co_parts_prefix(a.parts + 1 * CO_MAX_G, s_pre, s_w, E) + pt_front;
-        for (uint32_t tb = t0; tb < t1; tb += CO_KB) {
-            uint32_t io[CO_KB + 1], eid[CO_KB], pp[CO_KB];
+        uint32_t xrun = co_parts_prefix(a.parts + 1 * CO_MAX_G, s_pre, s_w, E) + pt_front;
+        auto drain = [&]() {
+            __syncwarp();
+            for (uint32_t i = lane; i < ln; i += 32) {
+                const uint32_t t = wl[2u * i], x = wl[2u * i + 1u];
+                const uint32_t o = (uint32_t)g.inc_off[t];
+                co_pt_fill_site(a, g, t, o, (uint32_t)g.inc_off[t + 1] - o, x);
+            }
+            __syncwarp();
+            ln = 0;
+        };
+        for (uint32_t tb = t0; tb < t1; tb += 32 * CO_KB) {
+            uint32_t io[CO_KB], io1[CO_KB], uu[CO_KB], eid[CO_KB], pp[CO_KB];
             int32_t pos[CO_KB], posm[CO_KB], chr[CO_KB], chrm[CO_KB];
 #pragma unroll
-            for (int q = 0; q <= CO_KB; ++q) io[q] = tb + q <= t1 ? (uint32_t)g.inc_off[tb + q] : 0u;
+            for (int q = 0; q < CO_KB; ++q) {
+                const uint32_t t = tb + q * 32 + lane;
+                io[q] = t < t1 ? (uint32_t)g.inc_off[t] : 0u; io1[q] = t < t1 ? (uint32_t)g.inc_off[t + 1] : 0u; uu[q] = t < t1 ? a.ncp[t] : 0u;
+            }
 #pragma unroll
-            for (int q = 0; q < CO_KB; ++q) eid[q] = tb + q < t1 ? a.inc_eid[io[q]] : 0u;
+            for (int q = 0; q < CO_KB; ++q) eid[q] = tb + q * 32 + lane < t1 ? a.inc_eid[io[q]] : 0u;
 #pragma unroll
-            for (int q = 0; q < CO_KB; ++q) pp[q] = tb + q < t1 ? a.site_of[eid[q] ^ 1u] : 0u;
+            for (int q = 0; q < CO_KB; ++q) pp[q] = tb + q * 32 + lane < t1 ? a.site_of[eid[q] ^ 1u] : 0u;
 #pragma unroll
             for (int q = 0; q < CO_KB; ++q) {
-                const bool lv = tb + q < t1;
+                const bool lv = tb + q * 32 + lane < t1 && io1[q] - io[q] == 1u;
                 pos[q] = lv ? g.site_pos[pp[q]] : 0; chr[q] = lv ? g.site_chrom[pp[q]] : 0;
                 posm[q] = lv && pp[q] > 0 ? g.site_pos[pp[q] - 1] : -1; chrm[q] = lv && pp[q] > 0 ? g.site_chrom[pp[q] - 1] : -1;
             }
 #pragma unroll
             for (int q = 0; q < CO_KB; ++q) {
-                if (tb + q >= t1) break;
-                const uint32_t t = tb + q, o = io[q], d = io[q + 1] - o;
-                g.pt_off[t] = (int32_t)x;
-                g.pt_off64[t] = (int64_t)x;
-                if (d == 1u) {
+                if (tb + q * 32 >= t1) break;                                       // warp-uniform
+                const uint32_t t = tb + q * 32 + lane;
+                uint32_t wt;
+                const uint32_t x = xrun + co_warp_excl(uu[q], wt);
+                xrun += wt;
+                const uint32_t o = io[q], d = io1[q] - o;
+                const bool live = t < t1, gen = live && d != 1u;
+                if (live) { g.pt_off[t] = (int32_t)x; g.pt_off64[t] = (int64_t)x; }
+                if (live && !gen) {
                     g.pt_site[x] = (int32_t)pp[q];
                     g.pc_pos[x] = pos[q];
                     g.einc_beg[x] = (int32_t)o;
@@ -955,12 +1024,16 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
                     g.einc_end[x] = (int32_t)(o + 1u);
                     a.e_src[x] = t;
                     atomicAdd(a.rp_cnt + ((pp[q] > 0 && posm[q] == pos[q] && chrm[q] == chr[q]) ? pp[q] - 1u : pp[q]), 1u);
-                    ++x;
-                } else {
-                    x = co_pt_fill_site(a, g, t, o, d, x);
+                }
+                const uint32_t gm = __ballot_sync(full, gen);
+                if (gm) {
+                    if (ln + 32u > (uint32_t)CO_WL) drain();
+                    if (gen) { const uint32_t i = ln + __popc(gm & lt_mask); wl[2u * i] = t; wl[2u * i + 1u] = x; }
+                    ln += __popc(gm);
                 }
             }
         }
+        drain();
         if (c == 0 && tid == 0) { g.pt_off[S] = (int32_t)E; g.pt_off64[S] = (int64_t)E; a.cnt[2] = E; }
     }
     co_grid_sync(a.bar, target);
@@ -968,50 +1041,71 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
     uint32_t cp_front;
     {   // competitors counted; the reverse-partner counts of the own sites are final since the barrier
         uint32_t run = 0, run2 = 0;
-        for (uint32_t tb = t0; tb < t1; tb += CO_KB) {
-            uint32_t xo[CO_KB + 1], pp[CO_KB], po0[CO_KB], po1[CO_KB], rc[CO_KB];
-#pragma unroll
-            for (int q = 0; q <= CO_KB; ++q) xo[q] = tb + q <= t1 ? (uint32_t)g.pt_off[tb + q] : 0u;
-#pragma unroll
-            for (int q = 0; q < CO_KB; ++q) { rc[q] = tb + q < t1 ? a.rp_cnt[tb + q] : 0u; pp[q] = tb + q < t1 ? (uint32_t)g.pt_site[xo[q]] : 0u; }
-#pragma unroll
-            for (int q = 0; q < CO_KB; ++q) { po0[q] = tb + q < t1 ? (uint32_t)g.pt_off[pp[q]] : 0u; po1[q] = tb + q < t1 ? (uint32_t)g.pt_off[pp[q] + 1u] : 0u; }
+        auto drain = [&]() {
+            __syncwarp();
+            for (uint32_t i0 = 0; i0 < ln; i0 += 32) {
+                uint32_t u = 0;
+                if (i0 + lane < ln) {
+                    const uint32_t t = wl[2u * (i0 + lane)];
+                    u = co_cp_count_site(g, t);
+                    a.ncp[t] = u;
+                }
+                run += __reduce_add_sync(full, u);
+            }
+            __syncwarp();
+            ln = 0;
+        };
+        for (uint32_t tb = t0; tb < t1; tb += 32 * CO_KB) {
+            uint32_t xo[CO_KB], xo1[CO_KB], pp[CO_KB], po0[CO_KB], po1[CO_KB], rc[CO_KB];
 #pragma unroll
             for (int q = 0; q < CO_KB; ++q) {
-                if (tb + q >= t1) break;
-                const uint32_t t = tb + q;
+                const uint32_t t = tb + q * 32 + lane;
+                xo[q] = t < t1 ? (uint32_t)g.pt_off[t] : 0u; xo1[q] = t < t1 ? (uint32_t)g.pt_off[t + 1] : 0u; rc[q] = t < t1 ? a.rp_cnt[t] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) pp[q] = tb + q * 32 + lane < t1 ? (uint32_t)g.pt_site[xo[q]] : 0u;
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                const bool lv = tb + q * 32 + lane < t1;
+                po0[q] = lv ? (uint32_t)g.pt_off[pp[q]] : 0u; po1[q] = lv ? (uint32_t)g.pt_off[pp[q] + 1u] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (tb + q * 32 >= t1) break;                                       // warp-uniform
+                const uint32_t t = tb + q * 32 + lane;
                 // one partner whose only partner is this site: nobody competes
-                const uint32_t u = (xo[q + 1] - xo[q] == 1u && po1[q] - po0[q] == 1u) ? 0u : co_cp_count_site(g, t);
-                a.ncp[t] = u;
-                a.loc_rp[t] = run2;                                                 // inside the thread for now
-                run += u;
-                run2 += rc[q];
+                const bool live = t < t1, none = live && xo1[q] - xo[q] == 1u && po1[q] - po0[q] == 1u, gen = live && !none;
+                if (none) a.ncp[t] = 0u;
+                uint32_t wt2;
+                const uint32_t ex2 = co_warp_excl(rc[q], wt2);
+                if (live) a.loc_rp[t] = run2 + ex2;                                 // inside the warp for now
+                run2 += wt2;
+                const uint32_t gm = __ballot_sync(full, gen);
+                if (gm) {
+                    if (ln + 32u > (uint32_t)CO_WL) drain();
+                    if (gen) wl[2u * (ln + __popc(gm & lt_mask))] = t;
+                    ln += __popc(gm);
+                }
             }
         }
+        drain();
         uint32_t tot, tot2;
-        cp_front = co_block_excl(run, s_w, tot);
-        const uint32_t rp_front = co_block_excl(run2, s_w, tot2);
-        for (uint32_t t = t0; t < t1; ++t) a.loc_rp[t] += rp_front;                 // read by other CTAs after the barrier
+        cp_front = co_warps_excl(run, s_w, tot);
+        const uint32_t rp_front = co_warps_excl(run2, s_w, tot2);
+        for (uint32_t t = t0 + lane; t < t1; t += 32) a.loc_rp[t] += rp_front;      // read by other CTAs after the barrier
         if (tid == 0) { a.parts[2 * CO_MAX_G + c] = tot; a.parts[3 * CO_MAX_G + c] = tot2; }
     }
     co_grid_sync(a.bar, target);
     co_stamp(nullptr, a.stamps, stamp++);
     {
         uint32_t C, RP;
-        uint32_t x = co_parts_prefix(a.parts + 2 * CO_MAX_G, s_pre, s_w, C) + cp_front;
+        uint32_t xrun = co_parts_prefix(a.parts + 2 * CO_MAX_G, s_pre, s_w, C) + cp_front;
         const uint32_t rpb = co_parts_prefix(a.parts + 3 * CO_MAX_G, s_pre2, s_w, RP);
-        for (uint32_t tb = t0; tb < t1; tb += CO_KB) {
-            uint32_t nc[CO_KB], lr[CO_KB];
-#pragma unroll
-            for (int q = 0; q < CO_KB; ++q) { nc[q] = tb + q < t1 ? a.ncp[tb + q] : 0u; lr[q] = tb + q < t1 ? a.loc_rp[tb + q] : 0u; }
-#pragma unroll
-            for (int q = 0; q < CO_KB; ++q) {
-                if (tb + q >= t1) break;
-                const uint32_t t = tb + q;
-                g.cp_off[t] = (int32_t)x;
-                g.cp_off64[t] = (int64_t)x;
-                g.rp_off[t] = (int32_t)(rpb + lr[q]);
-                if (nc[q] == 0u) continue;
+        auto drain = [&]() {
+            __syncwarp();
+            for (uint32_t i = lane; i < ln; i += 32) {
+                const uint32_t t = wl[2u * i];
+                uint32_t x = wl[2u * i + 1u];
                 const int32_t tp = g.site_pos[t];
                 for (int32_t last = INT_MIN;;) {
                     last = next_competitor(g, g.pt_off, t, tp, last);
@@ -1020,7 +1114,38 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
                     ++x;
                 }
             }
+            __syncwarp();
+            ln = 0;
+        };
+        for (uint32_t tb = t0; tb < t1; tb += 32 * CO_KB) {
+            uint32_t nc[CO_KB], lr[CO_KB];
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                const uint32_t t = tb + q * 32 + lane;
+                nc[q] = t < t1 ? a.ncp[t] : 0u; lr[q] = t < t1 ? a.loc_rp[t] : 0u;
+            }
+#pragma unroll
+            for (int q = 0; q < CO_KB; ++q) {
+                if (tb + q * 32 >= t1) break;                                       // warp-uniform
+                const uint32_t t = tb + q * 32 + lane;
+                uint32_t wt;
+                const uint32_t x = xrun + co_warp_excl(nc[q], wt);
+                xrun += wt;
+                const bool live = t < t1, gen = live && nc[q] != 0u;
+                if (live) {
+                    g.cp_off[t] = (int32_t)x;
+                    g.cp_off64[t] = (int64_t)x;
+                    g.rp_off[t] = (int32_t)(rpb + lr[q]);
+                }
+                const uint32_t gm = __ballot_sync(full, gen);
+                if (gm) {
+                    if (ln + 32u > (uint32_t)CO_WL) drain();
+                    if (gen) { const uint32_t i = ln + __popc(gm & lt_mask); wl[2u * i] = t; wl[2u * i + 1u] = x; }
+                    ln += __popc(gm);
+                }
+            }
         }
+        drain();
         if (c == 0 && tid == 0) {
             g.cp_off[S] = (int32_t)C; g.cp_off64[S] = (int64_t)C; g.rp_off[S] = (int32_t)RP;
             a.cnt[4] = C; a.cnt[5] = RP;
@@ -1067,7 +1192,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
     }
 }
 
-// CTAs of k_gb_coop on the current device (two per SM), 0 when the device cannot run it
+// CTAs of k_gb_coop on the current device (one per SM), 0 when the device cannot run it
 int coop_grid() {
     static std::atomic<int> grid_of[64];
     int dev = 0;
@@ -1081,7 +1206,9 @@ int coop_grid() {
     if (coop && cudaFuncSetAttribute((const void*)k_gb_coop, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)CO_SMEM) == cudaSuccess)
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_gb_coop, CO_THREADS, CO_SMEM);
     cudaGetLastError();
-    int want = 2;                                                                  // CTAs per SM (the phases are latency-bound: more warps per SM)
+    // one CTA per SM: measured against two on configs[1] (474k keys): 91 vs 96 us -- the barriers (3 - 4 us each with 148 arrivals,
+    // more with 296) weigh more than the extra warps bring; SPLISER_K1_CTAS_PER_SM=2 for experiments
+    int want = 1;
     if (const char* f = std::getenv("SPLISER_K1_CTAS_PER_SM")) want = std::max(1, atoi(f));
     gsz = (coop && per_sm >= 1 && sms >= 1) ? std::min(sms * std::min(per_sm, want), CO_MAX_G) : -1;
     if (const char* f = std::getenv("SPLISER_K1_LAUNCHES")) if (f[0] == '1') gsz = -1;

@@ -349,6 +349,56 @@ def test_host_and_device_graph_builders_agree(ctx, monkeypatch):
         assert len(dev["pos"]) > 1000 and len(dev["comp_pos"]) > 0
 
 
+def test_cooperative_and_per_phase_graph_builds_agree(ctx, tmp_path):
+    """K1 runs as ONE cooperative kernel (k_gb_coop); SPLISER_K1_LAUNCHES=1 selects the launch-per-phase build it replaced (the
+    choice is taken once per process, hence the child process).  Both must give the same table in every column -- stranded and
+    unstranded, a table with hub sites (many partners per site: the general per-site loops) and a one-junction table."""
+    import json
+    import os
+    import subprocess
+    import sys
+    import textwrap
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = tmp_path / "k1.py"
+    script.write_text(textwrap.dedent('''
+        import hashlib, json, sys
+        sys.path.insert(0, %r)
+        import numpy as np
+        import spliser_b200
+        from spliser_b200 import Junctions, synth
+        from oracle import c_oracle
+        out = {}
+        with spliser_b200.Context(0) as ctx:
+            for name, stranded in (("s", True), ("u", False)):
+                w = synth.generate(synth.config_small(150_000, seed=501 + stranded, stranded=stranded, paired=stranded))
+                j = w.junctions
+                cases = {"full": j, "one": Junctions(j.chrom[:1], j.left[:1], j.right[:1], j.score[:1], j.strand[:1])}
+                # hubs: every 7th junction gets the left end of its predecessor on the same chromosome
+                left = j.left.copy()
+                for i in range(7, len(left), 7):
+                    if j.chrom[i] == j.chrom[i - 1] and left[i - 1] < j.right[i]: left[i] = left[i - 1]
+                cases["hubs"] = Junctions(j.chrom, left, j.right, j.score, j.strand)
+                for cname, jj in cases.items():
+                    t = c_oracle.table_dict(ctx.process_records(w.records, len(w.chroms), jj, w.flags | 4))
+                    assert ctx.stats()["graph_on_device"] == 1.0
+                    d = c_oracle.diff_tables(t, c_oracle.process(w.records, len(w.chroms), jj, w.flags | 4, threads=8))
+                    assert d is None, (name, cname, d)
+                    h = hashlib.sha256()
+                    for k in sorted(t):
+                        h.update(k.encode()); h.update(np.ascontiguousarray(t[k]).tobytes())
+                    out[name + "/" + cname] = [h.hexdigest(), int(len(t["pos"])), int(len(t["comp_pos"]))]
+        print("DIGESTS " + json.dumps(out))
+    ''' % ROOT))
+    got = {}
+    for mode in ("0", "1"):
+        env = dict(os.environ, SPLISER_K1_LAUNCHES=mode)
+        res = subprocess.run([sys.executable, str(script)], capture_output=True, text=True, timeout=600, env=env)
+        assert res.returncode == 0, res.stdout[-1500:] + res.stderr[-1500:]
+        got[mode] = json.loads([l for l in res.stdout.splitlines() if l.startswith("DIGESTS ")][-1][8:])
+    assert got["0"] == got["1"], (got["0"], got["1"])
+    assert got["0"]["s/hubs"][1] > 1000 and got["0"]["s/hubs"][2] > got["0"]["s/full"][2]      # hubs make competitors
+
+
 def test_c4_shaped_recount_vs_c_oracle(ctx):
     """BASELINE configs[3] shape at reduced size: K samples of one genome (own reads, own junction subset); every site
     of the merged table that a sample lacks is re-counted in that sample's reads with the partner / competitor
