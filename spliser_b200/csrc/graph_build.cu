@@ -1193,8 +1193,13 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
 }
 
 // CTAs of k_gb_coop on the current device (one per SM), 0 when the device cannot run it
+static std::atomic<int> grid_of[64];
+void coop_disable() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64) grid_of[dev].store(-1);
+}
 int coop_grid() {
-    static std::atomic<int> grid_of[64];
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64) return 0;
@@ -1406,6 +1411,7 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
     }
     if (fresh || !m.ready) { err = "graph build: phase 1 without phase 0"; return false; }
 
+    bool coop_done = false;
     if (coop_g > 0) {
         CoopArgs ca{};
         ca.jc = d_jc; ca.jl = d_jl; ca.jr = d_jr; ca.js = d_js;
@@ -1420,22 +1426,28 @@ bool graph_build_device(GraphBuildMem& m, const int32_t* j_chrom, const int32_t*
         ca.cap = (uint32_t)std::min<size_t>(m.cap_c, 0xffffffffu);
         ca.g = g;
         void* params[] = {(void*)&ca};
-        SPL_LAUNCH;
-        GB_CU(cudaLaunchCooperativeKernel((const void*)k_gb_coop, dim3((unsigned)coop_g), dim3(CO_THREADS), params, CO_SMEM, st));
-        { SPL_LAUNCH; k_gb_sb_fill<<<148 * 8, 256, 0, st>>>(g, n_chrom, d_cnt); }
-        GB_CU(cudaGetLastError());
-        if (want_stamps && phase == 1) {
-            uint32_t h[CO_STAMPS] = {0};
-            GB_CU(cudaMemsetAsync(wb + w_stamps, 0, sizeof(h), st));
-            SPL_LAUNCH;
-            GB_CU(cudaLaunchCooperativeKernel((const void*)k_gb_coop, dim3((unsigned)coop_g), dim3(CO_THREADS), params, CO_SMEM, st));
-            GB_CU(cudaMemcpyAsync(h, wb + w_stamps, sizeof(h), cudaMemcpyDeviceToHost, st));
-            GB_CU(cudaStreamSynchronize(st));
-            fprintf(stderr, "[k1 stamps, us since kernel start, grid %d]", coop_g);
-            for (int q = 1; q < CO_STAMPS && h[q]; ++q) fprintf(stderr, " %.1f", (double)(uint32_t)(h[q] - h[0]) * 1e-3);
-            fprintf(stderr, "\n");
+        // a launch the device refuses (the grid does not fit at once: instrumented builds, a partitioned device) is not an error of
+        // the build: this device takes the launch-per-phase kernels from now on
+        const cudaError_t le = cudaLaunchCooperativeKernel((const void*)k_gb_coop, dim3((unsigned)coop_g), dim3(CO_THREADS), params, CO_SMEM, st);
+        if (le == cudaSuccess) { SPL_LAUNCH; coop_done = true; }
+        else { cudaGetLastError(); coop_disable(); }
+        if (coop_done) {
+            { SPL_LAUNCH; k_gb_sb_fill<<<148 * 8, 256, 0, st>>>(g, n_chrom, d_cnt); }
+            GB_CU(cudaGetLastError());
+            if (want_stamps && phase == 1) {
+                uint32_t h[CO_STAMPS] = {0};
+                GB_CU(cudaMemsetAsync(wb + w_stamps, 0, sizeof(h), st));
+                SPL_LAUNCH;
+                GB_CU(cudaLaunchCooperativeKernel((const void*)k_gb_coop, dim3((unsigned)coop_g), dim3(CO_THREADS), params, CO_SMEM, st));
+                GB_CU(cudaMemcpyAsync(h, wb + w_stamps, sizeof(h), cudaMemcpyDeviceToHost, st));
+                GB_CU(cudaStreamSynchronize(st));
+                fprintf(stderr, "[k1 stamps, us since kernel start, grid %d]", coop_g);
+                for (int q = 1; q < CO_STAMPS && h[q]; ++q) fprintf(stderr, " %.1f", (double)(uint32_t)(h[q] - h[0]) * 1e-3);
+                fprintf(stderr, "\n");
+            }
         }
-    } else {
+    }
+    if (!coop_done) {
     // ---- A: sites
     GB_CU(cudaMemsetAsync(d_cnt + 6, 0, 4, st));
     { SPL_LAUNCH; k_gb_keys_a<<<cdiv(J, 256), 256, 0, st>>>(d_jc, d_jl, d_jr, d_js, J, stranded ? 1 : 0, pb, vb, ka); }
