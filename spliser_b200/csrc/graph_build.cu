@@ -593,7 +593,7 @@ __device__ __forceinline__ void co_grid_sync(uint32_t* bar, uint32_t& target) {
     __syncthreads();
 }
 
-__device__ __forceinline__ void co_stamp(const uint32_t* /*unused*/, uint32_t* stamps, int k) {
+__device__ __forceinline__ void co_stamp(uint32_t* stamps, int k) {
     if (stamps && k < CO_STAMPS && blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -704,7 +704,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
     const int vb = a.vb, pb = a.pb;
     uint32_t target = 0;
     int stamp = 0;
-    co_stamp(nullptr, a.stamps, stamp++);
+    co_stamp(a.stamps, stamp++);
 
     // ---- scratch that the later phases add into; endpoint keys of this CTA's slice
     for (uint32_t i = c * CO_THREADS + tid; i < n2 + 64u; i += G * CO_THREADS) g.site_hot[i] = 0;
@@ -750,7 +750,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
                 a.hist[d * G + c] = h;
             }
             co_grid_sync(a.bar, target);
-            co_stamp(nullptr, a.stamps, stamp++);
+            co_stamp(a.stamps, stamp++);
             // one warp per digit: exclusive scan of the digit's counts over the CTAs, digit total
             for (uint32_t d = c + G * (uint32_t)warp; d < nb; d += G * CO_WARPS) {
                 uint32_t v[CO_MAX_G / 32];
@@ -770,7 +770,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
                 if (lane == 0) a.dtot[d] = run;
             }
             co_grid_sync(a.bar, target);
-            co_stamp(nullptr, a.stamps, stamp++);
+            co_stamp(a.stamps, stamp++);
             {   // base of digit d for this CTA = keys with a smaller digit + keys with digit d in the CTAs in front; then per warp
                 const uint32_t d0 = 2u * tid;
                 const uint32_t v0 = d0 < nb ? a.dtot[d0] : 0u, v1 = d0 + 1u < nb ? a.dtot[d0 + 1u] : 0u;
@@ -812,7 +812,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
                 }
             }
             co_grid_sync(a.bar, target);
-            co_stamp(nullptr, a.stamps, stamp++);
+            co_stamp(a.stamps, stamp++);
             uint64_t* t = in; in = out; out = t;
         }
     }
@@ -842,7 +842,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
         if (tid == 0) a.parts[0 * CO_MAX_G + c] = tot;
     }
     co_grid_sync(a.bar, target);
-    co_stamp(nullptr, a.stamps, stamp++);
+    co_stamp(a.stamps, stamp++);
     uint32_t S;
     {
         uint32_t run = co_parts_prefix(a.parts + 0 * CO_MAX_G, s_pre, s_w, S) + heads_in_front;   // heads in front of the round
@@ -900,7 +900,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
         if (c == 0 && tid == 0) { g.inc_off[S] = (int32_t)n2; a.cnt[0] = S; a.cnt[7] = S + 1u; }
     }
     co_grid_sync(a.bar, target);
-    co_stamp(nullptr, a.stamps, stamp++);
+    co_stamp(a.stamps, stamp++);
 
     // ---- layout of the bin index: running sum of the chromosomes' bin counts, one warp of the last CTA (only k_gb_sb_fill reads it)
     if (c == G - 1 && warp == 0) {
@@ -974,7 +974,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
         if (tid == 0) a.parts[1 * CO_MAX_G + c] = tot;
     }
     co_grid_sync(a.bar, target);
-    co_stamp(nullptr, a.stamps, stamp++);
+    co_stamp(a.stamps, stamp++);
     uint32_t E;
     {
         uint32_t xrun = co_parts_prefix(a.parts + 1 * CO_MAX_G, s_pre, s_w, E) + pt_front;
@@ -1037,7 +1037,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
         if (c == 0 && tid == 0) { g.pt_off[S] = (int32_t)E; g.pt_off64[S] = (int64_t)E; a.cnt[2] = E; }
     }
     co_grid_sync(a.bar, target);
-    co_stamp(nullptr, a.stamps, stamp++);
+    co_stamp(a.stamps, stamp++);
     uint32_t cp_front;
     {   // competitors counted; the reverse-partner counts of the own sites are final since the barrier
         uint32_t run = 0, run2 = 0;
@@ -1096,7 +1096,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
         if (tid == 0) { a.parts[2 * CO_MAX_G + c] = tot; a.parts[3 * CO_MAX_G + c] = tot2; }
     }
     co_grid_sync(a.bar, target);
-    co_stamp(nullptr, a.stamps, stamp++);
+    co_stamp(a.stamps, stamp++);
     {
         uint32_t C, RP;
         uint32_t xrun = co_parts_prefix(a.parts + 2 * CO_MAX_G, s_pre, s_w, C) + cp_front;
@@ -1184,7 +1184,7 @@ __global__ void __launch_bounds__(CO_THREADS, 2) k_gb_coop(const CoopArgs a) {
             }
         }
     }
-    co_stamp(nullptr, a.stamps, stamp++);
+    co_stamp(a.stamps, stamp++);
     __syncthreads();
     if (tid == 0) {
         __threadfence();
