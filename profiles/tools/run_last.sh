@@ -1,6 +1,6 @@
-# proof that the sanitizer runs go through k_gb_coop (the phase timeline is only printed by the cooperative path)
 set -x
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-SPLISER_K1_STAMPS=1 SPLISER_SANITIZE_SMALL=1 timeout 75 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -s -m gpu -k "test_appendix_a_known_answers" -p no:cacheprovider > gpurun_out/san_k1_stamps.log 2>&1
-grep -c "k1 stamps" gpurun_out/san_k1_stamps.log; grep "k1 stamps" gpurun_out/san_k1_stamps.log | head -2; tail -3 gpurun_out/san_k1_stamps.log
+SPLISER_K1_STAMPS=1 timeout 25 python profiles/tools/k1_grch38_stamps.py 8000000 > gpurun_out/k1_grch38_hint.json 2> gpurun_out/k1_grch38_hint.err
+cat gpurun_out/k1_grch38_hint.json; grep stamps gpurun_out/k1_grch38_hint.err
+timeout 12 python -m pytest tests/test_gpu_parity.py -m gpu -x -q --timeout 10 -k "appendix or golden_process_fuzz or graph_builders or dirty" 2>&1 | tail -2
